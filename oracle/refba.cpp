@@ -1,0 +1,1026 @@
+// refba -- CPU ORACLE for the bundle-adjustment hot path of lutao98/SqrtLM-SLAM.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing in the product path (sqrtlm-slam_b200/, include/) may link,
+// import or execute this file; only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline /
+// `--impl reference` legs use it, and only as the checker / the timed CPU baseline.
+//
+// It is a dependency-free FP64 restatement of the reference's default BA back-end (vendored g2o
+// driven by src/backend/g2oOptimizer.cc).  The reference itself cannot be compiled here (needs
+// Eigen, OpenCV, PCL, Ceres, ROS -- none installed, no network), so this is a "port" oracle.
+// PARITY UNPINNED UPSTREAM: the reference has no tests, golden vectors or fixtures;
+// the per-edge arithmetic is additionally pinned against the reference's prebuilt
+// Thirdparty/g2o/lib/libg2o.so where that binary exposes it (see oracle/pin_libg2o.py).
+//
+// Every function cites the reference file:line it follows (paths relative to /root/reference).
+// Eigen is not vendored in the reference; where g2o calls into Eigen (quaternion*vector,
+// Quaterniond(Matrix3d), toRotationMatrix, Matrix3d::inverse, SimplicialLDLT) the published Eigen 3
+// algorithm is restated -- exact-in-exact-arithmetic operations, so only rounding can differ.
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// SE3Quat  (Thirdparty/g2o/g2o/types/se3quat.h)
+// ---------------------------------------------------------------------------------------------
+struct Quat { double x, y, z, w; };
+struct SE3 { Quat r; double t[3]; };
+
+// Eigen::Quaternion::operator*(Quaternion)  (used by se3quat.h:104-110, `result._r*=tr2._r`)
+inline Quat qmul(const Quat& a, const Quat& b) {
+  Quat c;
+  c.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  c.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  c.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+  c.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  return c;
+}
+
+// Eigen::Quaternion::_transformVector: v + w*uv + vec x uv with uv = 2 (vec x v)   (se3quat.h:217-220 `_r*xyz`)
+inline void qrot(const Quat& q, const double v[3], double out[3]) {
+  double uv[3] = {q.y * v[2] - q.z * v[1], q.z * v[0] - q.x * v[2], q.x * v[1] - q.y * v[0]};
+  uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+  out[0] = v[0] + q.w * uv[0] + (q.y * uv[2] - q.z * uv[1]);
+  out[1] = v[1] + q.w * uv[1] + (q.z * uv[0] - q.x * uv[2]);
+  out[2] = v[2] + q.w * uv[2] + (q.x * uv[1] - q.y * uv[0]);
+}
+
+// Eigen::Quaternion::toRotationMatrix
+inline void qtoR(const Quat& q, double R[9]) {
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+  R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+
+// Eigen::Quaterniond(Matrix3d)  (se3quat.h:58, 256)
+inline Quat RtoQ(const double m[9]) {
+  double q[4];  // x y z w
+  double t = m[0] + m[4] + m[8];
+  if (t > 0) {
+    t = std::sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (m[7] - m[5]) * t;
+    q[1] = (m[2] - m[6]) * t;
+    q[2] = (m[3] - m[1]) * t;
+  } else {
+    int i = 0;
+    if (m[4] > m[0]) i = 1;
+    if (m[8] > m[i * 3 + i]) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(m[i * 3 + i] - m[j * 3 + j] - m[k * 3 + k] + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (m[k * 3 + j] - m[j * 3 + k]) * t;
+    q[j] = (m[j * 3 + i] + m[i * 3 + j]) * t;
+    q[k] = (m[k * 3 + i] + m[i * 3 + k]) * t;
+  }
+  return Quat{q[0], q[1], q[2], q[3]};
+}
+
+// SE3Quat::normalizeRotation  (se3quat.h:280-285)
+inline void normalizeRotation(SE3& T) {
+  if (T.r.w < 0) { T.r.x *= -1; T.r.y *= -1; T.r.z *= -1; T.r.w *= -1; }
+  const double n = std::sqrt(T.r.x * T.r.x + T.r.y * T.r.y + T.r.z * T.r.z + T.r.w * T.r.w);
+  T.r.x /= n; T.r.y /= n; T.r.z /= n; T.r.w /= n;
+}
+
+// SE3Quat::operator*  (se3quat.h:104-110)
+inline SE3 se3mul(const SE3& a, const SE3& b) {
+  SE3 r = a;
+  double rt[3];
+  qrot(a.r, b.t, rt);
+  r.t[0] += rt[0]; r.t[1] += rt[1]; r.t[2] += rt[2];
+  r.r = qmul(a.r, b.r);
+  normalizeRotation(r);
+  return r;
+}
+
+// SE3Quat::map  (se3quat.h:217-220)
+inline void se3map(const SE3& T, const double p[3], double out[3]) {
+  qrot(T.r, p, out);
+  out[0] += T.t[0]; out[1] += T.t[1]; out[2] += T.t[2];
+}
+
+inline void mat3mul(const double A[9], const double B[9], double C[9]) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) C[i * 3 + j] = A[i * 3 + 0] * B[0 * 3 + j] + A[i * 3 + 1] * B[1 * 3 + j] + A[i * 3 + 2] * B[2 * 3 + j];
+}
+
+// SE3Quat::exp  (se3quat.h:223-257); update = (omega, upsilon), rotation first.
+inline SE3 se3exp(const double upd[6]) {
+  const double om[3] = {upd[0], upd[1], upd[2]};
+  const double up[3] = {upd[3], upd[4], upd[5]};
+  const double theta = std::sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+  const double Om[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0};  // skew(), se3_ops.hpp:27-47
+  double Om2[9];
+  mat3mul(Om, Om, Om2);
+  double R[9], V[9];
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (theta < 0.00001) {
+    for (int i = 0; i < 9; i++) { R[i] = I[i] + Om[i] + Om2[i]; V[i] = R[i]; }  // sic, se3quat.h:237-243
+  } else {
+    const double a = std::sin(theta) / theta;
+    const double b = (1 - std::cos(theta)) / (theta * theta);
+    const double c = (theta - std::sin(theta)) / (std::pow(theta, 3));
+    for (int i = 0; i < 9; i++) { R[i] = I[i] + a * Om[i] + b * Om2[i]; V[i] = I[i] + b * Om[i] + c * Om2[i]; }
+  }
+  SE3 T;
+  T.r = RtoQ(R);
+  for (int i = 0; i < 3; i++) T.t[i] = V[i * 3 + 0] * up[0] + V[i * 3 + 1] * up[1] + V[i * 3 + 2] * up[2];
+  normalizeRotation(T);  // SE3Quat(const Quaterniond&, const Vector3d&) ctor, se3quat.h:62-64
+  return T;
+}
+
+// ---------------------------------------------------------------------------------------------
+// graph
+// ---------------------------------------------------------------------------------------------
+struct Edge {
+  int pose, point;
+  bool stereo;
+  double obs[3];
+  double info;    // invSigma2: information = invSigma2 * I_d  (g2oOptimizer.cc:226-227, 262-264)
+  double fx, fy, cx, cy, bf;
+  int level = 0;
+  bool robust = false;
+  double delta = 0, dsqr = 0;  // RobustKernelHuber::setDelta, robust_kernel_impl.cpp:65-69
+  double err[3] = {0, 0, 0};   // g2o's Edge::_error: only rewritten by computeError() on ACTIVE edges
+  double Jl[9];                // _jacobianOplusXi (d x 3)
+  double Jp[18];               // _jacobianOplusXj (d x 6)
+  int hpl = -1;                // index of the Hpl block shared by all edges with the same (pose,landmark)
+};
+
+struct TraceRow { double pass, iter, trial, lambda, chi_before, chi_trial, rho, accepted; };
+
+struct Graph {
+  int n_pose = 0, n_point = 0, n_obs = 0;
+  std::vector<SE3> pose;
+  std::vector<uint8_t> fixed;
+  std::vector<double> point;  // 3 per landmark
+  std::vector<Edge> edges;    // insertion order == internalId order == _activeEdges order (sparse_optimizer.cpp:482-487)
+  int threads = 1;
+
+  // ---- active set / index mapping (sparse_optimizer.cpp:166-190, 199-267)
+  std::vector<int> active;        // active edge ids, ascending
+  std::vector<int> pose_slot;     // hessianIndex of pose (or -1: fixed / inactive)
+  std::vector<int> point_slot;    // hessianIndex of landmark minus numPoses (or -1)
+  std::vector<int> slot_pose, slot_point;
+  int Np = 0, Nl = 0;
+
+  // ---- BlockSolver<6,3> storage (block_solver.hpp:143-295)
+  std::vector<double> Hpp, Hll, Hpl, b, x, coeff, bschur, Dinv;
+  std::vector<int> hpl_slot;                 // pose slot of each Hpl block
+  std::vector<int> lm_hpl_ptr, lm_hpl;       // CCS column per landmark: its Hpl blocks sorted by pose slot
+  // reduced system, scalar skyline (envelope) storage of the upper triangle, row-wise on the transposed lower
+  std::vector<int> sky_first;
+  std::vector<int64_t> sky_ptr;
+  std::vector<double> S, Sfac;
+  std::vector<double> diagBackupPose, diagBackupLm;
+
+  // ---- LM state (optimization_algorithm_levenberg.cpp:43-55)
+  double lambda = -1, ni = 2;
+  int nBad = 0;
+  const volatile bool* stop = nullptr;
+
+  // ---- state stack (push/pop/discardTop, sparse_optimizer.cpp:600-613; one level deep is all LM uses)
+  std::vector<SE3> pose_bak;
+  std::vector<double> point_bak;
+
+  std::vector<TraceRow> trace;
+  int cur_pass = 0;
+  double t_solve_s = 0;
+
+  bool terminate() const { return stop ? *stop : false; }  // sparse_optimizer.h:188
+};
+
+// EdgeSE3ProjectXYZ::cam_project / EdgeStereoSE3ProjectXYZ::cam_project
+// (types_six_dof_expmap.cpp:141-157).  The stereo version takes `const float& bf` and computes
+// `const float invz = 1.0f/trans_xyz[2]`: inverse depth is rounded to float32 and `bf*invz` is a
+// float*float product.
+inline void computeError(const Graph& g, Edge& e) {
+  double Xc[3];
+  se3map(g.pose[e.pose], &g.point[3 * e.point], Xc);
+  if (!e.stereo) {
+    // types_six_dof_expmap.h:90-95 + project2d (.cpp:37-42)
+    const double px = Xc[0] / Xc[2], py = Xc[1] / Xc[2];
+    e.err[0] = e.obs[0] - (px * e.fx + e.cx);
+    e.err[1] = e.obs[1] - (py * e.fy + e.cy);
+    e.err[2] = 0;
+  } else {
+    // types_six_dof_expmap.h:122-127 + .cpp:150-157
+    const float bf_f = (float)e.bf;
+    const float invz = (float)(1.0f / Xc[2]);
+    double res[3];
+    res[0] = Xc[0] * invz * e.fx + e.cx;
+    res[1] = Xc[1] * invz * e.fy + e.cy;
+    res[2] = res[0] - (double)(bf_f * invz);
+    e.err[0] = e.obs[0] - res[0];
+    e.err[1] = e.obs[1] - res[1];
+    e.err[2] = e.obs[2] - res[2];
+  }
+}
+
+// BaseEdge::chi2  (base_edge.h:58-61): _error.dot(information()*_error), information = info*I
+inline double chi2(const Edge& e) {
+  if (!e.stereo) return e.err[0] * (e.info * e.err[0]) + e.err[1] * (e.info * e.err[1]);
+  return e.err[0] * (e.info * e.err[0]) + e.err[1] * (e.info * e.err[1]) + e.err[2] * (e.info * e.err[2]);
+}
+
+// isDepthPositive  (types_six_dof_expmap.h:97-101, 129-133)
+inline bool depthPositive(const Graph& g, const Edge& e) {
+  double Xc[3];
+  se3map(g.pose[e.pose], &g.point[3 * e.point], Xc);
+  return Xc[2] > 0.0;
+}
+
+// RobustKernelHuber::robustify  (robust_kernel_impl.cpp:78-91)
+inline void robustify(const Edge& e, double c, double rho[3]) {
+  if (c <= e.dsqr) {
+    rho[0] = c; rho[1] = 1.; rho[2] = 0.;
+  } else {
+    const double sqrte = std::sqrt(c);
+    rho[0] = 2 * sqrte * e.delta - e.dsqr;
+    rho[1] = e.delta / sqrte;
+    rho[2] = -0.5 * rho[1] / c;
+  }
+}
+
+// linearizeOplus  (types_six_dof_expmap.cpp:103-139 mono, 188-234 stereo)
+inline void linearize(const Graph& g, Edge& e) {
+  const SE3& T = g.pose[e.pose];
+  double Xc[3], R[9];
+  se3map(T, &g.point[3 * e.point], Xc);
+  qtoR(T.r, R);
+  const double x = Xc[0], y = Xc[1], z = Xc[2], z_2 = z * z;
+  const double fx = e.fx, fy = e.fy;
+  double* Ji = e.Jl;
+  double* Jj = e.Jp;
+  if (!e.stereo) {
+    // _jacobianOplusXi = -1./z * tmp * R   (.cpp:114-124)
+    const double tmp[6] = {fx, 0, -x / z * fx, 0, fy, -y / z * fy};
+    for (int r = 0; r < 2; r++)
+      for (int c = 0; c < 3; c++) {
+        const double tr = tmp[r * 3 + 0] * R[0 * 3 + c] + tmp[r * 3 + 1] * R[1 * 3 + c] + tmp[r * 3 + 2] * R[2 * 3 + c];
+        Ji[r * 3 + c] = (-1. / z) * tr;
+      }
+    for (int c = 0; c < 3; c++) Ji[6 + c] = 0;
+  } else {
+    for (int c = 0; c < 3; c++) {
+      Ji[0 * 3 + c] = -fx * R[0 * 3 + c] / z + fx * x * R[2 * 3 + c] / z_2;
+      Ji[1 * 3 + c] = -fy * R[1 * 3 + c] / z + fy * y * R[2 * 3 + c] / z_2;
+      Ji[2 * 3 + c] = Ji[0 * 3 + c] - e.bf * R[2 * 3 + c] / z_2;
+    }
+  }
+  Jj[0] = x * y / z_2 * fx;
+  Jj[1] = -(1 + (x * x / z_2)) * fx;
+  Jj[2] = y / z * fx;
+  Jj[3] = -1. / z * fx;
+  Jj[4] = 0;
+  Jj[5] = x / z_2 * fx;
+  Jj[6] = (1 + y * y / z_2) * fy;
+  Jj[7] = -x * y / z_2 * fy;
+  Jj[8] = -x / z * fy;
+  Jj[9] = 0;
+  Jj[10] = -1. / z * fy;
+  Jj[11] = y / z_2 * fy;
+  if (e.stereo) {
+    Jj[12] = Jj[0] - e.bf * y / z_2;
+    Jj[13] = Jj[1] + e.bf * x / z_2;
+    Jj[14] = Jj[2];
+    Jj[15] = Jj[3];
+    Jj[16] = 0;
+    Jj[17] = Jj[5] - e.bf / z_2;
+  } else {
+    for (int c = 0; c < 6; c++) Jj[12 + c] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SparseOptimizer::initializeOptimization(level) + buildIndexMapping + BlockSolver::buildStructure
+// (sparse_optimizer.cpp:199-267, 166-190; block_solver.hpp:143-295)
+// ---------------------------------------------------------------------------------------------
+void initializeOptimization(Graph& g, int level) {
+  g.active.clear();
+  std::vector<uint8_t> pose_active(g.n_pose, 0), point_active(g.n_point, 0);
+  for (int k = 0; k < (int)g.edges.size(); k++) {
+    const Edge& e = g.edges[k];
+    if (level >= 0 && e.level != level) continue;
+    // allVerticesFixed(): landmark vertices are never fixed in BA, so every edge qualifies
+    g.active.push_back(k);
+    pose_active[e.pose] = 1;
+    point_active[e.point] = 1;
+  }
+  // index mapping: non-fixed, non-marginalised vertices first (poses), then marginalised (landmarks),
+  // each in ascending vertex-id order (sortVectorContainers, sparse_optimizer.cpp:482-487)
+  g.pose_slot.assign(g.n_pose, -1);
+  g.point_slot.assign(g.n_point, -1);
+  g.slot_pose.clear();
+  g.slot_point.clear();
+  for (int i = 0; i < g.n_pose; i++)
+    if (pose_active[i] && !g.fixed[i]) { g.pose_slot[i] = (int)g.slot_pose.size(); g.slot_pose.push_back(i); }
+  for (int i = 0; i < g.n_point; i++)
+    if (point_active[i]) { g.point_slot[i] = (int)g.slot_point.size(); g.slot_point.push_back(i); }
+  g.Np = (int)g.slot_pose.size();
+  g.Nl = (int)g.slot_point.size();
+}
+
+void buildStructure(Graph& g) {
+  const int Np = g.Np, Nl = g.Nl;
+  g.Hpp.assign((size_t)Np * 36, 0.0);
+  g.Hll.assign((size_t)Nl * 9, 0.0);
+  g.Dinv.assign((size_t)Nl * 9, 0.0);
+  g.b.assign((size_t)Np * 6 + (size_t)Nl * 3, 0.0);
+  g.x.assign(g.b.size(), 0.0);
+  g.coeff.assign(g.b.size(), 0.0);
+  g.bschur.assign((size_t)Np * 6, 0.0);
+  // Hpl blocks: one per distinct (pose slot, landmark slot) pair among active edges
+  std::vector<std::vector<std::pair<int, int>>> per_lm(Nl);  // (pose slot, block id)
+  g.hpl_slot.clear();
+  for (int k : g.active) {
+    Edge& e = g.edges[k];
+    e.hpl = -1;
+    const int ps = g.pose_slot[e.pose], ls = g.point_slot[e.point];
+    if (ps < 0) continue;
+    auto& lst = per_lm[ls];
+    int found = -1;
+    for (auto& pr : lst)
+      if (pr.first == ps) { found = pr.second; break; }
+    if (found < 0) {
+      found = (int)g.hpl_slot.size();
+      g.hpl_slot.push_back(ps);
+      lst.emplace_back(ps, found);
+    }
+    e.hpl = found;
+  }
+  g.Hpl.assign(g.hpl_slot.size() * 18, 0.0);
+  g.lm_hpl_ptr.assign(Nl + 1, 0);
+  g.lm_hpl.clear();
+  for (int l = 0; l < Nl; l++) {
+    std::sort(per_lm[l].begin(), per_lm[l].end());  // SparseBlockMatrixCCS column: rows ascending
+    for (auto& pr : per_lm[l]) g.lm_hpl.push_back(pr.second);
+    g.lm_hpl_ptr[l + 1] = (int)g.lm_hpl.size();
+  }
+  // Schur pattern -> scalar skyline of the reduced system (upper triangle stored by column == lower by row)
+  std::vector<int> first_blk(Np);
+  for (int i = 0; i < Np; i++) first_blk[i] = i;
+  for (int l = 0; l < Nl; l++) {
+    const int a = g.lm_hpl_ptr[l], bnd = g.lm_hpl_ptr[l + 1];
+    if (bnd <= a) continue;
+    const int mn = g.hpl_slot[g.lm_hpl[a]];
+    for (int k = a; k < bnd; k++) {
+      const int s = g.hpl_slot[g.lm_hpl[k]];
+      first_blk[s] = std::min(first_blk[s], mn);
+    }
+  }
+  g.sky_first.assign((size_t)Np * 6, 0);
+  g.sky_ptr.assign((size_t)Np * 6 + 1, 0);
+  for (int i = 0; i < Np; i++)
+    for (int r = 0; r < 6; r++) {
+      const int row = i * 6 + r;
+      g.sky_first[row] = first_blk[i] * 6;
+      g.sky_ptr[row + 1] = g.sky_ptr[row] + (row - g.sky_first[row] + 1);
+    }
+  g.S.assign((size_t)g.sky_ptr[(size_t)Np * 6], 0.0);
+  g.Sfac = g.S;
+}
+
+inline double& Sat(Graph& g, std::vector<double>& S, int row, int col) {  // row >= col
+  return S[g.sky_ptr[row] + (col - g.sky_first[row])];
+}
+
+// SparseOptimizer::computeActiveErrors (sparse_optimizer.cpp:61-88)
+void computeActiveErrors(Graph& g) {
+  const int n = (int)g.active.size();
+#pragma omp parallel for schedule(static) num_threads(g.threads) if (g.threads > 1)
+  for (int k = 0; k < n; k++) computeError(g, g.edges[g.active[k]]);
+}
+
+// SparseOptimizer::activeRobustChi2 (sparse_optimizer.cpp:100-114): sequential sum in edge order
+double activeRobustChi2(const Graph& g) {
+  double chi = 0.0, rho[3];
+  for (int k : g.active) {
+    const Edge& e = g.edges[k];
+    if (e.robust) {
+      robustify(e, chi2(e), rho);
+      chi += rho[0];
+    } else
+      chi += chi2(e);
+  }
+  return chi;
+}
+
+// BaseBinaryEdge::constructQuadraticForm (base_binary_edge.hpp:55-120); A = Jl (vertex 0 = landmark),
+// B = Jp (vertex 1 = pose).  Products are accumulated in Eigen's fixed-size evaluation order:
+// (A^T * W) * A etc. with W = w * I.
+inline void constructQuadraticForm(Graph& g, Edge& e, double* Hpp, double* bp_base) {
+  const int d = e.stereo ? 3 : 2;
+  const int ls = g.point_slot[e.point];
+  const int ps = g.pose_slot[e.pose];
+  double w = e.info;
+  double omega_r[3];
+  for (int i = 0; i < d; i++) omega_r[i] = -(e.info * e.err[i]);
+  if (e.robust) {
+    double rho[3];
+    robustify(e, chi2(e), rho);
+    w = rho[1] * e.info;  // robustInformation, base_edge.h:96-102 (second-order term commented out)
+    for (int i = 0; i < d; i++) omega_r[i] *= rho[1];
+  }
+  const double* A = e.Jl;
+  const double* B = e.Jp;
+  // landmark: from->b += A^T omega_r ; from->A += A^T W A
+  double* bl = &g.b[(size_t)g.Np * 6 + (size_t)ls * 3];
+  double* Hl = &g.Hll[(size_t)ls * 9];
+  for (int i = 0; i < 3; i++) {
+    double s = 0;
+    for (int r = 0; r < d; r++) s += A[r * 3 + i] * omega_r[r];
+    bl[i] += s;
+    for (int j = 0; j < 3; j++) {
+      double h = 0;
+      for (int r = 0; r < d; r++) h += (A[r * 3 + i] * w) * A[r * 3 + j];
+      Hl[i * 3 + j] += h;
+    }
+  }
+  if (ps >= 0) {
+    double* Wpl = &g.Hpl[(size_t)e.hpl * 18];  // 6x3: B^T W A
+    double* bp = bp_base + (size_t)ps * 6;
+    double* Hp = Hpp + (size_t)ps * 36;
+    for (int i = 0; i < 6; i++) {
+      double s = 0;
+      for (int r = 0; r < d; r++) s += B[r * 6 + i] * omega_r[r];
+      bp[i] += s;
+      for (int j = 0; j < 6; j++) {
+        double h = 0;
+        for (int r = 0; r < d; r++) h += (B[r * 6 + i] * w) * B[r * 6 + j];
+        Hp[i * 6 + j] += h;
+      }
+      for (int j = 0; j < 3; j++) {
+        double h = 0;
+        for (int r = 0; r < d; r++) h += (B[r * 6 + i] * w) * A[r * 3 + j];
+        Wpl[i * 3 + j] += h;
+      }
+    }
+  }
+}
+
+// BlockSolver::buildSystem (block_solver.hpp:502-560)
+void buildSystem(Graph& g) {
+  std::fill(g.b.begin(), g.b.end(), 0.0);
+  std::fill(g.Hpp.begin(), g.Hpp.end(), 0.0);
+  std::fill(g.Hll.begin(), g.Hll.end(), 0.0);
+  std::fill(g.Hpl.begin(), g.Hpl.end(), 0.0);
+  const int n = (int)g.active.size();
+  if (g.threads <= 1) {
+    for (int k = 0; k < n; k++) {
+      Edge& e = g.edges[g.active[k]];
+      linearize(g, e);
+      constructQuadraticForm(g, e, g.Hpp.data(), g.b.data());
+    }
+    return;
+  }
+  // best-effort multi-core variant (g2o's dormant G2O_OPENMP site, block_solver.hpp:526-528): Jacobians in
+  // parallel, landmark-side accumulation is race-free because edges arrive grouped by landmark; pose-side
+  // accumulators are per-thread and reduced afterwards (changes summation order => rounding only).
+#pragma omp parallel for schedule(static) num_threads(g.threads)
+  for (int k = 0; k < n; k++) linearize(g, g.edges[g.active[k]]);
+  // split active edges into landmark-aligned chunks
+  std::vector<int> cut(g.threads + 1, n);
+  cut[0] = 0;
+  for (int t = 1; t < g.threads; t++) {
+    int c = (int)((int64_t)n * t / g.threads);
+    while (c < n && c > 0 && g.edges[g.active[c]].point == g.edges[g.active[c - 1]].point) c++;
+    cut[t] = std::max(c, cut[t - 1]);
+  }
+  std::vector<std::vector<double>> Hloc(g.threads), bloc(g.threads);
+#pragma omp parallel num_threads(g.threads)
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num();
+#else
+    const int t = 0;
+#endif
+    Hloc[t].assign(g.Hpp.size(), 0.0);
+    bloc[t].assign((size_t)g.Np * 6, 0.0);
+    for (int k = cut[t]; k < cut[t + 1]; k++) constructQuadraticForm(g, g.edges[g.active[k]], Hloc[t].data(), bloc[t].data());
+  }
+  for (int t = 0; t < g.threads; t++) {
+    for (size_t i = 0; i < g.Hpp.size(); i++) g.Hpp[i] += Hloc[t][i];
+    for (size_t i = 0; i < (size_t)g.Np * 6; i++) g.b[i] += bloc[t][i];
+  }
+}
+
+// Eigen::Matrix3d::inverse() (cofactor form, compute_inverse_size3_helper)  (block_solver.hpp:389)
+inline void inv3(const double* m, double* inv) {
+  const double c00 = m[4] * m[8] - m[5] * m[7];
+  const double c10 = m[5] * m[6] - m[3] * m[8];
+  const double c20 = m[3] * m[7] - m[4] * m[6];
+  const double det = m[0] * c00 + m[1] * c10 + m[2] * c20;
+  const double invdet = 1.0 / det;
+  inv[0] = c00 * invdet;
+  inv[3] = c10 * invdet;
+  inv[6] = c20 * invdet;
+  inv[1] = (m[2] * m[7] - m[1] * m[8]) * invdet;
+  inv[4] = (m[0] * m[8] - m[2] * m[6]) * invdet;
+  inv[7] = (m[1] * m[6] - m[0] * m[7]) * invdet;
+  inv[2] = (m[1] * m[5] - m[2] * m[4]) * invdet;
+  inv[5] = (m[2] * m[3] - m[0] * m[5]) * invdet;
+  inv[8] = (m[0] * m[4] - m[1] * m[3]) * invdet;
+}
+
+// Eigen::SimplicialLDLT (no pivoting; fails on a zero pivot) on the skyline-stored reduced system
+// (linear_solver_eigen.h:94-124).  AMD ordering is irrelevant to the exact-arithmetic result.
+bool ldltSolve(Graph& g, const double* rhs, double* x) {
+  const int n = g.Np * 6;
+  g.Sfac = g.S;
+  std::vector<double>& L = g.Sfac;  // unit-lower L strictly below the diagonal, D on the diagonal
+  std::vector<double> dinv(n);
+  for (int i = 0; i < n; i++) {
+    const int fi = g.sky_first[i];
+    double* Li = &L[g.sky_ptr[i]] - fi;  // Li[c] = element (i,c)
+    // pass 1: Y_ij = L_ij*d_j = A_ij - sum_k Y_ik L_jk   (finished rows j already hold L_jk)
+    for (int j = fi; j < i; j++) {
+      const int fj = g.sky_first[j];
+      const double* Lj = &L[g.sky_ptr[j]] - fj;
+      double s = Li[j];
+      for (int k = std::max(fi, fj); k < j; k++) s -= Li[k] * Lj[k];
+      Li[j] = s;
+    }
+    // pass 2: d_i = A_ii - sum_j Y_ij L_ij ; convert the row from Y to L
+    double d = Li[i];
+    for (int j = fi; j < i; j++) {
+      const double lij = Li[j] * dinv[j];
+      d -= Li[j] * lij;
+      Li[j] = lij;
+    }
+    if (d == 0.0 || !std::isfinite(d)) return false;  // Eigen: info() != Success on a zero pivot
+    dinv[i] = 1.0 / d;
+    Li[i] = d;
+  }
+  for (int i = 0; i < n; i++) x[i] = rhs[i];
+  for (int i = 0; i < n; i++) {
+    const int fi = g.sky_first[i];
+    const double* Li = &L[g.sky_ptr[i]] - fi;
+    double s = x[i];
+    for (int k = fi; k < i; k++) s -= Li[k] * x[k];
+    x[i] = s;
+  }
+  for (int i = 0; i < n; i++) x[i] *= dinv[i];
+  for (int i = n - 1; i >= 0; i--) {
+    const int fi = g.sky_first[i];
+    const double* Li = &L[g.sky_ptr[i]] - fi;
+    const double xi = x[i];
+    for (int k = fi; k < i; k++) x[k] -= Li[k] * xi;
+  }
+  return true;
+}
+
+// BlockSolver::setLambda / restoreDiagonal (block_solver.hpp:564-604): lambda on EVERY diagonal of Hpp and Hll
+void setLambda(Graph& g, double lambda) {
+  g.diagBackupPose.resize((size_t)g.Np * 6);
+  g.diagBackupLm.resize((size_t)g.Nl * 3);
+  for (int i = 0; i < g.Np; i++)
+    for (int r = 0; r < 6; r++) {
+      double& dd = g.Hpp[(size_t)i * 36 + r * 6 + r];
+      g.diagBackupPose[(size_t)i * 6 + r] = dd;
+      dd += lambda;
+    }
+  for (int i = 0; i < g.Nl; i++)
+    for (int r = 0; r < 3; r++) {
+      double& dd = g.Hll[(size_t)i * 9 + r * 3 + r];
+      g.diagBackupLm[(size_t)i * 3 + r] = dd;
+      dd += lambda;
+    }
+}
+void restoreDiagonal(Graph& g) {
+  for (int i = 0; i < g.Np; i++)
+    for (int r = 0; r < 6; r++) g.Hpp[(size_t)i * 36 + r * 6 + r] = g.diagBackupPose[(size_t)i * 6 + r];
+  for (int i = 0; i < g.Nl; i++)
+    for (int r = 0; r < 3; r++) g.Hll[(size_t)i * 9 + r * 3 + r] = g.diagBackupLm[(size_t)i * 3 + r];
+}
+
+// Schur complement of one landmark into (S, coeff)  (block_solver.hpp:381-432)
+inline void schurLandmark(Graph& g, int l, std::vector<double>& S, double* coeff) {
+  const int Np = g.Np;
+  double* Dinv = &g.Dinv[(size_t)l * 9];
+  inv3(&g.Hll[(size_t)l * 9], Dinv);
+  const double* bl = &g.b[(size_t)Np * 6 + (size_t)l * 3];
+  double db[3];
+  for (int i = 0; i < 3; i++) db[i] = Dinv[i * 3 + 0] * bl[0] + Dinv[i * 3 + 1] * bl[1] + Dinv[i * 3 + 2] * bl[2];
+  const int a = g.lm_hpl_ptr[l], bnd = g.lm_hpl_ptr[l + 1];
+  for (int ko = a; ko < bnd; ko++) {
+    const int blk1 = g.lm_hpl[ko];
+    const int i1 = g.hpl_slot[blk1];
+    const double* Bi = &g.Hpl[(size_t)blk1 * 18];
+    double BDinv[18];
+    for (int r = 0; r < 6; r++)
+      for (int c = 0; c < 3; c++)
+        BDinv[r * 3 + c] = Bi[r * 3 + 0] * Dinv[0 * 3 + c] + Bi[r * 3 + 1] * Dinv[1 * 3 + c] + Bi[r * 3 + 2] * Dinv[2 * 3 + c];
+    for (int r = 0; r < 6; r++) coeff[(size_t)i1 * 6 + r] += Bi[r * 3 + 0] * db[0] + Bi[r * 3 + 1] * db[1] + Bi[r * 3 + 2] * db[2];
+    for (int ki = ko; ki < bnd; ki++) {  // upper triangle only: i2 >= i1
+      const int blk2 = g.lm_hpl[ki];
+      const int i2 = g.hpl_slot[blk2];
+      const double* Bj = &g.Hpl[(size_t)blk2 * 18];
+      // Hschur(i1,i2) -= BDinv * Bj^T ; stored as the lower-triangle element (row of i2, col of i1) transposed
+      for (int r = 0; r < 6; r++)
+        for (int c = 0; c < 6; c++) {
+          const double v = BDinv[r * 3 + 0] * Bj[c * 3 + 0] + BDinv[r * 3 + 1] * Bj[c * 3 + 1] + BDinv[r * 3 + 2] * Bj[c * 3 + 2];
+          const int gr = i1 * 6 + r, gc = i2 * 6 + c;  // gr <= gc within the upper triangle unless i1==i2
+          if (gc >= gr) S[g.sky_ptr[gc] + (gr - g.sky_first[gc])] -= v;
+        }
+    }
+  }
+}
+
+// BlockSolver::solve (block_solver.hpp:354-486)
+bool blockSolve(Graph& g) {
+  const int Np = g.Np, Nl = g.Nl;
+  // _Hschur = _Hpp (upper triangle)
+  std::fill(g.S.begin(), g.S.end(), 0.0);
+  for (int i = 0; i < Np; i++)
+    for (int r = 0; r < 6; r++)
+      for (int c = r; c < 6; c++) Sat(g, g.S, i * 6 + c, i * 6 + r) = g.Hpp[(size_t)i * 36 + r * 6 + c];
+  std::fill(g.coeff.begin(), g.coeff.begin() + (size_t)Np * 6, 0.0);
+  if (g.threads <= 1) {
+    for (int l = 0; l < Nl; l++) schurLandmark(g, l, g.S, g.coeff.data());
+  } else {
+    // g2o's dormant `#pragma omp parallel for` over landmarks (block_solver.hpp:378-380), with per-thread
+    // accumulators instead of per-block mutexes
+    std::vector<std::vector<double>> Sl(g.threads), cl(g.threads);
+#pragma omp parallel num_threads(g.threads)
+    {
+#ifdef _OPENMP
+      const int t = omp_get_thread_num();
+#else
+      const int t = 0;
+#endif
+      Sl[t].assign(g.S.size(), 0.0);
+      cl[t].assign((size_t)Np * 6, 0.0);
+#pragma omp for schedule(static)
+      for (int l = 0; l < Nl; l++) schurLandmark(g, l, Sl[t], cl[t].data());
+    }
+    for (int t = 0; t < g.threads; t++) {
+      for (size_t i = 0; i < g.S.size(); i++) g.S[i] += Sl[t][i];
+      for (size_t i = 0; i < (size_t)Np * 6; i++) g.coeff[i] += cl[t][i];
+    }
+  }
+  for (int i = 0; i < Np * 6; i++) g.bschur[i] = g.b[i] - g.coeff[i];
+  const bool ok = ldltSolve(g, g.bschur.data(), g.x.data());
+  if (!ok) return false;
+  // landmark back-substitution (block_solver.hpp:461-483): xl = Dinv * (bl - Hpl^T xp)
+  double* xl = g.x.data() + (size_t)Np * 6;
+  const double* bl = g.b.data() + (size_t)Np * 6;
+#pragma omp parallel for schedule(static) num_threads(g.threads) if (g.threads > 1)
+  for (int l = 0; l < Nl; l++) {
+    double cl[3] = {bl[l * 3 + 0], bl[l * 3 + 1], bl[l * 3 + 2]};
+    for (int k = g.lm_hpl_ptr[l]; k < g.lm_hpl_ptr[l + 1]; k++) {
+      const int blk = g.lm_hpl[k];
+      const double* Bi = &g.Hpl[(size_t)blk * 18];
+      const double* xp = &g.x[(size_t)g.hpl_slot[blk] * 6];
+      for (int c = 0; c < 3; c++) {
+        double s = 0;
+        for (int r = 0; r < 6; r++) s += Bi[r * 3 + c] * (-xp[r]);  // cp = -xp; rightMultiply adds B^T * cp
+        cl[c] += s;
+      }
+    }
+    const double* Dinv = &g.Dinv[(size_t)l * 9];
+    for (int i = 0; i < 3; i++) xl[l * 3 + i] = Dinv[i * 3 + 0] * cl[0] + Dinv[i * 3 + 1] * cl[1] + Dinv[i * 3 + 2] * cl[2];
+  }
+  return true;
+}
+
+// SparseOptimizer::update (sparse_optimizer.cpp:422-435) -> oplusImpl
+void updateState(Graph& g, const double* upd) {
+  for (int s = 0; s < g.Np; s++) {
+    SE3& T = g.pose[g.slot_pose[s]];
+    T = se3mul(se3exp(upd + (size_t)s * 6), T);  // VertexSE3Expmap::oplusImpl, types_six_dof_expmap.h:73-76
+  }
+  const double* ul = upd + (size_t)g.Np * 6;
+  for (int s = 0; s < g.Nl; s++) {
+    double* X = &g.point[(size_t)g.slot_point[s] * 3];  // VertexSBAPointXYZ::oplusImpl, types_sba.h:52-56
+    X[0] += ul[s * 3 + 0]; X[1] += ul[s * 3 + 1]; X[2] += ul[s * 3 + 2];
+  }
+}
+
+void pushState(Graph& g) { g.pose_bak = g.pose; g.point_bak = g.point; }  // only indexed vertices change, so a full copy is equivalent
+void popState(Graph& g) { g.pose = g.pose_bak; g.point = g.point_bak; }
+
+// OptimizationAlgorithmLevenberg::computeLambdaInit (optimization_algorithm_levenberg.cpp:166-180)
+double computeLambdaInit(const Graph& g) {
+  double maxDiagonal = 0.;
+  for (int i = 0; i < g.Np; i++)
+    for (int j = 0; j < 6; j++) maxDiagonal = std::max(std::fabs(g.Hpp[(size_t)i * 36 + j * 6 + j]), maxDiagonal);
+  for (int i = 0; i < g.Nl; i++)
+    for (int j = 0; j < 3; j++) maxDiagonal = std::max(std::fabs(g.Hll[(size_t)i * 9 + j * 3 + j]), maxDiagonal);
+  return 1e-5 * maxDiagonal;  // _tau
+}
+
+enum SolverResult { Terminate = 2, OK = 1, Fail = -1 };
+
+// OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:61-164)
+SolverResult lmSolve(Graph& g, int iteration) {
+  if (iteration == 0) buildStructure(g);
+  computeActiveErrors(g);
+  double currentChi = activeRobustChi2(g);
+  double tempChi = currentChi;
+  const double iniChi = currentChi;
+  buildSystem(g);
+  if (iteration == 0) {
+    g.lambda = computeLambdaInit(g);
+    g.ni = 2;
+    g.nBad = 0;
+  }
+  double rho = 0;
+  int qmax = 0;
+  do {
+    pushState(g);
+    setLambda(g, g.lambda);
+    const bool ok2 = blockSolve(g);
+    updateState(g, g.x.data());
+    restoreDiagonal(g);
+    computeActiveErrors(g);
+    tempChi = activeRobustChi2(g);
+    if (!ok2) tempChi = std::numeric_limits<double>::max();
+    rho = (currentChi - tempChi);
+    double scale = 0.;  // computeScale, :182-189
+    for (size_t j = 0; j < g.x.size(); j++) scale += g.x[j] * (g.lambda * g.x[j] + g.b[j]);
+    scale += 1e-3;
+    rho /= scale;
+    TraceRow tr{(double)g.cur_pass, (double)iteration, (double)qmax, g.lambda, currentChi, tempChi, rho, 0.0};
+    if (rho > 0 && std::isfinite(tempChi)) {
+      double alpha = 1. - std::pow((2 * rho - 1), 3);
+      alpha = std::min(alpha, 2. / 3.);
+      const double scaleFactor = std::max(1. / 3., alpha);
+      g.lambda *= scaleFactor;
+      g.ni = 2;
+      currentChi = tempChi;
+      tr.accepted = 1.0;  // discardTop
+    } else {
+      g.lambda *= g.ni;
+      g.ni *= 2;
+      popState(g);  // NB: edge errors keep the rejected trial's values (stale _error)
+    }
+    g.trace.push_back(tr);
+    qmax++;
+  } while (rho < 0 && qmax < 10 && !g.terminate());
+  if (qmax == 10 || rho == 0) return Terminate;
+  if ((iniChi - currentChi) * 1e3 < iniChi)
+    g.nBad++;
+  else
+    g.nBad = 0;
+  if (g.nBad >= 3) return Terminate;
+  return OK;
+}
+
+// SparseOptimizer::optimize (sparse_optimizer.cpp:354-419)
+int optimize(Graph& g, int iterations) {
+  if (g.Np + g.Nl == 0) return -1;
+  int cj = 0;
+  bool ok = true;
+  for (int i = 0; i < iterations && !g.terminate() && ok; i++) {
+    const SolverResult r = lmSolve(g, i);
+    ok = (r == OK);
+    ++cj;
+  }
+  return cj;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C API (ctypes / bench)
+// =============================================================================================
+extern "C" {
+
+struct refba { Graph g; std::vector<uint8_t> outlier; };
+
+// Graph construction mirrors g2oOptimizer::BundleAdjustment / LocalBundleAdjustment edge wiring
+// (src/backend/g2oOptimizer.cc:210-283, 875-916): obs with ur<0 -> EdgeSE3ProjectXYZ, else EdgeStereoSE3ProjectXYZ.
+refba* refba_create(int n_pose, int n_point, int n_obs, const double* pose_qt, const uint8_t* pose_fixed,
+                    const double* point_xyz, const int32_t* obs_pose, const int32_t* obs_point,
+                    const float* obs_meas, const double* cam) {
+  refba* h = new refba();
+  Graph& g = h->g;
+  g.n_pose = n_pose; g.n_point = n_point; g.n_obs = n_obs;
+  g.pose.resize(n_pose);
+  g.fixed.assign(pose_fixed, pose_fixed + n_pose);
+  for (int i = 0; i < n_pose; i++) {
+    const double* v = pose_qt + (size_t)i * 7;
+    SE3 T;
+    T.t[0] = v[0]; T.t[1] = v[1]; T.t[2] = v[2];
+    T.r = Quat{v[3], v[4], v[5], v[6]};
+    normalizeRotation(T);  // SE3Quat(R,t) ctor
+    g.pose[i] = T;
+  }
+  g.point.assign(point_xyz, point_xyz + (size_t)n_point * 3);
+  g.edges.resize(n_obs);
+  for (int k = 0; k < n_obs; k++) {
+    Edge& e = g.edges[k];
+    e.pose = obs_pose[k];
+    e.point = obs_point[k];
+    const float* m = obs_meas + (size_t)k * 4;
+    e.stereo = !(m[2] < 0);
+    e.obs[0] = m[0]; e.obs[1] = m[1]; e.obs[2] = e.stereo ? m[2] : 0.0;
+    e.info = m[3];
+    const double* c = cam + (size_t)e.pose * 5;
+    e.fx = c[0]; e.fy = c[1]; e.cx = c[2]; e.cy = c[3]; e.bf = c[4];
+  }
+  h->outlier.assign(n_obs, 0);
+  return h;
+}
+
+void refba_destroy(refba* h) { delete h; }
+void refba_set_threads(refba* h, int t) { h->g.threads = t < 1 ? 1 : t; }
+
+static void setHuber(Edge& e, float th2d, float th3d, bool robust) {
+  e.robust = robust;
+  const double d = e.stereo ? (double)th3d : (double)th2d;  // `const float thHuber.. = sqrt(..)` then setDelta(double)
+  e.delta = d;
+  e.dsqr = d * d;
+}
+
+// g2oOptimizer::LocalBundleAdjustment control flow (g2oOptimizer.cc:704-976, 1119-1142) with the stereo edge
+// wired as in ::BundleAdjustment (:247-283) and upstream ORB-SLAM2's stereo thresholds (thHuberStereo :853, 7.815).
+// third_pass_iters = 0 (north_star default) or 20 (the fork's unconditional lidar-coupling pass, :1113-1114).
+int refba_solve_local(refba* h, const volatile bool* stop, int third_pass_iters) {
+  Graph& g = h->g;
+  g.stop = stop;
+  g.trace.clear();
+  const float thHuberMono = std::sqrt(5.991);     // :851 `const float`
+  const float thHuberStereo = std::sqrt(7.815);   // :853
+  for (Edge& e : g.edges) { e.level = 0; setHuber(e, thHuberMono, thHuberStereo, true); }
+  if (stop && *stop) return 0;  // :923-928 early-out, map untouched
+  auto t0 = std::chrono::steady_clock::now();
+  g.cur_pass = 0;
+  initializeOptimization(g, 0);
+  optimize(g, 5);
+  bool bDoMore = true;
+  if (stop && *stop) bDoMore = false;
+  if (bDoMore) {
+    for (Edge& e : g.edges) {  // :947-970
+      const double thr = e.stereo ? 7.815 : 5.991;
+      if (chi2(e) > thr || !depthPositive(g, e)) e.level = 1;
+      e.robust = false;
+    }
+    g.cur_pass = 1;
+    initializeOptimization(g, 0);
+    optimize(g, 10);
+  }
+  if (third_pass_iters > 0) {
+    g.cur_pass = 2;
+    initializeOptimization(g, 0);
+    optimize(g, third_pass_iters);
+  }
+  for (size_t k = 0; k < g.edges.size(); k++) {  // :1125-1142
+    const Edge& e = g.edges[k];
+    const double thr = e.stereo ? 7.815 : 5.991;
+    h->outlier[k] = (chi2(e) > thr || !depthPositive(g, e)) ? 1 : 0;
+  }
+  g.t_solve_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return 1;
+}
+
+// g2oOptimizer::BundleAdjustment (g2oOptimizer.cc:110-362): single pass, optional Huber with
+// thHuber2D = sqrt(5.99), thHuber3D = sqrt(7.815) (:163-164), no outlier step.
+int refba_solve_global(refba* h, int iters, int robust, const volatile bool* stop) {
+  Graph& g = h->g;
+  g.stop = stop;
+  g.trace.clear();
+  const float thHuber2D = std::sqrt(5.99);
+  const float thHuber3D = std::sqrt(7.815);
+  for (Edge& e : g.edges) { e.level = 0; setHuber(e, thHuber2D, thHuber3D, robust != 0); }
+  auto t0 = std::chrono::steady_clock::now();
+  g.cur_pass = 0;
+  initializeOptimization(g, 0);
+  optimize(g, iters);
+  for (size_t k = 0; k < g.edges.size(); k++) h->outlier[k] = 0;
+  g.t_solve_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return 1;
+}
+
+double refba_solve_seconds(refba* h) { return h->g.t_solve_s; }
+
+void refba_get_poses(refba* h, double* out) {
+  for (int i = 0; i < h->g.n_pose; i++) {  // SE3Quat::toVector order
+    const SE3& T = h->g.pose[i];
+    double* v = out + (size_t)i * 7;
+    v[0] = T.t[0]; v[1] = T.t[1]; v[2] = T.t[2]; v[3] = T.r.x; v[4] = T.r.y; v[5] = T.r.z; v[6] = T.r.w;
+  }
+}
+void refba_get_points(refba* h, double* out) { std::memcpy(out, h->g.point.data(), h->g.point.size() * sizeof(double)); }
+void refba_get_outliers(refba* h, uint8_t* out) { std::memcpy(out, h->outlier.data(), h->outlier.size()); }
+int refba_trace_len(refba* h) { return (int)h->g.trace.size(); }
+void refba_get_trace(refba* h, double* out) { std::memcpy(out, h->g.trace.data(), h->g.trace.size() * sizeof(TraceRow)); }
+
+// ---- stage-level introspection used by the kernel parity tests --------------------------------
+
+// Residuals / Jacobians / robust weights of every edge at the CURRENT state.
+// err (n_obs,3), Jp (n_obs,18), Jl (n_obs,9), w (n_obs,) = rho1*invSigma2, rho0 (n_obs,) robustified chi2.
+// huber: 0 = none, 1 = LBA deltas (sqrt(5.991)/sqrt(7.815)), 2 = GBA deltas (sqrt(5.99)/sqrt(7.815)).
+void refba_linearize_all(refba* h, int huber, double* err, double* Jp, double* Jl, double* w, double* rho0) {
+  Graph& g = h->g;
+  const float t2 = huber == 2 ? std::sqrt(5.99) : std::sqrt(5.991);
+  const float t3 = std::sqrt(7.815);
+  for (size_t k = 0; k < g.edges.size(); k++) {
+    Edge& e = g.edges[k];
+    setHuber(e, t2, t3, huber != 0);
+    computeError(g, e);
+    linearize(g, e);
+    std::memcpy(err + k * 3, e.err, 3 * sizeof(double));
+    std::memcpy(Jp + k * 18, e.Jp, 18 * sizeof(double));
+    std::memcpy(Jl + k * 9, e.Jl, 9 * sizeof(double));
+    const double c = chi2(e);
+    double rho[3] = {c, 1, 0};
+    if (e.robust) robustify(e, c, rho);
+    w[k] = rho[1] * e.info;
+    rho0[k] = rho[0];
+  }
+}
+
+// One damped Schur solve at the current state with all level-0 edges: returns the dense reduced matrix
+// S (6Np x 6Np, symmetric), bschur (6Np), b (6Np+3Nl), x (6Np+3Nl), slot->pose, slot->point maps.
+// Returns Np; the caller sizes buffers from n_pose/n_point upper bounds.
+int refba_schur_solve(refba* h, int huber, double lambda, double* S_dense, double* bschur, double* b, double* x,
+                      int32_t* slot_pose, int32_t* slot_point, double* max_diag) {
+  Graph& g = h->g;
+  const float t2 = huber == 2 ? std::sqrt(5.99) : std::sqrt(5.991);
+  const float t3 = std::sqrt(7.815);
+  for (Edge& e : g.edges) { e.level = 0; setHuber(e, t2, t3, huber != 0); }
+  initializeOptimization(g, 0);
+  buildStructure(g);
+  computeActiveErrors(g);
+  buildSystem(g);
+  *max_diag = computeLambdaInit(g) / 1e-5;
+  setLambda(g, lambda);
+  const bool ok = blockSolve(g);
+  restoreDiagonal(g);
+  const int n = g.Np * 6;
+  for (int r = 0; r < n; r++)
+    for (int c = g.sky_first[r]; c <= r; c++) {
+      const double v = g.S[g.sky_ptr[r] + (c - g.sky_first[r])];
+      S_dense[(size_t)r * n + c] = v;
+      S_dense[(size_t)c * n + r] = v;
+    }
+  std::memcpy(bschur, g.bschur.data(), n * sizeof(double));
+  std::memcpy(b, g.b.data(), g.b.size() * sizeof(double));
+  std::memcpy(x, g.x.data(), g.x.size() * sizeof(double));
+  for (int i = 0; i < g.Np; i++) slot_pose[i] = g.slot_pose[i];
+  for (int i = 0; i < g.Nl; i++) slot_point[i] = g.slot_point[i];
+  return ok ? g.Np : -1;
+}
+
+// Apply oplus to one pose: out7 = exp(upd6) * in7   (VertexSE3Expmap::oplusImpl)
+void refba_pose_oplus(const double* in7, const double* upd6, double* out7) {
+  SE3 T;
+  T.t[0] = in7[0]; T.t[1] = in7[1]; T.t[2] = in7[2];
+  T.r = Quat{in7[3], in7[4], in7[5], in7[6]};
+  SE3 r = se3mul(se3exp(upd6), T);
+  out7[0] = r.t[0]; out7[1] = r.t[1]; out7[2] = r.t[2];
+  out7[3] = r.r.x; out7[4] = r.r.y; out7[5] = r.r.z; out7[6] = r.r.w;
+}
+
+// SE3Quat::exp alone: out7 = (t, q)
+void refba_se3_exp(const double* upd6, double* out7) {
+  SE3 r = se3exp(upd6);
+  out7[0] = r.t[0]; out7[1] = r.t[1]; out7[2] = r.t[2];
+  out7[3] = r.r.x; out7[4] = r.r.y; out7[5] = r.r.z; out7[6] = r.r.w;
+}
+
+// cam_project restatements: Xc(3) -> mono (2) / stereo (3)
+void refba_cam_project_mono(const double* Xc, double fx, double fy, double cx, double cy, double* out2) {
+  out2[0] = Xc[0] / Xc[2] * fx + cx;
+  out2[1] = Xc[1] / Xc[2] * fy + cy;
+}
+void refba_cam_project_stereo(const double* Xc, double fx, double fy, double cx, double cy, float bf, double* out3) {
+  const float invz = (float)(1.0f / Xc[2]);
+  out3[0] = Xc[0] * invz * fx + cx;
+  out3[1] = Xc[1] * invz * fy + cy;
+  out3[2] = out3[0] - (double)(bf * invz);
+}
+void refba_huber(double delta, double e, double* rho3) {
+  Edge ed;
+  ed.delta = delta; ed.dsqr = delta * delta;
+  robustify(ed, e, rho3);
+}
+
+int refba_max_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+"""ctypes binding of the CPU oracle (oracle/refba.cpp).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline /
+`--impl reference` legs; never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "librefba.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "refba.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        dp, fp, ip, up = (C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint8))
+        L.refba_create.restype = C.c_void_p
+        L.refba_create.argtypes = [C.c_int, C.c_int, C.c_int, dp, up, dp, ip, ip, fp, dp]
+        L.refba_destroy.argtypes = [C.c_void_p]
+        L.refba_set_threads.argtypes = [C.c_void_p, C.c_int]
+        L.refba_solve_local.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.refba_solve_global.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.refba_solve_seconds.restype = C.c_double
+        L.refba_solve_seconds.argtypes = [C.c_void_p]
+        L.refba_get_poses.argtypes = [C.c_void_p, dp]
+        L.refba_get_points.argtypes = [C.c_void_p, dp]
+        L.refba_get_outliers.argtypes = [C.c_void_p, up]
+        L.refba_trace_len.argtypes = [C.c_void_p]
+        L.refba_get_trace.argtypes = [C.c_void_p, dp]
+        L.refba_linearize_all.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, dp, dp]
+        L.refba_schur_solve.argtypes = [C.c_void_p, C.c_int, C.c_double, dp, dp, dp, dp, ip, ip, dp]
+        L.refba_pose_oplus.argtypes = [dp, dp, dp]
+        L.refba_se3_exp.argtypes = [dp, dp]
+        L.refba_cam_project_mono.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_double, dp]
+        L.refba_cam_project_stereo.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_float, dp]
+        L.refba_huber.argtypes = [C.c_double, C.c_double, dp]
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+TRACE_COLS = ("pass", "iter", "trial", "lambda", "chi_before", "chi_trial", "rho", "accepted")
+
+
+class RefBA:
+    """One g2o-style optimiser instance over a flat SoA problem (same layout as include/sqrtba.h)."""
+
+    def __init__(self, prob, threads: int = 1):
+        L = lib()
+        self.n_pose, self.n_point, self.n_obs = prob.n_pose, prob.n_point, prob.n_obs
+        self._keep = [np.ascontiguousarray(prob.pose_qt, np.float64), np.ascontiguousarray(prob.pose_fixed, np.uint8),
+                      np.ascontiguousarray(prob.point_xyz, np.float64), np.ascontiguousarray(prob.obs_pose, np.int32),
+                      np.ascontiguousarray(prob.obs_point, np.int32), np.ascontiguousarray(prob.obs_meas, np.float32),
+                      np.ascontiguousarray(prob.cam, np.float64)]
+        k = self._keep
+        self.h = L.refba_create(self.n_pose, self.n_point, self.n_obs, _p(k[0], C.c_double), _p(k[1], C.c_uint8),
+                                _p(k[2], C.c_double), _p(k[3], C.c_int32), _p(k[4], C.c_int32),
+                                _p(k[5], C.c_float), _p(k[6], C.c_double))
+        L.refba_set_threads(self.h, threads)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().refba_destroy(self.h)
+            self.h = None
+
+    def solve_local(self, third_pass_iters: int = 0, stop=None):
+        return lib().refba_solve_local(self.h, stop, third_pass_iters)
+
+    def solve_global(self, iters: int, robust: bool, stop=None):
+        return lib().refba_solve_global(self.h, iters, int(robust), stop)
+
+    def solve_seconds(self) -> float:
+        return lib().refba_solve_seconds(self.h)
+
+    def poses(self):
+        out = np.zeros((self.n_pose, 7))
+        lib().refba_get_poses(self.h, _p(out, C.c_double))
+        return out
+
+    def points(self):
+        out = np.zeros((self.n_point, 3))
+        lib().refba_get_points(self.h, _p(out, C.c_double))
+        return out
+
+    def outliers(self):
+        out = np.zeros(self.n_obs, np.uint8)
+        lib().refba_get_outliers(self.h, _p(out, C.c_uint8))
+        return out
+
+    def trace(self):
+        n = lib().refba_trace_len(self.h)
+        out = np.zeros((n, 8))
+        if n:
+            lib().refba_get_trace(self.h, _p(out, C.c_double))
+        return out
+
+    def linearize_all(self, huber: int = 1):
+        n = self.n_obs
+        err, Jp, Jl, w, rho0 = np.zeros((n, 3)), np.zeros((n, 18)), np.zeros((n, 9)), np.zeros(n), np.zeros(n)
+        lib().refba_linearize_all(self.h, huber, _p(err, C.c_double), _p(Jp, C.c_double), _p(Jl, C.c_double),
+                                  _p(w, C.c_double), _p(rho0, C.c_double))
+        return dict(err=err, Jp=Jp.reshape(n, 3, 6), Jl=Jl.reshape(n, 3, 3), w=w, rho0=rho0)
+
+    def schur_solve(self, lam: float, huber: int = 1):
+        npz, nl = self.n_pose, self.n_point
+        S = np.zeros((6 * npz, 6 * npz))
+        bs = np.zeros(6 * npz)
+        b = np.zeros(6 * npz + 3 * nl)
+        x = np.zeros(6 * npz + 3 * nl)
+        sp = np.zeros(npz, np.int32)
+        sl = np.zeros(nl, np.int32)
+        md = C.c_double(0)
+        # the C side writes S with leading dimension 6*Np, so hand it a scratch buffer and reshape afterwards
+        Np = lib().refba_schur_solve(self.h, huber, lam, _p(S, C.c_double), _p(bs, C.c_double), _p(b, C.c_double),
+                                     _p(x, C.c_double), _p(sp, C.c_int32), _p(sl, C.c_int32), C.byref(md))
+        if Np < 0:
+            raise RuntimeError("oracle LDLT failed")
+        n = 6 * Np
+        Sd = S.ravel()[: n * n].reshape(n, n).copy()
+        Nl = int((self.n_point))
+        # number of active landmarks = all (every landmark has >= 1 edge in generated problems)
+        return dict(Np=Np, S=Sd, bschur=bs[:n].copy(), b=b[: n + 3 * Nl].copy(), x=x[: n + 3 * Nl].copy(),
+                    slot_pose=sp[:Np].copy(), slot_point=sl[:Nl].copy(), max_diag=md.value)
+
+
+def pose_oplus(pose7, upd6):
+    a = np.ascontiguousarray(pose7, np.float64)
+    u = np.ascontiguousarray(upd6, np.float64)
+    out = np.zeros(7)
+    lib().refba_pose_oplus(_p(a, C.c_double), _p(u, C.c_double), _p(out, C.c_double))
+    return out
+
+
+def se3_exp(upd6):
+    u = np.ascontiguousarray(upd6, np.float64)
+    out = np.zeros(7)
+    lib().refba_se3_exp(_p(u, C.c_double), _p(out, C.c_double))
+    return out

@@ -1,0 +1,353 @@
+"""Seeded synthetic KITTI-00-shaped bundle-adjustment problems.
+
+The reference ships no data and no tests, so every workload in BASELINE.json is
+generated here.  Constants come from the reference's own KITTI config
+(cfg/KITTI00-02.yaml:8-11,18-19,25,42,45) and the pyramid sigma table is computed
+in float32 exactly as the ORB extractor does (src/frontend/ORBextractor.cc:482-505).
+
+All state crosses the BA boundary the way the reference's does: poses as float32
+4x4 Tcw matrices converted with the Converter::toSE3Quat recipe
+(src/utils/Converter.cc:55-68), points as float32 3-vectors, measurements as
+float32 (cv::KeyPoint::pt, mvuRight, mvInvLevelSigma2 are float containers,
+include/data_structure/KeyFrame.h:394,402-403,427).
+
+Layout produced (identical to what include/sqrtba.h consumes):
+  pose_qt   (n_pose,7) f64  tx,ty,tz,qx,qy,qz,qw   (SE3Quat::toVector order, se3quat.h:138-148)
+  pose_fixed(n_pose,)  u8
+  cam       (n_pose,5) f64  fx,fy,cx,cy,bf
+  point_xyz (n_point,3) f64
+  obs_pose  (n_obs,) i32 ; obs_point (n_obs,) i32  -- grouped by landmark, pose-sorted inside
+  obs_meas  (n_obs,4) f32  u,v,ur(<0 = monocular),invSigma2
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+import numpy as np
+
+# cfg/KITTI00-02.yaml -- the reference stores these as float (KeyFrame.h:394)
+FX = float(np.float32(718.856))
+FY = float(np.float32(718.856))
+CX = float(np.float32(607.1928))
+CY = float(np.float32(185.2157))
+BF = float(np.float32(386.1448))
+IMG_W, IMG_H = 1241.0, 376.0
+N_LEVELS = 8
+
+
+def inv_level_sigma2() -> np.ndarray:
+    """mvInvLevelSigma2 in float32, ORBextractor.cc:482-505 (scaleFactor_ is a double member
+    initialised from the float 1.2f, include/frontend/ORBextractor.h:187)."""
+    scale = float(np.float32(1.2))
+    sf = np.zeros(N_LEVELS, dtype=np.float32)
+    s2 = np.zeros(N_LEVELS, dtype=np.float32)
+    sf[0] = 1.0
+    s2[0] = 1.0
+    for i in range(1, N_LEVELS):
+        sf[i] = np.float32(float(sf[i - 1]) * scale)
+        s2[i] = np.float32(sf[i] * sf[i])
+    return (np.float32(1.0) / s2).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- small SO3/SE3 helpers (vectorised)
+
+def _skew(w):
+    z = np.zeros(w.shape[:-1])
+    return np.stack([np.stack([z, -w[..., 2], w[..., 1]], -1),
+                     np.stack([w[..., 2], z, -w[..., 0]], -1),
+                     np.stack([-w[..., 1], w[..., 0], z], -1)], -2)
+
+
+def so3_exp(w):
+    th = np.linalg.norm(w, axis=-1)[..., None, None]
+    K = _skew(w)
+    th_s = np.where(th < 1e-12, 1.0, th)
+    a = np.where(th < 1e-12, 1.0, np.sin(th_s) / th_s)
+    b = np.where(th < 1e-12, 0.5, (1 - np.cos(th_s)) / (th_s * th_s))
+    return np.eye(3) + a * K + b * (K @ K)
+
+
+def rotmat_to_quat_eigen(R):
+    """Eigen's Quaterniond(Matrix3d) branches (what SE3Quat(R,t) calls, se3quat.h:58),
+    followed by SE3Quat::normalizeRotation (se3quat.h:280-285). Returns (...,4) x,y,z,w."""
+    R = np.asarray(R, dtype=np.float64)
+    flat = R.reshape(-1, 3, 3)
+    out = np.zeros((flat.shape[0], 4))
+    for n, m in enumerate(flat):
+        t = m[0, 0] + m[1, 1] + m[2, 2]
+        if t > 0:
+            t = np.sqrt(t + 1.0)
+            w = 0.5 * t
+            t = 0.5 / t
+            q = [(m[2, 1] - m[1, 2]) * t, (m[0, 2] - m[2, 0]) * t, (m[1, 0] - m[0, 1]) * t, w]
+        else:
+            i = 0
+            if m[1, 1] > m[0, 0]:
+                i = 1
+            if m[2, 2] > m[i, i]:
+                i = 2
+            j = (i + 1) % 3
+            k = (j + 1) % 3
+            t = np.sqrt(m[i, i] - m[j, j] - m[k, k] + 1.0)
+            q = [0.0, 0.0, 0.0, 0.0]
+            q[i] = 0.5 * t
+            t = 0.5 / t
+            q[3] = (m[k, j] - m[j, k]) * t
+            q[j] = (m[j, i] + m[i, j]) * t
+            q[k] = (m[k, i] + m[i, k]) * t
+        q = np.array(q)
+        if q[3] < 0:
+            q = -q
+        out[n] = q / np.sqrt(np.dot(q, q))
+    return out.reshape(R.shape[:-2] + (4,))
+
+
+def quat_to_rotmat(q):
+    x, y, z, w = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    return np.stack([
+        np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+        np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+        np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], -2)
+
+
+# ----------------------------------------------------------------------------- problem container
+
+@dataclass
+class Problem:
+    pose_qt: np.ndarray
+    pose_fixed: np.ndarray
+    cam: np.ndarray
+    point_xyz: np.ndarray
+    obs_pose: np.ndarray
+    obs_point: np.ndarray
+    obs_meas: np.ndarray
+    name: str = ""
+    truth: dict = field(default_factory=dict)
+
+    @property
+    def n_pose(self):
+        return int(self.pose_qt.shape[0])
+
+    @property
+    def n_point(self):
+        return int(self.point_xyz.shape[0])
+
+    @property
+    def n_obs(self):
+        return int(self.obs_pose.shape[0])
+
+    @property
+    def n_free(self):
+        return int((self.pose_fixed == 0).sum())
+
+    def lm_ptr(self) -> np.ndarray:
+        cnt = np.bincount(self.obs_point, minlength=self.n_point)
+        return np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+
+    def copy(self) -> "Problem":
+        return Problem(self.pose_qt.copy(), self.pose_fixed.copy(), self.cam.copy(), self.point_xyz.copy(),
+                       self.obs_pose.copy(), self.obs_point.copy(), self.obs_meas.copy(), self.name, dict(self.truth))
+
+    def save(self, path):
+        np.savez_compressed(path, pose_qt=self.pose_qt, pose_fixed=self.pose_fixed, cam=self.cam,
+                            point_xyz=self.point_xyz, obs_pose=self.obs_pose, obs_point=self.obs_point,
+                            obs_meas=self.obs_meas, name=np.array(self.name))
+
+    @staticmethod
+    def load(path) -> "Problem":
+        z = np.load(path)
+        return Problem(z["pose_qt"], z["pose_fixed"], z["cam"], z["point_xyz"], z["obs_pose"], z["obs_point"],
+                       z["obs_meas"], str(z["name"]))
+
+
+# ----------------------------------------------------------------------------- generator
+
+def _trajectory(rng, n_kf, loop=False):
+    """KITTI-like forward motion: camera z forward, x right, y down. Returns R_wc (n,3,3), c_w (n,3)."""
+    step = rng.uniform(0.8, 1.5, n_kf)
+    dyaw = np.deg2rad(rng.normal(0.0, 1.5, n_kf))
+    if loop:
+        # a bit more than one full turn so the tail re-observes the head (loop-closure overlap)
+        dyaw = dyaw * 0.3 + 2.0 * np.pi * 1.04 / n_kf
+    yaw = np.cumsum(dyaw) - dyaw[0]
+    pitch = np.deg2rad(rng.normal(0.0, 0.2, n_kf))
+    roll = np.deg2rad(rng.normal(0.0, 0.2, n_kf))
+    # yaw about camera y (down) axis, pitch about x, roll about z
+    Ry = so3_exp(np.stack([np.zeros(n_kf), yaw, np.zeros(n_kf)], -1))
+    Rx = so3_exp(np.stack([pitch, np.zeros(n_kf), np.zeros(n_kf)], -1))
+    Rz = so3_exp(np.stack([np.zeros(n_kf), np.zeros(n_kf), roll], -1))
+    R_wc = Ry @ Rx @ Rz
+    fwd = R_wc[:, :, 2]
+    c = np.zeros((n_kf, 3))
+    c[1:] = np.cumsum(fwd[:-1] * step[1:, None], axis=0)
+    return R_wc, c
+
+
+def make_problem(seed: int, n_kf: int, n_fixed_head: int, n_points: int, mean_track: float,
+                 stereo: bool = True, outlier_frac: float = 0.05, loop: bool = False,
+                 cand_halfwidth: int | None = None, extra_fixed=(), name: str = "",
+                 max_track: int | None = None) -> Problem:
+    """n_kf keyframes in trajectory order; the first n_fixed_head are fixed (plus `extra_fixed` indices)."""
+    rng = np.random.default_rng(seed)
+    R_wc, c_w = _trajectory(rng, n_kf, loop=loop)
+    R_cw = np.swapaxes(R_wc, -1, -2)
+    t_cw = -np.einsum("nij,nj->ni", R_cw, c_w)
+
+    inv_s2 = inv_level_sigma2()
+
+    # ---- points: back-project a random pixel at a random depth from a random non-fixed "home" keyframe
+    lo_home = min(n_fixed_head, n_kf - 1)
+    home = rng.integers(lo_home, n_kf, n_points)
+    pu = rng.uniform(0, IMG_W, n_points)
+    pv = rng.uniform(0, IMG_H, n_points)
+    depth = rng.uniform(4.0, 60.0, n_points)
+    xc = np.stack([(pu - CX) / FX * depth, (pv - CY) / FY * depth, depth], -1)
+    Xw = np.einsum("nij,nj->ni", R_wc[home], xc) + c_w[home]
+
+    # ---- candidate keyframes per point
+    if cand_halfwidth is None:
+        cand = np.broadcast_to(np.arange(n_kf)[None, :], (n_points, n_kf))
+        valid = np.ones_like(cand, dtype=bool)
+    else:
+        off = np.arange(-cand_halfwidth, cand_halfwidth + 1)
+        if loop:
+            per = int(round(n_kf / 1.04))
+            off = np.concatenate([off, off + per, off - per])
+        cand = home[:, None] + off[None, :]
+        valid = (cand >= 0) & (cand < n_kf)
+        cand = np.clip(cand, 0, n_kf - 1)
+
+    # ---- true projections into candidates
+    Xc = np.einsum("pkij,pj->pki", R_cw[cand], Xw) + t_cw[cand]
+    z = Xc[..., 2]
+    zs = np.where(z > 0.5, z, 1.0)
+    u = FX * Xc[..., 0] / zs + CX
+    v = FY * Xc[..., 1] / zs + CY
+    vis = valid & (z > 0.5) & (z < 90.0) & (u >= 0) & (u < IMG_W) & (v >= 0) & (v < IMG_H)
+    vis[np.arange(n_points), np.argmax(cand == home[:, None], axis=1)] = True  # home always sees it
+
+    # ---- contiguous-in-time tracks: keep the L visible candidates nearest (by index) to the home keyframe
+    L = 2 + rng.poisson(max(mean_track - 2.0, 0.1), n_points)
+    if max_track is not None:
+        L = np.minimum(L, max_track)
+    dist = np.abs(cand - home[:, None]).astype(np.float64)
+    dist = dist + rng.uniform(0, 0.5, dist.shape)  # break ties between the two sides
+    dist[~vis] = np.inf
+    order = np.argsort(dist, axis=1)
+    rank = np.empty_like(order)
+    np.put_along_axis(rank, order, np.broadcast_to(np.arange(order.shape[1])[None, :], order.shape), axis=1)
+    keep = vis & (rank < L[:, None])
+
+    # drop points with fewer than 2 observations (cannot be triangulated; the front-end never creates them)
+    nobs_pt = keep.sum(1)
+    good = nobs_pt >= 2
+    keep = keep[good]
+    cand_g, Xw, depth_g = cand[good], Xw[good], depth[good]
+    u, v, z = u[good], v[good], z[good]
+    n_pt = int(good.sum())
+
+    pt_idx, col = np.nonzero(keep)  # row-major => grouped by landmark
+    kf_idx = cand_g[pt_idx, col]
+    # sort observations inside each landmark by keyframe index
+    o = np.lexsort((kf_idx, pt_idx))
+    pt_idx, col, kf_idx = pt_idx[o], col[o], kf_idx[o]
+    n_obs = pt_idx.size
+    ut, vt, zt = u[pt_idx, col], v[pt_idx, col], z[pt_idx, col]
+
+    # ---- measurements
+    level = np.minimum(rng.geometric(0.35, n_obs) - 1, N_LEVELS - 1)
+    sigma = 1.2 ** level
+    mu = ut + rng.normal(0, 1, n_obs) * sigma
+    mv = vt + rng.normal(0, 1, n_obs) * sigma
+    mur = ut - BF / zt + rng.normal(0, 1, n_obs) * sigma
+    is_out = rng.uniform(0, 1, n_obs) < outlier_frac
+    n_out = int(is_out.sum())
+    sgn = lambda n: rng.choice([-1.0, 1.0], n)
+    mu[is_out] += sgn(n_out) * rng.uniform(10, 50, n_out)
+    mv[is_out] += sgn(n_out) * rng.uniform(10, 50, n_out)
+    mur[is_out] += sgn(n_out) * rng.uniform(10, 50, n_out)
+    meas = np.zeros((n_obs, 4), dtype=np.float32)
+    meas[:, 0] = mu.astype(np.float32)
+    meas[:, 1] = mv.astype(np.float32)
+    if stereo:
+        # a real right-image coordinate is never negative; the adapter uses ur<0 as "monocular"
+        meas[:, 2] = np.maximum(mur, 0.0).astype(np.float32)
+    else:
+        meas[:, 2] = -1.0
+    meas[:, 3] = inv_s2[level]
+
+    # ---- initial estimates: perturbed truth, then rounded through the float32 map boundary
+    fixed = np.zeros(n_kf, dtype=np.uint8)
+    fixed[:n_fixed_head] = 1
+    for i in extra_fixed:
+        fixed[i] = 1
+    xi_r = np.deg2rad(rng.normal(0, 0.3, (n_kf, 3)))
+    xi_t = rng.normal(0, 0.05, (n_kf, 3))
+    free = fixed == 0
+    dR = so3_exp(xi_r)
+    R0 = np.where(free[:, None, None], dR @ R_cw, R_cw)
+    t0 = np.where(free[:, None], np.einsum("nij,nj->ni", dR, t_cw) + xi_t, t_cw)
+    R0f = R0.astype(np.float32).astype(np.float64)
+    t0f = t0.astype(np.float32).astype(np.float64)
+    q0 = rotmat_to_quat_eigen(R0f)
+    pose_qt = np.concatenate([t0f, q0], axis=1)
+
+    X0 = Xw + rng.normal(0, 1, Xw.shape) * (0.02 * depth_g)[:, None]
+    X0 = X0.astype(np.float32).astype(np.float64)
+
+    cam = np.tile(np.array([FX, FY, CX, CY, BF]), (n_kf, 1))
+    truth = dict(R_cw=R_cw, t_cw=t_cw, Xw=Xw, is_outlier=is_out)
+    return Problem(np.ascontiguousarray(pose_qt), fixed, np.ascontiguousarray(cam), np.ascontiguousarray(X0),
+                   kf_idx.astype(np.int32), pt_idx.astype(np.int32), meas, name, truth)
+
+
+# ----------------------------------------------------------------------------- the BASELINE.json configs
+
+def config_c0(seed=0, scale=1.0):
+    """C0: stereo local window, 20 free + 10 fixed KFs, ~6k points, ~70k observations."""
+    return make_problem(seed, 30, 10, int(6000 * scale), 11.7, stereo=True, name=f"C0-seed{seed}")
+
+
+def config_c1(seed=0, scale=1.0):
+    """C1: the same window in monocular mode; first window KF additionally fixed (gauge)."""
+    return make_problem(seed, 30, 10, int(6000 * scale), 11.7, stereo=False, extra_fixed=(10,),
+                        name=f"C1-seed{seed}")
+
+
+def config_c2(seed=0, scale=1.0):
+    """C2: large stereo window, 100 KFs (first fixed), 50k points, ~600k observations."""
+    return make_problem(seed, 100, 1, int(50000 * scale), 12.0, stereo=True, cand_halfwidth=40,
+                        name=f"C2-seed{seed}")
+
+
+def config_c3(seed=0, scale=1.0, n_kf=1500):
+    """C3: global BA, 1500 KFs on a loop (first fixed), 300k points, ~3M observations."""
+    return make_problem(seed, int(n_kf), 1, int(300000 * scale), 10.0, stereo=True, loop=True,
+                        cand_halfwidth=20, name=f"C3-seed{seed}")
+
+
+def small_window(seed=0, n_free=6, n_fixed=3, n_points=150, mean_track=5.0, stereo=True, outlier_frac=0.05,
+                 extra_fixed=()):
+    """Tiny window for oracle / parity tests."""
+    return make_problem(seed, n_free + n_fixed, n_fixed, n_points, mean_track, stereo=stereo,
+                        outlier_frac=outlier_frac, extra_fixed=extra_fixed, name=f"small-seed{seed}")
+
+
+def concat_windows(windows):
+    """Batch of independent windows (config C4) as one block-diagonal problem + CSR window offsets."""
+    pose_ptr = np.zeros(len(windows) + 1, dtype=np.int64)
+    point_ptr = np.zeros(len(windows) + 1, dtype=np.int64)
+    obs_ptr = np.zeros(len(windows) + 1, dtype=np.int64)
+    for i, w in enumerate(windows):
+        pose_ptr[i + 1] = pose_ptr[i] + w.n_pose
+        point_ptr[i + 1] = point_ptr[i] + w.n_point
+        obs_ptr[i + 1] = obs_ptr[i] + w.n_obs
+    p = Problem(
+        np.concatenate([w.pose_qt for w in windows]),
+        np.concatenate([w.pose_fixed for w in windows]),
+        np.concatenate([w.cam for w in windows]),
+        np.concatenate([w.point_xyz for w in windows]),
+        np.concatenate([w.obs_pose + pose_ptr[i] for i, w in enumerate(windows)]).astype(np.int32),
+        np.concatenate([w.obs_point + point_ptr[i] for i, w in enumerate(windows)]).astype(np.int32),
+        np.concatenate([w.obs_meas for w in windows]),
+        name=f"batch{len(windows)}")
+    return p, pose_ptr, point_ptr, obs_ptr
