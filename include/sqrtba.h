@@ -1,0 +1,140 @@
+/* sqrtba.h -- C ABI of the B200-native square-root Levenberg-Marquardt bundle-adjustment back-end.
+ *
+ * Drop-in boundary for the bundle-adjustment hot path of lutao98/SqrtLM-SLAM.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference checkout):
+ *
+ *   sqrtba_set_problem      <- graph construction in g2oOptimizer::LocalBundleAdjustment / ::BundleAdjustment
+ *                              (src/backend/g2oOptimizer.cc:805-919, 142-295): VertexSE3Expmap per keyframe,
+ *                              VertexSBAPointXYZ per map point, Edge(Stereo)SE3ProjectXYZ per observation
+ *   sqrtba_solve_local      <- the optimise part of Optimizer::LocalBundleAdjustment
+ *                              (include/backend/Optimizer.h:55, src/backend/g2oOptimizer.cc:923-976[,1113-1114])
+ *   sqrtba_solve_global     <- the optimise part of Optimizer::BundleAdjustment / GlobalBundleAdjustemnt
+ *                              (include/backend/Optimizer.h:50-53, src/backend/g2oOptimizer.cc:300-301)
+ *   sqrtba_get_poses/points <- vSE3->estimate() / vPoint->estimate() read-back (g2oOptimizer.cc:1167-1189, 308-361)
+ *   sqrtba_get_outliers     <- the chi2 / depth test that fills vToErase (g2oOptimizer.cc:1119-1142)
+ *   stop_flag               <- bool* pbStopFlag / optimizer.setForceStopFlag (g2oOptimizer.cc:797-798, 923-947)
+ *
+ * Conventions: plain C, host pointers unless a name says `_device`, caller keeps ownership of every buffer
+ * (inputs are copied), all functions return 0 on success and a negative sqrtba_status on failure and never
+ * throw; sqrtba_last_error() gives the message.  A handle is owned by one calling thread at a time; different
+ * handles may be used concurrently (the reference runs local and global BA on different threads).
+ * There is no CPU fallback: every solve runs on the CUDA device or fails with SQRTBA_ERR_CUDA.
+ */
+#ifndef SQRTBA_H_
+#define SQRTBA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sqrtba_handle sqrtba_handle;
+
+typedef enum {
+  SQRTBA_OK = 0,
+  SQRTBA_ERR_INVALID = -1, /* bad argument / problem not set */
+  SQRTBA_ERR_CUDA = -2,    /* CUDA runtime error or no device */
+  SQRTBA_ERR_ALLOC = -3,
+  SQRTBA_ERR_COMM = -4     /* NCCL / multi-GPU set-up error */
+} sqrtba_status;
+
+typedef struct {
+  int32_t device;            /* CUDA device ordinal */
+  double pcg_rtol;           /* PCG stops when sqrt(r'M^-1 r / r0'M^-1 r0) <= pcg_rtol (default 1e-9) */
+  int32_t pcg_max_iters;     /* hard cap per linear solve (default 300) */
+  int32_t third_pass_iters;  /* 0 = ORB-SLAM2 two-pass 5+10 (default); 20 = this fork's extra pass (g2oOptimizer.cc:1113) */
+  int32_t pcg_mode;          /* 0 = one launch per CG phase (default in round 1), 1 = persistent cooperative kernel */
+  int32_t pcg_check_every;   /* multi-launch mode: host polls the convergence counter every N iterations */
+  int32_t reserved[8];
+} sqrtba_config;
+
+/* one row per LM trial (g2o "levenbergIterations"), per window */
+typedef struct {
+  double pass;       /* 0,1,(2) */
+  double iter;       /* outer iteration index inside the pass */
+  double trial;      /* qmax before increment */
+  double lambda;     /* damping used for this trial */
+  double chi_before; /* currentChi */
+  double chi_trial;  /* tempChi */
+  double rho;        /* gain ratio */
+  double accepted;   /* 1/0 */
+  double cg_iters;   /* PCG iterations spent on this trial */
+  double cg_relres;  /* final sqrt(rz/rz0) */
+} sqrtba_trace_row;
+
+typedef struct {
+  int32_t n_windows;
+  int32_t lm_trials;        /* total trials (max over windows = lock-step macro steps) */
+  int32_t cg_iters_total;   /* matvec launches */
+  int32_t kernel_launches;  /* launches of this library's kernels during the last solve */
+  double ms_total;          /* device time of the last solve (CUDA events on the handle's stream) */
+  double ms_linearize, ms_qr, ms_pcg, ms_backsub, ms_cost; /* per-stage device time (events) */
+  double ms_matvec;         /* sum of matvec kernel time (multi-launch mode; 0 in persistent mode) */
+  double reserved[8];
+} sqrtba_stats;
+
+int sqrtba_default_config(sqrtba_config* cfg);
+int sqrtba_create(const sqrtba_config* cfg, sqrtba_handle** out);
+int sqrtba_destroy(sqrtba_handle* h);
+const char* sqrtba_last_error(const sqrtba_handle* h);
+const char* sqrtba_version(void);
+
+/* One problem = one BA graph.
+ *  pose_qt    n_pose x 7  tx,ty,tz,qx,qy,qz,qw  (SE3Quat::toVector, Thirdparty/g2o/g2o/types/se3quat.h:138-148), Tcw
+ *  pose_fixed n_pose      1 = vSE3->setFixed(true) (g2oOptimizer.cc:154, 813, 829)
+ *  cam        n_pose x 5  fx,fy,cx,cy,bf of the observing keyframe (KeyFrame.h:394)
+ *  point_xyz  n_point x 3 world position
+ *  obs_pose / obs_point   indices; observations MUST be grouped by landmark (non-decreasing obs_point), which is
+ *                         the order the reference adapter creates edges in (g2oOptimizer.cc:856-919)
+ *  obs_meas   n_obs x 4   float u, v, ur (ur < 0 => monocular EdgeSE3ProjectXYZ), invSigma2 */
+int sqrtba_set_problem(sqrtba_handle* h, int32_t n_pose, int32_t n_point, int32_t n_obs, const double* pose_qt,
+                       const uint8_t* pose_fixed, const double* cam, const double* point_xyz,
+                       const int32_t* obs_pose, const int32_t* obs_point, const float* obs_meas);
+
+/* Batch of independent windows (block-diagonal problem): same arrays concatenated, indices global, plus CSR
+ * offsets per window (n_win+1 entries each).  Every window runs its own LM (own lambda, accept/reject, stop). */
+int sqrtba_set_problem_batch(sqrtba_handle* h, int32_t n_win, const int64_t* win_pose_ptr,
+                             const int64_t* win_point_ptr, const int64_t* win_obs_ptr, const double* pose_qt,
+                             const uint8_t* pose_fixed, const double* cam, const double* point_xyz,
+                             const int32_t* obs_pose, const int32_t* obs_point, const float* obs_meas);
+
+/* Restore the initial estimate given to set_problem (device-to-device), so a solve can be repeated. */
+int sqrtba_reset_state(sqrtba_handle* h);
+
+/* Local BA: robust pass (5 its) -> chi2/depth outlier exclusion -> non-robust pass (10 its) [-> third pass].
+ * stop_flag may be NULL; it is polled on the host between LM trials, never read by the device. */
+int sqrtba_solve_local(sqrtba_handle* h, const volatile bool* stop_flag, sqrtba_stats* stats);
+/* Global BA: one pass of `iters` LM iterations, Huber iff robust (deltas sqrt(5.99)/sqrt(7.815)), no outlier step. */
+int sqrtba_solve_global(sqrtba_handle* h, int32_t iters, int32_t robust, const volatile bool* stop_flag,
+                        sqrtba_stats* stats);
+
+int sqrtba_get_poses(sqrtba_handle* h, double* pose_qt_out);   /* n_pose x 7 */
+int sqrtba_get_points(sqrtba_handle* h, double* point_xyz_out); /* n_point x 3 */
+int sqrtba_get_outliers(sqrtba_handle* h, uint8_t* flags_out);  /* n_obs, 1 = erase this observation */
+int sqrtba_get_trace_len(sqrtba_handle* h, int32_t window);
+int sqrtba_get_trace(sqrtba_handle* h, int32_t window, sqrtba_trace_row* rows_out, int32_t max_rows);
+
+/* ---- stage-level entry points (kernel parity tests, profiling) --------------------------------------------
+ * sqrtba_debug_linearize : run the fused residual+Jacobian+Huber kernel at the current state.
+ *    huber: 0 none, 1 local-BA deltas, 2 global-BA deltas.  Outputs (any may be NULL):
+ *    err n_obs x 3 (unweighted), Jp n_obs x 18, Jl n_obs x 9 (both scaled by sqrt(rho1*invSigma2)),
+ *    r n_obs x 3 (weighted residual), chi2 per window (robustified sum).
+ * sqrtba_debug_step      : one damped square-root step with the given lambda at the current linearisation:
+ *    landmark QR, block-Jacobi, PCG, back-substitution.  Outputs: dp 6 per free pose slot (pose order),
+ *    dl 3 per landmark, bs reduced rhs (6 per slot), cg_iters. State is NOT updated.
+ * sqrtba_debug_matvec    : y = (S_reduced) p for the current QR factors (p, y: 6 per free pose slot). */
+int sqrtba_debug_linearize(sqrtba_handle* h, int32_t huber, double* err, double* Jp, double* Jl, double* r,
+                           double* chi2);
+int sqrtba_debug_step(sqrtba_handle* h, double lambda, double* dp, double* dl, double* bs, int32_t* cg_iters);
+int sqrtba_debug_matvec(sqrtba_handle* h, const double* p, double* y);
+int sqrtba_num_free_poses(sqrtba_handle* h);
+
+/* Time `reps` launches of one stage kernel on the handle's stream with CUDA events (after `warmup` untimed
+ * launches); returns the average ms per launch.  stage: 0 matvec, 1 linearize, 2 landmark QR, 3 cost, 4 backsub. */
+int sqrtba_time_stage(sqrtba_handle* h, int32_t stage, int32_t warmup, int32_t reps, double* ms_avg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQRTBA_H_ */

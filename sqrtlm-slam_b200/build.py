@@ -1,0 +1,49 @@
+"""Builds the sm_100a shared library in-tree (libsqrtba.so next to this file) with nvcc.
+
+`python sqrtlm-slam_b200/build.py` or build.build_lib(); __graft_entry__.build() calls this."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libsqrtba.so")
+SOURCES = [os.path.join(HERE, "csrc", "sqrtba_solver.cu")]
+DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("sqrtba_kernels.cuh", "sqrtba_math.cuh")] + [
+    os.path.join(os.path.dirname(HERE), "include", "sqrtba.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+
+
+def nvcc_path() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + SOURCES
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libsqrtba.so")
+    with open(os.path.join(HERE, "ptxas_info.txt"), "w") as f:  # register / spill report of the last build
+        f.write(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,201 @@
+"""ctypes mirror of include/sqrtba.h -- the call a C++ host makes, exposed to Python tests and bench.py.
+
+No compute happens here and there is NO fallback: if libsqrtba.so is missing the import of `lib()` raises,
+and every solve goes through the C ABI to the CUDA device."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsqrtba.so")
+_lib = None
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("pcg_rtol", C.c_double), ("pcg_max_iters", C.c_int32),
+                ("third_pass_iters", C.c_int32), ("pcg_mode", C.c_int32), ("pcg_check_every", C.c_int32),
+                ("reserved", C.c_int32 * 8)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_windows", C.c_int32), ("lm_trials", C.c_int32), ("cg_iters_total", C.c_int32),
+                ("kernel_launches", C.c_int32), ("ms_total", C.c_double), ("ms_linearize", C.c_double),
+                ("ms_qr", C.c_double), ("ms_pcg", C.c_double), ("ms_backsub", C.c_double), ("ms_cost", C.c_double),
+                ("ms_matvec", C.c_double), ("reserved", C.c_double * 8)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+TRACE_COLS = ("pass", "iter", "trial", "lambda", "chi_before", "chi_trial", "rho", "accepted", "cg_iters", "cg_relres")
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with sqrtlm-slam_b200/build.py (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        vp, dp, fp, ip, up, lp = (C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32),
+                                  C.POINTER(C.c_uint8), C.POINTER(C.c_int64))
+        L.sqrtba_version.restype = C.c_char_p
+        L.sqrtba_last_error.restype = C.c_char_p
+        L.sqrtba_last_error.argtypes = [vp]
+        L.sqrtba_default_config.argtypes = [C.POINTER(Config)]
+        L.sqrtba_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+        L.sqrtba_destroy.argtypes = [vp]
+        L.sqrtba_set_problem.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, dp, up, dp, dp, ip, ip, fp]
+        L.sqrtba_set_problem_batch.argtypes = [vp, C.c_int32, lp, lp, lp, dp, up, dp, dp, ip, ip, fp]
+        L.sqrtba_reset_state.argtypes = [vp]
+        L.sqrtba_solve_local.argtypes = [vp, vp, C.POINTER(Stats)]
+        L.sqrtba_solve_global.argtypes = [vp, C.c_int32, C.c_int32, vp, C.POINTER(Stats)]
+        L.sqrtba_get_poses.argtypes = [vp, dp]
+        L.sqrtba_get_points.argtypes = [vp, dp]
+        L.sqrtba_get_outliers.argtypes = [vp, up]
+        L.sqrtba_get_trace_len.argtypes = [vp, C.c_int32]
+        L.sqrtba_get_trace.argtypes = [vp, C.c_int32, dp, C.c_int32]
+        L.sqrtba_debug_linearize.argtypes = [vp, C.c_int32, dp, dp, dp, dp, dp]
+        L.sqrtba_debug_step.argtypes = [vp, C.c_double, dp, dp, dp, ip]
+        L.sqrtba_debug_matvec.argtypes = [vp, dp, dp]
+        L.sqrtba_num_free_poses.argtypes = [vp]
+        L.sqrtba_time_stage.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, dp]
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class SqrtBAError(RuntimeError):
+    pass
+
+
+class SqrtBA:
+    """Thin owner of one sqrtba_handle.  Method names follow the C ABI."""
+
+    def __init__(self, device: int = 0, pcg_rtol: float = 1e-9, pcg_max_iters: int = 300, third_pass_iters: int = 0,
+                 pcg_mode: int = 0, pcg_check_every: int = 4, stage_timing: bool = False):
+        L = lib()
+        cfg = Config()
+        L.sqrtba_default_config(C.byref(cfg))
+        cfg.device, cfg.pcg_rtol, cfg.pcg_max_iters = device, pcg_rtol, pcg_max_iters
+        cfg.third_pass_iters, cfg.pcg_mode, cfg.pcg_check_every = third_pass_iters, pcg_mode, pcg_check_every
+        cfg.reserved[0] = 1 if stage_timing else 0
+        self.h = C.c_void_p()
+        rc = L.sqrtba_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            msg = L.sqrtba_last_error(None)
+            self.h = None
+            raise SqrtBAError(f"sqrtba_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.n_pose = self.n_point = self.n_obs = 0
+        self.n_win = 1
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sqrtba_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, what):
+        if rc < 0:
+            msg = lib().sqrtba_last_error(self.h)
+            raise SqrtBAError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+        return rc
+
+    def _arrays(self, prob):
+        return (np.ascontiguousarray(prob.pose_qt, np.float64), np.ascontiguousarray(prob.pose_fixed, np.uint8),
+                np.ascontiguousarray(prob.cam, np.float64), np.ascontiguousarray(prob.point_xyz, np.float64),
+                np.ascontiguousarray(prob.obs_pose, np.int32), np.ascontiguousarray(prob.obs_point, np.int32),
+                np.ascontiguousarray(prob.obs_meas, np.float32))
+
+    def set_problem(self, prob):
+        a = self._arrays(prob)
+        self.n_pose, self.n_point, self.n_obs, self.n_win = prob.n_pose, prob.n_point, prob.n_obs, 1
+        self._chk(lib().sqrtba_set_problem(self.h, prob.n_pose, prob.n_point, prob.n_obs, _p(a[0], C.c_double),
+                                           _p(a[1], C.c_uint8), _p(a[2], C.c_double), _p(a[3], C.c_double),
+                                           _p(a[4], C.c_int32), _p(a[5], C.c_int32), _p(a[6], C.c_float)),
+                  "sqrtba_set_problem")
+
+    def set_problem_batch(self, prob, pose_ptr, point_ptr, obs_ptr):
+        a = self._arrays(prob)
+        pp, tp, op = (np.ascontiguousarray(x, np.int64) for x in (pose_ptr, point_ptr, obs_ptr))
+        self.n_pose, self.n_point, self.n_obs, self.n_win = prob.n_pose, prob.n_point, prob.n_obs, len(pp) - 1
+        self._chk(lib().sqrtba_set_problem_batch(self.h, self.n_win, _p(pp, C.c_int64), _p(tp, C.c_int64),
+                                                 _p(op, C.c_int64), _p(a[0], C.c_double), _p(a[1], C.c_uint8),
+                                                 _p(a[2], C.c_double), _p(a[3], C.c_double), _p(a[4], C.c_int32),
+                                                 _p(a[5], C.c_int32), _p(a[6], C.c_float)), "sqrtba_set_problem_batch")
+
+    def reset_state(self):
+        self._chk(lib().sqrtba_reset_state(self.h), "sqrtba_reset_state")
+
+    def solve_local(self, stop=None) -> dict:
+        st = Stats()
+        self._chk(lib().sqrtba_solve_local(self.h, stop, C.byref(st)), "sqrtba_solve_local")
+        return st.as_dict()
+
+    def solve_global(self, iters: int, robust: bool, stop=None) -> dict:
+        st = Stats()
+        self._chk(lib().sqrtba_solve_global(self.h, iters, int(robust), stop, C.byref(st)), "sqrtba_solve_global")
+        return st.as_dict()
+
+    def poses(self):
+        out = np.zeros((self.n_pose, 7))
+        self._chk(lib().sqrtba_get_poses(self.h, _p(out, C.c_double)), "sqrtba_get_poses")
+        return out
+
+    def points(self):
+        out = np.zeros((self.n_point, 3))
+        self._chk(lib().sqrtba_get_points(self.h, _p(out, C.c_double)), "sqrtba_get_points")
+        return out
+
+    def outliers(self):
+        out = np.zeros(self.n_obs, np.uint8)
+        self._chk(lib().sqrtba_get_outliers(self.h, _p(out, C.c_uint8)), "sqrtba_get_outliers")
+        return out
+
+    def trace(self, window: int = 0):
+        n = self._chk(lib().sqrtba_get_trace_len(self.h, window), "sqrtba_get_trace_len")
+        out = np.zeros((n, len(TRACE_COLS)))
+        if n:
+            self._chk(lib().sqrtba_get_trace(self.h, window, _p(out, C.c_double), n), "sqrtba_get_trace")
+        return out
+
+    def num_free_poses(self) -> int:
+        return self._chk(lib().sqrtba_num_free_poses(self.h), "sqrtba_num_free_poses")
+
+    def debug_linearize(self, huber: int = 1):
+        n = self.n_obs
+        err, Jp, Jl, r = np.zeros((n, 3)), np.zeros((n, 18)), np.zeros((n, 9)), np.zeros((n, 3))
+        chi = np.zeros(self.n_win)
+        self._chk(lib().sqrtba_debug_linearize(self.h, huber, _p(err, C.c_double), _p(Jp, C.c_double),
+                                               _p(Jl, C.c_double), _p(r, C.c_double), _p(chi, C.c_double)),
+                  "sqrtba_debug_linearize")
+        return dict(err=err, Jp=Jp.reshape(n, 3, 6), Jl=Jl.reshape(n, 3, 3), r=r, chi2=chi)
+
+    def debug_step(self, lam: float):
+        ns = self.num_free_poses()
+        dp, dl, bs = np.zeros((max(ns, 1), 6)), np.zeros((self.n_point, 3)), np.zeros((max(ns, 1), 6))
+        it = C.c_int32(0)
+        self._chk(lib().sqrtba_debug_step(self.h, lam, _p(dp, C.c_double), _p(dl, C.c_double), _p(bs, C.c_double),
+                                          C.byref(it)), "sqrtba_debug_step")
+        return dict(dp=dp[:ns], dl=dl, bs=bs[:ns], cg_iters=it.value)
+
+    def debug_matvec(self, p):
+        p = np.ascontiguousarray(p, np.float64)
+        y = np.zeros_like(p)
+        self._chk(lib().sqrtba_debug_matvec(self.h, _p(p, C.c_double), _p(y, C.c_double)), "sqrtba_debug_matvec")
+        return y
+
+    def time_stage(self, stage: int, warmup: int = 3, reps: int = 20) -> float:
+        ms = C.c_double(0)
+        self._chk(lib().sqrtba_time_stage(self.h, stage, warmup, reps, C.byref(ms)), "sqrtba_time_stage")
+        return ms.value

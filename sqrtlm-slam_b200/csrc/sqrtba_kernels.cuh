@@ -1,0 +1,981 @@
+// CUDA kernels of the square-root LM bundle-adjustment path (sm_100a).
+//
+// Work decomposition.  Observations arrive grouped by landmark.  The host packs whole landmarks into "items"
+// of at most 32 observations; one warp owns one item, one lane owns one observation, so every per-landmark
+// reduction (Householder norms, Q1^T v, J_l^T r ...) is a segmented warp-shuffle reduction and every
+// per-observation plane access is a fully coalesced stream.  A landmark with more than 32 observations gets
+// an item of its own and the warp sweeps it in chunks of 32.  Items never straddle windows (batched BA).
+//
+// Storage is SoA by component ("planes" of n_obs doubles): Jp 18, Jl 9, Q1 9, r 3, err 3.
+// All arithmetic is FP64 (tolerances 1e-6 on cost / 1e-5 m on poses); the roofline is HBM bandwidth.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sqrtba_math.cuh"
+
+namespace sqrtba {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int CTA = 256;
+constexpr int WARPS = CTA / 32;
+
+enum Phase { PH_LIN = 0, PH_TRIAL = 1, PH_DONE = 2 };
+
+constexpr int TRACE_COLS = 10;
+
+struct WinCtl {
+  double lambda, ni, cur_chi, ini_chi, tmp_chi, rho;
+  unsigned long long maxdiag_bits;  // landmark-side max |diag(Hll)| as ordered bits (non-negative doubles)
+  double rz, rz0;
+  int iter, qmax, nbad, phase;
+  int max_iter, pass, cg_active, cg_iters;
+  int trace_len, need_restore, lin_count, pad;
+};
+
+struct Dev {
+  int n_pose, n_point, n_obs, n_win, n_slot, n_item;
+  // ---- problem (static)
+  const double* cam;       // n_pose*5
+  const int* pose_slot;    // n_pose: free slot or -1
+  const int* slot_pose;    // n_slot
+  const int* slot_win;     // n_slot
+  const int* pose_win;     // n_pose
+  const int* point_win;    // n_point
+  const float4* obs_meas;  // n_obs
+  const int* obs_pose;     // n_obs
+  const int* obs_point;    // n_obs
+  const int* obs_slot;     // n_obs: pose_slot[obs_pose]
+  const int* item_start;   // n_item
+  const int* item_cnt;     // n_item
+  const int* item_win;     // n_item
+  const int* win_item_ptr;  // n_win+1
+  const int* win_slot_ptr;  // n_win+1
+  // ---- state
+  double* pose;       // n_pose*7 (t,q)
+  double* point;      // n_point*3
+  double* pose_bak;
+  double* point_bak;
+  uint8_t* obs_level;  // n_obs (0 active, 1 excluded)
+  uint8_t* obs_outlier;
+  // ---- linearisation (planes)
+  double* err;  // 3 planes: g2o's stored _error (unweighted)
+  double* Jp;   // 18
+  double* Jl;   // 9
+  double* Q1;   // 9
+  double* r;    // 3
+  // ---- per landmark (planes of n_point)
+  double* R;   // 6: r00 r01 r02 r11 r12 r22
+  double* tl;  // 3: Q1^T r
+  double* bl;  // 3: -Jl^T r
+  double* dl;  // 3: landmark step
+  // ---- per slot
+  double* bp;   // 6*n_slot  -Jp^T r
+  double* hd;   // 6*n_slot  diag(Jp^T Jp)
+  double* bs;   // 6*n_slot  reduced rhs
+  double* D;    // 21*n_slot upper triangle of the block-Jacobi block (without lambda)
+  double* Dinv; // 36*n_slot
+  double* x;    // 6*n_slot  pose step
+  double* res;
+  double* z;
+  double* p;
+  double* q;
+  // ---- per item
+  double* chi_part;    // n_item
+  double* scale_part;  // n_item
+  // ---- control
+  WinCtl* ctl;      // n_win
+  double* trace;    // n_win * max_trace * TRACE_COLS
+  int max_trace;
+  int* counters;    // [0] windows done, [1] cg-active windows
+};
+
+// ------------------------------------------------------------------------------------------------ warp helpers
+
+struct Seg {
+  int start, end;  // lane range [start,end) of this lane's landmark inside the warp
+};
+
+__device__ __forceinline__ Seg seg_of(int key, int lane) {
+  const int prev = __shfl_up_sync(FULL, key, 1);
+  const bool head = (lane == 0) || (key != prev);
+  const unsigned heads = __ballot_sync(FULL, head);
+  Seg s;
+  s.start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+  const unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+  s.end = above ? (__ffs(above) - 1) : 32;
+  return s;
+}
+
+// sum over the lane's segment, result broadcast to every lane of the segment (fixed order => deterministic)
+__device__ __forceinline__ double seg_sum(double v, const Seg& s, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double t = __shfl_down_sync(FULL, v, off);
+    if (lane + off < s.end) v += t;
+  }
+  return __shfl_sync(FULL, v, s.start);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, off));
+  return v;
+}
+
+// reduction of one value over the whole landmark, for both item shapes:
+//   short item (LONG=false): segmented over the lane's landmark;  long item: whole warp
+template <bool LONG>
+__device__ __forceinline__ double lm_sum(double v, const Seg& s, int lane) {
+  if (LONG) return warp_sum(v);
+  return seg_sum(v, s, lane);
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {  // sh: WARPS doubles, result to all threads
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < WARPS; i++) t += sh[i];
+  return t;
+}
+
+__device__ __forceinline__ void atomic_max_pos(unsigned long long* addr, double v) {
+  atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
+
+// ------------------------------------------------------------------------------------------------ K0: zeroing
+
+// per-slot accumulators that the linearise kernel fills with atomics (only for windows that re-linearise)
+__global__ void k_zero_lin(Dev P) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P.n_slot) return;
+  if (P.ctl[P.slot_win[s]].phase != PH_LIN) return;
+#pragma unroll
+  for (int c = 0; c < 6; c++) { P.bp[s * 6 + c] = 0.0; P.hd[s * 6 + c] = 0.0; }
+}
+
+// per-slot accumulators of one trial (reduced rhs, block-Jacobi block)
+__global__ void k_zero_trial(Dev P) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P.n_slot) return;
+  if (P.ctl[P.slot_win[s]].phase != PH_TRIAL) return;
+#pragma unroll
+  for (int c = 0; c < 6; c++) P.bs[s * 6 + c] = 0.0;
+#pragma unroll
+  for (int c = 0; c < 21; c++) P.D[s * 21 + c] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------ K1: linearise
+// Fused residual + SE3/point Jacobians + Huber weighting (reference: computeActiveErrors + linearizeOplus +
+// the weighting half of constructQuadraticForm; sparse_optimizer.cpp:61-88, types_six_dof_expmap.cpp:103-234,
+// base_binary_edge.hpp:55-120).  Also produces what LM needs without ever forming H: chi2 (deterministic
+// per-item partials), b_p = -Jp^T r, b_l = -Jl^T r, diag(Jp^T Jp), max diag(Jl^T Jl).
+struct ObsLin {
+  double e[3], Jp[18], Jl[9], w, rho0;
+  bool depth_pos;
+};
+
+__device__ __forceinline__ void obs_eval(const Dev& P, int o, bool want_jac, bool robust, double d2, double d3,
+                                         ObsLin& L) {
+  const float4 m = __ldg(&P.obs_meas[o]);
+  const int ip = __ldg(&P.obs_pose[o]);
+  const int il = __ldg(&P.obs_point[o]);
+  double pose[7], X[3], cam[5], R[9], Xc[3];
+#pragma unroll
+  for (int i = 0; i < 7; i++) pose[i] = P.pose[ip * 7 + i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) X[i] = P.point[il * 3 + i];
+#pragma unroll
+  for (int i = 0; i < 5; i++) cam[i] = __ldg(&P.cam[ip * 5 + i]);
+  quat_to_R(pose + 3, R);
+  transform(R, pose, X, Xc);
+  const bool stereo = !(m.z < 0.0f);
+  reproj_error(Xc, m.x, m.y, m.z, cam, stereo, L.e);
+  L.depth_pos = Xc[2] > 0.0;
+  const double info = (double)m.w;
+  const double c = L.e[0] * (info * L.e[0]) + L.e[1] * (info * L.e[1]) + L.e[2] * (info * L.e[2]);
+  double rho1 = 1.0;
+  L.rho0 = c;
+  if (robust) {
+    const double delta = stereo ? d3 : d2;
+    huber(c, delta, delta * delta, &L.rho0, &rho1);
+  }
+  L.w = sqrt(rho1 * info);
+  if (want_jac) reproj_jacobians(R, Xc, cam, stereo, L.Jp, L.Jl);
+}
+
+__global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2, double d3, int force_all) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (w >= P.n_item) return;
+  const int win = P.item_win[w];
+  if (!force_all && P.ctl[win].phase != PH_LIN) return;
+  const int start = P.item_start[w], cnt = P.item_cnt[w];
+  const int No = P.n_obs, Nl = P.n_point;
+  const bool is_long = cnt > 32;
+  double chi_acc = 0.0, maxd = 0.0;
+  double bl_acc[3] = {0, 0, 0}, hl_acc[3] = {0, 0, 0};
+  for (int base = 0; base < cnt; base += 32) {
+    const int i = base + lane;
+    const bool act = i < cnt;
+    const int o = start + (act ? i : 0);
+    ObsLin L;
+    int slot = -1, lm = -1 - lane;
+    bool live = false;
+    if (act) {
+      lm = P.obs_point[o];
+      slot = P.obs_slot[o];
+      live = P.obs_level[o] == 0;
+      obs_eval(P, o, true, robust != 0, d2, d3, L);
+      if (live) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) P.err[(size_t)c * No + o] = L.e[c];
+        chi_acc += L.rho0;
+      }
+      // an excluded (level-1) edge contributes zero rows; select, do not multiply (its Jacobian may be inf/NaN)
+#pragma unroll
+      for (int c = 0; c < 18; c++) { L.Jp[c] = live ? L.Jp[c] * L.w : 0.0; P.Jp[(size_t)c * No + o] = L.Jp[c]; }
+#pragma unroll
+      for (int c = 0; c < 9; c++) { L.Jl[c] = live ? L.Jl[c] * L.w : 0.0; P.Jl[(size_t)c * No + o] = L.Jl[c]; }
+#pragma unroll
+      for (int c = 0; c < 3; c++) { L.e[c] = live ? L.e[c] * L.w : 0.0; P.r[(size_t)c * No + o] = L.e[c]; }
+      if (slot >= 0 && live) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          const double g = L.Jp[c] * L.e[0] + L.Jp[6 + c] * L.e[1] + L.Jp[12 + c] * L.e[2];
+          const double h = L.Jp[c] * L.Jp[c] + L.Jp[6 + c] * L.Jp[6 + c] + L.Jp[12 + c] * L.Jp[12 + c];
+          atomicAdd(&P.bp[slot * 6 + c], -g);
+          atomicAdd(&P.hd[slot * 6 + c], h);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 9; c++) L.Jl[c] = 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; c++) L.e[c] = 0.0;
+    }
+    // landmark-side gradient and Hessian diagonal
+    const Seg sg = seg_of(lm, lane);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double g = L.Jl[c] * L.e[0] + L.Jl[3 + c] * L.e[1] + L.Jl[6 + c] * L.e[2];
+      double h = L.Jl[c] * L.Jl[c] + L.Jl[3 + c] * L.Jl[3 + c] + L.Jl[6 + c] * L.Jl[6 + c];
+      if (is_long) {
+        bl_acc[c] += warp_sum(g);
+        hl_acc[c] += warp_sum(h);
+      } else {
+        g = seg_sum(g, sg, lane);
+        h = seg_sum(h, sg, lane);
+        if (act && lane == sg.start) P.bl[(size_t)c * Nl + lm] = -g;
+        maxd = fmax(maxd, h);
+      }
+    }
+  }
+  if (is_long) {
+    const int lm = P.obs_point[start];
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) P.bl[(size_t)c * Nl + lm] = -bl_acc[c];
+    }
+    maxd = fmax(hl_acc[0], fmax(hl_acc[1], hl_acc[2]));
+  }
+  chi_acc = warp_sum(chi_acc);
+  maxd = warp_max(maxd);
+  if (lane == 0) {
+    P.chi_part[w] = chi_acc;
+    atomic_max_pos(&P.ctl[win].maxdiag_bits, maxd);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K8a: LM begin
+// OptimizationAlgorithmLevenberg::solve up to the trial loop (optimization_algorithm_levenberg.cpp:75-100):
+// currentChi, iniChi, lambda init = tau * max diag(H) at iteration 0 (computeLambdaInit :166-180).
+__global__ void __launch_bounds__(CTA) k_lm_begin(Dev P) {
+  __shared__ double sh[WARPS];
+  const int win = blockIdx.x;
+  WinCtl& c = P.ctl[win];
+  if (c.phase != PH_LIN) return;
+  double chi = 0.0, md = 0.0;
+  for (int i = P.win_item_ptr[win] + threadIdx.x; i < P.win_item_ptr[win + 1]; i += CTA) chi += P.chi_part[i];
+  for (int i = P.win_slot_ptr[win] * 6 + threadIdx.x; i < P.win_slot_ptr[win + 1] * 6; i += CTA)
+    md = fmax(md, fabs(P.hd[i]));
+  chi = block_sum(chi, sh);
+  md = warp_max(md);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = md;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WARPS; i++) md = fmax(md, sh[i]);
+    md = fmax(md, __longlong_as_double((long long)c.maxdiag_bits));
+    c.maxdiag_bits = 0ull;
+    c.cur_chi = chi;
+    c.ini_chi = chi;
+    c.tmp_chi = chi;
+    if (c.iter == 0) {
+      c.lambda = 1e-5 * md;  // _tau
+      c.ni = 2.0;
+      c.nbad = 0;
+    }
+    c.qmax = 0;
+    c.rho = 0.0;
+    c.phase = PH_TRIAL;
+    c.lin_count++;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K2: landmark QR
+// In-place Householder QR of A_l = [sqrt(lambda) I3 ; J_l] (damping rows first, so reflector j touches damping
+// row j and every observation row), one lane per observation, norms/dots by (segmented) warp shuffles.
+// Replaces the per-landmark (Hll+lambda I)^-1 and Schur products of block_solver.hpp:381-432 without forming
+// them: keeps R (3x3), the observation rows of the thin factor Q1 (compact-WY: Q1_obs = -V T diag(v0)) and
+// t_l = Q1^T r.  Also emits the reduced right-hand side b_s = -sum Jp^T (r - Q1 t_l) and the 6x6 block-Jacobi
+// blocks sum Jp^T Jp - (Jp^T Q1)(Jp^T Q1)^T of the (never formed) reduced camera matrix.
+struct LmFactor {
+  double beta[3], v0[3], w01, w02, w12;
+  double Rm[6];
+  double M[6];  // upper-tri of T*diag(v0): m00 m01 m02 m11 m12 m22
+};
+
+__device__ __forceinline__ void wy_from_gram(LmFactor& F, double g01, double g02, double g12) {
+  const double T00 = F.beta[0], T11 = F.beta[1], T22 = F.beta[2];
+  const double T01 = -F.beta[1] * (T00 * g01);
+  const double T02 = -F.beta[2] * (T00 * g02 + T01 * g12);
+  const double T12 = -F.beta[2] * (T11 * g12);
+  F.M[0] = T00 * F.v0[0]; F.M[1] = T01 * F.v0[1]; F.M[2] = T02 * F.v0[2];
+  F.M[3] = T11 * F.v0[1]; F.M[4] = T12 * F.v0[2];
+  F.M[5] = T22 * F.v0[2];
+}
+
+// rows of V for one observation from its rows of J_l (a, 3x3 row-major): V0=a0, V1=a1-w01 a0, V2=a2-w02 a0-w12 V1
+__device__ __forceinline__ void v_rows(const double a[9], const LmFactor& F, double V[9]) {
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    V[r * 3 + 0] = a[r * 3 + 0];
+    V[r * 3 + 1] = a[r * 3 + 1] - F.w01 * V[r * 3 + 0];
+    V[r * 3 + 2] = a[r * 3 + 2] - F.w02 * V[r * 3 + 0] - F.w12 * V[r * 3 + 1];
+  }
+}
+__device__ __forceinline__ void q1_rows(const double V[9], const LmFactor& F, double Q[9]) {
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    Q[r * 3 + 0] = -(V[r * 3 + 0] * F.M[0]);
+    Q[r * 3 + 1] = -(V[r * 3 + 0] * F.M[1] + V[r * 3 + 1] * F.M[3]);
+    Q[r * 3 + 2] = -(V[r * 3 + 0] * F.M[2] + V[r * 3 + 1] * F.M[4] + V[r * 3 + 2] * F.M[5]);
+  }
+}
+
+// one Householder column step given the reduced sums; updates the factor
+__device__ __forceinline__ void hh_col(LmFactor& F, int j, double lam, double sl, double sig) {
+  const double norm = sqrt(lam + sig);
+  F.v0[j] = sl + norm;
+  F.beta[j] = 1.0 / (norm * F.v0[j]);
+  F.Rm[j == 0 ? 0 : (j == 1 ? 3 : 5)] = -norm;
+}
+
+__device__ __forceinline__ void load9(const double* planes, size_t stride, int o, double a[9]) {
+#pragma unroll
+  for (int c = 0; c < 9; c++) a[c] = planes[(size_t)c * stride + o];
+}
+
+// scatter of one observation's pose-side contributions for the trial: reduced rhs and block-Jacobi block
+__device__ __forceinline__ void scatter_trial(const Dev& P, int o, int slot, const double Q[9], const double rr[3],
+                                              const double tl[3]) {
+  const int No = P.n_obs;
+  double J[18];
+#pragma unroll
+  for (int c = 0; c < 18; c++) J[c] = P.Jp[(size_t)c * No + o];
+  double u[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) u[r] = rr[r] - (Q[r * 3] * tl[0] + Q[r * 3 + 1] * tl[1] + Q[r * 3 + 2] * tl[2]);
+#pragma unroll
+  for (int c = 0; c < 6; c++) atomicAdd(&P.bs[slot * 6 + c], -(J[c] * u[0] + J[6 + c] * u[1] + J[12 + c] * u[2]));
+  double G[18];  // Jp^T Q1 (6x3)
+#pragma unroll
+  for (int c = 0; c < 6; c++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) G[c * 3 + k] = J[c] * Q[k] + J[6 + c] * Q[3 + k] + J[12 + c] * Q[6 + k];
+  int idx = 0;
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = a; b < 6; b++) {
+      const double v = J[a] * J[b] + J[6 + a] * J[6 + b] + J[12 + a] * J[12 + b] -
+                       (G[a * 3] * G[b * 3] + G[a * 3 + 1] * G[b * 3 + 1] + G[a * 3 + 2] * G[b * 3 + 2]);
+      atomicAdd(&P.D[slot * 21 + idx], v);
+      idx++;
+    }
+}
+
+__global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_override) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (w >= P.n_item) return;
+  const int win = P.item_win[w];
+  if (!force_all && P.ctl[win].phase != PH_TRIAL) return;
+  const double lam = force_all ? lam_override : P.ctl[win].lambda;
+  const double sl = sqrt(lam);
+  const int start = P.item_start[w], cnt = P.item_cnt[w];
+  const int No = P.n_obs, Nl = P.n_point;
+  LmFactor F;
+  if (cnt <= 32) {
+    const bool act = lane < cnt;
+    const int o = start + (act ? lane : 0);
+    const int lm = act ? P.obs_point[o] : (-1 - lane);
+    const Seg sg = seg_of(lm, lane);
+    double a[9], rr[3];
+    if (act) {
+      load9(P.Jl, No, o, a);
+#pragma unroll
+      for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 9; c++) a[c] = 0.0;
+      rr[0] = rr[1] = rr[2] = 0.0;
+    }
+    // column 0
+    double s0 = seg_sum(a[0] * a[0] + a[3] * a[3] + a[6] * a[6], sg, lane);
+    double d01 = seg_sum(a[0] * a[1] + a[3] * a[4] + a[6] * a[7], sg, lane);
+    double d02 = seg_sum(a[0] * a[2] + a[3] * a[5] + a[6] * a[8], sg, lane);
+    hh_col(F, 0, lam, sl, s0);
+    F.w01 = F.beta[0] * d01;
+    F.w02 = F.beta[0] * d02;
+    F.Rm[1] = -F.w01 * F.v0[0];
+    F.Rm[2] = -F.w02 * F.v0[0];
+    double V[9];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      V[r * 3] = a[r * 3];
+      V[r * 3 + 1] = a[r * 3 + 1] - F.w01 * a[r * 3];
+      V[r * 3 + 2] = a[r * 3 + 2] - F.w02 * a[r * 3];
+    }
+    // column 1
+    double s1 = seg_sum(V[1] * V[1] + V[4] * V[4] + V[7] * V[7], sg, lane);
+    double d12 = seg_sum(V[1] * V[2] + V[4] * V[5] + V[7] * V[8], sg, lane);
+    hh_col(F, 1, lam, sl, s1);
+    F.w12 = F.beta[1] * d12;
+    F.Rm[4] = -F.w12 * F.v0[1];
+#pragma unroll
+    for (int r = 0; r < 3; r++) V[r * 3 + 2] -= F.w12 * V[r * 3 + 1];
+    // column 2
+    double s2 = seg_sum(V[2] * V[2] + V[5] * V[5] + V[8] * V[8], sg, lane);
+    hh_col(F, 2, lam, sl, s2);
+    // Gram of the reflector observation parts -> compact WY
+    double g01 = seg_sum(V[0] * V[1] + V[3] * V[4] + V[6] * V[7], sg, lane);
+    double g02 = seg_sum(V[0] * V[2] + V[3] * V[5] + V[6] * V[8], sg, lane);
+    double g12 = seg_sum(V[1] * V[2] + V[4] * V[5] + V[7] * V[8], sg, lane);
+    wy_from_gram(F, g01, g02, g12);
+    double Q[9];
+    q1_rows(V, F, Q);
+    double tl[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) tl[k] = seg_sum(Q[k] * rr[0] + Q[3 + k] * rr[1] + Q[6 + k] * rr[2], sg, lane);
+    if (act) {
+#pragma unroll
+      for (int c = 0; c < 9; c++) P.Q1[(size_t)c * No + o] = Q[c];
+      if (lane == sg.start) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) P.R[(size_t)c * Nl + lm] = F.Rm[c];
+#pragma unroll
+        for (int c = 0; c < 3; c++) P.tl[(size_t)c * Nl + lm] = tl[c];
+      }
+      const int slot = P.obs_slot[o];
+      if (slot >= 0) scatter_trial(P, o, slot, Q, rr, tl);
+    }
+  } else {
+    // long landmark: five sweeps over its rows (L1/L2 resident), whole-warp reductions
+    const int lm = P.obs_point[start];
+    double acc[3] = {0, 0, 0};
+    double a[9];
+    for (int i = lane; i < cnt; i += 32) {
+      load9(P.Jl, No, start + i, a);
+      acc[0] += a[0] * a[0] + a[3] * a[3] + a[6] * a[6];
+      acc[1] += a[0] * a[1] + a[3] * a[4] + a[6] * a[7];
+      acc[2] += a[0] * a[2] + a[3] * a[5] + a[6] * a[8];
+    }
+    hh_col(F, 0, lam, sl, warp_sum(acc[0]));
+    F.w01 = F.beta[0] * warp_sum(acc[1]);
+    F.w02 = F.beta[0] * warp_sum(acc[2]);
+    F.Rm[1] = -F.w01 * F.v0[0];
+    F.Rm[2] = -F.w02 * F.v0[0];
+    F.w12 = 0.0;
+    acc[0] = acc[1] = 0.0;
+    double V[9];
+    for (int i = lane; i < cnt; i += 32) {
+      load9(P.Jl, No, start + i, a);
+      v_rows(a, F, V);  // w12 = 0: V2 is the column-0-reduced third column
+      acc[0] += V[1] * V[1] + V[4] * V[4] + V[7] * V[7];
+      acc[1] += V[1] * V[2] + V[4] * V[5] + V[7] * V[8];
+    }
+    hh_col(F, 1, lam, sl, warp_sum(acc[0]));
+    F.w12 = F.beta[1] * warp_sum(acc[1]);
+    F.Rm[4] = -F.w12 * F.v0[1];
+    double g[4] = {0, 0, 0, 0};
+    for (int i = lane; i < cnt; i += 32) {
+      load9(P.Jl, No, start + i, a);
+      v_rows(a, F, V);
+      g[0] += V[2] * V[2] + V[5] * V[5] + V[8] * V[8];
+      g[1] += V[0] * V[1] + V[3] * V[4] + V[6] * V[7];
+      g[2] += V[0] * V[2] + V[3] * V[5] + V[6] * V[8];
+      g[3] += V[1] * V[2] + V[4] * V[5] + V[7] * V[8];
+    }
+    hh_col(F, 2, lam, sl, warp_sum(g[0]));
+    const double g01 = warp_sum(g[1]), g02 = warp_sum(g[2]), g12 = warp_sum(g[3]);
+    wy_from_gram(F, g01, g02, g12);
+    double tl[3] = {0, 0, 0}, Q[9], rr[3];
+    for (int i = lane; i < cnt; i += 32) {
+      const int o = start + i;
+      load9(P.Jl, No, o, a);
+      v_rows(a, F, V);
+      q1_rows(V, F, Q);
+#pragma unroll
+      for (int c = 0; c < 9; c++) P.Q1[(size_t)c * No + o] = Q[c];
+#pragma unroll
+      for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
+#pragma unroll
+      for (int k = 0; k < 3; k++) tl[k] += Q[k] * rr[0] + Q[3 + k] * rr[1] + Q[6 + k] * rr[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) tl[k] = warp_sum(tl[k]);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) P.R[(size_t)c * Nl + lm] = F.Rm[c];
+#pragma unroll
+      for (int c = 0; c < 3; c++) P.tl[(size_t)c * Nl + lm] = tl[c];
+    }
+    for (int i = lane; i < cnt; i += 32) {
+      const int o = start + i;
+      const int slot = P.obs_slot[o];
+      if (slot < 0) continue;
+      load9(P.Q1, No, o, Q);  // written by this same lane above
+#pragma unroll
+      for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
+      scatter_trial(P, o, slot, Q, rr, tl);
+    }
+  }
+}
+
+// 6x6 block-Jacobi inverse per pose slot: (D + lambda I)^-1
+__global__ void k_dinv(Dev P, int force_all, double lam_override) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P.n_slot) return;
+  const WinCtl& c = P.ctl[P.slot_win[s]];
+  if (!force_all && c.phase != PH_TRIAL) return;
+  const double lam = force_all ? lam_override : c.lambda;
+  double A[36], Ai[36];
+  int idx = 0;
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = a; b < 6; b++) {
+      const double v = P.D[s * 21 + idx] + (a == b ? lam : 0.0);
+      A[a * 6 + b] = v;
+      A[b * 6 + a] = v;
+      idx++;
+    }
+  if (!spd6_inverse(A, Ai)) {
+    for (int i = 0; i < 36; i++) Ai[i] = 0.0;
+    for (int i = 0; i < 6; i++) Ai[i * 6 + i] = 1.0 / fmax(fabs(A[i * 6 + i]), 1e-300);
+  }
+  for (int i = 0; i < 36; i++) P.Dinv[s * 36 + i] = Ai[i];
+}
+
+// ------------------------------------------------------------------------------------------------ K3: matvec
+// q += sum_l Jp^T (I - Q1 Q1^T) Jp p  over the landmarks of this warp's item (lambda*p is added by the CG
+// update).  Per observation: v = Jp p[slot] (d-vector), s_l = sum Q1^T v (3-vector, landmark reduction),
+// u = v - Q1 s_l, scatter-add Jp^T u.  Streams Jp (18) + Q1 (9) planes: 216 B/observation.
+// Observations of fixed poses have no pose columns (g2o hessianIndex -1): they are skipped entirely.
+__device__ __forceinline__ void matvec_obs_v(const Dev& P, const double* __restrict__ pvec, int o, int slot,
+                                             double J[18], double Q[9], double v[3]) {
+  const int No = P.n_obs;
+#pragma unroll
+  for (int c = 0; c < 18; c++) J[c] = P.Jp[(size_t)c * No + o];
+#pragma unroll
+  for (int c = 0; c < 9; c++) Q[c] = P.Q1[(size_t)c * No + o];
+  double pp[6];
+#pragma unroll
+  for (int c = 0; c < 6; c++) pp[c] = pvec[slot * 6 + c];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+    v[r] = J[r * 6] * pp[0] + J[r * 6 + 1] * pp[1] + J[r * 6 + 2] * pp[2] + J[r * 6 + 3] * pp[3] +
+           J[r * 6 + 4] * pp[4] + J[r * 6 + 5] * pp[5];
+}
+
+__device__ __forceinline__ void matvec_item(const Dev& P, const double* __restrict__ pvec, double* __restrict__ qvec,
+                                            int w, int lane) {
+  const int start = P.item_start[w], cnt = P.item_cnt[w];
+  if (cnt <= 32) {
+    const bool act = lane < cnt;
+    const int o = start + (act ? lane : 0);
+    const int lm = act ? P.obs_point[o] : (-1 - lane);
+    const int slot = act ? P.obs_slot[o] : -1;
+    const Seg sg = seg_of(lm, lane);
+    double J[18], Q[9], v[3] = {0, 0, 0}, sv[3];
+    if (slot >= 0) matvec_obs_v(P, pvec, o, slot, J, Q, v);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double t = (slot >= 0) ? (Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2]) : 0.0;
+      sv[k] = seg_sum(t, sg, lane);
+    }
+    if (slot >= 0) {
+#pragma unroll
+      for (int r = 0; r < 3; r++) v[r] -= Q[r * 3] * sv[0] + Q[r * 3 + 1] * sv[1] + Q[r * 3 + 2] * sv[2];
+#pragma unroll
+      for (int c = 0; c < 6; c++) atomicAdd(&qvec[slot * 6 + c], J[c] * v[0] + J[6 + c] * v[1] + J[12 + c] * v[2]);
+    }
+  } else {
+    double J[18], Q[9], v[3], sv[3] = {0, 0, 0};
+    for (int i = lane; i < cnt; i += 32) {
+      const int o = start + i;
+      const int slot = P.obs_slot[o];
+      if (slot < 0) continue;
+      matvec_obs_v(P, pvec, o, slot, J, Q, v);
+#pragma unroll
+      for (int k = 0; k < 3; k++) sv[k] += Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) sv[k] = warp_sum(sv[k]);
+    for (int i = lane; i < cnt; i += 32) {
+      const int o = start + i;
+      const int slot = P.obs_slot[o];
+      if (slot < 0) continue;
+      matvec_obs_v(P, pvec, o, slot, J, Q, v);
+#pragma unroll
+      for (int r = 0; r < 3; r++) v[r] -= Q[r * 3] * sv[0] + Q[r * 3 + 1] * sv[1] + Q[r * 3 + 2] * sv[2];
+#pragma unroll
+      for (int c = 0; c < 6; c++) atomicAdd(&qvec[slot * 6 + c], J[c] * v[0] + J[6 + c] * v[1] + J[12 + c] * v[2]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CTA) k_matvec(Dev P, const double* __restrict__ pvec, double* __restrict__ qvec,
+                                                int force_all) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (w >= P.n_item) return;
+  if (!force_all && !P.ctl[P.item_win[w]].cg_active) return;
+  matvec_item(P, pvec, qvec, w, lane);
+}
+
+// ------------------------------------------------------------------------------------------------ K4/K5: PCG vector ops
+// One CTA owns one window's pose-sized vectors, so dot products are block reductions with no global sync.
+__global__ void __launch_bounds__(CTA) k_cg_init(Dev P, int force_all) {
+  __shared__ double sh[WARPS];
+  const int win = blockIdx.x;
+  WinCtl& c = P.ctl[win];
+  if (!force_all && c.phase != PH_TRIAL) return;
+  const int s0 = P.win_slot_ptr[win], s1 = P.win_slot_ptr[win + 1];
+  double rz = 0.0;
+  for (int e = s0 * 6 + threadIdx.x; e < s1 * 6; e += CTA) {
+    const int s = e / 6, rr = e - s * 6;
+    double z = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) z += P.Dinv[s * 36 + rr * 6 + k] * P.bs[s * 6 + k];
+    const double b = P.bs[e];
+    P.x[e] = 0.0;
+    P.res[e] = b;
+    P.z[e] = z;
+    P.p[e] = z;
+    rz += b * z;
+  }
+  rz = block_sum(rz, sh);
+  if (threadIdx.x == 0) {
+    c.rz = rz;
+    c.rz0 = rz;
+    c.cg_iters = 0;
+    c.cg_active = (rz > 0.0) ? 1 : 0;
+    if (c.cg_active) atomicAdd(&P.counters[1], 1);
+  }
+}
+
+__global__ void __launch_bounds__(CTA) k_cg_step(Dev P, double tol2, int max_iters, int force_all, double lam_override) {
+  __shared__ double sh[WARPS];
+  const int win = blockIdx.x;
+  WinCtl& c = P.ctl[win];
+  if (!c.cg_active) return;
+  const double lam = force_all ? lam_override : c.lambda;
+  const int e0 = P.win_slot_ptr[win] * 6, e1 = P.win_slot_ptr[win + 1] * 6;
+  double pq = 0.0;
+  for (int e = e0 + threadIdx.x; e < e1; e += CTA) {
+    const double qq = P.q[e] + lam * P.p[e];
+    P.q[e] = qq;
+    pq += P.p[e] * qq;
+  }
+  pq = block_sum(pq, sh);
+  const double rz = c.rz;
+  const double alpha = rz / pq;
+  const bool broke = !(pq > 0.0) || !isfinite(alpha);
+  if (broke) {  // breakdown: keep the current iterate; LM will judge the step by its gain ratio
+    if (threadIdx.x == 0) { c.cg_active = 0; atomicSub(&P.counters[1], 1); }
+    return;
+  }
+  for (int e = e0 + threadIdx.x; e < e1; e += CTA) {
+    P.x[e] += alpha * P.p[e];
+    P.res[e] -= alpha * P.q[e];
+  }
+  __syncthreads();
+  double rzn = 0.0;
+  for (int e = e0 + threadIdx.x; e < e1; e += CTA) {
+    const int s = e / 6, rr = e - s * 6;
+    double z = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) z += P.Dinv[s * 36 + rr * 6 + k] * P.res[s * 6 + k];
+    P.z[e] = z;
+    rzn += P.res[e] * z;
+  }
+  rzn = block_sum(rzn, sh);
+  const double beta = rzn / rz;
+  for (int e = e0 + threadIdx.x; e < e1; e += CTA) P.p[e] = P.z[e] + beta * P.p[e];
+  if (threadIdx.x == 0) {
+    c.rz = rzn;
+    c.cg_iters++;
+    if (!(rzn > tol2 * c.rz0) || c.cg_iters >= max_iters) {
+      c.cg_active = 0;
+      atomicSub(&P.counters[1], 1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K6: back-substitution
+// dl = -R^-1 (t_l + sum_o Q1_o^T Jp_o dp[slot])  == g2o's Dinv (b_l - Hpl^T dp) (block_solver.hpp:461-483);
+// also the landmark part of computeScale: sum dl (lambda dl + b_l)  (optimization_algorithm_levenberg.cpp:182-189)
+__global__ void __launch_bounds__(CTA) k_backsub(Dev P, int force_all, double lam_override) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (w >= P.n_item) return;
+  const int win = P.item_win[w];
+  if (!force_all && P.ctl[win].phase != PH_TRIAL) return;
+  const double lam = force_all ? lam_override : P.ctl[win].lambda;
+  const int start = P.item_start[w], cnt = P.item_cnt[w];
+  const int Nl = P.n_point;
+  const bool is_long = cnt > 32;
+  double g[3] = {0, 0, 0};
+  double scale = 0.0;
+  int lm = -1 - lane;
+  Seg sg;
+  sg.start = 0; sg.end = 32;
+  bool act = false;
+  for (int base = 0; base < cnt; base += 32) {
+    const int i = base + lane;
+    act = i < cnt;
+    const int o = start + (act ? i : 0);
+    const int slot = act ? P.obs_slot[o] : -1;
+    if (act) lm = P.obs_point[o];
+    double J[18], Q[9], v[3];
+    double t[3] = {0, 0, 0};
+    if (slot >= 0) {
+      matvec_obs_v(P, P.x, o, slot, J, Q, v);
+#pragma unroll
+      for (int k = 0; k < 3; k++) t[k] = Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2];
+    }
+    if (is_long) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) g[k] += t[k];
+    } else {
+      sg = seg_of(lm, lane);
+#pragma unroll
+      for (int k = 0; k < 3; k++) g[k] = seg_sum(t[k], sg, lane);
+    }
+  }
+  bool head;
+  if (is_long) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) g[k] = warp_sum(g[k]);
+    lm = P.obs_point[start];
+    head = lane == 0;
+  } else {
+    head = act && lane == sg.start;
+  }
+  if (head) {
+    double Rm[6], tl[3], bl[3], d[3];
+#pragma unroll
+    for (int c = 0; c < 6; c++) Rm[c] = P.R[(size_t)c * Nl + lm];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { tl[c] = P.tl[(size_t)c * Nl + lm]; bl[c] = P.bl[(size_t)c * Nl + lm]; }
+    const double y0 = tl[0] + g[0], y1 = tl[1] + g[1], y2 = tl[2] + g[2];
+    d[2] = y2 / Rm[5];
+    d[1] = (y1 - Rm[4] * d[2]) / Rm[3];
+    d[0] = (y0 - Rm[1] * d[1] - Rm[2] * d[2]) / Rm[0];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      d[c] = -d[c];
+      P.dl[(size_t)c * Nl + lm] = d[c];
+      scale += d[c] * (lam * d[c] + bl[c]);
+    }
+  }
+  scale = warp_sum(scale);
+  if (lane == 0) P.scale_part[w] = scale;
+}
+
+// ------------------------------------------------------------------------------------------------ K7: state update
+// SparseOptimizer::update -> oplusImpl on every free vertex of the windows in a trial (sparse_optimizer.cpp:422-435);
+// push() is the device-to-device backup the host enqueues right before (sparse_optimizer.cpp:600-603).
+__global__ void k_update_pose(Dev P) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P.n_slot) return;
+  if (P.ctl[P.slot_win[s]].phase != PH_TRIAL) return;
+  const int ip = P.slot_pose[s];
+  double pose[7], xi[6];
+  for (int i = 0; i < 7; i++) pose[i] = P.pose[ip * 7 + i];
+  for (int i = 0; i < 6; i++) xi[i] = P.x[s * 6 + i];
+  pose_oplus(pose, xi);
+  for (int i = 0; i < 7; i++) P.pose[ip * 7 + i] = pose[i];
+}
+__global__ void k_update_point(Dev P) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= P.n_point) return;
+  if (P.ctl[P.point_win[l]].phase != PH_TRIAL) return;
+#pragma unroll
+  for (int c = 0; c < 3; c++) P.point[l * 3 + c] += P.dl[(size_t)c * P.n_point + l];
+}
+// pop(): restore the pre-trial estimate of the windows whose trial was rejected (sparse_optimizer.cpp:605-608)
+__global__ void k_restore(Dev P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n_pose) {
+    if (P.ctl[P.pose_win[i]].need_restore)
+      for (int c = 0; c < 7; c++) P.pose[i * 7 + c] = P.pose_bak[i * 7 + c];
+  }
+  if (i < P.n_point) {
+    if (P.ctl[P.point_win[i]].need_restore)
+      for (int c = 0; c < 3; c++) P.point[i * 3 + c] = P.point_bak[i * 3 + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K1b: trial cost
+// computeActiveErrors + activeRobustChi2 at the trial state (optimization_algorithm_levenberg.cpp:123-124):
+// rewrites the stored error of ACTIVE edges only -- level-1 edges keep their pass-1 value, and a rejected last
+// trial leaves the trial-state errors behind, exactly like g2o's _error.
+__global__ void __launch_bounds__(CTA) k_cost(Dev P, int robust, double d2, double d3) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (w >= P.n_item) return;
+  if (P.ctl[P.item_win[w]].phase != PH_TRIAL) return;
+  const int start = P.item_start[w], cnt = P.item_cnt[w];
+  const int No = P.n_obs;
+  double chi = 0.0;
+  for (int i = lane; i < cnt; i += 32) {
+    const int o = start + i;
+    if (P.obs_level[o] != 0) continue;
+    ObsLin L;
+    obs_eval(P, o, false, robust != 0, d2, d3, L);
+#pragma unroll
+    for (int c = 0; c < 3; c++) P.err[(size_t)c * No + o] = L.e[c];
+    chi += L.rho0;
+  }
+  chi = warp_sum(chi);
+  if (lane == 0) P.chi_part[w] = chi;
+}
+
+// ------------------------------------------------------------------------------------------------ K8b: LM decision
+// The body of the do-while of OptimizationAlgorithmLevenberg::solve and its exit logic
+// (optimization_algorithm_levenberg.cpp:126-163), one CTA per window.
+__global__ void __launch_bounds__(CTA) k_lm_decide(Dev P, int terminate) {
+  __shared__ double sh[WARPS];
+  const int win = blockIdx.x;
+  WinCtl& c = P.ctl[win];
+  if (c.phase != PH_TRIAL) {
+    if (threadIdx.x == 0) c.need_restore = 0;
+    return;
+  }
+  double chi = 0.0, scale = 0.0;
+  for (int i = P.win_item_ptr[win] + threadIdx.x; i < P.win_item_ptr[win + 1]; i += CTA) {
+    chi += P.chi_part[i];
+    scale += P.scale_part[i];
+  }
+  const double lam = c.lambda;
+  for (int e = P.win_slot_ptr[win] * 6 + threadIdx.x; e < P.win_slot_ptr[win + 1] * 6; e += CTA)
+    scale += P.x[e] * (lam * P.x[e] + P.bp[e]);
+  chi = block_sum(chi, sh);
+  scale = block_sum(scale, sh);
+  if (threadIdx.x != 0) return;
+  const double tempChi = chi;
+  double rho = (c.cur_chi - tempChi);
+  scale += 1e-3;
+  rho /= scale;
+  double* tr = nullptr;
+  if (c.trace_len < P.max_trace) tr = P.trace + ((size_t)win * P.max_trace + c.trace_len) * TRACE_COLS;
+  if (tr) {
+    tr[0] = c.pass; tr[1] = c.iter; tr[2] = c.qmax; tr[3] = lam; tr[4] = c.cur_chi; tr[5] = tempChi; tr[6] = rho;
+    tr[8] = c.cg_iters; tr[9] = (c.rz0 > 0.0) ? sqrt(fabs(c.rz) / c.rz0) : 0.0;
+  }
+  c.tmp_chi = tempChi;
+  c.rho = rho;
+  const bool good = (rho > 0.0) && isfinite(tempChi);
+  if (good) {
+    double alpha = 1.0 - pow((2.0 * rho - 1.0), 3.0);
+    alpha = fmin(alpha, 2.0 / 3.0);
+    const double scaleFactor = fmax(1.0 / 3.0, alpha);
+    c.lambda *= scaleFactor;
+    c.ni = 2.0;
+    c.cur_chi = tempChi;
+    c.need_restore = 0;
+  } else {
+    c.lambda *= c.ni;
+    c.ni *= 2.0;
+    c.need_restore = 1;
+  }
+  if (tr) tr[7] = good ? 1.0 : 0.0;
+  c.trace_len++;
+  c.qmax++;
+  const bool again = (rho < 0.0) && (c.qmax < 10) && !terminate;
+  if (again) return;  // stay in PH_TRIAL: same linearisation, new lambda
+  bool done = false;
+  if (c.qmax == 10 || rho == 0.0) {
+    done = true;  // Terminate
+  } else {
+    if ((c.ini_chi - c.cur_chi) * 1e3 < c.ini_chi) c.nbad++; else c.nbad = 0;
+    if (c.nbad >= 3) done = true;
+  }
+  c.iter++;
+  if (c.iter >= c.max_iter || terminate) done = true;
+  c.phase = done ? PH_DONE : PH_LIN;
+  if (done) atomicAdd(&P.counters[0], 1);
+}
+
+// start of one optimize(n) call: SparseOptimizer::optimize + the iteration==0 re-initialisation of lambda
+__global__ void k_pass_init(Dev P, int max_iter, int pass) {
+  const int win = blockIdx.x * blockDim.x + threadIdx.x;
+  if (win >= P.n_win) return;
+  WinCtl& c = P.ctl[win];
+  c.iter = 0;
+  c.qmax = 0;
+  c.nbad = 0;
+  c.phase = (max_iter > 0) ? PH_LIN : PH_DONE;
+  c.max_iter = max_iter;
+  c.pass = pass;
+  c.need_restore = 0;
+  c.cg_active = 0;
+  c.maxdiag_bits = 0ull;
+}
+
+// ------------------------------------------------------------------------------------------------ K9: outlier flags
+// mode 0: after pass 1 -> e->setLevel(1) (g2oOptimizer.cc:952-970); mode 1: final -> erase flag (:1125-1142).
+// chi2 comes from the STORED error (stale for level-1 edges by design), depth from the current estimates.
+__global__ void k_classify(Dev P, int mode, double thr2d, double thr3d) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= P.n_obs) return;
+  const float4 m = P.obs_meas[o];
+  const bool stereo = !(m.z < 0.0f);
+  const double info = (double)m.w;
+  const double e0 = P.err[o], e1 = P.err[(size_t)P.n_obs + o], e2 = P.err[(size_t)2 * P.n_obs + o];
+  const double c = e0 * (info * e0) + e1 * (info * e1) + e2 * (info * e2);
+  const int ip = P.obs_pose[o], il = P.obs_point[o];
+  double R[9], Xc[3];
+  quat_to_R(P.pose + ip * 7 + 3, R);
+  transform(R, P.pose + ip * 7, P.point + il * 3, Xc);
+  const bool bad = (c > (stereo ? thr3d : thr2d)) || !(Xc[2] > 0.0);
+  if (mode == 0) {
+    if (bad) P.obs_level[o] = 1;
+  } else {
+    P.obs_outlier[o] = bad ? 1 : 0;
+  }
+}
+
+}  // namespace sqrtba

@@ -1,0 +1,739 @@
+// Host orchestration of the sqrtba CUDA path + the extern "C" ABI declared in include/sqrtba.h.
+//
+// One handle = one CUDA stream + device buffers for one (possibly batched) BA problem.  The LM loop of the
+// reference (Thirdparty/g2o/g2o/core/sparse_optimizer.cpp:354-419 driving
+// optimization_algorithm_levenberg.cpp:61-164) is run in lock-step over all windows of the batch: every
+// "macro step" is  [linearise windows that accepted]  ->  landmark QR with each window's lambda  ->  PCG  ->
+// back-substitution  ->  trial update  ->  trial cost  ->  per-window accept/reject on the device.
+// The host only enqueues kernels, reads back two counters per macro step and polls the caller's stop flag
+// (bool* pbStopFlag, src/backend/g2oOptimizer.cc:797-798) -- it never touches problem data after upload.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sqrtba.h"
+#include "sqrtba_kernels.cuh"
+
+namespace sqrtba {
+
+#define CU_CHECK(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      char buf__[512];                                                                         \
+      snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      err_ = buf__;                                                                            \
+      return SQRTBA_ERR_CUDA;                                                                  \
+    }                                                                                          \
+  } while (0)
+
+template <class T>
+struct DBuf {  // device buffer that only grows
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+class Solver {
+ public:
+  explicit Solver(const sqrtba_config& cfg) : cfg_(cfg) {}
+  ~Solver() { destroy(); }
+
+  int init() {
+    int ndev = 0;
+    CU_CHECK(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0 || cfg_.device >= ndev) {
+      err_ = "no CUDA device (sqrtba has no CPU fallback)";
+      return SQRTBA_ERR_CUDA;
+    }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    CU_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CU_CHECK(cudaMallocHost((void**)&h_counters_, 4 * sizeof(int)));
+    CU_CHECK(cudaEventCreate(&ev0_));
+    CU_CHECK(cudaEventCreate(&ev1_));
+    for (auto& e : stage_ev_) CU_CHECK(cudaEventCreate(&e));
+    return SQRTBA_OK;
+  }
+
+  void destroy() {
+    if (stream_) {
+      cudaSetDevice(cfg_.device);
+      cudaStreamSynchronize(stream_);
+    }
+    release_all();
+    if (h_counters_) cudaFreeHost(h_counters_);
+    h_counters_ = nullptr;
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    for (auto& e : stage_ev_)
+      if (e) cudaEventDestroy(e);
+    ev0_ = ev1_ = nullptr;
+    if (stream_) cudaStreamDestroy(stream_);
+    stream_ = nullptr;
+  }
+
+  const char* last_error() const { return err_.c_str(); }
+
+  // ------------------------------------------------------------------------------------------ problem upload
+  int set_problem(int n_win, const int64_t* wpose, const int64_t* wpoint, const int64_t* wobs, int n_pose, int n_point,
+                  int n_obs, const double* pose_qt, const uint8_t* pose_fixed, const double* cam,
+                  const double* point_xyz, const int32_t* obs_pose, const int32_t* obs_point, const float* obs_meas) {
+    if (n_pose <= 0 || n_point <= 0 || n_obs <= 0 || n_win <= 0 || !pose_qt || !pose_fixed || !cam || !point_xyz ||
+        !obs_pose || !obs_point || !obs_meas) {
+      err_ = "set_problem: empty problem or null pointer";
+      return SQRTBA_ERR_INVALID;
+    }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    have_problem_ = false;
+    std::vector<int> pose_win(n_pose, 0), point_win(n_point, 0);
+    if (n_win > 1) {
+      if (!wpose || !wpoint || !wobs || wpose[n_win] != n_pose || wpoint[n_win] != n_point || wobs[n_win] != n_obs) {
+        err_ = "set_problem_batch: window offsets inconsistent with array sizes";
+        return SQRTBA_ERR_INVALID;
+      }
+      for (int w = 0; w < n_win; w++) {
+        if (wpose[w] > wpose[w + 1] || wpoint[w] > wpoint[w + 1] || wobs[w] > wobs[w + 1]) {
+          err_ = "set_problem_batch: window offsets must be non-decreasing";
+          return SQRTBA_ERR_INVALID;
+        }
+        for (int64_t i = wpose[w]; i < wpose[w + 1]; i++) pose_win[i] = w;
+        for (int64_t i = wpoint[w]; i < wpoint[w + 1]; i++) point_win[i] = w;
+      }
+    }
+    // free-pose slots in pose order (g2o: hessianIndex, poses first; sparse_optimizer.cpp:166-190)
+    std::vector<int> pose_slot(n_pose, -1), slot_pose, slot_win, win_slot_ptr(n_win + 1, 0);
+    for (int i = 0; i < n_pose; i++)
+      if (!pose_fixed[i]) {
+        pose_slot[i] = (int)slot_pose.size();
+        slot_pose.push_back(i);
+        slot_win.push_back(pose_win[i]);
+        win_slot_ptr[pose_win[i] + 1]++;
+      }
+    for (int w = 0; w < n_win; w++) win_slot_ptr[w + 1] += win_slot_ptr[w];
+    const int n_slot = (int)slot_pose.size();
+    // observations: validate, per-landmark counts
+    std::vector<int> obs_slot(n_obs), lm_cnt(n_point, 0);
+    for (int k = 0; k < n_obs; k++) {
+      const int ip = obs_pose[k], il = obs_point[k];
+      if (ip < 0 || ip >= n_pose || il < 0 || il >= n_point) {
+        err_ = "set_problem: observation index out of range";
+        return SQRTBA_ERR_INVALID;
+      }
+      if (k && il < obs_point[k - 1]) {
+        err_ = "set_problem: observations must be grouped by landmark (non-decreasing obs_point)";
+        return SQRTBA_ERR_INVALID;
+      }
+      if (pose_win[ip] != point_win[il]) {
+        err_ = "set_problem_batch: observation links a pose and a point of different windows";
+        return SQRTBA_ERR_INVALID;
+      }
+      obs_slot[k] = pose_slot[ip];
+      lm_cnt[il]++;
+    }
+    // items: whole landmarks packed into <=32 observations, never across windows; long landmarks alone
+    std::vector<int> item_start, item_cnt, item_win, win_item_ptr(n_win + 1, 0);
+    {
+      int o = 0, cur_start = 0, cur_cnt = 0, cur_win = -1;
+      auto flush = [&]() {
+        if (cur_cnt > 0) {
+          item_start.push_back(cur_start);
+          item_cnt.push_back(cur_cnt);
+          item_win.push_back(cur_win);
+          win_item_ptr[cur_win + 1]++;
+        }
+        cur_cnt = 0;
+      };
+      for (int l = 0; l < n_point; l++) {
+        const int k = lm_cnt[l];
+        if (k == 0) continue;
+        const int w = point_win[l];
+        if (k > 32) {
+          flush();
+          item_start.push_back(o);
+          item_cnt.push_back(k);
+          item_win.push_back(w);
+          win_item_ptr[w + 1]++;
+        } else {
+          if (cur_cnt > 0 && (cur_cnt + k > 32 || w != cur_win)) flush();
+          if (cur_cnt == 0) { cur_start = o; cur_win = w; }
+          cur_cnt += k;
+        }
+        o += k;
+      }
+      flush();
+    }
+    for (int w = 0; w < n_win; w++) win_item_ptr[w + 1] += win_item_ptr[w];
+    const int n_item = (int)item_start.size();
+
+    // ---- device allocation
+    P_ = Dev{};
+    P_.n_pose = n_pose; P_.n_point = n_point; P_.n_obs = n_obs; P_.n_win = n_win; P_.n_slot = n_slot; P_.n_item = n_item;
+    const size_t No = n_obs, Nl = n_point, Ns = std::max(n_slot, 1);
+    CU_CHECK(d_cam_.ensure((size_t)n_pose * 5));
+    CU_CHECK(d_pose_slot_.ensure(n_pose));
+    CU_CHECK(d_slot_pose_.ensure(Ns));
+    CU_CHECK(d_slot_win_.ensure(Ns));
+    CU_CHECK(d_pose_win_.ensure(n_pose));
+    CU_CHECK(d_point_win_.ensure(n_point));
+    CU_CHECK(d_meas_.ensure(No));
+    CU_CHECK(d_obs_pose_.ensure(No));
+    CU_CHECK(d_obs_point_.ensure(No));
+    CU_CHECK(d_obs_slot_.ensure(No));
+    CU_CHECK(d_item_start_.ensure(n_item));
+    CU_CHECK(d_item_cnt_.ensure(n_item));
+    CU_CHECK(d_item_win_.ensure(n_item));
+    CU_CHECK(d_win_item_ptr_.ensure(n_win + 1));
+    CU_CHECK(d_win_slot_ptr_.ensure(n_win + 1));
+    CU_CHECK(d_pose_.ensure((size_t)n_pose * 7));
+    CU_CHECK(d_pose0_.ensure((size_t)n_pose * 7));
+    CU_CHECK(d_pose_bak_.ensure((size_t)n_pose * 7));
+    CU_CHECK(d_point_.ensure(Nl * 3));
+    CU_CHECK(d_point0_.ensure(Nl * 3));
+    CU_CHECK(d_point_bak_.ensure(Nl * 3));
+    CU_CHECK(d_level_.ensure(No));
+    CU_CHECK(d_outlier_.ensure(No));
+    CU_CHECK(d_err_.ensure(No * 3));
+    CU_CHECK(d_Jp_.ensure(No * 18));
+    CU_CHECK(d_Jl_.ensure(No * 9));
+    CU_CHECK(d_Q1_.ensure(No * 9));
+    CU_CHECK(d_r_.ensure(No * 3));
+    CU_CHECK(d_R_.ensure(Nl * 6));
+    CU_CHECK(d_tl_.ensure(Nl * 3));
+    CU_CHECK(d_bl_.ensure(Nl * 3));
+    CU_CHECK(d_dl_.ensure(Nl * 3));
+    CU_CHECK(d_slotvec_.ensure(Ns * (6 * 8 + 21 + 36)));
+    CU_CHECK(d_chi_part_.ensure(n_item));
+    CU_CHECK(d_scale_part_.ensure(n_item));
+    CU_CHECK(d_ctl_.ensure(n_win));
+    max_trace_ = 200;
+    CU_CHECK(d_trace_.ensure((size_t)n_win * max_trace_ * TRACE_COLS));
+    CU_CHECK(d_counters_.ensure(4));
+
+    auto up = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_); };
+    CU_CHECK(up(d_cam_.p, cam, (size_t)n_pose * 5 * sizeof(double)));
+    CU_CHECK(up(d_pose_slot_.p, pose_slot.data(), n_pose * sizeof(int)));
+    if (n_slot) {
+      CU_CHECK(up(d_slot_pose_.p, slot_pose.data(), n_slot * sizeof(int)));
+      CU_CHECK(up(d_slot_win_.p, slot_win.data(), n_slot * sizeof(int)));
+    }
+    CU_CHECK(up(d_pose_win_.p, pose_win.data(), n_pose * sizeof(int)));
+    CU_CHECK(up(d_point_win_.p, point_win.data(), n_point * sizeof(int)));
+    CU_CHECK(up(d_meas_.p, obs_meas, No * sizeof(float4)));
+    CU_CHECK(up(d_obs_pose_.p, obs_pose, No * sizeof(int)));
+    CU_CHECK(up(d_obs_point_.p, obs_point, No * sizeof(int)));
+    CU_CHECK(up(d_obs_slot_.p, obs_slot.data(), No * sizeof(int)));
+    CU_CHECK(up(d_item_start_.p, item_start.data(), n_item * sizeof(int)));
+    CU_CHECK(up(d_item_cnt_.p, item_cnt.data(), n_item * sizeof(int)));
+    CU_CHECK(up(d_item_win_.p, item_win.data(), n_item * sizeof(int)));
+    CU_CHECK(up(d_win_item_ptr_.p, win_item_ptr.data(), (n_win + 1) * sizeof(int)));
+    CU_CHECK(up(d_win_slot_ptr_.p, win_slot_ptr.data(), (n_win + 1) * sizeof(int)));
+    // poses: normalise the quaternion the way SE3Quat's constructor does (se3quat.h:58-64)
+    std::vector<double> pq(pose_qt, pose_qt + (size_t)n_pose * 7);
+    for (int i = 0; i < n_pose; i++) quat_normalize_pos_w(&pq[(size_t)i * 7 + 3]);
+    CU_CHECK(up(d_pose0_.p, pq.data(), (size_t)n_pose * 7 * sizeof(double)));
+    CU_CHECK(up(d_point0_.p, point_xyz, Nl * 3 * sizeof(double)));
+    CU_CHECK(cudaStreamSynchronize(stream_));  // host staging vectors go out of scope
+
+    P_.cam = d_cam_.p; P_.pose_slot = d_pose_slot_.p; P_.slot_pose = d_slot_pose_.p; P_.slot_win = d_slot_win_.p;
+    P_.pose_win = d_pose_win_.p; P_.point_win = d_point_win_.p; P_.obs_meas = d_meas_.p; P_.obs_pose = d_obs_pose_.p;
+    P_.obs_point = d_obs_point_.p; P_.obs_slot = d_obs_slot_.p; P_.item_start = d_item_start_.p;
+    P_.item_cnt = d_item_cnt_.p; P_.item_win = d_item_win_.p; P_.win_item_ptr = d_win_item_ptr_.p;
+    P_.win_slot_ptr = d_win_slot_ptr_.p;
+    P_.pose = d_pose_.p; P_.point = d_point_.p; P_.pose_bak = d_pose_bak_.p; P_.point_bak = d_point_bak_.p;
+    P_.obs_level = d_level_.p; P_.obs_outlier = d_outlier_.p;
+    P_.err = d_err_.p; P_.Jp = d_Jp_.p; P_.Jl = d_Jl_.p; P_.Q1 = d_Q1_.p; P_.r = d_r_.p;
+    P_.R = d_R_.p; P_.tl = d_tl_.p; P_.bl = d_bl_.p; P_.dl = d_dl_.p;
+    double* sv = d_slotvec_.p;
+    P_.bp = sv; sv += Ns * 6;
+    P_.hd = sv; sv += Ns * 6;
+    P_.bs = sv; sv += Ns * 6;
+    P_.x = sv; sv += Ns * 6;
+    P_.res = sv; sv += Ns * 6;
+    P_.z = sv; sv += Ns * 6;
+    P_.p = sv; sv += Ns * 6;
+    P_.q = sv; sv += Ns * 6;
+    P_.D = sv; sv += Ns * 21;
+    P_.Dinv = sv;
+    P_.chi_part = d_chi_part_.p; P_.scale_part = d_scale_part_.p;
+    P_.ctl = d_ctl_.p; P_.trace = d_trace_.p; P_.max_trace = max_trace_; P_.counters = d_counters_.p;
+    have_problem_ = true;
+    return reset_state();
+  }
+
+  int reset_state() {
+    if (!have_problem_) { err_ = "no problem set"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    CU_CHECK(cudaMemcpyAsync(d_pose_.p, d_pose0_.p, (size_t)P_.n_pose * 7 * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    CU_CHECK(cudaMemcpyAsync(d_point_.p, d_point0_.p, (size_t)P_.n_point * 3 * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    CU_CHECK(cudaMemsetAsync(d_level_.p, 0, P_.n_obs, stream_));
+    CU_CHECK(cudaMemsetAsync(d_outlier_.p, 0, P_.n_obs, stream_));
+    CU_CHECK(cudaMemsetAsync(d_err_.p, 0, (size_t)P_.n_obs * 3 * sizeof(double), stream_));
+    CU_CHECK(cudaMemsetAsync(d_ctl_.p, 0, (size_t)P_.n_win * sizeof(WinCtl), stream_));
+    CU_CHECK(cudaMemsetAsync(d_slotvec_.p, 0, d_slotvec_.cap * sizeof(double), stream_));
+    CU_CHECK(cudaMemsetAsync(d_dl_.p, 0, (size_t)P_.n_point * 3 * sizeof(double), stream_));
+    CU_CHECK(cudaStreamSynchronize(stream_));
+    return SQRTBA_OK;
+  }
+
+  // ------------------------------------------------------------------------------------------ solve
+  int solve_local(const volatile bool* stop, sqrtba_stats* st) {
+    if (!have_problem_) { err_ = "no problem set"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    begin_stats();
+    // `const float thHuberMono = sqrt(5.991)` / thHuberStereo = sqrt(7.815) then setDelta(double) (g2oOptimizer.cc:851-853)
+    const double d2 = (double)(float)std::sqrt(5.991), d3 = (double)(float)std::sqrt(7.815);
+    CU_CHECK(cudaMemsetAsync(d_level_.p, 0, P_.n_obs, stream_));
+    CU_CHECK(clear_traces());
+    if (stop && *stop) return finish_stats(st);  // g2oOptimizer.cc:923-928: early out, estimates untouched
+    int rc = run_pass(5, 0, 1, d2, d3, stop);
+    if (rc) return rc;
+    const bool do_more = !(stop && *stop);  // :936-947
+    if (do_more) {
+      launch_classify(0, 5.991, 7.815);
+      rc = run_pass(10, 1, 0, d2, d3, stop);
+      if (rc) return rc;
+    }
+    if (cfg_.third_pass_iters > 0) {
+      rc = run_pass(cfg_.third_pass_iters, 2, 0, d2, d3, stop);
+      if (rc) return rc;
+    }
+    launch_classify(1, 5.991, 7.815);
+    return finish_stats(st);
+  }
+
+  int solve_global(int iters, int robust, const volatile bool* stop, sqrtba_stats* st) {
+    if (!have_problem_) { err_ = "no problem set"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    begin_stats();
+    const double d2 = (double)(float)std::sqrt(5.99), d3 = (double)(float)std::sqrt(7.815);  // g2oOptimizer.cc:163-164
+    CU_CHECK(cudaMemsetAsync(d_level_.p, 0, P_.n_obs, stream_));
+    CU_CHECK(cudaMemsetAsync(d_outlier_.p, 0, P_.n_obs, stream_));
+    CU_CHECK(clear_traces());
+    int rc = run_pass(iters, 0, robust ? 1 : 0, d2, d3, stop);
+    if (rc) return rc;
+    return finish_stats(st);
+  }
+
+  // ------------------------------------------------------------------------------------------ read-back
+  int get_poses(double* out) { return download(out, d_pose_.p, (size_t)P_.n_pose * 7 * sizeof(double)); }
+  int get_points(double* out) { return download(out, d_point_.p, (size_t)P_.n_point * 3 * sizeof(double)); }
+  int get_outliers(uint8_t* out) { return download(out, d_outlier_.p, (size_t)P_.n_obs); }
+  int trace_len(int win) {
+    if (!have_problem_ || win < 0 || win >= P_.n_win) return SQRTBA_ERR_INVALID;
+    WinCtl c;
+    if (download(&c, d_ctl_.p + win, sizeof(WinCtl))) return SQRTBA_ERR_CUDA;
+    return std::min(c.trace_len, max_trace_);
+  }
+  int get_trace(int win, sqrtba_trace_row* rows, int max_rows) {
+    const int n = trace_len(win);
+    if (n < 0) return n;
+    const int m = std::min(n, max_rows);
+    static_assert(sizeof(sqrtba_trace_row) == TRACE_COLS * sizeof(double), "trace row layout");
+    if (m > 0 && download(rows, d_trace_.p + (size_t)win * max_trace_ * TRACE_COLS, (size_t)m * sizeof(sqrtba_trace_row)))
+      return SQRTBA_ERR_CUDA;
+    return m;
+  }
+  int num_free() const { return have_problem_ ? P_.n_slot : SQRTBA_ERR_INVALID; }
+
+  // ------------------------------------------------------------------------------------------ stage-level entry points
+  int debug_linearize(int huber, double* err, double* Jp, double* Jl, double* r, double* chi2) {
+    if (!have_problem_) { err_ = "no problem set"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    const double d2 = (double)(float)std::sqrt(huber == 2 ? 5.99 : 5.991), d3 = (double)(float)std::sqrt(7.815);
+    k_pass_init<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_, 1, 0);
+    if (P_.n_slot) k_zero_lin<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
+    k_linearize<<<cdiv(P_.n_item, WARPS), CTA, 0, stream_>>>(P_, huber != 0, d2, d3, 1);
+    k_lm_begin<<<P_.n_win, CTA, 0, stream_>>>(P_);
+    CU_CHECK(cudaGetLastError());
+    const size_t No = P_.n_obs;
+    std::vector<double> tmp;
+    auto planes = [&](double* dst, const double* dsrc, int np) -> int {
+      if (!dst) return 0;
+      tmp.resize(No * np);
+      if (download(tmp.data(), dsrc, No * np * sizeof(double))) return SQRTBA_ERR_CUDA;
+      for (size_t o = 0; o < No; o++)
+        for (int c = 0; c < np; c++) dst[o * np + c] = tmp[(size_t)c * No + o];
+      return 0;
+    };
+    if (planes(err, d_err_.p, 3) || planes(Jp, d_Jp_.p, 18) || planes(Jl, d_Jl_.p, 9) || planes(r, d_r_.p, 3)) return SQRTBA_ERR_CUDA;
+    if (chi2) {
+      std::vector<WinCtl> c(P_.n_win);
+      if (download(c.data(), d_ctl_.p, c.size() * sizeof(WinCtl))) return SQRTBA_ERR_CUDA;
+      for (int w = 0; w < P_.n_win; w++) chi2[w] = c[w].cur_chi;
+    }
+    return SQRTBA_OK;
+  }
+
+  // one damped square-root step at the linearisation left by debug_linearize (or the last solve)
+  int debug_step(double lambda, double* dp, double* dl, double* bs, int* cg_iters) {
+    if (!have_problem_) { err_ = "no problem set"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    // put every window into PH_TRIAL with the requested lambda
+    std::vector<WinCtl> c(P_.n_win);
+    if (download(c.data(), d_ctl_.p, c.size() * sizeof(WinCtl))) return SQRTBA_ERR_CUDA;
+    for (auto& w : c) { w.phase = PH_TRIAL; w.lambda = lambda; }
+    CU_CHECK(cudaMemcpyAsync(d_ctl_.p, c.data(), c.size() * sizeof(WinCtl), cudaMemcpyHostToDevice, stream_));
+    CU_CHECK(cudaStreamSynchronize(stream_));
+    int rc = factor_and_solve();
+    if (rc) return rc;
+    k_backsub<<<cdiv(P_.n_item, WARPS), CTA, 0, stream_>>>(P_, 0, 0.0);
+    CU_CHECK(cudaGetLastError());
+    if (dp && P_.n_slot && download(dp, P_.x, (size_t)P_.n_slot * 6 * sizeof(double))) return SQRTBA_ERR_CUDA;
+    if (bs && P_.n_slot && download(bs, P_.bs, (size_t)P_.n_slot * 6 * sizeof(double))) return SQRTBA_ERR_CUDA;
+    if (dl) {
+      std::vector<double> tmp((size_t)P_.n_point * 3);
+      if (download(tmp.data(), d_dl_.p, tmp.size() * sizeof(double))) return SQRTBA_ERR_CUDA;
+      for (int l = 0; l < P_.n_point; l++)
+        for (int k = 0; k < 3; k++) dl[(size_t)l * 3 + k] = tmp[(size_t)k * P_.n_point + l];
+    }
+    if (cg_iters) {
+      if (download(c.data(), d_ctl_.p, c.size() * sizeof(WinCtl))) return SQRTBA_ERR_CUDA;
+      int m = 0;
+      for (auto& w : c) m = std::max(m, w.cg_iters);
+      *cg_iters = m;
+    }
+    return SQRTBA_OK;
+  }
+
+  int debug_matvec(const double* p, double* y) {
+    if (!have_problem_ || !P_.n_slot) { err_ = "no problem / no free pose"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    const size_t bytes = (size_t)P_.n_slot * 6 * sizeof(double);
+    CU_CHECK(cudaMemcpyAsync(P_.p, p, bytes, cudaMemcpyHostToDevice, stream_));
+    CU_CHECK(cudaMemsetAsync(P_.q, 0, bytes, stream_));
+    k_matvec<<<cdiv(P_.n_item, WARPS), CTA, 0, stream_>>>(P_, P_.p, P_.q, 1);
+    CU_CHECK(cudaGetLastError());
+    return download(y, P_.q, bytes);
+  }
+
+  int time_stage(int stage, int warmup, int reps, double* ms_avg) {
+    if (!have_problem_) { err_ = "no problem set"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    const double d2 = (double)(float)std::sqrt(5.991), d3 = (double)(float)std::sqrt(7.815);
+    const int gi = cdiv(P_.n_item, WARPS);
+    auto one = [&]() {
+      switch (stage) {
+        case 0: k_matvec<<<gi, CTA, 0, stream_>>>(P_, P_.p, P_.q, 1); break;
+        case 1: k_linearize<<<gi, CTA, 0, stream_>>>(P_, 1, d2, d3, 1); break;
+        case 2: k_qr<<<gi, CTA, 0, stream_>>>(P_, 1, 1.0); break;
+        case 3: k_cost<<<gi, CTA, 0, stream_>>>(P_, 1, d2, d3); break;
+        case 4: k_backsub<<<gi, CTA, 0, stream_>>>(P_, 1, 1.0); break;
+        default: break;
+      }
+    };
+    if (stage < 0 || stage > 4) { err_ = "time_stage: unknown stage"; return SQRTBA_ERR_INVALID; }
+    if (stage == 3) {  // the cost kernel only runs for windows in a trial
+      std::vector<WinCtl> c(P_.n_win);
+      if (download(c.data(), d_ctl_.p, c.size() * sizeof(WinCtl))) return SQRTBA_ERR_CUDA;
+      for (auto& w : c) w.phase = PH_TRIAL;
+      CU_CHECK(cudaMemcpyAsync(d_ctl_.p, c.data(), c.size() * sizeof(WinCtl), cudaMemcpyHostToDevice, stream_));
+      CU_CHECK(cudaStreamSynchronize(stream_));
+    }
+    for (int i = 0; i < warmup; i++) one();
+    CU_CHECK(cudaStreamSynchronize(stream_));
+    CU_CHECK(cudaEventRecord(ev0_, stream_));
+    for (int i = 0; i < reps; i++) one();
+    CU_CHECK(cudaEventRecord(ev1_, stream_));
+    CU_CHECK(cudaEventSynchronize(ev1_));
+    CU_CHECK(cudaGetLastError());
+    float ms = 0;
+    CU_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    *ms_avg = (double)ms / std::max(reps, 1);
+    return SQRTBA_OK;
+  }
+
+ private:
+  int download(void* dst, const void* src, size_t bytes) {
+    CU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream_));
+    CU_CHECK(cudaStreamSynchronize(stream_));
+    return SQRTBA_OK;
+  }
+  cudaError_t clear_traces() {
+    // trace_len lives in WinCtl; zero the whole control block (lambda etc. are re-initialised at iteration 0)
+    return cudaMemsetAsync(d_ctl_.p, 0, (size_t)P_.n_win * sizeof(WinCtl), stream_);
+  }
+  void launch_classify(int mode, double t2, double t3) {
+    k_classify<<<cdiv(P_.n_obs, 256), 256, 0, stream_>>>(P_, mode, t2, t3);
+    launches_++;
+  }
+
+  // QR + block-Jacobi + PCG for every window in PH_TRIAL
+  int factor_and_solve() {
+    const int gi = cdiv(P_.n_item, WARPS);
+    if (P_.n_slot) k_zero_trial<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
+    stage_begin(1);
+    k_qr<<<gi, CTA, 0, stream_>>>(P_, 0, 0.0);
+    stage_end(1);
+    launches_ += 2;
+    if (!P_.n_slot) return SQRTBA_OK;
+    k_dinv<<<cdiv(P_.n_slot, 64), 64, 0, stream_>>>(P_, 0, 0.0);
+    stage_begin(2);
+    CU_CHECK(cudaMemsetAsync(P_.counters + 1, 0, sizeof(int), stream_));
+    k_cg_init<<<P_.n_win, CTA, 0, stream_>>>(P_, 0);
+    launches_ += 2;
+    const double tol2 = cfg_.pcg_rtol * cfg_.pcg_rtol;
+    const int check = std::max(1, cfg_.pcg_check_every);
+    const size_t qbytes = (size_t)P_.n_slot * 6 * sizeof(double);
+    for (int it = 0; it < cfg_.pcg_max_iters; it++) {
+      CU_CHECK(cudaMemsetAsync(P_.q, 0, qbytes, stream_));
+      k_matvec<<<gi, CTA, 0, stream_>>>(P_, P_.p, P_.q, 0);
+      k_cg_step<<<P_.n_win, CTA, 0, stream_>>>(P_, tol2, cfg_.pcg_max_iters, 0, 0.0);
+      launches_ += 2;
+      cg_iters_total_++;
+      if ((it + 1) % check == 0) {
+        CU_CHECK(cudaMemcpyAsync(h_counters_, P_.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        CU_CHECK(cudaStreamSynchronize(stream_));
+        if (h_counters_[1] <= 0) break;
+      }
+    }
+    stage_end(2);
+    CU_CHECK(cudaGetLastError());
+    return SQRTBA_OK;
+  }
+
+  // one optimizer.optimize(iters) call over all windows (sparse_optimizer.cpp:354-419)
+  int run_pass(int iters, int pass, int robust, double d2, double d3, const volatile bool* stop) {
+    const int gi = cdiv(P_.n_item, WARPS);
+    k_pass_init<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_, iters, pass);
+    CU_CHECK(cudaMemsetAsync(P_.counters, 0, 2 * sizeof(int), stream_));
+    launches_++;
+    if (iters <= 0) return SQRTBA_OK;
+    const int max_macro = iters * 10 + 1;
+    for (int step = 0; step < max_macro; step++) {
+      const int term = (stop && *stop) ? 1 : 0;
+      if (term && step == 0) break;  // `for (i < iterations && !terminate())` before the first iteration
+      if (P_.n_slot) k_zero_lin<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
+      stage_begin(0);
+      k_linearize<<<gi, CTA, 0, stream_>>>(P_, robust, d2, d3, 0);
+      stage_end(0);
+      k_lm_begin<<<P_.n_win, CTA, 0, stream_>>>(P_);
+      launches_ += 3;
+      int rc = factor_and_solve();
+      if (rc) return rc;
+      stage_begin(3);
+      k_backsub<<<gi, CTA, 0, stream_>>>(P_, 0, 0.0);
+      stage_end(3);
+      CU_CHECK(cudaMemcpyAsync(d_pose_bak_.p, d_pose_.p, (size_t)P_.n_pose * 7 * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+      CU_CHECK(cudaMemcpyAsync(d_point_bak_.p, d_point_.p, (size_t)P_.n_point * 3 * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+      if (P_.n_slot) k_update_pose<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
+      k_update_point<<<cdiv(P_.n_point, 256), 256, 0, stream_>>>(P_);
+      stage_begin(4);
+      k_cost<<<gi, CTA, 0, stream_>>>(P_, robust, d2, d3);
+      stage_end(4);
+      k_lm_decide<<<P_.n_win, CTA, 0, stream_>>>(P_, term);
+      k_restore<<<cdiv(std::max(P_.n_pose, P_.n_point), 256), 256, 0, stream_>>>(P_);
+      launches_ += 6;
+      lm_trials_++;
+      CU_CHECK(cudaMemcpyAsync(h_counters_, P_.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+      CU_CHECK(cudaStreamSynchronize(stream_));
+      CU_CHECK(cudaGetLastError());
+      if (h_counters_[0] >= P_.n_win) break;
+    }
+    return SQRTBA_OK;
+  }
+
+  // ---- statistics: per-stage CUDA-event timing is accumulated lazily (events are read after the solve)
+  void begin_stats() {
+    launches_ = 0; lm_trials_ = 0; cg_iters_total_ = 0;
+    for (auto& v : stage_ms_) v = 0.0;
+    cudaEventRecord(ev0_, stream_);
+  }
+  void stage_begin(int s) {
+    if (!stage_timing_) return;
+    cudaEventRecord(stage_ev_[2 * s], stream_);
+  }
+  void stage_end(int s) {
+    if (!stage_timing_) return;
+    cudaEventRecord(stage_ev_[2 * s + 1], stream_);
+    cudaEventSynchronize(stage_ev_[2 * s + 1]);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, stage_ev_[2 * s], stage_ev_[2 * s + 1]);
+    stage_ms_[s] += ms;
+  }
+  int finish_stats(sqrtba_stats* st) {
+    CU_CHECK(cudaEventRecord(ev1_, stream_));
+    CU_CHECK(cudaEventSynchronize(ev1_));
+    CU_CHECK(cudaGetLastError());
+    float ms = 0;
+    CU_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    if (st) {
+      std::memset(st, 0, sizeof *st);
+      st->n_windows = P_.n_win;
+      st->lm_trials = lm_trials_;
+      st->cg_iters_total = cg_iters_total_;
+      st->kernel_launches = launches_;
+      st->ms_total = ms;
+      st->ms_linearize = stage_ms_[0];
+      st->ms_qr = stage_ms_[1];
+      st->ms_pcg = stage_ms_[2];
+      st->ms_backsub = stage_ms_[3];
+      st->ms_cost = stage_ms_[4];
+    }
+    return SQRTBA_OK;
+  }
+
+  void release_all() {
+    d_cam_.release(); d_pose_slot_.release(); d_slot_pose_.release(); d_slot_win_.release(); d_pose_win_.release();
+    d_point_win_.release(); d_meas_.release(); d_obs_pose_.release(); d_obs_point_.release(); d_obs_slot_.release();
+    d_item_start_.release(); d_item_cnt_.release(); d_item_win_.release(); d_win_item_ptr_.release();
+    d_win_slot_ptr_.release(); d_pose_.release(); d_pose0_.release(); d_pose_bak_.release(); d_point_.release();
+    d_point0_.release(); d_point_bak_.release(); d_level_.release(); d_outlier_.release(); d_err_.release();
+    d_Jp_.release(); d_Jl_.release(); d_Q1_.release(); d_r_.release(); d_R_.release(); d_tl_.release();
+    d_bl_.release(); d_dl_.release(); d_slotvec_.release(); d_chi_part_.release(); d_scale_part_.release();
+    d_ctl_.release(); d_trace_.release(); d_counters_.release();
+  }
+
+ public:
+  bool stage_timing_ = false;
+
+ private:
+  sqrtba_config cfg_;
+  std::string err_;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  cudaEvent_t stage_ev_[10] = {};
+  double stage_ms_[5] = {};
+  int* h_counters_ = nullptr;
+  bool have_problem_ = false;
+  int max_trace_ = 200;
+  int launches_ = 0, lm_trials_ = 0, cg_iters_total_ = 0;
+  Dev P_{};
+  DBuf<double> d_cam_, d_pose_, d_pose0_, d_pose_bak_, d_point_, d_point0_, d_point_bak_, d_err_, d_Jp_, d_Jl_, d_Q1_,
+      d_r_, d_R_, d_tl_, d_bl_, d_dl_, d_slotvec_, d_chi_part_, d_scale_part_, d_trace_;
+  DBuf<int> d_pose_slot_, d_slot_pose_, d_slot_win_, d_pose_win_, d_point_win_, d_obs_pose_, d_obs_point_, d_obs_slot_,
+      d_item_start_, d_item_cnt_, d_item_win_, d_win_item_ptr_, d_win_slot_ptr_, d_counters_;
+  DBuf<float4> d_meas_;
+  DBuf<uint8_t> d_level_, d_outlier_;
+  DBuf<WinCtl> d_ctl_;
+};
+
+}  // namespace sqrtba
+
+// =================================================================================================== C ABI
+using sqrtba::Solver;
+
+struct sqrtba_handle {
+  Solver* s;
+  std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+extern "C" {
+
+const char* sqrtba_version(void) { return "sqrtba 0.1 (sm_100a)"; }
+
+int sqrtba_default_config(sqrtba_config* cfg) {
+  if (!cfg) return SQRTBA_ERR_INVALID;
+  std::memset(cfg, 0, sizeof *cfg);
+  cfg->device = 0;
+  cfg->pcg_rtol = 1e-9;
+  cfg->pcg_max_iters = 300;
+  cfg->third_pass_iters = 0;
+  cfg->pcg_mode = 0;
+  cfg->pcg_check_every = 4;
+  return SQRTBA_OK;
+}
+
+int sqrtba_create(const sqrtba_config* cfg, sqrtba_handle** out) {
+  if (!out) return SQRTBA_ERR_INVALID;
+  *out = nullptr;
+  sqrtba_config c;
+  if (cfg) c = *cfg; else sqrtba_default_config(&c);
+  if (c.pcg_rtol <= 0) c.pcg_rtol = 1e-9;
+  if (c.pcg_max_iters <= 0) c.pcg_max_iters = 300;
+  if (c.pcg_check_every <= 0) c.pcg_check_every = 4;
+  sqrtba_handle* h = new (std::nothrow) sqrtba_handle();
+  if (!h) return SQRTBA_ERR_ALLOC;
+  h->s = new (std::nothrow) Solver(c);
+  if (!h->s) { delete h; return SQRTBA_ERR_ALLOC; }
+  h->s->stage_timing_ = c.reserved[0] != 0;
+  const int rc = h->s->init();
+  if (rc) {
+    g_create_err = h->s->last_error();
+    delete h->s;
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return SQRTBA_OK;
+}
+
+int sqrtba_destroy(sqrtba_handle* h) {
+  if (!h) return SQRTBA_ERR_INVALID;
+  delete h->s;
+  delete h;
+  return SQRTBA_OK;
+}
+
+const char* sqrtba_last_error(const sqrtba_handle* h) { return h ? h->s->last_error() : g_create_err.c_str(); }
+
+int sqrtba_set_problem(sqrtba_handle* h, int32_t n_pose, int32_t n_point, int32_t n_obs, const double* pose_qt,
+                       const uint8_t* pose_fixed, const double* cam, const double* point_xyz,
+                       const int32_t* obs_pose, const int32_t* obs_point, const float* obs_meas) {
+  if (!h) return SQRTBA_ERR_INVALID;
+  return h->s->set_problem(1, nullptr, nullptr, nullptr, n_pose, n_point, n_obs, pose_qt, pose_fixed, cam, point_xyz,
+                           obs_pose, obs_point, obs_meas);
+}
+
+int sqrtba_set_problem_batch(sqrtba_handle* h, int32_t n_win, const int64_t* win_pose_ptr,
+                             const int64_t* win_point_ptr, const int64_t* win_obs_ptr, const double* pose_qt,
+                             const uint8_t* pose_fixed, const double* cam, const double* point_xyz,
+                             const int32_t* obs_pose, const int32_t* obs_point, const float* obs_meas) {
+  if (!h || n_win <= 0 || !win_pose_ptr || !win_point_ptr || !win_obs_ptr) return SQRTBA_ERR_INVALID;
+  return h->s->set_problem(n_win, win_pose_ptr, win_point_ptr, win_obs_ptr, (int)win_pose_ptr[n_win],
+                           (int)win_point_ptr[n_win], (int)win_obs_ptr[n_win], pose_qt, pose_fixed, cam, point_xyz,
+                           obs_pose, obs_point, obs_meas);
+}
+
+int sqrtba_reset_state(sqrtba_handle* h) { return h ? h->s->reset_state() : SQRTBA_ERR_INVALID; }
+int sqrtba_solve_local(sqrtba_handle* h, const volatile bool* stop_flag, sqrtba_stats* stats) {
+  return h ? h->s->solve_local(stop_flag, stats) : SQRTBA_ERR_INVALID;
+}
+int sqrtba_solve_global(sqrtba_handle* h, int32_t iters, int32_t robust, const volatile bool* stop_flag,
+                        sqrtba_stats* stats) {
+  return h ? h->s->solve_global(iters, robust, stop_flag, stats) : SQRTBA_ERR_INVALID;
+}
+int sqrtba_get_poses(sqrtba_handle* h, double* out) { return (h && out) ? h->s->get_poses(out) : SQRTBA_ERR_INVALID; }
+int sqrtba_get_points(sqrtba_handle* h, double* out) { return (h && out) ? h->s->get_points(out) : SQRTBA_ERR_INVALID; }
+int sqrtba_get_outliers(sqrtba_handle* h, uint8_t* out) { return (h && out) ? h->s->get_outliers(out) : SQRTBA_ERR_INVALID; }
+int sqrtba_get_trace_len(sqrtba_handle* h, int32_t window) { return h ? h->s->trace_len(window) : SQRTBA_ERR_INVALID; }
+int sqrtba_get_trace(sqrtba_handle* h, int32_t window, sqrtba_trace_row* rows_out, int32_t max_rows) {
+  return (h && rows_out) ? h->s->get_trace(window, rows_out, max_rows) : SQRTBA_ERR_INVALID;
+}
+int sqrtba_debug_linearize(sqrtba_handle* h, int32_t huber, double* err, double* Jp, double* Jl, double* r,
+                           double* chi2) {
+  return h ? h->s->debug_linearize(huber, err, Jp, Jl, r, chi2) : SQRTBA_ERR_INVALID;
+}
+int sqrtba_debug_step(sqrtba_handle* h, double lambda, double* dp, double* dl, double* bs, int32_t* cg_iters) {
+  return h ? h->s->debug_step(lambda, dp, dl, bs, cg_iters) : SQRTBA_ERR_INVALID;
+}
+int sqrtba_debug_matvec(sqrtba_handle* h, const double* p, double* y) {
+  return (h && p && y) ? h->s->debug_matvec(p, y) : SQRTBA_ERR_INVALID;
+}
+int sqrtba_num_free_poses(sqrtba_handle* h) { return h ? h->s->num_free() : SQRTBA_ERR_INVALID; }
+int sqrtba_time_stage(sqrtba_handle* h, int32_t stage, int32_t warmup, int32_t reps, double* ms_avg) {
+  return (h && ms_avg) ? h->s->time_stage(stage, warmup, reps, ms_avg) : SQRTBA_ERR_INVALID;
+}
+
+}  // extern "C"

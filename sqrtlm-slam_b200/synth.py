@@ -327,7 +327,7 @@ def config_c3(seed=0, scale=1.0, n_kf=1500):
 
 def small_window(seed=0, n_free=6, n_fixed=3, n_points=150, mean_track=5.0, stereo=True, outlier_frac=0.05,
                  extra_fixed=()):
-    """Tiny window for oracle / parity tests."""
+    """Tiny window for parity tests."""
     return make_problem(seed, n_free + n_fixed, n_fixed, n_points, mean_track, stereo=stereo,
                         outlier_frac=outlier_frac, extra_fixed=extra_fixed, name=f"small-seed{seed}")
 

@@ -1,0 +1,51 @@
+"""CPU-only checks of the drop-in boundary: the library builds, loads without a GPU, exports every symbol that
+include/sqrtba.h declares, and fails loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "sqrtba.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(sqrtba_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    pkg.build.build_lib()
+    L = C.CDLL(pkg.capi.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/sqrtba.h but not exported"
+
+
+def test_struct_layouts_match_header(pkg):
+    assert C.sizeof(pkg.capi.Config) == 4 + 4 + 8 + 4 * 4 + 8 * 4  # device(+pad), rtol, 4 ints, reserved[8]
+    assert C.sizeof(pkg.capi.Stats) == 4 * 4 + 8 * 7 + 8 * 8
+    assert len(pkg.capi.TRACE_COLS) == 10
+
+
+def test_no_cpu_fallback_without_device(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pkg.SqrtBAError):
+        pkg.SqrtBA()
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under the package or include/ may reference it."""
+    bad = []
+    for base in (os.path.join(ROOT, "sqrtlm-slam_b200"), os.path.join(ROOT, "include")):
+        for dp, _, fs in os.walk(base):
+            for f in fs:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
+                    s = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"\boracle\b|refba", s):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad

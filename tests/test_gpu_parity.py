@@ -1,0 +1,236 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/sqrtba.h), against the CPU oracle.
+
+Tolerances are the ones BASELINE.json's north_star states: per-iteration cost relative error <= 1e-6,
+final keyframe pose RMS <= 1e-5 m / 1e-6 rad, identical outlier flags.  (The stereo residual of the reference
+rounds 1/z to float32, which makes its own cost reproducible only to ~1e-7 relative -- see test_oracle.py.)"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import refba
+
+pytestmark = pytest.mark.gpu
+
+COST_RTOL = 1e-6
+POSE_T_RMS = 1e-5
+POSE_R_RMS = 1e-6
+
+
+def quat_angle(qa, qb):
+    d = np.abs(np.sum(qa * qb, axis=-1)).clip(0, 1)
+    # angle of the relative rotation; use the vector part for accuracy near zero
+    rel_v = np.linalg.norm(qa[..., :3] * qb[..., 3:4] - qb[..., :3] * qa[..., 3:4]
+                           - np.cross(qa[..., :3], qb[..., :3]), axis=-1)
+    return 2 * np.arctan2(rel_v, d)
+
+
+def compare_solution(gpu, ref, prob, check_flags=True, pose_t=POSE_T_RMS, pose_r=POSE_R_RMS, window=0, trace_ref=None):
+    tg = gpu.trace(window)
+    tr = ref.trace() if trace_ref is None else trace_ref
+    n = min(len(tg), len(tr))
+    assert n > 0
+    # accept / reject sequence and costs per trial
+    assert len(tg) == len(tr), f"trial count differs: gpu {len(tg)} vs oracle {len(tr)}"
+    assert np.array_equal(tg[:, [0, 1, 2, 7]], tr[:, [0, 1, 2, 7]])
+    np.testing.assert_allclose(tg[:, 4], tr[:, 4], rtol=COST_RTOL)
+    np.testing.assert_allclose(tg[:, 5], tr[:, 5], rtol=COST_RTOL)
+    np.testing.assert_allclose(tg[:, 3], tr[:, 3], rtol=1e-5)  # lambda follows rho
+
+
+def pose_rms(Pg, Pr, free):
+    dt = np.linalg.norm(Pg[free, :3] - Pr[free, :3], axis=1)
+    da = quat_angle(Pg[free, 3:], Pr[free, 3:])
+    return float(np.sqrt(np.mean(dt ** 2))), float(np.sqrt(np.mean(da ** 2)))
+
+
+@pytest.fixture(scope="module")
+def ba(pkg):
+    h = pkg.SqrtBA()
+    yield h
+    h.close()
+
+
+@pytest.mark.parametrize("stereo,huber", [(True, 1), (False, 1), (True, 0), (True, 2)])
+def test_linearize_matches_oracle(ba, synth, stereo, huber):
+    prob = synth.small_window(11, n_free=6, n_fixed=3, n_points=300, stereo=stereo)
+    ba.set_problem(prob)
+    g = ba.debug_linearize(huber)
+    o = refba.RefBA(prob).linearize_all(huber)
+    sw = np.sqrt(o["w"])
+    # float32 inverse-depth rounding may flip on a last-bit difference of z: <= 1 float ulp of 1/z on u (~1e-5 px)
+    assert np.abs(g["err"] - o["err"]).max() <= (3e-5 if stereo else 1e-9)
+    np.testing.assert_allclose(g["Jp"], o["Jp"] * sw[:, None, None], rtol=1e-6 if stereo else 1e-10, atol=1e-8)
+    np.testing.assert_allclose(g["Jl"], o["Jl"] * sw[:, None, None], rtol=1e-6 if stereo else 1e-10, atol=1e-8)
+    np.testing.assert_allclose(g["chi2"][0], o["rho0"].sum(), rtol=1e-7 if stereo else 1e-12)
+
+
+@pytest.mark.parametrize("stereo", [True, False])
+def test_sqrt_step_matches_schur_step(ba, synth, stereo):
+    prob = synth.small_window(5, n_free=7, n_fixed=3, n_points=400, mean_track=6.0, stereo=stereo)
+    ba.set_problem(prob)
+    ba.debug_linearize(1)
+    lam = 25.0
+    g = ba.debug_step(lam)
+    s = refba.RefBA(prob).schur_solve(lam, huber=1)
+    Np = s["Np"]
+    assert Np == ba.num_free_poses()
+    scale_b = np.abs(s["bschur"]).max()
+    assert np.abs(g["bs"].ravel() - s["bschur"]).max() <= 1e-6 * scale_b
+    xp = s["x"][:6 * Np]
+    assert np.abs(g["dp"].ravel() - xp).max() <= 1e-6 * np.abs(xp).max()
+    xl = s["x"][6 * Np:]
+    assert np.abs(g["dl"].ravel() - xl).max() <= 1e-5 * np.abs(xl).max()
+    # the implicit operator against the explicit reduced camera matrix (lambda excluded from the kernel)
+    rng = np.random.default_rng(0)
+    p = rng.normal(size=(Np, 6))
+    y = ba.debug_matvec(p).ravel() + lam * p.ravel()
+    want = s["S"] @ p.ravel()
+    assert np.abs(y - want).max() <= 1e-8 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("stereo,seed", [(True, 0), (False, 1), (True, 2)])
+def test_local_ba_small_window(ba, synth, stereo, seed):
+    prob = synth.small_window(seed, n_free=8, n_fixed=4, n_points=500, mean_track=6.0, stereo=stereo)
+    ba.set_problem(prob)
+    st = ba.solve_local()
+    assert st["kernel_launches"] > 0
+    ref = refba.RefBA(prob)
+    ref.solve_local(0)
+    compare_solution(ba, ref, prob)
+    free = prob.pose_fixed == 0
+    t_rms, r_rms = pose_rms(ba.poses(), ref.poses(), free)
+    assert t_rms <= POSE_T_RMS and r_rms <= POSE_R_RMS, (t_rms, r_rms)
+    assert np.array_equal(ba.outliers(), ref.outliers())
+    np.testing.assert_allclose(ba.points(), ref.points(), rtol=1e-5, atol=1e-4)
+    # fixed poses never move
+    np.testing.assert_array_equal(ba.poses()[~free], ref.poses()[~free])
+
+
+def test_local_ba_kitti_window_c0(ba, synth):
+    prob = synth.config_c0(0)
+    ba.set_problem(prob)
+    ba.solve_local()
+    ref = refba.RefBA(prob)
+    ref.solve_local(0)
+    compare_solution(ba, ref, prob)
+    free = prob.pose_fixed == 0
+    t_rms, r_rms = pose_rms(ba.poses(), ref.poses(), free)
+    assert t_rms <= POSE_T_RMS and r_rms <= POSE_R_RMS, (t_rms, r_rms)
+    assert np.array_equal(ba.outliers(), ref.outliers())
+
+
+def test_local_ba_mono_c1(ba, synth):
+    prob = synth.config_c1(1, scale=0.5)
+    ba.set_problem(prob)
+    ba.solve_local()
+    ref = refba.RefBA(prob)
+    ref.solve_local(0)
+    compare_solution(ba, ref, prob)
+    t_rms, r_rms = pose_rms(ba.poses(), ref.poses(), prob.pose_fixed == 0)
+    assert t_rms <= POSE_T_RMS and r_rms <= POSE_R_RMS, (t_rms, r_rms)
+    assert np.array_equal(ba.outliers(), ref.outliers())
+
+
+def test_third_pass_variant(pkg, synth):
+    prob = synth.small_window(3, n_free=6, n_fixed=3, n_points=300)
+    h = pkg.SqrtBA(third_pass_iters=20)
+    h.set_problem(prob)
+    h.solve_local()
+    ref = refba.RefBA(prob)
+    ref.solve_local(20)
+    tg, tr = h.trace(), ref.trace()
+    assert tg[:, 0].max() == 2 and len(tg) == len(tr)
+    np.testing.assert_allclose(tg[:, 5], tr[:, 5], rtol=COST_RTOL)
+    assert np.array_equal(h.outliers(), ref.outliers())
+    h.close()
+
+
+@pytest.mark.parametrize("robust,iters", [(False, 10), (True, 20)])
+def test_global_ba_loop(ba, synth, robust, iters):
+    prob = synth.make_problem(7, 60, 1, 3000, 8.0, stereo=True, loop=True, cand_halfwidth=12, name="gba-small")
+    ba.set_problem(prob)
+    ba.solve_global(iters, robust)
+    ref = refba.RefBA(prob)
+    ref.solve_global(iters, robust)
+    compare_solution(ba, ref, prob)
+    t_rms, r_rms = pose_rms(ba.poses(), ref.poses(), prob.pose_fixed == 0)
+    assert t_rms <= POSE_T_RMS and r_rms <= POSE_R_RMS, (t_rms, r_rms)
+    assert ba.outliers().sum() == 0
+
+
+def test_long_tracks(ba, synth):
+    # landmarks seen by more than 32 keyframes take the chunked whole-warp path
+    prob = synth.make_problem(9, 64, 2, 400, 45.0, stereo=True, name="long-tracks")
+    k = np.diff(prob.lm_ptr())
+    assert k.max() > 32 and k.min() <= 32
+    ba.set_problem(prob)
+    ba.debug_linearize(1)
+    lam = 40.0
+    g = ba.debug_step(lam)
+    s = refba.RefBA(prob).schur_solve(lam, huber=1)
+    xp = s["x"][:6 * s["Np"]]
+    assert np.abs(g["dp"].ravel() - xp).max() <= 1e-6 * np.abs(xp).max()
+    xl = s["x"][6 * s["Np"]:]
+    assert np.abs(g["dl"].ravel() - xl).max() <= 1e-5 * np.abs(xl).max()
+    ba.reset_state()
+    ba.solve_local()
+    ref = refba.RefBA(prob)
+    ref.solve_local(0)
+    compare_solution(ba, ref, prob)
+    assert np.array_equal(ba.outliers(), ref.outliers())
+
+
+def test_batch_of_windows_equals_individual_solves(pkg, synth):
+    wins = [synth.small_window(20 + i, n_free=5 + i, n_fixed=2 + (i % 2), n_points=200 + 50 * i, stereo=(i != 2))
+            for i in range(4)]
+    prob, pp, tp, op = synth.concat_windows(wins)
+    h = pkg.SqrtBA()
+    h.set_problem_batch(prob, pp, tp, op)
+    st = h.solve_local()
+    assert st["n_windows"] == 4
+    P, X, F = h.poses(), h.points(), h.outliers()
+    for i, w in enumerate(wins):
+        ref = refba.RefBA(w)
+        ref.solve_local(0)
+        compare_solution(h, ref, w, window=i)
+        free = w.pose_fixed == 0
+        t_rms, r_rms = pose_rms(P[pp[i]:pp[i + 1]], ref.poses(), free)
+        assert t_rms <= POSE_T_RMS and r_rms <= POSE_R_RMS, (i, t_rms, r_rms)
+        assert np.array_equal(F[op[i]:op[i + 1]], ref.outliers())
+    h.close()
+
+
+def test_stop_flag_and_errors(pkg, synth):
+    prob = synth.small_window(0)
+    h = pkg.SqrtBA()
+    with pytest.raises(pkg.SqrtBAError):
+        h.solve_local()                       # no problem set
+    h.set_problem(prob)
+    flag = ctypes.c_bool(True)
+    h.solve_local(ctypes.byref(flag))         # pbStopFlag already raised: early out, estimates untouched
+    np.testing.assert_array_equal(h.points(), prob.point_xyz)
+    assert len(h.trace()) == 0
+    bad = prob.copy()
+    bad.obs_point = bad.obs_point[::-1].copy()  # not grouped by landmark
+    with pytest.raises(pkg.SqrtBAError):
+        h.set_problem(bad)
+    bad = prob.copy()
+    bad.obs_pose[0] = prob.n_pose + 5
+    with pytest.raises(pkg.SqrtBAError):
+        h.set_problem(bad)
+    # the handle is reusable after a rejected problem
+    h.set_problem(prob)
+    h.solve_local()
+    assert len(h.trace()) >= 15
+    h.close()
+
+
+def test_repeatable_after_reset(ba, synth):
+    prob = synth.small_window(2, n_points=300)
+    ba.set_problem(prob)
+    ba.solve_local()
+    a = ba.poses().copy()
+    ba.reset_state()
+    ba.solve_local()
+    np.testing.assert_allclose(ba.poses(), a, rtol=0, atol=1e-9)  # atomics reorder sums: not bit-identical

@@ -1,0 +1,84 @@
+"""The kernels' __host__ __device__ arithmetic (csrc/sqrtba_math.cuh), compiled for the host, against the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import refba
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def mc():
+    out = os.path.join(HERE, "_build", "libmathcheck.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    src = os.path.join(HERE, "cpu_math_check.cpp")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", out, src],
+                   check=True)
+    return C.CDLL(out)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@pytest.mark.parametrize("stereo", [True, False])
+def test_residual_and_jacobians_match_oracle(mc, synth, stereo):
+    prob = synth.small_window(4, n_points=120, stereo=stereo)
+    lin = refba.RefBA(prob).linearize_all(0)
+    e, Jp, Jl = np.zeros(3), np.zeros(18), np.zeros(9)
+    dpos = C.c_int(0)
+    for k in range(prob.n_obs):
+        pose = np.ascontiguousarray(prob.pose_qt[prob.obs_pose[k]])
+        X = np.ascontiguousarray(prob.point_xyz[prob.obs_point[k]])
+        cam = np.ascontiguousarray(prob.cam[prob.obs_pose[k]])
+        meas = np.ascontiguousarray(prob.obs_meas[k])
+        mc.mc_obs(_dp(pose), _dp(X), _dp(cam), meas.ctypes.data_as(C.POINTER(C.c_float)), _dp(e), _dp(Jp), _dp(Jl),
+                  C.byref(dpos))
+        # float32 inverse depth: a last-bit difference in z may flip the rounding (1 float ulp of 1/z ~ 1e-5 px)
+        assert np.abs(e - lin["err"][k]).max() <= (2e-5 if stereo else 1e-10)
+        np.testing.assert_allclose(Jp.reshape(3, 6), lin["Jp"][k], rtol=1e-12, atol=1e-10)
+        np.testing.assert_allclose(Jl.reshape(3, 3), lin["Jl"][k], rtol=1e-12, atol=1e-10)
+        assert dpos.value == 1
+
+
+def test_pose_oplus_matches_oracle(mc):
+    rng = np.random.default_rng(0)
+    for scale in (0.3, 1e-3, 1e-7, 0.0):
+        for _ in range(10):
+            q = rng.normal(size=4)
+            q /= np.linalg.norm(q)
+            if q[3] < 0:
+                q = -q
+            pose = np.concatenate([rng.normal(0, 30, 3), q])
+            xi = rng.normal(0, 1, 6) * scale
+            want = refba.pose_oplus(pose, xi)
+            got = pose.copy()
+            mc.mc_oplus(_dp(got), _dp(np.ascontiguousarray(xi)))
+            np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+
+
+def test_huber_matches_oracle(mc):
+    d = float(np.float32(np.sqrt(7.815)))
+    for c in (0.0, 1.0, d * d, d * d + 1e-9, 50.0, 1e6):
+        r0, r1 = C.c_double(0), C.c_double(0)
+        mc.mc_huber(C.c_double(c), C.c_double(d), C.byref(r0), C.byref(r1))
+        want = np.zeros(3)
+        refba.lib().refba_huber(d, c, _dp(want))
+        # last-bit slack: the oracle build may contract 2*s*delta - dsqr into an FMA
+        assert abs(r0.value - want[0]) <= 4e-16 * max(1.0, abs(want[0])) and r1.value == want[1]
+
+
+def test_spd6_inverse(mc):
+    rng = np.random.default_rng(1)
+    for _ in range(10):
+        B = rng.normal(size=(9, 6))
+        A = np.ascontiguousarray(B.T @ B + 1e-3 * np.eye(6))
+        Ai = np.zeros((6, 6))
+        assert mc.mc_spd6_inverse(_dp(A), _dp(Ai)) == 1
+        np.testing.assert_allclose(Ai @ A, np.eye(6), atol=1e-9)
+    A = np.ascontiguousarray(-np.eye(6))
+    assert mc.mc_spd6_inverse(_dp(A), _dp(np.zeros((6, 6)))) == 0
