@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- local bundle-adjustment throughput on KITTI-00-shaped windows (BASELINE.json metric).
+
+A "step" is one full ORB-SLAM2-style local BA (robust 5 LM iterations -> chi2/depth outlier exclusion ->
+10 LM iterations) over one batch of independent synthetic stereo windows of the C0 shape (20 free + 10 fixed
+keyframes, ~6k points, ~70k observations each; BASELINE.json configs[0]/[4]).  Windows are the unit that shards:
+every rank owns `--windows-per-gpu` windows, no data-path collective (weak scaling).
+
+  value   observations x LM trials per second with the batch already resident in HBM (solve only)
+  e2e     the same metric through the C ABI with HOST buffers: sqrtba_set_problem_batch (H2D) + solve + read-back (D2H)
+  roofline  PCG matvec kernel: algorithmic bytes (216 B per free-pose stereo observation) / CUDA-event time per launch
+  cpu_baseline  the oracle (g2o Schur-LM restatement, oracle/refba.cpp) on a bounded sample, 1 thread
+
+`--impl reference` times that CPU implementation with all host threads (one window per thread).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "local-BA observations/s (KITTI-00-shaped stereo windows, observations x LM trials per second)"
+UNIT = "obs/s"
+
+
+def load_pkg():
+    name = "sqrtlm_slam_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    path = os.path.join(ROOT, "sqrtlm-slam_b200", "__init__.py")
+    spec = importlib.util.spec_from_file_location(name, path, submodule_search_locations=[os.path.dirname(path)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_batch(pkg, n_windows: int, seed0: int):
+    wins = [pkg.synth.config_c0(seed0 + i) for i in range(n_windows)]
+    prob, pp, tp, op = pkg.synth.concat_windows(wins)
+    return wins, prob, pp, tp, op
+
+
+def pinned_copy(arr):
+    """Host staging buffers in pinned memory (the e2e leg copies from these)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    try:
+        t = t.pin_memory()
+    except Exception:
+        pass
+    return t
+
+
+def trials_times_obs(ba, wins):
+    tot = 0
+    ntr = 0
+    for i, w in enumerate(wins):
+        n = len(ba.trace(i))
+        tot += n * w.n_obs
+        ntr += n
+    return tot, ntr
+
+
+def cpu_solve_windows(wins, threads_total: int):
+    """Solve windows with the oracle, one window per worker thread (ctypes releases the GIL). Returns
+    (seconds, sum(n_obs * trials), sum(trials))."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import refba
+    refba.lib()
+
+    def one(w):
+        r = refba.RefBA(w, threads=1)
+        r.solve_local(0)
+        return len(r.trace()) * w.n_obs, len(r.trace())
+
+    t0 = time.perf_counter()
+    if threads_total <= 1:
+        res = [one(w) for w in wins]
+    else:
+        with ThreadPoolExecutor(max_workers=threads_total) as ex:
+            res = list(ex.map(one, wins))
+    dt = time.perf_counter() - t0
+    return dt, sum(r[0] for r in res), sum(r[1] for r in res)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; g2o itself cannot be built in this image)
+    on the same workload shape, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = load_pkg()
+    cores = os.cpu_count() or 1
+    n_sample = max(cores, 8) if args.cpu_windows <= 0 else args.cpu_windows
+    wins = [pkg.synth.config_c0(1000 + i) for i in range(n_sample)]
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_solve_windows(wins[:cores], cores)
+    tot_t = tot_work = tot_tr = 0
+    for _ in range(args.steps):
+        dt, work, ntr = cpu_solve_windows(wins, cores)
+        tot_t += dt
+        tot_work += work
+        tot_tr += ntr
+    value = tot_work / tot_t
+    sample = f"{n_sample} C0-shaped windows per step ({sum(w.n_obs for w in wins)} observations), one window per thread"
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "C4-style batch of independent KITTI-00-shaped stereo local-BA windows (C0 shape)",
+                   "windows_per_step": n_sample, "passes": "5+10 LM iterations, chi2 outlier exclusion"},
+        "lm_iters_per_s": tot_tr / tot_t,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sqrtba", choices=["sqrtba", "reference"])
+    ap.add_argument("--windows-per-gpu", type=int, default=256)
+    ap.add_argument("--cpu-windows", type=int, default=0, help="windows in the CPU sample (0 = auto)")
+    ap.add_argument("--pcg-mode", type=int, default=0)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pkg = load_pkg()
+    pkg.capi.lib()  # fails loudly if the CUDA library is missing
+    W = args.windows_per_gpu
+    wins, prob, pp, tp, op = make_batch(pkg, W, seed0=rank * 100000)
+    n_obs_rank = prob.n_obs
+    free_obs = int((prob.pose_fixed[prob.obs_pose] == 0).sum())
+
+    ba = pkg.SqrtBA(device=local, pcg_mode=args.pcg_mode)
+    ba.set_problem_batch(prob, pp, tp, op)
+
+    # ---- resident-input leg: value -------------------------------------------------------------
+    launches = 0
+    for _ in range(args.warmup):
+        ba.reset_state()
+        ba.solve_local()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    stats = None
+    for _ in range(args.steps):
+        ba.reset_state()
+        stats = ba.solve_local()
+        dev_ms += stats["ms_total"]
+        launches += stats["kernel_launches"]
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop()
+    work, ntr = trials_times_obs(ba, wins)       # per step (identical every step: same inputs)
+    sec = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(work), float(ntr), float(n_obs_rank)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    sec_max = float(sec.item())
+    work_all, ntr_all, nobs_all = (float(x) for x in tot.tolist())
+    value = work_all * args.steps / sec_max
+
+    # ---- roofline of the dominant kernel (PCG matvec), full batch active, inputs >> L2 -----------
+    ms_matvec = ba.time_stage(0, warmup=3, reps=20)
+    ms_lin = ba.time_stage(1, warmup=2, reps=5)
+    ms_qr = ba.time_stage(2, warmup=2, reps=5)
+    peaks, peak_kind = measured_peaks()
+    alg_bytes = free_obs * 216.0
+    achieved = alg_bytes / (ms_matvec * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind, "kernel": "k_matvec",
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_matvec,
+                "note": "216 B per free-pose stereo observation (Jp 3x6 + Q1 3x3, FP64); observations of fixed "
+                        "keyframes have no pose columns and are not streamed",
+                "other_kernels_ms": {"k_linearize": ms_lin, "k_qr": ms_qr},
+                "pcg_share_of_step": None}
+
+    # ---- end-to-end leg through the C ABI with host buffers -------------------------------------
+    host = [pinned_copy(a) for a in (prob.pose_qt, prob.pose_fixed, prob.cam, prob.point_xyz, prob.obs_pose,
+                                     prob.obs_point, prob.obs_meas)]
+    hprob = pkg.synth.Problem(*[t.numpy() for t in host])
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    d2h = prob.n_pose * 7 * 8 + prob.n_point * 3 * 8 + prob.n_obs
+    ba2 = pkg.SqrtBA(device=local, pcg_mode=args.pcg_mode)
+    for _ in range(min(args.warmup, 1)):
+        ba2.set_problem_batch(hprob, pp, tp, op)
+        ba2.solve_local()
+        ba2.poses(); ba2.points(); ba2.outliers()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ba2.set_problem_batch(hprob, pp, tp, op)
+        st2 = ba2.solve_local()
+        launches += st2["kernel_launches"]
+        ba2.poses(); ba2.points(); ba2.outliers()
+    barrier()
+    t1 = time.perf_counter()
+    sec2 = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(sec2, op=dist.ReduceOp.MAX)
+    e2e_value = work_all * args.steps / float(sec2.item())
+    ba2.close()
+
+    # ---- CPU baseline (oracle port, 1 thread, bounded sample) on rank 0 at N=1 -------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        n_cpu = args.cpu_windows if args.cpu_windows > 0 else 12
+        dt, wk, _ = cpu_solve_windows(wins[:n_cpu], 1)
+        cpu = {"value": wk / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"first {n_cpu} windows of the batch, full two-pass local BA each, {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sec_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4: batch of independent KITTI-00-shaped stereo local-BA windows (C0 shape: 20 free + "
+                                   "10 fixed keyframes, ~6k points, ~70k observations), two-pass 5+10 LM with chi2 outlier exclusion",
+                       "windows_per_gpu": W, "observations_per_gpu": n_obs_rank, "observations_total": int(nobs_all),
+                       "l2_policy": "inputs_larger_than_l2", "pcg_rtol": 1e-9, "pcg_mode": args.pcg_mode},
+            "lm_iters_per_s": ntr_all * args.steps / sec_max,
+            "windows_per_s": W * world * args.steps / sec_max,
+            "ms_per_step_device_events": dev_ms / args.steps,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * float(sec2.item()) / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "solve_stats_last_step": stats,
+        }
+        print(json.dumps(line), flush=True)
+    ba.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

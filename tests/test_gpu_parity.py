@@ -103,8 +103,8 @@ def test_local_ba_small_window(ba, synth, stereo, seed):
     assert t_rms <= POSE_T_RMS and r_rms <= POSE_R_RMS, (t_rms, r_rms)
     assert np.array_equal(ba.outliers(), ref.outliers())
     np.testing.assert_allclose(ba.points(), ref.points(), rtol=1e-5, atol=1e-4)
-    # fixed poses never move
-    np.testing.assert_array_equal(ba.poses()[~free], ref.poses()[~free])
+    # fixed poses never move (both sides only re-normalise the input quaternion: last-bit slack)
+    np.testing.assert_allclose(ba.poses()[~free], ref.poses()[~free], rtol=0, atol=1e-15)
 
 
 def test_local_ba_kitti_window_c0(ba, synth):
