@@ -51,6 +51,14 @@ struct Dev {
   const int* item_win;     // n_item
   const int* win_item_ptr;  // n_win+1
   const int* win_slot_ptr;  // n_win+1
+  // tile = the WARPS consecutive items one CTA owns.  Per tile: the distinct free-pose slots its (short) items
+  // touch, and for every such observation a local slot id + its rank in the tile's pose-sorted order, so that
+  // pose-side sums are reduced inside the CTA (shared memory, no atomics) and flushed once per (tile, slot).
+  int n_tile;
+  const int* tile_slot_ptr;   // n_tile+1 -> tile_slots
+  const int* tile_slots;      // global slot ids, ascending inside a tile
+  const int* tile_lptr;       // per tile n_local+1 offsets into the pose-sorted order; base = tile_slot_ptr[t] + t
+  const unsigned* obs_lp;     // n_obs: low 16 bits local slot (0xffff = fixed pose / long item), high 16 bits rank
   // ---- state
   double* pose;       // n_pose*7 (t,q)
   double* point;      // n_point*3
@@ -151,6 +159,32 @@ __device__ __forceinline__ void atomic_max_pos(unsigned long long* addr, double 
   atomicMax(addr, (unsigned long long)__double_as_longlong(v));
 }
 
+// CTA-level reduction of per-observation pose-side contributions.  Every free-pose observation of the tile owns
+// one column `rank` of c_sh[NV][CTA]; columns are ordered by pose slot, so the sum for (local slot, value) is a
+// contiguous run that exactly one thread adds up in a fixed order -> no shared-memory atomics, and the CTA issues
+// one global atomicAdd per (tile, slot, value) instead of one per observation.
+// target[slot*stride + offset + k] += sum.  Must be called by all threads of the CTA.
+template <int NV>
+__device__ __forceinline__ void tile_scatter(const Dev& P, double* c_sh, const double* vals, bool has, int rank,
+                                             double* __restrict__ target, int stride, int offset) {
+  const int t = blockIdx.x;
+  const int sp = P.tile_slot_ptr[t], nl = P.tile_slot_ptr[t + 1] - sp;
+  if (has) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) c_sh[k * CTA + rank] = vals[k];
+  }
+  __syncthreads();
+  const int* lptr = P.tile_lptr + sp + t;
+  for (int idx = threadIdx.x; idx < nl * NV; idx += CTA) {
+    const int ls = idx / NV, k = idx - ls * NV;
+    const int a = lptr[ls], b = lptr[ls + 1];
+    double sum = 0.0;
+    for (int j = a; j < b; j++) sum += c_sh[k * CTA + j];
+    atomicAdd(&target[(size_t)P.tile_slots[sp + ls] * stride + offset + k], sum);
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------------ K0: zeroing
 
 // per-slot accumulators that the linearise kernel fills with atomics (only for windows that re-linearise)
@@ -213,27 +247,36 @@ __device__ __forceinline__ void obs_eval(const Dev& P, int o, bool want_jac, boo
 }
 
 __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2, double d3, int force_all) {
+  __shared__ double c_sh[6 * CTA];
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (w >= P.n_item) return;
-  const int win = P.item_win[w];
-  if (!force_all && P.ctl[win].phase != PH_LIN) return;
-  const int start = P.item_start[w], cnt = P.item_cnt[w];
+  const bool valid = w < P.n_item;
+  const int win = valid ? P.item_win[w] : 0;
+  const bool on = valid && (force_all || P.ctl[win].phase == PH_LIN);
+  if (!__syncthreads_or(on)) return;
+  const int start = valid ? P.item_start[w] : 0, cnt = valid ? P.item_cnt[w] : 0;
   const int No = P.n_obs, Nl = P.n_point;
   const bool is_long = cnt > 32;
   double chi_acc = 0.0, maxd = 0.0;
-  double bl_acc[3] = {0, 0, 0}, hl_acc[3] = {0, 0, 0};
-  for (int base = 0; base < cnt; base += 32) {
-    const int i = base + lane;
-    const bool act = i < cnt;
-    const int o = start + (act ? i : 0);
+  double vb[6] = {0, 0, 0, 0, 0, 0}, vh[6] = {0, 0, 0, 0, 0, 0};  // this observation's -Jp^T r and diag(Jp^T Jp)
+  bool has = false;
+  int rank = 0;
+  if (valid && !is_long) {
+    const bool act = lane < cnt;
+    const int o = start + (act ? lane : 0);
+    int lm = -1 - lane;
     ObsLin L;
-    int slot = -1, lm = -1 - lane;
-    bool live = false;
+#pragma unroll
+    for (int c = 0; c < 9; c++) L.Jl[c] = 0.0;
+    L.e[0] = L.e[1] = L.e[2] = 0.0;
     if (act) {
+      const unsigned lp = P.obs_lp[o];
+      has = (lp & 0xffffu) != 0xffffu;
+      rank = (int)(lp >> 16);
       lm = P.obs_point[o];
-      slot = P.obs_slot[o];
-      live = P.obs_level[o] == 0;
+    }
+    if (act && on) {
+      const bool live = P.obs_level[o] == 0;
       obs_eval(P, o, true, robust != 0, d2, d3, L);
       if (live) {
 #pragma unroll
@@ -247,39 +290,66 @@ __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2,
       for (int c = 0; c < 9; c++) { L.Jl[c] = live ? L.Jl[c] * L.w : 0.0; P.Jl[(size_t)c * No + o] = L.Jl[c]; }
 #pragma unroll
       for (int c = 0; c < 3; c++) { L.e[c] = live ? L.e[c] * L.w : 0.0; P.r[(size_t)c * No + o] = L.e[c]; }
-      if (slot >= 0 && live) {
+      if (has) {
 #pragma unroll
         for (int c = 0; c < 6; c++) {
-          const double g = L.Jp[c] * L.e[0] + L.Jp[6 + c] * L.e[1] + L.Jp[12 + c] * L.e[2];
-          const double h = L.Jp[c] * L.Jp[c] + L.Jp[6 + c] * L.Jp[6 + c] + L.Jp[12 + c] * L.Jp[12 + c];
-          atomicAdd(&P.bp[slot * 6 + c], -g);
-          atomicAdd(&P.hd[slot * 6 + c], h);
+          vb[c] = -(L.Jp[c] * L.e[0] + L.Jp[6 + c] * L.e[1] + L.Jp[12 + c] * L.e[2]);
+          vh[c] = L.Jp[c] * L.Jp[c] + L.Jp[6 + c] * L.Jp[6 + c] + L.Jp[12 + c] * L.Jp[12 + c];
         }
       }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 9; c++) L.Jl[c] = 0.0;
-#pragma unroll
-      for (int c = 0; c < 3; c++) L.e[c] = 0.0;
     }
-    // landmark-side gradient and Hessian diagonal
-    const Seg sg = seg_of(lm, lane);
+    if (on) {  // warp-uniform: landmark-side gradient and Hessian diagonal by segmented shuffles
+      const Seg sg = seg_of(lm, lane);
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-      double g = L.Jl[c] * L.e[0] + L.Jl[3 + c] * L.e[1] + L.Jl[6 + c] * L.e[2];
-      double h = L.Jl[c] * L.Jl[c] + L.Jl[3 + c] * L.Jl[3 + c] + L.Jl[6 + c] * L.Jl[6 + c];
-      if (is_long) {
-        bl_acc[c] += warp_sum(g);
-        hl_acc[c] += warp_sum(h);
-      } else {
+      for (int c = 0; c < 3; c++) {
+        double g = L.Jl[c] * L.e[0] + L.Jl[3 + c] * L.e[1] + L.Jl[6 + c] * L.e[2];
+        double h = L.Jl[c] * L.Jl[c] + L.Jl[3 + c] * L.Jl[3 + c] + L.Jl[6 + c] * L.Jl[6 + c];
         g = seg_sum(g, sg, lane);
         h = seg_sum(h, sg, lane);
         if (act && lane == sg.start) P.bl[(size_t)c * Nl + lm] = -g;
         maxd = fmax(maxd, h);
       }
     }
-  }
-  if (is_long) {
+  } else if (on) {
+    // long landmark: chunks of 32 observations, whole-warp reductions, direct atomics on the pose side
+    double bl_acc[3] = {0, 0, 0}, hl_acc[3] = {0, 0, 0};
+    for (int base = 0; base < cnt; base += 32) {
+      const int i = base + lane;
+      const bool act = i < cnt;
+      const int o = start + (act ? i : 0);
+      ObsLin L;
+#pragma unroll
+      for (int c = 0; c < 9; c++) L.Jl[c] = 0.0;
+      L.e[0] = L.e[1] = L.e[2] = 0.0;
+      if (act) {
+        const int slot = P.obs_slot[o];
+        const bool live = P.obs_level[o] == 0;
+        obs_eval(P, o, true, robust != 0, d2, d3, L);
+        if (live) {
+#pragma unroll
+          for (int c = 0; c < 3; c++) P.err[(size_t)c * No + o] = L.e[c];
+          chi_acc += L.rho0;
+        }
+#pragma unroll
+        for (int c = 0; c < 18; c++) { L.Jp[c] = live ? L.Jp[c] * L.w : 0.0; P.Jp[(size_t)c * No + o] = L.Jp[c]; }
+#pragma unroll
+        for (int c = 0; c < 9; c++) { L.Jl[c] = live ? L.Jl[c] * L.w : 0.0; P.Jl[(size_t)c * No + o] = L.Jl[c]; }
+#pragma unroll
+        for (int c = 0; c < 3; c++) { L.e[c] = live ? L.e[c] * L.w : 0.0; P.r[(size_t)c * No + o] = L.e[c]; }
+        if (slot >= 0 && live) {
+#pragma unroll
+          for (int c = 0; c < 6; c++) {
+            atomicAdd(&P.bp[slot * 6 + c], -(L.Jp[c] * L.e[0] + L.Jp[6 + c] * L.e[1] + L.Jp[12 + c] * L.e[2]));
+            atomicAdd(&P.hd[slot * 6 + c], L.Jp[c] * L.Jp[c] + L.Jp[6 + c] * L.Jp[6 + c] + L.Jp[12 + c] * L.Jp[12 + c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        bl_acc[c] += warp_sum(L.Jl[c] * L.e[0] + L.Jl[3 + c] * L.e[1] + L.Jl[6 + c] * L.e[2]);
+        hl_acc[c] += warp_sum(L.Jl[c] * L.Jl[c] + L.Jl[3 + c] * L.Jl[3 + c] + L.Jl[6 + c] * L.Jl[6 + c]);
+      }
+    }
     const int lm = P.obs_point[start];
     if (lane == 0) {
 #pragma unroll
@@ -287,12 +357,16 @@ __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2,
     }
     maxd = fmax(hl_acc[0], fmax(hl_acc[1], hl_acc[2]));
   }
-  chi_acc = warp_sum(chi_acc);
-  maxd = warp_max(maxd);
-  if (lane == 0) {
-    P.chi_part[w] = chi_acc;
-    atomic_max_pos(&P.ctl[win].maxdiag_bits, maxd);
+  if (on) {
+    chi_acc = warp_sum(chi_acc);
+    maxd = warp_max(maxd);
+    if (lane == 0) {
+      P.chi_part[w] = chi_acc;
+      atomic_max_pos(&P.ctl[win].maxdiag_bits, maxd);
+    }
   }
+  tile_scatter<6>(P, c_sh, vb, has, rank, P.bp, 6, 0);
+  tile_scatter<6>(P, c_sh, vh, has, rank, P.hd, 6, 0);
 }
 
 // ------------------------------------------------------------------------------------------------ K8a: LM begin
@@ -385,9 +459,9 @@ __device__ __forceinline__ void load9(const double* planes, size_t stride, int o
   for (int c = 0; c < 9; c++) a[c] = planes[(size_t)c * stride + o];
 }
 
-// scatter of one observation's pose-side contributions for the trial: reduced rhs and block-Jacobi block
-__device__ __forceinline__ void scatter_trial(const Dev& P, int o, int slot, const double Q[9], const double rr[3],
-                                              const double tl[3]) {
+// one observation's pose-side contributions for the trial: reduced rhs (6) and block-Jacobi block (21, upper tri)
+__device__ __forceinline__ void trial_contrib(const Dev& P, int o, const double Q[9], const double rr[3],
+                                              const double tl[3], double out[27]) {
   const int No = P.n_obs;
   double J[18];
 #pragma unroll
@@ -396,100 +470,113 @@ __device__ __forceinline__ void scatter_trial(const Dev& P, int o, int slot, con
 #pragma unroll
   for (int r = 0; r < 3; r++) u[r] = rr[r] - (Q[r * 3] * tl[0] + Q[r * 3 + 1] * tl[1] + Q[r * 3 + 2] * tl[2]);
 #pragma unroll
-  for (int c = 0; c < 6; c++) atomicAdd(&P.bs[slot * 6 + c], -(J[c] * u[0] + J[6 + c] * u[1] + J[12 + c] * u[2]));
+  for (int c = 0; c < 6; c++) out[c] = -(J[c] * u[0] + J[6 + c] * u[1] + J[12 + c] * u[2]);
   double G[18];  // Jp^T Q1 (6x3)
 #pragma unroll
   for (int c = 0; c < 6; c++)
 #pragma unroll
     for (int k = 0; k < 3; k++) G[c * 3 + k] = J[c] * Q[k] + J[6 + c] * Q[3 + k] + J[12 + c] * Q[6 + k];
-  int idx = 0;
+  int idx = 6;
 #pragma unroll
   for (int a = 0; a < 6; a++)
 #pragma unroll
     for (int b = a; b < 6; b++) {
-      const double v = J[a] * J[b] + J[6 + a] * J[6 + b] + J[12 + a] * J[12 + b] -
-                       (G[a * 3] * G[b * 3] + G[a * 3 + 1] * G[b * 3 + 1] + G[a * 3 + 2] * G[b * 3 + 2]);
-      atomicAdd(&P.D[slot * 21 + idx], v);
+      out[idx] = J[a] * J[b] + J[6 + a] * J[6 + b] + J[12 + a] * J[12 + b] -
+                 (G[a * 3] * G[b * 3] + G[a * 3 + 1] * G[b * 3 + 1] + G[a * 3 + 2] * G[b * 3 + 2]);
       idx++;
     }
 }
 
 __global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_override) {
+  __shared__ double c_sh[7 * CTA];
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (w >= P.n_item) return;
-  const int win = P.item_win[w];
-  if (!force_all && P.ctl[win].phase != PH_TRIAL) return;
+  const bool valid = w < P.n_item;
+  const int win = valid ? P.item_win[w] : 0;
+  const bool on = valid && (force_all || P.ctl[win].phase == PH_TRIAL);
+  if (!__syncthreads_or(on)) return;
   const double lam = force_all ? lam_override : P.ctl[win].lambda;
   const double sl = sqrt(lam);
-  const int start = P.item_start[w], cnt = P.item_cnt[w];
+  const int start = valid ? P.item_start[w] : 0, cnt = valid ? P.item_cnt[w] : 0;
   const int No = P.n_obs, Nl = P.n_point;
+  double contrib[27];
+#pragma unroll
+  for (int c = 0; c < 27; c++) contrib[c] = 0.0;
+  bool has = false;
+  int rank = 0;
   LmFactor F;
-  if (cnt <= 32) {
+  if (valid && cnt <= 32) {
     const bool act = lane < cnt;
     const int o = start + (act ? lane : 0);
-    const int lm = act ? P.obs_point[o] : (-1 - lane);
-    const Seg sg = seg_of(lm, lane);
-    double a[9], rr[3];
+    int lm = -1 - lane;
     if (act) {
-      load9(P.Jl, No, o, a);
-#pragma unroll
-      for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
-    } else {
-#pragma unroll
-      for (int c = 0; c < 9; c++) a[c] = 0.0;
-      rr[0] = rr[1] = rr[2] = 0.0;
+      const unsigned lp = P.obs_lp[o];
+      has = (lp & 0xffffu) != 0xffffu;
+      rank = (int)(lp >> 16);
+      lm = P.obs_point[o];
     }
-    // column 0
-    double s0 = seg_sum(a[0] * a[0] + a[3] * a[3] + a[6] * a[6], sg, lane);
-    double d01 = seg_sum(a[0] * a[1] + a[3] * a[4] + a[6] * a[7], sg, lane);
-    double d02 = seg_sum(a[0] * a[2] + a[3] * a[5] + a[6] * a[8], sg, lane);
-    hh_col(F, 0, lam, sl, s0);
-    F.w01 = F.beta[0] * d01;
-    F.w02 = F.beta[0] * d02;
-    F.Rm[1] = -F.w01 * F.v0[0];
-    F.Rm[2] = -F.w02 * F.v0[0];
-    double V[9];
+    if (on) {
+      const Seg sg = seg_of(lm, lane);
+      double a[9], rr[3];
+      if (act) {
+        load9(P.Jl, No, o, a);
 #pragma unroll
-    for (int r = 0; r < 3; r++) {
-      V[r * 3] = a[r * 3];
-      V[r * 3 + 1] = a[r * 3 + 1] - F.w01 * a[r * 3];
-      V[r * 3 + 2] = a[r * 3 + 2] - F.w02 * a[r * 3];
-    }
-    // column 1
-    double s1 = seg_sum(V[1] * V[1] + V[4] * V[4] + V[7] * V[7], sg, lane);
-    double d12 = seg_sum(V[1] * V[2] + V[4] * V[5] + V[7] * V[8], sg, lane);
-    hh_col(F, 1, lam, sl, s1);
-    F.w12 = F.beta[1] * d12;
-    F.Rm[4] = -F.w12 * F.v0[1];
+        for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
+      } else {
 #pragma unroll
-    for (int r = 0; r < 3; r++) V[r * 3 + 2] -= F.w12 * V[r * 3 + 1];
-    // column 2
-    double s2 = seg_sum(V[2] * V[2] + V[5] * V[5] + V[8] * V[8], sg, lane);
-    hh_col(F, 2, lam, sl, s2);
-    // Gram of the reflector observation parts -> compact WY
-    double g01 = seg_sum(V[0] * V[1] + V[3] * V[4] + V[6] * V[7], sg, lane);
-    double g02 = seg_sum(V[0] * V[2] + V[3] * V[5] + V[6] * V[8], sg, lane);
-    double g12 = seg_sum(V[1] * V[2] + V[4] * V[5] + V[7] * V[8], sg, lane);
-    wy_from_gram(F, g01, g02, g12);
-    double Q[9];
-    q1_rows(V, F, Q);
-    double tl[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) tl[k] = seg_sum(Q[k] * rr[0] + Q[3 + k] * rr[1] + Q[6 + k] * rr[2], sg, lane);
-    if (act) {
-#pragma unroll
-      for (int c = 0; c < 9; c++) P.Q1[(size_t)c * No + o] = Q[c];
-      if (lane == sg.start) {
-#pragma unroll
-        for (int c = 0; c < 6; c++) P.R[(size_t)c * Nl + lm] = F.Rm[c];
-#pragma unroll
-        for (int c = 0; c < 3; c++) P.tl[(size_t)c * Nl + lm] = tl[c];
+        for (int c = 0; c < 9; c++) a[c] = 0.0;
+        rr[0] = rr[1] = rr[2] = 0.0;
       }
-      const int slot = P.obs_slot[o];
-      if (slot >= 0) scatter_trial(P, o, slot, Q, rr, tl);
+      // column 0
+      double s0 = seg_sum(a[0] * a[0] + a[3] * a[3] + a[6] * a[6], sg, lane);
+      double d01 = seg_sum(a[0] * a[1] + a[3] * a[4] + a[6] * a[7], sg, lane);
+      double d02 = seg_sum(a[0] * a[2] + a[3] * a[5] + a[6] * a[8], sg, lane);
+      hh_col(F, 0, lam, sl, s0);
+      F.w01 = F.beta[0] * d01;
+      F.w02 = F.beta[0] * d02;
+      F.Rm[1] = -F.w01 * F.v0[0];
+      F.Rm[2] = -F.w02 * F.v0[0];
+      double V[9];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        V[r * 3] = a[r * 3];
+        V[r * 3 + 1] = a[r * 3 + 1] - F.w01 * a[r * 3];
+        V[r * 3 + 2] = a[r * 3 + 2] - F.w02 * a[r * 3];
+      }
+      // column 1
+      double s1 = seg_sum(V[1] * V[1] + V[4] * V[4] + V[7] * V[7], sg, lane);
+      double d12 = seg_sum(V[1] * V[2] + V[4] * V[5] + V[7] * V[8], sg, lane);
+      hh_col(F, 1, lam, sl, s1);
+      F.w12 = F.beta[1] * d12;
+      F.Rm[4] = -F.w12 * F.v0[1];
+#pragma unroll
+      for (int r = 0; r < 3; r++) V[r * 3 + 2] -= F.w12 * V[r * 3 + 1];
+      // column 2
+      double s2 = seg_sum(V[2] * V[2] + V[5] * V[5] + V[8] * V[8], sg, lane);
+      hh_col(F, 2, lam, sl, s2);
+      // Gram of the reflector observation parts -> compact WY
+      double g01 = seg_sum(V[0] * V[1] + V[3] * V[4] + V[6] * V[7], sg, lane);
+      double g02 = seg_sum(V[0] * V[2] + V[3] * V[5] + V[6] * V[8], sg, lane);
+      double g12 = seg_sum(V[1] * V[2] + V[4] * V[5] + V[7] * V[8], sg, lane);
+      wy_from_gram(F, g01, g02, g12);
+      double Q[9];
+      q1_rows(V, F, Q);
+      double tl[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) tl[k] = seg_sum(Q[k] * rr[0] + Q[3 + k] * rr[1] + Q[6 + k] * rr[2], sg, lane);
+      if (act) {
+#pragma unroll
+        for (int c = 0; c < 9; c++) P.Q1[(size_t)c * No + o] = Q[c];
+        if (lane == sg.start) {
+#pragma unroll
+          for (int c = 0; c < 6; c++) P.R[(size_t)c * Nl + lm] = F.Rm[c];
+#pragma unroll
+          for (int c = 0; c < 3; c++) P.tl[(size_t)c * Nl + lm] = tl[c];
+        }
+        if (has) trial_contrib(P, o, Q, rr, tl, contrib);
+      }
     }
-  } else {
+  } else if (on) {
     // long landmark: five sweeps over its rows (L1/L2 resident), whole-warp reductions
     const int lm = P.obs_point[start];
     double acc[3] = {0, 0, 0};
@@ -550,6 +637,7 @@ __global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_ove
 #pragma unroll
       for (int c = 0; c < 3; c++) P.tl[(size_t)c * Nl + lm] = tl[c];
     }
+    double lc[27];
     for (int i = lane; i < cnt; i += 32) {
       const int o = start + i;
       const int slot = P.obs_slot[o];
@@ -557,10 +645,19 @@ __global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_ove
       load9(P.Q1, No, o, Q);  // written by this same lane above
 #pragma unroll
       for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
-      scatter_trial(P, o, slot, Q, rr, tl);
+      trial_contrib(P, o, Q, rr, tl, lc);
+#pragma unroll
+      for (int c = 0; c < 6; c++) atomicAdd(&P.bs[slot * 6 + c], lc[c]);
+#pragma unroll
+      for (int c = 0; c < 21; c++) atomicAdd(&P.D[slot * 21 + c], lc[6 + c]);
     }
   }
+  tile_scatter<6>(P, c_sh, contrib, has, rank, P.bs, 6, 0);
+  tile_scatter<7>(P, c_sh, contrib + 6, has, rank, P.D, 21, 0);
+  tile_scatter<7>(P, c_sh, contrib + 13, has, rank, P.D, 21, 7);
+  tile_scatter<7>(P, c_sh, contrib + 20, has, rank, P.D, 21, 14);
 }
+
 
 // 6x6 block-Jacobi inverse per pose slot: (D + lambda I)^-1
 __global__ void k_dinv(Dev P, int force_all, double lam_override) {
@@ -608,29 +705,69 @@ __device__ __forceinline__ void matvec_obs_v(const Dev& P, const double* __restr
            J[r * 6 + 4] * pp[4] + J[r * 6 + 5] * pp[5];
 }
 
-__device__ __forceinline__ void matvec_item(const Dev& P, const double* __restrict__ pvec, double* __restrict__ qvec,
-                                            int w, int lane) {
-  const int start = P.item_start[w], cnt = P.item_cnt[w];
-  if (cnt <= 32) {
+__global__ void __launch_bounds__(CTA) k_matvec(Dev P, const double* __restrict__ pvec, double* __restrict__ qvec,
+                                                int force_all) {
+  __shared__ double p_sh[6 * CTA];
+  __shared__ double c_sh[6 * CTA];
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x;
+  const int w = t * WARPS + (threadIdx.x >> 5);
+  const bool valid = w < P.n_item;
+  const bool on = valid && (force_all || P.ctl[P.item_win[w]].cg_active);
+  if (!__syncthreads_or(on)) return;
+  // stage the pose-sized vector entries this tile needs (its distinct free slots)
+  const int sp = P.tile_slot_ptr[t], nl = P.tile_slot_ptr[t + 1] - sp;
+  for (int i = threadIdx.x; i < nl * 6; i += CTA) {
+    const int ls = i / 6;
+    p_sh[i] = pvec[(size_t)P.tile_slots[sp + ls] * 6 + (i - ls * 6)];
+  }
+  __syncthreads();
+  const int start = valid ? P.item_start[w] : 0, cnt = valid ? P.item_cnt[w] : 0;
+  const int No = P.n_obs;
+  double out[6] = {0, 0, 0, 0, 0, 0};
+  bool has = false;
+  int rank = 0;
+  if (valid && cnt <= 32) {
     const bool act = lane < cnt;
     const int o = start + (act ? lane : 0);
-    const int lm = act ? P.obs_point[o] : (-1 - lane);
-    const int slot = act ? P.obs_slot[o] : -1;
-    const Seg sg = seg_of(lm, lane);
-    double J[18], Q[9], v[3] = {0, 0, 0}, sv[3];
-    if (slot >= 0) matvec_obs_v(P, pvec, o, slot, J, Q, v);
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const double t = (slot >= 0) ? (Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2]) : 0.0;
-      sv[k] = seg_sum(t, sg, lane);
+    int lm = -1 - lane, ls = 0xffff;
+    if (act) {
+      const unsigned lp = P.obs_lp[o];
+      ls = (int)(lp & 0xffffu);
+      has = ls != 0xffff;
+      rank = (int)(lp >> 16);
+      lm = P.obs_point[o];
     }
-    if (slot >= 0) {
+    if (on) {
+      const Seg sg = seg_of(lm, lane);
+      double J[18], Q[9], v[3] = {0, 0, 0}, sv[3];
+      if (has) {
 #pragma unroll
-      for (int r = 0; r < 3; r++) v[r] -= Q[r * 3] * sv[0] + Q[r * 3 + 1] * sv[1] + Q[r * 3 + 2] * sv[2];
+        for (int c = 0; c < 18; c++) J[c] = P.Jp[(size_t)c * No + o];
 #pragma unroll
-      for (int c = 0; c < 6; c++) atomicAdd(&qvec[slot * 6 + c], J[c] * v[0] + J[6 + c] * v[1] + J[12 + c] * v[2]);
+        for (int c = 0; c < 9; c++) Q[c] = P.Q1[(size_t)c * No + o];
+        double pp[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) pp[c] = p_sh[ls * 6 + c];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+          v[r] = J[r * 6] * pp[0] + J[r * 6 + 1] * pp[1] + J[r * 6 + 2] * pp[2] + J[r * 6 + 3] * pp[3] +
+                 J[r * 6 + 4] * pp[4] + J[r * 6 + 5] * pp[5];
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const double tt = has ? (Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2]) : 0.0;
+        sv[k] = seg_sum(tt, sg, lane);
+      }
+      if (has) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) v[r] -= Q[r * 3] * sv[0] + Q[r * 3 + 1] * sv[1] + Q[r * 3 + 2] * sv[2];
+#pragma unroll
+        for (int c = 0; c < 6; c++) out[c] = J[c] * v[0] + J[6 + c] * v[1] + J[12 + c] * v[2];
+      }
     }
-  } else {
+  } else if (on) {
+    // long landmark: two sweeps, direct atomics
     double J[18], Q[9], v[3], sv[3] = {0, 0, 0};
     for (int i = lane; i < cnt; i += 32) {
       const int o = start + i;
@@ -653,16 +790,9 @@ __device__ __forceinline__ void matvec_item(const Dev& P, const double* __restri
       for (int c = 0; c < 6; c++) atomicAdd(&qvec[slot * 6 + c], J[c] * v[0] + J[6 + c] * v[1] + J[12 + c] * v[2]);
     }
   }
+  tile_scatter<6>(P, c_sh, out, has, rank, qvec, 6, 0);
 }
 
-__global__ void __launch_bounds__(CTA) k_matvec(Dev P, const double* __restrict__ pvec, double* __restrict__ qvec,
-                                                int force_all) {
-  const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (w >= P.n_item) return;
-  if (!force_all && !P.ctl[P.item_win[w]].cg_active) return;
-  matvec_item(P, pvec, qvec, w, lane);
-}
 
 // ------------------------------------------------------------------------------------------------ K4/K5: PCG vector ops
 // One CTA owns one window's pose-sized vectors, so dot products are block reductions with no global sync.

@@ -184,10 +184,55 @@ class Solver {
     }
     for (int w = 0; w < n_win; w++) win_item_ptr[w + 1] += win_item_ptr[w];
     const int n_item = (int)item_start.size();
+    // tiles: the WARPS consecutive items of one CTA; distinct free slots per tile + per-observation (local slot, rank
+    // in the tile's pose-sorted order) for the in-CTA reduction of pose-side sums (see tile_scatter)
+    const int n_tile = cdiv(n_item, WARPS);
+    std::vector<int> tile_slot_ptr(n_tile + 1, 0), tile_slots, tile_lptr;
+    std::vector<unsigned> obs_lp(n_obs, 0xffffu);
+    {
+      std::vector<int> stamp(std::max(n_slot, 1), -1), local_of(std::max(n_slot, 1), 0), distinct, lptr, cursor;
+      tile_slots.reserve((size_t)n_tile * 24);
+      tile_lptr.reserve((size_t)n_tile * 25);
+      for (int t = 0; t < n_tile; t++) {
+        const int i0 = t * WARPS, i1 = std::min(n_item, i0 + WARPS);
+        distinct.clear();
+        for (int it = i0; it < i1; it++) {
+          if (item_cnt[it] > 32) continue;
+          for (int o = item_start[it]; o < item_start[it] + item_cnt[it]; o++) {
+            const int sl = obs_slot[o];
+            if (sl >= 0 && stamp[sl] != t) { stamp[sl] = t; distinct.push_back(sl); }
+          }
+        }
+        std::sort(distinct.begin(), distinct.end());
+        const int nl = (int)distinct.size();
+        for (int i = 0; i < nl; i++) local_of[distinct[i]] = i;
+        lptr.assign(nl + 1, 0);
+        for (int it = i0; it < i1; it++) {
+          if (item_cnt[it] > 32) continue;
+          for (int o = item_start[it]; o < item_start[it] + item_cnt[it]; o++)
+            if (obs_slot[o] >= 0) lptr[local_of[obs_slot[o]] + 1]++;
+        }
+        for (int i = 0; i < nl; i++) lptr[i + 1] += lptr[i];
+        cursor.assign(lptr.begin(), lptr.end());
+        for (int it = i0; it < i1; it++) {
+          if (item_cnt[it] > 32) continue;
+          for (int o = item_start[it]; o < item_start[it] + item_cnt[it]; o++) {
+            if (obs_slot[o] < 0) continue;
+            const int ls = local_of[obs_slot[o]];
+            const int rank = cursor[ls]++;
+            obs_lp[o] = (unsigned)ls | ((unsigned)rank << 16);
+          }
+        }
+        tile_slots.insert(tile_slots.end(), distinct.begin(), distinct.end());
+        tile_lptr.insert(tile_lptr.end(), lptr.begin(), lptr.end());
+        tile_slot_ptr[t + 1] = tile_slot_ptr[t] + nl;
+      }
+    }
 
     // ---- device allocation
     P_ = Dev{};
     P_.n_pose = n_pose; P_.n_point = n_point; P_.n_obs = n_obs; P_.n_win = n_win; P_.n_slot = n_slot; P_.n_item = n_item;
+    P_.n_tile = n_tile;
     const size_t No = n_obs, Nl = n_point, Ns = std::max(n_slot, 1);
     CU_CHECK(d_cam_.ensure((size_t)n_pose * 5));
     CU_CHECK(d_pose_slot_.ensure(n_pose));
@@ -204,6 +249,10 @@ class Solver {
     CU_CHECK(d_item_win_.ensure(n_item));
     CU_CHECK(d_win_item_ptr_.ensure(n_win + 1));
     CU_CHECK(d_win_slot_ptr_.ensure(n_win + 1));
+    CU_CHECK(d_tile_slot_ptr_.ensure(n_tile + 1));
+    CU_CHECK(d_tile_slots_.ensure(tile_slots.size()));
+    CU_CHECK(d_tile_lptr_.ensure(tile_lptr.size()));
+    CU_CHECK(d_obs_lp_.ensure(No));
     CU_CHECK(d_pose_.ensure((size_t)n_pose * 7));
     CU_CHECK(d_pose0_.ensure((size_t)n_pose * 7));
     CU_CHECK(d_pose_bak_.ensure((size_t)n_pose * 7));
@@ -247,6 +296,10 @@ class Solver {
     CU_CHECK(up(d_item_win_.p, item_win.data(), n_item * sizeof(int)));
     CU_CHECK(up(d_win_item_ptr_.p, win_item_ptr.data(), (n_win + 1) * sizeof(int)));
     CU_CHECK(up(d_win_slot_ptr_.p, win_slot_ptr.data(), (n_win + 1) * sizeof(int)));
+    CU_CHECK(up(d_tile_slot_ptr_.p, tile_slot_ptr.data(), (n_tile + 1) * sizeof(int)));
+    if (!tile_slots.empty()) CU_CHECK(up(d_tile_slots_.p, tile_slots.data(), tile_slots.size() * sizeof(int)));
+    CU_CHECK(up(d_tile_lptr_.p, tile_lptr.data(), tile_lptr.size() * sizeof(int)));
+    CU_CHECK(up(d_obs_lp_.p, obs_lp.data(), No * sizeof(unsigned)));
     // poses: normalise the quaternion the way SE3Quat's constructor does (se3quat.h:58-64)
     std::vector<double> pq(pose_qt, pose_qt + (size_t)n_pose * 7);
     for (int i = 0; i < n_pose; i++) quat_normalize_pos_w(&pq[(size_t)i * 7 + 3]);
@@ -259,6 +312,8 @@ class Solver {
     P_.obs_point = d_obs_point_.p; P_.obs_slot = d_obs_slot_.p; P_.item_start = d_item_start_.p;
     P_.item_cnt = d_item_cnt_.p; P_.item_win = d_item_win_.p; P_.win_item_ptr = d_win_item_ptr_.p;
     P_.win_slot_ptr = d_win_slot_ptr_.p;
+    P_.tile_slot_ptr = d_tile_slot_ptr_.p; P_.tile_slots = d_tile_slots_.p; P_.tile_lptr = d_tile_lptr_.p;
+    P_.obs_lp = d_obs_lp_.p;
     P_.pose = d_pose_.p; P_.point = d_point_.p; P_.pose_bak = d_pose_bak_.p; P_.point_bak = d_point_bak_.p;
     P_.obs_level = d_level_.p; P_.obs_outlier = d_outlier_.p;
     P_.err = d_err_.p; P_.Jp = d_Jp_.p; P_.Jl = d_Jl_.p; P_.Q1 = d_Q1_.p; P_.r = d_r_.p;
@@ -601,6 +656,7 @@ class Solver {
     d_Jp_.release(); d_Jl_.release(); d_Q1_.release(); d_r_.release(); d_R_.release(); d_tl_.release();
     d_bl_.release(); d_dl_.release(); d_slotvec_.release(); d_chi_part_.release(); d_scale_part_.release();
     d_ctl_.release(); d_trace_.release(); d_counters_.release();
+    d_tile_slot_ptr_.release(); d_tile_slots_.release(); d_tile_lptr_.release(); d_obs_lp_.release();
   }
 
  public:
@@ -621,7 +677,9 @@ class Solver {
   DBuf<double> d_cam_, d_pose_, d_pose0_, d_pose_bak_, d_point_, d_point0_, d_point_bak_, d_err_, d_Jp_, d_Jl_, d_Q1_,
       d_r_, d_R_, d_tl_, d_bl_, d_dl_, d_slotvec_, d_chi_part_, d_scale_part_, d_trace_;
   DBuf<int> d_pose_slot_, d_slot_pose_, d_slot_win_, d_pose_win_, d_point_win_, d_obs_pose_, d_obs_point_, d_obs_slot_,
-      d_item_start_, d_item_cnt_, d_item_win_, d_win_item_ptr_, d_win_slot_ptr_, d_counters_;
+      d_item_start_, d_item_cnt_, d_item_win_, d_win_item_ptr_, d_win_slot_ptr_, d_counters_, d_tile_slot_ptr_,
+      d_tile_slots_, d_tile_lptr_;
+  DBuf<unsigned> d_obs_lp_;
   DBuf<float4> d_meas_;
   DBuf<uint8_t> d_level_, d_outlier_;
   DBuf<WinCtl> d_ctl_;
