@@ -6,7 +6,8 @@
 // per-observation plane access is a fully coalesced stream.  A landmark with more than 32 observations gets
 // an item of its own and the warp sweeps it in chunks of 32.  Items never straddle windows (batched BA).
 //
-// Storage is SoA by component ("planes" of n_obs doubles): Jp 18, Jl 9, Q1 9, r 3, err 3.
+// Storage is SoA by component ("planes" of ld doubles): Jl 9, r 3, err 3; the matvec operand (Jp 18 + Q1 9) is
+// tile-blocked SoA (see Dev::JQ).
 // All arithmetic is FP64 (tolerances 1e-6 on cost / 1e-5 m on poses); the roofline is HBM bandwidth.
 #pragma once
 #include <cuda_runtime.h>
@@ -17,8 +18,12 @@
 namespace sqrtba {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int CTA = 256;
+constexpr int CTA = 128;            // item kernels: one CTA = one tile of up to WARPS items (warps)
 constexpr int WARPS = CTA / 32;
+constexpr int RCTA = 256;           // per-window reduction / vector kernels
+constexpr int RWARPS = RCTA / 32;
+constexpr int MAXSLOT = 128;        // "small window": all free poses of a window fit the CTA's shared accumulators
+constexpr int NPLANE = 27;          // matvec streams Jp (18) + Q1 (9) planes
 
 enum Phase { PH_LIN = 0, PH_TRIAL = 1, PH_DONE = 2 };
 
@@ -31,6 +36,17 @@ struct WinCtl {
   int iter, qmax, nbad, phase;
   int max_iter, pass, cg_active, cg_iters;
   int trace_len, need_restore, lin_count, pad;
+};
+
+struct TileInfo {
+  int item0, nitem;  // items [item0, item0+nitem)
+  int o0, o1;        // observation range [o0, o1)
+  int win;           // window of the tile
+  int nfree;         // observations that take part in the in-CTA reduction (ranks 0..nfree-1)
+  int nt;            // columns of this tile's JQ block: (o1-o0) rounded up to even (16-byte rows for TMA)
+  int pad0;
+  long long jq_off;  // offset (doubles) of the tile's [27][nt] block inside Dev::JQ
+  long long pad1;
 };
 
 struct Dev {
@@ -51,14 +67,15 @@ struct Dev {
   const int* item_win;     // n_item
   const int* win_item_ptr;  // n_win+1
   const int* win_slot_ptr;  // n_win+1
-  // tile = the WARPS consecutive items one CTA owns.  Per tile: the distinct free-pose slots its (short) items
-  // touch, and for every such observation a local slot id + its rank in the tile's pose-sorted order, so that
-  // pose-side sums are reduced inside the CTA (shared memory, no atomics) and flushed once per (tile, slot).
+  // tile = up to WARPS consecutive short items of ONE window (or one long item); one CTA per tile.
+  // obs_lp: low 16 bits = window-relative free slot when the problem is "smallwin" (0 otherwise), 0xffff = the
+  // observation takes no part in the in-CTA reduction (fixed pose or long item); high 16 bits = its rank in the
+  // tile's pose-sorted order.
   int n_tile;
-  const int* tile_slot_ptr;   // n_tile+1 -> tile_slots
-  const int* tile_slots;      // global slot ids, ascending inside a tile
-  const int* tile_lptr;       // per tile n_local+1 offsets into the pose-sorted order; base = tile_slot_ptr[t] + t
-  const unsigned* obs_lp;     // n_obs: low 16 bits local slot (0xffff = fixed pose / long item), high 16 bits rank
+  int ld;                     // leading dimension (stride) of every per-observation plane, multiple of 32
+  int smallwin;               // every window has <= MAXSLOT free poses
+  const struct TileInfo* tiles;
+  const unsigned* obs_lp;     // n_obs
   // ---- state
   double* pose;       // n_pose*7 (t,q)
   double* point;      // n_point*3
@@ -68,10 +85,12 @@ struct Dev {
   uint8_t* obs_outlier;
   // ---- linearisation (planes)
   double* err;  // 3 planes: g2o's stored _error (unweighted)
-  double* Jp;   // 18
   double* Jl;   // 9
-  double* Q1;   // 9
   double* r;    // 3
+  // matvec operand, TILE-BLOCKED: tile t owns the contiguous block JQ[jq_off .. jq_off + 27*nt) laid out [27][nt]:
+  // rows 0-17 = weighted Jp (3x6 row-major), rows 18-26 = observation rows of Q1 (3x3 row-major); column = o - o0.
+  // One tile = one contiguous 27*nt*8-byte chunk, so the matvec fetches it with a single TMA bulk copy.
+  double* JQ;
   // ---- per landmark (planes of n_point)
   double* R;   // 6: r00 r01 r02 r11 r12 r22
   double* tl;  // 3: Q1^T r
@@ -144,14 +163,14 @@ __device__ __forceinline__ double lm_sum(double v, const Seg& s, int lane) {
   return seg_sum(v, s, lane);
 }
 
-__device__ __forceinline__ double block_sum(double v, double* sh) {  // sh: WARPS doubles, result to all threads
+__device__ __forceinline__ double block_sum(double v, double* sh) {  // RCTA threads; sh: RWARPS doubles; result to all
   v = warp_sum(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
   __syncthreads();
   double t = 0.0;
 #pragma unroll
-  for (int i = 0; i < WARPS; i++) t += sh[i];
+  for (int i = 0; i < RWARPS; i++) t += sh[i];
   return t;
 }
 
@@ -159,30 +178,57 @@ __device__ __forceinline__ void atomic_max_pos(unsigned long long* addr, double 
   atomicMax(addr, (unsigned long long)__double_as_longlong(v));
 }
 
-// CTA-level reduction of per-observation pose-side contributions.  Every free-pose observation of the tile owns
-// one column `rank` of c_sh[NV][CTA]; columns are ordered by pose slot, so the sum for (local slot, value) is a
-// contiguous run that exactly one thread adds up in a fixed order -> no shared-memory atomics, and the CTA issues
-// one global atomicAdd per (tile, slot, value) instead of one per observation.
-// target[slot*stride + offset + k] += sum.  Must be called by all threads of the CTA.
+// CTA-level reduction of per-observation pose-side contributions.  Every participating observation of the tile owns
+// one column `rank` of c_sh[NV][CTA]; ranks are ordered by pose slot, so the sum for one (slot, value) is a
+// contiguous run that exactly one thread (the run head) adds up in a fixed order -> no shared-memory atomics, and the
+// CTA issues one global atomicAdd per (tile, slot, value) instead of one per observation.
+// target[key*stride + offset + k] += run sum.  Must be called by all threads of the CTA.
 template <int NV>
-__device__ __forceinline__ void tile_scatter(const Dev& P, double* c_sh, const double* vals, bool has, int rank,
-                                             double* __restrict__ target, int stride, int offset) {
-  const int t = blockIdx.x;
-  const int sp = P.tile_slot_ptr[t], nl = P.tile_slot_ptr[t + 1] - sp;
+__device__ __forceinline__ void tile_scatter(int nfree, int* key_sh, double* c_sh, const double* vals, bool has, int rank,
+                                             int key, double* __restrict__ target, int stride, int offset) {
   if (has) {
+    key_sh[rank] = key;
 #pragma unroll
     for (int k = 0; k < NV; k++) c_sh[k * CTA + rank] = vals[k];
   }
   __syncthreads();
-  const int* lptr = P.tile_lptr + sp + t;
-  for (int idx = threadIdx.x; idx < nl * NV; idx += CTA) {
-    const int ls = idx / NV, k = idx - ls * NV;
-    const int a = lptr[ls], b = lptr[ls + 1];
-    double sum = 0.0;
-    for (int j = a; j < b; j++) sum += c_sh[k * CTA + j];
-    atomicAdd(&target[(size_t)P.tile_slots[sp + ls] * stride + offset + k], sum);
+  for (int idx = threadIdx.x; idx < nfree * NV; idx += CTA) {
+    const int j = idx / NV, k = idx - j * NV;
+    const int kj = key_sh[j];
+    if (j == 0 || key_sh[j - 1] != kj) {
+      double sum = 0.0;
+      for (int jj = j; jj < nfree && key_sh[jj] == kj; jj++) sum += c_sh[k * CTA + jj];
+      atomicAdd(&target[(size_t)kj * stride + offset + k], sum);
+    }
   }
   __syncthreads();
+}
+
+// ---- TMA (bulk async copy) + mbarrier primitives, raw PTX (sm_90+/sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
 }
 
 // ------------------------------------------------------------------------------------------------ K0: zeroing
@@ -248,19 +294,22 @@ __device__ __forceinline__ void obs_eval(const Dev& P, int o, bool want_jac, boo
 
 __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2, double d3, int force_all) {
   __shared__ double c_sh[6 * CTA];
-  const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
-  const bool valid = w < P.n_item;
-  const int win = valid ? P.item_win[w] : 0;
-  const bool on = valid && (force_all || P.ctl[win].phase == PH_LIN);
-  if (!__syncthreads_or(on)) return;
+  __shared__ int key_sh[CTA];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const TileInfo ti = P.tiles[blockIdx.x];
+  const int w = ti.item0 + wid;
+  const bool valid = wid < ti.nitem;
+  const int win = ti.win;
+  if (!force_all && P.ctl[win].phase != PH_LIN) return;  // a tile lies inside one window: CTA-uniform
+  const bool on = valid;
   const int start = valid ? P.item_start[w] : 0, cnt = valid ? P.item_cnt[w] : 0;
-  const int No = P.n_obs, Nl = P.n_point;
+  const size_t No = (size_t)P.ld; const int Nl = P.n_point;
   const bool is_long = cnt > 32;
+  double* __restrict__ jq = P.JQ + ti.jq_off;
   double chi_acc = 0.0, maxd = 0.0;
   double vb[6] = {0, 0, 0, 0, 0, 0}, vh[6] = {0, 0, 0, 0, 0, 0};  // this observation's -Jp^T r and diag(Jp^T Jp)
   bool has = false;
-  int rank = 0;
+  int rank = 0, key = 0;
   if (valid && !is_long) {
     const bool act = lane < cnt;
     const int o = start + (act ? lane : 0);
@@ -273,6 +322,7 @@ __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2,
       const unsigned lp = P.obs_lp[o];
       has = (lp & 0xffffu) != 0xffffu;
       rank = (int)(lp >> 16);
+      key = P.obs_slot[o];
       lm = P.obs_point[o];
     }
     if (act && on) {
@@ -285,7 +335,7 @@ __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2,
       }
       // an excluded (level-1) edge contributes zero rows; select, do not multiply (its Jacobian may be inf/NaN)
 #pragma unroll
-      for (int c = 0; c < 18; c++) { L.Jp[c] = live ? L.Jp[c] * L.w : 0.0; P.Jp[(size_t)c * No + o] = L.Jp[c]; }
+      for (int c = 0; c < 18; c++) { L.Jp[c] = live ? L.Jp[c] * L.w : 0.0; jq[(size_t)c * ti.nt + (o - ti.o0)] = L.Jp[c]; }
 #pragma unroll
       for (int c = 0; c < 9; c++) { L.Jl[c] = live ? L.Jl[c] * L.w : 0.0; P.Jl[(size_t)c * No + o] = L.Jl[c]; }
 #pragma unroll
@@ -331,7 +381,7 @@ __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2,
           chi_acc += L.rho0;
         }
 #pragma unroll
-        for (int c = 0; c < 18; c++) { L.Jp[c] = live ? L.Jp[c] * L.w : 0.0; P.Jp[(size_t)c * No + o] = L.Jp[c]; }
+        for (int c = 0; c < 18; c++) { L.Jp[c] = live ? L.Jp[c] * L.w : 0.0; jq[(size_t)c * ti.nt + (o - ti.o0)] = L.Jp[c]; }
 #pragma unroll
         for (int c = 0; c < 9; c++) { L.Jl[c] = live ? L.Jl[c] * L.w : 0.0; P.Jl[(size_t)c * No + o] = L.Jl[c]; }
 #pragma unroll
@@ -365,21 +415,21 @@ __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2,
       atomic_max_pos(&P.ctl[win].maxdiag_bits, maxd);
     }
   }
-  tile_scatter<6>(P, c_sh, vb, has, rank, P.bp, 6, 0);
-  tile_scatter<6>(P, c_sh, vh, has, rank, P.hd, 6, 0);
+  tile_scatter<6>(ti.nfree, key_sh, c_sh, vb, has, rank, key, P.bp, 6, 0);
+  tile_scatter<6>(ti.nfree, key_sh, c_sh, vh, has, rank, key, P.hd, 6, 0);
 }
 
 // ------------------------------------------------------------------------------------------------ K8a: LM begin
 // OptimizationAlgorithmLevenberg::solve up to the trial loop (optimization_algorithm_levenberg.cpp:75-100):
 // currentChi, iniChi, lambda init = tau * max diag(H) at iteration 0 (computeLambdaInit :166-180).
-__global__ void __launch_bounds__(CTA) k_lm_begin(Dev P) {
-  __shared__ double sh[WARPS];
+__global__ void __launch_bounds__(RCTA) k_lm_begin(Dev P) {
+  __shared__ double sh[RWARPS];
   const int win = blockIdx.x;
   WinCtl& c = P.ctl[win];
   if (c.phase != PH_LIN) return;
   double chi = 0.0, md = 0.0;
-  for (int i = P.win_item_ptr[win] + threadIdx.x; i < P.win_item_ptr[win + 1]; i += CTA) chi += P.chi_part[i];
-  for (int i = P.win_slot_ptr[win] * 6 + threadIdx.x; i < P.win_slot_ptr[win + 1] * 6; i += CTA)
+  for (int i = P.win_item_ptr[win] + threadIdx.x; i < P.win_item_ptr[win + 1]; i += RCTA) chi += P.chi_part[i];
+  for (int i = P.win_slot_ptr[win] * 6 + threadIdx.x; i < P.win_slot_ptr[win + 1] * 6; i += RCTA)
     md = fmax(md, fabs(P.hd[i]));
   chi = block_sum(chi, sh);
   md = warp_max(md);
@@ -387,7 +437,7 @@ __global__ void __launch_bounds__(CTA) k_lm_begin(Dev P) {
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = md;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < WARPS; i++) md = fmax(md, sh[i]);
+    for (int i = 0; i < RWARPS; i++) md = fmax(md, sh[i]);
     md = fmax(md, __longlong_as_double((long long)c.maxdiag_bits));
     c.maxdiag_bits = 0ull;
     c.cur_chi = chi;
@@ -454,18 +504,17 @@ __device__ __forceinline__ void hh_col(LmFactor& F, int j, double lam, double sl
   F.Rm[j == 0 ? 0 : (j == 1 ? 3 : 5)] = -norm;
 }
 
-__device__ __forceinline__ void load9(const double* planes, size_t stride, int o, double a[9]) {
+__device__ __forceinline__ void load9(const double* planes, size_t stride, size_t o, double a[9]) {
 #pragma unroll
   for (int c = 0; c < 9; c++) a[c] = planes[(size_t)c * stride + o];
 }
 
 // one observation's pose-side contributions for the trial: reduced rhs (6) and block-Jacobi block (21, upper tri)
-__device__ __forceinline__ void trial_contrib(const Dev& P, int o, const double Q[9], const double rr[3],
-                                              const double tl[3], double out[27]) {
-  const int No = P.n_obs;
+__device__ __forceinline__ void trial_contrib(const double* __restrict__ jq, int nt, int col, const double Q[9],
+                                              const double rr[3], const double tl[3], double out[27]) {
   double J[18];
 #pragma unroll
-  for (int c = 0; c < 18; c++) J[c] = P.Jp[(size_t)c * No + o];
+  for (int c = 0; c < 18; c++) J[c] = jq[(size_t)c * nt + col];
   double u[3];
 #pragma unroll
   for (int r = 0; r < 3; r++) u[r] = rr[r] - (Q[r * 3] * tl[0] + Q[r * 3 + 1] * tl[1] + Q[r * 3 + 2] * tl[2]);
@@ -489,21 +538,25 @@ __device__ __forceinline__ void trial_contrib(const Dev& P, int o, const double 
 
 __global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_override) {
   __shared__ double c_sh[7 * CTA];
-  const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
-  const bool valid = w < P.n_item;
-  const int win = valid ? P.item_win[w] : 0;
-  const bool on = valid && (force_all || P.ctl[win].phase == PH_TRIAL);
-  if (!__syncthreads_or(on)) return;
+  __shared__ int key_sh[CTA];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const TileInfo ti = P.tiles[blockIdx.x];
+  const int w = ti.item0 + wid;
+  const bool valid = wid < ti.nitem;
+  const int win = ti.win;
+  if (!force_all && P.ctl[win].phase != PH_TRIAL) return;  // CTA-uniform
+  const bool on = valid;
   const double lam = force_all ? lam_override : P.ctl[win].lambda;
   const double sl = sqrt(lam);
   const int start = valid ? P.item_start[w] : 0, cnt = valid ? P.item_cnt[w] : 0;
-  const int No = P.n_obs, Nl = P.n_point;
+  const size_t No = (size_t)P.ld; const int Nl = P.n_point;
+  double* __restrict__ jq = P.JQ + ti.jq_off;
+  const int nt = ti.nt;
   double contrib[27];
 #pragma unroll
   for (int c = 0; c < 27; c++) contrib[c] = 0.0;
   bool has = false;
-  int rank = 0;
+  int rank = 0, key = 0;
   LmFactor F;
   if (valid && cnt <= 32) {
     const bool act = lane < cnt;
@@ -513,6 +566,7 @@ __global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_ove
       const unsigned lp = P.obs_lp[o];
       has = (lp & 0xffffu) != 0xffffu;
       rank = (int)(lp >> 16);
+      key = P.obs_slot[o];
       lm = P.obs_point[o];
     }
     if (on) {
@@ -566,14 +620,14 @@ __global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_ove
       for (int k = 0; k < 3; k++) tl[k] = seg_sum(Q[k] * rr[0] + Q[3 + k] * rr[1] + Q[6 + k] * rr[2], sg, lane);
       if (act) {
 #pragma unroll
-        for (int c = 0; c < 9; c++) P.Q1[(size_t)c * No + o] = Q[c];
+        for (int c = 0; c < 9; c++) jq[(size_t)(18 + c) * nt + (o - ti.o0)] = Q[c];
         if (lane == sg.start) {
 #pragma unroll
           for (int c = 0; c < 6; c++) P.R[(size_t)c * Nl + lm] = F.Rm[c];
 #pragma unroll
           for (int c = 0; c < 3; c++) P.tl[(size_t)c * Nl + lm] = tl[c];
         }
-        if (has) trial_contrib(P, o, Q, rr, tl, contrib);
+        if (has) trial_contrib(jq, nt, o - ti.o0, Q, rr, tl, contrib);
       }
     }
   } else if (on) {
@@ -623,7 +677,7 @@ __global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_ove
       v_rows(a, F, V);
       q1_rows(V, F, Q);
 #pragma unroll
-      for (int c = 0; c < 9; c++) P.Q1[(size_t)c * No + o] = Q[c];
+      for (int c = 0; c < 9; c++) jq[(size_t)(18 + c) * nt + (o - ti.o0)] = Q[c];
 #pragma unroll
       for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
 #pragma unroll
@@ -642,20 +696,20 @@ __global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_ove
       const int o = start + i;
       const int slot = P.obs_slot[o];
       if (slot < 0) continue;
-      load9(P.Q1, No, o, Q);  // written by this same lane above
+      load9(jq + (size_t)18 * nt, nt, o - ti.o0, Q);  // written by this same lane above
 #pragma unroll
       for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
-      trial_contrib(P, o, Q, rr, tl, lc);
+      trial_contrib(jq, nt, o - ti.o0, Q, rr, tl, lc);
 #pragma unroll
       for (int c = 0; c < 6; c++) atomicAdd(&P.bs[slot * 6 + c], lc[c]);
 #pragma unroll
       for (int c = 0; c < 21; c++) atomicAdd(&P.D[slot * 21 + c], lc[6 + c]);
     }
   }
-  tile_scatter<6>(P, c_sh, contrib, has, rank, P.bs, 6, 0);
-  tile_scatter<7>(P, c_sh, contrib + 6, has, rank, P.D, 21, 0);
-  tile_scatter<7>(P, c_sh, contrib + 13, has, rank, P.D, 21, 7);
-  tile_scatter<7>(P, c_sh, contrib + 20, has, rank, P.D, 21, 14);
+  tile_scatter<6>(ti.nfree, key_sh, c_sh, contrib, has, rank, key, P.bs, 6, 0);
+  tile_scatter<7>(ti.nfree, key_sh, c_sh, contrib + 6, has, rank, key, P.D, 21, 0);
+  tile_scatter<7>(ti.nfree, key_sh, c_sh, contrib + 13, has, rank, key, P.D, 21, 7);
+  tile_scatter<7>(ti.nfree, key_sh, c_sh, contrib + 20, has, rank, key, P.D, 21, 14);
 }
 
 
@@ -689,13 +743,13 @@ __global__ void k_dinv(Dev P, int force_all, double lam_override) {
 // update).  Per observation: v = Jp p[slot] (d-vector), s_l = sum Q1^T v (3-vector, landmark reduction),
 // u = v - Q1 s_l, scatter-add Jp^T u.  Streams Jp (18) + Q1 (9) planes: 216 B/observation.
 // Observations of fixed poses have no pose columns (g2o hessianIndex -1): they are skipped entirely.
-__device__ __forceinline__ void matvec_obs_v(const Dev& P, const double* __restrict__ pvec, int o, int slot,
-                                             double J[18], double Q[9], double v[3]) {
-  const int No = P.n_obs;
+__device__ __forceinline__ void matvec_obs_v(const double* __restrict__ jq, int nt, int col,
+                                             const double* __restrict__ pvec, int slot, double J[18], double Q[9],
+                                             double v[3]) {
 #pragma unroll
-  for (int c = 0; c < 18; c++) J[c] = P.Jp[(size_t)c * No + o];
+  for (int c = 0; c < 18; c++) J[c] = jq[(size_t)c * nt + col];
 #pragma unroll
-  for (int c = 0; c < 9; c++) Q[c] = P.Q1[(size_t)c * No + o];
+  for (int c = 0; c < 9; c++) Q[c] = jq[(size_t)(18 + c) * nt + col];
   double pp[6];
 #pragma unroll
   for (int c = 0; c < 6; c++) pp[c] = pvec[slot * 6 + c];
@@ -705,105 +759,228 @@ __device__ __forceinline__ void matvec_obs_v(const Dev& P, const double* __restr
            J[r * 6 + 4] * pp[4] + J[r * 6 + 5] * pp[5];
 }
 
+// long landmark (one warp, more than 32 observations): two sweeps, direct atomics
+__device__ __forceinline__ void matvec_long_item(const Dev& P, const double* __restrict__ jq, int nt,
+                                                 const double* __restrict__ pvec, double* __restrict__ qvec,
+                                                 int start, int cnt, int lane) {
+  double J[18], Q[9], v[3], sv[3] = {0, 0, 0};
+  for (int i = lane; i < cnt; i += 32) {
+    const int o = start + i;
+    const int slot = P.obs_slot[o];
+    if (slot < 0) continue;
+    matvec_obs_v(jq, nt, i, pvec, slot, J, Q, v);  // a long item is a tile of its own: column = i
+#pragma unroll
+    for (int k = 0; k < 3; k++) sv[k] += Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) sv[k] = warp_sum(sv[k]);
+  for (int i = lane; i < cnt; i += 32) {
+    const int o = start + i;
+    const int slot = P.obs_slot[o];
+    if (slot < 0) continue;
+    matvec_obs_v(jq, nt, i, pvec, slot, J, Q, v);
+#pragma unroll
+    for (int r = 0; r < 3; r++) v[r] -= Q[r * 3] * sv[0] + Q[r * 3 + 1] * sv[1] + Q[r * 3 + 2] * sv[2];
+#pragma unroll
+    for (int c = 0; c < 6; c++) atomicAdd(&qvec[slot * 6 + c], J[c] * v[0] + J[6 + c] * v[1] + J[12 + c] * v[2]);
+  }
+}
+
+// per-observation matvec math once J (3x6), Q (3x3) and p (6) are in registers; the landmark sum is a segmented shuffle
+__device__ __forceinline__ void matvec_lane(bool has, const double J[18], const double Q[9], const double pp[6],
+                                            const Seg& sg, int lane, double out[6]) {
+  double v[3] = {0, 0, 0}, sv[3];
+  if (has) {
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      v[r] = J[r * 6] * pp[0] + J[r * 6 + 1] * pp[1] + J[r * 6 + 2] * pp[2] + J[r * 6 + 3] * pp[3] +
+             J[r * 6 + 4] * pp[4] + J[r * 6 + 5] * pp[5];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double tt = has ? (Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2]) : 0.0;
+    sv[k] = seg_sum(tt, sg, lane);
+  }
+  if (has) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) v[r] -= Q[r * 3] * sv[0] + Q[r * 3 + 1] * sv[1] + Q[r * 3 + 2] * sv[2];
+#pragma unroll
+    for (int c = 0; c < 6; c++) out[c] = J[c] * v[0] + J[6 + c] * v[1] + J[12 + c] * v[2];
+  }
+}
+
+// General matvec (any window size): one CTA per tile, planes read straight from global memory, p gathered from L2,
+// pose-side sums reduced in the CTA and flushed with one atomic per (tile, slot, component).
 __global__ void __launch_bounds__(CTA) k_matvec(Dev P, const double* __restrict__ pvec, double* __restrict__ qvec,
                                                 int force_all) {
-  __shared__ double p_sh[6 * CTA];
   __shared__ double c_sh[6 * CTA];
-  const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x;
-  const int w = t * WARPS + (threadIdx.x >> 5);
-  const bool valid = w < P.n_item;
-  const bool on = valid && (force_all || P.ctl[P.item_win[w]].cg_active);
-  if (!__syncthreads_or(on)) return;
-  // stage the pose-sized vector entries this tile needs (its distinct free slots)
-  const int sp = P.tile_slot_ptr[t], nl = P.tile_slot_ptr[t + 1] - sp;
-  for (int i = threadIdx.x; i < nl * 6; i += CTA) {
-    const int ls = i / 6;
-    p_sh[i] = pvec[(size_t)P.tile_slots[sp + ls] * 6 + (i - ls * 6)];
-  }
-  __syncthreads();
+  __shared__ int key_sh[CTA];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const TileInfo ti = P.tiles[blockIdx.x];
+  if (!force_all && !P.ctl[ti.win].cg_active) return;  // CTA-uniform
+  const int w = ti.item0 + wid;
+  const bool valid = wid < ti.nitem;
   const int start = valid ? P.item_start[w] : 0, cnt = valid ? P.item_cnt[w] : 0;
-  const int No = P.n_obs;
+  const double* __restrict__ jq = P.JQ + ti.jq_off;
+  const int nt = ti.nt;
   double out[6] = {0, 0, 0, 0, 0, 0};
   bool has = false;
-  int rank = 0;
+  int rank = 0, key = 0;
   if (valid && cnt <= 32) {
     const bool act = lane < cnt;
     const int o = start + (act ? lane : 0);
-    int lm = -1 - lane, ls = 0xffff;
+    int lm = -1 - lane;
     if (act) {
       const unsigned lp = P.obs_lp[o];
-      ls = (int)(lp & 0xffffu);
-      has = ls != 0xffff;
+      has = (lp & 0xffffu) != 0xffffu;
       rank = (int)(lp >> 16);
+      key = P.obs_slot[o];
       lm = P.obs_point[o];
     }
-    if (on) {
-      const Seg sg = seg_of(lm, lane);
-      double J[18], Q[9], v[3] = {0, 0, 0}, sv[3];
-      if (has) {
+    const Seg sg = seg_of(lm, lane);
+    double J[18], Q[9], pp[6];
+    if (has) {
+      const int col = o - ti.o0;
 #pragma unroll
-        for (int c = 0; c < 18; c++) J[c] = P.Jp[(size_t)c * No + o];
+      for (int c = 0; c < 18; c++) J[c] = jq[(size_t)c * nt + col];
 #pragma unroll
-        for (int c = 0; c < 9; c++) Q[c] = P.Q1[(size_t)c * No + o];
-        double pp[6];
+      for (int c = 0; c < 9; c++) Q[c] = jq[(size_t)(18 + c) * nt + col];
 #pragma unroll
-        for (int c = 0; c < 6; c++) pp[c] = p_sh[ls * 6 + c];
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-          v[r] = J[r * 6] * pp[0] + J[r * 6 + 1] * pp[1] + J[r * 6 + 2] * pp[2] + J[r * 6 + 3] * pp[3] +
-                 J[r * 6 + 4] * pp[4] + J[r * 6 + 5] * pp[5];
-      }
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const double tt = has ? (Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2]) : 0.0;
-        sv[k] = seg_sum(tt, sg, lane);
-      }
-      if (has) {
-#pragma unroll
-        for (int r = 0; r < 3; r++) v[r] -= Q[r * 3] * sv[0] + Q[r * 3 + 1] * sv[1] + Q[r * 3 + 2] * sv[2];
-#pragma unroll
-        for (int c = 0; c < 6; c++) out[c] = J[c] * v[0] + J[6 + c] * v[1] + J[12 + c] * v[2];
-      }
+      for (int c = 0; c < 6; c++) pp[c] = pvec[(size_t)key * 6 + c];
     }
-  } else if (on) {
-    // long landmark: two sweeps, direct atomics
-    double J[18], Q[9], v[3], sv[3] = {0, 0, 0};
-    for (int i = lane; i < cnt; i += 32) {
-      const int o = start + i;
-      const int slot = P.obs_slot[o];
-      if (slot < 0) continue;
-      matvec_obs_v(P, pvec, o, slot, J, Q, v);
-#pragma unroll
-      for (int k = 0; k < 3; k++) sv[k] += Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2];
-    }
-#pragma unroll
-    for (int k = 0; k < 3; k++) sv[k] = warp_sum(sv[k]);
-    for (int i = lane; i < cnt; i += 32) {
-      const int o = start + i;
-      const int slot = P.obs_slot[o];
-      if (slot < 0) continue;
-      matvec_obs_v(P, pvec, o, slot, J, Q, v);
-#pragma unroll
-      for (int r = 0; r < 3; r++) v[r] -= Q[r * 3] * sv[0] + Q[r * 3 + 1] * sv[1] + Q[r * 3 + 2] * sv[2];
-#pragma unroll
-      for (int c = 0; c < 6; c++) atomicAdd(&qvec[slot * 6 + c], J[c] * v[0] + J[6 + c] * v[1] + J[12 + c] * v[2]);
-    }
+    matvec_lane(has, J, Q, pp, sg, lane, out);
+  } else if (valid) {
+    matvec_long_item(P, jq, nt, pvec, qvec, start, cnt, lane);
   }
-  tile_scatter<6>(P, c_sh, out, has, rank, qvec, 6, 0);
+  tile_scatter<6>(ti.nfree, key_sh, c_sh, out, has, rank, key, qvec, 6, 0);
 }
 
+// Small-window matvec: persistent CTAs over contiguous tile ranges, planes streamed by TMA bulk copies into an
+// S-stage shared-memory ring (mbarrier complete_tx), so the bytes in flight live in shared memory instead of
+// registers; p and the q accumulators of the current window stay in shared memory and q is flushed with one atomic
+// per (CTA, window, component).  Shared memory: S*27*CTA + 6*CTA + 12*MAXSLOT doubles + keys + barriers.
+template <int S>
+__global__ void __launch_bounds__(CTA) k_matvec_pipe(Dev P, const double* __restrict__ pvec, double* __restrict__ qvec,
+                                                     int force_all) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stage = reinterpret_cast<double*>(smem_raw);
+  double* c_sh = stage + (size_t)S * NPLANE * CTA;
+  double* p_sh = c_sh + 6 * CTA;
+  double* acc_sh = p_sh + 6 * MAXSLOT;
+  int* key_sh = reinterpret_cast<int*>(acc_sh + 6 * MAXSLOT);
+  uint64_t* full = reinterpret_cast<uint64_t*>(key_sh + CTA);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int t0 = (int)((long long)P.n_tile * blockIdx.x / gridDim.x);
+  const int t1 = (int)((long long)P.n_tile * (blockIdx.x + 1) / gridDim.x);
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto tile_on = [&](int t) -> bool { return force_all || P.ctl[P.tiles[t].win].cg_active; };
+  auto tile_tma = [&](int t) -> bool { return P.item_cnt[P.tiles[t].item0] <= 32; };
+  // ---- producer (thread 0): next active short tile -> stage n_issued % S
+  int t_load = t0, n_issued = 0;
+  auto issue_next = [&]() {
+    while (t_load < t1 && !(tile_on(t_load) && tile_tma(t_load))) t_load++;
+    if (t_load >= t1) return;
+    const TileInfo tl = P.tiles[t_load];
+    const int s = n_issued % S;
+    const uint32_t bytes = (uint32_t)(NPLANE * tl.nt * sizeof(double));  // one contiguous [27][nt] block
+    mbar_expect_tx(&full[s], bytes);
+    bulk_g2s(stage + (size_t)s * NPLANE * CTA, P.JQ + tl.jq_off, bytes, &full[s]);
+    n_issued++;
+    t_load++;
+  };
+  if (tid == 0)
+    for (int s = 0; s < S; s++) issue_next();
+  int n_done = 0, cur_win = -1, ws0 = 0, wn = 0;
+  for (int t = t0; t < t1; t++) {
+    if (!tile_on(t)) continue;  // CTA-uniform
+    const TileInfo ti = P.tiles[t];
+    if (ti.win != cur_win) {
+      // flush the finished window's accumulators (thread i owns index i in both loops), stage p of the new one
+      for (int i = tid; i < wn * 6; i += CTA) atomicAdd(&qvec[(size_t)ws0 * 6 + i], acc_sh[i]);
+      cur_win = ti.win;
+      ws0 = P.win_slot_ptr[cur_win];
+      wn = P.win_slot_ptr[cur_win + 1] - ws0;
+      __syncthreads();
+      for (int i = tid; i < wn * 6; i += CTA) {
+        acc_sh[i] = 0.0;
+        p_sh[i] = pvec[(size_t)ws0 * 6 + i];
+      }
+      __syncthreads();
+    }
+    const int w = ti.item0 + wid;
+    const bool valid = wid < ti.nitem;
+    const int start = valid ? P.item_start[w] : 0, cnt = valid ? P.item_cnt[w] : 0;
+    if (!tile_tma(t)) {  // CTA-uniform: a long landmark is a tile of its own
+      if (valid) matvec_long_item(P, P.JQ + ti.jq_off, ti.nt, pvec, qvec, start, cnt, lane);
+      continue;
+    }
+    const int s = n_done % S;
+    mbar_wait(&full[s], (uint32_t)((n_done / S) & 1));
+    const double* st = stage + (size_t)s * NPLANE * CTA;
+    const int nt = ti.nt;
+    double out[6] = {0, 0, 0, 0, 0, 0};
+    bool has = false;
+    int rank = 0, ls = 0;
+    if (valid) {
+      const bool act = lane < cnt;
+      const int o = start + (act ? lane : 0);
+      int lm = -1 - lane;
+      if (act) {
+        const unsigned lp = P.obs_lp[o];
+        ls = (int)(lp & 0xffffu);
+        has = ls != 0xffff;
+        rank = (int)(lp >> 16);
+        lm = P.obs_point[o];
+      }
+      const Seg sg = seg_of(lm, lane);
+      double J[18], Q[9], pp[6];
+      if (has) {
+        const int col = o - ti.o0;
+#pragma unroll
+        for (int c = 0; c < 18; c++) J[c] = st[c * nt + col];
+#pragma unroll
+        for (int c = 0; c < 9; c++) Q[c] = st[(18 + c) * nt + col];
+#pragma unroll
+        for (int c = 0; c < 6; c++) pp[c] = p_sh[ls * 6 + c];
+      }
+      matvec_lane(has, J, Q, pp, sg, lane, out);
+      if (has) {
+        key_sh[rank] = ls;
+#pragma unroll
+        for (int k = 0; k < 6; k++) c_sh[k * CTA + rank] = out[k];
+      }
+    }
+    __syncthreads();  // every thread has consumed stage s and published its column
+    if (tid == 0) issue_next();  // refill the stage that was just freed
+    for (int idx = tid; idx < ti.nfree * 6; idx += CTA) {
+      const int j = idx / 6, k = idx - j * 6;
+      const int kj = key_sh[j];
+      if (j == 0 || key_sh[j - 1] != kj) {
+        double sum = 0.0;
+        for (int jj = j; jj < ti.nfree && key_sh[jj] == kj; jj++) sum += c_sh[k * CTA + jj];
+        acc_sh[kj * 6 + k] += sum;
+      }
+    }
+    __syncthreads();
+    n_done++;
+  }
+  for (int i = tid; i < wn * 6; i += CTA) atomicAdd(&qvec[(size_t)ws0 * 6 + i], acc_sh[i]);
+}
 
 // ------------------------------------------------------------------------------------------------ K4/K5: PCG vector ops
 // One CTA owns one window's pose-sized vectors, so dot products are block reductions with no global sync.
-__global__ void __launch_bounds__(CTA) k_cg_init(Dev P, int force_all) {
-  __shared__ double sh[WARPS];
+__global__ void __launch_bounds__(RCTA) k_cg_init(Dev P, int force_all) {
+  __shared__ double sh[RWARPS];
   const int win = blockIdx.x;
   WinCtl& c = P.ctl[win];
   if (!force_all && c.phase != PH_TRIAL) return;
   const int s0 = P.win_slot_ptr[win], s1 = P.win_slot_ptr[win + 1];
   double rz = 0.0;
-  for (int e = s0 * 6 + threadIdx.x; e < s1 * 6; e += CTA) {
+  for (int e = s0 * 6 + threadIdx.x; e < s1 * 6; e += RCTA) {
     const int s = e / 6, rr = e - s * 6;
     double z = 0.0;
 #pragma unroll
@@ -825,15 +1002,15 @@ __global__ void __launch_bounds__(CTA) k_cg_init(Dev P, int force_all) {
   }
 }
 
-__global__ void __launch_bounds__(CTA) k_cg_step(Dev P, double tol2, int max_iters, int force_all, double lam_override) {
-  __shared__ double sh[WARPS];
+__global__ void __launch_bounds__(RCTA) k_cg_step(Dev P, double tol2, int max_iters, int force_all, double lam_override) {
+  __shared__ double sh[RWARPS];
   const int win = blockIdx.x;
   WinCtl& c = P.ctl[win];
   if (!c.cg_active) return;
   const double lam = force_all ? lam_override : c.lambda;
   const int e0 = P.win_slot_ptr[win] * 6, e1 = P.win_slot_ptr[win + 1] * 6;
   double pq = 0.0;
-  for (int e = e0 + threadIdx.x; e < e1; e += CTA) {
+  for (int e = e0 + threadIdx.x; e < e1; e += RCTA) {
     const double qq = P.q[e] + lam * P.p[e];
     P.q[e] = qq;
     pq += P.p[e] * qq;
@@ -846,13 +1023,13 @@ __global__ void __launch_bounds__(CTA) k_cg_step(Dev P, double tol2, int max_ite
     if (threadIdx.x == 0) { c.cg_active = 0; atomicSub(&P.counters[1], 1); }
     return;
   }
-  for (int e = e0 + threadIdx.x; e < e1; e += CTA) {
+  for (int e = e0 + threadIdx.x; e < e1; e += RCTA) {
     P.x[e] += alpha * P.p[e];
     P.res[e] -= alpha * P.q[e];
   }
   __syncthreads();
   double rzn = 0.0;
-  for (int e = e0 + threadIdx.x; e < e1; e += CTA) {
+  for (int e = e0 + threadIdx.x; e < e1; e += RCTA) {
     const int s = e / 6, rr = e - s * 6;
     double z = 0.0;
 #pragma unroll
@@ -862,7 +1039,7 @@ __global__ void __launch_bounds__(CTA) k_cg_step(Dev P, double tol2, int max_ite
   }
   rzn = block_sum(rzn, sh);
   const double beta = rzn / rz;
-  for (int e = e0 + threadIdx.x; e < e1; e += CTA) P.p[e] = P.z[e] + beta * P.p[e];
+  for (int e = e0 + threadIdx.x; e < e1; e += RCTA) P.p[e] = P.z[e] + beta * P.p[e];
   if (threadIdx.x == 0) {
     c.rz = rzn;
     c.cg_iters++;
@@ -877,15 +1054,17 @@ __global__ void __launch_bounds__(CTA) k_cg_step(Dev P, double tol2, int max_ite
 // dl = -R^-1 (t_l + sum_o Q1_o^T Jp_o dp[slot])  == g2o's Dinv (b_l - Hpl^T dp) (block_solver.hpp:461-483);
 // also the landmark part of computeScale: sum dl (lambda dl + b_l)  (optimization_algorithm_levenberg.cpp:182-189)
 __global__ void __launch_bounds__(CTA) k_backsub(Dev P, int force_all, double lam_override) {
-  const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (w >= P.n_item) return;
-  const int win = P.item_win[w];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const TileInfo ti = P.tiles[blockIdx.x];
+  if (wid >= ti.nitem) return;
+  const int w = ti.item0 + wid;
+  const int win = ti.win;
   if (!force_all && P.ctl[win].phase != PH_TRIAL) return;
   const double lam = force_all ? lam_override : P.ctl[win].lambda;
   const int start = P.item_start[w], cnt = P.item_cnt[w];
   const int Nl = P.n_point;
   const bool is_long = cnt > 32;
+  const double* __restrict__ jq = P.JQ + ti.jq_off;
   double g[3] = {0, 0, 0};
   double scale = 0.0;
   int lm = -1 - lane;
@@ -901,7 +1080,7 @@ __global__ void __launch_bounds__(CTA) k_backsub(Dev P, int force_all, double la
     double J[18], Q[9], v[3];
     double t[3] = {0, 0, 0};
     if (slot >= 0) {
-      matvec_obs_v(P, P.x, o, slot, J, Q, v);
+      matvec_obs_v(jq, ti.nt, o - ti.o0, P.x, slot, J, Q, v);
 #pragma unroll
       for (int k = 0; k < 3; k++) t[k] = Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2];
     }
@@ -988,7 +1167,7 @@ __global__ void __launch_bounds__(CTA) k_cost(Dev P, int robust, double d2, doub
   if (w >= P.n_item) return;
   if (P.ctl[P.item_win[w]].phase != PH_TRIAL) return;
   const int start = P.item_start[w], cnt = P.item_cnt[w];
-  const int No = P.n_obs;
+  const size_t No = (size_t)P.ld;
   double chi = 0.0;
   for (int i = lane; i < cnt; i += 32) {
     const int o = start + i;
@@ -1006,8 +1185,8 @@ __global__ void __launch_bounds__(CTA) k_cost(Dev P, int robust, double d2, doub
 // ------------------------------------------------------------------------------------------------ K8b: LM decision
 // The body of the do-while of OptimizationAlgorithmLevenberg::solve and its exit logic
 // (optimization_algorithm_levenberg.cpp:126-163), one CTA per window.
-__global__ void __launch_bounds__(CTA) k_lm_decide(Dev P, int terminate) {
-  __shared__ double sh[WARPS];
+__global__ void __launch_bounds__(RCTA) k_lm_decide(Dev P, int terminate) {
+  __shared__ double sh[RWARPS];
   const int win = blockIdx.x;
   WinCtl& c = P.ctl[win];
   if (c.phase != PH_TRIAL) {
@@ -1015,12 +1194,12 @@ __global__ void __launch_bounds__(CTA) k_lm_decide(Dev P, int terminate) {
     return;
   }
   double chi = 0.0, scale = 0.0;
-  for (int i = P.win_item_ptr[win] + threadIdx.x; i < P.win_item_ptr[win + 1]; i += CTA) {
+  for (int i = P.win_item_ptr[win] + threadIdx.x; i < P.win_item_ptr[win + 1]; i += RCTA) {
     chi += P.chi_part[i];
     scale += P.scale_part[i];
   }
   const double lam = c.lambda;
-  for (int e = P.win_slot_ptr[win] * 6 + threadIdx.x; e < P.win_slot_ptr[win + 1] * 6; e += CTA)
+  for (int e = P.win_slot_ptr[win] * 6 + threadIdx.x; e < P.win_slot_ptr[win + 1] * 6; e += RCTA)
     scale += P.x[e] * (lam * P.x[e] + P.bp[e]);
   chi = block_sum(chi, sh);
   scale = block_sum(scale, sh);
@@ -1094,7 +1273,7 @@ __global__ void k_classify(Dev P, int mode, double thr2d, double thr3d) {
   const float4 m = P.obs_meas[o];
   const bool stereo = !(m.z < 0.0f);
   const double info = (double)m.w;
-  const double e0 = P.err[o], e1 = P.err[(size_t)P.n_obs + o], e2 = P.err[(size_t)2 * P.n_obs + o];
+  const double e0 = P.err[o], e1 = P.err[(size_t)P.ld + o], e2 = P.err[(size_t)2 * P.ld + o];
   const double c = e0 * (info * e0) + e1 * (info * e1) + e2 * (info * e2);
   const int ip = P.obs_pose[o], il = P.obs_point[o];
   double R[9], Xc[3];

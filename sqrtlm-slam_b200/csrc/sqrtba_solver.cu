@@ -72,6 +72,14 @@ class Solver {
     CU_CHECK(cudaEventCreate(&ev0_));
     CU_CHECK(cudaEventCreate(&ev1_));
     for (auto& e : stage_ev_) CU_CHECK(cudaEventCreate(&e));
+    cudaDeviceProp prop;
+    CU_CHECK(cudaGetDeviceProperties(&prop, cfg_.device));
+    n_sm_ = prop.multiProcessorCount;
+    CU_CHECK(cudaFuncSetAttribute(k_matvec_pipe<PIPE_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pipe_smem_bytes()));
+    int per_sm = 0;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matvec_pipe<PIPE_STAGES>, CTA, pipe_smem_bytes()));
+    pipe_ctas_ = std::max(1, per_sm) * n_sm_;
     return SQRTBA_OK;
   }
 
@@ -184,56 +192,71 @@ class Solver {
     }
     for (int w = 0; w < n_win; w++) win_item_ptr[w + 1] += win_item_ptr[w];
     const int n_item = (int)item_start.size();
-    // tiles: the WARPS consecutive items of one CTA; distinct free slots per tile + per-observation (local slot, rank
-    // in the tile's pose-sorted order) for the in-CTA reduction of pose-side sums (see tile_scatter)
-    const int n_tile = cdiv(n_item, WARPS);
-    std::vector<int> tile_slot_ptr(n_tile + 1, 0), tile_slots, tile_lptr;
+    // tiles: up to WARPS consecutive short items of one window (a long item is a tile of its own); per observation the
+    // rank in the tile's pose-sorted order (for the in-CTA reduction of pose-side sums, see tile_scatter) and, when every
+    // window is small, its window-relative slot (the persistent matvec keeps p and q of the window in shared memory)
+    int max_win_slots = 0;
+    for (int w = 0; w < n_win; w++) max_win_slots = std::max(max_win_slots, win_slot_ptr[w + 1] - win_slot_ptr[w]);
+    const int smallwin = (max_win_slots <= MAXSLOT) ? 1 : 0;
+    std::vector<TileInfo> tiles;
+    long long jq_total = 0;
     std::vector<unsigned> obs_lp(n_obs, 0xffffu);
     {
       std::vector<int> stamp(std::max(n_slot, 1), -1), local_of(std::max(n_slot, 1), 0), distinct, lptr, cursor;
-      tile_slots.reserve((size_t)n_tile * 24);
-      tile_lptr.reserve((size_t)n_tile * 25);
-      for (int t = 0; t < n_tile; t++) {
-        const int i0 = t * WARPS, i1 = std::min(n_item, i0 + WARPS);
-        distinct.clear();
-        for (int it = i0; it < i1; it++) {
-          if (item_cnt[it] > 32) continue;
-          for (int o = item_start[it]; o < item_start[it] + item_cnt[it]; o++) {
+      tiles.reserve(n_item / WARPS + n_win + 1);
+      int it = 0;
+      while (it < n_item) {
+        TileInfo ti{};
+        ti.item0 = it;
+        ti.win = item_win[it];
+        ti.o0 = item_start[it];
+        if (item_cnt[it] > 32) {
+          ti.nitem = 1;
+        } else {
+          int n = 0;
+          while (it + n < n_item && n < WARPS && item_cnt[it + n] <= 32 && item_win[it + n] == ti.win) n++;
+          ti.nitem = n;
+        }
+        const int last = it + ti.nitem - 1;
+        ti.o1 = item_start[last] + item_cnt[last];
+        const int t = (int)tiles.size();
+        if (item_cnt[it] <= 32) {
+          distinct.clear();
+          for (int o = ti.o0; o < ti.o1; o++) {
             const int sl = obs_slot[o];
             if (sl >= 0 && stamp[sl] != t) { stamp[sl] = t; distinct.push_back(sl); }
           }
-        }
-        std::sort(distinct.begin(), distinct.end());
-        const int nl = (int)distinct.size();
-        for (int i = 0; i < nl; i++) local_of[distinct[i]] = i;
-        lptr.assign(nl + 1, 0);
-        for (int it = i0; it < i1; it++) {
-          if (item_cnt[it] > 32) continue;
-          for (int o = item_start[it]; o < item_start[it] + item_cnt[it]; o++)
+          std::sort(distinct.begin(), distinct.end());
+          const int nl = (int)distinct.size();
+          for (int i = 0; i < nl; i++) local_of[distinct[i]] = i;
+          lptr.assign(nl + 1, 0);
+          for (int o = ti.o0; o < ti.o1; o++)
             if (obs_slot[o] >= 0) lptr[local_of[obs_slot[o]] + 1]++;
-        }
-        for (int i = 0; i < nl; i++) lptr[i + 1] += lptr[i];
-        cursor.assign(lptr.begin(), lptr.end());
-        for (int it = i0; it < i1; it++) {
-          if (item_cnt[it] > 32) continue;
-          for (int o = item_start[it]; o < item_start[it] + item_cnt[it]; o++) {
+          for (int i = 0; i < nl; i++) lptr[i + 1] += lptr[i];
+          cursor.assign(lptr.begin(), lptr.end());
+          const int ws0 = win_slot_ptr[ti.win];
+          for (int o = ti.o0; o < ti.o1; o++) {
             if (obs_slot[o] < 0) continue;
-            const int ls = local_of[obs_slot[o]];
-            const int rank = cursor[ls]++;
-            obs_lp[o] = (unsigned)ls | ((unsigned)rank << 16);
+            const int rank = cursor[local_of[obs_slot[o]]]++;
+            const unsigned low = smallwin ? (unsigned)(obs_slot[o] - ws0) : 0u;
+            obs_lp[o] = low | ((unsigned)rank << 16);
           }
+          ti.nfree = lptr[nl];
         }
-        tile_slots.insert(tile_slots.end(), distinct.begin(), distinct.end());
-        tile_lptr.insert(tile_lptr.end(), lptr.begin(), lptr.end());
-        tile_slot_ptr[t + 1] = tile_slot_ptr[t] + nl;
+        ti.nt = ((ti.o1 - ti.o0) + 1) & ~1;
+        ti.jq_off = jq_total;
+        jq_total += (long long)NPLANE * ti.nt;
+        tiles.push_back(ti);
+        it += ti.nitem;
       }
     }
-
+    const int n_tile = (int)tiles.size();
+    const int ld = ((n_obs + 31) / 32) * 32;
     // ---- device allocation
     P_ = Dev{};
     P_.n_pose = n_pose; P_.n_point = n_point; P_.n_obs = n_obs; P_.n_win = n_win; P_.n_slot = n_slot; P_.n_item = n_item;
-    P_.n_tile = n_tile;
-    const size_t No = n_obs, Nl = n_point, Ns = std::max(n_slot, 1);
+    P_.n_tile = n_tile; P_.ld = ld; P_.smallwin = smallwin;
+    const size_t No = n_obs, Nl = n_point, Ns = std::max(n_slot, 1), Ld = ld;
     CU_CHECK(d_cam_.ensure((size_t)n_pose * 5));
     CU_CHECK(d_pose_slot_.ensure(n_pose));
     CU_CHECK(d_slot_pose_.ensure(Ns));
@@ -249,9 +272,7 @@ class Solver {
     CU_CHECK(d_item_win_.ensure(n_item));
     CU_CHECK(d_win_item_ptr_.ensure(n_win + 1));
     CU_CHECK(d_win_slot_ptr_.ensure(n_win + 1));
-    CU_CHECK(d_tile_slot_ptr_.ensure(n_tile + 1));
-    CU_CHECK(d_tile_slots_.ensure(tile_slots.size()));
-    CU_CHECK(d_tile_lptr_.ensure(tile_lptr.size()));
+    CU_CHECK(d_tiles_.ensure(n_tile));
     CU_CHECK(d_obs_lp_.ensure(No));
     CU_CHECK(d_pose_.ensure((size_t)n_pose * 7));
     CU_CHECK(d_pose0_.ensure((size_t)n_pose * 7));
@@ -261,11 +282,10 @@ class Solver {
     CU_CHECK(d_point_bak_.ensure(Nl * 3));
     CU_CHECK(d_level_.ensure(No));
     CU_CHECK(d_outlier_.ensure(No));
-    CU_CHECK(d_err_.ensure(No * 3));
-    CU_CHECK(d_Jp_.ensure(No * 18));
-    CU_CHECK(d_Jl_.ensure(No * 9));
-    CU_CHECK(d_Q1_.ensure(No * 9));
-    CU_CHECK(d_r_.ensure(No * 3));
+    CU_CHECK(d_err_.ensure(Ld * 3));
+    CU_CHECK(d_JQ_.ensure((size_t)jq_total));
+    CU_CHECK(d_Jl_.ensure(Ld * 9));
+    CU_CHECK(d_r_.ensure(Ld * 3));
     CU_CHECK(d_R_.ensure(Nl * 6));
     CU_CHECK(d_tl_.ensure(Nl * 3));
     CU_CHECK(d_bl_.ensure(Nl * 3));
@@ -296,9 +316,7 @@ class Solver {
     CU_CHECK(up(d_item_win_.p, item_win.data(), n_item * sizeof(int)));
     CU_CHECK(up(d_win_item_ptr_.p, win_item_ptr.data(), (n_win + 1) * sizeof(int)));
     CU_CHECK(up(d_win_slot_ptr_.p, win_slot_ptr.data(), (n_win + 1) * sizeof(int)));
-    CU_CHECK(up(d_tile_slot_ptr_.p, tile_slot_ptr.data(), (n_tile + 1) * sizeof(int)));
-    if (!tile_slots.empty()) CU_CHECK(up(d_tile_slots_.p, tile_slots.data(), tile_slots.size() * sizeof(int)));
-    CU_CHECK(up(d_tile_lptr_.p, tile_lptr.data(), tile_lptr.size() * sizeof(int)));
+    CU_CHECK(up(d_tiles_.p, tiles.data(), (size_t)n_tile * sizeof(TileInfo)));
     CU_CHECK(up(d_obs_lp_.p, obs_lp.data(), No * sizeof(unsigned)));
     // poses: normalise the quaternion the way SE3Quat's constructor does (se3quat.h:58-64)
     std::vector<double> pq(pose_qt, pose_qt + (size_t)n_pose * 7);
@@ -312,11 +330,11 @@ class Solver {
     P_.obs_point = d_obs_point_.p; P_.obs_slot = d_obs_slot_.p; P_.item_start = d_item_start_.p;
     P_.item_cnt = d_item_cnt_.p; P_.item_win = d_item_win_.p; P_.win_item_ptr = d_win_item_ptr_.p;
     P_.win_slot_ptr = d_win_slot_ptr_.p;
-    P_.tile_slot_ptr = d_tile_slot_ptr_.p; P_.tile_slots = d_tile_slots_.p; P_.tile_lptr = d_tile_lptr_.p;
+    P_.tiles = d_tiles_.p;
     P_.obs_lp = d_obs_lp_.p;
     P_.pose = d_pose_.p; P_.point = d_point_.p; P_.pose_bak = d_pose_bak_.p; P_.point_bak = d_point_bak_.p;
     P_.obs_level = d_level_.p; P_.obs_outlier = d_outlier_.p;
-    P_.err = d_err_.p; P_.Jp = d_Jp_.p; P_.Jl = d_Jl_.p; P_.Q1 = d_Q1_.p; P_.r = d_r_.p;
+    P_.err = d_err_.p; P_.JQ = d_JQ_.p; P_.Jl = d_Jl_.p; P_.r = d_r_.p;
     P_.R = d_R_.p; P_.tl = d_tl_.p; P_.bl = d_bl_.p; P_.dl = d_dl_.p;
     double* sv = d_slotvec_.p;
     P_.bp = sv; sv += Ns * 6;
@@ -331,6 +349,9 @@ class Solver {
     P_.Dinv = sv;
     P_.chi_part = d_chi_part_.p; P_.scale_part = d_scale_part_.p;
     P_.ctl = d_ctl_.p; P_.trace = d_trace_.p; P_.max_trace = max_trace_; P_.counters = d_counters_.p;
+    h_tiles_ = tiles;
+    // pad columns of the JQ blocks are streamed by the TMA copies: keep them defined
+    CU_CHECK(cudaMemsetAsync(d_JQ_.p, 0, (size_t)jq_total * sizeof(double), stream_));
     have_problem_ = true;
     return reset_state();
   }
@@ -342,7 +363,7 @@ class Solver {
     CU_CHECK(cudaMemcpyAsync(d_point_.p, d_point0_.p, (size_t)P_.n_point * 3 * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
     CU_CHECK(cudaMemsetAsync(d_level_.p, 0, P_.n_obs, stream_));
     CU_CHECK(cudaMemsetAsync(d_outlier_.p, 0, P_.n_obs, stream_));
-    CU_CHECK(cudaMemsetAsync(d_err_.p, 0, (size_t)P_.n_obs * 3 * sizeof(double), stream_));
+    CU_CHECK(cudaMemsetAsync(d_err_.p, 0, (size_t)P_.ld * 3 * sizeof(double), stream_));
     CU_CHECK(cudaMemsetAsync(d_ctl_.p, 0, (size_t)P_.n_win * sizeof(WinCtl), stream_));
     CU_CHECK(cudaMemsetAsync(d_slotvec_.p, 0, d_slotvec_.cap * sizeof(double), stream_));
     CU_CHECK(cudaMemsetAsync(d_dl_.p, 0, (size_t)P_.n_point * 3 * sizeof(double), stream_));
@@ -417,20 +438,27 @@ class Solver {
     const double d2 = (double)(float)std::sqrt(huber == 2 ? 5.99 : 5.991), d3 = (double)(float)std::sqrt(7.815);
     k_pass_init<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_, 1, 0);
     if (P_.n_slot) k_zero_lin<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
-    k_linearize<<<cdiv(P_.n_item, WARPS), CTA, 0, stream_>>>(P_, huber != 0, d2, d3, 1);
-    k_lm_begin<<<P_.n_win, CTA, 0, stream_>>>(P_);
+    k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, huber != 0, d2, d3, 1);
+    k_lm_begin<<<P_.n_win, RCTA, 0, stream_>>>(P_);
     CU_CHECK(cudaGetLastError());
-    const size_t No = P_.n_obs;
+    const size_t No = P_.n_obs, Ld = P_.ld;
     std::vector<double> tmp;
     auto planes = [&](double* dst, const double* dsrc, int np) -> int {
       if (!dst) return 0;
-      tmp.resize(No * np);
-      if (download(tmp.data(), dsrc, No * np * sizeof(double))) return SQRTBA_ERR_CUDA;
+      tmp.resize(Ld * np);
+      if (download(tmp.data(), dsrc, Ld * np * sizeof(double))) return SQRTBA_ERR_CUDA;
       for (size_t o = 0; o < No; o++)
-        for (int c = 0; c < np; c++) dst[o * np + c] = tmp[(size_t)c * No + o];
+        for (int c = 0; c < np; c++) dst[o * np + c] = tmp[(size_t)c * Ld + o];
       return 0;
     };
-    if (planes(err, d_err_.p, 3) || planes(Jp, d_Jp_.p, 18) || planes(Jl, d_Jl_.p, 9) || planes(r, d_r_.p, 3)) return SQRTBA_ERR_CUDA;
+    if (planes(err, d_err_.p, 3) || planes(Jl, d_Jl_.p, 9) || planes(r, d_r_.p, 3)) return SQRTBA_ERR_CUDA;
+    if (Jp) {  // un-block the tile-blocked matvec operand
+      tmp.resize(d_JQ_.cap);
+      if (download(tmp.data(), d_JQ_.p, d_JQ_.cap * sizeof(double))) return SQRTBA_ERR_CUDA;
+      for (const TileInfo& ti : h_tiles_)
+        for (int o = ti.o0; o < ti.o1; o++)
+          for (int c = 0; c < 18; c++) Jp[(size_t)o * 18 + c] = tmp[(size_t)ti.jq_off + (size_t)c * ti.nt + (o - ti.o0)];
+    }
     if (chi2) {
       std::vector<WinCtl> c(P_.n_win);
       if (download(c.data(), d_ctl_.p, c.size() * sizeof(WinCtl))) return SQRTBA_ERR_CUDA;
@@ -451,7 +479,7 @@ class Solver {
     CU_CHECK(cudaStreamSynchronize(stream_));
     int rc = factor_and_solve();
     if (rc) return rc;
-    k_backsub<<<cdiv(P_.n_item, WARPS), CTA, 0, stream_>>>(P_, 0, 0.0);
+    k_backsub<<<P_.n_tile, CTA, 0, stream_>>>(P_, 0, 0.0);
     CU_CHECK(cudaGetLastError());
     if (dp && P_.n_slot && download(dp, P_.x, (size_t)P_.n_slot * 6 * sizeof(double))) return SQRTBA_ERR_CUDA;
     if (bs && P_.n_slot && download(bs, P_.bs, (size_t)P_.n_slot * 6 * sizeof(double))) return SQRTBA_ERR_CUDA;
@@ -476,7 +504,7 @@ class Solver {
     const size_t bytes = (size_t)P_.n_slot * 6 * sizeof(double);
     CU_CHECK(cudaMemcpyAsync(P_.p, p, bytes, cudaMemcpyHostToDevice, stream_));
     CU_CHECK(cudaMemsetAsync(P_.q, 0, bytes, stream_));
-    k_matvec<<<cdiv(P_.n_item, WARPS), CTA, 0, stream_>>>(P_, P_.p, P_.q, 1);
+    launch_matvec(P_.p, P_.q, 1);
     CU_CHECK(cudaGetLastError());
     return download(y, P_.q, bytes);
   }
@@ -488,11 +516,11 @@ class Solver {
     const int gi = cdiv(P_.n_item, WARPS);
     auto one = [&]() {
       switch (stage) {
-        case 0: k_matvec<<<gi, CTA, 0, stream_>>>(P_, P_.p, P_.q, 1); break;
-        case 1: k_linearize<<<gi, CTA, 0, stream_>>>(P_, 1, d2, d3, 1); break;
-        case 2: k_qr<<<gi, CTA, 0, stream_>>>(P_, 1, 1.0); break;
+        case 0: launch_matvec(P_.p, P_.q, 1); break;
+        case 1: k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, 1, d2, d3, 1); break;
+        case 2: k_qr<<<P_.n_tile, CTA, 0, stream_>>>(P_, 1, 1.0); break;
         case 3: k_cost<<<gi, CTA, 0, stream_>>>(P_, 1, d2, d3); break;
-        case 4: k_backsub<<<gi, CTA, 0, stream_>>>(P_, 1, 1.0); break;
+        case 4: k_backsub<<<P_.n_tile, CTA, 0, stream_>>>(P_, 1, 1.0); break;
         default: break;
       }
     };
@@ -532,27 +560,42 @@ class Solver {
     launches_++;
   }
 
+  // matvec dispatch: persistent TMA-pipelined kernel when every window is small, general tile kernel otherwise
+  static constexpr int PIPE_STAGES = 3;
+  static constexpr size_t pipe_smem_bytes() {
+    return ((size_t)PIPE_STAGES * NPLANE * CTA + 6 * CTA + 12 * MAXSLOT) * sizeof(double) + CTA * sizeof(int) +
+           PIPE_STAGES * sizeof(uint64_t);
+  }
+  void launch_matvec(const double* pvec, double* qvec, int force_all) {
+    if (P_.smallwin && cfg_.reserved[1] == 0) {
+      const int grid = std::min(P_.n_tile, pipe_ctas_);
+      k_matvec_pipe<PIPE_STAGES><<<grid, CTA, pipe_smem_bytes(), stream_>>>(P_, pvec, qvec, force_all);
+    } else {
+      k_matvec<<<P_.n_tile, CTA, 0, stream_>>>(P_, pvec, qvec, force_all);
+    }
+  }
+
   // QR + block-Jacobi + PCG for every window in PH_TRIAL
   int factor_and_solve() {
     const int gi = cdiv(P_.n_item, WARPS);
     if (P_.n_slot) k_zero_trial<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
     stage_begin(1);
-    k_qr<<<gi, CTA, 0, stream_>>>(P_, 0, 0.0);
+    k_qr<<<P_.n_tile, CTA, 0, stream_>>>(P_, 0, 0.0);
     stage_end(1);
     launches_ += 2;
     if (!P_.n_slot) return SQRTBA_OK;
     k_dinv<<<cdiv(P_.n_slot, 64), 64, 0, stream_>>>(P_, 0, 0.0);
     stage_begin(2);
     CU_CHECK(cudaMemsetAsync(P_.counters + 1, 0, sizeof(int), stream_));
-    k_cg_init<<<P_.n_win, CTA, 0, stream_>>>(P_, 0);
+    k_cg_init<<<P_.n_win, RCTA, 0, stream_>>>(P_, 0);
     launches_ += 2;
     const double tol2 = cfg_.pcg_rtol * cfg_.pcg_rtol;
     const int check = std::max(1, cfg_.pcg_check_every);
     const size_t qbytes = (size_t)P_.n_slot * 6 * sizeof(double);
     for (int it = 0; it < cfg_.pcg_max_iters; it++) {
       CU_CHECK(cudaMemsetAsync(P_.q, 0, qbytes, stream_));
-      k_matvec<<<gi, CTA, 0, stream_>>>(P_, P_.p, P_.q, 0);
-      k_cg_step<<<P_.n_win, CTA, 0, stream_>>>(P_, tol2, cfg_.pcg_max_iters, 0, 0.0);
+      launch_matvec(P_.p, P_.q, 0);
+      k_cg_step<<<P_.n_win, RCTA, 0, stream_>>>(P_, tol2, cfg_.pcg_max_iters, 0, 0.0);
       launches_ += 2;
       cg_iters_total_++;
       if ((it + 1) % check == 0) {
@@ -579,14 +622,14 @@ class Solver {
       if (term && step == 0) break;  // `for (i < iterations && !terminate())` before the first iteration
       if (P_.n_slot) k_zero_lin<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
       stage_begin(0);
-      k_linearize<<<gi, CTA, 0, stream_>>>(P_, robust, d2, d3, 0);
+      k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, robust, d2, d3, 0);
       stage_end(0);
-      k_lm_begin<<<P_.n_win, CTA, 0, stream_>>>(P_);
+      k_lm_begin<<<P_.n_win, RCTA, 0, stream_>>>(P_);
       launches_ += 3;
       int rc = factor_and_solve();
       if (rc) return rc;
       stage_begin(3);
-      k_backsub<<<gi, CTA, 0, stream_>>>(P_, 0, 0.0);
+      k_backsub<<<P_.n_tile, CTA, 0, stream_>>>(P_, 0, 0.0);
       stage_end(3);
       CU_CHECK(cudaMemcpyAsync(d_pose_bak_.p, d_pose_.p, (size_t)P_.n_pose * 7 * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
       CU_CHECK(cudaMemcpyAsync(d_point_bak_.p, d_point_.p, (size_t)P_.n_point * 3 * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
@@ -595,7 +638,7 @@ class Solver {
       stage_begin(4);
       k_cost<<<gi, CTA, 0, stream_>>>(P_, robust, d2, d3);
       stage_end(4);
-      k_lm_decide<<<P_.n_win, CTA, 0, stream_>>>(P_, term);
+      k_lm_decide<<<P_.n_win, RCTA, 0, stream_>>>(P_, term);
       k_restore<<<cdiv(std::max(P_.n_pose, P_.n_point), 256), 256, 0, stream_>>>(P_);
       launches_ += 6;
       lm_trials_++;
@@ -653,10 +696,10 @@ class Solver {
     d_item_start_.release(); d_item_cnt_.release(); d_item_win_.release(); d_win_item_ptr_.release();
     d_win_slot_ptr_.release(); d_pose_.release(); d_pose0_.release(); d_pose_bak_.release(); d_point_.release();
     d_point0_.release(); d_point_bak_.release(); d_level_.release(); d_outlier_.release(); d_err_.release();
-    d_Jp_.release(); d_Jl_.release(); d_Q1_.release(); d_r_.release(); d_R_.release(); d_tl_.release();
+    d_JQ_.release(); d_Jl_.release(); d_r_.release(); d_R_.release(); d_tl_.release();
     d_bl_.release(); d_dl_.release(); d_slotvec_.release(); d_chi_part_.release(); d_scale_part_.release();
     d_ctl_.release(); d_trace_.release(); d_counters_.release();
-    d_tile_slot_ptr_.release(); d_tile_slots_.release(); d_tile_lptr_.release(); d_obs_lp_.release();
+    d_tiles_.release(); d_obs_lp_.release();
   }
 
  public:
@@ -673,13 +716,15 @@ class Solver {
   bool have_problem_ = false;
   int max_trace_ = 200;
   int launches_ = 0, lm_trials_ = 0, cg_iters_total_ = 0;
+  int n_sm_ = 148, pipe_ctas_ = 296;
   Dev P_{};
-  DBuf<double> d_cam_, d_pose_, d_pose0_, d_pose_bak_, d_point_, d_point0_, d_point_bak_, d_err_, d_Jp_, d_Jl_, d_Q1_,
+  DBuf<double> d_cam_, d_pose_, d_pose0_, d_pose_bak_, d_point_, d_point0_, d_point_bak_, d_err_, d_JQ_, d_Jl_,
       d_r_, d_R_, d_tl_, d_bl_, d_dl_, d_slotvec_, d_chi_part_, d_scale_part_, d_trace_;
   DBuf<int> d_pose_slot_, d_slot_pose_, d_slot_win_, d_pose_win_, d_point_win_, d_obs_pose_, d_obs_point_, d_obs_slot_,
-      d_item_start_, d_item_cnt_, d_item_win_, d_win_item_ptr_, d_win_slot_ptr_, d_counters_, d_tile_slot_ptr_,
-      d_tile_slots_, d_tile_lptr_;
+      d_item_start_, d_item_cnt_, d_item_win_, d_win_item_ptr_, d_win_slot_ptr_, d_counters_;
   DBuf<unsigned> d_obs_lp_;
+  DBuf<TileInfo> d_tiles_;
+  std::vector<TileInfo> h_tiles_;
   DBuf<float4> d_meas_;
   DBuf<uint8_t> d_level_, d_outlier_;
   DBuf<WinCtl> d_ctl_;
