@@ -79,7 +79,7 @@ class SqrtBA:
 
     def __init__(self, device: int = 0, pcg_rtol: float = 1e-9, pcg_max_iters: int = 300, third_pass_iters: int = 0,
                  pcg_mode: int = 0, pcg_check_every: int = 4, stage_timing: bool = False,
-                 general_matvec: bool = False):
+                 general_matvec: bool = False, pipe_stages: int = 0):
         L = lib()
         cfg = Config()
         L.sqrtba_default_config(C.byref(cfg))
@@ -87,6 +87,7 @@ class SqrtBA:
         cfg.third_pass_iters, cfg.pcg_mode, cfg.pcg_check_every = third_pass_iters, pcg_mode, pcg_check_every
         cfg.reserved[0] = 1 if stage_timing else 0
         cfg.reserved[1] = 1 if general_matvec else 0   # force the non-pipelined tile kernel (A/B profiling)
+        cfg.reserved[2] = pipe_stages                  # 0 = auto, 2/3 = forced TMA ring depth
         self.h = C.c_void_p()
         rc = L.sqrtba_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:

@@ -24,6 +24,8 @@ constexpr int RCTA = 256;           // per-window reduction / vector kernels
 constexpr int RWARPS = RCTA / 32;
 constexpr int MAXSLOT = 128;        // "small window": all free poses of a window fit the CTA's shared accumulators
 constexpr int NPLANE = 27;          // matvec streams Jp (18) + Q1 (9) planes
+constexpr int JQ_HDR = 8;           // doubles (64 bytes) of per-tile header in front of every JQ data block
+constexpr int JQ_ROWS = NPLANE + 1; // data planes + one 8-byte meta entry per column
 
 enum Phase { PH_LIN = 0, PH_TRIAL = 1, PH_DONE = 2 };
 
@@ -44,9 +46,10 @@ struct TileInfo {
   int win;           // window of the tile
   int nfree;         // observations that take part in the in-CTA reduction (ranks 0..nfree-1)
   int nt;            // columns of this tile's JQ block: (o1-o0) rounded up to even (16-byte rows for TMA)
-  int pad0;
-  long long jq_off;  // offset (doubles) of the tile's [27][nt] block inside Dev::JQ
-  long long pad1;
+  int is_long;       // the tile is one landmark with more than 32 observations
+  long long jq_off;  // offset (doubles) of the tile's [27][nt] data block inside Dev::JQ (its header sits right before)
+  int nrun;          // distinct free pose slots among the participating observations (= runs of equal slot by rank)
+  int blk_doubles;   // size of the whole JQ block (header + data + meta + run table), in doubles, even
 };
 
 struct Dev {
@@ -76,6 +79,8 @@ struct Dev {
   int smallwin;               // every window has <= MAXSLOT free poses
   const struct TileInfo* tiles;
   const unsigned* obs_lp;     // n_obs
+  const int* tile_run_ptr;    // n_tile+1 -> tile_runs (host-built run tables, copied into the JQ blocks by k_init_jq)
+  const int* tile_runs;
   // ---- state
   double* pose;       // n_pose*7 (t,q)
   double* point;      // n_point*3
@@ -87,9 +92,12 @@ struct Dev {
   double* err;  // 3 planes: g2o's stored _error (unweighted)
   double* Jl;   // 9
   double* r;    // 3
-  // matvec operand, TILE-BLOCKED: tile t owns the contiguous block JQ[jq_off .. jq_off + 27*nt) laid out [27][nt]:
-  // rows 0-17 = weighted Jp (3x6 row-major), rows 18-26 = observation rows of Q1 (3x3 row-major); column = o - o0.
-  // One tile = one contiguous 27*nt*8-byte chunk, so the matvec fetches it with a single TMA bulk copy.
+  // matvec operand, TILE-BLOCKED: tile t owns one contiguous block of JQ:
+  //   [JQ_HDR doubles header][27][nt] data][nt x 8-byte per-column meta][run table: nrun+1 offsets, nrun slots (int)]
+  // run table: ranks [run_ptr[r], run_ptr[r+1]) all belong to pose slot run_slot[r] (window-relative when smallwin)
+  // data rows 0-17 = weighted Jp (3x6 row-major), rows 18-26 = observation rows of Q1 (3x3 row-major), column = o - o0;
+  // meta = {obs_lp, landmark id}; header = 16 ints (see k_init_jq).  jq_off points at the data part.
+  // One tile = one contiguous chunk, so the matvec fetches everything it needs with a single TMA bulk copy.
   double* JQ;
   // ---- per landmark (planes of n_point)
   double* R;   // 6: r00 r01 r02 r11 r12 r22
@@ -181,24 +189,24 @@ __device__ __forceinline__ void atomic_max_pos(unsigned long long* addr, double 
 // CTA-level reduction of per-observation pose-side contributions.  Every participating observation of the tile owns
 // one column `rank` of c_sh[NV][CTA]; ranks are ordered by pose slot, so the sum for one (slot, value) is a
 // contiguous run that exactly one thread (the run head) adds up in a fixed order -> no shared-memory atomics, and the
-// CTA issues one global atomicAdd per (tile, slot, value) instead of one per observation.
-// target[key*stride + offset + k] += run sum.  Must be called by all threads of the CTA.
+// CTA issues one global atomicAdd per (tile, slot, value) instead of one per observation.  The runs come from the
+// tile's run table (host-built, stored at the tail of its JQ block).  Must be called by all threads of the CTA.
 template <int NV>
-__device__ __forceinline__ void tile_scatter(int nfree, int* key_sh, double* c_sh, const double* vals, bool has, int rank,
-                                             int key, double* __restrict__ target, int stride, int offset) {
+__device__ __forceinline__ void tile_scatter(const int* __restrict__ run_ptr, const int* __restrict__ run_slot, int nrun,
+                                             int slot_base, double* c_sh, const double* vals, bool has, int rank,
+                                             double* __restrict__ target, int stride, int offset) {
   if (has) {
-    key_sh[rank] = key;
 #pragma unroll
     for (int k = 0; k < NV; k++) c_sh[k * CTA + rank] = vals[k];
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < nfree * NV; idx += CTA) {
-    const int j = idx / NV, k = idx - j * NV;
-    const int kj = key_sh[j];
-    if (j == 0 || key_sh[j - 1] != kj) {
+  for (int idx = threadIdx.x; idx < nrun * 8; idx += CTA) {  // 8 threads per run, value k = idx & 7
+    const int r = idx >> 3, k = idx & 7;
+    if (k < NV) {
+      const int a = run_ptr[r], b = run_ptr[r + 1];
       double sum = 0.0;
-      for (int jj = j; jj < nfree && key_sh[jj] == kj; jj++) sum += c_sh[k * CTA + jj];
-      atomicAdd(&target[(size_t)kj * stride + offset + k], sum);
+      for (int j = a; j < b; j++) sum += c_sh[k * CTA + j];
+      atomicAdd(&target[(size_t)(slot_base + run_slot[r]) * stride + offset + k], sum);
     }
   }
   __syncthreads();
@@ -294,7 +302,6 @@ __device__ __forceinline__ void obs_eval(const Dev& P, int o, bool want_jac, boo
 
 __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2, double d3, int force_all) {
   __shared__ double c_sh[6 * CTA];
-  __shared__ int key_sh[CTA];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const TileInfo ti = P.tiles[blockIdx.x];
   const int w = ti.item0 + wid;
@@ -415,8 +422,10 @@ __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2,
       atomic_max_pos(&P.ctl[win].maxdiag_bits, maxd);
     }
   }
-  tile_scatter<6>(ti.nfree, key_sh, c_sh, vb, has, rank, key, P.bp, 6, 0);
-  tile_scatter<6>(ti.nfree, key_sh, c_sh, vh, has, rank, key, P.hd, 6, 0);
+  const int* runs = reinterpret_cast<const int*>(jq + (size_t)JQ_ROWS * ti.nt);
+  const int sbase = P.smallwin ? P.win_slot_ptr[win] : 0;
+  tile_scatter<6>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh, vb, has, rank, P.bp, 6, 0);
+  tile_scatter<6>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh, vh, has, rank, P.hd, 6, 0);
 }
 
 // ------------------------------------------------------------------------------------------------ K8a: LM begin
@@ -538,7 +547,6 @@ __device__ __forceinline__ void trial_contrib(const double* __restrict__ jq, int
 
 __global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_override) {
   __shared__ double c_sh[7 * CTA];
-  __shared__ int key_sh[CTA];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const TileInfo ti = P.tiles[blockIdx.x];
   const int w = ti.item0 + wid;
@@ -706,10 +714,12 @@ __global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_ove
       for (int c = 0; c < 21; c++) atomicAdd(&P.D[slot * 21 + c], lc[6 + c]);
     }
   }
-  tile_scatter<6>(ti.nfree, key_sh, c_sh, contrib, has, rank, key, P.bs, 6, 0);
-  tile_scatter<7>(ti.nfree, key_sh, c_sh, contrib + 6, has, rank, key, P.D, 21, 0);
-  tile_scatter<7>(ti.nfree, key_sh, c_sh, contrib + 13, has, rank, key, P.D, 21, 7);
-  tile_scatter<7>(ti.nfree, key_sh, c_sh, contrib + 20, has, rank, key, P.D, 21, 14);
+  const int* runs = reinterpret_cast<const int*>(jq + (size_t)JQ_ROWS * nt);
+  const int sbase = P.smallwin ? P.win_slot_ptr[win] : 0;
+  tile_scatter<6>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh, contrib, has, rank, P.bs, 6, 0);
+  tile_scatter<7>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh, contrib + 6, has, rank, P.D, 21, 0);
+  tile_scatter<7>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh, contrib + 13, has, rank, P.D, 21, 7);
+  tile_scatter<7>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh, contrib + 20, has, rank, P.D, 21, 14);
 }
 
 
@@ -814,7 +824,6 @@ __device__ __forceinline__ void matvec_lane(bool has, const double J[18], const 
 __global__ void __launch_bounds__(CTA) k_matvec(Dev P, const double* __restrict__ pvec, double* __restrict__ qvec,
                                                 int force_all) {
   __shared__ double c_sh[6 * CTA];
-  __shared__ int key_sh[CTA];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const TileInfo ti = P.tiles[blockIdx.x];
   if (!force_all && !P.ctl[ti.win].cg_active) return;  // CTA-uniform
@@ -852,121 +861,184 @@ __global__ void __launch_bounds__(CTA) k_matvec(Dev P, const double* __restrict_
   } else if (valid) {
     matvec_long_item(P, jq, nt, pvec, qvec, start, cnt, lane);
   }
-  tile_scatter<6>(ti.nfree, key_sh, c_sh, out, has, rank, key, qvec, 6, 0);
+  const int* runs = reinterpret_cast<const int*>(jq + (size_t)JQ_ROWS * nt);
+  const int sbase = P.smallwin ? P.win_slot_ptr[ti.win] : 0;
+  tile_scatter<6>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh, out, has, rank, qvec, 6, 0);
 }
 
-// Small-window matvec: persistent CTAs over contiguous tile ranges, planes streamed by TMA bulk copies into an
-// S-stage shared-memory ring (mbarrier complete_tx), so the bytes in flight live in shared memory instead of
-// registers; p and the q accumulators of the current window stay in shared memory and q is flushed with one atomic
-// per (CTA, window, component).  Shared memory: S*27*CTA + 6*CTA + 12*MAXSLOT doubles + keys + barriers.
+// Writes the static part of every JQ block: the 64-byte header and the per-column meta entries.
+// header ints: [0] nitem, [1] win, [2] first free slot of the window, [3] free slots of the window, [4] nfree,
+//              [5] nt, [6] o0, [7]/[8] jq_off lo/hi, [9..12] observations per item, [13] is_long, [14] nrun
+__global__ void k_init_jq(Dev P) {
+  const TileInfo ti = P.tiles[blockIdx.x];
+  double* blk = P.JQ + ti.jq_off;
+  if (threadIdx.x == 0) {
+    int* h = reinterpret_cast<int*>(blk - JQ_HDR);
+    h[0] = ti.nitem; h[1] = ti.win; h[2] = P.win_slot_ptr[ti.win];
+    h[3] = P.win_slot_ptr[ti.win + 1] - P.win_slot_ptr[ti.win];
+    h[4] = ti.nfree; h[5] = ti.nt; h[6] = ti.o0;
+    h[7] = (int)(ti.jq_off & 0xffffffffll); h[8] = (int)(ti.jq_off >> 32);
+    for (int i = 0; i < 4; i++) h[9 + i] = (i < ti.nitem) ? P.item_cnt[ti.item0 + i] : 0;
+    h[13] = ti.is_long; h[14] = ti.nrun; h[15] = 0;
+  }
+  int* runs = reinterpret_cast<int*>(blk + (size_t)JQ_ROWS * ti.nt);
+  const int r0 = P.tile_run_ptr[blockIdx.x], nr = P.tile_run_ptr[blockIdx.x + 1] - r0;
+  for (int i = threadIdx.x; i < nr; i += blockDim.x) runs[i] = P.tile_runs[r0 + i];
+  uint2* meta = reinterpret_cast<uint2*>(blk + (size_t)NPLANE * ti.nt);
+  for (int col = threadIdx.x; col < ti.nt; col += blockDim.x) {
+    const int o = ti.o0 + col;
+    uint2 m;
+    m.x = (o < ti.o1) ? P.obs_lp[o] : 0xffffu;
+    m.y = (o < ti.o1) ? (unsigned)P.obs_point[o] : 0xffffffffu;
+    meta[col] = m;
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Small-window matvec, warp-specialised and persistent.  One producer warp streams whole JQ blocks (header + 27 planes
+// + meta) of the CTA's contiguous tile range into an S-stage shared-memory ring with ONE TMA bulk copy per tile
+// (mbarrier complete_tx); four consumer warps wait on the stage, read everything from shared memory (no dependent
+// global loads on the critical path), and hand the stage back through an "empty" mbarrier.  p and the q accumulators
+// of the current window stay in shared memory; q is flushed with one atomic per (CTA, window, component).
+constexpr int PIPE_THREADS = CTA + 32;
+constexpr int JQ_STAGE_D = JQ_HDR + JQ_ROWS * CTA + (2 * CTA + 4) / 2;
 template <int S>
-__global__ void __launch_bounds__(CTA) k_matvec_pipe(Dev P, const double* __restrict__ pvec, double* __restrict__ qvec,
-                                                     int force_all) {
+__global__ void __launch_bounds__(PIPE_THREADS, 3) k_matvec_pipe(Dev P, const double* __restrict__ pvec,
+                                                               double* __restrict__ qvec, int force_all, int maxslot) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int STAGE_D = JQ_STAGE_D;  // doubles per stage: header + 28 rows + run table of a full tile
   double* stage = reinterpret_cast<double*>(smem_raw);
-  double* c_sh = stage + (size_t)S * NPLANE * CTA;
+  double* c_sh = stage + (size_t)S * STAGE_D;
   double* p_sh = c_sh + 6 * CTA;
-  double* acc_sh = p_sh + 6 * MAXSLOT;
-  int* key_sh = reinterpret_cast<int*>(acc_sh + 6 * MAXSLOT);
-  uint64_t* full = reinterpret_cast<uint64_t*>(key_sh + CTA);
+  double* acc_sh = p_sh + 6 * maxslot;
+  uint64_t* full = reinterpret_cast<uint64_t*>(acc_sh + 6 * maxslot);
+  uint64_t* empty = full + S;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int t0 = (int)((long long)P.n_tile * blockIdx.x / gridDim.x);
   const int t1 = (int)((long long)P.n_tile * (blockIdx.x + 1) / gridDim.x);
   if (tid == 0) {
-    for (int s = 0; s < S; s++) mbar_init(&full[s], 1);
+    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_fence_init();
   }
   __syncthreads();
-  auto tile_on = [&](int t) -> bool { return force_all || P.ctl[P.tiles[t].win].cg_active; };
-  auto tile_tma = [&](int t) -> bool { return P.item_cnt[P.tiles[t].item0] <= 32; };
-  // ---- producer (thread 0): next active short tile -> stage n_issued % S
-  int t_load = t0, n_issued = 0;
-  auto issue_next = [&]() {
-    while (t_load < t1 && !(tile_on(t_load) && tile_tma(t_load))) t_load++;
-    if (t_load >= t1) return;
-    const TileInfo tl = P.tiles[t_load];
-    const int s = n_issued % S;
-    const uint32_t bytes = (uint32_t)(NPLANE * tl.nt * sizeof(double));  // one contiguous [27][nt] block
-    mbar_expect_tx(&full[s], bytes);
-    bulk_g2s(stage + (size_t)s * NPLANE * CTA, P.JQ + tl.jq_off, bytes, &full[s]);
-    n_issued++;
-    t_load++;
-  };
-  if (tid == 0)
-    for (int s = 0; s < S; s++) issue_next();
-  int n_done = 0, cur_win = -1, ws0 = 0, wn = 0;
-  for (int t = t0; t < t1; t++) {
-    if (!tile_on(t)) continue;  // CTA-uniform
-    const TileInfo ti = P.tiles[t];
-    if (ti.win != cur_win) {
+  if (wid == WARPS) {
+    // ------------------------------------------------------------------ producer warp (one elected lane)
+    if (lane == 0) {
+      int n = 0, seen_win = -1;
+      bool win_on = true;
+      TileInfo nxt = P.tiles[t0 < t1 ? t0 : 0];
+      for (int t = t0; t < t1; t++) {
+        const TileInfo ti = nxt;
+        if (t + 1 < t1) nxt = P.tiles[t + 1];  // prefetch the next descriptor before blocking on the ring
+        if (ti.win != seen_win) {
+          seen_win = ti.win;
+          win_on = force_all || P.ctl[ti.win].cg_active;
+        }
+        if (!win_on) continue;
+        const int s = n % S;
+        if (n >= S) mbar_wait(&empty[s], (uint32_t)(((n / S) - 1) & 1));
+        const uint32_t bytes = ti.is_long ? (uint32_t)(JQ_HDR * sizeof(double))
+                                          : (uint32_t)(ti.blk_doubles * sizeof(double));
+        mbar_expect_tx(&full[s], bytes);
+        bulk_g2s(stage + (size_t)s * STAGE_D, P.JQ + ti.jq_off - JQ_HDR, bytes, &full[s]);
+        n++;
+      }
+      const int s = n % S;  // end-of-stream marker
+      if (n >= S) mbar_wait(&empty[s], (uint32_t)(((n / S) - 1) & 1));
+      reinterpret_cast<volatile int*>(stage + (size_t)s * STAGE_D)[0] = -1;
+      mbar_arrive(&full[s]);
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- consumer warps
+  int n = 0, cur_win = -1, ws0 = 0, wn = 0;
+  while (true) {
+    const int s = n % S;
+    mbar_wait(&full[s], (uint32_t)((n / S) & 1));
+    const double* st = stage + (size_t)s * STAGE_D;
+    const int* hdr = reinterpret_cast<const int*>(st);
+    const int nitem = reinterpret_cast<const volatile int*>(hdr)[0];
+    if (nitem < 0) break;
+    if (hdr[1] != cur_win) {
       // flush the finished window's accumulators (thread i owns index i in both loops), stage p of the new one
       for (int i = tid; i < wn * 6; i += CTA) atomicAdd(&qvec[(size_t)ws0 * 6 + i], acc_sh[i]);
-      cur_win = ti.win;
-      ws0 = P.win_slot_ptr[cur_win];
-      wn = P.win_slot_ptr[cur_win + 1] - ws0;
-      __syncthreads();
+      cur_win = hdr[1];
+      ws0 = hdr[2];
+      wn = hdr[3];
+      named_bar_sync(1, CTA);
       for (int i = tid; i < wn * 6; i += CTA) {
         acc_sh[i] = 0.0;
         p_sh[i] = pvec[(size_t)ws0 * 6 + i];
       }
-      __syncthreads();
+      named_bar_sync(1, CTA);
     }
-    const int w = ti.item0 + wid;
-    const bool valid = wid < ti.nitem;
-    const int start = valid ? P.item_start[w] : 0, cnt = valid ? P.item_cnt[w] : 0;
-    if (!tile_tma(t)) {  // CTA-uniform: a long landmark is a tile of its own
-      if (valid) matvec_long_item(P, P.JQ + ti.jq_off, ti.nt, pvec, qvec, start, cnt, lane);
+    const int nt = hdr[5];
+    if (hdr[13]) {  // a long landmark is a tile of its own: operands straight from global memory, direct atomics
+      const long long jq_off = ((long long)hdr[8] << 32) | (unsigned)hdr[7];
+      if (wid == 0) matvec_long_item(P, P.JQ + jq_off, nt, pvec, qvec, hdr[6], hdr[9], lane);
+      named_bar_sync(1, CTA);
+      if (tid == 0) mbar_arrive(&empty[s]);
+      n++;
       continue;
     }
-    const int s = n_done % S;
-    mbar_wait(&full[s], (uint32_t)((n_done / S) & 1));
-    const double* st = stage + (size_t)s * NPLANE * CTA;
-    const int nt = ti.nt;
+    const double* data = st + JQ_HDR;
+    const uint2* meta = reinterpret_cast<const uint2*>(data + (size_t)NPLANE * nt);
     double out[6] = {0, 0, 0, 0, 0, 0};
     bool has = false;
     int rank = 0, ls = 0;
-    if (valid) {
+    if (wid < nitem) {
+      const int col0 = (wid > 0 ? hdr[9] : 0) + (wid > 1 ? hdr[10] : 0) + (wid > 2 ? hdr[11] : 0);
+      const int cnt = hdr[9 + wid];
       const bool act = lane < cnt;
-      const int o = start + (act ? lane : 0);
+      const int col = col0 + (act ? lane : 0);
       int lm = -1 - lane;
       if (act) {
-        const unsigned lp = P.obs_lp[o];
-        ls = (int)(lp & 0xffffu);
+        const uint2 m = meta[col];
+        ls = (int)(m.x & 0xffffu);
         has = ls != 0xffff;
-        rank = (int)(lp >> 16);
-        lm = P.obs_point[o];
+        rank = (int)(m.x >> 16);
+        lm = (int)m.y;
       }
       const Seg sg = seg_of(lm, lane);
       double J[18], Q[9], pp[6];
       if (has) {
-        const int col = o - ti.o0;
 #pragma unroll
-        for (int c = 0; c < 18; c++) J[c] = st[c * nt + col];
+        for (int c = 0; c < 18; c++) J[c] = data[c * nt + col];
 #pragma unroll
-        for (int c = 0; c < 9; c++) Q[c] = st[(18 + c) * nt + col];
+        for (int c = 0; c < 9; c++) Q[c] = data[(18 + c) * nt + col];
 #pragma unroll
         for (int c = 0; c < 6; c++) pp[c] = p_sh[ls * 6 + c];
       }
       matvec_lane(has, J, Q, pp, sg, lane, out);
       if (has) {
-        key_sh[rank] = ls;
 #pragma unroll
         for (int k = 0; k < 6; k++) c_sh[k * CTA + rank] = out[k];
       }
     }
-    __syncthreads();  // every thread has consumed stage s and published its column
-    if (tid == 0) issue_next();  // refill the stage that was just freed
-    for (int idx = tid; idx < ti.nfree * 6; idx += CTA) {
-      const int j = idx / 6, k = idx - j * 6;
-      const int kj = key_sh[j];
-      if (j == 0 || key_sh[j - 1] != kj) {
-        double sum = 0.0;
-        for (int jj = j; jj < ti.nfree && key_sh[jj] == kj; jj++) sum += c_sh[k * CTA + jj];
-        acc_sh[kj * 6 + k] += sum;
+    named_bar_sync(1, CTA);  // every consumer has published its column
+    {  // pose-side reduction: 8 threads per run of equal slot (6 of them active), window accumulators in shared memory
+      const int nrun = hdr[14];
+      const int* run_ptr = reinterpret_cast<const int*>(data + (size_t)JQ_ROWS * nt);
+      const int* run_slot = run_ptr + nrun + 1;
+      for (int idx = tid; idx < nrun * 8; idx += CTA) {
+        const int r = idx >> 3, k = idx & 7;
+        if (k < 6) {
+          const int a = run_ptr[r], b = run_ptr[r + 1];
+          double sum = 0.0;
+          for (int j = a; j < b; j++) sum += c_sh[k * CTA + j];
+          acc_sh[run_slot[r] * 6 + k] += sum;
+        }
       }
     }
-    __syncthreads();
-    n_done++;
+    named_bar_sync(1, CTA);  // stage s (run table included) fully consumed; c_sh free for the next tile
+    if (tid == 0) mbar_arrive(&empty[s]);
+    n++;
   }
   for (int i = tid; i < wn * 6; i += CTA) atomicAdd(&qvec[(size_t)ws0 * 6 + i], acc_sh[i]);
 }

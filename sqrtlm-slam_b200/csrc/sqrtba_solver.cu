@@ -75,11 +75,10 @@ class Solver {
     cudaDeviceProp prop;
     CU_CHECK(cudaGetDeviceProperties(&prop, cfg_.device));
     n_sm_ = prop.multiProcessorCount;
-    CU_CHECK(cudaFuncSetAttribute(k_matvec_pipe<PIPE_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)pipe_smem_bytes()));
-    int per_sm = 0;
-    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matvec_pipe<PIPE_STAGES>, CTA, pipe_smem_bytes()));
-    pipe_ctas_ = std::max(1, per_sm) * n_sm_;
+    CU_CHECK(cudaFuncSetAttribute(k_matvec_pipe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pipe_smem_bytes(2, MAXSLOT)));
+    CU_CHECK(cudaFuncSetAttribute(k_matvec_pipe<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pipe_smem_bytes(3, MAXSLOT)));
     return SQRTBA_OK;
   }
 
@@ -199,6 +198,7 @@ class Solver {
     for (int w = 0; w < n_win; w++) max_win_slots = std::max(max_win_slots, win_slot_ptr[w + 1] - win_slot_ptr[w]);
     const int smallwin = (max_win_slots <= MAXSLOT) ? 1 : 0;
     std::vector<TileInfo> tiles;
+    std::vector<int> tile_run_ptr(1, 0), tile_runs;
     long long jq_total = 0;
     std::vector<unsigned> obs_lp(n_obs, 0xffffu);
     {
@@ -242,10 +242,18 @@ class Solver {
             obs_lp[o] = low | ((unsigned)rank << 16);
           }
           ti.nfree = lptr[nl];
+          ti.nrun = nl;
+          // run table: nl+1 rank offsets, then the nl slots (window-relative when every window is small)
+          tile_runs.insert(tile_runs.end(), lptr.begin(), lptr.end());
+          for (int i = 0; i < nl; i++) tile_runs.push_back(smallwin ? distinct[i] - ws0 : distinct[i]);
         }
+        tile_run_ptr.push_back((int)tile_runs.size());
         ti.nt = ((ti.o1 - ti.o0) + 1) & ~1;
-        ti.jq_off = jq_total;
-        jq_total += (long long)NPLANE * ti.nt;
+        ti.is_long = item_cnt[it] > 32 ? 1 : 0;
+        ti.jq_off = jq_total + JQ_HDR;
+        const int run_ints = ti.is_long ? 0 : 2 * ti.nrun + 1;
+        ti.blk_doubles = JQ_HDR + JQ_ROWS * ti.nt + 2 * ((run_ints + 3) / 4);
+        jq_total += ti.blk_doubles;
         tiles.push_back(ti);
         it += ti.nitem;
       }
@@ -274,6 +282,8 @@ class Solver {
     CU_CHECK(d_win_slot_ptr_.ensure(n_win + 1));
     CU_CHECK(d_tiles_.ensure(n_tile));
     CU_CHECK(d_obs_lp_.ensure(No));
+    CU_CHECK(d_tile_run_ptr_.ensure(n_tile + 1));
+    CU_CHECK(d_tile_runs_.ensure(tile_runs.size()));
     CU_CHECK(d_pose_.ensure((size_t)n_pose * 7));
     CU_CHECK(d_pose0_.ensure((size_t)n_pose * 7));
     CU_CHECK(d_pose_bak_.ensure((size_t)n_pose * 7));
@@ -317,6 +327,8 @@ class Solver {
     CU_CHECK(up(d_win_item_ptr_.p, win_item_ptr.data(), (n_win + 1) * sizeof(int)));
     CU_CHECK(up(d_win_slot_ptr_.p, win_slot_ptr.data(), (n_win + 1) * sizeof(int)));
     CU_CHECK(up(d_tiles_.p, tiles.data(), (size_t)n_tile * sizeof(TileInfo)));
+    CU_CHECK(up(d_tile_run_ptr_.p, tile_run_ptr.data(), (size_t)(n_tile + 1) * sizeof(int)));
+    if (!tile_runs.empty()) CU_CHECK(up(d_tile_runs_.p, tile_runs.data(), tile_runs.size() * sizeof(int)));
     CU_CHECK(up(d_obs_lp_.p, obs_lp.data(), No * sizeof(unsigned)));
     // poses: normalise the quaternion the way SE3Quat's constructor does (se3quat.h:58-64)
     std::vector<double> pq(pose_qt, pose_qt + (size_t)n_pose * 7);
@@ -332,6 +344,7 @@ class Solver {
     P_.win_slot_ptr = d_win_slot_ptr_.p;
     P_.tiles = d_tiles_.p;
     P_.obs_lp = d_obs_lp_.p;
+    P_.tile_run_ptr = d_tile_run_ptr_.p; P_.tile_runs = d_tile_runs_.p;
     P_.pose = d_pose_.p; P_.point = d_point_.p; P_.pose_bak = d_pose_bak_.p; P_.point_bak = d_point_bak_.p;
     P_.obs_level = d_level_.p; P_.obs_outlier = d_outlier_.p;
     P_.err = d_err_.p; P_.JQ = d_JQ_.p; P_.Jl = d_Jl_.p; P_.r = d_r_.p;
@@ -350,8 +363,24 @@ class Solver {
     P_.chi_part = d_chi_part_.p; P_.scale_part = d_scale_part_.p;
     P_.ctl = d_ctl_.p; P_.trace = d_trace_.p; P_.max_trace = max_trace_; P_.counters = d_counters_.p;
     h_tiles_ = tiles;
-    // pad columns of the JQ blocks are streamed by the TMA copies: keep them defined
+    max_win_slots_ = std::max(max_win_slots, 1);
+    // pad columns of the JQ blocks are streamed by the TMA copies: keep them defined; then headers + per-column meta
     CU_CHECK(cudaMemsetAsync(d_JQ_.p, 0, (size_t)jq_total * sizeof(double), stream_));
+    k_init_jq<<<n_tile, 128, 0, stream_>>>(P_);
+    CU_CHECK(cudaGetLastError());
+    if (smallwin) {  // pipeline depth / residency for this problem's window size
+      int best_ctas = 0;
+      for (int S : {2, 3}) {
+        int per_sm = 0;
+        const size_t bytes = pipe_smem_bytes(S, max_win_slots_);
+        cudaError_t e = (S == 2) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matvec_pipe<2>, PIPE_THREADS, bytes)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matvec_pipe<3>, PIPE_THREADS, bytes);
+        if (e != cudaSuccess) per_sm = 0;
+        if (cfg_.reserved[2] > 0 && S != cfg_.reserved[2]) continue;   // forced depth (profiling)
+        if (per_sm * S > best_ctas * pipe_stages_ || best_ctas == 0) { best_ctas = per_sm; pipe_stages_ = S; }
+      }
+      pipe_ctas_ = std::max(1, best_ctas) * n_sm_;
+    }
     have_problem_ = true;
     return reset_state();
   }
@@ -561,15 +590,17 @@ class Solver {
   }
 
   // matvec dispatch: persistent TMA-pipelined kernel when every window is small, general tile kernel otherwise
-  static constexpr int PIPE_STAGES = 3;
-  static constexpr size_t pipe_smem_bytes() {
-    return ((size_t)PIPE_STAGES * NPLANE * CTA + 6 * CTA + 12 * MAXSLOT) * sizeof(double) + CTA * sizeof(int) +
-           PIPE_STAGES * sizeof(uint64_t);
+  static size_t pipe_smem_bytes(int S, int maxslot) {
+    return ((size_t)S * JQ_STAGE_D + 6 * CTA + 12 * (size_t)maxslot) * sizeof(double) + 2 * S * sizeof(uint64_t);
   }
   void launch_matvec(const double* pvec, double* qvec, int force_all) {
     if (P_.smallwin && cfg_.reserved[1] == 0) {
       const int grid = std::min(P_.n_tile, pipe_ctas_);
-      k_matvec_pipe<PIPE_STAGES><<<grid, CTA, pipe_smem_bytes(), stream_>>>(P_, pvec, qvec, force_all);
+      const size_t bytes = pipe_smem_bytes(pipe_stages_, max_win_slots_);
+      if (pipe_stages_ == 2)
+        k_matvec_pipe<2><<<grid, PIPE_THREADS, bytes, stream_>>>(P_, pvec, qvec, force_all, max_win_slots_);
+      else
+        k_matvec_pipe<3><<<grid, PIPE_THREADS, bytes, stream_>>>(P_, pvec, qvec, force_all, max_win_slots_);
     } else {
       k_matvec<<<P_.n_tile, CTA, 0, stream_>>>(P_, pvec, qvec, force_all);
     }
@@ -699,7 +730,7 @@ class Solver {
     d_JQ_.release(); d_Jl_.release(); d_r_.release(); d_R_.release(); d_tl_.release();
     d_bl_.release(); d_dl_.release(); d_slotvec_.release(); d_chi_part_.release(); d_scale_part_.release();
     d_ctl_.release(); d_trace_.release(); d_counters_.release();
-    d_tiles_.release(); d_obs_lp_.release();
+    d_tiles_.release(); d_obs_lp_.release(); d_tile_run_ptr_.release(); d_tile_runs_.release();
   }
 
  public:
@@ -716,12 +747,13 @@ class Solver {
   bool have_problem_ = false;
   int max_trace_ = 200;
   int launches_ = 0, lm_trials_ = 0, cg_iters_total_ = 0;
-  int n_sm_ = 148, pipe_ctas_ = 296;
+  int n_sm_ = 148, pipe_ctas_ = 296, pipe_stages_ = 3, max_win_slots_ = 1;
   Dev P_{};
   DBuf<double> d_cam_, d_pose_, d_pose0_, d_pose_bak_, d_point_, d_point0_, d_point_bak_, d_err_, d_JQ_, d_Jl_,
       d_r_, d_R_, d_tl_, d_bl_, d_dl_, d_slotvec_, d_chi_part_, d_scale_part_, d_trace_;
   DBuf<int> d_pose_slot_, d_slot_pose_, d_slot_win_, d_pose_win_, d_point_win_, d_obs_pose_, d_obs_point_, d_obs_slot_,
-      d_item_start_, d_item_cnt_, d_item_win_, d_win_item_ptr_, d_win_slot_ptr_, d_counters_;
+      d_item_start_, d_item_cnt_, d_item_win_, d_win_item_ptr_, d_win_slot_ptr_, d_counters_, d_tile_run_ptr_,
+      d_tile_runs_;
   DBuf<unsigned> d_obs_lp_;
   DBuf<TileInfo> d_tiles_;
   std::vector<TileInfo> h_tiles_;

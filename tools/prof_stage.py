@@ -13,7 +13,8 @@ n_win = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 pkg = load_pkg()
 wins, prob, pp, tp, op = make_batch(pkg, n_win, 0)
-ba = pkg.SqrtBA(general_matvec=(os.environ.get('SQRTBA_GENERAL_MATVEC') == '1'))
+ba = pkg.SqrtBA(general_matvec=(os.environ.get('SQRTBA_GENERAL_MATVEC') == '1'),
+                pipe_stages=int(os.environ.get('SQRTBA_PIPE_STAGES', '0')))
 ba.set_problem_batch(prob, pp, tp, op)
 ba.debug_linearize(1)
 ba.debug_step(100.0)
