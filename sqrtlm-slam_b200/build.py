@@ -31,6 +31,16 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
+def build_variant(out_name: str, extra_flags: list[str]) -> str:
+    """Instrumented / experimental builds next to the product library (never loaded by default)."""
+    out = os.path.join(HERE, out_name)
+    res = subprocess.run([nvcc_path()] + NVCC_FLAGS + extra_flags + ["-o", out] + SOURCES, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building " + out_name)
+    return out
+
+
 def build_lib(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB

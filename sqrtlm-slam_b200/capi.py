@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsqrtba.so")
+LIB_PATH = os.environ.get("SQRTBA_LIB") or os.path.join(HERE, "libsqrtba.so")  # SQRTBA_LIB: instrumented builds
 _lib = None
 
 

@@ -123,6 +123,7 @@ struct Dev {
   double* trace;    // n_win * max_trace * TRACE_COLS
   int max_trace;
   int* counters;    // [0] windows done, [1] cg-active windows
+  long long* prof;  // optional (SQRTBA_PIPE_PROF builds): per-CTA cycle counters of the pipelined matvec
 };
 
 // ------------------------------------------------------------------------------------------------ warp helpers
@@ -909,15 +910,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 constexpr int PIPE_THREADS = CTA + 32;
 constexpr int JQ_STAGE_D = JQ_HDR + JQ_ROWS * CTA + (2 * CTA + 4) / 2;
 template <int S>
-__global__ void __launch_bounds__(PIPE_THREADS, 3) k_matvec_pipe(Dev P, const double* __restrict__ pvec,
+__global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__ pvec,
                                                                double* __restrict__ qvec, int force_all, int maxslot) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int STAGE_D = JQ_STAGE_D;  // doubles per stage: header + 28 rows + run table of a full tile
   double* stage = reinterpret_cast<double*>(smem_raw);
-  double* c_sh = stage + (size_t)S * STAGE_D;
-  double* p_sh = c_sh + 6 * CTA;
+  constexpr int CST = CTA + 1;  // padded row stride of c_sh: the 6 value-lanes of a run hit 6 different bank pairs
+  double* c_sh = stage + (size_t)S * STAGE_D;  // two buffers of [6][CST]
+  double* p_sh = c_sh + 2 * (6 * CST) + 2;      // component-major: p_sh[c * maxslot + slot]
   double* acc_sh = p_sh + 6 * maxslot;
-  uint64_t* full = reinterpret_cast<uint64_t*>(acc_sh + 6 * maxslot);
+  int* runs_sh = reinterpret_cast<int*>(acc_sh + 6 * maxslot);  // two buffers of 2*CTA+4 ints
+  uint64_t* full = reinterpret_cast<uint64_t*>(runs_sh + 2 * (2 * CTA + 4));
   uint64_t* empty = full + S;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int t0 = (int)((long long)P.n_tile * blockIdx.x / gridDim.x);
@@ -958,15 +961,24 @@ __global__ void __launch_bounds__(PIPE_THREADS, 3) k_matvec_pipe(Dev P, const do
   }
   // -------------------------------------------------------------------- consumer warps
   int n = 0, cur_win = -1, ws0 = 0, wn = 0;
+#ifdef SQRTBA_PIPE_PROF
+  long long tp[6] = {0, 0, 0, 0, 0, 0}, tc = clock64(), tn;
+#define PROF_MARK(i) { tn = clock64(); tp[i] += tn - tc; tc = tn; }
+#else
+#define PROF_MARK(i)
+#endif
   while (true) {
     const int s = n % S;
+    PROF_MARK(5)
     mbar_wait(&full[s], (uint32_t)((n / S) & 1));
+    PROF_MARK(0)
     const double* st = stage + (size_t)s * STAGE_D;
     const int* hdr = reinterpret_cast<const int*>(st);
     const int nitem = reinterpret_cast<const volatile int*>(hdr)[0];
     if (nitem < 0) break;
     if (hdr[1] != cur_win) {
-      // flush the finished window's accumulators (thread i owns index i in both loops), stage p of the new one
+      // flush the finished window's accumulators, stage p of the new one
+      named_bar_sync(1, CTA);  // previous tile's reduction complete
       for (int i = tid; i < wn * 6; i += CTA) atomicAdd(&qvec[(size_t)ws0 * 6 + i], acc_sh[i]);
       cur_win = hdr[1];
       ws0 = hdr[2];
@@ -974,7 +986,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 3) k_matvec_pipe(Dev P, const do
       named_bar_sync(1, CTA);
       for (int i = tid; i < wn * 6; i += CTA) {
         acc_sh[i] = 0.0;
-        p_sh[i] = pvec[(size_t)ws0 * 6 + i];
+        const int sl = i / 6;
+        p_sh[(i - sl * 6) * maxslot + sl] = pvec[(size_t)ws0 * 6 + i];
       }
       named_bar_sync(1, CTA);
     }
@@ -989,15 +1002,20 @@ __global__ void __launch_bounds__(PIPE_THREADS, 3) k_matvec_pipe(Dev P, const do
     }
     const double* data = st + JQ_HDR;
     const uint2* meta = reinterpret_cast<const uint2*>(data + (size_t)NPLANE * nt);
-    double out[6] = {0, 0, 0, 0, 0, 0};
-    bool has = false;
-    int rank = 0, ls = 0;
+    double* cb = c_sh + (size_t)(n & 1) * (6 * CST);       // double-buffered: no barrier needed after the reduction
+    int* rb = runs_sh + (size_t)(n & 1) * (2 * CTA + 4);
+    const int nrun = hdr[14];
+    {  // copy the tile's run table out of the stage so the stage can be released right after the first barrier
+      const int* rsrc = reinterpret_cast<const int*>(data + (size_t)JQ_ROWS * nt);
+      for (int i = tid; i < 2 * nrun + 1; i += CTA) rb[i] = rsrc[i];
+    }
     if (wid < nitem) {
       const int col0 = (wid > 0 ? hdr[9] : 0) + (wid > 1 ? hdr[10] : 0) + (wid > 2 ? hdr[11] : 0);
       const int cnt = hdr[9 + wid];
       const bool act = lane < cnt;
       const int col = col0 + (act ? lane : 0);
-      int lm = -1 - lane;
+      int lm = -1 - lane, rank = 0, ls = 0;
+      bool has = false;
       if (act) {
         const uint2 m = meta[col];
         ls = (int)(m.x & 0xffffu);
@@ -1006,41 +1024,61 @@ __global__ void __launch_bounds__(PIPE_THREADS, 3) k_matvec_pipe(Dev P, const do
         lm = (int)m.y;
       }
       const Seg sg = seg_of(lm, lane);
-      double J[18], Q[9], pp[6];
+      const double* dcol = data + col;
+      double J[18], v[3] = {0, 0, 0}, t[3] = {0, 0, 0};
       if (has) {
+        double pp[6];
 #pragma unroll
-        for (int c = 0; c < 18; c++) J[c] = data[c * nt + col];
+        for (int c = 0; c < 6; c++) pp[c] = p_sh[c * maxslot + ls];
 #pragma unroll
-        for (int c = 0; c < 9; c++) Q[c] = data[(18 + c) * nt + col];
+        for (int c = 0; c < 18; c++) J[c] = dcol[c * nt];
 #pragma unroll
-        for (int c = 0; c < 6; c++) pp[c] = p_sh[ls * 6 + c];
-      }
-      matvec_lane(has, J, Q, pp, sg, lane, out);
-      if (has) {
+        for (int r = 0; r < 3; r++)
+          v[r] = J[r * 6] * pp[0] + J[r * 6 + 1] * pp[1] + J[r * 6 + 2] * pp[2] + J[r * 6 + 3] * pp[3] +
+                 J[r * 6 + 4] * pp[4] + J[r * 6 + 5] * pp[5];
 #pragma unroll
-        for (int k = 0; k < 6; k++) c_sh[k * CTA + rank] = out[k];
-      }
-    }
-    named_bar_sync(1, CTA);  // every consumer has published its column
-    {  // pose-side reduction: 8 threads per run of equal slot (6 of them active), window accumulators in shared memory
-      const int nrun = hdr[14];
-      const int* run_ptr = reinterpret_cast<const int*>(data + (size_t)JQ_ROWS * nt);
-      const int* run_slot = run_ptr + nrun + 1;
-      for (int idx = tid; idx < nrun * 8; idx += CTA) {
-        const int r = idx >> 3, k = idx & 7;
-        if (k < 6) {
-          const int a = run_ptr[r], b = run_ptr[r + 1];
-          double sum = 0.0;
-          for (int j = a; j < b; j++) sum += c_sh[k * CTA + j];
-          acc_sh[run_slot[r] * 6 + k] += sum;
+        for (int r = 0; r < 3; r++) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) t[k] += dcol[(18 + r * 3 + k) * nt] * v[r];
         }
       }
+      double sv[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) sv[k] = seg_sum(t[k], sg, lane);
+      if (has) {
+        // Q1 rows are re-read from the stage instead of being kept live across the shuffles (register pressure)
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+          v[r] -= dcol[(18 + r * 3) * nt] * sv[0] + dcol[(19 + r * 3) * nt] * sv[1] + dcol[(20 + r * 3) * nt] * sv[2];
+#pragma unroll
+        for (int c = 0; c < 6; c++) cb[c * CST + rank] = J[c] * v[0] + J[6 + c] * v[1] + J[12 + c] * v[2];
+      }
     }
-    named_bar_sync(1, CTA);  // stage s (run table included) fully consumed; c_sh free for the next tile
+    PROF_MARK(1)
+    named_bar_sync(1, CTA);  // every consumer has drained stage s and published its column / the run table
     if (tid == 0) mbar_arrive(&empty[s]);
+    PROF_MARK(2)
+    // pose-side reduction: one thread per (run of equal slot, component); window accumulators stay in shared memory.
+    // The next tile's barrier orders these read-modify-writes against the following tile's, so no barrier here.
+    for (int idx = tid; idx < nrun * 6; idx += CTA) {
+      const int r = (idx * 10923) >> 16, k = idx - r * 6;
+      const int a = rb[r], b = rb[r + 1];
+      double sum = 0.0;
+      for (int j = a; j < b; j++) sum += cb[k * CST + j];
+      acc_sh[rb[nrun + 1 + r] * 6 + k] += sum;
+    }
+    PROF_MARK(3)
     n++;
   }
+  named_bar_sync(1, CTA);  // the last tile's reduction is complete before the accumulators are flushed
   for (int i = tid; i < wn * 6; i += CTA) atomicAdd(&qvec[(size_t)ws0 * 6 + i], acc_sh[i]);
+#ifdef SQRTBA_PIPE_PROF
+  if (P.prof && (tid & 31) == 0) {
+    long long* o = P.prof + ((size_t)blockIdx.x * WARPS + wid) * 8;
+    for (int i = 0; i < 6; i++) o[i] = tp[i];
+    o[6] = n;
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ K4/K5: PCG vector ops

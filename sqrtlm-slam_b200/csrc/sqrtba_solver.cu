@@ -362,6 +362,12 @@ class Solver {
     P_.Dinv = sv;
     P_.chi_part = d_chi_part_.p; P_.scale_part = d_scale_part_.p;
     P_.ctl = d_ctl_.p; P_.trace = d_trace_.p; P_.max_trace = max_trace_; P_.counters = d_counters_.p;
+    P_.prof = nullptr;
+#ifdef SQRTBA_PIPE_PROF
+    CU_CHECK(d_prof_.ensure((size_t)4096 * WARPS * 8));
+    CU_CHECK(cudaMemsetAsync(d_prof_.p, 0, d_prof_.cap * sizeof(long long), stream_));
+    P_.prof = d_prof_.p;
+#endif
     h_tiles_ = tiles;
     max_win_slots_ = std::max(max_win_slots, 1);
     // pad columns of the JQ blocks are streamed by the TMA copies: keep them defined; then headers + per-column meta
@@ -571,6 +577,20 @@ class Solver {
     float ms = 0;
     CU_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
     *ms_avg = (double)ms / std::max(reps, 1);
+#ifdef SQRTBA_PIPE_PROF
+    if (stage == 0 && P_.smallwin) {  // cycle breakdown of the last pipelined matvec launch, averaged over consumer warps
+      const int nw = std::min(P_.n_tile, pipe_ctas_) * WARPS;
+      std::vector<long long> hp((size_t)nw * 8);
+      if (download(hp.data(), d_prof_.p, hp.size() * sizeof(long long))) return SQRTBA_ERR_CUDA;
+      double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+      for (int w = 0; w < nw; w++)
+        for (int i = 0; i < 7; i++) acc[i] += (double)hp[(size_t)w * 8 + i];
+      const double tiles = acc[6] / WARPS;  // each consumer warp counts every tile of its CTA
+      fprintf(stderr, "[pipe prof] tiles/CTA %.1f | cycles per tile: wait_full %.0f phase1 %.0f barA %.0f phase2 %.0f barB+arrive %.0f loop %.0f\n",
+              acc[6] / nw, acc[0] / acc[6], acc[1] / acc[6], acc[2] / acc[6], acc[3] / acc[6], acc[4] / acc[6], acc[5] / acc[6]);
+      (void)tiles;
+    }
+#endif
     return SQRTBA_OK;
   }
 
@@ -591,7 +611,8 @@ class Solver {
 
   // matvec dispatch: persistent TMA-pipelined kernel when every window is small, general tile kernel otherwise
   static size_t pipe_smem_bytes(int S, int maxslot) {
-    return ((size_t)S * JQ_STAGE_D + 6 * CTA + 12 * (size_t)maxslot) * sizeof(double) + 2 * S * sizeof(uint64_t);
+    return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + 12 * (size_t)maxslot) * sizeof(double) +
+           2 * (2 * CTA + 4) * sizeof(int) + 2 * S * sizeof(uint64_t);
   }
   void launch_matvec(const double* pvec, double* qvec, int force_all) {
     if (P_.smallwin && cfg_.reserved[1] == 0) {
@@ -756,6 +777,7 @@ class Solver {
       d_tile_runs_;
   DBuf<unsigned> d_obs_lp_;
   DBuf<TileInfo> d_tiles_;
+  DBuf<long long> d_prof_;
   std::vector<TileInfo> h_tiles_;
   DBuf<float4> d_meas_;
   DBuf<uint8_t> d_level_, d_outlier_;
