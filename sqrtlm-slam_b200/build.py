@@ -55,5 +55,27 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_LIB = os.path.join(HERE, "libsqrtba_host.so")
+HOST_SOURCES = [os.path.join(HERE, "host", f) for f in ("sqrtbaOptimizer.cc", "harness.cc")]
+HOST_DEPS = HOST_SOURCES + [os.path.join(HERE, "host", f) for f in ("Optimizer.h", "map_types.h")]
+
+
+def build_host(force: bool = False) -> str:
+    """The C++ adapter (reference Optimizer API over the C ABI) + its test harness, against the header-compatible
+    map types.  Plain g++; links libsqrtba.so through an $ORIGIN rpath."""
+    build_lib()
+    if not force and os.path.exists(HOST_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_LIB) for d in HOST_DEPS + [LIB]):
+        return HOST_LIB
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", HOST_LIB] + HOST_SOURCES + [
+        "-L" + HERE, "-lsqrtba", "-Wl,-rpath,$ORIGIN", "-pthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building libsqrtba_host.so")
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

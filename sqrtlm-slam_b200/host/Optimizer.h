@@ -1,0 +1,40 @@
+// Mirror of the bundle-adjustment part of the reference facade (include/backend/Optimizer.h:42-56): same class, same
+// static signatures (the reference's spelling `GlobalBundleAdjustemnt` included), plus the new back-end selector value.
+#pragma once
+#include <vector>
+
+#ifdef SQRTBA_WITH_REFERENCE_HEADERS
+#include "data_structure/KeyFrame.h"
+#include "data_structure/Map.h"
+#include "data_structure/MapPoint.h"
+#include "utils/lidarconfig.h"
+#else
+#include "map_types.h"
+#endif
+
+namespace ORB_SLAM2 {
+
+class Optimizer {
+ public:
+  enum eSolver { CERES = 0, G2O = 1, MYOPT = 2, SQRTBA = 3 };
+  void static BundleAdjustment(const std::vector<KeyFrame*>& vpKF, const std::vector<MapPoint*>& vpMP,
+                               int nIterations = 5, bool* pbStopFlag = NULL, const unsigned long nLoopKF = 0,
+                               const bool bRobust = true);
+  void static GlobalBundleAdjustemnt(Map* pMap, int nIterations = 5, bool* pbStopFlag = NULL,
+                                     const unsigned long nLoopKF = 0, const bool bRobust = true);
+  void static LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* lidarconfig);
+};
+
+// the adapter that sits beside g2oOptimizer / CeresOptimizer / MyOptimizer (src/backend/)
+class sqrtbaOptimizer {
+ public:
+  void static BundleAdjustment(const std::vector<KeyFrame*>& vpKF, const std::vector<MapPoint*>& vpMP, int nIterations,
+                               bool* pbStopFlag, const unsigned long nLoopKF, const bool bRobust);
+  void static GlobalBundleAdjustemnt(Map* pMap, int nIterations, bool* pbStopFlag, const unsigned long nLoopKF,
+                                     const bool bRobust);
+  void static LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* lidarconfig);
+  // last error of the calling thread's handle ("" if none); the reference API itself is void / silent
+  static const char* LastError();
+};
+
+}  // namespace ORB_SLAM2

@@ -1,0 +1,101 @@
+// C harness around the adapter for the Python tests: builds a map of the header-compatible types from flat arrays,
+// calls ORB_SLAM2::Optimizer::{LocalBundleAdjustment,GlobalBundleAdjustemnt} exactly as LocalMapping / LoopClosing do
+// (src/backend/LocalMapping.cc:131, src/backend/LoopClosing.cc:987), and exposes the resulting map state.
+#include <cstdint>
+#include <memory>
+
+#include "Optimizer.h"
+
+using namespace ORB_SLAM2;
+
+struct hh_map {
+  Map map;
+  std::vector<std::unique_ptr<KeyFrame>> kfs;
+  std::vector<std::unique_ptr<MapPoint>> mps;
+  lidarConfig lidar;
+};
+
+extern "C" {
+
+hh_map* hh_build(int n_kf, const float* Tcw, const float* cam5, const float* inv_sigma2, int n_levels, int n_mp,
+                 const float* Xw, int n_obs, const int32_t* obs_kf, const int32_t* obs_mp, const float* obs_uvr,
+                 const int32_t* obs_octave) {
+  hh_map* m = new hh_map();
+  for (int i = 0; i < n_kf; i++) {
+    auto kf = std::make_unique<KeyFrame>();
+    kf->mnId = (unsigned long)i;
+    kf->Tcw.create(4, 4, CV_32F);
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) kf->Tcw.at<float>(r, c) = Tcw[i * 16 + r * 4 + c];
+    kf->fx = cam5[0]; kf->fy = cam5[1]; kf->cx = cam5[2]; kf->cy = cam5[3]; kf->mbf = cam5[4];
+    kf->mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + n_levels);
+    m->map.mspKeyFrames.push_back(kf.get());
+    m->kfs.push_back(std::move(kf));
+  }
+  for (int i = 0; i < n_mp; i++) {
+    auto mp = std::make_unique<MapPoint>();
+    mp->mnId = (unsigned long)i;
+    mp->mWorldPos.create(3, 1, CV_32F);
+    for (int r = 0; r < 3; r++) mp->mWorldPos.at<float>(r) = Xw[i * 3 + r];
+    m->map.mspMapPoints.push_back(mp.get());
+    m->mps.push_back(std::move(mp));
+  }
+  for (int k = 0; k < n_obs; k++) {
+    KeyFrame* kf = m->kfs[obs_kf[k]].get();
+    MapPoint* mp = m->mps[obs_mp[k]].get();
+    cv::KeyPoint kp;
+    kp.pt.x = obs_uvr[k * 3 + 0];
+    kp.pt.y = obs_uvr[k * 3 + 1];
+    kp.octave = obs_octave[k];
+    const size_t idx = kf->mvKeysUn.size();
+    kf->mvKeysUn.push_back(kp);
+    kf->mvuRight.push_back(obs_uvr[k * 3 + 2]);
+    kf->mvpMapPoints.push_back(mp);
+    mp->mObservations[kf] = idx;
+  }
+  return m;
+}
+
+void hh_destroy(hh_map* m) { delete m; }
+
+void hh_set_covisible(hh_map* m, int kf, const int32_t* list, int n) {
+  auto& v = m->kfs[kf]->mvpOrderedConnectedKeyFrames;
+  v.clear();
+  for (int i = 0; i < n; i++) v.push_back(m->kfs[list[i]].get());
+}
+
+void hh_set_bad(hh_map* m, int kf, int mp) {
+  if (kf >= 0) m->kfs[kf]->mbBad = true;
+  if (mp >= 0) m->mps[mp]->mbBad = true;
+}
+
+void hh_local_ba(hh_map* m, int kf, bool* stop) {
+  Optimizer::LocalBundleAdjustment(m->kfs[kf].get(), stop, &m->map, &m->lidar);
+}
+
+void hh_global_ba(hh_map* m, int iters, int robust, unsigned long nLoopKF, bool* stop) {
+  Optimizer::GlobalBundleAdjustemnt(&m->map, iters, stop, nLoopKF, robust != 0);
+}
+
+void hh_get_pose(hh_map* m, int kf, int gba, float* out16) {
+  const cv::Mat T = gba ? m->kfs[kf]->mTcwGBA : m->kfs[kf]->GetPose();
+  for (int i = 0; i < 16; i++) out16[i] = T.empty() ? 0.f : T.at<float>(i / 4, i % 4);
+}
+void hh_get_point(hh_map* m, int mp, int gba, float* out3) {
+  const cv::Mat P = gba ? m->mps[mp]->mPosGBA : m->mps[mp]->GetWorldPos();
+  for (int i = 0; i < 3; i++) out3[i] = P.empty() ? 0.f : P.at<float>(i);
+}
+int hh_has_observation(hh_map* m, int kf, int mp) {
+  auto obs = m->mps[mp]->GetObservations();
+  return obs.count(m->kfs[kf].get()) ? 1 : 0;
+}
+int hh_keyframe_sees(hh_map* m, int kf, int mp) {
+  for (MapPoint* p : m->kfs[kf]->GetMapPointMatches())
+    if (p == m->mps[mp].get()) return 1;
+  return 0;
+}
+int hh_point_updates(hh_map* m, int mp) { return m->mps[mp]->nUpdateNormalAndDepth; }
+unsigned long hh_gba_marker(hh_map* m, int kf) { return m->kfs[kf]->mnBAGlobalForKF; }
+const char* hh_last_error() { return sqrtbaOptimizer::LastError(); }
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Header-compatible stand-ins for the reference's map types, restricted to the member surface the BA adapters touch
+// (SURVEY.md §8(b)): include/data_structure/KeyFrame.h:83-84,134,226-250,306,345-403,427; MapPoint.h:82-88,108,129,
+// 161,230,242-287; Map.h:100,107,144; and the sliver of cv::Mat / cv::KeyPoint they use.  They let
+// sqrtbaOptimizer.cc compile and be tested in an image without OpenCV / PCL / ROS.  In the reference tree the adapter
+// includes the real headers instead -- same names, same signatures.
+#pragma once
+#include <algorithm>
+#include <cstddef>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#define CV_32F 5
+namespace cv {
+struct Point2f { float x = 0, y = 0; };
+struct KeyPoint { Point2f pt; int octave = 0; };
+class Mat {  // row-major float matrix, value semantics like a cloned cv::Mat
+ public:
+  Mat() {}
+  Mat(int r, int c, int /*type*/) { create(r, c, CV_32F); }
+  void create(int r, int c, int /*type*/) { rows = r; cols = c; d_.assign((size_t)r * c, 0.f); }
+  template <class T> T& at(int i, int j) { return d_[(size_t)i * cols + j]; }
+  template <class T> const T& at(int i, int j) const { return d_[(size_t)i * cols + j]; }
+  template <class T> T& at(int i) { return d_[(size_t)i]; }
+  template <class T> const T& at(int i) const { return d_[(size_t)i]; }
+  Mat clone() const { return *this; }
+  void copyTo(Mat& o) const { o = *this; }
+  bool empty() const { return d_.empty(); }
+  int rows = 0, cols = 0;
+ private:
+  std::vector<float> d_;
+};
+}  // namespace cv
+
+struct lidarConfig {  // include/utils/lidarconfig.h -- passed through LocalBundleAdjustment, unused by the visual passes
+  bool using_flat_point = false, using_sharp_point = false;
+  double distance_sq_threshold = 0, flat_optimized_weight = 0, corner_optimized_weight = 0;
+};
+
+namespace ORB_SLAM2 {
+class MapPoint;
+class Map;
+
+class KeyFrame {
+ public:
+  long unsigned int mnId = 0;
+  long unsigned int mnBALocalForKF = ~0ul, mnBAFixedForKF = ~0ul, mnBAGlobalForKF = 0;
+  cv::Mat mTcwGBA;
+  float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0;
+  std::vector<cv::KeyPoint> mvKeysUn;
+  std::vector<float> mvuRight;
+  std::vector<float> mvInvLevelSigma2;
+
+  cv::Mat GetPose() { std::unique_lock<std::mutex> l(mMutexPose); return Tcw.clone(); }
+  void SetPose(const cv::Mat& T) { std::unique_lock<std::mutex> l(mMutexPose); T.copyTo(Tcw); }
+  bool isBad() { return mbBad; }
+  std::vector<KeyFrame*> GetVectorCovisibleKeyFrames() { return mvpOrderedConnectedKeyFrames; }
+  std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+  void EraseMapPointMatch(MapPoint* pMP) {
+    for (auto& p : mvpMapPoints)
+      if (p == pMP) p = nullptr;
+  }
+  // test-side construction
+  cv::Mat Tcw;
+  bool mbBad = false;
+  std::vector<KeyFrame*> mvpOrderedConnectedKeyFrames;
+  std::vector<MapPoint*> mvpMapPoints;  // indexed by keypoint
+  std::mutex mMutexPose;
+};
+
+class MapPoint {
+ public:
+  long unsigned int mnId = 0;
+  long unsigned int mnBALocalForKF = ~0ul, mnBAGlobalForKF = 0;
+  cv::Mat mPosGBA;
+  int nUpdateNormalAndDepth = 0;
+
+  cv::Mat GetWorldPos() { std::unique_lock<std::mutex> l(mMutexPos); return mWorldPos.clone(); }
+  void SetWorldPos(const cv::Mat& P) { std::unique_lock<std::mutex> l(mMutexPos); P.copyTo(mWorldPos); }
+  std::map<KeyFrame*, size_t> GetObservations() { std::unique_lock<std::mutex> l(mMutexFeatures); return mObservations; }
+  void EraseObservation(KeyFrame* pKF) { std::unique_lock<std::mutex> l(mMutexFeatures); mObservations.erase(pKF); }
+  bool isBad() { return mbBad; }
+  void UpdateNormalAndDepth() { nUpdateNormalAndDepth++; }  // MapPoint.cc:531-575 is outside the BA path
+  cv::Mat mWorldPos;
+  bool mbBad = false;
+  std::map<KeyFrame*, size_t> mObservations;
+  std::mutex mMutexPos, mMutexFeatures;
+};
+
+class Map {
+ public:
+  std::vector<KeyFrame*> GetAllKeyFrames() { return mspKeyFrames; }
+  std::vector<MapPoint*> GetAllMapPoints() { return mspMapPoints; }
+  std::mutex mMutexMapUpdate;
+  std::vector<KeyFrame*> mspKeyFrames;
+  std::vector<MapPoint*> mspMapPoints;
+};
+}  // namespace ORB_SLAM2

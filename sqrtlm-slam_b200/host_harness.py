@@ -1,0 +1,106 @@
+"""ctypes wrapper of host/harness.cc: drives the C++ adapter (reference Optimizer API) from Python tests."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import build, synth
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build.build_host())
+        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        L.hh_build.restype = C.c_void_p
+        L.hh_build.argtypes = [C.c_int, fp, fp, fp, C.c_int, C.c_int, fp, C.c_int, ip, ip, fp, ip]
+        L.hh_destroy.argtypes = [C.c_void_p]
+        L.hh_set_covisible.argtypes = [C.c_void_p, C.c_int, ip, C.c_int]
+        L.hh_set_bad.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hh_local_ba.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.hh_global_ba.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_ulong, C.c_void_p]
+        L.hh_get_pose.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
+        L.hh_get_point.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
+        L.hh_has_observation.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hh_keyframe_sees.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hh_point_updates.argtypes = [C.c_void_p, C.c_int]
+        L.hh_gba_marker.restype = C.c_ulong
+        L.hh_gba_marker.argtypes = [C.c_void_p, C.c_int]
+        L.hh_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class MockMap:
+    """A map of header-compatible KeyFrame/MapPoint objects built from a synthetic Problem (keyframe i has mnId i)."""
+
+    def __init__(self, prob):
+        self.prob = prob
+        R = synth.quat_to_rotmat(prob.pose_qt[:, 3:])
+        T = np.tile(np.eye(4, dtype=np.float32), (prob.n_pose, 1, 1))
+        T[:, :3, :3] = R.astype(np.float32)
+        T[:, :3, 3] = prob.pose_qt[:, :3].astype(np.float32)
+        inv = synth.inv_level_sigma2()
+        octave = np.array([int(np.argmin(np.abs(inv - s))) for s in prob.obs_meas[:, 3]], np.int32)
+        assert np.all(inv[octave] == prob.obs_meas[:, 3])
+        self._keep = [np.ascontiguousarray(T), np.ascontiguousarray(prob.cam[0], np.float32), inv,
+                      np.ascontiguousarray(prob.point_xyz, np.float32), np.ascontiguousarray(prob.obs_pose, np.int32),
+                      np.ascontiguousarray(prob.obs_point, np.int32), np.ascontiguousarray(prob.obs_meas[:, :3], np.float32),
+                      octave]
+        k = self._keep
+        self.h = lib().hh_build(prob.n_pose, _f(k[0]), _f(k[1]), _f(k[2]), len(inv), prob.n_point, _f(k[3]), prob.n_obs,
+                                _i(k[4]), _i(k[5]), _f(k[6]), _i(k[7]))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().hh_destroy(self.h)
+            self.h = None
+
+    def set_covisible(self, kf, others):
+        a = np.ascontiguousarray(others, np.int32)
+        lib().hh_set_covisible(self.h, kf, _i(a), len(a))
+
+    def set_bad(self, kf=-1, mp=-1):
+        lib().hh_set_bad(self.h, kf, mp)
+
+    def local_ba(self, kf, stop=None):
+        lib().hh_local_ba(self.h, kf, stop)
+
+    def global_ba(self, iters, robust, n_loop_kf=0, stop=None):
+        lib().hh_global_ba(self.h, iters, int(robust), n_loop_kf, stop)
+
+    def pose(self, kf, gba=False):
+        out = np.zeros(16, np.float32)
+        lib().hh_get_pose(self.h, kf, int(gba), _f(out))
+        return out.reshape(4, 4)
+
+    def point(self, mp, gba=False):
+        out = np.zeros(3, np.float32)
+        lib().hh_get_point(self.h, mp, int(gba), _f(out))
+        return out
+
+    def has_observation(self, kf, mp):
+        return bool(lib().hh_has_observation(self.h, kf, mp))
+
+    def keyframe_sees(self, kf, mp):
+        return bool(lib().hh_keyframe_sees(self.h, kf, mp))
+
+    def point_updates(self, mp):
+        return lib().hh_point_updates(self.h, mp)
+
+    def gba_marker(self, kf):
+        return lib().hh_gba_marker(self.h, kf)
+
+    def last_error(self):
+        return lib().hh_last_error().decode()

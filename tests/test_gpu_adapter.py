@@ -1,0 +1,109 @@
+"""The C++ adapter (sqrtlm-slam_b200/host/sqrtbaOptimizer.cc) that keeps the reference's
+Optimizer::LocalBundleAdjustment / GlobalBundleAdjustemnt signatures (include/backend/Optimizer.h:50-56), driven the
+way LocalMapping / LoopClosing drive it, against the oracle on the same map.  Map state is float32 (cv::Mat CV_32F in
+the reference), so poses/points are compared after the same rounding."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import refba
+
+pytestmark = pytest.mark.gpu
+
+
+def f32_pose_matrix(pose7, synth):
+    R = synth.quat_to_rotmat(pose7[3:])
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = R.astype(np.float32)
+    T[:3, 3] = pose7[:3].astype(np.float32)
+    return T
+
+
+def test_local_ba_through_reference_api(pkg, synth):
+    prob = synth.make_problem(31, 14, 5, 900, 6.0, stereo=True, name="adapter-lba")
+    m = pkg.host_harness.MockMap(prob)
+    cur = prob.n_pose - 1
+    free = np.nonzero(prob.pose_fixed == 0)[0]
+    m.set_covisible(cur, [i for i in free if i != cur])      # local window = current KF + covisibles
+    m.local_ba(cur)
+    assert m.last_error() == ""
+    ref = refba.RefBA(prob)
+    ref.solve_local(0)
+    P, X, F = ref.poses(), ref.points(), ref.outliers()
+    for i in range(prob.n_pose):
+        want = f32_pose_matrix(P[i], synth) if prob.pose_fixed[i] == 0 else f32_pose_matrix(prob.pose_qt[i], synth)
+        np.testing.assert_allclose(m.pose(i), want, rtol=0, atol=2e-5)
+    for j in range(prob.n_point):
+        np.testing.assert_allclose(m.point(j), X[j].astype(np.float32), rtol=2e-6, atol=2e-5)
+        assert m.point_updates(j) == 1                         # UpdateNormalAndDepth once per local point
+    # outlier observations are erased both ways (g2oOptimizer.cc:1149-1161), inliers kept
+    for k in range(prob.n_obs):
+        kf, mp = int(prob.obs_pose[k]), int(prob.obs_point[k])
+        assert m.has_observation(kf, mp) == (F[k] == 0)
+        assert m.keyframe_sees(kf, mp) == (F[k] == 0)
+    assert 0 < F.sum() < prob.n_obs
+
+
+def test_local_ba_stop_flag_raised_leaves_map_untouched(pkg, synth):
+    prob = synth.small_window(4)
+    m = pkg.host_harness.MockMap(prob)
+    cur = prob.n_pose - 1
+    m.set_covisible(cur, [i for i in np.nonzero(prob.pose_fixed == 0)[0] if i != cur])
+    before = [m.pose(i).copy() for i in range(prob.n_pose)]
+    flag = ctypes.c_bool(True)
+    m.local_ba(cur, ctypes.byref(flag))
+    for i in range(prob.n_pose):
+        np.testing.assert_array_equal(m.pose(i), before[i])
+    assert all(m.point_updates(j) == 0 for j in range(prob.n_point))
+
+
+def test_local_ba_skips_bad_keyframes_and_points(pkg, synth):
+    prob = synth.small_window(6, n_free=6, n_fixed=3, n_points=200)
+    m = pkg.host_harness.MockMap(prob)
+    cur = prob.n_pose - 1
+    m.set_covisible(cur, [i for i in np.nonzero(prob.pose_fixed == 0)[0] if i != cur])
+    bad_kf, bad_mp = int(np.nonzero(prob.pose_fixed == 0)[0][0]), 5
+    m.set_bad(kf=bad_kf, mp=bad_mp)
+    p_before, x_before = m.pose(bad_kf).copy(), m.point(bad_mp).copy()
+    m.local_ba(cur)
+    np.testing.assert_array_equal(m.pose(bad_kf), p_before)   # bad KF is neither optimised nor written
+    np.testing.assert_array_equal(m.point(bad_mp), x_before)
+    assert m.point_updates(bad_mp) == 0
+    # reference: the same problem without the bad keyframe's observations and the bad point
+    keep = (prob.obs_pose != bad_kf) & (prob.obs_point != bad_mp)
+    q = prob.copy()
+    q.obs_pose, q.obs_point, q.obs_meas = prob.obs_pose[keep], prob.obs_point[keep], prob.obs_meas[keep]
+    used = np.unique(q.obs_point)
+    remap = -np.ones(prob.n_point, int)
+    remap[used] = np.arange(len(used))
+    q.obs_point = remap[q.obs_point].astype(np.int32)
+    q.point_xyz = prob.point_xyz[used]
+    q.pose_fixed = prob.pose_fixed.copy()
+    q.pose_fixed[bad_kf] = 1
+    ref = refba.RefBA(q)
+    ref.solve_local(0)
+    P = ref.poses()
+    for i in np.nonzero(prob.pose_fixed == 0)[0]:
+        if i != bad_kf:
+            np.testing.assert_allclose(m.pose(int(i)), f32_pose_matrix(P[i], synth), rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("n_loop_kf", [0, 7])
+def test_global_ba_through_reference_api(pkg, synth, n_loop_kf):
+    prob = synth.make_problem(17, 40, 1, 2000, 7.0, stereo=True, loop=True, cand_halfwidth=10, name="adapter-gba")
+    m = pkg.host_harness.MockMap(prob)
+    before = m.pose(3).copy()
+    m.global_ba(10, False, n_loop_kf)
+    ref = refba.RefBA(prob)
+    ref.solve_global(10, False)
+    P, X = ref.poses(), ref.points()
+    gba = n_loop_kf != 0
+    for i in range(prob.n_pose):
+        np.testing.assert_allclose(m.pose(i, gba=gba), f32_pose_matrix(P[i], synth), rtol=0, atol=2e-5)
+        if gba:   # staged result: mTcwGBA + marker, live pose untouched (g2oOptimizer.cc:324-329)
+            assert m.gba_marker(i) == n_loop_kf
+    if gba:
+        np.testing.assert_array_equal(m.pose(3), before)
+    for j in range(0, prob.n_point, 50):
+        np.testing.assert_allclose(m.point(j, gba=gba), X[j].astype(np.float32), rtol=2e-6, atol=2e-5)
