@@ -10,7 +10,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -52,7 +54,46 @@ struct DBuf {  // device buffer that only grows
   }
 };
 
+template <class T>
+struct HBuf {  // pinned host staging buffer that only grows (fast H2D, reused across set_problem calls)
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    if (cudaMallocHost((void**)&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return 1;
+    cap = n;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// run fn(k0,k1) over [0,n) in chunks on up to n_thr threads
+template <class F>
+static void parallel_chunks(long long n, long long chunk, int n_thr, F fn) {
+  const long long n_chunk = (n + chunk - 1) / chunk;
+  if (n_thr <= 1 || n_chunk <= 1) { fn(0, n); return; }
+  std::atomic<long long> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      const long long c = next.fetch_add(1);
+      if (c >= n_chunk) break;
+      fn(c * chunk, std::min(n, (c + 1) * chunk));
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < std::min<long long>(n_thr, n_chunk); t++) pool.emplace_back(worker);
+  worker();
+  for (auto& th : pool) th.join();
+}
 
 class Solver {
  public:
@@ -138,128 +179,203 @@ class Solver {
       }
     for (int w = 0; w < n_win; w++) win_slot_ptr[w + 1] += win_slot_ptr[w];
     const int n_slot = (int)slot_pose.size();
-    // observations: validate, per-landmark counts
-    std::vector<int> obs_slot(n_obs), lm_cnt(n_point, 0);
-    for (int k = 0; k < n_obs; k++) {
-      const int ip = obs_pose[k], il = obs_point[k];
-      if (ip < 0 || ip >= n_pose || il < 0 || il >= n_point) {
-        err_ = "set_problem: observation index out of range";
-        return SQRTBA_ERR_INVALID;
-      }
-      if (k && il < obs_point[k - 1]) {
-        err_ = "set_problem: observations must be grouped by landmark (non-decreasing obs_point)";
-        return SQRTBA_ERR_INVALID;
-      }
-      if (pose_win[ip] != point_win[il]) {
-        err_ = "set_problem_batch: observation links a pose and a point of different windows";
-        return SQRTBA_ERR_INVALID;
-      }
-      obs_slot[k] = pose_slot[ip];
-      lm_cnt[il]++;
-    }
-    // items: whole landmarks packed into <=32 observations, never across windows; long landmarks alone
-    std::vector<int> item_start, item_cnt, item_win, win_item_ptr(n_win + 1, 0);
-    {
-      int o = 0, cur_start = 0, cur_cnt = 0, cur_win = -1;
-      auto flush = [&]() {
-        if (cur_cnt > 0) {
-          item_start.push_back(cur_start);
-          item_cnt.push_back(cur_cnt);
-          item_win.push_back(cur_win);
-          win_item_ptr[cur_win + 1]++;
-        }
-        cur_cnt = 0;
-      };
-      for (int l = 0; l < n_point; l++) {
-        const int k = lm_cnt[l];
-        if (k == 0) continue;
-        const int w = point_win[l];
-        if (k > 32) {
-          flush();
-          item_start.push_back(o);
-          item_cnt.push_back(k);
-          item_win.push_back(w);
-          win_item_ptr[w + 1]++;
-        } else {
-          if (cur_cnt > 0 && (cur_cnt + k > 32 || w != cur_win)) flush();
-          if (cur_cnt == 0) { cur_start = o; cur_win = w; }
-          cur_cnt += k;
-        }
-        o += k;
-      }
-      flush();
-    }
-    for (int w = 0; w < n_win; w++) win_item_ptr[w + 1] += win_item_ptr[w];
-    const int n_item = (int)item_start.size();
-    // tiles: up to WARPS consecutive short items of one window (a long item is a tile of its own); per observation the
-    // rank in the tile's pose-sorted order (for the in-CTA reduction of pose-side sums, see tile_scatter) and, when every
-    // window is small, its window-relative slot (the persistent matvec keeps p and q of the window in shared memory)
+    // ---- observation pre-processing (multi-threaded; all outputs land in pinned staging buffers)
+    const int ld = ((n_obs + 31) / 32) * 32;
     int max_win_slots = 0;
     for (int w = 0; w < n_win; w++) max_win_slots = std::max(max_win_slots, win_slot_ptr[w + 1] - win_slot_ptr[w]);
     const int smallwin = (max_win_slots <= MAXSLOT) ? 1 : 0;
-    std::vector<TileInfo> tiles;
-    std::vector<int> tile_run_ptr(1, 0), tile_runs;
-    long long jq_total = 0;
-    std::vector<unsigned> obs_lp(n_obs, 0xffffu);
+    if (h_obs_slot_.ensure(n_obs) || h_obs_lp_.ensure(n_obs)) { err_ = "pinned host allocation failed"; return SQRTBA_ERR_ALLOC; }
+    int* obs_slot = h_obs_slot_.p;
+    unsigned* obs_lp = h_obs_lp_.p;
+    const int n_thr = std::max(1, std::min<int>(cfg_.reserved[3] > 0 ? cfg_.reserved[3] : (int)std::thread::hardware_concurrency(), 64));
+    // A. validate, free slot per observation, first observation of every landmark
+    std::vector<int> lm_first(n_point, -1), lm_cnt(n_point, 0);
     {
-      std::vector<int> stamp(std::max(n_slot, 1), -1), local_of(std::max(n_slot, 1), 0), distinct, lptr, cursor;
-      tiles.reserve(n_item / WARPS + n_win + 1);
-      int it = 0;
-      while (it < n_item) {
-        TileInfo ti{};
-        ti.item0 = it;
-        ti.win = item_win[it];
-        ti.o0 = item_start[it];
-        if (item_cnt[it] > 32) {
-          ti.nitem = 1;
-        } else {
-          int n = 0;
-          while (it + n < n_item && n < WARPS && item_cnt[it + n] <= 32 && item_win[it + n] == ti.win) n++;
-          ti.nitem = n;
+      std::atomic<int> bad(0);
+      parallel_chunks(n_obs, 1 << 16, n_thr, [&](long long k0, long long k1) {
+        for (long long k = k0; k < k1; k++) {
+          const int ip = obs_pose[k], il = obs_point[k];
+          if (ip < 0 || ip >= n_pose || il < 0 || il >= n_point) { bad.store(1); return; }
+          if (k && il < obs_point[k - 1]) { bad.store(2); return; }
+          if (pose_win[ip] != point_win[il]) { bad.store(3); return; }
+          obs_slot[k] = pose_slot[ip];
+          obs_lp[k] = 0xffffu;
+          if (k == 0 || il != obs_point[k - 1]) lm_first[il] = (int)k;
         }
-        const int last = it + ti.nitem - 1;
-        ti.o1 = item_start[last] + item_cnt[last];
-        const int t = (int)tiles.size();
-        if (item_cnt[it] <= 32) {
-          distinct.clear();
-          for (int o = ti.o0; o < ti.o1; o++) {
-            const int sl = obs_slot[o];
-            if (sl >= 0 && stamp[sl] != t) { stamp[sl] = t; distinct.push_back(sl); }
+      });
+      if (bad.load()) {
+        err_ = bad.load() == 1 ? "set_problem: observation index out of range"
+             : bad.load() == 2 ? "set_problem: observations must be grouped by landmark (non-decreasing obs_point)"
+                               : "set_problem_batch: observation links a pose and a point of different windows";
+        return SQRTBA_ERR_INVALID;
+      }
+      int next = n_obs;
+      for (int l = n_point - 1; l >= 0; l--)
+        if (lm_first[l] >= 0) { lm_cnt[l] = next - lm_first[l]; next = lm_first[l]; }
+    }
+    // B. work chunks: landmark ranges inside one window of roughly equal observation count.  Items and tiles never
+    //    span chunks (a chunk boundary merely ends an item early), so chunks are processed independently.
+    struct Chunk { int win, l0, l1; std::vector<int> it_start, it_cnt, run_ptr, runs; std::vector<TileInfo> tiles; long long jq = 0; };
+    std::vector<Chunk> chunks;
+    {
+      const long long target = std::max<long long>(1 << 15, (long long)n_obs / (8LL * n_thr));
+      for (int w = 0; w < n_win; w++) {
+        const int p0 = (n_win > 1) ? (int)wpoint[w] : 0, p1 = (n_win > 1) ? (int)wpoint[w + 1] : n_point;
+        int l0 = p0;
+        long long acc = 0;
+        for (int l = p0; l < p1; l++) {
+          acc += lm_cnt[l];
+          if (acc >= target || l == p1 - 1) {
+            Chunk c; c.win = w; c.l0 = l0; c.l1 = l + 1;
+            chunks.push_back(std::move(c));
+            l0 = l + 1; acc = 0;
           }
-          std::sort(distinct.begin(), distinct.end());
-          const int nl = (int)distinct.size();
-          for (int i = 0; i < nl; i++) local_of[distinct[i]] = i;
-          lptr.assign(nl + 1, 0);
-          for (int o = ti.o0; o < ti.o1; o++)
-            if (obs_slot[o] >= 0) lptr[local_of[obs_slot[o]] + 1]++;
-          for (int i = 0; i < nl; i++) lptr[i + 1] += lptr[i];
-          cursor.assign(lptr.begin(), lptr.end());
-          const int ws0 = win_slot_ptr[ti.win];
-          for (int o = ti.o0; o < ti.o1; o++) {
-            if (obs_slot[o] < 0) continue;
-            const int rank = cursor[local_of[obs_slot[o]]]++;
-            const unsigned low = smallwin ? (unsigned)(obs_slot[o] - ws0) : 0u;
-            obs_lp[o] = low | ((unsigned)rank << 16);
-          }
-          ti.nfree = lptr[nl];
-          ti.nrun = nl;
-          // run table: nl+1 rank offsets, then the nl slots (window-relative when every window is small)
-          tile_runs.insert(tile_runs.end(), lptr.begin(), lptr.end());
-          for (int i = 0; i < nl; i++) tile_runs.push_back(smallwin ? distinct[i] - ws0 : distinct[i]);
         }
-        tile_run_ptr.push_back((int)tile_runs.size());
-        ti.nt = ((ti.o1 - ti.o0) + 1) & ~1;
-        ti.is_long = item_cnt[it] > 32 ? 1 : 0;
-        ti.jq_off = jq_total + JQ_HDR;
-        const int run_ints = ti.is_long ? 0 : 2 * ti.nrun + 1;
-        ti.blk_doubles = JQ_HDR + JQ_ROWS * ti.nt + 2 * ((run_ints + 3) / 4);
-        jq_total += ti.blk_doubles;
-        tiles.push_back(ti);
-        it += ti.nitem;
       }
     }
-    const int n_tile = (int)tiles.size();
-    const int ld = ((n_obs + 31) / 32) * 32;
+    // C. per chunk: pack whole landmarks into items of <= 32 observations, items into tiles of <= WARPS items, and per
+    //    tile the pose-sorted ranks + run table (see tile_scatter / k_matvec_pipe)
+    {
+      std::atomic<int> next_chunk(0);
+      auto worker = [&]() {
+        std::vector<int> stamp(std::max(max_win_slots, 1), -1), local_of(std::max(max_win_slots, 1), 0), distinct, lptr, cursor;
+        for (;;) {
+          const int ci = next_chunk.fetch_add(1);
+          if (ci >= (int)chunks.size()) break;
+          Chunk& c = chunks[ci];
+          const int ws0 = win_slot_ptr[c.win];
+          std::fill(stamp.begin(), stamp.end(), -1);
+          int cur_start = 0, cur_cnt = 0;
+          auto flush = [&]() {
+            if (cur_cnt > 0) { c.it_start.push_back(cur_start); c.it_cnt.push_back(cur_cnt); }
+            cur_cnt = 0;
+          };
+          for (int l = c.l0; l < c.l1; l++) {
+            const int k = lm_cnt[l];
+            if (k == 0) continue;
+            if (k > 32) {
+              flush();
+              c.it_start.push_back(lm_first[l]);
+              c.it_cnt.push_back(k);
+            } else {
+              if (cur_cnt > 0 && cur_cnt + k > 32) flush();
+              if (cur_cnt == 0) cur_start = lm_first[l];
+              cur_cnt += k;
+            }
+          }
+          flush();
+          const int ni = (int)c.it_start.size();
+          c.run_ptr.push_back(0);
+          int it = 0;
+          while (it < ni) {
+            TileInfo ti{};
+            ti.item0 = it;  // chunk-local, rebased in the merge
+            ti.win = c.win;
+            ti.o0 = c.it_start[it];
+            ti.is_long = c.it_cnt[it] > 32 ? 1 : 0;
+            if (ti.is_long) {
+              ti.nitem = 1;
+            } else {
+              int n = 0;
+              while (it + n < ni && n < WARPS && c.it_cnt[it + n] <= 32) n++;
+              ti.nitem = n;
+            }
+            const int last = it + ti.nitem - 1;
+            ti.o1 = c.it_start[last] + c.it_cnt[last];
+            const int t = (int)c.tiles.size();
+            if (!ti.is_long) {
+              distinct.clear();
+              for (int o = ti.o0; o < ti.o1; o++) {
+                const int sl = obs_slot[o] - ws0;
+                if (obs_slot[o] >= 0 && stamp[sl] != t) { stamp[sl] = t; distinct.push_back(sl); }
+              }
+              std::sort(distinct.begin(), distinct.end());
+              const int nl = (int)distinct.size();
+              for (int i = 0; i < nl; i++) local_of[distinct[i]] = i;
+              lptr.assign(nl + 1, 0);
+              for (int o = ti.o0; o < ti.o1; o++)
+                if (obs_slot[o] >= 0) lptr[local_of[obs_slot[o] - ws0] + 1]++;
+              for (int i = 0; i < nl; i++) lptr[i + 1] += lptr[i];
+              cursor.assign(lptr.begin(), lptr.end());
+              for (int o = ti.o0; o < ti.o1; o++) {
+                if (obs_slot[o] < 0) continue;
+                const int rank = cursor[local_of[obs_slot[o] - ws0]]++;
+                const unsigned low = smallwin ? (unsigned)(obs_slot[o] - ws0) : 0u;
+                obs_lp[o] = low | ((unsigned)rank << 16);
+              }
+              ti.nfree = lptr[nl];
+              ti.nrun = nl;
+              // run table: nl+1 rank offsets, then the nl slots (window-relative when every window is small)
+              c.runs.insert(c.runs.end(), lptr.begin(), lptr.end());
+              for (int i = 0; i < nl; i++) c.runs.push_back(smallwin ? distinct[i] : distinct[i] + ws0);
+            }
+            c.run_ptr.push_back((int)c.runs.size());
+            ti.nt = ((ti.o1 - ti.o0) + 1) & ~1;
+            const int run_ints = ti.is_long ? 0 : 2 * ti.nrun + 1;
+            ti.blk_doubles = JQ_HDR + JQ_ROWS * ti.nt + 2 * ((run_ints + 3) / 4);
+            ti.jq_off = c.jq + JQ_HDR;  // chunk-local, rebased in the merge
+            c.jq += ti.blk_doubles;
+            c.tiles.push_back(ti);
+            it += ti.nitem;
+          }
+        }
+      };
+      std::vector<std::thread> pool;
+      for (int t = 1; t < n_thr; t++) pool.emplace_back(worker);
+      worker();
+      for (auto& th : pool) th.join();
+    }
+    // D. merge the chunks (offsets are prefix sums over chunks in order)
+    std::vector<long long> item_off(chunks.size() + 1, 0), tile_off(chunks.size() + 1, 0), run_off(chunks.size() + 1, 0),
+        jq_off(chunks.size() + 1, 0);
+    std::vector<int> win_item_ptr(n_win + 1, 0);
+    for (size_t c = 0; c < chunks.size(); c++) {
+      item_off[c + 1] = item_off[c] + (long long)chunks[c].it_start.size();
+      tile_off[c + 1] = tile_off[c] + (long long)chunks[c].tiles.size();
+      run_off[c + 1] = run_off[c] + (long long)chunks[c].runs.size();
+      jq_off[c + 1] = jq_off[c] + chunks[c].jq;
+      win_item_ptr[chunks[c].win + 1] += (int)chunks[c].it_start.size();
+    }
+    for (int w = 0; w < n_win; w++) win_item_ptr[w + 1] += win_item_ptr[w];
+    const int n_item = (int)item_off.back(), n_tile = (int)tile_off.back();
+    const long long jq_total = jq_off.back();
+    const size_t n_runs = (size_t)run_off.back();
+    if (h_item_start_.ensure(n_item) || h_item_cnt_.ensure(n_item) || h_item_win_.ensure(n_item) || h_tiles_pin_.ensure(n_tile) ||
+        h_tile_run_ptr_.ensure(n_tile + 1) || h_tile_runs_.ensure(n_runs)) {
+      err_ = "pinned host allocation failed";
+      return SQRTBA_ERR_ALLOC;
+    }
+    {
+      std::atomic<int> next_chunk(0);
+      auto worker = [&]() {
+        for (;;) {
+          const int ci = next_chunk.fetch_add(1);
+          if (ci >= (int)chunks.size()) break;
+          const Chunk& c = chunks[ci];
+          const long long io = item_off[ci], to = tile_off[ci], ro = run_off[ci];
+          for (size_t i = 0; i < c.it_start.size(); i++) {
+            h_item_start_.p[io + i] = c.it_start[i];
+            h_item_cnt_.p[io + i] = c.it_cnt[i];
+            h_item_win_.p[io + i] = c.win;
+          }
+          for (size_t t = 0; t < c.tiles.size(); t++) {
+            TileInfo ti = c.tiles[t];
+            ti.item0 += (int)io;
+            ti.jq_off += jq_off[ci];
+            h_tiles_pin_.p[to + t] = ti;
+            h_tile_run_ptr_.p[to + t] = (int)ro + c.run_ptr[t];
+          }
+          if (!c.runs.empty()) std::memcpy(h_tile_runs_.p + ro, c.runs.data(), c.runs.size() * sizeof(int));
+        }
+      };
+      std::vector<std::thread> pool;
+      for (int t = 1; t < n_thr; t++) pool.emplace_back(worker);
+      worker();
+      for (auto& th : pool) th.join();
+      h_tile_run_ptr_.p[n_tile] = (int)n_runs;
+    }
+    const int* item_start = h_item_start_.p;
+    (void)item_start;
     // ---- device allocation
     P_ = Dev{};
     P_.n_pose = n_pose; P_.n_point = n_point; P_.n_obs = n_obs; P_.n_win = n_win; P_.n_slot = n_slot; P_.n_item = n_item;
@@ -283,7 +399,7 @@ class Solver {
     CU_CHECK(d_tiles_.ensure(n_tile));
     CU_CHECK(d_obs_lp_.ensure(No));
     CU_CHECK(d_tile_run_ptr_.ensure(n_tile + 1));
-    CU_CHECK(d_tile_runs_.ensure(tile_runs.size()));
+    CU_CHECK(d_tile_runs_.ensure(n_runs));
     CU_CHECK(d_pose_.ensure((size_t)n_pose * 7));
     CU_CHECK(d_pose0_.ensure((size_t)n_pose * 7));
     CU_CHECK(d_pose_bak_.ensure((size_t)n_pose * 7));
@@ -320,16 +436,16 @@ class Solver {
     CU_CHECK(up(d_meas_.p, obs_meas, No * sizeof(float4)));
     CU_CHECK(up(d_obs_pose_.p, obs_pose, No * sizeof(int)));
     CU_CHECK(up(d_obs_point_.p, obs_point, No * sizeof(int)));
-    CU_CHECK(up(d_obs_slot_.p, obs_slot.data(), No * sizeof(int)));
-    CU_CHECK(up(d_item_start_.p, item_start.data(), n_item * sizeof(int)));
-    CU_CHECK(up(d_item_cnt_.p, item_cnt.data(), n_item * sizeof(int)));
-    CU_CHECK(up(d_item_win_.p, item_win.data(), n_item * sizeof(int)));
+    CU_CHECK(up(d_obs_slot_.p, h_obs_slot_.p, No * sizeof(int)));
+    CU_CHECK(up(d_item_start_.p, h_item_start_.p, n_item * sizeof(int)));
+    CU_CHECK(up(d_item_cnt_.p, h_item_cnt_.p, n_item * sizeof(int)));
+    CU_CHECK(up(d_item_win_.p, h_item_win_.p, n_item * sizeof(int)));
     CU_CHECK(up(d_win_item_ptr_.p, win_item_ptr.data(), (n_win + 1) * sizeof(int)));
     CU_CHECK(up(d_win_slot_ptr_.p, win_slot_ptr.data(), (n_win + 1) * sizeof(int)));
-    CU_CHECK(up(d_tiles_.p, tiles.data(), (size_t)n_tile * sizeof(TileInfo)));
-    CU_CHECK(up(d_tile_run_ptr_.p, tile_run_ptr.data(), (size_t)(n_tile + 1) * sizeof(int)));
-    if (!tile_runs.empty()) CU_CHECK(up(d_tile_runs_.p, tile_runs.data(), tile_runs.size() * sizeof(int)));
-    CU_CHECK(up(d_obs_lp_.p, obs_lp.data(), No * sizeof(unsigned)));
+    CU_CHECK(up(d_tiles_.p, h_tiles_pin_.p, (size_t)n_tile * sizeof(TileInfo)));
+    CU_CHECK(up(d_tile_run_ptr_.p, h_tile_run_ptr_.p, (size_t)(n_tile + 1) * sizeof(int)));
+    if (n_runs) CU_CHECK(up(d_tile_runs_.p, h_tile_runs_.p, n_runs * sizeof(int)));
+    CU_CHECK(up(d_obs_lp_.p, h_obs_lp_.p, No * sizeof(unsigned)));
     // poses: normalise the quaternion the way SE3Quat's constructor does (se3quat.h:58-64)
     std::vector<double> pq(pose_qt, pose_qt + (size_t)n_pose * 7);
     for (int i = 0; i < n_pose; i++) quat_normalize_pos_w(&pq[(size_t)i * 7 + 3]);
@@ -368,7 +484,7 @@ class Solver {
     CU_CHECK(cudaMemsetAsync(d_prof_.p, 0, d_prof_.cap * sizeof(long long), stream_));
     P_.prof = d_prof_.p;
 #endif
-    h_tiles_ = tiles;
+    h_tiles_.assign(h_tiles_pin_.p, h_tiles_pin_.p + n_tile);
     max_win_slots_ = std::max(max_win_slots, 1);
     // pad columns of the JQ blocks are streamed by the TMA copies: keep them defined; then headers + per-column meta
     CU_CHECK(cudaMemsetAsync(d_JQ_.p, 0, (size_t)jq_total * sizeof(double), stream_));
@@ -752,6 +868,8 @@ class Solver {
     d_bl_.release(); d_dl_.release(); d_slotvec_.release(); d_chi_part_.release(); d_scale_part_.release();
     d_ctl_.release(); d_trace_.release(); d_counters_.release();
     d_tiles_.release(); d_obs_lp_.release(); d_tile_run_ptr_.release(); d_tile_runs_.release();
+    h_obs_slot_.release(); h_item_start_.release(); h_item_cnt_.release(); h_item_win_.release();
+    h_tile_run_ptr_.release(); h_tile_runs_.release(); h_obs_lp_.release(); h_tiles_pin_.release();
   }
 
  public:
@@ -778,6 +896,9 @@ class Solver {
   DBuf<unsigned> d_obs_lp_;
   DBuf<TileInfo> d_tiles_;
   DBuf<long long> d_prof_;
+  HBuf<int> h_obs_slot_, h_item_start_, h_item_cnt_, h_item_win_, h_tile_run_ptr_, h_tile_runs_;
+  HBuf<unsigned> h_obs_lp_;
+  HBuf<TileInfo> h_tiles_pin_;
   std::vector<TileInfo> h_tiles_;
   DBuf<float4> d_meas_;
   DBuf<uint8_t> d_level_, d_outlier_;
