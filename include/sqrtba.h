@@ -115,6 +115,18 @@ int sqrtba_get_outliers(sqrtba_handle* h, uint8_t* flags_out);  /* n_obs, 1 = er
 int sqrtba_get_trace_len(sqrtba_handle* h, int32_t window);
 int sqrtba_get_trace(sqrtba_handle* h, int32_t window, sqrtba_trace_row* rows_out, int32_t max_rows);
 
+/* ---- multi-GPU: landmark-sharded bundle adjustment (global BA, BASELINE config 3) ---------------------------------
+ * One process (one handle) per GPU.  Every rank passes ALL poses (replicated, identical) and ITS OWN shard of the map
+ * points with all their observations to sqrtba_set_problem; the solve calls are collective.  Per CG iteration the
+ * ranks all-reduce the pose-sized matvec result (NCCL over NVLink); per LM trial a few pose-sized vectors and three
+ * scalars per window.  All ranks take identical LM decisions and end with identical poses; each holds its own points.
+ * sqrtba_comm_unique_id: rank 0 creates the NCCL id (128 bytes) and distributes it by any means (MPI, torch.distributed,
+ * a file); sqrtba_comm_init joins the communicator on the handle's device.  Without a communicator every handle is an
+ * independent single-GPU solver (batched windows shard by window with no collective at all). */
+int sqrtba_comm_unique_id(uint8_t* id128_out);
+int sqrtba_comm_init(sqrtba_handle* h, int32_t nranks, int32_t rank, const uint8_t* id128);
+int sqrtba_comm_destroy(sqrtba_handle* h);
+
 /* ---- stage-level entry points (kernel parity tests, profiling) --------------------------------------------
  * sqrtba_debug_linearize : run the fused residual+Jacobian+Huber kernel at the current state.
  *    huber: 0 none, 1 local-BA deltas, 2 global-BA deltas.  Outputs (any may be NULL):

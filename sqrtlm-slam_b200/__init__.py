@@ -9,3 +9,4 @@ from . import build  # noqa: F401
 from . import capi  # noqa: F401
 from .capi import SqrtBA, SqrtBAError  # noqa: F401
 from . import host_harness  # noqa: F401
+from . import multi  # noqa: F401

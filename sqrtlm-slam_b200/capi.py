@@ -62,6 +62,9 @@ def lib():
         L.sqrtba_debug_matvec.argtypes = [vp, dp, dp]
         L.sqrtba_num_free_poses.argtypes = [vp]
         L.sqrtba_time_stage.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, dp]
+        L.sqrtba_comm_unique_id.argtypes = [up]
+        L.sqrtba_comm_init.argtypes = [vp, C.c_int32, C.c_int32, up]
+        L.sqrtba_comm_destroy.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -197,6 +200,13 @@ class SqrtBA:
         y = np.zeros_like(p)
         self._chk(lib().sqrtba_debug_matvec(self.h, _p(p, C.c_double), _p(y, C.c_double)), "sqrtba_debug_matvec")
         return y
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._chk(lib().sqrtba_comm_init(self.h, nranks, rank, buf), "sqrtba_comm_init")
+
+    def comm_destroy(self):
+        self._chk(lib().sqrtba_comm_destroy(self.h), "sqrtba_comm_destroy")
 
     def time_stage(self, stage: int, warmup: int = 3, reps: int = 20) -> float:
         ms = C.c_double(0)

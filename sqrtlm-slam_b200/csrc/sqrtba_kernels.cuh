@@ -118,6 +118,9 @@ struct Dev {
   // ---- per item
   double* chi_part;    // n_item
   double* scale_part;  // n_item
+  // ---- per window partial sums that cross ranks in the landmark-sharded (multi-GPU) mode:
+  // wred[0*n_win + w] chi2, [1*n_win + w] landmark part of computeScale, [2*n_win + w] landmark-side max diagonal
+  double* wred;
   // ---- control
   WinCtl* ctl;      // n_win
   double* trace;    // n_win * max_trace * TRACE_COLS
@@ -432,24 +435,41 @@ __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2,
 // ------------------------------------------------------------------------------------------------ K8a: LM begin
 // OptimizationAlgorithmLevenberg::solve up to the trial loop (optimization_algorithm_levenberg.cpp:75-100):
 // currentChi, iniChi, lambda init = tau * max diag(H) at iteration 0 (computeLambdaInit :166-180).
+// Split in two so that, with landmarks sharded over several GPUs, the per-window partial sums (wred) and the pose-side
+// vectors can be all-reduced between the two kernels; with one GPU they simply run back to back.
+__global__ void __launch_bounds__(RCTA) k_lm_reduce_lin(Dev P) {
+  __shared__ double sh[RWARPS];
+  const int win = blockIdx.x;
+  WinCtl& c = P.ctl[win];
+  if (c.phase != PH_LIN) {  // nothing new from this window: contribute the neutral element
+    if (threadIdx.x == 0) { P.wred[win] = 0.0; P.wred[2 * P.n_win + win] = 0.0; }
+    return;
+  }
+  double chi = 0.0;
+  for (int i = P.win_item_ptr[win] + threadIdx.x; i < P.win_item_ptr[win + 1]; i += RCTA) chi += P.chi_part[i];
+  chi = block_sum(chi, sh);
+  if (threadIdx.x == 0) {
+    P.wred[win] = chi;
+    P.wred[2 * P.n_win + win] = __longlong_as_double((long long)c.maxdiag_bits);
+    c.maxdiag_bits = 0ull;
+  }
+}
+
 __global__ void __launch_bounds__(RCTA) k_lm_begin(Dev P) {
   __shared__ double sh[RWARPS];
   const int win = blockIdx.x;
   WinCtl& c = P.ctl[win];
   if (c.phase != PH_LIN) return;
-  double chi = 0.0, md = 0.0;
-  for (int i = P.win_item_ptr[win] + threadIdx.x; i < P.win_item_ptr[win + 1]; i += RCTA) chi += P.chi_part[i];
+  double md = 0.0;
   for (int i = P.win_slot_ptr[win] * 6 + threadIdx.x; i < P.win_slot_ptr[win + 1] * 6; i += RCTA)
     md = fmax(md, fabs(P.hd[i]));
-  chi = block_sum(chi, sh);
   md = warp_max(md);
-  __syncthreads();
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = md;
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 0; i < RWARPS; i++) md = fmax(md, sh[i]);
-    md = fmax(md, __longlong_as_double((long long)c.maxdiag_bits));
-    c.maxdiag_bits = 0ull;
+    md = fmax(md, P.wred[2 * P.n_win + win]);
+    const double chi = P.wred[win];
     c.cur_chi = chi;
     c.ini_chi = chi;
     c.tmp_chi = chi;
@@ -1295,6 +1315,23 @@ __global__ void __launch_bounds__(CTA) k_cost(Dev P, int robust, double d2, doub
 // ------------------------------------------------------------------------------------------------ K8b: LM decision
 // The body of the do-while of OptimizationAlgorithmLevenberg::solve and its exit logic
 // (optimization_algorithm_levenberg.cpp:126-163), one CTA per window.
+__global__ void __launch_bounds__(RCTA) k_lm_reduce_trial(Dev P) {
+  __shared__ double sh[RWARPS];
+  const int win = blockIdx.x;
+  if (P.ctl[win].phase != PH_TRIAL) {
+    if (threadIdx.x == 0) { P.wred[win] = 0.0; P.wred[P.n_win + win] = 0.0; }
+    return;
+  }
+  double chi = 0.0, scale = 0.0;
+  for (int i = P.win_item_ptr[win] + threadIdx.x; i < P.win_item_ptr[win + 1]; i += RCTA) {
+    chi += P.chi_part[i];
+    scale += P.scale_part[i];
+  }
+  chi = block_sum(chi, sh);
+  scale = block_sum(scale, sh);
+  if (threadIdx.x == 0) { P.wred[win] = chi; P.wred[P.n_win + win] = scale; }
+}
+
 __global__ void __launch_bounds__(RCTA) k_lm_decide(Dev P, int terminate) {
   __shared__ double sh[RWARPS];
   const int win = blockIdx.x;
@@ -1303,16 +1340,11 @@ __global__ void __launch_bounds__(RCTA) k_lm_decide(Dev P, int terminate) {
     if (threadIdx.x == 0) c.need_restore = 0;
     return;
   }
-  double chi = 0.0, scale = 0.0;
-  for (int i = P.win_item_ptr[win] + threadIdx.x; i < P.win_item_ptr[win + 1]; i += RCTA) {
-    chi += P.chi_part[i];
-    scale += P.scale_part[i];
-  }
+  double chi = P.wred[win], scale = 0.0;
   const double lam = c.lambda;
   for (int e = P.win_slot_ptr[win] * 6 + threadIdx.x; e < P.win_slot_ptr[win + 1] * 6; e += RCTA)
     scale += P.x[e] * (lam * P.x[e] + P.bp[e]);
-  chi = block_sum(chi, sh);
-  scale = block_sum(scale, sh);
+  scale = block_sum(scale, sh) + P.wred[P.n_win + win];
   if (threadIdx.x != 0) return;
   const double tempChi = chi;
   double rho = (c.cur_chi - tempChi);

@@ -8,6 +8,7 @@
 // The host only enqueues kernels, reads back two counters per macro step and polls the caller's stop flag
 // (bool* pbStopFlag, src/backend/g2oOptimizer.cc:797-798) -- it never touches problem data after upload.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -95,6 +96,34 @@ static void parallel_chunks(long long n, long long chunk, int n_thr, F fn) {
   for (auto& th : pool) th.join();
 }
 
+// NCCL is loaded at run time and only when a multi-GPU communicator is requested, so the single-GPU path has no
+// dependency on it.  (In a Python process that already imported torch, dlopen resolves to torch's bundled libnccl.)
+struct NcclApi {
+  struct UniqueId { char internal[128]; };
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  void* lib = nullptr;
+  bool load() {
+    if (lib) return true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) return false;
+    GetUniqueId = (int (*)(UniqueId*))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (int (*)(void**, int, UniqueId, int))dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { lib = nullptr; return false; }
+    return true;
+  }
+};
+static NcclApi g_nccl;
+
 class Solver {
  public:
   explicit Solver(const sqrtba_config& cfg) : cfg_(cfg) {}
@@ -128,6 +157,7 @@ class Solver {
       cudaSetDevice(cfg_.device);
       cudaStreamSynchronize(stream_);
     }
+    comm_destroy();
     release_all();
     if (h_counters_) cudaFreeHost(h_counters_);
     h_counters_ = nullptr;
@@ -420,6 +450,7 @@ class Solver {
     CU_CHECK(d_chi_part_.ensure(n_item));
     CU_CHECK(d_scale_part_.ensure(n_item));
     CU_CHECK(d_ctl_.ensure(n_win));
+    CU_CHECK(d_wred_.ensure((size_t)3 * n_win));
     max_trace_ = 200;
     CU_CHECK(d_trace_.ensure((size_t)n_win * max_trace_ * TRACE_COLS));
     CU_CHECK(d_counters_.ensure(4));
@@ -465,18 +496,18 @@ class Solver {
     P_.obs_level = d_level_.p; P_.obs_outlier = d_outlier_.p;
     P_.err = d_err_.p; P_.JQ = d_JQ_.p; P_.Jl = d_Jl_.p; P_.r = d_r_.p;
     P_.R = d_R_.p; P_.tl = d_tl_.p; P_.bl = d_bl_.p; P_.dl = d_dl_.p;
-    double* sv = d_slotvec_.p;
+    double* sv = d_slotvec_.p;  // [bp hd | bs D | x res z p q | Dinv]: the two groups that cross ranks are contiguous
     P_.bp = sv; sv += Ns * 6;
     P_.hd = sv; sv += Ns * 6;
     P_.bs = sv; sv += Ns * 6;
+    P_.D = sv; sv += Ns * 21;
     P_.x = sv; sv += Ns * 6;
     P_.res = sv; sv += Ns * 6;
     P_.z = sv; sv += Ns * 6;
     P_.p = sv; sv += Ns * 6;
     P_.q = sv; sv += Ns * 6;
-    P_.D = sv; sv += Ns * 21;
     P_.Dinv = sv;
-    P_.chi_part = d_chi_part_.p; P_.scale_part = d_scale_part_.p;
+    P_.chi_part = d_chi_part_.p; P_.scale_part = d_scale_part_.p; P_.wred = d_wred_.p;
     P_.ctl = d_ctl_.p; P_.trace = d_trace_.p; P_.max_trace = max_trace_; P_.counters = d_counters_.p;
     P_.prof = nullptr;
 #ifdef SQRTBA_PIPE_PROF
@@ -590,7 +621,7 @@ class Solver {
     k_pass_init<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_, 1, 0);
     if (P_.n_slot) k_zero_lin<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
     k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, huber != 0, d2, d3, 1);
-    k_lm_begin<<<P_.n_win, RCTA, 0, stream_>>>(P_);
+    if (int rc = begin_after_linearize()) return rc;
     CU_CHECK(cudaGetLastError());
     const size_t No = P_.n_obs, Ld = P_.ld;
     std::vector<double> tmp;
@@ -725,6 +756,52 @@ class Solver {
     launches_++;
   }
 
+  // second half of "linearise": cross-rank sums (landmark-sharded mode), then lambda init / currentChi per window
+  int begin_after_linearize() {
+    if (int rc = allreduce(P_.bp, (size_t)P_.n_slot * 12, false)) return rc;  // b_p and diag(Jp^T Jp)
+    k_lm_reduce_lin<<<P_.n_win, RCTA, 0, stream_>>>(P_);
+    if (int rc = allreduce(P_.wred, (size_t)P_.n_win, false)) return rc;                     // chi2: sum
+    if (int rc = allreduce(P_.wred + 2 * (size_t)P_.n_win, (size_t)P_.n_win, true)) return rc;  // landmark max diag: max
+    k_lm_begin<<<P_.n_win, RCTA, 0, stream_>>>(P_);
+    CU_CHECK(cudaGetLastError());
+    return SQRTBA_OK;
+  }
+
+  // in-place all-reduce over the ranks that share this problem (no-op for a single GPU)
+  int allreduce(double* buf, size_t count, bool is_max) {
+    if (!comm_ || count == 0) return SQRTBA_OK;
+    const int rc = g_nccl.AllReduce(buf, buf, count, /*ncclFloat64*/ 8, is_max ? /*ncclMax*/ 2 : /*ncclSum*/ 0, comm_, stream_);
+    if (rc != 0) {
+      err_ = std::string("ncclAllReduce failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+      return SQRTBA_ERR_COMM;
+    }
+    return SQRTBA_OK;
+  }
+
+ public:
+  int comm_init(int nranks, int rank, const uint8_t* id128) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id128) { err_ = "comm_init: bad arguments"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    if (!g_nccl.load()) { err_ = "comm_init: cannot load libnccl.so.2"; return SQRTBA_ERR_COMM; }
+    comm_destroy();
+    NcclApi::UniqueId id;
+    std::memcpy(id.internal, id128, 128);
+    const int rc = g_nccl.CommInitRank(&comm_, nranks, id, rank);
+    if (rc != 0) {
+      comm_ = nullptr;
+      err_ = std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+      return SQRTBA_ERR_COMM;
+    }
+    n_ranks_ = nranks;
+    return SQRTBA_OK;
+  }
+  void comm_destroy() {
+    if (comm_ && g_nccl.CommDestroy) g_nccl.CommDestroy(comm_);
+    comm_ = nullptr;
+    n_ranks_ = 1;
+  }
+
+ private:
   // matvec dispatch: persistent TMA-pipelined kernel when every window is small, general tile kernel otherwise
   static size_t pipe_smem_bytes(int S, int maxslot) {
     return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + 12 * (size_t)maxslot) * sizeof(double) +
@@ -752,6 +829,7 @@ class Solver {
     stage_end(1);
     launches_ += 2;
     if (!P_.n_slot) return SQRTBA_OK;
+    if (int rc = allreduce(P_.bs, (size_t)P_.n_slot * 27, false)) return rc;  // reduced rhs + block-Jacobi blocks
     k_dinv<<<cdiv(P_.n_slot, 64), 64, 0, stream_>>>(P_, 0, 0.0);
     stage_begin(2);
     CU_CHECK(cudaMemsetAsync(P_.counters + 1, 0, sizeof(int), stream_));
@@ -763,6 +841,7 @@ class Solver {
     for (int it = 0; it < cfg_.pcg_max_iters; it++) {
       CU_CHECK(cudaMemsetAsync(P_.q, 0, qbytes, stream_));
       launch_matvec(P_.p, P_.q, 0);
+      if (int rc = allreduce(P_.q, (size_t)P_.n_slot * 6, false)) return rc;  // the one exchange step of a CG iteration
       k_cg_step<<<P_.n_win, RCTA, 0, stream_>>>(P_, tol2, cfg_.pcg_max_iters, 0, 0.0);
       launches_ += 2;
       cg_iters_total_++;
@@ -792,8 +871,8 @@ class Solver {
       stage_begin(0);
       k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, robust, d2, d3, 0);
       stage_end(0);
-      k_lm_begin<<<P_.n_win, RCTA, 0, stream_>>>(P_);
-      launches_ += 3;
+      if (int rc = begin_after_linearize()) return rc;
+      launches_ += 4;
       int rc = factor_and_solve();
       if (rc) return rc;
       stage_begin(3);
@@ -806,9 +885,11 @@ class Solver {
       stage_begin(4);
       k_cost<<<gi, CTA, 0, stream_>>>(P_, robust, d2, d3);
       stage_end(4);
+      k_lm_reduce_trial<<<P_.n_win, RCTA, 0, stream_>>>(P_);
+      if (int rc = allreduce(P_.wred, (size_t)2 * P_.n_win, false)) return rc;  // trial chi2 + landmark part of the scale
       k_lm_decide<<<P_.n_win, RCTA, 0, stream_>>>(P_, term);
       k_restore<<<cdiv(std::max(P_.n_pose, P_.n_point), 256), 256, 0, stream_>>>(P_);
-      launches_ += 6;
+      launches_ += 7;
       lm_trials_++;
       CU_CHECK(cudaMemcpyAsync(h_counters_, P_.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
       CU_CHECK(cudaStreamSynchronize(stream_));
@@ -866,7 +947,7 @@ class Solver {
     d_point0_.release(); d_point_bak_.release(); d_level_.release(); d_outlier_.release(); d_err_.release();
     d_JQ_.release(); d_Jl_.release(); d_r_.release(); d_R_.release(); d_tl_.release();
     d_bl_.release(); d_dl_.release(); d_slotvec_.release(); d_chi_part_.release(); d_scale_part_.release();
-    d_ctl_.release(); d_trace_.release(); d_counters_.release();
+    d_ctl_.release(); d_trace_.release(); d_counters_.release(); d_wred_.release();
     d_tiles_.release(); d_obs_lp_.release(); d_tile_run_ptr_.release(); d_tile_runs_.release();
     h_obs_slot_.release(); h_item_start_.release(); h_item_cnt_.release(); h_item_win_.release();
     h_tile_run_ptr_.release(); h_tile_runs_.release(); h_obs_lp_.release(); h_tiles_pin_.release();
@@ -887,9 +968,11 @@ class Solver {
   int max_trace_ = 200;
   int launches_ = 0, lm_trials_ = 0, cg_iters_total_ = 0;
   int n_sm_ = 148, pipe_ctas_ = 296, pipe_stages_ = 3, max_win_slots_ = 1;
+  void* comm_ = nullptr;  // ncclComm_t
+  int n_ranks_ = 1;
   Dev P_{};
   DBuf<double> d_cam_, d_pose_, d_pose0_, d_pose_bak_, d_point_, d_point0_, d_point_bak_, d_err_, d_JQ_, d_Jl_,
-      d_r_, d_R_, d_tl_, d_bl_, d_dl_, d_slotvec_, d_chi_part_, d_scale_part_, d_trace_;
+      d_r_, d_R_, d_tl_, d_bl_, d_dl_, d_slotvec_, d_chi_part_, d_scale_part_, d_trace_, d_wred_;
   DBuf<int> d_pose_slot_, d_slot_pose_, d_slot_win_, d_pose_win_, d_point_win_, d_obs_pose_, d_obs_point_, d_obs_slot_,
       d_item_start_, d_item_cnt_, d_item_win_, d_win_item_ptr_, d_win_slot_ptr_, d_counters_, d_tile_run_ptr_,
       d_tile_runs_;
@@ -1010,6 +1093,22 @@ int sqrtba_debug_matvec(sqrtba_handle* h, const double* p, double* y) {
   return (h && p && y) ? h->s->debug_matvec(p, y) : SQRTBA_ERR_INVALID;
 }
 int sqrtba_num_free_poses(sqrtba_handle* h) { return h ? h->s->num_free() : SQRTBA_ERR_INVALID; }
+int sqrtba_comm_unique_id(uint8_t* id128) {
+  if (!id128) return SQRTBA_ERR_INVALID;
+  if (!sqrtba::g_nccl.load()) return SQRTBA_ERR_COMM;
+  sqrtba::NcclApi::UniqueId id;
+  if (sqrtba::g_nccl.GetUniqueId(&id) != 0) return SQRTBA_ERR_COMM;
+  std::memcpy(id128, id.internal, 128);
+  return SQRTBA_OK;
+}
+int sqrtba_comm_init(sqrtba_handle* h, int32_t nranks, int32_t rank, const uint8_t* id128) {
+  return h ? h->s->comm_init(nranks, rank, id128) : SQRTBA_ERR_INVALID;
+}
+int sqrtba_comm_destroy(sqrtba_handle* h) {
+  if (!h) return SQRTBA_ERR_INVALID;
+  h->s->comm_destroy();
+  return SQRTBA_OK;
+}
 int sqrtba_time_stage(sqrtba_handle* h, int32_t stage, int32_t warmup, int32_t reps, double* ms_avg) {
   return (h && ms_avg) ? h->s->time_stage(stage, warmup, reps, ms_avg) : SQRTBA_ERR_INVALID;
 }
