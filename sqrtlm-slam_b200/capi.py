@@ -80,9 +80,10 @@ class SqrtBAError(RuntimeError):
 class SqrtBA:
     """Thin owner of one sqrtba_handle.  Method names follow the C ABI."""
 
-    def __init__(self, device: int = 0, pcg_rtol: float = 1e-9, pcg_max_iters: int = 300, third_pass_iters: int = 0,
+    def __init__(self, device: int = 0, pcg_rtol: float = 1e-9, pcg_max_iters: int = 2000, third_pass_iters: int = 0,
                  pcg_mode: int = 0, pcg_check_every: int = 4, stage_timing: bool = False,
-                 general_matvec: bool = False, pipe_stages: int = 0):
+                 general_matvec: bool = False, pipe_stages: int = 0, host_threads: int = 0,
+                 no_reorder: bool = False, pipe_slots: int = 0):
         L = lib()
         cfg = Config()
         L.sqrtba_default_config(C.byref(cfg))
@@ -91,6 +92,9 @@ class SqrtBA:
         cfg.reserved[0] = 1 if stage_timing else 0
         cfg.reserved[1] = 1 if general_matvec else 0   # force the non-pipelined tile kernel (A/B profiling)
         cfg.reserved[2] = pipe_stages                  # 0 = auto, 2/3 = forced TMA ring depth
+        cfg.reserved[3] = host_threads                 # 0 = all host cores for set_problem's preprocessing
+        cfg.reserved[4] = 1 if no_reorder else 0       # keep the caller's landmark order in big windows (A/B profiling)
+        cfg.reserved[5] = pipe_slots                   # big windows: slots in the matvec's shared accumulator window
         self.h = C.c_void_p()
         rc = L.sqrtba_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:

@@ -76,7 +76,9 @@ struct Dev {
   // tile's pose-sorted order.
   int n_tile;
   int ld;                     // leading dimension (stride) of every per-observation plane, multiple of 32
-  int smallwin;               // every window has <= MAXSLOT free poses
+  int smallwin;               // window-relative slots fit 16 bits (every window has < 65535 free poses): obs_lp and the
+                              // run tables carry window-relative slots and the TMA-pipelined matvec is used
+  int pq_shared;              // every window has <= MAXSLOT free poses: p and q of a window live in shared memory
   const struct TileInfo* tiles;
   const unsigned* obs_lp;     // n_obs
   const int* tile_run_ptr;    // n_tile+1 -> tile_runs (host-built run tables, copied into the JQ blocks by k_init_jq)
@@ -889,7 +891,8 @@ __global__ void __launch_bounds__(CTA) k_matvec(Dev P, const double* __restrict_
 
 // Writes the static part of every JQ block: the 64-byte header and the per-column meta entries.
 // header ints: [0] nitem, [1] win, [2] first free slot of the window, [3] free slots of the window, [4] nfree,
-//              [5] nt, [6] o0, [7]/[8] jq_off lo/hi, [9..12] observations per item, [13] is_long, [14] nrun
+//              [5] nt, [6] o0, [7]/[8] jq_off lo/hi, [9..12] observations per item, [13] is_long, [14] nrun,
+//              [15] lowest run slot of the tile (-1: none)
 __global__ void k_init_jq(Dev P) {
   const TileInfo ti = P.tiles[blockIdx.x];
   double* blk = P.JQ + ti.jq_off;
@@ -900,7 +903,9 @@ __global__ void k_init_jq(Dev P) {
     h[4] = ti.nfree; h[5] = ti.nt; h[6] = ti.o0;
     h[7] = (int)(ti.jq_off & 0xffffffffll); h[8] = (int)(ti.jq_off >> 32);
     for (int i = 0; i < 4; i++) h[9 + i] = (i < ti.nitem) ? P.item_cnt[ti.item0 + i] : 0;
-    h[13] = ti.is_long; h[14] = ti.nrun; h[15] = 0;
+    h[13] = ti.is_long; h[14] = ti.nrun;
+    // lowest slot of the tile (run slots are sorted): anchors the shared accumulator window of the big-window matvec
+    h[15] = (ti.nrun > 0) ? P.tile_runs[P.tile_run_ptr[blockIdx.x] + ti.nrun + 1] : -1;
   }
   int* runs = reinterpret_cast<int*>(blk + (size_t)JQ_ROWS * ti.nt);
   const int r0 = P.tile_run_ptr[blockIdx.x], nr = P.tile_run_ptr[blockIdx.x + 1] - r0;
@@ -927,9 +932,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // (mbarrier complete_tx); four consumer warps wait on the stage, read everything from shared memory (no dependent
 // global loads on the critical path), and hand the stage back through an "empty" mbarrier.  p and the q accumulators
 // of the current window stay in shared memory; q is flushed with one atomic per (CTA, window, component).
+//
+// BIG = false: every window has <= MAXSLOT free poses; p and the q accumulators of the current window live in shared
+// memory (maxslot = free poses of the largest window).
+// BIG = true (global BA): p is gathered from global memory (L1/L2 resident: 48 bytes per pose) and the q accumulators
+// are a sliding WINDOW of `maxslot` consecutive slots anchored at the lowest slot of the tile being processed.  The
+// host orders the landmarks of a big window by their first free pose, so the consecutive tiles of one CTA touch a
+// narrow, slowly drifting band of poses; run sums that fall outside the window go straight to global atomics.
 constexpr int PIPE_THREADS = CTA + 32;
 constexpr int JQ_STAGE_D = JQ_HDR + JQ_ROWS * CTA + (2 * CTA + 4) / 2;
-template <int S>
+template <int S, bool BIG>
 __global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__ pvec,
                                                                double* __restrict__ qvec, int force_all, int maxslot) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -937,8 +949,8 @@ __global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__
   double* stage = reinterpret_cast<double*>(smem_raw);
   constexpr int CST = CTA + 1;  // padded row stride of c_sh: the 6 value-lanes of a run hit 6 different bank pairs
   double* c_sh = stage + (size_t)S * STAGE_D;  // two buffers of [6][CST]
-  double* p_sh = c_sh + 2 * (6 * CST) + 2;      // component-major: p_sh[c * maxslot + slot]
-  double* acc_sh = p_sh + 6 * maxslot;
+  double* p_sh = c_sh + 2 * (6 * CST) + 2;      // component-major: p_sh[c * maxslot + slot]  (unused when BIG)
+  double* acc_sh = p_sh + (BIG ? 0 : 6 * maxslot);
   int* runs_sh = reinterpret_cast<int*>(acc_sh + 6 * maxslot);  // two buffers of 2*CTA+4 ints
   uint64_t* full = reinterpret_cast<uint64_t*>(runs_sh + 2 * (2 * CTA + 4));
   uint64_t* empty = full + S;
@@ -981,6 +993,7 @@ __global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__
   }
   // -------------------------------------------------------------------- consumer warps
   int n = 0, cur_win = -1, ws0 = 0, wn = 0;
+  int abase = 0;  // BIG: first (window-relative) slot of the shared accumulator window
 #ifdef SQRTBA_PIPE_PROF
   long long tp[6] = {0, 0, 0, 0, 0, 0}, tc = clock64(), tn;
 #define PROF_MARK(i) { tn = clock64(); tp[i] += tn - tc; tc = tn; }
@@ -996,7 +1009,26 @@ __global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__
     const int* hdr = reinterpret_cast<const int*>(st);
     const int nitem = reinterpret_cast<const volatile int*>(hdr)[0];
     if (nitem < 0) break;
-    if (hdr[1] != cur_win) {
+    if (BIG) {
+      const int lo = hdr[15];
+      const bool new_win = hdr[1] != cur_win;
+      if (new_win || (lo >= 0 && (lo < abase || lo >= abase + (maxslot >> 1)))) {
+        // flush the accumulator window and re-anchor it at this tile's lowest slot
+        named_bar_sync(1, CTA);  // previous tile's reduction complete
+        const int aw = min(maxslot, wn - abase);
+        for (int i = tid; i < aw * 6; i += CTA) {
+          const double v = acc_sh[i];
+          if (v != 0.0) atomicAdd(&qvec[(size_t)(ws0 + abase) * 6 + i], v);
+        }
+        cur_win = hdr[1];
+        ws0 = hdr[2];
+        wn = hdr[3];
+        abase = max(0, min(lo, wn - maxslot));
+        named_bar_sync(1, CTA);
+        for (int i = tid; i < maxslot * 6; i += CTA) acc_sh[i] = 0.0;
+        named_bar_sync(1, CTA);
+      }
+    } else if (hdr[1] != cur_win) {
       // flush the finished window's accumulators, stage p of the new one
       named_bar_sync(1, CTA);  // previous tile's reduction complete
       for (int i = tid; i < wn * 6; i += CTA) atomicAdd(&qvec[(size_t)ws0 * 6 + i], acc_sh[i]);
@@ -1048,8 +1080,14 @@ __global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__
       double J[18], v[3] = {0, 0, 0}, t[3] = {0, 0, 0};
       if (has) {
         double pp[6];
+        if (BIG) {
+          const double* pg = pvec + (size_t)(ws0 + ls) * 6;
 #pragma unroll
-        for (int c = 0; c < 6; c++) pp[c] = p_sh[c * maxslot + ls];
+          for (int c = 0; c < 6; c++) pp[c] = __ldg(pg + c);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 6; c++) pp[c] = p_sh[c * maxslot + ls];
+        }
 #pragma unroll
         for (int c = 0; c < 18; c++) J[c] = dcol[c * nt];
 #pragma unroll
@@ -1085,13 +1123,27 @@ __global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__
       const int a = rb[r], b = rb[r + 1];
       double sum = 0.0;
       for (int j = a; j < b; j++) sum += cb[k * CST + j];
-      acc_sh[rb[nrun + 1 + r] * 6 + k] += sum;
+      if (BIG) {
+        const int sl = rb[nrun + 1 + r], rel = sl - abase;
+        if ((unsigned)rel < (unsigned)maxslot) acc_sh[rel * 6 + k] += sum;
+        else atomicAdd(&qvec[(size_t)(ws0 + sl) * 6 + k], sum);
+      } else {
+        acc_sh[rb[nrun + 1 + r] * 6 + k] += sum;
+      }
     }
     PROF_MARK(3)
     n++;
   }
   named_bar_sync(1, CTA);  // the last tile's reduction is complete before the accumulators are flushed
-  for (int i = tid; i < wn * 6; i += CTA) atomicAdd(&qvec[(size_t)ws0 * 6 + i], acc_sh[i]);
+  if (BIG) {
+    const int aw = min(maxslot, wn - abase);
+    for (int i = tid; i < aw * 6; i += CTA) {
+      const double v = acc_sh[i];
+      if (v != 0.0) atomicAdd(&qvec[(size_t)(ws0 + abase) * 6 + i], v);
+    }
+  } else {
+    for (int i = tid; i < wn * 6; i += CTA) atomicAdd(&qvec[(size_t)ws0 * 6 + i], acc_sh[i]);
+  }
 #ifdef SQRTBA_PIPE_PROF
   if (P.prof && (tid & 31) == 0) {
     long long* o = P.prof + ((size_t)blockIdx.x * WARPS + wid) * 8;

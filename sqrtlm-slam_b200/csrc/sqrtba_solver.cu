@@ -145,10 +145,14 @@ class Solver {
     cudaDeviceProp prop;
     CU_CHECK(cudaGetDeviceProperties(&prop, cfg_.device));
     n_sm_ = prop.multiProcessorCount;
-    CU_CHECK(cudaFuncSetAttribute(k_matvec_pipe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)pipe_smem_bytes(2, MAXSLOT)));
-    CU_CHECK(cudaFuncSetAttribute(k_matvec_pipe<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)pipe_smem_bytes(3, MAXSLOT)));
+    CU_CHECK(cudaFuncSetAttribute(k_matvec_pipe<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pipe_smem_bytes(2, MAXSLOT, false)));
+    CU_CHECK(cudaFuncSetAttribute(k_matvec_pipe<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pipe_smem_bytes(3, MAXSLOT, false)));
+    CU_CHECK(cudaFuncSetAttribute(k_matvec_pipe<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pipe_smem_bytes(2, MAXSLOT, false)));
+    CU_CHECK(cudaFuncSetAttribute(k_matvec_pipe<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pipe_smem_bytes(3, MAXSLOT, false)));
     return SQRTBA_OK;
   }
 
@@ -175,7 +179,12 @@ class Solver {
   // ------------------------------------------------------------------------------------------ problem upload
   int set_problem(int n_win, const int64_t* wpose, const int64_t* wpoint, const int64_t* wobs, int n_pose, int n_point,
                   int n_obs, const double* pose_qt, const uint8_t* pose_fixed, const double* cam,
-                  const double* point_xyz, const int32_t* obs_pose, const int32_t* obs_point, const float* obs_meas) {
+                  const double* point_xyz_in, const int32_t* obs_pose_in, const int32_t* obs_point_in,
+                  const float* obs_meas_in) {
+    const double* point_xyz = point_xyz_in;
+    const int32_t* obs_pose = obs_pose_in;
+    const int32_t* obs_point = obs_point_in;
+    const float* obs_meas = obs_meas_in;
     if (n_pose <= 0 || n_point <= 0 || n_obs <= 0 || n_win <= 0 || !pose_qt || !pose_fixed || !cam || !point_xyz ||
         !obs_pose || !obs_point || !obs_meas) {
       err_ = "set_problem: empty problem or null pointer";
@@ -213,7 +222,8 @@ class Solver {
     const int ld = ((n_obs + 31) / 32) * 32;
     int max_win_slots = 0;
     for (int w = 0; w < n_win; w++) max_win_slots = std::max(max_win_slots, win_slot_ptr[w + 1] - win_slot_ptr[w]);
-    const int smallwin = (max_win_slots <= MAXSLOT) ? 1 : 0;
+    const int smallwin = (max_win_slots < 65535) ? 1 : 0;       // window-relative slots fit the 16-bit meta field
+    const int pq_shared = (max_win_slots <= MAXSLOT) ? 1 : 0;  // p/q of a window fit the matvec CTA's shared memory
     if (h_obs_slot_.ensure(n_obs) || h_obs_lp_.ensure(n_obs)) { err_ = "pinned host allocation failed"; return SQRTBA_ERR_ALLOC; }
     int* obs_slot = h_obs_slot_.p;
     unsigned* obs_lp = h_obs_lp_.p;
@@ -242,6 +252,61 @@ class Solver {
       int next = n_obs;
       for (int l = n_point - 1; l >= 0; l--)
         if (lm_first[l] >= 0) { lm_cnt[l] = next - lm_first[l]; next = lm_first[l]; }
+    }
+    // A2. big windows (global BA): order the landmarks of each window by their first free pose, so that consecutive
+    //     tiles touch a narrow, slowly drifting band of pose slots (shared accumulator window of the matvec, few
+    //     distinct slots per tile for the run-table reductions, cache-resident pose gathers).  The order the caller
+    //     uses (std::set<MapPoint*> pointer order in the reference, g2oOptimizer.cc:117,176) is restored on read-back.
+    perm_.clear(); old_first_.clear(); new_first_.clear();
+    if (!pq_shared && smallwin && cfg_.reserved[4] == 0) {
+      std::vector<int> key(n_point);
+      parallel_chunks(n_point, 1 << 14, n_thr, [&](long long l0, long long l1) {
+        for (long long l = l0; l < l1; l++) {
+          int k = 0x7fffffff;
+          if (lm_first[l] >= 0)
+            for (int o = lm_first[l]; o < lm_first[l] + lm_cnt[l]; o++)
+              if (obs_slot[o] >= 0) k = std::min(k, obs_slot[o]);
+          key[l] = k;
+        }
+      });
+      perm_.resize(n_point);
+      for (int l = 0; l < n_point; l++) perm_[l] = l;
+      for (int w = 0; w < n_win; w++) {
+        const int p0 = (n_win > 1) ? (int)wpoint[w] : 0, p1 = (n_win > 1) ? (int)wpoint[w + 1] : n_point;
+        std::stable_sort(perm_.begin() + p0, perm_.begin() + p1, [&](int a, int b) { return key[a] < key[b]; });
+      }
+      old_first_ = lm_first;
+      new_first_.assign(n_point, -1);
+      std::vector<int> cnt_new(n_point, 0);
+      int pos = 0;
+      for (int j = 0; j < n_point; j++) {
+        const int l = perm_[j];
+        cnt_new[j] = lm_cnt[l];
+        if (lm_cnt[l] > 0) { new_first_[j] = pos; pos += lm_cnt[l]; }
+      }
+      if (h_perm_pose_.ensure(n_obs) || h_perm_point_.ensure(n_obs) || h_perm_meas_.ensure((size_t)n_obs * 4) ||
+          h_perm_xyz_.ensure((size_t)n_point * 3) || h_perm_slot_.ensure(n_obs)) {
+        err_ = "pinned host allocation failed";
+        return SQRTBA_ERR_ALLOC;
+      }
+      parallel_chunks(n_point, 1 << 12, n_thr, [&](long long j0, long long j1) {
+        for (long long j = j0; j < j1; j++) {
+          const int l = perm_[j];
+          for (int c = 0; c < 3; c++) h_perm_xyz_.p[j * 3 + c] = point_xyz_in[(size_t)l * 3 + c];
+          const int src = old_first_[l], dst = new_first_[j], k = cnt_new[j];
+          for (int i = 0; i < k; i++) {
+            h_perm_pose_.p[dst + i] = obs_pose_in[src + i];
+            h_perm_point_.p[dst + i] = (int)j;
+            h_perm_slot_.p[dst + i] = obs_slot[src + i];
+            std::memcpy(h_perm_meas_.p + (size_t)(dst + i) * 4, obs_meas_in + (size_t)(src + i) * 4, 4 * sizeof(float));
+          }
+        }
+      });
+      std::memcpy(obs_slot, h_perm_slot_.p, (size_t)n_obs * sizeof(int));
+      lm_first = new_first_;
+      lm_cnt.swap(cnt_new);
+      lm_count_new_ = lm_cnt;
+      point_xyz = h_perm_xyz_.p; obs_pose = h_perm_pose_.p; obs_point = h_perm_point_.p; obs_meas = h_perm_meas_.p;
     }
     // B. work chunks: landmark ranges inside one window of roughly equal observation count.  Items and tiles never
     //    span chunks (a chunk boundary merely ends an item early), so chunks are processed independently.
@@ -409,7 +474,7 @@ class Solver {
     // ---- device allocation
     P_ = Dev{};
     P_.n_pose = n_pose; P_.n_point = n_point; P_.n_obs = n_obs; P_.n_win = n_win; P_.n_slot = n_slot; P_.n_item = n_item;
-    P_.n_tile = n_tile; P_.ld = ld; P_.smallwin = smallwin;
+    P_.n_tile = n_tile; P_.ld = ld; P_.smallwin = smallwin; P_.pq_shared = pq_shared;
     const size_t No = n_obs, Nl = n_point, Ns = std::max(n_slot, 1), Ld = ld;
     CU_CHECK(d_cam_.ensure((size_t)n_pose * 5));
     CU_CHECK(d_pose_slot_.ensure(n_pose));
@@ -522,12 +587,19 @@ class Solver {
     k_init_jq<<<n_tile, 128, 0, stream_>>>(P_);
     CU_CHECK(cudaGetLastError());
     if (smallwin) {  // pipeline depth / residency for this problem's window size
+      // big windows: shared accumulator window of `pipe_slots_` consecutive slots (reserved[5] overrides)
+      pipe_slots_ = pq_shared ? max_win_slots_ : (cfg_.reserved[5] > 0 ? std::min(cfg_.reserved[5], MAXSLOT) : 48);
       int best_ctas = 0;
       for (int S : {2, 3}) {
         int per_sm = 0;
-        const size_t bytes = pipe_smem_bytes(S, max_win_slots_);
-        cudaError_t e = (S == 2) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matvec_pipe<2>, PIPE_THREADS, bytes)
-                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matvec_pipe<3>, PIPE_THREADS, bytes);
+        const size_t bytes = pipe_smem_bytes(S, pipe_slots_, !pq_shared);
+        cudaError_t e;
+        if (pq_shared)
+          e = (S == 2) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matvec_pipe<2, false>, PIPE_THREADS, bytes)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matvec_pipe<3, false>, PIPE_THREADS, bytes);
+        else
+          e = (S == 2) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matvec_pipe<2, true>, PIPE_THREADS, bytes)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matvec_pipe<3, true>, PIPE_THREADS, bytes);
         if (e != cudaSuccess) per_sm = 0;
         if (cfg_.reserved[2] > 0 && S != cfg_.reserved[2]) continue;   // forced depth (profiling)
         if (per_sm * S > best_ctas * pipe_stages_ || best_ctas == 0) { best_ctas = per_sm; pipe_stages_ = S; }
@@ -594,8 +666,39 @@ class Solver {
 
   // ------------------------------------------------------------------------------------------ read-back
   int get_poses(double* out) { return download(out, d_pose_.p, (size_t)P_.n_pose * 7 * sizeof(double)); }
-  int get_points(double* out) { return download(out, d_point_.p, (size_t)P_.n_point * 3 * sizeof(double)); }
-  int get_outliers(uint8_t* out) { return download(out, d_outlier_.p, (size_t)P_.n_obs); }
+  int get_points(double* out) {
+    if (perm_.empty()) return download(out, d_point_.p, (size_t)P_.n_point * 3 * sizeof(double));
+    std::vector<double> tmp((size_t)P_.n_point * 3);
+    if (int rc = download(tmp.data(), d_point_.p, tmp.size() * sizeof(double))) return rc;
+    unperm_points(tmp.data(), out, 3);
+    return SQRTBA_OK;
+  }
+  int get_outliers(uint8_t* out) {
+    if (perm_.empty()) return download(out, d_outlier_.p, (size_t)P_.n_obs);
+    std::vector<uint8_t> tmp((size_t)P_.n_obs);
+    if (int rc = download(tmp.data(), d_outlier_.p, tmp.size())) return rc;
+    unperm_obs(tmp.data(), out, 1);
+    return SQRTBA_OK;
+  }
+  // big windows are solved in an internal landmark order (set_problem step A2): back to the caller's order
+  template <class T>
+  void unperm_points(const T* in, T* out, int width) const {
+    for (size_t j = 0; j < perm_.size(); j++)
+      for (int c = 0; c < width; c++) out[(size_t)perm_[j] * width + c] = in[j * width + c];
+  }
+  template <class T>
+  void unperm_obs(const T* in, T* out, int width) const {
+    const int n_point = (int)perm_.size();
+    for (int j = 0; j < n_point; j++) {
+      if (new_first_[j] < 0) continue;
+      const int l = perm_[j];
+      const int next_new = (j + 1 < n_point && new_first_[j + 1] >= 0) ? new_first_[j + 1] : -1;
+      (void)next_new;
+      const size_t src = (size_t)new_first_[j], dst = (size_t)old_first_[l];
+      const size_t k = lm_count_new_[j];
+      std::memcpy(out + dst * width, in + src * width, k * width * sizeof(T));
+    }
+  }
   int trace_len(int win) {
     if (!have_problem_ || win < 0 || win >= P_.n_win) return SQRTBA_ERR_INVALID;
     WinCtl c;
@@ -629,17 +732,25 @@ class Solver {
       if (!dst) return 0;
       tmp.resize(Ld * np);
       if (download(tmp.data(), dsrc, Ld * np * sizeof(double))) return SQRTBA_ERR_CUDA;
+      std::vector<double> rows;
+      double* d = dst;
+      if (!perm_.empty()) { rows.resize(No * np); d = rows.data(); }
       for (size_t o = 0; o < No; o++)
-        for (int c = 0; c < np; c++) dst[o * np + c] = tmp[(size_t)c * Ld + o];
+        for (int c = 0; c < np; c++) d[o * np + c] = tmp[(size_t)c * Ld + o];
+      if (!perm_.empty()) unperm_obs(rows.data(), dst, np);
       return 0;
     };
     if (planes(err, d_err_.p, 3) || planes(Jl, d_Jl_.p, 9) || planes(r, d_r_.p, 3)) return SQRTBA_ERR_CUDA;
     if (Jp) {  // un-block the tile-blocked matvec operand
       tmp.resize(d_JQ_.cap);
       if (download(tmp.data(), d_JQ_.p, d_JQ_.cap * sizeof(double))) return SQRTBA_ERR_CUDA;
+      std::vector<double> rows;
+      double* d = Jp;
+      if (!perm_.empty()) { rows.resize(No * 18); d = rows.data(); }
       for (const TileInfo& ti : h_tiles_)
         for (int o = ti.o0; o < ti.o1; o++)
-          for (int c = 0; c < 18; c++) Jp[(size_t)o * 18 + c] = tmp[(size_t)ti.jq_off + (size_t)c * ti.nt + (o - ti.o0)];
+          for (int c = 0; c < 18; c++) d[(size_t)o * 18 + c] = tmp[(size_t)ti.jq_off + (size_t)c * ti.nt + (o - ti.o0)];
+      if (!perm_.empty()) unperm_obs(rows.data(), Jp, 18);
     }
     if (chi2) {
       std::vector<WinCtl> c(P_.n_win);
@@ -668,8 +779,10 @@ class Solver {
     if (dl) {
       std::vector<double> tmp((size_t)P_.n_point * 3);
       if (download(tmp.data(), d_dl_.p, tmp.size() * sizeof(double))) return SQRTBA_ERR_CUDA;
-      for (int l = 0; l < P_.n_point; l++)
-        for (int k = 0; k < 3; k++) dl[(size_t)l * 3 + k] = tmp[(size_t)k * P_.n_point + l];
+      for (int l = 0; l < P_.n_point; l++) {
+        const size_t lo = perm_.empty() ? (size_t)l : (size_t)perm_[l];
+        for (int k = 0; k < 3; k++) dl[lo * 3 + k] = tmp[(size_t)k * P_.n_point + l];
+      }
     }
     if (cg_iters) {
       if (download(c.data(), d_ctl_.p, c.size() * sizeof(WinCtl))) return SQRTBA_ERR_CUDA;
@@ -803,18 +916,25 @@ class Solver {
 
  private:
   // matvec dispatch: persistent TMA-pipelined kernel when every window is small, general tile kernel otherwise
-  static size_t pipe_smem_bytes(int S, int maxslot) {
-    return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + 12 * (size_t)maxslot) * sizeof(double) +
+  static size_t pipe_smem_bytes(int S, int maxslot, bool big) {
+    return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + (big ? 6 : 12) * (size_t)maxslot) * sizeof(double) +
            2 * (2 * CTA + 4) * sizeof(int) + 2 * S * sizeof(uint64_t);
   }
   void launch_matvec(const double* pvec, double* qvec, int force_all) {
     if (P_.smallwin && cfg_.reserved[1] == 0) {
       const int grid = std::min(P_.n_tile, pipe_ctas_);
-      const size_t bytes = pipe_smem_bytes(pipe_stages_, max_win_slots_);
-      if (pipe_stages_ == 2)
-        k_matvec_pipe<2><<<grid, PIPE_THREADS, bytes, stream_>>>(P_, pvec, qvec, force_all, max_win_slots_);
-      else
-        k_matvec_pipe<3><<<grid, PIPE_THREADS, bytes, stream_>>>(P_, pvec, qvec, force_all, max_win_slots_);
+      const bool big = !P_.pq_shared;
+      const size_t bytes = pipe_smem_bytes(pipe_stages_, pipe_slots_, big);
+      if (big) {
+        if (pipe_stages_ == 2)
+          k_matvec_pipe<2, true><<<grid, PIPE_THREADS, bytes, stream_>>>(P_, pvec, qvec, force_all, pipe_slots_);
+        else
+          k_matvec_pipe<3, true><<<grid, PIPE_THREADS, bytes, stream_>>>(P_, pvec, qvec, force_all, pipe_slots_);
+      } else if (pipe_stages_ == 2) {
+        k_matvec_pipe<2, false><<<grid, PIPE_THREADS, bytes, stream_>>>(P_, pvec, qvec, force_all, pipe_slots_);
+      } else {
+        k_matvec_pipe<3, false><<<grid, PIPE_THREADS, bytes, stream_>>>(P_, pvec, qvec, force_all, pipe_slots_);
+      }
     } else {
       k_matvec<<<P_.n_tile, CTA, 0, stream_>>>(P_, pvec, qvec, force_all);
     }
@@ -951,6 +1071,7 @@ class Solver {
     d_tiles_.release(); d_obs_lp_.release(); d_tile_run_ptr_.release(); d_tile_runs_.release();
     h_obs_slot_.release(); h_item_start_.release(); h_item_cnt_.release(); h_item_win_.release();
     h_tile_run_ptr_.release(); h_tile_runs_.release(); h_obs_lp_.release(); h_tiles_pin_.release();
+    h_perm_pose_.release(); h_perm_point_.release(); h_perm_slot_.release(); h_perm_meas_.release(); h_perm_xyz_.release();
   }
 
  public:
@@ -967,7 +1088,8 @@ class Solver {
   bool have_problem_ = false;
   int max_trace_ = 200;
   int launches_ = 0, lm_trials_ = 0, cg_iters_total_ = 0;
-  int n_sm_ = 148, pipe_ctas_ = 296, pipe_stages_ = 3, max_win_slots_ = 1;
+  int n_sm_ = 148, pipe_ctas_ = 296, pipe_stages_ = 3, max_win_slots_ = 1, pipe_slots_ = 1;
+  std::vector<int> perm_, old_first_, new_first_, lm_count_new_;  // landmark re-ordering of big windows: new -> old, first observation in either order
   void* comm_ = nullptr;  // ncclComm_t
   int n_ranks_ = 1;
   Dev P_{};
@@ -981,6 +1103,9 @@ class Solver {
   DBuf<long long> d_prof_;
   HBuf<int> h_obs_slot_, h_item_start_, h_item_cnt_, h_item_win_, h_tile_run_ptr_, h_tile_runs_;
   HBuf<unsigned> h_obs_lp_;
+  HBuf<int> h_perm_pose_, h_perm_point_, h_perm_slot_;
+  HBuf<float> h_perm_meas_;
+  HBuf<double> h_perm_xyz_;
   HBuf<TileInfo> h_tiles_pin_;
   std::vector<TileInfo> h_tiles_;
   DBuf<float4> d_meas_;
@@ -1009,7 +1134,7 @@ int sqrtba_default_config(sqrtba_config* cfg) {
   std::memset(cfg, 0, sizeof *cfg);
   cfg->device = 0;
   cfg->pcg_rtol = 1e-9;
-  cfg->pcg_max_iters = 300;
+  cfg->pcg_max_iters = 2000;
   cfg->third_pass_iters = 0;
   cfg->pcg_mode = 0;
   cfg->pcg_check_every = 4;
@@ -1022,7 +1147,7 @@ int sqrtba_create(const sqrtba_config* cfg, sqrtba_handle** out) {
   sqrtba_config c;
   if (cfg) c = *cfg; else sqrtba_default_config(&c);
   if (c.pcg_rtol <= 0) c.pcg_rtol = 1e-9;
-  if (c.pcg_max_iters <= 0) c.pcg_max_iters = 300;
+  if (c.pcg_max_iters <= 0) c.pcg_max_iters = 2000;
   if (c.pcg_check_every <= 0) c.pcg_check_every = 4;
   sqrtba_handle* h = new (std::nothrow) sqrtba_handle();
   if (!h) return SQRTBA_ERR_ALLOC;

@@ -159,6 +159,64 @@ def test_global_ba_loop(ba, synth, robust, iters):
     assert ba.outliers().sum() == 0
 
 
+def big_window_problem(synth, seed=17, n_kf=200, n_points=8000):
+    """More than 128 free poses in one window: the big-window matvec (sliding shared accumulator window, p gathered
+    from global memory) and the internal landmark re-ordering by first free pose.  Landmarks arrive in random order
+    (like the reference's std::set<MapPoint*> pointer order)."""
+    return synth.make_problem(seed, n_kf, 1, n_points, 9.0, stereo=True, loop=True, cand_halfwidth=15, name="gba-mid")
+
+
+def test_big_window_stage_parity(ba, synth):
+    prob = big_window_problem(synth)
+    assert prob.n_free > 128
+    ba.set_problem(prob)
+    g = ba.debug_linearize(2)
+    o = refba.RefBA(prob).linearize_all(2)
+    sw = np.sqrt(o["w"])
+    # outputs come back in the CALLER's landmark / observation order although the solve re-orders internally
+    assert np.abs(g["err"] - o["err"]).max() <= 3e-5
+    np.testing.assert_allclose(g["Jp"], o["Jp"] * sw[:, None, None], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(g["Jl"], o["Jl"] * sw[:, None, None], rtol=1e-6, atol=1e-8)
+    lam = 10.0
+    st = ba.debug_step(lam)
+    s = refba.RefBA(prob).schur_solve(lam, huber=2)
+    Np = s["Np"]
+    xp = s["x"][:6 * Np]
+    assert np.abs(st["dp"].ravel() - xp).max() <= 1e-6 * np.abs(xp).max()
+    xl = s["x"][6 * Np:]
+    assert np.abs(st["dl"].ravel() - xl).max() <= 1e-5 * np.abs(xl).max()
+    rng = np.random.default_rng(1)
+    p = rng.normal(size=(Np, 6))
+    y = ba.debug_matvec(p).ravel() + lam * p.ravel()
+    want = s["S"] @ p.ravel()
+    assert np.abs(y - want).max() <= 1e-8 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("robust,iters", [(False, 10), (True, 10)])
+def test_global_ba_big_window(ba, synth, robust, iters):
+    prob = big_window_problem(synth)
+    ba.set_problem(prob)
+    ba.solve_global(iters, robust)
+    ref = refba.RefBA(prob)
+    ref.solve_global(iters, robust)
+    compare_solution(ba, ref, prob)
+    t_rms, r_rms = pose_rms(ba.poses(), ref.poses(), prob.pose_fixed == 0)
+    assert t_rms <= POSE_T_RMS and r_rms <= POSE_R_RMS, (t_rms, r_rms)
+    np.testing.assert_allclose(ba.points(), ref.points(), rtol=1e-5, atol=1e-4)
+
+
+def test_local_ba_big_window_outlier_flags(ba, synth):
+    # local-BA control flow (two passes, outlier flags per observation) on a re-ordered big window
+    prob = big_window_problem(synth, seed=23, n_kf=150, n_points=4000)
+    ba.set_problem(prob)
+    ba.solve_local()
+    ref = refba.RefBA(prob)
+    ref.solve_local(0)
+    compare_solution(ba, ref, prob)
+    assert np.array_equal(ba.outliers(), ref.outliers())
+    np.testing.assert_allclose(ba.points(), ref.points(), rtol=1e-5, atol=1e-4)
+
+
 def test_long_tracks(ba, synth):
     # landmarks seen by more than 32 keyframes take the chunked whole-warp path
     prob = synth.make_problem(9, 64, 2, 400, 45.0, stereo=True, name="long-tracks")
