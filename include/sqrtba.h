@@ -44,7 +44,10 @@ typedef struct {
   double pcg_rtol;           /* PCG stops when sqrt(r'M^-1 r / r0'M^-1 r0) <= pcg_rtol (default 1e-9) */
   int32_t pcg_max_iters;     /* hard cap per linear solve (default 2000; a safety net -- global BA needs a few hundred) */
   int32_t third_pass_iters;  /* 0 = ORB-SLAM2 two-pass 5+10 (default); 20 = this fork's extra pass (g2oOptimizer.cc:1113) */
-  int32_t pcg_mode;          /* 0 = one launch per CG phase (default in round 1), 1 = persistent cooperative kernel */
+  int32_t pcg_mode;          /* 0 = auto: single-window problems run the whole PCG solve in ONE persistent cooperative
+                                kernel (grid barriers between the matvec and the vector updates, in-kernel NVLink
+                                exchange when landmark-sharded), batches use one launch per CG phase;
+                                1 = always one launch per phase; 2 = persistent whenever possible */
   int32_t pcg_check_every;   /* multi-launch mode: host polls the convergence counter every N iterations */
   int32_t reserved[8];
 } sqrtba_config;

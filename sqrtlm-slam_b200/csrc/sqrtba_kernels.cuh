@@ -776,16 +776,20 @@ __global__ void k_dinv(Dev P, int force_all, double lam_override) {
 // update).  Per observation: v = Jp p[slot] (d-vector), s_l = sum Q1^T v (3-vector, landmark reduction),
 // u = v - Q1 s_l, scatter-add Jp^T u.  Streams Jp (18) + Q1 (9) planes: 216 B/observation.
 // Observations of fixed poses have no pose columns (g2o hessianIndex -1): they are skipped entirely.
+// PSRC: where p lives -- 0 global (slot-major), 1 global read through L2 (rewritten by other CTAs during the kernel),
+// 2 shared memory, component-major with stride `pstride`
+template <int PSRC = 0>
 __device__ __forceinline__ void matvec_obs_v(const double* __restrict__ jq, int nt, int col,
-                                             const double* __restrict__ pvec, int slot, double J[18], double Q[9],
-                                             double v[3]) {
+                                             const double* pvec, int slot, double J[18], double Q[9],
+                                             double v[3], int pstride = 0) {
 #pragma unroll
   for (int c = 0; c < 18; c++) J[c] = jq[(size_t)c * nt + col];
 #pragma unroll
   for (int c = 0; c < 9; c++) Q[c] = jq[(size_t)(18 + c) * nt + col];
   double pp[6];
 #pragma unroll
-  for (int c = 0; c < 6; c++) pp[c] = pvec[slot * 6 + c];
+  for (int c = 0; c < 6; c++)
+    pp[c] = (PSRC == 2) ? pvec[c * pstride + slot] : ((PSRC == 1) ? __ldcg(pvec + slot * 6 + c) : pvec[slot * 6 + c]);
 #pragma unroll
   for (int r = 0; r < 3; r++)
     v[r] = J[r * 6] * pp[0] + J[r * 6 + 1] * pp[1] + J[r * 6 + 2] * pp[2] + J[r * 6 + 3] * pp[3] +
@@ -793,15 +797,16 @@ __device__ __forceinline__ void matvec_obs_v(const double* __restrict__ jq, int 
 }
 
 // long landmark (one warp, more than 32 observations): two sweeps, direct atomics
+template <int PSRC = 0>
 __device__ __forceinline__ void matvec_long_item(const Dev& P, const double* __restrict__ jq, int nt,
-                                                 const double* __restrict__ pvec, double* __restrict__ qvec,
-                                                 int start, int cnt, int lane) {
+                                                 const double* pvec, double* qvec,
+                                                 int start, int cnt, int lane, int pstride = 0) {
   double J[18], Q[9], v[3], sv[3] = {0, 0, 0};
   for (int i = lane; i < cnt; i += 32) {
     const int o = start + i;
     const int slot = P.obs_slot[o];
     if (slot < 0) continue;
-    matvec_obs_v(jq, nt, i, pvec, slot, J, Q, v);  // a long item is a tile of its own: column = i
+    matvec_obs_v<PSRC>(jq, nt, i, pvec, slot, J, Q, v, pstride);  // a long item is a tile of its own: column = i
 #pragma unroll
     for (int k = 0; k < 3; k++) sv[k] += Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2];
   }
@@ -811,7 +816,7 @@ __device__ __forceinline__ void matvec_long_item(const Dev& P, const double* __r
     const int o = start + i;
     const int slot = P.obs_slot[o];
     if (slot < 0) continue;
-    matvec_obs_v(jq, nt, i, pvec, slot, J, Q, v);
+    matvec_obs_v<PSRC>(jq, nt, i, pvec, slot, J, Q, v, pstride);
 #pragma unroll
     for (int r = 0; r < 3; r++) v[r] -= Q[r * 3] * sv[0] + Q[r * 3 + 1] * sv[1] + Q[r * 3 + 2] * sv[2];
 #pragma unroll
@@ -1012,7 +1017,7 @@ __global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__
     if (BIG) {
       const int lo = hdr[15];
       const bool new_win = hdr[1] != cur_win;
-      if (new_win || (lo >= 0 && (lo < abase || lo >= abase + (maxslot >> 1)))) {
+      if (new_win || (maxslot > 0 && lo >= 0 && (lo < abase || lo >= abase + (maxslot >> 1)))) {
         // flush the accumulator window and re-anchor it at this tile's lowest slot
         named_bar_sync(1, CTA);  // previous tile's reduction complete
         const int aw = min(maxslot, wn - abase);
@@ -1151,6 +1156,500 @@ __global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__
     o[6] = n;
   }
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------ K3-K5 fused: persistent PCG
+// Whole preconditioned-CG solve of ONE window (local BA window, large window, global BA) in a single cooperative launch:
+// the TMA-pipelined matvec above plus the CG vector updates, separated by grid barriers, so a CG iteration costs no
+// kernel launch and no host round trip.  A grid barrier is ~1.7 us on 444 CTAs (tools/microbench/gridbar.cu) and every
+// dependent L2 access ~0.5 us, so the design minimises barriers per iteration:
+//
+// BIG = false (<= MAXSLOT free poses: local BA): every CTA keeps the WHOLE CG state (p, res) replicated in shared
+//   memory and performs the vector updates redundantly with identical arithmetic -> ONE grid barrier per iteration
+//   (q complete).  q rotates through three buffers so that clearing never races with accumulation.
+// BIG = true (global BA): vector phases are chunked by pose (chunk = VSLOT poses, one CTA per chunk, six lanes per
+//   pose) -> THREE barriers per iteration: q complete | dot products | p complete.  The second dot product of textbook
+//   CG is taken from the recurrence  r'.z' = r.z - 2 alpha q.z + alpha^2 q.Dinv q, evaluated together with p.q and
+//   with the TRUE r.z of the current iterate (so the recurrence error never accumulates).
+//   With landmarks sharded over several GPUs the pose-sized partial products are exchanged INSIDE
+//   the kernel over NVLink peer memory: every rank stores its chunk of q into the receive buffer of every peer, raises
+//   a per-chunk flag (st.release.sys), waits for the peers' flags and adds the partial vectors in rank order -- all
+//   ranks hold bit-identical q, alpha, beta and iterates.  Dot products are per-chunk partials summed in chunk order
+//   by every CTA, so they do not depend on the grid size (ranks with different shards launch different grids).
+constexpr int VSLOT = 20;  // 4 warps x 5 poses x 6 lanes
+// !BIG: the per-CTA partial products are added into one of KQ copies of q (CTA b -> copy b % KQ).  FP64 atomics on
+// one L2 line serialise (~30 cycles each: 444 CTAs flushing the same 120 doubles cost ~8 us), so the copies cut the
+// depth of that queue; every CTA then adds the KQ copies in a fixed order.
+constexpr int KQ = 4;
+
+struct PcgArgs {
+  double tol2;
+  int max_iters;
+  int nranks, rank;
+  unsigned* gbar;                 // grid barrier arrival counter (monotonic; zeroed by the host before the launch)
+  double* part;                   // BIG: [nchunk][4] partial dot products
+  double* q3;                     // !BIG: three rotating buffers of KQ copies of q, [3][KQ][6*n_slot] (zeroed by the host)
+  double* dq;                     // BIG: Dinv * q
+  double* recv;                   // this rank's receive buffer  [2 (parity)][nranks][nelem_cap]
+  unsigned long long* flag;       // this rank's arrival flags   [nranks][nchunk_cap]
+  double* peer_recv[8];           // the same two buffers of every rank, peer-mapped (cudaIpc)
+  unsigned long long* peer_flag[8];
+  unsigned long long* seq_state;  // running exchange sequence number (device resident, advanced by the kernel)
+  int nelem_cap, nchunk_cap;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Barrier over the consumer threads of every CTA of a cooperative launch: CTA barrier, one thread does a release-add
+// on a monotonically increasing counter and acquire-spins until all CTAs of this generation arrived, CTA barrier.
+__device__ __forceinline__ void grid_bar(unsigned* bar, unsigned nblk, unsigned& gen, int tid) {
+  named_bar_sync(1, CTA);
+  if (tid == 0) {
+    gen++;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    const unsigned target = gen * nblk;
+    while (ld_acquire_gpu(bar) < target) {}
+  }
+  named_bar_sync(1, CTA);
+}
+
+// deterministic sum over the 128 consumer threads, result to all of them (slot: 0/1 selects the scratch cell)
+__device__ __forceinline__ double cta_sum(double v, double* red_sh, int which, int lane, int wid) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(FULL, v, off);
+  if (lane == 0) red_sh[which * 4 + wid] = v;
+  named_bar_sync(1, CTA);
+  return (red_sh[which * 4] + red_sh[which * 4 + 1]) + (red_sh[which * 4 + 2] + red_sh[which * 4 + 3]);
+}
+
+// per-lane matvec products of one staged tile: writes this observation's Jp^T u (6 values) into column `rank` of cb
+template <bool BIG>
+__device__ __forceinline__ void tile_products(const double* data, const int* hdr, int nt, int wid, int lane,
+                                              const double* p_sh, int maxslot, const double* pglob, double* cb) {
+  constexpr int CST = CTA + 1;
+  const uint2* meta = reinterpret_cast<const uint2*>(data + (size_t)NPLANE * nt);
+  const int col0 = (wid > 0 ? hdr[9] : 0) + (wid > 1 ? hdr[10] : 0) + (wid > 2 ? hdr[11] : 0);
+  const int cnt = hdr[9 + wid];
+  const bool act = lane < cnt;
+  const int col = col0 + (act ? lane : 0);
+  int lm = -1 - lane, rank = 0, ls = 0;
+  bool has = false;
+  if (act) {
+    const uint2 m = meta[col];
+    ls = (int)(m.x & 0xffffu);
+    has = ls != 0xffff;
+    rank = (int)(m.x >> 16);
+    lm = (int)m.y;
+  }
+  const Seg sg = seg_of(lm, lane);
+  const double* dcol = data + col;
+  double J[18], v[3] = {0, 0, 0}, t[3] = {0, 0, 0};
+  if (has) {
+    double pp[6];
+    if (BIG) {
+      const double* pg = pglob + (size_t)ls * 6;  // rewritten by other CTAs between iterations: L2 loads
+#pragma unroll
+      for (int cc = 0; cc < 6; cc++) pp[cc] = __ldcg(pg + cc);
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 6; cc++) pp[cc] = p_sh[cc * maxslot + ls];
+    }
+#pragma unroll
+    for (int cc = 0; cc < 18; cc++) J[cc] = dcol[cc * nt];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      v[r] = J[r * 6] * pp[0] + J[r * 6 + 1] * pp[1] + J[r * 6 + 2] * pp[2] + J[r * 6 + 3] * pp[3] +
+             J[r * 6 + 4] * pp[4] + J[r * 6 + 5] * pp[5];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) t[k] += dcol[(18 + r * 3 + k) * nt] * v[r];
+    }
+  }
+  double sv[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) sv[k] = seg_sum(t[k], sg, lane);
+  if (has) {
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      v[r] -= dcol[(18 + r * 3) * nt] * sv[0] + dcol[(19 + r * 3) * nt] * sv[1] + dcol[(20 + r * 3) * nt] * sv[2];
+#pragma unroll
+    for (int cc = 0; cc < 6; cc++) cb[cc * CST + rank] = J[cc] * v[0] + J[6 + cc] * v[1] + J[12 + cc] * v[2];
+  }
+}
+
+__host__ __device__ inline int pipe_run_cap(int maxslot, bool big) {  // ints per run-table buffer
+  return 2 * ((big || maxslot > CTA) ? CTA : maxslot) + 4;
+}
+
+template <int S, bool BIG>
+__global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, double lam_override, int use_override) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int STAGE_D = JQ_STAGE_D;
+  constexpr int CST = CTA + 1;
+  double* stage = reinterpret_cast<double*>(smem_raw);
+  double* c_sh = stage + (size_t)S * STAGE_D;            // two buffers of [6][CST]
+  double* p_sh = c_sh + 2 * (6 * CST) + 2;                // !BIG: p, component-major [c * maxslot + slot]
+  double* acc_sh = p_sh + (BIG ? 0 : 6 * maxslot);        // !BIG: q accumulators, then scratch of the vector phase
+  double* res_sh = acc_sh + (BIG ? 0 : 6 * maxslot);      // !BIG: residual, slot-major [slot * 6 + c]
+  double* red_sh = res_sh + (BIG ? 0 : 6 * maxslot);      // 8 doubles
+  uint64_t* full = reinterpret_cast<uint64_t*>(red_sh + 8);
+  uint64_t* empty = full + S;
+  volatile int* sig = reinterpret_cast<volatile int*>(empty + S);  // [0] approved iteration, [1] stop, [2] fills consumed
+  int* runs_sh = const_cast<int*>(sig) + 4;
+  const int rcap = pipe_run_cap(maxslot, BIG);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int t0 = (int)((long long)P.n_tile * blockIdx.x / gridDim.x);
+  const int t1 = (int)((long long)P.n_tile * (blockIdx.x + 1) / gridDim.x);
+  const int ntile = t1 - t0;
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_fence_init();
+    sig[0] = 0;
+    sig[1] = 0;
+    sig[2] = 0;
+  }
+  __syncthreads();
+  WinCtl& c = P.ctl[0];
+  if (!c.cg_active) return;  // grid-uniform: set by k_cg_init before this launch, cleared only after the last barrier
+  if (wid == WARPS) {
+    // ------------------------------------------------------------------ producer warp (one elected lane)
+    // JQ does not change during the solve, so the first tiles of the next iteration are prefetched speculatively while
+    // the consumers run the vector phases; past the ring depth the iteration must have been approved.
+    if (lane == 0 && ntile > 0) {
+      int n = 0;
+      TileInfo nxt = P.tiles[t0];
+      for (int it = 0;; it++) {
+        bool stop = false;
+        for (int k = 0; k < ntile; k++) {
+          if (it > 0 && k >= S) {
+            while (sig[0] < it && !sig[1]) {}
+            if (sig[1]) { stop = true; break; }
+          }
+          const TileInfo ti = nxt;
+          nxt = P.tiles[(k + 1 < ntile) ? t0 + k + 1 : t0];
+          const int s = n % S;
+          if (n >= S) mbar_wait(&empty[s], (uint32_t)(((n / S) - 1) & 1));
+          const uint32_t bytes = ti.is_long ? (uint32_t)(JQ_HDR * sizeof(double))
+                                            : (uint32_t)(ti.blk_doubles * sizeof(double));
+          mbar_expect_tx(&full[s], bytes);
+          bulk_g2s(stage + (size_t)s * STAGE_D, P.JQ + ti.jq_off - JQ_HDR, bytes, &full[s]);
+          n++;
+        }
+        if (!stop && it > 0 && ntile <= S) {  // every tile of this iteration was speculative: still needs the verdict
+          while (sig[0] < it && !sig[1]) {}
+          if (sig[1]) stop = true;
+        }
+        if (stop) break;
+      }
+      // drain: speculative copies of an iteration that never runs must land before the CTA's shared memory is released
+      const int used = sig[2];
+      for (int f = used; f < n; f++) mbar_wait(&full[f % S], (uint32_t)((f / S) & 1));
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- consumer warps
+  const double lam = use_override ? lam_override : c.lambda;
+  double rz = c.rz;
+  const double rz0 = c.rz0;
+  const int n6 = P.n_slot * 6;
+  const unsigned long long seq0 = (BIG && A.nranks > 1) ? *A.seq_state : 0ull;
+  unsigned long long seq_last = seq0;
+  const int nchunk = (P.n_slot + VSLOT - 1) / VSLOT;
+  const int vsl = wid * 5 + lane / 6, vcc = lane - (lane / 6) * 6;
+  const int vbase = min((lane / 6) * 6, 24);
+  unsigned gen = 0;
+  int n = 0, iters = 0;
+#ifdef SQRTBA_PIPE_PROF
+  long long tpp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tcc = clock64(), tnn;
+#define PROFP(i) { tnn = clock64(); tpp[i] += tnn - tcc; tcc = tnn; }
+#else
+#define PROFP(i)
+#endif
+  if (!BIG) {  // replicate the CG state
+    for (int e = tid; e < n6; e += CTA) {
+      const int sl = e / 6;
+      p_sh[(e - sl * 6) * maxslot + sl] = P.p[e];
+      res_sh[e] = P.res[e];
+      acc_sh[e] = 0.0;
+    }
+    named_bar_sync(1, CTA);
+  }
+  for (int it = 0;; it++) {
+    double* qcur = BIG ? P.q : A.q3 + ((size_t)(it % 3) * KQ + (blockIdx.x % KQ)) * n6;
+    PROFP(7)
+    // ================================================================== matvec over this CTA's tiles
+    for (int kt = 0; kt < ntile; kt++) {
+      const int s = n % S;
+      mbar_wait(&full[s], (uint32_t)((n / S) & 1));
+      const double* st = stage + (size_t)s * STAGE_D;
+      const int* hdr = reinterpret_cast<const int*>(st);
+      const int nitem = hdr[0];
+      const int nt = hdr[5];
+      if (hdr[13]) {  // long landmark: operands straight from global memory, direct atomics
+        const long long jq_off = ((long long)hdr[8] << 32) | (unsigned)hdr[7];
+        if (wid == 0) {
+          if (BIG) matvec_long_item<1>(P, P.JQ + jq_off, nt, P.p, qcur, hdr[6], hdr[9], lane);
+          else matvec_long_item<2>(P, P.JQ + jq_off, nt, p_sh, qcur, hdr[6], hdr[9], lane, maxslot);
+        }
+        named_bar_sync(1, CTA);
+        if (tid == 0) mbar_arrive(&empty[s]);
+        n++;
+        continue;
+      }
+      const double* data = st + JQ_HDR;
+      double* cb = c_sh + (size_t)(n & 1) * (6 * CST);
+      int* rb = runs_sh + (size_t)(n & 1) * rcap;
+      const int nrun = hdr[14];
+      {
+        const int* rsrc = reinterpret_cast<const int*>(data + (size_t)JQ_ROWS * nt);
+        for (int i = tid; i < 2 * nrun + 1; i += CTA) rb[i] = rsrc[i];
+      }
+      if (wid < nitem) tile_products<BIG>(data, hdr, nt, wid, lane, p_sh, maxslot, P.p, cb);
+      named_bar_sync(1, CTA);
+      if (tid == 0) mbar_arrive(&empty[s]);
+      for (int idx = tid; idx < nrun * 6; idx += CTA) {
+        const int r = (idx * 10923) >> 16, k = idx - r * 6;
+        const int a = rb[r], b = rb[r + 1];
+        double sum = 0.0;
+        for (int j = a; j < b; j++) sum += cb[k * CST + j];
+        if (BIG) atomicAdd(&qcur[(size_t)rb[nrun + 1 + r] * 6 + k], sum);
+        else acc_sh[rb[nrun + 1 + r] * 6 + k] += sum;
+      }
+      n++;
+    }
+    PROFP(3)
+    if (!BIG) {
+      named_bar_sync(1, CTA);
+      for (int e = tid; e < n6; e += CTA) atomicAdd(&qcur[e], acc_sh[e]);
+    }
+    PROFP(4)
+    grid_bar(A.gbar, gridDim.x, gen, tid);  // B1: q complete
+    PROFP(0)
+    if (!BIG) {
+      // ================================================================ replicated vector update (one barrier / iteration)
+      if (blockIdx.x == 0) {  // clear the buffer of iteration it+2: its readers (iteration it-1) all passed B1 above
+        double* qz = A.q3 + (size_t)((it + 2) % 3) * KQ * n6;
+        for (int e = tid; e < KQ * n6; e += CTA) qz[e] = 0.0;
+      }
+      constexpr int EPT = MAXSLOT * 6 / CTA;  // elements per thread
+      double d = 0.0;
+      {
+        const double* qall = A.q3 + (size_t)(it % 3) * KQ * n6;
+        double qg[EPT][KQ];
+#pragma unroll
+        for (int j = 0; j < EPT; j++) {
+          const int e = tid + j * CTA;
+#pragma unroll
+          for (int k = 0; k < KQ; k++) qg[j][k] = (e < n6) ? __ldcg(&qall[(size_t)k * n6 + e]) : 0.0;  // all loads in flight together
+        }
+#pragma unroll
+        for (int j = 0; j < EPT; j++) {
+          const int e = tid + j * CTA;
+          if (e < n6) {
+            const int sl = e / 6, cc = e - sl * 6;
+            const double pv = p_sh[cc * maxslot + sl];
+            double qs = qg[j][0];
+#pragma unroll
+            for (int k = 1; k < KQ; k++) qs += qg[j][k];
+            const double qv = qs + lam * pv;
+            acc_sh[e] = qv;
+            d += pv * qv;
+          }
+        }
+      }
+      PROFP(1)
+      const double pq = cta_sum(d, red_sh, 0, lane, wid);
+      const double alpha = rz / pq;
+      if (!(pq > 0.0) || !isfinite(alpha)) break;  // breakdown: keep the iterate, LM judges the step by its gain ratio
+      for (int e = tid; e < n6; e += CTA) {
+        res_sh[e] -= alpha * acc_sh[e];
+        if (blockIdx.x == 0) {  // the step itself is only needed once: fire-and-forget adds (x was zeroed by k_cg_init)
+          const int sl = e / 6, cc = e - sl * 6;
+          atomicAdd(&P.x[e], alpha * p_sh[cc * maxslot + sl]);
+        }
+      }
+      named_bar_sync(1, CTA);
+      d = 0.0;
+      {
+        double dg[EPT][6];
+#pragma unroll
+        for (int j = 0; j < EPT; j++) {
+          const int e = tid + j * CTA;
+          const double* Di = P.Dinv + (size_t)e * 6;  // row cc of block sl = 6 doubles at (sl*36 + cc*6) = e*6
+#pragma unroll
+          for (int k = 0; k < 6; k++) dg[j][k] = (e < n6) ? __ldg(Di + k) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < EPT; j++) {
+          const int e = tid + j * CTA;
+          if (e < n6) {
+            const int sl = e / 6;
+            const double* rs = res_sh + sl * 6;
+            double z = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) z += dg[j][k] * rs[k];
+            acc_sh[e] = z;
+            d += res_sh[e] * z;
+          }
+        }
+      }
+      PROFP(2)
+      const double rzn = cta_sum(d, red_sh, 1, lane, wid);
+      iters = it + 1;
+      const bool last = !(rzn > A.tol2 * rz0) || iters >= A.max_iters;
+      if (tid == 0) {
+        if (last) { sig[2] = n; __threadfence_block(); sig[1] = 1; }
+        else sig[0] = it + 1;
+      }
+      const double beta = rzn / rz;
+      rz = rzn;
+      if (last) break;
+      for (int e = tid; e < n6; e += CTA) {
+        const int sl = e / 6, cc = e - sl * 6;
+        p_sh[cc * maxslot + sl] = acc_sh[e] + beta * p_sh[cc * maxslot + sl];
+        acc_sh[e] = 0.0;
+      }
+      named_bar_sync(1, CTA);
+      PROFP(5)
+      continue;
+    }
+    // ================================================================== chunked vector update (BIG)
+    // ---- phase 1: [cross-rank sum of q]  q += lambda p,  Dq = Dinv q,  partial r.z, p.q, q.z, q.Dq
+    const unsigned long long seq = seq0 + (unsigned long long)it + 1ull;
+    const int par = (int)(seq & 1ull);
+    seq_last = seq;
+    for (int ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+      const int slot = ch * VSLOT + vsl;
+      const bool ok = lane < 30 && slot < P.n_slot;
+      const int e = slot * 6 + vcc;
+      double qv = ok ? __ldcg(&P.q[e]) : 0.0;
+      if (A.nranks > 1) {
+        if (ok) {
+          for (int r = 0; r < A.nranks; r++)
+            if (r != A.rank) A.peer_recv[r][((size_t)par * A.nranks + A.rank) * A.nelem_cap + e] = qv;
+        }
+        __threadfence_system();
+        named_bar_sync(1, CTA);
+        if (tid < A.nranks && tid != A.rank) {
+          st_release_sys(&A.peer_flag[tid][(size_t)A.rank * A.nchunk_cap + ch], seq);
+          while (ld_acquire_sys(&A.flag[(size_t)tid * A.nchunk_cap + ch]) < seq) {}
+        }
+        named_bar_sync(1, CTA);
+        if (ok) {
+          double tot = 0.0;
+          for (int r = 0; r < A.nranks; r++)
+            tot += (r == A.rank) ? qv : __ldcv(&A.recv[((size_t)par * A.nranks + r) * A.nelem_cap + e]);
+          qv = tot;
+        }
+      }
+      double pv = 0.0, zv = 0.0, rv = 0.0;
+      if (ok) {
+        pv = P.p[e];
+        zv = P.z[e];
+        rv = P.res[e];
+        qv += lam * pv;
+        P.q[e] = qv;
+      }
+      double dq = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const double qk = __shfl_sync(FULL, qv, vbase + k);
+        if (ok) dq += __ldg(&P.Dinv[(size_t)slot * 36 + vcc * 6 + k]) * qk;
+      }
+      if (ok) A.dq[e] = dq;
+      double d0 = rv * zv, d1 = pv * qv, d2 = qv * zv, d3 = qv * dq;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        d0 += __shfl_down_sync(FULL, d0, off);
+        d1 += __shfl_down_sync(FULL, d1, off);
+        d2 += __shfl_down_sync(FULL, d2, off);
+        d3 += __shfl_down_sync(FULL, d3, off);
+      }
+      named_bar_sync(1, CTA);  // red_sh free (previous chunk's partials consumed)
+      if (lane == 0) { red_sh[wid] = d0; red_sh[4 + wid] = d1; c_sh[wid] = d2; c_sh[4 + wid] = d3; }
+      named_bar_sync(1, CTA);
+      if (tid < 4) {
+        const double* src = (tid < 2) ? red_sh + tid * 4 : c_sh + (tid - 2) * 4;
+        A.part[(size_t)ch * 4 + tid] = (src[0] + src[1]) + (src[2] + src[3]);
+      }
+    }
+    PROFP(1)
+    grid_bar(A.gbar, gridDim.x, gen, tid);  // B2: partial dot products complete
+    PROFP(2)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int i = lane; i < nchunk; i += 32) {
+      const double2 ab = __ldcg(reinterpret_cast<const double2*>(A.part + (size_t)i * 4));
+      const double2 cd = __ldcg(reinterpret_cast<const double2*>(A.part + (size_t)i * 4 + 2));
+      s0 += ab.x; s1 += ab.y; s2 += cd.x; s3 += cd.y;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s0 += __shfl_down_sync(FULL, s0, off);
+      s1 += __shfl_down_sync(FULL, s1, off);
+      s2 += __shfl_down_sync(FULL, s2, off);
+      s3 += __shfl_down_sync(FULL, s3, off);
+    }
+    s0 = __shfl_sync(FULL, s0, 0); s1 = __shfl_sync(FULL, s1, 0); s2 = __shfl_sync(FULL, s2, 0); s3 = __shfl_sync(FULL, s3, 0);
+    rz = s0;  // true r.z of the current iterate
+    const double alpha = rz / s1;
+    if (!(s1 > 0.0) || !isfinite(alpha)) break;  // breakdown
+    double rzn = rz - 2.0 * alpha * s2 + alpha * alpha * s3;
+    if (!(rzn > 0.0)) rzn = 0.0;
+    iters = it + 1;
+    const bool last = !(rzn > A.tol2 * rz0) || iters >= A.max_iters;
+    if (tid == 0) {
+      if (last) { sig[2] = n; __threadfence_block(); sig[1] = 1; }
+      else sig[0] = it + 1;
+    }
+    const double beta = rzn / rz;
+    // ---- phase 2: x += alpha p, res -= alpha q, z -= alpha Dq, p = z + beta p, q = 0
+    for (int ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+      const int slot = ch * VSLOT + vsl;
+      if (lane < 30 && slot < P.n_slot) {
+        const int e = slot * 6 + vcc;
+        const double pv = P.p[e];
+        P.x[e] += alpha * pv;
+        P.res[e] -= alpha * P.q[e];
+        const double z = P.z[e] - alpha * A.dq[e];
+        P.z[e] = z;
+        P.p[e] = z + beta * pv;
+        P.q[e] = 0.0;
+      }
+    }
+    rz = rzn;
+    if (last) break;
+    PROFP(5)
+    grid_bar(A.gbar, gridDim.x, gen, tid);  // B3: p complete, q cleared
+    PROFP(6)
+  }
+#ifdef SQRTBA_PIPE_PROF
+  if (P.prof && tid == 0) {
+    long long* o = P.prof + (size_t)blockIdx.x * 16;
+    for (int i = 0; i < 8; i++) o[i] += tpp[i];
+    o[8] += iters;
+  }
+#endif
+  if (tid == 0 && !sig[1]) { sig[2] = n; __threadfence_block(); sig[1] = 1; }  // breakdown exit: release the producer
+  if (blockIdx.x == 0 && tid == 0) {
+    c.rz = rz;
+    c.cg_iters = iters;
+    c.cg_active = 0;
+    atomicAdd(&P.counters[2], iters);
+    if (BIG && A.nranks > 1) *A.seq_state = seq_last;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ K4/K5: PCG vector ops

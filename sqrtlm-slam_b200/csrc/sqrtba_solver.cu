@@ -104,6 +104,7 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   void* lib = nullptr;
   bool load() {
@@ -117,8 +118,9 @@ struct NcclApi {
     CommInitRank = (int (*)(void**, int, UniqueId, int))dlsym(lib, "ncclCommInitRank");
     CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
     AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
     GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
-    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { lib = nullptr; return false; }
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !AllGather) { lib = nullptr; return false; }
     return true;
   }
 };
@@ -153,6 +155,17 @@ class Solver {
                                   (int)pipe_smem_bytes(2, MAXSLOT, false)));
     CU_CHECK(cudaFuncSetAttribute(k_matvec_pipe<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pipe_smem_bytes(3, MAXSLOT, false)));
+    CU_CHECK(cudaFuncSetAttribute(k_pcg_persist<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)persist_smem_bytes(2, MAXSLOT, false)));
+    CU_CHECK(cudaFuncSetAttribute(k_pcg_persist<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)persist_smem_bytes(3, MAXSLOT, false)));
+    CU_CHECK(cudaFuncSetAttribute(k_pcg_persist<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)persist_smem_bytes(2, MAXSLOT, false)));
+    CU_CHECK(cudaFuncSetAttribute(k_pcg_persist<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)persist_smem_bytes(3, MAXSLOT, false)));
+    int coop = 0;
+    CU_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg_.device));
+    coop_ok_ = coop != 0;
     return SQRTBA_OK;
   }
 
@@ -587,8 +600,9 @@ class Solver {
     k_init_jq<<<n_tile, 128, 0, stream_>>>(P_);
     CU_CHECK(cudaGetLastError());
     if (smallwin) {  // pipeline depth / residency for this problem's window size
-      // big windows: shared accumulator window of `pipe_slots_` consecutive slots (reserved[5] overrides)
-      pipe_slots_ = pq_shared ? max_win_slots_ : (cfg_.reserved[5] > 0 ? std::min(cfg_.reserved[5], MAXSLOT) : 48);
+      // big windows: run sums go straight to global atomics (measured faster than a shared accumulator window:
+      // 5.70 vs 4.70 TB/s on C3); reserved[5] > 0 brings the window back for A/B profiling
+      pipe_slots_ = pq_shared ? max_win_slots_ : (cfg_.reserved[5] > 0 ? std::min(cfg_.reserved[5], MAXSLOT) : 0);
       int best_ctas = 0;
       for (int S : {2, 3}) {
         int per_sm = 0;
@@ -605,6 +619,34 @@ class Solver {
         if (per_sm * S > best_ctas * pipe_stages_ || best_ctas == 0) { best_ctas = per_sm; pipe_stages_ = S; }
       }
       pipe_ctas_ = std::max(1, best_ctas) * n_sm_;
+      // the persistent PCG kernel shares the ring configuration; its grid must be co-resident (cooperative launch)
+      int best = 0;
+      persist_stages_ = 2;
+      for (int S : {2, 3}) {
+        int per_sm = 0;
+        const size_t pbytes = persist_smem_bytes(S, pipe_slots_, !pq_shared);
+        cudaError_t e;
+        if (pq_shared)
+          e = (S == 2) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist<2, false>, PIPE_THREADS, pbytes)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist<3, false>, PIPE_THREADS, pbytes);
+        else
+          e = (S == 2) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist<2, true>, PIPE_THREADS, pbytes)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist<3, true>, PIPE_THREADS, pbytes);
+        if (e != cudaSuccess) per_sm = 0;
+        if (cfg_.reserved[2] > 0 && S != cfg_.reserved[2]) continue;
+        if (per_sm * S > best * persist_stages_ || best == 0) { best = per_sm; persist_stages_ = S; }
+      }
+      persist_ctas_ = best * n_sm_;
+    }
+    {
+      const int nchunk = (std::max(n_slot, 1) + VSLOT - 1) / VSLOT;
+      CU_CHECK(d_part_.ensure((size_t)4 * nchunk));
+      CU_CHECK(d_gbar_.ensure(2));
+      CU_CHECK(d_q3_.ensure((size_t)3 * KQ * 6 * std::max(n_slot, 1)));
+      CU_CHECK(d_dq_.ensure((size_t)6 * std::max(n_slot, 1)));
+      if (comm_) {
+        if (int rc = peer_setup((size_t)std::max(n_slot, 1) * 6, (size_t)nchunk)) return rc;
+      }
     }
     have_problem_ = true;
     return reset_state();
@@ -648,6 +690,7 @@ class Solver {
       if (rc) return rc;
     }
     launch_classify(1, 5.991, 7.815);
+    dump_persist_prof();
     return finish_stats(st);
   }
 
@@ -661,6 +704,7 @@ class Solver {
     CU_CHECK(clear_traces());
     int rc = run_pass(iters, 0, robust ? 1 : 0, d2, d3, stop);
     if (rc) return rc;
+    dump_persist_prof();
     return finish_stats(st);
   }
 
@@ -906,12 +950,37 @@ class Solver {
       return SQRTBA_ERR_COMM;
     }
     n_ranks_ = nranks;
+    rank_ = rank;
     return SQRTBA_OK;
   }
   void comm_destroy() {
+    if (stream_) cudaStreamSynchronize(stream_);
+    peer_release();
+    if (d_seq_) cudaFree(d_seq_);
+    d_seq_ = nullptr;
     if (comm_ && g_nccl.CommDestroy) g_nccl.CommDestroy(comm_);
     comm_ = nullptr;
     n_ranks_ = 1;
+    rank_ = 0;
+  }
+  int uses_peer_exchange() const { return (comm_ && peer_ok_) ? 1 : 0; }
+  void dump_persist_prof() {
+#ifdef SQRTBA_PIPE_PROF
+    const int grid = std::min(P_.n_tile, persist_ctas_);
+    std::vector<long long> hp((size_t)grid * 16);
+    if (download(hp.data(), d_prof_.p, hp.size() * sizeof(long long))) return;
+    double acc[9] = {};
+    double mx3 = 0;
+    for (int b = 0; b < grid; b++) {
+      for (int i = 0; i < 9; i++) acc[i] += (double)hp[(size_t)b * 16 + i];
+      mx3 = std::max(mx3, (double)hp[(size_t)b * 16 + 3]);
+    }
+    const double its = std::max(acc[8], 1.0);
+    fprintf(stderr, "[persist prof] grid %d, iterations/CTA %.0f | cycles per iteration (CTA average): tiles %.0f (max-CTA %.0f) flush %.0f "
+            "B1 %.0f ph1 %.0f B2|ph2 %.0f ph3 %.0f B3 %.0f other %.0f\n", grid, its / grid, acc[3] / its, mx3 / (its / grid), acc[4] / its,
+            acc[0] / its, acc[1] / its, acc[2] / its, acc[5] / its, acc[6] / its, acc[7] / its);
+    cudaMemsetAsync(d_prof_.p, 0, d_prof_.cap * sizeof(long long), stream_);
+#endif
   }
 
  private:
@@ -919,6 +988,10 @@ class Solver {
   static size_t pipe_smem_bytes(int S, int maxslot, bool big) {
     return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + (big ? 6 : 12) * (size_t)maxslot) * sizeof(double) +
            2 * (2 * CTA + 4) * sizeof(int) + 2 * S * sizeof(uint64_t);
+  }
+  static size_t persist_smem_bytes(int S, int maxslot, bool big) {
+    return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + (big ? 0 : 18) * (size_t)maxslot + 8) * sizeof(double) +
+           2 * S * sizeof(uint64_t) + 4 * sizeof(int) + 2 * (size_t)pipe_run_cap(maxslot, big) * sizeof(int);
   }
   void launch_matvec(const double* pvec, double* qvec, int force_all) {
     if (P_.smallwin && cfg_.reserved[1] == 0) {
@@ -940,6 +1013,129 @@ class Solver {
     }
   }
 
+  // pcg_mode: 0 = auto (persistent kernel for single-window problems, one launch per CG phase for batches),
+  //           1 = always one launch per phase, 2 = persistent whenever possible
+  bool use_persist() const {
+    if (cfg_.pcg_mode == 1 || !coop_ok_ || P_.n_win != 1 || !P_.smallwin || persist_ctas_ <= 0 || cfg_.reserved[1] != 0) return false;
+    if (comm_ && (!peer_ok_ || P_.pq_shared)) return false;  // sharded without peer-mapped buffers, or a small window: NCCL all-reduce per iteration
+    return true;
+  }
+  int launch_pcg_persist(double tol2, int use_override, double lam_override) {
+    PcgArgs A{};
+    A.tol2 = tol2;
+    A.max_iters = cfg_.pcg_max_iters;
+    A.nranks = comm_ ? n_ranks_ : 1;
+    A.rank = comm_ ? rank_ : 0;
+    A.gbar = d_gbar_.p;
+    A.part = d_part_.p;
+    A.q3 = d_q3_.p;
+    A.dq = d_dq_.p;
+    if (A.nranks > 1) {
+      A.recv = peer_recv_[rank_];
+      A.flag = peer_flag_[rank_];
+      for (int r = 0; r < n_ranks_; r++) { A.peer_recv[r] = peer_recv_[r]; A.peer_flag[r] = peer_flag_[r]; }
+      A.seq_state = d_seq_;
+      A.nelem_cap = (int)peer_nelem_cap_;
+      A.nchunk_cap = (int)peer_nchunk_cap_;
+    }
+    const bool big = !P_.pq_shared;
+    const int grid = std::min(P_.n_tile, persist_ctas_);
+    const size_t bytes = persist_smem_bytes(persist_stages_, pipe_slots_, big);
+    int maxslot = pipe_slots_;
+    void* args[] = {(void*)&P_, (void*)&A, (void*)&maxslot, (void*)&lam_override, (void*)&use_override};
+    const void* fn = big ? (persist_stages_ == 2 ? (const void*)k_pcg_persist<2, true> : (const void*)k_pcg_persist<3, true>)
+                         : (persist_stages_ == 2 ? (const void*)k_pcg_persist<2, false> : (const void*)k_pcg_persist<3, false>);
+    CU_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PIPE_THREADS), args, bytes, stream_));
+    return SQRTBA_OK;
+  }
+
+  // Peer-mapped exchange buffers of the landmark-sharded mode (collective: every rank calls with the same sizes).
+  // Each rank allocates its receive buffer and flags with cudaMalloc, the cudaIpc handles travel through an NCCL
+  // all-gather on the existing communicator, and every rank maps every peer's buffers.
+  int peer_setup(size_t nelem, size_t nchunk) {
+    if (!comm_ || n_ranks_ <= 1) return SQRTBA_OK;
+    if (peer_ok_ && nelem <= peer_nelem_cap_ && nchunk <= peer_nchunk_cap_) return SQRTBA_OK;
+    if (n_ranks_ > 8 || cfg_.reserved[6] != 0) { peer_ok_ = false; return SQRTBA_OK; }
+    peer_release();
+    peer_nelem_cap_ = nelem;
+    peer_nchunk_cap_ = nchunk;
+    const size_t recv_bytes = 2 * (size_t)n_ranks_ * nelem * sizeof(double);
+    const size_t flag_bytes = (size_t)n_ranks_ * nchunk * sizeof(unsigned long long);
+    double* recv = nullptr;
+    unsigned long long* flag = nullptr;
+    CU_CHECK(cudaMalloc((void**)&recv, recv_bytes));
+    CU_CHECK(cudaMalloc((void**)&flag, flag_bytes));
+    if (!d_seq_) CU_CHECK(cudaMalloc((void**)&d_seq_, sizeof(unsigned long long)));
+    CU_CHECK(cudaMemsetAsync(recv, 0, recv_bytes, stream_));
+    CU_CHECK(cudaMemsetAsync(flag, 0, flag_bytes, stream_));
+    CU_CHECK(cudaMemsetAsync(d_seq_, 0, sizeof(unsigned long long), stream_));
+    peer_recv_[rank_] = recv;
+    peer_flag_[rank_] = flag;
+    struct Handles { cudaIpcMemHandle_t recv, flag; };
+    static_assert(sizeof(Handles) == 128, "two 64-byte cudaIpc handles");
+    std::vector<Handles> hs(n_ranks_);
+    int ok = 1;
+    if (cudaIpcGetMemHandle(&hs[rank_].recv, recv) != cudaSuccess || cudaIpcGetMemHandle(&hs[rank_].flag, flag) != cudaSuccess) {
+      ok = 0;
+      cudaGetLastError();
+      std::memset(&hs[rank_], 0, sizeof(Handles));
+    }
+    Handles* d_h = nullptr;
+    CU_CHECK(cudaMalloc((void**)&d_h, sizeof(Handles) * n_ranks_));
+    CU_CHECK(cudaMemcpyAsync(d_h + rank_, &hs[rank_], sizeof(Handles), cudaMemcpyHostToDevice, stream_));
+    if (g_nccl.AllGather(d_h + rank_, d_h, sizeof(Handles), /*ncclInt8*/ 0, comm_, stream_) != 0) {
+      cudaFree(d_h);
+      err_ = "ncclAllGather of the peer handles failed";
+      return SQRTBA_ERR_COMM;
+    }
+    CU_CHECK(cudaMemcpyAsync(hs.data(), d_h, sizeof(Handles) * n_ranks_, cudaMemcpyDeviceToHost, stream_));
+    CU_CHECK(cudaStreamSynchronize(stream_));
+    cudaFree(d_h);
+    for (int r = 0; r < n_ranks_ && ok; r++) {
+      if (r == rank_) continue;
+      void *pr = nullptr, *pf = nullptr;
+      if (cudaIpcOpenMemHandle(&pr, hs[r].recv, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&pf, hs[r].flag, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        ok = 0;
+        cudaGetLastError();
+        if (pr) cudaIpcCloseMemHandle(pr);
+        break;
+      }
+      peer_recv_[r] = (double*)pr;
+      peer_flag_[r] = (unsigned long long*)pf;
+    }
+    // every rank must take the same path: agree on success (min over ranks)
+    double* d_ok = nullptr;
+    CU_CHECK(cudaMalloc((void**)&d_ok, sizeof(double)));
+    const double okd = ok;
+    CU_CHECK(cudaMemcpyAsync(d_ok, &okd, sizeof(double), cudaMemcpyHostToDevice, stream_));
+    double all_ok = 0.0;
+    const int rc = g_nccl.AllReduce(d_ok, d_ok, 1, /*ncclFloat64*/ 8, /*ncclMin*/ 3, comm_, stream_);
+    if (rc == 0) {
+      CU_CHECK(cudaMemcpyAsync(&all_ok, d_ok, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+      CU_CHECK(cudaStreamSynchronize(stream_));
+    }
+    cudaFree(d_ok);
+    peer_ok_ = (rc == 0) && all_ok > 0.5;
+    if (!peer_ok_) peer_release();
+    return SQRTBA_OK;
+  }
+  void peer_release() {
+    for (int r = 0; r < 8; r++) {
+      if (r == rank_) {
+        if (peer_recv_[r]) cudaFree(peer_recv_[r]);
+        if (peer_flag_[r]) cudaFree(peer_flag_[r]);
+      } else {
+        if (peer_recv_[r]) cudaIpcCloseMemHandle(peer_recv_[r]);
+        if (peer_flag_[r]) cudaIpcCloseMemHandle(peer_flag_[r]);
+      }
+      peer_recv_[r] = nullptr;
+      peer_flag_[r] = nullptr;
+    }
+    peer_ok_ = false;
+    peer_nelem_cap_ = peer_nchunk_cap_ = 0;
+  }
+
   // QR + block-Jacobi + PCG for every window in PH_TRIAL
   int factor_and_solve() {
     const int gi = cdiv(P_.n_item, WARPS);
@@ -958,6 +1154,16 @@ class Solver {
     const double tol2 = cfg_.pcg_rtol * cfg_.pcg_rtol;
     const int check = std::max(1, cfg_.pcg_check_every);
     const size_t qbytes = (size_t)P_.n_slot * 6 * sizeof(double);
+    if (use_persist()) {  // whole PCG solve in one cooperative launch (single-window problems)
+      if (P_.pq_shared) CU_CHECK(cudaMemsetAsync(d_q3_.p, 0, 3 * KQ * qbytes, stream_));
+      else CU_CHECK(cudaMemsetAsync(P_.q, 0, qbytes, stream_));
+      CU_CHECK(cudaMemsetAsync(d_gbar_.p, 0, 2 * sizeof(unsigned), stream_));
+      if (int rc = launch_pcg_persist(tol2, 0, 0.0)) return rc;
+      launches_ += 1;
+      stage_end(2);
+      CU_CHECK(cudaGetLastError());
+      return SQRTBA_OK;
+    }
     for (int it = 0; it < cfg_.pcg_max_iters; it++) {
       CU_CHECK(cudaMemsetAsync(P_.q, 0, qbytes, stream_));
       launch_matvec(P_.p, P_.q, 0);
@@ -1011,9 +1217,10 @@ class Solver {
       k_restore<<<cdiv(std::max(P_.n_pose, P_.n_point), 256), 256, 0, stream_>>>(P_);
       launches_ += 7;
       lm_trials_++;
-      CU_CHECK(cudaMemcpyAsync(h_counters_, P_.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+      CU_CHECK(cudaMemcpyAsync(h_counters_, P_.counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
       CU_CHECK(cudaStreamSynchronize(stream_));
       CU_CHECK(cudaGetLastError());
+      if (use_persist()) cg_iters_total_ = h_counters_[2];
       if (h_counters_[0] >= P_.n_win) break;
     }
     return SQRTBA_OK;
@@ -1023,6 +1230,7 @@ class Solver {
   void begin_stats() {
     launches_ = 0; lm_trials_ = 0; cg_iters_total_ = 0;
     for (auto& v : stage_ms_) v = 0.0;
+    cudaMemsetAsync(d_counters_.p + 2, 0, sizeof(int), stream_);
     cudaEventRecord(ev0_, stream_);
   }
   void stage_begin(int s) {
@@ -1069,6 +1277,7 @@ class Solver {
     d_bl_.release(); d_dl_.release(); d_slotvec_.release(); d_chi_part_.release(); d_scale_part_.release();
     d_ctl_.release(); d_trace_.release(); d_counters_.release(); d_wred_.release();
     d_tiles_.release(); d_obs_lp_.release(); d_tile_run_ptr_.release(); d_tile_runs_.release();
+    d_gbar_.release(); d_part_.release(); d_q3_.release(); d_dq_.release();
     h_obs_slot_.release(); h_item_start_.release(); h_item_cnt_.release(); h_item_win_.release();
     h_tile_run_ptr_.release(); h_tile_runs_.release(); h_obs_lp_.release(); h_tiles_pin_.release();
     h_perm_pose_.release(); h_perm_point_.release(); h_perm_slot_.release(); h_perm_meas_.release(); h_perm_xyz_.release();
@@ -1091,7 +1300,15 @@ class Solver {
   int n_sm_ = 148, pipe_ctas_ = 296, pipe_stages_ = 3, max_win_slots_ = 1, pipe_slots_ = 1;
   std::vector<int> perm_, old_first_, new_first_, lm_count_new_;  // landmark re-ordering of big windows: new -> old, first observation in either order
   void* comm_ = nullptr;  // ncclComm_t
-  int n_ranks_ = 1;
+  int n_ranks_ = 1, rank_ = 0;
+  bool coop_ok_ = false, peer_ok_ = false;
+  int persist_ctas_ = 0, persist_stages_ = 2;
+  double* peer_recv_[8] = {};
+  unsigned long long* peer_flag_[8] = {};
+  unsigned long long* d_seq_ = nullptr;
+  size_t peer_nelem_cap_ = 0, peer_nchunk_cap_ = 0;
+  DBuf<unsigned> d_gbar_;
+  DBuf<double> d_part_, d_q3_, d_dq_;
   Dev P_{};
   DBuf<double> d_cam_, d_pose_, d_pose0_, d_pose_bak_, d_point_, d_point0_, d_point_bak_, d_err_, d_JQ_, d_Jl_,
       d_r_, d_R_, d_tl_, d_bl_, d_dl_, d_slotvec_, d_chi_part_, d_scale_part_, d_trace_, d_wred_;

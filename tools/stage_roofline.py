@@ -38,7 +38,7 @@ def main():
     free_obs = int((prob.pose_fixed[prob.obs_pose] == 0).sum())
     variants = [dict()]
     if args.variants:
-        variants += [dict(pipe_stages=2, pipe_slots=48), dict(pipe_stages=3, pipe_slots=128), dict(pipe_stages=2, pipe_slots=128),
+        variants += [dict(pipe_slots=-1), dict(pipe_slots=24), dict(pipe_slots=32),
                      dict(no_reorder=True), dict(general_matvec=True)]
     for kw in variants:
         ba = pkg.SqrtBA(**kw)
