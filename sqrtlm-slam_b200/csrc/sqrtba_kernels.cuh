@@ -776,12 +776,24 @@ __global__ void k_dinv(Dev P, int force_all, double lam_override) {
 // update).  Per observation: v = Jp p[slot] (d-vector), s_l = sum Q1^T v (3-vector, landmark reduction),
 // u = v - Q1 s_l, scatter-add Jp^T u.  Streams Jp (18) + Q1 (9) planes: 216 B/observation.
 // Observations of fixed poses have no pose columns (g2o hessianIndex -1): they are skipped entirely.
+// The search direction of the persistent big-window PCG is never stored between iterations: owners apply the CG update
+// one phase late, and everybody else evaluates  p = (z - alpha Dq) + beta p_old  where it is needed.
+struct PEff {
+  const double *z, *dq, *p;
+  double alpha, beta;
+};
+// Plain (L1-cached) loads: the three vectors only change between grid barriers, whose acquire makes the owners' writes
+// visible to ordinary loads (the cooperative-groups grid.sync contract); repeated far-band poses then hit L1.
+__device__ __forceinline__ double peff_at(const PEff& pe, size_t e) {
+  return (pe.z[e] - pe.alpha * pe.dq[e]) + pe.beta * pe.p[e];
+}
+
 // PSRC: where p lives -- 0 global (slot-major), 1 global read through L2 (rewritten by other CTAs during the kernel),
-// 2 shared memory, component-major with stride `pstride`
+// 2 shared memory, component-major with stride `pstride`, 3 evaluated on the fly from a PEff
 template <int PSRC = 0>
 __device__ __forceinline__ void matvec_obs_v(const double* __restrict__ jq, int nt, int col,
                                              const double* pvec, int slot, double J[18], double Q[9],
-                                             double v[3], int pstride = 0) {
+                                             double v[3], int pstride = 0, const PEff* pe = nullptr) {
 #pragma unroll
   for (int c = 0; c < 18; c++) J[c] = jq[(size_t)c * nt + col];
 #pragma unroll
@@ -789,7 +801,8 @@ __device__ __forceinline__ void matvec_obs_v(const double* __restrict__ jq, int 
   double pp[6];
 #pragma unroll
   for (int c = 0; c < 6; c++)
-    pp[c] = (PSRC == 2) ? pvec[c * pstride + slot] : ((PSRC == 1) ? __ldcg(pvec + slot * 6 + c) : pvec[slot * 6 + c]);
+    pp[c] = (PSRC == 3) ? peff_at(*pe, (size_t)slot * 6 + c)
+                        : (PSRC == 2) ? pvec[c * pstride + slot] : ((PSRC == 1) ? __ldcg(pvec + slot * 6 + c) : pvec[slot * 6 + c]);
 #pragma unroll
   for (int r = 0; r < 3; r++)
     v[r] = J[r * 6] * pp[0] + J[r * 6 + 1] * pp[1] + J[r * 6 + 2] * pp[2] + J[r * 6 + 3] * pp[3] +
@@ -800,13 +813,13 @@ __device__ __forceinline__ void matvec_obs_v(const double* __restrict__ jq, int 
 template <int PSRC = 0>
 __device__ __forceinline__ void matvec_long_item(const Dev& P, const double* __restrict__ jq, int nt,
                                                  const double* pvec, double* qvec,
-                                                 int start, int cnt, int lane, int pstride = 0) {
+                                                 int start, int cnt, int lane, int pstride = 0, const PEff* pe = nullptr) {
   double J[18], Q[9], v[3], sv[3] = {0, 0, 0};
   for (int i = lane; i < cnt; i += 32) {
     const int o = start + i;
     const int slot = P.obs_slot[o];
     if (slot < 0) continue;
-    matvec_obs_v<PSRC>(jq, nt, i, pvec, slot, J, Q, v, pstride);  // a long item is a tile of its own: column = i
+    matvec_obs_v<PSRC>(jq, nt, i, pvec, slot, J, Q, v, pstride, pe);  // a long item is a tile of its own: column = i
 #pragma unroll
     for (int k = 0; k < 3; k++) sv[k] += Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2];
   }
@@ -816,7 +829,7 @@ __device__ __forceinline__ void matvec_long_item(const Dev& P, const double* __r
     const int o = start + i;
     const int slot = P.obs_slot[o];
     if (slot < 0) continue;
-    matvec_obs_v<PSRC>(jq, nt, i, pvec, slot, J, Q, v, pstride);
+    matvec_obs_v<PSRC>(jq, nt, i, pvec, slot, J, Q, v, pstride, pe);
 #pragma unroll
     for (int r = 0; r < 3; r++) v[r] -= Q[r * 3] * sv[0] + Q[r * 3 + 1] * sv[1] + Q[r * 3 + 2] * sv[2];
 #pragma unroll
@@ -1187,9 +1200,11 @@ struct PcgArgs {
   int max_iters;
   int nranks, rank;
   unsigned* gbar;                 // grid barrier arrival counter (monotonic; zeroed by the host before the launch)
+  const int* tile_ptr;            // [gridDim.x + 1] cost-balanced tile ranges of the CTAs
   double* part;                   // BIG: [nchunk][4] partial dot products
   double* q3;                     // !BIG: three rotating buffers of KQ copies of q, [3][KQ][6*n_slot] (zeroed by the host)
-  double* dq;                     // BIG: Dinv * q
+  double* dq;                     // BIG: Dinv * qf   (zeroed by the host)
+  double* qf;                     // BIG: q + lambda p (zeroed by the host)
   double* recv;                   // this rank's receive buffer  [2 (parity)][nranks][nelem_cap]
   unsigned long long* flag;       // this rank's arrival flags   [nranks][nchunk_cap]
   double* peer_recv[8];           // the same two buffers of every rank, peer-mapped (cudaIpc)
@@ -1237,7 +1252,7 @@ __device__ __forceinline__ double cta_sum(double v, double* red_sh, int which, i
 // per-lane matvec products of one staged tile: writes this observation's Jp^T u (6 values) into column `rank` of cb
 template <bool BIG>
 __device__ __forceinline__ void tile_products(const double* data, const int* hdr, int nt, int wid, int lane,
-                                              const double* p_sh, int maxslot, const double* pglob, double* cb) {
+                                              const double* p_sh, int maxslot, const PEff& pe, int abase, double* cb) {
   constexpr int CST = CTA + 1;
   const uint2* meta = reinterpret_cast<const uint2*>(data + (size_t)NPLANE * nt);
   const int col0 = (wid > 0 ? hdr[9] : 0) + (wid > 1 ? hdr[10] : 0) + (wid > 2 ? hdr[11] : 0);
@@ -1258,13 +1273,13 @@ __device__ __forceinline__ void tile_products(const double* data, const int* hdr
   double J[18], v[3] = {0, 0, 0}, t[3] = {0, 0, 0};
   if (has) {
     double pp[6];
-    if (BIG) {
-      const double* pg = pglob + (size_t)ls * 6;  // rewritten by other CTAs between iterations: L2 loads
+    const int rel = BIG ? ls - abase : ls;
+    if (!BIG || (unsigned)rel < (unsigned)maxslot) {  // BIG: inside the CTA's window of the search direction
 #pragma unroll
-      for (int cc = 0; cc < 6; cc++) pp[cc] = __ldcg(pg + cc);
-    } else {
+      for (int cc = 0; cc < 6; cc++) pp[cc] = p_sh[cc * maxslot + rel];
+    } else {                                           // outside (loop-closure observations, wide covisibility)
 #pragma unroll
-      for (int cc = 0; cc < 6; cc++) pp[cc] = p_sh[cc * maxslot + ls];
+      for (int cc = 0; cc < 6; cc++) pp[cc] = peff_at(pe, (size_t)ls * 6 + cc);
     }
 #pragma unroll
     for (int cc = 0; cc < 18; cc++) J[cc] = dcol[cc * nt];
@@ -1301,8 +1316,9 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
   constexpr int CST = CTA + 1;
   double* stage = reinterpret_cast<double*>(smem_raw);
   double* c_sh = stage + (size_t)S * STAGE_D;            // two buffers of [6][CST]
-  double* p_sh = c_sh + 2 * (6 * CST) + 2;                // !BIG: p, component-major [c * maxslot + slot]
-  double* acc_sh = p_sh + (BIG ? 0 : 6 * maxslot);        // !BIG: q accumulators, then scratch of the vector phase
+  double* p_sh = c_sh + 2 * (6 * CST) + 2;                // p, component-major [c * maxslot + slot]; BIG: a WINDOW of
+                                                          // maxslot consecutive slots starting at abase
+  double* acc_sh = p_sh + 6 * maxslot;                    // !BIG: q accumulators, then scratch of the vector phase
   double* res_sh = acc_sh + (BIG ? 0 : 6 * maxslot);      // !BIG: residual, slot-major [slot * 6 + c]
   double* red_sh = res_sh + (BIG ? 0 : 6 * maxslot);      // 8 doubles
   uint64_t* full = reinterpret_cast<uint64_t*>(red_sh + 8);
@@ -1311,8 +1327,7 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
   int* runs_sh = const_cast<int*>(sig) + 4;
   const int rcap = pipe_run_cap(maxslot, BIG);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int t0 = (int)((long long)P.n_tile * blockIdx.x / gridDim.x);
-  const int t1 = (int)((long long)P.n_tile * (blockIdx.x + 1) / gridDim.x);
+  const int t0 = A.tile_ptr[blockIdx.x], t1 = A.tile_ptr[blockIdx.x + 1];
   const int ntile = t1 - t0;
   if (tid == 0) {
     for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -1371,7 +1386,10 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
   const int vsl = wid * 5 + lane / 6, vcc = lane - (lane / 6) * 6;
   const int vbase = min((lane / 6) * 6, 24);
   unsigned gen = 0;
-  int n = 0, iters = 0;
+  int n = 0, iters = 0, abase = 0;
+  PEff pe;
+  pe.z = P.z; pe.dq = A.dq; pe.p = P.p;
+  pe.alpha = 0.0; pe.beta = 0.0;  // iteration 0: p = z (k_cg_init), Dq zeroed by the host
 #ifdef SQRTBA_PIPE_PROF
   long long tpp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tcc = clock64(), tnn;
 #define PROFP(i) { tnn = clock64(); tpp[i] += tnn - tcc; tcc = tnn; }
@@ -1398,10 +1416,25 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       const int* hdr = reinterpret_cast<const int*>(st);
       const int nitem = hdr[0];
       const int nt = hdr[5];
+      if (BIG) {
+        // slide the window of the search direction with the (sorted) landmarks: re-evaluate it when this tile starts
+        // below it or more than a few poses above its anchor
+        const int lo = hdr[15];
+        const int want = max(0, min(lo, P.n_slot - maxslot));
+        if (kt == 0 || (lo >= 0 && (want < abase || want > abase + 6))) {
+          named_bar_sync(1, CTA);  // every warp is done reading the old window
+          abase = want;
+          for (int i = tid; i < maxslot * 6; i += CTA) {
+            const int rel = i / 6, cc = i - rel * 6;
+            if (abase + rel < P.n_slot) p_sh[cc * maxslot + rel] = peff_at(pe, (size_t)(abase + rel) * 6 + cc);
+          }
+          named_bar_sync(1, CTA);
+        }
+      }
       if (hdr[13]) {  // long landmark: operands straight from global memory, direct atomics
         const long long jq_off = ((long long)hdr[8] << 32) | (unsigned)hdr[7];
         if (wid == 0) {
-          if (BIG) matvec_long_item<1>(P, P.JQ + jq_off, nt, P.p, qcur, hdr[6], hdr[9], lane);
+          if (BIG) matvec_long_item<3>(P, P.JQ + jq_off, nt, nullptr, qcur, hdr[6], hdr[9], lane, 0, &pe);
           else matvec_long_item<2>(P, P.JQ + jq_off, nt, p_sh, qcur, hdr[6], hdr[9], lane, maxslot);
         }
         named_bar_sync(1, CTA);
@@ -1417,7 +1450,7 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
         const int* rsrc = reinterpret_cast<const int*>(data + (size_t)JQ_ROWS * nt);
         for (int i = tid; i < 2 * nrun + 1; i += CTA) rb[i] = rsrc[i];
       }
-      if (wid < nitem) tile_products<BIG>(data, hdr, nt, wid, lane, p_sh, maxslot, P.p, cb);
+      if (wid < nitem) tile_products<BIG>(data, hdr, nt, wid, lane, p_sh, maxslot, pe, abase, cb);
       named_bar_sync(1, CTA);
       if (tid == 0) mbar_arrive(&empty[s]);
       for (int idx = tid; idx < nrun * 6; idx += CTA) {
@@ -1527,7 +1560,8 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       continue;
     }
     // ================================================================== chunked vector update (BIG)
-    // ---- phase 1: [cross-rank sum of q]  q += lambda p,  Dq = Dinv q,  partial r.z, p.q, q.z, q.Dq
+    // ---- owners: apply the PREVIOUS iteration's update (deferred so that nobody had to wait for it), then
+    //      [cross-rank sum of q]  qf = q + lambda p,  Dq = Dinv qf,  partial r.z, p.qf, qf.z, qf.Dq;  q = 0
     const unsigned long long seq = seq0 + (unsigned long long)it + 1ull;
     const int par = (int)(seq & 1ull);
     seq_last = seq;
@@ -1535,7 +1569,19 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       const int slot = ch * VSLOT + vsl;
       const bool ok = lane < 30 && slot < P.n_slot;
       const int e = slot * 6 + vcc;
-      double qv = ok ? __ldcg(&P.q[e]) : 0.0;
+      double qv = 0.0, pv = 0.0, zv = 0.0, rv = 0.0;
+      if (ok) {
+        qv = __ldcg(&P.q[e]);
+        const double po = P.p[e], dqo = A.dq[e], qfo = A.qf[e];
+        zv = P.z[e] - pe.alpha * dqo;
+        pv = zv + pe.beta * po;
+        rv = P.res[e] - pe.alpha * qfo;
+        P.x[e] += pe.alpha * po;
+        P.z[e] = zv;
+        P.p[e] = pv;
+        P.res[e] = rv;
+        P.q[e] = 0.0;
+      }
       if (A.nranks > 1) {
         if (ok) {
           for (int r = 0; r < A.nranks; r++)
@@ -1555,13 +1601,9 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
           qv = tot;
         }
       }
-      double pv = 0.0, zv = 0.0, rv = 0.0;
       if (ok) {
-        pv = P.p[e];
-        zv = P.z[e];
-        rv = P.res[e];
         qv += lam * pv;
-        P.q[e] = qv;
+        A.qf[e] = qv;
       }
       double dq = 0.0;
 #pragma unroll
@@ -1578,7 +1620,7 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
         d2 += __shfl_down_sync(FULL, d2, off);
         d3 += __shfl_down_sync(FULL, d3, off);
       }
-      named_bar_sync(1, CTA);  // red_sh free (previous chunk's partials consumed)
+      named_bar_sync(1, CTA);  // scratch free (previous chunk's partials consumed)
       if (lane == 0) { red_sh[wid] = d0; red_sh[4 + wid] = d1; c_sh[wid] = d2; c_sh[4 + wid] = d3; }
       named_bar_sync(1, CTA);
       if (tid < 4) {
@@ -1587,26 +1629,32 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       }
     }
     PROFP(1)
-    grid_bar(A.gbar, gridDim.x, gen, tid);  // B2: partial dot products complete
+    grid_bar(A.gbar, gridDim.x, gen, tid);  // B2: state of this iterate and the partial dot products complete
     PROFP(2)
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    for (int i = lane; i < nchunk; i += 32) {
-      const double2 ab = __ldcg(reinterpret_cast<const double2*>(A.part + (size_t)i * 4));
-      const double2 cd = __ldcg(reinterpret_cast<const double2*>(A.part + (size_t)i * 4 + 2));
-      s0 += ab.x; s1 += ab.y; s2 += cd.x; s3 += cd.y;
-    }
+    if (wid == 0) {  // one warp per CTA reads the partials (every CTA reads the same few lines)
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      for (int i = lane; i < nchunk; i += 32) {
+        const double2 ab = __ldcg(reinterpret_cast<const double2*>(A.part + (size_t)i * 4));
+        const double2 cd = __ldcg(reinterpret_cast<const double2*>(A.part + (size_t)i * 4 + 2));
+        s0 += ab.x; s1 += ab.y; s2 += cd.x; s3 += cd.y;
+      }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      s0 += __shfl_down_sync(FULL, s0, off);
-      s1 += __shfl_down_sync(FULL, s1, off);
-      s2 += __shfl_down_sync(FULL, s2, off);
-      s3 += __shfl_down_sync(FULL, s3, off);
+      for (int off = 16; off > 0; off >>= 1) {
+        s0 += __shfl_down_sync(FULL, s0, off);
+        s1 += __shfl_down_sync(FULL, s1, off);
+        s2 += __shfl_down_sync(FULL, s2, off);
+        s3 += __shfl_down_sync(FULL, s3, off);
+      }
+      if (lane == 0) { red_sh[0] = s0; red_sh[1] = s1; red_sh[2] = s2; red_sh[3] = s3; }
     }
-    s0 = __shfl_sync(FULL, s0, 0); s1 = __shfl_sync(FULL, s1, 0); s2 = __shfl_sync(FULL, s2, 0); s3 = __shfl_sync(FULL, s3, 0);
+    named_bar_sync(1, CTA);
+    const double s0 = red_sh[0], s1 = red_sh[1], s2 = red_sh[2], s3 = red_sh[3];
     rz = s0;  // true r.z of the current iterate
     const double alpha = rz / s1;
-    if (!(s1 > 0.0) || !isfinite(alpha)) break;  // breakdown
-    double rzn = rz - 2.0 * alpha * s2 + alpha * alpha * s3;
+    pe.alpha = 0.0;
+    pe.beta = 0.0;
+    if (!(s1 > 0.0) || !isfinite(alpha)) break;  // breakdown: keep the iterate, LM judges the step by its gain ratio
+    double rzn = rz - 2.0 * alpha * s2 + alpha * alpha * s3;  // r'.z' after the step (exact in exact arithmetic)
     if (!(rzn > 0.0)) rzn = 0.0;
     iters = it + 1;
     const bool last = !(rzn > A.tol2 * rz0) || iters >= A.max_iters;
@@ -1614,26 +1662,20 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       if (last) { sig[2] = n; __threadfence_block(); sig[1] = 1; }
       else sig[0] = it + 1;
     }
-    const double beta = rzn / rz;
-    // ---- phase 2: x += alpha p, res -= alpha q, z -= alpha Dq, p = z + beta p, q = 0
+    pe.alpha = alpha;
+    pe.beta = rzn / rz;
+    rz = rzn;
+    PROFP(5)
+    if (last) break;
+  }
+  if (BIG && pe.alpha != 0.0) {  // the last step is still pending
     for (int ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
       const int slot = ch * VSLOT + vsl;
       if (lane < 30 && slot < P.n_slot) {
         const int e = slot * 6 + vcc;
-        const double pv = P.p[e];
-        P.x[e] += alpha * pv;
-        P.res[e] -= alpha * P.q[e];
-        const double z = P.z[e] - alpha * A.dq[e];
-        P.z[e] = z;
-        P.p[e] = z + beta * pv;
-        P.q[e] = 0.0;
+        P.x[e] += pe.alpha * P.p[e];
       }
     }
-    rz = rzn;
-    if (last) break;
-    PROFP(5)
-    grid_bar(A.gbar, gridDim.x, gen, tid);  // B3: p complete, q cleared
-    PROFP(6)
   }
 #ifdef SQRTBA_PIPE_PROF
   if (P.prof && tid == 0) {

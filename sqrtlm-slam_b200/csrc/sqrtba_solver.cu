@@ -622,9 +622,10 @@ class Solver {
       // the persistent PCG kernel shares the ring configuration; its grid must be co-resident (cooperative launch)
       int best = 0;
       persist_stages_ = 2;
+      persist_slots_ = pq_shared ? max_win_slots_ : 48;  // big windows: slots in the shared window of the search direction
       for (int S : {2, 3}) {
         int per_sm = 0;
-        const size_t pbytes = persist_smem_bytes(S, pipe_slots_, !pq_shared);
+        const size_t pbytes = persist_smem_bytes(S, persist_slots_, !pq_shared);
         cudaError_t e;
         if (pq_shared)
           e = (S == 2) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist<2, false>, PIPE_THREADS, pbytes)
@@ -638,12 +639,45 @@ class Solver {
       }
       persist_ctas_ = best * n_sm_;
     }
+    persist_grid_ = std::min(n_tile, persist_ctas_);
+    if (smallwin && n_win == 1 && persist_grid_ > 0) {
+      // Static tile ranges of the persistent PCG kernel, balanced by cost instead of by count: an observation whose pose
+      // lies outside the CTA's shared window of the search direction (loop-closure tracks, very wide covisibility)
+      // evaluates it from global memory and costs about twice a windowed one.
+      std::vector<double> cum(n_tile + 1, 0.0);
+      for (int t = 0; t < n_tile; t++) {
+        const TileInfo& ti = h_tiles_pin_.p[t];
+        double cost = 16.0 + (ti.o1 - ti.o0);
+        if (!pq_shared && !ti.is_long && ti.nrun > 0) {
+          const int* runs = h_tile_runs_.p + h_tile_run_ptr_.p[t];
+          const int lo = runs[ti.nrun + 1];
+          for (int i = 0; i < ti.nrun; i++)
+            if (runs[ti.nrun + 1 + i] >= lo + persist_slots_ - 6) cost += 1.0 * (runs[i + 1] - runs[i]);
+        }
+        if (ti.is_long) cost += 2.0 * (ti.o1 - ti.o0);
+        cum[t + 1] = cum[t] + cost;
+      }
+      std::vector<int> ptr(persist_grid_ + 1, 0);
+      int t = 0;
+      for (int b = 1; b < persist_grid_; b++) {
+        const double target = cum[n_tile] * b / persist_grid_;
+        while (t < n_tile && cum[t + 1] <= target) t++;
+        // every CTA keeps at least one tile
+        t = std::max(t, ptr[b - 1] + 1);
+        t = std::min(t, n_tile - (persist_grid_ - b));
+        ptr[b] = t;
+      }
+      ptr[persist_grid_] = n_tile;
+      CU_CHECK(d_ptile_.ensure(persist_grid_ + 1));
+      CU_CHECK(cudaMemcpyAsync(d_ptile_.p, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+      CU_CHECK(cudaStreamSynchronize(stream_));
+    }
     {
       const int nchunk = (std::max(n_slot, 1) + VSLOT - 1) / VSLOT;
       CU_CHECK(d_part_.ensure((size_t)4 * nchunk));
       CU_CHECK(d_gbar_.ensure(2));
       CU_CHECK(d_q3_.ensure((size_t)3 * KQ * 6 * std::max(n_slot, 1)));
-      CU_CHECK(d_dq_.ensure((size_t)6 * std::max(n_slot, 1)));
+      CU_CHECK(d_dq_.ensure((size_t)12 * std::max(n_slot, 1)));  // Dq and qf
       if (comm_) {
         if (int rc = peer_setup((size_t)std::max(n_slot, 1) * 6, (size_t)nchunk)) return rc;
       }
@@ -966,7 +1000,7 @@ class Solver {
   int uses_peer_exchange() const { return (comm_ && peer_ok_) ? 1 : 0; }
   void dump_persist_prof() {
 #ifdef SQRTBA_PIPE_PROF
-    const int grid = std::min(P_.n_tile, persist_ctas_);
+    const int grid = persist_grid_;
     std::vector<long long> hp((size_t)grid * 16);
     if (download(hp.data(), d_prof_.p, hp.size() * sizeof(long long))) return;
     double acc[9] = {};
@@ -979,6 +1013,18 @@ class Solver {
     fprintf(stderr, "[persist prof] grid %d, iterations/CTA %.0f | cycles per iteration (CTA average): tiles %.0f (max-CTA %.0f) flush %.0f "
             "B1 %.0f ph1 %.0f B2|ph2 %.0f ph3 %.0f B3 %.0f other %.0f\n", grid, its / grid, acc[3] / its, mx3 / (its / grid), acc[4] / its,
             acc[0] / its, acc[1] / its, acc[2] / its, acc[5] / its, acc[6] / its, acc[7] / its);
+    {
+      std::vector<std::pair<long long, int>> v;
+      for (int b = 0; b < grid; b++) v.push_back({hp[(size_t)b * 16 + 3], b});
+      std::sort(v.begin(), v.end());
+      std::vector<int> ptr(grid + 1);
+      download(ptr.data(), d_ptile_.p, ptr.size() * sizeof(int));
+      fprintf(stderr, "[persist prof] slowest CTAs (cta:tiles:cycles/iter):");
+      for (int i = 0; i < 12; i++) { auto& x = v[grid - 1 - i]; fprintf(stderr, " %d:%d:%.0f", x.second, ptr[x.second + 1] - ptr[x.second], x.first / (its / grid)); }
+      fprintf(stderr, "\n[persist prof] fastest:");
+      for (int i = 0; i < 6; i++) { auto& x = v[i]; fprintf(stderr, " %d:%d:%.0f", x.second, ptr[x.second + 1] - ptr[x.second], x.first / (its / grid)); }
+      fprintf(stderr, "\n");
+    }
     cudaMemsetAsync(d_prof_.p, 0, d_prof_.cap * sizeof(long long), stream_);
 #endif
   }
@@ -990,7 +1036,7 @@ class Solver {
            2 * (2 * CTA + 4) * sizeof(int) + 2 * S * sizeof(uint64_t);
   }
   static size_t persist_smem_bytes(int S, int maxslot, bool big) {
-    return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + (big ? 0 : 18) * (size_t)maxslot + 8) * sizeof(double) +
+    return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + (big ? 6 : 18) * (size_t)maxslot + 8) * sizeof(double) +
            2 * S * sizeof(uint64_t) + 4 * sizeof(int) + 2 * (size_t)pipe_run_cap(maxslot, big) * sizeof(int);
   }
   void launch_matvec(const double* pvec, double* qvec, int force_all) {
@@ -1030,6 +1076,7 @@ class Solver {
     A.part = d_part_.p;
     A.q3 = d_q3_.p;
     A.dq = d_dq_.p;
+    A.qf = d_dq_.p + (size_t)6 * std::max(P_.n_slot, 1);
     if (A.nranks > 1) {
       A.recv = peer_recv_[rank_];
       A.flag = peer_flag_[rank_];
@@ -1039,9 +1086,10 @@ class Solver {
       A.nchunk_cap = (int)peer_nchunk_cap_;
     }
     const bool big = !P_.pq_shared;
-    const int grid = std::min(P_.n_tile, persist_ctas_);
-    const size_t bytes = persist_smem_bytes(persist_stages_, pipe_slots_, big);
-    int maxslot = pipe_slots_;
+    const int grid = persist_grid_;
+    A.tile_ptr = d_ptile_.p;
+    const size_t bytes = persist_smem_bytes(persist_stages_, persist_slots_, big);
+    int maxslot = persist_slots_;
     void* args[] = {(void*)&P_, (void*)&A, (void*)&maxslot, (void*)&lam_override, (void*)&use_override};
     const void* fn = big ? (persist_stages_ == 2 ? (const void*)k_pcg_persist<2, true> : (const void*)k_pcg_persist<3, true>)
                          : (persist_stages_ == 2 ? (const void*)k_pcg_persist<2, false> : (const void*)k_pcg_persist<3, false>);
@@ -1156,7 +1204,10 @@ class Solver {
     const size_t qbytes = (size_t)P_.n_slot * 6 * sizeof(double);
     if (use_persist()) {  // whole PCG solve in one cooperative launch (single-window problems)
       if (P_.pq_shared) CU_CHECK(cudaMemsetAsync(d_q3_.p, 0, 3 * KQ * qbytes, stream_));
-      else CU_CHECK(cudaMemsetAsync(P_.q, 0, qbytes, stream_));
+      else {
+        CU_CHECK(cudaMemsetAsync(P_.q, 0, qbytes, stream_));
+        CU_CHECK(cudaMemsetAsync(d_dq_.p, 0, 2 * qbytes, stream_));
+      }
       CU_CHECK(cudaMemsetAsync(d_gbar_.p, 0, 2 * sizeof(unsigned), stream_));
       if (int rc = launch_pcg_persist(tol2, 0, 0.0)) return rc;
       launches_ += 1;
@@ -1277,7 +1328,7 @@ class Solver {
     d_bl_.release(); d_dl_.release(); d_slotvec_.release(); d_chi_part_.release(); d_scale_part_.release();
     d_ctl_.release(); d_trace_.release(); d_counters_.release(); d_wred_.release();
     d_tiles_.release(); d_obs_lp_.release(); d_tile_run_ptr_.release(); d_tile_runs_.release();
-    d_gbar_.release(); d_part_.release(); d_q3_.release(); d_dq_.release();
+    d_gbar_.release(); d_part_.release(); d_q3_.release(); d_dq_.release(); d_ptile_.release();
     h_obs_slot_.release(); h_item_start_.release(); h_item_cnt_.release(); h_item_win_.release();
     h_tile_run_ptr_.release(); h_tile_runs_.release(); h_obs_lp_.release(); h_tiles_pin_.release();
     h_perm_pose_.release(); h_perm_point_.release(); h_perm_slot_.release(); h_perm_meas_.release(); h_perm_xyz_.release();
@@ -1302,7 +1353,8 @@ class Solver {
   void* comm_ = nullptr;  // ncclComm_t
   int n_ranks_ = 1, rank_ = 0;
   bool coop_ok_ = false, peer_ok_ = false;
-  int persist_ctas_ = 0, persist_stages_ = 2;
+  int persist_ctas_ = 0, persist_stages_ = 2, persist_slots_ = 1, persist_grid_ = 0;
+  DBuf<int> d_ptile_;
   double* peer_recv_[8] = {};
   unsigned long long* peer_flag_[8] = {};
   unsigned long long* d_seq_ = nullptr;
