@@ -189,6 +189,67 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_matvec_ncu_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+def run_extras(pkg, torch, dist, world, rank, local, barrier, args):
+    """(1) latency of ONE C0 window -- the call shape of Optimizer::LocalBundleAdjustment -- on rank 0;
+    (2) C3 global BA, landmarks sharded over all `world` ranks (strong scaling): time-to-converge of
+    solve_global(10 iterations, non-robust), the reference's loop-closing call (LoopClosing.cc:987-991)."""
+    out = {}
+    if rank == 0:
+        w = pkg.synth.config_c0(0)
+        ba = pkg.SqrtBA(device=local)
+        ba.set_problem(w)
+        ms = []
+        for _ in range(5):
+            ba.reset_state()
+            st = ba.solve_local()
+            ms.append(st["ms_total"])
+        tr = ba.trace()
+        best = min(ms[2:])
+        out["single_window"] = {"workload": "C0: one KITTI-00-shaped stereo window, two-pass 5+10 local BA",
+                                "n_obs": w.n_obs, "ms_per_local_ba": best, "lm_trials": len(tr),
+                                "lm_iters_per_s": len(tr) / (best * 1e-3), "obs_per_s": len(tr) * w.n_obs / (best * 1e-3),
+                                "cg_iters": st["cg_iters_total"], "persistent_pcg": st["persistent_pcg"]}
+        ba.close()
+    prob = pkg.synth.config_c3(0, scale=args.gba_scale, n_kf=max(int(1500 * args.gba_scale), 160))
+    shard, _, _ = pkg.multi.shard_by_landmark(prob, rank, world)
+    ba = pkg.SqrtBA(device=local)
+    if world > 1:
+        pkg.multi.init_comm(ba, rank, world)
+    ba.set_problem(shard)
+    times = []
+    st = None
+    for _ in range(3):
+        ba.reset_state()
+        barrier()
+        t0 = time.perf_counter()
+        st = ba.solve_global(10, False)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    tsec = torch.tensor([min(times[1:])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+    tr = ba.trace()
+    free_obs = int((prob.pose_fixed[prob.obs_pose] == 0).sum())
+    out["global_ba"] = {"workload": f"C3: {prob.n_pose} keyframes on a loop, {prob.n_point} points, {prob.n_obs} observations, "
+                                    "10 LM iterations, non-robust; landmarks sharded over the ranks",
+                        "n_gpus": world, "scaling": "strong", "time_to_converge_s": float(tsec.item()),
+                        "lm_trials": len(tr), "cg_iters_total": int(tr[:, 8].sum()), "final_chi2": float(tr[-1, 5]),
+                        "persistent_pcg": st["persistent_pcg"], "peer_exchange": st["peer_exchange"],
+                        "us_per_cg_iteration_incl_everything": 1e6 * float(tsec.item()) / max(int(tr[:, 8].sum()), 1),
+                        "matvec_algorithmic_bytes_all_ranks": free_obs * 216.0}
+    ba.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -199,6 +260,8 @@ def main():
     ap.add_argument("--cpu-windows", type=int, default=0, help="windows in the CPU sample (0 = auto)")
     ap.add_argument("--pcg-mode", type=int, default=0)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="skip the single-window latency and global-BA legs")
+    ap.add_argument("--gba-scale", type=float, default=1.0, help="scale of the C3 global-BA leg (1.0 = 1500 KFs, 3M obs)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -268,13 +331,21 @@ def main():
     peaks, peak_kind = measured_peaks()
     alg_bytes = free_obs * 216.0
     achieved = alg_bytes / (ms_matvec * 1e-3) / 1e9
+    tr_info = load_traffic()
+    traffic = None
+    if tr_info and tr_info.get("dram_bytes_per_free_obs"):
+        # per launch like `achieved`: the capture's DRAM bytes per free-pose observation x this launch's observations
+        traffic = tr_info["dram_bytes_per_free_obs"] * free_obs
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind, "kernel": "k_matvec",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": (tr_info or {}).get("source"),
+                "peak_kind": peak_kind, "kernel": "k_matvec_pipe<2,false>",
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_matvec,
                 "note": "216 B per free-pose stereo observation (Jp 3x6 + Q1 3x3, FP64); observations of fixed "
                         "keyframes have no pose columns and are not streamed",
                 "other_kernels_ms": {"k_linearize": ms_lin, "k_qr": ms_qr},
                 "pcg_share_of_step": None}
+
+    roofline["pcg_share_of_step"] = stats["cg_iters_total"] * ms_matvec / max(stats["ms_total"], 1e-9)
 
     # ---- end-to-end leg through the C ABI with host buffers -------------------------------------
     host = [pinned_copy(a) for a in (prob.pose_qt, prob.pose_fixed, prob.cam, prob.point_xyz, prob.obs_pose,
@@ -302,10 +373,15 @@ def main():
     e2e_value = work_all * args.steps / float(sec2.item())
     ba2.close()
 
+    # ---- the other two shapes of BASELINE.json's metric (reported beside the headline, not part of `value`) ----
+    extras = {}
+    if not args.skip_extras:
+        extras = run_extras(pkg, torch, dist, world, rank, local, barrier, args)
+
     # ---- CPU baseline (oracle port, 1 thread, bounded sample) on rank 0 at N=1 -------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        n_cpu = args.cpu_windows if args.cpu_windows > 0 else 12
+        n_cpu = args.cpu_windows if args.cpu_windows > 0 else 32
         dt, wk, _ = cpu_solve_windows(wins[:n_cpu], 1)
         cpu = {"value": wk / dt, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"first {n_cpu} windows of the batch, full two-pass local BA each, {dt:.1f} s"}
@@ -329,6 +405,8 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "solve_stats_last_step": stats,
+            "single_window": extras.get("single_window"),
+            "global_ba": extras.get("global_ba"),
         }
         print(json.dumps(line), flush=True)
     ba.close()

@@ -27,7 +27,10 @@ class Stats(C.Structure):
                 ("ms_matvec", C.c_double), ("reserved", C.c_double * 8)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d["persistent_pcg"] = int(self.reserved[0])
+        d["peer_exchange"] = int(self.reserved[1])
+        return d
 
 
 TRACE_COLS = ("pass", "iter", "trial", "lambda", "chi_before", "chi_trial", "rho", "accepted", "cg_iters", "cg_relres")

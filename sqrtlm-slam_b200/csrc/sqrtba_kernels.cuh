@@ -50,7 +50,17 @@ struct TileInfo {
   long long jq_off;  // offset (doubles) of the tile's [27][nt] data block inside Dev::JQ (its header sits right before)
   int nrun;          // distinct free pose slots among the participating observations (= runs of equal slot by rank)
   int blk_doubles;   // size of the whole JQ block (header + data + meta + run table), in doubles, even
+  int cnt[4];        // observations of each item of the tile (0 for absent items): saves the item_start / item_cnt lookups
 };
+
+// item geometry from the tile descriptor alone (items of a tile are consecutive observation ranges; selects, not
+// indexing, so the descriptor stays in registers)
+__device__ __forceinline__ int tile_item_cnt(const TileInfo& ti, int wid) {
+  return wid == 0 ? ti.cnt[0] : (wid == 1 ? ti.cnt[1] : (wid == 2 ? ti.cnt[2] : (wid == 3 ? ti.cnt[3] : 0)));
+}
+__device__ __forceinline__ int tile_item_start(const TileInfo& ti, int wid) {
+  return ti.o0 + (wid > 0 ? ti.cnt[0] : 0) + (wid > 1 ? ti.cnt[1] : 0) + (wid > 2 ? ti.cnt[2] : 0);
+}
 
 struct Dev {
   int n_pose, n_point, n_obs, n_win, n_slot, n_item;
@@ -218,6 +228,23 @@ __device__ __forceinline__ void tile_scatter(const int* __restrict__ run_ptr, co
   __syncthreads();
 }
 
+// Single-pass variant for kernels that reduce several per-observation vectors at once: every participating observation
+// has already written its NV values into column `rank` of c_sh[NV][SCST] (SCST = CTA + 1: the value-lanes of one run
+// fall into different banks); one thread per (run, value) adds the run up and issues ONE global atomic.  `addr(slot, k)`
+// maps value k of pose slot `slot` to its accumulator.  Must be called by all threads of the CTA after a __syncthreads().
+constexpr int SCST = CTA + 1;
+template <int NV, class Addr>
+__device__ __forceinline__ void tile_scatter_all(const int* __restrict__ run_ptr, const int* __restrict__ run_slot, int nrun,
+                                                 int slot_base, const double* c_sh, Addr addr) {
+  for (int idx = threadIdx.x; idx < nrun * NV; idx += CTA) {
+    const int r = idx / NV, k = idx - r * NV;
+    const int a = run_ptr[r], b = run_ptr[r + 1];
+    double sum = 0.0;
+    for (int j = a; j < b; j++) sum += c_sh[k * SCST + j];
+    atomicAdd(addr(slot_base + run_slot[r], k), sum);
+  }
+}
+
 // ---- TMA (bulk async copy) + mbarrier primitives, raw PTX (sm_90+/sm_100a)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -232,6 +259,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// TMA prefetch of a contiguous global range into L2 (no shared-memory destination, no registers): used to pull the
+// operands of a LATER phase of a kernel towards the SMs while the current phase computes.  size: multiple of 16 bytes.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -306,8 +338,8 @@ __device__ __forceinline__ void obs_eval(const Dev& P, int o, bool want_jac, boo
   if (want_jac) reproj_jacobians(R, Xc, cam, stereo, L.Jp, L.Jl);
 }
 
-__global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2, double d3, int force_all) {
-  __shared__ double c_sh[6 * CTA];
+__global__ void __launch_bounds__(CTA, 4) k_linearize(Dev P, int robust, double d2, double d3, int force_all) {
+  __shared__ double c_sh[12 * SCST];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const TileInfo ti = P.tiles[blockIdx.x];
   const int w = ti.item0 + wid;
@@ -315,10 +347,11 @@ __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2,
   const int win = ti.win;
   if (!force_all && P.ctl[win].phase != PH_LIN) return;  // a tile lies inside one window: CTA-uniform
   const bool on = valid;
-  const int start = valid ? P.item_start[w] : 0, cnt = valid ? P.item_cnt[w] : 0;
+  const int start = tile_item_start(ti, wid), cnt = tile_item_cnt(ti, wid);
   const size_t No = (size_t)P.ld; const int Nl = P.n_point;
   const bool is_long = cnt > 32;
   double* __restrict__ jq = P.JQ + ti.jq_off;
+  const uint2* __restrict__ meta = reinterpret_cast<const uint2*>(jq + (size_t)NPLANE * ti.nt);  // {obs_lp, landmark}
   double chi_acc = 0.0, maxd = 0.0;
   double vb[6] = {0, 0, 0, 0, 0, 0}, vh[6] = {0, 0, 0, 0, 0, 0};  // this observation's -Jp^T r and diag(Jp^T Jp)
   bool has = false;
@@ -332,11 +365,10 @@ __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2,
     for (int c = 0; c < 9; c++) L.Jl[c] = 0.0;
     L.e[0] = L.e[1] = L.e[2] = 0.0;
     if (act) {
-      const unsigned lp = P.obs_lp[o];
-      has = (lp & 0xffffu) != 0xffffu;
-      rank = (int)(lp >> 16);
-      key = P.obs_slot[o];
-      lm = P.obs_point[o];
+      const uint2 m = meta[o - ti.o0];
+      has = (m.x & 0xffffu) != 0xffffu;
+      rank = (int)(m.x >> 16);
+      lm = (int)m.y;
     }
     if (act && on) {
       const bool live = P.obs_level[o] == 0;
@@ -428,10 +460,17 @@ __global__ void __launch_bounds__(CTA) k_linearize(Dev P, int robust, double d2,
       atomic_max_pos(&P.ctl[win].maxdiag_bits, maxd);
     }
   }
+  if (has) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) { c_sh[c * SCST + rank] = vb[c]; c_sh[(6 + c) * SCST + rank] = vh[c]; }
+  }
+  __syncthreads();
   const int* runs = reinterpret_cast<const int*>(jq + (size_t)JQ_ROWS * ti.nt);
   const int sbase = P.smallwin ? P.win_slot_ptr[win] : 0;
-  tile_scatter<6>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh, vb, has, rank, P.bp, 6, 0);
-  tile_scatter<6>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh, vh, has, rank, P.hd, 6, 0);
+  double* bp = P.bp;
+  double* hd = P.hd;
+  tile_scatter_all<12>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh,
+                       [bp, hd](int slot, int k) { return (k < 6) ? bp + (size_t)slot * 6 + k : hd + (size_t)slot * 6 + (k - 6); });
 }
 
 // ------------------------------------------------------------------------------------------------ K8a: LM begin
@@ -568,50 +607,78 @@ __device__ __forceinline__ void trial_contrib(const double* __restrict__ jq, int
     }
 }
 
-__global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_override) {
-  __shared__ double c_sh[7 * CTA];
+// short-item variant of trial_contrib: the 27 values go straight into column `rank` of c_sh[27][SCST]
+__device__ __forceinline__ void trial_contrib_sh(const double* __restrict__ jq, int nt, int col, const double Q[9],
+                                                 const double rr[3], const double tl[3], double* c_sh, int rank) {
+  double J[18];
+#pragma unroll
+  for (int c = 0; c < 18; c++) J[c] = jq[(size_t)c * nt + col];
+  {
+    double u[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) u[r] = rr[r] - (Q[r * 3] * tl[0] + Q[r * 3 + 1] * tl[1] + Q[r * 3 + 2] * tl[2]);
+#pragma unroll
+    for (int c = 0; c < 6; c++) c_sh[c * SCST + rank] = -(J[c] * u[0] + J[6 + c] * u[1] + J[12 + c] * u[2]);
+  }
+  double G[18];  // Jp^T Q1 (6x3)
+#pragma unroll
+  for (int c = 0; c < 6; c++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) G[c * 3 + k] = J[c] * Q[k] + J[6 + c] * Q[3 + k] + J[12 + c] * Q[6 + k];
+  int idx = 6;
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = a; b < 6; b++) {
+      c_sh[idx * SCST + rank] = J[a] * J[b] + J[6 + a] * J[6 + b] + J[12 + a] * J[12 + b] -
+                                (G[a * 3] * G[b * 3] + G[a * 3 + 1] * G[b * 3 + 1] + G[a * 3 + 2] * G[b * 3 + 2]);
+      idx++;
+    }
+}
+
+__global__ void __launch_bounds__(CTA, 4) k_qr(Dev P, int force_all, double lam_override) {
+  __shared__ double c_sh[27 * SCST];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const TileInfo ti = P.tiles[blockIdx.x];
-  const int w = ti.item0 + wid;
   const bool valid = wid < ti.nitem;
   const int win = ti.win;
-  if (!force_all && P.ctl[win].phase != PH_TRIAL) return;  // CTA-uniform
+  const WinCtl& wc = P.ctl[win];
+  if (!force_all && wc.phase != PH_TRIAL) return;  // CTA-uniform
   const bool on = valid;
-  const double lam = force_all ? lam_override : P.ctl[win].lambda;
+  const double lam = force_all ? lam_override : wc.lambda;
   const double sl = sqrt(lam);
-  const int start = valid ? P.item_start[w] : 0, cnt = valid ? P.item_cnt[w] : 0;
+  // item geometry from the tile descriptor alone (items of a tile are consecutive observation ranges)
+  const int cnt = tile_item_cnt(ti, wid);
+  const int start = tile_item_start(ti, wid);
   const size_t No = (size_t)P.ld; const int Nl = P.n_point;
   double* __restrict__ jq = P.JQ + ti.jq_off;
   const int nt = ti.nt;
-  double contrib[27];
-#pragma unroll
-  for (int c = 0; c < 27; c++) contrib[c] = 0.0;
+  const uint2* __restrict__ meta = reinterpret_cast<const uint2*>(jq + (size_t)NPLANE * nt);  // {obs_lp, landmark} per column
+  // the 18 Jp rows are only needed after the factorisation: start pulling them into L2 now (one TMA prefetch per CTA)
+  if (threadIdx.x == 0 && !ti.is_long) bulk_prefetch_l2(jq, (uint32_t)(18 * nt * sizeof(double)));
   bool has = false;
-  int rank = 0, key = 0;
+  int rank = 0;
   LmFactor F;
   if (valid && cnt <= 32) {
     const bool act = lane < cnt;
     const int o = start + (act ? lane : 0);
     int lm = -1 - lane;
-    if (act) {
-      const unsigned lp = P.obs_lp[o];
-      has = (lp & 0xffffu) != 0xffffu;
-      rank = (int)(lp >> 16);
-      key = P.obs_slot[o];
-      lm = P.obs_point[o];
+    double a[9], rr[3];
+    if (act) {  // every load of this phase is issued before the first use
+      const uint2 m = meta[o - ti.o0];
+      load9(P.Jl, No, o, a);
+#pragma unroll
+      for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
+      has = (m.x & 0xffffu) != 0xffffu;
+      rank = (int)(m.x >> 16);
+      lm = (int)m.y;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 9; c++) a[c] = 0.0;
+      rr[0] = rr[1] = rr[2] = 0.0;
     }
     if (on) {
       const Seg sg = seg_of(lm, lane);
-      double a[9], rr[3];
-      if (act) {
-        load9(P.Jl, No, o, a);
-#pragma unroll
-        for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
-      } else {
-#pragma unroll
-        for (int c = 0; c < 9; c++) a[c] = 0.0;
-        rr[0] = rr[1] = rr[2] = 0.0;
-      }
       // column 0
       double s0 = seg_sum(a[0] * a[0] + a[3] * a[3] + a[6] * a[6], sg, lane);
       double d01 = seg_sum(a[0] * a[1] + a[3] * a[4] + a[6] * a[7], sg, lane);
@@ -658,7 +725,7 @@ __global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_ove
 #pragma unroll
           for (int c = 0; c < 3; c++) P.tl[(size_t)c * Nl + lm] = tl[c];
         }
-        if (has) trial_contrib(jq, nt, o - ti.o0, Q, rr, tl, contrib);
+        if (has) trial_contrib_sh(jq, nt, o - ti.o0, Q, rr, tl, c_sh, rank);
       }
     }
   } else if (on) {
@@ -737,12 +804,13 @@ __global__ void __launch_bounds__(CTA) k_qr(Dev P, int force_all, double lam_ove
       for (int c = 0; c < 21; c++) atomicAdd(&P.D[slot * 21 + c], lc[6 + c]);
     }
   }
+  __syncthreads();
   const int* runs = reinterpret_cast<const int*>(jq + (size_t)JQ_ROWS * nt);
   const int sbase = P.smallwin ? P.win_slot_ptr[win] : 0;
-  tile_scatter<6>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh, contrib, has, rank, P.bs, 6, 0);
-  tile_scatter<7>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh, contrib + 6, has, rank, P.D, 21, 0);
-  tile_scatter<7>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh, contrib + 13, has, rank, P.D, 21, 7);
-  tile_scatter<7>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh, contrib + 20, has, rank, P.D, 21, 14);
+  double* bs = P.bs;
+  double* D = P.D;
+  tile_scatter_all<27>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh,
+                       [bs, D](int slot, int k) { return (k < 6) ? bs + (size_t)slot * 6 + k : D + (size_t)slot * 21 + (k - 6); });
 }
 
 

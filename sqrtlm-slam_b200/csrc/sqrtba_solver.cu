@@ -390,6 +390,7 @@ class Solver {
             }
             const int last = it + ti.nitem - 1;
             ti.o1 = c.it_start[last] + c.it_cnt[last];
+            for (int i = 0; i < 4; i++) ti.cnt[i] = (i < ti.nitem) ? c.it_cnt[it + i] : 0;
             const int t = (int)c.tiles.size();
             if (!ti.is_long) {
               distinct.clear();
@@ -1314,6 +1315,9 @@ class Solver {
       st->ms_pcg = stage_ms_[2];
       st->ms_backsub = stage_ms_[3];
       st->ms_cost = stage_ms_[4];
+      st->reserved[0] = use_persist() ? 1.0 : 0.0;           // the PCG solves ran in the persistent cooperative kernel
+      st->reserved[1] = (comm_ && peer_ok_) ? 1.0 : 0.0;     // landmark-sharded: in-kernel NVLink exchange available
+      st->reserved[2] = persist_grid_;
     }
     return SQRTBA_OK;
   }

@@ -61,7 +61,8 @@ def main():
     out = {"workload": f"C3 global BA: {prob.n_pose} keyframes, {prob.n_point} points, {prob.n_obs} observations, "
                        f"{args.iters} iterations, robust={args.robust}",
            "n_gpus": world, "time_to_converge_s": float(tsec.item()), "lm_trials": len(tr),
-           "cg_iters_total": int(tr[:, 8].sum()), "final_chi2": float(tr[-1, 5]), "matvec_launches": st["cg_iters_total"]}
+           "cg_iters_total": int(tr[:, 8].sum()), "final_chi2": float(tr[-1, 5]), "matvec_launches": st["cg_iters_total"],
+           "persistent_pcg": st["persistent_pcg"], "peer_exchange": st["peer_exchange"], "kernel_launches": st["kernel_launches"]}
     if world > 1:
         allp = [None] * world
         dist.all_gather_object(allp, pts)
