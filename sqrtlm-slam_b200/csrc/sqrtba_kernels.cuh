@@ -1258,6 +1258,9 @@ __global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__
 //   ranks hold bit-identical q, alpha, beta and iterates.  Dot products are per-chunk partials summed in chunk order
 //   by every CTA, so they do not depend on the grid size (ranks with different shards launch different grids).
 constexpr int VSLOT = 20;  // 4 warps x 5 poses x 6 lanes
+#ifndef PERSIST_REREAD
+#define PERSIST_REREAD false
+#endif
 // !BIG: the per-CTA partial products are added into one of KQ copies of q (CTA b -> copy b % KQ).  FP64 atomics on
 // one L2 line serialise (~30 cycles each: 444 CTAs flushing the same 120 doubles cost ~8 us), so the copies cut the
 // depth of that queue; every CTA then adds the KQ copies in a fixed order.
@@ -1273,14 +1276,21 @@ struct PcgArgs {
   double* q3;                     // !BIG: three rotating buffers of KQ copies of q, [3][KQ][6*n_slot] (zeroed by the host)
   double* dq;                     // BIG: Dinv * qf   (zeroed by the host)
   double* qf;                     // BIG: q + lambda p (zeroed by the host)
-  double* recv;                   // this rank's receive buffer  [2 (parity)][nranks][nelem_cap]
-  unsigned long long* flag;       // this rank's arrival flags   [nranks][nchunk_cap]
-  double* peer_recv[8];           // the same two buffers of every rank, peer-mapped (cudaIpc)
-  unsigned long long* peer_flag[8];
+  uint4* recv;                    // this rank's receive buffer  [2 (parity)][nranks][nelem_cap] of 16-byte records
+                                  // {value lo, seq, value hi, seq}
+  uint4* const* peer_tbl;         // device table of the receive buffers of all ranks, peer-mapped (cudaIpc)
   unsigned long long* seq_state;  // running exchange sequence number (device resident, advanced by the kernel)
   int nelem_cap, nchunk_cap;
 };
 
+__device__ __forceinline__ void st_volatile_v4(uint4* p, const uint4& v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -1295,12 +1305,49 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   return v;
 }
 
+// Sum of one element of q over the ranks that share the problem, over NVLink peer memory, flag-in-data ("LL") style:
+// every 8-byte half-record {4 bytes of the value, 4-byte sequence number} is written with one store (8-byte stores are
+// not torn), so the receiver needs neither a fence nor a separate flag: it polls the record until both sequence
+// numbers match.  The partial values are added in rank order: identical bits on every rank.
+// (__noinline__: keeps its registers out of the matvec loop's allocation.)
+__device__ __forceinline__ double peer_sum(uint4* const* peer_tbl, const uint4* recv, int nranks, int rank, int nelem_cap,
+                                        double qv, int e, unsigned long long seq) {
+  const int par = (int)(seq & 1ull);
+  const unsigned sq = (unsigned)seq;
+  {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(qv);
+    const uint4 rec = make_uint4((unsigned)bits, sq, (unsigned)(bits >> 32), sq);
+#pragma unroll 1
+    for (int r = 0; r < nranks; r++)
+      if (r != rank) st_volatile_v4(peer_tbl[r] + ((size_t)par * nranks + rank) * nelem_cap + e, rec);
+  }
+  const uint4* mine = recv + (size_t)par * nranks * nelem_cap + e;
+  // rank order, two records in flight at a time (a deliberately small register footprint: see tile_products)
+  double tot = 0.0;
+#pragma unroll 1
+  for (int r = 0; r < nranks; r += 2) {
+    const bool h0 = r != rank, h1 = (r + 1 < nranks) && (r + 1 != rank);
+    uint4 v0 = make_uint4(0, sq, 0, sq), v1 = make_uint4(0, sq, 0, sq);
+    bool d0 = !h0, d1 = !h1;
+    while (!(d0 && d1)) {
+      if (!d0) v0 = ld_volatile_v4(mine + (size_t)r * nelem_cap);
+      if (!d1) v1 = ld_volatile_v4(mine + (size_t)(r + 1) * nelem_cap);
+      d0 = d0 || (v0.y == sq && v0.w == sq);
+      d1 = d1 || (v1.y == sq && v1.w == sq);
+    }
+    tot += h0 ? __longlong_as_double((long long)(((unsigned long long)v0.z << 32) | v0.x)) : (r == rank ? qv : 0.0);
+    if (r + 1 < nranks)
+      tot += h1 ? __longlong_as_double((long long)(((unsigned long long)v1.z << 32) | v1.x)) : qv;
+  }
+  return tot;
+}
+
 // Barrier over the consumer threads of every CTA of a cooperative launch: CTA barrier, one thread does a release-add
 // on a monotonically increasing counter and acquire-spins until all CTAs of this generation arrived, CTA barrier.
-__device__ __forceinline__ void grid_bar(unsigned* bar, unsigned nblk, unsigned& gen, int tid) {
+// `gen` = how many barriers this launch has completed including this one (the counter is monotonic).
+__device__ __forceinline__ void grid_bar(unsigned* bar, unsigned nblk, unsigned gen, int tid) {
   named_bar_sync(1, CTA);
   if (tid == 0) {
-    gen++;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     const unsigned target = gen * nblk;
     while (ld_acquire_gpu(bar) < target) {}
@@ -1318,7 +1365,10 @@ __device__ __forceinline__ double cta_sum(double v, double* red_sh, int which, i
 }
 
 // per-lane matvec products of one staged tile: writes this observation's Jp^T u (6 values) into column `rank` of cb
-template <bool BIG>
+// REREAD: Jp is re-read from the stage for the final product instead of being kept live across the shuffles -- slower
+// (+25 % per tile) but 36 registers lighter; used by the multi-GPU instantiation, whose exchange code otherwise pushes
+// ptxas into spilling those rows inside the loop (+80 % per tile).
+template <bool BIG, bool REREAD = false>
 __device__ __forceinline__ void tile_products(const double* data, const int* hdr, int nt, int wid, int lane,
                                               const double* p_sh, int maxslot, const PEff& pe, int abase, double* cb) {
   constexpr int CST = CTA + 1;
@@ -1368,8 +1418,14 @@ __device__ __forceinline__ void tile_products(const double* data, const int* hdr
 #pragma unroll
     for (int r = 0; r < 3; r++)
       v[r] -= dcol[(18 + r * 3) * nt] * sv[0] + dcol[(19 + r * 3) * nt] * sv[1] + dcol[(20 + r * 3) * nt] * sv[2];
+    if (REREAD) {
 #pragma unroll
-    for (int cc = 0; cc < 6; cc++) cb[cc * CST + rank] = J[cc] * v[0] + J[6 + cc] * v[1] + J[12 + cc] * v[2];
+      for (int cc = 0; cc < 6; cc++)
+        cb[cc * CST + rank] = dcol[cc * nt] * v[0] + dcol[(6 + cc) * nt] * v[1] + dcol[(12 + cc) * nt] * v[2];
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 6; cc++) cb[cc * CST + rank] = J[cc] * v[0] + J[6 + cc] * v[1] + J[12 + cc] * v[2];
+    }
   }
 }
 
@@ -1377,7 +1433,9 @@ __host__ __device__ inline int pipe_run_cap(int maxslot, bool big) {  // ints pe
   return 2 * ((big || maxslot > CTA) ? CTA : maxslot) + 4;
 }
 
-template <int S, bool BIG>
+// MULTI: landmark-sharded over several GPUs (compiled separately so that the exchange code cannot disturb the register
+// allocation of the single-GPU matvec loop)
+template <int S, bool BIG, bool MULTI = false>
 __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, double lam_override, int use_override) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int STAGE_D = JQ_STAGE_D;
@@ -1388,8 +1446,11 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
                                                           // maxslot consecutive slots starting at abase
   double* acc_sh = p_sh + 6 * maxslot;                    // !BIG: q accumulators, then scratch of the vector phase
   double* res_sh = acc_sh + (BIG ? 0 : 6 * maxslot);      // !BIG: residual, slot-major [slot * 6 + c]
-  double* red_sh = res_sh + (BIG ? 0 : 6 * maxslot);      // 8 doubles
-  uint64_t* full = reinterpret_cast<uint64_t*>(red_sh + 8);
+  double* red_sh = res_sh + (BIG ? 0 : 6 * maxslot);      // 8 doubles of reduction scratch
+  // CG scalars that live across iterations are parked here during the matvec phase instead of in registers: the hot
+  // loop needs every register it can get (ptxas otherwise spills the Jacobian rows around the shuffles)
+  volatile double* st_sh = red_sh + 8;                    // [0] r.z  [1] r0.z0  [2] lambda
+  uint64_t* full = reinterpret_cast<uint64_t*>(red_sh + 16);
   uint64_t* empty = full + S;
   volatile int* sig = reinterpret_cast<volatile int*>(empty + S);  // [0] approved iteration, [1] stop, [2] fills consumed
   int* runs_sh = const_cast<int*>(sig) + 4;
@@ -1444,22 +1505,20 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
     return;
   }
   // -------------------------------------------------------------------- consumer warps
-  const double lam = use_override ? lam_override : c.lambda;
-  double rz = c.rz;
-  const double rz0 = c.rz0;
+  if (tid == 0) {
+    st_sh[0] = c.rz;
+    st_sh[1] = c.rz0;
+    st_sh[2] = use_override ? lam_override : c.lambda;
+  }
   const int n6 = P.n_slot * 6;
-  const unsigned long long seq0 = (BIG && A.nranks > 1) ? *A.seq_state : 0ull;
-  unsigned long long seq_last = seq0;
-  const int nchunk = (P.n_slot + VSLOT - 1) / VSLOT;
-  const int vsl = wid * 5 + lane / 6, vcc = lane - (lane / 6) * 6;
-  const int vbase = min((lane / 6) * 6, 24);
-  unsigned gen = 0;
-  int n = 0, iters = 0, abase = 0;
+  int n = 0, abase = 0;
+  double rz_out = 0.0;
+  int iters_out = 0, exch_out = 0;
   PEff pe;
   pe.z = P.z; pe.dq = A.dq; pe.p = P.p;
   pe.alpha = 0.0; pe.beta = 0.0;  // iteration 0: p = z (k_cg_init), Dq zeroed by the host
 #ifdef SQRTBA_PIPE_PROF
-  long long tpp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tcc = clock64(), tnn;
+  long long tpp[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tcc = clock64(), tnn;
 #define PROFP(i) { tnn = clock64(); tpp[i] += tnn - tcc; tcc = tnn; }
 #else
 #define PROFP(i)
@@ -1471,8 +1530,8 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       res_sh[e] = P.res[e];
       acc_sh[e] = 0.0;
     }
-    named_bar_sync(1, CTA);
   }
+  named_bar_sync(1, CTA);
   for (int it = 0;; it++) {
     double* qcur = BIG ? P.q : A.q3 + ((size_t)(it % 3) * KQ + (blockIdx.x % KQ)) * n6;
     PROFP(7)
@@ -1518,7 +1577,7 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
         const int* rsrc = reinterpret_cast<const int*>(data + (size_t)JQ_ROWS * nt);
         for (int i = tid; i < 2 * nrun + 1; i += CTA) rb[i] = rsrc[i];
       }
-      if (wid < nitem) tile_products<BIG>(data, hdr, nt, wid, lane, p_sh, maxslot, pe, abase, cb);
+      if (wid < nitem) tile_products<BIG, MULTI && PERSIST_REREAD>(data, hdr, nt, wid, lane, p_sh, maxslot, pe, abase, cb);
       named_bar_sync(1, CTA);
       if (tid == 0) mbar_arrive(&empty[s]);
       for (int idx = tid; idx < nrun * 6; idx += CTA) {
@@ -1537,8 +1596,10 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       for (int e = tid; e < n6; e += CTA) atomicAdd(&qcur[e], acc_sh[e]);
     }
     PROFP(4)
-    grid_bar(A.gbar, gridDim.x, gen, tid);  // B1: q complete
+    grid_bar(A.gbar, gridDim.x, (unsigned)(BIG ? 2 * it + 1 : it + 1), tid);  // B1: q complete
     PROFP(0)
+    const double lam = st_sh[2], rz0 = st_sh[1];
+    double rz = st_sh[0];
     if (!BIG) {
       // ================================================================ replicated vector update (one barrier / iteration)
       if (blockIdx.x == 0) {  // clear the buffer of iteration it+2: its readers (iteration it-1) all passed B1 above
@@ -1574,7 +1635,11 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       PROFP(1)
       const double pq = cta_sum(d, red_sh, 0, lane, wid);
       const double alpha = rz / pq;
-      if (!(pq > 0.0) || !isfinite(alpha)) break;  // breakdown: keep the iterate, LM judges the step by its gain ratio
+      if (!(pq > 0.0) || !isfinite(alpha)) {  // breakdown: keep the iterate, LM judges the step by its gain ratio
+        rz_out = rz;
+        iters_out = it;
+        break;
+      }
       for (int e = tid; e < n6; e += CTA) {
         res_sh[e] -= alpha * acc_sh[e];
         if (blockIdx.x == 0) {  // the step itself is only needed once: fire-and-forget adds (x was zeroed by k_cg_init)
@@ -1609,15 +1674,18 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       }
       PROFP(2)
       const double rzn = cta_sum(d, red_sh, 1, lane, wid);
-      iters = it + 1;
-      const bool last = !(rzn > A.tol2 * rz0) || iters >= A.max_iters;
+      const bool last = !(rzn > A.tol2 * rz0) || it + 1 >= A.max_iters;
       if (tid == 0) {
         if (last) { sig[2] = n; __threadfence_block(); sig[1] = 1; }
         else sig[0] = it + 1;
+        st_sh[0] = rzn;  // read again after the next grid barrier
       }
       const double beta = rzn / rz;
-      rz = rzn;
-      if (last) break;
+      if (last) {
+        rz_out = rzn;
+        iters_out = it + 1;
+        break;
+      }
       for (int e = tid; e < n6; e += CTA) {
         const int sl = e / 6, cc = e - sl * 6;
         p_sh[cc * maxslot + sl] = acc_sh[e] + beta * p_sh[cc * maxslot + sl];
@@ -1630,9 +1698,11 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
     // ================================================================== chunked vector update (BIG)
     // ---- owners: apply the PREVIOUS iteration's update (deferred so that nobody had to wait for it), then
     //      [cross-rank sum of q]  qf = q + lambda p,  Dq = Dinv qf,  partial r.z, p.qf, qf.z, qf.Dq;  q = 0
-    const unsigned long long seq = seq0 + (unsigned long long)it + 1ull;
-    const int par = (int)(seq & 1ull);
-    seq_last = seq;
+    const unsigned long long seq = (MULTI ? *A.seq_state : 0ull) + (unsigned long long)it + 1ull;
+    const int nchunk = (P.n_slot + VSLOT - 1) / VSLOT;
+    const int vsl = wid * 5 + lane / 6, vcc = lane - (lane / 6) * 6;
+    const int vbase = min((lane / 6) * 6, 24);
+    exch_out = it + 1;
     for (int ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
       const int slot = ch * VSLOT + vsl;
       const bool ok = lane < 30 && slot < P.n_slot;
@@ -1650,25 +1720,9 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
         P.res[e] = rv;
         P.q[e] = 0.0;
       }
-      if (A.nranks > 1) {
-        if (ok) {
-          for (int r = 0; r < A.nranks; r++)
-            if (r != A.rank) A.peer_recv[r][((size_t)par * A.nranks + A.rank) * A.nelem_cap + e] = qv;
-        }
-        __threadfence_system();
-        named_bar_sync(1, CTA);
-        if (tid < A.nranks && tid != A.rank) {
-          st_release_sys(&A.peer_flag[tid][(size_t)A.rank * A.nchunk_cap + ch], seq);
-          while (ld_acquire_sys(&A.flag[(size_t)tid * A.nchunk_cap + ch]) < seq) {}
-        }
-        named_bar_sync(1, CTA);
-        if (ok) {
-          double tot = 0.0;
-          for (int r = 0; r < A.nranks; r++)
-            tot += (r == A.rank) ? qv : __ldcv(&A.recv[((size_t)par * A.nranks + r) * A.nelem_cap + e]);
-          qv = tot;
-        }
-      }
+      PROFP(9)
+      if (MULTI && ok) qv = peer_sum(A.peer_tbl, A.recv, A.nranks, A.rank, A.nelem_cap, qv, e, seq);
+      PROFP(10)
       if (ok) {
         qv += lam * pv;
         A.qf[e] = qv;
@@ -1680,6 +1734,7 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
         if (ok) dq += __ldg(&P.Dinv[(size_t)slot * 36 + vcc * 6 + k]) * qk;
       }
       if (ok) A.dq[e] = dq;
+      PROFP(11)
       double d0 = rv * zv, d1 = pv * qv, d2 = qv * zv, d3 = qv * dq;
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
@@ -1688,7 +1743,9 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
         d2 += __shfl_down_sync(FULL, d2, off);
         d3 += __shfl_down_sync(FULL, d3, off);
       }
+      PROFP(6)
       named_bar_sync(1, CTA);  // scratch free (previous chunk's partials consumed)
+      PROFP(8)
       if (lane == 0) { red_sh[wid] = d0; red_sh[4 + wid] = d1; c_sh[wid] = d2; c_sh[4 + wid] = d3; }
       named_bar_sync(1, CTA);
       if (tid < 4) {
@@ -1697,7 +1754,7 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       }
     }
     PROFP(1)
-    grid_bar(A.gbar, gridDim.x, gen, tid);  // B2: state of this iterate and the partial dot products complete
+    grid_bar(A.gbar, gridDim.x, (unsigned)(2 * it + 2), tid);  // B2: state of this iterate and the partial dot products complete
     PROFP(2)
     if (wid == 0) {  // one warp per CTA reads the partials (every CTA reads the same few lines)
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -1721,22 +1778,31 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
     const double alpha = rz / s1;
     pe.alpha = 0.0;
     pe.beta = 0.0;
-    if (!(s1 > 0.0) || !isfinite(alpha)) break;  // breakdown: keep the iterate, LM judges the step by its gain ratio
+    if (!(s1 > 0.0) || !isfinite(alpha)) {  // breakdown: keep the iterate, LM judges the step by its gain ratio
+      rz_out = rz;
+      iters_out = it;
+      break;
+    }
     double rzn = rz - 2.0 * alpha * s2 + alpha * alpha * s3;  // r'.z' after the step (exact in exact arithmetic)
     if (!(rzn > 0.0)) rzn = 0.0;
-    iters = it + 1;
-    const bool last = !(rzn > A.tol2 * rz0) || iters >= A.max_iters;
+    const bool last = !(rzn > A.tol2 * rz0) || it + 1 >= A.max_iters;
     if (tid == 0) {
       if (last) { sig[2] = n; __threadfence_block(); sig[1] = 1; }
       else sig[0] = it + 1;
+      st_sh[0] = rzn;
     }
     pe.alpha = alpha;
     pe.beta = rzn / rz;
-    rz = rzn;
     PROFP(5)
-    if (last) break;
+    if (last) {
+      rz_out = rzn;
+      iters_out = it + 1;
+      break;
+    }
   }
   if (BIG && pe.alpha != 0.0) {  // the last step is still pending
+    const int nchunk = (P.n_slot + VSLOT - 1) / VSLOT;
+    const int vsl = wid * 5 + lane / 6, vcc = lane - (lane / 6) * 6;
     for (int ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
       const int slot = ch * VSLOT + vsl;
       if (lane < 30 && slot < P.n_slot) {
@@ -1749,16 +1815,17 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
   if (P.prof && tid == 0) {
     long long* o = P.prof + (size_t)blockIdx.x * 16;
     for (int i = 0; i < 8; i++) o[i] += tpp[i];
-    o[8] += iters;
+    o[8] += iters_out;
+    o[9] += tpp[9]; o[10] += tpp[10]; o[11] += tpp[11]; o[12] += tpp[6]; o[13] += tpp[8];
   }
 #endif
   if (tid == 0 && !sig[1]) { sig[2] = n; __threadfence_block(); sig[1] = 1; }  // breakdown exit: release the producer
   if (blockIdx.x == 0 && tid == 0) {
-    c.rz = rz;
-    c.cg_iters = iters;
+    c.rz = rz_out;
+    c.cg_iters = iters_out;
     c.cg_active = 0;
-    atomicAdd(&P.counters[2], iters);
-    if (BIG && A.nranks > 1) *A.seq_state = seq_last;
+    atomicAdd(&P.counters[2], iters_out);
+    if (BIG && MULTI) *A.seq_state += (unsigned long long)exch_out;
   }
 }
 

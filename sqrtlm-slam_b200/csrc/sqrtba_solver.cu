@@ -163,6 +163,10 @@ class Solver {
                                   (int)persist_smem_bytes(2, MAXSLOT, false)));
     CU_CHECK(cudaFuncSetAttribute(k_pcg_persist<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)persist_smem_bytes(3, MAXSLOT, false)));
+    CU_CHECK(cudaFuncSetAttribute(k_pcg_persist<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)persist_smem_bytes(2, MAXSLOT, false)));
+    CU_CHECK(cudaFuncSetAttribute(k_pcg_persist<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)persist_smem_bytes(3, MAXSLOT, false)));
     int coop = 0;
     CU_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg_.device));
     coop_ok_ = coop != 0;
@@ -993,6 +997,8 @@ class Solver {
     peer_release();
     if (d_seq_) cudaFree(d_seq_);
     d_seq_ = nullptr;
+    if (d_peer_tbl_) cudaFree(d_peer_tbl_);
+    d_peer_tbl_ = nullptr;
     if (comm_ && g_nccl.CommDestroy) g_nccl.CommDestroy(comm_);
     comm_ = nullptr;
     n_ranks_ = 1;
@@ -1014,6 +1020,17 @@ class Solver {
     fprintf(stderr, "[persist prof] grid %d, iterations/CTA %.0f | cycles per iteration (CTA average): tiles %.0f (max-CTA %.0f) flush %.0f "
             "B1 %.0f ph1 %.0f B2|ph2 %.0f ph3 %.0f B3 %.0f other %.0f\n", grid, its / grid, acc[3] / its, mx3 / (its / grid), acc[4] / its,
             acc[0] / its, acc[1] / its, acc[2] / its, acc[5] / its, acc[6] / its, acc[7] / its);
+    {
+      const int nchunk = (std::max(P_.n_slot, 1) + VSLOT - 1) / VSLOT;
+      const int nown = std::min(nchunk, grid);
+      double o9 = 0, o10 = 0, o1 = 0, o2 = 0, o11 = 0, o12 = 0, o13 = 0;
+      for (int b = 0; b < nown; b++) { o9 += hp[(size_t)b * 16 + 9]; o10 += hp[(size_t)b * 16 + 10]; o1 += hp[(size_t)b * 16 + 1]; o2 += hp[(size_t)b * 16 + 2];
+        o11 += hp[(size_t)b * 16 + 11]; o12 += hp[(size_t)b * 16 + 12]; o13 += hp[(size_t)b * 16 + 13]; }
+      fprintf(stderr, "[persist prof] owner detail: Dq %.0f, dot shuffles %.0f, wait for the CTA's other warps %.0f\n", o11 / (its / grid * nown), o12 / (its / grid * nown), o13 / (its / grid * nown));
+      const double oi = its / grid * nown;
+      fprintf(stderr, "[persist prof] owner CTAs (%d): cycles per iteration: B1->exchange start %.0f, exchange %.0f, rest of phase 1 %.0f, B2 wait %.0f\n",
+              nown, o9 / oi, o10 / oi, o1 / oi, o2 / oi);
+    }
     {
       std::vector<std::pair<long long, int>> v;
       for (int b = 0; b < grid; b++) v.push_back({hp[(size_t)b * 16 + 3], b});
@@ -1037,7 +1054,7 @@ class Solver {
            2 * (2 * CTA + 4) * sizeof(int) + 2 * S * sizeof(uint64_t);
   }
   static size_t persist_smem_bytes(int S, int maxslot, bool big) {
-    return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + (big ? 6 : 18) * (size_t)maxslot + 8) * sizeof(double) +
+    return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + (big ? 6 : 18) * (size_t)maxslot + 16) * sizeof(double) +
            2 * S * sizeof(uint64_t) + 4 * sizeof(int) + 2 * (size_t)pipe_run_cap(maxslot, big) * sizeof(int);
   }
   void launch_matvec(const double* pvec, double* qvec, int force_all) {
@@ -1079,9 +1096,8 @@ class Solver {
     A.dq = d_dq_.p;
     A.qf = d_dq_.p + (size_t)6 * std::max(P_.n_slot, 1);
     if (A.nranks > 1) {
-      A.recv = peer_recv_[rank_];
-      A.flag = peer_flag_[rank_];
-      for (int r = 0; r < n_ranks_; r++) { A.peer_recv[r] = peer_recv_[r]; A.peer_flag[r] = peer_flag_[r]; }
+      A.recv = (uint4*)peer_recv_[rank_];
+      A.peer_tbl = (uint4* const*)d_peer_tbl_;
       A.seq_state = d_seq_;
       A.nelem_cap = (int)peer_nelem_cap_;
       A.nchunk_cap = (int)peer_nchunk_cap_;
@@ -1092,7 +1108,9 @@ class Solver {
     const size_t bytes = persist_smem_bytes(persist_stages_, persist_slots_, big);
     int maxslot = persist_slots_;
     void* args[] = {(void*)&P_, (void*)&A, (void*)&maxslot, (void*)&lam_override, (void*)&use_override};
-    const void* fn = big ? (persist_stages_ == 2 ? (const void*)k_pcg_persist<2, true> : (const void*)k_pcg_persist<3, true>)
+    const bool multi = A.nranks > 1;  // use_persist() admits several ranks only for big windows
+    const void* fn = big ? (multi ? (persist_stages_ == 2 ? (const void*)k_pcg_persist<2, true, true> : (const void*)k_pcg_persist<3, true, true>)
+                                  : (persist_stages_ == 2 ? (const void*)k_pcg_persist<2, true> : (const void*)k_pcg_persist<3, true>))
                          : (persist_stages_ == 2 ? (const void*)k_pcg_persist<2, false> : (const void*)k_pcg_persist<3, false>);
     CU_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PIPE_THREADS), args, bytes, stream_));
     return SQRTBA_OK;
@@ -1108,7 +1126,7 @@ class Solver {
     peer_release();
     peer_nelem_cap_ = nelem;
     peer_nchunk_cap_ = nchunk;
-    const size_t recv_bytes = 2 * (size_t)n_ranks_ * nelem * sizeof(double);
+    const size_t recv_bytes = 2 * (size_t)n_ranks_ * nelem * 16;  // 16-byte {value, sequence} records
     const size_t flag_bytes = (size_t)n_ranks_ * nchunk * sizeof(unsigned long long);
     double* recv = nullptr;
     unsigned long long* flag = nullptr;
@@ -1166,6 +1184,11 @@ class Solver {
     }
     cudaFree(d_ok);
     peer_ok_ = (rc == 0) && all_ok > 0.5;
+    if (peer_ok_) {
+      if (!d_peer_tbl_) CU_CHECK(cudaMalloc((void**)&d_peer_tbl_, 8 * sizeof(void*)));
+      CU_CHECK(cudaMemcpyAsync(d_peer_tbl_, peer_recv_, 8 * sizeof(void*), cudaMemcpyHostToDevice, stream_));
+      CU_CHECK(cudaStreamSynchronize(stream_));
+    }
     if (!peer_ok_) peer_release();
     return SQRTBA_OK;
   }
@@ -1362,6 +1385,7 @@ class Solver {
   double* peer_recv_[8] = {};
   unsigned long long* peer_flag_[8] = {};
   unsigned long long* d_seq_ = nullptr;
+  void** d_peer_tbl_ = nullptr;
   size_t peer_nelem_cap_ = 0, peer_nchunk_cap_ = 0;
   DBuf<unsigned> d_gbar_;
   DBuf<double> d_part_, d_q3_, d_dq_;
