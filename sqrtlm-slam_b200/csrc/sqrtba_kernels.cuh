@@ -51,6 +51,7 @@ struct TileInfo {
   int nrun;          // distinct free pose slots among the participating observations (= runs of equal slot by rank)
   int blk_doubles;   // size of the whole JQ block (header + data + meta + run table), in doubles, even
   int cnt[4];        // observations of each item of the tile (0 for absent items): saves the item_start / item_cnt lookups
+  int fcnt[4];       // free-pose observations of each item: the JQ block of a short tile only has columns for those
 };
 
 // item geometry from the tile descriptor alone (items of a tile are consecutive observation ranges; selects, not
@@ -60,6 +61,15 @@ __device__ __forceinline__ int tile_item_cnt(const TileInfo& ti, int wid) {
 }
 __device__ __forceinline__ int tile_item_start(const TileInfo& ti, int wid) {
   return ti.o0 + (wid > 0 ? ti.cnt[0] : 0) + (wid > 1 ? ti.cnt[1] : 0) + (wid > 2 ? ti.cnt[2] : 0);
+}
+
+// Column of a free-pose observation inside its tile's JQ block.  Short tiles store columns for FREE-pose observations
+// only (in landmark order): observations of fixed keyframes have no pose columns (g2o hessianIndex -1), so neither the
+// matvec nor the back-substitution ever reads them -- leaving them out cuts the dominant kernel's DRAM traffic by the
+// share of fixed-keyframe observations (14 % on the KITTI-shaped windows).  Must be called by all lanes of the warp.
+__device__ __forceinline__ int tile_fcol(const TileInfo& ti, int wid, bool has, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, has);
+  return (wid > 0 ? ti.fcnt[0] : 0) + (wid > 1 ? ti.fcnt[1] : 0) + (wid > 2 ? ti.fcnt[2] : 0) + __popc(m & ((1u << lane) - 1u));
 }
 
 struct Dev {
@@ -351,7 +361,6 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize(Dev P, int robust, double 
   const size_t No = (size_t)P.ld; const int Nl = P.n_point;
   const bool is_long = cnt > 32;
   double* __restrict__ jq = P.JQ + ti.jq_off;
-  const uint2* __restrict__ meta = reinterpret_cast<const uint2*>(jq + (size_t)NPLANE * ti.nt);  // {obs_lp, landmark}
   double chi_acc = 0.0, maxd = 0.0;
   double vb[6] = {0, 0, 0, 0, 0, 0}, vh[6] = {0, 0, 0, 0, 0, 0};  // this observation's -Jp^T r and diag(Jp^T Jp)
   bool has = false;
@@ -365,11 +374,12 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize(Dev P, int robust, double 
     for (int c = 0; c < 9; c++) L.Jl[c] = 0.0;
     L.e[0] = L.e[1] = L.e[2] = 0.0;
     if (act) {
-      const uint2 m = meta[o - ti.o0];
-      has = (m.x & 0xffffu) != 0xffffu;
-      rank = (int)(m.x >> 16);
-      lm = (int)m.y;
+      const unsigned lp = P.obs_lp[o];
+      has = (lp & 0xffffu) != 0xffffu;
+      rank = (int)(lp >> 16);
+      lm = P.obs_point[o];
     }
+    const int fcol = tile_fcol(ti, wid, has, lane);
     if (act && on) {
       const bool live = P.obs_level[o] == 0;
       obs_eval(P, o, true, robust != 0, d2, d3, L);
@@ -380,7 +390,7 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize(Dev P, int robust, double 
       }
       // an excluded (level-1) edge contributes zero rows; select, do not multiply (its Jacobian may be inf/NaN)
 #pragma unroll
-      for (int c = 0; c < 18; c++) { L.Jp[c] = live ? L.Jp[c] * L.w : 0.0; jq[(size_t)c * ti.nt + (o - ti.o0)] = L.Jp[c]; }
+      for (int c = 0; c < 18; c++) { L.Jp[c] = live ? L.Jp[c] * L.w : 0.0; if (has) jq[(size_t)c * ti.nt + fcol] = L.Jp[c]; }
 #pragma unroll
       for (int c = 0; c < 9; c++) { L.Jl[c] = live ? L.Jl[c] * L.w : 0.0; P.Jl[(size_t)c * No + o] = L.Jl[c]; }
 #pragma unroll
@@ -653,7 +663,6 @@ __global__ void __launch_bounds__(CTA, 4) k_qr(Dev P, int force_all, double lam_
   const size_t No = (size_t)P.ld; const int Nl = P.n_point;
   double* __restrict__ jq = P.JQ + ti.jq_off;
   const int nt = ti.nt;
-  const uint2* __restrict__ meta = reinterpret_cast<const uint2*>(jq + (size_t)NPLANE * nt);  // {obs_lp, landmark} per column
   // the 18 Jp rows are only needed after the factorisation: start pulling them into L2 now (one TMA prefetch per CTA)
   if (threadIdx.x == 0 && !ti.is_long) bulk_prefetch_l2(jq, (uint32_t)(18 * nt * sizeof(double)));
   bool has = false;
@@ -665,18 +674,19 @@ __global__ void __launch_bounds__(CTA, 4) k_qr(Dev P, int force_all, double lam_
     int lm = -1 - lane;
     double a[9], rr[3];
     if (act) {  // every load of this phase is issued before the first use
-      const uint2 m = meta[o - ti.o0];
+      const unsigned lp = P.obs_lp[o];
+      lm = P.obs_point[o];
       load9(P.Jl, No, o, a);
 #pragma unroll
       for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
-      has = (m.x & 0xffffu) != 0xffffu;
-      rank = (int)(m.x >> 16);
-      lm = (int)m.y;
+      has = (lp & 0xffffu) != 0xffffu;
+      rank = (int)(lp >> 16);
     } else {
 #pragma unroll
       for (int c = 0; c < 9; c++) a[c] = 0.0;
       rr[0] = rr[1] = rr[2] = 0.0;
     }
+    const int fcol = tile_fcol(ti, wid, has, lane);
     if (on) {
       const Seg sg = seg_of(lm, lane);
       // column 0
@@ -717,15 +727,17 @@ __global__ void __launch_bounds__(CTA, 4) k_qr(Dev P, int force_all, double lam_
 #pragma unroll
       for (int k = 0; k < 3; k++) tl[k] = seg_sum(Q[k] * rr[0] + Q[3 + k] * rr[1] + Q[6 + k] * rr[2], sg, lane);
       if (act) {
+        if (has) {
 #pragma unroll
-        for (int c = 0; c < 9; c++) jq[(size_t)(18 + c) * nt + (o - ti.o0)] = Q[c];
+          for (int c = 0; c < 9; c++) jq[(size_t)(18 + c) * nt + fcol] = Q[c];
+        }
         if (lane == sg.start) {
 #pragma unroll
           for (int c = 0; c < 6; c++) P.R[(size_t)c * Nl + lm] = F.Rm[c];
 #pragma unroll
           for (int c = 0; c < 3; c++) P.tl[(size_t)c * Nl + lm] = tl[c];
         }
-        if (has) trial_contrib_sh(jq, nt, o - ti.o0, Q, rr, tl, c_sh, rank);
+        if (has) trial_contrib_sh(jq, nt, fcol, Q, rr, tl, c_sh, rank);
       }
     }
   } else if (on) {
@@ -956,9 +968,10 @@ __global__ void __launch_bounds__(CTA) k_matvec(Dev P, const double* __restrict_
       lm = P.obs_point[o];
     }
     const Seg sg = seg_of(lm, lane);
+    const int fcol = tile_fcol(ti, wid, has, lane);
     double J[18], Q[9], pp[6];
     if (has) {
-      const int col = o - ti.o0;
+      const int col = fcol;
 #pragma unroll
       for (int c = 0; c < 18; c++) J[c] = jq[(size_t)c * nt + col];
 #pragma unroll
@@ -988,7 +1001,8 @@ __global__ void k_init_jq(Dev P) {
     h[3] = P.win_slot_ptr[ti.win + 1] - P.win_slot_ptr[ti.win];
     h[4] = ti.nfree; h[5] = ti.nt; h[6] = ti.o0;
     h[7] = (int)(ti.jq_off & 0xffffffffll); h[8] = (int)(ti.jq_off >> 32);
-    for (int i = 0; i < 4; i++) h[9 + i] = (i < ti.nitem) ? P.item_cnt[ti.item0 + i] : 0;
+    // matvec lanes = columns: free-pose observations per item (a long tile keeps one column per observation)
+    for (int i = 0; i < 4; i++) h[9 + i] = ti.is_long ? (i == 0 ? ti.cnt[0] : 0) : ti.fcnt[i];
     h[13] = ti.is_long; h[14] = ti.nrun;
     // lowest slot of the tile (run slots are sorted): anchors the shared accumulator window of the big-window matvec
     h[15] = (ti.nrun > 0) ? P.tile_runs[P.tile_run_ptr[blockIdx.x] + ti.nrun + 1] : -1;
@@ -997,13 +1011,25 @@ __global__ void k_init_jq(Dev P) {
   const int r0 = P.tile_run_ptr[blockIdx.x], nr = P.tile_run_ptr[blockIdx.x + 1] - r0;
   for (int i = threadIdx.x; i < nr; i += blockDim.x) runs[i] = P.tile_runs[r0 + i];
   uint2* meta = reinterpret_cast<uint2*>(blk + (size_t)NPLANE * ti.nt);
-  for (int col = threadIdx.x; col < ti.nt; col += blockDim.x) {
-    const int o = ti.o0 + col;
-    uint2 m;
-    m.x = (o < ti.o1) ? P.obs_lp[o] : 0xffffu;
-    m.y = (o < ti.o1) ? (unsigned)P.obs_point[o] : 0xffffffffu;
-    meta[col] = m;
+  if (ti.is_long) {
+    for (int col = threadIdx.x; col < ti.nt; col += blockDim.x) {
+      const int o = ti.o0 + col;
+      uint2 m;
+      m.x = (o < ti.o1) ? P.obs_lp[o] : 0xffffu;
+      m.y = (o < ti.o1) ? (unsigned)P.obs_point[o] : 0xffffffffu;
+      meta[col] = m;
+    }
+    return;
   }
+  // short tile (blockDim.x = 128 = one warp per item): one meta entry per FREE-pose observation, in landmark order
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int cnt = tile_item_cnt(ti, wid), start = tile_item_start(ti, wid);
+  const bool act = wid < ti.nitem && lane < cnt;
+  const unsigned lp = act ? P.obs_lp[start + lane] : 0xffffu;
+  const bool has = (lp & 0xffffu) != 0xffffu;
+  const int fcol = tile_fcol(ti, wid, has, lane);
+  if (has) meta[fcol] = make_uint2(lp, (unsigned)P.obs_point[start + lane]);
+  if (threadIdx.x == 0 && (ti.nfree & 1)) meta[ti.nfree] = make_uint2(0xffffu, 0xffffffffu);  // pad column
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -1937,8 +1963,9 @@ __global__ void __launch_bounds__(CTA) k_backsub(Dev P, int force_all, double la
     if (act) lm = P.obs_point[o];
     double J[18], Q[9], v[3];
     double t[3] = {0, 0, 0};
+    const int fcol = is_long ? i : tile_fcol(ti, wid, slot >= 0, lane);  // long tiles keep a column per observation
     if (slot >= 0) {
-      matvec_obs_v(jq, ti.nt, o - ti.o0, P.x, slot, J, Q, v);
+      matvec_obs_v(jq, ti.nt, fcol, P.x, slot, J, Q, v);
 #pragma unroll
       for (int k = 0; k < 3; k++) t[k] = Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2];
     }

@@ -423,7 +423,13 @@ class Solver {
               for (int i = 0; i < nl; i++) c.runs.push_back(smallwin ? distinct[i] : distinct[i] + ws0);
             }
             c.run_ptr.push_back((int)c.runs.size());
-            ti.nt = ((ti.o1 - ti.o0) + 1) & ~1;
+            for (int i = 0; i < 4; i++) {
+              ti.fcnt[i] = 0;
+              if (i < ti.nitem && !ti.is_long)
+                for (int o = c.it_start[it + i]; o < c.it_start[it + i] + c.it_cnt[it + i]; o++) ti.fcnt[i] += obs_slot[o] >= 0;
+            }
+            // columns of the JQ block: free-pose observations only (a long tile keeps one per observation); even
+            ti.nt = ((ti.is_long ? (ti.o1 - ti.o0) : ti.nfree) + 1) & ~1;
             const int run_ints = ti.is_long ? 0 : 2 * ti.nrun + 1;
             ti.blk_doubles = JQ_HDR + JQ_ROWS * ti.nt + 2 * ((run_ints + 3) / 4);
             ti.jq_off = c.jq + JQ_HDR;  // chunk-local, rebased in the merge
@@ -830,9 +836,16 @@ class Solver {
       std::vector<double> rows;
       double* d = Jp;
       if (!perm_.empty()) { rows.resize(No * 18); d = rows.data(); }
-      for (const TileInfo& ti : h_tiles_)
-        for (int o = ti.o0; o < ti.o1; o++)
-          for (int c = 0; c < 18; c++) d[(size_t)o * 18 + c] = tmp[(size_t)ti.jq_off + (size_t)c * ti.nt + (o - ti.o0)];
+      for (const TileInfo& ti : h_tiles_) {  // fixed-keyframe observations have no pose columns: zeros
+        int fcol = 0;
+        for (int o = ti.o0; o < ti.o1; o++) {
+          const bool free_pose = h_obs_slot_.p[o] >= 0;
+          const int col = ti.is_long ? (o - ti.o0) : fcol;
+          for (int c = 0; c < 18; c++)
+            d[(size_t)o * 18 + c] = (free_pose || ti.is_long) ? tmp[(size_t)ti.jq_off + (size_t)c * ti.nt + col] : 0.0;
+          fcol += free_pose;
+        }
+      }
       if (!perm_.empty()) unperm_obs(rows.data(), Jp, 18);
     }
     if (chi2) {
