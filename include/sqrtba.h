@@ -130,6 +130,24 @@ int sqrtba_comm_unique_id(uint8_t* id128_out);
 int sqrtba_comm_init(sqrtba_handle* h, int32_t nranks, int32_t rank, const uint8_t* id128);
 int sqrtba_comm_destroy(sqrtba_handle* h);
 
+/* ---- pose-only optimisation (tracking thread) --------------------------------------------------------------------
+ * Replaces Optimizer::PoseOptimization (include/backend/Optimizer.h:58-60 -> src/backend/g2oOptimizer.cc:385-559,
+ * 655-690; the lidar block :560-640 is not covered): one SE3 vertex per frame, one unary reprojection edge per matched
+ * map point (EdgeSE3ProjectXYZOnlyPose when ur < 0, EdgeStereoSE3ProjectXYZOnlyPose otherwise -- the reference fork
+ * only creates the monocular ones, :441-483), Huber deltas sqrt(5.991)/sqrt(7.815), four rounds of optimize(10) from
+ * the same initial pose with chi2 re-classification in between, kernels dropped from the third classification on.
+ * A batch of frames (relocalisation candidates) is one launch: frame f owns observations
+ * [frame_obs_ptr[f], frame_obs_ptr[f+1]).  Independent of sqrtba_set_problem (the handle only lends stream/buffers).
+ *   pose_qt     n_frames x 7 in/out (Tcw, SE3Quat::toVector order)     cam  n_frames x 5 (fx,fy,cx,cy,bf)
+ *   obs_xyz     n_obs x 3 world positions of the matched map points    obs_meas n_obs x 4 float u,v,ur,invSigma2
+ *   outlier_out n_obs (Frame::mvbOutlier)    inliers_out n_frames (the function's return value; 0 if < 3 observations)
+ * sqrtba_pose_opt_trace: LM trials of one frame of the LAST call, rows of 8 doubles
+ *   (round, iteration, trial, lambda, chi2 before, chi2 trial, rho, accepted); returns the number of rows. */
+int sqrtba_pose_opt(sqrtba_handle* h, int32_t n_frames, const int64_t* frame_obs_ptr, double* pose_qt, const double* cam,
+                    const double* obs_xyz, const float* obs_meas, uint8_t* outlier_out, int32_t* inliers_out,
+                    sqrtba_stats* stats);
+int sqrtba_pose_opt_trace(sqrtba_handle* h, int32_t frame, double* rows_out, int32_t max_rows);
+
 /* ---- stage-level entry points (kernel parity tests, profiling) --------------------------------------------
  * sqrtba_debug_linearize : run the fused residual+Jacobian+Huber kernel at the current state.
  *    huber: 0 none, 1 local-BA deltas, 2 global-BA deltas.  Outputs (any may be NULL):

@@ -1015,6 +1015,261 @@ void refba_huber(double delta, double e, double* rho3) {
   robustify(ed, e, rho3);
 }
 
+// =============================================================================================
+// Pose-only optimisation: g2oOptimizer::PoseOptimization, src/backend/g2oOptimizer.cc:385-559,
+// 655-690 (the lidar block :560-640 is out of scope).  One VertexSE3Expmap, one unary EdgeSE3ProjectXYZOnlyPose per
+// observation with ur<0 (the fork leaves the stereo branch empty, :481-483; an observation with ur>=0 is wired as the
+// vendored EdgeStereoSE3ProjectXYZOnlyPose, types_six_dof_expmap.h:175-202, the way upstream ORB-SLAM2 does).
+// BlockSolver_6_3 + LinearSolverDense (linear_solver_dense.h:65-113: Eigen LDLT of the 6x6 block, isPositive() or fail)
+// + OptimizationAlgorithmLevenberg; 4 rounds x optimize(10) from the SAME initial pose, chi2 re-classification after
+// each round (float chi2 against float thresholds), Huber kernels dropped from round 2 on.
+// =============================================================================================
+namespace {
+struct PEdge {
+  bool stereo;
+  double obs[3], info, Xw[3];
+  int level = 0;
+  bool robust = true;
+  double delta, dsqr;
+  double err[3] = {0, 0, 0};
+  double J[18];
+};
+struct PoseProblem {
+  SE3 T, Tbak;
+  double fx, fy, cx, cy, bf;
+  std::vector<PEdge> e;
+  std::vector<int> active;
+  double H[36], b[6], x[6];
+  double lambda = -1, ni = 2;
+  int nBad = 0;
+  std::vector<TraceRow> trace;
+  int round = 0;
+};
+// EdgeSE3ProjectXYZOnlyPose::computeError (types_six_dof_expmap.h:152-156, .cpp:290-296) /
+// EdgeStereoSE3ProjectXYZOnlyPose::computeError (.h:184-188, .cpp:299-306: float invz, DOUBLE bf)
+inline void pComputeError(const PoseProblem& P, PEdge& e) {
+  double Xc[3];
+  se3map(P.T, e.Xw, Xc);
+  if (!e.stereo) {
+    const double px = Xc[0] / Xc[2], py = Xc[1] / Xc[2];
+    e.err[0] = e.obs[0] - (px * P.fx + P.cx);
+    e.err[1] = e.obs[1] - (py * P.fy + P.cy);
+    e.err[2] = 0;
+  } else {
+    const float invz = (float)(1.0f / Xc[2]);
+    const double r0 = Xc[0] * invz * P.fx + P.cx, r1 = Xc[1] * invz * P.fy + P.cy;
+    e.err[0] = e.obs[0] - r0;
+    e.err[1] = e.obs[1] - r1;
+    e.err[2] = e.obs[2] - (r0 - P.bf * invz);
+  }
+}
+inline double pChi2(const PEdge& e) {
+  if (!e.stereo) return e.err[0] * (e.info * e.err[0]) + e.err[1] * (e.info * e.err[1]);
+  return e.err[0] * (e.info * e.err[0]) + e.err[1] * (e.info * e.err[1]) + e.err[2] * (e.info * e.err[2]);
+}
+// linearizeOplus (.cpp:266-288 mono, 335-364 stereo): invz = 1/z, invz_2 = invz*invz
+inline void pLinearize(const PoseProblem& P, PEdge& e) {
+  double Xc[3];
+  se3map(P.T, e.Xw, Xc);
+  const double x = Xc[0], y = Xc[1], invz = 1.0 / Xc[2], invz_2 = invz * invz, fx = P.fx, fy = P.fy;
+  double* J = e.J;
+  J[0] = x * y * invz_2 * fx;
+  J[1] = -(1 + (x * x * invz_2)) * fx;
+  J[2] = y * invz * fx;
+  J[3] = -invz * fx;
+  J[4] = 0;
+  J[5] = x * invz_2 * fx;
+  J[6] = (1 + y * y * invz_2) * fy;
+  J[7] = -x * y * invz_2 * fy;
+  J[8] = -x * invz * fy;
+  J[9] = 0;
+  J[10] = -invz * fy;
+  J[11] = y * invz_2 * fy;
+  if (e.stereo) {
+    J[12] = J[0] - P.bf * y * invz_2;
+    J[13] = J[1] + P.bf * x * invz_2;
+    J[14] = J[2];
+    J[15] = J[3];
+    J[16] = 0;
+    J[17] = J[5] - P.bf * invz_2;
+  } else {
+    for (int c = 0; c < 6; c++) J[12 + c] = 0;
+  }
+}
+inline void pRobustify(const PEdge& e, double c, double rho[3]) {
+  if (c <= e.dsqr) { rho[0] = c; rho[1] = 1.; rho[2] = 0.; }
+  else { const double sq = std::sqrt(c); rho[0] = 2 * sq * e.delta - e.dsqr; rho[1] = e.delta / sq; rho[2] = -0.5 * rho[1] / c; }
+}
+void pComputeActiveErrors(PoseProblem& P) { for (int k : P.active) pComputeError(P, P.e[k]); }
+double pActiveRobustChi2(const PoseProblem& P) {  // sparse_optimizer.cpp:100-114
+  double chi = 0;
+  for (int k : P.active) {
+    const PEdge& e = P.e[k];
+    const double c = pChi2(e);
+    if (e.robust) { double rho[3]; pRobustify(e, c, rho); chi += rho[0]; } else chi += c;
+  }
+  return chi;
+}
+// BaseUnaryEdge::constructQuadraticForm (base_unary_edge.hpp:42-72) over the active edges
+void pBuildSystem(PoseProblem& P) {
+  for (double& v : P.H) v = 0;
+  for (double& v : P.b) v = 0;
+  for (int k : P.active) {
+    PEdge& e = P.e[k];
+    pLinearize(P, e);
+    double w = e.info, rho1 = 1.0;
+    if (e.robust) { double rho[3]; pRobustify(e, pChi2(e), rho); rho1 = rho[1]; w = rho[1] * e.info; }
+    const int d = e.stereo ? 3 : 2;
+    for (int i = 0; i < 6; i++) {
+      double g = 0;
+      for (int r = 0; r < d; r++) g += e.J[r * 6 + i] * (e.info * e.err[r]);
+      P.b[i] -= rho1 * g;
+      for (int j = 0; j < 6; j++) {
+        double h = 0;
+        for (int r = 0; r < d; r++) h += e.J[r * 6 + i] * (w * e.J[r * 6 + j]);
+        P.H[i * 6 + j] += h;
+      }
+    }
+  }
+}
+// Eigen::LDLT + isPositive() (linear_solver_dense.h:105-111), restated without pivoting
+bool pSolve6(const double* H, const double* b, double* x) {
+  double L[36] = {0}, D[6];
+  for (int j = 0; j < 6; j++) {
+    double d = H[j * 6 + j];
+    for (int k = 0; k < j; k++) d -= L[j * 6 + k] * L[j * 6 + k] * D[k];
+    if (!(d > 0.0)) return false;
+    D[j] = d;
+    for (int i = j + 1; i < 6; i++) {
+      double v = H[i * 6 + j];
+      for (int k = 0; k < j; k++) v -= L[i * 6 + k] * L[j * 6 + k] * D[k];
+      L[i * 6 + j] = v / d;
+    }
+  }
+  double y[6];
+  for (int i = 0; i < 6; i++) { double v = b[i]; for (int k = 0; k < i; k++) v -= L[i * 6 + k] * y[k]; y[i] = v; }
+  for (int i = 0; i < 6; i++) y[i] /= D[i];
+  for (int i = 5; i >= 0; i--) { double v = y[i]; for (int k = i + 1; k < 6; k++) v -= L[k * 6 + i] * x[k]; x[i] = v; }
+  return true;
+}
+// OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:61-164) for the one-vertex graph
+SolverResult pLmSolve(PoseProblem& P, int iteration) {
+  pComputeActiveErrors(P);
+  double currentChi = pActiveRobustChi2(P);
+  double tempChi = currentChi;
+  const double iniChi = currentChi;
+  pBuildSystem(P);
+  if (iteration == 0) {
+    double md = 0;
+    for (int j = 0; j < 6; j++) md = std::max(std::fabs(P.H[j * 6 + j]), md);
+    P.lambda = 1e-5 * md;
+    P.ni = 2;
+    P.nBad = 0;
+  }
+  double rho = 0;
+  int qmax = 0;
+  do {
+    P.Tbak = P.T;
+    double Hd[36];
+    std::memcpy(Hd, P.H, sizeof Hd);
+    for (int j = 0; j < 6; j++) Hd[j * 6 + j] += P.lambda;
+    const bool ok2 = pSolve6(Hd, P.b, P.x);
+    if (!ok2) for (double& v : P.x) v = 0;  // BlockSolver::solve leaves x untouched on failure; the step is rejected below
+    P.T = se3mul(se3exp(P.x), P.T);
+    pComputeActiveErrors(P);
+    tempChi = pActiveRobustChi2(P);
+    if (!ok2) tempChi = std::numeric_limits<double>::max();
+    rho = (currentChi - tempChi);
+    double scale = 0.;
+    for (int j = 0; j < 6; j++) scale += P.x[j] * (P.lambda * P.x[j] + P.b[j]);
+    scale += 1e-3;
+    rho /= scale;
+    TraceRow tr{(double)P.round, (double)iteration, (double)qmax, P.lambda, currentChi, tempChi, rho, 0.0};
+    if (rho > 0 && std::isfinite(tempChi)) {
+      double alpha = 1. - std::pow((2 * rho - 1), 3);
+      alpha = std::min(alpha, 2. / 3.);
+      P.lambda *= std::max(1. / 3., alpha);
+      P.ni = 2;
+      currentChi = tempChi;
+      tr.accepted = 1.0;
+    } else {
+      P.lambda *= P.ni;
+      P.ni *= 2;
+      P.T = P.Tbak;  // pop: edge errors keep the rejected trial's values
+    }
+    P.trace.push_back(tr);
+    qmax++;
+  } while (rho < 0 && qmax < 10);
+  if (qmax == 10 || rho == 0) return Terminate;
+  if ((iniChi - currentChi) * 1e3 < iniChi) P.nBad++; else P.nBad = 0;
+  if (P.nBad >= 3) return Terminate;
+  return OK;
+}
+}  // namespace
+
+// pose7 in/out (SE3Quat::toVector order), cam = fx,fy,cx,cy,bf, xyz n x 3 (the reference copies float map points into
+// double Xw, g2oOptimizer.cc:472-475), meas n x 4 float (u, v, ur<0 => mono, invSigma2).  outlier: n flags
+// (Frame::mvbOutlier).  trace: up to max_trace rows of 8 doubles (round, iter, trial, lambda, chi_before, chi_trial,
+// rho, accepted); *n_trace = rows written.  Returns nInitialCorrespondences - nBad (0 if fewer than 3 observations).
+int refba_pose_opt(double* pose7, const double* cam, int n, const double* xyz, const float* meas, uint8_t* outlier,
+                   double* trace, int max_trace, int* n_trace) {
+  PoseProblem P;
+  P.T.t[0] = pose7[0]; P.T.t[1] = pose7[1]; P.T.t[2] = pose7[2];
+  P.T.r = Quat{pose7[3], pose7[4], pose7[5], pose7[6]};
+  normalizeRotation(P.T);
+  const SE3 T0 = P.T;
+  P.fx = cam[0]; P.fy = cam[1]; P.cx = cam[2]; P.cy = cam[3]; P.bf = cam[4];
+  const float deltaMono = std::sqrt(5.991), deltaStereo = std::sqrt(7.815);  // :426-428
+  P.e.resize(n);
+  for (int i = 0; i < n; i++) {
+    PEdge& e = P.e[i];
+    e.stereo = !(meas[i * 4 + 2] < 0.0f);
+    e.obs[0] = meas[i * 4 + 0]; e.obs[1] = meas[i * 4 + 1]; e.obs[2] = e.stereo ? meas[i * 4 + 2] : 0.0;
+    e.info = meas[i * 4 + 3];
+    for (int c = 0; c < 3; c++) e.Xw[c] = xyz[i * 3 + c];
+    e.delta = e.stereo ? deltaStereo : deltaMono;
+    e.dsqr = e.delta * e.delta;
+    outlier[i] = 0;
+  }
+  if (n_trace) *n_trace = 0;
+  if (n < 3) return 0;  // :491-492
+  const float chi2Mono[4] = {5.991f, 5.991f, 5.991f, 5.991f}, chi2Stereo[4] = {7.815f, 7.815f, 7.815f, 7.815f};
+  int nBad = 0;
+  for (int it = 0; it < 4; it++) {
+    P.T = T0;  // vSE3->setEstimate(Converter::toSE3Quat(pFrame->mTcw)), :510
+    P.round = it;
+    P.active.clear();
+    for (int i = 0; i < n; i++) if (P.e[i].level == 0) P.active.push_back(i);
+    if (!P.active.empty()) {  // optimize(10), sparse_optimizer.cpp:354-419
+      bool ok = true;
+      for (int i = 0; i < 10 && ok; i++) ok = (pLmSolve(P, i) == OK);
+    }
+    nBad = 0;
+    for (int i = 0; i < n; i++) {  // :518-547
+      PEdge& e = P.e[i];
+      if (outlier[i]) pComputeError(P, e);
+      const float chi2 = (float)pChi2(e);
+      if (chi2 > (e.stereo ? chi2Stereo[it] : chi2Mono[it])) { outlier[i] = 1; e.level = 1; nBad++; }
+      else { outlier[i] = 0; e.level = 0; }
+      if (it == 2) e.robust = false;
+    }
+    if (n < 10) break;  // optimizer.edges().size()<10, :549-550
+  }
+  nBad = 0;
+  for (int i = 0; i < n; i++) {  // final classification, :656-680 (double 5.991 / upstream stereo 7.815)
+    PEdge& e = P.e[i];
+    if (outlier[i]) pComputeError(P, e);
+    const float chi2 = (float)pChi2(e);
+    if ((double)chi2 > (e.stereo ? 7.815 : 5.991)) { outlier[i] = 1; nBad++; } else outlier[i] = 0;
+  }
+  pose7[0] = P.T.t[0]; pose7[1] = P.T.t[1]; pose7[2] = P.T.t[2];
+  pose7[3] = P.T.r.x; pose7[4] = P.T.r.y; pose7[5] = P.T.r.z; pose7[6] = P.T.r.w;
+  const int nt = std::min<int>((int)P.trace.size(), max_trace);
+  if (trace && nt > 0) std::memcpy(trace, P.trace.data(), (size_t)nt * sizeof(TraceRow));
+  if (n_trace) *n_trace = nt;
+  return n - nBad;
+}
+
 int refba_max_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

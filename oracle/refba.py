@@ -49,6 +49,7 @@ def lib():
         L.refba_cam_project_mono.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_double, dp]
         L.refba_cam_project_stereo.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_float, dp]
         L.refba_huber.argtypes = [C.c_double, C.c_double, dp]
+        L.refba_pose_opt.argtypes = [dp, dp, C.c_int, dp, fp, up, dp, C.c_int, ip]
         _lib = L
     return _lib
 
@@ -154,3 +155,20 @@ def se3_exp(upd6):
     out = np.zeros(7)
     lib().refba_se3_exp(_p(u, C.c_double), _p(out, C.c_double))
     return out
+
+
+def pose_opt(pose7, cam5, xyz, meas):
+    """g2oOptimizer::PoseOptimization restated (oracle/refba.cpp: refba_pose_opt).
+    Returns (pose7_out, outlier flags, inliers, trace[rows, 8])."""
+    L = lib()
+    pose = np.ascontiguousarray(pose7, np.float64).copy()
+    cam = np.ascontiguousarray(cam5, np.float64)
+    xyz = np.ascontiguousarray(xyz, np.float64)
+    meas = np.ascontiguousarray(meas, np.float32)
+    n = xyz.shape[0]
+    out = np.zeros(max(n, 1), np.uint8)
+    tr = np.zeros((400, 8))
+    nt = C.c_int32(0)
+    inl = L.refba_pose_opt(_p(pose, C.c_double), _p(cam, C.c_double), n, _p(xyz, C.c_double), _p(meas, C.c_float),
+                           _p(out, C.c_uint8), _p(tr, C.c_double), 400, C.byref(nt))
+    return pose, out[:n], int(inl), tr[:nt.value]

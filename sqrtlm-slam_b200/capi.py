@@ -65,6 +65,8 @@ def lib():
         L.sqrtba_debug_matvec.argtypes = [vp, dp, dp]
         L.sqrtba_num_free_poses.argtypes = [vp]
         L.sqrtba_time_stage.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, dp]
+        L.sqrtba_pose_opt.argtypes = [vp, C.c_int32, lp, dp, dp, dp, fp, up, ip, C.POINTER(Stats)]
+        L.sqrtba_pose_opt_trace.argtypes = [vp, C.c_int32, dp, C.c_int32]
         L.sqrtba_comm_unique_id.argtypes = [up]
         L.sqrtba_comm_init.argtypes = [vp, C.c_int32, C.c_int32, up]
         L.sqrtba_comm_destroy.argtypes = [vp]
@@ -207,6 +209,27 @@ class SqrtBA:
         y = np.zeros_like(p)
         self._chk(lib().sqrtba_debug_matvec(self.h, _p(p, C.c_double), _p(y, C.c_double)), "sqrtba_debug_matvec")
         return y
+
+    def pose_opt(self, frame_ptr, pose_qt, cam, obs_xyz, obs_meas):
+        """sqrtba_pose_opt on a batch of frames.  Returns (poses, outlier flags, inliers per frame, stats)."""
+        fp_ = np.ascontiguousarray(frame_ptr, np.int64)
+        nf = len(fp_) - 1
+        pose = np.ascontiguousarray(pose_qt, np.float64).reshape(nf, 7).copy()
+        cam = np.ascontiguousarray(cam, np.float64).reshape(nf, 5)
+        xyz = np.ascontiguousarray(obs_xyz, np.float64).reshape(-1, 3)
+        meas = np.ascontiguousarray(obs_meas, np.float32).reshape(-1, 4)
+        out = np.zeros(max(int(fp_[-1]), 1), np.uint8)
+        inl = np.zeros(nf, np.int32)
+        st = Stats()
+        self._chk(lib().sqrtba_pose_opt(self.h, nf, _p(fp_, C.c_int64), _p(pose, C.c_double), _p(cam, C.c_double),
+                                        _p(xyz, C.c_double), _p(meas, C.c_float), _p(out, C.c_uint8), _p(inl, C.c_int32),
+                                        C.byref(st)), "sqrtba_pose_opt")
+        return pose, out[:int(fp_[-1])], inl, st.as_dict()
+
+    def pose_opt_trace(self, frame: int = 0):
+        rows = np.zeros((400, 8))
+        n = self._chk(lib().sqrtba_pose_opt_trace(self.h, frame, _p(rows, C.c_double), 400), "sqrtba_pose_opt_trace")
+        return rows[:n]
 
     def comm_init(self, nranks: int, rank: int, unique_id: bytes):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)

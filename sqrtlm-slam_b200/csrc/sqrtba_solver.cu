@@ -21,6 +21,7 @@
 
 #include "../../include/sqrtba.h"
 #include "sqrtba_kernels.cuh"
+#include "sqrtba_poseopt.cuh"
 
 namespace sqrtba {
 
@@ -805,6 +806,72 @@ class Solver {
   }
   int num_free() const { return have_problem_ ? P_.n_slot : SQRTBA_ERR_INVALID; }
 
+  // ------------------------------------------------------------------------------------------ pose-only optimisation
+  // g2oOptimizer::PoseOptimization for a batch of frames (one CTA per frame, one launch); independent of set_problem.
+  int pose_opt(int n_frames, const int64_t* frame_ptr, double* pose_qt, const double* cam, const double* obs_xyz,
+               const float* obs_meas, uint8_t* outlier_out, int32_t* inliers_out, sqrtba_stats* st) {
+    if (n_frames <= 0 || !frame_ptr || !pose_qt || !cam || !inliers_out) { err_ = "pose_opt: bad arguments"; return SQRTBA_ERR_INVALID; }
+    const long long n_obs = frame_ptr[n_frames];
+    if (frame_ptr[0] != 0 || n_obs < 0 || (n_obs > 0 && (!obs_xyz || !obs_meas || !outlier_out))) {
+      err_ = "pose_opt: bad observation arrays";
+      return SQRTBA_ERR_INVALID;
+    }
+    for (int f = 0; f < n_frames; f++)
+      if (frame_ptr[f] > frame_ptr[f + 1]) { err_ = "pose_opt: frame offsets must be non-decreasing"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    const size_t No = (size_t)std::max<long long>(n_obs, 1);
+    CU_CHECK(d_po_ptr_.ensure(n_frames + 1));
+    CU_CHECK(d_po_pose_.ensure((size_t)n_frames * 7));
+    CU_CHECK(d_po_cam_.ensure((size_t)n_frames * 5));
+    CU_CHECK(d_po_xyz_.ensure(No * 3));
+    CU_CHECK(d_po_meas_.ensure(No));
+    CU_CHECK(d_po_err_.ensure(No * 3));
+    CU_CHECK(d_po_level_.ensure(No));
+    CU_CHECK(d_po_outlier_.ensure(No));
+    CU_CHECK(d_po_inl_.ensure(2 * (size_t)n_frames));
+    CU_CHECK(d_po_trace_.ensure((size_t)n_frames * PO_MAX_TRACE * PO_TRACE_COLS));
+    auto up = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_); };
+    static_assert(sizeof(long long) == sizeof(int64_t), "frame offsets");
+    CU_CHECK(cudaEventRecord(ev0_, stream_));
+    CU_CHECK(up(d_po_ptr_.p, frame_ptr, (size_t)(n_frames + 1) * sizeof(int64_t)));
+    CU_CHECK(up(d_po_pose_.p, pose_qt, (size_t)n_frames * 7 * sizeof(double)));
+    CU_CHECK(up(d_po_cam_.p, cam, (size_t)n_frames * 5 * sizeof(double)));
+    if (n_obs > 0) {
+      CU_CHECK(up(d_po_xyz_.p, obs_xyz, (size_t)n_obs * 3 * sizeof(double)));
+      CU_CHECK(up(d_po_meas_.p, obs_meas, (size_t)n_obs * sizeof(float4)));
+    }
+    PoseOptArgs A{};
+    A.n_frames = n_frames; A.frame_ptr = d_po_ptr_.p; A.pose = d_po_pose_.p; A.cam = d_po_cam_.p; A.xyz = d_po_xyz_.p;
+    A.meas = d_po_meas_.p; A.err = d_po_err_.p; A.level = d_po_level_.p; A.outlier = d_po_outlier_.p;
+    A.inliers = d_po_inl_.p; A.trace = d_po_trace_.p; A.trace_len = d_po_inl_.p + n_frames;
+    k_pose_opt<<<n_frames, PO_CTA, 0, stream_>>>(A);
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaMemcpyAsync(pose_qt, d_po_pose_.p, (size_t)n_frames * 7 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    CU_CHECK(cudaMemcpyAsync(inliers_out, d_po_inl_.p, (size_t)n_frames * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    if (n_obs > 0) CU_CHECK(cudaMemcpyAsync(outlier_out, d_po_outlier_.p, (size_t)n_obs, cudaMemcpyDeviceToHost, stream_));
+    CU_CHECK(cudaEventRecord(ev1_, stream_));
+    CU_CHECK(cudaEventSynchronize(ev1_));
+    po_frames_ = n_frames;
+    if (st) {
+      std::memset(st, 0, sizeof *st);
+      float ms = 0;
+      CU_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+      st->n_windows = n_frames;
+      st->kernel_launches = 1;
+      st->ms_total = ms;
+    }
+    return SQRTBA_OK;
+  }
+  int pose_opt_trace(int frame, double* rows, int max_rows) {
+    if (frame < 0 || frame >= po_frames_ || !rows) { err_ = "pose_opt_trace: no such frame"; return SQRTBA_ERR_INVALID; }
+    int len = 0;
+    if (download(&len, d_po_inl_.p + po_frames_ + frame, sizeof(int))) return SQRTBA_ERR_CUDA;
+    const int m = std::min(std::min(len, max_rows), PO_MAX_TRACE);
+    if (m > 0 && download(rows, d_po_trace_.p + (size_t)frame * PO_MAX_TRACE * PO_TRACE_COLS, (size_t)m * PO_TRACE_COLS * sizeof(double)))
+      return SQRTBA_ERR_CUDA;
+    return m;
+  }
+
   // ------------------------------------------------------------------------------------------ stage-level entry points
   int debug_linearize(int huber, double* err, double* Jp, double* Jl, double* r, double* chi2) {
     if (!have_problem_) { err_ = "no problem set"; return SQRTBA_ERR_INVALID; }
@@ -1369,6 +1436,8 @@ class Solver {
     d_ctl_.release(); d_trace_.release(); d_counters_.release(); d_wred_.release();
     d_tiles_.release(); d_obs_lp_.release(); d_tile_run_ptr_.release(); d_tile_runs_.release();
     d_gbar_.release(); d_part_.release(); d_q3_.release(); d_dq_.release(); d_ptile_.release();
+    d_po_ptr_.release(); d_po_pose_.release(); d_po_cam_.release(); d_po_xyz_.release(); d_po_err_.release(); d_po_trace_.release();
+    d_po_meas_.release(); d_po_level_.release(); d_po_outlier_.release(); d_po_inl_.release();
     h_obs_slot_.release(); h_item_start_.release(); h_item_cnt_.release(); h_item_win_.release();
     h_tile_run_ptr_.release(); h_tile_runs_.release(); h_obs_lp_.release(); h_tiles_pin_.release();
     h_perm_pose_.release(); h_perm_point_.release(); h_perm_slot_.release(); h_perm_meas_.release(); h_perm_xyz_.release();
@@ -1402,6 +1471,12 @@ class Solver {
   size_t peer_nelem_cap_ = 0, peer_nchunk_cap_ = 0;
   DBuf<unsigned> d_gbar_;
   DBuf<double> d_part_, d_q3_, d_dq_;
+  DBuf<long long> d_po_ptr_;
+  DBuf<double> d_po_pose_, d_po_cam_, d_po_xyz_, d_po_err_, d_po_trace_;
+  DBuf<float4> d_po_meas_;
+  DBuf<uint8_t> d_po_level_, d_po_outlier_;
+  DBuf<int> d_po_inl_;
+  int po_frames_ = 0;
   Dev P_{};
   DBuf<double> d_cam_, d_pose_, d_pose0_, d_pose_bak_, d_point_, d_point0_, d_point_bak_, d_err_, d_JQ_, d_Jl_,
       d_r_, d_R_, d_tl_, d_bl_, d_dl_, d_slotvec_, d_chi_part_, d_scale_part_, d_trace_, d_wred_;
@@ -1528,6 +1603,15 @@ int sqrtba_debug_matvec(sqrtba_handle* h, const double* p, double* y) {
   return (h && p && y) ? h->s->debug_matvec(p, y) : SQRTBA_ERR_INVALID;
 }
 int sqrtba_num_free_poses(sqrtba_handle* h) { return h ? h->s->num_free() : SQRTBA_ERR_INVALID; }
+int sqrtba_pose_opt(sqrtba_handle* h, int32_t n_frames, const int64_t* frame_obs_ptr, double* pose_qt, const double* cam,
+                    const double* obs_xyz, const float* obs_meas, uint8_t* outlier_out, int32_t* inliers_out,
+                    sqrtba_stats* stats) {
+  return h ? h->s->pose_opt(n_frames, frame_obs_ptr, pose_qt, cam, obs_xyz, obs_meas, outlier_out, inliers_out, stats)
+           : SQRTBA_ERR_INVALID;
+}
+int sqrtba_pose_opt_trace(sqrtba_handle* h, int32_t frame, double* rows_out, int32_t max_rows) {
+  return h ? h->s->pose_opt_trace(frame, rows_out, max_rows) : SQRTBA_ERR_INVALID;
+}
 int sqrtba_comm_unique_id(uint8_t* id128) {
   if (!id128) return SQRTBA_ERR_INVALID;
   if (!sqrtba::g_nccl.load()) return SQRTBA_ERR_COMM;

@@ -4,6 +4,7 @@
 #include <vector>
 
 #ifdef SQRTBA_WITH_REFERENCE_HEADERS
+#include "data_structure/Frame.h"
 #include "data_structure/KeyFrame.h"
 #include "data_structure/Map.h"
 #include "data_structure/MapPoint.h"
@@ -33,6 +34,11 @@ class sqrtbaOptimizer {
   void static GlobalBundleAdjustemnt(Map* pMap, int nIterations, bool* pbStopFlag, const unsigned long nLoopKF,
                                      const bool bRobust);
   void static LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* lidarconfig);
+  // the visual part of Optimizer::PoseOptimization (include/backend/Optimizer.h:58-59), same shape as the reference's
+  // CeresOptimizer::PoseOptimization(Frame*) / MyOptimizer::PoseOptimization(Frame*) adapters (Optimizer.cc:55-60)
+  int static PoseOptimization(Frame* pFrame);
+  // relocalisation: several candidate frames in one launch (Tracking.cc:2466-2517 calls PoseOptimization per candidate)
+  void static PoseOptimizationBatch(const std::vector<Frame*>& frames, std::vector<int>& inliers);
   // last error of the calling thread's handle ("" if none); the reference API itself is void / silent
   static const char* LastError();
 };

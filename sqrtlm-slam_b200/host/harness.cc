@@ -98,4 +98,45 @@ int hh_point_updates(hh_map* m, int mp) { return m->mps[mp]->nUpdateNormalAndDep
 unsigned long hh_gba_marker(hh_map* m, int kf) { return m->kfs[kf]->mnBAGlobalForKF; }
 const char* hh_last_error() { return sqrtbaOptimizer::LastError(); }
 
+// ---- pose-only optimisation: a Frame with n keypoints, every one matched to its own map point
+struct hh_frame {
+  Frame frame;
+  std::vector<std::unique_ptr<MapPoint>> mps;
+};
+hh_frame* hh_frame_build(const float* Tcw16, const float* cam5, const float* inv_sigma2, int n_levels, int n,
+                         const float* Xw, const float* uvr, const int32_t* octave) {
+  hh_frame* f = new hh_frame();
+  Frame& F = f->frame;
+  F.N = n;
+  F.mTcw.create(4, 4, CV_32F);
+  for (int i = 0; i < 16; i++) F.mTcw.at<float>(i / 4, i % 4) = Tcw16[i];
+  F.fx = cam5[0]; F.fy = cam5[1]; F.cx = cam5[2]; F.cy = cam5[3]; F.mbf = cam5[4];
+  F.mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + n_levels);
+  F.mvKeysUn.resize(n); F.mvuRight.resize(n); F.mvpMapPoints.resize(n); F.mvbOutlier.assign(n, false);
+  for (int i = 0; i < n; i++) {
+    auto mp = std::make_unique<MapPoint>();
+    mp->mWorldPos.create(3, 1, CV_32F);
+    for (int c = 0; c < 3; c++) mp->mWorldPos.at<float>(c) = Xw[i * 3 + c];
+    F.mvKeysUn[i].pt.x = uvr[i * 3]; F.mvKeysUn[i].pt.y = uvr[i * 3 + 1]; F.mvKeysUn[i].octave = octave[i];
+    F.mvuRight[i] = uvr[i * 3 + 2];
+    F.mvpMapPoints[i] = mp.get();
+    f->mps.push_back(std::move(mp));
+  }
+  return f;
+}
+void hh_frame_destroy(hh_frame* f) { delete f; }
+void hh_frame_unmatch(hh_frame* f, int i) { f->frame.mvpMapPoints[i] = nullptr; }
+int hh_pose_opt(hh_frame* f) { return sqrtbaOptimizer::PoseOptimization(&f->frame); }
+void hh_pose_opt_batch(hh_frame** fs, int n, int32_t* inliers) {
+  std::vector<Frame*> v;
+  for (int i = 0; i < n; i++) v.push_back(&fs[i]->frame);
+  std::vector<int> inl;
+  sqrtbaOptimizer::PoseOptimizationBatch(v, inl);
+  for (int i = 0; i < n; i++) inliers[i] = inl[i];
+}
+void hh_frame_get(hh_frame* f, float* Tcw16, uint8_t* outlier) {
+  for (int i = 0; i < 16; i++) Tcw16[i] = f->frame.mTcw.at<float>(i / 4, i % 4);
+  for (int i = 0; i < f->frame.N; i++) outlier[i] = f->frame.mvbOutlier[i] ? 1 : 0;
+}
+
 }  // extern "C"

@@ -86,6 +86,23 @@ class MapPoint {
   bool mbBad = false;
   std::map<KeyFrame*, size_t> mObservations;
   std::mutex mMutexPos, mMutexFeatures;
+  static std::mutex mGlobalMutex;  // MapPoint.h:252, held while PoseOptimization copies map points (g2oOptimizer.cc:433)
+};
+
+// include/data_structure/Frame.h -- the members g2oOptimizer::PoseOptimization touches (g2oOptimizer.cc:405-559,655-690):
+// mTcw (:407,510), N (:412), mvpMapPoints (:436), mvuRight (:442), mvbOutlier (:445,525-541,663-677), mvKeysUn (:449),
+// mvInvLevelSigma2 (:457), fx fy cx cy (:465-468) [mbf for the stereo edge of upstream ORB-SLAM2], SetPose (:557)
+class Frame {
+ public:
+  int N = 0;
+  cv::Mat mTcw;
+  float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0;
+  std::vector<cv::KeyPoint> mvKeysUn;
+  std::vector<float> mvuRight;
+  std::vector<float> mvInvLevelSigma2;
+  std::vector<MapPoint*> mvpMapPoints;
+  std::vector<bool> mvbOutlier;
+  void SetPose(const cv::Mat& T) { T.copyTo(mTcw); }
 };
 
 class Map {

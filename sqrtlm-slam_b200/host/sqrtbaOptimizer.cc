@@ -22,6 +22,10 @@
 
 namespace ORB_SLAM2 {
 
+#ifndef SQRTBA_WITH_REFERENCE_HEADERS
+std::mutex MapPoint::mGlobalMutex;
+#endif
+
 namespace {
 
 struct Handle {
@@ -302,6 +306,65 @@ void sqrtbaOptimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map
 
 // ---- the facade (src/backend/Optimizer.cc:26-79) with the new selector value
 Optimizer::eSolver solver = Optimizer::SQRTBA;
+
+// g2oOptimizer::PoseOptimization (g2oOptimizer.cc:385-559, 655-690) for one or several frames.  Edge wiring as in the
+// reference: a matched map point with mvuRight < 0 becomes a monocular edge; the fork leaves the stereo branch empty
+// (:481-483), so a point with a right coordinate is neither optimised nor counted -- define SQRTBA_POSEOPT_STEREO to get
+// upstream ORB-SLAM2's stereo edges instead.
+void sqrtbaOptimizer::PoseOptimizationBatch(const std::vector<Frame*>& frames, std::vector<int>& inliers) {
+  inliers.assign(frames.size(), 0);
+  Handle& H = tl_handle;
+  if (frames.empty() || !H.get()) return;
+  const int nf = (int)frames.size();
+  std::vector<int64_t> ptr(nf + 1, 0);
+  std::vector<double> pose((size_t)nf * 7), cam((size_t)nf * 5), xyz;
+  std::vector<float> meas;
+  std::vector<std::pair<int, int>> ref;  // (frame, keypoint index) of every edge
+  {
+    std::unique_lock<std::mutex> lock(MapPoint::mGlobalMutex);  // :433
+    for (int f = 0; f < nf; f++) {
+      Frame* F = frames[f];
+      toSE3Quat(F->mTcw, &pose[(size_t)f * 7]);
+      cam[f * 5 + 0] = F->fx; cam[f * 5 + 1] = F->fy; cam[f * 5 + 2] = F->cx; cam[f * 5 + 3] = F->cy; cam[f * 5 + 4] = F->mbf;
+      for (int i = 0; i < F->N; i++) {
+        MapPoint* pMP = F->mvpMapPoints[i];
+        if (!pMP) continue;
+        const bool mono = F->mvuRight[i] < 0;
+#ifndef SQRTBA_POSEOPT_STEREO
+        if (!mono) continue;
+#endif
+        F->mvbOutlier[i] = false;
+        const cv::KeyPoint& kp = F->mvKeysUn[i];
+        const cv::Mat Xw = pMP->GetWorldPos();
+        for (int c = 0; c < 3; c++) xyz.push_back(Xw.at<float>(c));
+        meas.push_back(kp.pt.x);
+        meas.push_back(kp.pt.y);
+        meas.push_back(mono ? -1.f : F->mvuRight[i]);
+        meas.push_back(F->mvInvLevelSigma2[kp.octave]);
+        ref.emplace_back(f, i);
+      }
+      ptr[f + 1] = (int64_t)ref.size();
+    }
+  }
+  std::vector<uint8_t> out(std::max<size_t>(ref.size(), 1), 0);
+  std::vector<int32_t> inl(nf, 0);
+  if (sqrtba_pose_opt(H.h, nf, ptr.data(), pose.data(), cam.data(), xyz.data(), meas.data(), out.data(), inl.data(), nullptr) !=
+      SQRTBA_OK) {
+    H.err = sqrtba_last_error(H.h);
+    return;
+  }
+  for (size_t k = 0; k < ref.size(); k++) frames[ref[k].first]->mvbOutlier[ref[k].second] = out[k] != 0;
+  for (int f = 0; f < nf; f++) {
+    if (ptr[f + 1] - ptr[f] >= 3) frames[f]->SetPose(toCvMat(&pose[(size_t)f * 7]));  // :491-492: nothing happens below 3
+    inliers[f] = inl[f];
+  }
+}
+
+int sqrtbaOptimizer::PoseOptimization(Frame* pFrame) {
+  std::vector<int> inl;
+  PoseOptimizationBatch(std::vector<Frame*>{pFrame}, inl);
+  return inl.empty() ? 0 : inl[0];
+}
 
 void Optimizer::GlobalBundleAdjustemnt(Map* pMap, int nIterations, bool* pbStopFlag, const unsigned long nLoopKF,
                                        const bool bRobust) {

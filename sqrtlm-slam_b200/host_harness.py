@@ -30,6 +30,14 @@ def lib():
         L.hh_gba_marker.restype = C.c_ulong
         L.hh_gba_marker.argtypes = [C.c_void_p, C.c_int]
         L.hh_last_error.restype = C.c_char_p
+        up = C.POINTER(C.c_uint8)
+        L.hh_frame_build.restype = C.c_void_p
+        L.hh_frame_build.argtypes = [fp, fp, fp, C.c_int, C.c_int, fp, fp, ip]
+        L.hh_frame_destroy.argtypes = [C.c_void_p]
+        L.hh_frame_unmatch.argtypes = [C.c_void_p, C.c_int]
+        L.hh_pose_opt.argtypes = [C.c_void_p]
+        L.hh_pose_opt_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, ip]
+        L.hh_frame_get.argtypes = [C.c_void_p, fp, up]
         _lib = L
     return _lib
 
@@ -104,3 +112,44 @@ class MockMap:
 
     def last_error(self):
         return lib().hh_last_error().decode()
+
+
+class MockFrame:
+    """A header-compatible Frame (every keypoint matched to its own MapPoint) for Optimizer::PoseOptimization."""
+
+    def __init__(self, pose7, cam5, xyz, meas):
+        T = np.eye(4, dtype=np.float32)
+        T[:3, :3] = synth.quat_to_rotmat(np.asarray(pose7)[3:]).astype(np.float32)
+        T[:3, 3] = np.asarray(pose7)[:3].astype(np.float32)
+        inv = synth.inv_level_sigma2()
+        octave = np.array([int(np.argmin(np.abs(inv - s))) for s in meas[:, 3]], np.int32)
+        assert np.all(inv[octave] == meas[:, 3])
+        self.n = len(xyz)
+        self._keep = [np.ascontiguousarray(T), np.ascontiguousarray(cam5, np.float32), inv,
+                      np.ascontiguousarray(xyz, np.float32), np.ascontiguousarray(meas[:, :3], np.float32), octave]
+        k = self._keep
+        self.h = lib().hh_frame_build(_f(k[0]), _f(k[1]), _f(k[2]), len(inv), self.n, _f(k[3]), _f(k[4]), _i(k[5]))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().hh_frame_destroy(self.h)
+            self.h = None
+
+    def unmatch(self, i):
+        lib().hh_frame_unmatch(self.h, i)
+
+    def pose_optimization(self) -> int:
+        return lib().hh_pose_opt(self.h)
+
+    def state(self):
+        T = np.zeros(16, np.float32)
+        out = np.zeros(max(self.n, 1), np.uint8)
+        lib().hh_frame_get(self.h, _f(T), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return T.reshape(4, 4), out[:self.n]
+
+
+def pose_optimization_batch(frames):
+    arr = (C.c_void_p * len(frames))(*[f.h for f in frames])
+    inl = np.zeros(len(frames), np.int32)
+    lib().hh_pose_opt_batch(arr, len(frames), _i(inl))
+    return inl

@@ -351,3 +351,41 @@ def concat_windows(windows):
         np.concatenate([w.obs_meas for w in windows]),
         name=f"batch{len(windows)}")
     return p, pose_ptr, point_ptr, obs_ptr
+
+
+def frame_problem(seed=0, n_points=1500, stereo=False, outlier_frac=0.1, pose_noise=(0.05, 0.3)):
+    """One tracked frame for pose-only optimisation (g2oOptimizer::PoseOptimization): map points in front of the
+    camera, their measurements in the frame, a perturbed initial pose.  Returns (pose7, cam5, xyz[n,3], meas[n,4])
+    plus the true pose and the injected-outlier mask.  Map points and the pose cross the boundary as float32, the way
+    Frame::mTcw (cv::Mat CV_32F) and MapPoint::GetWorldPos() do (g2oOptimizer.cc:407, 472-475)."""
+    rng = np.random.default_rng(seed)
+    R_wc, c_w = _trajectory(rng, 3)
+    R_cw = np.swapaxes(R_wc, -1, -2)[1]
+    t_cw = -R_cw @ c_w[1]
+    pu = rng.uniform(0, IMG_W, n_points)
+    pv = rng.uniform(0, IMG_H, n_points)
+    depth = rng.uniform(4.0, 60.0, n_points)
+    xc = np.stack([(pu - CX) / FX * depth, (pv - CY) / FY * depth, depth], -1)
+    Xw = (xc - t_cw) @ R_cw  # R_cw^T (xc - t)
+    inv_s2 = inv_level_sigma2()
+    level = np.minimum(rng.geometric(0.35, n_points) - 1, N_LEVELS - 1)
+    sigma = 1.2 ** level
+    mu = pu + rng.normal(0, 1, n_points) * sigma
+    mv = pv + rng.normal(0, 1, n_points) * sigma
+    mur = pu - BF / depth + rng.normal(0, 1, n_points) * sigma
+    is_out = rng.uniform(0, 1, n_points) < outlier_frac
+    k = int(is_out.sum())
+    mu[is_out] += rng.choice([-1.0, 1.0], k) * rng.uniform(10, 50, k)
+    mv[is_out] += rng.choice([-1.0, 1.0], k) * rng.uniform(10, 50, k)
+    mur[is_out] += rng.choice([-1.0, 1.0], k) * rng.uniform(10, 50, k)
+    meas = np.zeros((n_points, 4), dtype=np.float32)
+    meas[:, 0], meas[:, 1] = mu, mv
+    meas[:, 2] = np.maximum(mur, 0.0) if stereo else -1.0
+    meas[:, 3] = inv_s2[level]
+    dR = so3_exp(np.deg2rad(rng.normal(0, pose_noise[1], 3)))
+    R0 = (dR @ R_cw).astype(np.float32).astype(np.float64)
+    t0 = (dR @ t_cw + rng.normal(0, pose_noise[0], 3)).astype(np.float32).astype(np.float64)
+    pose7 = np.concatenate([t0, rotmat_to_quat_eigen(R0)])
+    cam = np.array([FX, FY, CX, CY, BF])
+    truth = dict(R_cw=R_cw, t_cw=t_cw, is_outlier=is_out)
+    return pose7, cam, Xw.astype(np.float32).astype(np.float64), meas, truth

@@ -107,3 +107,36 @@ def test_global_ba_through_reference_api(pkg, synth, n_loop_kf):
         np.testing.assert_array_equal(m.pose(3), before)
     for j in range(0, prob.n_point, 50):
         np.testing.assert_allclose(m.point(j, gba=gba), X[j].astype(np.float32), rtol=2e-6, atol=2e-5)
+
+
+def test_pose_optimization_through_reference_api(pkg, synth):
+    """sqrtbaOptimizer::PoseOptimization(Frame*) against the oracle: same inlier count, same mvbOutlier flags, the pose
+    written back through Frame::SetPose (float32).  The fork only wires monocular edges (g2oOptimizer.cc:441-483): a
+    keypoint with a right coordinate is ignored, an unmatched keypoint too."""
+    pose0, cam, xyz, meas, _ = synth.frame_problem(seed=77, n_points=900, stereo=False, outlier_frac=0.1)
+    meas = meas.copy()
+    meas[5::40, 2] = 300.0                                    # a few keypoints with a right coordinate: skipped by the fork
+    fr = pkg.host_harness.MockFrame(pose0, cam, xyz, meas)
+    for i in (3, 17):
+        fr.unmatch(i)
+    used = np.ones(len(xyz), bool)
+    used[5::40] = False
+    used[[3, 17]] = False
+    rp, rf, ri, _ = refba.pose_opt(pose0, cam, xyz[used], meas[used])
+    inl = fr.pose_optimization()
+    assert pkg.host_harness.lib().hh_last_error().decode() == ""
+    assert inl == ri
+    T, flags = fr.state()
+    assert np.array_equal(flags[used], rf)
+    assert not flags[~used].any()
+    np.testing.assert_allclose(T, f32_pose_matrix(rp, synth), rtol=0, atol=2e-6)
+    # batch entry point (relocalisation candidates): same result per frame
+    frames = [pkg.host_harness.MockFrame(*synth.frame_problem(seed=80 + k, n_points=400 + 100 * k)[:4]) for k in range(3)]
+    inl_b = pkg.host_harness.pose_optimization_batch(frames)
+    for k, f in enumerate(frames):
+        p0, c, x, m, _ = synth.frame_problem(seed=80 + k, n_points=400 + 100 * k)
+        rp, rf, ri, _ = refba.pose_opt(p0, c, x, m)
+        assert inl_b[k] == ri
+        Tk, fk = f.state()
+        assert np.array_equal(fk, rf)
+        np.testing.assert_allclose(Tk, f32_pose_matrix(rp, synth), rtol=0, atol=2e-6)
