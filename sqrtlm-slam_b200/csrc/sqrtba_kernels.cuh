@@ -1746,6 +1746,11 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
         P.res[e] = rv;
         P.q[e] = 0.0;
       }
+      // this thread's row of the block-Jacobi inverse: requested BEFORE the exchange so that its latency (an HBM miss
+      // after the tiles streamed through L2) hides behind the NVLink round trip
+      double dv[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) dv[k] = ok ? __ldg(&P.Dinv[(size_t)slot * 36 + vcc * 6 + k]) : 0.0;
       PROFP(9)
       if (MULTI && ok) qv = peer_sum(A.peer_tbl, A.recv, A.nranks, A.rank, A.nelem_cap, qv, e, seq);
       PROFP(10)
@@ -1757,7 +1762,7 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
 #pragma unroll
       for (int k = 0; k < 6; k++) {
         const double qk = __shfl_sync(FULL, qv, vbase + k);
-        if (ok) dq += __ldg(&P.Dinv[(size_t)slot * 36 + vcc * 6 + k]) * qk;
+        dq += dv[k] * qk;
       }
       if (ok) A.dq[e] = dq;
       PROFP(11)
