@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize(Dev P, int robust, double 
   double chi_acc = 0.0, maxd = 0.0;
   double vb[6] = {0, 0, 0, 0, 0, 0}, vh[6] = {0, 0, 0, 0, 0, 0};  // this observation's -Jp^T r and diag(Jp^T Jp)
   bool has = false;
-  int rank = 0, key = 0;
+  int rank = 0;
   if (valid && !is_long) {
     const bool act = lane < cnt;
     const int o = start + (act ? lane : 0);
@@ -1306,7 +1306,7 @@ struct PcgArgs {
                                   // {value lo, seq, value hi, seq}
   uint4* const* peer_tbl;         // device table of the receive buffers of all ranks, peer-mapped (cudaIpc)
   unsigned long long* seq_state;  // running exchange sequence number (device resident, advanced by the kernel)
-  int nelem_cap, nchunk_cap;
+  int nelem_cap;
 };
 
 __device__ __forceinline__ void st_volatile_v4(uint4* p, const uint4& v) {
@@ -1315,14 +1315,6 @@ __device__ __forceinline__ void st_volatile_v4(uint4* p, const uint4& v) {
 __device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
   uint4 v;
   asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {

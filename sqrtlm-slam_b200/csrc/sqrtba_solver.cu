@@ -494,8 +494,6 @@ class Solver {
       for (auto& th : pool) th.join();
       h_tile_run_ptr_.p[n_tile] = (int)n_runs;
     }
-    const int* item_start = h_item_start_.p;
-    (void)item_start;
     // ---- device allocation
     P_ = Dev{};
     P_.n_pose = n_pose; P_.n_point = n_point; P_.n_obs = n_obs; P_.n_win = n_win; P_.n_slot = n_slot; P_.n_item = n_item;
@@ -691,7 +689,7 @@ class Solver {
       CU_CHECK(d_q3_.ensure((size_t)3 * KQ * 6 * std::max(n_slot, 1)));
       CU_CHECK(d_dq_.ensure((size_t)12 * std::max(n_slot, 1)));  // Dq and qf
       if (comm_) {
-        if (int rc = peer_setup((size_t)std::max(n_slot, 1) * 6, (size_t)nchunk)) return rc;
+        if (int rc = peer_setup((size_t)std::max(n_slot, 1) * 6)) return rc;
       }
     }
     have_problem_ = true;
@@ -1180,7 +1178,6 @@ class Solver {
       A.peer_tbl = (uint4* const*)d_peer_tbl_;
       A.seq_state = d_seq_;
       A.nelem_cap = (int)peer_nelem_cap_;
-      A.nchunk_cap = (int)peer_nchunk_cap_;
     }
     const bool big = !P_.pq_shared;
     const int grid = persist_grid_;
@@ -1196,60 +1193,50 @@ class Solver {
     return SQRTBA_OK;
   }
 
-  // Peer-mapped exchange buffers of the landmark-sharded mode (collective: every rank calls with the same sizes).
-  // Each rank allocates its receive buffer and flags with cudaMalloc, the cudaIpc handles travel through an NCCL
-  // all-gather on the existing communicator, and every rank maps every peer's buffers.
-  int peer_setup(size_t nelem, size_t nchunk) {
+  // Peer-mapped exchange buffers of the landmark-sharded mode (collective: every rank calls with the same size).
+  // Each rank allocates its receive buffer with cudaMalloc, the cudaIpc handles travel through an NCCL all-gather on
+  // the existing communicator, and every rank maps every peer's buffer.  If any rank cannot map a peer (no P2P), all
+  // ranks agree to fall back to ncclAllReduce per CG iteration.
+  int peer_setup(size_t nelem) {
     if (!comm_ || n_ranks_ <= 1) return SQRTBA_OK;
-    if (peer_ok_ && nelem <= peer_nelem_cap_ && nchunk <= peer_nchunk_cap_) return SQRTBA_OK;
+    if (peer_ok_ && nelem <= peer_nelem_cap_) return SQRTBA_OK;
     if (n_ranks_ > 8 || cfg_.reserved[6] != 0) { peer_ok_ = false; return SQRTBA_OK; }
     peer_release();
     peer_nelem_cap_ = nelem;
-    peer_nchunk_cap_ = nchunk;
-    const size_t recv_bytes = 2 * (size_t)n_ranks_ * nelem * 16;  // 16-byte {value, sequence} records
-    const size_t flag_bytes = (size_t)n_ranks_ * nchunk * sizeof(unsigned long long);
+    const size_t recv_bytes = 2 * (size_t)n_ranks_ * nelem * 16;  // 16-byte {value, sequence} records, two parities
     double* recv = nullptr;
-    unsigned long long* flag = nullptr;
     CU_CHECK(cudaMalloc((void**)&recv, recv_bytes));
-    CU_CHECK(cudaMalloc((void**)&flag, flag_bytes));
     if (!d_seq_) CU_CHECK(cudaMalloc((void**)&d_seq_, sizeof(unsigned long long)));
     CU_CHECK(cudaMemsetAsync(recv, 0, recv_bytes, stream_));
-    CU_CHECK(cudaMemsetAsync(flag, 0, flag_bytes, stream_));
     CU_CHECK(cudaMemsetAsync(d_seq_, 0, sizeof(unsigned long long), stream_));
     peer_recv_[rank_] = recv;
-    peer_flag_[rank_] = flag;
-    struct Handles { cudaIpcMemHandle_t recv, flag; };
-    static_assert(sizeof(Handles) == 128, "two 64-byte cudaIpc handles");
-    std::vector<Handles> hs(n_ranks_);
+    std::vector<cudaIpcMemHandle_t> hs(n_ranks_);
     int ok = 1;
-    if (cudaIpcGetMemHandle(&hs[rank_].recv, recv) != cudaSuccess || cudaIpcGetMemHandle(&hs[rank_].flag, flag) != cudaSuccess) {
+    if (cudaIpcGetMemHandle(&hs[rank_], recv) != cudaSuccess) {
       ok = 0;
       cudaGetLastError();
-      std::memset(&hs[rank_], 0, sizeof(Handles));
+      std::memset(&hs[rank_], 0, sizeof(cudaIpcMemHandle_t));
     }
-    Handles* d_h = nullptr;
-    CU_CHECK(cudaMalloc((void**)&d_h, sizeof(Handles) * n_ranks_));
-    CU_CHECK(cudaMemcpyAsync(d_h + rank_, &hs[rank_], sizeof(Handles), cudaMemcpyHostToDevice, stream_));
-    if (g_nccl.AllGather(d_h + rank_, d_h, sizeof(Handles), /*ncclInt8*/ 0, comm_, stream_) != 0) {
+    cudaIpcMemHandle_t* d_h = nullptr;
+    CU_CHECK(cudaMalloc((void**)&d_h, sizeof(cudaIpcMemHandle_t) * n_ranks_));
+    CU_CHECK(cudaMemcpyAsync(d_h + rank_, &hs[rank_], sizeof(cudaIpcMemHandle_t), cudaMemcpyHostToDevice, stream_));
+    if (g_nccl.AllGather(d_h + rank_, d_h, sizeof(cudaIpcMemHandle_t), /*ncclInt8*/ 0, comm_, stream_) != 0) {
       cudaFree(d_h);
       err_ = "ncclAllGather of the peer handles failed";
       return SQRTBA_ERR_COMM;
     }
-    CU_CHECK(cudaMemcpyAsync(hs.data(), d_h, sizeof(Handles) * n_ranks_, cudaMemcpyDeviceToHost, stream_));
+    CU_CHECK(cudaMemcpyAsync(hs.data(), d_h, sizeof(cudaIpcMemHandle_t) * n_ranks_, cudaMemcpyDeviceToHost, stream_));
     CU_CHECK(cudaStreamSynchronize(stream_));
     cudaFree(d_h);
     for (int r = 0; r < n_ranks_ && ok; r++) {
       if (r == rank_) continue;
-      void *pr = nullptr, *pf = nullptr;
-      if (cudaIpcOpenMemHandle(&pr, hs[r].recv, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-          cudaIpcOpenMemHandle(&pf, hs[r].flag, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      void* pr = nullptr;
+      if (cudaIpcOpenMemHandle(&pr, hs[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
         ok = 0;
         cudaGetLastError();
-        if (pr) cudaIpcCloseMemHandle(pr);
         break;
       }
       peer_recv_[r] = (double*)pr;
-      peer_flag_[r] = (unsigned long long*)pf;
     }
     // every rank must take the same path: agree on success (min over ranks)
     double* d_ok = nullptr;
@@ -1274,18 +1261,14 @@ class Solver {
   }
   void peer_release() {
     for (int r = 0; r < 8; r++) {
-      if (r == rank_) {
-        if (peer_recv_[r]) cudaFree(peer_recv_[r]);
-        if (peer_flag_[r]) cudaFree(peer_flag_[r]);
-      } else {
-        if (peer_recv_[r]) cudaIpcCloseMemHandle(peer_recv_[r]);
-        if (peer_flag_[r]) cudaIpcCloseMemHandle(peer_flag_[r]);
+      if (peer_recv_[r]) {
+        if (r == rank_) cudaFree(peer_recv_[r]);
+        else cudaIpcCloseMemHandle(peer_recv_[r]);
       }
       peer_recv_[r] = nullptr;
-      peer_flag_[r] = nullptr;
     }
     peer_ok_ = false;
-    peer_nelem_cap_ = peer_nchunk_cap_ = 0;
+    peer_nelem_cap_ = 0;
   }
 
   // QR + block-Jacobi + PCG for every window in PH_TRIAL
@@ -1465,10 +1448,9 @@ class Solver {
   int persist_ctas_ = 0, persist_stages_ = 2, persist_slots_ = 1, persist_grid_ = 0;
   DBuf<int> d_ptile_;
   double* peer_recv_[8] = {};
-  unsigned long long* peer_flag_[8] = {};
   unsigned long long* d_seq_ = nullptr;
   void** d_peer_tbl_ = nullptr;
-  size_t peer_nelem_cap_ = 0, peer_nchunk_cap_ = 0;
+  size_t peer_nelem_cap_ = 0;
   DBuf<unsigned> d_gbar_;
   DBuf<double> d_part_, d_q3_, d_dq_;
   DBuf<long long> d_po_ptr_;
