@@ -7,9 +7,12 @@
 // It is a dependency-free FP64 restatement of the reference's default BA back-end (vendored g2o
 // driven by src/backend/g2oOptimizer.cc).  The reference itself cannot be compiled here (needs
 // Eigen, OpenCV, PCL, Ceres, ROS -- none installed, no network), so this is a "port" oracle.
-// PARITY UNPINNED UPSTREAM: the reference has no tests, golden vectors or fixtures;
-// the per-edge arithmetic is additionally pinned against the reference's prebuilt
-// Thirdparty/g2o/lib/libg2o.so where that binary exposes it (see oracle/pin_libg2o.py).
+// PARITY PARTLY PINNED: the reference has no tests, golden vectors or fixtures, so the solver-level
+// behaviour (Schur/LM control flow, outlier policy) is unpinned upstream.  The per-edge arithmetic IS pinned against
+// the reference's own compiled code: its tree ships a prebuilt Thirdparty/g2o/lib/libg2o.so that exports
+// SE3Quat::exp, project2d, the mono / stereo cam_project and RobustKernelHuber::robustify; oracle/pin_libg2o.py calls
+// them through ctypes and tests/test_pin_libg2o.py checks this file against the recorded outputs
+// (tests/golden/libg2o_vectors.npz).  That check found one quirk the sources hide in a header: `float dsqr`.
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 // Eigen is not vendored in the reference; where g2o calls into Eigen (quaternion*vector,
@@ -157,7 +160,9 @@ struct Edge {
   double fx, fy, cx, cy, bf;
   int level = 0;
   bool robust = false;
-  double delta = 0, dsqr = 0;  // RobustKernelHuber::setDelta, robust_kernel_impl.cpp:65-69
+  double delta = 0, dsqr = 0;  // RobustKernelHuber::setDelta, robust_kernel_impl.cpp:65-69.  NB the reference stores
+                               // dsqr in a FLOAT member (robust_kernel_impl.h:84): delta^2 is rounded to float32 -- found by
+                               // pinning against the prebuilt libg2o.so (oracle/pin_libg2o.py)
   double err[3] = {0, 0, 0};   // g2o's Edge::_error: only rewritten by computeError() on ACTIVE edges
   double Jl[9];                // _jacobianOplusXi (d x 3)
   double Jp[18];               // _jacobianOplusXj (d x 6)
@@ -848,7 +853,7 @@ static void setHuber(Edge& e, float th2d, float th3d, bool robust) {
   e.robust = robust;
   const double d = e.stereo ? (double)th3d : (double)th2d;  // `const float thHuber.. = sqrt(..)` then setDelta(double)
   e.delta = d;
-  e.dsqr = d * d;
+  e.dsqr = (double)(float)(d * d);  // `float dsqr`, robust_kernel_impl.h:84
 }
 
 // g2oOptimizer::LocalBundleAdjustment control flow (g2oOptimizer.cc:704-976, 1119-1142) with the stereo edge
@@ -1011,7 +1016,7 @@ void refba_cam_project_stereo(const double* Xc, double fx, double fy, double cx,
 }
 void refba_huber(double delta, double e, double* rho3) {
   Edge ed;
-  ed.delta = delta; ed.dsqr = delta * delta;
+  ed.delta = delta; ed.dsqr = (double)(float)(delta * delta);
   robustify(ed, e, rho3);
 }
 
@@ -1228,7 +1233,7 @@ int refba_pose_opt(double* pose7, const double* cam, int n, const double* xyz, c
     e.info = meas[i * 4 + 3];
     for (int c = 0; c < 3; c++) e.Xw[c] = xyz[i * 3 + c];
     e.delta = e.stereo ? deltaStereo : deltaMono;
-    e.dsqr = e.delta * e.delta;
+    e.dsqr = (double)(float)(e.delta * e.delta);  // `float dsqr`, robust_kernel_impl.h:84
     outlier[i] = 0;
   }
   if (n_trace) *n_trace = 0;

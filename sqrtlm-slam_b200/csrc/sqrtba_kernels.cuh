@@ -342,7 +342,7 @@ __device__ __forceinline__ void obs_eval(const Dev& P, int o, bool want_jac, boo
   L.rho0 = c;
   if (robust) {
     const double delta = stereo ? d3 : d2;
-    huber(c, delta, delta * delta, &L.rho0, &rho1);
+    huber(c, delta, huber_dsqr(delta), &L.rho0, &rho1);
   }
   L.w = sqrt(rho1 * info);
   if (want_jac) reproj_jacobians(R, Xc, cam, stereo, L.Jp, L.Jl);

@@ -54,7 +54,9 @@ SQ_HD void reproj_error(const double Xc[3], float u, float v, float ur, const do
   }
 }
 
-// Huber: rho0 (robustified chi2) and rho1 (weight); delta/dsqr as RobustKernelHuber::setDelta stores them
+// Huber: rho0 (robustified chi2) and rho1 (weight); delta/dsqr as RobustKernelHuber::setDelta stores them -- the
+// reference keeps dsqr in a FLOAT member (core/robust_kernel_impl.h:84), so callers pass huber_dsqr(delta)
+SQ_HD double huber_dsqr(double delta) { return (double)(float)(delta * delta); }
 SQ_HD void huber(double c, double delta, double dsqr, double* rho0, double* rho1) {
   if (c <= dsqr) {
     *rho0 = c;

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(PO_CTA) k_pose_opt(PoseOptArgs A) {
         for (int c = 0; c < 3; c++) A.err[o * 3 + c] = E.e[c];
         const double c2 = po_chi2(E.e, E.info, E.stereo);
         double rho0 = c2, rho1 = 1.0;
-        if (robust) { const double d = E.stereo ? dStereo : dMono; huber(c2, d, d * d, &rho0, &rho1); }
+        if (robust) { const double d = E.stereo ? dStereo : dMono; huber(c2, d, huber_dsqr(d), &rho0, &rho1); }
         acc[27] += rho0;
         acc[28] += 1.0;
         const double w = rho1 * E.info;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(PO_CTA) k_pose_opt(PoseOptArgs A) {
           for (int c = 0; c < 3; c++) A.err[o * 3 + c] = E.e[c];  // a rejected trial leaves these behind (stale _error)
           const double c2 = po_chi2(E.e, E.info, E.stereo);
           double rho0 = c2, rho1 = 1.0;
-          if (robust) { const double d = E.stereo ? dStereo : dMono; huber(c2, d, d * d, &rho0, &rho1); }
+          if (robust) { const double d = E.stereo ? dStereo : dMono; huber(c2, d, huber_dsqr(d), &rho0, &rho1); }
           chi[0] += rho0;
         }
         po_reduce<1>(chi, sh_part, sh_red);

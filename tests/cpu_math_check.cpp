@@ -13,7 +13,7 @@ void mc_obs(const double* pose7, const double* X, const double* cam, const float
   sqrtba::reproj_jacobians(R, Xc, cam, stereo, Jp, Jl);
   *depth_pos = Xc[2] > 0.0;
 }
-void mc_huber(double c, double delta, double* rho0, double* rho1) { sqrtba::huber(c, delta, delta * delta, rho0, rho1); }
+void mc_huber(double c, double delta, double* rho0, double* rho1) { sqrtba::huber(c, delta, sqrtba::huber_dsqr(delta), rho0, rho1); }
 void mc_oplus(double* pose7, const double* xi) { sqrtba::pose_oplus(pose7, xi); }
 int mc_spd6_inverse(const double* A, double* Ai) { return sqrtba::spd6_inverse(A, Ai) ? 1 : 0; }
 }

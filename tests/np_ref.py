@@ -70,10 +70,11 @@ class NpBA:
     def rho(self, k):
         c = self.chi2(k)
         d = self.delta[k]
-        if not self.robust or c <= d * d:
+        dsqr = float(np.float32(d * d))   # RobustKernelHuber keeps delta^2 in a float member (robust_kernel_impl.h:84)
+        if not self.robust or c <= dsqr:
             return c, 1.0
         s = np.sqrt(c)
-        return 2 * s * d - d * d, d / s
+        return 2 * s * d - dsqr, d / s
 
     def robust_chi2(self, active):
         return sum(self.rho(k)[0] for k in active)

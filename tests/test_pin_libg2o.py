@@ -1,0 +1,76 @@
+"""The oracle against the reference's OWN compiled code.
+
+`oracle/pin_libg2o.py` calls the per-edge functions that the reference's prebuilt `Thirdparty/g2o/lib/libg2o.so` exports
+(SE3Quat::exp, project2d, mono / stereo cam_project incl. the float32 inverse-depth quirk, RobustKernelHuber::robustify)
+and stores inputs + outputs in `tests/golden/libg2o_vectors.npz` (committed; regenerate with `python oracle/pin_libg2o.py`
+where /root/reference exists).  Here the oracle's restatements of those functions must reproduce the binary's outputs --
+to a few ulps, since the binary and the oracle are compiled with different FMA contraction."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import pin_libg2o, refba
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "libg2o_vectors.npz")
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    assert os.path.exists(GOLD), "tests/golden/libg2o_vectors.npz is a committed fixture"
+    return np.load(GOLD)
+
+
+def test_se3_exp_matches_reference_binary(gold):
+    L = refba.lib()
+    for u, want in zip(gold["upd"], gold["exp"]):
+        out = np.zeros(7)
+        L.refba_se3_exp(_dp(np.ascontiguousarray(u)), _dp(out))
+        np.testing.assert_allclose(out, want, rtol=0, atol=4e-15 * max(1.0, np.abs(want).max()))
+    # both branches of se3quat.h:237-254 are in the fixture
+    th = np.linalg.norm(gold["upd"][:, :3], axis=1)
+    assert (th < 1e-5).sum() >= 10 and (th > 1e-2).sum() >= 100
+
+
+def test_projection_matches_reference_binary(gold):
+    L = refba.lib()
+    cam = gold["cam"]
+    for x, pm, ps, p2 in zip(gold["xyz"], gold["cam_mono"], gold["cam_stereo"], gold["project2d"]):
+        x = np.ascontiguousarray(x)
+        o2, o3 = np.zeros(2), np.zeros(3)
+        L.refba_cam_project_mono(_dp(x), cam[0], cam[1], cam[2], cam[3], _dp(o2))
+        np.testing.assert_allclose(o2, pm, rtol=4e-16, atol=0)
+        np.testing.assert_allclose((o2 - cam[2:4]) / cam[:2], p2, rtol=0, atol=1e-13)
+        L.refba_cam_project_stereo(_dp(x), cam[0], cam[1], cam[2], cam[3], C.c_float(cam[4]), _dp(o3))
+        np.testing.assert_allclose(o3, ps, rtol=4e-16, atol=0)
+    # the quirk is real: the binary's stereo u differs from the double-precision u by float rounding of 1/z
+    du = np.abs(gold["cam_stereo"][:, 0] - gold["cam_mono"][:, 0])
+    assert du.max() > 1e-7 and du.max() < 1e-3
+
+
+def test_huber_matches_reference_binary(gold):
+    L = refba.lib()
+    delta = float(gold["delta"])
+    for e2, want in zip(gold["e2"], gold["huber"]):
+        rho = np.zeros(3)
+        L.refba_huber(delta, float(e2), _dp(rho))
+        np.testing.assert_allclose(rho, want, rtol=4e-16, atol=0)
+    assert (gold["huber"][:, 1] == 1.0).sum() > 50 and (gold["huber"][:, 1] < 1.0).sum() > 50
+
+
+@pytest.mark.skipif(not pin_libg2o.available(), reason="the reference checkout is not present on this machine")
+def test_committed_fixture_is_what_the_binary_computes(tmp_path, gold):
+    # in a clean interpreter: the prebuilt binary is not loaded into the test process
+    out = str(tmp_path / "g.npz")
+    script = os.path.join(os.path.dirname(os.path.abspath(pin_libg2o.__file__)), "pin_libg2o.py")
+    subprocess.run([sys.executable, script, out], check=True, capture_output=True)
+    fresh = np.load(out)
+    for k in gold.files:
+        assert np.array_equal(fresh[k], gold[k]), k
