@@ -10,6 +10,7 @@ returned by value comes back through a hidden first pointer; `this` follows it):
   g2o::EdgeSE3ProjectXYZ::cam_project(Vector3d const&) const           types_six_dof_expmap.cpp:141-147
   g2o::EdgeStereoSE3ProjectXYZ::cam_project(Vector3d const&, float const&) const      .cpp:150-157 (float invz quirk)
   g2o::RobustKernelHuber::robustify(double, Vector3d&) const           core/robust_kernel_impl.cpp:78-91
+  g2o::VertexSE3Expmap::VertexSE3Expmap / setToOriginImpl / oplusImpl  types_six_dof_expmap.h:59-76 (a REAL vertex object)
 
 The edge / kernel objects are never constructed: the methods are const and only read a few scalar members (fx, fy, cx,
 cy), whose byte offsets inside `this` are found by probing (set one candidate slot of a zeroed block to 1.0 and watch
@@ -33,6 +34,9 @@ SYM = {
     "cam_stereo": "_ZNK3g2o23EdgeStereoSE3ProjectXYZ11cam_projectERKN5Eigen6MatrixIdLi3ELi1ELi0ELi3ELi1EEERKf",
     "huber": "_ZNK3g2o17RobustKernelHuber9robustifyEdRN5Eigen6MatrixIdLi3ELi1ELi0ELi3ELi1EEE",
     "set_delta": "_ZN3g2o17RobustKernelHuber8setDeltaEd",
+    "vtx_ctor": "_ZN3g2o15VertexSE3ExpmapC1Ev",
+    "vtx_origin": "_ZN3g2o15VertexSE3Expmap15setToOriginImplEv",
+    "vtx_oplus": "_ZN3g2o15VertexSE3Expmap9oplusImplEPKd",
 }
 THIS_DOUBLES = 256  # probe window: 2 KB of `this`
 
@@ -63,6 +67,11 @@ class LibG2O:
         self.f["huber"].argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         self.f["set_delta"].restype = None
         self.f["set_delta"].argtypes = [C.c_void_p, C.c_double]
+        for k in ("vtx_ctor", "vtx_origin"):
+            self.f[k].restype = None
+            self.f[k].argtypes = [C.c_void_p]
+        self.f["vtx_oplus"].restype = None
+        self.f["vtx_oplus"].argtypes = [C.c_void_p, C.c_void_p]
         self._mono_off = self._probe_cam(stereo=False)
         self._stereo_off = self._probe_cam(stereo=True)
 
@@ -105,6 +114,35 @@ class LibG2O:
         self.f["exp"](out.ctypes.data, u.ctypes.data)
         return np.array([out[4], out[5], out[6], out[0], out[1], out[2], out[3]])  # (t, q) like SE3Quat::toVector
 
+    def oplus_chain(self, updates):
+        """VertexSE3Expmap::oplusImpl applied in sequence from the origin (types_six_dof_expmap.h:73-76: estimate <-
+        exp(update) * estimate, i.e. SE3Quat::operator* + normalizeRotation, se3quat.h:104-110,280-285).  A real vertex
+        object is built with the binary's own constructor; its `_estimate` (an SE3Quat: q.x q.y q.z q.w | t) is located
+        by looking for the identity quaternion that setToOriginImpl writes.  Returns the estimate as (t, q)."""
+        this = _aligned(512)                       # 4 KB: room for the whole BaseVertex<6, SE3Quat>
+        self.f["vtx_ctor"](this.ctypes.data)
+        self.f["vtx_origin"](this.ctypes.data)
+        off = None
+        for i in range(0, 500, 2):                 # SE3Quat is at least 16-byte aligned
+            if this[i] == 0 and this[i + 1] == 0 and this[i + 2] == 0 and this[i + 3] == 1.0 and not this[i + 4:i + 7].any():
+                u = _aligned(6)
+                u[:] = [0.1, -0.2, 0.3, 1.0, 2.0, 3.0]
+                probe = this.copy()                # the copy keeps the vptr etc.; only used to confirm the slot moves
+                before = this[i:i + 7].copy()
+                self.f["vtx_oplus"](this.ctypes.data, u.ctypes.data)
+                if not np.array_equal(this[i:i + 7], before):
+                    off = i
+                    break
+                del probe
+        assert off is not None, "VertexSE3Expmap::_estimate not found"
+        self.f["vtx_origin"](this.ctypes.data)
+        for upd in updates:
+            u = _aligned(6)
+            u[:] = upd
+            self.f["vtx_oplus"](this.ctypes.data, u.ctypes.data)
+        e = this[off:off + 7]
+        return np.array([e[4], e[5], e[6], e[0], e[1], e[2], e[3]])
+
     def project2d(self, xyz):
         out = _aligned(2)
         v = _aligned(4)
@@ -144,7 +182,9 @@ def make_golden(path: str, n: int = 300, seed: int = 0):
                project2d=np.stack([g.project2d(x) for x in xyz]),
                cam_mono=np.stack([g.cam_project(x, cam, False) for x in xyz]),
                cam_stereo=np.stack([g.cam_project(x, cam, True) for x in xyz]),
-               huber=np.stack([g.huber(delta, e) for e in e2]))
+               huber=np.stack([g.huber(delta, e) for e in e2]),
+               # chains of three oplus updates from the origin: composition + re-normalisation of the reference
+               oplus=np.stack([g.oplus_chain(upd[3 * k:3 * k + 3]) for k in range(n // 3)]))
     np.savez(path, **out)
     return out
 

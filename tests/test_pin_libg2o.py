@@ -74,3 +74,17 @@ def test_committed_fixture_is_what_the_binary_computes(tmp_path, gold):
     fresh = np.load(out)
     for k in gold.files:
         assert np.array_equal(fresh[k], gold[k]), k
+
+
+def test_pose_oplus_chain_matches_reference_binary(gold):
+    """VertexSE3Expmap::oplusImpl on a real vertex object of the binary: three updates from the origin
+    (left-multiplication, quaternion product, normalizeRotation) -- the oracle's refba_pose_oplus and the kernels'
+    pose_oplus (compiled for the host, tests/cpu_math_check.cpp) must land on the same pose."""
+    L = refba.lib()
+    for k, want in enumerate(gold["oplus"]):
+        pose = np.array([0, 0, 0, 0, 0, 0, 1.0])
+        for u in gold["upd"][3 * k:3 * k + 3]:
+            out = np.zeros(7)
+            L.refba_pose_oplus(_dp(pose), _dp(np.ascontiguousarray(u)), _dp(out))
+            pose = out
+        np.testing.assert_allclose(pose, want, rtol=0, atol=1e-14 * max(1.0, np.abs(want).max()))
