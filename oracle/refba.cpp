@@ -12,7 +12,9 @@
 // the reference's own compiled code: its tree ships a prebuilt Thirdparty/g2o/lib/libg2o.so that exports
 // SE3Quat::exp, project2d, the mono / stereo cam_project and RobustKernelHuber::robustify; oracle/pin_libg2o.py calls
 // them through ctypes and tests/test_pin_libg2o.py checks this file against the recorded outputs
-// (tests/golden/libg2o_vectors.npz).  That check found one quirk the sources hide in a header: `float dsqr`.
+// (tests/golden/libg2o_vectors.npz); oracle/pin_libg2o_edges.py does the same with REAL vertex and edge objects of that
+// binary (oplusImpl, computeError, linearizeOplus): residuals and Jacobians agree to 1e-15.  The check found one quirk
+// the sources hide in a header: `float dsqr`.
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 // Eigen is not vendored in the reference; where g2o calls into Eigen (quaternion*vector,

@@ -69,8 +69,9 @@ def test_huber_matches_reference_binary(gold):
 def test_committed_fixture_is_what_the_binary_computes(tmp_path, gold):
     # in a clean interpreter: the prebuilt binary is not loaded into the test process
     out = str(tmp_path / "g.npz")
-    script = os.path.join(os.path.dirname(os.path.abspath(pin_libg2o.__file__)), "pin_libg2o.py")
-    subprocess.run([sys.executable, script, out], check=True, capture_output=True)
+    odir = os.path.dirname(os.path.abspath(pin_libg2o.__file__))
+    for script in ("pin_libg2o.py", "pin_libg2o_edges.py"):   # the second appends the edge_* arrays
+        subprocess.run([sys.executable, os.path.join(odir, script), out], check=True, capture_output=True)
     fresh = np.load(out)
     for k in gold.files:
         assert np.array_equal(fresh[k], gold[k]), k
@@ -88,3 +89,26 @@ def test_pose_oplus_chain_matches_reference_binary(gold):
             L.refba_pose_oplus(_dp(pose), _dp(np.ascontiguousarray(u)), _dp(out))
             pose = out
         np.testing.assert_allclose(pose, want, rtol=0, atol=1e-14 * max(1.0, np.abs(want).max()))
+
+
+@pytest.mark.parametrize("tag,stereo", [("mono", False), ("stereo", True)])
+def test_edge_error_and_jacobians_match_reference_binary(gold, synth, tag, stereo):
+    """REAL EdgeSE3ProjectXYZ / EdgeStereoSE3ProjectXYZ objects of the binary (oracle/pin_libg2o_edges.py): computeError()
+    and linearizeOplus() on random poses, points and measurements -- the oracle's residual and both Jacobians agree to
+    rounding (the finite-difference check of test_oracle.py can only see the stereo Jacobian to 2e-2 because of the
+    float32 inverse depth; this one is exact)."""
+    d = 3 if stereo else 2
+    cam = gold["edge_cam"]
+    for k in range(len(gold[f"edge_{tag}_X"])):
+        m = np.zeros((1, 4), np.float32)
+        m[0, :3] = gold[f"edge_{tag}_meas"][k]
+        m[0, 3] = 1.0
+        if not stereo:
+            m[0, 2] = -1.0
+        prob = synth.Problem(gold[f"edge_{tag}_pose"][k][None].copy(), np.zeros(1, np.uint8), cam[None].copy(),
+                             gold[f"edge_{tag}_X"][k][None].copy(), np.zeros(1, np.int32), np.zeros(1, np.int32), m)
+        lin = refba.RefBA(prob).linearize_all(0)
+        e, Jp, Jl = lin["err"][0][:d], lin["Jp"][0][:d], lin["Jl"][0][:d]
+        np.testing.assert_allclose(e, gold[f"edge_{tag}_err"][k], rtol=0, atol=1e-14 * max(1.0, np.abs(e).max()))
+        np.testing.assert_allclose(Jp, gold[f"edge_{tag}_Jp"][k], rtol=0, atol=4e-15 * np.abs(Jp).max())
+        np.testing.assert_allclose(Jl, gold[f"edge_{tag}_Jl"][k], rtol=0, atol=4e-15 * np.abs(Jl).max())
