@@ -646,46 +646,16 @@ __device__ __forceinline__ void trial_contrib_sh(const double* __restrict__ jq, 
     }
 }
 
-__global__ void __launch_bounds__(CTA, 4) k_qr(Dev P, int force_all, double lam_override) {
-  __shared__ double c_sh[27 * SCST];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const TileInfo ti = P.tiles[blockIdx.x];
-  const bool valid = wid < ti.nitem;
-  const int win = ti.win;
-  const WinCtl& wc = P.ctl[win];
-  if (!force_all && wc.phase != PH_TRIAL) return;  // CTA-uniform
-  const bool on = valid;
-  const double lam = force_all ? lam_override : wc.lambda;
+// ---- the two item shapes of the landmark QR, shared by the plain and the pipelined kernel
+// short item: operands of this lane's observation are already in registers (a = its rows of J_l, rr = its residual)
+__device__ __forceinline__ void qr_short_item(const Dev& P, const TileInfo& ti, int wid, int lane, bool act, int o, int lm,
+                                              bool has, int rank, const double a[9], const double rr[3], double lam,
+                                              double* c_sh) {
   const double sl = sqrt(lam);
-  // item geometry from the tile descriptor alone (items of a tile are consecutive observation ranges)
-  const int cnt = tile_item_cnt(ti, wid);
-  const int start = tile_item_start(ti, wid);
-  const size_t No = (size_t)P.ld; const int Nl = P.n_point;
+  const int Nl = P.n_point, nt = ti.nt;
+  const bool on = true;
   double* __restrict__ jq = P.JQ + ti.jq_off;
-  const int nt = ti.nt;
-  // the 18 Jp rows are only needed after the factorisation: start pulling them into L2 now (one TMA prefetch per CTA)
-  if (threadIdx.x == 0 && !ti.is_long) bulk_prefetch_l2(jq, (uint32_t)(18 * nt * sizeof(double)));
-  bool has = false;
-  int rank = 0;
   LmFactor F;
-  if (valid && cnt <= 32) {
-    const bool act = lane < cnt;
-    const int o = start + (act ? lane : 0);
-    int lm = -1 - lane;
-    double a[9], rr[3];
-    if (act) {  // every load of this phase is issued before the first use
-      const unsigned lp = P.obs_lp[o];
-      lm = P.obs_point[o];
-      load9(P.Jl, No, o, a);
-#pragma unroll
-      for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
-      has = (lp & 0xffffu) != 0xffffu;
-      rank = (int)(lp >> 16);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 9; c++) a[c] = 0.0;
-      rr[0] = rr[1] = rr[2] = 0.0;
-    }
     const int fcol = tile_fcol(ti, wid, has, lane);
     if (on) {
       const Seg sg = seg_of(lm, lane);
@@ -740,7 +710,15 @@ __global__ void __launch_bounds__(CTA, 4) k_qr(Dev P, int force_all, double lam_
         if (has) trial_contrib_sh(jq, nt, fcol, Q, rr, tl, c_sh, rank);
       }
     }
-  } else if (on) {
+}
+
+// long landmark (one warp, more than 32 observations): operands straight from global memory, direct atomics
+__device__ __forceinline__ void qr_long_item(const Dev& P, const TileInfo& ti, int lane, int start, int cnt, double lam) {
+  const double sl = sqrt(lam);
+  const size_t No = (size_t)P.ld;
+  const int Nl = P.n_point, nt = ti.nt;
+  double* __restrict__ jq = P.JQ + ti.jq_off;
+  LmFactor F;
     // long landmark: five sweeps over its rows (L1/L2 resident), whole-warp reductions
     const int lm = P.obs_point[start];
     double acc[3] = {0, 0, 0};
@@ -815,9 +793,48 @@ __global__ void __launch_bounds__(CTA, 4) k_qr(Dev P, int force_all, double lam_
 #pragma unroll
       for (int c = 0; c < 21; c++) atomicAdd(&P.D[slot * 21 + c], lc[6 + c]);
     }
+}
+
+__global__ void __launch_bounds__(CTA, 4) k_qr(Dev P, int force_all, double lam_override) {
+  __shared__ double c_sh[27 * SCST];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const TileInfo ti = P.tiles[blockIdx.x];
+  const bool valid = wid < ti.nitem;
+  const int win = ti.win;
+  const WinCtl& wc = P.ctl[win];
+  if (!force_all && wc.phase != PH_TRIAL) return;  // CTA-uniform
+  const double lam = force_all ? lam_override : wc.lambda;
+  const int cnt = tile_item_cnt(ti, wid);
+  const int start = tile_item_start(ti, wid);
+  const size_t No = (size_t)P.ld;
+  double* __restrict__ jq = P.JQ + ti.jq_off;
+  // the 18 Jp rows are only needed after the factorisation: start pulling them into L2 now (one TMA prefetch per CTA)
+  if (threadIdx.x == 0 && !ti.is_long) bulk_prefetch_l2(jq, (uint32_t)(18 * ti.nt * sizeof(double)));
+  if (valid && cnt <= 32) {
+    const bool act = lane < cnt;
+    const int o = start + (act ? lane : 0);
+    int lm = -1 - lane, rank = 0;
+    bool has = false;
+    double a[9], rr[3];
+    if (act) {  // every load of this phase is issued before the first use
+      const unsigned lp = P.obs_lp[o];
+      lm = P.obs_point[o];
+      load9(P.Jl, No, o, a);
+#pragma unroll
+      for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
+      has = (lp & 0xffffu) != 0xffffu;
+      rank = (int)(lp >> 16);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 9; c++) a[c] = 0.0;
+      rr[0] = rr[1] = rr[2] = 0.0;
+    }
+    qr_short_item(P, ti, wid, lane, act, o, lm, has, rank, a, rr, lam, c_sh);
+  } else if (valid) {
+    qr_long_item(P, ti, lane, start, cnt, lam);
   }
   __syncthreads();
-  const int* runs = reinterpret_cast<const int*>(jq + (size_t)JQ_ROWS * nt);
+  const int* runs = reinterpret_cast<const int*>(jq + (size_t)JQ_ROWS * ti.nt);
   const int sbase = P.smallwin ? P.win_slot_ptr[win] : 0;
   double* bs = P.bs;
   double* D = P.D;
@@ -825,6 +842,120 @@ __global__ void __launch_bounds__(CTA, 4) k_qr(Dev P, int force_all, double lam_
                        [bs, D](int slot, int k) { return (k < 6) ? bs + (size_t)slot * 6 + k : D + (size_t)slot * 21 + (k - 6); });
 }
 
+// Pipelined variant: every CTA walks QR_TPB consecutive tiles and stages the NEXT tile's operands (this lane's rows of
+// J_l, its residual, its meta words -- 14 cp.async per thread -- plus the tile descriptor two tiles ahead) in shared
+// memory while it factorises the current one, so the three dependent global-load phases of the plain kernel
+// (descriptor -> operands -> Jp) no longer sit on the critical path; the Jp rows and the run table of the next tile are
+// pulled into L2 by a TMA prefetch.  Per-lane data is private (a lane reads back exactly what it copied), so the only
+// barrier the staging needs is the one that publishes the tile descriptors.
+constexpr int QR_TPB = 8;
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr size_t QR_PIPE_SMEM = (27 * SCST + 2 * 12 * CTA) * sizeof(double) + 2 * CTA * (sizeof(unsigned) + sizeof(int)) + 3 * 80;
+__global__ void __launch_bounds__(CTA, 4) k_qr_pipe(Dev P, int force_all, double lam_override) {
+  extern __shared__ __align__(16) unsigned char qr_smem[];
+  static_assert(sizeof(TileInfo) == 80, "tile descriptors are staged with five 16-byte copies");
+  TileInfo* ti_sh = reinterpret_cast<TileInfo*>(qr_smem);                       // [3]
+  double* c_sh = reinterpret_cast<double*>(qr_smem + 3 * 80);                   // [27][SCST]
+  double(*op_sh)[12][CTA] = reinterpret_cast<double(*)[12][CTA]>(c_sh + 27 * SCST);  // [2]: 9 rows of J_l, 3 of r, column = thread
+  unsigned(*lp_sh)[CTA] = reinterpret_cast<unsigned(*)[CTA]>(op_sh + 2);        // [2]
+  int(*lm_sh)[CTA] = reinterpret_cast<int(*)[CTA]>(lp_sh + 2);                  // [2]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int t0 = blockIdx.x * QR_TPB, t1 = min(t0 + QR_TPB, P.n_tile);
+  const size_t No = (size_t)P.ld;
+  // stage the operands of tile t (descriptor `ti`) into buffer b; returns nothing -- completion via wait_group
+  auto stage = [&](const TileInfo& ti, int b) {
+    if (ti.is_long) return;
+    const int cnt = tile_item_cnt(ti, wid), start = tile_item_start(ti, wid);
+    if (wid < ti.nitem && lane < cnt) {
+      const int o = start + lane;
+#pragma unroll
+      for (int c = 0; c < 9; c++) cp_async8(&op_sh[b][c][tid], P.Jl + (size_t)c * No + o);
+#pragma unroll
+      for (int c = 0; c < 3; c++) cp_async8(&op_sh[b][9 + c][tid], P.r + (size_t)c * No + o);
+      cp_async4(&lp_sh[b][tid], P.obs_lp + o);
+      cp_async4(&lm_sh[b][tid], P.obs_point + o);
+    }
+    if (tid == 0) bulk_prefetch_l2(P.JQ + ti.jq_off - JQ_HDR, (uint32_t)(ti.blk_doubles * sizeof(double)));
+  };
+  if (tid < 5) {
+    cp_async16(reinterpret_cast<char*>(&ti_sh[0]) + tid * 16, reinterpret_cast<const char*>(P.tiles + t0) + tid * 16);
+    if (t0 + 1 < t1)
+      cp_async16(reinterpret_cast<char*>(&ti_sh[1]) + tid * 16, reinterpret_cast<const char*>(P.tiles + t0 + 1) + tid * 16);
+  }
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  stage(ti_sh[0], 0);
+  cp_async_commit();
+  // window state of the tile being processed next (phase, lambda): loaded one tile ahead as well
+  int nphase = force_all ? PH_TRIAL : P.ctl[ti_sh[0].win].phase;
+  double nlam = force_all ? lam_override : P.ctl[ti_sh[0].win].lambda;
+  for (int k = 0; k < t1 - t0; k++) {
+    const int buf = k & 1;
+    cp_async_wait_all();  // operands of tile k (own lanes) and the descriptor of tile k+1 have landed
+    __syncthreads();      // ... and the descriptor is visible to everybody; c_sh of the previous tile is free
+    const TileInfo ti = ti_sh[k % 3];
+    const int phase = nphase;
+    const double lam = nlam;
+    if (k + 1 < t1 - t0) {
+      const TileInfo& tn = ti_sh[(k + 1) % 3];
+      if (k + 2 < t1 - t0 && tid < 5)
+        cp_async16(reinterpret_cast<char*>(&ti_sh[(k + 2) % 3]) + tid * 16,
+                   reinterpret_cast<const char*>(P.tiles + t0 + k + 2) + tid * 16);
+      stage(tn, buf ^ 1);
+      if (!force_all) { nphase = P.ctl[tn.win].phase; nlam = P.ctl[tn.win].lambda; }
+    }
+    cp_async_commit();
+    if (phase != PH_TRIAL) continue;  // CTA-uniform: the tile's window is not in a trial
+    const bool valid = wid < ti.nitem;
+    const int cnt = tile_item_cnt(ti, wid);
+    const int start = tile_item_start(ti, wid);
+    if (valid && cnt <= 32) {
+      const bool act = lane < cnt;
+      const int o = start + (act ? lane : 0);
+      int lm = -1 - lane, rank = 0;
+      bool has = false;
+      double a[9], rr[3];
+      if (act) {
+        const unsigned lp = lp_sh[buf][tid];
+        lm = lm_sh[buf][tid];
+#pragma unroll
+        for (int c = 0; c < 9; c++) a[c] = op_sh[buf][c][tid];
+#pragma unroll
+        for (int c = 0; c < 3; c++) rr[c] = op_sh[buf][9 + c][tid];
+        has = (lp & 0xffffu) != 0xffffu;
+        rank = (int)(lp >> 16);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 9; c++) a[c] = 0.0;
+        rr[0] = rr[1] = rr[2] = 0.0;
+      }
+      qr_short_item(P, ti, wid, lane, act, o, lm, has, rank, a, rr, lam, c_sh);
+    } else if (valid) {
+      qr_long_item(P, ti, lane, start, cnt, lam);
+    }
+    __syncthreads();
+    const double* jq = P.JQ + ti.jq_off;
+    const int* runs = reinterpret_cast<const int*>(jq + (size_t)JQ_ROWS * ti.nt);
+    const int sbase = P.smallwin ? P.win_slot_ptr[ti.win] : 0;
+    double* bs = P.bs;
+    double* D = P.D;
+    tile_scatter_all<27>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh,
+                         [bs, D](int slot, int k2) { return (k2 < 6) ? bs + (size_t)slot * 6 + k2 : D + (size_t)slot * 21 + (k2 - 6); });
+  }
+  cp_async_wait_all();
+}
 
 // 6x6 block-Jacobi inverse per pose slot: (D + lambda I)^-1
 __global__ void k_dinv(Dev P, int force_all, double lam_override) {

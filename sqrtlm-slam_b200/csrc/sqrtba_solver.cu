@@ -168,6 +168,7 @@ class Solver {
                                   (int)persist_smem_bytes(2, MAXSLOT, false)));
     CU_CHECK(cudaFuncSetAttribute(k_pcg_persist<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)persist_smem_bytes(3, MAXSLOT, false)));
+    CU_CHECK(cudaFuncSetAttribute(k_qr_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QR_PIPE_SMEM));
     int coop = 0;
     CU_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg_.device));
     coop_ok_ = coop != 0;
@@ -974,7 +975,7 @@ class Solver {
       switch (stage) {
         case 0: launch_matvec(P_.p, P_.q, 1); break;
         case 1: k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, 1, d2, d3, 1); break;
-        case 2: k_qr<<<P_.n_tile, CTA, 0, stream_>>>(P_, 1, 1.0); break;
+        case 2: launch_qr(1, 1.0); break;
         case 3: k_cost<<<gi, CTA, 0, stream_>>>(P_, 1, d2, d3); break;
         case 4: k_backsub<<<P_.n_tile, CTA, 0, stream_>>>(P_, 1, 1.0); break;
         default: break;
@@ -1135,6 +1136,11 @@ class Solver {
     return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + (big ? 6 : 18) * (size_t)maxslot + 16) * sizeof(double) +
            2 * S * sizeof(uint64_t) + 4 * sizeof(int) + 2 * (size_t)pipe_run_cap(maxslot, big) * sizeof(int);
   }
+  // landmark QR: cp.async-pipelined kernel (QR_TPB tiles per CTA); reserved[7] != 0 selects the plain one-tile-per-CTA kernel
+  void launch_qr(int force_all, double lam_override) {
+    if (cfg_.reserved[7] != 0) k_qr<<<P_.n_tile, CTA, 0, stream_>>>(P_, force_all, lam_override);
+    else k_qr_pipe<<<cdiv(P_.n_tile, QR_TPB), CTA, QR_PIPE_SMEM, stream_>>>(P_, force_all, lam_override);
+  }
   void launch_matvec(const double* pvec, double* qvec, int force_all) {
     if (P_.smallwin && cfg_.reserved[1] == 0) {
       const int grid = std::min(P_.n_tile, pipe_ctas_);
@@ -1276,7 +1282,7 @@ class Solver {
     const int gi = cdiv(P_.n_item, WARPS);
     if (P_.n_slot) k_zero_trial<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
     stage_begin(1);
-    k_qr<<<P_.n_tile, CTA, 0, stream_>>>(P_, 0, 0.0);
+    launch_qr(0, 0.0);
     stage_end(1);
     launches_ += 2;
     if (!P_.n_slot) return SQRTBA_OK;
