@@ -353,7 +353,9 @@ def main():
     hprob = pkg.synth.Problem(*[t.numpy() for t in host])
     h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = prob.n_pose * 7 * 8 + prob.n_point * 3 * 8 + prob.n_obs
-    ba2 = pkg.SqrtBA(device=local, pcg_mode=args.pcg_mode)
+    # host-side preprocessing threads of set_problem: the ranks of one box share its cores
+    host_threads = max(1, (os.cpu_count() or 1) // max(int(os.environ.get("LOCAL_WORLD_SIZE", world)), 1))
+    ba2 = pkg.SqrtBA(device=local, pcg_mode=args.pcg_mode, host_threads=host_threads)
     for _ in range(min(args.warmup, 1)):
         ba2.set_problem_batch(hprob, pp, tp, op)
         ba2.solve_local()
