@@ -189,6 +189,8 @@ class Solver {
     for (auto& e : stage_ev_)
       if (e) cudaEventDestroy(e);
     ev0_ = ev1_ = nullptr;
+    for (auto& e : mv_events_) cudaEventDestroy(e);
+    mv_events_.clear();
     if (stream_) cudaStreamDestroy(stream_);
     stream_ = nullptr;
   }
@@ -1163,6 +1165,15 @@ class Solver {
 
   // pcg_mode: 0 = auto (persistent kernel for single-window problems, one launch per CG phase for batches),
   //           1 = always one launch per phase, 2 = persistent whenever possible
+  bool grow_mv_events() {
+    if (mv_events_.size() >= 8192) return false;  // 4096 timed launches per solve are plenty
+    for (int i = 0; i < 256; i++) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreate(&e) != cudaSuccess) return false;
+      mv_events_.push_back(e);
+    }
+    return true;
+  }
   bool use_persist() const {
     if (cfg_.pcg_mode == 1 || !coop_ok_ || P_.n_win != 1 || !P_.smallwin || persist_ctas_ <= 0 || cfg_.reserved[1] != 0) return false;
     if (comm_ && (!peer_ok_ || P_.pq_shared)) return false;  // sharded without peer-mapped buffers, or a small window: NCCL all-reduce per iteration
@@ -1310,7 +1321,12 @@ class Solver {
     }
     for (int it = 0; it < cfg_.pcg_max_iters; it++) {
       CU_CHECK(cudaMemsetAsync(P_.q, 0, qbytes, stream_));
+      // live duration of the dominant kernel: an event pair per launch, read back after the solve (no extra sync)
+      cudaEvent_t ea = nullptr, eb = nullptr;
+      if (mv_used_ + 2 <= (int)mv_events_.size() || grow_mv_events()) { ea = mv_events_[mv_used_]; eb = mv_events_[mv_used_ + 1]; mv_used_ += 2; }
+      if (ea) cudaEventRecord(ea, stream_);
       launch_matvec(P_.p, P_.q, 0);
+      if (eb) cudaEventRecord(eb, stream_);
       if (int rc = allreduce(P_.q, (size_t)P_.n_slot * 6, false)) return rc;  // the one exchange step of a CG iteration
       k_cg_step<<<P_.n_win, RCTA, 0, stream_>>>(P_, tol2, cfg_.pcg_max_iters, 0, 0.0);
       launches_ += 2;
@@ -1374,6 +1390,7 @@ class Solver {
   void begin_stats() {
     launches_ = 0; lm_trials_ = 0; cg_iters_total_ = 0;
     for (auto& v : stage_ms_) v = 0.0;
+    mv_used_ = 0;
     cudaMemsetAsync(d_counters_.p + 2, 0, sizeof(int), stream_);
     cudaEventRecord(ev0_, stream_);
   }
@@ -1407,6 +1424,12 @@ class Solver {
       st->ms_pcg = stage_ms_[2];
       st->ms_backsub = stage_ms_[3];
       st->ms_cost = stage_ms_[4];
+      double mv = 0.0;
+      for (int i = 0; i + 1 < mv_used_; i += 2) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, mv_events_[i], mv_events_[i + 1]) == cudaSuccess) mv += t;
+      }
+      st->ms_matvec = mv;  // sum over the matvec launches of this solve (0 when the persistent PCG kernel ran)
       st->reserved[0] = use_persist() ? 1.0 : 0.0;           // the PCG solves ran in the persistent cooperative kernel
       st->reserved[1] = (comm_ && peer_ok_) ? 1.0 : 0.0;     // landmark-sharded: in-kernel NVLink exchange available
       st->reserved[2] = persist_grid_;
@@ -1452,6 +1475,8 @@ class Solver {
   int n_ranks_ = 1, rank_ = 0;
   bool coop_ok_ = false, peer_ok_ = false;
   int persist_ctas_ = 0, persist_stages_ = 2, persist_slots_ = 1, persist_grid_ = 0;
+  std::vector<cudaEvent_t> mv_events_;
+  int mv_used_ = 0;
   DBuf<int> d_ptile_;
   double* peer_recv_[8] = {};
   unsigned long long* d_seq_ = nullptr;
