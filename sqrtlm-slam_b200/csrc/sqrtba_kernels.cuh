@@ -302,6 +302,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
+// ---- cp.async (LDGSTS) staging primitives
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------ K0: zeroing
 
 // per-slot accumulators that the linearise kernel fills with atomics (only for windows that re-linearise)
@@ -334,11 +347,15 @@ struct ObsLin {
   bool depth_pos;
 };
 
+// the observation's own words (measurement, pose index, landmark index) already in registers
+__device__ __forceinline__ void obs_eval_ops(const Dev& P, const float4 m, int ip, int il, bool want_jac, bool robust,
+                                             double d2, double d3, ObsLin& L);
 __device__ __forceinline__ void obs_eval(const Dev& P, int o, bool want_jac, bool robust, double d2, double d3,
                                          ObsLin& L) {
-  const float4 m = __ldg(&P.obs_meas[o]);
-  const int ip = __ldg(&P.obs_pose[o]);
-  const int il = __ldg(&P.obs_point[o]);
+  obs_eval_ops(P, __ldg(&P.obs_meas[o]), __ldg(&P.obs_pose[o]), __ldg(&P.obs_point[o]), want_jac, robust, d2, d3, L);
+}
+__device__ __forceinline__ void obs_eval_ops(const Dev& P, const float4 m, int ip, int il, bool want_jac, bool robust,
+                                             double d2, double d3, ObsLin& L) {
   double pose[7], X[3], cam[5], R[9], Xc[3];
 #pragma unroll
   for (int i = 0; i < 7; i++) pose[i] = P.pose[ip * 7 + i];
@@ -363,14 +380,31 @@ __device__ __forceinline__ void obs_eval(const Dev& P, int o, bool want_jac, boo
   if (want_jac) reproj_jacobians(R, Xc, cam, stereo, L.Jp, L.Jl);
 }
 
-__global__ void __launch_bounds__(CTA, 4) k_linearize(Dev P, int robust, double d2, double d3, int force_all) {
-  __shared__ double c_sh[12 * SCST];
+// per-observation words of one lane, loadable one tile ahead of their use (8 registers)
+struct LinOps {
+  float4 m;
+  int ip, lm;
+  unsigned lp;
+  int live;
+};
+__device__ __forceinline__ LinOps lin_load_ops(const Dev& P, int o) {
+  LinOps q;
+  q.m = __ldg(&P.obs_meas[o]);
+  q.ip = __ldg(&P.obs_pose[o]);
+  q.lm = __ldg(&P.obs_point[o]);
+  q.lp = __ldg(&P.obs_lp[o]);
+  q.live = P.obs_level[o] == 0;
+  return q;
+}
+
+// One tile of the linearisation.  PRE: the lanes of short items already hold their LinOps (pipelined kernel).
+template <bool PRE>
+__device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti, const LinOps& pre, int robust, double d2,
+                                               double d3, double* c_sh) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const TileInfo ti = P.tiles[blockIdx.x];
   const int w = ti.item0 + wid;
   const bool valid = wid < ti.nitem;
   const int win = ti.win;
-  if (!force_all && P.ctl[win].phase != PH_LIN) return;  // a tile lies inside one window: CTA-uniform
   const bool on = valid;
   const int start = tile_item_start(ti, wid), cnt = tile_item_cnt(ti, wid);
   const size_t No = (size_t)P.ld; const int Nl = P.n_point;
@@ -388,16 +422,17 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize(Dev P, int robust, double 
 #pragma unroll
     for (int c = 0; c < 9; c++) L.Jl[c] = 0.0;
     L.e[0] = L.e[1] = L.e[2] = 0.0;
+    LinOps q = pre;
     if (act) {
-      const unsigned lp = P.obs_lp[o];
-      has = (lp & 0xffffu) != 0xffffu;
-      rank = (int)(lp >> 16);
-      lm = P.obs_point[o];
+      if (!PRE) q = lin_load_ops(P, o);
+      has = (q.lp & 0xffffu) != 0xffffu;
+      rank = (int)(q.lp >> 16);
+      lm = q.lm;
     }
     const int fcol = tile_fcol(ti, wid, has, lane);
     if (act && on) {
-      const bool live = P.obs_level[o] == 0;
-      obs_eval(P, o, true, robust != 0, d2, d3, L);
+      const bool live = q.live != 0;
+      obs_eval_ops(P, q.m, q.ip, q.lm, true, robust != 0, d2, d3, L);
       if (live) {
 #pragma unroll
         for (int c = 0; c < 3; c++) P.err[(size_t)c * No + o] = L.e[c];
@@ -496,6 +531,63 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize(Dev P, int robust, double 
   double* hd = P.hd;
   tile_scatter_all<12>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh,
                        [bp, hd](int slot, int k) { return (k < 6) ? bp + (size_t)slot * 6 + k : hd + (size_t)slot * 6 + (k - 6); });
+}
+
+__global__ void __launch_bounds__(CTA, 4) k_linearize(Dev P, int robust, double d2, double d3, int force_all) {
+  __shared__ double c_sh[12 * SCST];
+  const TileInfo ti = P.tiles[blockIdx.x];
+  if (!force_all && P.ctl[ti.win].phase != PH_LIN) return;  // a tile lies inside one window: CTA-uniform
+  LinOps none{};
+  linearize_tile<false>(P, ti, none, robust, d2, d3, c_sh);
+}
+
+// Pipelined variant (same idea as k_qr_pipe): every CTA walks LIN_TPB consecutive tiles; the tile descriptor two tiles
+// ahead is staged in shared memory with cp.async and every lane loads its own observation words (measurement, pose and
+// landmark index, meta, level: 8 registers) for the NEXT tile while it linearises the current one, so only the
+// L2-resident pose / point gathers stay on the critical path.
+constexpr int LIN_TPB = 8;
+__global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, double d2, double d3, int force_all) {
+  __shared__ double c_sh[12 * SCST];
+  __shared__ __align__(16) TileInfo ti_sh[3];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int t0 = blockIdx.x * LIN_TPB, t1 = min(t0 + LIN_TPB, P.n_tile);
+  auto ops_of = [&](const TileInfo& ti) {
+    LinOps q{};
+    if (!ti.is_long) {
+      const int cnt = tile_item_cnt(ti, wid), start = tile_item_start(ti, wid);
+      if (wid < ti.nitem && lane < cnt) q = lin_load_ops(P, start + lane);
+    }
+    return q;
+  };
+  if (tid < 5) {
+    cp_async16(reinterpret_cast<char*>(&ti_sh[0]) + tid * 16, reinterpret_cast<const char*>(P.tiles + t0) + tid * 16);
+    if (t0 + 1 < t1)
+      cp_async16(reinterpret_cast<char*>(&ti_sh[1]) + tid * 16, reinterpret_cast<const char*>(P.tiles + t0 + 1) + tid * 16);
+  }
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  LinOps nxt = ops_of(ti_sh[0]);
+  int nphase = force_all ? PH_LIN : P.ctl[ti_sh[0].win].phase;
+  for (int k = 0; k < t1 - t0; k++) {
+    cp_async_wait_all();  // descriptor of tile k+1
+    __syncthreads();      // ... visible to everybody; c_sh of the previous tile is free
+    const TileInfo ti = ti_sh[k % 3];
+    const LinOps cur = nxt;
+    const int phase = nphase;
+    if (k + 1 < t1 - t0) {
+      const TileInfo& tn = ti_sh[(k + 1) % 3];
+      if (k + 2 < t1 - t0 && tid < 5)
+        cp_async16(reinterpret_cast<char*>(&ti_sh[(k + 2) % 3]) + tid * 16,
+                   reinterpret_cast<const char*>(P.tiles + t0 + k + 2) + tid * 16);
+      nxt = ops_of(tn);
+      if (!force_all) nphase = P.ctl[tn.win].phase;
+    }
+    cp_async_commit();
+    if (phase != PH_LIN) continue;  // CTA-uniform
+    linearize_tile<true>(P, ti, cur, robust, d2, d3, c_sh);
+  }
+  cp_async_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------ K8a: LM begin
@@ -864,17 +956,6 @@ __global__ void __launch_bounds__(CTA, 4) k_qr(Dev P, int force_all, double lam_
 // pulled into L2 by a TMA prefetch.  Per-lane data is private (a lane reads back exactly what it copied), so the only
 // barrier the staging needs is the one that publishes the tile descriptors.
 constexpr int QR_TPB = 8;
-__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 constexpr size_t QR_PIPE_SMEM = (27 * SCST + 2 * 12 * CTA) * sizeof(double) + 2 * CTA * (sizeof(unsigned) + sizeof(int)) + 3 * 80;
 __global__ void __launch_bounds__(CTA, 4) k_qr_pipe(Dev P, int force_all, double lam_override) {

@@ -880,7 +880,7 @@ class Solver {
     const double d2 = (double)(float)std::sqrt(huber == 2 ? 5.99 : 5.991), d3 = (double)(float)std::sqrt(7.815);
     k_pass_init<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_, 1, 0);
     if (P_.n_slot) k_zero_lin<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
-    k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, huber != 0, d2, d3, 1);
+    launch_linearize(huber != 0, d2, d3, 1);
     if (int rc = begin_after_linearize()) return rc;
     CU_CHECK(cudaGetLastError());
     const size_t No = P_.n_obs, Ld = P_.ld;
@@ -976,7 +976,7 @@ class Solver {
     auto one = [&]() {
       switch (stage) {
         case 0: launch_matvec(P_.p, P_.q, 1); break;
-        case 1: k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, 1, d2, d3, 1); break;
+        case 1: launch_linearize(1, d2, d3, 1); break;
         case 2: launch_qr(1, 1.0); break;
         case 3: k_cost<<<gi, CTA, 0, stream_>>>(P_, 1, d2, d3); break;
         case 4: k_backsub<<<P_.n_tile, CTA, 0, stream_>>>(P_, 1, 1.0); break;
@@ -1137,6 +1137,10 @@ class Solver {
   static size_t persist_smem_bytes(int S, int maxslot, bool big) {
     return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + (big ? 6 : 18) * (size_t)maxslot + 16) * sizeof(double) +
            2 * S * sizeof(uint64_t) + 4 * sizeof(int) + 2 * (size_t)pipe_run_cap(maxslot, big) * sizeof(int);
+  }
+  void launch_linearize(int robust, double d2, double d3, int force_all) {
+    if (cfg_.reserved[7] != 0) k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
+    else k_linearize_pipe<<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
   }
   // landmark QR: cp.async-pipelined kernel (QR_TPB tiles per CTA); reserved[7] != 0 selects the plain one-tile-per-CTA kernel
   void launch_qr(int force_all, double lam_override) {
@@ -1355,7 +1359,7 @@ class Solver {
       if (term && step == 0) break;  // `for (i < iterations && !terminate())` before the first iteration
       if (P_.n_slot) k_zero_lin<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
       stage_begin(0);
-      k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, robust, d2, d3, 0);
+      launch_linearize(robust, d2, d3, 0);
       stage_end(0);
       if (int rc = begin_after_linearize()) return rc;
       launches_ += 4;
