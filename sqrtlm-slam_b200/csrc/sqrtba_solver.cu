@@ -329,6 +329,19 @@ class Solver {
       lm_count_new_ = lm_cnt;
       point_xyz = h_perm_xyz_.p; obs_pose = h_perm_pose_.p; obs_point = h_perm_point_.p; obs_meas = h_perm_meas_.p;
     }
+    // The caller's big arrays (or their re-ordered copies) are final now: start their host-to-device copies so that they
+    // overlap the remaining host-side preprocessing (truly asynchronous when the caller's buffers are pinned).
+    auto up = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_); };
+    CU_CHECK(d_cam_.ensure((size_t)n_pose * 5));
+    CU_CHECK(d_meas_.ensure((size_t)n_obs));
+    CU_CHECK(d_obs_pose_.ensure((size_t)n_obs));
+    CU_CHECK(d_obs_point_.ensure((size_t)n_obs));
+    CU_CHECK(d_point0_.ensure((size_t)n_point * 3));
+    CU_CHECK(up(d_cam_.p, cam, (size_t)n_pose * 5 * sizeof(double)));
+    CU_CHECK(up(d_meas_.p, obs_meas, (size_t)n_obs * sizeof(float4)));
+    CU_CHECK(up(d_obs_pose_.p, obs_pose, (size_t)n_obs * sizeof(int)));
+    CU_CHECK(up(d_obs_point_.p, obs_point, (size_t)n_obs * sizeof(int)));
+    CU_CHECK(up(d_point0_.p, point_xyz, (size_t)n_point * 3 * sizeof(double)));
     // B. work chunks: landmark ranges inside one window of roughly equal observation count.  Items and tiles never
     //    span chunks (a chunk boundary merely ends an item early), so chunks are processed independently.
     struct Chunk { int win, l0, l1; std::vector<int> it_start, it_cnt, run_ptr, runs; std::vector<TileInfo> tiles; long long jq = 0; };
@@ -466,6 +479,7 @@ class Solver {
     if (h_item_start_.ensure(n_item) || h_item_cnt_.ensure(n_item) || h_item_win_.ensure(n_item) || h_tiles_pin_.ensure(n_tile) ||
         h_tile_run_ptr_.ensure(n_tile + 1) || h_tile_runs_.ensure(n_runs)) {
       err_ = "pinned host allocation failed";
+      cudaStreamSynchronize(stream_);  // the early host-to-device copies still read the caller's buffers
       return SQRTBA_ERR_ALLOC;
     }
     {
@@ -546,8 +560,6 @@ class Solver {
     CU_CHECK(d_trace_.ensure((size_t)n_win * max_trace_ * TRACE_COLS));
     CU_CHECK(d_counters_.ensure(4));
 
-    auto up = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_); };
-    CU_CHECK(up(d_cam_.p, cam, (size_t)n_pose * 5 * sizeof(double)));
     CU_CHECK(up(d_pose_slot_.p, pose_slot.data(), n_pose * sizeof(int)));
     if (n_slot) {
       CU_CHECK(up(d_slot_pose_.p, slot_pose.data(), n_slot * sizeof(int)));
@@ -555,9 +567,6 @@ class Solver {
     }
     CU_CHECK(up(d_pose_win_.p, pose_win.data(), n_pose * sizeof(int)));
     CU_CHECK(up(d_point_win_.p, point_win.data(), n_point * sizeof(int)));
-    CU_CHECK(up(d_meas_.p, obs_meas, No * sizeof(float4)));
-    CU_CHECK(up(d_obs_pose_.p, obs_pose, No * sizeof(int)));
-    CU_CHECK(up(d_obs_point_.p, obs_point, No * sizeof(int)));
     CU_CHECK(up(d_obs_slot_.p, h_obs_slot_.p, No * sizeof(int)));
     CU_CHECK(up(d_item_start_.p, h_item_start_.p, n_item * sizeof(int)));
     CU_CHECK(up(d_item_cnt_.p, h_item_cnt_.p, n_item * sizeof(int)));
@@ -572,7 +581,6 @@ class Solver {
     std::vector<double> pq(pose_qt, pose_qt + (size_t)n_pose * 7);
     for (int i = 0; i < n_pose; i++) quat_normalize_pos_w(&pq[(size_t)i * 7 + 3]);
     CU_CHECK(up(d_pose0_.p, pq.data(), (size_t)n_pose * 7 * sizeof(double)));
-    CU_CHECK(up(d_point0_.p, point_xyz, Nl * 3 * sizeof(double)));
     CU_CHECK(cudaStreamSynchronize(stream_));  // host staging vectors go out of scope
 
     P_.cam = d_cam_.p; P_.pose_slot = d_pose_slot_.p; P_.slot_pose = d_slot_pose_.p; P_.slot_win = d_slot_win_.p;
