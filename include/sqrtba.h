@@ -163,6 +163,22 @@ int sqrtba_debug_step(sqrtba_handle* h, double lambda, double* dp, double* dl, d
 int sqrtba_debug_matvec(sqrtba_handle* h, const double* p, double* y);
 int sqrtba_num_free_poses(sqrtba_handle* h);
 
+/* The host-side plan of sqrtba_set_problem[_batch] WITHOUT a device (pure host code, used by the CPU tests of the host
+ * logic): landmarks packed into items (<= 32 observations, one warp), items into tiles (<= 4 items of one window, one
+ * CTA), per tile the pose-sorted ranks + run table, and for windows with more than 128 free poses the internal landmark
+ * order (sorted by first free pose).  Outputs (any may be NULL):
+ *   summary8       n_item, n_tile, n_run_ints, slots_fit_16_bits, pq_shared, reordered, jq_doubles lo31, jq_doubles hi
+ *   tiles20        per tile (20 ints): item0, nitem, o0, o1, win, nfree, nt, is_long, nrun, cnt[4], fcnt[4],
+ *                  blk_doubles, jq_off lo31, jq_off hi  (first max_tiles tiles)
+ *   obs_lp         n_obs meta words (low 16 bits: window-relative free slot or 0xffff; high 16: rank in the tile)
+ *   tile_run_ptr / tile_runs   CSR of the run tables (nrun+1 rank offsets, then nrun slots)
+ *   landmark_order n_point: internal index -> caller's landmark index
+ * Observation indices in tiles20 / obs_lp refer to the INTERNAL order when the problem was re-ordered. */
+int sqrtba_debug_plan(int32_t n_win, const int64_t* win_pose_ptr, const int64_t* win_point_ptr, const int64_t* win_obs_ptr,
+                      int32_t n_pose, int32_t n_point, int32_t n_obs, const uint8_t* pose_fixed, const int32_t* obs_pose,
+                      const int32_t* obs_point, int32_t host_threads, int32_t* summary8, int32_t* tiles20, int32_t max_tiles,
+                      uint32_t* obs_lp, int32_t* tile_run_ptr, int32_t* tile_runs, int64_t max_runs, int32_t* landmark_order);
+
 /* Time `reps` launches of one stage kernel on the handle's stream with CUDA events (after `warmup` untimed
  * launches); returns the average ms per launch.  stage: 0 matvec, 1 linearize, 2 landmark QR, 3 cost, 4 backsub. */
 int sqrtba_time_stage(sqrtba_handle* h, int32_t stage, int32_t warmup, int32_t reps, double* ms_avg);

@@ -64,6 +64,8 @@ def lib():
         L.sqrtba_debug_step.argtypes = [vp, C.c_double, dp, dp, dp, ip]
         L.sqrtba_debug_matvec.argtypes = [vp, dp, dp]
         L.sqrtba_num_free_poses.argtypes = [vp]
+        L.sqrtba_debug_plan.argtypes = [C.c_int32, lp, lp, lp, C.c_int32, C.c_int32, C.c_int32, up, ip, ip, C.c_int32, ip, ip,
+                                        C.c_int32, C.POINTER(C.c_uint32), ip, ip, C.c_int64, ip]
         L.sqrtba_time_stage.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, dp]
         L.sqrtba_pose_opt.argtypes = [vp, C.c_int32, lp, dp, dp, dp, fp, up, ip, C.POINTER(Stats)]
         L.sqrtba_pose_opt_trace.argtypes = [vp, C.c_int32, dp, C.c_int32]
@@ -243,3 +245,45 @@ class SqrtBA:
         ms = C.c_double(0)
         self._chk(lib().sqrtba_time_stage(self.h, stage, warmup, reps, C.byref(ms)), "sqrtba_time_stage")
         return ms.value
+
+
+TILE_COLS = ("item0", "nitem", "o0", "o1", "win", "nfree", "nt", "is_long", "nrun",
+             "cnt0", "cnt1", "cnt2", "cnt3", "fcnt0", "fcnt1", "fcnt2", "fcnt3", "blk_doubles", "jq_off_lo", "jq_off_hi")
+
+
+def debug_plan(prob, pose_ptr=None, point_ptr=None, obs_ptr=None, host_threads: int = 0) -> dict:
+    """Host-side plan of set_problem[_batch] (items, tiles, run tables, landmark order) -- needs no GPU.
+
+    Two calls: the first sizes the outputs from the summary, the second fills them.
+    """
+    if pose_ptr is None:
+        pose_ptr, point_ptr, obs_ptr = [0, prob.n_pose], [0, prob.n_point], [0, prob.n_obs]
+    pp, tp, op = (np.ascontiguousarray(x, np.int64) for x in (pose_ptr, point_ptr, obs_ptr))
+    fx = np.ascontiguousarray(prob.pose_fixed, np.uint8)
+    opose = np.ascontiguousarray(prob.obs_pose, np.int32)
+    opoint = np.ascontiguousarray(prob.obs_point, np.int32)
+    n_win = len(pp) - 1
+    summ = np.zeros(8, np.int32)
+
+    def call(tiles, lp_, rptr, runs, perm):
+        rc = lib().sqrtba_debug_plan(
+            n_win, _p(pp, C.c_int64), _p(tp, C.c_int64), _p(op, C.c_int64), prob.n_pose, prob.n_point, prob.n_obs,
+            _p(fx, C.c_uint8), _p(opose, C.c_int32), _p(opoint, C.c_int32), host_threads, _p(summ, C.c_int32),
+            None if tiles is None else _p(tiles, C.c_int32), 0 if tiles is None else len(tiles),
+            None if lp_ is None else _p(lp_, C.c_uint32), None if rptr is None else _p(rptr, C.c_int32),
+            None if runs is None else _p(runs, C.c_int32), 0 if runs is None else len(runs),
+            None if perm is None else _p(perm, C.c_int32))
+        if rc != 0:
+            raise SqrtBAError(f"sqrtba_debug_plan failed with code {rc}")
+
+    call(None, None, None, None, None)
+    n_item, n_tile, n_runs = int(summ[0]), int(summ[1]), int(summ[2])
+    tiles = np.zeros((n_tile, 20), np.int32)
+    obs_lp = np.zeros(prob.n_obs, np.uint32)
+    run_ptr = np.zeros(n_tile + 1, np.int32)
+    runs = np.zeros(max(n_runs, 1), np.int32)
+    perm = np.zeros(prob.n_point, np.int32)
+    call(tiles, obs_lp, run_ptr, runs, perm)
+    return dict(n_item=n_item, n_tile=n_tile, n_run_ints=n_runs, smallwin=bool(summ[3]), pq_shared=bool(summ[4]),
+                reordered=bool(summ[5]), jq_doubles=int(summ[6]) + (int(summ[7]) << 31), tiles=tiles, obs_lp=obs_lp,
+                tile_run_ptr=run_ptr, tile_runs=runs[:n_runs], landmark_order=perm)

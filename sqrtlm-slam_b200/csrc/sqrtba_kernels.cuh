@@ -45,7 +45,8 @@ struct TileInfo {
   int o0, o1;        // observation range [o0, o1)
   int win;           // window of the tile
   int nfree;         // observations that take part in the in-CTA reduction (ranks 0..nfree-1)
-  int nt;            // columns of this tile's JQ block: (o1-o0) rounded up to even (16-byte rows for TMA)
+  int nt;            // columns of this tile's JQ block, rounded up to even (16-byte rows for TMA): one per FREE-pose
+                     // observation (short tiles) or one per observation (long tiles)
   int is_long;       // the tile is one landmark with more than 32 observations
   long long jq_off;  // offset (doubles) of the tile's [27][nt] data block inside Dev::JQ (its header sits right before)
   int nrun;          // distinct free pose slots among the participating observations (= runs of equal slot by rank)

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <thread>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -60,17 +61,24 @@ template <class T>
 struct HBuf {  // pinned host staging buffer that only grows (fast H2D, reused across set_problem calls)
   T* p = nullptr;
   size_t cap = 0;
-  int ensure(size_t n) {
+  bool pinned = true;
+  int ensure(size_t n, bool want_pinned = true) {
     if (n <= cap) return 0;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-    if (cudaMallocHost((void**)&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return 1;
+    release();
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    if (want_pinned && cudaMallocHost((void**)&p, bytes) == cudaSuccess) {
+      pinned = true;
+    } else {  // plan-only mode (no device needed): ordinary memory
+      if (want_pinned) cudaGetLastError();
+      p = (T*)std::malloc(bytes);
+      pinned = false;
+      if (!p) return 1;
+    }
     cap = n;
     return 0;
   }
   void release() {
-    if (p) cudaFreeHost(p);
+    if (p) { if (pinned) cudaFreeHost(p); else std::free(p); }
     p = nullptr;
     cap = 0;
   }
@@ -211,7 +219,7 @@ class Solver {
       err_ = "set_problem: empty problem or null pointer";
       return SQRTBA_ERR_INVALID;
     }
-    CU_CHECK(cudaSetDevice(cfg_.device));
+    if (!plan_only_) CU_CHECK(cudaSetDevice(cfg_.device));
     have_problem_ = false;
     std::vector<int> pose_win(n_pose, 0), point_win(n_point, 0);
     if (n_win > 1) {
@@ -245,7 +253,7 @@ class Solver {
     for (int w = 0; w < n_win; w++) max_win_slots = std::max(max_win_slots, win_slot_ptr[w + 1] - win_slot_ptr[w]);
     const int smallwin = (max_win_slots < 65535) ? 1 : 0;       // window-relative slots fit the 16-bit meta field
     const int pq_shared = (max_win_slots <= MAXSLOT) ? 1 : 0;  // p/q of a window fit the matvec CTA's shared memory
-    if (h_obs_slot_.ensure(n_obs) || h_obs_lp_.ensure(n_obs)) { err_ = "pinned host allocation failed"; return SQRTBA_ERR_ALLOC; }
+    if (h_obs_slot_.ensure(n_obs, !plan_only_) || h_obs_lp_.ensure(n_obs, !plan_only_)) { err_ = "pinned host allocation failed"; return SQRTBA_ERR_ALLOC; }
     int* obs_slot = h_obs_slot_.p;
     unsigned* obs_lp = h_obs_lp_.p;
     const int n_thr = std::max(1, std::min<int>(cfg_.reserved[3] > 0 ? cfg_.reserved[3] : (int)std::thread::hardware_concurrency(), 64));
@@ -305,8 +313,8 @@ class Solver {
         cnt_new[j] = lm_cnt[l];
         if (lm_cnt[l] > 0) { new_first_[j] = pos; pos += lm_cnt[l]; }
       }
-      if (h_perm_pose_.ensure(n_obs) || h_perm_point_.ensure(n_obs) || h_perm_meas_.ensure((size_t)n_obs * 4) ||
-          h_perm_xyz_.ensure((size_t)n_point * 3) || h_perm_slot_.ensure(n_obs)) {
+      if (h_perm_pose_.ensure(n_obs, !plan_only_) || h_perm_point_.ensure(n_obs, !plan_only_) || h_perm_meas_.ensure((size_t)n_obs * 4, !plan_only_) ||
+          h_perm_xyz_.ensure((size_t)n_point * 3, !plan_only_) || h_perm_slot_.ensure(n_obs, !plan_only_)) {
         err_ = "pinned host allocation failed";
         return SQRTBA_ERR_ALLOC;
       }
@@ -332,6 +340,7 @@ class Solver {
     // The caller's big arrays (or their re-ordered copies) are final now: start their host-to-device copies so that they
     // overlap the remaining host-side preprocessing (truly asynchronous when the caller's buffers are pinned).
     auto up = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_); };
+    if (!plan_only_) {
     CU_CHECK(d_cam_.ensure((size_t)n_pose * 5));
     CU_CHECK(d_meas_.ensure((size_t)n_obs));
     CU_CHECK(d_obs_pose_.ensure((size_t)n_obs));
@@ -342,6 +351,7 @@ class Solver {
     CU_CHECK(up(d_obs_pose_.p, obs_pose, (size_t)n_obs * sizeof(int)));
     CU_CHECK(up(d_obs_point_.p, obs_point, (size_t)n_obs * sizeof(int)));
     CU_CHECK(up(d_point0_.p, point_xyz, (size_t)n_point * 3 * sizeof(double)));
+    }
     // B. work chunks: landmark ranges inside one window of roughly equal observation count.  Items and tiles never
     //    span chunks (a chunk boundary merely ends an item early), so chunks are processed independently.
     struct Chunk { int win, l0, l1; std::vector<int> it_start, it_cnt, run_ptr, runs; std::vector<TileInfo> tiles; long long jq = 0; };
@@ -476,8 +486,8 @@ class Solver {
     const int n_item = (int)item_off.back(), n_tile = (int)tile_off.back();
     const long long jq_total = jq_off.back();
     const size_t n_runs = (size_t)run_off.back();
-    if (h_item_start_.ensure(n_item) || h_item_cnt_.ensure(n_item) || h_item_win_.ensure(n_item) || h_tiles_pin_.ensure(n_tile) ||
-        h_tile_run_ptr_.ensure(n_tile + 1) || h_tile_runs_.ensure(n_runs)) {
+    if (h_item_start_.ensure(n_item, !plan_only_) || h_item_cnt_.ensure(n_item, !plan_only_) || h_item_win_.ensure(n_item, !plan_only_) || h_tiles_pin_.ensure(n_tile, !plan_only_) ||
+        h_tile_run_ptr_.ensure(n_tile + 1, !plan_only_) || h_tile_runs_.ensure(n_runs, !plan_only_)) {
       err_ = "pinned host allocation failed";
       cudaStreamSynchronize(stream_);  // the early host-to-device copies still read the caller's buffers
       return SQRTBA_ERR_ALLOC;
@@ -511,6 +521,9 @@ class Solver {
       for (auto& th : pool) th.join();
       h_tile_run_ptr_.p[n_tile] = (int)n_runs;
     }
+    plan_n_item_ = n_item; plan_n_tile_ = n_tile; plan_n_runs_ = (long long)n_runs; plan_jq_total_ = jq_total;
+    plan_smallwin_ = smallwin; plan_pq_shared_ = pq_shared;
+    if (plan_only_) return SQRTBA_OK;  // sqrtba_debug_plan: the host-side tiling only, no device needed
     // ---- device allocation
     P_ = Dev{};
     P_.n_pose = n_pose; P_.n_point = n_point; P_.n_obs = n_obs; P_.n_win = n_win; P_.n_slot = n_slot; P_.n_item = n_item;
@@ -814,6 +827,28 @@ class Solver {
     return m;
   }
   int num_free() const { return have_problem_ ? P_.n_slot : SQRTBA_ERR_INVALID; }
+
+  // host-side plan of the last set_problem (plan-only mode): tile table, meta words, run tables, landmark order
+  void plan_export(int32_t* summary, int32_t* tiles20, int32_t max_tiles, uint32_t* obs_lp, int32_t* run_ptr, int32_t* runs,
+                   int64_t max_runs, int32_t* perm, int32_t n_obs, int32_t n_point) const {
+    if (summary) {
+      summary[0] = plan_n_item_; summary[1] = plan_n_tile_; summary[2] = (int32_t)plan_n_runs_;
+      summary[3] = plan_smallwin_; summary[4] = plan_pq_shared_; summary[5] = perm_.empty() ? 0 : 1;
+      summary[6] = (int32_t)(plan_jq_total_ & 0x7fffffff); summary[7] = (int32_t)(plan_jq_total_ >> 31);
+    }
+    for (int t = 0; tiles20 && t < std::min(plan_n_tile_, max_tiles); t++) {
+      const TileInfo& ti = h_tiles_pin_.p[t];
+      int32_t* o = tiles20 + (size_t)t * 20;
+      o[0] = ti.item0; o[1] = ti.nitem; o[2] = ti.o0; o[3] = ti.o1; o[4] = ti.win; o[5] = ti.nfree; o[6] = ti.nt;
+      o[7] = ti.is_long; o[8] = ti.nrun;
+      for (int i = 0; i < 4; i++) { o[9 + i] = ti.cnt[i]; o[13 + i] = ti.fcnt[i]; }
+      o[17] = ti.blk_doubles; o[18] = (int32_t)(ti.jq_off & 0x7fffffff); o[19] = (int32_t)(ti.jq_off >> 31);
+    }
+    if (obs_lp) std::memcpy(obs_lp, h_obs_lp_.p, (size_t)n_obs * sizeof(uint32_t));
+    if (run_ptr) std::memcpy(run_ptr, h_tile_run_ptr_.p, (size_t)(std::min(plan_n_tile_, max_tiles) + 1) * sizeof(int32_t));
+    if (runs) std::memcpy(runs, h_tile_runs_.p, (size_t)std::min<long long>(plan_n_runs_, max_runs) * sizeof(int32_t));
+    if (perm) for (int l = 0; l < n_point; l++) perm[l] = perm_.empty() ? l : perm_[l];
+  }
 
   // ------------------------------------------------------------------------------------------ pose-only optimisation
   // g2oOptimizer::PoseOptimization for a batch of frames (one CTA per frame, one launch); independent of set_problem.
@@ -1469,6 +1504,9 @@ class Solver {
 
  public:
   bool stage_timing_ = false;
+  bool plan_only_ = false;
+  int plan_n_item_ = 0, plan_n_tile_ = 0, plan_smallwin_ = 0, plan_pq_shared_ = 0;
+  long long plan_n_runs_ = 0, plan_jq_total_ = 0;
 
  private:
   sqrtba_config cfg_;
@@ -1628,6 +1666,25 @@ int sqrtba_debug_matvec(sqrtba_handle* h, const double* p, double* y) {
   return (h && p && y) ? h->s->debug_matvec(p, y) : SQRTBA_ERR_INVALID;
 }
 int sqrtba_num_free_poses(sqrtba_handle* h) { return h ? h->s->num_free() : SQRTBA_ERR_INVALID; }
+int sqrtba_debug_plan(int32_t n_win, const int64_t* win_pose_ptr, const int64_t* win_point_ptr, const int64_t* win_obs_ptr,
+                      int32_t n_pose, int32_t n_point, int32_t n_obs, const uint8_t* pose_fixed, const int32_t* obs_pose,
+                      const int32_t* obs_point, int32_t host_threads, int32_t* summary8, int32_t* tiles20, int32_t max_tiles,
+                      uint32_t* obs_lp, int32_t* tile_run_ptr, int32_t* tile_runs, int64_t max_runs, int32_t* landmark_order) {
+  if (!pose_fixed || !obs_pose || !obs_point || n_pose <= 0 || n_point <= 0 || n_obs <= 0 || n_win <= 0) return SQRTBA_ERR_INVALID;
+  sqrtba_config c;
+  sqrtba_default_config(&c);
+  c.reserved[3] = host_threads;
+  Solver s(c);
+  s.plan_only_ = true;
+  // the plan never reads values, only indices: give the value arrays harmless stand-ins
+  std::vector<double> pose((size_t)n_pose * 7, 0.0), cam((size_t)n_pose * 5, 0.0), xyz((size_t)n_point * 3, 0.0);
+  std::vector<float> meas((size_t)n_obs * 4, 0.f);
+  const int rc = s.set_problem(n_win, win_pose_ptr, win_point_ptr, win_obs_ptr, n_pose, n_point, n_obs, pose.data(), pose_fixed,
+                               cam.data(), xyz.data(), obs_pose, obs_point, meas.data());
+  if (rc != SQRTBA_OK) return rc;
+  s.plan_export(summary8, tiles20, max_tiles, obs_lp, tile_run_ptr, tile_runs, max_runs, landmark_order, n_obs, n_point);
+  return SQRTBA_OK;
+}
 int sqrtba_pose_opt(sqrtba_handle* h, int32_t n_frames, const int64_t* frame_obs_ptr, double* pose_qt, const double* cam,
                     const double* obs_xyz, const float* obs_meas, uint8_t* outlier_out, int32_t* inliers_out,
                     sqrtba_stats* stats) {
