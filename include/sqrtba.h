@@ -148,6 +148,54 @@ int sqrtba_pose_opt(sqrtba_handle* h, int32_t n_frames, const int64_t* frame_obs
                     sqrtba_stats* stats);
 int sqrtba_pose_opt_trace(sqrtba_handle* h, int32_t frame, double* rows_out, int32_t max_rows);
 
+/* ---- lidar tight-coupling pass of this fork's LocalBundleAdjustment (src/backend/g2oOptimizer.cc:979-1117) ----
+ * After the two visual passes the reference (1) builds a local lidar map from the flat / corner feature clouds of every
+ * OTHER local keyframe, moved to the world frame with the freshly optimised poses (:985-1013), (2) matches every
+ * feature point of the current keyframe to its nearest map point (pcl::KdTreeFLANN, k = 1) and keeps matches with a
+ * squared distance below lidarConfig::distance_sq_threshold (:1043-1049, :1081-1087), (3) adds one unary edge per match
+ * to the current keyframe's pose -- EdgeLidarFlatPoint (point-to-plane) / EdgeLidarCornerPoint (point-to-point),
+ * types_six_dof_expmap.h:206-262, information = flat/corner_optimized_weight, no robust kernel -- and (4) runs
+ * optimize(20) over visual + lidar edges (:1113-1114).  Here all four steps run on the device inside
+ * sqrtba_solve_local, between pass 2 and the final outlier test, when cfg.third_pass_iters > 0 (20 in the reference).
+ *
+ * sqrtba_set_lidar        hands over the clouds (copied; valid until the next sqrtba_set_problem).  Single-window,
+ *                         single-GPU handles only.  Points are float32 as in pcl::PointXYZI:
+ *     flat_xyz/flat_normal/corner_xyz  the current keyframe's surface_points_less_flat_(+_normal_) /
+ *                         corner_points_less_sharp_ in ITS OWN frame (KeyFrame.h:438-442)
+ *     map_*_xyz/map_*_pose the same clouds of the other local keyframes, each point in its keyframe's frame, with the
+ *                         pose index of that keyframe
+ *     numeric_jacobian    1: central differences with delta = 1e-9 exactly as BaseUnaryEdge::linearizeOplus
+ *                         (base_unary_edge.hpp:82-123), the reference's behaviour; 0: closed-form Jacobians
+ * sqrtba_set_lidar_edges  explicit correspondences instead (callers with their own association, tests): n_flat flat edges
+ *                         followed by n_corner corner edges; point_cam/point_world/normal are n x 3, weight n (0 = no edge)
+ * sqrtba_get_lidar_matches after a solve: per current feature point (flat then corner) the matched map index or -1;
+ *                         returns the number of entries.   sqrtba_num_lidar_edges: edges that took part. */
+typedef struct sqrtba_lidar {
+  int32_t cur_pose;
+  int32_t n_flat;
+  const float* flat_xyz;
+  const float* flat_normal;
+  int32_t n_corner;
+  int32_t numeric_jacobian;
+  const float* corner_xyz;
+  int64_t n_map_flat;
+  const float* map_flat_xyz;
+  const int32_t* map_flat_pose;
+  int64_t n_map_corner;
+  const float* map_corner_xyz;
+  const int32_t* map_corner_pose;
+  double distance_sq_threshold; /* lidarConfig::distance_sq_threshold (cfg/lidar_slam.yaml:52) */
+  double flat_weight;           /* lidarConfig::flat_optimized_weight */
+  double corner_weight;         /* lidarConfig::corner_optimized_weight */
+  int32_t use_flat;             /* lidarConfig::using_flat_point */
+  int32_t use_corner;           /* lidarConfig::using_sharp_point */
+} sqrtba_lidar;
+int sqrtba_set_lidar(sqrtba_handle* h, const sqrtba_lidar* clouds);
+int sqrtba_set_lidar_edges(sqrtba_handle* h, int32_t cur_pose, int32_t n_flat, int32_t n_corner, const double* point_cam,
+                           const double* point_world, const double* normal, const double* weight, int32_t numeric_jacobian);
+int sqrtba_get_lidar_matches(sqrtba_handle* h, int32_t* match_out);
+int sqrtba_num_lidar_edges(sqrtba_handle* h);
+
 /* ---- stage-level entry points (kernel parity tests, profiling) --------------------------------------------
  * sqrtba_debug_linearize : run the fused residual+Jacobian+Huber kernel at the current state.
  *    huber: 0 none, 1 local-BA deltas, 2 global-BA deltas.  Outputs (any may be NULL):

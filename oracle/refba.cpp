@@ -211,6 +211,30 @@ struct Graph {
   int cur_pass = 0;
   double t_solve_s = 0;
 
+  // ---- lidar tight-coupling pass (g2oOptimizer.cc:979-1117): unary edges on the current keyframe, added after the
+  // second visual pass; `lidar` holds the clouds for the kd-tree association, `uedges` the resulting edges
+  struct UEdge {  // EdgeLidarFlatPoint / EdgeLidarCornerPoint, types_six_dof_expmap.h:206-262 (D = 1, no robust kernel)
+    int pose;
+    bool corner;
+    double pc[3], qw[3], n[3];  // curpoint_cameraframe_, lastpoint_worldframe_, curr_point_norm
+    double info;                // flat_optimized_weight / corner_optimized_weight
+    double err = 0;
+    double J[6];
+  };
+  std::vector<UEdge> uedges;
+  bool uactive = false;      // the edges exist in the graph only from the third pass on
+  bool unary_numeric = true; // BaseUnaryEdge::linearizeOplus central differences (the reference) vs closed form
+  struct Lidar {
+    bool set = false;
+    int cur_pose = 0;
+    std::vector<float> flat, flat_n, corner;                 // current keyframe, its own frame
+    std::vector<float> map_flat, map_corner;                 // the other local keyframes, each point in its keyframe's frame
+    std::vector<int32_t> map_flat_pose, map_corner_pose;
+    double thr = 0, w_flat = 0, w_corner = 0;
+    bool use_flat = false, use_corner = false;
+    std::vector<int32_t> match;                              // per current point: matched map index or -1
+  } lidar;
+
   bool terminate() const { return stop ? *stop : false; }  // sparse_optimizer.h:188
 };
 
@@ -317,6 +341,71 @@ inline void linearize(const Graph& g, Edge& e) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// lidar unary edges (types_six_dof_expmap.h:206-262)
+// ---------------------------------------------------------------------------------------------
+// computeError of both edge types: with M = estimate.to_homogeneous_matrix().inverse(), Rwc = M.block(0,0,3,3),
+// Ow = M.col(3).head(3):  d = Rwc.inverse() * (lastpoint_worldframe_ - Ow) - curpoint_cameraframe_;
+// flat: d.dot(curr_point_norm) (:223-224), corner: d.norm() (:252).  The two matrix inverses of a rigid transform are
+// restated in closed form (Rwc = R^T, Ow = -R^T t, Rwc^-1 = R); Eigen's general inverse differs from that by rounding.
+inline double uError(const SE3& T, const Graph::UEdge& e) {
+  double R[9];
+  qtoR(T.r, R);
+  double Ow[3], v[3], d[3];
+  for (int i = 0; i < 3; i++) Ow[i] = -(R[0 * 3 + i] * T.t[0] + R[1 * 3 + i] * T.t[1] + R[2 * 3 + i] * T.t[2]);
+  for (int i = 0; i < 3; i++) v[i] = e.qw[i] - Ow[i];
+  for (int i = 0; i < 3; i++) d[i] = (R[i * 3 + 0] * v[0] + R[i * 3 + 1] * v[1] + R[i * 3 + 2] * v[2]) - e.pc[i];
+  if (e.corner) return std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  return d[0] * e.n[0] + d[1] * e.n[1] + d[2] * e.n[2];
+}
+
+// BaseUnaryEdge::linearizeOplus (base_unary_edge.hpp:82-123): central differences, delta = 1e-9, through the vertex's
+// own oplus (push / oplus / computeError / pop per direction).  unary_numeric = false: the closed form
+// d err / d(omega, upsilon) = [Xc x g, g] with Xc = R q + t and g = n (flat) or d/|d| (corner).
+inline void uLinearize(const Graph& g, Graph::UEdge& e) {
+  const SE3& T = g.pose[e.pose];
+  if (g.unary_numeric) {
+    const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+    for (int d = 0; d < 6; d++) {
+      double add[6] = {0, 0, 0, 0, 0, 0};
+      add[d] = delta;
+      const double e1 = uError(se3mul(se3exp(add), T), e);
+      add[d] = -delta;
+      const double e2 = uError(se3mul(se3exp(add), T), e);
+      e.J[d] = scalar * (e1 - e2);
+    }
+    return;
+  }
+  double Xc[3], gr[3];
+  se3map(T, e.qw, Xc);
+  if (e.corner) {
+    const double d[3] = {Xc[0] - e.pc[0], Xc[1] - e.pc[1], Xc[2] - e.pc[2]};
+    const double n = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    for (int i = 0; i < 3; i++) gr[i] = n > 0 ? d[i] / n : 0.0;
+  } else {
+    for (int i = 0; i < 3; i++) gr[i] = e.n[i];
+  }
+  e.J[0] = Xc[1] * gr[2] - Xc[2] * gr[1];
+  e.J[1] = Xc[2] * gr[0] - Xc[0] * gr[2];
+  e.J[2] = Xc[0] * gr[1] - Xc[1] * gr[0];
+  e.J[3] = gr[0]; e.J[4] = gr[1]; e.J[5] = gr[2];
+}
+
+// BaseUnaryEdge::constructQuadraticForm without robust kernel (base_unary_edge.hpp:58-61)
+inline void uQuadraticForm(Graph& g, const Graph::UEdge& e) {
+  const int ps = g.pose_slot[e.pose];
+  if (ps < 0) return;
+  double* bp = &g.b[(size_t)ps * 6];
+  double* Hp = &g.Hpp[(size_t)ps * 36];
+  for (int i = 0; i < 6; i++) {
+    bp[i] -= e.J[i] * e.info * e.err;
+    for (int j = 0; j < 6; j++) Hp[i * 6 + j] += e.J[i] * e.info * e.J[j];
+  }
+}
+
+// a unary edge is active unless its only vertex is fixed (sparse_optimizer.cpp:218-235 allVerticesFixed)
+inline bool uActive(const Graph& g, const Graph::UEdge& e) { return g.uactive && !g.fixed[e.pose]; }
+
+// ---------------------------------------------------------------------------------------------
 // SparseOptimizer::initializeOptimization(level) + buildIndexMapping + BlockSolver::buildStructure
 // (sparse_optimizer.cpp:199-267, 166-190; block_solver.hpp:143-295)
 // ---------------------------------------------------------------------------------------------
@@ -331,6 +420,9 @@ void initializeOptimization(Graph& g, int level) {
     pose_active[e.pose] = 1;
     point_active[e.point] = 1;
   }
+  if (level <= 0)  // the lidar edges are created with the default level 0
+    for (const Graph::UEdge& e : g.uedges)
+      if (uActive(g, e)) pose_active[e.pose] = 1;
   // index mapping: non-fixed, non-marginalised vertices first (poses), then marginalised (landmarks),
   // each in ascending vertex-id order (sortVectorContainers, sparse_optimizer.cpp:482-487)
   g.pose_slot.assign(g.n_pose, -1);
@@ -414,6 +506,8 @@ void computeActiveErrors(Graph& g) {
   const int n = (int)g.active.size();
 #pragma omp parallel for schedule(static) num_threads(g.threads) if (g.threads > 1)
   for (int k = 0; k < n; k++) computeError(g, g.edges[g.active[k]]);
+  for (Graph::UEdge& e : g.uedges)
+    if (uActive(g, e)) e.err = uError(g.pose[e.pose], e);
 }
 
 // SparseOptimizer::activeRobustChi2 (sparse_optimizer.cpp:100-114): sequential sum in edge order
@@ -427,6 +521,8 @@ double activeRobustChi2(const Graph& g) {
     } else
       chi += chi2(e);
   }
+  for (const Graph::UEdge& e : g.uedges)  // inserted after every visual edge -> last in _activeEdges
+    if (uActive(g, e)) chi += e.err * (e.info * e.err);
   return chi;
 }
 
@@ -484,7 +580,16 @@ inline void constructQuadraticForm(Graph& g, Edge& e, double* Hpp, double* bp_ba
 }
 
 // BlockSolver::buildSystem (block_solver.hpp:502-560)
+void buildSystemVisual(Graph& g);
 void buildSystem(Graph& g) {
+  buildSystemVisual(g);
+  for (Graph::UEdge& e : g.uedges)
+    if (uActive(g, e)) {
+      uLinearize(g, e);
+      uQuadraticForm(g, e);
+    }
+}
+void buildSystemVisual(Graph& g) {
   std::fill(g.b.begin(), g.b.end(), 0.0);
   std::fill(g.Hpp.begin(), g.Hpp.end(), 0.0);
   std::fill(g.Hll.begin(), g.Hll.end(), 0.0);
@@ -861,9 +966,139 @@ static void setHuber(Edge& e, float th2d, float th3d, bool robust) {
 // g2oOptimizer::LocalBundleAdjustment control flow (g2oOptimizer.cc:704-976, 1119-1142) with the stereo edge
 // wired as in ::BundleAdjustment (:247-283) and upstream ORB-SLAM2's stereo thresholds (thHuberStereo :853, 7.815).
 // third_pass_iters = 0 (north_star default) or 20 (the fork's unconditional lidar-coupling pass, :1113-1114).
+// ---- lidar pass: association (g2oOptimizer.cc:981-1107) ------------------------------------------------------------
+// Twc of a keyframe the way the reference gets it: Converter::toCvMat(SE3Quat) (double -> CV_32F 4x4, Converter.cc)
+// followed by cv::Mat::inv().  OpenCV inverts the float matrix by LU; here the inverse of the float-rounded rigid
+// transform is written in closed form, evaluated in double and rounded to float (agrees to float rounding).
+static void twcFloat(const SE3& T, float Rwc[9], float Ow[3]) {
+  double R[9];
+  qtoR(T.r, R);
+  float Rf[9], tf[3];
+  for (int i = 0; i < 9; i++) Rf[i] = (float)R[i];
+  for (int i = 0; i < 3; i++) tf[i] = (float)T.t[i];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) Rwc[i * 3 + j] = Rf[j * 3 + i];
+  for (int i = 0; i < 3; i++)
+    Ow[i] = (float)(-((double)Rf[0 * 3 + i] * tf[0] + (double)Rf[1 * 3 + i] * tf[1] + (double)Rf[2 * 3 + i] * tf[2]));
+}
+// pcl::transformPointCloud(in, out, Eigen::Affine3d): the product is evaluated in double and cast to the float fields
+static void toWorldFloat(const float Rwc[9], const float Ow[3], const float* p, float* out) {
+  for (int i = 0; i < 3; i++)
+    out[i] = (float)((double)Rwc[i * 3 + 0] * p[0] + (double)Rwc[i * 3 + 1] * p[1] + (double)Rwc[i * 3 + 2] * p[2] + (double)Ow[i]);
+}
+// pcl::KdTreeFLANN<PointI>::nearestKSearch(k=1): exact nearest neighbour under flann::L2_Simple<float> (float
+// accumulation of squared differences, no fused multiply-add in a generic x86-64 build).  Brute force here; ties go
+// to the smallest index (a kd-tree may return either).
+__attribute__((optimize("fp-contract=off"))) static int nearestFloat(const std::vector<float>& map, const float* q, float* d2out) {
+  int best = -1;
+  float bd = std::numeric_limits<float>::infinity();
+  const size_t n = map.size() / 3;
+  for (size_t i = 0; i < n; i++) {
+    float r = 0.f;
+    for (int k = 0; k < 3; k++) {
+      const float diff = q[k] - map[i * 3 + k];
+      r += diff * diff;
+    }
+    if (r < bd) { bd = r; best = (int)i; }
+  }
+  *d2out = bd;
+  return best;
+}
+
+static void lidarAssociate(Graph& g) {
+  Graph::Lidar& L = g.lidar;
+  g.uedges.clear();
+  const size_t nf = L.flat.size() / 3, nc = L.corner.size() / 3;
+  L.match.assign(nf + nc, -1);
+  auto worldMap = [&](const std::vector<float>& pts, const std::vector<int32_t>& pose) {
+    std::vector<float> out(pts.size());
+    for (size_t i = 0; i < pose.size(); i++) {
+      float Rwc[9], Ow[3];
+      twcFloat(g.pose[pose[i]], Rwc, Ow);
+      toWorldFloat(Rwc, Ow, &pts[i * 3], &out[i * 3]);
+    }
+    return out;
+  };
+  float Rc[9], Oc[3];
+  twcFloat(g.pose[L.cur_pose], Rc, Oc);
+  auto pass = [&](const std::vector<float>& cur, const std::vector<float>& mapw, bool corner, size_t off) {
+    if (mapw.empty()) return;
+    for (size_t i = 0; i < cur.size() / 3; i++) {
+      float qw[3], d2;
+      toWorldFloat(Rc, Oc, &cur[i * 3], qw);
+      const int j = nearestFloat(mapw, qw, &d2);
+      if (!(d2 < L.thr)) continue;  // float compared against the double threshold, :1049/:1087
+      L.match[off + i] = j;
+      Graph::UEdge e;
+      e.pose = L.cur_pose;
+      e.corner = corner;
+      for (int k = 0; k < 3; k++) {
+        e.pc[k] = cur[i * 3 + k];
+        e.qw[k] = mapw[(size_t)j * 3 + k];
+        e.n[k] = corner ? 0.0 : L.flat_n[i * 3 + k];
+      }
+      e.info = corner ? L.w_corner : L.w_flat;
+      g.uedges.push_back(e);
+    }
+  };
+  if (L.use_flat) pass(L.flat, worldMap(L.map_flat, L.map_flat_pose), false, 0);
+  if (L.use_corner) pass(L.corner, worldMap(L.map_corner, L.map_corner_pose), true, nf);
+}
+
+// explicit correspondences (what the association would produce); w[i] == 0 -> no edge.  Flat edges first.
+void refba_set_lidar_edges(refba* h, int cur_pose, int n_flat, int n_corner, const double* pc, const double* qw,
+                           const double* normal, const double* w, int numeric_jacobian) {
+  Graph& g = h->g;
+  g.lidar.set = false;
+  g.uedges.clear();
+  g.unary_numeric = numeric_jacobian != 0;
+  for (int i = 0; i < n_flat + n_corner; i++) {
+    if (!(w[i] > 0)) continue;
+    Graph::UEdge e;
+    e.pose = cur_pose;
+    e.corner = i >= n_flat;
+    for (int k = 0; k < 3; k++) {
+      e.pc[k] = pc[i * 3 + k];
+      e.qw[k] = qw[i * 3 + k];
+      e.n[k] = e.corner ? 0.0 : normal[i * 3 + k];
+    }
+    e.info = w[i];
+    g.uedges.push_back(e);
+  }
+}
+
+// the clouds of the lidar pass: current keyframe features (own frame) and the features of the other local keyframes
+// (each in its keyframe's frame, with the pose index of that keyframe); thresholds/weights from lidarConfig
+void refba_set_lidar(refba* h, int cur_pose, int n_flat, const float* flat_xyz, const float* flat_normal, int n_corner,
+                     const float* corner_xyz, int64_t n_map_flat, const float* map_flat_xyz, const int32_t* map_flat_pose,
+                     int64_t n_map_corner, const float* map_corner_xyz, const int32_t* map_corner_pose,
+                     double distance_sq_threshold, double flat_weight, double corner_weight, int use_flat, int use_corner,
+                     int numeric_jacobian) {
+  Graph::Lidar& L = h->g.lidar;
+  L.set = true;
+  L.cur_pose = cur_pose;
+  L.flat.assign(flat_xyz, flat_xyz + (size_t)n_flat * 3);
+  L.flat_n.assign(flat_normal, flat_normal + (size_t)n_flat * 3);
+  L.corner.assign(corner_xyz, corner_xyz + (size_t)n_corner * 3);
+  L.map_flat.assign(map_flat_xyz, map_flat_xyz + (size_t)n_map_flat * 3);
+  L.map_flat_pose.assign(map_flat_pose, map_flat_pose + n_map_flat);
+  L.map_corner.assign(map_corner_xyz, map_corner_xyz + (size_t)n_map_corner * 3);
+  L.map_corner_pose.assign(map_corner_pose, map_corner_pose + n_map_corner);
+  L.thr = distance_sq_threshold; L.w_flat = flat_weight; L.w_corner = corner_weight;
+  L.use_flat = use_flat != 0; L.use_corner = use_corner != 0;
+  h->g.unary_numeric = numeric_jacobian != 0;
+  h->g.uedges.clear();
+}
+int refba_lidar_num_matches(refba* h) { return (int)h->g.lidar.match.size(); }
+void refba_get_lidar_matches(refba* h, int32_t* out) {
+  std::memcpy(out, h->g.lidar.match.data(), h->g.lidar.match.size() * sizeof(int32_t));
+}
+int refba_num_lidar_edges(refba* h) { return (int)h->g.uedges.size(); }
+
 int refba_solve_local(refba* h, const volatile bool* stop, int third_pass_iters) {
   Graph& g = h->g;
   g.stop = stop;
+  g.uactive = false;
   g.trace.clear();
   const float thHuberMono = std::sqrt(5.991);     // :851 `const float`
   const float thHuberStereo = std::sqrt(7.815);   // :853
@@ -887,6 +1122,8 @@ int refba_solve_local(refba* h, const volatile bool* stop, int third_pass_iters)
   }
   if (third_pass_iters > 0) {
     g.cur_pass = 2;
+    if (g.lidar.set) lidarAssociate(g);  // local lidar map + kd-tree matches at the pass-2 estimates, :981-1107
+    g.uactive = !g.uedges.empty();
     initializeOptimization(g, 0);
     optimize(g, third_pass_iters);
   }

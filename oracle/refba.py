@@ -49,6 +49,12 @@ def lib():
         L.refba_cam_project_mono.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_double, dp]
         L.refba_cam_project_stereo.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_float, dp]
         L.refba_huber.argtypes = [C.c_double, C.c_double, dp]
+        L.refba_set_lidar_edges.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_int]
+        L.refba_set_lidar.argtypes = [C.c_void_p, C.c_int, C.c_int, fp, fp, C.c_int, fp, C.c_int64, fp, ip, C.c_int64, fp, ip,
+                                      C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]
+        L.refba_lidar_num_matches.argtypes = [C.c_void_p]
+        L.refba_get_lidar_matches.argtypes = [C.c_void_p, ip]
+        L.refba_num_lidar_edges.argtypes = [C.c_void_p]
         L.refba_pose_opt.argtypes = [dp, dp, C.c_int, dp, fp, up, dp, C.c_int, ip]
         _lib = L
     return _lib
@@ -87,6 +93,34 @@ class RefBA:
 
     def solve_global(self, iters: int, robust: bool, stop=None):
         return lib().refba_solve_global(self.h, iters, int(robust), stop)
+
+    def set_lidar_edges(self, cur_pose, pc, qw, normal, w, n_flat, numeric_jacobian=True):
+        """Explicit lidar correspondences for the third pass (flat edges first; w == 0 -> no edge)."""
+        pc, qw, normal, w = (np.ascontiguousarray(a, np.float64) for a in (pc, qw, normal, w))
+        n = len(w)
+        lib().refba_set_lidar_edges(self.h, cur_pose, n_flat, n - n_flat, _p(pc, C.c_double), _p(qw, C.c_double),
+                                    _p(normal, C.c_double), _p(w, C.c_double), int(numeric_jacobian))
+
+    def set_lidar(self, ld, numeric_jacobian=True):
+        """Clouds of the lidar pass (synth.LidarData); the association runs inside solve_local before the third pass."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        a = [f32(ld.flat_xyz), f32(ld.flat_normal), f32(ld.corner_xyz), f32(ld.map_flat_xyz), i32(ld.map_flat_pose),
+             f32(ld.map_corner_xyz), i32(ld.map_corner_pose)]
+        lib().refba_set_lidar(self.h, ld.cur_pose, len(a[0]), _p(a[0], C.c_float), _p(a[1], C.c_float), len(a[2]),
+                              _p(a[2], C.c_float), len(a[3]), _p(a[3], C.c_float), _p(a[4], C.c_int32), len(a[5]),
+                              _p(a[5], C.c_float), _p(a[6], C.c_int32), ld.distance_sq_threshold, ld.flat_weight,
+                              ld.corner_weight, int(ld.use_flat), int(ld.use_corner), int(numeric_jacobian))
+
+    def lidar_matches(self):
+        n = lib().refba_lidar_num_matches(self.h)
+        out = np.full(n, -1, np.int32)
+        if n:
+            lib().refba_get_lidar_matches(self.h, _p(out, C.c_int32))
+        return out
+
+    def num_lidar_edges(self) -> int:
+        return lib().refba_num_lidar_edges(self.h)
 
     def solve_seconds(self) -> float:
         return lib().refba_solve_seconds(self.h)

@@ -33,6 +33,16 @@ class Stats(C.Structure):
         return d
 
 
+class Lidar(C.Structure):  # include/sqrtba.h: sqrtba_lidar
+    _fields_ = [("cur_pose", C.c_int32), ("n_flat", C.c_int32), ("flat_xyz", C.POINTER(C.c_float)),
+                ("flat_normal", C.POINTER(C.c_float)), ("n_corner", C.c_int32), ("numeric_jacobian", C.c_int32),
+                ("corner_xyz", C.POINTER(C.c_float)), ("n_map_flat", C.c_int64), ("map_flat_xyz", C.POINTER(C.c_float)),
+                ("map_flat_pose", C.POINTER(C.c_int32)), ("n_map_corner", C.c_int64),
+                ("map_corner_xyz", C.POINTER(C.c_float)), ("map_corner_pose", C.POINTER(C.c_int32)),
+                ("distance_sq_threshold", C.c_double), ("flat_weight", C.c_double), ("corner_weight", C.c_double),
+                ("use_flat", C.c_int32), ("use_corner", C.c_int32)]
+
+
 TRACE_COLS = ("pass", "iter", "trial", "lambda", "chi_before", "chi_trial", "rho", "accepted", "cg_iters", "cg_relres")
 
 
@@ -69,6 +79,10 @@ def lib():
         L.sqrtba_time_stage.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, dp]
         L.sqrtba_pose_opt.argtypes = [vp, C.c_int32, lp, dp, dp, dp, fp, up, ip, C.POINTER(Stats)]
         L.sqrtba_pose_opt_trace.argtypes = [vp, C.c_int32, dp, C.c_int32]
+        L.sqrtba_set_lidar.argtypes = [vp, C.POINTER(Lidar)]
+        L.sqrtba_set_lidar_edges.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, dp, dp, dp, dp, C.c_int32]
+        L.sqrtba_get_lidar_matches.argtypes = [vp, ip]
+        L.sqrtba_num_lidar_edges.argtypes = [vp]
         L.sqrtba_comm_unique_id.argtypes = [up]
         L.sqrtba_comm_init.argtypes = [vp, C.c_int32, C.c_int32, up]
         L.sqrtba_comm_destroy.argtypes = [vp]
@@ -151,6 +165,35 @@ class SqrtBA:
                                                  _p(op, C.c_int64), _p(a[0], C.c_double), _p(a[1], C.c_uint8),
                                                  _p(a[2], C.c_double), _p(a[3], C.c_double), _p(a[4], C.c_int32),
                                                  _p(a[5], C.c_int32), _p(a[6], C.c_float)), "sqrtba_set_problem_batch")
+
+    def set_lidar(self, ld, numeric_jacobian: bool = True):
+        """Clouds of the lidar tight-coupling pass (synth.LidarData layout); needs third_pass_iters > 0 to take part."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        a = [f32(ld.flat_xyz), f32(ld.flat_normal), f32(ld.corner_xyz), f32(ld.map_flat_xyz), i32(ld.map_flat_pose),
+             f32(ld.map_corner_xyz), i32(ld.map_corner_pose)]
+        c = Lidar(cur_pose=ld.cur_pose, n_flat=len(a[0]), flat_xyz=_p(a[0], C.c_float), flat_normal=_p(a[1], C.c_float),
+                  n_corner=len(a[2]), numeric_jacobian=int(numeric_jacobian), corner_xyz=_p(a[2], C.c_float),
+                  n_map_flat=len(a[3]), map_flat_xyz=_p(a[3], C.c_float), map_flat_pose=_p(a[4], C.c_int32),
+                  n_map_corner=len(a[5]), map_corner_xyz=_p(a[5], C.c_float), map_corner_pose=_p(a[6], C.c_int32),
+                  distance_sq_threshold=ld.distance_sq_threshold, flat_weight=ld.flat_weight,
+                  corner_weight=ld.corner_weight, use_flat=int(ld.use_flat), use_corner=int(ld.use_corner))
+        self._chk(lib().sqrtba_set_lidar(self.h, C.byref(c)), "sqrtba_set_lidar")
+        self._n_lidar = len(a[0]) + len(a[2])
+
+    def set_lidar_edges(self, cur_pose, pc, qw, normal, w, n_flat, numeric_jacobian: bool = True):
+        pc, qw, normal, w = (np.ascontiguousarray(a, np.float64) for a in (pc, qw, normal, w))
+        self._chk(lib().sqrtba_set_lidar_edges(self.h, cur_pose, n_flat, len(w) - n_flat, _p(pc, C.c_double),
+                                               _p(qw, C.c_double), _p(normal, C.c_double), _p(w, C.c_double),
+                                               int(numeric_jacobian)), "sqrtba_set_lidar_edges")
+
+    def lidar_matches(self) -> np.ndarray:
+        out = np.full(max(getattr(self, "_n_lidar", 0), 1), -1, np.int32)
+        n = self._chk(lib().sqrtba_get_lidar_matches(self.h, _p(out, C.c_int32)), "sqrtba_get_lidar_matches")
+        return out[:n]
+
+    def num_lidar_edges(self) -> int:
+        return self._chk(lib().sqrtba_num_lidar_edges(self.h), "sqrtba_num_lidar_edges")
 
     def reset_state(self):
         self._chk(lib().sqrtba_reset_state(self.h), "sqrtba_reset_state")

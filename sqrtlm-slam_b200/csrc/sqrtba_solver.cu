@@ -23,6 +23,7 @@
 #include "../../include/sqrtba.h"
 #include "sqrtba_kernels.cuh"
 #include "sqrtba_poseopt.cuh"
+#include "sqrtba_lidar.cuh"
 
 namespace sqrtba {
 
@@ -221,6 +222,7 @@ class Solver {
     }
     if (!plan_only_) CU_CHECK(cudaSetDevice(cfg_.device));
     have_problem_ = false;
+    lidar_edges_set_ = lidar_assoc_set_ = lidar_active_ = false;  // pose indices of the old problem
     std::vector<int> pose_win(n_pose, 0), point_win(n_point, 0);
     if (n_win > 1) {
       if (!wpose || !wpoint || !wobs || wpose[n_win] != n_pose || wpoint[n_win] != n_point || wobs[n_win] != n_obs) {
@@ -754,7 +756,10 @@ class Solver {
       if (rc) return rc;
     }
     if (cfg_.third_pass_iters > 0) {
+      if (lidar_assoc_set_)
+        if ((rc = lidar_associate())) return rc;
       rc = run_pass(cfg_.third_pass_iters, 2, 0, d2, d3, stop);
+      lidar_active_ = false;
       if (rc) return rc;
     }
     launch_classify(1, 5.991, 7.815);
@@ -852,6 +857,124 @@ class Solver {
 
   // ------------------------------------------------------------------------------------------ pose-only optimisation
   // g2oOptimizer::PoseOptimization for a batch of frames (one CTA per frame, one launch); independent of set_problem.
+  // ------------------------------------------------------------------------------------------ lidar pass (row N4)
+  int lidar_check(int cur_pose, const char* who) {
+    if (!have_problem_) { err_ = std::string(who) + ": no problem set"; return SQRTBA_ERR_INVALID; }
+    if (P_.n_win != 1 || comm_) { err_ = std::string(who) + ": the lidar pass belongs to one local-BA window on one GPU"; return SQRTBA_ERR_INVALID; }
+    if (cur_pose < 0 || cur_pose >= P_.n_pose) { err_ = std::string(who) + ": pose index out of range"; return SQRTBA_ERR_INVALID; }
+    return SQRTBA_OK;
+  }
+  int lidar_alloc_edges(int n_edge) {
+    const size_t n = (size_t)std::max(n_edge, 1);
+    CU_CHECK(d_l_pc_.ensure(n * 3));
+    CU_CHECK(d_l_qw_.ensure(n * 3));
+    CU_CHECK(d_l_nv_.ensure(n * 3));
+    CU_CHECK(d_l_w_.ensure(n));
+    CU_CHECK(d_l_acc_.ensure(LD_ACC));
+    CU_CHECK(d_l_match_.ensure(n));
+    lidar_.pc = d_l_pc_.p; lidar_.qw = d_l_qw_.p; lidar_.nv = d_l_nv_.p; lidar_.w = d_l_w_.p; lidar_.acc = d_l_acc_.p;
+    return SQRTBA_OK;
+  }
+  // explicit correspondences: what the association would produce (flat edges first, weight 0 = no edge)
+  int set_lidar_edges(int cur_pose, int n_flat, int n_corner, const double* pc, const double* qw, const double* normal,
+                      const double* w, int numeric) {
+    if (int rc = lidar_check(cur_pose, "set_lidar_edges")) return rc;
+    const int n = n_flat + n_corner;
+    if (n_flat < 0 || n_corner < 0 || (n > 0 && (!pc || !qw || !normal || !w))) { err_ = "set_lidar_edges: bad arrays"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    if (int rc = lidar_alloc_edges(n)) return rc;
+    if (n > 0) {
+      CU_CHECK(cudaMemcpyAsync(d_l_pc_.p, pc, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, stream_));
+      CU_CHECK(cudaMemcpyAsync(d_l_qw_.p, qw, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, stream_));
+      CU_CHECK(cudaMemcpyAsync(d_l_nv_.p, normal, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, stream_));
+      CU_CHECK(cudaMemcpyAsync(d_l_w_.p, w, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream_));
+      CU_CHECK(cudaStreamSynchronize(stream_));  // the caller's arrays may go away
+    }
+    lidar_.n_edge = n; lidar_.n_flat = n_flat; lidar_.pose = cur_pose; lidar_.numeric = numeric ? 1 : 0;
+    lidar_edges_set_ = n > 0;
+    lidar_assoc_set_ = false;
+    return SQRTBA_OK;
+  }
+  // the clouds of the pass; the association itself runs on the device inside solve_local, at the pass-2 estimates
+  int set_lidar(const sqrtba_lidar* c) {
+    if (!c) { err_ = "set_lidar: null"; return SQRTBA_ERR_INVALID; }
+    if (int rc = lidar_check(c->cur_pose, "set_lidar")) return rc;
+    if (c->n_flat < 0 || c->n_corner < 0 || c->n_map_flat < 0 || c->n_map_corner < 0 ||
+        (c->n_flat > 0 && (!c->flat_xyz || !c->flat_normal)) || (c->n_corner > 0 && !c->corner_xyz) ||
+        (c->n_map_flat > 0 && (!c->map_flat_xyz || !c->map_flat_pose)) ||
+        (c->n_map_corner > 0 && (!c->map_corner_xyz || !c->map_corner_pose)) ||
+        c->n_map_flat > 0x7fffffffLL || c->n_map_corner > 0x7fffffffLL) {
+      err_ = "set_lidar: bad arrays";
+      return SQRTBA_ERR_INVALID;
+    }
+    for (long long i = 0; i < c->n_map_flat; i++)
+      if (c->map_flat_pose[i] < 0 || c->map_flat_pose[i] >= P_.n_pose) { err_ = "set_lidar: map pose index out of range"; return SQRTBA_ERR_INVALID; }
+    for (long long i = 0; i < c->n_map_corner; i++)
+      if (c->map_corner_pose[i] < 0 || c->map_corner_pose[i] >= P_.n_pose) { err_ = "set_lidar: map pose index out of range"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    const int n = c->n_flat + c->n_corner;
+    if (int rc = lidar_alloc_edges(n)) return rc;
+    const size_t nf = (size_t)std::max(c->n_flat, 1), nc = (size_t)std::max(c->n_corner, 1);
+    const size_t mf = (size_t)std::max<long long>(c->n_map_flat, 1), mc = (size_t)std::max<long long>(c->n_map_corner, 1);
+    CU_CHECK(d_lc_flat_.ensure(nf * 3)); CU_CHECK(d_lc_normal_.ensure(nf * 3)); CU_CHECK(d_lc_corner_.ensure(nc * 3));
+    CU_CHECK(d_lm_flat_.ensure(mf * 3)); CU_CHECK(d_lm_flat_w_.ensure(mf * 3)); CU_CHECK(d_lm_flat_pose_.ensure(mf));
+    CU_CHECK(d_lm_corner_.ensure(mc * 3)); CU_CHECK(d_lm_corner_w_.ensure(mc * 3)); CU_CHECK(d_lm_corner_pose_.ensure(mc));
+    CU_CHECK(d_lc_world_.ensure((size_t)std::max(n, 1) * 3)); CU_CHECK(d_l_best_.ensure((size_t)std::max(n, 1)));
+    auto up = [&](void* dst, const void* src, size_t bytes) {
+      return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_) : cudaSuccess;
+    };
+    CU_CHECK(up(d_lc_flat_.p, c->flat_xyz, (size_t)c->n_flat * 3 * sizeof(float)));
+    CU_CHECK(up(d_lc_normal_.p, c->flat_normal, (size_t)c->n_flat * 3 * sizeof(float)));
+    CU_CHECK(up(d_lc_corner_.p, c->corner_xyz, (size_t)c->n_corner * 3 * sizeof(float)));
+    CU_CHECK(up(d_lm_flat_.p, c->map_flat_xyz, (size_t)c->n_map_flat * 3 * sizeof(float)));
+    CU_CHECK(up(d_lm_flat_pose_.p, c->map_flat_pose, (size_t)c->n_map_flat * sizeof(int)));
+    CU_CHECK(up(d_lm_corner_.p, c->map_corner_xyz, (size_t)c->n_map_corner * 3 * sizeof(float)));
+    CU_CHECK(up(d_lm_corner_pose_.p, c->map_corner_pose, (size_t)c->n_map_corner * sizeof(int)));
+    CU_CHECK(cudaStreamSynchronize(stream_));
+    LidarAssoc& A = assoc_;
+    A.pose = c->cur_pose; A.n_flat = c->n_flat; A.n_corner = c->n_corner;
+    A.flat = d_lc_flat_.p; A.flat_n = d_lc_normal_.p; A.corner = d_lc_corner_.p;
+    A.n_map_flat = c->n_map_flat; A.n_map_corner = c->n_map_corner;
+    A.map_flat = d_lm_flat_.p; A.map_flat_pose = d_lm_flat_pose_.p; A.map_corner = d_lm_corner_.p; A.map_corner_pose = d_lm_corner_pose_.p;
+    A.map_flat_w = d_lm_flat_w_.p; A.map_corner_w = d_lm_corner_w_.p; A.cur_w = d_lc_world_.p;
+    A.best = d_l_best_.p; A.match = d_l_match_.p;
+    A.thr = c->distance_sq_threshold; A.w_flat = c->flat_weight; A.w_corner = c->corner_weight;
+    A.use_flat = c->use_flat ? 1 : 0; A.use_corner = c->use_corner ? 1 : 0;
+    lidar_.n_edge = n; lidar_.n_flat = c->n_flat; lidar_.pose = c->cur_pose; lidar_.numeric = c->numeric_jacobian ? 1 : 0;
+    lidar_assoc_set_ = n > 0;
+    lidar_edges_set_ = false;
+    return SQRTBA_OK;
+  }
+  // local lidar map + nearest-neighbour matches + edges, all at the current device estimates (g2oOptimizer.cc:981-1107)
+  int lidar_associate() {
+    const LidarAssoc& A = assoc_;
+    const int n = A.n_flat + A.n_corner;
+    if (A.n_map_flat > 0) k_lidar_to_world<<<cdiv((int)A.n_map_flat, 256), 256, 0, stream_>>>(P_, A, 0);
+    if (A.n_map_corner > 0) k_lidar_to_world<<<cdiv((int)A.n_map_corner, 256), 256, 0, stream_>>>(P_, A, 1);
+    k_lidar_to_world<<<cdiv(n, 256), 256, 0, stream_>>>(P_, A, 2);
+    if (A.use_flat && A.n_flat > 0 && A.n_map_flat > 0)
+      k_lidar_nn<<<dim3(cdiv(A.n_flat, LD_NN_CTA), cdiv((int)A.n_map_flat, LD_NN_CHUNK)), LD_NN_CTA, 0, stream_>>>(A, 0);
+    if (A.use_corner && A.n_corner > 0 && A.n_map_corner > 0)
+      k_lidar_nn<<<dim3(cdiv(A.n_corner, LD_NN_CTA), cdiv((int)A.n_map_corner, LD_NN_CHUNK)), LD_NN_CTA, 0, stream_>>>(A, 1);
+    k_lidar_edges<<<cdiv(n, 256), 256, 0, stream_>>>(A, lidar_);
+    launches_ += 6;
+    CU_CHECK(cudaGetLastError());
+    return SQRTBA_OK;
+  }
+  int get_lidar_matches(int32_t* out) {
+    if (!lidar_assoc_set_ || !out) { err_ = "get_lidar_matches: no lidar clouds set"; return SQRTBA_ERR_INVALID; }
+    if (download(out, d_l_match_.p, (size_t)lidar_.n_edge * sizeof(int))) return SQRTBA_ERR_CUDA;
+    return lidar_.n_edge;
+  }
+  int num_lidar_edges() {
+    if (!lidar_assoc_set_ && !lidar_edges_set_) return 0;
+    std::vector<double> w((size_t)lidar_.n_edge);
+    if (download(w.data(), d_l_w_.p, w.size() * sizeof(double))) return SQRTBA_ERR_CUDA;
+    int n = 0;
+    for (double v : w) n += v > 0.0;
+    return n;
+  }
+
   int pose_opt(int n_frames, const int64_t* frame_ptr, double* pose_qt, const double* cam, const double* obs_xyz,
                const float* obs_meas, uint8_t* outlier_out, int32_t* inliers_out, sqrtba_stats* st) {
     if (n_frames <= 0 || !frame_ptr || !pose_qt || !cam || !inliers_out) { err_ = "pose_opt: bad arguments"; return SQRTBA_ERR_INVALID; }
@@ -1223,6 +1346,7 @@ class Solver {
   }
   bool use_persist() const {
     if (cfg_.pcg_mode == 1 || !coop_ok_ || P_.n_win != 1 || !P_.smallwin || persist_ctas_ <= 0 || cfg_.reserved[1] != 0) return false;
+    if (lidar_active_) return false;  // the unary term H_u p is added between the matvec and the CG update (multi-launch loop)
     if (comm_ && (!peer_ok_ || P_.pq_shared)) return false;  // sharded without peer-mapped buffers, or a small window: NCCL all-reduce per iteration
     return true;
   }
@@ -1345,6 +1469,7 @@ class Solver {
     launches_ += 2;
     if (!P_.n_slot) return SQRTBA_OK;
     if (int rc = allreduce(P_.bs, (size_t)P_.n_slot * 27, false)) return rc;  // reduced rhs + block-Jacobi blocks
+    if (lidar_active_) { k_lidar_trial_add<<<1, 32, 0, stream_>>>(P_, lidar_); launches_++; }
     k_dinv<<<cdiv(P_.n_slot, 64), 64, 0, stream_>>>(P_, 0, 0.0);
     stage_begin(2);
     CU_CHECK(cudaMemsetAsync(P_.counters + 1, 0, sizeof(int), stream_));
@@ -1375,6 +1500,7 @@ class Solver {
       launch_matvec(P_.p, P_.q, 0);
       if (eb) cudaEventRecord(eb, stream_);
       if (int rc = allreduce(P_.q, (size_t)P_.n_slot * 6, false)) return rc;  // the one exchange step of a CG iteration
+      if (lidar_active_) { k_lidar_matvec<<<1, 32, 0, stream_>>>(P_, lidar_, P_.p, P_.q); launches_++; }
       k_cg_step<<<P_.n_win, RCTA, 0, stream_>>>(P_, tol2, cfg_.pcg_max_iters, 0, 0.0);
       launches_ += 2;
       cg_iters_total_++;
@@ -1392,6 +1518,7 @@ class Solver {
   // one optimizer.optimize(iters) call over all windows (sparse_optimizer.cpp:354-419)
   int run_pass(int iters, int pass, int robust, double d2, double d3, const volatile bool* stop) {
     const int gi = cdiv(P_.n_item, WARPS);
+    lidar_active_ = pass == 2 && (lidar_edges_set_ || lidar_assoc_set_);  // the edges join the graph for the third pass only
     k_pass_init<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_, iters, pass);
     CU_CHECK(cudaMemsetAsync(P_.counters, 0, 2 * sizeof(int), stream_));
     launches_++;
@@ -1404,6 +1531,7 @@ class Solver {
       stage_begin(0);
       launch_linearize(robust, d2, d3, 0);
       stage_end(0);
+      if (lidar_active_) { k_lidar_lin<<<1, LD_CTA, 0, stream_>>>(P_, lidar_); launches_++; }
       if (int rc = begin_after_linearize()) return rc;
       launches_ += 4;
       int rc = factor_and_solve();
@@ -1418,6 +1546,7 @@ class Solver {
       stage_begin(4);
       k_cost<<<gi, CTA, 0, stream_>>>(P_, robust, d2, d3);
       stage_end(4);
+      if (lidar_active_) { k_lidar_cost<<<1, LD_CTA, 0, stream_>>>(P_, lidar_); launches_++; }
       k_lm_reduce_trial<<<P_.n_win, RCTA, 0, stream_>>>(P_);
       if (int rc = allreduce(P_.wred, (size_t)2 * P_.n_win, false)) return rc;  // trial chi2 + landmark part of the scale
       k_lm_decide<<<P_.n_win, RCTA, 0, stream_>>>(P_, term);
@@ -1495,6 +1624,9 @@ class Solver {
     d_ctl_.release(); d_trace_.release(); d_counters_.release(); d_wred_.release();
     d_tiles_.release(); d_obs_lp_.release(); d_tile_run_ptr_.release(); d_tile_runs_.release();
     d_gbar_.release(); d_part_.release(); d_q3_.release(); d_dq_.release(); d_ptile_.release();
+    d_l_pc_.release(); d_l_qw_.release(); d_l_nv_.release(); d_l_w_.release(); d_l_acc_.release(); d_l_match_.release();
+    d_lm_flat_pose_.release(); d_lm_corner_pose_.release(); d_lc_flat_.release(); d_lc_normal_.release(); d_lc_corner_.release();
+    d_lc_world_.release(); d_lm_flat_.release(); d_lm_flat_w_.release(); d_lm_corner_.release(); d_lm_corner_w_.release(); d_l_best_.release();
     d_po_ptr_.release(); d_po_pose_.release(); d_po_cam_.release(); d_po_xyz_.release(); d_po_err_.release(); d_po_trace_.release();
     d_po_meas_.release(); d_po_level_.release(); d_po_outlier_.release(); d_po_inl_.release();
     h_obs_slot_.release(); h_item_start_.release(); h_item_cnt_.release(); h_item_win_.release();
@@ -1534,6 +1666,14 @@ class Solver {
   size_t peer_nelem_cap_ = 0;
   DBuf<unsigned> d_gbar_;
   DBuf<double> d_part_, d_q3_, d_dq_;
+  // lidar pass
+  LidarDev lidar_{};
+  LidarAssoc assoc_{};
+  bool lidar_edges_set_ = false, lidar_assoc_set_ = false, lidar_active_ = false;
+  DBuf<double> d_l_pc_, d_l_qw_, d_l_nv_, d_l_w_, d_l_acc_;
+  DBuf<int> d_l_match_, d_lm_flat_pose_, d_lm_corner_pose_;
+  DBuf<float> d_lc_flat_, d_lc_normal_, d_lc_corner_, d_lc_world_, d_lm_flat_, d_lm_flat_w_, d_lm_corner_, d_lm_corner_w_;
+  DBuf<unsigned long long> d_l_best_;
   DBuf<long long> d_po_ptr_;
   DBuf<double> d_po_pose_, d_po_cam_, d_po_xyz_, d_po_err_, d_po_trace_;
   DBuf<float4> d_po_meas_;
@@ -1694,6 +1834,14 @@ int sqrtba_pose_opt(sqrtba_handle* h, int32_t n_frames, const int64_t* frame_obs
 int sqrtba_pose_opt_trace(sqrtba_handle* h, int32_t frame, double* rows_out, int32_t max_rows) {
   return h ? h->s->pose_opt_trace(frame, rows_out, max_rows) : SQRTBA_ERR_INVALID;
 }
+int sqrtba_set_lidar(sqrtba_handle* h, const sqrtba_lidar* clouds) { return h ? h->s->set_lidar(clouds) : SQRTBA_ERR_INVALID; }
+int sqrtba_set_lidar_edges(sqrtba_handle* h, int32_t cur_pose, int32_t n_flat, int32_t n_corner, const double* point_cam,
+                           const double* point_world, const double* normal, const double* weight, int32_t numeric_jacobian) {
+  return h ? h->s->set_lidar_edges(cur_pose, n_flat, n_corner, point_cam, point_world, normal, weight, numeric_jacobian)
+           : SQRTBA_ERR_INVALID;
+}
+int sqrtba_get_lidar_matches(sqrtba_handle* h, int32_t* match_out) { return h ? h->s->get_lidar_matches(match_out) : SQRTBA_ERR_INVALID; }
+int sqrtba_num_lidar_edges(sqrtba_handle* h) { return h ? h->s->num_lidar_edges() : SQRTBA_ERR_INVALID; }
 int sqrtba_comm_unique_id(uint8_t* id128) {
   if (!id128) return SQRTBA_ERR_INVALID;
   if (!sqrtba::g_nccl.load()) return SQRTBA_ERR_COMM;

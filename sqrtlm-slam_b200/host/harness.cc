@@ -69,6 +69,26 @@ void hh_set_bad(hh_map* m, int kf, int mp) {
   if (mp >= 0) m->mps[mp]->mbBad = true;
 }
 
+// lidar features of one keyframe (own frame) and the lidarConfig fields of the lidar pass
+void hh_set_lidar_cloud(hh_map* m, int kf, int n_flat, const float* flat_xyz, const float* flat_normal, int n_corner,
+                        const float* corner_xyz) {
+  KeyFrame* k = m->kfs[kf].get();
+  auto fill = [](PointIRTCloud& c, int n, const float* xyz) {
+    c.points.resize((size_t)n);
+    for (int i = 0; i < n; i++) { c.points[i].x = xyz[i * 3]; c.points[i].y = xyz[i * 3 + 1]; c.points[i].z = xyz[i * 3 + 2]; }
+  };
+  fill(k->surface_points_less_flat_, n_flat, flat_xyz);
+  fill(k->surface_points_less_flat_normal_, flat_normal ? n_flat : 0, flat_normal);
+  fill(k->corner_points_less_sharp_, n_corner, corner_xyz);
+}
+void hh_set_lidar_config(hh_map* m, int use_flat, int use_corner, double thr, double w_flat, double w_corner) {
+  m->lidar.using_flat_point = use_flat != 0;
+  m->lidar.using_sharp_point = use_corner != 0;
+  m->lidar.distance_sq_threshold = thr;
+  m->lidar.flat_optimized_weight = w_flat;
+  m->lidar.corner_optimized_weight = w_corner;
+}
+
 void hh_local_ba(hh_map* m, int kf, bool* stop) {
   Optimizer::LocalBundleAdjustment(m->kfs[kf].get(), stop, &m->map, &m->lidar);
 }

@@ -33,9 +33,17 @@ class Mat {  // row-major float matrix, value semantics like a cloned cv::Mat
 };
 }  // namespace cv
 
-struct lidarConfig {  // include/utils/lidarconfig.h -- passed through LocalBundleAdjustment, unused by the visual passes
+struct lidarConfig {  // include/utils/lidarconfig.h:51-56 -- the fields the lidar pass of LocalBundleAdjustment reads
   bool using_flat_point = false, using_sharp_point = false;
   double distance_sq_threshold = 0, flat_optimized_weight = 0, corner_optimized_weight = 0;
+};
+
+// include/data_structure/point_types.h:16-23,52-53: PointXYZIRT and pcl::PointCloud<PointIRT>, cut down to what
+// g2oOptimizer.cc:994-1096 touches (points[i].x/y/z, size())
+struct PointIRT { float x = 0, y = 0, z = 0; };
+struct PointIRTCloud {
+  std::vector<PointIRT> points;
+  size_t size() const { return points.size(); }
 };
 
 namespace ORB_SLAM2 {
@@ -61,6 +69,8 @@ class KeyFrame {
     for (auto& p : mvpMapPoints)
       if (p == pMP) p = nullptr;
   }
+  // lidar features of the keyframe in its own frame (KeyFrame.h:437-442)
+  PointIRTCloud corner_points_less_sharp_, surface_points_less_flat_, surface_points_less_flat_normal_;
   // test-side construction
   cv::Mat Tcw;
   bool mbBad = false;

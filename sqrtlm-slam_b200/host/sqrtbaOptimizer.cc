@@ -34,10 +34,13 @@ struct Handle {
   ~Handle() {
     if (h) sqrtba_destroy(h);
   }
+  int third_pass_iters = 0;
+  explicit Handle(int third = 0) : third_pass_iters(third) {}
   sqrtba_handle* get() {
     if (!h) {
       sqrtba_config cfg;
       sqrtba_default_config(&cfg);
+      cfg.third_pass_iters = third_pass_iters;
       if (sqrtba_create(&cfg, &h) != SQRTBA_OK) {
         err = sqrtba_last_error(nullptr);
         h = nullptr;
@@ -47,6 +50,7 @@ struct Handle {
   }
 };
 thread_local Handle tl_handle;  // LocalMapping and the GBA thread each get their own (Optimizer.h is re-entrant across threads)
+thread_local Handle tl_handle_lidar(20);  // local BA with the fork's lidar pass: optimize(20) after the two visual passes (:1113-1114)
 
 // Converter::toSE3Quat (src/utils/Converter.cc:55-68) without Eigen: float 4x4 Tcw -> (t, unit quaternion with w >= 0)
 void toSE3Quat(const cv::Mat& T, double out7[7]) {
@@ -177,7 +181,7 @@ bool upload(Handle& H, const Gathered& g) {
 
 }  // namespace
 
-const char* sqrtbaOptimizer::LastError() { return tl_handle.err.c_str(); }
+const char* sqrtbaOptimizer::LastError() { return tl_handle.err.empty() ? tl_handle_lidar.err.c_str() : tl_handle.err.c_str(); }
 
 void sqrtbaOptimizer::GlobalBundleAdjustemnt(Map* pMap, int nIterations, bool* pbStopFlag, const unsigned long nLoopKF,
                                              const bool bRobust) {
@@ -232,7 +236,54 @@ void sqrtbaOptimizer::BundleAdjustment(const std::vector<KeyFrame*>& vpKFs, cons
   }
 }
 
-void sqrtbaOptimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* /*lidarconfig*/) {
+namespace {
+// The clouds of the lidar pass (g2oOptimizer.cc:985-1013, 1033-1107) in the layout of sqrtba_set_lidar: the current
+// keyframe's features in its own frame, and the features of every OTHER local keyframe tagged with that keyframe's pose
+// index.  The reference moves the map clouds to the world frame and searches a kd-tree on the host; both happen on the
+// device here, at the estimates of the second pass.
+struct LidarClouds {
+  std::vector<float> flat, flat_n, corner, map_flat, map_corner;
+  std::vector<int32_t> map_flat_pose, map_corner_pose;
+};
+void append(const PointIRTCloud& c, std::vector<float>& xyz, std::vector<int32_t>* pose, int idx) {
+  for (const PointIRT& p : c.points) {
+    xyz.push_back(p.x); xyz.push_back(p.y); xyz.push_back(p.z);
+    if (pose) pose->push_back(idx);
+  }
+}
+bool set_lidar(sqrtba_handle* h, const Gathered& g, KeyFrame* pKF, const lidarConfig* cfg) {
+  LidarClouds L;
+  int cur = -1;
+  for (size_t i = 0; i < g.kfs.size(); i++) {
+    KeyFrame* kf = g.kfs[i];
+    if (kf == pKF) { cur = (int)i; continue; }
+    if (kf->mnBALocalForKF != pKF->mnId) continue;  // lLocalKeyFrames only (:986-992); fixed keyframes add nothing
+    append(kf->corner_points_less_sharp_, L.map_corner, &L.map_corner_pose, (int)i);
+    append(kf->surface_points_less_flat_, L.map_flat, &L.map_flat_pose, (int)i);
+  }
+  if (cur < 0) return false;
+  append(pKF->surface_points_less_flat_, L.flat, nullptr, 0);
+  append(pKF->surface_points_less_flat_normal_, L.flat_n, nullptr, 0);
+  append(pKF->corner_points_less_sharp_, L.corner, nullptr, 0);
+  if (L.flat_n.size() != L.flat.size()) return false;  // the normal cloud is index-aligned with the flat cloud (:1060-1062)
+  sqrtba_lidar c{};
+  c.cur_pose = cur;
+  c.n_flat = (int32_t)(L.flat.size() / 3); c.flat_xyz = L.flat.data(); c.flat_normal = L.flat_n.data();
+  c.n_corner = (int32_t)(L.corner.size() / 3); c.corner_xyz = L.corner.data();
+  c.numeric_jacobian = 1;  // BaseUnaryEdge::linearizeOplus, as the reference
+  c.n_map_flat = (int64_t)L.map_flat_pose.size(); c.map_flat_xyz = L.map_flat.data(); c.map_flat_pose = L.map_flat_pose.data();
+  c.n_map_corner = (int64_t)L.map_corner_pose.size(); c.map_corner_xyz = L.map_corner.data(); c.map_corner_pose = L.map_corner_pose.data();
+  c.distance_sq_threshold = cfg->distance_sq_threshold;
+  c.flat_weight = cfg->flat_optimized_weight;
+  c.corner_weight = cfg->corner_optimized_weight;
+  c.use_flat = cfg->using_flat_point;
+  c.use_corner = cfg->using_sharp_point;
+  if (c.n_flat + c.n_corner == 0) return true;  // nothing to match: the plain third pass
+  return sqrtba_set_lidar(h, &c) == SQRTBA_OK;
+}
+}  // namespace
+
+void sqrtbaOptimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* lidarconfig) {
   // ---- local keyframes: pKF + its covisible keyframes (g2oOptimizer.cc:709-727)
   std::list<KeyFrame*> lLocalKeyFrames;
   lLocalKeyFrames.push_back(pKF);
@@ -273,9 +324,16 @@ void sqrtbaOptimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map
          [cur](KeyFrame* kf) { return kf->mnBALocalForKF != cur || kf->mnId == 0; },  // :813, :829
          [](KeyFrame* kf) { return !kf->isBad(); }, g);                                // :872
   if (pbStopFlag && *pbStopFlag) return;  // :923-928
-  Handle& H = tl_handle;
-  if (!upload(H, g)) return;
+  // the fork's third pass (lidar edges on pKF + optimize(20), :979-1117) runs when the configuration asks for lidar
+  // features; without them the two-pass schedule of ORB-SLAM2 is used
+  const bool with_lidar = lidarconfig && (lidarconfig->using_flat_point || lidarconfig->using_sharp_point);
+  Handle& H = with_lidar ? tl_handle_lidar : tl_handle;
+  if (!upload(H, g)) { tl_handle.err = H.err; return; }
   sqrtba_handle* h = H.get();
+  if (with_lidar && !set_lidar(h, g, pKF, lidarconfig)) {
+    tl_handle.err = sqrtba_last_error(h);
+    return;
+  }
   if (sqrtba_solve_local(h, pbStopFlag, nullptr) != SQRTBA_OK) {
     H.err = sqrtba_last_error(h);
     return;

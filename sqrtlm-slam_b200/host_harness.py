@@ -20,6 +20,8 @@ def lib():
         L.hh_destroy.argtypes = [C.c_void_p]
         L.hh_set_covisible.argtypes = [C.c_void_p, C.c_int, ip, C.c_int]
         L.hh_set_bad.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hh_set_lidar_cloud.argtypes = [C.c_void_p, C.c_int, C.c_int, fp, fp, C.c_int, fp]
+        L.hh_set_lidar_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
         L.hh_local_ba.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hh_global_ba.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_ulong, C.c_void_p]
         L.hh_get_pose.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
@@ -81,6 +83,19 @@ class MockMap:
 
     def set_bad(self, kf=-1, mp=-1):
         lib().hh_set_bad(self.h, kf, mp)
+
+    def set_lidar(self, ld):
+        """Lidar clouds of synth.LidarData put on the keyframes (KeyFrame.h:437-442) + the lidarConfig of the pass."""
+        L = lib()
+        c32 = lambda a: np.ascontiguousarray(a, np.float32)
+        f, n, c = c32(ld.flat_xyz), c32(ld.flat_normal), c32(ld.corner_xyz)
+        L.hh_set_lidar_cloud(self.h, ld.cur_pose, len(f), _f(f), _f(n), len(c), _f(c))
+        for k in np.unique(np.concatenate([ld.map_flat_pose, ld.map_corner_pose])):
+            f = c32(ld.map_flat_xyz[ld.map_flat_pose == k])
+            c = c32(ld.map_corner_xyz[ld.map_corner_pose == k])
+            L.hh_set_lidar_cloud(self.h, int(k), len(f), _f(f), None, len(c), _f(c))
+        L.hh_set_lidar_config(self.h, int(ld.use_flat), int(ld.use_corner), ld.distance_sq_threshold, ld.flat_weight,
+                              ld.corner_weight)
 
     def local_ba(self, kf, stop=None):
         lib().hh_local_ba(self.h, kf, stop)

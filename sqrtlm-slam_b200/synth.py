@@ -389,3 +389,79 @@ def frame_problem(seed=0, n_points=1500, stereo=False, outlier_frac=0.1, pose_no
     cam = np.array([FX, FY, CX, CY, BF])
     truth = dict(R_cw=R_cw, t_cw=t_cw, is_outlier=is_out)
     return pose7, cam, Xw.astype(np.float32).astype(np.float64), meas, truth
+
+
+# ----------------------------------------------------------------------------- lidar feature clouds (row N4)
+
+@dataclass
+class LidarData:
+    """Inputs of the lidar tight-coupling pass (include/sqrtba.h: sqrtba_lidar), all float32 like pcl::PointXYZI.
+
+    Defaults of the thresholds / weights: include/utils/lidarconfig.h:53-56 (cfg/lidar_slam.yaml:52-61 only uses the
+    flat points; both kinds are generated so both edge types are exercised)."""
+    cur_pose: int
+    flat_xyz: np.ndarray
+    flat_normal: np.ndarray
+    corner_xyz: np.ndarray
+    map_flat_xyz: np.ndarray
+    map_flat_pose: np.ndarray
+    map_corner_xyz: np.ndarray
+    map_corner_pose: np.ndarray
+    distance_sq_threshold: float = 0.2
+    flat_weight: float = 50.0
+    corner_weight: float = 30.0
+    use_flat: bool = True
+    use_corner: bool = True
+
+
+def lidar_data(prob: Problem, seed: int = 0, cur_pose: int | None = None, n_flat: int = 1200, n_corner: int = 300,
+               sigma: float = 0.02) -> LidarData:
+    """Synthetic lidar features for a window made by make_problem: a ground plane 1.65 m below the cameras, two walls
+    and a row of vertical poles, seen from every FREE keyframe (the local keyframes) at its TRUE pose, expressed in
+    that keyframe's frame with `sigma` metres of noise.  The current keyframe (default: the newest free one) gets the
+    feature + normal clouds of KeyFrame.h:438-442; the others form the local map."""
+    rng = np.random.default_rng(10_000 + seed)
+    R_cw, t_cw = prob.truth["R_cw"], prob.truth["t_cw"]
+    free = np.flatnonzero(prob.pose_fixed == 0)
+    if cur_pose is None:
+        cur_pose = int(free[-1])
+    c_w = -np.einsum("nji,nj->ni", R_cw, t_cw)  # camera centres
+    x_mid = float(np.mean(c_w[free, 0]))
+    z_lo, z_hi = float(c_w[free, 2].min()) - 10.0, float(c_w[free, 2].max()) + 30.0
+    poles = np.stack([x_mid + rng.choice([-6.0, 6.0], 40), np.zeros(40), rng.uniform(z_lo, z_hi, 40)], -1)
+
+    def sample_flat(k, n):
+        which = rng.integers(0, 3, n)  # 0 ground, 1 left wall, 2 right wall
+        z = c_w[k, 2] + rng.uniform(-5.0, 30.0, n)
+        x = np.where(which == 0, c_w[k, 0] + rng.uniform(-12.0, 12.0, n), np.where(which == 1, x_mid - 8.0, x_mid + 8.0))
+        y = np.where(which == 0, 1.65, rng.uniform(-3.0, 1.65, n))
+        nw = np.where((which == 0)[:, None], np.array([0.0, -1.0, 0.0]),
+                      np.where((which == 1)[:, None], np.array([1.0, 0.0, 0.0]), np.array([-1.0, 0.0, 0.0])))
+        return np.stack([x, y, z], -1), nw
+
+    def sample_corner(k, n):
+        near = np.argsort(np.abs(poles[:, 2] - (c_w[k, 2] + 10.0)))[:12]
+        p = poles[rng.choice(near, n)]
+        p = p.copy()
+        p[:, 1] = rng.uniform(-2.5, 1.5, n)
+        return p
+
+    def to_kf(k, pw):
+        return np.einsum("ij,nj->ni", R_cw[k], pw) + t_cw[k] + rng.normal(0, sigma, pw.shape)
+
+    fw, nw = sample_flat(cur_pose, n_flat)
+    flat = to_kf(cur_pose, fw)
+    nrm = np.einsum("ij,nj->ni", R_cw[cur_pose], nw) + rng.normal(0, 0.01, nw.shape)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    corner = to_kf(cur_pose, sample_corner(cur_pose, n_corner))
+    mf, mfp, mc, mcp = [], [], [], []
+    for k in free:
+        if k == cur_pose:
+            continue
+        mf.append(to_kf(k, sample_flat(k, n_flat)[0]))
+        mfp.append(np.full(n_flat, k, np.int32))
+        mc.append(to_kf(k, sample_corner(k, n_corner)))
+        mcp.append(np.full(n_corner, k, np.int32))
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    return LidarData(cur_pose, f32(flat), f32(nrm), f32(corner), f32(np.concatenate(mf)), np.concatenate(mfp),
+                     f32(np.concatenate(mc)), np.concatenate(mcp))

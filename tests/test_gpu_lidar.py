@@ -1,0 +1,179 @@
+"""GPU parity of the lidar tight-coupling pass (g2oOptimizer.cc:979-1117) through the C ABI
+(sqrtba_set_lidar / sqrtba_set_lidar_edges + sqrtba_solve_local with third_pass_iters = 20) against the oracle:
+identical nearest-neighbour matches, per-trial costs within 1e-6 relative, poses within 1e-5 m / 1e-6 rad,
+identical outlier flags.  The reference evaluates the unary Jacobians by central differences with delta = 1e-9
+(base_unary_edge.hpp:82-123); both that mode and the closed form are compared."""
+import numpy as np
+import pytest
+
+from oracle import refba
+from test_gpu_parity import COST_RTOL, POSE_R_RMS, POSE_T_RMS, pose_rms
+
+pytestmark = pytest.mark.gpu
+
+
+def same_matches(mg, mr):
+    """The association runs at the pass-2 estimates, which agree to ~1e-9 between the PCG and the LDLT solve; after
+    the float32 rounding of Tcw (Converter::toCvMat) a last-bit flip can move a map point by ~1e-6 m, enough to swap two
+    equidistant candidates or cross the distance threshold for a rare query."""
+    assert len(mg) == len(mr)
+    assert (mg != mr).mean() <= 0.003, f"{(mg != mr).sum()} of {len(mg)} matches differ"
+
+
+def compare(h, ref, prob):
+    tg, tr = h.trace(), ref.trace()
+    assert len(tg) == len(tr), f"trial count differs: gpu {len(tg)} vs oracle {len(tr)}"
+    assert tg[:, 0].max() == 2
+    assert np.array_equal(tg[:, [0, 1, 2, 7]], tr[:, [0, 1, 2, 7]])
+    np.testing.assert_allclose(tg[:, 4], tr[:, 4], rtol=COST_RTOL)
+    np.testing.assert_allclose(tg[:, 5], tr[:, 5], rtol=COST_RTOL)
+    np.testing.assert_allclose(tg[:, 3], tr[:, 3], rtol=1e-5)
+    t_rms, r_rms = pose_rms(h.poses(), ref.poses(), prob.pose_fixed == 0)
+    assert t_rms <= POSE_T_RMS and r_rms <= POSE_R_RMS, (t_rms, r_rms)
+    assert np.array_equal(h.outliers(), ref.outliers())
+
+
+@pytest.mark.parametrize("numeric", [True, False])
+def test_lidar_pass_small_window(pkg, synth, numeric):
+    prob = synth.small_window(1, n_free=6, n_fixed=3, n_points=300)
+    ld = synth.lidar_data(prob, seed=1, n_flat=400, n_corner=100)
+    h = pkg.SqrtBA(third_pass_iters=20)
+    h.set_problem(prob)
+    h.set_lidar(ld, numeric_jacobian=numeric)
+    st = h.solve_local()
+    assert st["persistent_pcg"] in (0, 1)
+    ref = refba.RefBA(prob)
+    ref.set_lidar(ld, numeric_jacobian=numeric)
+    ref.solve_local(20)
+    same_matches(h.lidar_matches(), ref.lidar_matches())
+    assert abs(h.num_lidar_edges() - ref.num_lidar_edges()) <= 2 and ref.num_lidar_edges() > 100
+    compare(h, ref, prob)
+    # the edges matter: the plain third pass ends somewhere else
+    plain = refba.RefBA(prob)
+    plain.solve_local(20)
+    assert np.abs(plain.poses() - ref.poses()).max() > 1e-4
+    # a new problem drops the clouds (their pose indices belong to the old one)
+    h.set_problem(prob)
+    h.solve_local()
+    np.testing.assert_allclose(h.poses(), plain.poses(), rtol=0, atol=1e-6)
+    h.close()
+
+
+def test_lidar_pass_kitti_window(pkg, synth):
+    prob = synth.config_c0(0)
+    ld = synth.lidar_data(prob, seed=0)  # 1200 flat + 300 corner features per keyframe, 19 keyframes in the local map
+    h = pkg.SqrtBA(third_pass_iters=20)
+    h.set_problem(prob)
+    h.set_lidar(ld)
+    h.solve_local()
+    ref = refba.RefBA(prob)
+    ref.set_lidar(ld)
+    ref.solve_local(20)
+    mg, mr = h.lidar_matches(), ref.lidar_matches()
+    same_matches(mg, mr)
+    assert (mg >= 0).sum() > 500
+    compare(h, ref, prob)
+    h.close()
+
+
+def test_explicit_edges_and_flat_only(pkg, synth):
+    prob = synth.small_window(4, n_free=5, n_fixed=3, n_points=250)
+    cur = int(np.flatnonzero(prob.pose_fixed == 0)[-1])
+    rng = np.random.default_rng(0)
+    n_flat, n_corner = 200, 60
+    n = n_flat + n_corner
+    pc = np.stack([rng.uniform(-8, 8, n), rng.uniform(-2, 1.65, n), rng.uniform(3, 25, n)], -1)
+    nrm = rng.normal(size=(n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    R = synth.quat_to_rotmat(prob.pose_qt[cur, 3:])
+    qw = (pc + rng.normal(0, 0.05, (n, 3)) - prob.pose_qt[cur, :3]) @ R
+    w = np.where(rng.random(n) < 0.8, 40.0, 0.0)  # some points without a correspondence
+    for numeric in (True, False):
+        h = pkg.SqrtBA(third_pass_iters=20)
+        h.set_problem(prob)
+        h.set_lidar_edges(cur, pc, qw, nrm, w, n_flat, numeric_jacobian=numeric)
+        h.solve_local()
+        ref = refba.RefBA(prob)
+        ref.set_lidar_edges(cur, pc, qw, nrm, w, n_flat, numeric_jacobian=numeric)
+        ref.solve_local(20)
+        assert h.num_lidar_edges() == ref.num_lidar_edges() == int((w > 0).sum())
+        compare(h, ref, prob)
+        h.close()
+    # cfg/lidar_slam.yaml:59-60: flat points only
+    ld = synth.lidar_data(prob, seed=4, n_flat=300, n_corner=80)
+    ld.use_corner = False
+    h = pkg.SqrtBA(third_pass_iters=20)
+    h.set_problem(prob)
+    h.set_lidar(ld)
+    h.solve_local()
+    ref = refba.RefBA(prob)
+    ref.set_lidar(ld)
+    ref.solve_local(20)
+    m = h.lidar_matches()
+    same_matches(m, ref.lidar_matches())
+    assert (m[300:] == -1).all() and (m[:300] >= 0).any()
+    compare(h, ref, prob)
+    h.close()
+
+
+def test_lidar_edge_cases(pkg, synth):
+    prob = synth.small_window(2, n_free=5, n_fixed=3, n_points=200)
+    ld = synth.lidar_data(prob, seed=2, n_flat=200, n_corner=50)
+    plain = refba.RefBA(prob)
+    plain.solve_local(20)
+    h = pkg.SqrtBA(third_pass_iters=20)
+    # no problem yet
+    with pytest.raises(pkg.SqrtBAError):
+        h.set_lidar(ld)
+    h.set_problem(prob)
+    # bad pose index
+    bad = type(ld)(**{**ld.__dict__, "cur_pose": prob.n_pose})
+    with pytest.raises(pkg.SqrtBAError):
+        h.set_lidar(bad)
+    # a map far away: no match, the pass is the plain third pass
+    far = type(ld)(**{**ld.__dict__, "map_flat_xyz": ld.map_flat_xyz + 500.0, "map_corner_xyz": ld.map_corner_xyz + 500.0})
+    h.set_lidar(far)
+    h.solve_local()
+    assert h.num_lidar_edges() == 0 and (h.lidar_matches() == -1).all()
+    np.testing.assert_allclose(h.poses(), plain.poses(), rtol=0, atol=1e-6)
+    # current keyframe fixed: its unary edges are not active (sparse_optimizer.cpp:218-235)
+    fixed_cur = int(np.flatnonzero(prob.pose_fixed == 1)[0])
+    ld_fixed = type(ld)(**{**ld.__dict__, "cur_pose": fixed_cur})
+    h.set_problem(prob)
+    h.set_lidar(ld_fixed)
+    h.solve_local()
+    np.testing.assert_allclose(h.poses(), plain.poses(), rtol=0, atol=1e-6)
+    h.close()
+    # batches of windows and sharded handles do not take lidar clouds
+    wins = [synth.small_window(s, n_free=4, n_fixed=2, n_points=100) for s in range(2)]
+    batch, pp, tp, op = synth.concat_windows(wins)
+    hb = pkg.SqrtBA(third_pass_iters=20)
+    hb.set_problem_batch(batch, pp, tp, op)
+    with pytest.raises(pkg.SqrtBAError):
+        hb.set_lidar(ld)
+    hb.close()
+
+
+def test_local_ba_with_lidar_through_reference_api(pkg, synth):
+    """Optimizer::LocalBundleAdjustment(pKF, stop, map, lidarconfig) with clouds on the keyframes (KeyFrame.h:437-442)."""
+    prob = synth.make_problem(33, 12, 4, 700, 6.0, stereo=True, name="adapter-lidar")
+    ld = synth.lidar_data(prob, seed=3, n_flat=500, n_corner=120)
+    cur = ld.cur_pose
+    m = pkg.host_harness.MockMap(prob)
+    free = np.nonzero(prob.pose_fixed == 0)[0]
+    m.set_covisible(cur, [i for i in free if i != cur])
+    m.set_lidar(ld)
+    m.local_ba(cur)
+    assert m.last_error() == ""
+    ref = refba.RefBA(prob)
+    ref.set_lidar(ld)
+    ref.solve_local(20)
+    assert ref.num_lidar_edges() > 100
+    P = ref.poses()
+    for i in free:
+        R = synth.quat_to_rotmat(P[i, 3:])
+        np.testing.assert_allclose(m.pose(i)[:3, :3], R.astype(np.float32), rtol=0, atol=2e-5)
+        np.testing.assert_allclose(m.pose(i)[:3, 3], P[i, :3].astype(np.float32), rtol=0, atol=2e-5)
+    F = ref.outliers()
+    for k in range(0, prob.n_obs, 7):
+        assert m.has_observation(int(prob.obs_pose[k]), int(prob.obs_point[k])) == (F[k] == 0)
