@@ -104,7 +104,7 @@ class SqrtBA:
     def __init__(self, device: int = 0, pcg_rtol: float = 1e-9, pcg_max_iters: int = 2000, third_pass_iters: int = 0,
                  pcg_mode: int = 0, pcg_check_every: int = 4, stage_timing: bool = False,
                  general_matvec: bool = False, pipe_stages: int = 0, host_threads: int = 0,
-                 no_reorder: bool = False, pipe_slots: int = 0, plain_qr: bool = False):
+                 no_reorder: bool = False, pipe_slots: int = 0, plain_qr: bool = False, qr_variant: int = 0):
         L = lib()
         cfg = Config()
         L.sqrtba_default_config(C.byref(cfg))
@@ -116,7 +116,7 @@ class SqrtBA:
         cfg.reserved[3] = host_threads                 # 0 = all host cores for set_problem's preprocessing
         cfg.reserved[4] = 1 if no_reorder else 0       # keep the caller's landmark order in big windows (A/B profiling)
         cfg.reserved[5] = pipe_slots                   # big windows: slots in the matvec's shared accumulator window
-        cfg.reserved[7] = 1 if plain_qr else 0         # one-tile-per-CTA landmark QR instead of the cp.async pipeline
+        cfg.reserved[7] = 1 if plain_qr else qr_variant  # 1: one-tile-per-CTA kernels; 2-4: A/B variants of the pipelined QR
         self.h = C.c_void_p()
         rc = L.sqrtba_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:

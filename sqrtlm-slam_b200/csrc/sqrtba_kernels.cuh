@@ -401,7 +401,7 @@ __device__ __forceinline__ LinOps lin_load_ops(const Dev& P, int o) {
 // One tile of the linearisation.  PRE: the lanes of short items already hold their LinOps (pipelined kernel).
 template <bool PRE>
 __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti, const LinOps& pre, int robust, double d2,
-                                               double d3, double* c_sh) {
+                                               double d3, double* c_sh, const int* runs_staged = nullptr) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int w = ti.item0 + wid;
   const bool valid = wid < ti.nitem;
@@ -526,7 +526,7 @@ __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti,
     for (int c = 0; c < 6; c++) { c_sh[c * SCST + rank] = vb[c]; c_sh[(6 + c) * SCST + rank] = vh[c]; }
   }
   __syncthreads();
-  const int* runs = reinterpret_cast<const int*>(jq + (size_t)JQ_ROWS * ti.nt);
+  const int* runs = runs_staged ? runs_staged : reinterpret_cast<const int*>(jq + (size_t)JQ_ROWS * ti.nt);
   const int sbase = P.smallwin ? P.win_slot_ptr[win] : 0;
   double* bp = P.bp;
   double* hd = P.hd;
@@ -547,11 +547,23 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize(Dev P, int robust, double 
 // landmark index, meta, level: 8 registers) for the NEXT tile while it linearises the current one, so only the
 // L2-resident pose / point gathers stay on the critical path.
 constexpr int LIN_TPB = 8;
+constexpr int LIN_RUN_INTS = 2 * CTA + 2;
+// STAGE: the run table of the next tile is copied to shared memory with cp.async together with the descriptor (it sits
+// at the cold tail of the tile's JQ block, which nothing else touches before the pose-side reduction needs it), and the
+// landmark coordinates of the following tiles -- consecutive in memory, landmarks are tiled in order -- are pulled into
+// L2 by a TMA prefetch, so the only exposed global latency left is the L1/L2-resident pose gather.
+template <bool STAGE>
 __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, double d2, double d3, int force_all) {
   __shared__ double c_sh[12 * SCST];
   __shared__ __align__(16) TileInfo ti_sh[3];
+  __shared__ int run_sh[STAGE ? 2 : 1][STAGE ? LIN_RUN_INTS : 1];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int t0 = blockIdx.x * LIN_TPB, t1 = min(t0 + LIN_TPB, P.n_tile);
+  auto stage_runs = [&](const TileInfo& ti, int rb) {
+    if (!STAGE || ti.is_long) return;
+    const int* runs = reinterpret_cast<const int*>(P.JQ + ti.jq_off + (size_t)JQ_ROWS * ti.nt);
+    for (int i = tid; i < 2 * ti.nrun + 1; i += CTA) cp_async4(&run_sh[rb][i], runs + i);
+  };
   auto ops_of = [&](const TileInfo& ti) {
     LinOps q{};
     if (!ti.is_long) {
@@ -569,9 +581,11 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, do
   cp_async_wait_all();
   __syncthreads();
   LinOps nxt = ops_of(ti_sh[0]);
+  stage_runs(ti_sh[0], 0);
+  cp_async_commit();
   int nphase = force_all ? PH_LIN : P.ctl[ti_sh[0].win].phase;
   for (int k = 0; k < t1 - t0; k++) {
-    cp_async_wait_all();  // descriptor of tile k+1
+    cp_async_wait_all();  // descriptor of tile k+1 (and the run table of tile k)
     __syncthreads();      // ... visible to everybody; c_sh of the previous tile is free
     const TileInfo ti = ti_sh[k % 3];
     const LinOps cur = nxt;
@@ -582,11 +596,23 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, do
         cp_async16(reinterpret_cast<char*>(&ti_sh[(k + 2) % 3]) + tid * 16,
                    reinterpret_cast<const char*>(P.tiles + t0 + k + 2) + tid * 16);
       nxt = ops_of(tn);
+      stage_runs(tn, (k + 1) & 1);
       if (!force_all) nphase = P.ctl[tn.win].phase;
     }
     cp_async_commit();
     if (phase != PH_LIN) continue;  // CTA-uniform
-    linearize_tile<true>(P, ti, cur, robust, d2, d3, c_sh);
+    if (STAGE && !ti.is_long) {
+      // the last lane of the tile's last item knows the tile's last landmark: pull the coordinates of the next ~96
+      // landmarks (the next two or three tiles of this CTA) towards L2
+      const int li = ti.nitem - 1;
+      if (wid == li && lane == tile_item_cnt(ti, li) - 1) {
+        long long first = ((long long)cur.lm + 1) & ~1ll;  // 16-byte aligned start
+        long long bytes = ((long long)P.n_point - first) * 24;
+        bytes = (bytes < 2304 ? bytes : 2304) & ~15ll;
+        if (bytes > 0) bulk_prefetch_l2(P.point + first * 3, (uint32_t)bytes);
+      }
+    }
+    linearize_tile<true>(P, ti, cur, robust, d2, d3, c_sh, (STAGE && !ti.is_long) ? run_sh[k & 1] : nullptr);
   }
   cp_async_wait_all();
 }
@@ -820,6 +846,122 @@ __device__ __forceinline__ void qr_short_item(const Dev& P, const TileInfo& ti, 
     }
 }
 
+// trial_contrib_sh with the observation's Jp rows already in registers (loaded early, see qr_short_item_v2)
+__device__ __forceinline__ void trial_contrib_regs(const double J[18], const double Q[9], const double rr[3],
+                                                   const double tl[3], double* c_sh, int rank) {
+  {
+    double u[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) u[r] = rr[r] - (Q[r * 3] * tl[0] + Q[r * 3 + 1] * tl[1] + Q[r * 3 + 2] * tl[2]);
+#pragma unroll
+    for (int c = 0; c < 6; c++) c_sh[c * SCST + rank] = -(J[c] * u[0] + J[6 + c] * u[1] + J[12 + c] * u[2]);
+  }
+  double G[18];  // Jp^T Q1 (6x3)
+#pragma unroll
+  for (int c = 0; c < 6; c++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) G[c * 3 + k] = J[c] * Q[k] + J[6 + c] * Q[3 + k] + J[12 + c] * Q[6 + k];
+  int idx = 6;
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = a; b < 6; b++) {
+      c_sh[idx * SCST + rank] = J[a] * J[b] + J[6 + a] * J[6 + b] + J[12 + a] * J[12 + b] -
+                                (G[a * 3] * G[b * 3] + G[a * 3 + 1] * G[b * 3 + 1] + G[a * 3 + 2] * G[b * 3 + 2]);
+      idx++;
+    }
+}
+
+// Second version of the short item, used by the pipelined kernel.  Same factorisation, shorter critical path:
+//  * nine segmented reductions in three dependent groups instead of thirteen in five.  The Gram entries of the
+//    reflectors follow from sums that are already there -- with norm_j = sqrt(lambda + sigma_j) the column-j reflector
+//    leaves  sum V_j . V_k = d_jk * sqrt(lambda) / norm_j  (k > j, before later updates) -- and t_l = Q1^T r is
+//    -M^T (V^T r), where V^T r comes from c_j = sum a_j . r (reduced together with the first group) by the same
+//    column updates as V itself;
+//  * the 18 Jp rows of the observation are requested right after the first group (read-only path: the kernel only
+//    writes rows 18-26 of the block), so their L2 latency is covered by the remaining two reduction groups.
+template <int JPOS>  // where the Jp rows are requested: 0 = right before they are used, 1 = after reduction group 1, 2 = after group 2
+__device__ __forceinline__ void qr_short_item_v2(const Dev& P, const TileInfo& ti, int wid, int lane, bool act, int lm,
+                                                 bool has, int rank, const double a[9], const double rr[3], double lam,
+                                                 double* c_sh) {
+  const double sl = sqrt(lam);
+  const int Nl = P.n_point, nt = ti.nt;
+  double* __restrict__ jq = P.JQ + ti.jq_off;
+  LmFactor F;
+  const int fcol = tile_fcol(ti, wid, has, lane);
+  const Seg sg = seg_of(lm, lane);
+  // group 1: column 0 and the three products with the residual
+  const double s0 = seg_sum(a[0] * a[0] + a[3] * a[3] + a[6] * a[6], sg, lane);
+  const double d01 = seg_sum(a[0] * a[1] + a[3] * a[4] + a[6] * a[7], sg, lane);
+  const double d02 = seg_sum(a[0] * a[2] + a[3] * a[5] + a[6] * a[8], sg, lane);
+  const double c0 = seg_sum(a[0] * rr[0] + a[3] * rr[1] + a[6] * rr[2], sg, lane);
+  const double c1 = seg_sum(a[1] * rr[0] + a[4] * rr[1] + a[7] * rr[2], sg, lane);
+  const double c2 = seg_sum(a[2] * rr[0] + a[5] * rr[1] + a[8] * rr[2], sg, lane);
+  double J[18];
+  auto load_J = [&]() {
+    if (act && has) {
+      const double* __restrict__ jr = jq + fcol;
+#pragma unroll
+      for (int c = 0; c < 18; c++) J[c] = __ldg(jr + (size_t)c * nt);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 18; c++) J[c] = 0.0;
+    }
+  };
+  if (JPOS == 1) load_J();
+  hh_col(F, 0, lam, sl, s0);
+  const double norm0 = -F.Rm[0];
+  F.w01 = F.beta[0] * d01;
+  F.w02 = F.beta[0] * d02;
+  F.Rm[1] = -F.w01 * F.v0[0];
+  F.Rm[2] = -F.w02 * F.v0[0];
+  double V[9];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    V[r * 3] = a[r * 3];
+    V[r * 3 + 1] = a[r * 3 + 1] - F.w01 * a[r * 3];
+    V[r * 3 + 2] = a[r * 3 + 2] - F.w02 * a[r * 3];
+  }
+  // group 2: column 1
+  const double s1 = seg_sum(V[1] * V[1] + V[4] * V[4] + V[7] * V[7], sg, lane);
+  const double d12 = seg_sum(V[1] * V[2] + V[4] * V[5] + V[7] * V[8], sg, lane);
+  if (JPOS == 2) load_J();
+  hh_col(F, 1, lam, sl, s1);
+  const double norm1 = -F.Rm[3];
+  F.w12 = F.beta[1] * d12;
+  F.Rm[4] = -F.w12 * F.v0[1];
+#pragma unroll
+  for (int r = 0; r < 3; r++) V[r * 3 + 2] -= F.w12 * V[r * 3 + 1];
+  // group 3: column 2
+  const double s2 = seg_sum(V[2] * V[2] + V[5] * V[5] + V[8] * V[8], sg, lane);
+  hh_col(F, 2, lam, sl, s2);
+  const double g01 = d01 * (sl / norm0);
+  const double g02 = d02 * (sl / norm0) - F.w12 * g01;
+  const double g12 = d12 * (sl / norm1);
+  wy_from_gram(F, g01, g02, g12);
+  double Q[9];
+  q1_rows(V, F, Q);
+  const double u0 = c0, u1 = c1 - F.w01 * c0, u2 = c2 - F.w02 * c0 - F.w12 * u1;
+  double tl[3];
+  tl[0] = -(F.M[0] * u0);
+  tl[1] = -(F.M[1] * u0 + F.M[3] * u1);
+  tl[2] = -(F.M[2] * u0 + F.M[4] * u1 + F.M[5] * u2);
+  if (JPOS == 0) load_J();
+  if (act) {
+    if (has) {
+#pragma unroll
+      for (int c = 0; c < 9; c++) jq[(size_t)(18 + c) * nt + fcol] = Q[c];
+    }
+    if (lane == sg.start) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) P.R[(size_t)c * Nl + lm] = F.Rm[c];
+#pragma unroll
+      for (int c = 0; c < 3; c++) P.tl[(size_t)c * Nl + lm] = tl[c];
+    }
+    if (has) trial_contrib_regs(J, Q, rr, tl, c_sh, rank);
+  }
+}
+
 // long landmark (one warp, more than 32 observations): operands straight from global memory, direct atomics
 __device__ __forceinline__ void qr_long_item(const Dev& P, const TileInfo& ti, int lane, int start, int cnt, double lam) {
   const double sl = sqrt(lam);
@@ -1048,6 +1190,107 @@ __global__ void __launch_bounds__(CTA, 4) k_qr_pipe(Dev P, int force_all, double
     const int sbase = P.smallwin ? P.win_slot_ptr[ti.win] : 0;
     double* bs = P.bs;
     double* D = P.D;
+    tile_scatter_all<27>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh,
+                         [bs, D](int slot, int k2) { return (k2 < 6) ? bs + (size_t)slot * 6 + k2 : D + (size_t)slot * 21 + (k2 - 6); });
+  }
+  cp_async_wait_all();
+}
+
+// Second version of the pipelined kernel (the default): qr_short_item_v2, the run table of the next tile staged in
+// shared memory together with its operands (the pose-side reduction no longer starts with a dependent L2 round trip),
+// and ONE operand buffer -- a lane copies the next tile's operands into the slots it has just read its own from, so no
+// second buffer and no extra barrier are needed.
+constexpr int QR_RUN_INTS = 2 * CTA + 2;  // a tile has at most CTA runs: nrun + 1 offsets, nrun slots
+constexpr size_t QR_PIPE2_SMEM = (27 * SCST + 12 * CTA) * sizeof(double) + CTA * (sizeof(unsigned) + sizeof(int)) +
+                                 2 * QR_RUN_INTS * sizeof(int) + 3 * 80;
+template <int JPOS, int MINB>
+__global__ void __launch_bounds__(CTA, MINB) k_qr_pipe2(Dev P, int force_all, double lam_override) {
+  extern __shared__ __align__(16) unsigned char qr_smem[];
+  TileInfo* ti_sh = reinterpret_cast<TileInfo*>(qr_smem);                             // [3]
+  double* c_sh = reinterpret_cast<double*>(qr_smem + 3 * 80);                         // [27][SCST]
+  double(*op_sh)[CTA] = reinterpret_cast<double(*)[CTA]>(c_sh + 27 * SCST);           // [12]: 9 rows of J_l, 3 of r
+  unsigned* lp_sh = reinterpret_cast<unsigned*>(op_sh + 12);                          // [CTA]
+  int* lm_sh = reinterpret_cast<int*>(lp_sh + CTA);                                   // [CTA]
+  int(*run_sh)[QR_RUN_INTS] = reinterpret_cast<int(*)[QR_RUN_INTS]>(lm_sh + CTA);     // [2]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int t0 = blockIdx.x * QR_TPB, t1 = min(t0 + QR_TPB, P.n_tile);
+  const size_t No = (size_t)P.ld;
+  auto stage = [&](const TileInfo& ti, int rb) {
+    if (ti.is_long) return;
+    const int cnt = tile_item_cnt(ti, wid), start = tile_item_start(ti, wid);
+    if (wid < ti.nitem && lane < cnt) {
+      const int o = start + lane;
+#pragma unroll
+      for (int c = 0; c < 9; c++) cp_async8(&op_sh[c][tid], P.Jl + (size_t)c * No + o);
+#pragma unroll
+      for (int c = 0; c < 3; c++) cp_async8(&op_sh[9 + c][tid], P.r + (size_t)c * No + o);
+      cp_async4(&lp_sh[tid], P.obs_lp + o);
+      cp_async4(&lm_sh[tid], P.obs_point + o);
+    }
+    const int* runs = reinterpret_cast<const int*>(P.JQ + ti.jq_off + (size_t)JQ_ROWS * ti.nt);
+    for (int i = tid; i < 2 * ti.nrun + 1; i += CTA) cp_async4(&run_sh[rb][i], runs + i);
+    if (tid == 0) bulk_prefetch_l2(P.JQ + ti.jq_off, (uint32_t)(18 * ti.nt * sizeof(double)));
+  };
+  if (tid < 5) {
+    cp_async16(reinterpret_cast<char*>(&ti_sh[0]) + tid * 16, reinterpret_cast<const char*>(P.tiles + t0) + tid * 16);
+    if (t0 + 1 < t1)
+      cp_async16(reinterpret_cast<char*>(&ti_sh[1]) + tid * 16, reinterpret_cast<const char*>(P.tiles + t0 + 1) + tid * 16);
+  }
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  stage(ti_sh[0], 0);
+  cp_async_commit();
+  int nphase = force_all ? PH_TRIAL : P.ctl[ti_sh[0].win].phase;
+  double nlam = force_all ? lam_override : P.ctl[ti_sh[0].win].lambda;
+  for (int k = 0; k < t1 - t0; k++) {
+    cp_async_wait_all();  // operands + run table of tile k, descriptor of tile k+1
+    __syncthreads();      // ... visible to everybody; c_sh and the other run buffer are free
+    const TileInfo ti = ti_sh[k % 3];
+    const int phase = nphase;
+    const double lam = nlam;
+    const bool valid = wid < ti.nitem;
+    const int cnt = tile_item_cnt(ti, wid);
+    const int start = tile_item_start(ti, wid);
+    const bool is_short = valid && cnt <= 32;
+    const bool act = is_short && lane < cnt;
+    int lm = -1 - lane, rank = 0;
+    bool has = false;
+    double a[9], rr[3];
+    if (act) {  // this lane's operands, copied by itself one tile ago
+      const unsigned lp = lp_sh[tid];
+      lm = lm_sh[tid];
+#pragma unroll
+      for (int c = 0; c < 9; c++) a[c] = op_sh[c][tid];
+#pragma unroll
+      for (int c = 0; c < 3; c++) rr[c] = op_sh[9 + c][tid];
+      has = (lp & 0xffffu) != 0xffffu;
+      rank = (int)(lp >> 16);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 9; c++) a[c] = 0.0;
+      rr[0] = rr[1] = rr[2] = 0.0;
+    }
+    if (k + 1 < t1 - t0) {  // the slots just read are free again: bring in tile k+1
+      const TileInfo& tn = ti_sh[(k + 1) % 3];
+      if (k + 2 < t1 - t0 && tid < 5)
+        cp_async16(reinterpret_cast<char*>(&ti_sh[(k + 2) % 3]) + tid * 16,
+                   reinterpret_cast<const char*>(P.tiles + t0 + k + 2) + tid * 16);
+      stage(tn, (k + 1) & 1);
+      if (!force_all) { nphase = P.ctl[tn.win].phase; nlam = P.ctl[tn.win].lambda; }
+    }
+    cp_async_commit();
+    if (phase != PH_TRIAL) continue;  // CTA-uniform: the tile's window is not in a trial
+    if (is_short) {
+      qr_short_item_v2<JPOS>(P, ti, wid, lane, act, lm, has, rank, a, rr, lam, c_sh);
+    } else if (valid) {
+      qr_long_item(P, ti, lane, start, cnt, lam);
+    }
+    __syncthreads();
+    const int sbase = P.smallwin ? P.win_slot_ptr[ti.win] : 0;
+    double* bs = P.bs;
+    double* D = P.D;
+    const int* runs = run_sh[k & 1];
     tile_scatter_all<27>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh,
                          [bs, D](int slot, int k2) { return (k2 < 6) ? bs + (size_t)slot * 6 + k2 : D + (size_t)slot * 21 + (k2 - 6); });
   }

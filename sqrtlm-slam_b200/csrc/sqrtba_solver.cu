@@ -178,6 +178,8 @@ class Solver {
     CU_CHECK(cudaFuncSetAttribute(k_pcg_persist<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)persist_smem_bytes(3, MAXSLOT, false)));
     CU_CHECK(cudaFuncSetAttribute(k_qr_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QR_PIPE_SMEM));
+    CU_CHECK(cudaFuncSetAttribute(k_qr_pipe2<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QR_PIPE2_SMEM));
+    CU_CHECK(cudaFuncSetAttribute(k_qr_pipe2<0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QR_PIPE2_SMEM));
     int coop = 0;
     CU_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg_.device));
     coop_ok_ = coop != 0;
@@ -1305,13 +1307,18 @@ class Solver {
            2 * S * sizeof(uint64_t) + 4 * sizeof(int) + 2 * (size_t)pipe_run_cap(maxslot, big) * sizeof(int);
   }
   void launch_linearize(int robust, double d2, double d3, int force_all) {
-    if (cfg_.reserved[7] != 0) k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
-    else k_linearize_pipe<<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
+    if (cfg_.reserved[7] == 1) k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
+    else if (cfg_.reserved[7] == 2) k_linearize_pipe<false><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
+    else k_linearize_pipe<true><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
   }
   // landmark QR: cp.async-pipelined kernel (QR_TPB tiles per CTA); reserved[7] != 0 selects the plain one-tile-per-CTA kernel
   void launch_qr(int force_all, double lam_override) {
-    if (cfg_.reserved[7] != 0) k_qr<<<P_.n_tile, CTA, 0, stream_>>>(P_, force_all, lam_override);
-    else k_qr_pipe<<<cdiv(P_.n_tile, QR_TPB), CTA, QR_PIPE_SMEM, stream_>>>(P_, force_all, lam_override);
+    // reserved[7]: 0 = pipelined v2 (default), 1 = plain one-tile-per-CTA kernels, 2 = first pipelined version,
+    // 5 = v2 compiled for 5 CTAs/SM (96 registers) (A/B)
+    if (cfg_.reserved[7] == 1) k_qr<<<P_.n_tile, CTA, 0, stream_>>>(P_, force_all, lam_override);
+    else if (cfg_.reserved[7] == 2) k_qr_pipe<<<cdiv(P_.n_tile, QR_TPB), CTA, QR_PIPE_SMEM, stream_>>>(P_, force_all, lam_override);
+    else if (cfg_.reserved[7] == 5) k_qr_pipe2<0, 5><<<cdiv(P_.n_tile, QR_TPB), CTA, QR_PIPE2_SMEM, stream_>>>(P_, force_all, lam_override);
+    else k_qr_pipe2<0, 4><<<cdiv(P_.n_tile, QR_TPB), CTA, QR_PIPE2_SMEM, stream_>>>(P_, force_all, lam_override);
   }
   void launch_matvec(const double* pvec, double* qvec, int force_all) {
     if (P_.smallwin && cfg_.reserved[1] == 0) {

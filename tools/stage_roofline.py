@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--windows", type=int, default=256)
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--variants", action="store_true", help="A/B the big-window matvec knobs")
+    ap.add_argument("--qr-variants", action="store_true", help="A/B the pipelined landmark-QR variants")
     ap.add_argument("--reps", type=int, default=20)
     args = ap.parse_args()
     pkg = load_pkg()
@@ -40,6 +41,8 @@ def main():
     if args.variants:
         variants += [dict(plain_qr=True),
                      dict(no_reorder=True), dict(general_matvec=True)]
+    if args.qr_variants:
+        variants += [dict(qr_variant=v) for v in (2, 5)]
     for kw in variants:
         ba = pkg.SqrtBA(**kw)
         if batch:
@@ -53,7 +56,7 @@ def main():
         out = {"config": args.config, "variant": kw, "n_obs": prob.n_obs, "free_obs": free_obs, "n_point": prob.n_point,
                "n_free_pose": prob.n_free, "peak_gbs": peaks["hbm_gbs"], "peak_kind": kind, "kernels": {}}
         stages = [(0, "k_matvec"), (1, "k_linearize"), (2, "k_qr"), (3, "k_cost"), (4, "k_backsub")]
-        for stage, name in (stages if not kw else (stages[1:3] if kw.get("plain_qr") else stages[:1])):
+        for stage, name in (stages if not kw else (stages[1:3] if kw.get("plain_qr") else (stages[1:3] if "qr_variant" in kw else stages[:1]))):
             ms = ba.time_stage(stage, warmup=3, reps=args.reps)
             gbs = bytes_of[stage] / (ms * 1e-3) / 1e9
             out["kernels"][name] = {"ms": round(ms, 5), "alg_MB": round(bytes_of[stage] / 1e6, 2), "GBs": round(gbs, 1),
