@@ -394,7 +394,7 @@ __device__ __forceinline__ LinOps lin_load_ops(const Dev& P, int o) {
   q.ip = __ldg(&P.obs_pose[o]);
   q.lm = __ldg(&P.obs_point[o]);
   q.lp = __ldg(&P.obs_lp[o]);
-  q.live = P.obs_level[o] == 0;
+  q.live = P.obs_level[o];  // raw level byte; compared where it is used, so this pre-load never waits for the data
   return q;
 }
 
@@ -411,6 +411,7 @@ __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti,
   const size_t No = (size_t)P.ld; const int Nl = P.n_point;
   const bool is_long = cnt > 32;
   double* __restrict__ jq = P.JQ + ti.jq_off;
+  const int sbase = P.smallwin ? P.win_slot_ptr[win] : 0;  // for the pose-side reduction at the end: requested now
   double chi_acc = 0.0, maxd = 0.0;
   double vb[6] = {0, 0, 0, 0, 0, 0}, vh[6] = {0, 0, 0, 0, 0, 0};  // this observation's -Jp^T r and diag(Jp^T Jp)
   bool has = false;
@@ -432,7 +433,7 @@ __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti,
     }
     const int fcol = tile_fcol(ti, wid, has, lane);
     if (act && on) {
-      const bool live = q.live != 0;
+      const bool live = q.live == 0;
       obs_eval_ops(P, q.m, q.ip, q.lm, true, robust != 0, d2, d3, L);
       if (live) {
 #pragma unroll
@@ -527,7 +528,6 @@ __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti,
   }
   __syncthreads();
   const int* runs = runs_staged ? runs_staged : reinterpret_cast<const int*>(jq + (size_t)JQ_ROWS * ti.nt);
-  const int sbase = P.smallwin ? P.win_slot_ptr[win] : 0;
   double* bp = P.bp;
   double* hd = P.hd;
   tile_scatter_all<12>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh,
@@ -1281,13 +1281,13 @@ __global__ void __launch_bounds__(CTA, MINB) k_qr_pipe2(Dev P, int force_all, do
     }
     cp_async_commit();
     if (phase != PH_TRIAL) continue;  // CTA-uniform: the tile's window is not in a trial
+    const int sbase = P.smallwin ? P.win_slot_ptr[ti.win] : 0;  // for the reduction below: requested before the factorisation
     if (is_short) {
       qr_short_item_v2<JPOS>(P, ti, wid, lane, act, lm, has, rank, a, rr, lam, c_sh);
     } else if (valid) {
       qr_long_item(P, ti, lane, start, cnt, lam);
     }
     __syncthreads();
-    const int sbase = P.smallwin ? P.win_slot_ptr[ti.win] : 0;
     double* bs = P.bs;
     double* D = P.D;
     const int* runs = run_sh[k & 1];
