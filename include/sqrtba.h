@@ -24,6 +24,9 @@
 #define SQRTBA_H_
 
 #include <stdint.h>
+#ifndef __cplusplus
+#include <stdbool.h> /* the stop flags are the reference's `bool* pbStopFlag` */
+#endif
 
 #ifdef __cplusplus
 extern "C" {

@@ -30,6 +30,34 @@ def test_struct_layouts_match_header(pkg):
     assert len(pkg.capi.TRACE_COLS) == 10
 
 
+def test_ctypes_structs_match_the_compiled_header(pkg, tmp_path):
+    """sizeof / offsetof of every struct of include/sqrtba.h as gcc sees them, against the ctypes mirrors in capi.py
+    (the header is plain C: it must also compile as C)."""
+    import subprocess
+    structs = {"sqrtba_config": pkg.capi.Config, "sqrtba_stats": pkg.capi.Stats, "sqrtba_lidar": pkg.capi.Lidar}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "sqrtba.h"', "int main(void) {"]
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for ln in out:
+        if not ln:
+            continue
+        cname, field, val = ln.split()
+        ct = structs[cname]
+        want = C.sizeof(ct) if field == "size" else getattr(ct, field).offset
+        assert int(val) == want, f"{cname}.{field}: header {val}, ctypes {want}"
+        seen += 1
+    assert seen == sum(len(ct._fields_) + 1 for ct in structs.values())
+
+
 def test_no_cpu_fallback_without_device(pkg):
     import torch
     if torch.cuda.is_available():
