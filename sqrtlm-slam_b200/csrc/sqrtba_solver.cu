@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <thread>
 #include <cstdio>
@@ -222,6 +223,16 @@ class Solver {
       err_ = "set_problem: empty problem or null pointer";
       return SQRTBA_ERR_INVALID;
     }
+    // SQRTBA_HOST_TIMING=1: wall time of the host-side steps on stderr (set_problem is the part of the end-to-end call
+    // that is neither a copy nor a kernel)
+    static const bool host_timing = std::getenv("SQRTBA_HOST_TIMING") != nullptr;
+    auto tick = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      if (!host_timing) return;
+      const auto now = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[sqrtba host] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count());
+      tick = now;
+    };
     if (!plan_only_) CU_CHECK(cudaSetDevice(cfg_.device));
     have_problem_ = false;
     lidar_edges_set_ = lidar_assoc_set_ = lidar_active_ = false;  // pose indices of the old problem
@@ -251,6 +262,7 @@ class Solver {
       }
     for (int w = 0; w < n_win; w++) win_slot_ptr[w + 1] += win_slot_ptr[w];
     const int n_slot = (int)slot_pose.size();
+    lap("windows + slots");
     // ---- observation pre-processing (multi-threaded; all outputs land in pinned staging buffers)
     const int ld = ((n_obs + 31) / 32) * 32;
     int max_win_slots = 0;
@@ -286,6 +298,7 @@ class Solver {
       for (int l = n_point - 1; l >= 0; l--)
         if (lm_first[l] >= 0) { lm_cnt[l] = next - lm_first[l]; next = lm_first[l]; }
     }
+    lap("A validate + slots per obs");
     // A2. big windows (global BA): order the landmarks of each window by their first free pose, so that consecutive
     //     tiles touch a narrow, slowly drifting band of pose slots (shared accumulator window of the matvec, few
     //     distinct slots per tile for the run-table reductions, cache-resident pose gathers).  The order the caller
@@ -341,6 +354,7 @@ class Solver {
       lm_count_new_ = lm_cnt;
       point_xyz = h_perm_xyz_.p; obs_pose = h_perm_pose_.p; obs_point = h_perm_point_.p; obs_meas = h_perm_meas_.p;
     }
+    lap("A2 landmark order");
     // The caller's big arrays (or their re-ordered copies) are final now: start their host-to-device copies so that they
     // overlap the remaining host-side preprocessing (truly asynchronous when the caller's buffers are pinned).
     auto up = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_); };
@@ -356,6 +370,7 @@ class Solver {
     CU_CHECK(up(d_obs_point_.p, obs_point, (size_t)n_obs * sizeof(int)));
     CU_CHECK(up(d_point0_.p, point_xyz, (size_t)n_point * 3 * sizeof(double)));
     }
+    lap("early uploads issued");
     // B. work chunks: landmark ranges inside one window of roughly equal observation count.  Items and tiles never
     //    span chunks (a chunk boundary merely ends an item early), so chunks are processed independently.
     struct Chunk { int win, l0, l1; std::vector<int> it_start, it_cnt, run_ptr, runs; std::vector<TileInfo> tiles; long long jq = 0; };
@@ -376,6 +391,7 @@ class Solver {
         }
       }
     }
+    lap("B chunks");
     // C. per chunk: pack whole landmarks into items of <= 32 observations, items into tiles of <= WARPS items, and per
     //    tile the pose-sorted ranks + run table (see tile_scatter / k_matvec_pipe)
     {
@@ -475,6 +491,7 @@ class Solver {
       worker();
       for (auto& th : pool) th.join();
     }
+    lap("C items/tiles/run tables");
     // D. merge the chunks (offsets are prefix sums over chunks in order)
     std::vector<long long> item_off(chunks.size() + 1, 0), tile_off(chunks.size() + 1, 0), run_off(chunks.size() + 1, 0),
         jq_off(chunks.size() + 1, 0);
@@ -525,6 +542,7 @@ class Solver {
       for (auto& th : pool) th.join();
       h_tile_run_ptr_.p[n_tile] = (int)n_runs;
     }
+    lap("D merge");
     plan_n_item_ = n_item; plan_n_tile_ = n_tile; plan_n_runs_ = (long long)n_runs; plan_jq_total_ = jq_total;
     plan_smallwin_ = smallwin; plan_pq_shared_ = pq_shared;
     if (plan_only_) return SQRTBA_OK;  // sqrtba_debug_plan: the host-side tiling only, no device needed
