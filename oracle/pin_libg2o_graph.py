@@ -1,0 +1,255 @@
+"""Graph-level pinning: a REAL g2o::SparseOptimizer of the reference's prebuilt libg2o.so.
+
+pin_libg2o.py pins the per-edge functions and pin_libg2o_edges.py whole edge objects; this script goes one level up and
+pins the graph semantics the BA control flow relies on against the binary itself:
+
+  * index mapping of initializeOptimization(level) (sparse_optimizer.cpp:166-190, 199-267, 482-487): free poses first,
+    marginalised landmarks second, each in ascending vertex id whatever the insertion order; fixed vertices and
+    vertices whose edges are all at another level get no index;
+  * computeActiveErrors (sparse_optimizer.cpp:61-88) rewrites `_error` of ACTIVE edges only -- an edge moved to level 1
+    keeps the error it had (the stale-_error rule behind the local-BA outlier test, g2oOptimizer.cc:947-976,1119-1142);
+  * activeChi2 / activeRobustChi2 (sparse_optimizer.cpp:90-114) over the active edges, Huber with the float dsqr;
+  * update(double*) (sparse_optimizer.cpp:422-435) consumes the increment in index order and applies oplusImpl;
+    push()/pop() restore the estimates.
+
+Objects are built with the binary's own constructors in raw 64-byte aligned blocks; the few inline setters (setId,
+setFixed, setMarginalized, setLevel, setRobustKernel, setInformation) are replaced by writes at member offsets that are
+CHECKED against constructor defaults first (id -1 at byte 8, hessianIndex -1 at 80, dimension at 88 for vertices;
+id -1 at 32, dimension at 36, level at 40, robust kernel at 48 for edges; `_information` between `_measurement` and
+`_error`, both located by pin_libg2o_edges.Edges.layout).  Huber kernels come from the binary's
+RobustKernelCreator<RobustKernelHuber>::construct().  TEST INFRASTRUCTURE ONLY.  Run as a script in a clean interpreter;
+appends `graph_*` arrays to tests/golden/libg2o_vectors.npz."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import pin_libg2o as P  # noqa: E402
+import pin_libg2o_edges as PE  # noqa: E402
+
+SYM = {
+    "opt_ctor": ("_ZN3g2o15SparseOptimizerC1Ev", None, 1),
+    "add_vertex": ("_ZN3g2o16OptimizableGraph9addVertexEPNS_10HyperGraph6VertexEPNS0_4DataE", C.c_bool, 3),
+    "add_edge": ("_ZN3g2o16OptimizableGraph7addEdgeEPNS_10HyperGraph4EdgeE", C.c_bool, 2),
+    "init": ("_ZN3g2o15SparseOptimizer22initializeOptimizationEi", C.c_bool, None),
+    "errors": ("_ZN3g2o15SparseOptimizer19computeActiveErrorsEv", None, 1),
+    "chi2": ("_ZNK3g2o15SparseOptimizer10activeChi2Ev", C.c_double, 1),
+    "rchi2": ("_ZNK3g2o15SparseOptimizer16activeRobustChi2Ev", C.c_double, 1),
+    "update": ("_ZN3g2o15SparseOptimizer6updateEPKd", None, 2),
+    "push": ("_ZN3g2o15SparseOptimizer4pushEv", None, 1),
+    "pop": ("_ZN3g2o15SparseOptimizer3popEv", None, 1),
+    "huber_new": ("_ZN3g2o19RobustKernelCreatorINS_17RobustKernelHuberEE9constructEv", C.c_void_p, 1),
+}
+V_ID, V_HIDX, V_FIXED, V_MARG, V_DIM = 8, 80, 84, 85, 88          # byte offsets inside a vertex
+E_ID, E_DIM, E_LEVEL, E_KERNEL = 32, 36, 40, 48                    # byte offsets inside an edge
+POINT_ID0 = 100                                                    # vertex id of landmark j is POINT_ID0 + j
+
+
+class Graph:
+    def __init__(self):
+        self.ed = PE.Edges()
+        L = self.ed.g.L
+        self.f = {}
+        for k, (name, res, nargs) in SYM.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = [C.c_void_p, C.c_int] if nargs is None else [C.c_void_p] * nargs
+            self.f[k] = fn
+        self.lay = {True: self.ed.layout(True), False: self.ed.layout(False)}
+        self.opt = P._aligned(8192)
+        self.f["opt_ctor"](self.opt.ctypes.data)
+        self.keep, self.poses, self.points, self.edges = [], {}, {}, []
+        self.pose_est_off = None
+
+    # ---- vertices
+    def _check_vertex(self, v, dim):
+        i32 = v.view(np.int32)
+        assert i32[V_ID // 4] == -1 and i32[V_HIDX // 4] == -1 and i32[V_DIM // 4] == dim, "unexpected vertex layout"
+        assert v.view(np.uint8)[V_FIXED] == 0 and v.view(np.uint8)[V_MARG] == 0
+
+    def add_pose(self, idx, upd, fixed):
+        v = self.ed._pose_vertex(np.zeros(6))
+        self._check_vertex(v, 6)
+        if self.pose_est_off is None:  # _estimate: identity quaternion (x y z w) followed by t = 0 after setToOriginImpl
+            for i in range(0, 500, 2):
+                if v[i + 3] == 1.0 and not v[i:i + 3].any() and not v[i + 4:i + 7].any():
+                    self.pose_est_off = i
+                    break
+            assert self.pose_est_off is not None
+        u = P._aligned(6)
+        u[:] = upd
+        self.ed.g.f["vtx_oplus"](v.ctypes.data, u.ctypes.data)
+        v.view(np.int32)[V_ID // 4] = idx
+        v.view(np.uint8)[V_FIXED] = 1 if fixed else 0
+        assert self.f["add_vertex"](self.opt.ctypes.data, v.ctypes.data, None)
+        self.poses[idx] = v
+
+    def add_point(self, j, X):
+        v = self.ed._point_vertex(np.asarray(X, float))
+        i32 = v.view(np.int32)
+        assert i32[V_ID // 4] == -1 and i32[V_HIDX // 4] == -1 and i32[V_DIM // 4] == 3, "unexpected vertex layout"
+        assert np.array_equal(v[19:22], X), "VertexSBAPointXYZ::_estimate is not where it was found"
+        i32[V_ID // 4] = POINT_ID0 + j
+        v.view(np.uint8)[V_MARG] = 1                                 # setMarginalized(true), g2oOptimizer.cc:868
+        assert self.f["add_vertex"](self.opt.ctypes.data, v.ctypes.data, None)
+        self.points[j] = v
+
+    def pose_estimate(self, idx):
+        e = self.poses[idx][self.pose_est_off:self.pose_est_off + 7]
+        return np.array([e[4], e[5], e[6], e[0], e[1], e[2], e[3]])  # (t, q) like SE3Quat::toVector
+
+    def point_estimate(self, j):
+        return self.points[j][19:22].copy()
+
+    # ---- edges
+    def add_edge(self, pose, point, meas, info, cam, delta):
+        stereo = not (meas[2] < 0)
+        lay, d = self.lay[stereo], 3 if stereo else 2
+        off = self.ed.g._stereo_off if stereo else self.ed.g._mono_off
+        e, vbeg = self.ed._edge(stereo)
+        i32 = e.view(np.int32)
+        assert i32[E_ID // 4] == -1 and i32[E_DIM // 4] == d and i32[E_LEVEL // 4] == 0 and e.view(np.uint64)[E_KERNEL // 8] == 0
+        ptrs = (C.c_uint64 * 2).from_address(vbeg)
+        ptrs[0], ptrs[1] = self.points[point].ctypes.data, self.poses[pose].ctypes.data   # vertex 0 = landmark, 1 = pose
+        for k, val in zip(("fx", "fy", "cx", "cy"), cam[:4]):
+            e[off[k]] = val
+        if stereo:
+            e[lay["bf"]] = cam[4]
+        e[lay["meas"]:lay["meas"] + d] = meas[:d]
+        io = lay["err"] - d * d                                      # _information sits right before _error
+        assert io >= lay["meas"] + d
+        e[io:io + d * d] = (np.eye(d) * info).ravel()
+        rk = self.f["huber_new"](None)                               # new RobustKernelHuber (with its vtable)
+        self.ed.g.f["set_delta"](rk, float(delta))
+        e.view(np.uint64)[E_KERNEL // 8] = rk
+        assert self.f["add_edge"](self.opt.ctypes.data, e.ctypes.data)
+        self.edges.append((e, stereo, rk))
+
+    def set_levels(self, levels, robust):
+        for (e, stereo, rk), lv in zip(self.edges, levels):
+            e.view(np.int32)[E_LEVEL // 4] = int(lv)
+            e.view(np.uint64)[E_KERNEL // 8] = rk if robust else 0   # e->setRobustKernel(0), g2oOptimizer.cc:969
+
+    def errors(self):
+        out = np.zeros((len(self.edges), 3))
+        for k, (e, stereo, _) in enumerate(self.edges):
+            lay = self.lay[stereo]
+            out[k, :lay["d"]] = e[lay["err"]:lay["err"] + lay["d"]]
+        return out
+
+    def phase(self, levels, robust, update, n_pose, n_point):
+        """set levels -> initializeOptimization(0) -> computeActiveErrors -> chi2s -> push, update, pop check -> update."""
+        o = self.opt.ctypes.data
+        self.set_levels(levels, robust)
+        assert self.f["init"](o, 0)
+        self.f["errors"](o)
+        pidx = np.array([self.poses[i].view(np.int32)[V_HIDX // 4] for i in range(n_pose)], np.int32)
+        lidx = np.array([self.points[j].view(np.int32)[V_HIDX // 4] for j in range(n_point)], np.int32)
+        err = self.errors()
+        chi, rchi = self.f["chi2"](o), self.f["rchi2"](o)
+        before = [self.pose_estimate(i) for i in range(n_pose)] + [self.point_estimate(j) for j in range(n_point)]
+        u = P._aligned(len(update) + 8)
+        u[:len(update)] = update
+        self.f["push"](o)
+        self.f["update"](o, u.ctypes.data)
+        moved = [self.pose_estimate(i) for i in range(n_pose)] + [self.point_estimate(j) for j in range(n_point)]
+        self.f["pop"](o)
+        after = [self.pose_estimate(i) for i in range(n_pose)] + [self.point_estimate(j) for j in range(n_point)]
+        assert all(np.array_equal(a, b) for a, b in zip(before, after)), "pop() did not restore the estimates"
+        assert any(not np.array_equal(a, b) for a, b in zip(before, moved))
+        self.f["update"](o, u.ctypes.data)                            # keep the update for the next phase
+        poses = np.stack([self.pose_estimate(i) for i in range(n_pose)])
+        points = np.stack([self.point_estimate(j) for j in range(n_point)])
+        return dict(pose_index=pidx, point_index=lidx, err=err, chi2=chi, robust_chi2=rchi, poses=poses, points=points)
+
+
+def scenario(seed=7):
+    """A small local-BA-shaped graph: 6 poses (0 and 3 fixed), 8 landmarks, 30 mono/stereo observations."""
+    rng = np.random.default_rng(seed)
+    n_pose, n_point = 6, 8
+    cam = np.array([718.856, 718.856, 607.1928, 185.2157, 386.1448]).astype(np.float32).astype(np.float64)
+    upd = rng.normal(0, 1, (n_pose, 6)) * np.array([0.03, 0.03, 0.03, 0.5, 0.2, 0.5])
+    fixed = np.array([1, 0, 0, 1, 0, 0], np.uint8)
+    X = np.stack([rng.uniform(-6, 6, n_point), rng.uniform(-2, 2, n_point), rng.uniform(8, 30, n_point)], 1)
+    obs = []
+    for j in range(n_point):
+        for i in rng.choice(n_pose, size=int(rng.integers(3, 5)), replace=False):
+            obs.append((int(i), j))
+    obs.sort(key=lambda t: (t[1], t[0]))                              # grouped by landmark, pose-sorted inside
+    obs = np.array(obs, np.int32)
+    n_obs = len(obs)
+    stereo = rng.random(n_obs) < 0.6
+    info = np.float32(1.0) / (np.float32(1.2) ** rng.integers(0, 6, n_obs)).astype(np.float32) ** 2
+    return dict(n_pose=n_pose, n_point=n_point, cam=cam, upd=upd, fixed=fixed, X=X, obs=obs, stereo=stereo,
+                info=info.astype(np.float32), rng=rng)
+
+
+def make(path, seed=7):
+    S = scenario(seed)
+    rng = S["rng"]
+    G = Graph()
+    order = rng.permutation(S["n_pose"])                             # insertion order != id order
+    for i in order:
+        G.add_pose(int(i), S["upd"][i], bool(S["fixed"][i]))
+    for j in rng.permutation(S["n_point"]):
+        G.add_point(int(j), S["X"][j])
+    pose0 = np.stack([G.pose_estimate(i) for i in range(S["n_pose"])])
+    # measurements: projection at the current estimates + noise, some gross errors so that Huber's outlier branch is hit
+    Rm = []
+    for p in pose0:
+        x, y, z, w = p[3:]
+        Rm.append(np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                            [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                            [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]))
+    meas = np.zeros((len(S["obs"]), 4), np.float32)
+    for k, (i, j) in enumerate(S["obs"]):
+        Xc = Rm[i] @ S["X"][j] + pose0[i, :3]
+        u = S["cam"][0] * Xc[0] / Xc[2] + S["cam"][2] + rng.normal(0, 1.0) + (25.0 if k % 7 == 3 else 0.0)
+        v = S["cam"][1] * Xc[1] / Xc[2] + S["cam"][3] + rng.normal(0, 1.0)
+        ur = u - S["cam"][4] / Xc[2] + rng.normal(0, 1.0) if S["stereo"][k] else -1.0
+        meas[k] = (u, v, ur, S["info"][k])
+    d2, d3 = float(np.float32(np.sqrt(5.991))), float(np.float32(np.sqrt(7.815)))   # g2oOptimizer.cc:851-853
+    for k, (i, j) in enumerate(S["obs"]):
+        G.add_edge(int(i), int(j), meas[k].astype(np.float64), float(meas[k, 3]), S["cam"], d3 if S["stereo"][k] else d2)
+    n_obs = len(S["obs"])
+    # phase A: everything at level 0, Huber on (pass 1 of local BA)
+    levA = np.zeros(n_obs, np.int32)
+    nfreeA = int((S["fixed"] == 0).sum())
+    updA = rng.normal(0, 1, 6 * nfreeA + 3 * S["n_point"]) * 0.01
+    A = G.phase(levA, True, updA, S["n_pose"], S["n_point"])
+    # phase B: kernels off; some edges to level 1 -- among them EVERY edge of landmark 2 and every edge of free pose 4,
+    # which therefore drop out of the index mapping (g2oOptimizer.cc:947-970 + sparse_optimizer.cpp:218-259)
+    levB = (rng.random(n_obs) < 0.15).astype(np.int32)
+    levB[S["obs"][:, 1] == 2] = 1
+    levB[S["obs"][:, 0] == 4] = 1
+    B0 = dict(pose_active=np.zeros(S["n_pose"], bool), point_active=np.zeros(S["n_point"], bool))
+    for k, (i, j) in enumerate(S["obs"]):
+        if levB[k] == 0:
+            B0["pose_active"][i] = True
+            B0["point_active"][j] = True
+    nB = int((B0["pose_active"] & (S["fixed"] == 0)).sum()) * 6 + int(B0["point_active"].sum()) * 3
+    updB = rng.normal(0, 1, nB) * 0.01
+    B = G.phase(levB, False, updB, S["n_pose"], S["n_point"])
+    out = dict(np.load(path)) if os.path.exists(path) else {}
+    out.update(graph_pose=pose0, graph_fixed=S["fixed"], graph_X=S["X"], graph_obs=S["obs"], graph_meas=meas,
+               graph_cam=S["cam"], graph_levA=levA, graph_updA=updA, graph_levB=levB, graph_updB=updB)
+    for tag, R in (("A", A), ("B", B)):
+        for k, v in R.items():
+            out[f"graph_{tag}_{k}"] = np.asarray(v)
+    np.savez(path, **out)
+    return out
+
+
+if __name__ == "__main__":
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = sys.argv[1] if len(sys.argv) > 1 else os.path.join(here, "tests", "golden", "libg2o_vectors.npz")
+    o = make(p)
+    print("wrote", p, "| phase A index:", o["graph_A_pose_index"], o["graph_A_point_index"], "| phase B index:",
+          o["graph_B_pose_index"], o["graph_B_point_index"], "| chi2", o["graph_A_chi2"], o["graph_A_robust_chi2"],
+          o["graph_B_chi2"])
+    sys.stdout.flush()
+    os._exit(0)

@@ -7,14 +7,18 @@
 // It is a dependency-free FP64 restatement of the reference's default BA back-end (vendored g2o
 // driven by src/backend/g2oOptimizer.cc).  The reference itself cannot be compiled here (needs
 // Eigen, OpenCV, PCL, Ceres, ROS -- none installed, no network), so this is a "port" oracle.
-// PARITY PARTLY PINNED: the reference has no tests, golden vectors or fixtures, so the solver-level
-// behaviour (Schur/LM control flow, outlier policy) is unpinned upstream.  The per-edge arithmetic IS pinned against
+// PARITY PARTLY PINNED: the reference has no tests, golden vectors or fixtures, so the linear algebra
+// and the LM policy (Schur complement, LDLT, lambda/accept rules; BlockSolver and LinearSolverEigen are header-only and
+// absent from the shipped binary) and the lidar pass are unpinned upstream.  The per-edge arithmetic IS pinned against
 // the reference's own compiled code: its tree ships a prebuilt Thirdparty/g2o/lib/libg2o.so that exports
 // SE3Quat::exp, project2d, the mono / stereo cam_project and RobustKernelHuber::robustify; oracle/pin_libg2o.py calls
 // them through ctypes and tests/test_pin_libg2o.py checks this file against the recorded outputs
 // (tests/golden/libg2o_vectors.npz); oracle/pin_libg2o_edges.py does the same with REAL vertex and edge objects of that
 // binary (oplusImpl, computeError, linearizeOplus): residuals and Jacobians agree to 1e-15.  The check found one quirk
-// the sources hide in a header: `float dsqr`.
+// the sources hide in a header: `float dsqr`.  oracle/pin_libg2o_graph.py pins the GRAPH semantics against a real
+// g2o::SparseOptimizer of that binary: index mapping of initializeOptimization (free poses, then landmarks, ascending
+// id; fixed and edge-less vertices excluded), computeActiveErrors leaving level-1 edges' _error stale, activeChi2 /
+// activeRobustChi2, update() in index order, push/pop (refba_debug_phase below reproduces all of it exactly).
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 // Eigen is not vendored in the reference; where g2o calls into Eigen (quaternion*vector,
@@ -1169,6 +1173,34 @@ int refba_trace_len(refba* h) { return (int)h->g.trace.size(); }
 void refba_get_trace(refba* h, double* out) { std::memcpy(out, h->g.trace.data(), h->g.trace.size() * sizeof(TraceRow)); }
 
 // ---- stage-level introspection used by the kernel parity tests --------------------------------
+
+// One "phase" of graph-level semantics, used to pin the oracle against a REAL g2o::SparseOptimizer of the reference's
+// prebuilt binary (oracle/pin_libg2o_graph.py): set the edge levels and robust flags, initializeOptimization(0),
+// computeActiveErrors(), report the index mapping (hessianIndex of every vertex; landmarks offset by the number of
+// free poses as in g2o), every edge's stored _error (inactive edges keep what they had), activeChi2 and
+// activeRobustChi2, then -- if `update` is given -- SparseOptimizer::update(update) and the resulting estimates.
+void refba_debug_phase(refba* h, const int32_t* levels, int robust, int32_t* pose_index, int32_t* point_index,
+                       double* err, double* chi2_out, const double* update, double* poses, double* points) {
+  Graph& g = h->g;
+  const float thHuberMono = std::sqrt(5.991), thHuberStereo = std::sqrt(7.815);
+  for (size_t k = 0; k < g.edges.size(); k++) {
+    g.edges[k].level = levels[k];
+    setHuber(g.edges[k], thHuberMono, thHuberStereo, robust != 0);
+  }
+  initializeOptimization(g, 0);
+  computeActiveErrors(g);
+  for (int i = 0; i < g.n_pose; i++) pose_index[i] = g.pose_slot[i];
+  for (int i = 0; i < g.n_point; i++) point_index[i] = g.point_slot[i] < 0 ? -1 : g.Np + g.point_slot[i];
+  for (size_t k = 0; k < g.edges.size(); k++)
+    for (int c = 0; c < 3; c++) err[k * 3 + c] = g.edges[k].err[c];
+  double plain = 0.0;
+  for (int k : g.active) plain += chi2(g.edges[k]);  // SparseOptimizer::activeChi2, sparse_optimizer.cpp:90-98
+  chi2_out[0] = plain;
+  chi2_out[1] = activeRobustChi2(g);
+  if (update) updateState(g, update);
+  refba_get_poses(h, poses);
+  refba_get_points(h, points);
+}
 
 // Residuals / Jacobians / robust weights of every edge at the CURRENT state.
 // err (n_obs,3), Jp (n_obs,18), Jl (n_obs,9), w (n_obs,) = rho1*invSigma2, rho0 (n_obs,) robustified chi2.

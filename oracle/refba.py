@@ -55,6 +55,7 @@ def lib():
         L.refba_lidar_num_matches.argtypes = [C.c_void_p]
         L.refba_get_lidar_matches.argtypes = [C.c_void_p, ip]
         L.refba_num_lidar_edges.argtypes = [C.c_void_p]
+        L.refba_debug_phase.argtypes = [C.c_void_p, ip, C.c_int, ip, ip, dp, dp, dp, dp, dp]
         L.refba_pose_opt.argtypes = [dp, dp, C.c_int, dp, fp, up, dp, C.c_int, ip]
         _lib = L
     return _lib
@@ -93,6 +94,18 @@ class RefBA:
 
     def solve_global(self, iters: int, robust: bool, stop=None):
         return lib().refba_solve_global(self.h, iters, int(robust), stop)
+
+    def debug_phase(self, levels, robust, update=None):
+        """initializeOptimization(0) + computeActiveErrors + chi2 [+ update] with the given edge levels (refba_debug_phase)."""
+        lv = np.ascontiguousarray(levels, np.int32)
+        pi, li = np.zeros(self.n_pose, np.int32), np.zeros(self.n_point, np.int32)
+        err, chi = np.zeros((self.n_obs, 3)), np.zeros(2)
+        P, X = np.zeros((self.n_pose, 7)), np.zeros((self.n_point, 3))
+        up = None if update is None else np.ascontiguousarray(update, np.float64)
+        lib().refba_debug_phase(self.h, _p(lv, C.c_int32), int(robust), _p(pi, C.c_int32), _p(li, C.c_int32),
+                                _p(err, C.c_double), _p(chi, C.c_double), None if up is None else _p(up, C.c_double),
+                                _p(P, C.c_double), _p(X, C.c_double))
+        return dict(pose_index=pi, point_index=li, err=err, chi2=chi[0], robust_chi2=chi[1], poses=P, points=X)
 
     def set_lidar_edges(self, cur_pose, pc, qw, normal, w, n_flat, numeric_jacobian=True):
         """Explicit lidar correspondences for the third pass (flat edges first; w == 0 -> no edge)."""

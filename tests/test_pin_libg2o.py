@@ -70,7 +70,7 @@ def test_committed_fixture_is_what_the_binary_computes(tmp_path, gold):
     # in a clean interpreter: the prebuilt binary is not loaded into the test process
     out = str(tmp_path / "g.npz")
     odir = os.path.dirname(os.path.abspath(pin_libg2o.__file__))
-    for script in ("pin_libg2o.py", "pin_libg2o_edges.py"):   # the second appends the edge_* arrays
+    for script in ("pin_libg2o.py", "pin_libg2o_edges.py", "pin_libg2o_graph.py"):   # each appends its arrays
         subprocess.run([sys.executable, os.path.join(odir, script), out], check=True, capture_output=True)
     fresh = np.load(out)
     for k in gold.files:
@@ -112,3 +112,39 @@ def test_edge_error_and_jacobians_match_reference_binary(gold, synth, tag, stere
         np.testing.assert_allclose(e, gold[f"edge_{tag}_err"][k], rtol=0, atol=1e-14 * max(1.0, np.abs(e).max()))
         np.testing.assert_allclose(Jp, gold[f"edge_{tag}_Jp"][k], rtol=0, atol=4e-15 * np.abs(Jp).max())
         np.testing.assert_allclose(Jl, gold[f"edge_{tag}_Jl"][k], rtol=0, atol=4e-15 * np.abs(Jl).max())
+
+
+def test_graph_semantics_match_reference_binary(gold, synth):
+    """A REAL g2o::SparseOptimizer of the binary (oracle/pin_libg2o_graph.py) on a small local-BA-shaped graph, two
+    phases like the two passes of local BA: (A) all edges at level 0 with Huber kernels, (B) kernels off and some edges
+    at level 1 -- including every edge of one landmark and of one free pose.  Pinned: the index mapping of
+    initializeOptimization (free poses first, landmarks second, ascending id, fixed / edge-less vertices excluded),
+    computeActiveErrors touching active edges only (level-1 edges keep their phase-A _error), activeChi2 and
+    activeRobustChi2, and SparseOptimizer::update consuming the increment in index order."""
+    g = {k[len("graph_"):]: gold[k] for k in gold.files if k.startswith("graph_")}
+    n_pose, n_point = len(g["pose"]), len(g["X"])
+    prob = synth.Problem(g["pose"].copy(), g["fixed"].astype(np.uint8), np.tile(g["cam"], (n_pose, 1)), g["X"].copy(),
+                         g["obs"][:, 0].astype(np.int32), g["obs"][:, 1].astype(np.int32), g["meas"].astype(np.float32))
+    r = refba.RefBA(prob)
+    A = r.debug_phase(g["levA"], True, g["updA"])
+    B = r.debug_phase(g["levB"], False, g["updB"])
+    for tag, got in (("A", A), ("B", B)):
+        assert np.array_equal(got["pose_index"], g[f"{tag}_pose_index"]), tag
+        assert np.array_equal(got["point_index"], g[f"{tag}_point_index"]), tag
+        np.testing.assert_allclose(got["err"], g[f"{tag}_err"], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(got["chi2"], float(g[f"{tag}_chi2"]), rtol=1e-12)
+        np.testing.assert_allclose(got["robust_chi2"], float(g[f"{tag}_robust_chi2"]), rtol=1e-12)
+        np.testing.assert_allclose(got["poses"], g[f"{tag}_poses"], rtol=0, atol=1e-14)
+        np.testing.assert_allclose(got["points"], g[f"{tag}_points"], rtol=0, atol=1e-14)
+    # what the fixture exercises
+    assert g["A_robust_chi2"] < g["A_chi2"]                      # Huber's outlier branch was hit
+    assert (g["A_pose_index"][g["fixed"] == 1] == -1).all() and (g["A_pose_index"][g["fixed"] == 0] >= 0).all()
+    free_inactive = (g["B_pose_index"] == -1) & (g["fixed"] == 0)
+    assert free_inactive.sum() == 1 and (g["B_point_index"] == -1).sum() >= 1
+    lv1 = g["levB"] == 1
+    assert lv1.sum() >= 5 and np.array_equal(g["B_err"][lv1], g["A_err"][lv1])      # stale _error of level-1 edges
+    assert not np.array_equal(g["B_err"][~lv1], g["A_err"][~lv1])                  # active ones were recomputed
+    # an excluded vertex is not moved by update()
+    i = int(np.flatnonzero(free_inactive)[0])
+    assert np.array_equal(g["B_poses"][i], g["A_poses"][i])
+    assert not np.array_equal(g["A_poses"][1], g["pose"][1])
