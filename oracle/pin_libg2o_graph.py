@@ -10,7 +10,11 @@ pins the graph semantics the BA control flow relies on (SURVEY.md 8(a) rows A8, 
     keeps the error it had (the stale-_error rule behind the local-BA outlier test, g2oOptimizer.cc:947-976,1119-1142);
   * activeChi2 / activeRobustChi2 (sparse_optimizer.cpp:90-114) over the active edges, Huber with the float dsqr;
   * update(double*) (sparse_optimizer.cpp:422-435) consumes the increment in index order and applies oplusImpl;
-    push()/pop() restore the estimates.
+    push()/pop() restore the estimates;
+  * the normal equations (row A7): with the vertices' Hessian blocks and every edge's off-diagonal block mapped onto
+    our own memory (mapHessianMemory, as BlockSolver::buildStructure does, block_solver.hpp:143-295), the binary's
+    linearizeOplus + constructQuadraticForm of every active edge (base_binary_edge.hpp:55-120; Huber weighting through
+    robustInformation, base_edge.h:96-102) give Hpp, Hll, the 6x3 pose-landmark blocks and the gradient b.
 
 Objects are built with the binary's own constructors in raw 64-byte aligned blocks; the few inline setters (setId,
 setFixed, setMarginalized, setLevel, setRobustKernel, setInformation) are replaced by writes at member offsets that are
@@ -43,6 +47,14 @@ SYM = {
     "push": ("_ZN3g2o15SparseOptimizer4pushEv", None, 1),
     "pop": ("_ZN3g2o15SparseOptimizer3popEv", None, 1),
     "huber_new": ("_ZN3g2o19RobustKernelCreatorINS_17RobustKernelHuberEE9constructEv", C.c_void_p, 1),
+    "pose_map": ("_ZN3g2o10BaseVertexILi6ENS_7SE3QuatEE16mapHessianMemoryEPd", None, 2),
+    "pose_clear": ("_ZN3g2o10BaseVertexILi6ENS_7SE3QuatEE18clearQuadraticFormEv", None, 1),
+    "pt_map": ("_ZN3g2o10BaseVertexILi3EN5Eigen6MatrixIdLi3ELi1ELi0ELi3ELi1EEEE16mapHessianMemoryEPd", None, 2),
+    "pt_clear": ("_ZN3g2o10BaseVertexILi3EN5Eigen6MatrixIdLi3ELi1ELi0ELi3ELi1EEEE18clearQuadraticFormEv", None, 1),
+    "e3_map": ("_ZN3g2o14BaseBinaryEdgeILi3EN5Eigen6MatrixIdLi3ELi1ELi0ELi3ELi1EEENS_17VertexSBAPointXYZENS_15VertexSE3ExpmapEE16mapHessianMemoryEPdiib", None, -1),
+    "e2_map": ("_ZN3g2o14BaseBinaryEdgeILi2EN5Eigen6MatrixIdLi2ELi1ELi0ELi2ELi1EEENS_17VertexSBAPointXYZENS_15VertexSE3ExpmapEE16mapHessianMemoryEPdiib", None, -1),
+    "e3_quad": ("_ZN3g2o14BaseBinaryEdgeILi3EN5Eigen6MatrixIdLi3ELi1ELi0ELi3ELi1EEENS_17VertexSBAPointXYZENS_15VertexSE3ExpmapEE22constructQuadraticFormEv", None, 1),
+    "e2_quad": ("_ZN3g2o14BaseBinaryEdgeILi2EN5Eigen6MatrixIdLi2ELi1ELi0ELi2ELi1EEENS_17VertexSBAPointXYZENS_15VertexSE3ExpmapEE22constructQuadraticFormEv", None, 1),
 }
 V_ID, V_HIDX, V_FIXED, V_MARG, V_DIM = 8, 80, 84, 85, 88          # byte offsets inside a vertex
 E_ID, E_DIM, E_LEVEL, E_KERNEL = 32, 36, 40, 48                    # byte offsets inside an edge
@@ -57,7 +69,8 @@ class Graph:
         for k, (name, res, nargs) in SYM.items():
             fn = getattr(L, name)
             fn.restype = res
-            fn.argtypes = [C.c_void_p, C.c_int] if nargs is None else [C.c_void_p] * nargs
+            fn.argtypes = ([C.c_void_p, C.c_int] if nargs is None else
+                           [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_bool] if nargs == -1 else [C.c_void_p] * nargs)
             self.f[k] = fn
         self.lay = {True: self.ed.layout(True), False: self.ed.layout(False)}
         self.opt = P._aligned(8192)
@@ -141,6 +154,57 @@ class Graph:
             out[k, :lay["d"]] = e[lay["err"]:lay["err"] + lay["d"]]
         return out
 
+    def system(self, levels, fixed, obs):
+        """Hpp / Hll / per-edge Hpl (6x3) / b of the active edges at the current estimates, assembled by the binary."""
+        n_pose, n_point = len(self.poses), len(self.points)
+        Hpp = [P._aligned(36) for _ in range(n_pose)]
+        Hll = [P._aligned(12) for _ in range(n_point)]
+        Hpl = [P._aligned(20) for _ in self.edges]
+        for i in range(n_pose):
+            self.f["pose_map"](self.poses[i].ctypes.data, Hpp[i].ctypes.data)
+        for j in range(n_point):
+            self.f["pt_map"](self.points[j].ctypes.data, Hll[j].ctypes.data)
+        snap = {("p", i): self.poses[i].copy() for i in range(n_pose)}
+        snap.update({("l", j): self.points[j].copy() for j in range(n_point)})
+        for i in range(n_pose):
+            self.f["pose_clear"](self.poses[i].ctypes.data)
+        for j in range(n_point):
+            self.f["pt_clear"](self.points[j].ctypes.data)
+        jws = []
+        for k, (e, stereo, _) in enumerate(self.edges):
+            if levels[k] != 0:
+                continue
+            tag = "e3" if stereo else "e2"
+            if not fixed[obs[k][0]]:   # BlockSolver maps the pose-landmark block transposed: pose index < landmark index
+                self.f[tag + "_map"](e.ctypes.data, Hpl[k].ctypes.data, 0, 1, True)
+            jw = P._aligned(64)
+            self.ed.f["jw_ctor"](jw.ctypes.data)
+            self.ed.f["jw_size"](jw.ctypes.data, e.ctypes.data)
+            assert self.ed.f["jw_alloc"](jw.ctypes.data)
+            self.ed.f["stereo_lin" if stereo else "mono_lin"](e.ctypes.data, jw.ctypes.data)
+            self.f[tag + "_quad"](e.ctypes.data)
+            jws.append(jw)
+        # _b of a vertex: the D consecutive doubles that constructQuadraticForm moved (found by diffing the object)
+        def b_of(kind, idx, D):
+            v = self.poses[idx] if kind == "p" else self.points[idx]
+            ch = np.flatnonzero(v.view(np.uint64) != snap[(kind, idx)].view(np.uint64))   # bitwise: some slots hold NaN patterns
+            if len(ch) == 0:
+                return np.zeros(D)
+            assert ch.max() - ch.min() < D, (kind, idx, ch)
+            return ch.min()
+        boff = {}
+        for kind, n, D in (("p", n_pose, 6), ("l", n_point, 3)):
+            offs = [b_of(kind, i, D) for i in range(n)]
+            offs = [o for o in offs if not isinstance(o, np.ndarray)]
+            # the first changed slot may not be _b[0] if _b[0] stayed 0: take the smallest over all vertices of the kind
+            boff[kind] = min(offs)
+        bp = np.stack([self.poses[i][boff["p"]:boff["p"] + 6] for i in range(n_pose)])
+        bl = np.stack([self.points[j][boff["l"]:boff["l"] + 3] for j in range(n_point)])
+        H6 = np.stack([h[:36].reshape(6, 6).T for h in Hpp])       # Eigen blocks are column-major
+        H3 = np.stack([h[:9].reshape(3, 3).T for h in Hll])
+        Hx = np.stack([h[:18].reshape(3, 6).T for h in Hpl])       # 6x3 column-major -> (6, 3)
+        return dict(Hpp=H6, Hll=H3, Hpl=Hx, b_pose=bp, b_point=bl), jws
+
     def phase(self, levels, robust, update, n_pose, n_point):
         """set levels -> initializeOptimization(0) -> computeActiveErrors -> chi2s -> push, update, pop check -> update."""
         o = self.opt.ctypes.data
@@ -220,6 +284,10 @@ def make(path, seed=7):
     levA = np.zeros(n_obs, np.int32)
     nfreeA = int((S["fixed"] == 0).sum())
     updA = rng.normal(0, 1, 6 * nfreeA + 3 * S["n_point"]) * 0.01
+    G.set_levels(levA, True)
+    assert G.f["init"](G.opt.ctypes.data, 0)
+    G.f["errors"](G.opt.ctypes.data)
+    sysA, keep_jw = G.system(levA, S["fixed"], S["obs"])            # normal equations of pass 1 at the initial estimates
     A = G.phase(levA, True, updA, S["n_pose"], S["n_point"])
     # phase B: kernels off; some edges to level 1 -- among them EVERY edge of landmark 2 and every edge of free pose 4,
     # which therefore drop out of the index mapping (g2oOptimizer.cc:947-970 + sparse_optimizer.cpp:218-259)
@@ -237,6 +305,8 @@ def make(path, seed=7):
     out = dict(np.load(path)) if os.path.exists(path) else {}
     out.update(graph_pose=pose0, graph_fixed=S["fixed"], graph_X=S["X"], graph_obs=S["obs"], graph_meas=meas,
                graph_cam=S["cam"], graph_levA=levA, graph_updA=updA, graph_levB=levB, graph_updB=updB)
+    for k, v in sysA.items():
+        out[f"graph_sysA_{k}"] = v
     for tag, R in (("A", A), ("B", B)):
         for k, v in R.items():
             out[f"graph_{tag}_{k}"] = np.asarray(v)

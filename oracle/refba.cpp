@@ -7,7 +7,7 @@
 // It is a dependency-free FP64 restatement of the reference's default BA back-end (vendored g2o
 // driven by src/backend/g2oOptimizer.cc).  The reference itself cannot be compiled here (needs
 // Eigen, OpenCV, PCL, Ceres, ROS -- none installed, no network), so this is a "port" oracle.
-// PARITY PARTLY PINNED: the reference has no tests, golden vectors or fixtures, so the linear algebra
+// PARITY PARTLY PINNED: the reference has no tests, golden vectors or fixtures, so the reduced solve
 // and the LM policy (Schur complement, LDLT, lambda/accept rules; BlockSolver and LinearSolverEigen are header-only and
 // absent from the shipped binary) and the lidar pass are unpinned upstream.  The per-edge arithmetic IS pinned against
 // the reference's own compiled code: its tree ships a prebuilt Thirdparty/g2o/lib/libg2o.so that exports
@@ -18,7 +18,9 @@
 // the sources hide in a header: `float dsqr`.  oracle/pin_libg2o_graph.py pins the GRAPH semantics against a real
 // g2o::SparseOptimizer of that binary: index mapping of initializeOptimization (free poses, then landmarks, ascending
 // id; fixed and edge-less vertices excluded), computeActiveErrors leaving level-1 edges' _error stale, activeChi2 /
-// activeRobustChi2, update() in index order, push/pop (refba_debug_phase below reproduces all of it exactly).
+// activeRobustChi2, update() in index order, push/pop, and the normal equations that the binary's linearizeOplus +
+// constructQuadraticForm accumulate into mapped Hessian blocks (refba_debug_phase / refba_debug_system below
+// reproduce all of it: indices exactly, numbers to 1e-12).
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 // Eigen is not vendored in the reference; where g2o calls into Eigen (quaternion*vector,
@@ -1200,6 +1202,38 @@ void refba_debug_phase(refba* h, const int32_t* levels, int robust, int32_t* pos
   if (update) updateState(g, update);
   refba_get_poses(h, poses);
   refba_get_points(h, points);
+}
+
+// The normal equations of the active set chosen by the last refba_debug_phase, at the current state:
+// buildStructure + computeActiveErrors + buildSystem (linearizeOplus + constructQuadraticForm of every active edge,
+// base_binary_edge.hpp:55-120, block_solver.hpp:502-560).  Hpp: 36 per pose (row-major 6x6, zero for poses without an
+// index), Hll: 9 per landmark, Hpl: 18 per EDGE (6x3 row-major: B^T W A of the (pose, landmark) block the edge adds to;
+// zero when the pose is fixed or the edge inactive), b: 6 per pose then 3 per landmark (vertex order, not index order).
+void refba_debug_system(refba* h, double* Hpp, double* Hll, double* Hpl, double* b) {
+  Graph& g = h->g;
+  buildStructure(g);
+  computeActiveErrors(g);
+  buildSystem(g);
+  std::fill(Hpp, Hpp + (size_t)g.n_pose * 36, 0.0);
+  std::fill(Hll, Hll + (size_t)g.n_point * 9, 0.0);
+  std::fill(Hpl, Hpl + g.edges.size() * 18, 0.0);
+  std::fill(b, b + (size_t)g.n_pose * 6 + (size_t)g.n_point * 3, 0.0);
+  for (int i = 0; i < g.n_pose; i++) {
+    const int s = g.pose_slot[i];
+    if (s < 0) continue;
+    std::memcpy(Hpp + (size_t)i * 36, &g.Hpp[(size_t)s * 36], 36 * sizeof(double));
+    std::memcpy(b + (size_t)i * 6, &g.b[(size_t)s * 6], 6 * sizeof(double));
+  }
+  for (int j = 0; j < g.n_point; j++) {
+    const int s = g.point_slot[j];
+    if (s < 0) continue;
+    std::memcpy(Hll + (size_t)j * 9, &g.Hll[(size_t)s * 9], 9 * sizeof(double));
+    std::memcpy(b + (size_t)g.n_pose * 6 + (size_t)j * 3, &g.b[(size_t)g.Np * 6 + (size_t)s * 3], 3 * sizeof(double));
+  }
+  for (int k : g.active) {
+    const Edge& e = g.edges[k];
+    if (e.hpl >= 0 && g.pose_slot[e.pose] >= 0) std::memcpy(Hpl + (size_t)k * 18, &g.Hpl[(size_t)e.hpl * 18], 18 * sizeof(double));
+  }
 }
 
 // Residuals / Jacobians / robust weights of every edge at the CURRENT state.

@@ -56,6 +56,7 @@ def lib():
         L.refba_get_lidar_matches.argtypes = [C.c_void_p, ip]
         L.refba_num_lidar_edges.argtypes = [C.c_void_p]
         L.refba_debug_phase.argtypes = [C.c_void_p, ip, C.c_int, ip, ip, dp, dp, dp, dp, dp]
+        L.refba_debug_system.argtypes = [C.c_void_p, dp, dp, dp, dp]
         L.refba_pose_opt.argtypes = [dp, dp, C.c_int, dp, fp, up, dp, C.c_int, ip]
         _lib = L
     return _lib
@@ -106,6 +107,15 @@ class RefBA:
                                 _p(err, C.c_double), _p(chi, C.c_double), None if up is None else _p(up, C.c_double),
                                 _p(P, C.c_double), _p(X, C.c_double))
         return dict(pose_index=pi, point_index=li, err=err, chi2=chi[0], robust_chi2=chi[1], poses=P, points=X)
+
+    def debug_system(self):
+        """Normal equations of the active set of the last debug_phase (refba_debug_system): Hpp per pose, Hll per
+        landmark, Hpl per edge (6x3), b per vertex."""
+        Hpp, Hll = np.zeros((self.n_pose, 6, 6)), np.zeros((self.n_point, 3, 3))
+        Hpl, b = np.zeros((self.n_obs, 6, 3)), np.zeros(self.n_pose * 6 + self.n_point * 3)
+        lib().refba_debug_system(self.h, _p(Hpp, C.c_double), _p(Hll, C.c_double), _p(Hpl, C.c_double), _p(b, C.c_double))
+        return dict(Hpp=Hpp, Hll=Hll, Hpl=Hpl, b_pose=b[:self.n_pose * 6].reshape(-1, 6),
+                    b_point=b[self.n_pose * 6:].reshape(-1, 3))
 
     def set_lidar_edges(self, cur_pose, pc, qw, normal, w, n_flat, numeric_jacobian=True):
         """Explicit lidar correspondences for the third pass (flat edges first; w == 0 -> no edge)."""

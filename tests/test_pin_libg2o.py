@@ -120,12 +120,23 @@ def test_graph_semantics_match_reference_binary(gold, synth):
     at level 1 -- including every edge of one landmark and of one free pose.  Pinned: the index mapping of
     initializeOptimization (free poses first, landmarks second, ascending id, fixed / edge-less vertices excluded),
     computeActiveErrors touching active edges only (level-1 edges keep their phase-A _error), activeChi2 and
-    activeRobustChi2, and SparseOptimizer::update consuming the increment in index order."""
+    activeRobustChi2, SparseOptimizer::update consuming the increment in index order, and the normal equations
+    (Hpp, Hll, the 6x3 pose-landmark blocks, b) that constructQuadraticForm accumulates."""
     g = {k[len("graph_"):]: gold[k] for k in gold.files if k.startswith("graph_")}
     n_pose, n_point = len(g["pose"]), len(g["X"])
     prob = synth.Problem(g["pose"].copy(), g["fixed"].astype(np.uint8), np.tile(g["cam"], (n_pose, 1)), g["X"].copy(),
                          g["obs"][:, 0].astype(np.int32), g["obs"][:, 1].astype(np.int32), g["meas"].astype(np.float32))
     r = refba.RefBA(prob)
+    # row A7: the normal equations of phase A at the initial estimates, assembled by the binary's own linearizeOplus +
+    # constructQuadraticForm (Huber weighting through robustInformation) into blocks mapped the way BlockSolver maps them
+    r.debug_phase(g["levA"], True, None)
+    sysA = r.debug_system()
+    for k in ("Hpp", "Hll", "Hpl", "b_pose", "b_point"):
+        want = g[f"sysA_{k}"]
+        np.testing.assert_allclose(sysA[k], want, rtol=0, atol=1e-13 * np.abs(want).max(), err_msg=k)
+    assert not g["sysA_Hpp"][g["fixed"] == 1].any() and not g["sysA_b_pose"][g["fixed"] == 1].any()   # fixed: no blocks
+    assert not g["sysA_Hpl"][g["fixed"][g["obs"][:, 0]] == 1].any()
+    assert np.abs(g["sysA_Hpl"][g["fixed"][g["obs"][:, 0]] == 0]).min(axis=(1, 2)).max() > 0
     A = r.debug_phase(g["levA"], True, g["updA"])
     B = r.debug_phase(g["levB"], False, g["updB"])
     for tag, got in (("A", A), ("B", B)):
