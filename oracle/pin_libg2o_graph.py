@@ -198,6 +198,7 @@ class Graph:
             offs = [o for o in offs if not isinstance(o, np.ndarray)]
             # the first changed slot may not be _b[0] if _b[0] stayed 0: take the smallest over all vertices of the kind
             boff[kind] = min(offs)
+        self.boff = boff
         bp = np.stack([self.poses[i][boff["p"]:boff["p"] + 6] for i in range(n_pose)])
         bl = np.stack([self.points[j][boff["l"]:boff["l"] + 3] for j in range(n_point)])
         H6 = np.stack([h[:36].reshape(6, 6).T for h in Hpp])       # Eigen blocks are column-major
@@ -229,6 +230,151 @@ class Graph:
         poses = np.stack([self.pose_estimate(i) for i in range(n_pose)])
         points = np.stack([self.point_estimate(j) for j in range(n_point)])
         return dict(pose_index=pidx, point_index=lidx, err=err, chi2=chi, robust_chi2=rchi, poses=poses, points=points)
+
+
+class FakeSolver:
+    """A g2o::Solver (core/solver.h:43-150) implemented HERE and handed to the binary's own
+    OptimizationAlgorithmLevenberg: a hand-made vtable of ctypes callbacks in declaration order (two destructor
+    slots, init, buildStructure, updateStructure, buildSystem, solve, computeMarginals, setLambda, restoreDiagonal,
+    supportsSchur, schur, setSchur, setWriteDebug, writeDebug, saveHessian) in front of the members the inline accessors
+    read (_optimizer, _x, _b, _xSize, _maxXSize, _isLevenberg, _additionalVectorSpace).  The linear algebra is the
+    binary's linearizeOplus + constructQuadraticForm into blocks mapped here (what BlockSolver::buildSystem does,
+    block_solver.hpp:502-560), lambda on every diagonal (setLambda, :564-589) and ONE dense solve of the full system
+    (exactly what Schur complement + LDLT + back-substitution compute, :354-486).  Everything else -- lambda_0, the gain
+    ratio, the lambda/nu policy, trial loop, push/pop/discardTop, stop rules -- is the reference binary's code."""
+
+    def __init__(self, G, fixed, obs, levels):
+        self.G, self.fixed, self.obs, self.levels = G, fixed, obs, levels
+        self.log = []          # ("lambda", value) / ("solve", |x|) in call order
+        vp, b, d = C.c_void_p, C.c_bool, C.c_double
+        sig = [(None, [vp]), (None, [vp]), (b, [vp, vp, b]), (b, [vp, b]), (b, [vp, vp, vp]), (b, [vp]), (b, [vp]),
+               (b, [vp, vp, vp]), (b, [vp, d, b]), (None, [vp]), (b, [vp]), (b, [vp]), (None, [vp, b]), (None, [vp, b]),
+               (b, [vp]), (b, [vp, vp])]
+        impl = [self._noop, self._noop, self._init, self._build_structure, self._false3, self._build_system, self._solve,
+                self._false3, self._set_lambda, self._restore, self._false1, self._false1, self._noop2, self._noop2,
+                self._false1, self._false2]
+        self.cbs = [C.CFUNCTYPE(r, *a)(f) for (r, a), f in zip(sig, impl)]
+        self.vtable = (C.c_void_p * (len(self.cbs) + 2))()
+        for i, cb in enumerate(self.cbs):
+            self.vtable[i + 2] = C.cast(cb, C.c_void_p).value           # [0] offset-to-top, [1] RTTI stay 0
+        self.obj = P._aligned(16)
+        u = self.obj.view(np.uint64)
+        u[0] = C.addressof(self.vtable) + 16
+        u[1] = G.opt.ctypes.data                                          # _optimizer
+        u[6] = 1                                                          # _isLevenberg
+
+    # ---- trivial slots
+    def _noop(self, this): return None
+    def _noop2(self, this, flag): return None
+    def _false1(self, this): return False
+    def _false2(self, this, a): return False
+    def _false3(self, this, a, b): return False
+    def _init(self, this, opt, online): return True
+
+    def _build_structure(self, this, zero):
+        G = self.G
+        n_pose, n_point = len(G.poses), len(G.points)
+        ent = [(int(G.poses[i].view(np.int32)[V_HIDX // 4]), "p", i) for i in range(n_pose)]
+        ent += [(int(G.points[j].view(np.int32)[V_HIDX // 4]), "l", j) for j in range(n_point)]
+        ent = sorted(e for e in ent if e[0] >= 0)
+        self.off, n = {}, 0
+        for _, kind, i in ent:
+            self.off[(kind, i)] = n
+            n += 6 if kind == "p" else 3
+        self.n = n
+        self.Hpp = {i: P._aligned(36) for (k, i) in self.off if k == "p"}
+        self.Hll = {j: P._aligned(12) for (k, j) in self.off if k == "l"}
+        for i, h in self.Hpp.items():
+            G.f["pose_map"](G.poses[i].ctypes.data, h.ctypes.data)
+        for j, h in self.Hll.items():
+            G.f["pt_map"](G.points[j].ctypes.data, h.ctypes.data)
+        self.Hpl, self.jw = {}, {}
+        for k, (e, stereo, _) in enumerate(G.edges):
+            if self.levels[k] != 0:
+                continue
+            i, j = int(self.obs[k][0]), int(self.obs[k][1])
+            if ("p", i) in self.off and ("l", j) in self.off:
+                self.Hpl[k] = P._aligned(20)
+                G.f[("e3" if stereo else "e2") + "_map"](e.ctypes.data, self.Hpl[k].ctypes.data, 0, 1, True)
+            jw = P._aligned(64)
+            G.ed.f["jw_ctor"](jw.ctypes.data)
+            G.ed.f["jw_size"](jw.ctypes.data, e.ctypes.data)
+            assert G.ed.f["jw_alloc"](jw.ctypes.data)
+            self.jw[k] = jw
+        self.x, self.b = P._aligned(n + 8), P._aligned(n + 8)
+        u = self.obj.view(np.uint64)
+        u[2], u[3], u[4], u[5] = self.x.ctypes.data, self.b.ctypes.data, n, n
+        return True
+
+    def _build_system(self, this):
+        G = self.G
+        for h in list(self.Hpp.values()) + list(self.Hll.values()) + list(self.Hpl.values()):
+            h[:] = 0.0
+        for (kind, i) in self.off:
+            G.f["pose_clear" if kind == "p" else "pt_clear"]((G.poses if kind == "p" else G.points)[i].ctypes.data)
+        for k, jw in self.jw.items():
+            e, stereo, _ = G.edges[k]
+            G.ed.f["stereo_lin" if stereo else "mono_lin"](e.ctypes.data, jw.ctypes.data)
+            G.f[("e3" if stereo else "e2") + "_quad"](e.ctypes.data)
+        for (kind, i), o in self.off.items():                            # v->copyB(_b + colInHessian)
+            D = 6 if kind == "p" else 3
+            v = (G.poses if kind == "p" else G.points)[i]
+            self.b[o:o + D] = v[G.boff[kind]:G.boff[kind] + D]
+        return True
+
+    def _diag(self):
+        for i, h in self.Hpp.items():
+            yield h, [r * 6 + r for r in range(6)]
+        for j, h in self.Hll.items():
+            yield h, [r * 3 + r for r in range(3)]
+
+    def _set_lambda(self, this, lam, backup):
+        self.log.append(("lambda", float(lam)))
+        if backup:
+            self.backup = [(h, idx, h[idx].copy()) for h, idx in self._diag()]
+        for h, idx in self._diag():
+            h[idx] += lam
+        return True
+
+    def _restore(self, this):
+        for h, idx, val in self.backup:
+            h[idx] = val
+        return None
+
+    def _solve(self, this):
+        H = np.zeros((self.n, self.n))
+        for i, h in self.Hpp.items():
+            o = self.off[("p", i)]
+            H[o:o + 6, o:o + 6] = h[:36].reshape(6, 6).T
+        for j, h in self.Hll.items():
+            o = self.off[("l", j)]
+            H[o:o + 3, o:o + 3] = h[:9].reshape(3, 3).T
+        for k, h in self.Hpl.items():
+            op, ol = self.off[("p", int(self.obs[k][0]))], self.off[("l", int(self.obs[k][1]))]
+            blk = h[:18].reshape(3, 6).T                                 # 6x3
+            H[op:op + 6, ol:ol + 3] += blk
+            H[ol:ol + 3, op:op + 6] += blk.T
+        x = np.linalg.solve(H, self.b[:self.n])
+        self.x[:self.n] = x
+        self.log.append(("solve", float(np.linalg.norm(x))))
+        return True
+
+
+def run_lm(G, fixed, obs, levels, iters):
+    """SparseOptimizer::optimize(iters) of the binary with its own OptimizationAlgorithmLevenberg on top of FakeSolver."""
+    L = G.ed.g.L
+    lm_ctor = L._ZN3g2o30OptimizationAlgorithmLevenbergC1EPNS_6SolverE
+    lm_ctor.restype, lm_ctor.argtypes = None, [C.c_void_p, C.c_void_p]
+    set_alg = L._ZN3g2o15SparseOptimizer12setAlgorithmEPNS_21OptimizationAlgorithmE
+    set_alg.restype, set_alg.argtypes = None, [C.c_void_p, C.c_void_p]
+    optimize = L._ZN3g2o15SparseOptimizer8optimizeEib
+    optimize.restype, optimize.argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_bool]
+    solver = FakeSolver(G, fixed, obs, levels)
+    alg = P._aligned(1024)
+    lm_ctor(alg.ctypes.data, solver.obj.ctypes.data)
+    set_alg(G.opt.ctypes.data, alg.ctypes.data)
+    n_it = optimize(G.opt.ctypes.data, iters, False)
+    return n_it, solver, alg
 
 
 def scenario(seed=7):
@@ -314,10 +460,92 @@ def make(path, seed=7):
     return out
 
 
+def _rot(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def lm_scenario(exp, seed, rs, ts, xs, outliers, n_pose=7, n_point=30):
+    """A small BA problem that is far from its optimum (pose noise rs rad / ts m, landmark noise xs m, gross outliers):
+    Levenberg needs rejected trials and gain ratios in the unclamped range, and stops by its own rule."""
+    rng = np.random.default_rng(seed)
+    cam = np.array([718.856, 718.856, 607.1928, 185.2157, 386.1448]).astype(np.float32).astype(np.float64)
+    upd_t = rng.normal(0, 1, (n_pose, 6)) * np.array([0.03, 0.03, 0.03, 0.8, 0.2, 0.8])
+    fixed = np.zeros(n_pose, np.uint8)
+    fixed[0] = fixed[3] = 1
+    pose_t = np.stack([exp(u) for u in upd_t])
+    upd0 = upd_t + rng.normal(0, 1, (n_pose, 6)) * np.array([rs, rs, rs, ts, ts, ts]) * (fixed == 0)[:, None]
+    X = np.stack([rng.uniform(-8, 8, n_point), rng.uniform(-3, 3, n_point), rng.uniform(8, 35, n_point)], 1)
+    X0 = X + rng.normal(0, xs, X.shape)
+    obs = []
+    for j in range(n_point):
+        for i in rng.choice(n_pose, size=int(rng.integers(3, 6)), replace=False):
+            obs.append((int(i), j))
+    obs.sort(key=lambda t: (t[1], t[0]))
+    obs = np.array(obs, np.int32)
+    stereo = rng.random(len(obs)) < 0.6
+    info = (np.float32(1.0) / (np.float32(1.2) ** rng.integers(0, 6, len(obs))).astype(np.float32) ** 2).astype(np.float32)
+    meas = np.zeros((len(obs), 4), np.float32)
+    for k, (i, j) in enumerate(obs):
+        Xc = _rot(pose_t[i, 3:]) @ X[j] + pose_t[i, :3]
+        out = rng.random() < outliers
+        u = cam[0] * Xc[0] / Xc[2] + cam[2] + rng.normal(0, 1) + (rng.uniform(20, 60) if out else 0)
+        v = cam[1] * Xc[1] / Xc[2] + cam[3] + rng.normal(0, 1)
+        ur = u - cam[4] / Xc[2] + rng.normal(0, 1) if stereo[k] else -1.0
+        meas[k] = (u, v, ur, info[k])
+    return dict(cam=cam, upd0=upd0, fixed=fixed, X0=X0, obs=obs, meas=meas, n_pose=n_pose, n_point=n_point)
+
+
+def make_lm(path, iters=30):
+    """The reference binary's SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve on FakeSolver: records
+    the lambda handed to every trial (a complete fingerprint of the gain ratios and of the accept / reject / stop
+    decisions), the number of iterations optimize() returns and the final estimates, as `lm<k>_*` arrays."""
+    out = dict(np.load(path)) if os.path.exists(path) else {}
+    cases = [(17, 0.25, 1.5, 4.0, 0.15, True), (34, 0.08, 0.6, 1.5, 0.10, False)]
+    keep = []
+    for c, (seed, rs, ts, xs, of, robust) in enumerate(cases):
+        G = Graph()
+        S = lm_scenario(G.ed.g.se3_exp, seed, rs, ts, xs, of)
+        for i in range(S["n_pose"]):
+            G.add_pose(i, S["upd0"][i], bool(S["fixed"][i]))
+        for j in range(S["n_point"]):
+            G.add_point(j, S["X0"][j])
+        pose0 = np.stack([G.pose_estimate(i) for i in range(S["n_pose"])])
+        d2, d3 = float(np.float32(np.sqrt(5.99))), float(np.float32(np.sqrt(7.815)))   # g2oOptimizer.cc:163-164 (GBA)
+        for k, (i, j) in enumerate(S["obs"]):
+            m = S["meas"][k].astype(np.float64)
+            G.add_edge(int(i), int(j), m, float(m[3]), S["cam"], d3 if not (m[2] < 0) else d2)
+        lev = np.zeros(len(S["obs"]), np.int32)
+        G.set_levels(lev, robust)
+        o = G.opt.ctypes.data
+        assert G.f["init"](o, 0)
+        G.f["errors"](o)
+        chi0 = G.f["rchi2"](o)
+        G.system(lev, S["fixed"], S["obs"])                          # locates the vertices' _b
+        n_it, solver, alg = run_lm(G, S["fixed"], S["obs"], lev, iters)
+        G.f["errors"](o)
+        chi1 = G.f["rchi2"](o)
+        lam = np.array([v for k, v in solver.log if k == "lambda"])
+        out.update({f"lm{c}_pose0": pose0, f"lm{c}_fixed": S["fixed"], f"lm{c}_X0": S["X0"], f"lm{c}_obs": S["obs"],
+                    f"lm{c}_meas": S["meas"], f"lm{c}_cam": S["cam"], f"lm{c}_robust": np.array(int(robust)),
+                    f"lm{c}_iters": np.array(iters), f"lm{c}_lambda": lam, f"lm{c}_n_iterations": np.array(n_it),
+                    f"lm{c}_chi2": np.array([chi0, chi1]),
+                    f"lm{c}_poses": np.stack([G.pose_estimate(i) for i in range(S["n_pose"])]),
+                    f"lm{c}_points": np.stack([G.point_estimate(j) for j in range(S["n_point"])])})
+        keep.append((G, solver, alg))
+        print(f"lm case {c}: optimize -> {n_it} iterations, {len(lam)} trials, "
+              f"{int((lam[1:] > lam[:-1]).sum())} rejected, chi2 {chi0:.1f} -> {chi1:.1f}")
+    np.savez(path, **out)
+    return out
+
+
 if __name__ == "__main__":
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = sys.argv[1] if len(sys.argv) > 1 else os.path.join(here, "tests", "golden", "libg2o_vectors.npz")
     o = make(p)
+    make_lm(p)
     print("wrote", p, "| phase A index:", o["graph_A_pose_index"], o["graph_A_point_index"], "| phase B index:",
           o["graph_B_pose_index"], o["graph_B_point_index"], "| chi2", o["graph_A_chi2"], o["graph_A_robust_chi2"],
           o["graph_B_chi2"])

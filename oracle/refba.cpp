@@ -7,9 +7,10 @@
 // It is a dependency-free FP64 restatement of the reference's default BA back-end (vendored g2o
 // driven by src/backend/g2oOptimizer.cc).  The reference itself cannot be compiled here (needs
 // Eigen, OpenCV, PCL, Ceres, ROS -- none installed, no network), so this is a "port" oracle.
-// PARITY PARTLY PINNED: the reference has no tests, golden vectors or fixtures, so the reduced solve
-// and the LM policy (Schur complement, LDLT, lambda/accept rules; BlockSolver and LinearSolverEigen are header-only and
-// absent from the shipped binary) and the lidar pass are unpinned upstream.  The per-edge arithmetic IS pinned against
+// PARITY PARTLY PINNED: the reference has no tests, golden vectors or fixtures.  Unpinned upstream: the
+// Schur complement + sparse LDLT numerics (BlockSolver and LinearSolverEigen are header-only and absent from the
+// shipped binary; exact-in-exact-arithmetic operations), the adapter control flow of g2oOptimizer.cc (two passes,
+// outlier policy: needs OpenCV/PCL types) and the lidar pass.  Everything else IS pinned against
 // the reference's own compiled code: its tree ships a prebuilt Thirdparty/g2o/lib/libg2o.so that exports
 // SE3Quat::exp, project2d, the mono / stereo cam_project and RobustKernelHuber::robustify; oracle/pin_libg2o.py calls
 // them through ctypes and tests/test_pin_libg2o.py checks this file against the recorded outputs
@@ -20,7 +21,10 @@
 // id; fixed and edge-less vertices excluded), computeActiveErrors leaving level-1 edges' _error stale, activeChi2 /
 // activeRobustChi2, update() in index order, push/pop, and the normal equations that the binary's linearizeOplus +
 // constructQuadraticForm accumulate into mapped Hessian blocks (refba_debug_phase / refba_debug_system below
-// reproduce all of it: indices exactly, numbers to 1e-12).
+// reproduce all of it: indices exactly, numbers to 1e-12).  The same script runs the binary's own
+// SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve on a g2o::Solver it supplies (vtable of callbacks;
+// the binary's constructQuadraticForm + a dense solve): lmSolve / optimize below reproduce its lambda sequence trial by
+// trial, including rejected trials, both clamps of the lambda factor and the _nBad stop rule.
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 // Eigen is not vendored in the reference; where g2o calls into Eigen (quaternion*vector,

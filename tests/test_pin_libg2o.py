@@ -159,3 +159,44 @@ def test_graph_semantics_match_reference_binary(gold, synth):
     i = int(np.flatnonzero(free_inactive)[0])
     assert np.array_equal(g["B_poses"][i], g["A_poses"][i])
     assert not np.array_equal(g["A_poses"][1], g["pose"][1])
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_levenberg_policy_matches_reference_binary(gold, synth, case):
+    """Row A10/A11 against the binary: its own SparseOptimizer::optimize(30) + OptimizationAlgorithmLevenberg::solve ran
+    on a g2o::Solver implemented in oracle/pin_libg2o_graph.py (normal equations from the binary's
+    constructQuadraticForm, lambda on every diagonal, one dense solve), on two problems far from their optimum -- one
+    with Huber kernels, one without.  The lambda handed to each trial is a complete fingerprint of lambda_0 = tau * max
+    diag(H), every gain ratio rho = (chi - chi_trial) / (x.(lambda x + b) + 1e-3), the 1 - (2 rho - 1)^3 factor with
+    its clamps, the lambda * nu / nu * 2 rule after a rejection and the accept / reject / stop decisions; the oracle's
+    Schur + LDLT path must reproduce it trial by trial, stop after the same iteration and land on the same estimates."""
+    g = {k[len(f"lm{case}_"):]: gold[k] for k in gold.files if k.startswith(f"lm{case}_")}
+    n_pose = len(g["pose0"])
+    prob = synth.Problem(g["pose0"].copy(), g["fixed"].astype(np.uint8), np.tile(g["cam"], (n_pose, 1)), g["X0"].copy(),
+                         g["obs"][:, 0].astype(np.int32), g["obs"][:, 1].astype(np.int32), g["meas"].astype(np.float32))
+    r = refba.RefBA(prob)
+    r.solve_global(int(g["iters"]), bool(g["robust"]))
+    tr = r.trace()
+    lam = g["lambda"]
+    assert len(tr) == len(lam), f"oracle made {len(tr)} trials, the binary {len(lam)}"
+    # exact up to the point where a factor is unclamped; from there lambda carries the ~1e-7 reproducibility of the
+    # stereo cost (float32 inverse depth) through rho
+    np.testing.assert_allclose(tr[:, 3], lam, rtol=1e-6)
+    first_unclamped = int(np.argmax(~(np.isclose(lam[1:] / lam[:-1], 1 / 3) | (lam[1:] > lam[:-1]) |
+                                      np.isclose(lam[1:] / lam[:-1], 2 / 3)))) or len(lam)
+    np.testing.assert_allclose(tr[:first_unclamped, 3], lam[:first_unclamped], rtol=1e-12)
+    assert int(tr[:, 1].max()) + 1 == int(g["n_iterations"]) < int(g["iters"])      # both stop by the _nBad rule
+    np.testing.assert_allclose(tr[0, 4], g["chi2"][0], rtol=1e-12)
+    # the stereo residual rounds 1/z to float32 (types_six_dof_expmap.cpp:151): two exact solvers that differ by 1e-13
+    # in the state can see that rounding flip, so cost and estimates are reproducible to ~1e-7 relative, not to 1e-12
+    np.testing.assert_allclose(tr[tr[:, 7] == 1][-1, 5], g["chi2"][1], rtol=1e-7)
+    # (and the toy problems stop by the _nBad rule on a weakly constrained valley: 1e-13 per step grows to ~1e-7 m)
+    np.testing.assert_allclose(r.poses(), g["poses"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(r.points(), g["points"], rtol=0, atol=1e-5)
+    # what the fixture exercises: rejected trials (lambda grows), consecutive rejections (nu doubles), unclamped factors
+    ratio = lam[1:] / lam[:-1]
+    assert (ratio > 1).sum() >= 4 and (ratio > 7).sum() >= 1                      # nu = 2, 4, 8, ... in a row
+    assert np.isclose(ratio, 1 / 3).any() and np.isclose(ratio, 2 / 3).any()      # both clamps of the factor
+    if case == 1:
+        assert ((ratio > 1 / 3 + 1e-6) & (ratio < 2 / 3 - 1e-6)).sum() >= 1      # and the cubic in between
+    assert np.array_equal(tr[:-1, 7] == 0, ratio > 1)                             # a rejected trial <=> lambda grows
