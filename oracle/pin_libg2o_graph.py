@@ -541,11 +541,74 @@ def make_lm(path, iters=30):
     return out
 
 
+def make_lba(path):
+    """The two-pass schedule of g2oOptimizer::LocalBundleAdjustment (g2oOptimizer.cc:923-976, 1119-1142) driven over the
+    binary's objects: optimize(5) with Huber kernels; every edge with chi2() > 5.991 / 7.815 or non-positive depth goes
+    to level 1 and every kernel is dropped; initializeOptimization(0); optimize(10); the same test again gives the
+    outlier flags.  chi2() and isDepthPositive() are inline in the reference (base_edge.h:58-61,
+    types_six_dof_expmap.h:97-101,129-133) and evaluated here from the binary's stored `_error` / estimates, so the
+    stale-_error rule (level-1 edges keep their pass-1 error and are always flagged) comes from the binary itself."""
+    out = dict(np.load(path)) if os.path.exists(path) else {}
+    G = Graph()
+    S = lm_scenario(G.ed.g.se3_exp, 5, 0.02, 0.15, 0.4, 0.15, n_pose=8, n_point=40)
+    for i in range(S["n_pose"]):
+        G.add_pose(i, S["upd0"][i], bool(S["fixed"][i]))
+    for j in range(S["n_point"]):
+        G.add_point(j, S["X0"][j])
+    pose0 = np.stack([G.pose_estimate(i) for i in range(S["n_pose"])])
+    d2, d3 = float(np.float32(np.sqrt(5.991))), float(np.float32(np.sqrt(7.815)))   # g2oOptimizer.cc:851-853
+    for k, (i, j) in enumerate(S["obs"]):
+        m = S["meas"][k].astype(np.float64)
+        G.add_edge(int(i), int(j), m, float(m[3]), S["cam"], d3 if not (m[2] < 0) else d2)
+    n_obs = len(S["obs"])
+    o = G.opt.ctypes.data
+
+    def classify():
+        err = G.errors()
+        flags = np.zeros(n_obs, np.uint8)
+        for k, (i, j) in enumerate(S["obs"]):
+            stereo = G.edges[k][1]
+            info = float(S["meas"][k, 3])
+            d = 3 if stereo else 2
+            chi = float(sum(err[k, c] * (info * err[k, c]) for c in range(d)))     # _error.dot(information() * _error)
+            P7 = G.pose_estimate(int(i))
+            z = (_rot(P7[3:]) @ G.point_estimate(int(j)) + P7[:3])[2]
+            flags[k] = 1 if (chi > (7.815 if stereo else 5.991) or not (z > 0.0)) else 0
+        return flags
+
+    lev = np.zeros(n_obs, np.int32)
+    G.set_levels(lev, True)
+    assert G.f["init"](o, 0)
+    G.f["errors"](o)
+    G.system(lev, S["fixed"], S["obs"])
+    n1, solver, alg = run_lm(G, S["fixed"], S["obs"], lev, 5)
+    lam1 = [v for k, v in solver.log if k == "lambda"]
+    lev2 = classify().astype(np.int32)                              # :947-970
+    solver.levels[:] = lev2
+    G.set_levels(lev2, False)
+    assert G.f["init"](o, 0)
+    optimize = G.ed.g.L._ZN3g2o15SparseOptimizer8optimizeEib
+    n2 = optimize(o, 10, False)
+    lam2 = [v for k, v in solver.log if k == "lambda"][len(lam1):]
+    flags = classify()                                              # :1125-1142
+    out.update(lba_pose0=pose0, lba_fixed=S["fixed"], lba_X0=S["X0"], lba_obs=S["obs"], lba_meas=S["meas"],
+               lba_cam=S["cam"], lba_lambda1=np.array(lam1), lba_lambda2=np.array(lam2),
+               lba_n_iterations=np.array([n1, n2]), lba_level2=lev2, lba_outlier=flags,
+               lba_poses=np.stack([G.pose_estimate(i) for i in range(S["n_pose"])]),
+               lba_points=np.stack([G.point_estimate(j) for j in range(S["n_point"])]))
+    print(f"lba: pass 1 {n1} iterations / {len(lam1)} trials, {int(lev2.sum())} of {n_obs} edges to level 1, "
+          f"pass 2 {n2} iterations / {len(lam2)} trials, {int(flags.sum())} outliers, "
+          f"{int(((lev2 == 1) & (flags == 1)).sum())} of them frozen since pass 1")
+    np.savez(path, **out)
+    return out, (G, solver, alg)
+
+
 if __name__ == "__main__":
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = sys.argv[1] if len(sys.argv) > 1 else os.path.join(here, "tests", "golden", "libg2o_vectors.npz")
     o = make(p)
     make_lm(p)
+    _keep = make_lba(p)
     print("wrote", p, "| phase A index:", o["graph_A_pose_index"], o["graph_A_point_index"], "| phase B index:",
           o["graph_B_pose_index"], o["graph_B_point_index"], "| chi2", o["graph_A_chi2"], o["graph_A_robust_chi2"],
           o["graph_B_chi2"])

@@ -24,7 +24,9 @@
 // reproduce all of it: indices exactly, numbers to 1e-12).  The same script runs the binary's own
 // SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve on a g2o::Solver it supplies (vtable of callbacks;
 // the binary's constructQuadraticForm + a dense solve): lmSolve / optimize below reproduce its lambda sequence trial by
-// trial, including rejected trials, both clamps of the lambda factor and the _nBad stop rule.
+// trial, including rejected trials, both clamps of the lambda factor and the _nBad stop rule; and the two-pass
+// local-BA schedule driven over the binary's objects gives the lambda sequences, level-1 set, outlier flags and
+// estimates that refba_solve_local gives.
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 // Eigen is not vendored in the reference; where g2o calls into Eigen (quaternion*vector,
