@@ -603,12 +603,248 @@ def make_lba(path):
     return out, (G, solver, alg)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# pose-only optimisation: g2oOptimizer::PoseOptimization over the binary's objects
+# ---------------------------------------------------------------------------------------------------------------------
+class PoseOnly:
+    """One VertexSE3Expmap + EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose edges of the binary
+    (types_six_dof_expmap.h:143-202).  Their constructors are inline, so the objects are laid out here the way the
+    inline constructors would (the exported vtable, a one-element `_vertices` vector, id -1, dimension D; everything
+    else zero) at the member offsets checked for the binary edges; Xw / fx.. are located by probing cam_project."""
+    U = {False: dict(vt="_ZTVN3g2o25EdgeSE3ProjectXYZOnlyPoseE", err="_ZN3g2o25EdgeSE3ProjectXYZOnlyPose12computeErrorEv",
+                     cam="_ZNK3g2o25EdgeSE3ProjectXYZOnlyPose11cam_projectERKN5Eigen6MatrixIdLi3ELi1ELi0ELi3ELi1EEE",
+                     lin="_ZN3g2o13BaseUnaryEdgeILi2EN5Eigen6MatrixIdLi2ELi1ELi0ELi2ELi1EEENS_15VertexSE3ExpmapEE14linearizeOplusERNS_17JacobianWorkspaceE",
+                     quad="_ZN3g2o13BaseUnaryEdgeILi2EN5Eigen6MatrixIdLi2ELi1ELi0ELi2ELi1EEENS_15VertexSE3ExpmapEE22constructQuadraticFormEv"),
+         True: dict(vt="_ZTVN3g2o31EdgeStereoSE3ProjectXYZOnlyPoseE", err="_ZN3g2o31EdgeStereoSE3ProjectXYZOnlyPose12computeErrorEv",
+                    cam="_ZNK3g2o31EdgeStereoSE3ProjectXYZOnlyPose11cam_projectERKN5Eigen6MatrixIdLi3ELi1ELi0ELi3ELi1EEE",
+                    lin="_ZN3g2o13BaseUnaryEdgeILi3EN5Eigen6MatrixIdLi3ELi1ELi0ELi3ELi1EEENS_15VertexSE3ExpmapEE14linearizeOplusERNS_17JacobianWorkspaceE",
+                    quad="_ZN3g2o13BaseUnaryEdgeILi3EN5Eigen6MatrixIdLi3ELi1ELi0ELi3ELi1EEENS_15VertexSE3ExpmapEE22constructQuadraticFormEv")}
+
+    def __init__(self):
+        self.G = Graph()
+        L = self.G.ed.g.L
+        self.fn = {}
+        for st, d in self.U.items():
+            f = {}
+            f["vt"] = C.addressof(C.c_char.in_dll(L, d["vt"])) + 16
+            for k in ("err", "quad"):
+                f[k] = getattr(L, d[k]); f[k].restype = None; f[k].argtypes = [C.c_void_p]
+            f["lin"] = getattr(L, d["lin"]); f["lin"].restype = None; f["lin"].argtypes = [C.c_void_p, C.c_void_p]
+            f["cam"] = getattr(L, d["cam"]); f["cam"].restype = C.c_void_p; f["cam"].argtypes = [C.c_void_p] * 3
+            self.fn[st] = f
+        self.cam_off = {st: self._probe_cam(st) for st in (False, True)}
+        self.edges, self.keep = [], []
+
+    def _probe_cam(self, stereo):
+        found = {}
+        xyz = P._aligned(4)
+        xyz[:3] = [2.0, 3.0, 1.0]
+        for i in range(20, 80):
+            this = P._aligned(256)
+            this[i] = 1.0
+            out = P._aligned(4)
+            self.fn[stereo]["cam"](out.ctypes.data, this.ctypes.data, xyz.ctypes.data)
+            r = out[:3]
+            if r[0] == 2.0 and r[1] == 0.0:
+                found["fx"] = i
+            elif r[0] == 1.0 and r[1] == 0.0:
+                found["cx"] = i
+            elif r[1] == 3.0 and r[0] == 0.0:
+                found["fy"] = i
+            elif r[1] == 1.0 and r[0] == 0.0:
+                found["cy"] = i
+            elif stereo and r[0] == 0.0 and r[1] == 0.0 and r[2] != 0.0:
+                found["bf"] = i
+        assert {"fx", "fy", "cx", "cy"} <= set(found) and (not stereo or "bf" in found), found
+        assert found["fy"] == found["fx"] + 1 and found["cx"] == found["fx"] + 2 and found["cy"] == found["fx"] + 3
+        return found
+
+    def add_edge(self, Xw, meas, cam, delta):
+        G = self.G
+        stereo = not (meas[2] < 0)
+        d = 3 if stereo else 2
+        lay, off = G.lay[stereo], self.cam_off[stereo]
+        e = P._aligned(PE.OBJ)
+        u, i32 = e.view(np.uint64), e.view(np.int32)
+        u[0] = self.fn[stereo]["vt"]
+        slot = P._aligned(2)                                          # storage of the one-element _vertices vector
+        slot.view(np.uint64)[0] = G.poses[0].ctypes.data
+        u[1], u[2], u[3] = slot.ctypes.data, slot.ctypes.data + 8, slot.ctypes.data + 8
+        i32[E_ID // 4], i32[E_DIM // 4], i32[E_LEVEL // 4] = -1, d, 0
+        e[lay["meas"]:lay["meas"] + d] = meas[:d]
+        io = lay["err"] - d * d
+        e[io:io + d * d] = (np.eye(d) * float(meas[3])).ravel()
+        e[off["fx"] - 3:off["fx"]] = Xw                               # Vector3d Xw sits right before fx
+        for k, val in zip(("fx", "fy", "cx", "cy"), cam[:4]):
+            e[off[k]] = val
+        if stereo:
+            e[off["bf"]] = cam[4]
+        rk = G.f["huber_new"](None)
+        G.ed.g.f["set_delta"](rk, float(delta))
+        u[E_KERNEL // 8] = rk
+        assert G.f["add_edge"](G.opt.ctypes.data, e.ctypes.data)
+        jw = P._aligned(64)
+        G.ed.f["jw_ctor"](jw.ctypes.data)
+        G.ed.f["jw_size"](jw.ctypes.data, e.ctypes.data)
+        assert G.ed.f["jw_alloc"](jw.ctypes.data)
+        self.edges.append(dict(e=e, stereo=stereo, d=d, rk=rk, jw=jw, info=float(meas[3]), lay=lay))
+        self.keep.append(slot)
+
+    def error(self, k):
+        ed = self.edges[k]
+        return ed["e"][ed["lay"]["err"]:ed["lay"]["err"] + ed["d"]].copy()
+
+    def chi2(self, k):
+        ed, err = self.edges[k], self.error(k)
+        return float(sum(err[c] * (ed["info"] * err[c]) for c in range(ed["d"])))
+
+    def set_level(self, k, lv):
+        self.edges[k]["e"].view(np.int32)[E_LEVEL // 4] = lv
+
+    def level(self, k):
+        return int(self.edges[k]["e"].view(np.int32)[E_LEVEL // 4])
+
+
+class FakeSolverUnary(FakeSolver):
+    """The dense 6x6 case (LinearSolverDense in the reference, linear_solver_dense.h:65-113): one pose, unary edges."""
+
+    def __init__(self, po):
+        self.po = po
+        super().__init__(po.G, None, None, None)
+
+    def _build_structure(self, this, zero):
+        G = self.G
+        assert G.poses[0].view(np.int32)[V_HIDX // 4] == 0
+        self.n = 6
+        self.H = P._aligned(36)
+        G.f["pose_map"](G.poses[0].ctypes.data, self.H.ctypes.data)
+        self.x, self.b = P._aligned(16), P._aligned(16)
+        u = self.obj.view(np.uint64)
+        u[2], u[3], u[4], u[5] = self.x.ctypes.data, self.b.ctypes.data, 6, 6
+        return True
+
+    def _build_system(self, this):
+        G, po = self.G, self.po
+        self.H[:] = 0.0
+        G.f["pose_clear"](G.poses[0].ctypes.data)
+        for k, ed in enumerate(po.edges):
+            if po.level(k) != 0:
+                continue
+            po.fn[ed["stereo"]]["lin"](ed["e"].ctypes.data, ed["jw"].ctypes.data)
+            po.fn[ed["stereo"]]["quad"](ed["e"].ctypes.data)
+        self.b[:6] = G.poses[0][G.boff["p"]:G.boff["p"] + 6]
+        return True
+
+    def _diag(self):
+        yield self.H, [r * 6 + r for r in range(6)]
+
+    def _solve(self, this):
+        x = np.linalg.solve(self.H[:36].reshape(6, 6).T, self.b[:6])
+        self.x[:6] = x
+        self.log.append(("solve", float(np.linalg.norm(x))))
+        return True
+
+
+def make_poseopt(path, seed=3, n=150):
+    """g2oOptimizer::PoseOptimization (g2oOptimizer.cc:385-559, 655-690) over the binary: four rounds of
+    setEstimate(initial) / initializeOptimization(0) / optimize(10), after each the chi2 re-classification
+    (computeError() on the edges that were outliers, `const float chi2 = e->chi2()`, level 1 / 0, kernels dropped in the
+    third round), then the final classification.  Records lambda per trial and round, flags, inlier count, pose."""
+    out = dict(np.load(path)) if os.path.exists(path) else {}
+    po = PoseOnly()
+    G = po.G
+    rng = np.random.default_rng(seed)
+    cam = np.array([718.856, 718.856, 607.1928, 185.2157, 386.1448]).astype(np.float32).astype(np.float64)
+    upd_t = rng.normal(0, 1, 6) * np.array([0.05, 0.05, 0.05, 1.0, 0.3, 1.0])
+    pose_t = G.ed.g.se3_exp(upd_t)
+    upd0 = upd_t + rng.normal(0, 1, 6) * np.array([0.03, 0.03, 0.03, 0.3, 0.3, 0.3])
+    Xc = np.stack([rng.uniform(-10, 10, n), rng.uniform(-4, 4, n), rng.uniform(5, 50, n)], 1)
+    R = _rot(pose_t[3:])
+    Xw = ((Xc - pose_t[:3]) @ R).astype(np.float32).astype(np.float64)     # map points are float in the reference
+    meas = np.zeros((n, 4), np.float32)
+    for k in range(n):
+        c = R @ Xw[k] + pose_t[:3]
+        bad = rng.random() < 0.2
+        u = cam[0] * c[0] / c[2] + cam[2] + rng.normal(0, 1) + (rng.uniform(8, 40) * rng.choice([-1, 1]) if bad else 0)
+        v = cam[1] * c[1] / c[2] + cam[3] + rng.normal(0, 1)
+        ur = u - cam[4] / c[2] + rng.normal(0, 1) if rng.random() < 0.5 else -1.0
+        meas[k] = (u, v, ur, np.float32(1.0) / np.float32(1.2) ** (2 * int(rng.integers(0, 5))))
+    G.add_pose(0, upd0, False)
+    pose0 = G.pose_estimate(0)
+    est0 = G.poses[0][G.pose_est_off:G.pose_est_off + 7].copy()
+    dm, ds = float(np.float32(np.sqrt(5.991))), float(np.float32(np.sqrt(7.815)))   # g2oOptimizer.cc:426-428
+    for k in range(n):
+        m = meas[k].astype(np.float64)
+        po.add_edge(Xw[k], m, cam, ds if not (m[2] < 0) else dm)
+    o = G.opt.ctypes.data
+    # locate the pose vertex's _b (differential probe on a throw-away quadratic form)
+    assert G.f["init"](o, 0)
+    G.f["errors"](o)
+    Hs = P._aligned(36)
+    G.f["pose_map"](G.poses[0].ctypes.data, Hs.ctypes.data)
+    G.f["pose_clear"](G.poses[0].ctypes.data)
+    snap = G.poses[0].copy()
+    ed0 = po.edges[0]
+    po.fn[ed0["stereo"]]["lin"](ed0["e"].ctypes.data, ed0["jw"].ctypes.data)
+    po.fn[ed0["stereo"]]["quad"](ed0["e"].ctypes.data)
+    ch = np.flatnonzero(G.poses[0].view(np.uint64) != snap.view(np.uint64))
+    assert 0 < len(ch) <= 6 and ch.max() - ch.min() < 6, ch
+    G.boff = {"p": int(ch.min())}
+    G.f["pose_clear"](G.poses[0].ctypes.data)
+
+    L = G.ed.g.L
+    lm_ctor = L._ZN3g2o30OptimizationAlgorithmLevenbergC1EPNS_6SolverE
+    lm_ctor.restype, lm_ctor.argtypes = None, [C.c_void_p, C.c_void_p]
+    set_alg = L._ZN3g2o15SparseOptimizer12setAlgorithmEPNS_21OptimizationAlgorithmE
+    set_alg.restype, set_alg.argtypes = None, [C.c_void_p, C.c_void_p]
+    optimize = L._ZN3g2o15SparseOptimizer8optimizeEib
+    optimize.restype, optimize.argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_bool]
+    solver = FakeSolverUnary(po)
+    alg = P._aligned(1024)
+    lm_ctor(alg.ctypes.data, solver.obj.ctypes.data)
+    set_alg(o, alg.ctypes.data)
+
+    outlier = np.zeros(n, np.uint8)
+    lam_rounds, n_its = [], []
+    for it in range(4):
+        G.poses[0][G.pose_est_off:G.pose_est_off + 7] = est0             # vSE3->setEstimate(initial), :510
+        assert G.f["init"](o, 0)
+        before = len(solver.log)
+        n_its.append(optimize(o, 10, False))
+        lam_rounds.append([v for k, v in solver.log[before:] if k == "lambda"])
+        for k, ed in enumerate(po.edges):                                # :518-547
+            if outlier[k]:
+                po.fn[ed["stereo"]]["err"](ed["e"].ctypes.data)
+            chi = np.float32(po.chi2(k))
+            if chi > np.float32(7.815 if ed["stereo"] else 5.991):
+                outlier[k] = 1
+                po.set_level(k, 1)
+            else:
+                outlier[k] = 0
+                po.set_level(k, 0)
+            if it == 2:
+                ed["e"].view(np.uint64)[E_KERNEL // 8] = 0
+    for k, ed in enumerate(po.edges):                                    # final classification, :656-680
+        if outlier[k]:
+            po.fn[ed["stereo"]]["err"](ed["e"].ctypes.data)
+        chi = np.float32(po.chi2(k))
+        outlier[k] = 1 if float(chi) > (7.815 if ed["stereo"] else 5.991) else 0
+    lam = np.concatenate([np.array(r) for r in lam_rounds])
+    out.update(po_pose0=pose0, po_cam=cam, po_xyz=Xw, po_meas=meas, po_lambda=lam,
+               po_round_trials=np.array([len(r) for r in lam_rounds]), po_n_iterations=np.array(n_its),
+               po_outlier=outlier, po_inliers=np.array(n - int(outlier.sum())), po_pose=G.pose_estimate(0))
+    print(f"pose-only: trials per round {[len(r) for r in lam_rounds]}, iterations {n_its}, {int(outlier.sum())} of {n} outliers")
+    np.savez(path, **out)
+    return out, (po, solver, alg)
+
+
 if __name__ == "__main__":
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = sys.argv[1] if len(sys.argv) > 1 else os.path.join(here, "tests", "golden", "libg2o_vectors.npz")
     o = make(p)
     make_lm(p)
     _keep = make_lba(p)
+    _keep2 = make_poseopt(p)
     print("wrote", p, "| phase A index:", o["graph_A_pose_index"], o["graph_A_point_index"], "| phase B index:",
           o["graph_B_pose_index"], o["graph_B_point_index"], "| chi2", o["graph_A_chi2"], o["graph_A_robust_chi2"],
           o["graph_B_chi2"])

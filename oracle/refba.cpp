@@ -26,7 +26,8 @@
 // the binary's constructQuadraticForm + a dense solve): lmSolve / optimize below reproduce its lambda sequence trial by
 // trial, including rejected trials, both clamps of the lambda factor and the _nBad stop rule; and the two-pass
 // local-BA schedule driven over the binary's objects gives the lambda sequences, level-1 set, outlier flags and
-// estimates that refba_solve_local gives.
+// estimates that refba_solve_local gives; likewise refba_pose_opt against the four-round pose-only schedule over the
+// binary's EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose objects.
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 // Eigen is not vendored in the reference; where g2o calls into Eigen (quaternion*vector,

@@ -227,3 +227,20 @@ def test_two_pass_local_ba_matches_reference_binary(gold, synth):
     assert (g["lambda2"][1:] > g["lambda2"][:-1]).any()
     assert 10 < g["level2"].sum() < len(g["level2"]) // 2
     assert (g["outlier"][g["level2"] == 1] == 1).all()
+
+
+def test_pose_only_optimisation_matches_reference_binary(gold):
+    """g2oOptimizer::PoseOptimization (g2oOptimizer.cc:385-559, 655-690) driven over the binary's own VertexSE3Expmap,
+    EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose objects, Huber kernels and Levenberg loop
+    (oracle/pin_libg2o_graph.py: make_poseopt): four rounds of optimize(10) from the initial pose with the chi2
+    re-classification in between.  The oracle's refba_pose_opt -- the checker of the pose-only CUDA kernel -- must make
+    the same trials in every round with the same lambda, flag the same observations and end on the same pose."""
+    g = {k[len("po_"):]: gold[k] for k in gold.files if k.startswith("po_")}
+    pose, outlier, inliers, tr = refba.pose_opt(g["pose0"], g["cam"], g["xyz"], g["meas"])
+    assert [int((tr[:, 0] == r).sum()) for r in range(4)] == list(g["round_trials"])
+    assert [int(tr[tr[:, 0] == r][:, 1].max()) + 1 for r in range(4)] == list(g["n_iterations"])
+    np.testing.assert_allclose(tr[:, 3], g["lambda"], rtol=1e-6)
+    assert np.array_equal(outlier, g["outlier"]) and inliers == int(g["inliers"])
+    np.testing.assert_allclose(pose, g["pose"], rtol=0, atol=1e-12)
+    assert 20 < g["outlier"].sum() < 60 and (g["meas"][:, 2] < 0).any() and (g["meas"][:, 2] >= 0).any()
+    assert (g["lambda"][1:] > g["lambda"][:-1]).sum() >= 4      # rejected trials inside the rounds
