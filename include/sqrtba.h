@@ -52,7 +52,16 @@ typedef struct {
                                 exchange when landmark-sharded), batches use one launch per CG phase;
                                 1 = always one launch per phase; 2 = persistent whenever possible */
   int32_t pcg_check_every;   /* multi-launch mode: host polls the convergence counter every N iterations */
-  int32_t reserved[8];
+  int32_t reserved[8];       /* tuning / A-B knobs, all 0 by default:
+                                [0] record per-stage CUDA-event times (stats.ms_linearize ...)
+                                [1] 1 = general (non-TMA) matvec kernel instead of the pipelined one
+                                [2] force the depth of the matvec's shared-memory ring (2 or 3 stages)
+                                [3] host threads of sqrtba_set_problem's preprocessing (0 = all cores)
+                                [4] 1 = keep the caller's landmark order in big windows (no internal re-ordering)
+                                [5] big-window matvec: pose slots of a shared-memory accumulator window (0 = global atomics)
+                                [6] 1 = landmark-sharded global BA without peer-mapped buffers (NCCL all-reduce per iteration)
+                                [7] linearise / landmark-QR kernel variant: 0 = pipelined v2 (default), 1 = one tile per
+                                    CTA, 2 = first pipelined version, 5 = v2 QR compiled for 5 CTAs/SM */
 } sqrtba_config;
 
 /* one row per LM trial (g2o "levenbergIterations"), per window */
@@ -77,7 +86,8 @@ typedef struct {
   double ms_total;          /* device time of the last solve (CUDA events on the handle's stream) */
   double ms_linearize, ms_qr, ms_pcg, ms_backsub, ms_cost; /* per-stage device time (events) */
   double ms_matvec;         /* sum of matvec kernel time (multi-launch mode; 0 in persistent mode) */
-  double reserved[8];
+  double reserved[8];       /* [0] 1 = the persistent PCG kernel ran, [1] 1 = in-kernel NVLink exchange was active,
+                               [2] grid of the persistent kernel */
 } sqrtba_stats;
 
 int sqrtba_default_config(sqrtba_config* cfg);
