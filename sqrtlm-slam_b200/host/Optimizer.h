@@ -41,6 +41,17 @@ class sqrtbaOptimizer {
   void static PoseOptimizationBatch(const std::vector<Frame*>& frames, std::vector<int>& inliers);
   // last error of the calling thread's handle ("" if none); the reference API itself is void / silent
   static const char* LastError();
+  // the flat problem (layout of sqrtba_set_problem) that LocalBundleAdjustment / BundleAdjustment build from the map,
+  // without solving it: lets the window selection and the gather be tested and timed on a machine without a GPU
+  struct FlatProblem {
+    std::vector<double> pose_qt, cam, point_xyz;
+    std::vector<unsigned char> pose_fixed;
+    std::vector<int> obs_pose, obs_point;
+    std::vector<float> obs_meas;
+    std::vector<unsigned long> kf_ids, mp_ids;
+  };
+  void static GatherLocalWindow(KeyFrame* pKF, FlatProblem& out);
+  void static GatherGlobal(const std::vector<KeyFrame*>& vpKF, const std::vector<MapPoint*>& vpMP, FlatProblem& out);
 };
 
 }  // namespace ORB_SLAM2

@@ -1,6 +1,7 @@
 // C harness around the adapter for the Python tests: builds a map of the header-compatible types from flat arrays,
 // calls ORB_SLAM2::Optimizer::{LocalBundleAdjustment,GlobalBundleAdjustemnt} exactly as LocalMapping / LoopClosing do
 // (src/backend/LocalMapping.cc:131, src/backend/LoopClosing.cc:987), and exposes the resulting map state.
+#include <algorithm>
 #include <cstdint>
 #include <memory>
 
@@ -87,6 +88,27 @@ void hh_set_lidar_config(hh_map* m, int use_flat, int use_corner, double thr, do
   m->lidar.distance_sq_threshold = thr;
   m->lidar.flat_optimized_weight = w_flat;
   m->lidar.corner_optimized_weight = w_corner;
+}
+
+// the flat problem of the adapter's gather (no solve, no GPU): sizes first, then the arrays
+static sqrtbaOptimizer::FlatProblem g_flat;
+void hh_gather(hh_map* m, int kf /* >= 0: local window of that keyframe, -1: whole map */, int32_t* sizes3) {
+  if (kf >= 0) sqrtbaOptimizer::GatherLocalWindow(m->kfs[kf].get(), g_flat);
+  else sqrtbaOptimizer::GatherGlobal(m->map.GetAllKeyFrames(), m->map.GetAllMapPoints(), g_flat);
+  sizes3[0] = (int32_t)g_flat.kf_ids.size(); sizes3[1] = (int32_t)g_flat.mp_ids.size(); sizes3[2] = (int32_t)g_flat.obs_pose.size();
+}
+void hh_gather_get(double* pose_qt, uint8_t* pose_fixed, double* cam, double* point_xyz, int32_t* obs_pose, int32_t* obs_point,
+                   float* obs_meas, int64_t* kf_ids, int64_t* mp_ids) {
+  const auto& f = g_flat;
+  std::copy(f.pose_qt.begin(), f.pose_qt.end(), pose_qt);
+  std::copy(f.pose_fixed.begin(), f.pose_fixed.end(), pose_fixed);
+  std::copy(f.cam.begin(), f.cam.end(), cam);
+  std::copy(f.point_xyz.begin(), f.point_xyz.end(), point_xyz);
+  std::copy(f.obs_pose.begin(), f.obs_pose.end(), obs_pose);
+  std::copy(f.obs_point.begin(), f.obs_point.end(), obs_point);
+  std::copy(f.obs_meas.begin(), f.obs_meas.end(), obs_meas);
+  for (size_t i = 0; i < f.kf_ids.size(); i++) kf_ids[i] = (int64_t)f.kf_ids[i];
+  for (size_t i = 0; i < f.mp_ids.size(); i++) mp_ids[i] = (int64_t)f.mp_ids[i];
 }
 
 void hh_local_ba(hh_map* m, int kf, bool* stop) {

@@ -12,10 +12,14 @@
 // Error convention of the reference is kept: void, silent; the last sqrtba error string is available for logging.
 #include "Optimizer.h"
 
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdint>
 #include <cstdio>
 #include <list>
+#include <thread>
+#include <unordered_map>
 #include <string>
 
 #include "../../include/sqrtba.h"
@@ -119,16 +123,84 @@ struct Gathered {
   std::vector<std::pair<KeyFrame*, MapPoint*>> obs_ref;
 };
 
-// kf_fixed(kf) decides setFixed; usable(kf) mirrors the per-observation filters of the reference adapters
+// One observation of a map point as MapPoint::GetObservations() reports it
+struct ObsRec { KeyFrame* kf; size_t idx; };
+
+// The observation lists of many map points, copied ONCE from the map (MapPoint::GetObservations() returns a copy of a
+// std::map under the point's mutex, MapPoint.cc:212-215 -- ~12 node allocations per point; the reference walks it twice
+// per local-BA call, :759-780 and :870-919) into one flat array.  Filled on all host cores.
+struct ObsCache {
+  std::vector<size_t> ptr;   // n_mp + 1
+  std::vector<ObsRec> rec;
+};
+
+int host_threads(size_t work_items) {
+  static const int hw = [] {
+    const char* e = std::getenv("SQRTBA_ADAPTER_THREADS");   // override for measurements
+    return e ? std::max(1, std::atoi(e)) : (int)std::max(1u, std::thread::hardware_concurrency());
+  }();
+  return (int)std::max<size_t>(1, std::min<size_t>({(size_t)hw, (size_t)16, work_items / 512 + 1}));
+}
+
+template <class F>
+void parallel_ranges(size_t n, int n_thr, F f) {   // f(thread, begin, end) over contiguous ranges
+  if (n_thr <= 1) { f(0, (size_t)0, n); return; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < n_thr; t++) pool.emplace_back([=] { f(t, n * t / n_thr, n * (t + 1) / n_thr); });
+  for (auto& th : pool) th.join();
+}
+
+void fill_obs_cache(const std::vector<MapPoint*>& mps, ObsCache& c) {
+  const int T = host_threads(mps.size());
+  std::vector<std::vector<ObsRec>> part(T);
+  std::vector<std::vector<size_t>> cnt(T);
+  parallel_ranges(mps.size(), T, [&](int t, size_t a, size_t b) {
+    part[t].reserve((b - a) * 12);
+    cnt[t].reserve(b - a);
+    for (size_t i = a; i < b; i++) {
+      const std::map<KeyFrame*, size_t> observations = mps[i]->GetObservations();
+      for (auto& kv : observations) part[t].push_back(ObsRec{kv.first, kv.second});
+      cnt[t].push_back(observations.size());
+    }
+  });
+  c.ptr.assign(1, 0);
+  c.ptr.reserve(mps.size() + 1);
+  size_t total = 0;
+  for (auto& p : part) total += p.size();
+  c.rec.clear();
+  c.rec.reserve(total);
+  for (int t = 0; t < T; t++) {
+    for (size_t n : cnt[t]) c.ptr.push_back(c.ptr.back() + n);
+    c.rec.insert(c.rec.end(), part[t].begin(), part[t].end());
+  }
+}
+
+// kf_fixed(kf) decides setFixed; usable(kf) mirrors the per-observation filters of the reference adapters.
+// `cache` (optional) holds the observation lists of `mps` in the order given (copied earlier by the caller).
+// Two parallel sweeps over the map points in mnId order -- count the usable observations, then (after a prefix sum) fill
+// the flat arrays in place -- so nothing is merged or re-allocated and the result does not depend on the thread count.
 template <class FixedFn, class UsableFn>
-void gather(std::vector<KeyFrame*> kfs, std::vector<MapPoint*> mps, FixedFn kf_fixed, UsableFn usable, Gathered& g) {
+void gather(std::vector<KeyFrame*> kfs, std::vector<MapPoint*> mps, FixedFn kf_fixed, UsableFn usable, Gathered& g,
+            const ObsCache* cache = nullptr) {
+  ObsCache own;
+  if (!cache) {
+    fill_obs_cache(mps, own);
+    cache = &own;
+  }
   std::sort(kfs.begin(), kfs.end(), [](KeyFrame* a, KeyFrame* b) { return a->mnId < b->mnId; });
-  std::sort(mps.begin(), mps.end(), [](MapPoint* a, MapPoint* b) { return a->mnId < b->mnId; });
-  std::map<KeyFrame*, int> kf_index;
+  std::vector<size_t> order(mps.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return mps[a]->mnId < mps[b]->mnId; });
+  std::unordered_map<KeyFrame*, int> kf_index;
+  kf_index.reserve(kfs.size() * 2);
+  std::vector<uint8_t> kf_usable(kfs.size());
   g.kfs = kfs;
+  g.pose_qt.reserve(kfs.size() * 7);
+  g.cam.reserve(kfs.size() * 5);
   for (size_t i = 0; i < kfs.size(); i++) {
     KeyFrame* kf = kfs[i];
     kf_index[kf] = (int)i;
+    kf_usable[i] = usable(kf) ? 1 : 0;
     double p[7];
     toSE3Quat(kf->GetPose(), p);
     g.pose_qt.insert(g.pose_qt.end(), p, p + 7);
@@ -136,33 +208,67 @@ void gather(std::vector<KeyFrame*> kfs, std::vector<MapPoint*> mps, FixedFn kf_f
     const double c[5] = {kf->fx, kf->fy, kf->cx, kf->cy, kf->mbf};
     g.cam.insert(g.cam.end(), c, c + 5);
   }
-  for (MapPoint* mp : mps) {
-    const std::map<KeyFrame*, size_t> observations = mp->GetObservations();
-    std::vector<std::pair<int, size_t>> obs;  // (pose index, keypoint index)
-    for (auto& kv : observations) {
-      auto it = kf_index.find(kv.first);
-      if (it == kf_index.end() || !usable(kv.first)) continue;
-      obs.emplace_back(it->second, kv.second);
+  const size_t n = order.size();
+  const int T = host_threads(n);
+  // sweep 1: pose index of every cached observation (-1: keyframe not in the problem or not usable), count per point
+  std::vector<int> rec_pose(cache->rec.size());
+  std::vector<size_t> cnt(n + 1, 0);  // cnt[r + 1] = usable observations of the r-th point in mnId order
+  parallel_ranges(n, T, [&](int, size_t a, size_t b) {
+    for (size_t r = a; r < b; r++) {
+      size_t c = 0;
+      for (size_t k = cache->ptr[order[r]]; k < cache->ptr[order[r] + 1]; k++) {
+        auto it = kf_index.find(cache->rec[k].kf);
+        const int ip = (it != kf_index.end() && kf_usable[it->second]) ? it->second : -1;
+        rec_pose[k] = ip;
+        c += ip >= 0;
+      }
+      cnt[r + 1] = c;
     }
-    if (obs.empty()) continue;  // vbNotIncludedMP (g2oOptimizer.cc:287-295)
-    std::sort(obs.begin(), obs.end());
-    const int ip = (int)g.mps.size();
-    g.mps.push_back(mp);
-    const cv::Mat X = mp->GetWorldPos();
-    for (int i = 0; i < 3; i++) g.point_xyz.push_back(X.at<float>(i));
-    for (auto& o : obs) {
-      KeyFrame* kf = kfs[o.first];
-      const cv::KeyPoint& kp = kf->mvKeysUn[o.second];
-      const float ur = kf->mvuRight[o.second];
-      g.obs_pose.push_back(o.first);
-      g.obs_point.push_back(ip);
-      g.obs_meas.push_back(kp.pt.x);
-      g.obs_meas.push_back(kp.pt.y);
-      g.obs_meas.push_back(ur < 0 ? -1.f : ur);  // mvuRight < 0 => monocular edge (g2oOptimizer.cc:208, 877)
-      g.obs_meas.push_back(kf->mvInvLevelSigma2[kp.octave]);
-      g.obs_ref.emplace_back(kf, mp);
-    }
+  });
+  // prefix sums: observation offset and compact point index (points without a usable observation drop out,
+  // vbNotIncludedMP, g2oOptimizer.cc:287-295)
+  std::vector<size_t> pt_index(n + 1, 0);
+  for (size_t r = 0; r < n; r++) {
+    pt_index[r + 1] = pt_index[r] + (cnt[r + 1] > 0);
+    cnt[r + 1] += cnt[r];
   }
+  const size_t n_pt = pt_index[n], n_ob = cnt[n];
+  g.mps.resize(n_pt);
+  g.point_xyz.resize(n_pt * 3);
+  g.obs_pose.resize(n_ob);
+  g.obs_point.resize(n_ob);
+  g.obs_meas.resize(n_ob * 4);
+  g.obs_ref.resize(n_ob);
+  // sweep 2: fill in place, observations of a point sorted by pose index
+  parallel_ranges(n, T, [&](int, size_t a, size_t b) {
+    std::vector<std::pair<int, size_t>> obs;  // (pose index, keypoint index), reused
+    for (size_t r = a; r < b; r++) {
+      if (cnt[r + 1] == cnt[r]) continue;
+      MapPoint* mp = mps[order[r]];
+      obs.clear();
+      for (size_t k = cache->ptr[order[r]]; k < cache->ptr[order[r] + 1]; k++)
+        if (rec_pose[k] >= 0) obs.emplace_back(rec_pose[k], cache->rec[k].idx);
+      std::sort(obs.begin(), obs.end());
+      const size_t ip = pt_index[r];
+      g.mps[ip] = mp;
+      const cv::Mat X = mp->GetWorldPos();
+      for (int i = 0; i < 3; i++) g.point_xyz[ip * 3 + i] = X.at<float>(i);
+      size_t o = cnt[r];
+      for (auto& ob : obs) {
+        KeyFrame* kf = kfs[ob.first];
+        const cv::KeyPoint& kp = kf->mvKeysUn[ob.second];
+        const float ur = kf->mvuRight[ob.second];
+        g.obs_pose[o] = ob.first;
+        g.obs_point[o] = (int32_t)ip;
+        g.obs_meas[o * 4 + 0] = kp.pt.x;
+        g.obs_meas[o * 4 + 1] = kp.pt.y;
+        g.obs_meas[o * 4 + 2] = ur < 0 ? -1.f : ur;  // mvuRight < 0 => monocular edge (g2oOptimizer.cc:208, 877)
+        g.obs_meas[o * 4 + 3] = kf->mvInvLevelSigma2[kp.octave];
+        g.obs_ref[o] = std::make_pair(kf, mp);
+        o++;
+      }
+    }
+  });
 }
 
 bool upload(Handle& H, const Gathered& g) {
@@ -283,7 +389,18 @@ bool set_lidar(sqrtba_handle* h, const Gathered& g, KeyFrame* pKF, const lidarCo
 }
 }  // namespace
 
-void sqrtbaOptimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* lidarconfig) {
+namespace {
+// Window selection + gather of LocalBundleAdjustment (g2oOptimizer.cc:709-780, 805-919): everything the host does
+// before the solve.  SQRTBA_HOST_TIMING=1 prints the wall time of each step on stderr.
+void gather_local_window(KeyFrame* pKF, Gathered& g) {
+  static const bool host_timing = std::getenv("SQRTBA_HOST_TIMING") != nullptr;
+  auto tick = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!host_timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[sqrtba adapter] %-24s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count());
+    tick = now;
+  };
   // ---- local keyframes: pKF + its covisible keyframes (g2oOptimizer.cc:709-727)
   std::list<KeyFrame*> lLocalKeyFrames;
   lLocalKeyFrames.push_back(pKF);
@@ -303,26 +420,37 @@ void sqrtbaOptimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map
         pMP->mnBALocalForKF = pKF->mnId;
       }
   }
-  // ---- fixed keyframes: other observers of the local points (:759-780)
+  lap("local keyframes + points");
+  // ---- fixed keyframes: other observers of the local points (:759-780).  The observation lists are copied from the
+  //      map once, on all host cores, and serve both this loop and the gather below (the reference copies every
+  //      std::map twice, :761 and :870)
+  std::vector<MapPoint*> mps(lLocalMapPoints.begin(), lLocalMapPoints.end());
+  ObsCache cache;
+  fill_obs_cache(mps, cache);
+  lap("observation copies");
   std::list<KeyFrame*> lFixedCameras;
-  for (MapPoint* mp : lLocalMapPoints) {
-    std::map<KeyFrame*, size_t> observations = mp->GetObservations();
-    for (auto& kv : observations) {
-      KeyFrame* pKFi = kv.first;
-      if (pKFi->mnBALocalForKF != pKF->mnId && pKFi->mnBAFixedForKF != pKF->mnId) {
-        pKFi->mnBAFixedForKF = pKF->mnId;
-        if (!pKFi->isBad()) lFixedCameras.push_back(pKFi);
-      }
+  for (const ObsRec& r : cache.rec) {
+    KeyFrame* pKFi = r.kf;
+    if (pKFi->mnBALocalForKF != pKF->mnId && pKFi->mnBAFixedForKF != pKF->mnId) {
+      pKFi->mnBAFixedForKF = pKF->mnId;
+      if (!pKFi->isBad()) lFixedCameras.push_back(pKFi);
     }
   }
+  lap("window selection");
   std::vector<KeyFrame*> kfs(lLocalKeyFrames.begin(), lLocalKeyFrames.end());
   kfs.insert(kfs.end(), lFixedCameras.begin(), lFixedCameras.end());
-  std::vector<MapPoint*> mps(lLocalMapPoints.begin(), lLocalMapPoints.end());
   const unsigned long cur = pKF->mnId;
-  Gathered g;
   gather(kfs, mps,
          [cur](KeyFrame* kf) { return kf->mnBALocalForKF != cur || kf->mnId == 0; },  // :813, :829
-         [](KeyFrame* kf) { return !kf->isBad(); }, g);                                // :872
+         [](KeyFrame* kf) { return !kf->isBad(); }, g, &cache);                        // :872
+  lap("gather");
+}
+}  // namespace
+
+void sqrtbaOptimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* lidarconfig) {
+  const unsigned long cur = pKF->mnId;
+  Gathered g;
+  gather_local_window(pKF, g);
   if (pbStopFlag && *pbStopFlag) return;  // :923-928
   // the fork's third pass (lidar edges on pKF + optimize(20), :979-1117) runs when the configuration asks for lidar
   // features; without them the two-pass schedule of ORB-SLAM2 is used
@@ -360,6 +488,31 @@ void sqrtbaOptimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map
     g.mps[i]->SetWorldPos(toCvMat3(&X[i * 3]));
     g.mps[i]->UpdateNormalAndDepth();
   }
+}
+
+// ---- the flat problems the adapters hand to the C ABI, without solving (host-side tests, no GPU needed)
+static void to_flat(const Gathered& g, sqrtbaOptimizer::FlatProblem& out) {
+  out.pose_qt = g.pose_qt; out.cam = g.cam; out.point_xyz = g.point_xyz; out.pose_fixed = g.pose_fixed;
+  out.obs_pose = g.obs_pose; out.obs_point = g.obs_point; out.obs_meas = g.obs_meas;
+  out.kf_ids.clear(); out.mp_ids.clear();
+  for (KeyFrame* kf : g.kfs) out.kf_ids.push_back(kf->mnId);
+  for (MapPoint* mp : g.mps) out.mp_ids.push_back(mp->mnId);
+}
+void sqrtbaOptimizer::GatherLocalWindow(KeyFrame* pKF, FlatProblem& out) {
+  Gathered g;
+  gather_local_window(pKF, g);
+  to_flat(g, out);
+}
+void sqrtbaOptimizer::GatherGlobal(const std::vector<KeyFrame*>& vpKFs, const std::vector<MapPoint*>& vpMP, FlatProblem& out) {
+  std::vector<KeyFrame*> kfs;
+  std::vector<MapPoint*> mps;
+  for (KeyFrame* kf : vpKFs)
+    if (!kf->isBad()) kfs.push_back(kf);
+  for (MapPoint* mp : vpMP)
+    if (!mp->isBad()) mps.push_back(mp);
+  Gathered g;
+  gather(kfs, mps, [](KeyFrame* kf) { return kf->mnId == 0; }, [](KeyFrame* kf) { return !kf->isBad(); }, g);
+  to_flat(g, out);
 }
 
 // ---- the facade (src/backend/Optimizer.cc:26-79) with the new selector value

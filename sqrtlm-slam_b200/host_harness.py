@@ -14,7 +14,7 @@ def lib():
     global _lib
     if _lib is None:
         L = C.CDLL(build.build_host())
-        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        fp, ip, up = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
         L.hh_build.restype = C.c_void_p
         L.hh_build.argtypes = [C.c_int, fp, fp, fp, C.c_int, C.c_int, fp, C.c_int, ip, ip, fp, ip]
         L.hh_destroy.argtypes = [C.c_void_p]
@@ -22,6 +22,9 @@ def lib():
         L.hh_set_bad.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.hh_set_lidar_cloud.argtypes = [C.c_void_p, C.c_int, C.c_int, fp, fp, C.c_int, fp]
         L.hh_set_lidar_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.hh_gather.argtypes = [C.c_void_p, C.c_int, ip]
+        L.hh_gather_get.argtypes = [C.POINTER(C.c_double), up, C.POINTER(C.c_double), C.POINTER(C.c_double), ip, ip, fp,
+                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.hh_local_ba.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hh_global_ba.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_ulong, C.c_void_p]
         L.hh_get_pose.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
@@ -32,7 +35,6 @@ def lib():
         L.hh_gba_marker.restype = C.c_ulong
         L.hh_gba_marker.argtypes = [C.c_void_p, C.c_int]
         L.hh_last_error.restype = C.c_char_p
-        up = C.POINTER(C.c_uint8)
         L.hh_frame_build.restype = C.c_void_p
         L.hh_frame_build.argtypes = [fp, fp, fp, C.c_int, C.c_int, fp, fp, ip]
         L.hh_frame_destroy.argtypes = [C.c_void_p]
@@ -96,6 +98,23 @@ class MockMap:
             L.hh_set_lidar_cloud(self.h, int(k), len(f), _f(f), None, len(c), _f(c))
         L.hh_set_lidar_config(self.h, int(ld.use_flat), int(ld.use_corner), ld.distance_sq_threshold, ld.flat_weight,
                               ld.corner_weight)
+
+    def gather(self, kf=-1):
+        """The flat problem the adapter builds for LocalBundleAdjustment(kf) (kf >= 0) or for the whole map (-1),
+        without solving it -- needs no GPU.  Returns a dict of arrays in the layout of sqrtba_set_problem + the ids."""
+        L = lib()
+        sz = np.zeros(3, np.int32)
+        L.hh_gather(self.h, kf, _i(sz))
+        nk, nm, no = (int(v) for v in sz)
+        out = dict(pose_qt=np.zeros((nk, 7)), pose_fixed=np.zeros(nk, np.uint8), cam=np.zeros((nk, 5)),
+                   point_xyz=np.zeros((nm, 3)), obs_pose=np.zeros(no, np.int32), obs_point=np.zeros(no, np.int32),
+                   obs_meas=np.zeros((no, 4), np.float32), kf_ids=np.zeros(nk, np.int64), mp_ids=np.zeros(nm, np.int64))
+        dp = C.POINTER(C.c_double)
+        L.hh_gather_get(out["pose_qt"].ctypes.data_as(dp), out["pose_fixed"].ctypes.data_as(C.POINTER(C.c_uint8)),
+                        out["cam"].ctypes.data_as(dp), out["point_xyz"].ctypes.data_as(dp), _i(out["obs_pose"]),
+                        _i(out["obs_point"]), _f(out["obs_meas"]), out["kf_ids"].ctypes.data_as(C.POINTER(C.c_int64)),
+                        out["mp_ids"].ctypes.data_as(C.POINTER(C.c_int64)))
+        return out
 
     def local_ba(self, kf, stop=None):
         lib().hh_local_ba(self.h, kf, stop)

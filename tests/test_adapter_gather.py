@@ -1,0 +1,101 @@
+"""The host half of the adapter (sqrtlm-slam_b200/host/sqrtbaOptimizer.cc) on CPU: window selection and gather of
+Optimizer::LocalBundleAdjustment (g2oOptimizer.cc:709-780, 805-919) and the gather of BundleAdjustment (:137-295), from a
+map of header-compatible KeyFrame / MapPoint objects to the flat arrays of sqrtba_set_problem -- without solving, so no
+GPU is needed.  The solve itself is covered by tests/test_gpu_adapter.py."""
+import os
+
+import numpy as np
+import pytest
+
+
+def expected_pose_qt(prob, synth):
+    """What the adapter reads: float32 Tcw matrices converted as Converter::toSE3Quat does."""
+    Rf = synth.quat_to_rotmat(prob.pose_qt[:, 3:]).astype(np.float32).astype(np.float64)
+    t = prob.pose_qt[:, :3].astype(np.float32).astype(np.float64)
+    return np.concatenate([t, synth.rotmat_to_quat_eigen(Rf)], axis=1)
+
+
+def check_against_problem(flat, prob, synth, fixed):
+    assert np.array_equal(flat["kf_ids"], np.arange(prob.n_pose))
+    assert np.array_equal(flat["mp_ids"], np.arange(prob.n_point))
+    np.testing.assert_allclose(flat["pose_qt"], expected_pose_qt(prob, synth), rtol=0, atol=1e-15)
+    assert np.array_equal(flat["pose_fixed"], fixed)
+    np.testing.assert_allclose(flat["cam"], np.tile(prob.cam[0].astype(np.float32).astype(np.float64), (prob.n_pose, 1)))
+    assert np.array_equal(flat["point_xyz"], prob.point_xyz.astype(np.float32).astype(np.float64))
+    # observations: grouped by landmark in ascending id, pose-sorted inside -- exactly the generator's order
+    assert np.array_equal(flat["obs_point"], prob.obs_point)
+    assert np.array_equal(flat["obs_pose"], prob.obs_pose)
+    assert np.array_equal(flat["obs_meas"], prob.obs_meas)
+
+
+def test_local_window_gather(pkg, synth):
+    prob = synth.make_problem(31, 14, 5, 900, 6.0, stereo=True, name="gather-lba")
+    m = pkg.host_harness.MockMap(prob)
+    cur = prob.n_pose - 1
+    free = np.nonzero(prob.pose_fixed == 0)[0]
+    m.set_covisible(cur, [int(i) for i in free if i != cur])
+    flat = m.gather(cur)
+    # local keyframes are free except mnId 0 (g2oOptimizer.cc:813), every other observer of a local point is fixed
+    check_against_problem(flat, prob, synth, prob.pose_fixed)
+    assert 0 < flat["pose_fixed"].sum() < prob.n_pose
+
+
+def test_gather_is_thread_count_invariant(pkg, synth, monkeypatch):
+    import subprocess
+    import sys
+    code = (
+        "import importlib, sys, numpy as np\n"
+        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "pkg = importlib.import_module('sqrtlm-slam_b200')\n"
+        "prob = pkg.synth.make_problem(7, 12, 4, 3000, 7.0, stereo=True)\n"
+        "m = pkg.host_harness.MockMap(prob)\n"
+        "cur = prob.n_pose - 1\n"
+        "m.set_covisible(cur, [int(i) for i in np.nonzero(prob.pose_fixed == 0)[0] if i != cur])\n"
+        "f = m.gather(cur)\n"
+        "import hashlib\n"
+        "print(hashlib.sha1(b''.join(np.ascontiguousarray(f[k]).tobytes() for k in sorted(f))).hexdigest())\n")
+    digests = set()
+    for t in ("1", "3", "8"):
+        env = dict(os.environ, SQRTBA_ADAPTER_THREADS=t)
+        digests.add(subprocess.run([sys.executable, "-c", code], env=env, check=True, capture_output=True, text=True).stdout.strip())
+    assert len(digests) == 1, digests
+
+
+def test_local_window_skips_bad_and_unrelated(pkg, synth):
+    prob = synth.small_window(6, n_free=6, n_fixed=3, n_points=200)
+    m = pkg.host_harness.MockMap(prob)
+    cur = prob.n_pose - 1
+    free = [int(i) for i in np.nonzero(prob.pose_fixed == 0)[0]]
+    bad_kf, bad_mp = free[0], 5
+    m.set_covisible(cur, [i for i in free if i != cur])
+    m.set_bad(kf=bad_kf, mp=bad_mp)
+    flat = m.gather(cur)
+    assert bad_kf not in flat["kf_ids"] and bad_mp not in flat["mp_ids"]
+    local_kfs = [i for i in free if i != bad_kf]
+    local_pts = np.unique(prob.obs_point[np.isin(prob.obs_pose, local_kfs)])   # seen by a (good) local keyframe
+    keep = (prob.obs_pose != bad_kf) & (prob.obs_point != bad_mp) & np.isin(prob.obs_point, local_pts)
+    kf_of = {int(k): i for i, k in enumerate(flat["kf_ids"])}
+    mp_of = {int(k): i for i, k in enumerate(flat["mp_ids"])}
+    # every surviving observation is there, in the same order, with compacted indices
+    want_pose = np.array([kf_of[int(p)] for p in prob.obs_pose[keep]])
+    want_point = np.array([mp_of[int(p)] for p in prob.obs_point[keep]])
+    assert np.array_equal(flat["obs_pose"], want_pose) and np.array_equal(flat["obs_point"], want_point)
+    assert np.array_equal(flat["obs_meas"], prob.obs_meas[keep])
+    # a window made of only two keyframes: the other observers of their points become fixed, unrelated ones drop out
+    m2 = pkg.host_harness.MockMap(prob)
+    m2.set_covisible(cur, [free[-2]])
+    f2 = m2.gather(cur)
+    loc = {cur, free[-2]}
+    fixed_ids = set(int(k) for k, f in zip(f2["kf_ids"], f2["pose_fixed"]) if f)
+    assert loc.isdisjoint(fixed_ids - {0}) and set(int(k) for k in f2["kf_ids"]) >= loc
+    seen_by_local = np.isin(prob.obs_pose, list(loc))
+    assert set(int(p) for p in f2["mp_ids"]) == set(int(p) for p in np.unique(prob.obs_point[seen_by_local]))
+
+
+def test_global_gather(pkg, synth):
+    prob = synth.make_problem(11, 10, 1, 500, 5.0, stereo=True, name="gather-gba")
+    m = pkg.host_harness.MockMap(prob)
+    flat = m.gather(-1)
+    fixed = np.zeros(prob.n_pose, np.uint8)
+    fixed[0] = 1  # only mnId 0 (g2oOptimizer.cc:154)
+    check_against_problem(flat, prob, synth, fixed)
