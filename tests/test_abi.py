@@ -77,3 +77,39 @@ def test_product_never_imports_oracle():
                     if re.search(r"\boracle\b|refba", s):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_hot_kernels_carry_the_blackwell_instructions(pkg):
+    """SASS of the built library (sm_100a): the matvec / persistent-PCG kernels move their tiles with TMA bulk copies
+    (UBLKCP) completed on mbarriers (SYNCS); the pipelined landmark QR and linearisation stage the next tile with
+    cp.async (LDGSTS) and prefetch into L2 with the TMA prefetch (UBLKPF).  Guards against a build that silently lost
+    them (wrong arch flag, a fallback path)."""
+    import collections
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump is not installed")
+    pkg.build.build_lib()
+    sass = subprocess.run(["cuobjdump", "-sass", pkg.capi.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    fn, cnt = None, collections.defaultdict(collections.Counter)
+    for line in sass.split("\n"):
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            continue
+        for k in ("UBLKCP", "UBLKPF", "SYNCS", "LDGSTS", "DFMA"):
+            if k in line:
+                cnt[fn][k] += 1
+
+    def kernels(sub):
+        ks = [c for f, c in cnt.items() if sub in f]
+        assert ks, f"no kernel named *{sub}* in the library"
+        return ks
+
+    for c in kernels("k_matvec_pipe") + kernels("k_pcg_persist"):
+        assert c["UBLKCP"] >= 1 and c["SYNCS"] >= 8 and c["DFMA"] > 50, c
+    for c in kernels("k_qr_pipe2"):
+        assert c["LDGSTS"] >= 14 and c["UBLKPF"] >= 1 and c["DFMA"] > 300, c
+    for c in kernels("k_linearize_pipeILb1E"):
+        assert c["LDGSTS"] >= 2 and c["UBLKPF"] >= 1 and c["DFMA"] > 150, c
