@@ -51,6 +51,10 @@ class sqrtbaOptimizer {
     std::vector<unsigned long> kf_ids, mp_ids;
   };
   void static GatherLocalWindow(KeyFrame* pKF, FlatProblem& out);
+  // the write-back half of LocalBundleAdjustment (outlier erasure, SetPose, SetWorldPos + UpdateNormalAndDepth under
+  // mMutexMapUpdate) applied to a result given in the layout of GatherLocalWindow -- again for tests without a GPU
+  void static ApplyLocalResult(KeyFrame* pKF, Map* pMap, const std::vector<double>& pose_qt,
+                               const std::vector<double>& point_xyz, const std::vector<unsigned char>& outlier);
   void static GatherGlobal(const std::vector<KeyFrame*>& vpKF, const std::vector<MapPoint*>& vpMP, FlatProblem& out);
 };
 

@@ -111,6 +111,13 @@ void hh_gather_get(double* pose_qt, uint8_t* pose_fixed, double* cam, double* po
   for (size_t i = 0; i < f.mp_ids.size(); i++) mp_ids[i] = (int64_t)f.mp_ids[i];
 }
 
+void hh_apply_local(hh_map* m, int kf, int n_kf, const double* pose_qt, int n_mp, const double* point_xyz, int n_obs,
+                    const uint8_t* outlier) {
+  sqrtbaOptimizer::ApplyLocalResult(m->kfs[kf].get(), &m->map, std::vector<double>(pose_qt, pose_qt + (size_t)n_kf * 7),
+                                    std::vector<double>(point_xyz, point_xyz + (size_t)n_mp * 3),
+                                    std::vector<unsigned char>(outlier, outlier + n_obs));
+}
+
 void hh_local_ba(hh_map* m, int kf, bool* stop) {
   Optimizer::LocalBundleAdjustment(m->kfs[kf].get(), stop, &m->map, &m->lidar);
 }

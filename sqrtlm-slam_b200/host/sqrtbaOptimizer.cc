@@ -329,17 +329,19 @@ void sqrtbaOptimizer::BundleAdjustment(const std::vector<KeyFrame*>& vpKFs, cons
       kf->mnBAGlobalForKF = nLoopKF;
     }
   }
-  for (size_t i = 0; i < g.mps.size(); i++) {  // :334-361
-    MapPoint* mp = g.mps[i];
-    if (nLoopKF == 0) {
-      mp->SetWorldPos(toCvMat3(&X[i * 3]));
-      mp->UpdateNormalAndDepth();
-    } else {
-      mp->mPosGBA.create(3, 1, CV_32F);
-      toCvMat3(&X[i * 3]).copyTo(mp->mPosGBA);
-      mp->mnBAGlobalForKF = nLoopKF;
+  parallel_ranges(g.mps.size(), host_threads(g.mps.size()), [&](int, size_t a, size_t b) {  // :334-361, per-point state only
+    for (size_t i = a; i < b; i++) {
+      MapPoint* mp = g.mps[i];
+      if (nLoopKF == 0) {
+        mp->SetWorldPos(toCvMat3(&X[i * 3]));
+        mp->UpdateNormalAndDepth();
+      } else {
+        mp->mPosGBA.create(3, 1, CV_32F);
+        toCvMat3(&X[i * 3]).copyTo(mp->mPosGBA);
+        mp->mnBAGlobalForKF = nLoopKF;
+      }
     }
-  }
+  });
 }
 
 namespace {
@@ -447,6 +449,32 @@ void gather_local_window(KeyFrame* pKF, Gathered& g) {
 }
 }  // namespace
 
+namespace {
+// Erase the outlier observations and write the estimates back under the map mutex (g2oOptimizer.cc:1145-1189).  The
+// erasures and SetPose stay serial (they touch shared keyframes); SetWorldPos + UpdateNormalAndDepth only touch their
+// own map point (per-point mutexes, MapPoint.cc:118-124, 531-575) and read keyframe poses that are final by then, so
+// they run on all host cores -- UpdateNormalAndDepth copies the point's observation map again and is the bulk of the
+// time mMutexMapUpdate is held, which is time the tracking thread waits.
+void write_back_local(const Gathered& g, unsigned long cur, const double* P, const double* X, const uint8_t* flags, Map* pMap) {
+  std::unique_lock<std::mutex> lock(pMap->mMutexMapUpdate);
+  for (size_t k = 0; k < g.obs_ref.size(); k++)
+    if (flags[k]) {
+      KeyFrame* pKFi = g.obs_ref[k].first;
+      MapPoint* pMPi = g.obs_ref[k].second;
+      pKFi->EraseMapPointMatch(pMPi);
+      pMPi->EraseObservation(pKFi);
+    }
+  for (size_t i = 0; i < g.kfs.size(); i++)
+    if (g.kfs[i]->mnBALocalForKF == cur) g.kfs[i]->SetPose(toCvMat(&P[i * 7]));
+  parallel_ranges(g.mps.size(), host_threads(g.mps.size()), [&](int, size_t a, size_t b) {
+    for (size_t i = a; i < b; i++) {
+      g.mps[i]->SetWorldPos(toCvMat3(&X[i * 3]));
+      g.mps[i]->UpdateNormalAndDepth();
+    }
+  });
+}
+}  // namespace
+
 void sqrtbaOptimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* lidarconfig) {
   const unsigned long cur = pKF->mnId;
   Gathered g;
@@ -473,21 +501,7 @@ void sqrtbaOptimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map
     H.err = sqrtba_last_error(h);
     return;
   }
-  // ---- erase outlier observations and write the estimates back under the map mutex (:1145-1189)
-  std::unique_lock<std::mutex> lock(pMap->mMutexMapUpdate);
-  for (size_t k = 0; k < flags.size(); k++)
-    if (flags[k]) {
-      KeyFrame* pKFi = g.obs_ref[k].first;
-      MapPoint* pMPi = g.obs_ref[k].second;
-      pKFi->EraseMapPointMatch(pMPi);
-      pMPi->EraseObservation(pKFi);
-    }
-  for (size_t i = 0; i < g.kfs.size(); i++)
-    if (g.kfs[i]->mnBALocalForKF == cur) g.kfs[i]->SetPose(toCvMat(&P[i * 7]));
-  for (size_t i = 0; i < g.mps.size(); i++) {
-    g.mps[i]->SetWorldPos(toCvMat3(&X[i * 3]));
-    g.mps[i]->UpdateNormalAndDepth();
-  }
+  write_back_local(g, cur, P.data(), X.data(), flags.data(), pMap);
 }
 
 // ---- the flat problems the adapters hand to the C ABI, without solving (host-side tests, no GPU needed)
@@ -502,6 +516,13 @@ void sqrtbaOptimizer::GatherLocalWindow(KeyFrame* pKF, FlatProblem& out) {
   Gathered g;
   gather_local_window(pKF, g);
   to_flat(g, out);
+}
+void sqrtbaOptimizer::ApplyLocalResult(KeyFrame* pKF, Map* pMap, const std::vector<double>& pose_qt,
+                                       const std::vector<double>& point_xyz, const std::vector<unsigned char>& outlier) {
+  Gathered g;
+  gather_local_window(pKF, g);
+  if (pose_qt.size() != g.kfs.size() * 7 || point_xyz.size() != g.mps.size() * 3 || outlier.size() != g.obs_ref.size()) return;
+  write_back_local(g, pKF->mnId, pose_qt.data(), point_xyz.data(), outlier.data(), pMap);
 }
 void sqrtbaOptimizer::GatherGlobal(const std::vector<KeyFrame*>& vpKFs, const std::vector<MapPoint*>& vpMP, FlatProblem& out) {
   std::vector<KeyFrame*> kfs;

@@ -25,6 +25,8 @@ def lib():
         L.hh_gather.argtypes = [C.c_void_p, C.c_int, ip]
         L.hh_gather_get.argtypes = [C.POINTER(C.c_double), up, C.POINTER(C.c_double), C.POINTER(C.c_double), ip, ip, fp,
                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.hh_apply_local.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double),
+                                     C.c_int, up]
         L.hh_local_ba.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hh_global_ba.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_ulong, C.c_void_p]
         L.hh_get_pose.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
@@ -115,6 +117,15 @@ class MockMap:
                         _i(out["obs_point"]), _f(out["obs_meas"]), out["kf_ids"].ctypes.data_as(C.POINTER(C.c_int64)),
                         out["mp_ids"].ctypes.data_as(C.POINTER(C.c_int64)))
         return out
+
+    def apply_local(self, kf, pose_qt, point_xyz, outlier):
+        """The write-back half of LocalBundleAdjustment(kf) with a result given in the layout of gather(kf)."""
+        P = np.ascontiguousarray(pose_qt, np.float64)
+        X = np.ascontiguousarray(point_xyz, np.float64)
+        F = np.ascontiguousarray(outlier, np.uint8)
+        dp = C.POINTER(C.c_double)
+        lib().hh_apply_local(self.h, kf, len(P), P.ctypes.data_as(dp), len(X), X.ctypes.data_as(dp), len(F),
+                             F.ctypes.data_as(C.POINTER(C.c_uint8)))
 
     def local_ba(self, kf, stop=None):
         lib().hh_local_ba(self.h, kf, stop)

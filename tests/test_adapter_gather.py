@@ -99,3 +99,37 @@ def test_global_gather(pkg, synth):
     fixed = np.zeros(prob.n_pose, np.uint8)
     fixed[0] = 1  # only mnId 0 (g2oOptimizer.cc:154)
     check_against_problem(flat, prob, synth, fixed)
+
+
+def test_local_write_back(pkg, synth):
+    """Outlier erasure both ways, SetPose for local keyframes only (float32 Tcw), SetWorldPos + one UpdateNormalAndDepth
+    per local point (g2oOptimizer.cc:1145-1189) -- the parallel write-back must do exactly that."""
+    prob = synth.make_problem(5, 12, 4, 2500, 6.0, stereo=True, name="write-back")   # enough points for several threads
+    m = pkg.host_harness.MockMap(prob)
+    cur = prob.n_pose - 1
+    free = np.nonzero(prob.pose_fixed == 0)[0]
+    m.set_covisible(cur, [int(i) for i in free if i != cur])
+    flat = m.gather(cur)
+    rng = np.random.default_rng(0)
+    P = flat["pose_qt"].copy()
+    P[:, :3] += rng.normal(0, 0.1, (len(P), 3))
+    X = flat["point_xyz"] + rng.normal(0, 0.05, flat["point_xyz"].shape)
+    F = (rng.random(len(flat["obs_pose"])) < 0.1).astype(np.uint8)
+    # a fresh map: the window-selection markers (mnBALocalForKF) of the gather above would hide the points from a second
+    # selection with the same keyframe id, exactly as in the reference
+    m = pkg.host_harness.MockMap(prob)
+    m.set_covisible(cur, [int(i) for i in free if i != cur])
+    before = [m.pose(i).copy() for i in range(prob.n_pose)]
+    m.apply_local(cur, P, X, F)
+    for i in range(prob.n_pose):
+        if prob.pose_fixed[i]:
+            np.testing.assert_array_equal(m.pose(i), before[i])          # fixed keyframes are not written
+        else:
+            np.testing.assert_allclose(m.pose(i)[:3, 3], P[i, :3].astype(np.float32), rtol=0, atol=0)
+            np.testing.assert_allclose(m.pose(i)[:3, :3], synth.quat_to_rotmat(P[i, 3:]).astype(np.float32), rtol=0, atol=1e-7)
+    for j in range(prob.n_point):
+        np.testing.assert_array_equal(m.point(j), X[j].astype(np.float32))
+        assert m.point_updates(j) == 1
+    for k in range(prob.n_obs):
+        kf, mp = int(prob.obs_pose[k]), int(prob.obs_point[k])
+        assert m.has_observation(kf, mp) == (F[k] == 0) and m.keyframe_sees(kf, mp) == (F[k] == 0)
