@@ -11,8 +11,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libsqrtba.so")
 SOURCES = [os.path.join(HERE, "csrc", "sqrtba_solver.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("sqrtba_kernels.cuh", "sqrtba_math.cuh")] + [
-    os.path.join(os.path.dirname(HERE), "include", "sqrtba.h")]
+DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("sqrtba_kernels.cuh", "sqrtba_math.cuh", "sqrtba_poseopt.cuh",
+                                                            "sqrtba_lidar.cuh")] + [
+    os.path.join(HERE, "host", "host_pool.h"), os.path.join(os.path.dirname(HERE), "include", "sqrtba.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 
@@ -57,7 +58,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
 
 HOST_LIB = os.path.join(HERE, "libsqrtba_host.so")
 HOST_SOURCES = [os.path.join(HERE, "host", f) for f in ("sqrtbaOptimizer.cc", "harness.cc")]
-HOST_DEPS = HOST_SOURCES + [os.path.join(HERE, "host", f) for f in ("Optimizer.h", "map_types.h")]
+HOST_DEPS = HOST_SOURCES + [os.path.join(HERE, "host", f) for f in ("Optimizer.h", "map_types.h", "host_pool.h")]
 
 
 def build_host(force: bool = False) -> str:

@@ -25,6 +25,7 @@
 #include "sqrtba_kernels.cuh"
 #include "sqrtba_poseopt.cuh"
 #include "sqrtba_lidar.cuh"
+#include "../host/host_pool.h"
 
 namespace sqrtba {
 
@@ -87,25 +88,6 @@ struct HBuf {  // pinned host staging buffer that only grows (fast H2D, reused a
 };
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
-
-// run fn(k0,k1) over [0,n) in chunks on up to n_thr threads
-template <class F>
-static void parallel_chunks(long long n, long long chunk, int n_thr, F fn) {
-  const long long n_chunk = (n + chunk - 1) / chunk;
-  if (n_thr <= 1 || n_chunk <= 1) { fn(0, n); return; }
-  std::atomic<long long> next(0);
-  auto worker = [&]() {
-    for (;;) {
-      const long long c = next.fetch_add(1);
-      if (c >= n_chunk) break;
-      fn(c * chunk, std::min(n, (c + 1) * chunk));
-    }
-  };
-  std::vector<std::thread> pool;
-  for (int t = 1; t < std::min<long long>(n_thr, n_chunk); t++) pool.emplace_back(worker);
-  worker();
-  for (auto& th : pool) th.join();
-}
 
 // NCCL is loaded at run time and only when a multi-GPU communicator is requested, so the single-GPU path has no
 // dependency on it.  (In a Python process that already imported torch, dlopen resolves to torch's bundled libnccl.)
@@ -277,7 +259,7 @@ class Solver {
     std::vector<int> lm_first(n_point, -1), lm_cnt(n_point, 0);
     {
       std::atomic<int> bad(0);
-      parallel_chunks(n_obs, 1 << 16, n_thr, [&](long long k0, long long k1) {
+      pool_.chunks(n_obs, 1 << 16, n_thr, [&](long long k0, long long k1) {
         for (long long k = k0; k < k1; k++) {
           const int ip = obs_pose[k], il = obs_point[k];
           if (ip < 0 || ip >= n_pose || il < 0 || il >= n_point) { bad.store(1); return; }
@@ -306,7 +288,7 @@ class Solver {
     perm_.clear(); old_first_.clear(); new_first_.clear();
     if (!pq_shared && smallwin && cfg_.reserved[4] == 0) {
       std::vector<int> key(n_point);
-      parallel_chunks(n_point, 1 << 14, n_thr, [&](long long l0, long long l1) {
+      pool_.chunks(n_point, 1 << 14, n_thr, [&](long long l0, long long l1) {
         for (long long l = l0; l < l1; l++) {
           int k = 0x7fffffff;
           if (lm_first[l] >= 0)
@@ -335,7 +317,7 @@ class Solver {
         err_ = "pinned host allocation failed";
         return SQRTBA_ERR_ALLOC;
       }
-      parallel_chunks(n_point, 1 << 12, n_thr, [&](long long j0, long long j1) {
+      pool_.chunks(n_point, 1 << 12, n_thr, [&](long long j0, long long j1) {
         for (long long j = j0; j < j1; j++) {
           const int l = perm_[j];
           for (int c = 0; c < 3; c++) h_perm_xyz_.p[j * 3 + c] = point_xyz_in[(size_t)l * 3 + c];
@@ -376,7 +358,7 @@ class Solver {
     struct Chunk { int win, l0, l1; std::vector<int> it_start, it_cnt, run_ptr, runs; std::vector<TileInfo> tiles; long long jq = 0; };
     std::vector<Chunk> chunks;
     {
-      const long long target = std::max<long long>(1 << 15, (long long)n_obs / (8LL * n_thr));
+      const long long target = std::max<long long>(1 << 13, (long long)n_obs / (8LL * n_thr));
       for (int w = 0; w < n_win; w++) {
         const int p0 = (n_win > 1) ? (int)wpoint[w] : 0, p1 = (n_win > 1) ? (int)wpoint[w + 1] : n_point;
         int l0 = p0;
@@ -486,10 +468,8 @@ class Solver {
           }
         }
       };
-      std::vector<std::thread> pool;
-      for (int t = 1; t < n_thr; t++) pool.emplace_back(worker);
-      worker();
-      for (auto& th : pool) th.join();
+      const int n_work = std::min<int>(n_thr, (int)chunks.size());  // never more workers than chunks
+      pool_.run(n_work, n_work, [&](int) { worker(); });
     }
     lap("C items/tiles/run tables");
     // D. merge the chunks (offsets are prefix sums over chunks in order)
@@ -536,10 +516,8 @@ class Solver {
           if (!c.runs.empty()) std::memcpy(h_tile_runs_.p + ro, c.runs.data(), c.runs.size() * sizeof(int));
         }
       };
-      std::vector<std::thread> pool;
-      for (int t = 1; t < n_thr; t++) pool.emplace_back(worker);
-      worker();
-      for (auto& th : pool) th.join();
+      const int n_work = std::min<int>(n_thr, (int)chunks.size());
+      pool_.run(n_work, n_work, [&](int) { worker(); });
       h_tile_run_ptr_.p[n_tile] = (int)n_runs;
     }
     lap("D merge");
@@ -1662,6 +1640,7 @@ class Solver {
  public:
   bool stage_timing_ = false;
   bool plan_only_ = false;
+  HostPool pool_;  // helper threads of set_problem, created on first use and kept for the life of the handle
   int plan_n_item_ = 0, plan_n_tile_ = 0, plan_smallwin_ = 0, plan_pq_shared_ = 0;
   long long plan_n_runs_ = 0, plan_jq_total_ = 0;
 

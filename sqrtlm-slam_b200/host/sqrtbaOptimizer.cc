@@ -23,6 +23,7 @@
 #include <string>
 
 #include "../../include/sqrtba.h"
+#include "host_pool.h"
 
 namespace ORB_SLAM2 {
 
@@ -142,12 +143,13 @@ int host_threads(size_t work_items) {
   return (int)std::max<size_t>(1, std::min<size_t>({(size_t)hw, (size_t)16, work_items / 512 + 1}));
 }
 
+// helper threads of the calling thread (LocalMapping and the global-BA thread each get their own), created on first
+// use and parked between loops
+thread_local sqrtba::HostPool tl_pool;
+
 template <class F>
-void parallel_ranges(size_t n, int n_thr, F f) {   // f(thread, begin, end) over contiguous ranges
-  if (n_thr <= 1) { f(0, (size_t)0, n); return; }
-  std::vector<std::thread> pool;
-  for (int t = 0; t < n_thr; t++) pool.emplace_back([=] { f(t, n * t / n_thr, n * (t + 1) / n_thr); });
-  for (auto& th : pool) th.join();
+void parallel_ranges(size_t n, int n_thr, F f) {   // f(part, begin, end) over n_thr contiguous ranges
+  tl_pool.ranges(n, n_thr, f);
 }
 
 void fill_obs_cache(const std::vector<MapPoint*>& mps, ObsCache& c) {
