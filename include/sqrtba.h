@@ -61,7 +61,8 @@ typedef struct {
                                 [5] big-window matvec: pose slots of a shared-memory accumulator window (0 = global atomics)
                                 [6] 1 = landmark-sharded global BA without peer-mapped buffers (NCCL all-reduce per iteration)
                                 [7] linearise / landmark-QR kernel variant: 0 = pipelined v2 (default), 1 = one tile per
-                                    CTA, 2 = first pipelined version, 5 = v2 QR compiled for 5 CTAs/SM */
+                                    CTA, 2 = first pipelined version, 5 = v2 QR compiled for 5 CTAs/SM, 6 = linearisation with
+                                    L1 prefetch of the next tile's pose / landmark lines (experimental, not yet measured) */
 } sqrtba_config;
 
 /* one row per LM trial (g2o "levenbergIterations"), per window */

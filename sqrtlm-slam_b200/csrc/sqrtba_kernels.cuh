@@ -398,10 +398,12 @@ __device__ __forceinline__ LinOps lin_load_ops(const Dev& P, int o) {
   return q;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // One tile of the linearisation.  PRE: the lanes of short items already hold their LinOps (pipelined kernel).
 template <bool PRE>
 __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti, const LinOps& pre, int robust, double d2,
-                                               double d3, double* c_sh, const int* runs_staged = nullptr) {
+                                               double d3, double* c_sh, const int* runs_staged = nullptr,
+                                               int pf_pose = -1, int pf_point = -1) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int w = ti.item0 + wid;
   const bool valid = wid < ti.nitem;
@@ -526,6 +528,13 @@ __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti,
 #pragma unroll
     for (int c = 0; c < 6; c++) { c_sh[c * SCST + rank] = vb[c]; c_sh[(6 + c) * SCST + rank] = vh[c]; }
   }
+  if (pf_pose >= 0) {  // the arithmetic of this tile is done and the next tile's indices arrived long ago: pull its
+                       // pose (56 B: two lines at most), camera and landmark lines into L1 while the reduction runs
+    prefetch_l1(P.pose + (size_t)pf_pose * 7);
+    prefetch_l1(P.pose + (size_t)pf_pose * 7 + 6);
+    prefetch_l1(P.cam + (size_t)pf_pose * 5);
+    prefetch_l1(P.point + (size_t)pf_point * 3);
+  }
   __syncthreads();
   const int* runs = runs_staged ? runs_staged : reinterpret_cast<const int*>(jq + (size_t)JQ_ROWS * ti.nt);
   double* bp = P.bp;
@@ -552,7 +561,10 @@ constexpr int LIN_RUN_INTS = 2 * CTA + 2;
 // at the cold tail of the tile's JQ block, which nothing else touches before the pose-side reduction needs it), and the
 // landmark coordinates of the following tiles -- consecutive in memory, landmarks are tiled in order -- are pulled into
 // L2 by a TMA prefetch, so the only exposed global latency left is the L1/L2-resident pose gather.
-template <bool STAGE>
+// PF (experimental, off by default; A/B knob reserved[7] = 6): when the arithmetic of a tile is done, the indices of
+// the next tile's observations have long arrived in registers -- linearize_tile prefetches their pose, camera and
+// landmark lines into L1 before the pose-side reduction, so the gathers at the top of the next tile hit L1, not L2.
+template <bool STAGE, bool PF = false>
 __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, double d2, double d3, int force_all) {
   __shared__ double c_sh[12 * SCST];
   __shared__ __align__(16) TileInfo ti_sh[3];
@@ -612,7 +624,13 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, do
         if (bytes > 0) bulk_prefetch_l2(P.point + first * 3, (uint32_t)bytes);
       }
     }
-    linearize_tile<true>(P, ti, cur, robust, d2, d3, c_sh, (STAGE && !ti.is_long) ? run_sh[k & 1] : nullptr);
+    bool pf = false;  // lanes that own an observation of the next tile prefetch its operands (PF only)
+    if (PF && k + 1 < t1 - t0) {
+      const TileInfo& tn = ti_sh[(k + 1) % 3];
+      pf = !tn.is_long && wid < tn.nitem && lane < tile_item_cnt(tn, wid);
+    }
+    linearize_tile<true>(P, ti, cur, robust, d2, d3, c_sh, (STAGE && !ti.is_long) ? run_sh[k & 1] : nullptr,
+                         pf ? nxt.ip : -1, pf ? nxt.lm : -1);
   }
   cp_async_wait_all();
 }

@@ -1305,6 +1305,7 @@ class Solver {
   void launch_linearize(int robust, double d2, double d3, int force_all) {
     if (cfg_.reserved[7] == 1) k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
     else if (cfg_.reserved[7] == 2) k_linearize_pipe<false><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
+    else if (cfg_.reserved[7] == 6) k_linearize_pipe<true, true><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
     else k_linearize_pipe<true><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
   }
   // landmark QR: cp.async-pipelined kernel (QR_TPB tiles per CTA); reserved[7] != 0 selects the plain one-tile-per-CTA kernel

@@ -42,7 +42,7 @@ def main():
         variants += [dict(plain_qr=True),
                      dict(no_reorder=True), dict(general_matvec=True)]
     if args.qr_variants:
-        variants += [dict(qr_variant=v) for v in (2, 5)]
+        variants += [dict(qr_variant=v) for v in (2, 5, 6)]
     for kw in variants:
         ba = pkg.SqrtBA(**kw)
         if batch:
