@@ -21,8 +21,17 @@ setFixed, setMarginalized, setLevel, setRobustKernel, setInformation) are replac
 CHECKED against constructor defaults first (id -1 at byte 8, hessianIndex -1 at 80, dimension at 88 for vertices;
 id -1 at 32, dimension at 36, level at 40, robust kernel at 48 for edges; `_information` between `_measurement` and
 `_error`, both located by pin_libg2o_edges.Edges.layout).  Huber kernels come from the binary's
-RobustKernelCreator<RobustKernelHuber>::construct().  TEST INFRASTRUCTURE ONLY.  Run as a script in a clean interpreter;
-appends `graph_*` arrays to tests/golden/libg2o_vectors.npz."""
+RobustKernelCreator<RobustKernelHuber>::construct().
+
+Beyond the graph semantics the script runs the binary's own optimisation loops -- SparseOptimizer::optimize +
+OptimizationAlgorithmLevenberg::solve -- on a g2o::Solver implemented here (FakeSolver: a vtable of ctypes callbacks):
+  * make_lm      two problems far from their optimum, optimize(30): the lambda of every trial, iterations, estimates;
+  * make_lba     the two-pass schedule of LocalBundleAdjustment (5 + 10 iterations, chi2 / depth classification between);
+  * make_poseopt the four-round schedule of PoseOptimization over real EdgeSE3ProjectXYZOnlyPose /
+                 EdgeStereoSE3ProjectXYZOnlyPose objects (inline constructors: laid out around the exported vtables).
+
+TEST INFRASTRUCTURE ONLY.  Run as a script in a clean interpreter; appends `graph_*`, `lm<k>_*`, `lba_*` and `po_*`
+arrays to tests/golden/libg2o_vectors.npz (tests/test_pin_libg2o.py compares the oracle with them)."""
 from __future__ import annotations
 
 import ctypes as C
