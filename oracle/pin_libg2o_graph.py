@@ -28,10 +28,12 @@ OptimizationAlgorithmLevenberg::solve -- on a g2o::Solver implemented here (Fake
   * make_lm      two problems far from their optimum, optimize(30): the lambda of every trial, iterations, estimates;
   * make_lba     the two-pass schedule of LocalBundleAdjustment (5 + 10 iterations, chi2 / depth classification between);
   * make_poseopt the four-round schedule of PoseOptimization over real EdgeSE3ProjectXYZOnlyPose /
-                 EdgeStereoSE3ProjectXYZOnlyPose objects (inline constructors: laid out around the exported vtables).
+                 EdgeStereoSE3ProjectXYZOnlyPose objects (inline constructors: laid out around the exported vtables);
+  * make_sim3 / make_posegraph   g2o::Sim3 arithmetic and the optimisation of OptimizeEssentialGraph (VertexSim3Expmap,
+                 EdgeSim3 with numeric Jacobians, lambda_0 = 1e-16) -- the oracle of SURVEY row N3.
 
-TEST INFRASTRUCTURE ONLY.  Run as a script in a clean interpreter; appends `graph_*`, `lm<k>_*`, `lba_*` and `po_*`
-arrays to tests/golden/libg2o_vectors.npz (tests/test_pin_libg2o.py compares the oracle with them)."""
+TEST INFRASTRUCTURE ONLY.  Run as a script in a clean interpreter; appends `graph_*`, `lm<k>_*`, `lba_*`, `po_*`, `sim3_*`
+and `pg<k>_*` arrays to tests/golden/libg2o_vectors.npz (tests/test_pin_libg2o.py compares the oracle with them)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -847,6 +849,324 @@ def make_poseopt(path, seed=3, n=150):
     return out, (po, solver, alg)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# essential-graph (Sim3 pose-graph) optimisation, SURVEY.md 8(f) N3: g2o::Sim3, VertexSim3Expmap, EdgeSim3 of the binary
+# ---------------------------------------------------------------------------------------------------------------------
+class Sim3Graph:
+    """VertexSim3Expmap / EdgeSim3 objects (types_seven_dof_expmap.h:48-110) built with the binary's constructors; the
+    estimate (Sim3: quaternion x y z w | t | s), `_fix_scale` and `_b` are located by probing, the measurement goes in
+    through BaseEdge<7,Sim3>::setMeasurement, information / error through informationData() / errorData()."""
+    S = {
+        "v_ctor": ("_ZN3g2o16VertexSim3ExpmapC1Ev", None, 1), "v_origin": ("_ZN3g2o16VertexSim3Expmap15setToOriginImplEv", None, 1),
+        "v_oplus": ("_ZN3g2o16VertexSim3Expmap9oplusImplEPKd", None, 2),
+        "v_map": ("_ZN3g2o10BaseVertexILi7ENS_4Sim3EE16mapHessianMemoryEPd", None, 2),
+        "v_clear": ("_ZN3g2o10BaseVertexILi7ENS_4Sim3EE18clearQuadraticFormEv", None, 1),
+        "sim3_exp": ("_ZN3g2o4Sim3C1ERKN5Eigen6MatrixIdLi7ELi1ELi0ELi7ELi1EEE", None, 2),
+        "e_ctor": ("_ZN3g2o8EdgeSim3C1Ev", None, 1), "e_err": ("_ZN3g2o8EdgeSim312computeErrorEv", None, 1),
+        "e_meas": ("_ZN3g2o8BaseEdgeILi7ENS_4Sim3EE14setMeasurementERKS1_", None, 2),
+        "e_info": ("_ZN3g2o8BaseEdgeILi7ENS_4Sim3EE15informationDataEv", C.c_void_p, 1),
+        "e_errd": ("_ZN3g2o8BaseEdgeILi7ENS_4Sim3EE9errorDataEv", C.c_void_p, 1),
+        "e_lin": ("_ZN3g2o14BaseBinaryEdgeILi7ENS_4Sim3ENS_16VertexSim3ExpmapES2_E14linearizeOplusERNS_17JacobianWorkspaceE", None, 2),
+        "e_quad": ("_ZN3g2o14BaseBinaryEdgeILi7ENS_4Sim3ENS_16VertexSim3ExpmapES2_E22constructQuadraticFormEv", None, 1),
+        "e_map": ("_ZN3g2o14BaseBinaryEdgeILi7ENS_4Sim3ENS_16VertexSim3ExpmapES2_E16mapHessianMemoryEPdiib", None, -1),
+        "lam_init": ("_ZN3g2o30OptimizationAlgorithmLevenberg17setUserLambdaInitEd", None, -2),
+    }
+
+    def __init__(self):
+        self.G = Graph()
+        L = self.G.ed.g.L
+        self.f = {}
+        for k, (name, res, nargs) in self.S.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = ([C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_bool] if nargs == -1 else
+                           [C.c_void_p, C.c_double] if nargs == -2 else [C.c_void_p] * nargs)
+            self.f[k] = fn
+        self.verts, self.edges = [], []
+        v = self.new_vertex_block()
+        # _estimate: identity quaternion, t = 0, s = 1 after setToOriginImpl
+        self.est = None
+        for i in range(0, 400, 2):
+            if list(v[i:i + 8]) == [0, 0, 0, 1, 0, 0, 0, 1]:
+                u = P._aligned(8)
+                u[:7] = [0.1, 0.2, -0.1, 1, 2, 3, 0.3]
+                before = v[i:i + 8].copy()
+                self.f["v_oplus"](v.ctypes.data, u.ctypes.data)
+                if not np.array_equal(before, v[i:i + 8]):
+                    self.est = i
+                    break
+        assert self.est is not None, "VertexSim3Expmap::_estimate not found"
+        # _fix_scale: the bool after the four Vector2d members that makes oplus ignore update[6]
+        self.fix_off = None
+        for byte in range((self.est + 8) * 8, (self.est + 8) * 8 + 256):
+            w = self.new_vertex_block()
+            if w.view(np.uint8)[byte] != 0:
+                continue
+            w.view(np.uint8)[byte] = 1
+            u = P._aligned(8)
+            u[:7] = [0, 0, 0, 0, 0, 0, 0.5]
+            self.f["v_oplus"](w.ctypes.data, u.ctypes.data)
+            if w[self.est + 7] == 1.0:
+                self.fix_off = byte
+                break
+        assert self.fix_off is not None, "VertexSim3Expmap::_fix_scale not found"
+
+    def new_vertex_block(self):
+        v = P._aligned(PE.OBJ)
+        self.f["v_ctor"](v.ctypes.data)
+        self.f["v_origin"](v.ctypes.data)
+        return v
+
+    def exp(self, upd7):
+        out, u = P._aligned(8), P._aligned(8)
+        u[:7] = upd7
+        self.f["sim3_exp"](out.ctypes.data, u.ctypes.data)
+        return out.copy()
+
+    def oplus(self, s8, upd7, fix_scale):
+        v = self.new_vertex_block()
+        v[self.est:self.est + 8] = s8
+        v.view(np.uint8)[self.fix_off] = 1 if fix_scale else 0
+        u = P._aligned(8)
+        u[:7] = upd7
+        self.f["v_oplus"](v.ctypes.data, u.ctypes.data)
+        return v[self.est:self.est + 8].copy()
+
+    def add_vertex(self, idx, s8, fixed, fix_scale):
+        v = self.new_vertex_block()
+        i32 = v.view(np.int32)
+        assert i32[V_ID // 4] == -1 and i32[V_HIDX // 4] == -1 and i32[V_DIM // 4] == 7
+        v[self.est:self.est + 8] = s8
+        i32[V_ID // 4] = idx
+        v.view(np.uint8)[V_FIXED] = 1 if fixed else 0
+        v.view(np.uint8)[self.fix_off] = 1 if fix_scale else 0
+        assert self.G.f["add_vertex"](self.G.opt.ctypes.data, v.ctypes.data, None)
+        self.verts.append(v)
+
+    def estimate(self, i):
+        return self.verts[i][self.est:self.est + 8].copy()
+
+    def new_edge(self, vi, vj, meas8):
+        e = P._aligned(PE.OBJ)
+        self.f["e_ctor"](e.ctypes.data)
+        vec = PE._vector_slots(e, 16)
+        assert vec and vec[0][0] == 1
+        ptrs = (C.c_uint64 * 2).from_address(vec[0][1])
+        ptrs[0], ptrs[1] = vi.ctypes.data, vj.ctypes.data
+        m = P._aligned(8)
+        m[:] = meas8
+        self.f["e_meas"](e.ctypes.data, m.ctypes.data)
+        info = np.ctypeslib.as_array((C.c_double * 49).from_address(self.f["e_info"](e.ctypes.data)))
+        info[:] = np.eye(7).ravel()
+        return e
+
+    def edge_error(self, meas8, a8, b8):
+        va, vb = self.new_vertex_block(), self.new_vertex_block()
+        va[self.est:self.est + 8] = a8
+        vb[self.est:self.est + 8] = b8
+        e = self.new_edge(va, vb, meas8)
+        self.f["e_err"](e.ctypes.data)
+        return np.ctypeslib.as_array((C.c_double * 7).from_address(self.f["e_errd"](e.ctypes.data))).copy()
+
+    def add_edge(self, i, j, meas8):
+        e = self.new_edge(self.verts[i], self.verts[j], meas8)
+        assert self.G.f["add_edge"](self.G.opt.ctypes.data, e.ctypes.data)
+        jw = P._aligned(64)
+        self.G.ed.f["jw_ctor"](jw.ctypes.data)
+        self.G.ed.f["jw_size"](jw.ctypes.data, e.ctypes.data)
+        assert self.G.ed.f["jw_alloc"](jw.ctypes.data)
+        self.edges.append(dict(e=e, i=i, j=j, jw=jw))
+
+
+class FakeSolverSim3(FakeSolver):
+    """BlockSolver_7_3 without marginalised vertices (g2oOptimizer.cc:1220-1230): every free vertex in the one system."""
+
+    def __init__(self, sg):
+        self.sg = sg
+        super().__init__(sg.G, None, None, None)
+
+    def _build_structure(self, this, zero):
+        sg = self.sg
+        ent = sorted((int(v.view(np.int32)[V_HIDX // 4]), i) for i, v in enumerate(sg.verts))
+        self.off = {i: 7 * k for k, (h, i) in enumerate(e for e in ent if e[0] >= 0)}
+        self.n = 7 * len(self.off)
+        self.Hv = {i: P._aligned(52) for i in self.off}
+        for i, h in self.Hv.items():
+            sg.f["v_map"](sg.verts[i].ctypes.data, h.ctypes.data)
+        self.He = {}
+        for k, ed in enumerate(sg.edges):
+            if ed["i"] in self.off and ed["j"] in self.off:
+                self.He[k] = P._aligned(52)
+                sg.f["e_map"](ed["e"].ctypes.data, self.He[k].ctypes.data, 0, 1, False)
+        self.x, self.b = P._aligned(self.n + 8), P._aligned(self.n + 8)
+        u = self.obj.view(np.uint64)
+        u[2], u[3], u[4], u[5] = self.x.ctypes.data, self.b.ctypes.data, self.n, self.n
+        return True
+
+    def _build_system(self, this):
+        sg = self.sg
+        for h in list(self.Hv.values()) + list(self.He.values()):
+            h[:] = 0.0
+        for i in self.off:
+            sg.f["v_clear"](sg.verts[i].ctypes.data)
+        for ed in sg.edges:
+            sg.f["e_lin"](ed["e"].ctypes.data, ed["jw"].ctypes.data)
+            sg.f["e_quad"](ed["e"].ctypes.data)
+        for i, o in self.off.items():
+            self.b[o:o + 7] = sg.verts[i][sg.b_off:sg.b_off + 7]
+        return True
+
+    def _diag(self):
+        for i, h in self.Hv.items():
+            yield h, [r * 7 + r for r in range(7)]
+
+    def _solve(self, this):
+        H = np.zeros((self.n, self.n))
+        for i, h in self.Hv.items():
+            o = self.off[i]
+            H[o:o + 7, o:o + 7] = h[:49].reshape(7, 7).T
+        for k, h in self.He.items():
+            oi, oj = self.off[self.sg.edges[k]["i"]], self.off[self.sg.edges[k]["j"]]
+            blk = h[:49].reshape(7, 7).T                                  # Ji^T Jj
+            H[oi:oi + 7, oj:oj + 7] += blk
+            H[oj:oj + 7, oi:oi + 7] += blk.T
+        x = np.linalg.solve(H, self.b[:self.n])
+        self.x[:self.n] = x
+        self.log.append(("solve", float(np.linalg.norm(x))))
+        return True
+
+
+def _sim3_mul(a, b):
+    """numpy helper for building scenarios only (not a pinned quantity): Sim3 product of 8-vectors."""
+    def qm(p, q):
+        x1, y1, z1, w1 = p
+        x2, y2, z2, w2 = q
+        return np.array([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2,
+                         w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2])
+    return np.concatenate([qm(a[:4], b[:4]), a[7] * (_rot(a[:4]) @ b[4:7]) + a[4:7], [a[7] * b[7]]])
+
+
+def _sim3_inv(a):
+    qi = np.array([-a[0], -a[1], -a[2], a[3]])
+    return np.concatenate([qi, _rot(qi) @ (-a[4:7] / a[7]), [1.0 / a[7]]])
+
+
+def make_sim3(path, n=200, seed=11):
+    """Sim3 arithmetic of the binary: exp (Sim3(Vector7d)), oplusImpl with and without _fix_scale, EdgeSim3 error
+    (= log of C * v1 * v2^-1, which exercises operator*, inverse and log)."""
+    out = dict(np.load(path)) if os.path.exists(path) else {}
+    sg = Sim3Graph()
+    rng = np.random.default_rng(seed)
+    upd = rng.normal(0, 1, (n, 7)) * np.array([0.4, 0.4, 0.4, 2, 2, 2, 0.3])
+    upd[:10, :3] *= 1e-7          # theta < eps
+    upd[5:20, 6] *= 1e-7          # |sigma| < eps (rows 5-9 have both small)
+    ex = np.stack([sg.exp(u) for u in upd])
+    upd2 = rng.normal(0, 1, (n, 7)) * np.array([0.05, 0.05, 0.05, 0.3, 0.3, 0.3, 0.05])
+    op_free = np.stack([sg.oplus(ex[k], upd2[k], False) for k in range(n)])
+    op_fix = np.stack([sg.oplus(ex[k], upd2[k], True) for k in range(n)])
+    # edge error: v2 close to meas * v1 so that the log stays in its principal range, plus small-angle / small-scale cases
+    v1 = ex
+    pert = rng.normal(0, 1, (n, 7)) * np.array([0.2, 0.2, 0.2, 1, 1, 1, 0.2])
+    pert[:10, :3] *= 1e-7
+    pert[5:20, 6] *= 1e-8
+    meas = np.stack([sg.exp(rng.normal(0, 1, 7) * np.array([0.3, 0.3, 0.3, 1, 1, 1, 0.2])) for _ in range(n)])
+    v2 = np.stack([_sim3_mul(_sim3_inv(sg.exp(pert[k])), _sim3_mul(meas[k], v1[k])) for k in range(n)])
+    err = np.stack([sg.edge_error(meas[k], v1[k], v2[k]) for k in range(n)])
+    out.update(sim3_upd=upd, sim3_exp=ex, sim3_upd2=upd2, sim3_oplus_free=op_free, sim3_oplus_fix=op_fix,
+               sim3_meas=meas, sim3_v1=v1, sim3_v2=v2, sim3_err=err)
+    np.savez(path, **out)
+    print(f"sim3: estimate at double {sg.est}, _fix_scale at byte {sg.fix_off}, max |edge error| {np.abs(err).max():.3f}")
+    return out
+
+
+def make_posegraph(path):
+    """The optimisation of g2oOptimizer::OptimizeEssentialGraph (g2oOptimizer.cc:1212-1232, 1472-1478) on the binary:
+    VertexSim3Expmap per keyframe (one fixed), EdgeSim3 with identity information, Levenberg with
+    setUserLambdaInit(1e-16), optimize(20) -- on a drifting loop with a closing edge, once with fixed scale (stereo)
+    and once with free scale (monocular)."""
+    out = dict(np.load(path)) if os.path.exists(path) else {}
+    keep = []
+    for case, fix_scale in enumerate((True, False)):
+        sg = Sim3Graph()
+        G = sg.G
+        rng = np.random.default_rng(21 + case)
+        n = 24
+        # ground truth: a circle; odometry = true relative motion + noise (+ scale drift when the scale is free)
+        truth = []
+        for k in range(n):
+            ang = 2 * np.pi * k / n
+            q = np.array([0, np.sin(ang / 2), 0, np.cos(ang / 2)])
+            c = np.array([10 * np.sin(ang), 0.0, 10 * (1 - np.cos(ang))])
+            truth.append(np.concatenate([q, -_rot(q) @ c, [1.0]]))      # S_kw
+        edges, meas = [], []
+        est = [truth[0].copy()]
+        for k in range(1, n):
+            rel = _sim3_mul(truth[k], _sim3_inv(truth[k - 1]))          # S_k,k-1
+            noise = sg.exp(rng.normal(0, 1, 7) * np.array([0.01, 0.01, 0.01, 0.05, 0.02, 0.05, 0.0 if fix_scale else 0.01]))
+            m = _sim3_mul(noise, rel)
+            edges.append((k - 1, k))                                     # vertex 0 = i, vertex 1 = j, measurement S_ji
+            meas.append(m)
+            est.append(_sim3_mul(m, est[k - 1]))                         # dead reckoning: drifts
+        edges.append((n - 1, 0))                                         # the loop closes
+        meas.append(_sim3_mul(truth[0], _sim3_inv(truth[n - 1])))
+        for k in range(2, n, 5):                                         # a few covisibility edges
+            edges.append((k - 2, k))
+            meas.append(_sim3_mul(truth[k], _sim3_inv(truth[k - 2])))
+        est, meas, edges = np.stack(est), np.stack(meas), np.array(edges, np.int32)
+        fixed = np.zeros(n, np.uint8)
+        fixed[0] = 1                                                     # pLoopKF
+        for k in range(n):
+            sg.add_vertex(k, est[k], bool(fixed[k]), fix_scale)
+        for (i, j), m in zip(edges, meas):
+            sg.add_edge(int(i), int(j), m)
+        o = G.opt.ctypes.data
+        assert G.f["init"](o, 0)
+        G.f["errors"](o)
+        chi0 = G.f["chi2"](o)
+        # locate _b of the Sim3 vertex
+        Hs = P._aligned(52)
+        sg.f["v_map"](sg.verts[1].ctypes.data, Hs.ctypes.data)
+        sg.f["v_clear"](sg.verts[1].ctypes.data)
+        snap = sg.verts[1].copy()
+        e0 = sg.edges[0]
+        He = P._aligned(52)
+        sg.f["e_map"](e0["e"].ctypes.data, He.ctypes.data, 0, 1, False)
+        Hz = P._aligned(52)
+        sg.f["v_map"](sg.verts[0].ctypes.data, Hz.ctypes.data)
+        sg.f["e_lin"](e0["e"].ctypes.data, e0["jw"].ctypes.data)
+        sg.f["e_quad"](e0["e"].ctypes.data)
+        ch = np.flatnonzero(sg.verts[1].view(np.uint64) != snap.view(np.uint64))
+        # _b is the first run of changed doubles (7 long; its scale component stays 0 when the scale is fixed); further
+        # up the object the backup stack's bookkeeping moves too (push / pop of the numeric Jacobian)
+        assert len(ch) >= 3 and (ch < ch.min() + 7).sum() >= 3 and ch.min() > V_DIM // 8, ch
+        sg.b_off = int(ch.min())
+        sg.f["v_clear"](sg.verts[1].ctypes.data)
+        L = G.ed.g.L
+        lm_ctor = L._ZN3g2o30OptimizationAlgorithmLevenbergC1EPNS_6SolverE
+        lm_ctor.restype, lm_ctor.argtypes = None, [C.c_void_p, C.c_void_p]
+        set_alg = L._ZN3g2o15SparseOptimizer12setAlgorithmEPNS_21OptimizationAlgorithmE
+        set_alg.restype, set_alg.argtypes = None, [C.c_void_p, C.c_void_p]
+        optimize = L._ZN3g2o15SparseOptimizer8optimizeEib
+        optimize.restype, optimize.argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_bool]
+        solver = FakeSolverSim3(sg)
+        alg = P._aligned(1024)
+        lm_ctor(alg.ctypes.data, solver.obj.ctypes.data)
+        sg.f["lam_init"](alg.ctypes.data, 1e-16)                         # solver->setUserLambdaInit(1e-16), :1230
+        set_alg(o, alg.ctypes.data)
+        n_it = optimize(o, 20, False)
+        G.f["errors"](o)
+        chi1 = G.f["chi2"](o)
+        lam = np.array([v for k, v in solver.log if k == "lambda"])
+        out.update({f"pg{case}_vert0": est, f"pg{case}_fixed": fixed, f"pg{case}_fix_scale": np.array(int(fix_scale)),
+                    f"pg{case}_edges": edges, f"pg{case}_meas": meas, f"pg{case}_lambda": lam,
+                    f"pg{case}_n_iterations": np.array(n_it), f"pg{case}_chi2": np.array([chi0, chi1]),
+                    f"pg{case}_vert": np.stack([sg.estimate(k) for k in range(n)])})
+        keep.append((sg, solver, alg, Hs, He, Hz))
+        print(f"pose graph (fix_scale={fix_scale}): optimize -> {n_it} iterations, {len(lam)} trials, chi2 {chi0:.4f} -> {chi1:.6f}")
+    np.savez(path, **out)
+    return out, keep
+
+
 if __name__ == "__main__":
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = sys.argv[1] if len(sys.argv) > 1 else os.path.join(here, "tests", "golden", "libg2o_vectors.npz")
@@ -854,6 +1174,8 @@ if __name__ == "__main__":
     make_lm(p)
     _keep = make_lba(p)
     _keep2 = make_poseopt(p)
+    make_sim3(p)
+    _keep3 = make_posegraph(p)
     print("wrote", p, "| phase A index:", o["graph_A_pose_index"], o["graph_A_point_index"], "| phase B index:",
           o["graph_B_pose_index"], o["graph_B_point_index"], "| chi2", o["graph_A_chi2"], o["graph_A_robust_chi2"],
           o["graph_B_chi2"])

@@ -27,7 +27,8 @@
 // trial, including rejected trials, both clamps of the lambda factor and the _nBad stop rule; and the two-pass
 // local-BA schedule driven over the binary's objects gives the lambda sequences, level-1 set, outlier flags and
 // estimates that refba_solve_local gives; likewise refba_pose_opt against the four-round pose-only schedule over the
-// binary's EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose objects.
+// binary's EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose objects, and refba_sim3_* / refba_pose_graph
+// (essential-graph optimisation, no CUDA counterpart yet) against the binary's Sim3, VertexSim3Expmap and EdgeSim3.
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 // Eigen is not vendored in the reference; where g2o calls into Eigen (quaternion*vector,
@@ -1585,6 +1586,394 @@ int refba_pose_opt(double* pose7, const double* cam, int n, const double* xyz, c
   if (trace && nt > 0) std::memcpy(trace, P.trace.data(), (size_t)nt * sizeof(TraceRow));
   if (n_trace) *n_trace = nt;
   return n - nBad;
+}
+
+// =====================================================================================================
+// Essential-graph (Sim3 pose-graph) optimisation -- SURVEY.md 8(f) row N3, oracle only (no CUDA counterpart yet).
+// Restates g2o's Sim3 (types/sim3.h:40-285), VertexSim3Expmap::oplusImpl and EdgeSim3::computeError
+// (types/types_seven_dof_expmap.h:48-110), the NUMERIC Jacobians EdgeSim3 inherits (base_binary_edge.hpp:122-195:
+// central differences, delta 1e-9, through the vertex's own oplus), constructQuadraticForm with identity information,
+// and the optimisation set up by g2oOptimizer::OptimizeEssentialGraph (g2oOptimizer.cc:1212-1232, 1472-1478):
+// Levenberg with setUserLambdaInit(1e-16), no marginalised vertices (BlockSolver_7_3 solves the whole system).
+// Pinned against the reference binary by oracle/pin_libg2o_graph.py (make_sim3, make_posegraph).
+// =====================================================================================================
+namespace {
+struct Sim3 { Quat r; double t[3]; double s; };
+
+// Sim3(const Vector7d& update): exp map, update = (omega, upsilon, sigma)   (sim3.h:68-144)
+inline Sim3 sim3exp(const double u[7]) {
+  const double om[3] = {u[0], u[1], u[2]}, up[3] = {u[3], u[4], u[5]}, sigma = u[6];
+  const double theta = std::sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+  const double Om[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0};
+  double Om2[9];
+  mat3mul(Om, Om, Om2);
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  Sim3 S;
+  S.s = std::exp(sigma);
+  double R[9], A, B, C;
+  const double eps = 0.00001;
+  if (std::fabs(sigma) < eps) {
+    C = 1;
+    if (theta < eps) {
+      A = 1. / 2.; B = 1. / 6.;
+      for (int i = 0; i < 9; i++) R[i] = I[i] + Om[i] + Om2[i];
+    } else {
+      const double theta2 = theta * theta;
+      A = (1 - std::cos(theta)) / theta2;
+      B = (theta - std::sin(theta)) / (theta2 * theta);
+      for (int i = 0; i < 9; i++) R[i] = I[i] + std::sin(theta) / theta * Om[i] + (1 - std::cos(theta)) / (theta * theta) * Om2[i];
+    }
+  } else {
+    C = (S.s - 1) / sigma;
+    if (theta < eps) {
+      const double sigma2 = sigma * sigma;
+      A = ((sigma - 1) * S.s + 1) / sigma2;
+      B = ((0.5 * sigma2 - sigma + 1) * S.s) / (sigma2 * sigma);
+      for (int i = 0; i < 9; i++) R[i] = I[i] + Om[i] + Om2[i];
+    } else {
+      for (int i = 0; i < 9; i++) R[i] = I[i] + std::sin(theta) / theta * Om[i] + (1 - std::cos(theta)) / (theta * theta) * Om2[i];
+      const double a = S.s * std::sin(theta), b = S.s * std::cos(theta);
+      const double theta2 = theta * theta, sigma2 = sigma * sigma, c = theta2 + sigma2;
+      A = (a * sigma + (1 - b) * theta) / (theta * c);
+      B = (C - ((b - 1) * sigma + a * theta) / c) * 1. / theta2;
+    }
+  }
+  S.r = RtoQ(R);
+  double W[9];
+  for (int i = 0; i < 9; i++) W[i] = A * Om[i] + B * Om2[i] + C * I[i];
+  for (int i = 0; i < 3; i++) S.t[i] = W[i * 3] * up[0] + W[i * 3 + 1] * up[1] + W[i * 3 + 2] * up[2];
+  return S;
+}
+
+// Eigen's PartialPivLU solve of a 3x3 system (Matrix3d::lu().solve, sim3.h:224)
+inline void lu3solve(const double Win[9], const double b[3], double x[3]) {
+  double A[9];
+  std::memcpy(A, Win, sizeof A);
+  int perm[3] = {0, 1, 2};
+  for (int k = 0; k < 3; k++) {
+    int piv = k;
+    for (int i = k + 1; i < 3; i++)
+      if (std::fabs(A[i * 3 + k]) > std::fabs(A[piv * 3 + k])) piv = i;
+    if (piv != k) {
+      for (int j = 0; j < 3; j++) std::swap(A[k * 3 + j], A[piv * 3 + j]);
+      std::swap(perm[k], perm[piv]);
+    }
+    for (int i = k + 1; i < 3; i++) {
+      A[i * 3 + k] /= A[k * 3 + k];
+      for (int j = k + 1; j < 3; j++) A[i * 3 + j] -= A[i * 3 + k] * A[k * 3 + j];
+    }
+  }
+  double y[3];
+  for (int i = 0; i < 3; i++) {
+    y[i] = b[perm[i]];
+    for (int j = 0; j < i; j++) y[i] -= A[i * 3 + j] * y[j];
+  }
+  for (int i = 2; i >= 0; i--) {
+    x[i] = y[i];
+    for (int j = i + 1; j < 3; j++) x[i] -= A[i * 3 + j] * x[j];
+    x[i] /= A[i * 3 + i];
+  }
+}
+
+// Sim3::log   (sim3.h:150-235)
+inline void sim3log(const Sim3& S, double res[7]) {
+  const double sigma = std::log(S.s);
+  double R[9];
+  qtoR(S.r, R);
+  const double d = 0.5 * (R[0] + R[4] + R[8] - 1);
+  const double dR[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};  // deltaR, se3_ops.hpp:40-47
+  const double eps = 0.00001;
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  double om[3], A, B, C;
+  if (std::fabs(sigma) < eps) {
+    C = 1;
+    if (d > 1 - eps) {
+      for (int i = 0; i < 3; i++) om[i] = 0.5 * dR[i];
+      A = 1. / 2.; B = 1. / 6.;
+    } else {
+      const double theta = std::acos(d), theta2 = theta * theta;
+      for (int i = 0; i < 3; i++) om[i] = theta / (2 * std::sqrt(1 - d * d)) * dR[i];
+      A = (1 - std::cos(theta)) / theta2;
+      B = (theta - std::sin(theta)) / (theta2 * theta);
+    }
+  } else {
+    C = (S.s - 1) / sigma;
+    if (d > 1 - eps) {
+      const double sigma2 = sigma * sigma;
+      for (int i = 0; i < 3; i++) om[i] = 0.5 * dR[i];
+      A = ((sigma - 1) * S.s + 1) / sigma2;
+      B = ((0.5 * sigma2 - sigma + 1) * S.s) / (sigma2 * sigma);
+    } else {
+      const double theta = std::acos(d);
+      for (int i = 0; i < 3; i++) om[i] = theta / (2 * std::sqrt(1 - d * d)) * dR[i];
+      const double theta2 = theta * theta;
+      const double a = S.s * std::sin(theta), b = S.s * std::cos(theta), c = theta2 + sigma * sigma;
+      A = (a * sigma + (1 - b) * theta) / (theta * c);
+      B = (C - ((b - 1) * sigma + a * theta) / c) * 1. / theta2;
+    }
+  }
+  const double Om[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0};
+  double Om2[9], W[9], ups[3];
+  mat3mul(Om, Om, Om2);
+  for (int i = 0; i < 9; i++) W[i] = A * Om[i] + B * Om2[i] + C * I[i];
+  lu3solve(W, S.t, ups);
+  for (int i = 0; i < 3; i++) { res[i] = om[i]; res[i + 3] = ups[i]; }
+  res[6] = sigma;
+}
+
+// Sim3::operator* and inverse (sim3.h:238-278).  No re-normalisation of the quaternion, unlike SE3Quat.
+inline Sim3 sim3mul(const Sim3& a, const Sim3& b) {
+  Sim3 r;
+  r.r = qmul(a.r, b.r);
+  double rt[3];
+  qrot(a.r, b.t, rt);
+  for (int i = 0; i < 3; i++) r.t[i] = a.s * rt[i] + a.t[i];
+  r.s = a.s * b.s;
+  return r;
+}
+inline Sim3 sim3inv(const Sim3& a) {
+  Sim3 r;
+  r.r = Quat{-a.r.x, -a.r.y, -a.r.z, a.r.w};
+  const double v[3] = {(-1. / a.s) * a.t[0], (-1. / a.s) * a.t[1], (-1. / a.s) * a.t[2]};
+  qrot(r.r, v, r.t);
+  r.s = 1. / a.s;
+  return r;
+}
+inline Sim3 sim3from8(const double* v) {  // (qx, qy, qz, qw, tx, ty, tz, s): Sim3::operator[] order
+  Sim3 S;
+  S.r = Quat{v[0], v[1], v[2], v[3]};
+  S.t[0] = v[4]; S.t[1] = v[5]; S.t[2] = v[6];
+  S.s = v[7];
+  return S;
+}
+inline void sim3to8(const Sim3& S, double* v) {
+  v[0] = S.r.x; v[1] = S.r.y; v[2] = S.r.z; v[3] = S.r.w;
+  v[4] = S.t[0]; v[5] = S.t[1]; v[6] = S.t[2]; v[7] = S.s;
+}
+// VertexSim3Expmap::oplusImpl (types_seven_dof_expmap.h:63-72)
+inline Sim3 sim3oplus(const Sim3& est, const double upd[7], bool fix_scale) {
+  double u[7];
+  std::memcpy(u, upd, sizeof u);
+  if (fix_scale) u[6] = 0;
+  return sim3mul(sim3exp(u), est);
+}
+// EdgeSim3::computeError (types_seven_dof_expmap.h:95-103): log(C * v1 * v2^-1)
+inline void sim3edgeError(const Sim3& C, const Sim3& v1, const Sim3& v2, double e[7]) {
+  sim3log(sim3mul(sim3mul(C, v1), sim3inv(v2)), e);
+}
+
+struct PoseGraph {
+  int n = 0;
+  std::vector<Sim3> v, bak;
+  std::vector<uint8_t> fixed;
+  bool fix_scale = true;
+  struct E { int i, j; Sim3 meas; double err[7]; double Ji[49], Jj[49]; };
+  std::vector<E> e;
+  std::vector<int> slot;  // hessianIndex
+  int N = 0;              // free vertices
+  std::vector<double> H, b, x;
+  std::vector<TraceRow> trace;
+};
+
+inline void pgErrors(PoseGraph& G) {
+  for (auto& e : G.e) sim3edgeError(e.meas, G.v[e.i], G.v[e.j], e.err);
+}
+inline double pgChi2(const PoseGraph& G) {  // information = identity
+  double c = 0;
+  for (const auto& e : G.e) {
+    double s = 0;
+    for (int k = 0; k < 7; k++) s += e.err[k] * e.err[k];
+    c += s;
+  }
+  return c;
+}
+// BaseBinaryEdge::linearizeOplus, numeric version (base_binary_edge.hpp:122-195)
+inline void pgLinearize(PoseGraph& G, PoseGraph::E& e) {
+  const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+  for (int side = 0; side < 2; side++) {
+    const int vi = side == 0 ? e.i : e.j;
+    double* J = side == 0 ? e.Ji : e.Jj;
+    if (G.fixed[vi]) continue;
+    const Sim3 keep = G.v[vi];
+    for (int d = 0; d < 7; d++) {
+      double add[7] = {0, 0, 0, 0, 0, 0, 0}, e1[7], e2[7];
+      add[d] = delta;
+      G.v[vi] = sim3oplus(keep, add, G.fix_scale);
+      sim3edgeError(e.meas, G.v[e.i], G.v[e.j], e1);
+      add[d] = -delta;
+      G.v[vi] = sim3oplus(keep, add, G.fix_scale);
+      sim3edgeError(e.meas, G.v[e.i], G.v[e.j], e2);
+      G.v[vi] = keep;
+      for (int r = 0; r < 7; r++) J[r * 7 + d] = scalar * (e1[r] - e2[r]);
+    }
+  }
+}
+inline void pgBuildSystem(PoseGraph& G) {
+  const int n = G.N * 7;
+  std::fill(G.H.begin(), G.H.end(), 0.0);
+  std::fill(G.b.begin(), G.b.end(), 0.0);
+  for (auto& e : G.e) {
+    pgLinearize(G, e);
+    const int si = G.slot[e.i], sj = G.slot[e.j];
+    // constructQuadraticForm without robust kernel, omega = I (base_binary_edge.hpp:97-117)
+    if (si >= 0)
+      for (int a = 0; a < 7; a++) {
+        double s = 0;
+        for (int r = 0; r < 7; r++) s += e.Ji[r * 7 + a] * e.err[r];
+        G.b[si * 7 + a] -= s;
+        for (int c = 0; c < 7; c++) {
+          double h = 0;
+          for (int r = 0; r < 7; r++) h += e.Ji[r * 7 + a] * e.Ji[r * 7 + c];
+          G.H[(size_t)(si * 7 + a) * n + si * 7 + c] += h;
+        }
+      }
+    if (sj >= 0)
+      for (int a = 0; a < 7; a++) {
+        double s = 0;
+        for (int r = 0; r < 7; r++) s += e.Jj[r * 7 + a] * e.err[r];
+        G.b[sj * 7 + a] -= s;
+        for (int c = 0; c < 7; c++) {
+          double h = 0;
+          for (int r = 0; r < 7; r++) h += e.Jj[r * 7 + a] * e.Jj[r * 7 + c];
+          G.H[(size_t)(sj * 7 + a) * n + sj * 7 + c] += h;
+        }
+      }
+    if (si >= 0 && sj >= 0)
+      for (int a = 0; a < 7; a++)
+        for (int c = 0; c < 7; c++) {
+          double h = 0;
+          for (int r = 0; r < 7; r++) h += e.Ji[r * 7 + a] * e.Jj[r * 7 + c];
+          G.H[(size_t)(si * 7 + a) * n + sj * 7 + c] += h;
+          G.H[(size_t)(sj * 7 + c) * n + si * 7 + a] += h;
+        }
+  }
+}
+// dense LDL^T solve of (H + lambda I) x = b (stands for LinearSolverEigen's sparse Cholesky: an exact solve)
+inline bool pgSolve(PoseGraph& G, double lambda) {
+  const int n = G.N * 7;
+  std::vector<double> A(G.H);
+  for (int i = 0; i < n; i++) A[(size_t)i * n + i] += lambda;
+  std::vector<double> D(n);
+  for (int j = 0; j < n; j++) {
+    double d = A[(size_t)j * n + j];
+    for (int k = 0; k < j; k++) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k] * D[k];
+    if (!(d > 0)) return false;
+    D[j] = d;
+    for (int i = j + 1; i < n; i++) {
+      double l = A[(size_t)i * n + j];
+      for (int k = 0; k < j; k++) l -= A[(size_t)i * n + k] * A[(size_t)j * n + k] * D[k];
+      A[(size_t)i * n + j] = l / d;
+    }
+  }
+  std::vector<double>& x = G.x;
+  for (int i = 0; i < n; i++) {
+    double v = G.b[i];
+    for (int k = 0; k < i; k++) v -= A[(size_t)i * n + k] * x[k];
+    x[i] = v;
+  }
+  for (int i = 0; i < n; i++) x[i] /= D[i];
+  for (int i = n - 1; i >= 0; i--)
+    for (int k = i + 1; k < n; k++) x[i] -= A[(size_t)k * n + i] * x[k];
+  return true;
+}
+}  // namespace
+
+// arithmetic probes (8-vectors are qx,qy,qz,qw,tx,ty,tz,s)
+void refba_sim3_exp(const double* upd7, double* out8) { sim3to8(sim3exp(upd7), out8); }
+void refba_sim3_log(const double* in8, double* out7) { sim3log(sim3from8(in8), out7); }
+void refba_sim3_oplus(const double* in8, const double* upd7, int fix_scale, double* out8) {
+  sim3to8(sim3oplus(sim3from8(in8), upd7, fix_scale != 0), out8);
+}
+void refba_sim3_edge_error(const double* meas8, const double* v1_8, const double* v2_8, double* err7) {
+  sim3edgeError(sim3from8(meas8), sim3from8(v1_8), sim3from8(v2_8), err7);
+}
+
+// Sim3 pose-graph optimisation as OptimizeEssentialGraph sets it up: LM, lambda_0 = lambda_init (1e-16 in the reference),
+// `iters` iterations, identity information, vertices in ascending id.  vertices n x 8 in/out; edges (i, j) with
+// measurement S_ji (vertex 0 = i, vertex 1 = j).  trace rows as in refba_get_trace.  Returns the iterations performed.
+int refba_pose_graph(int n, double* vert8, const uint8_t* fixed, int fix_scale, int n_e, const int32_t* edge_ij,
+                     const double* meas8, int iters, double lambda_init, double* trace, int max_trace, int* n_trace) {
+  PoseGraph G;
+  G.n = n;
+  G.fix_scale = fix_scale != 0;
+  G.v.resize(n);
+  G.fixed.assign(fixed, fixed + n);
+  for (int i = 0; i < n; i++) G.v[i] = sim3from8(vert8 + (size_t)i * 8);
+  G.e.resize(n_e);
+  for (int k = 0; k < n_e; k++) {
+    G.e[k].i = edge_ij[2 * k];
+    G.e[k].j = edge_ij[2 * k + 1];
+    G.e[k].meas = sim3from8(meas8 + (size_t)k * 8);
+  }
+  // index mapping: non-fixed vertices that have an edge, ascending id
+  std::vector<uint8_t> act(n, 0);
+  for (auto& e : G.e) { act[e.i] = 1; act[e.j] = 1; }
+  G.slot.assign(n, -1);
+  for (int i = 0; i < n; i++)
+    if (act[i] && !G.fixed[i]) G.slot[i] = G.N++;
+  const int dim = G.N * 7;
+  G.H.assign((size_t)dim * dim, 0.0);
+  G.b.assign(dim, 0.0);
+  G.x.assign(dim, 0.0);
+  double lambda = 0, ni = 2;
+  int nBad = 0, done = 0;
+  bool ok = true;
+  for (int it = 0; it < iters && ok && dim > 0; it++) {  // SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve
+    pgErrors(G);
+    double currentChi = pgChi2(G), tempChi = currentChi;
+    const double iniChi = currentChi;
+    pgBuildSystem(G);
+    if (it == 0) {
+      if (lambda_init > 0) lambda = lambda_init;  // computeLambdaInit: _userLambdaInit (optimization_algorithm_levenberg.cpp:168-169)
+      else {
+        double md = 0;
+        for (int i = 0; i < dim; i++) md = std::max(md, std::fabs(G.H[(size_t)i * dim + i]));
+        lambda = 1e-5 * md;
+      }
+      ni = 2;
+      nBad = 0;
+    }
+    double rho = 0;
+    int qmax = 0;
+    do {
+      G.bak = G.v;
+      const bool ok2 = pgSolve(G, lambda);
+      for (int i = 0; i < n; i++)
+        if (G.slot[i] >= 0) G.v[i] = sim3oplus(G.v[i], &G.x[(size_t)G.slot[i] * 7], G.fix_scale);
+      pgErrors(G);
+      tempChi = pgChi2(G);
+      if (!ok2) tempChi = std::numeric_limits<double>::max();
+      rho = currentChi - tempChi;
+      double scale = 0;
+      for (int j = 0; j < dim; j++) scale += G.x[j] * (lambda * G.x[j] + G.b[j]);
+      scale += 1e-3;
+      rho /= scale;
+      TraceRow tr{0.0, (double)it, (double)qmax, lambda, currentChi, tempChi, rho, 0.0};
+      if (rho > 0 && std::isfinite(tempChi)) {
+        double alpha = 1. - std::pow((2 * rho - 1), 3);
+        alpha = std::min(alpha, 2. / 3.);
+        lambda *= std::max(1. / 3., alpha);
+        ni = 2;
+        currentChi = tempChi;
+        tr.accepted = 1.0;
+      } else {
+        lambda *= ni;
+        ni *= 2;
+        G.v = G.bak;
+      }
+      G.trace.push_back(tr);
+      qmax++;
+    } while (rho < 0 && qmax < 10);
+    done++;
+    if (qmax == 10 || rho == 0) { ok = false; break; }
+    if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
+    if (nBad >= 3) ok = false;
+  }
+  for (int i = 0; i < n; i++) sim3to8(G.v[i], vert8 + (size_t)i * 8);
+  const int nt = std::min<int>((int)G.trace.size(), max_trace);
+  if (trace && nt > 0) std::memcpy(trace, G.trace.data(), (size_t)nt * sizeof(TraceRow));
+  if (n_trace) *n_trace = nt;
+  return done;
 }
 
 int refba_max_threads() {

@@ -57,6 +57,11 @@ def lib():
         L.refba_num_lidar_edges.argtypes = [C.c_void_p]
         L.refba_debug_phase.argtypes = [C.c_void_p, ip, C.c_int, ip, ip, dp, dp, dp, dp, dp]
         L.refba_debug_system.argtypes = [C.c_void_p, dp, dp, dp, dp]
+        L.refba_sim3_exp.argtypes = [dp, dp]
+        L.refba_sim3_log.argtypes = [dp, dp]
+        L.refba_sim3_oplus.argtypes = [dp, dp, C.c_int, dp]
+        L.refba_sim3_edge_error.argtypes = [dp, dp, dp, dp]
+        L.refba_pose_graph.argtypes = [C.c_int, dp, up, C.c_int, C.c_int, ip, dp, C.c_int, C.c_double, dp, C.c_int, ip]
         L.refba_pose_opt.argtypes = [dp, dp, C.c_int, dp, fp, up, dp, C.c_int, ip]
         _lib = L
     return _lib
@@ -229,3 +234,42 @@ def pose_opt(pose7, cam5, xyz, meas):
     inl = L.refba_pose_opt(_p(pose, C.c_double), _p(cam, C.c_double), n, _p(xyz, C.c_double), _p(meas, C.c_float),
                            _p(out, C.c_uint8), _p(tr, C.c_double), 400, C.byref(nt))
     return pose, out[:n], int(inl), tr[:nt.value]
+
+
+# ---- essential-graph (Sim3 pose-graph) optimisation, SURVEY.md 8(f) N3 (oracle only); 8-vectors are qx,qy,qz,qw,tx,ty,tz,s
+def sim3_exp(upd7):
+    u, out = np.ascontiguousarray(upd7, np.float64), np.zeros(8)
+    lib().refba_sim3_exp(_p(u, C.c_double), _p(out, C.c_double))
+    return out
+
+
+def sim3_log(s8):
+    a, out = np.ascontiguousarray(s8, np.float64), np.zeros(7)
+    lib().refba_sim3_log(_p(a, C.c_double), _p(out, C.c_double))
+    return out
+
+
+def sim3_oplus(s8, upd7, fix_scale):
+    a, u, out = np.ascontiguousarray(s8, np.float64), np.ascontiguousarray(upd7, np.float64), np.zeros(8)
+    lib().refba_sim3_oplus(_p(a, C.c_double), _p(u, C.c_double), int(fix_scale), _p(out, C.c_double))
+    return out
+
+
+def sim3_edge_error(meas8, v1, v2):
+    m, a, b, out = (np.ascontiguousarray(x, np.float64) for x in (meas8, v1, v2, np.zeros(7)))
+    lib().refba_sim3_edge_error(_p(m, C.c_double), _p(a, C.c_double), _p(b, C.c_double), _p(out, C.c_double))
+    return out
+
+
+def pose_graph(vert8, fixed, fix_scale, edge_ij, meas8, iters=20, lambda_init=1e-16):
+    """g2oOptimizer::OptimizeEssentialGraph's optimisation restated (refba_pose_graph).
+    Returns (vertices n x 8, trace rows x 8, iterations performed)."""
+    V = np.ascontiguousarray(vert8, np.float64).copy()
+    fx = np.ascontiguousarray(fixed, np.uint8)
+    E = np.ascontiguousarray(edge_ij, np.int32)
+    M = np.ascontiguousarray(meas8, np.float64)
+    tr = np.zeros((iters * 10 + 1, 8))
+    nt = C.c_int32(0)
+    done = lib().refba_pose_graph(len(V), _p(V, C.c_double), _p(fx, C.c_uint8), int(fix_scale), len(E), _p(E, C.c_int32),
+                                  _p(M, C.c_double), iters, lambda_init, _p(tr, C.c_double), len(tr), C.byref(nt))
+    return V, tr[:nt.value], done

@@ -244,3 +244,43 @@ def test_pose_only_optimisation_matches_reference_binary(gold):
     np.testing.assert_allclose(pose, g["pose"], rtol=0, atol=1e-12)
     assert 20 < g["outlier"].sum() < 60 and (g["meas"][:, 2] < 0).any() and (g["meas"][:, 2] >= 0).any()
     assert (g["lambda"][1:] > g["lambda"][:-1]).sum() >= 4      # rejected trials inside the rounds
+
+
+def test_sim3_arithmetic_matches_reference_binary(gold):
+    """Row N3 groundwork: g2o::Sim3(Vector7d) (the exponential map with its four small-angle / small-scale branches,
+    sim3.h:68-144), VertexSim3Expmap::oplusImpl with and without _fix_scale, and EdgeSim3::computeError = log(C * v1 *
+    v2^-1) (operator*, inverse, log incl. the 3x3 LU solve) on real objects of the binary."""
+    for u, want in zip(gold["sim3_upd"], gold["sim3_exp"]):
+        np.testing.assert_allclose(refba.sim3_exp(u), want, rtol=0, atol=4e-15 * max(1.0, np.abs(want).max()))
+    for s8, u, free, fix in zip(gold["sim3_exp"], gold["sim3_upd2"], gold["sim3_oplus_free"], gold["sim3_oplus_fix"]):
+        np.testing.assert_allclose(refba.sim3_oplus(s8, u, False), free, rtol=0, atol=4e-15 * max(1.0, np.abs(free).max()))
+        np.testing.assert_allclose(refba.sim3_oplus(s8, u, True), fix, rtol=0, atol=4e-15 * max(1.0, np.abs(fix).max()))
+        assert fix[7] == s8[7] and free[7] != s8[7]                      # _fix_scale really pins the scale
+    for m, a, b, want in zip(gold["sim3_meas"], gold["sim3_v1"], gold["sim3_v2"], gold["sim3_err"]):
+        np.testing.assert_allclose(refba.sim3_edge_error(m, a, b), want, rtol=0, atol=1e-13 * max(1.0, np.abs(want).max()))
+    th = np.linalg.norm(gold["sim3_upd"][:, :3], axis=1)
+    sg = np.abs(gold["sim3_upd"][:, 6])
+    for small_t in (True, False):                                        # all four branches of the exponential
+        for small_s in (True, False):
+            assert (((th < 1e-5) == small_t) & ((sg < 1e-5) == small_s)).sum() >= 5
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_essential_graph_optimisation_matches_reference_binary(gold, case):
+    """The optimisation g2oOptimizer::OptimizeEssentialGraph sets up (g2oOptimizer.cc:1212-1232, 1472-1478) run by the
+    binary itself -- VertexSim3Expmap / EdgeSim3 objects, numeric Jacobians (central differences, delta 1e-9), identity
+    information, Levenberg with setUserLambdaInit(1e-16), optimize(20) -- on a drifting loop with a closing edge, with
+    fixed (stereo) and free (monocular) scale.  refba_pose_graph must make the same trials with the same lambda, stop in
+    the same iteration (both end through ten rejected trials in a row, the qmax == 10 rule) and reach the same cost."""
+    g = {k[len(f"pg{case}_"):]: gold[k] for k in gold.files if k.startswith(f"pg{case}_")}
+    V, tr, done = refba.pose_graph(g["vert0"], g["fixed"], int(g["fix_scale"]), g["edges"], g["meas"], 20, 1e-16)
+    assert done == int(g["n_iterations"]) and len(tr) == len(g["lambda"])
+    np.testing.assert_allclose(tr[:, 3], g["lambda"], rtol=1e-6)
+    assert tr[0, 3] == 1e-16
+    np.testing.assert_allclose(tr[0, 4], g["chi2"][0], rtol=1e-12)
+    np.testing.assert_allclose(tr[tr[:, 7] == 1][-1, 5], g["chi2"][1], rtol=1e-6)
+    # numeric Jacobians with delta = 1e-9 carry ~1e-7 of noise per entry: the estimates agree to that, amplified
+    np.testing.assert_allclose(V, g["vert"], rtol=0, atol=1e-4)
+    assert g["chi2"][1] < 0.05 * g["chi2"][0]
+    last = tr[tr[:, 1] == tr[-1, 1]]
+    assert len(last) >= 10 and (last[:9, 7] == 0).all()                  # the run ends on the ten-trials rule
