@@ -1,6 +1,7 @@
 // Host build of sqrtlm-slam_b200/csrc/sqrtba_math.cuh (the __host__ __device__ arithmetic the CUDA kernels use),
 // so the per-observation formulas can be compared against the oracle on a machine without a GPU.
 #include "../sqrtlm-slam_b200/csrc/sqrtba_math.cuh"
+#include "../sqrtlm-slam_b200/csrc/sqrtba_sim3.cuh"
 
 extern "C" {
 void mc_obs(const double* pose7, const double* X, const double* cam, const float* meas4, double* e, double* Jp,
@@ -16,4 +17,8 @@ void mc_obs(const double* pose7, const double* X, const double* cam, const float
 void mc_huber(double c, double delta, double* rho0, double* rho1) { sqrtba::huber(c, delta, sqrtba::huber_dsqr(delta), rho0, rho1); }
 void mc_oplus(double* pose7, const double* xi) { sqrtba::pose_oplus(pose7, xi); }
 int mc_spd6_inverse(const double* A, double* Ai) { return sqrtba::spd6_inverse(A, Ai) ? 1 : 0; }
+void mc_sim3_exp(const double* u7, double* out8) { sqrtba::sim3_exp(u7, out8); }
+void mc_sim3_log(const double* s8, double* out7) { sqrtba::sim3_log(s8, out7); }
+void mc_sim3_oplus(double* est8, const double* u7, int fix_scale) { sqrtba::sim3_oplus(est8, u7, fix_scale != 0); }
+void mc_sim3_edge_error(const double* c8, const double* a8, const double* b8, double* err7) { sqrtba::sim3_edge_error(c8, a8, b8, err7); }
 }

@@ -82,3 +82,27 @@ def test_spd6_inverse(mc):
         np.testing.assert_allclose(Ai @ A, np.eye(6), atol=1e-9)
     A = np.ascontiguousarray(-np.eye(6))
     assert mc.mc_spd6_inverse(_dp(A), _dp(np.zeros((6, 6)))) == 0
+
+
+def test_sim3_arithmetic_matches_reference_binary(mc):
+    """csrc/sqrtba_sim3.cuh (the arithmetic of the future essential-graph kernel) compiled for the host,
+    against vectors recorded from the reference's own binary (oracle/pin_libg2o_graph.py: make_sim3)."""
+    gold = np.load(os.path.join(HERE, "golden", "libg2o_vectors.npz"))
+    for u, want in zip(gold["sim3_upd"], gold["sim3_exp"]):
+        out = np.zeros(8)
+        mc.mc_sim3_exp(_dp(np.ascontiguousarray(u)), _dp(out))
+        np.testing.assert_allclose(out, want, rtol=0, atol=4e-15 * max(1.0, np.abs(want).max()))
+    for s8, u, free, fix in zip(gold["sim3_exp"], gold["sim3_upd2"], gold["sim3_oplus_free"], gold["sim3_oplus_fix"]):
+        for flag, want in ((0, free), (1, fix)):
+            est = np.ascontiguousarray(s8).copy()
+            mc.mc_sim3_oplus(_dp(est), _dp(np.ascontiguousarray(u)), flag)
+            np.testing.assert_allclose(est, want, rtol=0, atol=4e-15 * max(1.0, np.abs(want).max()))
+    for m, a, b, want in zip(gold["sim3_meas"], gold["sim3_v1"], gold["sim3_v2"], gold["sim3_err"]):
+        out = np.zeros(7)
+        mc.mc_sim3_edge_error(_dp(np.ascontiguousarray(m)), _dp(np.ascontiguousarray(a)), _dp(np.ascontiguousarray(b)), _dp(out))
+        np.testing.assert_allclose(out, want, rtol=0, atol=1e-13 * max(1.0, np.abs(want).max()))
+        back = np.zeros(8)                                   # exp(log(.)) closes on the same element
+        mc.mc_sim3_exp(_dp(out), _dp(back))
+        lg = np.zeros(7)
+        mc.mc_sim3_log(_dp(back), _dp(lg))
+        np.testing.assert_allclose(lg, out, rtol=0, atol=1e-12 * max(1.0, np.abs(out).max()))
