@@ -1141,6 +1141,21 @@ def make_posegraph(path):
         assert len(ch) >= 3 and (ch < ch.min() + 7).sum() >= 3 and ch.min() > V_DIM // 8, ch
         sg.b_off = int(ch.min())
         sg.f["v_clear"](sg.verts[1].ctypes.data)
+        # the numeric Jacobians of every edge at the initial estimates (BaseBinaryEdge::linearizeOplus, central
+        # differences through oplusImpl): read from the JacobianWorkspace, 7x7 column-major per vertex
+        e_all, Ji_all, Jj_all = [], [], []
+        for ed in sg.edges:
+            sg.f["e_err"](ed["e"].ctypes.data)
+            sg.f["e_lin"](ed["e"].ctypes.data, ed["jw"].ctypes.data)
+            ws = PE._vector_slots(ed["jw"], 32)
+            assert ws, "JacobianWorkspace::_workspace not found"
+            pw = (C.c_uint64 * 4).from_address(ws[0][1])
+            Ji = np.ctypeslib.as_array((C.c_double * 49).from_address(pw[0])).copy().reshape(7, 7).T
+            Jj = np.ctypeslib.as_array((C.c_double * 49).from_address(pw[2])).copy().reshape(7, 7).T
+            e_all.append(np.ctypeslib.as_array((C.c_double * 7).from_address(sg.f["e_errd"](ed["e"].ctypes.data))).copy())
+            Ji_all.append(Ji if not fixed[ed["i"]] else np.zeros((7, 7)))   # a fixed vertex's Jacobian is never computed
+            Jj_all.append(Jj if not fixed[ed["j"]] else np.zeros((7, 7)))
+        out.update({f"pg{case}_err0": np.stack(e_all), f"pg{case}_Ji0": np.stack(Ji_all), f"pg{case}_Jj0": np.stack(Jj_all)})
         L = G.ed.g.L
         lm_ctor = L._ZN3g2o30OptimizationAlgorithmLevenbergC1EPNS_6SolverE
         lm_ctor.restype, lm_ctor.argtypes = None, [C.c_void_p, C.c_void_p]

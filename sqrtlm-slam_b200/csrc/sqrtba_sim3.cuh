@@ -163,4 +163,29 @@ SQ_HD void sim3_edge_error(const double C8[8], const double v1[8], const double 
   sim3_log(c, err);
 }
 
+// EdgeSim3's Jacobians are the numeric ones it inherits (BaseBinaryEdge::linearizeOplus, base_binary_edge.hpp:122-195):
+// per non-fixed vertex and per tangent direction d, oplus(+delta e_d) and oplus(-delta e_d) on that vertex (through
+// oplusImpl, so a fixed scale zeroes column 6), column d = (e(+) - e(-)) / (2 delta), delta = 1e-9.  Ji, Jj: 7x7
+// row-major (row = error component); the Jacobian of a fixed vertex is left untouched.
+SQ_HD void sim3_edge_linearize(const double C8[8], const double v1[8], const double v2[8], bool fixed1, bool fixed2,
+                               bool fix_scale, double Ji[49], double Jj[49]) {
+  const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+  for (int side = 0; side < 2; side++) {
+    if (side == 0 ? fixed1 : fixed2) continue;
+    double* J = side == 0 ? Ji : Jj;
+    for (int d = 0; d < 7; d++) {
+      double add[7] = {0, 0, 0, 0, 0, 0, 0}, p[8], e1[7], e2[7];
+      add[d] = delta;
+      for (int i = 0; i < 8; i++) p[i] = side == 0 ? v1[i] : v2[i];
+      sim3_oplus(p, add, fix_scale);
+      sim3_edge_error(C8, side == 0 ? p : v1, side == 0 ? v2 : p, e1);
+      add[d] = -delta;
+      for (int i = 0; i < 8; i++) p[i] = side == 0 ? v1[i] : v2[i];
+      sim3_oplus(p, add, fix_scale);
+      sim3_edge_error(C8, side == 0 ? p : v1, side == 0 ? v2 : p, e2);
+      for (int r = 0; r < 7; r++) J[r * 7 + d] = scalar * (e1[r] - e2[r]);
+    }
+  }
+}
+
 }  // namespace sqrtba

@@ -20,5 +20,9 @@ int mc_spd6_inverse(const double* A, double* Ai) { return sqrtba::spd6_inverse(A
 void mc_sim3_exp(const double* u7, double* out8) { sqrtba::sim3_exp(u7, out8); }
 void mc_sim3_log(const double* s8, double* out7) { sqrtba::sim3_log(s8, out7); }
 void mc_sim3_oplus(double* est8, const double* u7, int fix_scale) { sqrtba::sim3_oplus(est8, u7, fix_scale != 0); }
+void mc_sim3_edge_linearize(const double* c8, const double* a8, const double* b8, int f1, int f2, int fix_scale, double* Ji,
+                            double* Jj) {
+  sqrtba::sim3_edge_linearize(c8, a8, b8, f1 != 0, f2 != 0, fix_scale != 0, Ji, Jj);
+}
 void mc_sim3_edge_error(const double* c8, const double* a8, const double* b8, double* err7) { sqrtba::sim3_edge_error(c8, a8, b8, err7); }
 }

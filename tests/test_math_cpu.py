@@ -106,3 +106,29 @@ def test_sim3_arithmetic_matches_reference_binary(mc):
         lg = np.zeros(7)
         mc.mc_sim3_log(_dp(back), _dp(lg))
         np.testing.assert_allclose(lg, out, rtol=0, atol=1e-12 * max(1.0, np.abs(out).max()))
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_sim3_edge_jacobians_match_reference_binary(mc, case):
+    """The numeric Jacobians EdgeSim3 inherits (central differences with delta = 1e-9 through oplusImpl), as the binary
+    writes them into its JacobianWorkspace for every edge of the pose-graph fixtures, against sim3_edge_linearize.  The
+    scheme amplifies rounding by 1/(2 delta) = 5e8, so two implementations agree to ~1e-5 (entries reach ~10), not to rounding."""
+    gold = np.load(os.path.join(HERE, "golden", "libg2o_vectors.npz"))
+    g = {k[len(f"pg{case}_"):]: gold[k] for k in gold.files if k.startswith(f"pg{case}_")}
+    fix_scale = int(g["fix_scale"])
+    seen_free = 0
+    for (i, j), m, e0, Ji0, Jj0 in zip(g["edges"], g["meas"], g["err0"], g["Ji0"], g["Jj0"]):
+        a, b = np.ascontiguousarray(g["vert0"][i]), np.ascontiguousarray(g["vert0"][j])
+        err = np.zeros(7)
+        mc.mc_sim3_edge_error(_dp(np.ascontiguousarray(m)), _dp(a), _dp(b), _dp(err))
+        np.testing.assert_allclose(err, e0, rtol=0, atol=1e-13)
+        Ji, Jj = np.zeros((7, 7)), np.zeros((7, 7))
+        mc.mc_sim3_edge_linearize(_dp(np.ascontiguousarray(m)), _dp(a), _dp(b), int(g["fixed"][i]), int(g["fixed"][j]),
+                                  fix_scale, _dp(Ji), _dp(Jj))
+        np.testing.assert_allclose(Ji, Ji0, rtol=0, atol=2e-5)
+        np.testing.assert_allclose(Jj, Jj0, rtol=0, atol=2e-5)
+        if not g["fixed"][i]:
+            seen_free += 1
+            assert np.abs(Ji0).max() > 0.5
+            assert (np.abs(Ji0[:, 6]).max() == 0.0) == bool(fix_scale)      # a fixed scale zeroes the last column
+    assert seen_free > 10
