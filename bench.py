@@ -218,6 +218,17 @@ def run_extras(pkg, torch, dist, world, rank, local, barrier, args):
                                 "n_obs": w.n_obs, "ms_per_local_ba": best, "lm_trials": len(tr),
                                 "lm_iters_per_s": len(tr) / (best * 1e-3), "obs_per_s": len(tr) * w.n_obs / (best * 1e-3),
                                 "cg_iters": st["cg_iters_total"], "persistent_pcg": st["persistent_pcg"]}
+        try:  # the whole C-ABI call sequence of one LocalBundleAdjustment from host buffers (wall clock, best of 5)
+            wall = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                ba.set_problem(w)
+                ba.solve_local()
+                ba.poses(), ba.points(), ba.outliers()
+                wall.append(time.perf_counter() - t0)
+            out["single_window"]["ms_per_call_set_solve_get"] = 1e3 * min(wall[1:])
+        except Exception as exc:  # an extra, never fatal for the bench line
+            out["single_window"]["ms_per_call_set_solve_get_error"] = repr(exc)
         ba.close()
     prob = pkg.synth.config_c3(0, scale=args.gba_scale, n_kf=max(int(1500 * args.gba_scale), 160))
     shard, _, _ = pkg.multi.shard_by_landmark(prob, rank, world)
