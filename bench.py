@@ -133,9 +133,9 @@ def trials_times_obs(ba, wins):
     return tot, ntr
 
 
-def cpu_solve_windows(wins, threads_total: int):
+def cpu_solve_windows(wins, threads_total: int, keep: bool = False):
     """Solve windows with the oracle, one window per worker thread (ctypes releases the GIL). Returns
-    (seconds, sum(n_obs * trials), sum(trials))."""
+    (seconds, sum(n_obs * trials), sum(trials)[, per-window (trace, poses, outliers)])."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import refba
     refba.lib()
@@ -143,7 +143,8 @@ def cpu_solve_windows(wins, threads_total: int):
     def one(w):
         r = refba.RefBA(w, threads=1)
         r.solve_local(0)
-        return len(r.trace()) * w.n_obs, len(r.trace())
+        tr = r.trace()
+        return len(tr) * w.n_obs, len(tr), ((tr, r.poses(), r.outliers()) if keep else None)
 
     t0 = time.perf_counter()
     if threads_total <= 1:
@@ -152,7 +153,39 @@ def cpu_solve_windows(wins, threads_total: int):
         with ThreadPoolExecutor(max_workers=threads_total) as ex:
             res = list(ex.map(one, wins))
     dt = time.perf_counter() - t0
-    return dt, sum(r[0] for r in res), sum(r[1] for r in res)
+    out = (dt, sum(r[0] for r in res), sum(r[1] for r in res))
+    return out + ([r[2] for r in res],) if keep else out
+
+
+def quat_angle(qa, qb):
+    d = np.abs(np.sum(qa * qb, axis=-1)).clip(0, 1)
+    rel_v = np.linalg.norm(qa[..., :3] * qb[..., 3:4] - qb[..., :3] * qa[..., 3:4] - np.cross(qa[..., :3], qb[..., :3]), axis=-1)
+    return 2 * np.arctan2(rel_v, d)
+
+
+def parity_report(tg, pg, fg, tr, pr, fr, free):
+    """north_star's tolerances on one window: identical trial sequence, per-trial cost <= 1e-6 relative, pose RMS
+    <= 1e-5 m / 1e-6 rad, identical outlier flags.  Returns (ok, worst cost error, pose RMS m, pose RMS rad)."""
+    same = len(tg) == len(tr) and np.array_equal(tg[:, [0, 1, 2, 7]], tr[:, [0, 1, 2, 7]])
+    cost = float(np.max(np.abs(tg[:, 5] - tr[:, 5]) / np.abs(tr[:, 5]))) if same else float("inf")
+    t_rms = float(np.sqrt(np.mean(np.sum((pg[free, :3] - pr[free, :3]) ** 2, axis=1))))
+    r_rms = float(np.sqrt(np.mean(quat_angle(pg[free, 3:], pr[free, 3:]) ** 2)))
+    flags = fg is None or bool(np.array_equal(fg, fr))
+    ok = bool(same and cost <= 1e-6 and t_rms <= 1e-5 and r_rms <= 1e-6 and flags)
+    return ok, cost, t_rms, r_rms
+
+
+WORKLOAD = ("C4: batch of independent KITTI-00-shaped stereo local-BA windows (C0 shape: 20 free + 10 fixed keyframes, "
+            "~6k points, ~70k observations), two-pass 5+10 LM with chi2 outlier exclusion")
+
+
+def bench_config(args, n_obs_rank=None, nobs_all=None):
+    cfg = {"workload": WORKLOAD, "windows_per_gpu": args.windows_per_gpu, "l2_policy": "inputs_larger_than_l2",
+           "pcg_rtol": 1e-9, "pcg_mode": args.pcg_mode}
+    if n_obs_rank is not None:
+        cfg["observations_per_gpu"] = n_obs_rank
+        cfg["observations_total"] = int(nobs_all)
+    return cfg
 
 
 def run_reference(args):
@@ -163,10 +196,18 @@ def run_reference(args):
         return
     pkg = load_pkg()
     cores = os.cpu_count() or 1
-    n_sample = max(cores, 8) if args.cpu_windows <= 0 else args.cpu_windows
-    wins = [pkg.synth.config_c0(1000 + i) for i in range(n_sample)]
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_solve_windows(wins[:cores], cores)
+    # the GPU arm's step is args.windows_per_gpu windows (seeds 0..W-1 on rank 0); a CPU step is the first n_sample of
+    # them, sized from a timed warm-up so that `--steps` steps end within a few minutes on this box's cores
+    first = [pkg.synth.config_c0(i) for i in range(min(cores, args.windows_per_gpu))]
+    t_w = cpu_solve_windows(first, cores)[0]           # ~ one window per core: seconds per window and thread
+    if args.cpu_windows > 0:
+        n_sample = args.cpu_windows
+    else:
+        budget_s = 150.0
+        n_sample = int(budget_s * cores / (max(args.steps, 1) * max(t_w, 1e-3)))
+        n_sample = max(min(n_sample, args.windows_per_gpu), min(cores, args.windows_per_gpu))
+    wins = first + [pkg.synth.config_c0(i) for i in range(len(first), n_sample)]
+    wins = wins[:n_sample]
     tot_t = tot_work = tot_tr = 0
     for _ in range(args.steps):
         dt, work, ntr = cpu_solve_windows(wins, cores)
@@ -174,13 +215,14 @@ def run_reference(args):
         tot_work += work
         tot_tr += ntr
     value = tot_work / tot_t
-    sample = f"{n_sample} C0-shaped windows per step ({sum(w.n_obs for w in wins)} observations), one window per thread"
+    sample = (f"the first {n_sample} of the batch's {args.windows_per_gpu} windows per step "
+              f"({sum(w.n_obs for w in wins)} observations), full two-pass local BA each, one window per thread")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "C4-style batch of independent KITTI-00-shaped stereo local-BA windows (C0 shape)",
-                   "windows_per_step": n_sample, "passes": "5+10 LM iterations, chi2 outlier exclusion"},
+        "config": bench_config(args),
+        "sample_windows_per_step": n_sample,
         "lm_iters_per_s": tot_tr / tot_t,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -198,38 +240,102 @@ def load_traffic():
         return None
 
 
+def single_window_leg(pkg, prob, local, label, reps=5):
+    """Latency of ONE window -- the call shape of Optimizer::LocalBundleAdjustment: device time of the two-pass solve
+    (best of `reps` after two warm-up solves) and wall time of the whole C-ABI call sequence from host buffers."""
+    ba = pkg.SqrtBA(device=local)
+    ba.set_problem(prob)
+    ms = []
+    st = None
+    for _ in range(reps):
+        ba.reset_state()
+        st = ba.solve_local()
+        ms.append(st["ms_total"])
+    tr = ba.trace()
+    best = min(ms[2:])
+    out = {"workload": label, "n_obs": prob.n_obs, "n_free_poses": prob.n_free, "ms_per_local_ba": best,
+           "lm_trials": len(tr), "lm_iters_per_s": len(tr) / (best * 1e-3), "obs_per_s": len(tr) * prob.n_obs / (best * 1e-3),
+           "cg_iters": st["cg_iters_total"], "persistent_pcg": st["persistent_pcg"], "kernel_launches": st["kernel_launches"]}
+    try:  # the whole C-ABI call sequence of one LocalBundleAdjustment from host buffers (wall clock, best of reps)
+        wall = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            ba.set_problem(prob)
+            ba.solve_local()
+            ba.poses(), ba.points(), ba.outliers()
+            wall.append(time.perf_counter() - t0)
+        out["ms_per_call_set_solve_get"] = 1e3 * min(wall[1:])
+    except Exception as exc:  # an extra, never fatal for the bench line
+        out["ms_per_call_set_solve_get_error"] = repr(exc)
+    res = (ba.trace(), ba.poses(), ba.outliers())
+    ba.close()
+    return out, res
+
+
+def oracle_local(prob, threads):
+    from oracle import refba
+    r = refba.RefBA(prob, threads=threads)
+    t0 = time.perf_counter()
+    r.solve_local(0)
+    return time.perf_counter() - t0, (r.trace(), r.poses(), r.outliers())
+
+
 def run_extras(pkg, torch, dist, world, rank, local, barrier, args):
-    """(1) latency of ONE C0 window -- the call shape of Optimizer::LocalBundleAdjustment -- on rank 0;
-    (2) C3 global BA, landmarks sharded over all `world` ranks (strong scaling): time-to-converge of
-    solve_global(10 iterations, non-robust), the reference's loop-closing call (LoopClosing.cc:987-991)."""
+    """The other shapes of BASELINE.json's metric, beside the headline batch:
+    (1) C0 / C1 single-window latency and LM iterations/s on rank 0;
+    (2) C2 (100 keyframes, ~600k observations, one GPU): latency, per-kernel GB/s against the HBM peak, the rate of the
+        persistent PCG kernel's matvec phase, oracle beside it;
+    (3) C3 global BA, landmarks sharded over all `world` ranks (strong scaling): time-to-converge of
+        solve_global(10 iterations, non-robust), the reference's loop-closing call (LoopClosing.cc:987-991); at N=1 the
+        oracle's time-to-converge on the host cores (1 thread and all cores) and a parity check against it."""
     out = {}
+    cpu_ok = rank == 0 and world == 1 and not args.skip_cpu_baseline
+    cores = os.cpu_count() or 1
+    peaks, _ = measured_peaks()
     if rank == 0:
-        w = pkg.synth.config_c0(0)
-        ba = pkg.SqrtBA(device=local)
-        ba.set_problem(w)
-        ms = []
-        for _ in range(5):
-            ba.reset_state()
-            st = ba.solve_local()
-            ms.append(st["ms_total"])
-        tr = ba.trace()
-        best = min(ms[2:])
-        out["single_window"] = {"workload": "C0: one KITTI-00-shaped stereo window, two-pass 5+10 local BA",
-                                "n_obs": w.n_obs, "ms_per_local_ba": best, "lm_trials": len(tr),
-                                "lm_iters_per_s": len(tr) / (best * 1e-3), "obs_per_s": len(tr) * w.n_obs / (best * 1e-3),
-                                "cg_iters": st["cg_iters_total"], "persistent_pcg": st["persistent_pcg"]}
-        try:  # the whole C-ABI call sequence of one LocalBundleAdjustment from host buffers (wall clock, best of 5)
-            wall = []
-            for _ in range(5):
-                t0 = time.perf_counter()
-                ba.set_problem(w)
-                ba.solve_local()
-                ba.poses(), ba.points(), ba.outliers()
-                wall.append(time.perf_counter() - t0)
-            out["single_window"]["ms_per_call_set_solve_get"] = 1e3 * min(wall[1:])
-        except Exception as exc:  # an extra, never fatal for the bench line
-            out["single_window"]["ms_per_call_set_solve_get_error"] = repr(exc)
+        for key, prob, label in (("single_window", pkg.synth.config_c0(0), "C0: one KITTI-00-shaped stereo window, two-pass 5+10 local BA"),
+                                 ("mono_window", pkg.synth.config_c1(0), "C1: the same window in monocular mode (EdgeSE3ProjectXYZ), gauge fixed by the first window keyframe")):
+            leg, res = single_window_leg(pkg, prob, local, label)
+            if cpu_ok:
+                dt, ref = oracle_local(prob, 1)
+                ok, cost, t_rms, r_rms = parity_report(*res, *ref, prob.pose_fixed == 0)
+                leg["cpu_baseline"] = {"value": len(ref[0]) * prob.n_obs / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                       "ms_per_local_ba": 1e3 * dt, "lm_iters_per_s": len(ref[0]) / dt,
+                                       "sample": "the same window, full two-pass local BA"}
+                leg["parity_vs_oracle"] = {"ok": ok, "cost_rel_err_max": cost, "pose_t_rms_m": t_rms, "pose_r_rms_rad": r_rms}
+            out[key] = leg
+        # ---- C2
+        prob = pkg.synth.config_c2(0)
+        leg, res = single_window_leg(pkg, prob, local, "C2: large stereo window, 100 keyframes (99 free), ~50k points, ~600k observations, two-pass 5+10 local BA", reps=4)
+        free_obs = int((prob.pose_fixed[prob.obs_pose] == 0).sum())
+        ba = pkg.SqrtBA(device=local, stage_timing=True)
+        ba.set_problem(prob)
+        ba.solve_local()
+        ba.reset_state()
+        st = ba.solve_local()
+        us_cg = 1e3 * st["ms_pcg"] / max(st["cg_iters_total"], 1)
+        stage_ms = {"k_matvec_pipe": ba.time_stage(0, 3, 20), "k_linearize_pipe": ba.time_stage(1, 2, 10),
+                    "k_qr_pipe2": ba.time_stage(2, 2, 10), "k_backsub": ba.time_stage(4, 2, 10)}
         ba.close()
+        n_lm = prob.n_point
+        alg = {"k_matvec_pipe": free_obs * 216.0, "k_linearize_pipe": prob.n_obs * 288.0,
+               "k_qr_pipe2": prob.n_obs * 312.0 + n_lm * 72.0, "k_backsub": free_obs * 216.0 + n_lm * 168.0}
+        leg["roofline"] = {"bound": "hbm", "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "kernels": {k: {"ms": v, "algorithmic_bytes": alg[k], "achieved": alg[k] / (v * 1e-3) / 1e9,
+                                           "frac": alg[k] / (v * 1e-3) / 1e9 / peaks["hbm_gbs"]} for k, v in stage_ms.items()},
+                           "persistent_pcg": {"us_per_cg_iteration": us_cg, "achieved": free_obs * 216.0 / (us_cg * 1e-6) / 1e9,
+                                              "frac": free_obs * 216.0 / (us_cg * 1e-6) / 1e9 / peaks["hbm_gbs"],
+                                              "note": "one CG iteration of k_pcg_persist = matvec over all tiles + grid barrier + vector update"},
+                           "note": "working set per CG iteration ~ 110 MB: close to the 126 MB L2, so these are HBM/L2 mixed rates"}
+        if cpu_ok:
+            dt, ref = oracle_local(prob, 1)
+            dta, _ = oracle_local(prob, cores)
+            ok, cost, t_rms, r_rms = parity_report(*res, *ref, prob.pose_fixed == 0)
+            leg["cpu_baseline"] = {"value": len(ref[0]) * prob.n_obs / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                   "ms_per_local_ba": 1e3 * dt, "ms_per_local_ba_all_cores": 1e3 * dta, "all_cores": cores,
+                                   "sample": "the same window, full two-pass local BA"}
+            leg["parity_vs_oracle"] = {"ok": ok, "cost_rel_err_max": cost, "pose_t_rms_m": t_rms, "pose_r_rms_rad": r_rms}
+        out["large_window"] = leg
     prob = pkg.synth.config_c3(0, scale=args.gba_scale, n_kf=max(int(1500 * args.gba_scale), 160))
     shard, _, _ = pkg.multi.shard_by_landmark(prob, rank, world)
     ba = pkg.SqrtBA(device=local)
@@ -250,13 +356,34 @@ def run_extras(pkg, torch, dist, world, rank, local, barrier, args):
         dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
     tr = ba.trace()
     free_obs = int((prob.pose_fixed[prob.obs_pose] == 0).sum())
+    cg_total = max(int(tr[:, 8].sum()), 1)
+    us_iter = 1e6 * float(tsec.item()) / cg_total
     out["global_ba"] = {"workload": f"C3: {prob.n_pose} keyframes on a loop, {prob.n_point} points, {prob.n_obs} observations, "
                                     "10 LM iterations, non-robust; landmarks sharded over the ranks",
                         "n_gpus": world, "scaling": "strong", "time_to_converge_s": float(tsec.item()),
                         "lm_trials": len(tr), "cg_iters_total": int(tr[:, 8].sum()), "final_chi2": float(tr[-1, 5]),
                         "persistent_pcg": st["persistent_pcg"], "peer_exchange": st["peer_exchange"],
-                        "us_per_cg_iteration_incl_everything": 1e6 * float(tsec.item()) / max(int(tr[:, 8].sum()), 1),
-                        "matvec_algorithmic_bytes_all_ranks": free_obs * 216.0}
+                        "us_per_cg_iteration_incl_everything": us_iter,
+                        "matvec_algorithmic_bytes_all_ranks": free_obs * 216.0,
+                        "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"] * world,
+                                     "achieved": free_obs * 216.0 / (us_iter * 1e-6) / 1e9,
+                                     "frac": free_obs * 216.0 / (us_iter * 1e-6) / 1e9 / (peaks["hbm_gbs"] * world),
+                                     "note": "whole time-to-converge / CG iterations, i.e. linearise, QR, barriers and the "
+                                             "NVLink exchange all charged to the matvec's algorithmic bytes; peak = N x one GPU"}}
+    if cpu_ok:  # the reference's CPU algorithm on the same map: time-to-converge, 1 thread (faithful) and all cores
+        from oracle import refba
+        pg = ba.poses()
+        res = {}
+        for thr in ([1, cores] if cores > 1 else [1]):
+            r = refba.RefBA(prob, threads=thr)
+            t0 = time.perf_counter()
+            r.solve_global(10, False)
+            res[thr] = time.perf_counter() - t0
+        ok, cost, t_rms, r_rms = parity_report(tr, pg, None, r.trace(), r.poses(), None, prob.pose_fixed == 0)
+        out["global_ba"]["cpu_baseline"] = {"value": res[1], "unit": "s (time-to-converge, lower is better)", "cores": 1,
+                                            "kind": "port", "all_cores_value": res.get(cores), "all_cores": cores,
+                                            "sample": "the same C3 map, solve_global(10 iterations, non-robust), whole solve"}
+        out["global_ba"]["parity_vs_oracle"] = {"ok": ok, "cost_rel_err_max": cost, "pose_t_rms_m": t_rms, "pose_r_rms_rad": r_rms}
     ba.close()
     return out
 
@@ -397,21 +524,32 @@ def main():
 
     # ---- CPU baseline (oracle port, 1 thread, bounded sample) on rank 0 at N=1 -------------------
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         n_cpu = args.cpu_windows if args.cpu_windows > 0 else 32
-        dt, wk, _ = cpu_solve_windows(wins[:n_cpu], 1)
+        dt, wk, _, refs = cpu_solve_windows(wins[:n_cpu], 1, keep=True)
         cpu = {"value": wk / dt, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"first {n_cpu} windows of the batch, full two-pass local BA each, {dt:.1f} s"}
+        # the oracle solved these windows anyway: compare them with what the GPU produced for the same windows in the
+        # last timed step (trial sequence, per-trial cost, pose RMS, outlier flags -- north_star's tolerances)
+        Pg, Fg = ba.poses(), ba.outliers()
+        bad, worst = [], [0.0, 0.0, 0.0]
+        for i, (w, (rt, rp, rf)) in enumerate(zip(wins[:n_cpu], refs)):
+            ok, cost, t_rms, r_rms = parity_report(ba.trace(i), Pg[pp[i]:pp[i + 1]], Fg[op[i]:op[i + 1]], rt, rp, rf, w.pose_fixed == 0)
+            worst = [max(worst[0], cost), max(worst[1], t_rms), max(worst[2], r_rms)]
+            if not ok:
+                bad.append(i)
+        parity = {"parity_checked_windows": n_cpu, "windows_failing": bad, "cost_rel_err_max": worst[0],
+                  "pose_t_rms_m_max": worst[1], "pose_r_rms_rad_max": worst[2],
+                  "tolerances": "identical trial sequence and outlier flags, cost 1e-6, pose RMS 1e-5 m / 1e-6 rad"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sec_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C4: batch of independent KITTI-00-shaped stereo local-BA windows (C0 shape: 20 free + "
-                                   "10 fixed keyframes, ~6k points, ~70k observations), two-pass 5+10 LM with chi2 outlier exclusion",
-                       "windows_per_gpu": W, "observations_per_gpu": n_obs_rank, "observations_total": int(nobs_all),
-                       "l2_policy": "inputs_larger_than_l2", "pcg_rtol": 1e-9, "pcg_mode": args.pcg_mode},
+            "config": bench_config(args),
+            "observations_per_gpu": n_obs_rank, "observations_total": int(nobs_all),
             "lm_iters_per_s": ntr_all * args.steps / sec_max,
             "windows_per_s": W * world * args.steps / sec_max,
             "ms_per_step_device_events": dev_ms / args.steps,
@@ -421,8 +559,12 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity_checked_windows": (parity or {}).get("parity_checked_windows", 0),
+            "parity": parity,
             "solve_stats_last_step": stats,
             "single_window": extras.get("single_window"),
+            "mono_window": extras.get("mono_window"),
+            "large_window": extras.get("large_window"),
             "global_ba": extras.get("global_ba"),
         }
         print(json.dumps(line), flush=True)

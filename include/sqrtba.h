@@ -120,7 +120,9 @@ int sqrtba_set_problem_batch(sqrtba_handle* h, int32_t n_win, const int64_t* win
 int sqrtba_reset_state(sqrtba_handle* h);
 
 /* Local BA: robust pass (5 its) -> chi2/depth outlier exclusion -> non-robust pass (10 its) [-> third pass].
- * stop_flag may be NULL; it is polled on the host between LM trials, never read by the device. */
+ * stop_flag may be NULL; it is polled on the host between LM trials, never read by the device.  With a communicator
+ * (sqrtba_comm_init) the solve calls are collective and every poll max-reduces the ranks' flags over NCCL, so all
+ * ranks stop in the same LM step even if their callers raise the flag at different moments. */
 int sqrtba_solve_local(sqrtba_handle* h, const volatile bool* stop_flag, sqrtba_stats* stats);
 /* Global BA: one pass of `iters` LM iterations, Huber iff robust (deltas sqrt(5.99)/sqrt(7.815)), no outlier step. */
 int sqrtba_solve_global(sqrtba_handle* h, int32_t iters, int32_t robust, const volatile bool* stop_flag,

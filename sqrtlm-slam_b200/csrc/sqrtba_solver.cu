@@ -133,7 +133,7 @@ class Solver {
     }
     CU_CHECK(cudaSetDevice(cfg_.device));
     CU_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    CU_CHECK(cudaMallocHost((void**)&h_counters_, 4 * sizeof(int)));
+    CU_CHECK(cudaMallocHost((void**)&h_counters_, 8 * sizeof(int)));
     CU_CHECK(cudaEventCreate(&ev0_));
     CU_CHECK(cudaEventCreate(&ev1_));
     for (auto& e : stage_ev_) CU_CHECK(cudaEventCreate(&e));
@@ -220,8 +220,9 @@ class Solver {
     lidar_edges_set_ = lidar_assoc_set_ = lidar_active_ = false;  // pose indices of the old problem
     std::vector<int> pose_win(n_pose, 0), point_win(n_point, 0);
     if (n_win > 1) {
-      if (!wpose || !wpoint || !wobs || wpose[n_win] != n_pose || wpoint[n_win] != n_point || wobs[n_win] != n_obs) {
-        err_ = "set_problem_batch: window offsets inconsistent with array sizes";
+      if (!wpose || !wpoint || !wobs || wpose[n_win] != n_pose || wpoint[n_win] != n_point || wobs[n_win] != n_obs ||
+          wpose[0] != 0 || wpoint[0] != 0 || wobs[0] != 0) {
+        err_ = "set_problem_batch: window offsets inconsistent with array sizes (every offset array starts at 0 and ends at the array size)";
         return SQRTBA_ERR_INVALID;
       }
       for (int w = 0; w < n_win; w++) {
@@ -265,6 +266,7 @@ class Solver {
           if (ip < 0 || ip >= n_pose || il < 0 || il >= n_point) { bad.store(1); return; }
           if (k && il < obs_point[k - 1]) { bad.store(2); return; }
           if (pose_win[ip] != point_win[il]) { bad.store(3); return; }
+          if (n_win > 1 && (k < wobs[point_win[il]] || k >= wobs[point_win[il] + 1])) { bad.store(4); return; }
           obs_slot[k] = pose_slot[ip];
           obs_lp[k] = 0xffffu;
           if (k == 0 || il != obs_point[k - 1]) lm_first[il] = (int)k;
@@ -273,7 +275,8 @@ class Solver {
       if (bad.load()) {
         err_ = bad.load() == 1 ? "set_problem: observation index out of range"
              : bad.load() == 2 ? "set_problem: observations must be grouped by landmark (non-decreasing obs_point)"
-                               : "set_problem_batch: observation links a pose and a point of different windows";
+             : bad.load() == 3 ? "set_problem_batch: observation links a pose and a point of different windows"
+                               : "set_problem_batch: observation lies outside the observation range of its window";
         return SQRTBA_ERR_INVALID;
       }
       int next = n_obs;
@@ -571,7 +574,7 @@ class Solver {
     CU_CHECK(d_wred_.ensure((size_t)3 * n_win));
     max_trace_ = 200;
     CU_CHECK(d_trace_.ensure((size_t)n_win * max_trace_ * TRACE_COLS));
-    CU_CHECK(d_counters_.ensure(4));
+    CU_CHECK(d_counters_.ensure(8));
 
     CU_CHECK(up(d_pose_slot_.p, pose_slot.data(), n_pose * sizeof(int)));
     if (n_slot) {
@@ -744,10 +747,13 @@ class Solver {
     const double d2 = (double)(float)std::sqrt(5.991), d3 = (double)(float)std::sqrt(7.815);
     CU_CHECK(cudaMemsetAsync(d_level_.p, 0, P_.n_obs, stream_));
     CU_CHECK(clear_traces());
-    if (stop && *stop) return finish_stats(st);  // g2oOptimizer.cc:923-928: early out, estimates untouched
-    int rc = run_pass(5, 0, 1, d2, d3, stop);
+    int term = 0, rc = 0;
+    if ((rc = poll_stop(stop, &term))) return rc;
+    if (term) return finish_stats(st);  // g2oOptimizer.cc:923-928: early out, estimates untouched
+    rc = run_pass(5, 0, 1, d2, d3, stop);
     if (rc) return rc;
-    const bool do_more = !(stop && *stop);  // :936-947
+    if ((rc = poll_stop(stop, &term))) return rc;
+    const bool do_more = !term;  // :936-947
     if (do_more) {
       launch_classify(0, 5.991, 7.815);
       rc = run_pass(10, 1, 0, d2, d3, stop);
@@ -756,7 +762,8 @@ class Solver {
     if (cfg_.third_pass_iters > 0) {
       if (lidar_assoc_set_)
         if ((rc = lidar_associate())) return rc;
-      rc = run_pass(cfg_.third_pass_iters, 2, 0, d2, d3, stop);
+      // the Huber kernels are only dropped inside `if (bDoMore)` (:947-970): a skipped second pass leaves them on
+      rc = run_pass(cfg_.third_pass_iters, 2, do_more ? 0 : 1, d2, d3, stop);
       lidar_active_ = false;
       if (rc) return rc;
     }
@@ -1208,6 +1215,27 @@ class Solver {
     return SQRTBA_OK;
   }
 
+  // The caller's stop flag (bool* pbStopFlag).  Landmark-sharded over several ranks every LM step issues collectives,
+  // so all ranks must act on the SAME value: the flags are max-reduced (a rank that sees the flag a step earlier than
+  // its peers would otherwise leave the loop while they block in the next all-reduce).  One extra small all-reduce +
+  // read-back per LM trial; single-GPU solves just read the flag.
+  int poll_stop(const volatile bool* stop, int* term) {
+    const int local = (stop && *stop) ? 1 : 0;
+    *term = local;
+    if (!comm_) return SQRTBA_OK;
+    h_counters_[3] = local;
+    CU_CHECK(cudaMemcpyAsync(d_counters_.p + 3, h_counters_ + 3, sizeof(int), cudaMemcpyHostToDevice, stream_));
+    const int rc = g_nccl.AllReduce(d_counters_.p + 3, d_counters_.p + 3, 1, /*ncclInt32*/ 2, /*ncclMax*/ 2, comm_, stream_);
+    if (rc != 0) {
+      err_ = std::string("ncclAllReduce (stop flag) failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+      return SQRTBA_ERR_COMM;
+    }
+    CU_CHECK(cudaMemcpyAsync(h_counters_ + 3, d_counters_.p + 3, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CU_CHECK(cudaStreamSynchronize(stream_));
+    *term = h_counters_[3];
+    return SQRTBA_OK;
+  }
+
   // in-place all-reduce over the ranks that share this problem (no-op for a single GPU)
   int allreduce(double* buf, size_t count, bool is_max) {
     if (!comm_ || count == 0) return SQRTBA_OK;
@@ -1529,7 +1557,8 @@ class Solver {
     if (iters <= 0) return SQRTBA_OK;
     const int max_macro = iters * 10 + 1;
     for (int step = 0; step < max_macro; step++) {
-      const int term = (stop && *stop) ? 1 : 0;
+      int term = 0;
+      if (int rc = poll_stop(stop, &term)) return rc;
       if (term && step == 0) break;  // `for (i < iterations && !terminate())` before the first iteration
       if (P_.n_slot) k_zero_lin<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
       stage_begin(0);

@@ -39,6 +39,18 @@ class sqrtbaOptimizer {
   int static PoseOptimization(Frame* pFrame);
   // relocalisation: several candidate frames in one launch (Tracking.cc:2466-2517 calls PoseOptimization per candidate)
   void static PoseOptimizationBatch(const std::vector<Frame*>& frames, std::vector<int>& inliers);
+  // Behaviour switches of the local-BA adapter.  The defaults are what THIS reference does:
+  //  * local_ba_stereo_edges = false: the fork's local BA only creates monocular edges -- an observation with a right
+  //    coordinate falls into an empty branch (g2oOptimizer.cc:914-916) and takes no part in the optimisation or in the
+  //    outlier erasure.  true = upstream ORB-SLAM2's stereo edges (the solver supports them; thresholds :853).
+  //  * local_ba_two_pass = false: the fork ALWAYS runs initializeOptimization(0); optimize(20) after the lidar block,
+  //    with or without lidar features or matches (:1113-1114), i.e. the schedule is 5 + 10 + 20.  true = upstream
+  //    ORB-SLAM2's two-pass 5 + 10 schedule (what BASELINE.json's configs time).
+  struct Options {
+    bool local_ba_stereo_edges = false;
+    bool local_ba_two_pass = false;
+  };
+  static Options& options();
   // last error of the calling thread's handle ("" if none); the reference API itself is void / silent
   static const char* LastError();
   // the flat problem (layout of sqrtba_set_problem) that LocalBundleAdjustment / BundleAdjustment build from the map,

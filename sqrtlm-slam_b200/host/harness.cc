@@ -118,6 +118,10 @@ void hh_apply_local(hh_map* m, int kf, int n_kf, const double* pose_qt, int n_mp
                                     std::vector<unsigned char>(outlier, outlier + n_obs));
 }
 
+void hh_set_options(int local_ba_stereo_edges, int local_ba_two_pass) {
+  sqrtbaOptimizer::options().local_ba_stereo_edges = local_ba_stereo_edges != 0;
+  sqrtbaOptimizer::options().local_ba_two_pass = local_ba_two_pass != 0;
+}
 void hh_local_ba(hh_map* m, int kf, bool* stop) {
   Optimizer::LocalBundleAdjustment(m->kfs[kf].get(), stop, &m->map, &m->lidar);
 }

@@ -4,10 +4,10 @@
 //   LocalBundleAdjustment   window selection as g2oOptimizer.cc:709-780, gather instead of graph construction
 //                           (:805-919), solve (:923-976), outlier erase + write-back (:1119-1189)
 //   BundleAdjustment        g2oOptimizer.cc:110-362, GlobalBundleAdjustemnt :80-89
+// Defaults follow the reference fork (sqrtbaOptimizer::options(), Optimizer.h): local BA creates monocular edges only
+// -- observations with mvuRight >= 0 fall into the fork's empty stereo branch (g2oOptimizer.cc:914-916) -- and always
+// ends with the third optimize(20) (:1113-1114); upstream ORB-SLAM2's stereo edges / two-pass schedule are opt-in.
 // Differences that are deliberate:
-//   * stereo observations (mvuRight >= 0) get the stereo edge in local BA too, as upstream ORB-SLAM2 does; the
-//     reference's local BA silently drops them (empty branch, g2oOptimizer.cc:914-916) although it declares their
-//     thresholds (:853).
 //   * vertices are handed over in ascending mnId order -- the order g2o itself imposes (sparse_optimizer.cpp:482-487).
 // Error convention of the reference is kept: void, silent; the last sqrtba error string is available for logging.
 #include "Optimizer.h"
@@ -122,6 +122,9 @@ struct Gathered {
   std::vector<int32_t> obs_pose, obs_point;
   std::vector<float> obs_meas;
   std::vector<std::pair<KeyFrame*, MapPoint*>> obs_ref;
+  // local map points without a usable observation: vertices without edges in the reference's graph (:856-866) -- their
+  // estimate cannot move, but the write-back still visits them (SetWorldPos + UpdateNormalAndDepth, :1180-1188)
+  std::vector<MapPoint*> edgeless;
 };
 
 // One observation of a map point as MapPoint::GetObservations() reports it
@@ -181,9 +184,10 @@ void fill_obs_cache(const std::vector<MapPoint*>& mps, ObsCache& c) {
 // `cache` (optional) holds the observation lists of `mps` in the order given (copied earlier by the caller).
 // Two parallel sweeps over the map points in mnId order -- count the usable observations, then (after a prefix sum) fill
 // the flat arrays in place -- so nothing is merged or re-allocated and the result does not depend on the thread count.
+// drop_stereo: observations with a right coordinate are left out (the fork's local BA, g2oOptimizer.cc:883-916).
 template <class FixedFn, class UsableFn>
 void gather(std::vector<KeyFrame*> kfs, std::vector<MapPoint*> mps, FixedFn kf_fixed, UsableFn usable, Gathered& g,
-            const ObsCache* cache = nullptr) {
+            const ObsCache* cache = nullptr, bool drop_stereo = false) {
   ObsCache own;
   if (!cache) {
     fill_obs_cache(mps, own);
@@ -220,7 +224,8 @@ void gather(std::vector<KeyFrame*> kfs, std::vector<MapPoint*> mps, FixedFn kf_f
       size_t c = 0;
       for (size_t k = cache->ptr[order[r]]; k < cache->ptr[order[r] + 1]; k++) {
         auto it = kf_index.find(cache->rec[k].kf);
-        const int ip = (it != kf_index.end() && kf_usable[it->second]) ? it->second : -1;
+        int ip = (it != kf_index.end() && kf_usable[it->second]) ? it->second : -1;
+        if (ip >= 0 && drop_stereo && !(cache->rec[k].kf->mvuRight[cache->rec[k].idx] < 0)) ip = -1;
         rec_pose[k] = ip;
         c += ip >= 0;
       }
@@ -232,6 +237,7 @@ void gather(std::vector<KeyFrame*> kfs, std::vector<MapPoint*> mps, FixedFn kf_f
   std::vector<size_t> pt_index(n + 1, 0);
   for (size_t r = 0; r < n; r++) {
     pt_index[r + 1] = pt_index[r] + (cnt[r + 1] > 0);
+    if (cnt[r + 1] == 0) g.edgeless.push_back(mps[order[r]]);
     cnt[r + 1] += cnt[r];
   }
   const size_t n_pt = pt_index[n], n_ob = cnt[n];
@@ -446,7 +452,8 @@ void gather_local_window(KeyFrame* pKF, Gathered& g) {
   const unsigned long cur = pKF->mnId;
   gather(kfs, mps,
          [cur](KeyFrame* kf) { return kf->mnBALocalForKF != cur || kf->mnId == 0; },  // :813, :829
-         [](KeyFrame* kf) { return !kf->isBad(); }, g, &cache);                        // :872
+         [](KeyFrame* kf) { return !kf->isBad(); }, g, &cache,                         // :872
+         !sqrtbaOptimizer::options().local_ba_stereo_edges);                           // :883-916
   lap("gather");
 }
 }  // namespace
@@ -474,18 +481,28 @@ void write_back_local(const Gathered& g, unsigned long cur, const double* P, con
       g.mps[i]->UpdateNormalAndDepth();
     }
   });
+  // points that had no edge keep their position (float -> double -> float is exact) but see the new keyframe poses
+  for (MapPoint* mp : g.edgeless) mp->UpdateNormalAndDepth();
 }
 }  // namespace
+
+sqrtbaOptimizer::Options& sqrtbaOptimizer::options() {
+  static Options o;
+  return o;
+}
 
 void sqrtbaOptimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* lidarconfig) {
   const unsigned long cur = pKF->mnId;
   Gathered g;
   gather_local_window(pKF, g);
   if (pbStopFlag && *pbStopFlag) return;  // :923-928
-  // the fork's third pass (lidar edges on pKF + optimize(20), :979-1117) runs when the configuration asks for lidar
-  // features; without them the two-pass schedule of ORB-SLAM2 is used
-  const bool with_lidar = lidarconfig && (lidarconfig->using_flat_point || lidarconfig->using_sharp_point);
-  Handle& H = with_lidar ? tl_handle_lidar : tl_handle;
+  // The fork runs its third optimize(20) unconditionally after the lidar block (:1113-1114) -- with both feature kinds
+  // switched off, or without a single match, it is simply 20 more iterations over the visual edges.  The lidar clouds
+  // are handed over only when the configuration asks for a feature kind.  options().local_ba_two_pass selects upstream
+  // ORB-SLAM2's 5 + 10 schedule instead (then there is no pass the lidar edges could join).
+  const bool two_pass = options().local_ba_two_pass;
+  const bool with_lidar = !two_pass && lidarconfig && (lidarconfig->using_flat_point || lidarconfig->using_sharp_point);
+  Handle& H = two_pass ? tl_handle : tl_handle_lidar;
   if (!upload(H, g)) { tl_handle.err = H.err; return; }
   sqrtba_handle* h = H.get();
   if (with_lidar && !set_lidar(h, g, pKF, lidarconfig)) {

@@ -28,6 +28,7 @@ def lib():
         L.hh_apply_local.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double),
                                      C.c_int, up]
         L.hh_local_ba.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.hh_set_options.argtypes = [C.c_int, C.c_int]
         L.hh_global_ba.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_ulong, C.c_void_p]
         L.hh_get_pose.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
         L.hh_get_point.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
@@ -54,6 +55,13 @@ def _f(a):
 
 def _i(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def set_options(stereo_edges: bool, two_pass: bool):
+    """sqrtbaOptimizer::options() (host/Optimizer.h).  The C++ defaults are the reference fork's behaviour (monocular
+    edges only, always a third optimize(20)); the methods below default to upstream ORB-SLAM2's (stereo edges, two
+    passes -- the schedule BASELINE.json's configs name) and say so at every call."""
+    lib().hh_set_options(int(stereo_edges), int(two_pass))
 
 
 class MockMap:
@@ -101,10 +109,11 @@ class MockMap:
         L.hh_set_lidar_config(self.h, int(ld.use_flat), int(ld.use_corner), ld.distance_sq_threshold, ld.flat_weight,
                               ld.corner_weight)
 
-    def gather(self, kf=-1):
+    def gather(self, kf=-1, stereo_edges=True):
         """The flat problem the adapter builds for LocalBundleAdjustment(kf) (kf >= 0) or for the whole map (-1),
         without solving it -- needs no GPU.  Returns a dict of arrays in the layout of sqrtba_set_problem + the ids."""
         L = lib()
+        set_options(stereo_edges, True)
         sz = np.zeros(3, np.int32)
         L.hh_gather(self.h, kf, _i(sz))
         nk, nm, no = (int(v) for v in sz)
@@ -118,8 +127,9 @@ class MockMap:
                         out["mp_ids"].ctypes.data_as(C.POINTER(C.c_int64)))
         return out
 
-    def apply_local(self, kf, pose_qt, point_xyz, outlier):
+    def apply_local(self, kf, pose_qt, point_xyz, outlier, stereo_edges=True):
         """The write-back half of LocalBundleAdjustment(kf) with a result given in the layout of gather(kf)."""
+        set_options(stereo_edges, True)
         P = np.ascontiguousarray(pose_qt, np.float64)
         X = np.ascontiguousarray(point_xyz, np.float64)
         F = np.ascontiguousarray(outlier, np.uint8)
@@ -127,7 +137,10 @@ class MockMap:
         lib().hh_apply_local(self.h, kf, len(P), P.ctypes.data_as(dp), len(X), X.ctypes.data_as(dp), len(F),
                              F.ctypes.data_as(C.POINTER(C.c_uint8)))
 
-    def local_ba(self, kf, stop=None):
+    def local_ba(self, kf, stop=None, stereo_edges=True, two_pass=True):
+        """Optimizer::LocalBundleAdjustment(kf, stop, map, lidarconfig).  stereo_edges=False, two_pass=False is the
+        reference fork's behaviour and the adapter's own default (g2oOptimizer.cc:914-916, 1113-1114)."""
+        set_options(stereo_edges, two_pass)
         lib().hh_local_ba(self.h, kf, stop)
 
     def global_ba(self, iters, robust, n_loop_kf=0, stop=None):

@@ -133,3 +133,47 @@ def test_local_write_back(pkg, synth):
     for k in range(prob.n_obs):
         kf, mp = int(prob.obs_pose[k]), int(prob.obs_point[k])
         assert m.has_observation(kf, mp) == (F[k] == 0) and m.keyframe_sees(kf, mp) == (F[k] == 0)
+
+
+def mixed_mono_stereo(prob, seed=0, frac=0.5):
+    """Every `frac` of the points loses the right coordinate in ALL its observations (monocular points), the others stay
+    stereo -- so the fork's local BA (monocular edges only) sees whole points drop out."""
+    q = prob.copy()
+    rng = np.random.default_rng(seed)
+    mono_pt = rng.random(prob.n_point) < frac
+    q.obs_meas = prob.obs_meas.copy()
+    q.obs_meas[mono_pt[prob.obs_point], 2] = -1.0
+    return q, mono_pt
+
+
+def test_fork_default_drops_stereo_observations(pkg, synth):
+    """The reference fork's local BA leaves the stereo branch empty (g2oOptimizer.cc:914-916): the adapter's default
+    (options().local_ba_stereo_edges = false) hands over the monocular observations only; points without one stay in
+    the map, keep their position and still get their UpdateNormalAndDepth at write-back (:1180-1188)."""
+    prob = synth.make_problem(11, 10, 3, 600, 5.0, stereo=True, name="fork-default")
+    q, mono_pt = mixed_mono_stereo(prob, seed=1)
+    m = pkg.host_harness.MockMap(q)
+    cur = q.n_pose - 1
+    free = np.nonzero(q.pose_fixed == 0)[0]
+    m.set_covisible(cur, [int(i) for i in free if i != cur])
+    flat = m.gather(cur, stereo_edges=False)
+    keep = q.obs_meas[:, 2] < 0
+    assert 0 < keep.sum() < q.n_obs
+    assert len(flat["obs_pose"]) == keep.sum() and (flat["obs_meas"][:, 2] < 0).all()
+    used = np.unique(q.obs_point[keep])
+    assert np.array_equal(flat["mp_ids"], used)
+    np.testing.assert_array_equal(flat["obs_meas"], q.obs_meas[keep])
+    np.testing.assert_array_equal(flat["mp_ids"][flat["obs_point"]], q.obs_point[keep])
+    # write-back: every local point is visited once, the edge-less ones keep their position
+    m = pkg.host_harness.MockMap(q)
+    m.set_covisible(cur, [int(i) for i in free if i != cur])
+    X = flat["point_xyz"] + 0.01
+    before = [m.point(j).copy() for j in range(q.n_point)]
+    m.apply_local(cur, flat["pose_qt"], X, np.zeros(len(flat["obs_pose"]), np.uint8), stereo_edges=False)
+    used_set = set(int(u) for u in used)
+    for j in range(q.n_point):
+        assert m.point_updates(j) == 1
+        if j in used_set:
+            np.testing.assert_array_equal(m.point(j), X[list(used).index(j)].astype(np.float32))
+        else:
+            np.testing.assert_array_equal(m.point(j), before[j])

@@ -45,6 +45,47 @@ def test_local_ba_through_reference_api(pkg, synth):
     assert 0 < F.sum() < prob.n_obs
 
 
+def test_local_ba_fork_defaults_through_reference_api(pkg, synth):
+    """The adapter's DEFAULT behaviour is the reference fork's: monocular edges only (the stereo branch of its local BA
+    is empty, g2oOptimizer.cc:914-916) and the 5 + 10 + 20 schedule (the third optimize(20) runs unconditionally,
+    :1113-1114).  Oracle: the same window without the stereo observations, solve_local(20)."""
+    from test_adapter_gather import mixed_mono_stereo
+    prob = synth.make_problem(41, 14, 5, 1200, 6.0, stereo=True, name="adapter-fork")
+    q, _ = mixed_mono_stereo(prob, seed=2, frac=0.6)
+    m = pkg.host_harness.MockMap(q)
+    cur = q.n_pose - 1
+    free = np.nonzero(q.pose_fixed == 0)[0]
+    m.set_covisible(cur, [i for i in free if i != cur])
+    m.local_ba(cur, stereo_edges=False, two_pass=False)
+    assert m.last_error() == ""
+    keep = q.obs_meas[:, 2] < 0
+    used = np.unique(q.obs_point[keep])
+    remap = -np.ones(q.n_point, int)
+    remap[used] = np.arange(len(used))
+    sub = q.copy()
+    sub.obs_pose, sub.obs_meas = q.obs_pose[keep], q.obs_meas[keep]
+    sub.obs_point = remap[q.obs_point[keep]].astype(np.int32)
+    sub.point_xyz = q.point_xyz[used]
+    ref = refba.RefBA(sub)
+    ref.solve_local(20)
+    assert ref.trace()[:, 0].max() == 2
+    P, X, F = ref.poses(), ref.points(), ref.outliers()
+    for i in free:
+        np.testing.assert_allclose(m.pose(int(i)), f32_pose_matrix(P[i], synth), rtol=0, atol=2e-5)
+    for jj, j in enumerate(used):
+        np.testing.assert_allclose(m.point(int(j)), X[jj].astype(np.float32), rtol=2e-6, atol=2e-5)
+    for j in range(q.n_point):
+        assert m.point_updates(j) == 1
+        if remap[j] < 0:  # no monocular observation: a vertex without edges, never moved
+            np.testing.assert_array_equal(m.point(j), q.point_xyz[j].astype(np.float32))
+    ko = np.nonzero(keep)[0]
+    for kk, k in enumerate(ko):
+        kf, mp = int(q.obs_pose[k]), int(q.obs_point[k])
+        assert m.has_observation(kf, mp) == (F[kk] == 0)
+    for k in np.nonzero(~keep)[0][::5]:   # stereo observations are never erased: they had no edge
+        assert m.has_observation(int(q.obs_pose[k]), int(q.obs_point[k]))
+
+
 def test_local_ba_stop_flag_raised_leaves_map_untouched(pkg, synth):
     prob = synth.small_window(4)
     m = pkg.host_harness.MockMap(prob)

@@ -168,7 +168,7 @@ def test_local_ba_with_lidar_through_reference_api(pkg, synth):
     free = np.nonzero(prob.pose_fixed == 0)[0]
     m.set_covisible(cur, [i for i in free if i != cur])
     m.set_lidar(ld)
-    m.local_ba(cur)
+    m.local_ba(cur, two_pass=False)   # the fork's 5 + 10 + 20 schedule; stereo edges as upstream ORB-SLAM2
     assert m.last_error() == ""
     # The association is discrete: the reference rounds Twc to float32 before it moves the clouds, and one swapped
     # nearest neighbour shifts the optimum by ~1e-5 m.  So the oracle must start from exactly what the adapter reads

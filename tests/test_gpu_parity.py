@@ -111,29 +111,93 @@ def test_local_ba_small_window(ba, synth, stereo, seed):
     np.testing.assert_allclose(ba.poses()[~free], ref.poses()[~free], rtol=0, atol=1e-15)
 
 
-def test_local_ba_kitti_window_c0(ba, synth):
-    prob = synth.config_c0(0)
-    ba.set_problem(prob)
-    ba.solve_local()
-    ref = refba.RefBA(prob)
-    ref.solve_local(0)
-    compare_solution(ba, ref, prob)
-    free = prob.pose_fixed == 0
-    t_rms, r_rms = pose_rms(ba.poses(), ref.poses(), free)
-    assert t_rms <= POSE_T_RMS and r_rms <= POSE_R_RMS, (t_rms, r_rms)
-    assert np.array_equal(ba.outliers(), ref.outliers())
+def _oracle_threads():
+    import os
+    return max(1, min(os.cpu_count() or 1, 32))
 
 
-def test_local_ba_mono_c1(ba, synth):
-    prob = synth.config_c1(1, scale=0.5)
+def _full_local_parity(ba, prob, threads=1):
+    """Two-pass local BA on one full-size BASELINE window: identical trial sequence, per-trial cost <= 1e-6, lambda,
+    pose RMS <= 1e-5 m / 1e-6 rad, identical outlier flags (g2oOptimizer.cc:704-976)."""
     ba.set_problem(prob)
-    ba.solve_local()
-    ref = refba.RefBA(prob)
+    st = ba.solve_local()
+    assert st["kernel_launches"] > 0
+    ref = refba.RefBA(prob, threads=threads)
     ref.solve_local(0)
     compare_solution(ba, ref, prob)
     t_rms, r_rms = pose_rms(ba.poses(), ref.poses(), prob.pose_fixed == 0)
     assert t_rms <= POSE_T_RMS and r_rms <= POSE_R_RMS, (t_rms, r_rms)
     assert np.array_equal(ba.outliers(), ref.outliers())
+    np.testing.assert_allclose(ba.points(), ref.points(), rtol=1e-5, atol=1e-4)
+    return st
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4])
+def test_local_ba_kitti_window_c0(ba, synth, seed):
+    # BASELINE configs[0] at full size, seeds 0-4 (SURVEY.md 8(d))
+    prob = synth.config_c0(seed)
+    assert prob.n_free == 20 and prob.n_pose == 30
+    _full_local_parity(ba, prob)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_local_ba_mono_c1(ba, synth, seed):
+    # BASELINE configs[1] at full size: monocular edges, gauge fixed by the first window keyframe
+    prob = synth.config_c1(seed)
+    assert not (prob.obs_meas[:, 2] >= 0).any()
+    _full_local_parity(ba, prob)
+
+
+def test_local_ba_large_window_c2(ba, synth):
+    # BASELINE configs[2] at full size: 100 keyframes / 50k points / ~600k observations on one GPU.  99 free poses:
+    # the p/q-in-shared-memory matvec with the largest window it supports and the persistent one-barrier PCG.
+    prob = synth.config_c2(0)
+    assert prob.n_free == 99 and prob.n_obs > 500000
+    st = _full_local_parity(ba, prob, threads=_oracle_threads())
+    assert st["persistent_pcg"] == 1
+
+
+def test_global_ba_c3_full(ba, synth):
+    # BASELINE configs[3] at full size on ONE GPU: 1500 keyframes on a loop / 300k points / ~3M observations,
+    # 10 non-robust iterations (the loop-closing call, LoopClosing.cc:987-991) against the oracle's Schur + LDLT
+    prob = synth.config_c3(0)
+    assert prob.n_pose == 1500 and prob.n_obs > 2500000
+    ba.set_problem(prob)
+    st = ba.solve_global(10, False)
+    assert st["persistent_pcg"] == 1
+    ref = refba.RefBA(prob, threads=_oracle_threads())
+    ref.solve_global(10, False)
+    compare_solution(ba, ref, prob)
+    t_rms, r_rms = pose_rms(ba.poses(), ref.poses(), prob.pose_fixed == 0)
+    assert t_rms <= POSE_T_RMS and r_rms <= POSE_R_RMS, (t_rms, r_rms)
+    np.testing.assert_allclose(ba.points(), ref.points(), rtol=1e-5, atol=1e-4)
+    assert ba.outliers().sum() == 0
+
+
+def test_batch_c4_slice_equals_oracle(pkg, synth):
+    # BASELINE configs[4]: a slice of the real batch (full C0-shaped windows, the bench's seeds) solved as ONE batched
+    # problem -- per-window lambda / accept state on the device -- against the oracle window by window
+    from concurrent.futures import ThreadPoolExecutor
+    wins = [synth.config_c0(i) for i in range(12)]
+    prob, pp, tp, op = synth.concat_windows(wins)
+    h = pkg.SqrtBA()
+    h.set_problem_batch(prob, pp, tp, op)
+    st = h.solve_local()
+    assert st["n_windows"] == len(wins) and st["persistent_pcg"] == 0
+
+    def one(w):
+        r = refba.RefBA(w)
+        r.solve_local(0)
+        return r
+    with ThreadPoolExecutor(max_workers=_oracle_threads()) as ex:
+        refs = list(ex.map(one, wins))
+    P, F = h.poses(), h.outliers()
+    for i, (w, ref) in enumerate(zip(wins, refs)):
+        compare_solution(h, ref, w, window=i)
+        t_rms, r_rms = pose_rms(P[pp[i]:pp[i + 1]], ref.poses(), w.pose_fixed == 0)
+        assert t_rms <= POSE_T_RMS and r_rms <= POSE_R_RMS, (i, t_rms, r_rms)
+        assert np.array_equal(F[op[i]:op[i + 1]], ref.outliers()), i
+    h.close()
 
 
 def test_third_pass_variant(pkg, synth):
