@@ -50,7 +50,10 @@ typedef struct {
   int32_t pcg_mode;          /* 0 = auto: single-window problems run the whole PCG solve in ONE persistent cooperative
                                 kernel (grid barriers between the matvec and the vector updates, in-kernel NVLink
                                 exchange when landmark-sharded), batches use one launch per CG phase;
-                                1 = always one launch per phase; 2 = persistent whenever possible */
+                                1 = always one launch per phase; 2 = persistent whenever possible;
+                                3 = like 0 but without the CUDA graph of the LM macro step (A/B: single-window problems
+                                otherwise run every LM trial as ONE graph launch and read its verdict from mapped
+                                pinned memory instead of synchronising the stream) */
   int32_t pcg_check_every;   /* multi-launch mode: host polls the convergence counter every N iterations */
   int32_t reserved[8];       /* tuning / A-B knobs, all 0 by default:
                                 [0] record per-stage CUDA-event times (stats.ms_linearize ...)
@@ -120,7 +123,9 @@ int sqrtba_set_problem_batch(sqrtba_handle* h, int32_t n_win, const int64_t* win
 int sqrtba_reset_state(sqrtba_handle* h);
 
 /* Local BA: robust pass (5 its) -> chi2/depth outlier exclusion -> non-robust pass (10 its) [-> third pass].
- * stop_flag may be NULL; it is polled on the host between LM trials, never read by the device.  With a communicator
+ * stop_flag may be NULL.  The host polls it before every LM iteration (g2o: `for (i < iterations && !terminate())`)
+ * and mirrors it into mapped pinned memory, where the LM decision kernel reads it at the end of every trial (g2o's
+ * do-while condition); the caller's bool itself is never read by the device.  With a communicator
  * (sqrtba_comm_init) the solve calls are collective and every poll max-reduces the ranks' flags over NCCL, so all
  * ranks stop in the same LM step even if their callers raise the flag at different moments. */
 int sqrtba_solve_local(sqrtba_handle* h, const volatile bool* stop_flag, sqrtba_stats* stats);

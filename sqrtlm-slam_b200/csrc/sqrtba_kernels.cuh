@@ -37,7 +37,8 @@ struct WinCtl {
   double rz, rz0;
   int iter, qmax, nbad, phase;
   int max_iter, pass, cg_active, cg_iters;
-  int trace_len, need_restore, lin_count, pad;
+  int trace_len, need_restore, lin_count;
+  int robust;  // Huber kernels on in this pass (set by k_pass_init; kernels launched with robust < 0 read it here)
 };
 
 struct TileInfo {
@@ -547,6 +548,7 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize(Dev P, int robust, double 
   __shared__ double c_sh[12 * SCST];
   const TileInfo ti = P.tiles[blockIdx.x];
   if (!force_all && P.ctl[ti.win].phase != PH_LIN) return;  // a tile lies inside one window: CTA-uniform
+  if (robust < 0) robust = P.ctl[ti.win].robust;
   LinOps none{};
   linearize_tile<false>(P, ti, none, robust, d2, d3, c_sh);
 }
@@ -596,12 +598,14 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, do
   stage_runs(ti_sh[0], 0);
   cp_async_commit();
   int nphase = force_all ? PH_LIN : P.ctl[ti_sh[0].win].phase;
+  int nrob = robust < 0 ? P.ctl[ti_sh[0].win].robust : robust;  // robust < 0: the pass's setting, from the control block
   for (int k = 0; k < t1 - t0; k++) {
     cp_async_wait_all();  // descriptor of tile k+1 (and the run table of tile k)
     __syncthreads();      // ... visible to everybody; c_sh of the previous tile is free
     const TileInfo ti = ti_sh[k % 3];
     const LinOps cur = nxt;
     const int phase = nphase;
+    const int rob = nrob;
     if (k + 1 < t1 - t0) {
       const TileInfo& tn = ti_sh[(k + 1) % 3];
       if (k + 2 < t1 - t0 && tid < 5)
@@ -610,6 +614,7 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, do
       nxt = ops_of(tn);
       stage_runs(tn, (k + 1) & 1);
       if (!force_all) nphase = P.ctl[tn.win].phase;
+      if (robust < 0) nrob = P.ctl[tn.win].robust;
     }
     cp_async_commit();
     if (phase != PH_LIN) continue;  // CTA-uniform
@@ -629,7 +634,7 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, do
       const TileInfo& tn = ti_sh[(k + 1) % 3];
       pf = !tn.is_long && wid < tn.nitem && lane < tile_item_cnt(tn, wid);
     }
-    linearize_tile<true>(P, ti, cur, robust, d2, d3, c_sh, (STAGE && !ti.is_long) ? run_sh[k & 1] : nullptr,
+    linearize_tile<true>(P, ti, cur, rob, d2, d3, c_sh, (STAGE && !ti.is_long) ? run_sh[k & 1] : nullptr,
                          pf ? nxt.ip : -1, pf ? nxt.lm : -1);
   }
   cp_async_wait_all();
@@ -640,9 +645,7 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, do
 // currentChi, iniChi, lambda init = tau * max diag(H) at iteration 0 (computeLambdaInit :166-180).
 // Split in two so that, with landmarks sharded over several GPUs, the per-window partial sums (wred) and the pose-side
 // vectors can be all-reduced between the two kernels; with one GPU they simply run back to back.
-__global__ void __launch_bounds__(RCTA) k_lm_reduce_lin(Dev P) {
-  __shared__ double sh[RWARPS];
-  const int win = blockIdx.x;
+__device__ __forceinline__ void lm_reduce_lin_body(const Dev& P, int win, double* sh) {
   WinCtl& c = P.ctl[win];
   if (c.phase != PH_LIN) {  // nothing new from this window: contribute the neutral element
     if (threadIdx.x == 0) { P.wred[win] = 0.0; P.wred[2 * P.n_win + win] = 0.0; }
@@ -657,16 +660,19 @@ __global__ void __launch_bounds__(RCTA) k_lm_reduce_lin(Dev P) {
     c.maxdiag_bits = 0ull;
   }
 }
-
-__global__ void __launch_bounds__(RCTA) k_lm_begin(Dev P) {
+__global__ void __launch_bounds__(RCTA) k_lm_reduce_lin(Dev P) {
   __shared__ double sh[RWARPS];
-  const int win = blockIdx.x;
+  lm_reduce_lin_body(P, blockIdx.x, sh);
+}
+
+__device__ __forceinline__ void lm_begin_body(const Dev& P, int win, double* sh) {
   WinCtl& c = P.ctl[win];
   if (c.phase != PH_LIN) return;
   double md = 0.0;
   for (int i = P.win_slot_ptr[win] * 6 + threadIdx.x; i < P.win_slot_ptr[win + 1] * 6; i += RCTA)
     md = fmax(md, fabs(P.hd[i]));
   md = warp_max(md);
+  __syncthreads();
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = md;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -686,6 +692,26 @@ __global__ void __launch_bounds__(RCTA) k_lm_begin(Dev P) {
     c.phase = PH_TRIAL;
     c.lin_count++;
   }
+}
+__global__ void __launch_bounds__(RCTA) k_lm_begin(Dev P) {
+  __shared__ double sh[RWARPS];
+  lm_begin_body(P, blockIdx.x, sh);
+}
+
+// Single-rank fusion of the three small kernels between the linearisation and the landmark QR (one launch instead of
+// three; used by the CUDA-graph macro step of single-window problems): per-window chi2 / max-diagonal reduction, the LM
+// "begin" step, and the zeroing of this trial's pose-side accumulators (reduced rhs, block-Jacobi blocks).
+__global__ void __launch_bounds__(RCTA) k_trial_begin(Dev P) {
+  __shared__ double sh[RWARPS];
+  const int win = blockIdx.x;
+  lm_reduce_lin_body(P, win, sh);
+  __syncthreads();
+  lm_begin_body(P, win, sh);
+  __syncthreads();  // thread 0's phase write is visible to the CTA
+  if (P.ctl[win].phase != PH_TRIAL) return;
+  const int s0 = P.win_slot_ptr[win], s1 = P.win_slot_ptr[win + 1];
+  for (int i = s0 * 6 + threadIdx.x; i < s1 * 6; i += RCTA) P.bs[i] = 0.0;
+  for (int i = s0 * 21 + threadIdx.x; i < s1 * 21; i += RCTA) P.D[i] = 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------ K2: landmark QR
@@ -1316,12 +1342,7 @@ __global__ void __launch_bounds__(CTA, MINB) k_qr_pipe2(Dev P, int force_all, do
 }
 
 // 6x6 block-Jacobi inverse per pose slot: (D + lambda I)^-1
-__global__ void k_dinv(Dev P, int force_all, double lam_override) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= P.n_slot) return;
-  const WinCtl& c = P.ctl[P.slot_win[s]];
-  if (!force_all && c.phase != PH_TRIAL) return;
-  const double lam = force_all ? lam_override : c.lambda;
+__device__ __forceinline__ void dinv_slot(const Dev& P, int s, double lam) {
   double A[36], Ai[36];
   int idx = 0;
 #pragma unroll
@@ -1338,6 +1359,13 @@ __global__ void k_dinv(Dev P, int force_all, double lam_override) {
     for (int i = 0; i < 6; i++) Ai[i * 6 + i] = 1.0 / fmax(fabs(A[i * 6 + i]), 1e-300);
   }
   for (int i = 0; i < 36; i++) P.Dinv[s * 36 + i] = Ai[i];
+}
+__global__ void k_dinv(Dev P, int force_all, double lam_override) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P.n_slot) return;
+  const WinCtl& c = P.ctl[P.slot_win[s]];
+  if (!force_all && c.phase != PH_TRIAL) return;
+  dinv_slot(P, s, force_all ? lam_override : c.lambda);
 }
 
 // ------------------------------------------------------------------------------------------------ K3: matvec
@@ -1815,7 +1843,7 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 // every 8-byte half-record {4 bytes of the value, 4-byte sequence number} is written with one store (8-byte stores are
 // not torn), so the receiver needs neither a fence nor a separate flag: it polls the record until both sequence
 // numbers match.  The partial values are added in rank order: identical bits on every rank.
-// (__noinline__: keeps its registers out of the matvec loop's allocation.)
+// (__noinline__: its registers -- eight records in flight -- stay out of the matvec loop's allocation.)
 __device__ __forceinline__ double peer_sum(uint4* const* peer_tbl, const uint4* recv, int nranks, int rank, int nelem_cap,
                                         double qv, int e, unsigned long long seq) {
   const int par = (int)(seq & 1ull);
@@ -1823,27 +1851,36 @@ __device__ __forceinline__ double peer_sum(uint4* const* peer_tbl, const uint4* 
   {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(qv);
     const uint4 rec = make_uint4((unsigned)bits, sq, (unsigned)(bits >> 32), sq);
-#pragma unroll 1
-    for (int r = 0; r < nranks; r++)
-      if (r != rank) st_volatile_v4(peer_tbl[r] + ((size_t)par * nranks + rank) * nelem_cap + e, rec);
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      if (r < nranks && r != rank) st_volatile_v4(peer_tbl[r] + ((size_t)par * nranks + rank) * nelem_cap + e, rec);
   }
   const uint4* mine = recv + (size_t)par * nranks * nelem_cap + e;
-  // rank order, two records in flight at a time (a deliberately small register footprint: see tile_products)
+  // four peers' records in flight at a time (two L2 round trips at eight ranks when the data is already there instead
+  // of four; eight at a time cost the matvec loop registers), re-polling only the ones that have not arrived; the sum
+  // itself is taken in rank order
   double tot = 0.0;
 #pragma unroll 1
-  for (int r = 0; r < nranks; r += 2) {
-    const bool h0 = r != rank, h1 = (r + 1 < nranks) && (r + 1 != rank);
-    uint4 v0 = make_uint4(0, sq, 0, sq), v1 = make_uint4(0, sq, 0, sq);
-    bool d0 = !h0, d1 = !h1;
-    while (!(d0 && d1)) {
-      if (!d0) v0 = ld_volatile_v4(mine + (size_t)r * nelem_cap);
-      if (!d1) v1 = ld_volatile_v4(mine + (size_t)(r + 1) * nelem_cap);
-      d0 = d0 || (v0.y == sq && v0.w == sq);
-      d1 = d1 || (v1.y == sq && v1.w == sq);
+  for (int r0 = 0; r0 < nranks; r0 += 4) {
+    uint4 v[4];
+    unsigned pending = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      v[j] = make_uint4(0, sq, 0, sq);
+      if (r0 + j < nranks && r0 + j != rank) pending |= 1u << j;
     }
-    tot += h0 ? __longlong_as_double((long long)(((unsigned long long)v0.z << 32) | v0.x)) : (r == rank ? qv : 0.0);
-    if (r + 1 < nranks)
-      tot += h1 ? __longlong_as_double((long long)(((unsigned long long)v1.z << 32) | v1.x)) : qv;
+    while (pending) {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (pending & (1u << j)) v[j] = ld_volatile_v4(mine + (size_t)(r0 + j) * nelem_cap);
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if ((pending & (1u << j)) && v[j].y == sq && v[j].w == sq) pending &= ~(1u << j);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (r0 + j < nranks)
+        tot += (r0 + j == rank) ? qv : __longlong_as_double((long long)(((unsigned long long)v[j].z << 32) | v[j].x));
   }
   return tot;
 }
@@ -2101,6 +2138,21 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       for (int e = tid; e < n6; e += CTA) atomicAdd(&qcur[e], acc_sh[e]);
     }
     PROFP(4)
+    // BIG: an owner CTA requests everything of its (first) chunk that does not depend on this iteration's matvec --
+    // the vectors it wrote itself one iteration ago and its rows of the block-Jacobi inverse -- BEFORE the barrier, so
+    // that after it only q itself is a dependent L2 round trip
+    double pf_po = 0.0, pf_dq = 0.0, pf_qf = 0.0, pf_z = 0.0, pf_r = 0.0, pf_dv[6] = {0, 0, 0, 0, 0, 0};
+    if (BIG) {
+      const int slot0 = (int)blockIdx.x * VSLOT + wid * 5 + lane / 6;
+      if ((int)blockIdx.x * VSLOT < P.n_slot && lane < 30 && slot0 < P.n_slot) {
+        const int e0 = slot0 * 6 + (lane - (lane / 6) * 6);
+        pf_po = P.p[e0]; pf_dq = A.dq[e0]; pf_qf = A.qf[e0]; pf_z = P.z[e0]; pf_r = P.res[e0];
+        if (!MULTI) {  // sharded: the inverse's rows are requested right before the exchange and hide behind it
+#pragma unroll
+          for (int k = 0; k < 6; k++) pf_dv[k] = __ldg(&P.Dinv[(size_t)e0 * 6 + k]);
+        }
+      }
+    }
     grid_bar(A.gbar, gridDim.x, (unsigned)(BIG ? 2 * it + 1 : it + 1), tid);  // B1: q complete
     PROFP(0)
     const double lam = st_sh[2], rz0 = st_sh[1];
@@ -2213,23 +2265,24 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       const bool ok = lane < 30 && slot < P.n_slot;
       const int e = slot * 6 + vcc;
       double qv = 0.0, pv = 0.0, zv = 0.0, rv = 0.0;
+      const bool first = ch == (int)blockIdx.x;  // this chunk's state was requested before the barrier
+      double dv[6];
       if (ok) {
         qv = __ldcg(&P.q[e]);
-        const double po = P.p[e], dqo = A.dq[e], qfo = A.qf[e];
-        zv = P.z[e] - pe.alpha * dqo;
+        const double po = first ? pf_po : P.p[e], dqo = first ? pf_dq : A.dq[e], qfo = first ? pf_qf : A.qf[e];
+        zv = (first ? pf_z : P.z[e]) - pe.alpha * dqo;
         pv = zv + pe.beta * po;
-        rv = P.res[e] - pe.alpha * qfo;
+        rv = (first ? pf_r : P.res[e]) - pe.alpha * qfo;
         P.x[e] += pe.alpha * po;
         P.z[e] = zv;
         P.p[e] = pv;
         P.res[e] = rv;
         P.q[e] = 0.0;
       }
-      // this thread's row of the block-Jacobi inverse: requested BEFORE the exchange so that its latency (an HBM miss
-      // after the tiles streamed through L2) hides behind the NVLink round trip
-      double dv[6];
+      // this thread's row of the block-Jacobi inverse (later chunks of a CTA: requested before the exchange so that its
+      // latency hides behind the NVLink round trip)
 #pragma unroll
-      for (int k = 0; k < 6; k++) dv[k] = ok ? __ldg(&P.Dinv[(size_t)slot * 36 + vcc * 6 + k]) : 0.0;
+      for (int k = 0; k < 6; k++) dv[k] = (first && !MULTI) ? pf_dv[k] : (ok ? __ldg(&P.Dinv[(size_t)slot * 36 + vcc * 6 + k]) : 0.0);
       PROFP(9)
       if (MULTI && ok) qv = peer_sum(A.peer_tbl, A.recv, A.nranks, A.rank, A.nelem_cap, qv, e, seq);
       PROFP(10)
@@ -2267,11 +2320,25 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
     grid_bar(A.gbar, gridDim.x, (unsigned)(2 * it + 2), tid);  // B2: state of this iterate and the partial dot products complete
     PROFP(2)
     if (wid == 0) {  // one warp per CTA reads the partials (every CTA reads the same few lines)
+      // three records per lane in flight at a time (96 chunks = 1920 poses per L2 round trip instead of one round trip
+      // per record); the summation order is unchanged, so every rank still gets the same bits
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      for (int i = lane; i < nchunk; i += 32) {
-        const double2 ab = __ldcg(reinterpret_cast<const double2*>(A.part + (size_t)i * 4));
-        const double2 cd = __ldcg(reinterpret_cast<const double2*>(A.part + (size_t)i * 4 + 2));
-        s0 += ab.x; s1 += ab.y; s2 += cd.x; s3 += cd.y;
+      for (int i0 = lane; i0 < nchunk; i0 += 96) {
+        double2 ab[3], cd[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const int i = i0 + 32 * j;
+          if (i < nchunk) {
+            ab[j] = __ldcg(reinterpret_cast<const double2*>(A.part + (size_t)i * 4));
+            cd[j] = __ldcg(reinterpret_cast<const double2*>(A.part + (size_t)i * 4 + 2));
+          } else {
+            ab[j] = make_double2(0.0, 0.0);
+            cd[j] = make_double2(0.0, 0.0);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          if (i0 + 32 * j < nchunk) { s0 += ab[j].x; s1 += ab[j].y; s2 += cd[j].x; s3 += cd[j].y; }
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
@@ -2341,9 +2408,7 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
 
 // ------------------------------------------------------------------------------------------------ K4/K5: PCG vector ops
 // One CTA owns one window's pose-sized vectors, so dot products are block reductions with no global sync.
-__global__ void __launch_bounds__(RCTA) k_cg_init(Dev P, int force_all) {
-  __shared__ double sh[RWARPS];
-  const int win = blockIdx.x;
+__device__ __forceinline__ void cg_init_body(const Dev& P, int win, int force_all, double* sh) {
   WinCtl& c = P.ctl[win];
   if (!force_all && c.phase != PH_TRIAL) return;
   const int s0 = P.win_slot_ptr[win], s1 = P.win_slot_ptr[win + 1];
@@ -2368,6 +2433,26 @@ __global__ void __launch_bounds__(RCTA) k_cg_init(Dev P, int force_all) {
     c.cg_active = (rz > 0.0) ? 1 : 0;
     if (c.cg_active) atomicAdd(&P.counters[1], 1);
   }
+}
+__global__ void __launch_bounds__(RCTA) k_cg_init(Dev P, int force_all) {
+  __shared__ double sh[RWARPS];
+  cg_init_body(P, blockIdx.x, force_all, sh);
+}
+
+// Single-window fusion of everything between the landmark QR and the persistent PCG kernel (CUDA-graph macro step):
+// block-Jacobi inverses, CG start vectors, and the zeroing the host used to enqueue as memset nodes (q buffers of the
+// persistent kernel, its grid-barrier counter, the "PCG active" counter).  One CTA (the problem has one window).
+__global__ void __launch_bounds__(RCTA) k_cg_prep(Dev P, double* zero_a, int n_a, double* zero_b, int n_b, unsigned* gbar) {
+  __shared__ double sh[RWARPS];
+  const WinCtl& c = P.ctl[0];
+  if (threadIdx.x == 0) { P.counters[1] = 0; gbar[0] = 0u; gbar[1] = 0u; }
+  for (int i = threadIdx.x; i < n_a; i += RCTA) zero_a[i] = 0.0;
+  for (int i = threadIdx.x; i < n_b; i += RCTA) zero_b[i] = 0.0;
+  if (c.phase != PH_TRIAL) return;
+  const double lam = c.lambda;
+  for (int s = threadIdx.x; s < P.n_slot; s += RCTA) dinv_slot(P, s, lam);
+  __syncthreads();
+  cg_init_body(P, 0, 0, sh);
 }
 
 __global__ void __launch_bounds__(RCTA) k_cg_step(Dev P, double tol2, int max_iters, int force_all, double lam_override) {
@@ -2513,11 +2598,33 @@ __global__ void k_update_point(Dev P) {
 #pragma unroll
   for (int c = 0; c < 3; c++) P.point[l * 3 + c] += P.dl[(size_t)c * P.n_point + l];
 }
+// push() + update() in one launch (CUDA-graph macro step): every free pose / point of a window in a trial saves its own
+// estimate right before it moves, so no device-to-device copy of the whole state is needed.  (Fixed poses never move
+// and k_restore never touches them.)
+__global__ void k_push_update(Dev P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n_slot && P.ctl[P.slot_win[i]].phase == PH_TRIAL) {
+    const int ip = P.slot_pose[i];
+    double pose[7], xi[6];
+    for (int k = 0; k < 7; k++) { pose[k] = P.pose[ip * 7 + k]; P.pose_bak[ip * 7 + k] = pose[k]; }
+    for (int k = 0; k < 6; k++) xi[k] = P.x[i * 6 + k];
+    pose_oplus(pose, xi);
+    for (int k = 0; k < 7; k++) P.pose[ip * 7 + k] = pose[k];
+  }
+  if (i < P.n_point && P.ctl[P.point_win[i]].phase == PH_TRIAL) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const double v = P.point[i * 3 + c];
+      P.point_bak[i * 3 + c] = v;
+      P.point[i * 3 + c] = v + P.dl[(size_t)c * P.n_point + i];
+    }
+  }
+}
 // pop(): restore the pre-trial estimate of the windows whose trial was rejected (sparse_optimizer.cpp:605-608)
 __global__ void k_restore(Dev P) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < P.n_pose) {
-    if (P.ctl[P.pose_win[i]].need_restore)
+    if (P.pose_slot[i] >= 0 && P.ctl[P.pose_win[i]].need_restore)  // fixed poses never moved
       for (int c = 0; c < 7; c++) P.pose[i * 7 + c] = P.pose_bak[i * 7 + c];
   }
   if (i < P.n_point) {
@@ -2534,7 +2641,9 @@ __global__ void __launch_bounds__(CTA) k_cost(Dev P, int robust, double d2, doub
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (w >= P.n_item) return;
-  if (P.ctl[P.item_win[w]].phase != PH_TRIAL) return;
+  const WinCtl& wc = P.ctl[P.item_win[w]];
+  if (wc.phase != PH_TRIAL) return;
+  if (robust < 0) robust = wc.robust;  // captured macro step: the pass's setting lives in the window's control block
   const int start = P.item_start[w], cnt = P.item_cnt[w];
   const size_t No = (size_t)P.ld;
   double chi = 0.0;
@@ -2554,9 +2663,7 @@ __global__ void __launch_bounds__(CTA) k_cost(Dev P, int robust, double d2, doub
 // ------------------------------------------------------------------------------------------------ K8b: LM decision
 // The body of the do-while of OptimizationAlgorithmLevenberg::solve and its exit logic
 // (optimization_algorithm_levenberg.cpp:126-163), one CTA per window.
-__global__ void __launch_bounds__(RCTA) k_lm_reduce_trial(Dev P) {
-  __shared__ double sh[RWARPS];
-  const int win = blockIdx.x;
+__device__ __forceinline__ void lm_reduce_trial_body(const Dev& P, int win, double* sh) {
   if (P.ctl[win].phase != PH_TRIAL) {
     if (threadIdx.x == 0) { P.wred[win] = 0.0; P.wred[P.n_win + win] = 0.0; }
     return;
@@ -2570,10 +2677,15 @@ __global__ void __launch_bounds__(RCTA) k_lm_reduce_trial(Dev P) {
   scale = block_sum(scale, sh);
   if (threadIdx.x == 0) { P.wred[win] = chi; P.wred[P.n_win + win] = scale; }
 }
-
-__global__ void __launch_bounds__(RCTA) k_lm_decide(Dev P, int terminate) {
+__global__ void __launch_bounds__(RCTA) k_lm_reduce_trial(Dev P) {
   __shared__ double sh[RWARPS];
-  const int win = blockIdx.x;
+  lm_reduce_trial_body(P, blockIdx.x, sh);
+}
+
+// term_host: optional pointer into mapped pinned host memory that mirrors the caller's stop flag (bool* pbStopFlag):
+// read HERE, at the end of the trial -- the point where g2o's do-while evaluates terminate()
+// (optimization_algorithm_levenberg.cpp:161) -- instead of at the top of the macro step on the host.
+__device__ __forceinline__ void lm_decide_body(const Dev& P, int win, int terminate, const volatile int* term_host, double* sh) {
   WinCtl& c = P.ctl[win];
   if (c.phase != PH_TRIAL) {
     if (threadIdx.x == 0) c.need_restore = 0;
@@ -2585,6 +2697,7 @@ __global__ void __launch_bounds__(RCTA) k_lm_decide(Dev P, int terminate) {
     scale += P.x[e] * (lam * P.x[e] + P.bp[e]);
   scale = block_sum(scale, sh) + P.wred[P.n_win + win];
   if (threadIdx.x != 0) return;
+  if (term_host && *term_host) terminate = 1;
   const double tempChi = chi;
   double rho = (c.cur_chi - tempChi);
   scale += 1e-3;
@@ -2628,9 +2741,52 @@ __global__ void __launch_bounds__(RCTA) k_lm_decide(Dev P, int terminate) {
   c.phase = done ? PH_DONE : PH_LIN;
   if (done) atomicAdd(&P.counters[0], 1);
 }
+__global__ void __launch_bounds__(RCTA) k_lm_decide(Dev P, int terminate) {
+  __shared__ double sh[RWARPS];
+  lm_decide_body(P, blockIdx.x, terminate, nullptr, sh);
+}
+
+// What the host reads after every macro step, in mapped pinned memory: no copy, no stream synchronisation -- the host
+// spins on `seq` (written last, after a system-scope fence).
+struct HostCtl {
+  volatile int term;         // host -> device: the caller's stop flag was seen raised
+  volatile int seq;          // device -> host: macro steps published so far
+  volatile int counters[3];  // windows done, PCG-active windows, CG iterations of the solve so far
+  int pad[3];
+};
+
+// Single-window fusion of the trial's tail (CUDA-graph macro step): cost / scale reduction, the LM decision with the
+// stop flag read from mapped host memory, zeroing of the gradient accumulators when the window re-linearises next, and
+// the publication of the step's counters to the host.
+__global__ void __launch_bounds__(RCTA) k_decide_publish(Dev P, HostCtl* hc) {
+  __shared__ double sh[RWARPS];
+  lm_reduce_trial_body(P, 0, sh);
+  __syncthreads();
+  lm_decide_body(P, 0, 0, &hc->term, sh);
+  __syncthreads();
+  if (P.ctl[0].phase == PH_LIN)
+    for (int i = threadIdx.x; i < P.n_slot * 6; i += RCTA) { P.bp[i] = 0.0; P.hd[i] = 0.0; }
+  if (threadIdx.x == 0) {
+    hc->counters[0] = P.counters[0];
+    hc->counters[1] = P.counters[1];
+    hc->counters[2] = P.counters[2];
+    const int seq = ++P.counters[5];
+    __threadfence_system();
+    hc->seq = seq;
+  }
+}
+
+// the stop flag was seen raised at the top of an iteration: `for (i < iterations && !terminate())` does not start it
+// (sparse_optimizer.cpp:383) -- windows that would have re-linearised or re-tried are finished as they are
+__global__ void k_terminate(Dev P) {
+  const int win = blockIdx.x * blockDim.x + threadIdx.x;
+  if (win >= P.n_win) return;
+  WinCtl& c = P.ctl[win];
+  if (c.phase != PH_DONE) { c.phase = PH_DONE; c.need_restore = 0; c.cg_active = 0; }
+}
 
 // start of one optimize(n) call: SparseOptimizer::optimize + the iteration==0 re-initialisation of lambda
-__global__ void k_pass_init(Dev P, int max_iter, int pass) {
+__global__ void k_pass_init(Dev P, int max_iter, int pass, int robust) {
   const int win = blockIdx.x * blockDim.x + threadIdx.x;
   if (win >= P.n_win) return;
   WinCtl& c = P.ctl[win];
@@ -2640,6 +2796,7 @@ __global__ void k_pass_init(Dev P, int max_iter, int pass) {
   c.phase = (max_iter > 0) ? PH_LIN : PH_DONE;
   c.max_iter = max_iter;
   c.pass = pass;
+  c.robust = robust;
   c.need_restore = 0;
   c.cg_active = 0;
   c.maxdiag_bits = 0ull;

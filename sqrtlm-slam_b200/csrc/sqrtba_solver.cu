@@ -134,6 +134,9 @@ class Solver {
     CU_CHECK(cudaSetDevice(cfg_.device));
     CU_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CU_CHECK(cudaMallocHost((void**)&h_counters_, 8 * sizeof(int)));
+    CU_CHECK(cudaHostAlloc((void**)&h_ctl_, sizeof(HostCtl), cudaHostAllocMapped));
+    std::memset((void*)h_ctl_, 0, sizeof(HostCtl));
+    CU_CHECK(cudaHostGetDevicePointer((void**)&d_ctl_host_, (void*)h_ctl_, 0));
     CU_CHECK(cudaEventCreate(&ev0_));
     CU_CHECK(cudaEventCreate(&ev1_));
     for (auto& e : stage_ev_) CU_CHECK(cudaEventCreate(&e));
@@ -178,6 +181,10 @@ class Solver {
     release_all();
     if (h_counters_) cudaFreeHost(h_counters_);
     h_counters_ = nullptr;
+    if (step_exec_) cudaGraphExecDestroy(step_exec_);
+    step_exec_ = nullptr;
+    if (h_ctl_) cudaFreeHost((void*)h_ctl_);
+    h_ctl_ = nullptr;
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     for (auto& e : stage_ev_)
@@ -720,6 +727,7 @@ class Solver {
       }
     }
     have_problem_ = true;
+    step_graph_valid_ = false;  // the captured macro step carries this problem's sizes and pointers
     return reset_state();
   }
 
@@ -1049,7 +1057,7 @@ class Solver {
     if (!have_problem_) { err_ = "no problem set"; return SQRTBA_ERR_INVALID; }
     CU_CHECK(cudaSetDevice(cfg_.device));
     const double d2 = (double)(float)std::sqrt(huber == 2 ? 5.99 : 5.991), d3 = (double)(float)std::sqrt(7.815);
-    k_pass_init<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_, 1, 0);
+    k_pass_init<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_, 1, 0, huber != 0 ? 1 : 0);
     if (P_.n_slot) k_zero_lin<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
     launch_linearize(huber != 0, d2, d3, 1);
     if (int rc = begin_after_linearize()) return rc;
@@ -1547,19 +1555,129 @@ class Solver {
     return SQRTBA_OK;
   }
 
+  // ---- single-window problems: one LM macro step = ONE CUDA graph launch, verdict read from mapped host memory
+  // A C0-shaped window spends ~150 us per LM trial in kernels; enqueueing ~20 small launches + memsets per trial and a
+  // stream synchronisation + copy to read three counters cost about as much again.  The graph has 10 kernel nodes (the
+  // small per-window kernels fused: k_trial_begin, k_cg_prep, k_push_update, k_decide_publish), the cooperative PCG
+  // kernel included; the last decision kernel writes the step's counters and a sequence number into mapped pinned
+  // memory (HostCtl) and the host spins on it.  The stop flag is mirrored into the same block, so the device reads it
+  // where g2o's do-while evaluates terminate() -- at the end of the trial.
+  bool use_graph() const {
+    return graph_ok_ && cfg_.pcg_mode != 3 && !stage_timing_ && !comm_ && P_.n_win == 1 && P_.n_slot > 0 && use_persist();
+  }
+  int enqueue_step(double d2, double d3) {
+    const int gi = cdiv(P_.n_item, WARPS);
+    const int n6 = P_.n_slot * 6;
+    launch_linearize(-1, d2, d3, 0);
+    k_trial_begin<<<1, RCTA, 0, stream_>>>(P_);
+    launch_qr(0, 0.0);
+    if (P_.pq_shared) k_cg_prep<<<1, RCTA, 0, stream_>>>(P_, d_q3_.p, 3 * KQ * n6, nullptr, 0, d_gbar_.p);
+    else k_cg_prep<<<1, RCTA, 0, stream_>>>(P_, P_.q, n6, d_dq_.p, 2 * n6, d_gbar_.p);
+    const double tol2 = cfg_.pcg_rtol * cfg_.pcg_rtol;
+    if (int rc = launch_pcg_persist(tol2, 0, 0.0)) return rc;
+    k_backsub<<<P_.n_tile, CTA, 0, stream_>>>(P_, 0, 0.0);
+    k_push_update<<<cdiv(std::max(P_.n_slot, P_.n_point), 256), 256, 0, stream_>>>(P_);
+    k_cost<<<gi, CTA, 0, stream_>>>(P_, -1, d2, d3);
+    k_decide_publish<<<1, RCTA, 0, stream_>>>(P_, d_ctl_host_);
+    k_restore<<<cdiv(std::max(P_.n_pose, P_.n_point), 256), 256, 0, stream_>>>(P_);
+    return SQRTBA_OK;
+  }
+  static constexpr int STEP_NODES = 10;
+  // (re)capture the macro step for the current problem; an existing executable graph is updated in place
+  int ensure_step_graph(double d2, double d3) {
+    if (step_graph_valid_ && step_d2_ == d2 && step_d3_ == d3) return SQRTBA_OK;
+    static const bool host_timing = std::getenv("SQRTBA_HOST_TIMING") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); graph_ok_ = false; return SQRTBA_OK; }
+    const int rc = enqueue_step(d2, d3);
+    const cudaError_t le = cudaGetLastError();
+    const cudaError_t ce = cudaStreamEndCapture(stream_, &g);
+    if (rc || le != cudaSuccess || ce != cudaSuccess || !g) {  // e.g. a driver that cannot capture cooperative launches
+      cudaGetLastError();
+      if (g) cudaGraphDestroy(g);
+      graph_ok_ = false;
+      return SQRTBA_OK;  // the caller falls back to one launch per kernel
+    }
+    if (step_exec_) {
+      cudaGraphExecUpdateResultInfo info;
+      if (cudaGraphExecUpdate(step_exec_, g, &info) != cudaSuccess) {
+        cudaGetLastError();
+        cudaGraphExecDestroy(step_exec_);
+        step_exec_ = nullptr;
+      }
+    }
+    if (!step_exec_ && cudaGraphInstantiate(&step_exec_, g, 0) != cudaSuccess) {
+      cudaGetLastError();
+      step_exec_ = nullptr;
+      graph_ok_ = false;
+    }
+    cudaGraphDestroy(g);
+    step_graph_valid_ = step_exec_ != nullptr;
+    step_d2_ = d2; step_d3_ = d3;
+    if (host_timing)
+      std::fprintf(stderr, "[sqrtba host] %-28s %8.3f ms\n", "macro-step graph (re)capture",
+                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    return SQRTBA_OK;
+  }
+  int run_pass_graph(int iters, const volatile bool* stop) {
+    const int max_macro = iters * 10 + 1;
+    for (int step = 0; step < max_macro; step++) {
+      if (stop && *stop) {  // `for (i < iterations && !terminate())`: the next iteration does not start
+        if (step > 0) { k_terminate<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_); launches_++; }
+        break;
+      }
+      h_ctl_->term = 0;
+      const int want = ++step_seq_;
+      CU_CHECK(cudaGraphLaunch(step_exec_, stream_));
+      unsigned spins = 0;
+      while (h_ctl_->seq < want) {
+        if (stop && *stop) h_ctl_->term = 1;  // seen by k_decide_publish when the trial ends
+        if ((++spins & 0xfffu) == 0) {
+          const cudaError_t q = cudaStreamQuery(stream_);
+          if (q == cudaSuccess) {
+            if (h_ctl_->seq >= want) break;
+            err_ = "LM macro step finished without publishing its counters";
+            return SQRTBA_ERR_CUDA;
+          }
+          if (q != cudaErrorNotReady) {
+            err_ = std::string("LM macro step failed: ") + cudaGetErrorString(q);
+            return SQRTBA_ERR_CUDA;
+          }
+        }
+        __builtin_ia32_pause();
+      }
+      launches_ += STEP_NODES;
+      lm_trials_++;
+      cg_iters_total_ = h_ctl_->counters[2];
+      if (h_ctl_->counters[0] >= P_.n_win) break;
+    }
+    return SQRTBA_OK;
+  }
+
   // one optimizer.optimize(iters) call over all windows (sparse_optimizer.cpp:354-419)
   int run_pass(int iters, int pass, int robust, double d2, double d3, const volatile bool* stop) {
     const int gi = cdiv(P_.n_item, WARPS);
     lidar_active_ = pass == 2 && (lidar_edges_set_ || lidar_assoc_set_);  // the edges join the graph for the third pass only
-    k_pass_init<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_, iters, pass);
+    k_pass_init<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_, iters, pass, robust);
     CU_CHECK(cudaMemsetAsync(P_.counters, 0, 2 * sizeof(int), stream_));
     launches_++;
     if (iters <= 0) return SQRTBA_OK;
+    if (use_graph()) {
+      if (int rc = ensure_step_graph(d2, d3)) return rc;
+      if (step_graph_valid_) {
+        if (P_.n_slot) { k_zero_lin<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_); launches_++; }  // later steps: k_decide_publish
+        return run_pass_graph(iters, stop);
+      }
+    }
     const int max_macro = iters * 10 + 1;
     for (int step = 0; step < max_macro; step++) {
       int term = 0;
       if (int rc = poll_stop(stop, &term)) return rc;
-      if (term && step == 0) break;  // `for (i < iterations && !terminate())` before the first iteration
+      if (term) {  // `for (i < iterations && !terminate())`: the next iteration does not start (sparse_optimizer.cpp:383)
+        if (step > 0) { k_terminate<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_); launches_++; }
+        break;
+      }
       if (P_.n_slot) k_zero_lin<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
       stage_begin(0);
       launch_linearize(robust, d2, d3, 0);
@@ -1582,6 +1700,9 @@ class Solver {
       if (lidar_active_) { k_lidar_cost<<<1, LD_CTA, 0, stream_>>>(P_, lidar_); launches_++; }
       k_lm_reduce_trial<<<P_.n_win, RCTA, 0, stream_>>>(P_);
       if (int rc = allreduce(P_.wred, (size_t)2 * P_.n_win, false)) return rc;  // trial chi2 + landmark part of the scale
+      // the flag is looked at again where g2o's do-while evaluates terminate(): after the trial's solve was enqueued
+      // (single-rank only: sharded ranks must act on the value they agreed on at the top of the step)
+      if (!comm_ && stop && *stop) term = 1;
       k_lm_decide<<<P_.n_win, RCTA, 0, stream_>>>(P_, term);
       k_restore<<<cdiv(std::max(P_.n_pose, P_.n_point), 256), 256, 0, stream_>>>(P_);
       launches_ += 7;
@@ -1600,7 +1721,9 @@ class Solver {
     launches_ = 0; lm_trials_ = 0; cg_iters_total_ = 0;
     for (auto& v : stage_ms_) v = 0.0;
     mv_used_ = 0;
-    cudaMemsetAsync(d_counters_.p + 2, 0, sizeof(int), stream_);
+    cudaMemsetAsync(d_counters_.p + 2, 0, 6 * sizeof(int), stream_);  // CG iterations, stop-flag scratch, published steps
+    step_seq_ = 0;
+    if (h_ctl_) { h_ctl_->seq = 0; h_ctl_->term = 0; }
     cudaEventRecord(ev0_, stream_);
   }
   void stage_begin(int s) {
@@ -1682,6 +1805,12 @@ class Solver {
   cudaEvent_t stage_ev_[10] = {};
   double stage_ms_[5] = {};
   int* h_counters_ = nullptr;
+  volatile HostCtl* h_ctl_ = nullptr;   // mapped pinned memory: the device publishes every macro step here
+  HostCtl* d_ctl_host_ = nullptr;       // its device-side address
+  cudaGraphExec_t step_exec_ = nullptr; // the captured LM macro step of single-window problems
+  bool step_graph_valid_ = false, graph_ok_ = true;
+  double step_d2_ = 0.0, step_d3_ = 0.0;
+  int step_seq_ = 0;
   bool have_problem_ = false;
   int max_trace_ = 200;
   int launches_ = 0, lm_trials_ = 0, cg_iters_total_ = 0;

@@ -361,3 +361,57 @@ def test_repeatable_after_reset(ba, synth):
     ba.reset_state()
     ba.solve_local()
     np.testing.assert_allclose(ba.poses(), a, rtol=0, atol=1e-9)  # atomics reorder sums: not bit-identical
+
+
+def test_graph_step_equals_plain_launches(pkg, synth):
+    # single-window problems run every LM trial as one CUDA-graph launch (fused small kernels, verdict through mapped
+    # pinned memory); pcg_mode=3 keeps the persistent PCG kernel but launches kernel by kernel: same trials, same result
+    for prob, glob in ((synth.config_c0(3), False), (big_window_problem(synth, seed=29, n_kf=140, n_points=3000), True)):
+        out = []
+        for mode in (0, 3):
+            h = pkg.SqrtBA(pcg_mode=mode)
+            h.set_problem(prob)
+            st = h.solve_global(6, True) if glob else h.solve_local()
+            assert st["persistent_pcg"] == 1
+            out.append((h.trace(), h.poses(), h.points(), h.outliers(), st["kernel_launches"]))
+            # a second problem on the same handle re-captures / updates the graph
+            h.set_problem(synth.small_window(1, n_points=200))
+            h.solve_local()
+            h.close()
+        (ta, pa, xa, fa, la), (tb, pb, xb, fb, lb) = out
+        assert la < lb                                             # fewer launches per trial
+        assert len(ta) == len(tb) and np.array_equal(ta[:, [0, 1, 2, 7]], tb[:, [0, 1, 2, 7]])
+        np.testing.assert_allclose(ta[:, 5], tb[:, 5], rtol=1e-9)
+        np.testing.assert_allclose(pa, pb, rtol=0, atol=1e-8)
+        np.testing.assert_allclose(xa, xb, rtol=0, atol=1e-7)
+        assert np.array_equal(fa, fb)
+
+
+@pytest.mark.parametrize("batch", [False, True])
+def test_stop_flag_raised_during_the_solve(pkg, synth, batch):
+    # pbStopFlag raised by another thread while the solve runs (LocalMapping::InterruptBA): the solve returns early,
+    # no hang, estimates stay finite and the trace is a prefix-like shorter run
+    import threading
+    import time
+    wins = [synth.config_c0(10 + i) for i in range(4 if batch else 1)]
+    h = pkg.SqrtBA()
+    if batch:
+        prob, pp, tp, op = synth.concat_windows(wins)
+        h.set_problem_batch(prob, pp, tp, op)
+    else:
+        h.set_problem(wins[0])
+    h.solve_local()
+    full = len(h.trace())
+    h.reset_state()
+    flag = ctypes.c_bool(False)
+    t = threading.Thread(target=lambda: (time.sleep(0.0015), setattr(flag, "value", True)))
+    t.start()
+    h.solve_local(ctypes.byref(flag))
+    t.join()
+    n = len(h.trace())
+    assert n <= full and np.isfinite(h.poses()).all() and np.isfinite(h.points()).all()
+    # raised before the call: nothing runs at all
+    h.reset_state()
+    h.solve_local(ctypes.byref(flag))
+    assert len(h.trace()) == 0
+    h.close()

@@ -36,6 +36,13 @@ __global__ void k(unsigned* bar, int iters, double* sink) {
         const unsigned target = gen * gridDim.x;
         while (ld_relaxed_gpu(&bar[0]) < target) { __nanosleep(32); }
         __threadfence();
+      } else if (MODE == 4) {  // arrivals and the release flag on DIFFERENT lines: the last arriver (it sees it in the
+                               // value its atomic returns) publishes the generation, everybody else spins on a
+                               // read-only line that no atomic is queued on
+        unsigned prev;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&bar[0]) : "memory");
+        if (prev == gen * gridDim.x - 1) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&bar[32]), "r"(gen) : "memory");
+        else while (ld_acquire_gpu(&bar[32]) < gen) {}
       } else if (MODE == 3) {  // as 1, acquire load instead of relaxed + fence
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&bar[0]) : "memory");
         const unsigned target = gen * gridDim.x;
@@ -49,7 +56,7 @@ __global__ void k(unsigned* bar, int iters, double* sink) {
 }
 template <int MODE>
 void run(int grid, int iters, unsigned* bar) {
-  cudaMemset(bar, 0, 8);
+  cudaMemset(bar, 0, 1024);
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
   int it = iters;
@@ -57,7 +64,7 @@ void run(int grid, int iters, unsigned* bar) {
   void* args[] = {&bar, &it, &sink};
   cudaLaunchCooperativeKernel((void*)k<MODE>, dim3(grid), dim3(160), args, 70 * 1024, 0);
   cudaDeviceSynchronize();
-  cudaMemset(bar, 0, 8);
+  cudaMemset(bar, 0, 1024);
   cudaEventRecord(a);
   cudaLaunchCooperativeKernel((void*)k<MODE>, dim3(grid), dim3(160), args, 70 * 1024, 0);
   cudaEventRecord(b);
@@ -68,16 +75,18 @@ void run(int grid, int iters, unsigned* bar) {
 }
 int main() {
   unsigned* bar;
-  cudaMalloc(&bar, 8);
+  cudaMalloc(&bar, 1024);
   cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70 * 1024);
   cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70 * 1024);
   cudaFuncSetAttribute(k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70 * 1024);
   cudaFuncSetAttribute(k<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70 * 1024);
+  cudaFuncSetAttribute(k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70 * 1024);
   for (int grid : {148, 296, 444}) {
     run<0>(grid, 2000, bar);
     run<1>(grid, 2000, bar);
     run<2>(grid, 2000, bar);
     run<3>(grid, 2000, bar);
+    run<4>(grid, 2000, bar);
   }
   return 0;
 }
