@@ -23,7 +23,10 @@ constexpr int WARPS = CTA / 32;
 constexpr int RCTA = 256;           // per-window reduction / vector kernels
 constexpr int RWARPS = RCTA / 32;
 constexpr int MAXSLOT = 128;        // "small window": all free poses of a window fit the CTA's shared accumulators
-constexpr int NPLANE = 27;          // matvec streams Jp (18) + Q1 (9) planes
+constexpr int JG = 4;               // geometry rows of the matvec operand: {x/z, y/z, 1/z, w} per observation -- the weighted
+                                    // 3x6 pose Jacobian is rebuilt from them in registers (jp_compact, sqrtba_math.cuh)
+constexpr int NPLANE = JG + 9;      // matvec streams the geometry rows (4) + Q1 (9): 104 bytes per observation
+constexpr unsigned LP_STEREO = 0x80000000u;  // obs_lp / meta bit: the edge is a stereo edge (third residual row exists)
 constexpr int JQ_HDR = 8;           // doubles (64 bytes) of per-tile header in front of every JQ data block
 constexpr int JQ_ROWS = NPLANE + 1; // data planes + one 8-byte meta entry per column
 
@@ -92,10 +95,11 @@ struct Dev {
   const int* item_win;     // n_item
   const int* win_item_ptr;  // n_win+1
   const int* win_slot_ptr;  // n_win+1
+  const double* slot_cam;   // n_slot*3: fx, fy, bf of the keyframe in that free slot (for jp_compact)
   // tile = up to WARPS consecutive short items of ONE window (or one long item); one CTA per tile.
   // obs_lp: low 16 bits = window-relative free slot when the problem is "smallwin" (0 otherwise), 0xffff = the
-  // observation takes no part in the in-CTA reduction (fixed pose or long item); high 16 bits = its rank in the
-  // tile's pose-sorted order.
+  // observation takes no part in the in-CTA reduction (fixed pose or long item); bits 16-30 = its rank in the
+  // tile's pose-sorted order; bit 31 (LP_STEREO) = stereo edge.
   int n_tile;
   int ld;                     // leading dimension (stride) of every per-observation plane, multiple of 32
   int smallwin;               // window-relative slots fit 16 bits (every window has < 65535 free poses): obs_lp and the
@@ -117,9 +121,10 @@ struct Dev {
   double* Jl;   // 9
   double* r;    // 3
   // matvec operand, TILE-BLOCKED: tile t owns one contiguous block of JQ:
-  //   [JQ_HDR doubles header][27][nt] data][nt x 8-byte per-column meta][run table: nrun+1 offsets, nrun slots (int)]
+  //   [JQ_HDR doubles header][13][nt] data][nt x 8-byte per-column meta][run table: nrun+1 offsets, nrun slots (int)]
   // run table: ranks [run_ptr[r], run_ptr[r+1]) all belong to pose slot run_slot[r] (window-relative when smallwin)
-  // data rows 0-17 = weighted Jp (3x6 row-major), rows 18-26 = observation rows of Q1 (3x3 row-major), column = o - o0;
+  // data rows 0-3 = {x/z, y/z, 1/z, w} (the weighted 3x6 Jp is a function of these and of the keyframe's fx, fy, bf:
+  // jp_compact), rows 4-12 = observation rows of Q1 (3x3 row-major), column = free-pose observation;
   // meta = {obs_lp, landmark id}; header = 16 ints (see k_init_jq).  jq_off points at the data part.
   // One tile = one contiguous chunk, so the matvec fetches everything it needs with a single TMA bulk copy.
   double* JQ;
@@ -345,8 +350,10 @@ __global__ void k_zero_trial(Dev P) {
 // base_binary_edge.hpp:55-120).  Also produces what LM needs without ever forming H: chi2 (deterministic
 // per-item partials), b_p = -Jp^T r, b_l = -Jl^T r, diag(Jp^T Jp), max diag(Jl^T Jl).
 struct ObsLin {
-  double e[3], Jp[18], Jl[9], w, rho0;
-  bool depth_pos;
+  double e[3], Jl[9], w, rho0;
+  double g[4];   // {x/z, y/z, 1/z, w}: what the matvec operand stores instead of the 3x6 pose block
+  double cam3[3];  // fx, fy, bf of the observing keyframe
+  bool depth_pos, stereo;
 };
 
 // the observation's own words (measurement, pose index, landmark index) already in registers
@@ -379,7 +386,13 @@ __device__ __forceinline__ void obs_eval_ops(const Dev& P, const float4 m, int i
     huber(c, delta, huber_dsqr(delta), &L.rho0, &rho1);
   }
   L.w = sqrt(rho1 * info);
-  if (want_jac) reproj_jacobians(R, Xc, cam, stereo, L.Jp, L.Jl);
+  L.stereo = stereo;
+  if (want_jac) {
+    reproj_jacobian_point(R, Xc, cam, stereo, L.Jl);
+    const double iz = 1.0 / Xc[2];
+    L.g[0] = Xc[0] * iz; L.g[1] = Xc[1] * iz; L.g[2] = iz; L.g[3] = L.w;
+    L.cam3[0] = cam[0]; L.cam3[1] = cam[1]; L.cam3[2] = cam[4];
+  }
 }
 
 // per-observation words of one lane, loadable one tile ahead of their use (8 registers)
@@ -431,7 +444,7 @@ __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti,
     if (act) {
       if (!PRE) q = lin_load_ops(P, o);
       has = (q.lp & 0xffffu) != 0xffffu;
-      rank = (int)(q.lp >> 16);
+      rank = (int)((q.lp >> 16) & 0x7fffu);
       lm = q.lm;
     }
     const int fcol = tile_fcol(ti, wid, has, lane);
@@ -445,16 +458,18 @@ __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti,
       }
       // an excluded (level-1) edge contributes zero rows; select, do not multiply (its Jacobian may be inf/NaN)
 #pragma unroll
-      for (int c = 0; c < 18; c++) { L.Jp[c] = live ? L.Jp[c] * L.w : 0.0; if (has) jq[(size_t)c * ti.nt + fcol] = L.Jp[c]; }
+      for (int c = 0; c < JG; c++) { L.g[c] = live ? L.g[c] : 0.0; if (has) jq[(size_t)c * ti.nt + fcol] = L.g[c]; }
 #pragma unroll
       for (int c = 0; c < 9; c++) { L.Jl[c] = live ? L.Jl[c] * L.w : 0.0; P.Jl[(size_t)c * No + o] = L.Jl[c]; }
 #pragma unroll
       for (int c = 0; c < 3; c++) { L.e[c] = live ? L.e[c] * L.w : 0.0; P.r[(size_t)c * No + o] = L.e[c]; }
       if (has) {
+        double Jp[18];
+        jp_full(jp_compact(L.g, L.cam3[0], L.cam3[1], L.cam3[2], L.stereo), L.stereo, Jp);
 #pragma unroll
         for (int c = 0; c < 6; c++) {
-          vb[c] = -(L.Jp[c] * L.e[0] + L.Jp[6 + c] * L.e[1] + L.Jp[12 + c] * L.e[2]);
-          vh[c] = L.Jp[c] * L.Jp[c] + L.Jp[6 + c] * L.Jp[6 + c] + L.Jp[12 + c] * L.Jp[12 + c];
+          vb[c] = -(Jp[c] * L.e[0] + Jp[6 + c] * L.e[1] + Jp[12 + c] * L.e[2]);
+          vh[c] = Jp[c] * Jp[c] + Jp[6 + c] * Jp[6 + c] + Jp[12 + c] * Jp[12 + c];
         }
       }
     }
@@ -491,16 +506,18 @@ __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti,
           chi_acc += L.rho0;
         }
 #pragma unroll
-        for (int c = 0; c < 18; c++) { L.Jp[c] = live ? L.Jp[c] * L.w : 0.0; jq[(size_t)c * ti.nt + (o - ti.o0)] = L.Jp[c]; }
+        for (int c = 0; c < JG; c++) { L.g[c] = live ? L.g[c] : 0.0; jq[(size_t)c * ti.nt + (o - ti.o0)] = L.g[c]; }
 #pragma unroll
         for (int c = 0; c < 9; c++) { L.Jl[c] = live ? L.Jl[c] * L.w : 0.0; P.Jl[(size_t)c * No + o] = L.Jl[c]; }
 #pragma unroll
         for (int c = 0; c < 3; c++) { L.e[c] = live ? L.e[c] * L.w : 0.0; P.r[(size_t)c * No + o] = L.e[c]; }
         if (slot >= 0 && live) {
+          double Jp[18];
+          jp_full(jp_compact(L.g, L.cam3[0], L.cam3[1], L.cam3[2], L.stereo), L.stereo, Jp);
 #pragma unroll
           for (int c = 0; c < 6; c++) {
-            atomicAdd(&P.bp[slot * 6 + c], -(L.Jp[c] * L.e[0] + L.Jp[6 + c] * L.e[1] + L.Jp[12 + c] * L.e[2]));
-            atomicAdd(&P.hd[slot * 6 + c], L.Jp[c] * L.Jp[c] + L.Jp[6 + c] * L.Jp[6 + c] + L.Jp[12 + c] * L.Jp[12 + c]);
+            atomicAdd(&P.bp[slot * 6 + c], -(Jp[c] * L.e[0] + Jp[6 + c] * L.e[1] + Jp[12 + c] * L.e[2]));
+            atomicAdd(&P.hd[slot * 6 + c], Jp[c] * Jp[c] + Jp[6 + c] * Jp[6 + c] + Jp[12 + c] * Jp[12 + c]);
           }
         }
       }
@@ -768,12 +785,23 @@ __device__ __forceinline__ void load9(const double* planes, size_t stride, size_
   for (int c = 0; c < 9; c++) a[c] = planes[(size_t)c * stride + o];
 }
 
-// one observation's pose-side contributions for the trial: reduced rhs (6) and block-Jacobi block (21, upper tri)
-__device__ __forceinline__ void trial_contrib(const double* __restrict__ jq, int nt, int col, const double Q[9],
-                                              const double rr[3], const double tl[3], double out[27]) {
-  double J[18];
+// this observation's weighted 3x6 pose block, rebuilt from the geometry rows of its JQ column (`slot` = global free slot)
+__device__ __forceinline__ void load_Jp(const Dev& P, const double* __restrict__ jq, int nt, int col, int slot, bool stereo,
+                                        double J[18]) {
+  double g[JG];
 #pragma unroll
-  for (int c = 0; c < 18; c++) J[c] = jq[(size_t)c * nt + col];
+  for (int c = 0; c < JG; c++) g[c] = __ldg(jq + (size_t)c * nt + col);
+  const double* cam = P.slot_cam + (size_t)slot * 3;
+  jp_full(jp_compact(g, __ldg(cam), __ldg(cam + 1), __ldg(cam + 2), stereo), stereo, J);
+}
+// global free slot of an observation from its meta word (window-relative slot in the low 16 bits when smallwin)
+__device__ __forceinline__ int slot_of(const Dev& P, unsigned lp, int sbase, int o) {
+  return P.smallwin ? sbase + (int)(lp & 0xffffu) : P.obs_slot[o];
+}
+
+// one observation's pose-side contributions for the trial: reduced rhs (6) and block-Jacobi block (21, upper tri)
+__device__ __forceinline__ void trial_contrib(const double J[18], const double Q[9],
+                                              const double rr[3], const double tl[3], double out[27]) {
   double u[3];
 #pragma unroll
   for (int r = 0; r < 3; r++) u[r] = rr[r] - (Q[r * 3] * tl[0] + Q[r * 3 + 1] * tl[1] + Q[r * 3 + 2] * tl[2]);
@@ -796,11 +824,8 @@ __device__ __forceinline__ void trial_contrib(const double* __restrict__ jq, int
 }
 
 // short-item variant of trial_contrib: the 27 values go straight into column `rank` of c_sh[27][SCST]
-__device__ __forceinline__ void trial_contrib_sh(const double* __restrict__ jq, int nt, int col, const double Q[9],
-                                                 const double rr[3], const double tl[3], double* c_sh, int rank) {
-  double J[18];
-#pragma unroll
-  for (int c = 0; c < 18; c++) J[c] = jq[(size_t)c * nt + col];
+__device__ __forceinline__ void trial_contrib_regs(const double J[18], const double Q[9], const double rr[3],
+                                                   const double tl[3], double* c_sh, int rank) {
   {
     double u[3];
 #pragma unroll
@@ -827,8 +852,8 @@ __device__ __forceinline__ void trial_contrib_sh(const double* __restrict__ jq, 
 // ---- the two item shapes of the landmark QR, shared by the plain and the pipelined kernel
 // short item: operands of this lane's observation are already in registers (a = its rows of J_l, rr = its residual)
 __device__ __forceinline__ void qr_short_item(const Dev& P, const TileInfo& ti, int wid, int lane, bool act, int o, int lm,
-                                              bool has, int rank, const double a[9], const double rr[3], double lam,
-                                              double* c_sh) {
+                                              bool has, int rank, int slot, bool stereo, const double a[9],
+                                              const double rr[3], double lam, double* c_sh) {
   const double sl = sqrt(lam);
   const int Nl = P.n_point, nt = ti.nt;
   const bool on = true;
@@ -877,7 +902,7 @@ __device__ __forceinline__ void qr_short_item(const Dev& P, const TileInfo& ti, 
       if (act) {
         if (has) {
 #pragma unroll
-          for (int c = 0; c < 9; c++) jq[(size_t)(18 + c) * nt + fcol] = Q[c];
+          for (int c = 0; c < 9; c++) jq[(size_t)(JG + c) * nt + fcol] = Q[c];
         }
         if (lane == sg.start) {
 #pragma unroll
@@ -885,34 +910,12 @@ __device__ __forceinline__ void qr_short_item(const Dev& P, const TileInfo& ti, 
 #pragma unroll
           for (int c = 0; c < 3; c++) P.tl[(size_t)c * Nl + lm] = tl[c];
         }
-        if (has) trial_contrib_sh(jq, nt, fcol, Q, rr, tl, c_sh, rank);
+        if (has) {
+          double J[18];
+          load_Jp(P, jq, nt, fcol, slot, stereo, J);
+          trial_contrib_regs(J, Q, rr, tl, c_sh, rank);
+        }
       }
-    }
-}
-
-// trial_contrib_sh with the observation's Jp rows already in registers (loaded early, see qr_short_item_v2)
-__device__ __forceinline__ void trial_contrib_regs(const double J[18], const double Q[9], const double rr[3],
-                                                   const double tl[3], double* c_sh, int rank) {
-  {
-    double u[3];
-#pragma unroll
-    for (int r = 0; r < 3; r++) u[r] = rr[r] - (Q[r * 3] * tl[0] + Q[r * 3 + 1] * tl[1] + Q[r * 3 + 2] * tl[2]);
-#pragma unroll
-    for (int c = 0; c < 6; c++) c_sh[c * SCST + rank] = -(J[c] * u[0] + J[6 + c] * u[1] + J[12 + c] * u[2]);
-  }
-  double G[18];  // Jp^T Q1 (6x3)
-#pragma unroll
-  for (int c = 0; c < 6; c++)
-#pragma unroll
-    for (int k = 0; k < 3; k++) G[c * 3 + k] = J[c] * Q[k] + J[6 + c] * Q[3 + k] + J[12 + c] * Q[6 + k];
-  int idx = 6;
-#pragma unroll
-  for (int a = 0; a < 6; a++)
-#pragma unroll
-    for (int b = a; b < 6; b++) {
-      c_sh[idx * SCST + rank] = J[a] * J[b] + J[6 + a] * J[6 + b] + J[12 + a] * J[12 + b] -
-                                (G[a * 3] * G[b * 3] + G[a * 3 + 1] * G[b * 3 + 1] + G[a * 3 + 2] * G[b * 3 + 2]);
-      idx++;
     }
 }
 
@@ -926,8 +929,8 @@ __device__ __forceinline__ void trial_contrib_regs(const double J[18], const dou
 //    writes rows 18-26 of the block), so their L2 latency is covered by the remaining two reduction groups.
 template <int JPOS>  // where the Jp rows are requested: 0 = right before they are used, 1 = after reduction group 1, 2 = after group 2
 __device__ __forceinline__ void qr_short_item_v2(const Dev& P, const TileInfo& ti, int wid, int lane, bool act, int lm,
-                                                 bool has, int rank, const double a[9], const double rr[3], double lam,
-                                                 double* c_sh) {
+                                                 bool has, int rank, int slot, bool stereo, const double a[9],
+                                                 const double rr[3], double lam, double* c_sh) {
   const double sl = sqrt(lam);
   const int Nl = P.n_point, nt = ti.nt;
   double* __restrict__ jq = P.JQ + ti.jq_off;
@@ -944,9 +947,7 @@ __device__ __forceinline__ void qr_short_item_v2(const Dev& P, const TileInfo& t
   double J[18];
   auto load_J = [&]() {
     if (act && has) {
-      const double* __restrict__ jr = jq + fcol;
-#pragma unroll
-      for (int c = 0; c < 18; c++) J[c] = __ldg(jr + (size_t)c * nt);
+      load_Jp(P, jq, nt, fcol, slot, stereo, J);
     } else {
 #pragma unroll
       for (int c = 0; c < 18; c++) J[c] = 0.0;
@@ -994,7 +995,7 @@ __device__ __forceinline__ void qr_short_item_v2(const Dev& P, const TileInfo& t
   if (act) {
     if (has) {
 #pragma unroll
-      for (int c = 0; c < 9; c++) jq[(size_t)(18 + c) * nt + fcol] = Q[c];
+      for (int c = 0; c < 9; c++) jq[(size_t)(JG + c) * nt + fcol] = Q[c];
     }
     if (lane == sg.start) {
 #pragma unroll
@@ -1059,7 +1060,7 @@ __device__ __forceinline__ void qr_long_item(const Dev& P, const TileInfo& ti, i
       v_rows(a, F, V);
       q1_rows(V, F, Q);
 #pragma unroll
-      for (int c = 0; c < 9; c++) jq[(size_t)(18 + c) * nt + (o - ti.o0)] = Q[c];
+      for (int c = 0; c < 9; c++) jq[(size_t)(JG + c) * nt + (o - ti.o0)] = Q[c];
 #pragma unroll
       for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
 #pragma unroll
@@ -1078,10 +1079,12 @@ __device__ __forceinline__ void qr_long_item(const Dev& P, const TileInfo& ti, i
       const int o = start + i;
       const int slot = P.obs_slot[o];
       if (slot < 0) continue;
-      load9(jq + (size_t)18 * nt, nt, o - ti.o0, Q);  // written by this same lane above
+      load9(jq + (size_t)JG * nt, nt, o - ti.o0, Q);  // written by this same lane above
 #pragma unroll
       for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
-      trial_contrib(jq, nt, o - ti.o0, Q, rr, tl, lc);
+      double J[18];
+      load_Jp(P, jq, nt, o - ti.o0, slot, (P.obs_lp[o] & LP_STEREO) != 0, J);
+      trial_contrib(J, Q, rr, tl, lc);
 #pragma unroll
       for (int c = 0; c < 6; c++) atomicAdd(&P.bs[slot * 6 + c], lc[c]);
 #pragma unroll
@@ -1103,12 +1106,12 @@ __global__ void __launch_bounds__(CTA, 4) k_qr(Dev P, int force_all, double lam_
   const size_t No = (size_t)P.ld;
   double* __restrict__ jq = P.JQ + ti.jq_off;
   // the 18 Jp rows are only needed after the factorisation: start pulling them into L2 now (one TMA prefetch per CTA)
-  if (threadIdx.x == 0 && !ti.is_long) bulk_prefetch_l2(jq, (uint32_t)(18 * ti.nt * sizeof(double)));
+  if (threadIdx.x == 0 && !ti.is_long) bulk_prefetch_l2(jq, (uint32_t)(JG * ti.nt * sizeof(double)));
   if (valid && cnt <= 32) {
     const bool act = lane < cnt;
     const int o = start + (act ? lane : 0);
-    int lm = -1 - lane, rank = 0;
-    bool has = false;
+    int lm = -1 - lane, rank = 0, slot = 0;
+    bool has = false, stereo = false;
     double a[9], rr[3];
     if (act) {  // every load of this phase is issued before the first use
       const unsigned lp = P.obs_lp[o];
@@ -1117,13 +1120,15 @@ __global__ void __launch_bounds__(CTA, 4) k_qr(Dev P, int force_all, double lam_
 #pragma unroll
       for (int c = 0; c < 3; c++) rr[c] = P.r[(size_t)c * No + o];
       has = (lp & 0xffffu) != 0xffffu;
-      rank = (int)(lp >> 16);
+      rank = (int)((lp >> 16) & 0x7fffu);
+      stereo = (lp & LP_STEREO) != 0;
+      if (has) slot = slot_of(P, lp, P.smallwin ? P.win_slot_ptr[win] : 0, o);
     } else {
 #pragma unroll
       for (int c = 0; c < 9; c++) a[c] = 0.0;
       rr[0] = rr[1] = rr[2] = 0.0;
     }
-    qr_short_item(P, ti, wid, lane, act, o, lm, has, rank, a, rr, lam, c_sh);
+    qr_short_item(P, ti, wid, lane, act, o, lm, has, rank, slot, stereo, a, rr, lam, c_sh);
   } else if (valid) {
     qr_long_item(P, ti, lane, start, cnt, lam);
   }
@@ -1207,8 +1212,8 @@ __global__ void __launch_bounds__(CTA, 4) k_qr_pipe(Dev P, int force_all, double
     if (valid && cnt <= 32) {
       const bool act = lane < cnt;
       const int o = start + (act ? lane : 0);
-      int lm = -1 - lane, rank = 0;
-      bool has = false;
+      int lm = -1 - lane, rank = 0, slot = 0;
+      bool has = false, stereo = false;
       double a[9], rr[3];
       if (act) {
         const unsigned lp = lp_sh[buf][tid];
@@ -1218,13 +1223,15 @@ __global__ void __launch_bounds__(CTA, 4) k_qr_pipe(Dev P, int force_all, double
 #pragma unroll
         for (int c = 0; c < 3; c++) rr[c] = op_sh[buf][9 + c][tid];
         has = (lp & 0xffffu) != 0xffffu;
-        rank = (int)(lp >> 16);
+        rank = (int)((lp >> 16) & 0x7fffu);
+        stereo = (lp & LP_STEREO) != 0;
+        if (has) slot = slot_of(P, lp, P.smallwin ? P.win_slot_ptr[ti.win] : 0, o);
       } else {
 #pragma unroll
         for (int c = 0; c < 9; c++) a[c] = 0.0;
         rr[0] = rr[1] = rr[2] = 0.0;
       }
-      qr_short_item(P, ti, wid, lane, act, o, lm, has, rank, a, rr, lam, c_sh);
+      qr_short_item(P, ti, wid, lane, act, o, lm, has, rank, slot, stereo, a, rr, lam, c_sh);
     } else if (valid) {
       qr_long_item(P, ti, lane, start, cnt, lam);
     }
@@ -1273,7 +1280,7 @@ __global__ void __launch_bounds__(CTA, MINB) k_qr_pipe2(Dev P, int force_all, do
     }
     const int* runs = reinterpret_cast<const int*>(P.JQ + ti.jq_off + (size_t)JQ_ROWS * ti.nt);
     for (int i = tid; i < 2 * ti.nrun + 1; i += CTA) cp_async4(&run_sh[rb][i], runs + i);
-    if (tid == 0) bulk_prefetch_l2(P.JQ + ti.jq_off, (uint32_t)(18 * ti.nt * sizeof(double)));
+    if (tid == 0) bulk_prefetch_l2(P.JQ + ti.jq_off, (uint32_t)(JG * ti.nt * sizeof(double)));
   };
   if (tid < 5) {
     cp_async16(reinterpret_cast<char*>(&ti_sh[0]) + tid * 16, reinterpret_cast<const char*>(P.tiles + t0) + tid * 16);
@@ -1299,17 +1306,19 @@ __global__ void __launch_bounds__(CTA, MINB) k_qr_pipe2(Dev P, int force_all, do
     const bool is_short = valid && cnt <= 32;
     const bool act = is_short && lane < cnt;
     int lm = -1 - lane, rank = 0;
+    unsigned lpw = 0xffffu;
     bool has = false;
     double a[9], rr[3];
     if (act) {  // this lane's operands, copied by itself one tile ago
       const unsigned lp = lp_sh[tid];
+      lpw = lp;
       lm = lm_sh[tid];
 #pragma unroll
       for (int c = 0; c < 9; c++) a[c] = op_sh[c][tid];
 #pragma unroll
       for (int c = 0; c < 3; c++) rr[c] = op_sh[9 + c][tid];
       has = (lp & 0xffffu) != 0xffffu;
-      rank = (int)(lp >> 16);
+      rank = (int)((lp >> 16) & 0x7fffu);
     } else {
 #pragma unroll
       for (int c = 0; c < 9; c++) a[c] = 0.0;
@@ -1327,7 +1336,8 @@ __global__ void __launch_bounds__(CTA, MINB) k_qr_pipe2(Dev P, int force_all, do
     if (phase != PH_TRIAL) continue;  // CTA-uniform: the tile's window is not in a trial
     const int sbase = P.smallwin ? P.win_slot_ptr[ti.win] : 0;  // for the reduction below: requested before the factorisation
     if (is_short) {
-      qr_short_item_v2<JPOS>(P, ti, wid, lane, act, lm, has, rank, a, rr, lam, c_sh);
+      const int slot = has ? slot_of(P, lpw, sbase, start + lane) : 0;
+      qr_short_item_v2<JPOS>(P, ti, wid, lane, act, lm, has, rank, slot, (lpw & LP_STEREO) != 0, a, rr, lam, c_sh);
     } else if (valid) {
       qr_long_item(P, ti, lane, start, cnt, lam);
     }
@@ -1388,13 +1398,12 @@ __device__ __forceinline__ double peff_at(const PEff& pe, size_t e) {
 // PSRC: where p lives -- 0 global (slot-major), 1 global read through L2 (rewritten by other CTAs during the kernel),
 // 2 shared memory, component-major with stride `pstride`, 3 evaluated on the fly from a PEff
 template <int PSRC = 0>
-__device__ __forceinline__ void matvec_obs_v(const double* __restrict__ jq, int nt, int col,
-                                             const double* pvec, int slot, double J[18], double Q[9],
+__device__ __forceinline__ void matvec_obs_v(const Dev& P, const double* __restrict__ jq, int nt, int col,
+                                             const double* pvec, int slot, bool stereo, double J[18], double Q[9],
                                              double v[3], int pstride = 0, const PEff* pe = nullptr) {
+  load_Jp(P, jq, nt, col, slot, stereo, J);
 #pragma unroll
-  for (int c = 0; c < 18; c++) J[c] = jq[(size_t)c * nt + col];
-#pragma unroll
-  for (int c = 0; c < 9; c++) Q[c] = jq[(size_t)(18 + c) * nt + col];
+  for (int c = 0; c < 9; c++) Q[c] = jq[(size_t)(JG + c) * nt + col];
   double pp[6];
 #pragma unroll
   for (int c = 0; c < 6; c++)
@@ -1416,7 +1425,7 @@ __device__ __forceinline__ void matvec_long_item(const Dev& P, const double* __r
     const int o = start + i;
     const int slot = P.obs_slot[o];
     if (slot < 0) continue;
-    matvec_obs_v<PSRC>(jq, nt, i, pvec, slot, J, Q, v, pstride, pe);  // a long item is a tile of its own: column = i
+    matvec_obs_v<PSRC>(P, jq, nt, i, pvec, slot, (P.obs_lp[o] & LP_STEREO) != 0, J, Q, v, pstride, pe);  // a long item is a tile of its own: column = i
 #pragma unroll
     for (int k = 0; k < 3; k++) sv[k] += Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2];
   }
@@ -1426,7 +1435,7 @@ __device__ __forceinline__ void matvec_long_item(const Dev& P, const double* __r
     const int o = start + i;
     const int slot = P.obs_slot[o];
     if (slot < 0) continue;
-    matvec_obs_v<PSRC>(jq, nt, i, pvec, slot, J, Q, v, pstride, pe);
+    matvec_obs_v<PSRC>(P, jq, nt, i, pvec, slot, (P.obs_lp[o] & LP_STEREO) != 0, J, Q, v, pstride, pe);
 #pragma unroll
     for (int r = 0; r < 3; r++) v[r] -= Q[r * 3] * sv[0] + Q[r * 3 + 1] * sv[1] + Q[r * 3 + 2] * sv[2];
 #pragma unroll
@@ -1477,10 +1486,12 @@ __global__ void __launch_bounds__(CTA) k_matvec(Dev P, const double* __restrict_
     const bool act = lane < cnt;
     const int o = start + (act ? lane : 0);
     int lm = -1 - lane;
+    bool stereo = false;
     if (act) {
       const unsigned lp = P.obs_lp[o];
       has = (lp & 0xffffu) != 0xffffu;
-      rank = (int)(lp >> 16);
+      rank = (int)((lp >> 16) & 0x7fffu);
+      stereo = (lp & LP_STEREO) != 0;
       key = P.obs_slot[o];
       lm = P.obs_point[o];
     }
@@ -1489,10 +1500,9 @@ __global__ void __launch_bounds__(CTA) k_matvec(Dev P, const double* __restrict_
     double J[18], Q[9], pp[6];
     if (has) {
       const int col = fcol;
+      load_Jp(P, jq, nt, col, key, stereo, J);
 #pragma unroll
-      for (int c = 0; c < 18; c++) J[c] = jq[(size_t)c * nt + col];
-#pragma unroll
-      for (int c = 0; c < 9; c++) Q[c] = jq[(size_t)(18 + c) * nt + col];
+      for (int c = 0; c < 9; c++) Q[c] = jq[(size_t)(JG + c) * nt + col];
 #pragma unroll
       for (int c = 0; c < 6; c++) pp[c] = pvec[(size_t)key * 6 + c];
     }
@@ -1571,7 +1581,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 constexpr int PIPE_THREADS = CTA + 32;
 constexpr int JQ_STAGE_D = JQ_HDR + JQ_ROWS * CTA + (2 * CTA + 4) / 2;
 template <int S, bool BIG>
-__global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__ pvec,
+__global__ void __maxnreg__(96) k_matvec_pipe(Dev P, const double* __restrict__ pvec,
                                                                double* __restrict__ qvec, int force_all, int maxslot) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int STAGE_D = JQ_STAGE_D;  // doubles per stage: header + 28 rows + run table of a full tile
@@ -1580,7 +1590,8 @@ __global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__
   double* c_sh = stage + (size_t)S * STAGE_D;  // two buffers of [6][CST]
   double* p_sh = c_sh + 2 * (6 * CST) + 2;      // component-major: p_sh[c * maxslot + slot]  (unused when BIG)
   double* acc_sh = p_sh + (BIG ? 0 : 6 * maxslot);
-  int* runs_sh = reinterpret_cast<int*>(acc_sh + 6 * maxslot);  // two buffers of 2*CTA+4 ints
+  double* cam_sh = acc_sh + 6 * maxslot;                         // !BIG: fx, fy, bf of the window's slots [c * maxslot + slot]
+  int* runs_sh = reinterpret_cast<int*>(cam_sh + (BIG ? 0 : 3 * maxslot));  // two buffers of 2*CTA+4 ints
   uint64_t* full = reinterpret_cast<uint64_t*>(runs_sh + 2 * (2 * CTA + 4));
   uint64_t* empty = full + S;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1670,6 +1681,10 @@ __global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__
         const int sl = i / 6;
         p_sh[(i - sl * 6) * maxslot + sl] = pvec[(size_t)ws0 * 6 + i];
       }
+      for (int i = tid; i < wn * 3; i += CTA) {
+        const int sl = i / 3;
+        cam_sh[(i - sl * 3) * maxslot + sl] = __ldg(P.slot_cam + (size_t)ws0 * 3 + i);
+      }
       named_bar_sync(1, CTA);
     }
     const int nt = hdr[5];
@@ -1696,37 +1711,41 @@ __global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__
       const bool act = lane < cnt;
       const int col = col0 + (act ? lane : 0);
       int lm = -1 - lane, rank = 0, ls = 0;
-      bool has = false;
+      bool has = false, stereo = false;
       if (act) {
         const uint2 m = meta[col];
         ls = (int)(m.x & 0xffffu);
         has = ls != 0xffff;
-        rank = (int)(m.x >> 16);
+        rank = (int)((m.x >> 16) & 0x7fffu);
+        stereo = (m.x & LP_STEREO) != 0;
         lm = (int)m.y;
       }
       const Seg sg = seg_of(lm, lane);
       const double* dcol = data + col;
-      double J[18], v[3] = {0, 0, 0}, t[3] = {0, 0, 0};
+      double v[3] = {0, 0, 0}, t[3] = {0, 0, 0};
+      JpC Jc;
       if (has) {
-        double pp[6];
+        double pp[6], g[JG], cm[3];
         if (BIG) {
           const double* pg = pvec + (size_t)(ws0 + ls) * 6;
 #pragma unroll
           for (int c = 0; c < 6; c++) pp[c] = __ldg(pg + c);
+#pragma unroll
+          for (int c = 0; c < 3; c++) cm[c] = __ldg(P.slot_cam + (size_t)(ws0 + ls) * 3 + c);
         } else {
 #pragma unroll
           for (int c = 0; c < 6; c++) pp[c] = p_sh[c * maxslot + ls];
+#pragma unroll
+          for (int c = 0; c < 3; c++) cm[c] = cam_sh[c * maxslot + ls];
         }
 #pragma unroll
-        for (int c = 0; c < 18; c++) J[c] = dcol[c * nt];
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-          v[r] = J[r * 6] * pp[0] + J[r * 6 + 1] * pp[1] + J[r * 6 + 2] * pp[2] + J[r * 6 + 3] * pp[3] +
-                 J[r * 6 + 4] * pp[4] + J[r * 6 + 5] * pp[5];
+        for (int c = 0; c < JG; c++) g[c] = dcol[c * nt];
+        Jc = jp_compact(g, cm[0], cm[1], cm[2], stereo);  // the weighted 3x6 pose block, 13 distinct entries
+        jp_mul(Jc, stereo, pp, v);
 #pragma unroll
         for (int r = 0; r < 3; r++) {
 #pragma unroll
-          for (int k = 0; k < 3; k++) t[k] += dcol[(18 + r * 3 + k) * nt] * v[r];
+          for (int k = 0; k < 3; k++) t[k] += dcol[(JG + r * 3 + k) * nt] * v[r];
         }
       }
       double sv[3];
@@ -1736,9 +1755,11 @@ __global__ void __maxnreg__(120) k_matvec_pipe(Dev P, const double* __restrict__
         // Q1 rows are re-read from the stage instead of being kept live across the shuffles (register pressure)
 #pragma unroll
         for (int r = 0; r < 3; r++)
-          v[r] -= dcol[(18 + r * 3) * nt] * sv[0] + dcol[(19 + r * 3) * nt] * sv[1] + dcol[(20 + r * 3) * nt] * sv[2];
+          v[r] -= dcol[(JG + r * 3) * nt] * sv[0] + dcol[(JG + 1 + r * 3) * nt] * sv[1] + dcol[(JG + 2 + r * 3) * nt] * sv[2];
+        double out[6];
+        jp_mulT(Jc, stereo, v, out);
 #pragma unroll
-        for (int c = 0; c < 6; c++) cb[c * CST + rank] = J[c] * v[0] + J[6 + c] * v[1] + J[12 + c] * v[2];
+        for (int c = 0; c < 6; c++) cb[c * CST + rank] = out[c];
       }
     }
     PROF_MARK(1)
@@ -1912,7 +1933,7 @@ __device__ __forceinline__ double cta_sum(double v, double* red_sh, int which, i
 // (+25 % per tile) but 36 registers lighter; used by the multi-GPU instantiation, whose exchange code otherwise pushes
 // ptxas into spilling those rows inside the loop (+80 % per tile).
 template <bool BIG, bool REREAD = false>
-__device__ __forceinline__ void tile_products(const double* data, const int* hdr, int nt, int wid, int lane,
+__device__ __forceinline__ void tile_products(const Dev& P, const double* data, const int* hdr, int nt, int wid, int lane,
                                               const double* p_sh, int maxslot, const PEff& pe, int abase, double* cb) {
   constexpr int CST = CTA + 1;
   const uint2* meta = reinterpret_cast<const uint2*>(data + (size_t)NPLANE * nt);
@@ -1921,19 +1942,21 @@ __device__ __forceinline__ void tile_products(const double* data, const int* hdr
   const bool act = lane < cnt;
   const int col = col0 + (act ? lane : 0);
   int lm = -1 - lane, rank = 0, ls = 0;
-  bool has = false;
+  bool has = false, stereo = false;
   if (act) {
     const uint2 m = meta[col];
     ls = (int)(m.x & 0xffffu);
     has = ls != 0xffff;
-    rank = (int)(m.x >> 16);
+    rank = (int)((m.x >> 16) & 0x7fffu);
+    stereo = (m.x & LP_STEREO) != 0;
     lm = (int)m.y;
   }
   const Seg sg = seg_of(lm, lane);
   const double* dcol = data + col;
-  double J[18], v[3] = {0, 0, 0}, t[3] = {0, 0, 0};
+  double v[3] = {0, 0, 0}, t[3] = {0, 0, 0};
+  JpC Jc;
   if (has) {
-    double pp[6];
+    double pp[6], g[JG], cm[3];
     const int rel = BIG ? ls - abase : ls;
     if (!BIG || (unsigned)rel < (unsigned)maxslot) {  // BIG: inside the CTA's window of the search direction
 #pragma unroll
@@ -1942,16 +1965,17 @@ __device__ __forceinline__ void tile_products(const double* data, const int* hdr
 #pragma unroll
       for (int cc = 0; cc < 6; cc++) pp[cc] = peff_at(pe, (size_t)ls * 6 + cc);
     }
+    // one window per problem here: the window-relative slot is the global one (intrinsics: three L1-resident doubles)
 #pragma unroll
-    for (int cc = 0; cc < 18; cc++) J[cc] = dcol[cc * nt];
+    for (int cc = 0; cc < 3; cc++) cm[cc] = __ldg(P.slot_cam + (size_t)ls * 3 + cc);
 #pragma unroll
-    for (int r = 0; r < 3; r++)
-      v[r] = J[r * 6] * pp[0] + J[r * 6 + 1] * pp[1] + J[r * 6 + 2] * pp[2] + J[r * 6 + 3] * pp[3] +
-             J[r * 6 + 4] * pp[4] + J[r * 6 + 5] * pp[5];
+    for (int cc = 0; cc < JG; cc++) g[cc] = dcol[cc * nt];
+    Jc = jp_compact(g, cm[0], cm[1], cm[2], stereo);
+    jp_mul(Jc, stereo, pp, v);
 #pragma unroll
     for (int r = 0; r < 3; r++) {
 #pragma unroll
-      for (int k = 0; k < 3; k++) t[k] += dcol[(18 + r * 3 + k) * nt] * v[r];
+      for (int k = 0; k < 3; k++) t[k] += dcol[(JG + r * 3 + k) * nt] * v[r];
     }
   }
   double sv[3];
@@ -1960,15 +1984,11 @@ __device__ __forceinline__ void tile_products(const double* data, const int* hdr
   if (has) {
 #pragma unroll
     for (int r = 0; r < 3; r++)
-      v[r] -= dcol[(18 + r * 3) * nt] * sv[0] + dcol[(19 + r * 3) * nt] * sv[1] + dcol[(20 + r * 3) * nt] * sv[2];
-    if (REREAD) {
+      v[r] -= dcol[(JG + r * 3) * nt] * sv[0] + dcol[(JG + 1 + r * 3) * nt] * sv[1] + dcol[(JG + 2 + r * 3) * nt] * sv[2];
+    double out[6];
+    jp_mulT(Jc, stereo, v, out);
 #pragma unroll
-      for (int cc = 0; cc < 6; cc++)
-        cb[cc * CST + rank] = dcol[cc * nt] * v[0] + dcol[(6 + cc) * nt] * v[1] + dcol[(12 + cc) * nt] * v[2];
-    } else {
-#pragma unroll
-      for (int cc = 0; cc < 6; cc++) cb[cc * CST + rank] = J[cc] * v[0] + J[6 + cc] * v[1] + J[12 + cc] * v[2];
-    }
+    for (int cc = 0; cc < 6; cc++) cb[cc * CST + rank] = out[cc];
   }
 }
 
@@ -2120,7 +2140,7 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
         const int* rsrc = reinterpret_cast<const int*>(data + (size_t)JQ_ROWS * nt);
         for (int i = tid; i < 2 * nrun + 1; i += CTA) rb[i] = rsrc[i];
       }
-      if (wid < nitem) tile_products<BIG, MULTI && PERSIST_REREAD>(data, hdr, nt, wid, lane, p_sh, maxslot, pe, abase, cb);
+      if (wid < nitem) tile_products<BIG, MULTI && PERSIST_REREAD>(P, data, hdr, nt, wid, lane, p_sh, maxslot, pe, abase, cb);
       named_bar_sync(1, CTA);
       if (tid == 0) mbar_arrive(&empty[s]);
       for (int idx = tid; idx < nrun * 6; idx += CTA) {
@@ -2534,7 +2554,7 @@ __global__ void __launch_bounds__(CTA) k_backsub(Dev P, int force_all, double la
     double t[3] = {0, 0, 0};
     const int fcol = is_long ? i : tile_fcol(ti, wid, slot >= 0, lane);  // long tiles keep a column per observation
     if (slot >= 0) {
-      matvec_obs_v(jq, ti.nt, fcol, P.x, slot, J, Q, v);
+      matvec_obs_v(P, jq, ti.nt, fcol, P.x, slot, (P.obs_lp[o] & LP_STEREO) != 0, J, Q, v);
 #pragma unroll
       for (int k = 0; k < 3; k++) t[k] = Q[k] * v[0] + Q[3 + k] * v[1] + Q[6 + k] * v[2];
     }

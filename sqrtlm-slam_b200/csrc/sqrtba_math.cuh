@@ -109,6 +109,73 @@ SQ_HD void reproj_jacobians(const double R[9], const double Xc[3], const double 
   }
 }
 
+// ---- the pose Jacobian as a function of four numbers per observation ------------------------------------------------
+// The weighted 3x6 pose block of an edge depends on the camera-frame point only through x/z, y/z and 1/z (and on the
+// keyframe's fx, fy, bf): 13 distinct non-zero entries out of 18.  The PCG operand therefore stores
+//   g = { x/z, y/z, 1/z, w }      (w = sqrt(rho1 * invSigma2); an excluded edge stores four zeros)
+// per observation -- 32 bytes instead of 144 -- and every kernel that needs the block rebuilds it in registers with the
+// SAME function, so the gradient, the block-Jacobi blocks, the reduced right-hand side and the matvec all see identical
+// values.  (types_six_dof_expmap.cpp:126-138, 188-234 written in these variables.)
+struct JpC {  // the 13 distinct entries, named by their position in the 3x6 row-major block
+  double j0, j1, j2, j3, j5, j6, j7, j8, j10, j11, j12, j13, j17;
+};
+SQ_HD JpC jp_compact(const double g[4], double fx, double fy, double bf, bool stereo) {
+  const double a = g[0], b = g[1], iz = g[2], w = g[3];
+  const double fxw = fx * w, fyw = fy * w;
+  JpC J;
+  J.j0 = a * b * fxw;
+  J.j1 = -(1.0 + a * a) * fxw;
+  J.j2 = b * fxw;
+  J.j3 = -iz * fxw;
+  J.j5 = a * iz * fxw;
+  J.j6 = (1.0 + b * b) * fyw;
+  J.j7 = -a * b * fyw;
+  J.j8 = -a * fyw;
+  J.j10 = -iz * fyw;
+  J.j11 = b * iz * fyw;
+  const double bw = stereo ? bf * w * iz : 0.0;
+  J.j12 = stereo ? J.j0 - bw * b : 0.0;
+  J.j13 = stereo ? J.j1 + bw * a : 0.0;
+  J.j17 = stereo ? J.j5 - bw * iz : 0.0;
+  return J;
+}
+// v = Jp * p (6-vector); the third row is zero for a monocular edge
+SQ_HD void jp_mul(const JpC& J, bool stereo, const double p[6], double v[3]) {
+  v[0] = J.j0 * p[0] + J.j1 * p[1] + J.j2 * p[2] + J.j3 * p[3] + J.j5 * p[5];
+  v[1] = J.j6 * p[0] + J.j7 * p[1] + J.j8 * p[2] + J.j10 * p[4] + J.j11 * p[5];
+  v[2] = stereo ? (J.j12 * p[0] + J.j13 * p[1] + J.j2 * p[2] + J.j3 * p[3] + J.j17 * p[5]) : 0.0;
+}
+// out = Jp^T * u
+SQ_HD void jp_mulT(const JpC& J, bool stereo, const double u[3], double out[6]) {
+  const double u02 = stereo ? u[0] + u[2] : u[0];
+  const double u2 = stereo ? u[2] : 0.0;
+  out[0] = J.j0 * u[0] + J.j6 * u[1] + J.j12 * u2;
+  out[1] = J.j1 * u[0] + J.j7 * u[1] + J.j13 * u2;
+  out[2] = J.j2 * u02 + J.j8 * u[1];
+  out[3] = J.j3 * u02;
+  out[4] = J.j10 * u[1];
+  out[5] = J.j5 * u[0] + J.j11 * u[1] + J.j17 * u2;
+}
+// the full 3x6 row-major block (the landmark QR's block-Jacobi products, debug read-back)
+SQ_HD void jp_full(const JpC& J, bool stereo, double Jp[18]) {
+  Jp[0] = J.j0; Jp[1] = J.j1; Jp[2] = J.j2; Jp[3] = J.j3; Jp[4] = 0.0; Jp[5] = J.j5;
+  Jp[6] = J.j6; Jp[7] = J.j7; Jp[8] = J.j8; Jp[9] = 0.0; Jp[10] = J.j10; Jp[11] = J.j11;
+  Jp[12] = J.j12; Jp[13] = J.j13; Jp[14] = stereo ? J.j2 : 0.0; Jp[15] = stereo ? J.j3 : 0.0; Jp[16] = 0.0; Jp[17] = J.j17;
+}
+// Jacobian wrt the world point only (3x3 row-major; third row zero for a monocular edge) -- the Jl half of
+// reproj_jacobians
+SQ_HD void reproj_jacobian_point(const double R[9], const double Xc[3], const double cam[5], bool stereo, double Jl[9]) {
+  const double x = Xc[0], y = Xc[1], z = Xc[2];
+  const double iz = 1.0 / z, iz2 = iz * iz;
+  const double fx = cam[0], fy = cam[1], bf = cam[4];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    Jl[c] = -fx * R[c] * iz + fx * x * R[6 + c] * iz2;
+    Jl[3 + c] = -fy * R[3 + c] * iz + fy * y * R[6 + c] * iz2;
+    Jl[6 + c] = stereo ? Jl[c] - bf * R[6 + c] * iz2 : 0.0;
+  }
+}
+
 // ---- SE3 left update  T <- exp(xi) * T, state stored as (tx,ty,tz,qx,qy,qz,qw) ---------------------
 
 SQ_HD void quat_mul(const double a[4], const double b[4], double c[4]) {  // (x,y,z,w)

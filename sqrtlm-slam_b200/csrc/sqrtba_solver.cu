@@ -346,6 +346,10 @@ class Solver {
       lm_count_new_ = lm_cnt;
       point_xyz = h_perm_xyz_.p; obs_pose = h_perm_pose_.p; obs_point = h_perm_point_.p; obs_meas = h_perm_meas_.p;
     }
+    // every observation's meta word starts as "takes no part in the in-CTA reduction" + the stereo bit (final order)
+    pool_.chunks(n_obs, 1 << 16, n_thr, [&](long long k0, long long k1) {
+      for (long long k = k0; k < k1; k++) obs_lp[k] = 0xffffu | (!(obs_meas[(size_t)k * 4 + 2] < 0.0f) ? LP_STEREO : 0u);
+    });
     lap("A2 landmark order");
     // The caller's big arrays (or their re-ordered copies) are final now: start their host-to-device copies so that they
     // overlap the remaining host-side preprocessing (truly asynchronous when the caller's buffers are pinned).
@@ -453,7 +457,7 @@ class Solver {
                 if (obs_slot[o] < 0) continue;
                 const int rank = cursor[local_of[obs_slot[o] - ws0]]++;
                 const unsigned low = smallwin ? (unsigned)(obs_slot[o] - ws0) : 0u;
-                obs_lp[o] = low | ((unsigned)rank << 16);
+                obs_lp[o] = low | ((unsigned)rank << 16) | (obs_lp[o] & LP_STEREO);
               }
               ti.nfree = lptr[nl];
               ti.nrun = nl;
@@ -543,6 +547,7 @@ class Solver {
     CU_CHECK(d_pose_slot_.ensure(n_pose));
     CU_CHECK(d_slot_pose_.ensure(Ns));
     CU_CHECK(d_slot_win_.ensure(Ns));
+    CU_CHECK(d_slot_cam_.ensure(Ns * 3));
     CU_CHECK(d_pose_win_.ensure(n_pose));
     CU_CHECK(d_point_win_.ensure(n_point));
     CU_CHECK(d_meas_.ensure(No));
@@ -588,6 +593,12 @@ class Solver {
       CU_CHECK(up(d_slot_pose_.p, slot_pose.data(), n_slot * sizeof(int)));
       CU_CHECK(up(d_slot_win_.p, slot_win.data(), n_slot * sizeof(int)));
     }
+    h_slot_cam_.assign((size_t)Ns * 3, 0.0);
+    for (int sl = 0; sl < n_slot; sl++) {  // fx, fy, bf of the keyframe in every free slot (jp_compact's intrinsics)
+      const double* c5 = cam + (size_t)slot_pose[sl] * 5;
+      h_slot_cam_[(size_t)sl * 3] = c5[0]; h_slot_cam_[(size_t)sl * 3 + 1] = c5[1]; h_slot_cam_[(size_t)sl * 3 + 2] = c5[4];
+    }
+    CU_CHECK(up(d_slot_cam_.p, h_slot_cam_.data(), h_slot_cam_.size() * sizeof(double)));
     CU_CHECK(up(d_pose_win_.p, pose_win.data(), n_pose * sizeof(int)));
     CU_CHECK(up(d_point_win_.p, point_win.data(), n_point * sizeof(int)));
     CU_CHECK(up(d_obs_slot_.p, h_obs_slot_.p, No * sizeof(int)));
@@ -611,6 +622,7 @@ class Solver {
     P_.obs_point = d_obs_point_.p; P_.obs_slot = d_obs_slot_.p; P_.item_start = d_item_start_.p;
     P_.item_cnt = d_item_cnt_.p; P_.item_win = d_item_win_.p; P_.win_item_ptr = d_win_item_ptr_.p;
     P_.win_slot_ptr = d_win_slot_ptr_.p;
+    P_.slot_cam = d_slot_cam_.p;
     P_.tiles = d_tiles_.p;
     P_.obs_lp = d_obs_lp_.p;
     P_.tile_run_ptr = d_tile_run_ptr_.p; P_.tile_runs = d_tile_runs_.p;
@@ -660,7 +672,9 @@ class Solver {
                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matvec_pipe<3, true>, PIPE_THREADS, bytes);
         if (e != cudaSuccess) per_sm = 0;
         if (cfg_.reserved[2] > 0 && S != cfg_.reserved[2]) continue;   // forced depth (profiling)
-        if (per_sm * S > best_ctas * pipe_stages_ || best_ctas == 0) { best_ctas = per_sm; pipe_stages_ = S; }
+        // With the 104-byte columns a tile is 14 KB and the kernel is bound by the per-tile dependency chain of a CTA
+        // (meta -> operands -> segmented sums -> run sums), not by bytes in flight: resident CTAs first, depth second
+        if (per_sm > best_ctas || (per_sm == best_ctas && S > pipe_stages_) || best_ctas == 0) { best_ctas = per_sm; pipe_stages_ = S; }
       }
       pipe_ctas_ = std::max(1, best_ctas) * n_sm_;
       // the persistent PCG kernel shares the ring configuration; its grid must be co-resident (cooperative launch)
@@ -1088,8 +1102,16 @@ class Solver {
         for (int o = ti.o0; o < ti.o1; o++) {
           const bool free_pose = h_obs_slot_.p[o] >= 0;
           const int col = ti.is_long ? (o - ti.o0) : fcol;
-          for (int c = 0; c < 18; c++)
-            d[(size_t)o * 18 + c] = (free_pose || ti.is_long) ? tmp[(size_t)ti.jq_off + (size_t)c * ti.nt + col] : 0.0;
+          double Jp[18];
+          for (int c = 0; c < 18; c++) Jp[c] = 0.0;
+          if (free_pose) {  // the block stores {x/z, y/z, 1/z, w}; the 3x6 Jacobian is rebuilt the way the kernels do
+            double g[JG];
+            for (int c = 0; c < JG; c++) g[c] = tmp[(size_t)ti.jq_off + (size_t)c * ti.nt + col];
+            const double* cm = &h_slot_cam_[(size_t)h_obs_slot_.p[o] * 3];
+            const bool stereo = (h_obs_lp_.p[o] & LP_STEREO) != 0;
+            jp_full(jp_compact(g, cm[0], cm[1], cm[2], stereo), stereo, Jp);
+          }
+          for (int c = 0; c < 18; c++) d[(size_t)o * 18 + c] = Jp[c];
           fcol += free_pose;
         }
       }
@@ -1331,7 +1353,7 @@ class Solver {
  private:
   // matvec dispatch: persistent TMA-pipelined kernel when every window is small, general tile kernel otherwise
   static size_t pipe_smem_bytes(int S, int maxslot, bool big) {
-    return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + (big ? 6 : 12) * (size_t)maxslot) * sizeof(double) +
+    return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + (big ? 6 : 15) * (size_t)maxslot) * sizeof(double) +
            2 * (2 * CTA + 4) * sizeof(int) + 2 * S * sizeof(uint64_t);
   }
   static size_t persist_smem_bytes(int S, int maxslot, bool big) {
@@ -1770,7 +1792,7 @@ class Solver {
   }
 
   void release_all() {
-    d_cam_.release(); d_pose_slot_.release(); d_slot_pose_.release(); d_slot_win_.release(); d_pose_win_.release();
+    d_cam_.release(); d_slot_cam_.release(); d_pose_slot_.release(); d_slot_pose_.release(); d_slot_win_.release(); d_pose_win_.release();
     d_point_win_.release(); d_meas_.release(); d_obs_pose_.release(); d_obs_point_.release(); d_obs_slot_.release();
     d_item_start_.release(); d_item_cnt_.release(); d_item_win_.release(); d_win_item_ptr_.release();
     d_win_slot_ptr_.release(); d_pose_.release(); d_pose0_.release(); d_pose_bak_.release(); d_point_.release();
@@ -1846,6 +1868,8 @@ class Solver {
   Dev P_{};
   DBuf<double> d_cam_, d_pose_, d_pose0_, d_pose_bak_, d_point_, d_point0_, d_point_bak_, d_err_, d_JQ_, d_Jl_,
       d_r_, d_R_, d_tl_, d_bl_, d_dl_, d_slotvec_, d_chi_part_, d_scale_part_, d_trace_, d_wred_;
+  DBuf<double> d_slot_cam_;
+  std::vector<double> h_slot_cam_;
   DBuf<int> d_pose_slot_, d_slot_pose_, d_slot_win_, d_pose_win_, d_point_win_, d_obs_pose_, d_obs_point_, d_obs_slot_,
       d_item_start_, d_item_cnt_, d_item_win_, d_win_item_ptr_, d_win_slot_ptr_, d_counters_, d_tile_run_ptr_,
       d_tile_runs_;

@@ -14,7 +14,7 @@ capi = importlib.import_module("sqrtlm-slam_b200.capi")
 synth = importlib.import_module("sqrtlm-slam_b200.synth")
 
 T = {k: i for i, k in enumerate(capi.TILE_COLS)}
-JQ_HDR, JQ_ROWS = 8, 28  # sqrtba_kernels.cuh
+JQ_HDR, JQ_ROWS = 8, 14  # sqrtba_kernels.cuh: 4 geometry rows {x/z, y/z, 1/z, w} + 9 rows of Q1 + the 8-byte meta entries
 
 
 def internal_order(prob, plan):
@@ -109,7 +109,7 @@ def check_plan(prob, plan, pose_ptr, obs_ptr):
         # meta words: low half = window-relative slot, high half = rank; ranks are a bijection onto [0, nfree) and
         # every rank falls inside the run of its slot
         lp = plan["obs_lp"][o0:o1][fr]
-        lo, rank = (lp & 0xFFFF).astype(np.int64), (lp >> 16).astype(np.int64)
+        lo, rank = (lp & 0xFFFF).astype(np.int64), ((lp >> 16) & 0x7FFF).astype(np.int64)   # bit 31: stereo edge
         assert np.array_equal(lo, oslot[o0:o1][fr])
         assert np.array_equal(np.sort(rank), np.arange(ti[T["nfree"]]))
         run_of_rank = np.searchsorted(roff, rank, side="right") - 1
