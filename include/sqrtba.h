@@ -217,6 +217,22 @@ int sqrtba_set_lidar_edges(sqrtba_handle* h, int32_t cur_pose, int32_t n_flat, i
 int sqrtba_get_lidar_matches(sqrtba_handle* h, int32_t* match_out);
 int sqrtba_num_lidar_edges(sqrtba_handle* h);
 
+/* ---- essential-graph (Sim3 pose-graph) optimisation: the loop-closing step before global BA ------
+ * Replaces the optimiser of g2oOptimizer::OptimizeEssentialGraph (include/backend/Optimizer.h:62-67,
+ * src/backend/g2oOptimizer.cc:1212-1460): VertexSim3Expmap vertices, EdgeSim3 edges (identity information, the numeric
+ * Jacobians that edge type inherits), Levenberg with setUserLambdaInit(lambda_init) and `iters` iterations (reference:
+ * 1e-16 and 20), exact sparse Cholesky per trial.  The adapter builds the graph from the map (spanning tree, loop
+ * edges, covisibility >= 100, new loop connections) and applies the result (g2oOptimizer.cc:1462-1520).
+ *   vert8    n_vert x 8, in/out: qx qy qz qw | tx ty tz | s  (g2o::Sim3 operator[] order), S_iw of every keyframe
+ *   fixed    n_vert: 1 = setFixed (the loop keyframe)     fix_scale: VertexSim3Expmap::_fix_scale (stereo / RGB-D)
+ *   edge_ij  n_edge x 2: vertex 0 = i, vertex 1 = j;  meas8 n_edge x 8: S_ji
+ * Vertices without an edge and fixed vertices are not moved.  Independent of sqrtba_set_problem.
+ * sqrtba_pose_graph_trace: LM trials of the LAST call, rows of 8 doubles (pass, iteration, trial, lambda, chi2 before,
+ * chi2 of the trial, rho, accepted); rows_out == NULL returns the number of rows. */
+int sqrtba_pose_graph(sqrtba_handle* h, int32_t n_vert, double* vert8, const uint8_t* fixed, int32_t fix_scale, int32_t n_edge,
+                      const int32_t* edge_ij, const double* meas8, int32_t iters, double lambda_init, sqrtba_stats* stats);
+int sqrtba_pose_graph_trace(sqrtba_handle* h, double* rows_out, int32_t max_rows);
+
 /* ---- stage-level entry points (kernel parity tests, profiling) --------------------------------------------
  * sqrtba_debug_linearize : run the fused residual+Jacobian+Huber kernel at the current state.
  *    huber: 0 none, 1 local-BA deltas, 2 global-BA deltas.  Outputs (any may be NULL):

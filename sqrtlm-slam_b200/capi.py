@@ -79,6 +79,8 @@ def lib():
         L.sqrtba_time_stage.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, dp]
         L.sqrtba_pose_opt.argtypes = [vp, C.c_int32, lp, dp, dp, dp, fp, up, ip, C.POINTER(Stats)]
         L.sqrtba_pose_opt_trace.argtypes = [vp, C.c_int32, dp, C.c_int32]
+        L.sqrtba_pose_graph.argtypes = [vp, C.c_int32, dp, up, C.c_int32, C.c_int32, ip, dp, C.c_int32, C.c_double, C.POINTER(Stats)]
+        L.sqrtba_pose_graph_trace.argtypes = [vp, dp, C.c_int32]
         L.sqrtba_set_lidar.argtypes = [vp, C.POINTER(Lidar)]
         L.sqrtba_set_lidar_edges.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, dp, dp, dp, dp, C.c_int32]
         L.sqrtba_get_lidar_matches.argtypes = [vp, ip]
@@ -208,18 +210,26 @@ class SqrtBA:
         self._chk(lib().sqrtba_solve_global(self.h, iters, int(robust), stop, C.byref(st)), "sqrtba_solve_global")
         return st.as_dict()
 
-    def poses(self):
-        out = np.zeros((self.n_pose, 7))
+    # the getters copy into a caller buffer (`out`: C-contiguous, right dtype and size; pinned host memory makes the
+    # device-to-host copy a plain DMA) or allocate a fresh pageable array
+    def poses(self, out=None):
+        if out is None:
+            out = np.empty((self.n_pose, 7))
+        assert out.dtype == np.float64 and out.size == self.n_pose * 7 and out.flags.c_contiguous
         self._chk(lib().sqrtba_get_poses(self.h, _p(out, C.c_double)), "sqrtba_get_poses")
         return out
 
-    def points(self):
-        out = np.zeros((self.n_point, 3))
+    def points(self, out=None):
+        if out is None:
+            out = np.empty((self.n_point, 3))
+        assert out.dtype == np.float64 and out.size == self.n_point * 3 and out.flags.c_contiguous
         self._chk(lib().sqrtba_get_points(self.h, _p(out, C.c_double)), "sqrtba_get_points")
         return out
 
-    def outliers(self):
-        out = np.zeros(self.n_obs, np.uint8)
+    def outliers(self, out=None):
+        if out is None:
+            out = np.empty(self.n_obs, np.uint8)
+        assert out.dtype == np.uint8 and out.size == self.n_obs and out.flags.c_contiguous
         self._chk(lib().sqrtba_get_outliers(self.h, _p(out, C.c_uint8)), "sqrtba_get_outliers")
         return out
 
@@ -276,6 +286,21 @@ class SqrtBA:
         rows = np.zeros((400, 8))
         n = self._chk(lib().sqrtba_pose_opt_trace(self.h, frame, _p(rows, C.c_double), 400), "sqrtba_pose_opt_trace")
         return rows[:n]
+
+    def pose_graph(self, vert8, fixed, fix_scale, edge_ij, meas8, iters: int = 20, lambda_init: float = 1e-16):
+        """sqrtba_pose_graph: returns (vertices n x 8 after the optimisation, LM trace rows x 8, stats)."""
+        V = np.ascontiguousarray(vert8, np.float64).copy()
+        fx = np.ascontiguousarray(fixed, np.uint8)
+        E = np.ascontiguousarray(edge_ij, np.int32)
+        M = np.ascontiguousarray(meas8, np.float64)
+        st = Stats()
+        self._chk(lib().sqrtba_pose_graph(self.h, len(V), _p(V, C.c_double), _p(fx, C.c_uint8), int(fix_scale), len(E),
+                                          _p(E, C.c_int32), _p(M, C.c_double), iters, lambda_init, C.byref(st)), "sqrtba_pose_graph")
+        n = lib().sqrtba_pose_graph_trace(self.h, None, 0)
+        tr = np.zeros((max(n, 0), 8))
+        if n > 0:
+            lib().sqrtba_pose_graph_trace(self.h, _p(tr, C.c_double), n)
+        return V, tr, st.as_dict()
 
     def comm_init(self, nranks: int, rank: int, unique_id: bytes):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)

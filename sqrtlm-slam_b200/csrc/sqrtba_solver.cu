@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -25,6 +26,7 @@
 #include "sqrtba_kernels.cuh"
 #include "sqrtba_poseopt.cuh"
 #include "sqrtba_lidar.cuh"
+#include "sqrtba_posegraph.cuh"
 #include "../host/host_pool.h"
 
 namespace sqrtba {
@@ -275,7 +277,8 @@ class Solver {
           if (pose_win[ip] != point_win[il]) { bad.store(3); return; }
           if (n_win > 1 && (k < wobs[point_win[il]] || k >= wobs[point_win[il] + 1])) { bad.store(4); return; }
           obs_slot[k] = pose_slot[ip];
-          obs_lp[k] = 0xffffu;
+          // meta word: "takes no part in the in-CTA reduction" until step C says otherwise + the stereo bit
+          obs_lp[k] = 0xffffu | (!(obs_meas[(size_t)k * 4 + 2] < 0.0f) ? LP_STEREO : 0u);
           if (k == 0 || il != obs_point[k - 1]) lm_first[il] = (int)k;
         }
       });
@@ -346,10 +349,10 @@ class Solver {
       lm_count_new_ = lm_cnt;
       point_xyz = h_perm_xyz_.p; obs_pose = h_perm_pose_.p; obs_point = h_perm_point_.p; obs_meas = h_perm_meas_.p;
     }
-    // every observation's meta word starts as "takes no part in the in-CTA reduction" + the stereo bit (final order)
-    pool_.chunks(n_obs, 1 << 16, n_thr, [&](long long k0, long long k1) {
-      for (long long k = k0; k < k1; k++) obs_lp[k] = 0xffffu | (!(obs_meas[(size_t)k * 4 + 2] < 0.0f) ? LP_STEREO : 0u);
-    });
+    if (!perm_.empty())  // re-ordered observations: the stereo bits follow the new order
+      pool_.chunks(n_obs, 1 << 16, n_thr, [&](long long k0, long long k1) {
+        for (long long k = k0; k < k1; k++) obs_lp[k] = 0xffffu | (!(obs_meas[(size_t)k * 4 + 2] < 0.0f) ? LP_STEREO : 0u);
+      });
     lap("A2 landmark order");
     // The caller's big arrays (or their re-ordered copies) are final now: start their host-to-device copies so that they
     // overlap the remaining host-side preprocessing (truly asynchronous when the caller's buffers are pinned).
@@ -695,6 +698,9 @@ class Solver {
         if (cfg_.reserved[2] > 0 && S != cfg_.reserved[2]) continue;
         if (per_sm * S > best * persist_stages_ || best == 0) { best = per_sm; persist_stages_ = S; }
       }
+      // (4 CTAs/SM at 96 registers was measured SLOWER for the persistent kernel -- C0 5.4 vs 4.7 ms: every extra CTA adds
+      // arrivals to the grid barrier, flush atomics on the q copies and a redundant vector update)
+      if (const char* e = std::getenv("SQRTBA_PERSIST_CTAS_PER_SM")) best = std::max(1, std::min(best, std::atoi(e)));  // A/B
       persist_ctas_ = best * n_sm_;
     }
     persist_grid_ = std::min(n_tile, persist_ctas_);
@@ -1064,6 +1070,206 @@ class Solver {
     if (m > 0 && download(rows, d_po_trace_.p + (size_t)frame * PO_MAX_TRACE * PO_TRACE_COLS, (size_t)m * PO_TRACE_COLS * sizeof(double)))
       return SQRTBA_ERR_CUDA;
     return m;
+  }
+
+
+  // ------------------------------------------------------------------------------------------ essential graph (row N3)
+  // The optimisation of g2oOptimizer::OptimizeEssentialGraph (g2oOptimizer.cc:1212-1460) for a pose graph the adapter
+  // has built: Levenberg with lambda_0 = lambda_init (setUserLambdaInit, 1e-16 in the reference; <= 0: tau * max diag),
+  // `iters` iterations, exact block-skyline Cholesky per trial (csrc/sqrtba_posegraph.cuh).  Independent of set_problem.
+  int pose_graph(int n_vert, double* vert8, const uint8_t* fixed, int fix_scale, int n_edge, const int32_t* edge_ij,
+                 const double* meas8, int iters, double lambda_init, sqrtba_stats* st) {
+    if (n_vert <= 0 || n_edge < 0 || !vert8 || !fixed || (n_edge > 0 && (!edge_ij || !meas8)) || iters < 0) {
+      err_ = "pose_graph: bad arguments";
+      return SQRTBA_ERR_INVALID;
+    }
+    for (int k = 0; k < 2 * n_edge; k++)
+      if (edge_ij[k] < 0 || edge_ij[k] >= n_vert) { err_ = "pose_graph: edge vertex out of range"; return SQRTBA_ERR_INVALID; }
+    for (int k = 0; k < n_edge; k++)
+      if (edge_ij[2 * k] == edge_ij[2 * k + 1]) { err_ = "pose_graph: an edge joins a vertex with itself"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    pg_trace_.clear();
+    // index mapping: non-fixed vertices that have an edge, ascending id (sparse_optimizer.cpp:166-190, 482-487)
+    std::vector<int> slot(n_vert, -1), slot_vert;
+    {
+      std::vector<uint8_t> act(n_vert, 0);
+      for (int k = 0; k < 2 * n_edge; k++) act[edge_ij[k]] = 1;
+      for (int i = 0; i < n_vert; i++)
+        if (act[i] && !fixed[i]) { slot[i] = (int)slot_vert.size(); slot_vert.push_back(i); }
+    }
+    const int n_slot = (int)slot_vert.size();
+    if (st) std::memset(st, 0, sizeof *st);
+    if (n_slot == 0 || iters == 0) return SQRTBA_OK;  // nothing to optimise: estimates untouched
+    // block skyline: row r stores the block columns [first[r], r]
+    std::vector<int> first(n_slot);
+    for (int r = 0; r < n_slot; r++) first[r] = r;
+    for (int k = 0; k < n_edge; k++) {
+      const int a = slot[edge_ij[2 * k]], b = slot[edge_ij[2 * k + 1]];
+      if (a < 0 || b < 0) continue;
+      const int hi = std::max(a, b), lo = std::min(a, b);
+      first[hi] = std::min(first[hi], lo);
+    }
+    std::vector<long long> rowptr(n_slot + 1, 0);
+    for (int r = 0; r < n_slot; r++) rowptr[r + 1] = rowptr[r] + (r - first[r] + 1);
+    const long long n_blocks = rowptr[n_slot];
+    if (n_blocks > (1ll << 23)) {  // 8M blocks = 3.3 GB per copy: the natural (keyframe id) order does not fit this graph
+      err_ = "pose_graph: the block skyline of this graph in keyframe-id order is too large";
+      return SQRTBA_ERR_INVALID;
+    }
+    std::vector<int> col_ptr(n_slot + 1, 0), col_rows((size_t)(n_blocks - n_slot));
+    for (int r = 0; r < n_slot; r++)
+      for (int c = first[r]; c < r; c++) col_ptr[c + 1]++;
+    for (int c = 0; c < n_slot; c++) col_ptr[c + 1] += col_ptr[c];
+    {
+      std::vector<int> cur(col_ptr.begin(), col_ptr.end() - 1);
+      for (int r = 0; r < n_slot; r++)   // ascending r: every column's row list comes out sorted
+        for (int c = first[r]; c < r; c++) col_rows[(size_t)cur[c]++] = r;
+    }
+    // the edges of every free vertex in ascending edge index (deterministic assembly, no atomics)
+    std::vector<int> inc_ptr(n_slot + 1, 0), inc_edge;
+    for (int k = 0; k < 2 * n_edge; k++)
+      if (slot[edge_ij[k]] >= 0) inc_ptr[slot[edge_ij[k]] + 1]++;
+    for (int r = 0; r < n_slot; r++) inc_ptr[r + 1] += inc_ptr[r];
+    inc_edge.resize((size_t)inc_ptr[n_slot]);
+    {
+      std::vector<int> cur(inc_ptr.begin(), inc_ptr.end() - 1);
+      for (int k = 0; k < n_edge; k++)
+        for (int side = 0; side < 2; side++) {
+          const int sl = slot[edge_ij[2 * k + side]];
+          if (sl >= 0) inc_edge[(size_t)cur[sl]++] = 2 * k + side;
+        }
+    }
+    const int n_err_cta = std::max(cdiv(n_edge, 256), 1);
+    const size_t Nv = n_vert, Ne = (size_t)std::max(n_edge, 1), Ns = n_slot, Nb = (size_t)n_blocks;
+    CU_CHECK(d_pg_inc_ptr_.ensure(Ns + 1)); CU_CHECK(d_pg_inc_edge_.ensure(std::max<size_t>(inc_edge.size(), 1)));
+    CU_CHECK(d_pg_chi_part_.ensure(n_err_cta));
+    CU_CHECK(d_pg_vert_.ensure(Nv * 8)); CU_CHECK(d_pg_bak_.ensure(Nv * 8)); CU_CHECK(d_pg_fixed_.ensure(Nv));
+    CU_CHECK(d_pg_slot_.ensure(Nv)); CU_CHECK(d_pg_slot_vert_.ensure(Ns)); CU_CHECK(d_pg_edge_.ensure(Ne * 2));
+    CU_CHECK(d_pg_meas_.ensure(Ne * 8)); CU_CHECK(d_pg_err_.ensure(Ne * 7)); CU_CHECK(d_pg_Ji_.ensure(Ne * 49));
+    CU_CHECK(d_pg_Jj_.ensure(Ne * 49)); CU_CHECK(d_pg_first_.ensure(Ns)); CU_CHECK(d_pg_rowptr_.ensure(Ns + 1));
+    CU_CHECK(d_pg_H_.ensure(Nb * 49)); CU_CHECK(d_pg_L_.ensure(Nb * 49)); CU_CHECK(d_pg_Linv_.ensure(Ns * 49));
+    CU_CHECK(d_pg_col_ptr_.ensure(Ns + 1)); CU_CHECK(d_pg_col_rows_.ensure(std::max<size_t>(col_rows.size(), 1)));
+    CU_CHECK(d_pg_b_.ensure(Ns * 7)); CU_CHECK(d_pg_y_.ensure(Ns * 7)); CU_CHECK(d_pg_x_.ensure(Ns * 7)); CU_CHECK(d_pg_scal_.ensure(4));
+    auto up = [&](void* dst, const void* src, size_t bytes) {
+      return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_) : cudaSuccess;
+    };
+    CU_CHECK(cudaEventRecord(ev0_, stream_));
+    CU_CHECK(up(d_pg_vert_.p, vert8, Nv * 8 * sizeof(double)));
+    CU_CHECK(up(d_pg_fixed_.p, fixed, Nv));
+    CU_CHECK(up(d_pg_slot_.p, slot.data(), Nv * sizeof(int)));
+    CU_CHECK(up(d_pg_slot_vert_.p, slot_vert.data(), Ns * sizeof(int)));
+    CU_CHECK(up(d_pg_edge_.p, edge_ij, (size_t)n_edge * 2 * sizeof(int)));
+    CU_CHECK(up(d_pg_meas_.p, meas8, (size_t)n_edge * 8 * sizeof(double)));
+    CU_CHECK(up(d_pg_first_.p, first.data(), Ns * sizeof(int)));
+    CU_CHECK(up(d_pg_rowptr_.p, rowptr.data(), (Ns + 1) * sizeof(long long)));
+    CU_CHECK(up(d_pg_col_ptr_.p, col_ptr.data(), (Ns + 1) * sizeof(int)));
+    CU_CHECK(up(d_pg_col_rows_.p, col_rows.data(), col_rows.size() * sizeof(int)));
+    CU_CHECK(up(d_pg_inc_ptr_.p, inc_ptr.data(), (Ns + 1) * sizeof(int)));
+    CU_CHECK(up(d_pg_inc_edge_.p, inc_edge.data(), inc_edge.size() * sizeof(int)));
+    PgDev G{};
+    G.n_vert = n_vert; G.n_edge = n_edge; G.n_slot = n_slot; G.fix_scale = fix_scale ? 1 : 0;
+    G.vert = d_pg_vert_.p; G.vert_bak = d_pg_bak_.p; G.fixed = d_pg_fixed_.p; G.slot = d_pg_slot_.p; G.slot_vert = d_pg_slot_vert_.p;
+    G.edge_ij = d_pg_edge_.p; G.meas = d_pg_meas_.p; G.err = d_pg_err_.p; G.Ji = d_pg_Ji_.p; G.Jj = d_pg_Jj_.p;
+    G.first = d_pg_first_.p; G.rowptr = d_pg_rowptr_.p; G.H = d_pg_H_.p; G.L = d_pg_L_.p; G.Linv = d_pg_Linv_.p;
+    G.col_ptr = d_pg_col_ptr_.p; G.col_rows = d_pg_col_rows_.p; G.b = d_pg_b_.p; G.y = d_pg_y_.p; G.x = d_pg_x_.p; G.scal = d_pg_scal_.p;
+    G.chi_part = d_pg_chi_part_.p; G.inc_ptr = d_pg_inc_ptr_.p; G.inc_edge = d_pg_inc_edge_.p;
+    int launches = 0;
+    double h_scal[4];
+    std::vector<double> h_part(n_err_cta, 0.0);
+    // computeActiveErrors + activeChi2: per-CTA partial sums, added up in order here (reproducible); with_scal also
+    // reads the solve's scalars in the same synchronisation
+    auto chi2_now = [&](double* out, bool with_scal) -> int {
+      if (n_edge > 0) { k_pg_errors<<<n_err_cta, 256, 0, stream_>>>(G); launches++; }
+      else CU_CHECK(cudaMemsetAsync(G.chi_part, 0, sizeof(double), stream_));
+      CU_CHECK(cudaMemcpyAsync(h_part.data(), G.chi_part, (size_t)n_err_cta * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+      if (with_scal) CU_CHECK(cudaMemcpyAsync(h_scal, G.scal, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+      CU_CHECK(cudaStreamSynchronize(stream_));
+      CU_CHECK(cudaGetLastError());
+      double c = 0.0;
+      for (double v : h_part) c += v;
+      *out = c;
+      return SQRTBA_OK;
+    };
+    double lambda = 0.0, ni = 2.0;
+    int nbad = 0;
+    bool ok = true;
+    for (int it = 0; it < iters && ok; it++) {  // SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve
+      double currentChi = 0.0;
+      if (int rc = chi2_now(&currentChi, false)) return rc;
+      double tempChi = currentChi;
+      const double iniChi = currentChi;
+      CU_CHECK(cudaMemsetAsync(G.H, 0, Nb * 49 * sizeof(double), stream_));
+      if (n_edge > 0) { k_pg_linearize<<<cdiv((long long)n_edge * 14, 128), 128, 0, stream_>>>(G); launches++; }
+      k_pg_assemble<<<cdiv((long long)n_slot * 49, 256), 256, 0, stream_>>>(G);
+      launches++;
+      if (it == 0) {
+        if (lambda_init > 0) {
+          lambda = lambda_init;  // computeLambdaInit returns _userLambdaInit (optimization_algorithm_levenberg.cpp:168-169)
+        } else {                // tau * max diag(H)
+          std::vector<double> Hh(Nb * 49);
+          if (download(Hh.data(), G.H, Hh.size() * sizeof(double))) return SQRTBA_ERR_CUDA;
+          double md = 0.0;
+          for (int r = 0; r < n_slot; r++)
+            for (int a = 0; a < 7; a++) md = std::max(md, std::fabs(Hh[(size_t)(rowptr[r] + (r - first[r])) * 49 + a * 8]));
+          lambda = 1e-5 * md;
+        }
+        ni = 2.0;
+        nbad = 0;
+      }
+      double rho = 0.0;
+      int qmax = 0;
+      do {
+        k_pg_prepare<<<cdiv(std::max<long long>(n_blocks * 49, (long long)n_slot * 7), 256), 256, 0, stream_>>>(G, n_blocks);
+        k_pg_damp<<<cdiv(n_slot * 7, 256), 256, 0, stream_>>>(G, lambda);
+        k_pg_factor_solve<<<1, PG_THREADS, 0, stream_>>>(G, lambda);
+        k_pg_update<<<cdiv(n_slot, 128), 128, 0, stream_>>>(G);   // push + update
+        launches += 4;
+        if (int rc = chi2_now(&tempChi, true)) return rc;
+        if (h_scal[2] != 0.0) tempChi = std::numeric_limits<double>::max();  // Cholesky failure => the step is rejected
+        rho = currentChi - tempChi;
+        const double scale = h_scal[1] + 1e-3;
+        rho /= scale;
+        double row[8] = {0.0, (double)it, (double)qmax, lambda, currentChi, tempChi, rho, 0.0};
+        if (rho > 0 && std::isfinite(tempChi)) {
+          double alpha = 1. - std::pow((2 * rho - 1), 3);
+          alpha = std::min(alpha, 2. / 3.);
+          lambda *= std::max(1. / 3., alpha);
+          ni = 2;
+          currentChi = tempChi;
+          row[7] = 1.0;
+        } else {
+          lambda *= ni;
+          ni *= 2;
+          k_pg_restore<<<cdiv(n_slot, 128), 128, 0, stream_>>>(G);  // pop
+          launches++;
+        }
+        pg_trace_.insert(pg_trace_.end(), row, row + 8);
+        qmax++;
+      } while (rho < 0 && qmax < 10);
+      if (qmax == 10 || rho == 0) { ok = false; break; }
+      if ((iniChi - currentChi) * 1e3 < iniChi) nbad++; else nbad = 0;
+      if (nbad >= 3) ok = false;
+    }
+    CU_CHECK(cudaMemcpyAsync(vert8, G.vert, Nv * 8 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    CU_CHECK(cudaEventRecord(ev1_, stream_));
+    CU_CHECK(cudaEventSynchronize(ev1_));
+    CU_CHECK(cudaGetLastError());
+    if (st) {
+      float ms = 0;
+      CU_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+      st->n_windows = 1;
+      st->lm_trials = (int)(pg_trace_.size() / 8);
+      st->kernel_launches = launches;
+      st->ms_total = ms;
+      st->reserved[3] = (double)n_blocks;  // 7x7 blocks of the skyline
+      st->reserved[4] = (double)n_slot;
+    }
+    return SQRTBA_OK;
+  }
+  int pose_graph_trace(double* rows, int max_rows) {
+    const int n = (int)(pg_trace_.size() / 8), m = std::min(n, std::max(max_rows, 0));
+    if (m > 0 && rows) std::memcpy(rows, pg_trace_.data(), (size_t)m * 8 * sizeof(double));
+    return rows ? m : n;
   }
 
   // ------------------------------------------------------------------------------------------ stage-level entry points
@@ -1807,6 +2013,11 @@ class Solver {
     d_lc_world_.release(); d_lm_flat_.release(); d_lm_flat_w_.release(); d_lm_corner_.release(); d_lm_corner_w_.release(); d_l_best_.release();
     d_po_ptr_.release(); d_po_pose_.release(); d_po_cam_.release(); d_po_xyz_.release(); d_po_err_.release(); d_po_trace_.release();
     d_po_meas_.release(); d_po_level_.release(); d_po_outlier_.release(); d_po_inl_.release();
+    d_pg_vert_.release(); d_pg_bak_.release(); d_pg_meas_.release(); d_pg_err_.release(); d_pg_Ji_.release(); d_pg_Jj_.release();
+    d_pg_H_.release(); d_pg_L_.release(); d_pg_Linv_.release(); d_pg_b_.release(); d_pg_y_.release(); d_pg_x_.release();
+    d_pg_scal_.release(); d_pg_fixed_.release(); d_pg_slot_.release(); d_pg_slot_vert_.release(); d_pg_edge_.release();
+    d_pg_first_.release(); d_pg_col_ptr_.release(); d_pg_col_rows_.release(); d_pg_rowptr_.release();
+    d_pg_inc_ptr_.release(); d_pg_inc_edge_.release(); d_pg_chi_part_.release();
     h_obs_slot_.release(); h_item_start_.release(); h_item_cnt_.release(); h_item_win_.release();
     h_tile_run_ptr_.release(); h_tile_runs_.release(); h_obs_lp_.release(); h_tiles_pin_.release();
     h_perm_pose_.release(); h_perm_point_.release(); h_perm_slot_.release(); h_perm_meas_.release(); h_perm_xyz_.release();
@@ -1865,6 +2076,14 @@ class Solver {
   DBuf<uint8_t> d_po_level_, d_po_outlier_;
   DBuf<int> d_po_inl_;
   int po_frames_ = 0;
+  // essential-graph optimisation (independent of set_problem)
+  DBuf<double> d_pg_vert_, d_pg_bak_, d_pg_meas_, d_pg_err_, d_pg_Ji_, d_pg_Jj_, d_pg_H_, d_pg_L_, d_pg_Linv_, d_pg_b_, d_pg_y_,
+      d_pg_x_, d_pg_scal_;
+  DBuf<uint8_t> d_pg_fixed_;
+  DBuf<int> d_pg_slot_, d_pg_slot_vert_, d_pg_edge_, d_pg_first_, d_pg_col_ptr_, d_pg_col_rows_, d_pg_inc_ptr_, d_pg_inc_edge_;
+  DBuf<double> d_pg_chi_part_;
+  DBuf<long long> d_pg_rowptr_;
+  std::vector<double> pg_trace_;
   Dev P_{};
   DBuf<double> d_cam_, d_pose_, d_pose0_, d_pose_bak_, d_point_, d_point0_, d_point_bak_, d_err_, d_JQ_, d_Jl_,
       d_r_, d_R_, d_tl_, d_bl_, d_dl_, d_slotvec_, d_chi_part_, d_scale_part_, d_trace_, d_wred_;
@@ -2020,6 +2239,14 @@ int sqrtba_pose_opt(sqrtba_handle* h, int32_t n_frames, const int64_t* frame_obs
 }
 int sqrtba_pose_opt_trace(sqrtba_handle* h, int32_t frame, double* rows_out, int32_t max_rows) {
   return h ? h->s->pose_opt_trace(frame, rows_out, max_rows) : SQRTBA_ERR_INVALID;
+}
+int sqrtba_pose_graph(sqrtba_handle* h, int32_t n_vert, double* vert8, const uint8_t* fixed, int32_t fix_scale, int32_t n_edge,
+                      const int32_t* edge_ij, const double* meas8, int32_t iters, double lambda_init, sqrtba_stats* stats) {
+  return h ? h->s->pose_graph(n_vert, vert8, fixed, fix_scale, n_edge, edge_ij, meas8, iters, lambda_init, stats)
+           : SQRTBA_ERR_INVALID;
+}
+int sqrtba_pose_graph_trace(sqrtba_handle* h, double* rows_out, int32_t max_rows) {
+  return h ? h->s->pose_graph_trace(rows_out, max_rows) : SQRTBA_ERR_INVALID;
 }
 int sqrtba_set_lidar(sqrtba_handle* h, const sqrtba_lidar* clouds) { return h ? h->s->set_lidar(clouds) : SQRTBA_ERR_INVALID; }
 int sqrtba_set_lidar_edges(sqrtba_handle* h, int32_t cur_pose, int32_t n_flat, int32_t n_corner, const double* point_cam,

@@ -465,3 +465,70 @@ def lidar_data(prob: Problem, seed: int = 0, cur_pose: int | None = None, n_flat
     f32 = lambda a: np.ascontiguousarray(a, np.float32)
     return LidarData(cur_pose, f32(flat), f32(nrm), f32(corner), f32(np.concatenate(mf)), np.concatenate(mfp),
                      f32(np.concatenate(mc)), np.concatenate(mcp))
+
+
+# ----------------------------------------------------------------------------- essential graph (Sim3 pose graph, row N3)
+# Sim3 as 8 numbers in g2o's operator[] order: qx qy qz qw | tx ty tz | s   (types/sim3.h)
+
+def _q_mul(a, b):
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                     aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _q_rot(q, v):
+    return quat_to_rotmat(q) @ v
+
+
+def sim3_mul(a, b):
+    return np.concatenate([_q_mul(a[:4], b[:4]), a[7] * _q_rot(a[:4], b[4:7]) + a[4:7], [a[7] * b[7]]])
+
+
+def sim3_inv(a):
+    qi = np.array([-a[0], -a[1], -a[2], a[3]])
+    return np.concatenate([qi, _q_rot(qi, (-1.0 / a[7]) * a[4:7]), [1.0 / a[7]]])
+
+
+def sim3_small(rng, s_rot, s_t, s_scale):
+    """A small random similarity: rotation vector ~ N(0, s_rot), translation ~ N(0, s_t), log-scale ~ N(0, s_scale)."""
+    w = rng.normal(0, s_rot, 3)
+    th = np.linalg.norm(w)
+    q = np.concatenate([np.sin(th / 2) * w / th, [np.cos(th / 2)]]) if th > 0 else np.array([0, 0, 0, 1.0])
+    return np.concatenate([q, rng.normal(0, s_t, 3), [float(np.exp(rng.normal(0, s_scale))) if s_scale > 0 else 1.0]])
+
+
+def pose_graph(seed=0, n_kf=200, fix_scale=True, covis_span=4, covis_prob=0.5, n_loop=6, radius=60.0):
+    """An essential graph the way OptimizeEssentialGraph sees it after a loop closure (g2oOptimizer.cc:1212-1460):
+    keyframes on a closed loop, dead-reckoned estimates that drift (in scale too when it is free), spanning-tree edges
+    (parent = previous keyframe), covisibility edges to older neighbours, and `n_loop` loop edges between the end of the
+    trajectory and its start, measured from the true geometry.  Vertex 0 (the loop keyframe) is fixed.
+    Returns (vert0 n x 8 [S_iw], fixed n, edge_ij m x 2 [vertex 0 = i, vertex 1 = j], meas m x 8 [S_ji])."""
+    rng = np.random.default_rng(seed)
+    truth = []
+    for k in range(n_kf):
+        ang = 2 * np.pi * k / n_kf
+        q = np.array([0, np.sin(ang / 2), 0, np.cos(ang / 2)])
+        c = np.array([radius * np.sin(ang), 0.3 * np.sin(3 * ang), radius * (1 - np.cos(ang))])
+        truth.append(np.concatenate([q, -_q_rot(q, c), [1.0]]))  # S_kw
+    edges, meas = [], []
+    est = [truth[0].copy()]
+    sc = 0.0 if fix_scale else 0.004
+    for k in range(1, n_kf):  # spanning tree: child k -> parent k-1, measurement S_parent,child (vertex 0 = child)
+        rel = sim3_mul(truth[k], sim3_inv(truth[k - 1]))  # S_k,k-1
+        m = sim3_mul(sim3_small(rng, 0.004, 0.03, sc), rel)
+        est.append(sim3_mul(m, est[k - 1]))                # dead reckoning
+        edges.append((k, k - 1))
+        meas.append(sim3_inv(m))                           # S_ji with i = k, j = k-1
+    for k in range(2, n_kf):  # covisibility edges to older neighbours (pKFn->mnId < pKF->mnId), from the estimates' own
+        for d in range(2, covis_span + 1):  # relative pose as the reference does (Sji = Sjw * Swi of the SAME estimates)
+            if k - d >= 0 and rng.random() < covis_prob:
+                edges.append((k, k - d))
+                meas.append(sim3_mul(est[k - d], sim3_inv(est[k])))
+    for t in range(n_loop):   # loop edges: the last keyframes see the first ones again; measured by the loop detector
+        i, j = n_kf - 1 - t, t % 3
+        edges.append((i, j))
+        meas.append(sim3_mul(sim3_mul(sim3_small(rng, 0.001, 0.01, 0.0), truth[j]), sim3_inv(truth[i])))
+    fixed = np.zeros(n_kf, np.uint8)
+    fixed[0] = 1
+    return np.stack(est), fixed, np.array(edges, np.int32), np.stack(meas)
