@@ -1,6 +1,8 @@
 // Mirror of the bundle-adjustment part of the reference facade (include/backend/Optimizer.h:42-56): same class, same
 // static signatures (the reference's spelling `GlobalBundleAdjustemnt` included), plus the new back-end selector value.
 #pragma once
+#include <map>
+#include <set>
 #include <vector>
 
 #ifdef SQRTBA_WITH_REFERENCE_HEADERS
@@ -24,6 +26,11 @@ class Optimizer {
   void static GlobalBundleAdjustemnt(Map* pMap, int nIterations = 5, bool* pbStopFlag = NULL,
                                      const unsigned long nLoopKF = 0, const bool bRobust = true);
   void static LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* lidarconfig);
+  // include/backend/Optimizer.h:62-67
+  void static OptimizeEssentialGraph(Map* pMap, KeyFrame* pLoopKF, KeyFrame* pCurKF,
+                                     const LoopClosing::KeyFrameAndPose& NonCorrectedSim3,
+                                     const LoopClosing::KeyFrameAndPose& CorrectedSim3,
+                                     const std::map<KeyFrame*, std::set<KeyFrame*>>& LoopConnections, const bool& bFixScale);
 };
 
 // the adapter that sits beside g2oOptimizer / CeresOptimizer / MyOptimizer (src/backend/)
@@ -39,6 +46,24 @@ class sqrtbaOptimizer {
   int static PoseOptimization(Frame* pFrame);
   // relocalisation: several candidate frames in one launch (Tracking.cc:2466-2517 calls PoseOptimization per candidate)
   void static PoseOptimizationBatch(const std::vector<Frame*>& frames, std::vector<int>& inliers);
+  // g2oOptimizer::OptimizeEssentialGraph (src/backend/g2oOptimizer.cc:1212-1520): the graph is built from the map by the
+  // reference's rules (keyframe vertices, new loop connections, spanning tree, loop edges, covisibility >= 100), the
+  // optimisation runs on the device (sqrtba_pose_graph), poses and map points are corrected under mMutexMapUpdate
+  void static OptimizeEssentialGraph(Map* pMap, KeyFrame* pLoopKF, KeyFrame* pCurKF,
+                                     const LoopClosing::KeyFrameAndPose& NonCorrectedSim3,
+                                     const LoopClosing::KeyFrameAndPose& CorrectedSim3,
+                                     const std::map<KeyFrame*, std::set<KeyFrame*>>& LoopConnections, const bool& bFixScale);
+  // the graph that OptimizeEssentialGraph hands to sqrtba_pose_graph, without optimising (host-side tests, no GPU):
+  // vertices indexed by keyframe mnId (8 doubles each, absent / bad keyframes are zero rows with present = 0)
+  struct PoseGraphProblem {
+    std::vector<double> vert8, meas8;
+    std::vector<unsigned char> fixed, present;
+    std::vector<int> edge_ij;
+  };
+  void static GatherEssentialGraph(Map* pMap, KeyFrame* pLoopKF, KeyFrame* pCurKF,
+                                   const LoopClosing::KeyFrameAndPose& NonCorrectedSim3,
+                                   const LoopClosing::KeyFrameAndPose& CorrectedSim3,
+                                   const std::map<KeyFrame*, std::set<KeyFrame*>>& LoopConnections, PoseGraphProblem& out);
   // Behaviour switches of the local-BA adapter.  The defaults are what THIS reference does:
   //  * local_ba_stereo_edges = false: the fork's local BA only creates monocular edges -- an observation with a right
   //    coordinate falls into an empty branch (g2oOptimizer.cc:914-916) and takes no part in the optimisation or in the

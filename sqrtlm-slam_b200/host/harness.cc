@@ -118,6 +118,56 @@ void hh_apply_local(hh_map* m, int kf, int n_kf, const double* pose_qt, int n_mp
                                     std::vector<unsigned char>(outlier, outlier + n_obs));
 }
 
+// ---- essential graph: spanning tree, loop edges, covisibility weights, reference keyframes; then the reference call
+void hh_set_parent(hh_map* m, int kf, int parent) {
+  m->kfs[kf]->mpParent = m->kfs[parent].get();
+  m->kfs[parent]->mspChildrens.insert(m->kfs[kf].get());
+}
+void hh_add_loop_edge(hh_map* m, int a, int b) {
+  m->kfs[a]->mspLoopEdges.insert(m->kfs[b].get());
+  m->kfs[b]->mspLoopEdges.insert(m->kfs[a].get());
+}
+void hh_set_weight(hh_map* m, int a, int b, int w) {
+  m->kfs[a]->mConnectedKeyFrameWeights[m->kfs[b].get()] = w;
+  m->kfs[b]->mConnectedKeyFrameWeights[m->kfs[a].get()] = w;
+}
+void hh_set_ref_kf(hh_map* m, int mp, int kf, long corrected_by, long corrected_ref) {
+  m->mps[mp]->mpRefKF = m->kfs[kf].get();
+  if (corrected_by >= 0) { m->mps[mp]->mnCorrectedByKF = (unsigned long)corrected_by; m->mps[mp]->mnCorrectedReference = (unsigned long)corrected_ref; }
+}
+static g2o::Sim3 sim3_from8(const double* v) {
+  g2o::Sim3 S;
+  S.r.x_ = v[0]; S.r.y_ = v[1]; S.r.z_ = v[2]; S.r.w_ = v[3];
+  S.t[0] = v[4]; S.t[1] = v[5]; S.t[2] = v[6];
+  S.s = v[7];
+  return S;
+}
+// mode 0: gather only (sizes3 <- n_vert, n_edge, -), mode 1: Optimizer::OptimizeEssentialGraph
+static sqrtbaOptimizer::PoseGraphProblem g_pg;
+void hh_essential_graph(hh_map* m, int mode, int loop_kf, int cur_kf, int n_corr, const int32_t* corr_kf, const double* corr8,
+                        const double* noncorr8, int n_conn, const int32_t* conn_ab, int fix_scale, int32_t* sizes3) {
+  LoopClosing::KeyFrameAndPose Corrected, NonCorrected;
+  for (int k = 0; k < n_corr; k++) {
+    Corrected[m->kfs[corr_kf[k]].get()] = sim3_from8(corr8 + (size_t)k * 8);
+    NonCorrected[m->kfs[corr_kf[k]].get()] = sim3_from8(noncorr8 + (size_t)k * 8);
+  }
+  std::map<KeyFrame*, std::set<KeyFrame*>> Conn;
+  for (int k = 0; k < n_conn; k++) Conn[m->kfs[conn_ab[2 * k]].get()].insert(m->kfs[conn_ab[2 * k + 1]].get());
+  if (mode == 0) {
+    sqrtbaOptimizer::GatherEssentialGraph(&m->map, m->kfs[loop_kf].get(), m->kfs[cur_kf].get(), NonCorrected, Corrected, Conn, g_pg);
+    sizes3[0] = (int)g_pg.fixed.size(); sizes3[1] = (int)(g_pg.edge_ij.size() / 2); sizes3[2] = 0;
+  } else {
+    const bool fs = fix_scale != 0;
+    Optimizer::OptimizeEssentialGraph(&m->map, m->kfs[loop_kf].get(), m->kfs[cur_kf].get(), NonCorrected, Corrected, Conn, fs);
+  }
+}
+void hh_essential_graph_get(double* vert8, uint8_t* fixed, uint8_t* present, int32_t* edge_ij, double* meas8) {
+  std::copy(g_pg.vert8.begin(), g_pg.vert8.end(), vert8);
+  std::copy(g_pg.fixed.begin(), g_pg.fixed.end(), fixed);
+  std::copy(g_pg.present.begin(), g_pg.present.end(), present);
+  std::copy(g_pg.edge_ij.begin(), g_pg.edge_ij.end(), edge_ij);
+  std::copy(g_pg.meas8.begin(), g_pg.meas8.end(), meas8);
+}
 void hh_set_options(int local_ba_stereo_edges, int local_ba_two_pass) {
   sqrtbaOptimizer::options().local_ba_stereo_edges = local_ba_stereo_edges != 0;
   sqrtbaOptimizer::options().local_ba_two_pass = local_ba_two_pass != 0;

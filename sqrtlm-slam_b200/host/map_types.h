@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
 #include <vector>
 
 #define CV_32F 5
@@ -46,6 +47,21 @@ struct PointIRTCloud {
   size_t size() const { return points.size(); }
 };
 
+// Thirdparty/g2o/g2o/types/sim3.h: the accessor surface of g2o::Sim3 that the essential-graph adapter uses
+// (rotation().x() .. w(), translation()[i], scale()); the real class stores an Eigen quaternion and vector
+namespace g2o {
+struct Sim3Quat { double x_ = 0, y_ = 0, z_ = 0, w_ = 1; double x() const { return x_; } double y() const { return y_; }
+                  double z() const { return z_; } double w() const { return w_; } };
+struct Sim3 {
+  Sim3Quat r;
+  double t[3] = {0, 0, 0};
+  double s = 1.0;
+  const Sim3Quat& rotation() const { return r; }
+  const double* translation() const { return t; }
+  double scale() const { return s; }
+};
+}  // namespace g2o
+
 namespace ORB_SLAM2 {
 class MapPoint;
 class Map;
@@ -69,6 +85,27 @@ class KeyFrame {
     for (auto& p : mvpMapPoints)
       if (p == pMP) p = nullptr;
   }
+  // spanning tree / loop edges / covisibility weights: what OptimizeEssentialGraph reads (KeyFrame.h:136-159)
+  KeyFrame* GetParent() { return mpParent; }
+  std::set<KeyFrame*> GetLoopEdges() { return mspLoopEdges; }
+  bool hasChild(KeyFrame* pKF) { return mspChildrens.count(pKF) != 0; }
+  int GetWeight(KeyFrame* pKF) { auto it = mConnectedKeyFrameWeights.find(pKF); return it == mConnectedKeyFrameWeights.end() ? 0 : it->second; }
+  std::vector<KeyFrame*> GetCovisiblesByWeight(const int& w) {  // ordered by decreasing weight (KeyFrame.cc:222-240)
+    std::vector<std::pair<int, KeyFrame*>> v;
+    for (auto& kv : mConnectedKeyFrameWeights)
+      if (kv.second >= w) v.emplace_back(-kv.second, kv.first);
+    std::stable_sort(v.begin(), v.end(), [](const std::pair<int, KeyFrame*>& a, const std::pair<int, KeyFrame*>& b) { return a.first < b.first; });
+    std::vector<KeyFrame*> out;
+    for (auto& e : v) out.push_back(e.second);
+    return out;
+  }
+  cv::Mat GetRotation() { std::unique_lock<std::mutex> l(mMutexPose); cv::Mat R(3, 3, CV_32F);
+                          for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R.at<float>(i, j) = Tcw.at<float>(i, j); return R; }
+  cv::Mat GetTranslation() { std::unique_lock<std::mutex> l(mMutexPose); cv::Mat t(3, 1, CV_32F);
+                             for (int i = 0; i < 3; i++) t.at<float>(i) = Tcw.at<float>(i, 3); return t; }
+  KeyFrame* mpParent = nullptr;
+  std::set<KeyFrame*> mspLoopEdges, mspChildrens;
+  std::map<KeyFrame*, int> mConnectedKeyFrameWeights;
   // lidar features of the keyframe in its own frame (KeyFrame.h:437-442)
   PointIRTCloud corner_points_less_sharp_, surface_points_less_flat_, surface_points_less_flat_normal_;
   // test-side construction
@@ -84,6 +121,9 @@ class MapPoint {
   long unsigned int mnId = 0;
   long unsigned int mnBALocalForKF = ~0ul, mnBAGlobalForKF = 0;
   cv::Mat mPosGBA;
+  long unsigned int mnCorrectedByKF = 0, mnCorrectedReference = 0;  // MapPoint.h:281-282 (set by LoopClosing::CorrectLoop)
+  KeyFrame* GetReferenceKeyFrame() { return mpRefKF; }
+  KeyFrame* mpRefKF = nullptr;
   int nUpdateNormalAndDepth = 0;
 
   cv::Mat GetWorldPos() { std::unique_lock<std::mutex> l(mMutexPos); return mWorldPos.clone(); }
@@ -119,8 +159,14 @@ class Map {
  public:
   std::vector<KeyFrame*> GetAllKeyFrames() { return mspKeyFrames; }
   std::vector<MapPoint*> GetAllMapPoints() { return mspMapPoints; }
+  long unsigned int GetMaxKFid() { long unsigned int m = 0; for (KeyFrame* k : mspKeyFrames) m = std::max(m, k->mnId); return m; }
   std::mutex mMutexMapUpdate;
   std::vector<KeyFrame*> mspKeyFrames;
   std::vector<MapPoint*> mspMapPoints;
+};
+// include/backend/LoopClosing.h:63-65
+class LoopClosing {
+ public:
+  typedef std::map<KeyFrame*, g2o::Sim3, std::less<KeyFrame*>> KeyFrameAndPose;
 };
 }  // namespace ORB_SLAM2

@@ -23,6 +23,7 @@
 #include <string>
 
 #include "../../include/sqrtba.h"
+#include "../csrc/sqrtba_sim3.cuh"  // g2o::Sim3's product / inverse restated (host build of the device arithmetic)
 #include "host_pool.h"
 
 namespace ORB_SLAM2 {
@@ -523,6 +524,191 @@ void sqrtbaOptimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map
   write_back_local(g, cur, P.data(), X.data(), flags.data(), pMap);
 }
 
+
+// ---- essential graph (g2oOptimizer::OptimizeEssentialGraph, src/backend/g2oOptimizer.cc:1212-1520) -------------------
+namespace {
+// g2o::Sim3 <-> the 8 doubles of sqrtba_pose_graph (qx qy qz qw | tx ty tz | s)
+void sim3_to8(const g2o::Sim3& S, double* o) {
+  o[0] = S.rotation().x(); o[1] = S.rotation().y(); o[2] = S.rotation().z(); o[3] = S.rotation().w();
+  o[4] = S.translation()[0]; o[5] = S.translation()[1]; o[6] = S.translation()[2];
+  o[7] = S.scale();
+}
+// g2o::Sim3(Rcw, tcw, 1.0) from the keyframe's float pose (:1276-1280): Eigen's Quaterniond(Matrix3d), not normalised
+void pose_to_sim3(KeyFrame* pKF, double* o) {
+  const cv::Mat R = pKF->GetRotation(), t = pKF->GetTranslation();
+  double m[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) m[i * 3 + j] = R.at<float>(i, j);
+  sqrtba::R_to_quat(m, o);
+  for (int i = 0; i < 3; i++) o[4 + i] = t.at<float>(i);
+  o[7] = 1.0;
+}
+
+struct EssentialGraph {
+  std::vector<KeyFrame*> vpKFs;
+  std::vector<double> vScw;          // (nMaxKFid + 1) x 8: the vertices' initial estimates, indexed by mnId (:1244)
+  std::vector<uint8_t> fixed, present;
+  std::vector<int32_t> edge_ij;
+  std::vector<double> meas8;
+};
+
+void build_essential_graph(Map* pMap, KeyFrame* pLoopKF, KeyFrame* pCurKF, const LoopClosing::KeyFrameAndPose& NonCorrectedSim3,
+                           const LoopClosing::KeyFrameAndPose& CorrectedSim3,
+                           const std::map<KeyFrame*, std::set<KeyFrame*>>& LoopConnections, EssentialGraph& G) {
+  G.vpKFs = pMap->GetAllKeyFrames();
+  const size_t nMax = pMap->GetMaxKFid();
+  G.vScw.assign((nMax + 1) * 8, 0.0);
+  G.fixed.assign(nMax + 1, 0);
+  G.present.assign(nMax + 1, 0);
+  const int minFeat = 100;  // :1251
+  // Step 2 (:1258-1298): one vertex per good keyframe, the Sim3-corrected pose where loop closing has one
+  for (KeyFrame* pKF : G.vpKFs) {
+    if (pKF->isBad()) continue;
+    const size_t id = pKF->mnId;
+    auto it = CorrectedSim3.find(pKF);
+    if (it != CorrectedSim3.end()) sim3_to8(it->second, &G.vScw[id * 8]);
+    else pose_to_sim3(pKF, &G.vScw[id * 8]);
+    G.present[id] = 1;
+    if (pKF == pLoopKF) G.fixed[id] = 1;
+  }
+  auto S = [&](size_t id) { return &G.vScw[id * 8]; };
+  auto add_edge = [&](size_t i, size_t j, const double* Sjw, const double* Swi) {  // measurement S_ji = S_jw * S_wi
+    if (i > nMax || j > nMax || !G.present[i] || !G.present[j]) return;  // the reference would dereference a null vertex
+    double Sji[8];
+    sqrtba::sim3_mul(Sjw, Swi, Sji);
+    G.edge_ij.push_back((int32_t)i);
+    G.edge_ij.push_back((int32_t)j);
+    G.meas8.insert(G.meas8.end(), Sji, Sji + 8);
+  };
+  std::set<std::pair<unsigned long, unsigned long>> sInsertedEdges;
+  // Step 3 (:1306-1336): the new connections the loop fusion created
+  for (auto& kv : LoopConnections) {
+    KeyFrame* pKF = kv.first;
+    const unsigned long nIDi = pKF->mnId;
+    if (nIDi > nMax || !G.present[nIDi]) continue;
+    double Swi[8];
+    sqrtba::sim3_inv(S(nIDi), Swi);
+    for (KeyFrame* pKFn : kv.second) {
+      const unsigned long nIDj = pKFn->mnId;
+      if ((nIDi != pCurKF->mnId || nIDj != pLoopKF->mnId) && pKF->GetWeight(pKFn) < minFeat) continue;
+      if (nIDj > nMax || !G.present[nIDj]) continue;
+      add_edge(nIDi, nIDj, S(nIDj), Swi);
+      sInsertedEdges.insert(std::make_pair(std::min(nIDi, nIDj), std::max(nIDi, nIDj)));
+    }
+  }
+  // Step 4 (:1339-1448): spanning tree, earlier loop edges, strong covisibility -- relative poses from BEFORE the correction
+  auto prior = [&](KeyFrame* pKF, double* out) {  // S_kw: the non-corrected pose if loop closing recorded one
+    auto it = NonCorrectedSim3.find(pKF);
+    if (it != NonCorrectedSim3.end()) sim3_to8(it->second, out);
+    else std::memcpy(out, S(pKF->mnId), 8 * sizeof(double));
+  };
+  for (KeyFrame* pKF : G.vpKFs) {
+    const unsigned long nIDi = pKF->mnId;
+    if (pKF->isBad()) continue;  // (the reference would index a vertex that was never added)
+    double Siw[8], Swi[8];
+    prior(pKF, Siw);
+    sqrtba::sim3_inv(Siw, Swi);
+    KeyFrame* pParentKF = pKF->GetParent();
+    if (pParentKF && !pParentKF->isBad()) {
+      double Sjw[8];
+      prior(pParentKF, Sjw);
+      add_edge(nIDi, pParentKF->mnId, Sjw, Swi);
+    }
+    const std::set<KeyFrame*> sLoopEdges = pKF->GetLoopEdges();
+    for (KeyFrame* pLKF : sLoopEdges)
+      if (pLKF->mnId < pKF->mnId && !pLKF->isBad()) {
+        double Slw[8];
+        prior(pLKF, Slw);
+        add_edge(nIDi, pLKF->mnId, Slw, Swi);
+      }
+    const std::vector<KeyFrame*> vpConnectedKFs = pKF->GetCovisiblesByWeight(minFeat);
+    for (KeyFrame* pKFn : vpConnectedKFs)
+      if (pKFn && pKFn != pParentKF && !pKF->hasChild(pKFn) && !sLoopEdges.count(pKFn))
+        if (!pKFn->isBad() && pKFn->mnId < pKF->mnId) {
+          if (sInsertedEdges.count(std::make_pair(std::min(pKF->mnId, pKFn->mnId), std::max(pKF->mnId, pKFn->mnId)))) continue;
+          double Snw[8];
+          prior(pKFn, Snw);
+          add_edge(nIDi, pKFn->mnId, Snw, Swi);
+        }
+  }
+}
+}  // namespace
+
+void sqrtbaOptimizer::GatherEssentialGraph(Map* pMap, KeyFrame* pLoopKF, KeyFrame* pCurKF,
+                                           const LoopClosing::KeyFrameAndPose& NonCorrectedSim3,
+                                           const LoopClosing::KeyFrameAndPose& CorrectedSim3,
+                                           const std::map<KeyFrame*, std::set<KeyFrame*>>& LoopConnections, PoseGraphProblem& out) {
+  EssentialGraph G;
+  build_essential_graph(pMap, pLoopKF, pCurKF, NonCorrectedSim3, CorrectedSim3, LoopConnections, G);
+  out.vert8 = G.vScw; out.meas8 = G.meas8; out.fixed = G.fixed; out.present = G.present;
+  out.edge_ij.assign(G.edge_ij.begin(), G.edge_ij.end());
+}
+
+void sqrtbaOptimizer::OptimizeEssentialGraph(Map* pMap, KeyFrame* pLoopKF, KeyFrame* pCurKF,
+                                             const LoopClosing::KeyFrameAndPose& NonCorrectedSim3,
+                                             const LoopClosing::KeyFrameAndPose& CorrectedSim3,
+                                             const std::map<KeyFrame*, std::set<KeyFrame*>>& LoopConnections, const bool& bFixScale) {
+  EssentialGraph G;
+  build_essential_graph(pMap, pLoopKF, pCurKF, NonCorrectedSim3, CorrectedSim3, LoopConnections, G);
+  Handle& H = tl_handle;
+  sqrtba_handle* h = H.get();
+  if (!h) return;
+  std::vector<double> est = G.vScw;  // absent ids are vertices without edges for the solver: never touched
+  const int n_vert = (int)G.fixed.size();
+  // solver->setUserLambdaInit(1e-16); optimizer.optimize(20)  (:1230, :1452-1453)
+  if (sqrtba_pose_graph(h, n_vert, est.data(), G.fixed.data(), bFixScale ? 1 : 0, (int)(G.edge_ij.size() / 2), G.edge_ij.data(),
+                        G.meas8.data(), 20, 1e-16, nullptr) != SQRTBA_OK) {
+    H.err = sqrtba_last_error(h);
+    return;
+  }
+  std::unique_lock<std::mutex> lock(pMap->mMutexMapUpdate);  // :1456
+  // SE3 pose recovery (:1459-1476): Sim3 [sR t; 0 1] -> SE3 [R t/s; 0 1]
+  std::vector<double> vCorrectedSwc(est.size(), 0.0);
+  for (KeyFrame* pKFi : G.vpKFs) {
+    const size_t id = pKFi->mnId;
+    if (id >= G.present.size() || !G.present[id]) continue;  // (a bad keyframe has no vertex)
+    const double* Siw = &est[id * 8];
+    sqrtba::sim3_inv(Siw, &vCorrectedSwc[id * 8]);
+    double R[9];
+    sqrtba::quat_to_R(Siw, R);  // Quaterniond::toRotationMatrix
+    const double inv_s = 1. / Siw[7];
+    cv::Mat Tiw(4, 4, CV_32F);  // Converter::toCvSE3
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) Tiw.at<float>(i, j) = (float)R[i * 3 + j];
+      Tiw.at<float>(i, 3) = (float)(Siw[4 + i] * inv_s);
+    }
+    Tiw.at<float>(3, 3) = 1.f;
+    pKFi->SetPose(Tiw);
+  }
+  // map points (:1479-1518): through their reference keyframe, from its pose before to its pose after the optimisation
+  const std::vector<MapPoint*> vpMPs = pMap->GetAllMapPoints();
+  parallel_ranges(vpMPs.size(), host_threads(vpMPs.size()), [&](int, size_t a, size_t b) {
+    for (size_t i = a; i < b; i++) {
+      MapPoint* pMP = vpMPs[i];
+      if (pMP->isBad()) continue;
+      size_t nIDr;
+      if (pMP->mnCorrectedByKF == pCurKF->mnId) {
+        nIDr = pMP->mnCorrectedReference;
+      } else {
+        KeyFrame* pRefKF = pMP->GetReferenceKeyFrame();
+        nIDr = pRefKF->mnId;
+      }
+      if (nIDr >= G.present.size() || !G.present[nIDr]) continue;
+      const double* Srw = &G.vScw[nIDr * 8];
+      const double* Swr = &vCorrectedSwc[nIDr * 8];
+      const cv::Mat P3Dw = pMP->GetWorldPos();
+      const double X[3] = {P3Dw.at<float>(0), P3Dw.at<float>(1), P3Dw.at<float>(2)};
+      double rc[3], c[3], rw[3], w[3];
+      sqrtba::sim3_rotate(Srw, X, rc);  // Sim3::map: s * (r * xyz) + t
+      for (int k = 0; k < 3; k++) c[k] = Srw[7] * rc[k] + Srw[4 + k];
+      sqrtba::sim3_rotate(Swr, c, rw);
+      for (int k = 0; k < 3; k++) w[k] = Swr[7] * rw[k] + Swr[4 + k];
+      pMP->SetWorldPos(toCvMat3(w));
+      pMP->UpdateNormalAndDepth();
+    }
+  });
+}
+
 // ---- the flat problems the adapters hand to the C ABI, without solving (host-side tests, no GPU needed)
 static void to_flat(const Gathered& g, sqrtbaOptimizer::FlatProblem& out) {
   out.pose_qt = g.pose_qt; out.cam = g.cam; out.point_xyz = g.point_xyz; out.pose_fixed = g.pose_fixed;
@@ -624,6 +810,12 @@ void Optimizer::GlobalBundleAdjustemnt(Map* pMap, int nIterations, bool* pbStopF
 void Optimizer::BundleAdjustment(const std::vector<KeyFrame*>& vpKFs, const std::vector<MapPoint*>& vpMP, int nIterations,
                                  bool* pbStopFlag, const unsigned long nLoopKF, const bool bRobust) {
   sqrtbaOptimizer::BundleAdjustment(vpKFs, vpMP, nIterations, pbStopFlag, nLoopKF, bRobust);
+}
+void Optimizer::OptimizeEssentialGraph(Map* pMap, KeyFrame* pLoopKF, KeyFrame* pCurKF,
+                                       const LoopClosing::KeyFrameAndPose& NonCorrectedSim3,
+                                       const LoopClosing::KeyFrameAndPose& CorrectedSim3,
+                                       const std::map<KeyFrame*, std::set<KeyFrame*>>& LoopConnections, const bool& bFixScale) {
+  sqrtbaOptimizer::OptimizeEssentialGraph(pMap, pLoopKF, pCurKF, NonCorrectedSim3, CorrectedSim3, LoopConnections, bFixScale);
 }
 void Optimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* lidarconfig) {
   sqrtbaOptimizer::LocalBundleAdjustment(pKF, pbStopFlag, pMap, lidarconfig);

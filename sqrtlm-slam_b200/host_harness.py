@@ -29,6 +29,13 @@ def lib():
                                      C.c_int, up]
         L.hh_local_ba.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hh_set_options.argtypes = [C.c_int, C.c_int]
+        dpp = C.POINTER(C.c_double)
+        L.hh_set_parent.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hh_add_loop_edge.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hh_set_weight.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.hh_set_ref_kf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_long]
+        L.hh_essential_graph.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, ip, dpp, dpp, C.c_int, ip, C.c_int, ip]
+        L.hh_essential_graph_get.argtypes = [dpp, up, up, ip, dpp]
         L.hh_global_ba.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_ulong, C.c_void_p]
         L.hh_get_pose.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
         L.hh_get_point.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
@@ -84,10 +91,61 @@ class MockMap:
         self.h = lib().hh_build(prob.n_pose, _f(k[0]), _f(k[1]), _f(k[2]), len(inv), prob.n_point, _f(k[3]), prob.n_obs,
                                 _i(k[4]), _i(k[5]), _f(k[6]), _i(k[7]))
 
+    @classmethod
+    def from_poses(cls, Tcw, points):
+        """A map of keyframes (float 4x4 Tcw each, mnId = index) and map points without observations: what the
+        essential-graph adapter needs (spanning tree / loop edges / weights are set with the methods below)."""
+        self = cls.__new__(cls)
+        self.prob = None
+        T = np.ascontiguousarray(Tcw, np.float32)
+        X = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        cam = np.array([synth.FX, synth.FY, synth.CX, synth.CY, synth.BF], np.float32)
+        inv = synth.inv_level_sigma2()
+        e_i, e_f = np.zeros(1, np.int32), np.zeros(3, np.float32)
+        self._keep = [T, cam, inv, X, e_i, e_f]
+        self.h = lib().hh_build(len(T), _f(T), _f(cam), _f(inv), len(inv), len(X), _f(X), 0, _i(e_i), _i(e_i), _f(e_f), _i(e_i))
+        return self
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().hh_destroy(self.h)
             self.h = None
+
+    # ---- essential graph (Optimizer::OptimizeEssentialGraph)
+    def set_parent(self, kf, parent):
+        lib().hh_set_parent(self.h, kf, parent)
+
+    def add_loop_edge(self, a, b):
+        lib().hh_add_loop_edge(self.h, a, b)
+
+    def set_weight(self, a, b, w):
+        lib().hh_set_weight(self.h, a, b, w)
+
+    def set_ref_kf(self, mp, kf, corrected_by=-1, corrected_ref=0):
+        lib().hh_set_ref_kf(self.h, mp, kf, corrected_by, corrected_ref)
+
+    def essential_graph(self, loop_kf, cur_kf, corrected, non_corrected, connections, fix_scale, optimise):
+        """corrected / non_corrected: {kf: Sim3 as 8 doubles} (LoopClosing::KeyFrameAndPose, same keys); connections:
+        [(kf, kf)] (LoopConnections).  optimise=False returns the graph the adapter would hand to sqrtba_pose_graph
+        (no GPU needed); optimise=True runs Optimizer::OptimizeEssentialGraph on the map."""
+        L = lib()
+        ids = np.array(sorted(corrected), np.int32)
+        c8 = np.ascontiguousarray([corrected[int(k)] for k in ids], np.float64).reshape(-1, 8)
+        n8 = np.ascontiguousarray([non_corrected[int(k)] for k in ids], np.float64).reshape(-1, 8)
+        conn = np.ascontiguousarray(connections, np.int32).reshape(-1, 2)
+        sz = np.zeros(3, np.int32)
+        dp = C.POINTER(C.c_double)
+        L.hh_essential_graph(self.h, 1 if optimise else 0, loop_kf, cur_kf, len(ids), _i(ids), c8.ctypes.data_as(dp),
+                             n8.ctypes.data_as(dp), len(conn), _i(conn), int(fix_scale), _i(sz))
+        if optimise:
+            return None
+        nv, ne = int(sz[0]), int(sz[1])
+        out = dict(vert8=np.zeros((nv, 8)), fixed=np.zeros(nv, np.uint8), present=np.zeros(nv, np.uint8),
+                   edge_ij=np.zeros((ne, 2), np.int32), meas8=np.zeros((ne, 8)))
+        up = C.POINTER(C.c_uint8)
+        L.hh_essential_graph_get(out["vert8"].ctypes.data_as(dp), out["fixed"].ctypes.data_as(up), out["present"].ctypes.data_as(up),
+                                 _i(out["edge_ij"]), out["meas8"].ctypes.data_as(dp))
+        return out
 
     def set_covisible(self, kf, others):
         a = np.ascontiguousarray(others, np.int32)

@@ -66,9 +66,10 @@ def so3_exp(w):
     return np.eye(3) + a * K + b * (K @ K)
 
 
-def rotmat_to_quat_eigen(R):
+def rotmat_to_quat_eigen(R, normalize=True):
     """Eigen's Quaterniond(Matrix3d) branches (what SE3Quat(R,t) calls, se3quat.h:58),
-    followed by SE3Quat::normalizeRotation (se3quat.h:280-285). Returns (...,4) x,y,z,w."""
+    followed by SE3Quat::normalizeRotation (se3quat.h:280-285) unless normalize=False (g2o::Sim3(R,t,s) keeps the
+    quaternion as Eigen returns it, sim3.h:60-66). Returns (...,4) x,y,z,w."""
     R = np.asarray(R, dtype=np.float64)
     flat = R.reshape(-1, 3, 3)
     out = np.zeros((flat.shape[0], 4))
@@ -95,6 +96,9 @@ def rotmat_to_quat_eigen(R):
             q[j] = (m[j, i] + m[i, j]) * t
             q[k] = (m[k, i] + m[i, k]) * t
         q = np.array(q)
+        if not normalize:
+            out[n] = q
+            continue
         if q[3] < 0:
             q = -q
         out[n] = q / np.sqrt(np.dot(q, q))

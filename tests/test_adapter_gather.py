@@ -177,3 +177,27 @@ def test_fork_default_drops_stereo_observations(pkg, synth):
             np.testing.assert_array_equal(m.point(j), X[list(used).index(j)].astype(np.float32))
         else:
             np.testing.assert_array_equal(m.point(j), before[j])
+
+
+def test_essential_graph_gather(pkg, synth):
+    """The graph sqrtbaOptimizer::OptimizeEssentialGraph builds from the map (no GPU): vertices = Sim3-corrected poses
+    where loop closing has them, the keyframe's own pose otherwise; edges by the reference's rules
+    (g2oOptimizer.cc:1306-1448): new loop connections (weight >= 100 except the loop pair itself), spanning tree,
+    earlier loop edges, covisibility >= 100 to older keyframes unless already inserted; relative poses from the
+    NON-corrected estimates."""
+    import essential_graph_case as egc
+    case = egc.build(pkg, synth)
+    g = case["map"].essential_graph(case["loop_kf"], case["cur_kf"], case["corrected"], case["non_corrected"],
+                                    case["connections"], True, optimise=False)
+    vert, edges, meas = egc.expected_graph(case, synth)
+    assert g["present"].all() and g["fixed"].sum() == 1 and g["fixed"][case["loop_kf"]] == 1
+    np.testing.assert_allclose(g["vert8"], vert, rtol=0, atol=1e-12)
+    got = {(int(i), int(j)): mm for (i, j), mm in zip(g["edge_ij"], g["meas8"])}
+    want = {e: mm for e, mm in zip(edges, meas)}
+    assert len(got) == len(g["edge_ij"]) and set(got) == set(want)
+    for e in want:
+        np.testing.assert_allclose(got[e], want[e], rtol=0, atol=1e-12)
+    # spot checks of the rules
+    cur, n = case["cur_kf"], case["n_kf"]
+    assert (cur, 0) in got and (cur, 1) in got and (cur - 1, 1) in got and (cur - 2, 2) not in got
+    assert (12, 3) in got and (4, 2) in got and (5, 3) not in got and (6, 3) not in got

@@ -181,3 +181,37 @@ def test_pose_optimization_through_reference_api(pkg, synth):
         Tk, fk = f.state()
         assert np.array_equal(fk, rf)
         np.testing.assert_allclose(Tk, f32_pose_matrix(rp, synth), rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("fix_scale", [True, False])
+def test_essential_graph_through_reference_api(pkg, synth, fix_scale):
+    """Optimizer::OptimizeEssentialGraph(pMap, pLoopKF, pCurKF, NonCorrectedSim3, CorrectedSim3, LoopConnections,
+    bFixScale) (include/backend/Optimizer.h:62-67) on a mock map after a loop closure: keyframe poses become
+    [R | t/s] of the optimised Sim3 (g2oOptimizer.cc:1459-1476), every good map point moves with its reference keyframe
+    (:1479-1518).  Expected values: the oracle's pose-graph optimisation of the graph the adapter gathers."""
+    import essential_graph_case as egc
+    case = egc.build(pkg, synth, n_kf=48, seed=5, fix_scale=fix_scale)
+    m = case["map"]
+    args = (case["loop_kf"], case["cur_kf"], case["corrected"], case["non_corrected"], case["connections"], fix_scale)
+    g = m.essential_graph(*args, optimise=False)
+    Vr, trr, _ = refba.pose_graph(g["vert8"], g["fixed"], fix_scale, g["edge_ij"], g["meas8"], iters=20)
+    assert trr[trr[:, 7] == 1][-1, 5] < 0.2 * trr[0, 4]
+    m.essential_graph(*args, optimise=True)
+    assert m.last_error() == ""
+    scale = 1.0 + np.abs(Vr[:, 4:7]).max()
+    moved = 0.0
+    for k in range(case["n_kf"]):
+        R = synth.quat_to_rotmat(Vr[k, :4] / np.linalg.norm(Vr[k, :4]))
+        T = m.pose(k)
+        np.testing.assert_allclose(T[:3, :3], R.astype(np.float32), rtol=0, atol=2e-5)
+        np.testing.assert_allclose(T[:3, 3], (Vr[k, 4:7] / Vr[k, 7]).astype(np.float32), rtol=0, atol=2e-5 * scale)
+        moved = max(moved, float(np.abs(T[:3, 3] - case["T"][k, :3, 3]).max()))
+    assert moved > 0.005                                                 # the drift was actually distributed
+    np.testing.assert_array_equal(m.pose(case["loop_kf"]), case["T"][case["loop_kf"]] if fix_scale else m.pose(case["loop_kf"]))
+    for j in range(0, len(case["pts"]), 3):                               # Swr_corrected.map(Srw.map(P))
+        r = int(case["ref"][j])
+        X = case["pts"][j].astype(np.float64)
+        c = synth.sim3_mul(g["vert8"][r], np.concatenate([[0, 0, 0, 1.0], X, [1.0]]))[4:7]
+        w = synth.sim3_mul(synth.sim3_inv(Vr[r]), np.concatenate([[0, 0, 0, 1.0], c, [1.0]]))[4:7]
+        np.testing.assert_allclose(m.point(j), w.astype(np.float32), rtol=0, atol=5e-5 * scale)
+        assert m.point_updates(j) == 1

@@ -86,7 +86,9 @@ def test_essential_graph_matches_oracle(ba, synth, n_kf, fix_scale, seed):
     assert np.all(tr[:k][~acc, 5] > tr[:k][~acc, 4]) and np.all(trr[:k][~acc, 5] > trr[:k][~acc, 4])
     fg, fr = tr[tr[:, 7] == 1][-1, 5], trr[trr[:, 7] == 1][-1, 5]
     assert abs(fg - fr) <= 1e-6 * chi0
-    sim3_close(V, Vr, 1e-5)
+    # free scale: the optimum is flat along a near-gauge direction, so the numeric-Jacobian noise moves the estimates
+    # more than the cost (same bound as the oracle's own check against the binary)
+    sim3_close(V, Vr, 1e-5 if fix_scale else 1e-4)
     assert fg < 1e-2 * chi0                                              # the loop closes: the drift is distributed
 
 
