@@ -3,6 +3,7 @@
 // (src/backend/LocalMapping.cc:131, src/backend/LoopClosing.cc:987), and exposes the resulting map state.
 #include <algorithm>
 #include <cstdint>
+#include <list>
 #include <memory>
 
 #include "Optimizer.h"
@@ -168,6 +169,63 @@ void hh_essential_graph_get(double* vert8, uint8_t* fixed, uint8_t* present, int
   std::copy(g_pg.edge_ij.begin(), g_pg.edge_ij.end(), edge_ij);
   std::copy(g_pg.meas8.begin(), g_pg.meas8.end(), meas8);
 }
+// ---- what LoopClosing::RunGlobalBundleAdjustment does with the staged global-BA result (src/backend/LoopClosing.cc:
+// 1014-1103), restated as the CALLER's code for the integration test: keyframes and points that did not take part in
+// the optimisation (created while it ran) follow their parent / reference keyframe.  Float 4x4 arithmetic like cv::Mat.
+static cv::Mat mul4(const cv::Mat& A, const cv::Mat& B) {
+  cv::Mat Cm(4, 4, CV_32F);
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      float acc = 0.f;
+      for (int k = 0; k < 4; k++) acc += A.at<float>(i, k) * B.at<float>(k, j);
+      Cm.at<float>(i, j) = acc;
+    }
+  return Cm;
+}
+void hh_forget_gba(hh_map* m, int kf, int mp) {  // as if created after the global BA started
+  if (kf >= 0) m->kfs[kf]->mnBAGlobalForKF = 0;
+  if (mp >= 0) m->mps[mp]->mnBAGlobalForKF = 0;
+}
+void hh_apply_gba(hh_map* m, unsigned long nLoopKF) {
+  std::unique_lock<std::mutex> lock(m->map.mMutexMapUpdate);
+  std::list<KeyFrame*> lpKFtoCheck(m->map.mvpKeyFrameOrigins.begin(), m->map.mvpKeyFrameOrigins.end());
+  while (!lpKFtoCheck.empty()) {
+    KeyFrame* pKF = lpKFtoCheck.front();
+    const std::set<KeyFrame*> sChilds = pKF->GetChilds();
+    cv::Mat Twc = pKF->GetPoseInverse();
+    for (KeyFrame* pChild : sChilds) {
+      if (pChild->mnBAGlobalForKF != nLoopKF) {
+        cv::Mat Tchildc = mul4(pChild->GetPose(), Twc);
+        pChild->mTcwGBA = mul4(Tchildc, pKF->mTcwGBA);
+        pChild->mnBAGlobalForKF = nLoopKF;
+      }
+      lpKFtoCheck.push_back(pChild);
+    }
+    pKF->mTcwBefGBA = pKF->GetPose();
+    pKF->SetPose(pKF->mTcwGBA);
+    lpKFtoCheck.pop_front();
+  }
+  for (MapPoint* pMP : m->map.GetAllMapPoints()) {
+    if (pMP->isBad()) continue;
+    if (pMP->mnBAGlobalForKF == nLoopKF) {
+      pMP->SetWorldPos(pMP->mPosGBA);
+    } else {
+      KeyFrame* pRefKF = pMP->GetReferenceKeyFrame();
+      if (!pRefKF || pRefKF->mnBAGlobalForKF != nLoopKF) continue;
+      const cv::Mat& B = pRefKF->mTcwBefGBA;
+      const cv::Mat X = pMP->GetWorldPos();
+      float Xc[3];
+      for (int i = 0; i < 3; i++)
+        Xc[i] = B.at<float>(i, 0) * X.at<float>(0) + B.at<float>(i, 1) * X.at<float>(1) + B.at<float>(i, 2) * X.at<float>(2) + B.at<float>(i, 3);
+      const cv::Mat Twc = pRefKF->GetPoseInverse();
+      cv::Mat W(3, 1, CV_32F);
+      for (int i = 0; i < 3; i++)
+        W.at<float>(i) = Twc.at<float>(i, 0) * Xc[0] + Twc.at<float>(i, 1) * Xc[1] + Twc.at<float>(i, 2) * Xc[2] + Twc.at<float>(i, 3);
+      pMP->SetWorldPos(W);
+    }
+  }
+}
+void hh_set_origin(hh_map* m, int kf) { m->map.mvpKeyFrameOrigins.push_back(m->kfs[kf].get()); }
 void hh_set_options(int local_ba_stereo_edges, int local_ba_two_pass) {
   sqrtbaOptimizer::options().local_ba_stereo_edges = local_ba_stereo_edges != 0;
   sqrtbaOptimizer::options().local_ba_two_pass = local_ba_two_pass != 0;

@@ -103,6 +103,19 @@ class KeyFrame {
                           for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R.at<float>(i, j) = Tcw.at<float>(i, j); return R; }
   cv::Mat GetTranslation() { std::unique_lock<std::mutex> l(mMutexPose); cv::Mat t(3, 1, CV_32F);
                              for (int i = 0; i < 3; i++) t.at<float>(i) = Tcw.at<float>(i, 3); return t; }
+  std::set<KeyFrame*> GetChilds() { return mspChildrens; }
+  cv::Mat GetPoseInverse() {  // Twc = [Rcw^T | -Rcw^T tcw], float as in KeyFrame::SetPose (KeyFrame.cc:102-124)
+    std::unique_lock<std::mutex> l(mMutexPose);
+    cv::Mat Twc(4, 4, CV_32F);
+    for (int i = 0; i < 3; i++) {
+      float o = 0.f;
+      for (int j = 0; j < 3; j++) { Twc.at<float>(i, j) = Tcw.at<float>(j, i); o += Tcw.at<float>(j, i) * Tcw.at<float>(j, 3); }
+      Twc.at<float>(i, 3) = -o;
+    }
+    Twc.at<float>(3, 3) = 1.f;
+    return Twc;
+  }
+  cv::Mat mTcwBefGBA;  // KeyFrame.h:389
   KeyFrame* mpParent = nullptr;
   std::set<KeyFrame*> mspLoopEdges, mspChildrens;
   std::map<KeyFrame*, int> mConnectedKeyFrameWeights;
@@ -163,6 +176,7 @@ class Map {
   std::mutex mMutexMapUpdate;
   std::vector<KeyFrame*> mspKeyFrames;
   std::vector<MapPoint*> mspMapPoints;
+  std::vector<KeyFrame*> mvpKeyFrameOrigins;  // Map.h:138
 };
 // include/backend/LoopClosing.h:63-65
 class LoopClosing {

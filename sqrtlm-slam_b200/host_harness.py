@@ -30,6 +30,9 @@ def lib():
         L.hh_local_ba.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hh_set_options.argtypes = [C.c_int, C.c_int]
         dpp = C.POINTER(C.c_double)
+        L.hh_forget_gba.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hh_apply_gba.argtypes = [C.c_void_p, C.c_ulong]
+        L.hh_set_origin.argtypes = [C.c_void_p, C.c_int]
         L.hh_set_parent.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.hh_add_loop_edge.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.hh_set_weight.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -110,6 +113,17 @@ class MockMap:
         if getattr(self, "h", None):
             lib().hh_destroy(self.h)
             self.h = None
+
+    # ---- the caller's use of the staged global-BA result (LoopClosing::RunGlobalBundleAdjustment, LoopClosing.cc:1014-1103)
+    def set_origin(self, kf):
+        lib().hh_set_origin(self.h, kf)
+
+    def forget_gba(self, kf=-1, mp=-1):
+        """Reset the global-BA marker of a keyframe / point: as if it was created while the optimisation ran."""
+        lib().hh_forget_gba(self.h, kf, mp)
+
+    def apply_gba(self, n_loop_kf):
+        lib().hh_apply_gba(self.h, n_loop_kf)
 
     # ---- essential graph (Optimizer::OptimizeEssentialGraph)
     def set_parent(self, kf, parent):

@@ -215,3 +215,48 @@ def test_essential_graph_through_reference_api(pkg, synth, fix_scale):
         w = synth.sim3_mul(synth.sim3_inv(Vr[r]), np.concatenate([[0, 0, 0, 1.0], c, [1.0]]))[4:7]
         np.testing.assert_allclose(m.point(j), w.astype(np.float32), rtol=0, atol=5e-5 * scale)
         assert m.point_updates(j) == 1
+
+
+def test_global_ba_result_propagation_by_the_caller(pkg, synth):
+    """Loop closing calls GlobalBundleAdjustemnt(map, 10, &stop, nLoopKF, false) and then spreads the STAGED result
+    (mTcwGBA / mPosGBA / mnBAGlobalForKF, written by the adapter) over the spanning tree: keyframes and points created
+    while the optimisation ran follow their parent / reference keyframe (LoopClosing.cc:987-1103; restated as caller
+    code in host/harness.cc).  Checks that the adapter stages exactly what that code consumes."""
+    prob = synth.make_problem(19, 30, 1, 1500, 7.0, stereo=True, loop=True, cand_halfwidth=8, name="gba-propagate")
+    m = pkg.host_harness.MockMap(prob)
+    for k in range(1, prob.n_pose):
+        m.set_parent(k, k - 1)
+    m.set_origin(0)
+    ref_kf = np.full(prob.n_point, -1)
+    for o in range(prob.n_obs):
+        if ref_kf[prob.obs_point[o]] < 0:
+            ref_kf[prob.obs_point[o]] = prob.obs_pose[o]
+    for j in range(prob.n_point):
+        m.set_ref_kf(j, int(ref_kf[j]))
+    n_loop = 9
+    m.global_ba(10, False, n_loop)
+    late_kf, late_mp = prob.n_pose - 1, int(np.nonzero(ref_kf == 5)[0][0])
+    m.forget_gba(kf=late_kf, mp=late_mp)
+    before = [m.pose(i).copy() for i in range(prob.n_pose)]
+    staged = [m.pose(i, gba=True).copy() for i in range(prob.n_pose)]
+    x_before = m.point(late_mp).copy()
+    m.apply_gba(n_loop)
+    ref = refba.RefBA(prob)
+    ref.solve_global(10, False)
+    P, X = ref.poses(), ref.points()
+    for i in range(prob.n_pose - 1):
+        np.testing.assert_array_equal(m.pose(i), staged[i])
+        np.testing.assert_allclose(m.pose(i), f32_pose_matrix(P[i], synth), rtol=0, atol=2e-5)
+    # the late keyframe keeps its pose RELATIVE to its parent: Tchild * Twc_parent(before) * TcwGBA_parent
+    par = late_kf - 1
+    want = before[late_kf].astype(np.float64) @ np.linalg.inv(before[par].astype(np.float64)) @ staged[par].astype(np.float64)
+    np.testing.assert_allclose(m.pose(late_kf), want, rtol=0, atol=5e-5)
+    assert m.gba_marker(late_kf) == n_loop
+    for j in range(0, prob.n_point, 40):
+        if j != late_mp:
+            np.testing.assert_allclose(m.point(j), X[j].astype(np.float32), rtol=2e-6, atol=2e-5)
+    # the late point moves with its reference keyframe: Twc_after * (Tcw_before * X)
+    r = int(ref_kf[late_mp])
+    Xc = before[r][:3, :3].astype(np.float64) @ x_before.astype(np.float64) + before[r][:3, 3]
+    Ta = np.linalg.inv(m.pose(r).astype(np.float64))
+    np.testing.assert_allclose(m.point(late_mp), Ta[:3, :3] @ Xc + Ta[:3, 3], rtol=0, atol=5e-5)
