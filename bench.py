@@ -8,7 +8,8 @@ every rank owns `--windows-per-gpu` windows, no data-path collective (weak scali
 
   value   observations x LM trials per second with the batch already resident in HBM (solve only)
   e2e     the same metric through the C ABI with HOST buffers: sqrtba_set_problem_batch (H2D) + solve + read-back (D2H)
-  roofline  PCG matvec kernel: algorithmic bytes (216 B per free-pose stereo observation) / CUDA-event time per launch
+  roofline  PCG matvec kernel: SURVEY 8(d)'s algorithmic bytes (216 B per free-pose stereo observation) / CUDA-event time
+            per launch, beside the bytes the kernel's own layout moves (104 B: the 3x6 pose block is rebuilt from four numbers)
   cpu_baseline  the oracle (g2o Schur-LM restatement, oracle/refba.cpp) on a bounded sample, 1 thread
 
 `--impl reference` times that CPU implementation with all host threads (one window per thread).
@@ -30,6 +31,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+ALG_MATVEC = 216.0     # canonical bytes per free-pose stereo observation of the matvec / back-substitution
+LAYOUT_MATVEC = 104.0  # bytes per free-pose observation the kernels actually stream (4 geometry rows + 9 rows of Q1)
 METRIC = "local-BA observations/s (KITTI-00-shaped stereo windows, observations x LM trials per second)"
 UNIT = "obs/s"
 
@@ -233,7 +236,7 @@ def run_reference(args):
 
 def load_traffic():
     """dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_matvec_ncu_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_matvec_ncu_traffic.json")
     try:
         return json.load(open(p))
     except Exception:
@@ -318,15 +321,18 @@ def run_extras(pkg, torch, dist, world, rank, local, barrier, args):
                     "k_qr_pipe2": ba.time_stage(2, 2, 10), "k_backsub": ba.time_stage(4, 2, 10)}
         ba.close()
         n_lm = prob.n_point
-        alg = {"k_matvec_pipe": free_obs * 216.0, "k_linearize_pipe": prob.n_obs * 288.0,
-               "k_qr_pipe2": prob.n_obs * 312.0 + n_lm * 72.0, "k_backsub": free_obs * 216.0 + n_lm * 168.0}
+        # SURVEY 8(d) / DESIGN.md section 4 figures (canonical layout), as in round 1
+        alg = {"k_matvec_pipe": free_obs * ALG_MATVEC, "k_linearize_pipe": prob.n_obs * 288.0,
+               "k_qr_pipe2": prob.n_obs * 312.0 + n_lm * 72.0, "k_backsub": free_obs * ALG_MATVEC + n_lm * 168.0}
         leg["roofline"] = {"bound": "hbm", "peak": peaks["hbm_gbs"], "unit": "GB/s",
                            "kernels": {k: {"ms": v, "algorithmic_bytes": alg[k], "achieved": alg[k] / (v * 1e-3) / 1e9,
                                            "frac": alg[k] / (v * 1e-3) / 1e9 / peaks["hbm_gbs"]} for k, v in stage_ms.items()},
-                           "persistent_pcg": {"us_per_cg_iteration": us_cg, "achieved": free_obs * 216.0 / (us_cg * 1e-6) / 1e9,
-                                              "frac": free_obs * 216.0 / (us_cg * 1e-6) / 1e9 / peaks["hbm_gbs"],
+                           "persistent_pcg": {"us_per_cg_iteration": us_cg, "achieved": free_obs * ALG_MATVEC / (us_cg * 1e-6) / 1e9,
+                                              "frac": free_obs * ALG_MATVEC / (us_cg * 1e-6) / 1e9 / peaks["hbm_gbs"],
+                                              "achieved_moved": free_obs * LAYOUT_MATVEC / (us_cg * 1e-6) / 1e9,
                                               "note": "one CG iteration of k_pcg_persist = matvec over all tiles + grid barrier + vector update"},
-                           "note": "working set per CG iteration ~ 110 MB: close to the 126 MB L2, so these are HBM/L2 mixed rates"}
+                           "note": "SURVEY 8(d) bytes; the layout moves 104 B per free observation, so one CG iteration touches "
+                                   "~61 MB: L2-resident on this GPU (126 MB) -- these are L2 rates, not HBM rates"}
         if cpu_ok:
             dt, ref = oracle_local(prob, 1)
             dta, _ = oracle_local(prob, cores)
@@ -364,10 +370,11 @@ def run_extras(pkg, torch, dist, world, rank, local, barrier, args):
                         "lm_trials": len(tr), "cg_iters_total": int(tr[:, 8].sum()), "final_chi2": float(tr[-1, 5]),
                         "persistent_pcg": st["persistent_pcg"], "peer_exchange": st["peer_exchange"],
                         "us_per_cg_iteration_incl_everything": us_iter,
-                        "matvec_algorithmic_bytes_all_ranks": free_obs * 216.0,
+                        "matvec_algorithmic_bytes_all_ranks": free_obs * ALG_MATVEC,
+                        "matvec_layout_bytes_all_ranks": free_obs * LAYOUT_MATVEC,
                         "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"] * world,
-                                     "achieved": free_obs * 216.0 / (us_iter * 1e-6) / 1e9,
-                                     "frac": free_obs * 216.0 / (us_iter * 1e-6) / 1e9 / (peaks["hbm_gbs"] * world),
+                                     "achieved": free_obs * ALG_MATVEC / (us_iter * 1e-6) / 1e9,
+                                     "frac": free_obs * ALG_MATVEC / (us_iter * 1e-6) / 1e9 / (peaks["hbm_gbs"] * world),
                                      "note": "whole time-to-converge / CG iterations, i.e. linearise, QR, barriers and the "
                                              "NVLink exchange all charged to the matvec's algorithmic bytes; peak = N x one GPU"}}
     if cpu_ok:  # the reference's CPU algorithm on the same map: time-to-converge, 1 thread (faithful) and all cores
@@ -467,7 +474,8 @@ def main():
     ms_lin = ba.time_stage(1, warmup=2, reps=5)
     ms_qr = ba.time_stage(2, warmup=2, reps=5)
     peaks, peak_kind = measured_peaks()
-    alg_bytes = free_obs * 216.0
+    alg_bytes = free_obs * ALG_MATVEC          # the figure roofline.achieved is defined on
+    moved_bytes = free_obs * LAYOUT_MATVEC     # what this kernel's operand layout streams per launch
     achieved = alg_bytes / (ms_matvec * 1e-3) / 1e9
     tr_info = load_traffic()
     traffic = None
@@ -478,8 +486,14 @@ def main():
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": (tr_info or {}).get("source"),
                 "peak_kind": peak_kind, "kernel": "k_matvec_pipe<2,false>",
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_matvec,
-                "note": "216 B per free-pose stereo observation (Jp 3x6 + Q1 3x3, FP64); observations of fixed "
-                        "keyframes have no pose columns and are not streamed",
+                "moved": {"layout_bytes_per_launch": moved_bytes, "achieved": moved_bytes / (ms_matvec * 1e-3) / 1e9,
+                          "frac": moved_bytes / (ms_matvec * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                          "note": "the operand stores {x/z, y/z, 1/z, w} + Q1 (104 B per free-pose observation) and rebuilds "
+                                  "the 3x6 pose block in registers: DRAM traffic is about half of the algorithmic figure, and "
+                                  "the kernel is bound by the per-tile dependency chain (issue slots 58 % busy at 20 warps/SM, "
+                                  "profiles/r02_matvec_compactJ_ncu_full.txt), no longer by HBM"},
+                "note": "achieved = SURVEY 8(d)'s 216 B per free-pose stereo observation (Jp 3x6 + Q1 3x3, FP64) x the "
+                        "launch's observations / time, as in round 1; observations of fixed keyframes have no pose columns",
                 "other_kernels_ms": {"k_linearize": ms_lin, "k_qr": ms_qr},
                 "pcg_share_of_step": None}
 

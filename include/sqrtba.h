@@ -65,7 +65,9 @@ typedef struct {
                                 [6] 1 = landmark-sharded global BA without peer-mapped buffers (NCCL all-reduce per iteration)
                                 [7] linearise / landmark-QR kernel variant: 0 = pipelined v2 (default), 1 = one tile per
                                     CTA, 2 = first pipelined version, 5 = v2 QR compiled for 5 CTAs/SM, 6 = linearisation with
-                                    L1 prefetch of the next tile's pose / landmark lines (experimental, not yet measured) */
+                                    L1 prefetch of the next tile's pose / landmark lines (experimental), 7 = fused
+                                    linearise + landmark QR kernel for the iterations whose lambda is known and the retries
+                                    (parity-tested; measured slower than the two separate kernels) */
 } sqrtba_config;
 
 /* one row per LM trial (g2o "levenbergIterations"), per window */
@@ -265,7 +267,8 @@ int sqrtba_debug_plan(int32_t n_win, const int64_t* win_pose_ptr, const int64_t*
                       uint32_t* obs_lp, int32_t* tile_run_ptr, int32_t* tile_runs, int64_t max_runs, int32_t* landmark_order);
 
 /* Time `reps` launches of one stage kernel on the handle's stream with CUDA events (after `warmup` untimed
- * launches); returns the average ms per launch.  stage: 0 matvec, 1 linearize, 2 landmark QR, 3 cost, 4 backsub. */
+ * launches); returns the average ms per launch.  stage: 0 matvec, 1 linearize, 2 landmark QR, 3 cost, 4 backsub,
+ * 5 fused linearise + landmark QR. */
 int sqrtba_time_stage(sqrtba_handle* h, int32_t stage, int32_t warmup, int32_t reps, double* ms_avg);
 
 #ifdef __cplusplus

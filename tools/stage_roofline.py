@@ -51,11 +51,13 @@ def main():
             ba.set_problem(prob)
         ba.debug_linearize(1)
         ba.debug_step(100.0)
+        # SURVEY 8(d) figures (canonical layout); 5 = fused linearise + QR: 264 B per observation + 168 B per landmark
         bytes_of = {0: free_obs * 216.0, 1: prob.n_obs * 288.0, 2: prob.n_obs * 312.0 + prob.n_point * 72.0,
-                    3: prob.n_obs * 24.0, 4: free_obs * 216.0 + prob.n_point * 168.0}
+                    3: prob.n_obs * 24.0, 4: free_obs * 216.0 + prob.n_point * 168.0,
+                    5: prob.n_obs * 264.0 + prob.n_point * 168.0}
         out = {"config": args.config, "variant": kw, "n_obs": prob.n_obs, "free_obs": free_obs, "n_point": prob.n_point,
                "n_free_pose": prob.n_free, "peak_gbs": peaks["hbm_gbs"], "peak_kind": kind, "kernels": {}}
-        stages = [(0, "k_matvec"), (1, "k_linearize"), (2, "k_qr"), (3, "k_cost"), (4, "k_backsub")]
+        stages = [(0, "k_matvec"), (1, "k_linearize"), (2, "k_qr"), (3, "k_cost"), (4, "k_backsub"), (5, "k_linqr_fused")]
         for stage, name in (stages if not kw else (stages[1:3] if kw.get("plain_qr") else (stages[1:3] if "qr_variant" in kw else stages[:1]))):
             ms = ba.time_stage(stage, warmup=3, reps=args.reps)
             gbs = bytes_of[stage] / (ms * 1e-3) / 1e9
