@@ -2979,7 +2979,7 @@ __global__ void __launch_bounds__(RCTA) k_lm_reduce_trial(Dev P) {
 
 // term_host: optional pointer into mapped pinned host memory that mirrors the caller's stop flag (bool* pbStopFlag):
 // read HERE, at the end of the trial -- the point where g2o's do-while evaluates terminate()
-// (optimization_algorithm_levenberg.cpp:161) -- instead of at the top of the macro step on the host.
+// (optimization_algorithm_levenberg.cpp:149) -- instead of at the top of the macro step on the host.
 __device__ __forceinline__ void lm_decide_body(const Dev& P, int win, int terminate, const volatile int* term_host, double* sh) {
   WinCtl& c = P.ctl[win];
   if (c.phase != PH_TRIAL) {
@@ -3076,7 +3076,7 @@ __global__ void __launch_bounds__(RCTA) k_decide_publish(Dev P, HostCtl* hc) {
 }
 
 // the stop flag was seen raised at the top of an iteration: `for (i < iterations && !terminate())` does not start it
-// (sparse_optimizer.cpp:383) -- windows that would have re-linearised or re-tried are finished as they are
+// (sparse_optimizer.cpp:376) -- windows that would have re-linearised or re-tried are finished as they are
 __global__ void k_terminate(Dev P) {
   const int win = blockIdx.x * blockDim.x + threadIdx.x;
   if (win >= P.n_win) return;

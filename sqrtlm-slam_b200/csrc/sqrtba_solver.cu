@@ -1913,7 +1913,7 @@ class Solver {
     for (int step = 0; step < max_macro; step++) {
       int term = 0;
       if (int rc = poll_stop(stop, &term)) return rc;
-      if (term) {  // `for (i < iterations && !terminate())`: the next iteration does not start (sparse_optimizer.cpp:383)
+      if (term) {  // `for (i < iterations && !terminate())`: the next iteration does not start (sparse_optimizer.cpp:376)
         if (step > 0) { k_terminate<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_); launches_++; }
         break;
       }

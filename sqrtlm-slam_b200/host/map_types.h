@@ -85,12 +85,12 @@ class KeyFrame {
     for (auto& p : mvpMapPoints)
       if (p == pMP) p = nullptr;
   }
-  // spanning tree / loop edges / covisibility weights: what OptimizeEssentialGraph reads (KeyFrame.h:136-159)
+  // spanning tree / loop edges / covisibility weights: what OptimizeEssentialGraph reads (KeyFrame.h:149-210)
   KeyFrame* GetParent() { return mpParent; }
   std::set<KeyFrame*> GetLoopEdges() { return mspLoopEdges; }
   bool hasChild(KeyFrame* pKF) { return mspChildrens.count(pKF) != 0; }
   int GetWeight(KeyFrame* pKF) { auto it = mConnectedKeyFrameWeights.find(pKF); return it == mConnectedKeyFrameWeights.end() ? 0 : it->second; }
-  std::vector<KeyFrame*> GetCovisiblesByWeight(const int& w) {  // ordered by decreasing weight (KeyFrame.cc:222-240)
+  std::vector<KeyFrame*> GetCovisiblesByWeight(const int& w) {  // ordered by decreasing weight (KeyFrame.cc:268-287)
     std::vector<std::pair<int, KeyFrame*>> v;
     for (auto& kv : mConnectedKeyFrameWeights)
       if (kv.second >= w) v.emplace_back(-kv.second, kv.first);
@@ -134,7 +134,7 @@ class MapPoint {
   long unsigned int mnId = 0;
   long unsigned int mnBALocalForKF = ~0ul, mnBAGlobalForKF = 0;
   cv::Mat mPosGBA;
-  long unsigned int mnCorrectedByKF = 0, mnCorrectedReference = 0;  // MapPoint.h:281-282 (set by LoopClosing::CorrectLoop)
+  long unsigned int mnCorrectedByKF = 0, mnCorrectedReference = 0;  // MapPoint.h:282-283 (set by LoopClosing::CorrectLoop)
   KeyFrame* GetReferenceKeyFrame() { return mpRefKF; }
   KeyFrame* mpRefKF = nullptr;
   int nUpdateNormalAndDepth = 0;
@@ -176,9 +176,9 @@ class Map {
   std::mutex mMutexMapUpdate;
   std::vector<KeyFrame*> mspKeyFrames;
   std::vector<MapPoint*> mspMapPoints;
-  std::vector<KeyFrame*> mvpKeyFrameOrigins;  // Map.h:138
+  std::vector<KeyFrame*> mvpKeyFrameOrigins;  // Map.h:141
 };
-// include/backend/LoopClosing.h:63-65
+// include/backend/LoopClosing.h:60-65
 class LoopClosing {
  public:
   typedef std::map<KeyFrame*, g2o::Sim3, std::less<KeyFrame*>> KeyFrameAndPose;

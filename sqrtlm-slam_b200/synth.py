@@ -69,7 +69,7 @@ def so3_exp(w):
 def rotmat_to_quat_eigen(R, normalize=True):
     """Eigen's Quaterniond(Matrix3d) branches (what SE3Quat(R,t) calls, se3quat.h:58),
     followed by SE3Quat::normalizeRotation (se3quat.h:280-285) unless normalize=False (g2o::Sim3(R,t,s) keeps the
-    quaternion as Eigen returns it, sim3.h:60-66). Returns (...,4) x,y,z,w."""
+    quaternion as Eigen returns it, sim3.h:63-66). Returns (...,4) x,y,z,w."""
     R = np.asarray(R, dtype=np.float64)
     flat = R.reshape(-1, 3, 3)
     out = np.zeros((flat.shape[0], 4))
