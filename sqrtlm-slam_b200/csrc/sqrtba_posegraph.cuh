@@ -168,30 +168,44 @@ __global__ void __launch_bounds__(PG_THREADS) k_pg_factor_solve(PgDev G, double 
     const long long dk = G.rowptr[k] + (k - G.first[k]);
     if (tid < 49) Akk[tid] = G.L[(size_t)dk * 49 + tid];
     __syncthreads();
-    if (tid == 0) {  // 7x7 Cholesky of the pivot and the inverse of its factor
+    if (tid < 32) {  // 7x7 Cholesky of the pivot by one warp: lane r < 7 owns row r in registers, the pivot row travels
+                     // by shuffles (a single-thread version over shared memory is one chain of dependent 30-cycle
+                     // accesses: 8 us per pivot)
+      const int r = tid;
+      double a[7], l[7];
+#pragma unroll
+      for (int c = 0; c < 7; c++) { a[c] = (r < 7) ? Akk[r * 7 + c] : 0.0; l[c] = 0.0; }
       bool ok = true;
+#pragma unroll
       for (int c = 0; c < 7; c++) {
-        double d = Akk[c * 7 + c];
-        for (int s = 0; s < c; s++) d -= Lkk[c * 7 + s] * Lkk[c * 7 + s];
+        double v = a[c];  // row r, column c minus the part already eliminated:  sum_{s<c} L[r][s] * L[c][s]
+#pragma unroll
+        for (int s2 = 0; s2 < 7; s2++)
+          if (s2 < c) v -= l[s2] * __shfl_sync(0xffffffffu, l[s2], c);
+        double d = __shfl_sync(0xffffffffu, v, c);  // the pivot's own diagonal entry
         if (!(d > 0.0) || !isfinite(d)) { ok = false; d = 1.0; }
-        const double l = sqrt(d);
-        Lkk[c * 7 + c] = l;
-        for (int r = c + 1; r < 7; r++) {
-          double v = Akk[r * 7 + c];
-          for (int s = 0; s < c; s++) v -= Lkk[r * 7 + s] * Lkk[c * 7 + s];
-          Lkk[r * 7 + c] = v / l;
-        }
-        for (int r = 0; r < c; r++) Lkk[r * 7 + c] = 0.0;
+        const double lcc = sqrt(d);
+        l[c] = (r == c) ? lcc : ((r > c) ? v / lcc : 0.0);
       }
-      for (int c = 0; c < 7; c++) {  // inverse of the lower-triangular factor, column by column
-        for (int r = 0; r < 7; r++) {
-          if (r < c) { Lki[r * 7 + c] = 0.0; continue; }
-          double v = (r == c) ? 1.0 : 0.0;
-          for (int s = c; s < r; s++) v -= Lkk[r * 7 + s] * Lki[s * 7 + c];
-          Lki[r * 7 + c] = v / Lkk[r * 7 + r];
-        }
+      if (r < 7) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) Lkk[r * 7 + c] = l[c];
       }
-      if (!ok) fail = 1;
+      __syncwarp();
+      if (r < 7) {  // lane r: column r of the inverse of L by forward substitution (L read from shared memory: broadcasts)
+        double x[7];
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+          double v = (i == r) ? 1.0 : 0.0;
+#pragma unroll
+          for (int s2 = 0; s2 < 7; s2++)
+            if (s2 < i) v -= Lkk[i * 7 + s2] * x[s2];
+          x[i] = (i < r) ? 0.0 : v / Lkk[i * 7 + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 7; i++) Lki[i * 7 + r] = x[i];
+      }
+      if (r == 0 && !ok) fail = 1;
     }
     __syncthreads();
     if (tid < 49) {
@@ -251,16 +265,19 @@ __global__ void __launch_bounds__(PG_THREADS) k_pg_factor_solve(PgDev G, double 
     }
     __syncthreads();
   }
-  // forward substitution  L y = b  (y holds b on entry)
+  // forward substitution  L y = b  and backward substitution  L^T x = y, in place on one shared-memory vector
+  extern __shared__ double ysh[];  // 7 * n_slot doubles (dynamic), preceded by nothing
+  for (int t = tid; t < n * 7; t += PG_THREADS) ysh[t] = G.y[t];
+  __syncthreads();
   for (int k = 0; k < n; k++) {
     if (tid < 7) {
       double v = 0.0;
 #pragma unroll
-      for (int s = 0; s < 7; s++) v += G.Linv[(size_t)k * 49 + tid * 7 + s] * G.y[(size_t)k * 7 + s];
+      for (int s2 = 0; s2 < 7; s2++) v += G.Linv[(size_t)k * 49 + tid * 7 + s2] * ysh[k * 7 + s2];
       yk[tid] = v;
     }
     __syncthreads();
-    if (tid < 7) G.y[(size_t)k * 7 + tid] = yk[tid];
+    if (tid < 7) ysh[k * 7 + tid] = yk[tid];
     const int c0 = G.col_ptr[k], m = G.col_ptr[k + 1] - c0;
     for (int t = tid; t < m * 7; t += PG_THREADS) {
       const int a = t / 7, p = t - a * 7;
@@ -268,12 +285,11 @@ __global__ void __launch_bounds__(PG_THREADS) k_pg_factor_solve(PgDev G, double 
       const double* Lik = G.L + (size_t)(G.rowptr[i] + (k - G.first[i])) * 49 + p * 7;
       double v = 0.0;
 #pragma unroll
-      for (int s = 0; s < 7; s++) v += Lik[s] * yk[s];
-      G.y[(size_t)i * 7 + p] -= v;
+      for (int s2 = 0; s2 < 7; s2++) v += Lik[s2] * yk[s2];
+      ysh[i * 7 + p] -= v;
     }
     __syncthreads();
   }
-  // backward substitution  L^T x = y
   for (int k = n - 1; k >= 0; k--) {
     const int c0 = G.col_ptr[k], m = G.col_ptr[k + 1] - c0;
     const int q = tid >> 5, lane = tid & 31;  // warp q < 7 gathers component q of  sum_i L_ik^T x_i
@@ -282,23 +298,24 @@ __global__ void __launch_bounds__(PG_THREADS) k_pg_factor_solve(PgDev G, double 
       for (int a = lane; a < m; a += 32) {
         const int i = G.col_rows[c0 + a];
         const double* Lik = G.L + (size_t)(G.rowptr[i] + (k - G.first[i])) * 49;
-        const double* xi = G.x + (size_t)i * 7;
 #pragma unroll
-        for (int p = 0; p < 7; p++) v += Lik[p * 7 + q] * xi[p];
+        for (int p = 0; p < 7; p++) v += Lik[p * 7 + q] * ysh[i * 7 + p];
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      if (lane == 0) yk[q] = G.y[(size_t)k * 7 + q] - v;
+      if (lane == 0) yk[q] = ysh[k * 7 + q] - v;
     }
     __syncthreads();
     if (tid < 7) {  // x_k = Lkk^-T * yk
       double v = 0.0;
 #pragma unroll
-      for (int s = 0; s < 7; s++) v += G.Linv[(size_t)k * 49 + s * 7 + tid] * yk[s];
-      G.x[(size_t)k * 7 + tid] = v;
+      for (int s2 = 0; s2 < 7; s2++) v += G.Linv[(size_t)k * 49 + s2 * 7 + tid] * yk[s2];
+      ysh[k * 7 + tid] = v;
     }
     __syncthreads();
   }
+  for (int t = tid; t < n * 7; t += PG_THREADS) G.x[t] = ysh[t];
+  __syncthreads();
   // computeScale: sum_j x_j (lambda x_j + b_j)   (optimization_algorithm_levenberg.cpp:182-189)
   double sc = 0.0;
   for (int t = tid; t < n * 7; t += PG_THREADS) sc += G.x[t] * (lambda * G.x[t] + G.b[t]);

@@ -165,6 +165,7 @@ class Solver {
                                   (int)persist_smem_bytes(2, MAXSLOT, false)));
     CU_CHECK(cudaFuncSetAttribute(k_pcg_persist<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)persist_smem_bytes(3, MAXSLOT, false)));
+    CU_CHECK(cudaFuncSetAttribute(k_pg_factor_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU_CHECK(cudaFuncSetAttribute(k_qr_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QR_PIPE_SMEM));
     CU_CHECK(cudaFuncSetAttribute(k_qr_pipe2<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QR_PIPE2_SMEM));
     CU_CHECK(cudaFuncSetAttribute(k_qr_pipe2<0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QR_PIPE2_SMEM));
@@ -1117,6 +1118,10 @@ class Solver {
     std::vector<long long> rowptr(n_slot + 1, 0);
     for (int r = 0; r < n_slot; r++) rowptr[r + 1] = rowptr[r] + (r - first[r] + 1);
     const long long n_blocks = rowptr[n_slot];
+    if ((size_t)n_slot * 7 * sizeof(double) > 160 * 1024) {  // the solve keeps its work vector in shared memory
+      err_ = "pose_graph: more than 2900 free keyframes (shared-memory work vector of the triangular solves)";
+      return SQRTBA_ERR_INVALID;
+    }
     if (n_blocks > (1ll << 23)) {  // 8M blocks = 3.3 GB per copy: the natural (keyframe id) order does not fit this graph
       err_ = "pose_graph: the block skyline of this graph in keyframe-id order is too large";
       return SQRTBA_ERR_INVALID;
@@ -1226,7 +1231,16 @@ class Solver {
       do {
         k_pg_prepare<<<cdiv(std::max<long long>(n_blocks * 49, (long long)n_slot * 7), 256), 256, 0, stream_>>>(G, n_blocks);
         k_pg_damp<<<cdiv(n_slot * 7, 256), 256, 0, stream_>>>(G, lambda);
-        k_pg_factor_solve<<<1, PG_THREADS, 0, stream_>>>(G, lambda);
+        static const bool pg_timing = std::getenv("SQRTBA_HOST_TIMING") != nullptr;
+        if (pg_timing) cudaEventRecord(stage_ev_[0], stream_);
+        k_pg_factor_solve<<<1, PG_THREADS, (size_t)n_slot * 7 * sizeof(double), stream_>>>(G, lambda);
+        if (pg_timing) {
+          cudaEventRecord(stage_ev_[1], stream_);
+          cudaEventSynchronize(stage_ev_[1]);
+          float fms = 0;
+          cudaEventElapsedTime(&fms, stage_ev_[0], stage_ev_[1]);
+          std::fprintf(stderr, "[sqrtba host] pose graph: factor + solve %8.3f ms (%d block rows, %lld blocks)\n", fms, n_slot, n_blocks);
+        }
         k_pg_update<<<cdiv(n_slot, 128), 128, 0, stream_>>>(G);   // push + update
         launches += 4;
         if (int rc = chi2_now(&tempChi, true)) return rc;
