@@ -53,7 +53,13 @@ typedef struct {
                                 1 = always one launch per phase; 2 = persistent whenever possible;
                                 3 = like 0 but without the CUDA graph of the LM macro step (A/B: single-window problems
                                 otherwise run every LM trial as ONE graph launch and read its verdict from mapped
-                                pinned memory instead of synchronising the stream) */
+                                pinned memory instead of synchronising the stream);
+                                4 = reproducible: every pose-side sum leaves the CTAs as per-(CTA, window) partial vectors
+                                that are added in a fixed order -- no floating-point atomics anywhere, bit-identical
+                                results from run to run; one launch per CG phase (a single window pays for it: the
+                                persistent PCG kernel is what makes C0 fast).  Needs <= 128 free poses per window, no
+                                landmark with more than 32 observations, one GPU; otherwise the default path runs and
+                                stats.reserved[5] says 0 */
   int32_t pcg_check_every;   /* multi-launch mode: host polls the convergence counter every N iterations */
   int32_t reserved[8];       /* tuning / A-B knobs, all 0 by default:
                                 [0] record per-stage CUDA-event times (stats.ms_linearize ...)
@@ -93,7 +99,7 @@ typedef struct {
   double ms_linearize, ms_qr, ms_pcg, ms_backsub, ms_cost; /* per-stage device time (events) */
   double ms_matvec;         /* sum of matvec kernel time (multi-launch mode; 0 in persistent mode) */
   double reserved[8];       /* [0] 1 = the persistent PCG kernel ran, [1] 1 = in-kernel NVLink exchange was active,
-                               [2] grid of the persistent kernel */
+                               [2] grid of the persistent kernel, [5] 1 = reproducible mode (pcg_mode 4) was active */
 } sqrtba_stats;
 
 int sqrtba_default_config(sqrtba_config* cfg);

@@ -30,6 +30,7 @@ class Stats(C.Structure):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
         d["persistent_pcg"] = int(self.reserved[0])
         d["peer_exchange"] = int(self.reserved[1])
+        d["reproducible"] = int(self.reserved[5])
         return d
 
 

@@ -105,6 +105,13 @@ struct Dev {
   int smallwin;               // window-relative slots fit 16 bits (every window has < 65535 free poses): obs_lp and the
                               // run tables carry window-relative slots and the TMA-pipelined matvec is used
   int pq_shared;              // every window has <= MAXSLOT free poses: p and q of a window live in shared memory
+  int det;                    // reproducible mode (pcg_mode = 4): pose-side sums leave the CTAs as per-(CTA, window)
+                              // partial vectors that are added up in a fixed order, never through atomics
+  int maxslot;                // det: free poses of the largest window (stride of the partial vectors)
+  double* part_lin;           // det: [(linearise CTA + window)][12 * maxslot]  b_p | diag(Jp^T Jp) per slot
+  double* part_qr;            // det: [(QR CTA + window)][27 * maxslot]         reduced rhs | block-Jacobi block per slot
+  double* part_q;             // det: [(matvec CTA + window)][6 * maxslot]      partial q per slot
+  const int* win_tile_ptr;    // n_win + 1: tile range of every window
   int fused;                  // k_linqr_pipe serves the iterations with a known lambda and the retries; the separate
                               // linearise / QR kernels only the first trial of a pass (see lin_phase / qr_phase)
   const struct TileInfo* tiles;
@@ -293,6 +300,32 @@ __device__ __forceinline__ void tile_scatter_all(const int* __restrict__ run_ptr
     const double sum = run_sum(c_sh + k * SCST, a, b);
     atomicAdd(addr(slot_base + run_slot[r], k), sum);
   }
+}
+
+// Reproducible mode: the run sums of a tile are added to the CTA's shared accumulators acc[slot * NV + k] (window-relative
+// slot; a slot occurs once per tile, tiles follow each other behind a CTA barrier: fixed order), and a CTA's accumulators
+// leave it as ONE partial vector per (CTA, window) visit -- visit = CTA + window is unique because both grow along a
+// CTA's consecutive tiles -- that a per-window reduction adds up in visit order.
+template <int NV>
+__device__ __forceinline__ void tile_scatter_acc(const int* __restrict__ run_ptr, const int* __restrict__ run_slot, int nrun,
+                                                 const double* c_sh, double* acc) {
+  for (int idx = threadIdx.x; idx < nrun * NV; idx += CTA) {
+    const int r = idx / NV, k = idx - r * NV;
+    acc[run_slot[r] * NV + k] += run_sum(c_sh + k * SCST, run_ptr[r], run_ptr[r + 1]);
+  }
+}
+template <int NV>
+__device__ __forceinline__ void det_flush(double* __restrict__ part, int visit, int maxslot, int wn, double* acc) {
+  __syncthreads();
+  double* dst = part + (size_t)visit * NV * maxslot;
+  for (int i = threadIdx.x; i < NV * wn; i += CTA) { dst[i] = acc[i]; acc[i] = 0.0; }
+  __syncthreads();
+}
+// sum of element i over the visits [c_lo + win, c_hi + win] of a window, in order
+__device__ __forceinline__ double det_sum(const double* __restrict__ part, int c_lo, int c_hi, int win, size_t stride, int i) {
+  double v = 0.0;
+  for (int c = c_lo; c <= c_hi; c++) v += part[(size_t)(c + win) * stride + i];
+  return v;
 }
 
 // ---- TMA (bulk async copy) + mbarrier primitives, raw PTX (sm_90+/sm_100a)
@@ -498,7 +531,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 template <bool PRE>
 __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti, const LinOps& pre, int robust, double d2,
                                                double d3, double* c_sh, const int* runs_staged = nullptr,
-                                               int pf_pose = -1, int pf_point = -1) {
+                                               int pf_pose = -1, int pf_point = -1, double* acc_det = nullptr) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int w = ti.item0 + wid;
   const bool valid = wid < ti.nitem;
@@ -592,6 +625,7 @@ __device__ __forceinline__ void linearize_tile(const Dev& P, const TileInfo& ti,
   const int* runs = runs_staged ? runs_staged : reinterpret_cast<const int*>(jq + (size_t)JQ_ROWS * ti.nt);
   double* bp = P.bp;
   double* hd = P.hd;
+  if (acc_det) { tile_scatter_acc<12>(runs, runs + ti.nrun + 1, ti.nrun, c_sh, acc_det); return; }
   tile_scatter_all<12>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh,
                        [bp, hd](int slot, int k) { return (k < 6) ? bp + (size_t)slot * 6 + k : hd + (size_t)slot * 6 + (k - 6); });
 }
@@ -623,8 +657,14 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, do
   __shared__ double c_sh[12 * SCST];
   __shared__ __align__(16) TileInfo ti_sh[3];
   __shared__ int run_sh[STAGE ? 2 : 1][STAGE ? LIN_RUN_INTS : 1];
+  extern __shared__ double lin_acc[];  // reproducible mode: 12 * maxslot accumulators of the window being walked
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int t0 = blockIdx.x * LIN_TPB, t1 = min(t0 + LIN_TPB, P.n_tile);
+  int det_win = -1;
+  if (P.det) {
+    for (int i = tid; i < 12 * P.maxslot; i += CTA) lin_acc[i] = 0.0;
+    __syncthreads();
+  }
   auto stage_runs = [&](const TileInfo& ti, int rb) {
     if (!STAGE || ti.is_long) return;
     const int* runs = reinterpret_cast<const int*>(P.JQ + ti.jq_off + (size_t)JQ_ROWS * ti.nt);
@@ -670,6 +710,11 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, do
     }
     cp_async_commit();
     if (phase != PH_LIN) continue;  // CTA-uniform
+    if (P.det && ti.win != det_win) {  // a new window starts: the finished one leaves the CTA as one partial vector
+      if (det_win >= 0)
+        det_flush<12>(P.part_lin, blockIdx.x + det_win, P.maxslot, P.win_slot_ptr[det_win + 1] - P.win_slot_ptr[det_win], lin_acc);
+      det_win = ti.win;
+    }
     if (STAGE && !ti.is_long) {
       // the last lane of the tile's last item knows the tile's last landmark: pull the coordinates of the next ~96
       // landmarks (the next two or three tiles of this CTA) towards L2
@@ -687,9 +732,11 @@ __global__ void __launch_bounds__(CTA, 4) k_linearize_pipe(Dev P, int robust, do
       pf = !tn.is_long && wid < tn.nitem && lane < tile_item_cnt(tn, wid);
     }
     linearize_tile<true>(P, ti, cur, rob, d2, d3, c_sh, (STAGE && !ti.is_long) ? run_sh[k & 1] : nullptr,
-                         pf ? nxt.ip : -1, pf ? nxt.lm : -1);
+                         pf ? nxt.ip : -1, pf ? nxt.lm : -1, P.det ? lin_acc : nullptr);
   }
   cp_async_wait_all();
+  if (P.det && det_win >= 0)
+    det_flush<12>(P.part_lin, blockIdx.x + det_win, P.maxslot, P.win_slot_ptr[det_win + 1] - P.win_slot_ptr[det_win], lin_acc);
 }
 
 // ------------------------------------------------------------------------------------------------ K8a: LM begin
@@ -702,6 +749,15 @@ __device__ __forceinline__ void lm_reduce_lin_body(const Dev& P, int win, double
   if (c.phase != PH_LIN) {  // nothing new from this window: contribute the neutral element
     if (threadIdx.x == 0) { P.wred[win] = 0.0; P.wred[2 * P.n_win + win] = 0.0; }
     return;
+  }
+  if (P.det && P.win_tile_ptr[win + 1] > P.win_tile_ptr[win]) {  // b_p and diag(Jp^T Jp): the CTAs' partial vectors in order
+    const int c_lo = P.win_tile_ptr[win] / LIN_TPB, c_hi = (P.win_tile_ptr[win + 1] - 1) / LIN_TPB;
+    const int s0 = P.win_slot_ptr[win], wn = P.win_slot_ptr[win + 1] - s0;
+    for (int i = threadIdx.x; i < 12 * wn; i += RCTA) {
+      const double v = det_sum(P.part_lin, c_lo, c_hi, win, (size_t)12 * P.maxslot, i);
+      const int sl = i / 12, k = i - sl * 12;
+      if (k < 6) P.bp[(size_t)(s0 + sl) * 6 + k] = v; else P.hd[(size_t)(s0 + sl) * 6 + (k - 6)] = v;
+    }
   }
   double chi = 0.0;
   for (int i = P.win_item_ptr[win] + threadIdx.x; i < P.win_item_ptr[win + 1]; i += RCTA) chi += P.chi_part[i];
@@ -1343,9 +1399,15 @@ __global__ void __launch_bounds__(CTA, MINB) k_qr_pipe2(Dev P, int force_all, do
   unsigned* lp_sh = reinterpret_cast<unsigned*>(op_sh + 12);                          // [CTA]
   int* lm_sh = reinterpret_cast<int*>(lp_sh + CTA);                                   // [CTA]
   int(*run_sh)[QR_RUN_INTS] = reinterpret_cast<int(*)[QR_RUN_INTS]>(lm_sh + CTA);     // [2]
+  double* qr_acc = reinterpret_cast<double*>(qr_smem + QR_PIPE2_SMEM);                // reproducible mode: [27 * maxslot]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int t0 = blockIdx.x * QR_TPB, t1 = min(t0 + QR_TPB, P.n_tile);
   const size_t No = (size_t)P.ld;
+  int det_win = -1;
+  if (P.det) {
+    for (int i = tid; i < 27 * P.maxslot; i += CTA) qr_acc[i] = 0.0;
+    __syncthreads();
+  }
   auto stage = [&](const TileInfo& ti, int rb) {
     if (ti.is_long) return;
     const int cnt = tile_item_cnt(ti, wid), start = tile_item_start(ti, wid);
@@ -1415,6 +1477,11 @@ __global__ void __launch_bounds__(CTA, MINB) k_qr_pipe2(Dev P, int force_all, do
     cp_async_commit();
     if (phase != PH_TRIAL) continue;  // CTA-uniform: the tile's window is not in a trial
     const int sbase = P.smallwin ? P.win_slot_ptr[ti.win] : 0;  // for the reduction below: requested before the factorisation
+    if (P.det && ti.win != det_win) {  // a new window starts: the finished one leaves the CTA as one partial vector
+      if (det_win >= 0)
+        det_flush<27>(P.part_qr, blockIdx.x + det_win, P.maxslot, P.win_slot_ptr[det_win + 1] - P.win_slot_ptr[det_win], qr_acc);
+      det_win = ti.win;
+    }
     if (is_short) {
       const int slot = has ? slot_of(P, lpw, sbase, start + lane) : 0;
       qr_short_item_v2<JPOS>(P, ti, wid, lane, act, lm, has, rank, slot, (lpw & LP_STEREO) != 0, a, rr, lam, c_sh);
@@ -1425,10 +1492,27 @@ __global__ void __launch_bounds__(CTA, MINB) k_qr_pipe2(Dev P, int force_all, do
     double* bs = P.bs;
     double* D = P.D;
     const int* runs = run_sh[k & 1];
-    tile_scatter_all<27>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh,
-                         [bs, D](int slot, int k2) { return (k2 < 6) ? bs + (size_t)slot * 6 + k2 : D + (size_t)slot * 21 + (k2 - 6); });
+    if (P.det) tile_scatter_acc<27>(runs, runs + ti.nrun + 1, ti.nrun, c_sh, qr_acc);
+    else
+      tile_scatter_all<27>(runs, runs + ti.nrun + 1, ti.nrun, sbase, c_sh,
+                           [bs, D](int slot, int k2) { return (k2 < 6) ? bs + (size_t)slot * 6 + k2 : D + (size_t)slot * 21 + (k2 - 6); });
   }
   cp_async_wait_all();
+  if (P.det && det_win >= 0)
+    det_flush<27>(P.part_qr, blockIdx.x + det_win, P.maxslot, P.win_slot_ptr[det_win + 1] - P.win_slot_ptr[det_win], qr_acc);
+}
+
+// Reproducible mode: reduced right-hand side and block-Jacobi blocks of a window = its QR CTAs' partial vectors in order
+__global__ void __launch_bounds__(RCTA) k_reduce_qr(Dev P) {
+  const int win = blockIdx.x;
+  if (qr_phase(P, P.ctl[win]) != PH_TRIAL || P.win_tile_ptr[win + 1] <= P.win_tile_ptr[win]) return;
+  const int c_lo = P.win_tile_ptr[win] / QR_TPB, c_hi = (P.win_tile_ptr[win + 1] - 1) / QR_TPB;
+  const int s0 = P.win_slot_ptr[win], wn = P.win_slot_ptr[win + 1] - s0;
+  for (int i = threadIdx.x; i < 27 * wn; i += RCTA) {
+    const double v = det_sum(P.part_qr, c_lo, c_hi, win, (size_t)27 * P.maxslot, i);
+    const int sl = i / 27, k = i - sl * 27;
+    if (k < 6) P.bs[(size_t)(s0 + sl) * 6 + k] = v; else P.D[(size_t)(s0 + sl) * 21 + (k - 6)] = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ K1+K2 fused
@@ -1946,7 +2030,12 @@ __global__ void __maxnreg__(96) k_matvec_pipe(Dev P, const double* __restrict__ 
     } else if (hdr[1] != cur_win) {
       // flush the finished window's accumulators, stage p of the new one
       named_bar_sync(1, CTA);  // previous tile's reduction complete
-      for (int i = tid; i < wn * 6; i += CTA) atomicAdd(&qvec[(size_t)ws0 * 6 + i], acc_sh[i]);
+      if (P.det) {  // reproducible mode: one partial vector per (CTA, window) visit, summed in order by k_cg_step
+        if (cur_win >= 0)
+          for (int i = tid; i < wn * 6; i += CTA) P.part_q[(size_t)(blockIdx.x + cur_win) * 6 * P.maxslot + i] = acc_sh[i];
+      } else {
+        for (int i = tid; i < wn * 6; i += CTA) atomicAdd(&qvec[(size_t)ws0 * 6 + i], acc_sh[i]);
+      }
       cur_win = hdr[1];
       ws0 = hdr[2];
       wn = hdr[3];
@@ -2065,6 +2154,9 @@ __global__ void __maxnreg__(96) k_matvec_pipe(Dev P, const double* __restrict__ 
       const double v = acc_sh[i];
       if (v != 0.0) atomicAdd(&qvec[(size_t)(ws0 + abase) * 6 + i], v);
     }
+  } else if (P.det) {
+    if (cur_win >= 0)
+      for (int i = tid; i < wn * 6; i += CTA) P.part_q[(size_t)(blockIdx.x + cur_win) * 6 * P.maxslot + i] = acc_sh[i];
   } else {
     for (int i = tid; i < wn * 6; i += CTA) atomicAdd(&qvec[(size_t)ws0 * 6 + i], acc_sh[i]);
   }
@@ -2750,16 +2842,27 @@ __global__ void __launch_bounds__(RCTA) k_cg_prep(Dev P, double* zero_a, int n_a
   cg_init_body(P, 0, 0, sh);
 }
 
-__global__ void __launch_bounds__(RCTA) k_cg_step(Dev P, double tol2, int max_iters, int force_all, double lam_override) {
+__global__ void __launch_bounds__(RCTA) k_cg_step(Dev P, double tol2, int max_iters, int force_all, double lam_override,
+                                                  int det_grid) {
   __shared__ double sh[RWARPS];
   const int win = blockIdx.x;
   WinCtl& c = P.ctl[win];
   if (!c.cg_active) return;
   const double lam = force_all ? lam_override : c.lambda;
   const int e0 = P.win_slot_ptr[win] * 6, e1 = P.win_slot_ptr[win + 1] * 6;
+  // reproducible mode (det_grid = grid of the matvec launch): q of the window = the partial vectors of the matvec CTAs
+  // that own its tiles, in CTA order.  CTA c owns tiles [n_tile c / G, n_tile (c+1) / G): tile t belongs to
+  // ceil((t+1) G / n_tile) - 1
+  int c_lo = 0, c_hi = -1;
+  if (det_grid > 0 && P.win_tile_ptr[win + 1] > P.win_tile_ptr[win]) {
+    const long long G = det_grid, nt = P.n_tile;
+    c_lo = (int)((((long long)P.win_tile_ptr[win] + 1) * G + nt - 1) / nt - 1);
+    c_hi = (int)(((long long)P.win_tile_ptr[win + 1] * G + nt - 1) / nt - 1);
+  }
   double pq = 0.0;
   for (int e = e0 + threadIdx.x; e < e1; e += RCTA) {
-    const double qq = P.q[e] + lam * P.p[e];
+    const double qraw = det_grid > 0 ? det_sum(P.part_q, c_lo, c_hi, win, (size_t)6 * P.maxslot, e - e0) : P.q[e];
+    const double qq = qraw + lam * P.p[e];
     P.q[e] = qq;
     pq += P.p[e] * qq;
   }

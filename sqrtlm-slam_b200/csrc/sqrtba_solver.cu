@@ -752,6 +752,33 @@ class Solver {
         if (int rc = peer_setup((size_t)std::max(n_slot, 1) * 6)) return rc;
       }
     }
+    {  // tile range of every window (tiles are ordered by window) + the reproducible mode's partial vectors
+      std::vector<int> wtp(n_win + 1, 0);
+      bool any_long = false;
+      for (int t = 0; t < n_tile; t++) { wtp[h_tiles_pin_.p[t].win + 1]++; any_long |= h_tiles_pin_.p[t].is_long != 0; }
+      for (int w = 0; w < n_win; w++) wtp[w + 1] += wtp[w];
+      CU_CHECK(d_win_tile_ptr_.ensure(n_win + 1));
+      CU_CHECK(cudaMemcpyAsync(d_win_tile_ptr_.p, wtp.data(), wtp.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+      CU_CHECK(cudaStreamSynchronize(stream_));
+      P_.win_tile_ptr = d_win_tile_ptr_.p;
+      P_.maxslot = max_win_slots_;
+      // pcg_mode = 4: fixed-order reductions everywhere.  Needs every window's free poses in the CTAs' shared accumulators
+      // (<= 128), no landmark with more than 32 observations (those go through direct atomics), one GPU
+      det_active_ = cfg_.pcg_mode == 4 && pq_shared && smallwin && !any_long && !comm_ && n_slot > 0 && cfg_.reserved[7] == 0 &&
+                    cfg_.reserved[1] == 0;
+      P_.det = det_active_ ? 1 : 0;
+      if (det_active_) {
+        const size_t ms = (size_t)max_win_slots_;
+        const size_t v_lin = (size_t)cdiv(n_tile, LIN_TPB) + n_win, v_qr = (size_t)cdiv(n_tile, QR_TPB) + n_win;
+        const size_t v_q = (size_t)std::min(n_tile, pipe_ctas_) + n_win;
+        CU_CHECK(d_part_lin_.ensure(v_lin * 12 * ms));
+        CU_CHECK(d_part_qr_.ensure(v_qr * 27 * ms));
+        CU_CHECK(d_part_q_.ensure(v_q * 6 * ms));
+        P_.part_lin = d_part_lin_.p; P_.part_qr = d_part_qr_.p; P_.part_q = d_part_q_.p;
+        CU_CHECK(cudaFuncSetAttribute(k_qr_pipe2<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(QR_PIPE2_SMEM + 27 * MAXSLOT * sizeof(double))));
+      }
+    }
     have_problem_ = true;
     step_graph_valid_ = false;  // the captured macro step carries this problem's sizes and pointers
     return reset_state();
@@ -1292,8 +1319,15 @@ class Solver {
   }
 
   // ------------------------------------------------------------------------------------------ stage-level entry points
+  // the stage-level entry points below use the kernels' atomic flushes (they launch single stages out of sequence)
+  struct DetOff {
+    Dev& P; int saved;
+    explicit DetOff(Dev& p) : P(p), saved(p.det) { P.det = 0; }
+    ~DetOff() { P.det = saved; }
+  };
   int debug_linearize(int huber, double* err, double* Jp, double* Jl, double* r, double* chi2) {
     if (!have_problem_) { err_ = "no problem set"; return SQRTBA_ERR_INVALID; }
+    DetOff det_off(P_);
     CU_CHECK(cudaSetDevice(cfg_.device));
     const double d2 = (double)(float)std::sqrt(huber == 2 ? 5.99 : 5.991), d3 = (double)(float)std::sqrt(7.815);
     k_pass_init<<<cdiv(P_.n_win, 128), 128, 0, stream_>>>(P_, 1, 0, huber != 0 ? 1 : 0);
@@ -1353,6 +1387,7 @@ class Solver {
   // one damped square-root step at the linearisation left by debug_linearize (or the last solve)
   int debug_step(double lambda, double* dp, double* dl, double* bs, int* cg_iters) {
     if (!have_problem_) { err_ = "no problem set"; return SQRTBA_ERR_INVALID; }
+    DetOff det_off(P_);
     CU_CHECK(cudaSetDevice(cfg_.device));
     // put every window into PH_TRIAL with the requested lambda
     std::vector<WinCtl> c(P_.n_win);
@@ -1385,6 +1420,7 @@ class Solver {
 
   int debug_matvec(const double* p, double* y) {
     if (!have_problem_ || !P_.n_slot) { err_ = "no problem / no free pose"; return SQRTBA_ERR_INVALID; }
+    DetOff det_off(P_);
     CU_CHECK(cudaSetDevice(cfg_.device));
     const size_t bytes = (size_t)P_.n_slot * 6 * sizeof(double);
     CU_CHECK(cudaMemcpyAsync(P_.p, p, bytes, cudaMemcpyHostToDevice, stream_));
@@ -1396,6 +1432,7 @@ class Solver {
 
   int time_stage(int stage, int warmup, int reps, double* ms_avg) {
     if (!have_problem_) { err_ = "no problem set"; return SQRTBA_ERR_INVALID; }
+    DetOff det_off(P_);
     CU_CHECK(cudaSetDevice(cfg_.device));
     const double d2 = (double)(float)std::sqrt(5.991), d3 = (double)(float)std::sqrt(7.815);
     const int gi = cdiv(P_.n_item, WARPS);
@@ -1590,7 +1627,8 @@ class Solver {
     if (cfg_.reserved[7] == 1) k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
     else if (cfg_.reserved[7] == 2) k_linearize_pipe<false><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
     else if (cfg_.reserved[7] == 6) k_linearize_pipe<true, true><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
-    else k_linearize_pipe<true><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);  // 0 and 7
+    else k_linearize_pipe<true><<<cdiv(P_.n_tile, LIN_TPB), CTA, P_.det ? 12 * (size_t)P_.maxslot * sizeof(double) : 0, stream_>>>(
+        P_, robust, d2, d3, force_all);  // 0 and 7
   }
   // fused linearisation + landmark QR for the windows whose lambda is already known (iterations > 0, retries)
   void launch_linqr(int robust, double d2, double d3) {
@@ -1603,7 +1641,9 @@ class Solver {
     if (cfg_.reserved[7] == 1) k_qr<<<P_.n_tile, CTA, 0, stream_>>>(P_, force_all, lam_override);
     else if (cfg_.reserved[7] == 2) k_qr_pipe<<<cdiv(P_.n_tile, QR_TPB), CTA, QR_PIPE_SMEM, stream_>>>(P_, force_all, lam_override);
     else if (cfg_.reserved[7] == 5) k_qr_pipe2<0, 5><<<cdiv(P_.n_tile, QR_TPB), CTA, QR_PIPE2_SMEM, stream_>>>(P_, force_all, lam_override);
-    else k_qr_pipe2<0, 4><<<cdiv(P_.n_tile, QR_TPB), CTA, QR_PIPE2_SMEM, stream_>>>(P_, force_all, lam_override);
+    else k_qr_pipe2<0, 4><<<cdiv(P_.n_tile, QR_TPB), CTA, QR_PIPE2_SMEM + (P_.det ? 27 * (size_t)P_.maxslot * sizeof(double) : 0), stream_>>>(
+        P_, force_all, lam_override);
+    if (P_.det) { k_reduce_qr<<<P_.n_win, RCTA, 0, stream_>>>(P_); launches_++; }  // the CTAs' partial vectors, in order
   }
   void launch_matvec(const double* pvec, double* qvec, int force_all) {
     if (P_.smallwin && cfg_.reserved[1] == 0) {
@@ -1639,6 +1679,7 @@ class Solver {
   bool use_persist() const {
     if (cfg_.pcg_mode == 1 || !coop_ok_ || P_.n_win != 1 || !P_.smallwin || persist_ctas_ <= 0 || cfg_.reserved[1] != 0) return false;
     if (lidar_active_) return false;  // the unary term H_u p is added between the matvec and the CG update (multi-launch loop)
+    if (cfg_.pcg_mode == 4) return false;  // reproducible mode: one launch per CG phase, fixed-order sums in k_cg_step
     if (comm_ && (!peer_ok_ || P_.pq_shared)) return false;  // sharded without peer-mapped buffers, or a small window: NCCL all-reduce per iteration
     return true;
   }
@@ -1793,7 +1834,7 @@ class Solver {
       if (eb) cudaEventRecord(eb, stream_);
       if (int rc = allreduce(P_.q, (size_t)P_.n_slot * 6, false)) return rc;  // the one exchange step of a CG iteration
       if (lidar_active_) { k_lidar_matvec<<<1, 32, 0, stream_>>>(P_, lidar_, P_.p, P_.q); launches_++; }
-      k_cg_step<<<P_.n_win, RCTA, 0, stream_>>>(P_, tol2, cfg_.pcg_max_iters, 0, 0.0);
+      k_cg_step<<<P_.n_win, RCTA, 0, stream_>>>(P_, tol2, cfg_.pcg_max_iters, 0, 0.0, P_.det ? std::min(P_.n_tile, pipe_ctas_) : 0);
       launches_ += 2;
       cg_iters_total_++;
       if ((it + 1) % check == 0) {
@@ -2019,6 +2060,7 @@ class Solver {
       st->reserved[0] = use_persist() ? 1.0 : 0.0;           // the PCG solves ran in the persistent cooperative kernel
       st->reserved[1] = (comm_ && peer_ok_) ? 1.0 : 0.0;     // landmark-sharded: in-kernel NVLink exchange available
       st->reserved[2] = persist_grid_;
+      st->reserved[5] = det_active_ ? 1.0 : 0.0;             // reproducible mode active (pcg_mode = 4 and the problem qualifies)
     }
     return SQRTBA_OK;
   }
@@ -2033,6 +2075,7 @@ class Solver {
     d_bl_.release(); d_dl_.release(); d_slotvec_.release(); d_chi_part_.release(); d_scale_part_.release();
     d_ctl_.release(); d_trace_.release(); d_counters_.release(); d_wred_.release();
     d_tiles_.release(); d_obs_lp_.release(); d_tile_run_ptr_.release(); d_tile_runs_.release();
+    d_win_tile_ptr_.release(); d_part_lin_.release(); d_part_qr_.release(); d_part_q_.release();
     d_gbar_.release(); d_part_.release(); d_q3_.release(); d_dq_.release(); d_ptile_.release();
     d_l_pc_.release(); d_l_qw_.release(); d_l_nv_.release(); d_l_w_.release(); d_l_acc_.release(); d_l_match_.release();
     d_lm_flat_pose_.release(); d_lm_corner_pose_.release(); d_lc_flat_.release(); d_lc_normal_.release(); d_lc_corner_.release();
@@ -2081,7 +2124,9 @@ class Solver {
   int persist_ctas_ = 0, persist_stages_ = 2, persist_slots_ = 1, persist_grid_ = 0;
   std::vector<cudaEvent_t> mv_events_;
   int mv_used_ = 0;
-  DBuf<int> d_ptile_;
+  DBuf<int> d_ptile_, d_win_tile_ptr_;
+  DBuf<double> d_part_lin_, d_part_qr_, d_part_q_;
+  bool det_active_ = false;
   double* peer_recv_[8] = {};
   unsigned long long* d_seq_ = nullptr;
   void** d_peer_tbl_ = nullptr;

@@ -445,3 +445,43 @@ def test_fused_linearize_qr_variant(pkg, synth):
         np.testing.assert_allclose(pa, pb, rtol=0, atol=1e-8)
         np.testing.assert_allclose(xa, xb, rtol=0, atol=1e-7)
         assert np.array_equal(fa, fb)
+
+
+def test_reproducible_mode_is_bit_identical(pkg, synth):
+    # pcg_mode = 4: every pose-side sum is a fixed-order reduction of per-(CTA, window) partial vectors -- no floating-point
+    # atomics -- so two solves of the same problem agree in EVERY bit (trace, poses, points, flags), for one window and
+    # for a batch; the result still matches the oracle and the default (atomic) path to rounding
+    wins = [synth.config_c0(50 + i) for i in range(5)]
+    prob, pp, tp, op = synth.concat_windows(wins)
+    for batch in (False, True):
+        h = pkg.SqrtBA(pcg_mode=4)
+        if batch:
+            h.set_problem_batch(prob, pp, tp, op)
+        else:
+            h.set_problem(wins[0])
+        runs = []
+        for _ in range(3):
+            h.reset_state()
+            st = h.solve_local()
+            assert st["reproducible"] == 1 and st["persistent_pcg"] == 0
+            runs.append(([h.trace(i).copy() for i in range(len(wins) if batch else 1)], h.poses().copy(), h.points().copy(),
+                         h.outliers().copy()))
+        for r in runs[1:]:
+            for ta, tb in zip(runs[0][0], r[0]):
+                assert np.array_equal(ta, tb)
+            assert np.array_equal(runs[0][1], r[1]) and np.array_equal(runs[0][2], r[2]) and np.array_equal(runs[0][3], r[3])
+        # against the oracle (first window) and against the default path
+        ref = refba.RefBA(wins[0])
+        ref.solve_local(0)
+        compare_solution(h, ref, wins[0], window=0)
+        n0 = wins[0].n_pose
+        t_rms, r_rms = pose_rms(h.poses()[:n0], ref.poses(), wins[0].pose_fixed == 0)
+        assert t_rms <= POSE_T_RMS and r_rms <= POSE_R_RMS
+        assert np.array_equal(h.outliers()[:wins[0].n_obs], ref.outliers())
+        h.close()
+    # a problem that does not qualify (more than 128 free poses in a window) runs the default path and says so
+    h = pkg.SqrtBA(pcg_mode=4)
+    h.set_problem(big_window_problem(synth, seed=37, n_kf=140, n_points=2500))
+    st = h.solve_global(3, False)
+    assert st["reproducible"] == 0 and len(h.trace()) >= 3
+    h.close()
