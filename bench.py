@@ -321,6 +321,42 @@ def pose_only_leg(pkg, local, cpu_ok):
     return out
 
 
+def sim3_leg(pkg, local, cpu_ok):
+    """Optimizer::OptimizeSim3 (LoopClosing::ComputeSim3, per loop candidate): one candidate pair with 150 matches and a
+    batch of 16 candidates through sqrtba_optimize_sim3 (host buffers in, S12 + flags out: the call IS end to end)."""
+    import numpy as np
+    ba = pkg.SqrtBA(device=local)
+    c = pkg.synth.sim3_pair(seed=5, n_matches=150)
+    dev, wall = [], []
+    for _ in range(8):
+        t0 = time.perf_counter()
+        S, keep, n_in, st = ba.optimize_sim3([0, len(c[2])], c[0], c[1], c[2], c[3], c[4], 10.0, False)
+        wall.append(time.perf_counter() - t0)
+        dev.append(st["ms_total"])
+    out = {"workload": "one keyframe pair, 150 matches (300 edges), optimize(5) + chi2 test + optimize(10), numeric Jacobians (g2oOptimizer.cc:1560-1796)",
+           "ms_per_pair_device": min(dev[2:]), "ms_per_pair_call": 1e3 * min(wall[2:]), "inliers": int(n_in[0]),
+           "lm_trials": len(ba.optimize_sim3_trace(0))}
+    cases = [pkg.synth.sim3_pair(seed=200 + k, n_matches=150) for k in range(16)]
+    ptr = np.concatenate([[0], np.cumsum([len(k[2]) for k in cases])])
+    arrs = [np.stack([k[0] for k in cases]), np.stack([k[1] for k in cases])] + [np.concatenate([k[i] for k in cases]) for i in (2, 3, 4)]
+    wall = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        ba.optimize_sim3(ptr, *arrs, 10.0, False)
+        wall.append(time.perf_counter() - t0)
+    out["batch_16_pairs_ms_per_call"] = 1e3 * min(wall[1:])
+    if cpu_ok:
+        from oracle import refba
+        t0 = time.perf_counter()
+        So, keep_o, nin_o, _ = refba.optimize_sim3(c[0], c[1], c[2], c[3], c[4], 10.0, False)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 1e3 * dt, "unit": "ms per pair (lower is better)", "cores": 1, "kind": "port",
+                               "sample": "the same pair"}
+        out["parity_vs_oracle"] = {"ok": bool(nin_o == int(n_in[0]) and np.array_equal(keep, keep_o) and np.abs(S[0] - So).max() <= 1e-6)}
+    ba.close()
+    return out
+
+
 def essential_graph_leg(pkg, local, cpu_ok):
     """Optimizer::OptimizeEssentialGraph at KITTI-00 length: 1500 keyframes on a drifting loop, spanning tree +
     covisibility + loop edges, Levenberg with lambda_0 = 1e-16, 20 iterations (g2oOptimizer.cc:1212-1460)."""
@@ -402,6 +438,7 @@ def run_extras(pkg, torch, dist, world, rank, local, barrier, args):
     if rank == 0:
         out["pose_only"] = pose_only_leg(pkg, local, cpu_ok)
         out["essential_graph"] = essential_graph_leg(pkg, local, cpu_ok)
+        out["sim3_candidates"] = sim3_leg(pkg, local, cpu_ok)
     prob = pkg.synth.config_c3(0, scale=args.gba_scale, n_kf=max(int(1500 * args.gba_scale), 160))
     shard, _, _ = pkg.multi.shard_by_landmark(prob, rank, world)
     ba = pkg.SqrtBA(device=local)
@@ -645,6 +682,7 @@ def main():
             "large_window": extras.get("large_window"),
             "pose_only": extras.get("pose_only"),
             "essential_graph": extras.get("essential_graph"),
+            "sim3_candidates": extras.get("sim3_candidates"),
             "global_ba": extras.get("global_ba"),
         }
         print(json.dumps(line), flush=True)

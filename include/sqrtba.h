@@ -241,6 +241,29 @@ int sqrtba_pose_graph(sqrtba_handle* h, int32_t n_vert, double* vert8, const uin
                       const int32_t* edge_ij, const double* meas8, int32_t iters, double lambda_init, sqrtba_stats* stats);
 int sqrtba_pose_graph_trace(sqrtba_handle* h, double* rows_out, int32_t max_rows);
 
+/* ---- Sim3 alignment of a loop candidate: the optimisation inside LoopClosing::ComputeSim3 -------
+ * Replaces Optimizer::OptimizeSim3 (include/backend/Optimizer.h:68-69 -> src/backend/g2oOptimizer.cc:1560-1796; called from
+ * src/backend/LoopClosing.cc:513 with th2 = 10): ONE free
+ * VertexSim3Expmap S12 carrying both cameras' intrinsics; the matched map points enter as fixed vertices in their own
+ * camera frames; per match EdgeSim3ProjectXYZ (point of keyframe 2 into image 1) and EdgeInverseSim3ProjectXYZ (point of
+ * keyframe 1 into image 2), information invSigma2 * I, Huber delta = (float)sqrt(th2), numeric Jacobians (1e-9 central
+ * differences) as inherited by both edge types; BlockSolverX + LinearSolverDense + Levenberg: optimize(5), drop every
+ * match with chi2 > th2 on either edge, give up with fewer than 10 left, optimize(10 if something was dropped else 5),
+ * count the matches that still pass.  A batch of candidate pairs is one launch: pair k owns matches
+ * [pair_match_ptr[k], pair_match_ptr[k+1]).  Independent of sqrtba_set_problem.
+ *   sim3_12    n_pairs x 8 in/out (qx qy qz qw | t | s); untouched for a pair that gives up
+ *   cam8       n_pairs x 8: fx1 fy1 cx1 cy1 fx2 fy2 cx2 cy2
+ *   p1c, p2c   n_match x 3: the matched map points, R1w * X1 + t1w and R2w * X2 + t2w (:1650-1662)
+ *   match_meas n_match x 6 float: u1 v1 invSigma2_1 u2 v2 invSigma2_2 (undistorted keypoints, :1680-1712)
+ *   keep_out   n_match: 1 while vpMatches1 keeps the match, 0 = set to NULL by the reference
+ *   inliers_out n_pairs: the function's return value nIn (0 when it gives up)
+ * sqrtba_optimize_sim3_trace: LM trials of one pair of the LAST call, rows of 8 doubles (pass, iteration, trial, lambda,
+ *   chi2 before, chi2 of the trial, rho, accepted); returns the number of rows. */
+int sqrtba_optimize_sim3(sqrtba_handle* h, int32_t n_pairs, const int64_t* pair_match_ptr, double* sim3_12, const double* cam8,
+                         const double* p1c, const double* p2c, const float* match_meas, float th2, int32_t fix_scale,
+                         uint8_t* keep_out, int32_t* inliers_out, sqrtba_stats* stats);
+int sqrtba_optimize_sim3_trace(sqrtba_handle* h, int32_t pair, double* rows_out, int32_t max_rows);
+
 /* ---- stage-level entry points (kernel parity tests, profiling) --------------------------------------------
  * sqrtba_debug_linearize : run the fused residual+Jacobian+Huber kernel at the current state.
  *    huber: 0 none, 1 local-BA deltas, 2 global-BA deltas.  Outputs (any may be NULL):

@@ -30,10 +30,11 @@ OptimizationAlgorithmLevenberg::solve -- on a g2o::Solver implemented here (Fake
   * make_poseopt the four-round schedule of PoseOptimization over real EdgeSE3ProjectXYZOnlyPose /
                  EdgeStereoSE3ProjectXYZOnlyPose objects (inline constructors: laid out around the exported vtables);
   * make_sim3 / make_posegraph   g2o::Sim3 arithmetic and the optimisation of OptimizeEssentialGraph (VertexSim3Expmap,
-                 EdgeSim3 with numeric Jacobians, lambda_0 = 1e-16) -- the oracle of SURVEY row N3.
+                 EdgeSim3 with numeric Jacobians, lambda_0 = 1e-16) -- the oracle of SURVEY row N3;
+  * make_sim3opt the schedule of OptimizeSim3 over real EdgeSim3ProjectXYZ / EdgeInverseSim3ProjectXYZ objects.
 
-TEST INFRASTRUCTURE ONLY.  Run as a script in a clean interpreter; appends `graph_*`, `lm<k>_*`, `lba_*`, `po_*`, `sim3_*`
-and `pg<k>_*` arrays to tests/golden/libg2o_vectors.npz (tests/test_pin_libg2o.py compares the oracle with them)."""
+TEST INFRASTRUCTURE ONLY.  Run as a script in a clean interpreter; appends `graph_*`, `lm<k>_*`, `lba_*`, `po_*`, `sim3_*`,
+`pg<k>_*` and `s3o<k>_*` arrays to tests/golden/libg2o_vectors.npz (tests/test_pin_libg2o.py compares the oracle with them)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -1182,6 +1183,246 @@ def make_posegraph(path):
     return out, keep
 
 
+class FakeSolverSim3Dense(FakeSolver):
+    """The one-vertex dense case of OptimizeSim3 (BlockSolverX + LinearSolverDense, g2oOptimizer.cc:1565-1573): the
+    7x7 block of the Sim3 vertex, the fixed points contribute no unknowns."""
+
+    def __init__(self, so):
+        self.so = so
+        super().__init__(so.sg.G, None, None, None)
+
+    def _build_structure(self, this, zero):
+        so = self.so
+        assert so.vs.view(np.int32)[V_HIDX // 4] == 0
+        self.n = 7
+        self.H = P._aligned(52)
+        so.sg.f["v_map"](so.vs.ctypes.data, self.H.ctypes.data)
+        self.x, self.b = P._aligned(16), P._aligned(16)
+        u = self.obj.view(np.uint64)
+        u[2], u[3], u[4], u[5] = self.x.ctypes.data, self.b.ctypes.data, 7, 7
+        return True
+
+    def _build_system(self, this):
+        so = self.so
+        self.H[:] = 0.0
+        so.sg.f["v_clear"](so.vs.ctypes.data)
+        for ed in so.edges:
+            if ed["e"].view(np.int32)[E_LEVEL // 4] != 0:
+                continue
+            so.f["lin"](ed["e"].ctypes.data, ed["jw"].ctypes.data)
+            so.f["quad"](ed["e"].ctypes.data)
+        self.b[:7] = so.vs[so.b_off:so.b_off + 7]
+        return True
+
+    def _diag(self):
+        yield self.H, [r * 7 + r for r in range(7)]
+
+    def _solve(self, this):
+        x = np.linalg.solve(self.H[:49].reshape(7, 7).T, self.b[:7])
+        self.x[:7] = x
+        self.log.append(("solve", float(np.linalg.norm(x))))
+        return True
+
+
+class Sim3Opt:
+    """The graph of g2oOptimizer::OptimizeSim3 (g2oOptimizer.cc:1560-1796) out of the binary's objects: one
+    VertexSim3Expmap (with both cameras' intrinsics -- the four Vector2d members in front of `_fix_scale`,
+    types_seven_dof_expmap.h:71-72), fixed VertexSBAPointXYZ, EdgeSim3ProjectXYZ / EdgeInverseSim3ProjectXYZ with Huber
+    kernels.  optimizer.removeEdge is replaced by setLevel(1): either way the edge leaves the active set of the next
+    initializeOptimization(0) and the order of the others is kept."""
+    B2 = "_ZN3g2o14BaseBinaryEdgeILi2EN5Eigen6MatrixIdLi2ELi1ELi0ELi2ELi1EEENS_17VertexSBAPointXYZENS_16VertexSim3ExpmapEE"
+    E2 = "_ZN3g2o8BaseEdgeILi2EN5Eigen6MatrixIdLi2ELi1ELi0ELi2ELi1EEEE"
+    S = {
+        "e12_ctor": ("_ZN3g2o18EdgeSim3ProjectXYZC1Ev", None, 1), "e21_ctor": ("_ZN3g2o25EdgeInverseSim3ProjectXYZC1Ev", None, 1),
+        "e12_err": ("_ZN3g2o18EdgeSim3ProjectXYZ12computeErrorEv", None, 1),
+        "e21_err": ("_ZN3g2o25EdgeInverseSim3ProjectXYZ12computeErrorEv", None, 1),
+        "lin": (B2 + "14linearizeOplusERNS_17JacobianWorkspaceE", None, 2), "quad": (B2 + "22constructQuadraticFormEv", None, 1),
+        "meas": (E2 + "14setMeasurementERKS3_", None, 2), "info": (E2 + "15informationDataEv", C.c_void_p, 1),
+        "errd": (E2 + "9errorDataEv", C.c_void_p, 1), "chi2": ("_ZNK3g2o8BaseEdgeILi2EN5Eigen6MatrixIdLi2ELi1ELi0ELi2ELi1EEEE4chi2Ev", C.c_double, 1),
+    }
+
+    def __init__(self, s12, cam8, fix_scale):
+        self.sg = Sim3Graph()
+        L = self.sg.G.ed.g.L
+        self.f = {}
+        for k, (name, res, nargs) in self.S.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, [C.c_void_p] * nargs
+            self.f[k] = fn
+        sg = self.sg
+        assert sg.fix_off % 8 == 0
+        self.cam_off = sg.fix_off // 8 - 8                 # _principle_point1, _principle_point2, _focal_length1, _focal_length2
+        sg.add_vertex(0, s12, False, fix_scale)
+        self.vs = sg.verts[0]
+        fx1, fy1, cx1, cy1, fx2, fy2, cx2, cy2 = cam8
+        self.vs[self.cam_off:self.cam_off + 8] = [cx1, cy1, cx2, cy2, fx1, fy1, fx2, fy2]
+        self.edges, self.points = [], []
+
+    def _point(self, vid, X):
+        G = self.sg.G
+        v = G.ed._point_vertex(np.asarray(X, float))
+        i32 = v.view(np.int32)
+        assert i32[V_ID // 4] == -1 and i32[V_DIM // 4] == 3 and np.array_equal(v[19:22], X)
+        i32[V_ID // 4] = vid
+        v.view(np.uint8)[V_FIXED] = 1
+        assert G.f["add_vertex"](G.opt.ctypes.data, v.ctypes.data, None)
+        self.points.append(v)
+        return v
+
+    def _edge(self, kind, vp, obs, info, delta):
+        G = self.sg.G
+        e = P._aligned(PE.OBJ)
+        self.f[kind + "_ctor"](e.ctypes.data)
+        i32 = e.view(np.int32)
+        assert i32[E_ID // 4] == -1 and i32[E_DIM // 4] == 2 and i32[E_LEVEL // 4] == 0 and e.view(np.uint64)[E_KERNEL // 8] == 0
+        vec = PE._vector_slots(e, 16)
+        assert vec
+        ptrs = (C.c_uint64 * 2).from_address(vec[0][1])
+        ptrs[0], ptrs[1] = vp.ctypes.data, self.vs.ctypes.data           # vertex 0 = point, vertex 1 = the Sim3
+        m = P._aligned(2)
+        m[:] = obs
+        self.f["meas"](e.ctypes.data, m.ctypes.data)
+        inf = np.ctypeslib.as_array((C.c_double * 4).from_address(self.f["info"](e.ctypes.data)))
+        inf[:] = (np.eye(2) * info).ravel()
+        rk = G.f["huber_new"](None)
+        G.ed.g.f["set_delta"](rk, float(delta))
+        e.view(np.uint64)[E_KERNEL // 8] = rk
+        assert G.f["add_edge"](G.opt.ctypes.data, e.ctypes.data)
+        jw = P._aligned(64)
+        G.ed.f["jw_ctor"](jw.ctypes.data)
+        G.ed.f["jw_size"](jw.ctypes.data, e.ctypes.data)
+        assert G.ed.f["jw_alloc"](jw.ctypes.data)
+        ed = dict(e=e, kind=kind, jw=jw, rk=rk)
+        self.edges.append(ed)
+        return ed
+
+    def add_match(self, i, P1c, P2c, meas6, delta):
+        v1, v2 = self._point(2 * i + 1, P1c), self._point(2 * (i + 1), P2c)
+        e12 = self._edge("e12", v2, meas6[0:2], meas6[2], delta)       # x1 = S12 * X2
+        e21 = self._edge("e21", v1, meas6[3:5], meas6[5], delta)       # x2 = S21 * X1
+        return e12, e21
+
+    def error(self, ed):
+        self.f[ed["kind"] + "_err"](ed["e"].ctypes.data)
+        return self.stored_error(ed)
+
+    def stored_error(self, ed):
+        return np.ctypeslib.as_array((C.c_double * 2).from_address(self.f["errd"](ed["e"].ctypes.data))).copy()
+
+    def jacobian(self, ed):
+        """numeric 2x7 Jacobian w.r.t. the Sim3 (vertex 1) out of the JacobianWorkspace (column-major)"""
+        self.f["lin"](ed["e"].ctypes.data, ed["jw"].ctypes.data)
+        ws = PE._vector_slots(ed["jw"], 32)
+        assert ws, "JacobianWorkspace::_workspace not found"
+        pw = (C.c_uint64 * 4).from_address(ws[0][1])
+        return np.ctypeslib.as_array((C.c_double * 14).from_address(pw[2])).copy().reshape(7, 2).T
+
+    def chi2(self, ed):
+        return self.f["chi2"](ed["e"].ctypes.data)
+
+    def set_level(self, ed, lvl):
+        ed["e"].view(np.int32)[E_LEVEL // 4] = lvl
+
+
+def make_sim3opt(path):
+    """g2oOptimizer::OptimizeSim3 over the binary (fixed and free scale): errors and numeric Jacobians of both edge types
+    at the initial estimate, then the whole schedule -- optimize(5), chi2 test on the stored errors, optimize(10 / 5),
+    final count -- with the binary's Levenberg; records lambda per trial, kept matches, nIn and the final S12."""
+    out = dict(np.load(path)) if os.path.exists(path) else {}
+    keep_alive = []
+    for case, fix_scale in enumerate((True, False)):
+        rng = np.random.default_rng(40 + case)
+        n = 48
+        cam8 = np.array([718.856, 718.856, 607.1928, 185.2157, 707.0912, 707.0912, 601.8873, 183.1104]).astype(np.float32).astype(np.float64)
+        sg0 = Sim3Graph()
+        S12 = sg0.exp(rng.normal(0, 1, 7) * np.array([0.05, 0.05, 0.05, 0.6, 0.2, 0.6, 0.0 if fix_scale else 0.1]))
+        S21 = _sim3_inv(S12)
+        p1 = np.stack([rng.uniform(-8, 8, n), rng.uniform(-3, 3, n), rng.uniform(5, 40, n)], 1)
+        p2 = np.stack([S21[7] * (_rot(S21[:4]) @ x) + S21[4:7] for x in p1]) * (1 + rng.normal(0, 0.01, (n, 1)))
+        p1, p2 = p1.astype(np.float32).astype(np.float64), p2.astype(np.float32).astype(np.float64)
+        meas = np.zeros((n, 6), np.float32)
+        for k in range(n):
+            bad = rng.random() < 0.2
+            jump = rng.uniform(8, 40) * rng.choice([-1, 1]) if bad else 0.0
+            meas[k, 0] = cam8[0] * p1[k, 0] / p1[k, 2] + cam8[2] + rng.normal(0, 1) + (jump if k % 2 == 0 else 0)
+            meas[k, 1] = cam8[1] * p1[k, 1] / p1[k, 2] + cam8[3] + rng.normal(0, 1)
+            meas[k, 2] = np.float32(1.0) / np.float32(1.2) ** (2 * int(rng.integers(0, 5)))
+            meas[k, 3] = cam8[4] * p2[k, 0] / p2[k, 2] + cam8[6] + rng.normal(0, 1) + (jump if k % 2 == 1 else 0)
+            meas[k, 4] = cam8[5] * p2[k, 1] / p2[k, 2] + cam8[7] + rng.normal(0, 1)
+            meas[k, 5] = np.float32(1.0) / np.float32(1.2) ** (2 * int(rng.integers(0, 5)))
+        noise = sg0.exp(rng.normal(0, 1, 7) * np.array([0.01, 0.01, 0.01, 0.05, 0.05, 0.05, 0.0 if fix_scale else 0.02]))
+        s0 = _sim3_mul(noise, S12)
+        th2 = np.float32(10.0)                                           # LoopClosing.cc: OptimizeSim3(..., 10, mbFixScale)
+        delta = float(np.float32(np.sqrt(th2)))                          # const float deltaHuber = sqrt(th2), :1619
+        so = Sim3Opt(s0, cam8, fix_scale)
+        sg, G = so.sg, so.sg.G
+        pairs = [so.add_match(k, p1[k], p2[k], meas[k].astype(np.float64), delta) for k in range(n)]
+        o = G.opt.ctypes.data
+        assert G.f["init"](o, 0)
+        # locate _b of the Sim3 vertex (differential probe on a throw-away quadratic form)
+        Hs = P._aligned(52)
+        sg.f["v_map"](so.vs.ctypes.data, Hs.ctypes.data)
+        sg.f["v_clear"](so.vs.ctypes.data)
+        snap = so.vs.copy()
+        so.error(pairs[0][0])
+        so.f["lin"](pairs[0][0]["e"].ctypes.data, pairs[0][0]["jw"].ctypes.data)
+        so.f["quad"](pairs[0][0]["e"].ctypes.data)
+        ch = np.flatnonzero(so.vs.view(np.uint64) != snap.view(np.uint64))
+        assert len(ch) >= 3 and (ch < ch.min() + 7).sum() >= 3 and ch.min() > V_DIM // 8, ch
+        so.b_off = int(ch.min())
+        sg.f["v_clear"](so.vs.ctypes.data)
+        e12_0 = np.stack([so.error(a) for a, _ in pairs])
+        e21_0 = np.stack([so.error(b) for _, b in pairs])
+        J12_0 = np.stack([so.jacobian(a) for a, _ in pairs])
+        J21_0 = np.stack([so.jacobian(b) for _, b in pairs])
+        L = G.ed.g.L
+        lm_ctor = L._ZN3g2o30OptimizationAlgorithmLevenbergC1EPNS_6SolverE
+        lm_ctor.restype, lm_ctor.argtypes = None, [C.c_void_p, C.c_void_p]
+        set_alg = L._ZN3g2o15SparseOptimizer12setAlgorithmEPNS_21OptimizationAlgorithmE
+        set_alg.restype, set_alg.argtypes = None, [C.c_void_p, C.c_void_p]
+        optimize = L._ZN3g2o15SparseOptimizer8optimizeEib
+        optimize.restype, optimize.argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_bool]
+        solver = FakeSolverSim3Dense(so)
+        alg = P._aligned(1024)
+        lm_ctor(alg.ctypes.data, solver.obj.ctypes.data)
+        set_alg(o, alg.ctypes.data)
+        assert G.f["init"](o, 0)
+        it1 = optimize(o, 5, False)
+        n_l1 = sum(1 for k, _ in solver.log if k == "lambda")
+        keep = np.ones(n, np.uint8)
+        nBad = 0
+        for k, (a, b) in enumerate(pairs):
+            if so.chi2(a) > th2 or so.chi2(b) > th2:                      # stored _error, float th2 promoted
+                keep[k] = 0
+                so.set_level(a, 1)
+                so.set_level(b, 1)
+                nBad += 1
+        more = 10 if nBad > 0 else 5
+        assert n - nBad >= 10
+        assert G.f["init"](o, 0)
+        it2 = optimize(o, more, False)
+        nIn = 0
+        for k, (a, b) in enumerate(pairs):
+            if not keep[k]:
+                continue
+            if so.chi2(a) > th2 or so.chi2(b) > th2:
+                keep[k] = 0
+            else:
+                nIn += 1
+        lam = np.array([v for k, v in solver.log if k == "lambda"])
+        pre = f"s3o{case}_"
+        out.update({pre + "s0": s0, pre + "cam8": cam8, pre + "p1c": p1, pre + "p2c": p2, pre + "meas6": meas,
+                    pre + "fix_scale": np.array(int(fix_scale)), pre + "th2": np.array(th2), pre + "e12_0": e12_0,
+                    pre + "e21_0": e21_0, pre + "J12_0": J12_0, pre + "J21_0": J21_0, pre + "lambda": lam,
+                    pre + "n_trials_pass0": np.array(n_l1), pre + "iterations": np.array([it1, it2]),
+                    pre + "keep": keep, pre + "nIn": np.array(nIn), pre + "nBad": np.array(nBad),
+                    pre + "s12": sg.estimate(0)})
+        keep_alive.append((so, solver, alg, Hs))
+        print(f"OptimizeSim3 (fix_scale={fix_scale}): {it1}+{it2} iterations, {len(lam)} trials, nBad {nBad}, nIn {nIn} of {n}")
+    np.savez(path, **out)
+    return out, keep_alive
+
+
 if __name__ == "__main__":
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = sys.argv[1] if len(sys.argv) > 1 else os.path.join(here, "tests", "golden", "libg2o_vectors.npz")
@@ -1191,6 +1432,7 @@ if __name__ == "__main__":
     _keep2 = make_poseopt(p)
     make_sim3(p)
     _keep3 = make_posegraph(p)
+    _keep4 = make_sim3opt(p)
     print("wrote", p, "| phase A index:", o["graph_A_pose_index"], o["graph_A_point_index"], "| phase B index:",
           o["graph_B_pose_index"], o["graph_B_point_index"], "| chi2", o["graph_A_chi2"], o["graph_A_robust_chi2"],
           o["graph_B_chi2"])

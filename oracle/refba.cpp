@@ -28,7 +28,7 @@
 // local-BA schedule driven over the binary's objects gives the lambda sequences, level-1 set, outlier flags and
 // estimates that refba_solve_local gives; likewise refba_pose_opt against the four-round pose-only schedule over the
 // binary's EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose objects, and refba_sim3_* / refba_pose_graph
-// (essential-graph optimisation, no CUDA counterpart yet) against the binary's Sim3, VertexSim3Expmap and EdgeSim3.
+// (essential-graph optimisation) against the binary's Sim3, VertexSim3Expmap and EdgeSim3.
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 // Eigen is not vendored in the reference; where g2o calls into Eigen (quaternion*vector,
@@ -1974,6 +1974,251 @@ int refba_pose_graph(int n, double* vert8, const uint8_t* fixed, int fix_scale, 
   if (trace && nt > 0) std::memcpy(trace, G.trace.data(), (size_t)nt * sizeof(TraceRow));
   if (n_trace) *n_trace = nt;
   return done;
+}
+
+// =====================================================================================================
+// Sim3 alignment of a loop-candidate keyframe pair: g2oOptimizer::OptimizeSim3,
+// src/backend/g2oOptimizer.cc:1560-1796.  ONE free VertexSim3Expmap (S12, carrying both cameras' focal lengths and
+// principal points), the matched map points as FIXED vertices in their own camera frames, and per match two binary
+// edges with a Huber kernel of delta = (float)sqrt(th2):
+//   EdgeSim3ProjectXYZ        e12 = obs1 - cam_map1(project(S12.map(P2c)))            (types_seven_dof_expmap.h:130-149)
+//   EdgeInverseSim3ProjectXYZ e21 = obs2 - cam_map2(project(S12.inverse().map(P1c)))  (:152-171)
+// Both edges leave linearizeOplus to BaseBinaryEdge (the analytic one is commented out, types_seven_dof_expmap.cpp), so
+// the 2x7 Jacobian is the NUMERIC one (base_binary_edge.hpp:122-195, delta 1e-9, central differences through oplusImpl)
+// and only the Sim3 side is linearised (the point vertex is fixed).  BlockSolverX + LinearSolverDense + Levenberg:
+// optimize(5), drop the pairs with chi2 > th2 on either edge (stored errors, i.e. possibly those of a rejected last
+// trial), give up (return 0, S12 untouched) with fewer than 10 pairs left, optimize(10 if something was dropped else 5),
+// count the pairs that still pass.
+namespace {
+struct S3Pair { double P1c[3], P2c[3], obs1[2], obs2[2], info1, info2; double e12[2], e21[2]; bool on = true; };
+struct Sim3Problem {
+  Sim3 S, Sbak;
+  bool fix_scale;
+  double f1[2], c1[2], f2[2], c2[2];
+  double delta, dsqr;
+  std::vector<S3Pair> m;
+  double H[49], b[7], x[7];
+  double lambda = -1, ni = 2;
+  int nBad = 0, round = 0;
+  std::vector<TraceRow> trace;
+};
+inline void sim3map(const Sim3& S, const double* p, double* out) {  // Sim3::map, sim3.h:144-146
+  double r[3];
+  qrot(S.r, p, r);
+  for (int i = 0; i < 3; i++) out[i] = S.s * r[i] + S.t[i];
+}
+inline void s3Error12(const Sim3Problem& P, const Sim3& S, const S3Pair& m, double e[2]) {
+  double X[3];
+  sim3map(S, m.P2c, X);
+  e[0] = m.obs1[0] - (X[0] / X[2] * P.f1[0] + P.c1[0]);
+  e[1] = m.obs1[1] - (X[1] / X[2] * P.f1[1] + P.c1[1]);
+}
+inline void s3Error21(const Sim3Problem& P, const Sim3& S, const S3Pair& m, double e[2]) {
+  double X[3];
+  sim3map(sim3inv(S), m.P1c, X);
+  e[0] = m.obs2[0] - (X[0] / X[2] * P.f2[0] + P.c2[0]);
+  e[1] = m.obs2[1] - (X[1] / X[2] * P.f2[1] + P.c2[1]);
+}
+inline void s3ComputeActiveErrors(Sim3Problem& P) {
+  for (auto& m : P.m) if (m.on) { s3Error12(P, P.S, m, m.e12); s3Error21(P, P.S, m, m.e21); }
+}
+inline void s3Rho(const Sim3Problem& P, double c, double rho[2]) {
+  if (c <= P.dsqr) { rho[0] = c; rho[1] = 1.; }
+  else { const double sq = std::sqrt(c); rho[0] = 2 * sq * P.delta - P.dsqr; rho[1] = P.delta / sq; }
+}
+inline double s3Chi2(const double e[2], double info) { return e[0] * (info * e[0]) + e[1] * (info * e[1]); }
+inline double s3ActiveRobustChi2(const Sim3Problem& P) {
+  double chi = 0, rho[2];
+  for (const auto& m : P.m) if (m.on) {
+    s3Rho(P, s3Chi2(m.e12, m.info1), rho); chi += rho[0];
+    s3Rho(P, s3Chi2(m.e21, m.info2), rho); chi += rho[0];
+  }
+  return chi;
+}
+inline void s3AddEdge(Sim3Problem& P, const double e[2], double info, const double J[14]) {
+  double rho[2];
+  s3Rho(P, s3Chi2(e, info), rho);
+  const double w = rho[1] * info;
+  for (int i = 0; i < 7; i++) {
+    P.b[i] -= rho[1] * (J[i] * (info * e[0]) + J[7 + i] * (info * e[1]));
+    for (int j = 0; j < 7; j++) P.H[i * 7 + j] += J[i] * (w * J[j]) + J[7 + i] * (w * J[7 + j]);
+  }
+}
+inline void s3BuildSystem(Sim3Problem& P) {
+  for (double& v : P.H) v = 0;
+  for (double& v : P.b) v = 0;
+  const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+  for (auto& m : P.m) {
+    if (!m.on) continue;
+    double J12[14], J21[14];
+    for (int d = 0; d < 7; d++) {
+      double add[7] = {0, 0, 0, 0, 0, 0, 0}, a[2], c[2];
+      add[d] = delta;
+      const Sim3 Sp = sim3oplus(P.S, add, P.fix_scale);
+      add[d] = -delta;
+      const Sim3 Sm = sim3oplus(P.S, add, P.fix_scale);
+      s3Error12(P, Sp, m, a); s3Error12(P, Sm, m, c);
+      J12[d] = scalar * (a[0] - c[0]); J12[7 + d] = scalar * (a[1] - c[1]);
+      s3Error21(P, Sp, m, a); s3Error21(P, Sm, m, c);
+      J21[d] = scalar * (a[0] - c[0]); J21[7 + d] = scalar * (a[1] - c[1]);
+    }
+    s3AddEdge(P, m.e12, m.info1, J12);
+    s3AddEdge(P, m.e21, m.info2, J21);
+  }
+}
+// Eigen::LDLT + isPositive() (linear_solver_dense.h), restated without pivoting, 7x7
+inline bool s3Solve7(const double* H, const double* b, double* x) {
+  double L[49] = {0}, D[7], y[7];
+  for (int j = 0; j < 7; j++) {
+    double d = H[j * 7 + j];
+    for (int k = 0; k < j; k++) d -= L[j * 7 + k] * L[j * 7 + k] * D[k];
+    if (!(d > 0.0)) return false;
+    D[j] = d;
+    for (int i = j + 1; i < 7; i++) {
+      double v = H[i * 7 + j];
+      for (int k = 0; k < j; k++) v -= L[i * 7 + k] * L[j * 7 + k] * D[k];
+      L[i * 7 + j] = v / d;
+    }
+  }
+  for (int i = 0; i < 7; i++) { double v = b[i]; for (int k = 0; k < i; k++) v -= L[i * 7 + k] * y[k]; y[i] = v; }
+  for (int i = 0; i < 7; i++) y[i] /= D[i];
+  for (int i = 6; i >= 0; i--) { double v = y[i]; for (int k = i + 1; k < 7; k++) v -= L[k * 7 + i] * x[k]; x[i] = v; }
+  return true;
+}
+SolverResult s3LmSolve(Sim3Problem& P, int iteration) {  // optimization_algorithm_levenberg.cpp:61-164
+  s3ComputeActiveErrors(P);
+  double currentChi = s3ActiveRobustChi2(P), tempChi = currentChi;
+  const double iniChi = currentChi;
+  s3BuildSystem(P);
+  if (iteration == 0) {
+    double md = 0;
+    for (int j = 0; j < 7; j++) md = std::max(std::fabs(P.H[j * 7 + j]), md);
+    P.lambda = 1e-5 * md;
+    P.ni = 2;
+    P.nBad = 0;
+  }
+  double rho = 0;
+  int qmax = 0;
+  do {
+    P.Sbak = P.S;
+    double Hd[49];
+    std::memcpy(Hd, P.H, sizeof Hd);
+    for (int j = 0; j < 7; j++) Hd[j * 7 + j] += P.lambda;
+    const bool ok2 = s3Solve7(Hd, P.b, P.x);
+    if (!ok2) for (double& v : P.x) v = 0;
+    P.S = sim3oplus(P.S, P.x, P.fix_scale);
+    s3ComputeActiveErrors(P);
+    tempChi = s3ActiveRobustChi2(P);
+    if (!ok2) tempChi = std::numeric_limits<double>::max();
+    rho = (currentChi - tempChi);
+    double scale = 0.;
+    for (int j = 0; j < 7; j++) scale += P.x[j] * (P.lambda * P.x[j] + P.b[j]);
+    scale += 1e-3;
+    rho /= scale;
+    TraceRow tr{(double)P.round, (double)iteration, (double)qmax, P.lambda, currentChi, tempChi, rho, 0.0};
+    if (rho > 0 && std::isfinite(tempChi)) {
+      double alpha = 1. - std::pow((2 * rho - 1), 3);
+      alpha = std::min(alpha, 2. / 3.);
+      P.lambda *= std::max(1. / 3., alpha);
+      P.ni = 2;
+      currentChi = tempChi;
+      tr.accepted = 1.0;
+    } else {
+      P.lambda *= P.ni;
+      P.ni *= 2;
+      P.S = P.Sbak;
+    }
+    P.trace.push_back(tr);
+    qmax++;
+  } while (rho < 0 && qmax < 10);
+  if (qmax == 10 || rho == 0) return Terminate;
+  if ((iniChi - currentChi) * 1e3 < iniChi) P.nBad++; else P.nBad = 0;
+  if (P.nBad >= 3) return Terminate;
+  return OK;
+}
+}  // namespace
+
+// s12 in/out (qx qy qz qw | t | s); cam8 = fx1 fy1 cx1 cy1 fx2 fy2 cx2 cy2; p1c / p2c: n x 3 (the matched map points
+// in the frames of keyframe 1 / 2); meas6: n x 6 float (u1 v1 invSigma2_1 u2 v2 invSigma2_2).  keep[i] = 1 while
+// vpMatches1 keeps the match.  Returns nIn (0 -- and s12 untouched -- when fewer than 10 pairs survive the first test).
+int refba_optimize_sim3(double* s12, const double* cam8, int n, const double* p1c, const double* p2c, const float* meas6,
+                        float th2, int fix_scale, uint8_t* keep, double* trace, int max_trace, int* n_trace) {
+  Sim3Problem P;
+  P.S = sim3from8(s12);
+  P.fix_scale = fix_scale != 0;
+  P.f1[0] = cam8[0]; P.f1[1] = cam8[1]; P.c1[0] = cam8[2]; P.c1[1] = cam8[3];
+  P.f2[0] = cam8[4]; P.f2[1] = cam8[5]; P.c2[0] = cam8[6]; P.c2[1] = cam8[7];
+  const float deltaHuber = std::sqrt(th2);  // :1619
+  P.delta = deltaHuber;
+  P.dsqr = (double)(float)(P.delta * P.delta);
+  P.m.resize(n);
+  for (int i = 0; i < n; i++) {
+    S3Pair& m = P.m[i];
+    for (int c = 0; c < 3; c++) { m.P1c[c] = p1c[i * 3 + c]; m.P2c[c] = p2c[i * 3 + c]; }
+    m.obs1[0] = meas6[i * 6]; m.obs1[1] = meas6[i * 6 + 1]; m.info1 = meas6[i * 6 + 2];
+    m.obs2[0] = meas6[i * 6 + 3]; m.obs2[1] = meas6[i * 6 + 4]; m.info2 = meas6[i * 6 + 5];
+    m.e12[0] = m.e12[1] = m.e21[0] = m.e21[1] = 0;
+    keep[i] = 1;
+  }
+  auto optimize = [&](int iters) {  // sparse_optimizer.cpp:354-419; no active edge -> nothing happens
+    bool any = false;
+    for (auto& m : P.m) any |= m.on;
+    bool ok = any;
+    for (int i = 0; i < iters && ok; i++) ok = (s3LmSolve(P, i) == OK);
+  };
+  auto finish = [&](int ret) {
+    const int nt = std::min<int>((int)P.trace.size(), max_trace);
+    if (trace && nt > 0) std::memcpy(trace, P.trace.data(), (size_t)nt * sizeof(TraceRow));
+    if (n_trace) *n_trace = nt;
+    return ret;
+  };
+  P.round = 0;
+  optimize(5);
+  int nBad = 0;
+  for (int i = 0; i < n; i++) {
+    S3Pair& m = P.m[i];
+    if (s3Chi2(m.e12, m.info1) > th2 || s3Chi2(m.e21, m.info2) > th2) { keep[i] = 0; m.on = false; nBad++; }
+  }
+  const int more = nBad > 0 ? 10 : 5;
+  if (n - nBad < 10) return finish(0);
+  P.round = 1;
+  optimize(more);
+  int nIn = 0;
+  for (int i = 0; i < n; i++) {
+    S3Pair& m = P.m[i];
+    if (!m.on) continue;
+    if (s3Chi2(m.e12, m.info1) > th2 || s3Chi2(m.e21, m.info2) > th2) keep[i] = 0; else nIn++;
+  }
+  sim3to8(P.S, s12);
+  return finish(nIn);
+}
+
+// errors and numeric Jacobians (2x7 row-major each) of one match's two edges at S12 -- for the pin against the binary
+void refba_sim3_match_linearize(const double* s12, const double* cam8, const double* p1c, const double* p2c,
+                                const float* meas6, int fix_scale, double* e12, double* e21, double* J12, double* J21) {
+  Sim3Problem P;
+  P.S = sim3from8(s12);
+  P.fix_scale = fix_scale != 0;
+  P.f1[0] = cam8[0]; P.f1[1] = cam8[1]; P.c1[0] = cam8[2]; P.c1[1] = cam8[3];
+  P.f2[0] = cam8[4]; P.f2[1] = cam8[5]; P.c2[0] = cam8[6]; P.c2[1] = cam8[7];
+  S3Pair m;
+  for (int c = 0; c < 3; c++) { m.P1c[c] = p1c[c]; m.P2c[c] = p2c[c]; }
+  m.obs1[0] = meas6[0]; m.obs1[1] = meas6[1]; m.info1 = meas6[2];
+  m.obs2[0] = meas6[3]; m.obs2[1] = meas6[4]; m.info2 = meas6[5];
+  s3Error12(P, P.S, m, e12);
+  s3Error21(P, P.S, m, e21);
+  const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+  for (int d = 0; d < 7; d++) {
+    double add[7] = {0, 0, 0, 0, 0, 0, 0}, a[2], c[2];
+    add[d] = delta;
+    const Sim3 Sp = sim3oplus(P.S, add, P.fix_scale);
+    add[d] = -delta;
+    const Sim3 Sm = sim3oplus(P.S, add, P.fix_scale);
+    s3Error12(P, Sp, m, a); s3Error12(P, Sm, m, c);
+    J12[d] = scalar * (a[0] - c[0]); J12[7 + d] = scalar * (a[1] - c[1]);
+    s3Error21(P, Sp, m, a); s3Error21(P, Sm, m, c);
+    J21[d] = scalar * (a[0] - c[0]); J21[7 + d] = scalar * (a[1] - c[1]);
+  }
 }
 
 int refba_max_threads() {

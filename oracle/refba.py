@@ -236,7 +236,7 @@ def pose_opt(pose7, cam5, xyz, meas):
     return pose, out[:n], int(inl), tr[:nt.value]
 
 
-# ---- essential-graph (Sim3 pose-graph) optimisation, SURVEY.md 8(f) N3 (oracle only); 8-vectors are qx,qy,qz,qw,tx,ty,tz,s
+# ---- essential-graph (Sim3 pose-graph) optimisation; 8-vectors are qx,qy,qz,qw,tx,ty,tz,s
 def sim3_exp(upd7):
     u, out = np.ascontiguousarray(upd7, np.float64), np.zeros(8)
     lib().refba_sim3_exp(_p(u, C.c_double), _p(out, C.c_double))
@@ -273,3 +273,40 @@ def pose_graph(vert8, fixed, fix_scale, edge_ij, meas8, iters=20, lambda_init=1e
     done = lib().refba_pose_graph(len(V), _p(V, C.c_double), _p(fx, C.c_uint8), int(fix_scale), len(E), _p(E, C.c_int32),
                                   _p(M, C.c_double), iters, lambda_init, _p(tr, C.c_double), len(tr), C.byref(nt))
     return V, tr[:nt.value], done
+
+
+def optimize_sim3(s12, cam8, p1c, p2c, meas6, th2=10.0, fix_scale=False):
+    """g2oOptimizer::OptimizeSim3 restated (refba_optimize_sim3).
+    Returns (s12_out 8, keep flags n, nIn, trace[rows, 8])."""
+    L = lib()
+    S = np.ascontiguousarray(s12, np.float64).copy()
+    cam = np.ascontiguousarray(cam8, np.float64)
+    a, b = np.ascontiguousarray(p1c, np.float64), np.ascontiguousarray(p2c, np.float64)
+    m = np.ascontiguousarray(meas6, np.float32)
+    n = a.shape[0]
+    keep = np.zeros(max(n, 1), np.uint8)
+    tr = np.zeros((150, 8))
+    nt = C.c_int32(0)
+    L.refba_optimize_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.refba_optimize_sim3.restype = C.c_int
+    n_in = L.refba_optimize_sim3(S.ctypes.data, cam.ctypes.data, n, a.ctypes.data, b.ctypes.data, m.ctypes.data,
+                                 C.c_float(th2), int(fix_scale), keep.ctypes.data, tr.ctypes.data, len(tr), C.byref(nt))
+    return S, keep[:n], int(n_in), tr[:nt.value]
+
+
+def sim3_match_linearize(s12, cam8, p1c, p2c, meas6, fix_scale):
+    """(e12[n,2], e21[n,2], J12[n,2,7], J21[n,2,7]) of every match at s12 (refba_sim3_match_linearize)."""
+    L = lib()
+    S = np.ascontiguousarray(s12, np.float64)
+    cam = np.ascontiguousarray(cam8, np.float64)
+    a, b = np.ascontiguousarray(p1c, np.float64), np.ascontiguousarray(p2c, np.float64)
+    m = np.ascontiguousarray(meas6, np.float32)
+    n = a.shape[0]
+    e12, e21, J12, J21 = np.zeros((n, 2)), np.zeros((n, 2)), np.zeros((n, 2, 7)), np.zeros((n, 2, 7))
+    L.refba_sim3_match_linearize.argtypes = [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 4
+    L.refba_sim3_match_linearize.restype = None
+    for k in range(n):
+        L.refba_sim3_match_linearize(S.ctypes.data, cam.ctypes.data, a[k].ctypes.data, b[k].ctypes.data, m[k].ctypes.data,
+                                     int(fix_scale), e12[k].ctypes.data, e21[k].ctypes.data, J12[k].ctypes.data, J21[k].ctypes.data)
+    return e12, e21, J12, J21

@@ -82,6 +82,8 @@ def lib():
         L.sqrtba_pose_opt_trace.argtypes = [vp, C.c_int32, dp, C.c_int32]
         L.sqrtba_pose_graph.argtypes = [vp, C.c_int32, dp, up, C.c_int32, C.c_int32, ip, dp, C.c_int32, C.c_double, C.POINTER(Stats)]
         L.sqrtba_pose_graph_trace.argtypes = [vp, dp, C.c_int32]
+        L.sqrtba_optimize_sim3.argtypes = [vp, C.c_int32, lp, dp, dp, dp, dp, fp, C.c_float, C.c_int32, up, ip, C.POINTER(Stats)]
+        L.sqrtba_optimize_sim3_trace.argtypes = [vp, C.c_int32, dp, C.c_int32]
         L.sqrtba_set_lidar.argtypes = [vp, C.POINTER(Lidar)]
         L.sqrtba_set_lidar_edges.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, dp, dp, dp, dp, C.c_int32]
         L.sqrtba_get_lidar_matches.argtypes = [vp, ip]
@@ -302,6 +304,29 @@ class SqrtBA:
         if n > 0:
             lib().sqrtba_pose_graph_trace(self.h, _p(tr, C.c_double), n)
         return V, tr, st.as_dict()
+
+    def optimize_sim3(self, pair_ptr, s12, cam8, p1c, p2c, meas6, th2: float = 10.0, fix_scale: bool = False):
+        """sqrtba_optimize_sim3 over a batch of keyframe pairs: returns (s12 n_pairs x 8, keep flags per match,
+        nIn per pair, stats)."""
+        ptr = np.ascontiguousarray(pair_ptr, np.int64)
+        S = np.ascontiguousarray(s12, np.float64).reshape(-1, 8).copy()
+        cam = np.ascontiguousarray(cam8, np.float64).reshape(-1, 8)
+        a, b = np.ascontiguousarray(p1c, np.float64), np.ascontiguousarray(p2c, np.float64)
+        m = np.ascontiguousarray(meas6, np.float32)
+        n_pairs = len(ptr) - 1
+        keep = np.zeros(max(int(ptr[-1]), 1), np.uint8)
+        n_in = np.zeros(n_pairs, np.int32)
+        st = Stats()
+        self._chk(lib().sqrtba_optimize_sim3(self.h, n_pairs, _p(ptr, C.c_int64), _p(S, C.c_double), _p(cam, C.c_double),
+                                             _p(a, C.c_double), _p(b, C.c_double), _p(m, C.c_float), C.c_float(th2),
+                                             int(fix_scale), _p(keep, C.c_uint8), _p(n_in, C.c_int32), C.byref(st)),
+                  "sqrtba_optimize_sim3")
+        return S, keep[:int(ptr[-1])], n_in, st.as_dict()
+
+    def optimize_sim3_trace(self, pair: int) -> np.ndarray:
+        rows = np.zeros((150, 8))
+        n = self._chk(lib().sqrtba_optimize_sim3_trace(self.h, pair, _p(rows, C.c_double), 150), "sqrtba_optimize_sim3_trace")
+        return rows[:n]
 
     def comm_init(self, nranks: int, rank: int, unique_id: bytes):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)

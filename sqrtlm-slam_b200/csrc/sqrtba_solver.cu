@@ -27,6 +27,7 @@
 #include "sqrtba_poseopt.cuh"
 #include "sqrtba_lidar.cuh"
 #include "sqrtba_posegraph.cuh"
+#include "sqrtba_sim3opt.cuh"
 #include "../host/host_pool.h"
 
 namespace sqrtba {
@@ -1085,6 +1086,7 @@ class Solver {
     CU_CHECK(cudaEventRecord(ev1_, stream_));
     CU_CHECK(cudaEventSynchronize(ev1_));
     po_frames_ = n_frames;
+    s3_pairs_ = 0;  // shared buffers
     if (st) {
       std::memset(st, 0, sizeof *st);
       float ms = 0;
@@ -1105,6 +1107,75 @@ class Solver {
     return m;
   }
 
+
+  // -------------------------------------------------------------------------------------- Sim3 of a loop candidate (row N3)
+  // g2oOptimizer::OptimizeSim3 (g2oOptimizer.cc:1560-1796) for a batch of keyframe pairs, one CTA each
+  // (csrc/sqrtba_sim3opt.cuh).  Independent of set_problem.
+  int optimize_sim3(int n_pairs, const int64_t* pair_ptr, double* s12, const double* cam8, const double* p1c,
+                    const double* p2c, const float* meas6, float th2, int fix_scale, uint8_t* keep_out, int32_t* n_in_out,
+                    sqrtba_stats* st) {
+    if (n_pairs <= 0 || !pair_ptr || !s12 || !cam8 || !n_in_out || !(th2 > 0.0f)) { err_ = "optimize_sim3: bad arguments"; return SQRTBA_ERR_INVALID; }
+    const long long n_m = pair_ptr[n_pairs];
+    if (pair_ptr[0] != 0 || n_m < 0 || (n_m > 0 && (!p1c || !p2c || !meas6 || !keep_out))) {
+      err_ = "optimize_sim3: bad match arrays";
+      return SQRTBA_ERR_INVALID;
+    }
+    for (int f = 0; f < n_pairs; f++)
+      if (pair_ptr[f] > pair_ptr[f + 1]) { err_ = "optimize_sim3: pair offsets must be non-decreasing"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    const size_t Nm = (size_t)std::max<long long>(n_m, 1);
+    CU_CHECK(d_po_ptr_.ensure(n_pairs + 1));
+    CU_CHECK(d_po_pose_.ensure((size_t)n_pairs * 8));
+    CU_CHECK(d_po_cam_.ensure((size_t)n_pairs * 8));
+    CU_CHECK(d_po_xyz_.ensure(Nm * 6));
+    CU_CHECK(d_s3_meas_.ensure(Nm * 6));
+    CU_CHECK(d_po_err_.ensure(Nm * 4));
+    CU_CHECK(d_po_level_.ensure(Nm));
+    CU_CHECK(d_po_outlier_.ensure(Nm));
+    CU_CHECK(d_po_inl_.ensure(2 * (size_t)n_pairs));
+    CU_CHECK(d_po_trace_.ensure((size_t)n_pairs * S3_MAX_TRACE * S3_TRACE_COLS));
+    auto up = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_); };
+    CU_CHECK(cudaEventRecord(ev0_, stream_));
+    CU_CHECK(up(d_po_ptr_.p, pair_ptr, (size_t)(n_pairs + 1) * sizeof(int64_t)));
+    CU_CHECK(up(d_po_pose_.p, s12, (size_t)n_pairs * 8 * sizeof(double)));
+    CU_CHECK(up(d_po_cam_.p, cam8, (size_t)n_pairs * 8 * sizeof(double)));
+    if (n_m > 0) {
+      CU_CHECK(up(d_po_xyz_.p, p1c, (size_t)n_m * 3 * sizeof(double)));
+      CU_CHECK(up(d_po_xyz_.p + Nm * 3, p2c, (size_t)n_m * 3 * sizeof(double)));
+      CU_CHECK(up(d_s3_meas_.p, meas6, (size_t)n_m * 6 * sizeof(float)));
+    }
+    Sim3OptArgs A{};
+    A.n_pairs = n_pairs; A.pair_ptr = d_po_ptr_.p; A.s12 = d_po_pose_.p; A.cam8 = d_po_cam_.p; A.p1c = d_po_xyz_.p;
+    A.p2c = d_po_xyz_.p + Nm * 3; A.meas6 = d_s3_meas_.p; A.err = d_po_err_.p; A.on = d_po_level_.p; A.keep = d_po_outlier_.p;
+    A.n_in = d_po_inl_.p; A.trace = d_po_trace_.p; A.trace_len = d_po_inl_.p + n_pairs; A.th2 = th2; A.fix_scale = fix_scale;
+    k_sim3_opt<<<n_pairs, PO_CTA, 0, stream_>>>(A);
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaMemcpyAsync(s12, d_po_pose_.p, (size_t)n_pairs * 8 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    CU_CHECK(cudaMemcpyAsync(n_in_out, d_po_inl_.p, (size_t)n_pairs * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    if (n_m > 0) CU_CHECK(cudaMemcpyAsync(keep_out, d_po_outlier_.p, (size_t)n_m, cudaMemcpyDeviceToHost, stream_));
+    CU_CHECK(cudaEventRecord(ev1_, stream_));
+    CU_CHECK(cudaEventSynchronize(ev1_));
+    s3_pairs_ = n_pairs;
+    po_frames_ = 0;  // the pose-only trace buffers were reused
+    if (st) {
+      std::memset(st, 0, sizeof *st);
+      float ms = 0;
+      CU_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+      st->n_windows = n_pairs;
+      st->kernel_launches = 1;
+      st->ms_total = ms;
+    }
+    return SQRTBA_OK;
+  }
+  int optimize_sim3_trace(int pair, double* rows, int max_rows) {
+    if (pair < 0 || pair >= s3_pairs_ || !rows) { err_ = "optimize_sim3_trace: no such pair"; return SQRTBA_ERR_INVALID; }
+    int len = 0;
+    if (download(&len, d_po_inl_.p + s3_pairs_ + pair, sizeof(int))) return SQRTBA_ERR_CUDA;
+    const int m = std::min(std::min(len, max_rows), S3_MAX_TRACE);
+    if (m > 0 && download(rows, d_po_trace_.p + (size_t)pair * S3_MAX_TRACE * S3_TRACE_COLS, (size_t)m * S3_TRACE_COLS * sizeof(double)))
+      return SQRTBA_ERR_CUDA;
+    return m;
+  }
 
   // ------------------------------------------------------------------------------------------ essential graph (row N3)
   // The optimisation of g2oOptimizer::OptimizeEssentialGraph (g2oOptimizer.cc:1212-1460) for a pose graph the adapter
@@ -2081,7 +2152,7 @@ class Solver {
     d_lm_flat_pose_.release(); d_lm_corner_pose_.release(); d_lc_flat_.release(); d_lc_normal_.release(); d_lc_corner_.release();
     d_lc_world_.release(); d_lm_flat_.release(); d_lm_flat_w_.release(); d_lm_corner_.release(); d_lm_corner_w_.release(); d_l_best_.release();
     d_po_ptr_.release(); d_po_pose_.release(); d_po_cam_.release(); d_po_xyz_.release(); d_po_err_.release(); d_po_trace_.release();
-    d_po_meas_.release(); d_po_level_.release(); d_po_outlier_.release(); d_po_inl_.release();
+    d_po_meas_.release(); d_s3_meas_.release(); d_po_level_.release(); d_po_outlier_.release(); d_po_inl_.release();
     d_pg_vert_.release(); d_pg_bak_.release(); d_pg_meas_.release(); d_pg_err_.release(); d_pg_Ji_.release(); d_pg_Jj_.release();
     d_pg_H_.release(); d_pg_L_.release(); d_pg_Linv_.release(); d_pg_b_.release(); d_pg_y_.release(); d_pg_x_.release();
     d_pg_scal_.release(); d_pg_fixed_.release(); d_pg_slot_.release(); d_pg_slot_vert_.release(); d_pg_edge_.release();
@@ -2147,6 +2218,8 @@ class Solver {
   DBuf<uint8_t> d_po_level_, d_po_outlier_;
   DBuf<int> d_po_inl_;
   int po_frames_ = 0;
+  DBuf<float> d_s3_meas_;
+  int s3_pairs_ = 0;
   // essential-graph optimisation (independent of set_problem)
   DBuf<double> d_pg_vert_, d_pg_bak_, d_pg_meas_, d_pg_err_, d_pg_Ji_, d_pg_Jj_, d_pg_H_, d_pg_L_, d_pg_Linv_, d_pg_b_, d_pg_y_,
       d_pg_x_, d_pg_scal_;
@@ -2318,6 +2391,16 @@ int sqrtba_pose_graph(sqrtba_handle* h, int32_t n_vert, double* vert8, const uin
 }
 int sqrtba_pose_graph_trace(sqrtba_handle* h, double* rows_out, int32_t max_rows) {
   return h ? h->s->pose_graph_trace(rows_out, max_rows) : SQRTBA_ERR_INVALID;
+}
+int sqrtba_optimize_sim3(sqrtba_handle* h, int32_t n_pairs, const int64_t* pair_match_ptr, double* sim3_12, const double* cam8,
+                         const double* p1c, const double* p2c, const float* match_meas, float th2, int32_t fix_scale,
+                         uint8_t* keep_out, int32_t* inliers_out, sqrtba_stats* stats) {
+  return h ? h->s->optimize_sim3(n_pairs, pair_match_ptr, sim3_12, cam8, p1c, p2c, match_meas, th2, fix_scale, keep_out,
+                                 inliers_out, stats)
+           : SQRTBA_ERR_INVALID;
+}
+int sqrtba_optimize_sim3_trace(sqrtba_handle* h, int32_t pair, double* rows_out, int32_t max_rows) {
+  return h ? h->s->optimize_sim3_trace(pair, rows_out, max_rows) : SQRTBA_ERR_INVALID;
 }
 int sqrtba_set_lidar(sqrtba_handle* h, const sqrtba_lidar* clouds) { return h ? h->s->set_lidar(clouds) : SQRTBA_ERR_INVALID; }
 int sqrtba_set_lidar_edges(sqrtba_handle* h, int32_t cur_pose, int32_t n_flat, int32_t n_corner, const double* point_cam,

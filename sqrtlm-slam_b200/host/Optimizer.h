@@ -31,6 +31,9 @@ class Optimizer {
                                      const LoopClosing::KeyFrameAndPose& NonCorrectedSim3,
                                      const LoopClosing::KeyFrameAndPose& CorrectedSim3,
                                      const std::map<KeyFrame*, std::set<KeyFrame*>>& LoopConnections, const bool& bFixScale);
+  // include/backend/Optimizer.h:68-69
+  static int OptimizeSim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches1, g2o::Sim3& g2oS12,
+                          const float th2, const bool bFixScale);
 };
 
 // the adapter that sits beside g2oOptimizer / CeresOptimizer / MyOptimizer (src/backend/)
@@ -64,6 +67,19 @@ class sqrtbaOptimizer {
                                    const LoopClosing::KeyFrameAndPose& NonCorrectedSim3,
                                    const LoopClosing::KeyFrameAndPose& CorrectedSim3,
                                    const std::map<KeyFrame*, std::set<KeyFrame*>>& LoopConnections, PoseGraphProblem& out);
+  // g2oOptimizer::OptimizeSim3 (src/backend/g2oOptimizer.cc:1560-1796): the matches are gathered by the reference's
+  // rules (both map points good, the second one observed in pKF2; points moved into their keyframe's frame in float),
+  // the optimisation runs on the device (sqrtba_optimize_sim3), dropped matches are set to NULL in vpMatches1
+  static int OptimizeSim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches1, g2o::Sim3& g2oS12,
+                          const float th2, const bool bFixScale);
+  // the arrays OptimizeSim3 hands to sqrtba_optimize_sim3, without optimising (host-side tests, no GPU)
+  struct Sim3Problem {
+    double cam8[8];
+    std::vector<double> p1c, p2c;
+    std::vector<float> meas6;
+    std::vector<size_t> index;  // vnIndexEdge: position in vpMatches1 of every match
+  };
+  void static GatherSim3(KeyFrame* pKF1, KeyFrame* pKF2, const std::vector<MapPoint*>& vpMatches1, Sim3Problem& out);
   // Behaviour switches of the local-BA adapter.  The defaults are what THIS reference does:
   //  * local_ba_stereo_edges = false: the fork's local BA only creates monocular edges -- an observation with a right
   //    coordinate falls into an empty branch (g2oOptimizer.cc:914-916) and takes no part in the optimisation or in the

@@ -31,6 +31,9 @@ hh_map* hh_build(int n_kf, const float* Tcw, const float* cam5, const float* inv
       for (int c = 0; c < 4; c++) kf->Tcw.at<float>(r, c) = Tcw[i * 16 + r * 4 + c];
     kf->fx = cam5[0]; kf->fy = cam5[1]; kf->cx = cam5[2]; kf->cy = cam5[3]; kf->mbf = cam5[4];
     kf->mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + n_levels);
+    kf->mK.create(3, 3, CV_32F);
+    kf->mK.at<float>(0, 0) = cam5[0]; kf->mK.at<float>(1, 1) = cam5[1]; kf->mK.at<float>(0, 2) = cam5[2];
+    kf->mK.at<float>(1, 2) = cam5[3]; kf->mK.at<float>(2, 2) = 1.f;
     m->map.mspKeyFrames.push_back(kf.get());
     m->kfs.push_back(std::move(kf));
   }
@@ -225,6 +228,43 @@ void hh_apply_gba(hh_map* m, unsigned long nLoopKF) {
     }
   }
 }
+// ---- OptimizeSim3: match_mp[i] = index of the map point matched to keypoint i of kf1 (-1: no match), in/out
+static std::vector<MapPoint*> hh_matches(hh_map* m, int n, const int32_t* match_mp) {
+  std::vector<MapPoint*> v((size_t)n, nullptr);
+  for (int i = 0; i < n; i++)
+    if (match_mp[i] >= 0) v[i] = m->mps[match_mp[i]].get();
+  return v;
+}
+void hh_set_K(hh_map* m, int kf, float fx, float fy, float cx, float cy) {
+  cv::Mat& K = m->kfs[kf]->mK;
+  K.at<float>(0, 0) = fx; K.at<float>(1, 1) = fy; K.at<float>(0, 2) = cx; K.at<float>(1, 2) = cy;
+}
+int hh_gather_sim3(hh_map* m, int kf1, int kf2, int n, const int32_t* match_mp, double* cam8, double* p1c, double* p2c,
+                   float* meas6, int32_t* index) {
+  sqrtbaOptimizer::Sim3Problem P;
+  sqrtbaOptimizer::GatherSim3(m->kfs[kf1].get(), m->kfs[kf2].get(), hh_matches(m, n, match_mp), P);
+  std::copy(P.cam8, P.cam8 + 8, cam8);
+  std::copy(P.p1c.begin(), P.p1c.end(), p1c);
+  std::copy(P.p2c.begin(), P.p2c.end(), p2c);
+  std::copy(P.meas6.begin(), P.meas6.end(), meas6);
+  for (size_t k = 0; k < P.index.size(); k++) index[k] = (int32_t)P.index[k];
+  return (int)P.index.size();
+}
+int hh_optimize_sim3(hh_map* m, int kf1, int kf2, int n, int32_t* match_mp, double* s12, float th2, int fix_scale) {
+  std::vector<MapPoint*> v = hh_matches(m, n, match_mp);
+  g2o::Sim3 S;
+  S.r.x_ = s12[0]; S.r.y_ = s12[1]; S.r.z_ = s12[2]; S.r.w_ = s12[3];
+  S.t[0] = s12[4]; S.t[1] = s12[5]; S.t[2] = s12[6];
+  S.s = s12[7];
+  const int nIn = Optimizer::OptimizeSim3(m->kfs[kf1].get(), m->kfs[kf2].get(), v, S, th2, fix_scale != 0);
+  for (int i = 0; i < n; i++)
+    if (!v[i]) match_mp[i] = -1;
+  s12[0] = S.rotation().x(); s12[1] = S.rotation().y(); s12[2] = S.rotation().z(); s12[3] = S.rotation().w();
+  for (int i = 0; i < 3; i++) s12[4 + i] = S.translation()[i];
+  s12[7] = S.scale();
+  return nIn;
+}
+
 void hh_set_origin(hh_map* m, int kf) { m->map.mvpKeyFrameOrigins.push_back(m->kfs[kf].get()); }
 void hh_set_options(int local_ba_stereo_edges, int local_ba_two_pass) {
   sqrtbaOptimizer::options().local_ba_stereo_edges = local_ba_stereo_edges != 0;

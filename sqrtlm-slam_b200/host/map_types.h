@@ -72,6 +72,7 @@ class KeyFrame {
   long unsigned int mnBALocalForKF = ~0ul, mnBAFixedForKF = ~0ul, mnBAGlobalForKF = 0;
   cv::Mat mTcwGBA;
   float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0;
+  cv::Mat mK;  // KeyFrame.h:434 (const in the reference): 3x3 float calibration matrix, read by OptimizeSim3
   std::vector<cv::KeyPoint> mvKeysUn;
   std::vector<float> mvuRight;
   std::vector<float> mvInvLevelSigma2;
@@ -144,6 +145,11 @@ class MapPoint {
   std::map<KeyFrame*, size_t> GetObservations() { std::unique_lock<std::mutex> l(mMutexFeatures); return mObservations; }
   void EraseObservation(KeyFrame* pKF) { std::unique_lock<std::mutex> l(mMutexFeatures); mObservations.erase(pKF); }
   bool isBad() { return mbBad; }
+  int GetIndexInKeyFrame(KeyFrame* pKF) {  // MapPoint.h:137, MapPoint.cc:493-500
+    std::unique_lock<std::mutex> l(mMutexFeatures);
+    auto it = mObservations.find(pKF);
+    return it == mObservations.end() ? -1 : (int)it->second;
+  }
   void UpdateNormalAndDepth() { nUpdateNormalAndDepth++; }  // MapPoint.cc:531-575 is outside the BA path
   cv::Mat mWorldPos;
   bool mbBad = false;

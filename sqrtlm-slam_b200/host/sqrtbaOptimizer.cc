@@ -709,6 +709,86 @@ void sqrtbaOptimizer::OptimizeEssentialGraph(Map* pMap, KeyFrame* pLoopKF, KeyFr
   });
 }
 
+// ---- Sim3 of a loop candidate (g2oOptimizer::OptimizeSim3, src/backend/g2oOptimizer.cc:1560-1796) --------------------
+namespace {
+#ifdef SQRTBA_WITH_REFERENCE_HEADERS
+g2o::Sim3 sim3_from8(const double* v) {
+  return g2o::Sim3(Eigen::Quaterniond(v[3], v[0], v[1], v[2]), Eigen::Vector3d(v[4], v[5], v[6]), v[7]);
+}
+#else
+g2o::Sim3 sim3_from8(const double* v) {
+  g2o::Sim3 S;
+  S.r.x_ = v[0]; S.r.y_ = v[1]; S.r.z_ = v[2]; S.r.w_ = v[3];
+  S.t[0] = v[4]; S.t[1] = v[5]; S.t[2] = v[6];
+  S.s = v[7];
+  return S;
+}
+#endif
+// R * X + t on CV_32F matrices the way cv::Mat evaluates it (:1650-1651, :1660-1661): one GEMM with the translation as
+// its additive term -- double accumulator, ONE rounding to float -- then Converter::toVector3d
+void to_camera(const cv::Mat& R, const cv::Mat& t, const cv::Mat& Xw, double* out) {
+  for (int i = 0; i < 3; i++) {
+    double a = 0.0;
+    for (int j = 0; j < 3; j++) a += (double)R.at<float>(i, j) * (double)Xw.at<float>(j);
+    out[i] = (double)(float)(a + (double)t.at<float>(i));
+  }
+}
+}  // namespace
+
+void sqrtbaOptimizer::GatherSim3(KeyFrame* pKF1, KeyFrame* pKF2, const std::vector<MapPoint*>& vpMatches1, Sim3Problem& out) {
+  const cv::Mat& K1 = pKF1->mK;
+  const cv::Mat& K2 = pKF2->mK;
+  out.cam8[0] = K1.at<float>(0, 0); out.cam8[1] = K1.at<float>(1, 1); out.cam8[2] = K1.at<float>(0, 2); out.cam8[3] = K1.at<float>(1, 2);
+  out.cam8[4] = K2.at<float>(0, 0); out.cam8[5] = K2.at<float>(1, 1); out.cam8[6] = K2.at<float>(0, 2); out.cam8[7] = K2.at<float>(1, 2);
+  const cv::Mat R1w = pKF1->GetRotation(), t1w = pKF1->GetTranslation();
+  const cv::Mat R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+  const int N = (int)vpMatches1.size();
+  const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches();
+  out.p1c.clear(); out.p2c.clear(); out.meas6.clear(); out.index.clear();
+  for (int i = 0; i < N; i++) {
+    if (!vpMatches1[i]) continue;
+    MapPoint* pMP1 = vpMapPoints1[i];
+    MapPoint* pMP2 = vpMatches1[i];
+    const int i2 = pMP2->GetIndexInKeyFrame(pKF2);
+    if (!pMP1 || !pMP2) continue;                                  // :1640-1668
+    if (pMP1->isBad() || pMP2->isBad() || i2 < 0) continue;
+    double c1[3], c2[3];
+    to_camera(R1w, t1w, pMP1->GetWorldPos(), c1);
+    to_camera(R2w, t2w, pMP2->GetWorldPos(), c2);
+    out.p1c.insert(out.p1c.end(), c1, c1 + 3);
+    out.p2c.insert(out.p2c.end(), c2, c2 + 3);
+    const cv::KeyPoint& kpUn1 = pKF1->mvKeysUn[i];
+    const cv::KeyPoint& kpUn2 = pKF2->mvKeysUn[i2];
+    const float m[6] = {kpUn1.pt.x, kpUn1.pt.y, pKF1->mvInvLevelSigma2[kpUn1.octave],
+                        kpUn2.pt.x, kpUn2.pt.y, pKF2->mvInvLevelSigma2[kpUn2.octave]};
+    out.meas6.insert(out.meas6.end(), m, m + 6);
+    out.index.push_back((size_t)i);
+  }
+}
+
+int sqrtbaOptimizer::OptimizeSim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches1, g2o::Sim3& g2oS12,
+                                  const float th2, const bool bFixScale) {
+  Sim3Problem P;
+  GatherSim3(pKF1, pKF2, vpMatches1, P);
+  Handle& H = tl_handle;
+  sqrtba_handle* h = H.get();
+  if (!h) return 0;
+  const int64_t ptr[2] = {0, (int64_t)P.index.size()};
+  double s12[8];
+  sim3_to8(g2oS12, s12);
+  std::vector<uint8_t> keep(std::max<size_t>(P.index.size(), 1), 1);
+  int32_t nIn = 0;
+  if (sqrtba_optimize_sim3(h, 1, ptr, s12, P.cam8, P.p1c.data(), P.p2c.data(), P.meas6.data(), th2, bFixScale ? 1 : 0,
+                           keep.data(), &nIn, nullptr) != SQRTBA_OK) {
+    H.err = sqrtba_last_error(h);
+    return 0;
+  }
+  for (size_t k = 0; k < P.index.size(); k++)
+    if (!keep[k]) vpMatches1[P.index[k]] = static_cast<MapPoint*>(NULL);  // :1733, :1773
+  g2oS12 = sim3_from8(s12);  // comes back untouched when the reference returns early (:1755-1756)
+  return nIn;
+}
+
 // ---- the flat problems the adapters hand to the C ABI, without solving (host-side tests, no GPU needed)
 static void to_flat(const Gathered& g, sqrtbaOptimizer::FlatProblem& out) {
   out.pose_qt = g.pose_qt; out.cam = g.cam; out.point_xyz = g.point_xyz; out.pose_fixed = g.pose_fixed;
@@ -819,6 +899,10 @@ void Optimizer::OptimizeEssentialGraph(Map* pMap, KeyFrame* pLoopKF, KeyFrame* p
 }
 void Optimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* lidarconfig) {
   sqrtbaOptimizer::LocalBundleAdjustment(pKF, pbStopFlag, pMap, lidarconfig);
+}
+int Optimizer::OptimizeSim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches1, g2o::Sim3& g2oS12,
+                            const float th2, const bool bFixScale) {
+  return sqrtbaOptimizer::OptimizeSim3(pKF1, pKF2, vpMatches1, g2oS12, th2, bFixScale);
 }
 
 }  // namespace ORB_SLAM2

@@ -40,6 +40,9 @@ def lib():
         L.hh_essential_graph.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, ip, dpp, dpp, C.c_int, ip, C.c_int, ip]
         L.hh_essential_graph_get.argtypes = [dpp, up, up, ip, dpp]
         L.hh_global_ba.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_ulong, C.c_void_p]
+        L.hh_set_K.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.hh_gather_sim3.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, ip, dpp, dpp, dpp, fp, ip]
+        L.hh_optimize_sim3.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, ip, dpp, C.c_float, C.c_int]
         L.hh_get_pose.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
         L.hh_get_point.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
         L.hh_has_observation.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -160,6 +163,62 @@ class MockMap:
         L.hh_essential_graph_get(out["vert8"].ctypes.data_as(dp), out["fixed"].ctypes.data_as(up), out["present"].ctypes.data_as(up),
                                  _i(out["edge_ij"]), out["meas8"].ctypes.data_as(dp))
         return out
+
+    # ---- Sim3 of a loop candidate (Optimizer::OptimizeSim3)
+    @classmethod
+    def sim3_candidates(cls, case, seed=0, cam2=None):
+        """Two keyframes and two sets of map points out of a synth.sim3_pair case: keyframe 0 sees map points 0..n-1
+        at its keypoints 0..n-1, keyframe 1 sees map points n..2n-1 at SHUFFLED keypoints; map point n+i is the match
+        of keypoint i of keyframe 0.  Returns (map, match_mp)."""
+        s0, cam8, p1c, p2c, meas, _ = case
+        rng = np.random.default_rng(seed)
+        n = len(p1c)
+        T = np.tile(np.eye(4), (2, 1, 1))
+        for k in range(2):
+            T[k, :3, :3] = synth.so3_exp(rng.normal(0, 0.4, 3))
+            T[k, :3, 3] = rng.normal(0, 5.0, 3)
+        T = T.astype(np.float32)
+        Xw = np.concatenate([(p1c - T[0, :3, 3].astype(float)) @ T[0, :3, :3].astype(float),
+                             (p2c - T[1, :3, 3].astype(float)) @ T[1, :3, :3].astype(float)]).astype(np.float32)
+        inv = synth.inv_level_sigma2()
+        oct1 = np.array([int(np.argmin(np.abs(inv - v))) for v in meas[:, 2]], np.int32)
+        oct2 = np.array([int(np.argmin(np.abs(inv - v))) for v in meas[:, 5]], np.int32)
+        order = rng.permutation(n)                                   # keypoint j of keyframe 1 belongs to map point n + order[j]
+        obs_kf = np.concatenate([np.zeros(n, np.int32), np.ones(n, np.int32)])
+        obs_mp = np.concatenate([np.arange(n), n + order]).astype(np.int32)
+        uvr = np.zeros((2 * n, 3), np.float32)
+        uvr[:n, :2], uvr[n:, :2], uvr[:, 2] = meas[:, 0:2], meas[order, 3:5], -1.0
+        octave = np.concatenate([oct1, oct2[order]]).astype(np.int32)
+        cam = np.array([cam8[0], cam8[1], cam8[2], cam8[3], synth.BF], np.float32)
+        self = cls.__new__(cls)
+        self.prob = None
+        self._keep = [np.ascontiguousarray(T), cam, inv, np.ascontiguousarray(Xw), obs_kf, obs_mp, np.ascontiguousarray(uvr), octave]
+        k = self._keep
+        self.h = lib().hh_build(2, _f(k[0]), _f(k[1]), _f(k[2]), len(inv), 2 * n, _f(k[3]), 2 * n, _i(k[4]), _i(k[5]), _f(k[6]), _i(k[7]))
+        if cam2 is not None:
+            lib().hh_set_K(self.h, 1, *[float(v) for v in cam2])
+        self.Tcw, self.Xw = T, Xw
+        return self, (n + np.arange(n)).astype(np.int32)
+
+    def gather_sim3(self, kf1, kf2, match_mp):
+        """The arrays OptimizeSim3 would hand to sqrtba_optimize_sim3 (no GPU needed)."""
+        mm = np.ascontiguousarray(match_mp, np.int32)
+        n = len(mm)
+        cam8, p1c, p2c = np.zeros(8), np.zeros((n, 3)), np.zeros((n, 3))
+        meas, index = np.zeros((n, 6), np.float32), np.zeros(n, np.int32)
+        dp = C.POINTER(C.c_double)
+        m = lib().hh_gather_sim3(self.h, kf1, kf2, n, _i(mm), cam8.ctypes.data_as(dp), p1c.ctypes.data_as(dp),
+                                 p2c.ctypes.data_as(dp), _f(meas), _i(index))
+        return dict(cam8=cam8, p1c=p1c[:m], p2c=p2c[:m], meas6=meas[:m], index=index[:m])
+
+    def optimize_sim3(self, kf1, kf2, match_mp, s12, th2=10.0, fix_scale=False):
+        """Optimizer::OptimizeSim3(pKF1, pKF2, vpMatches1, g2oS12, th2, bFixScale): returns (nIn, matches after the
+        call with -1 where the reference writes NULL, S12 after the call)."""
+        mm = np.ascontiguousarray(match_mp, np.int32).copy()
+        S = np.ascontiguousarray(s12, np.float64).copy()
+        n_in = lib().hh_optimize_sim3(self.h, kf1, kf2, len(mm), _i(mm), S.ctypes.data_as(C.POINTER(C.c_double)),
+                                      C.c_float(th2), int(fix_scale))
+        return int(n_in), mm, S
 
     def set_covisible(self, kf, others):
         a = np.ascontiguousarray(others, np.int32)

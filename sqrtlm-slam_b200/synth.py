@@ -502,6 +502,44 @@ def sim3_small(rng, s_rot, s_t, s_scale):
     return np.concatenate([q, rng.normal(0, s_t, 3), [float(np.exp(rng.normal(0, s_scale))) if s_scale > 0 else 1.0]])
 
 
+def sim3_pair(seed=0, n_matches=150, fix_scale=False, outlier_frac=0.15, point_noise=0.01, init_noise=(0.01, 0.05, 0.02)):
+    """A loop-candidate keyframe pair for g2oOptimizer::OptimizeSim3 (g2oOptimizer.cc:1560-1796): matched map points
+    expressed in the frame of keyframe 1 (P1c) and of keyframe 2 (P2c), their keypoints in both images, and an initial
+    S12 as a RANSAC Sim3Solver would hand it over (truth times a small similarity).  Map points cross the boundary as
+    float32 (cv::Mat CV_32F products, :1650-1662).  Returns (s12_init 8, cam8, p1c[n,3], p2c[n,3], meas6[n,6] float32,
+    truth dict)."""
+    rng = np.random.default_rng(seed)
+    S12 = sim3_small(rng, 0.08, 0.8, 0.0 if fix_scale else 0.15)
+    S21 = sim3_inv(S12)
+    n = n_matches
+    pu, pv = rng.uniform(40, IMG_W - 40, n), rng.uniform(40, IMG_H - 40, n)
+    depth = rng.uniform(5.0, 40.0, n)
+    p1 = np.stack([(pu - CX) / FX * depth, (pv - CY) / FY * depth, depth], -1)
+    p2 = np.array([S21[7] * _q_rot(S21[:4], x) + S21[4:7] for x in p1])
+    p2 *= 1.0 + rng.normal(0, point_noise, (n, 1))  # the two maps disagree a little about every point
+    p2[:, 2] = np.maximum(p2[:, 2], 1.0)
+    inv_s2 = inv_level_sigma2()
+    l1 = np.minimum(rng.geometric(0.35, n) - 1, N_LEVELS - 1)
+    l2 = np.minimum(rng.geometric(0.35, n) - 1, N_LEVELS - 1)
+    meas = np.zeros((n, 6), np.float32)
+    meas[:, 0] = pu + rng.normal(0, 1, n) * 1.2 ** l1
+    meas[:, 1] = pv + rng.normal(0, 1, n) * 1.2 ** l1
+    meas[:, 2] = inv_s2[l1]
+    meas[:, 3] = p2[:, 0] / p2[:, 2] * FX + CX + rng.normal(0, 1, n) * 1.2 ** l2
+    meas[:, 4] = p2[:, 1] / p2[:, 2] * FY + CY + rng.normal(0, 1, n) * 1.2 ** l2
+    meas[:, 5] = inv_s2[l2]
+    is_out = rng.uniform(0, 1, n) < outlier_frac
+    k = int(is_out.sum())
+    side = rng.integers(0, 2, k) * 3
+    rows = np.nonzero(is_out)[0]
+    meas[rows, side] += (rng.choice([-1.0, 1.0], k) * rng.uniform(8, 60, k)).astype(np.float32)
+    meas[rows, side + 1] += (rng.choice([-1.0, 1.0], k) * rng.uniform(8, 60, k)).astype(np.float32)
+    s0 = sim3_mul(sim3_small(rng, init_noise[0], init_noise[1], 0.0 if fix_scale else init_noise[2]), S12)
+    cam8 = np.array([FX, FY, CX, CY, FX, FY, CX, CY])
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    return s0, cam8, f32(p1), f32(p2), meas, dict(S12=S12, is_outlier=is_out)
+
+
 def pose_graph(seed=0, n_kf=200, fix_scale=True, covis_span=4, covis_prob=0.5, n_loop=6, radius=60.0):
     """An essential graph the way OptimizeEssentialGraph sees it after a loop closure (g2oOptimizer.cc:1212-1460):
     keyframes on a closed loop, dead-reckoned estimates that drift (in scale too when it is free), spanning-tree edges

@@ -201,3 +201,37 @@ def test_essential_graph_gather(pkg, synth):
     cur, n = case["cur_kf"], case["n_kf"]
     assert (cur, 0) in got and (cur, 1) in got and (cur - 1, 1) in got and (cur - 2, 2) not in got
     assert (12, 3) in got and (4, 2) in got and (5, 3) not in got and (6, 3) not in got
+
+
+def test_sim3_gather(pkg, synth):
+    """The arrays sqrtbaOptimizer::OptimizeSim3 builds from the two keyframes (no GPU), by the reference's rules
+    (g2oOptimizer.cc:1622-1712): a match is used when both map points are good and the second is observed in pKF2; the
+    points are moved into their own keyframe's frame on the FLOAT matrices (R * X + t as one cv::Mat GEMM: double
+    accumulator, one rounding); keypoints and level sigmas come from keypoint i of pKF1 and from the keypoint of pKF2
+    that observes the matched point; both cameras' mK feed the vertex."""
+    from importlib import import_module
+    hh = import_module(pkg.__name__ + ".host_harness")
+    case = synth.sim3_pair(seed=3, n_matches=60)
+    cam2 = (700.0, 705.0, 600.5, 180.25)
+    m, match = hh.MockMap.sim3_candidates(case, seed=1, cam2=cam2)
+    n = len(match)
+    match = match.copy()
+    match[[4, 17]] = -1                       # no match for these keypoints
+    m.set_bad(mp=9)                           # pMP1 bad
+    m.set_bad(mp=n + 30)                      # pMP2 bad
+    match[40] = 12                            # a point that pKF2 does not observe: GetIndexInKeyFrame < 0
+    g = m.gather_sim3(0, 1, match)
+    used = [i for i in range(n) if i not in (4, 17, 9, 30, 40)]
+    assert list(g["index"]) == used
+    np.testing.assert_array_equal(g["cam8"], np.concatenate([np.float32(case[1][:4]), np.float32(cam2)]).astype(np.float64))
+    T, Xw = m.Tcw.astype(np.float64), m.Xw.astype(np.float64)
+
+    def to_cam(k, X):
+        return (T[k, :3, :3] @ X + T[k, :3, 3]).astype(np.float32).astype(np.float64)
+
+    for row, i in enumerate(used):
+        np.testing.assert_array_equal(g["p1c"][row], to_cam(0, Xw[i]))
+        np.testing.assert_array_equal(g["p2c"][row], to_cam(1, Xw[n + i]))
+    np.testing.assert_array_equal(g["meas6"], case[4][used])
+    # the float round trip through world coordinates keeps the points within float precision of the generator's
+    np.testing.assert_allclose(g["p1c"], case[2][used], rtol=0, atol=2e-4)

@@ -260,3 +260,30 @@ def test_global_ba_result_propagation_by_the_caller(pkg, synth):
     Xc = before[r][:3, :3].astype(np.float64) @ x_before.astype(np.float64) + before[r][:3, 3]
     Ta = np.linalg.inv(m.pose(r).astype(np.float64))
     np.testing.assert_allclose(m.point(late_mp), Ta[:3, :3] @ Xc + Ta[:3, 3], rtol=0, atol=5e-5)
+
+
+@pytest.mark.parametrize("fix_scale", [False, True])
+def test_optimize_sim3_through_reference_api(pkg, synth, fix_scale):
+    """Optimizer::OptimizeSim3(pKF1, pKF2, vpMatches1, g2oS12, th2, bFixScale) (include/backend/Optimizer.h:68-69) as
+    LoopClosing::ComputeSim3 calls it (LoopClosing.cc:513): returns nIn, writes the refined S12 and sets the matches it
+    rejects to NULL (g2oOptimizer.cc:1733, 1773).  Expected values: the oracle on the arrays the adapter gathers."""
+    case = synth.sim3_pair(seed=8, n_matches=120, fix_scale=fix_scale)
+    m, match = pkg.host_harness.MockMap.sim3_candidates(case, seed=2)
+    match = match.copy()
+    match[[3, 50]] = -1
+    g = m.gather_sim3(0, 1, match)
+    So, keep_o, nin_o, _ = refba.optimize_sim3(case[0], g["cam8"], g["p1c"], g["p2c"], g["meas6"], 10.0, fix_scale)
+    n_in, after, S = m.optimize_sim3(0, 1, match, case[0], 10.0, fix_scale)
+    assert m.last_error() == ""
+    assert n_in == nin_o and 60 < n_in < 118
+    want = match.copy()
+    want[g["index"][keep_o == 0]] = -1
+    assert np.array_equal(after, want) and (after == -1).sum() > 5
+    sgn = np.sign(np.sum(S[:4] * So[:4]))
+    np.testing.assert_allclose(S[:4] * sgn, So[:4], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(S[4:], So[4:], rtol=0, atol=1e-5)
+    # too few matches: the reference returns 0 and leaves g2oS12 alone, but has already dropped what failed the first test
+    few = np.full(len(match), -1, np.int32)
+    few[:8] = match[:8] if (match[:8] >= 0).all() else match[5:13]
+    n_in2, after2, S2 = m.optimize_sim3(0, 1, few, case[0], 10.0, fix_scale)
+    assert n_in2 == 0 and np.array_equal(S2, case[0])

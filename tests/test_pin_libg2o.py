@@ -284,3 +284,33 @@ def test_essential_graph_optimisation_matches_reference_binary(gold, case):
     assert g["chi2"][1] < 0.05 * g["chi2"][0]
     last = tr[tr[:, 1] == tr[-1, 1]]
     assert len(last) >= 10 and (last[:9, 7] == 0).all()                  # the run ends on the ten-trials rule
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_optimize_sim3_matches_reference_binary(gold, case):
+    """g2oOptimizer::OptimizeSim3 (g2oOptimizer.cc:1560-1796) run by the binary itself (oracle/pin_libg2o_graph.py:
+    make_sim3opt) -- one VertexSim3Expmap carrying both cameras, fixed VertexSBAPointXYZ, EdgeSim3ProjectXYZ /
+    EdgeInverseSim3ProjectXYZ with Huber kernels and their inherited NUMERIC Jacobians, Levenberg on a dense 7x7 --
+    with fixed and free scale: optimize(5), chi2 test on the stored errors, optimize(10), final count.
+    The oracle must reproduce both edges' errors and Jacobians at the initial estimate BIT FOR BIT, make the same
+    trials with the same lambda while the decisions are above the noise of the 1e-9 differences, keep exactly the same
+    matches and end on the same S12."""
+    pre = f"s3o{case}_"
+    g = {k[len(pre):]: gold[k] for k in gold.files if k.startswith(pre)}
+    fs = bool(g["fix_scale"])
+    e12, e21, J12, J21 = refba.sim3_match_linearize(g["s0"], g["cam8"], g["p1c"], g["p2c"], g["meas6"], fs)
+    assert np.array_equal(e12, g["e12_0"]) and np.array_equal(e21, g["e21_0"])
+    assert np.array_equal(J12, g["J12_0"]) and np.array_equal(J21, g["J21_0"])
+    assert fs == (not J12[:, :, 6].any()) and np.abs(J12[:, :, :6]).max() > 100
+    S, keep, n_in, tr = refba.optimize_sim3(g["s0"], g["cam8"], g["p1c"], g["p2c"], g["meas6"], float(g["th2"]), fs)
+    assert np.array_equal(keep, g["keep"]) and n_in == int(g["nIn"])
+    assert int(g["nBad"]) >= 5 and n_in >= 30                                  # the fixture drops matches in the first test
+    np.testing.assert_allclose(S, g["s12"], rtol=0, atol=1e-6)
+    # the first pass is far from convergence: identical trials; near the optimum the sign of a 1e-9-relative change of
+    # the cost decides between accept / reject, in the binary as here
+    n0 = int(g["n_trials_pass0"])
+    assert int((tr[:, 0] == 0).sum()) >= min(n0, 4)
+    m = min(n0, int((tr[:, 0] == 0).sum()), 4)
+    np.testing.assert_allclose(tr[:m, 3], g["lambda"][:m], rtol=1e-6)
+    k1 = int(np.argmax(tr[:, 0] == 1))
+    np.testing.assert_allclose(tr[k1:k1 + 3, 3], g["lambda"][n0:n0 + 3], rtol=1e-6)   # lambda_0 of pass 2 and the next two
