@@ -2,9 +2,9 @@
 // as __host__ __device__ code like sqrtba_math.cuh: g2o::Sim3 (Thirdparty/g2o/g2o/types/sim3.h:40-285),
 // VertexSim3Expmap::oplusImpl and EdgeSim3::computeError (types/types_seven_dof_expmap.h:48-110).
 //
-// Status: the arithmetic only.  It is compiled for the host by tests/cpu_math_check.cpp and checked against vectors
-// recorded from the reference's own binary (tests/golden/libg2o_vectors.npz: sim3_*); the kernel that uses it -- a
-// pose-graph Levenberg on the device -- is the next step of row N3 and is not written yet.
+// The arithmetic only: it is compiled for the host by tests/cpu_math_check.cpp and checked against vectors recorded from
+// the reference's own binary (tests/golden/libg2o_vectors.npz: sim3_*).  Used by csrc/sqrtba_posegraph.cuh (essential
+// graph), csrc/sqrtba_sim3opt.cuh (OptimizeSim3) and the host adapter.
 //
 // A Sim3 is stored as 8 doubles in g2o's operator[] order: qx qy qz qw | tx ty tz | s.
 #pragma once
