@@ -288,9 +288,9 @@ def pose_only_leg(pkg, local, cpu_ok):
     candidates through sqrtba_pose_opt (host buffers in, pose + flags out: the call IS end to end)."""
     import numpy as np
     ba = pkg.SqrtBA(device=local)
-    p0, cam, xyz, meas, _ = pkg.synth.frame_problem(seed=5, n_points=1500)
+    p0, cam, xyz, meas, truth = pkg.synth.frame_problem(seed=5, n_points=1500)
     dev, wall = [], []
-    for _ in range(8):
+    for _rep in range(8):
         t0 = time.perf_counter()
         gp, gf, gi, st = ba.pose_opt([0, len(xyz)], p0, cam, xyz, meas)
         wall.append(time.perf_counter() - t0)
@@ -298,6 +298,15 @@ def pose_only_leg(pkg, local, cpu_ok):
     out = {"workload": "one frame, 1500 matched map points, 4 x optimize(10) with chi2 re-classification (g2oOptimizer.cc:385-559)",
            "ms_per_frame_device": min(dev[2:]), "ms_per_frame_call": 1e3 * min(wall[2:]), "inliers": int(gi[0]),
            "lm_trials": len(ba.pose_opt_trace(0))}
+    # the same frame with this fork's lidar block (g2oOptimizer.cc:560-640): 800 flat + 200 sharp points against a
+    # 20 000-point local lidar map, exact nearest neighbour on the device, fifth optimize(10) over visual + lidar edges
+    ld = pkg.synth.frame_lidar(truth, seed=5)
+    dev = []
+    for _k in range(6):
+        lp, lf, li, lnm, st = ba.pose_opt_lidar(p0, cam, xyz, meas, ld)
+        dev.append(st["ms_total"])
+    out["with_lidar_block"] = {"ms_per_frame_device": min(dev[2:]), "flat_matches": lnm[0], "corner_matches": lnm[1],
+                               "map_points": int(len(ld.map_xyz)), "kernel_launches": st["kernel_launches"], "inliers": li}
     frames = [pkg.synth.frame_problem(seed=100 + k, n_points=1500) for k in range(64)]
     ptr = np.concatenate([[0], np.cumsum([len(f[2]) for f in frames])])
     P0 = np.stack([f[0] for f in frames]); CAM = np.stack([f[1] for f in frames])
@@ -317,6 +326,10 @@ def pose_only_leg(pkg, local, cpu_ok):
         out["cpu_baseline"] = {"value": 1e3 * dt, "unit": "ms per frame (lower is better)", "cores": 1, "kind": "port",
                                "sample": "the same frame"}
         out["parity_vs_oracle"] = {"ok": bool(ri == int(gi[0]) and np.array_equal(gf, rf) and np.abs(gp[0] - rp).max() <= 1e-7)}
+        t0 = time.perf_counter()
+        rp, rf, ri, _t, rnm = refba.pose_opt_lidar(p0, cam, xyz, meas, ld)
+        out["with_lidar_block"]["cpu_baseline_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["with_lidar_block"]["parity_vs_oracle"] = {"ok": bool(ri == li and np.array_equal(lf, rf) and rnm == lnm and np.abs(lp - rp).max() <= 1e-6)}
     ba.close()
     return out
 

@@ -161,7 +161,7 @@ int sqrtba_comm_destroy(sqrtba_handle* h);
 
 /* ---- pose-only optimisation (tracking thread) --------------------------------------------------------------------
  * Replaces Optimizer::PoseOptimization (include/backend/Optimizer.h:58-60 -> src/backend/g2oOptimizer.cc:385-559,
- * 655-690; the lidar block :560-640 is not covered): one SE3 vertex per frame, one unary reprojection edge per matched
+ * 655-690; the lidar block :560-640 is sqrtba_pose_opt_lidar below): one SE3 vertex per frame, one unary reprojection edge per matched
  * map point (EdgeSE3ProjectXYZOnlyPose when ur < 0, EdgeStereoSE3ProjectXYZOnlyPose otherwise -- the reference fork
  * only creates the monocular ones, :441-483), Huber deltas sqrt(5.991)/sqrt(7.815), four rounds of optimize(10) from
  * the same initial pose with chi2 re-classification in between, kernels dropped from the third classification on.
@@ -176,6 +176,28 @@ int sqrtba_pose_opt(sqrtba_handle* h, int32_t n_frames, const int64_t* frame_obs
                     const double* obs_xyz, const float* obs_meas, uint8_t* outlier_out, int32_t* inliers_out,
                     sqrtba_stats* stats);
 int sqrtba_pose_opt_trace(sqrtba_handle* h, int32_t frame, double* rows_out, int32_t max_rows);
+
+/* The same with the lidar block this fork adds to PoseOptimization (src/backend/g2oOptimizer.cc:560-640, facade
+ * include/backend/Optimizer.h:58-59: PoseOptimization(pFrame, local_lidarmap_cloud_ptr, kdtree_local_map, lidarconfig)):
+ * when the local lidar map holds more than 100 points, the frame's flat / sharp feature points (Frame.h:273-277) are
+ * moved to the world frame with the pose of the four visual rounds, matched to their nearest map point (k = 1; exact
+ * search on the device instead of the caller's kd-tree) and kept below distance_sq_threshold; every match becomes an
+ * EdgeLidarFlatPoint / EdgeLidarCornerPoint on the pose (types_six_dof_expmap.h:206-262, numeric Jacobians, information
+ * = weight, no kernel); the estimate restarts from the float-rounded pose (:557, :632) for a fifth optimize(10) over the
+ * level-0 visual edges and the lidar edges, then the final classification.  One frame per call.  With n_map <= 100 or
+ * fewer than 3 observations the call is sqrtba_pose_opt.  n_match2_out (may be NULL): matched flat / corner points, the
+ * two counts the reference prints (:626-627).  sqrtba_pose_opt_trace(h, 0, ...) then holds the trials of all five
+ * rounds (round index 4 = the lidar round). */
+typedef struct {
+  int32_t n_flat;  const float* flat_xyz;  const float* flat_normal; /* Frame::surface_points_flat_ / _flat_normal_, n x 3 */
+  int32_t n_corner; const float* corner_xyz;                          /* Frame::corner_points_sharp_ */
+  int64_t n_map;   const float* map_xyz;                              /* local_lidarmap_cloud_ptr, world frame, n x 3 */
+  double distance_sq_threshold, flat_weight, corner_weight;           /* lidarConfig (cfg/lidar_slam.yaml:52-61) */
+  int32_t use_flat, use_corner;                                       /* lidarConfig::using_flat_point / using_sharp_point */
+} sqrtba_frame_lidar;
+int sqrtba_pose_opt_lidar(sqrtba_handle* h, double* pose_qt, const double* cam, int32_t n_obs, const double* obs_xyz,
+                          const float* obs_meas, uint8_t* outlier_out, int32_t* inliers_out, const sqrtba_frame_lidar* lidar,
+                          int32_t* n_match2_out, sqrtba_stats* stats);
 
 /* ---- lidar tight-coupling pass of this fork's LocalBundleAdjustment (src/backend/g2oOptimizer.cc:979-1117) ----
  * After the two visual passes the reference (1) builds a local lidar map from the flat / corner feature clouds of every

@@ -1362,6 +1362,7 @@ struct PoseProblem {
   int nBad = 0;
   std::vector<TraceRow> trace;
   int round = 0;
+  std::vector<Graph::UEdge> u;  // lidar edges of the fifth optimisation (g2oOptimizer.cc:560-640), no robust kernel
 };
 // EdgeSE3ProjectXYZOnlyPose::computeError (types_six_dof_expmap.h:152-156, .cpp:290-296) /
 // EdgeStereoSE3ProjectXYZOnlyPose::computeError (.h:184-188, .cpp:299-306: float invz, DOUBLE bf)
@@ -1418,7 +1419,10 @@ inline void pRobustify(const PEdge& e, double c, double rho[3]) {
   if (c <= e.dsqr) { rho[0] = c; rho[1] = 1.; rho[2] = 0.; }
   else { const double sq = std::sqrt(c); rho[0] = 2 * sq * e.delta - e.dsqr; rho[1] = e.delta / sq; rho[2] = -0.5 * rho[1] / c; }
 }
-void pComputeActiveErrors(PoseProblem& P) { for (int k : P.active) pComputeError(P, P.e[k]); }
+void pComputeActiveErrors(PoseProblem& P) {
+  for (int k : P.active) pComputeError(P, P.e[k]);
+  for (Graph::UEdge& e : P.u) e.err = uError(P.T, e);
+}
 double pActiveRobustChi2(const PoseProblem& P) {  // sparse_optimizer.cpp:100-114
   double chi = 0;
   for (int k : P.active) {
@@ -1426,6 +1430,7 @@ double pActiveRobustChi2(const PoseProblem& P) {  // sparse_optimizer.cpp:100-11
     const double c = pChi2(e);
     if (e.robust) { double rho[3]; pRobustify(e, c, rho); chi += rho[0]; } else chi += c;
   }
+  for (const Graph::UEdge& e : P.u) chi += e.err * e.info * e.err;  // added after the visual edges -> last in _activeEdges
   return chi;
 }
 // BaseUnaryEdge::constructQuadraticForm (base_unary_edge.hpp:42-72) over the active edges
@@ -1447,6 +1452,21 @@ void pBuildSystem(PoseProblem& P) {
         for (int r = 0; r < d; r++) h += e.J[r * 6 + i] * (w * e.J[r * 6 + j]);
         P.H[i * 6 + j] += h;
       }
+    }
+  }
+  for (Graph::UEdge& e : P.u) {  // BaseUnaryEdge numeric linearizeOplus + constructQuadraticForm (base_unary_edge.hpp:58-123)
+    const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+    for (int d = 0; d < 6; d++) {
+      double add[6] = {0, 0, 0, 0, 0, 0};
+      add[d] = delta;
+      const double e1 = uError(se3mul(se3exp(add), P.T), e);
+      add[d] = -delta;
+      const double e2 = uError(se3mul(se3exp(add), P.T), e);
+      e.J[d] = scalar * (e1 - e2);
+    }
+    for (int i = 0; i < 6; i++) {
+      P.b[i] -= e.J[i] * e.info * e.err;
+      for (int j = 0; j < 6; j++) P.H[i * 6 + j] += e.J[i] * e.info * e.J[j];
     }
   }
 }
@@ -1529,8 +1549,15 @@ SolverResult pLmSolve(PoseProblem& P, int iteration) {
 // double Xw, g2oOptimizer.cc:472-475), meas n x 4 float (u, v, ur<0 => mono, invSigma2).  outlier: n flags
 // (Frame::mvbOutlier).  trace: up to max_trace rows of 8 doubles (round, iter, trial, lambda, chi_before, chi_trial,
 // rho, accepted); *n_trace = rows written.  Returns nInitialCorrespondences - nBad (0 if fewer than 3 observations).
-int refba_pose_opt(double* pose7, const double* cam, int n, const double* xyz, const float* meas, uint8_t* outlier,
-                   double* trace, int max_trace, int* n_trace) {
+struct refba_frame_lidar {  // the clouds and lidarConfig fields the lidar block of PoseOptimization reads (:560-640)
+  int32_t n_flat; const float* flat_xyz; const float* flat_normal;  // Frame::surface_points_flat_ / _normal_
+  int32_t n_corner; const float* corner_xyz;                        // Frame::corner_points_sharp_
+  int64_t n_map; const float* map_xyz;                              // local_lidarmap_cloud_ptr (world frame)
+  double distance_sq_threshold, flat_weight, corner_weight;
+  int32_t use_flat, use_corner;
+};
+static int poseOptRun(double* pose7, const double* cam, int n, const double* xyz, const float* meas, uint8_t* outlier,
+                      double* trace, int max_trace, int* n_trace, const refba_frame_lidar* L, int32_t* n_match2) {
   PoseProblem P;
   P.T.t[0] = pose7[0]; P.T.t[1] = pose7[1]; P.T.t[2] = pose7[2];
   P.T.r = Quat{pose7[3], pose7[4], pose7[5], pose7[6]};
@@ -1573,6 +1600,50 @@ int refba_pose_opt(double* pose7, const double* cam, int n, const double* xyz, c
     }
     if (n < 10) break;  // optimizer.edges().size()<10, :549-550
   }
+  if (n_match2) n_match2[0] = n_match2[1] = 0;
+  if (L && L->n_map > 100) {  // optimizer for lidar and visual, :560-640
+    // pose_temp = Converter::toCvMat(vSE3->estimate()).inv(): the float pose, inverted (closed form, see twcFloat)
+    float Rc[9], Oc[3];
+    twcFloat(P.T, Rc, Oc);
+    const std::vector<float> mapw(L->map_xyz, L->map_xyz + (size_t)L->n_map * 3);
+    auto pass = [&](const float* cur, const float* nrm, int cnt, bool corner) {
+      for (int i = 0; i < cnt; i++) {
+        float qw[3], d2;
+        toWorldFloat(Rc, Oc, cur + (size_t)i * 3, qw);
+        const int j = nearestFloat(mapw, qw, &d2);
+        if (!(d2 < L->distance_sq_threshold)) continue;  // float against the double threshold, :579 / :611
+        Graph::UEdge e;
+        e.pose = 0;
+        e.corner = corner;
+        for (int k = 0; k < 3; k++) {
+          e.pc[k] = cur[(size_t)i * 3 + k];
+          e.qw[k] = mapw[(size_t)j * 3 + k];
+          e.n[k] = corner ? 0.0 : nrm[(size_t)i * 3 + k];
+        }
+        e.info = corner ? L->corner_weight : L->flat_weight;
+        P.u.push_back(e);
+        if (n_match2) n_match2[corner ? 1 : 0]++;
+      }
+    };
+    if (L->use_flat) pass(L->flat_xyz, L->flat_normal, L->n_flat, false);
+    if (L->use_corner) pass(L->corner_xyz, nullptr, L->n_corner, true);
+    // vSE3->setEstimate(Converter::toSE3Quat(pFrame->mTcw)) after pFrame->SetPose(pose): the float round trip (:632)
+    {
+      double R[9];
+      qtoR(P.T.r, R);
+      for (double& v : R) v = (double)(float)v;
+      for (double& v : P.T.t) v = (double)(float)v;
+      P.T.r = RtoQ(R);
+      normalizeRotation(P.T);
+    }
+    P.round = 4;
+    P.active.clear();
+    for (int i = 0; i < n; i++) if (P.e[i].level == 0) P.active.push_back(i);
+    if (!P.active.empty() || !P.u.empty()) {
+      bool ok = true;
+      for (int i = 0; i < 10 && ok; i++) ok = (pLmSolve(P, i) == OK);
+    }
+  }
   nBad = 0;
   for (int i = 0; i < n; i++) {  // final classification, :656-680 (double 5.991 / upstream stereo 7.815)
     PEdge& e = P.e[i];
@@ -1586,6 +1657,20 @@ int refba_pose_opt(double* pose7, const double* cam, int n, const double* xyz, c
   if (trace && nt > 0) std::memcpy(trace, P.trace.data(), (size_t)nt * sizeof(TraceRow));
   if (n_trace) *n_trace = nt;
   return n - nBad;
+}
+int refba_pose_opt(double* pose7, const double* cam, int n, const double* xyz, const float* meas, uint8_t* outlier,
+                   double* trace, int max_trace, int* n_trace) {
+  return poseOptRun(pose7, cam, n, xyz, meas, outlier, trace, max_trace, n_trace, nullptr, nullptr);
+}
+// the same with this fork's lidar block (g2oOptimizer.cc:560-640): when the local lidar map has more than 100 points,
+// the frame's flat / sharp feature points -- moved to the world frame with the pose of the four visual rounds -- are
+// matched to their nearest map point (k = 1, squared distance below the threshold), every match becomes an
+// EdgeLidarFlatPoint / EdgeLidarCornerPoint on the pose (numeric Jacobians, information = weight, no kernel), and a
+// fifth optimize(10) runs from the float-rounded pose over the level-0 visual edges and the lidar edges.
+// n_match2: matched flat / corner points (the two counts the reference prints, :626-627).
+int refba_pose_opt_lidar(double* pose7, const double* cam, int n, const double* xyz, const float* meas, uint8_t* outlier,
+                         double* trace, int max_trace, int* n_trace, const refba_frame_lidar* lidar, int32_t* n_match2) {
+  return poseOptRun(pose7, cam, n, xyz, meas, outlier, trace, max_trace, n_trace, lidar, n_match2);
 }
 
 // =====================================================================================================

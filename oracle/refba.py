@@ -310,3 +310,40 @@ def sim3_match_linearize(s12, cam8, p1c, p2c, meas6, fix_scale):
         L.refba_sim3_match_linearize(S.ctypes.data, cam.ctypes.data, a[k].ctypes.data, b[k].ctypes.data, m[k].ctypes.data,
                                      int(fix_scale), e12[k].ctypes.data, e21[k].ctypes.data, J12[k].ctypes.data, J21[k].ctypes.data)
     return e12, e21, J12, J21
+
+
+class FrameLidarC(C.Structure):
+    _fields_ = [("n_flat", C.c_int32), ("flat_xyz", C.c_void_p), ("flat_normal", C.c_void_p), ("n_corner", C.c_int32),
+                ("corner_xyz", C.c_void_p), ("n_map", C.c_int64), ("map_xyz", C.c_void_p),
+                ("distance_sq_threshold", C.c_double), ("flat_weight", C.c_double), ("corner_weight", C.c_double),
+                ("use_flat", C.c_int32), ("use_corner", C.c_int32)]
+
+
+def frame_lidar_struct(ld):
+    """(ctypes struct, keep-alive list) for a synth.FrameLidar -- same layout as sqrtba_frame_lidar (include/sqrtba.h)."""
+    keep = [np.ascontiguousarray(a, np.float32) for a in (ld.flat_xyz, ld.flat_normal, ld.corner_xyz, ld.map_xyz)]
+    s = FrameLidarC(len(keep[0]), keep[0].ctypes.data, keep[1].ctypes.data, len(keep[2]), keep[2].ctypes.data,
+                    len(keep[3]), keep[3].ctypes.data, ld.distance_sq_threshold, ld.flat_weight, ld.corner_weight,
+                    int(ld.use_flat), int(ld.use_corner))
+    return s, keep
+
+
+def pose_opt_lidar(pose7, cam5, xyz, meas, ld):
+    """g2oOptimizer::PoseOptimization with this fork's lidar block restated (refba_pose_opt_lidar).
+    Returns (pose7_out, outlier flags, inliers, trace[rows, 8], (flat matches, corner matches))."""
+    L = lib()
+    pose = np.ascontiguousarray(pose7, np.float64).copy()
+    cam = np.ascontiguousarray(cam5, np.float64)
+    xyz = np.ascontiguousarray(xyz, np.float64)
+    meas = np.ascontiguousarray(meas, np.float32)
+    n = xyz.shape[0]
+    out = np.zeros(max(n, 1), np.uint8)
+    tr = np.zeros((500, 8))
+    nt = C.c_int32(0)
+    nm = np.zeros(2, np.int32)
+    st, keep = frame_lidar_struct(ld)
+    L.refba_pose_opt_lidar.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3
+    L.refba_pose_opt_lidar.restype = C.c_int
+    inl = L.refba_pose_opt_lidar(pose.ctypes.data, cam.ctypes.data, n, xyz.ctypes.data, meas.ctypes.data, out.ctypes.data,
+                                 tr.ctypes.data, 500, C.addressof(nt), C.addressof(st), nm.ctypes.data)
+    return pose, out[:n], int(inl), tr[:nt.value], (int(nm[0]), int(nm[1]))

@@ -34,6 +34,14 @@ class Stats(C.Structure):
         return d
 
 
+class FrameLidar(C.Structure):
+    """sqrtba_frame_lidar (include/sqrtba.h)"""
+    _fields_ = [("n_flat", C.c_int32), ("flat_xyz", C.c_void_p), ("flat_normal", C.c_void_p), ("n_corner", C.c_int32),
+                ("corner_xyz", C.c_void_p), ("n_map", C.c_int64), ("map_xyz", C.c_void_p),
+                ("distance_sq_threshold", C.c_double), ("flat_weight", C.c_double), ("corner_weight", C.c_double),
+                ("use_flat", C.c_int32), ("use_corner", C.c_int32)]
+
+
 class Lidar(C.Structure):  # include/sqrtba.h: sqrtba_lidar
     _fields_ = [("cur_pose", C.c_int32), ("n_flat", C.c_int32), ("flat_xyz", C.POINTER(C.c_float)),
                 ("flat_normal", C.POINTER(C.c_float)), ("n_corner", C.c_int32), ("numeric_jacobian", C.c_int32),
@@ -80,6 +88,7 @@ def lib():
         L.sqrtba_time_stage.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, dp]
         L.sqrtba_pose_opt.argtypes = [vp, C.c_int32, lp, dp, dp, dp, fp, up, ip, C.POINTER(Stats)]
         L.sqrtba_pose_opt_trace.argtypes = [vp, C.c_int32, dp, C.c_int32]
+        L.sqrtba_pose_opt_lidar.argtypes = [vp, dp, dp, C.c_int32, dp, fp, up, ip, C.c_void_p, ip, C.POINTER(Stats)]
         L.sqrtba_pose_graph.argtypes = [vp, C.c_int32, dp, up, C.c_int32, C.c_int32, ip, dp, C.c_int32, C.c_double, C.POINTER(Stats)]
         L.sqrtba_pose_graph_trace.argtypes = [vp, dp, C.c_int32]
         L.sqrtba_optimize_sim3.argtypes = [vp, C.c_int32, lp, dp, dp, dp, dp, fp, C.c_float, C.c_int32, up, ip, C.POINTER(Stats)]
@@ -286,9 +295,28 @@ class SqrtBA:
         return pose, out[:int(fp_[-1])], inl, st.as_dict()
 
     def pose_opt_trace(self, frame: int = 0):
-        rows = np.zeros((400, 8))
-        n = self._chk(lib().sqrtba_pose_opt_trace(self.h, frame, _p(rows, C.c_double), 400), "sqrtba_pose_opt_trace")
+        rows = np.zeros((500, 8))
+        n = self._chk(lib().sqrtba_pose_opt_trace(self.h, frame, _p(rows, C.c_double), 500), "sqrtba_pose_opt_trace")
         return rows[:n]
+
+    def pose_opt_lidar(self, pose_qt, cam, obs_xyz, obs_meas, ld):
+        """sqrtba_pose_opt_lidar on one frame (ld: synth.FrameLidar).  Returns (pose 7, outlier flags, inliers,
+        (flat matches, corner matches), stats)."""
+        pose = np.ascontiguousarray(pose_qt, np.float64).reshape(7).copy()
+        cam = np.ascontiguousarray(cam, np.float64).reshape(5)
+        xyz = np.ascontiguousarray(obs_xyz, np.float64).reshape(-1, 3)
+        meas = np.ascontiguousarray(obs_meas, np.float32).reshape(-1, 4)
+        keep = [np.ascontiguousarray(a, np.float32) for a in (ld.flat_xyz, ld.flat_normal, ld.corner_xyz, ld.map_xyz)]
+        fl = FrameLidar(len(keep[0]), keep[0].ctypes.data, keep[1].ctypes.data, len(keep[2]), keep[2].ctypes.data,
+                        len(keep[3]), keep[3].ctypes.data, ld.distance_sq_threshold, ld.flat_weight, ld.corner_weight,
+                        int(ld.use_flat), int(ld.use_corner))
+        out = np.zeros(max(len(xyz), 1), np.uint8)
+        inl, nm = np.zeros(1, np.int32), np.zeros(2, np.int32)
+        st = Stats()
+        self._chk(lib().sqrtba_pose_opt_lidar(self.h, _p(pose, C.c_double), _p(cam, C.c_double), len(xyz), _p(xyz, C.c_double),
+                                              _p(meas, C.c_float), _p(out, C.c_uint8), _p(inl, C.c_int32), C.addressof(fl),
+                                              _p(nm, C.c_int32), C.byref(st)), "sqrtba_pose_opt_lidar")
+        return pose, out[:len(xyz)], int(inl[0]), (int(nm[0]), int(nm[1])), st.as_dict()
 
     def pose_graph(self, vert8, fixed, fix_scale, edge_ij, meas8, iters: int = 20, lambda_init: float = 1e-16):
         """sqrtba_pose_graph: returns (vertices n x 8 after the optimisation, LM trace rows x 8, stats)."""

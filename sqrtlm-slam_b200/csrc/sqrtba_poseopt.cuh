@@ -1,5 +1,5 @@
 // Pose-only optimisation: the CUDA counterpart of g2oOptimizer::PoseOptimization
-// (src/backend/g2oOptimizer.cc:385-559, 655-690 -- the lidar block :560-640 is out of scope), the per-frame sibling of
+// (src/backend/g2oOptimizer.cc:385-559, 655-690; the lidar block :560-640 is csrc/sqrtba_poseopt_lidar.cuh), the per-frame sibling of
 // local BA that the tracking thread calls on every frame (Tracking.cc:1347,1547,1617,2466-2517).
 //
 // One CTA per frame, the whole 4 x optimize(10) schedule in ONE launch: every LM trial is a sweep of the CTA over the
@@ -17,7 +17,7 @@ namespace sqrtba {
 constexpr int PO_CTA = 256;
 constexpr int PO_WARPS = PO_CTA / 32;
 constexpr int PO_TRACE_COLS = 8;   // round, iter, trial, lambda, chi_before, chi_trial, rho, accepted
-constexpr int PO_MAX_TRACE = 400;  // 4 rounds x 10 iterations x <= 10 trials
+constexpr int PO_MAX_TRACE = 500;  // (4 rounds + the lidar round) x 10 iterations x <= 10 trials
 
 struct PoseOptArgs {
   int n_frames;
@@ -32,6 +32,7 @@ struct PoseOptArgs {
   int* inliers;                // n_frames
   double* trace;               // n_frames x PO_MAX_TRACE x PO_TRACE_COLS
   int* trace_len;              // n_frames
+  int skip_final;              // 1: stop after the rounds (pose, err, level, outlier stay for k_pose_opt_lidar)
 };
 
 struct PoEdge {
@@ -316,6 +317,11 @@ __global__ void __launch_bounds__(PO_CTA) k_pose_opt(PoseOptArgs A) {
     }
     __syncthreads();
     if (n < 10) break;  // optimizer.edges().size() < 10, :549-550
+  }
+  if (A.skip_final) {  // the lidar block follows (csrc/sqrtba_poseopt_lidar.cuh): it classifies after its own round
+    if (tid == 0) A.trace_len[f] = trace_len;
+    if (tid < 7) A.pose[f * 7 + tid] = sh_pose[tid];
+    return;
   }
   // ---- final classification (:656-680): double thresholds, same stale/recomputed error rule
   double nb[1] = {0.0};

@@ -28,6 +28,7 @@
 #include "sqrtba_lidar.cuh"
 #include "sqrtba_posegraph.cuh"
 #include "sqrtba_sim3opt.cuh"
+#include "sqrtba_poseopt_lidar.cuh"
 #include "../host/host_pool.h"
 
 namespace sqrtba {
@@ -1097,6 +1098,112 @@ class Solver {
     }
     return SQRTBA_OK;
   }
+  // ------------------------------------------------------------------------ pose-only optimisation with the lidar block
+  // g2oOptimizer::PoseOptimization as the tracking thread of this fork calls it (g2oOptimizer.cc:385-690, lidar block
+  // :560-640): the four visual rounds (k_pose_opt), then -- when the local lidar map has more than 100 points -- the
+  // association at the new pose, the float round trip of the estimate and a fifth optimize(10) over visual + lidar edges
+  // (csrc/sqrtba_poseopt_lidar.cuh).  One frame per call; independent of set_problem.
+  int pose_opt_lidar(double* pose_qt, const double* cam, int n_obs, const double* obs_xyz, const float* obs_meas,
+                     uint8_t* outlier_out, int32_t* inliers_out, const sqrtba_frame_lidar* c, int32_t* n_match2_out,
+                     sqrtba_stats* st) {
+    if (!c) { err_ = "pose_opt_lidar: null lidar block"; return SQRTBA_ERR_INVALID; }
+    if (c->n_flat < 0 || c->n_corner < 0 || c->n_map < 0 || c->n_map > 0x7fffffffLL ||
+        (c->n_flat > 0 && (!c->flat_xyz || !c->flat_normal)) || (c->n_corner > 0 && !c->corner_xyz) || (c->n_map > 0 && !c->map_xyz)) {
+      err_ = "pose_opt_lidar: bad lidar arrays";
+      return SQRTBA_ERR_INVALID;
+    }
+    if (n_match2_out) n_match2_out[0] = n_match2_out[1] = 0;
+    const int64_t ptr[2] = {0, n_obs};
+    const bool lidar_round = c->n_map > 100 && n_obs >= 3;  // :491-492 returns before the lidar block; :560 needs > 100 map points
+    if (!lidar_round) return pose_opt(1, ptr, pose_qt, cam, obs_xyz, obs_meas, outlier_out, inliers_out, st);
+    if (!pose_qt || !cam || !inliers_out || !obs_xyz || !obs_meas || !outlier_out) { err_ = "pose_opt_lidar: bad arguments"; return SQRTBA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(cfg_.device));
+    const size_t No = (size_t)n_obs;
+    CU_CHECK(d_po_ptr_.ensure(2));
+    CU_CHECK(d_po_pose_.ensure(8));
+    CU_CHECK(d_po_cam_.ensure(8));
+    CU_CHECK(d_po_xyz_.ensure(No * 3));
+    CU_CHECK(d_po_meas_.ensure(No));
+    CU_CHECK(d_po_err_.ensure(No * 3));
+    CU_CHECK(d_po_level_.ensure(No));
+    CU_CHECK(d_po_outlier_.ensure(No));
+    CU_CHECK(d_po_inl_.ensure(4));
+    CU_CHECK(d_po_trace_.ensure((size_t)PO_MAX_TRACE * PO_TRACE_COLS));
+    const int n = c->n_flat + c->n_corner;
+    const size_t ne = (size_t)std::max(n, 1);
+    CU_CHECK(d_fl_pc_.ensure(ne * 3)); CU_CHECK(d_fl_qw_.ensure(ne * 3)); CU_CHECK(d_fl_nv_.ensure(ne * 3)); CU_CHECK(d_fl_w_.ensure(ne));
+    CU_CHECK(d_fl_match_.ensure(ne)); CU_CHECK(d_fl_best_.ensure(ne)); CU_CHECK(d_fl_world_.ensure(ne * 3));
+    CU_CHECK(d_fl_flat_.ensure((size_t)std::max(c->n_flat, 1) * 3)); CU_CHECK(d_fl_normal_.ensure((size_t)std::max(c->n_flat, 1) * 3));
+    CU_CHECK(d_fl_corner_.ensure((size_t)std::max(c->n_corner, 1) * 3)); CU_CHECK(d_fl_map_.ensure((size_t)c->n_map * 3));
+    auto up = [&](void* dst, const void* src, size_t bytes) {
+      return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_) : cudaSuccess;
+    };
+    CU_CHECK(cudaEventRecord(ev0_, stream_));
+    CU_CHECK(up(d_po_ptr_.p, ptr, sizeof ptr));
+    CU_CHECK(up(d_po_pose_.p, pose_qt, 7 * sizeof(double)));
+    CU_CHECK(up(d_po_cam_.p, cam, 5 * sizeof(double)));
+    CU_CHECK(up(d_po_xyz_.p, obs_xyz, No * 3 * sizeof(double)));
+    CU_CHECK(up(d_po_meas_.p, obs_meas, No * sizeof(float4)));
+    CU_CHECK(up(d_fl_flat_.p, c->flat_xyz, (size_t)c->n_flat * 3 * sizeof(float)));
+    CU_CHECK(up(d_fl_normal_.p, c->flat_normal, (size_t)c->n_flat * 3 * sizeof(float)));
+    CU_CHECK(up(d_fl_corner_.p, c->corner_xyz, (size_t)c->n_corner * 3 * sizeof(float)));
+    CU_CHECK(up(d_fl_map_.p, c->map_xyz, (size_t)c->n_map * 3 * sizeof(float)));
+    PoseOptArgs A{};
+    A.n_frames = 1; A.frame_ptr = d_po_ptr_.p; A.pose = d_po_pose_.p; A.cam = d_po_cam_.p; A.xyz = d_po_xyz_.p;
+    A.meas = d_po_meas_.p; A.err = d_po_err_.p; A.level = d_po_level_.p; A.outlier = d_po_outlier_.p;
+    A.inliers = d_po_inl_.p; A.trace = d_po_trace_.p; A.trace_len = d_po_inl_.p + 1; A.skip_final = 1;
+    k_pose_opt<<<1, PO_CTA, 0, stream_>>>(A);
+    // association at the pose of the four rounds: both point kinds against the one local map cloud (world frame already)
+    LidarAssoc S{};
+    S.pose = 0; S.n_flat = c->n_flat; S.n_corner = c->n_corner;
+    S.flat = d_fl_flat_.p; S.flat_n = d_fl_normal_.p; S.corner = d_fl_corner_.p;
+    S.n_map_flat = S.n_map_corner = c->n_map;
+    S.map_flat_w = S.map_corner_w = d_fl_map_.p;
+    S.cur_w = d_fl_world_.p; S.best = d_fl_best_.p; S.match = d_fl_match_.p;
+    S.thr = c->distance_sq_threshold; S.w_flat = c->flat_weight; S.w_corner = c->corner_weight;
+    S.use_flat = c->use_flat ? 1 : 0; S.use_corner = c->use_corner ? 1 : 0;
+    LidarDev L{};
+    L.n_edge = n; L.n_flat = c->n_flat; L.pose = 0; L.numeric = 1;
+    L.pc = d_fl_pc_.p; L.qw = d_fl_qw_.p; L.nv = d_fl_nv_.p; L.w = d_fl_w_.p; L.acc = nullptr;
+    int launched = 1;
+    if (n > 0) {
+      Dev Pf{};
+      Pf.pose = d_po_pose_.p;
+      k_lidar_to_world<<<cdiv(n, 256), 256, 0, stream_>>>(Pf, S, 2);
+      if (S.use_flat && S.n_flat > 0) {
+        k_lidar_nn<<<dim3(cdiv(S.n_flat, LD_NN_CTA), cdiv((int)c->n_map, LD_NN_CHUNK)), LD_NN_CTA, 0, stream_>>>(S, 0);
+        launched++;
+      }
+      if (S.use_corner && S.n_corner > 0) {
+        k_lidar_nn<<<dim3(cdiv(S.n_corner, LD_NN_CTA), cdiv((int)c->n_map, LD_NN_CHUNK)), LD_NN_CTA, 0, stream_>>>(S, 1);
+        launched++;
+      }
+      k_lidar_edges<<<cdiv(n, 256), 256, 0, stream_>>>(S, L);
+      launched += 2;
+    }
+    k_pose_opt_lidar<<<1, PO_CTA, 0, stream_>>>(A, L, d_po_inl_.p + 2);
+    launched++;
+    CU_CHECK(cudaGetLastError());
+    int32_t nm[2] = {0, 0};
+    CU_CHECK(cudaMemcpyAsync(pose_qt, d_po_pose_.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    CU_CHECK(cudaMemcpyAsync(inliers_out, d_po_inl_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CU_CHECK(cudaMemcpyAsync(nm, d_po_inl_.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CU_CHECK(cudaMemcpyAsync(outlier_out, d_po_outlier_.p, No, cudaMemcpyDeviceToHost, stream_));
+    CU_CHECK(cudaEventRecord(ev1_, stream_));
+    CU_CHECK(cudaEventSynchronize(ev1_));
+    if (n_match2_out) { n_match2_out[0] = nm[0]; n_match2_out[1] = nm[1]; }
+    po_frames_ = 1;
+    s3_pairs_ = 0;
+    if (st) {
+      std::memset(st, 0, sizeof *st);
+      float ms = 0;
+      CU_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+      st->n_windows = 1;
+      st->kernel_launches = launched;
+      st->ms_total = ms;
+    }
+    return SQRTBA_OK;
+  }
   int pose_opt_trace(int frame, double* rows, int max_rows) {
     if (frame < 0 || frame >= po_frames_ || !rows) { err_ = "pose_opt_trace: no such frame"; return SQRTBA_ERR_INVALID; }
     int len = 0;
@@ -2152,7 +2259,8 @@ class Solver {
     d_lm_flat_pose_.release(); d_lm_corner_pose_.release(); d_lc_flat_.release(); d_lc_normal_.release(); d_lc_corner_.release();
     d_lc_world_.release(); d_lm_flat_.release(); d_lm_flat_w_.release(); d_lm_corner_.release(); d_lm_corner_w_.release(); d_l_best_.release();
     d_po_ptr_.release(); d_po_pose_.release(); d_po_cam_.release(); d_po_xyz_.release(); d_po_err_.release(); d_po_trace_.release();
-    d_po_meas_.release(); d_s3_meas_.release(); d_po_level_.release(); d_po_outlier_.release(); d_po_inl_.release();
+    d_po_meas_.release(); d_s3_meas_.release(); d_fl_pc_.release(); d_fl_qw_.release(); d_fl_nv_.release(); d_fl_w_.release(); d_fl_match_.release();
+    d_fl_best_.release(); d_fl_world_.release(); d_fl_flat_.release(); d_fl_normal_.release(); d_fl_corner_.release(); d_fl_map_.release(); d_po_level_.release(); d_po_outlier_.release(); d_po_inl_.release();
     d_pg_vert_.release(); d_pg_bak_.release(); d_pg_meas_.release(); d_pg_err_.release(); d_pg_Ji_.release(); d_pg_Jj_.release();
     d_pg_H_.release(); d_pg_L_.release(); d_pg_Linv_.release(); d_pg_b_.release(); d_pg_y_.release(); d_pg_x_.release();
     d_pg_scal_.release(); d_pg_fixed_.release(); d_pg_slot_.release(); d_pg_slot_vert_.release(); d_pg_edge_.release();
@@ -2219,6 +2327,10 @@ class Solver {
   DBuf<int> d_po_inl_;
   int po_frames_ = 0;
   DBuf<float> d_s3_meas_;
+  DBuf<double> d_fl_pc_, d_fl_qw_, d_fl_nv_, d_fl_w_;
+  DBuf<int> d_fl_match_;
+  DBuf<unsigned long long> d_fl_best_;
+  DBuf<float> d_fl_world_, d_fl_flat_, d_fl_normal_, d_fl_corner_, d_fl_map_;
   int s3_pairs_ = 0;
   // essential-graph optimisation (independent of set_problem)
   DBuf<double> d_pg_vert_, d_pg_bak_, d_pg_meas_, d_pg_err_, d_pg_Ji_, d_pg_Jj_, d_pg_H_, d_pg_L_, d_pg_Linv_, d_pg_b_, d_pg_y_,
@@ -2379,6 +2491,12 @@ int sqrtba_pose_opt(sqrtba_handle* h, int32_t n_frames, const int64_t* frame_obs
                     const double* obs_xyz, const float* obs_meas, uint8_t* outlier_out, int32_t* inliers_out,
                     sqrtba_stats* stats) {
   return h ? h->s->pose_opt(n_frames, frame_obs_ptr, pose_qt, cam, obs_xyz, obs_meas, outlier_out, inliers_out, stats)
+           : SQRTBA_ERR_INVALID;
+}
+int sqrtba_pose_opt_lidar(sqrtba_handle* h, double* pose_qt, const double* cam, int32_t n_obs, const double* obs_xyz,
+                          const float* obs_meas, uint8_t* outlier_out, int32_t* inliers_out, const sqrtba_frame_lidar* lidar,
+                          int32_t* n_match2_out, sqrtba_stats* stats) {
+  return h ? h->s->pose_opt_lidar(pose_qt, cam, n_obs, obs_xyz, obs_meas, outlier_out, inliers_out, lidar, n_match2_out, stats)
            : SQRTBA_ERR_INVALID;
 }
 int sqrtba_pose_opt_trace(sqrtba_handle* h, int32_t frame, double* rows_out, int32_t max_rows) {

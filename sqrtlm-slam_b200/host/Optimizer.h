@@ -26,6 +26,9 @@ class Optimizer {
   void static GlobalBundleAdjustemnt(Map* pMap, int nIterations = 5, bool* pbStopFlag = NULL,
                                      const unsigned long nLoopKF = 0, const bool bRobust = true);
   void static LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* lidarconfig);
+  // include/backend/Optimizer.h:58-59
+  int static PoseOptimization(Frame* pFrame, PointICloudPtr local_lidarmap_cloud_ptr,
+                              pcl::KdTreeFLANN<PointI>::Ptr kdtree_local_map, const lidarConfig* lidarconfig);
   // include/backend/Optimizer.h:62-67
   void static OptimizeEssentialGraph(Map* pMap, KeyFrame* pLoopKF, KeyFrame* pCurKF,
                                      const LoopClosing::KeyFrameAndPose& NonCorrectedSim3,
@@ -47,6 +50,10 @@ class sqrtbaOptimizer {
   // the visual part of Optimizer::PoseOptimization (include/backend/Optimizer.h:58-59), same shape as the reference's
   // CeresOptimizer::PoseOptimization(Frame*) / MyOptimizer::PoseOptimization(Frame*) adapters (Optimizer.cc:55-60)
   int static PoseOptimization(Frame* pFrame);
+  // g2oOptimizer::PoseOptimization with the fork's lidar block (src/backend/g2oOptimizer.cc:385-690): the frame's flat /
+  // sharp points against the tracker's local lidar map; the kd-tree argument is unused (exact search on the device)
+  int static PoseOptimization(Frame* pFrame, PointICloudPtr local_lidarmap_cloud_ptr,
+                              pcl::KdTreeFLANN<PointI>::Ptr kdtree_local_map, const lidarConfig* lidarconfig);
   // relocalisation: several candidate frames in one launch (Tracking.cc:2466-2517 calls PoseOptimization per candidate)
   void static PoseOptimizationBatch(const std::vector<Frame*>& frames, std::vector<int>& inliers);
   // g2oOptimizer::OptimizeEssentialGraph (src/backend/g2oOptimizer.cc:1212-1520): the graph is built from the map by the

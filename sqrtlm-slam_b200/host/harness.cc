@@ -328,6 +328,26 @@ hh_frame* hh_frame_build(const float* Tcw16, const float* cam5, const float* inv
 void hh_frame_destroy(hh_frame* f) { delete f; }
 void hh_frame_unmatch(hh_frame* f, int i) { f->frame.mvpMapPoints[i] = nullptr; }
 int hh_pose_opt(hh_frame* f) { return sqrtbaOptimizer::PoseOptimization(&f->frame); }
+// Optimizer::PoseOptimization(pFrame, local_lidarmap_cloud_ptr, kdtree_local_map, lidarconfig) as Tracking calls it
+// (Tracking.cc:1347, 1547, 1617)
+int hh_pose_opt_lidar(hh_frame* f, int n_flat, const float* flat_xyz, const float* flat_normal, int n_corner,
+                      const float* corner_xyz, int n_map, const float* map_xyz, int use_flat, int use_corner, double thr,
+                      double w_flat, double w_corner) {
+  auto fill = [](PointIRTCloud& c, int n, const float* xyz) {
+    c.points.resize((size_t)n);
+    for (int i = 0; i < n; i++) { c.points[i].x = xyz[i * 3]; c.points[i].y = xyz[i * 3 + 1]; c.points[i].z = xyz[i * 3 + 2]; }
+  };
+  fill(f->frame.surface_points_flat_, n_flat, flat_xyz);
+  fill(f->frame.surface_points_flat_normal_, n_flat, flat_normal);
+  fill(f->frame.corner_points_sharp_, n_corner, corner_xyz);
+  PointICloudPtr map = std::make_shared<PointICloud>();
+  map->points.resize((size_t)n_map);
+  for (int i = 0; i < n_map; i++) { map->points[i].x = map_xyz[i * 3]; map->points[i].y = map_xyz[i * 3 + 1]; map->points[i].z = map_xyz[i * 3 + 2]; }
+  lidarConfig cfg;
+  cfg.using_flat_point = use_flat != 0; cfg.using_sharp_point = use_corner != 0;
+  cfg.distance_sq_threshold = thr; cfg.flat_optimized_weight = w_flat; cfg.corner_optimized_weight = w_corner;
+  return Optimizer::PoseOptimization(&f->frame, map, pcl::KdTreeFLANN<PointI>::Ptr(), &cfg);
+}
 void hh_pose_opt_batch(hh_frame** fs, int n, int32_t* inliers) {
   std::vector<Frame*> v;
   for (int i = 0; i < n; i++) v.push_back(&fs[i]->frame);

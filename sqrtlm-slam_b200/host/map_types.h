@@ -8,6 +8,7 @@
 #include <cstddef>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <set>
 #include <vector>
@@ -46,6 +47,19 @@ struct PointIRTCloud {
   std::vector<PointIRT> points;
   size_t size() const { return points.size(); }
 };
+
+// include/data_structure/point_types.h:42-45: PointI = pcl::PointXYZI, PointICloud(Ptr) -- the tracker's local lidar map
+// handed to PoseOptimization (Tracking.cc:1347) -- and the kd-tree over it (pcl::KdTreeFLANN<PointI>::Ptr; the sqrtba
+// adapter searches on the device and only takes the pointer to keep the reference's signature)
+struct PointI { float x = 0, y = 0, z = 0, intensity = 0; };
+struct PointICloud {
+  std::vector<PointI> points;
+  size_t size() const { return points.size(); }
+};
+typedef std::shared_ptr<PointICloud> PointICloudPtr;
+namespace pcl {
+template <class T> struct KdTreeFLANN { typedef std::shared_ptr<KdTreeFLANN<T>> Ptr; };
+}  // namespace pcl
 
 // Thirdparty/g2o/g2o/types/sim3.h: the accessor surface of g2o::Sim3 that the essential-graph adapter uses
 // (rotation().x() .. w(), translation()[i], scale()); the real class stores an Eigen quaternion and vector
@@ -171,6 +185,8 @@ class Frame {
   std::vector<float> mvInvLevelSigma2;
   std::vector<MapPoint*> mvpMapPoints;
   std::vector<bool> mvbOutlier;
+  // lidar features of the frame in its own frame (Frame.h:273-277), read by the lidar block of PoseOptimization
+  PointIRTCloud corner_points_sharp_, surface_points_flat_, surface_points_flat_normal_;
   void SetPose(const cv::Mat& T) { T.copyTo(mTcw); }
 };
 

@@ -883,6 +883,70 @@ int sqrtbaOptimizer::PoseOptimization(Frame* pFrame) {
   return inl.empty() ? 0 : inl[0];
 }
 
+// with the fork's lidar block (g2oOptimizer.cc:560-640): same gather for the visual edges, the frame's flat / sharp
+// feature clouds and the tracker's local lidar map go along (pcl point fields x y z, packed to n x 3 floats)
+int sqrtbaOptimizer::PoseOptimization(Frame* pFrame, PointICloudPtr local_lidarmap_cloud_ptr,
+                                      pcl::KdTreeFLANN<PointI>::Ptr /*kdtree_local_map*/, const lidarConfig* lidarconfig) {
+  if (!local_lidarmap_cloud_ptr || !lidarconfig || !(local_lidarmap_cloud_ptr->size() > 100)) return PoseOptimization(pFrame);
+  Handle& H = tl_handle;
+  if (!H.get()) return 0;
+  Frame* F = pFrame;
+  double pose[7], cam[5] = {F->fx, F->fy, F->cx, F->cy, F->mbf};
+  std::vector<double> xyz;
+  std::vector<float> meas;
+  std::vector<int> ref;
+  {
+    std::unique_lock<std::mutex> lock(MapPoint::mGlobalMutex);  // :433
+    toSE3Quat(F->mTcw, pose);
+    for (int i = 0; i < F->N; i++) {
+      MapPoint* pMP = F->mvpMapPoints[i];
+      if (!pMP) continue;
+      const bool mono = F->mvuRight[i] < 0;
+#ifndef SQRTBA_POSEOPT_STEREO
+      if (!mono) continue;
+#endif
+      F->mvbOutlier[i] = false;
+      const cv::KeyPoint& kp = F->mvKeysUn[i];
+      const cv::Mat Xw = pMP->GetWorldPos();
+      for (int c = 0; c < 3; c++) xyz.push_back(Xw.at<float>(c));
+      meas.push_back(kp.pt.x);
+      meas.push_back(kp.pt.y);
+      meas.push_back(mono ? -1.f : F->mvuRight[i]);
+      meas.push_back(F->mvInvLevelSigma2[kp.octave]);
+      ref.push_back(i);
+    }
+  }
+  auto pack = [](const auto& cloud, std::vector<float>& out) {
+    out.resize(cloud.points.size() * 3);
+    for (size_t i = 0; i < cloud.points.size(); i++) {
+      out[i * 3] = cloud.points[i].x; out[i * 3 + 1] = cloud.points[i].y; out[i * 3 + 2] = cloud.points[i].z;
+    }
+  };
+  std::vector<float> flat, nrm, corner, map;
+  pack(F->surface_points_flat_, flat);
+  pack(F->surface_points_flat_normal_, nrm);
+  pack(F->corner_points_sharp_, corner);
+  pack(*local_lidarmap_cloud_ptr, map);
+  sqrtba_frame_lidar L;
+  std::memset(&L, 0, sizeof L);
+  L.n_flat = (int32_t)std::min(flat.size(), nrm.size()) / 3; L.flat_xyz = flat.data(); L.flat_normal = nrm.data();
+  L.n_corner = (int32_t)(corner.size() / 3); L.corner_xyz = corner.data();
+  L.n_map = (int64_t)(map.size() / 3); L.map_xyz = map.data();
+  L.distance_sq_threshold = lidarconfig->distance_sq_threshold;
+  L.flat_weight = lidarconfig->flat_optimized_weight; L.corner_weight = lidarconfig->corner_optimized_weight;
+  L.use_flat = lidarconfig->using_flat_point ? 1 : 0; L.use_corner = lidarconfig->using_sharp_point ? 1 : 0;
+  std::vector<uint8_t> out(std::max<size_t>(ref.size(), 1), 0);
+  int32_t inl = 0;
+  if (sqrtba_pose_opt_lidar(H.h, pose, cam, (int32_t)ref.size(), xyz.data(), meas.data(), out.data(), &inl, &L, nullptr, nullptr) !=
+      SQRTBA_OK) {
+    H.err = sqrtba_last_error(H.h);
+    return 0;
+  }
+  for (size_t k = 0; k < ref.size(); k++) F->mvbOutlier[ref[k]] = out[k] != 0;
+  if (ref.size() >= 3) F->SetPose(toCvMat(pose));  // :491-492: nothing happens below 3
+  return inl;
+}
+
 void Optimizer::GlobalBundleAdjustemnt(Map* pMap, int nIterations, bool* pbStopFlag, const unsigned long nLoopKF,
                                        const bool bRobust) {
   sqrtbaOptimizer::GlobalBundleAdjustemnt(pMap, nIterations, pbStopFlag, nLoopKF, bRobust);
@@ -899,6 +963,10 @@ void Optimizer::OptimizeEssentialGraph(Map* pMap, KeyFrame* pLoopKF, KeyFrame* p
 }
 void Optimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, const lidarConfig* lidarconfig) {
   sqrtbaOptimizer::LocalBundleAdjustment(pKF, pbStopFlag, pMap, lidarconfig);
+}
+int Optimizer::PoseOptimization(Frame* pFrame, PointICloudPtr local_lidarmap_cloud_ptr,
+                                pcl::KdTreeFLANN<PointI>::Ptr kdtree_local_map, const lidarConfig* lidarconfig) {
+  return sqrtbaOptimizer::PoseOptimization(pFrame, local_lidarmap_cloud_ptr, kdtree_local_map, lidarconfig);
 }
 int Optimizer::OptimizeSim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches1, g2o::Sim3& g2oS12,
                             const float th2, const bool bFixScale) {

@@ -56,6 +56,8 @@ def lib():
         L.hh_frame_destroy.argtypes = [C.c_void_p]
         L.hh_frame_unmatch.argtypes = [C.c_void_p, C.c_int]
         L.hh_pose_opt.argtypes = [C.c_void_p]
+        L.hh_pose_opt_lidar.argtypes = [C.c_void_p, C.c_int, fp, fp, C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, C.c_double,
+                                        C.c_double, C.c_double]
         L.hh_pose_opt_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, ip]
         L.hh_frame_get.argtypes = [C.c_void_p, fp, up]
         _lib = L
@@ -329,6 +331,14 @@ class MockFrame:
 
     def pose_optimization(self) -> int:
         return lib().hh_pose_opt(self.h)
+
+    def pose_optimization_lidar(self, ld) -> int:
+        """Optimizer::PoseOptimization(pFrame, local_lidarmap_cloud_ptr, kdtree_local_map, lidarconfig) with the clouds
+        of a synth.FrameLidar put on the frame (Frame.h:273-277) and into a PointICloud."""
+        c32 = lambda a: np.ascontiguousarray(a, np.float32)
+        f, n, c, m = c32(ld.flat_xyz), c32(ld.flat_normal), c32(ld.corner_xyz), c32(ld.map_xyz)
+        return lib().hh_pose_opt_lidar(self.h, len(f), _f(f), _f(n), len(c), _f(c), len(m), _f(m), int(ld.use_flat),
+                                       int(ld.use_corner), ld.distance_sq_threshold, ld.flat_weight, ld.corner_weight)
 
     def state(self):
         T = np.zeros(16, np.float32)

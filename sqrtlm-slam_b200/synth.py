@@ -471,6 +471,61 @@ def lidar_data(prob: Problem, seed: int = 0, cur_pose: int | None = None, n_flat
                      f32(np.concatenate(mc)), np.concatenate(mcp))
 
 
+@dataclass
+class FrameLidar:
+    """Inputs of the lidar block of PoseOptimization (include/sqrtba.h: sqrtba_frame_lidar; g2oOptimizer.cc:560-640): the
+    frame's flat / sharp feature points in its own frame (Frame.h:273-277) and the local lidar map in the world frame
+    (Tracking's local_lidarmap_cloud_ptr_), float32 like the pcl point types."""
+    flat_xyz: np.ndarray
+    flat_normal: np.ndarray
+    corner_xyz: np.ndarray
+    map_xyz: np.ndarray
+    distance_sq_threshold: float = 0.2
+    flat_weight: float = 50.0
+    corner_weight: float = 30.0
+    use_flat: bool = True
+    use_corner: bool = True
+
+
+def frame_lidar(truth, seed: int = 0, n_flat: int = 800, n_corner: int = 200, n_map: int = 20000, sigma: float = 0.02,
+                miss_frac: float = 0.1) -> FrameLidar:
+    """Lidar features for a frame made by frame_problem (truth = its last return value): a ground plane 1.65 m below
+    the camera, two walls and vertical poles.  The map cloud samples the scene in the world frame, the frame's feature
+    points sample it again, seen from the TRUE pose with `sigma` metres of noise; `miss_frac` of them are moved away
+    from every map point (no correspondence)."""
+    rng = np.random.default_rng(20_000 + seed)
+    R_cw, t_cw = truth["R_cw"], truth["t_cw"]
+    c_w = -R_cw.T @ t_cw
+    poles = np.stack([c_w[0] + rng.choice([-6.0, 6.0], 24), np.zeros(24), c_w[2] + rng.uniform(-5.0, 30.0, 24)], -1)
+
+    def flat(n):
+        which = rng.integers(0, 3, n)
+        z = c_w[2] + rng.uniform(-5.0, 30.0, n)
+        x = np.where(which == 0, c_w[0] + rng.uniform(-12.0, 12.0, n), np.where(which == 1, c_w[0] - 8.0, c_w[0] + 8.0))
+        y = np.where(which == 0, c_w[1] + 1.65, c_w[1] + rng.uniform(-3.0, 1.65, n))
+        nw = np.where((which == 0)[:, None], np.array([0.0, -1.0, 0.0]),
+                      np.where((which == 1)[:, None], np.array([1.0, 0.0, 0.0]), np.array([-1.0, 0.0, 0.0])))
+        return np.stack([x, y, z], -1), nw
+
+    def corner(n):
+        p = poles[rng.integers(0, len(poles), n)].copy()
+        p[:, 1] = c_w[1] + rng.uniform(-2.5, 1.5, n)
+        return p
+
+    n_mc = n_map // 5
+    mapw = np.concatenate([flat(n_map - n_mc)[0], corner(n_mc)])
+    fw, nw = flat(n_flat)
+    cw = corner(n_corner)
+    miss_f, miss_c = rng.uniform(0, 1, n_flat) < miss_frac, rng.uniform(0, 1, n_corner) < miss_frac
+    fw[miss_f, 1] -= 6.0                                  # above everything
+    cw[miss_c, 0] += 30.0
+    to_cam = lambda pw: pw @ R_cw.T + t_cw + rng.normal(0, sigma, pw.shape)
+    nrm = nw @ R_cw.T + rng.normal(0, 0.01, nw.shape)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    return FrameLidar(f32(to_cam(fw)), f32(nrm), f32(to_cam(cw)), f32(mapw))
+
+
 # ----------------------------------------------------------------------------- essential graph (Sim3 pose graph, row N3)
 # Sim3 as 8 numbers in g2o's operator[] order: qx qy qz qw | tx ty tz | s   (types/sim3.h)
 

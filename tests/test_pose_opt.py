@@ -1,4 +1,5 @@
-"""Pose-only optimisation (g2oOptimizer::PoseOptimization, g2oOptimizer.cc:385-559,655-690).
+"""Pose-only optimisation (g2oOptimizer::PoseOptimization, g2oOptimizer.cc:385-690, the
+fork's lidar block :560-640 included).
 
 CPU part: the oracle restatement behaves like the reference describes (converges from the tracked pose, flags the
 injected gross outliers, returns inliers = correspondences - bad, gives up below 3 correspondences).
@@ -103,3 +104,103 @@ def test_pose_opt_batch_equals_individual_and_edge_cases(pkg, synth):
     assert gi[5] == 0
     assert ba.pose_opt_trace(6)[:, 0].max() == 0
     ba.close()
+
+
+# ---- the lidar block of this fork's PoseOptimization (g2oOptimizer.cc:560-640)
+
+def lidar_frames(synth):
+    """(frame, lidar) pairs: a well-constrained frame where the lidar edges are a small correction, a frame with few
+    visual points and heavy lidar weights (the lidar edges steer the pose), one with corner points only, and one with
+    fewer than 10 visual edges (the visual schedule stops after one round, the kernels stay on)."""
+    out = []
+    f = synth.frame_problem(seed=50, n_points=700)
+    out.append((f, synth.frame_lidar(f[4], seed=0)))
+    f = synth.frame_problem(seed=51, n_points=40, pose_noise=(0.08, 0.4))
+    ld = synth.frame_lidar(f[4], seed=1, n_flat=600, n_corner=150, n_map=12000)
+    ld.flat_weight, ld.corner_weight = 5000.0, 3000.0
+    out.append((f, ld))
+    f = synth.frame_problem(seed=52, n_points=300, stereo=True)
+    ld = synth.frame_lidar(f[4], seed=2, n_flat=300, n_corner=200, n_map=6000)
+    ld.use_flat = False
+    out.append((f, ld))
+    f = synth.frame_problem(seed=53, n_points=8, outlier_frac=0.0)
+    ld = synth.frame_lidar(f[4], seed=3, n_flat=400, n_corner=100, n_map=8000)
+    ld.flat_weight = 500.0
+    out.append((f, ld))
+    return out
+
+
+def test_oracle_pose_opt_lidar_block(synth):
+    """The restated lidar block: needs more than 100 map points, matches most feature points (the generator moves 10 %
+    away), runs a fifth round from the float-rounded pose, and with heavy weights pulls a weakly constrained pose
+    towards the truth."""
+    (f, ld) = lidar_frames(synth)[1]
+    pose0, cam, xyz, meas, truth = f
+    plain = refba.pose_opt(pose0, cam, xyz, meas)
+    pose, flags, inl, tr, nm = refba.pose_opt_lidar(pose0, cam, xyz, meas, ld)
+    assert 0.8 * len(ld.flat_xyz) < nm[0] <= 0.95 * len(ld.flat_xyz) and 0.8 * len(ld.corner_xyz) < nm[1] <= 0.95 * len(ld.corner_xyz)
+    assert set(tr[:, 0].astype(int)) == {0, 1, 2, 3, 4} and tr[tr[:, 0] == 4][0, 1] == 0
+    n4 = int((tr[:, 0] < 4).sum())
+    assert np.array_equal(tr[:n4], plain[3])                        # the four visual rounds are untouched
+    # the fifth round starts from the float-rounded result of the fourth
+    t_true = truth["t_cw"]
+    assert np.abs(pose[:3] - t_true).max() < np.abs(plain[0][:3] - t_true).max()
+    assert inl == len(xyz) - int(flags.sum())
+    # a small map switches the block off (:560): identical to the plain call
+    small = type(ld)(ld.flat_xyz, ld.flat_normal, ld.corner_xyz, ld.map_xyz[:100])
+    p2, f2, i2, t2, nm2 = refba.pose_opt_lidar(pose0, cam, xyz, meas, small)
+    assert np.array_equal(p2, plain[0]) and np.array_equal(f2, plain[1]) and i2 == plain[2] and nm2 == (0, 0)
+
+
+@pytest.mark.gpu
+def test_pose_opt_lidar_matches_oracle(pkg, synth):
+    """sqrtba_pose_opt_lidar against the oracle: identical matches, the four visual rounds trial for trial, the lidar
+    round within the noise of its numeric Jacobians (1e-9 central differences: ~1e-7 relative per entry), identical
+    outlier flags and inlier counts, pose to 1e-6."""
+    ba = pkg.SqrtBA()
+    for k, (f, ld) in enumerate(lidar_frames(synth)):
+        pose0, cam, xyz, meas, _ = f
+        rp, rf, ri, rt, rnm = refba.pose_opt_lidar(pose0, cam, xyz, meas, ld)
+        gp, gf, gi, gnm, st = ba.pose_opt_lidar(pose0, cam, xyz, meas, ld)
+        assert gnm == rnm and (gnm[0] > 0 or not ld.use_flat) and gnm[1] > 0, k
+        assert st["kernel_launches"] >= 4
+        gt = ba.pose_opt_trace(0)
+        compare_traces(gt[gt[:, 0] < 4], rt[rt[:, 0] < 4])
+        g4, r4 = gt[gt[:, 0] == 4], rt[rt[:, 0] == 4]
+        assert len(g4) >= 1 and len(r4) >= 1
+        np.testing.assert_allclose(g4[0, 4], r4[0, 4], rtol=1e-9)          # cost at the float-rounded pose: no Jacobian in it
+        np.testing.assert_allclose(g4[0, 3], r4[0, 3], rtol=1e-5)          # lambda_0 = tau * max diag(H)
+        np.testing.assert_allclose(g4[0, 5], r4[0, 5], rtol=1e-6)
+        acc_g, acc_r = g4[g4[:, 7] == 1], r4[r4[:, 7] == 1]
+        np.testing.assert_allclose(acc_g[-1, 5], acc_r[-1, 5], rtol=1e-7)  # both end at the same cost
+        np.testing.assert_allclose(gp, rp, rtol=0, atol=1e-6)
+        assert np.array_equal(gf, rf) and gi == ri, k
+    # the block is off below 101 map points and below 3 observations: the call is sqrtba_pose_opt
+    (f, ld) = lidar_frames(synth)[0]
+    small = type(ld)(ld.flat_xyz, ld.flat_normal, ld.corner_xyz, ld.map_xyz[:100])
+    gp, gf, gi, gnm, st = ba.pose_opt_lidar(f[0], f[1], f[2], f[3], small)
+    pp, pf, pi, _ = ba.pose_opt([0, len(f[2])], f[0], f[1], f[2], f[3])
+    assert np.array_equal(gp, pp[0]) and np.array_equal(gf, pf) and gi == int(pi[0]) and gnm == (0, 0) and st["kernel_launches"] == 1
+    tiny = synth.frame_problem(seed=9, n_points=2)
+    gp, gf, gi, gnm, st = ba.pose_opt_lidar(tiny[0], tiny[1], tiny[2], tiny[3], ld)
+    assert gi == 0 and np.array_equal(gp, tiny[0]) and gnm == (0, 0)
+    ba.close()
+
+
+@pytest.mark.gpu
+def test_pose_optimization_with_lidar_through_reference_api(pkg, synth):
+    """Optimizer::PoseOptimization(pFrame, local_lidarmap_cloud_ptr, kdtree_local_map, lidarconfig)
+    (include/backend/Optimizer.h:58-59) on a mock Frame carrying its flat / sharp clouds: pose, mvbOutlier and the
+    returned inlier count against the oracle on what the adapter gathers."""
+    (f, ld) = lidar_frames(synth)[1]
+    pose0, cam, xyz, meas, _ = f
+    fr = pkg.host_harness.MockFrame(pose0, cam, xyz, meas)
+    T0, _ = fr.state()
+    p0 = np.concatenate([T0[:3, 3].astype(np.float64), synth.rotmat_to_quat_eigen(T0[:3, :3].astype(np.float64))])
+    rp, rf, ri, rt, rnm = refba.pose_opt_lidar(p0, cam.astype(np.float32).astype(np.float64), xyz, meas, ld)
+    inl = fr.pose_optimization_lidar(ld)
+    assert inl == ri and rnm[0] > 100
+    T, flags = fr.state()
+    assert np.array_equal(flags, rf)
+    np.testing.assert_allclose(T[:3, 3], rp[:3].astype(np.float32), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(T[:3, :3], synth.quat_to_rotmat(rp[3:]).astype(np.float32), rtol=0, atol=2e-6)
