@@ -713,20 +713,22 @@ class Solver {
     }
     persist_grid_ = std::min(n_tile, persist_ctas_);
     if (smallwin && n_win == 1 && persist_grid_ > 0) {
-      // Static tile ranges of the persistent PCG kernel, balanced by cost instead of by count: an observation whose pose
-      // lies outside the CTA's shared window of the search direction (loop-closure tracks, very wide covisibility)
-      // evaluates it from global memory and costs about twice a windowed one.
+      // Static tile ranges of the persistent PCG kernel, balanced by a cost model in SM cycles fitted to the per-CTA cycle
+      // counters of the instrumented build (tools/runs/r2_v.sh; 8-way shard of C3, C2): a tile is a latency chain, not a
+      // bandwidth item -- 2700 cycles whatever it holds, + ~80 per item (warp) and ~3 per observation; an observation
+      // whose pose lies outside the CTA's shared window of the search direction (loop-closure tracks, very wide
+      // covisibility) gathers it from global memory; a long landmark is swept by one warp.
       std::vector<double> cum(n_tile + 1, 0.0);
       for (int t = 0; t < n_tile; t++) {
         const TileInfo& ti = h_tiles_pin_.p[t];
-        double cost = 16.0 + (ti.o1 - ti.o0);
+        double cost = 2700.0 + 80.0 * ti.nitem + 3.0 * (ti.o1 - ti.o0);
         if (!pq_shared && !ti.is_long && ti.nrun > 0) {
           const int* runs = h_tile_runs_.p + h_tile_run_ptr_.p[t];
           const int lo = runs[ti.nrun + 1];
           for (int i = 0; i < ti.nrun; i++)
-            if (runs[ti.nrun + 1 + i] >= lo + persist_slots_ - 6) cost += 1.0 * (runs[i + 1] - runs[i]);
+            if (runs[ti.nrun + 1 + i] >= lo + persist_slots_ - 6) cost += 40.0 * (runs[i + 1] - runs[i]);
         }
-        if (ti.is_long) cost += 2.0 * (ti.o1 - ti.o0);
+        if (ti.is_long) cost += 60.0 * (ti.o1 - ti.o0);
         cum[t + 1] = cum[t] + cost;
       }
       std::vector<int> ptr(persist_grid_ + 1, 0);
@@ -1786,6 +1788,34 @@ class Solver {
       fprintf(stderr, "\n[persist prof] fastest:");
       for (int i = 0; i < 6; i++) { auto& x = v[i]; fprintf(stderr, " %d:%d:%.0f", x.second, ptr[x.second + 1] - ptr[x.second], x.first / (its / grid)); }
       fprintf(stderr, "\n");
+    }
+    if (const char* path = std::getenv("SQRTBA_PROF_CSV")) {  // per-CTA cycles + the features a cost model can use
+      std::vector<int> ptr(grid + 1);
+      download(ptr.data(), d_ptile_.p, ptr.size() * sizeof(int));
+      if (FILE* f = std::fopen(path, "a")) {
+        std::fprintf(f, "cta,cycles,tiles,obs,nrun,outside,slides,long_obs,items\n");
+        const bool big = max_win_slots_ > MAXSLOT;
+        for (int b = 0; b < grid; b++) {
+          long long obs = 0, nrun = 0, outside = 0, slides = 0, lobs = 0, items = 0;
+          int abase = 0;
+          for (int t = ptr[b]; t < ptr[b + 1]; t++) {
+            const TileInfo& ti = h_tiles_pin_.p[t];
+            obs += ti.o1 - ti.o0; nrun += ti.nrun; items += ti.nitem;
+            if (ti.is_long) lobs += ti.o1 - ti.o0;
+            if (big && !ti.is_long && ti.nrun > 0) {
+              const int* runs = h_tile_runs_.p + h_tile_run_ptr_.p[t];
+              const int lo = runs[ti.nrun + 1];
+              const int want = std::max(0, std::min(lo, P_.n_slot - persist_slots_));
+              if (t == ptr[b] || want < abase || want > abase + 6) { abase = want; slides++; }
+              for (int i = 0; i < ti.nrun; i++)
+                if (runs[ti.nrun + 1 + i] >= abase + persist_slots_ || runs[ti.nrun + 1 + i] < abase) outside += runs[i + 1] - runs[i];
+            }
+          }
+          std::fprintf(f, "%d,%.0f,%d,%lld,%lld,%lld,%lld,%lld,%lld\n", b, hp[(size_t)b * 16 + 3] / (its / grid), ptr[b + 1] - ptr[b], obs, nrun,
+                       outside, slides, lobs, items);
+        }
+        std::fclose(f);
+      }
     }
     cudaMemsetAsync(d_prof_.p, 0, d_prof_.cap * sizeof(long long), stream_);
 #endif
