@@ -11,8 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libsqrtba.so")
 SOURCES = [os.path.join(HERE, "csrc", "sqrtba_solver.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("sqrtba_kernels.cuh", "sqrtba_math.cuh", "sqrtba_poseopt.cuh",
-                                                            "sqrtba_lidar.cuh")] + [
+DEPS = SOURCES + sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith(".cuh")) + [
     os.path.join(HERE, "host", "host_pool.h"), os.path.join(os.path.dirname(HERE), "include", "sqrtba.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]

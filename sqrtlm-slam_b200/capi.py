@@ -31,6 +31,7 @@ class Stats(C.Structure):
         d["persistent_pcg"] = int(self.reserved[0])
         d["peer_exchange"] = int(self.reserved[1])
         d["reproducible"] = int(self.reserved[5])
+        d["chunk_precond"] = int(self.reserved[6])
         return d
 
 

@@ -2188,6 +2188,14 @@ __global__ void __maxnreg__(96) k_matvec_pipe(Dev P, const double* __restrict__ 
 //   ranks hold bit-identical q, alpha, beta and iterates.  Dot products are per-chunk partials summed in chunk order
 //   by every CTA, so they do not depend on the grid size (ranks with different shards launch different grids).
 constexpr int VSLOT = 20;  // 4 warps x 5 poses x 6 lanes
+// CHUNK (global BA, persistent kernel): the preconditioner is block-Jacobi with ONE block per chunk of VSLOT consecutive
+// pose slots (120 x 120) instead of one per pose (6 x 6): the landmarks of a big window are ordered by their first pose,
+// so most of the coupling of a pose is with its neighbours in the same chunk -- 2.2-2.4x fewer CG iterations on the
+// KITTI-shaped loop (sqrtba_chunkprec.cuh builds and inverts the blocks).  The owner CTA of a chunk keeps the inverse in
+// shared memory for the whole solve: strictly-lower triangle, packed, FP32 (28.6 KB; entrywise rounding of an SPD
+// inverse whose Jacobi-scaled condition number is a few hundred keeps it SPD), diagonal in a register.
+constexpr int CHB = VSLOT * 6;
+constexpr int CH_PACK = CHB * (CHB - 1) / 2;
 #ifndef PERSIST_REREAD
 #define PERSIST_REREAD false
 #endif
@@ -2211,6 +2219,8 @@ struct PcgArgs {
   uint4* const* peer_tbl;         // device table of the receive buffers of all ranks, peer-mapped (cudaIpc)
   unsigned long long* seq_state;  // running exchange sequence number (device resident, advanced by the kernel)
   int nelem_cap;
+  const float* cpack;             // CHUNK: [nchunk][CH_PACK] strictly-lower triangle of every chunk's inverse block (FP32)
+  const float* cdiag;             // CHUNK: [nchunk][CHB] its diagonal
 };
 
 __device__ __forceinline__ void st_volatile_v4(uint4* p, const uint4& v) {
@@ -2365,8 +2375,9 @@ __host__ __device__ inline int pipe_run_cap(int maxslot, bool big) {  // ints pe
 
 // MULTI: landmark-sharded over several GPUs (compiled separately so that the exchange code cannot disturb the register
 // allocation of the single-GPU matvec loop)
-template <int S, bool BIG, bool MULTI = false>
+template <int S, bool BIG, bool MULTI = false, bool CHUNK = false>
 __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, double lam_override, int use_override) {
+  static_assert(!CHUNK || BIG, "the chunk preconditioner belongs to the big-window path");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int STAGE_D = JQ_STAGE_D;
   constexpr int CST = CTA + 1;
@@ -2385,6 +2396,7 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
   volatile int* sig = reinterpret_cast<volatile int*>(empty + S);  // [0] approved iteration, [1] stop, [2] fills consumed
   int* runs_sh = const_cast<int*>(sig) + 4;
   const int rcap = pipe_run_cap(maxslot, BIG);
+  float* cpk_sh = reinterpret_cast<float*>(runs_sh + 2 * rcap);  // CHUNK: this CTA's chunk inverse, strictly lower, packed
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int t0 = A.tile_ptr[blockIdx.x], t1 = A.tile_ptr[blockIdx.x + 1];
   const int ntile = t1 - t0;
@@ -2453,6 +2465,13 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
 #else
 #define PROFP(i)
 #endif
+  if (CHUNK) {  // owner of a chunk: its inverse block stays in shared memory for the whole solve (the host guarantees
+                // gridDim.x >= number of chunks, so a CTA owns at most one)
+    if ((int)blockIdx.x * VSLOT < P.n_slot) {
+      const float* src = A.cpack + (size_t)blockIdx.x * CH_PACK;
+      for (int i = tid; i < CH_PACK; i += CTA) cpk_sh[i] = __ldg(src + i);
+    }
+  }
   if (!BIG) {  // replicate the CG state
     for (int e = tid; e < n6; e += CTA) {
       const int sl = e / 6;
@@ -2534,7 +2553,8 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       if ((int)blockIdx.x * VSLOT < P.n_slot && lane < 30 && slot0 < P.n_slot) {
         const int e0 = slot0 * 6 + (lane - (lane / 6) * 6);
         pf_po = P.p[e0]; pf_dq = A.dq[e0]; pf_qf = A.qf[e0]; pf_z = P.z[e0]; pf_r = P.res[e0];
-        if (!MULTI) {  // sharded: the inverse's rows are requested right before the exchange and hide behind it
+        if (CHUNK) pf_dv[0] = (double)__ldg(A.cdiag + (size_t)blockIdx.x * CHB + wid * 30 + lane);
+        else if (!MULTI) {  // sharded: the inverse's rows are requested right before the exchange and hide behind it
 #pragma unroll
           for (int k = 0; k < 6; k++) pf_dv[k] = __ldg(&P.Dinv[(size_t)e0 * 6 + k]);
         }
@@ -2668,8 +2688,10 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       }
       // this thread's row of the block-Jacobi inverse (later chunks of a CTA: requested before the exchange so that its
       // latency hides behind the NVLink round trip)
+      if (!CHUNK) {
 #pragma unroll
-      for (int k = 0; k < 6; k++) dv[k] = (first && !MULTI) ? pf_dv[k] : (ok ? __ldg(&P.Dinv[(size_t)slot * 36 + vcc * 6 + k]) : 0.0);
+        for (int k = 0; k < 6; k++) dv[k] = (first && !MULTI) ? pf_dv[k] : (ok ? __ldg(&P.Dinv[(size_t)slot * 36 + vcc * 6 + k]) : 0.0);
+      }
       PROFP(9)
       if (MULTI && ok) qv = peer_sum(A.peer_tbl, A.recv, A.nranks, A.rank, A.nelem_cap, qv, e, seq);
       PROFP(10)
@@ -2678,10 +2700,40 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
         A.qf[e] = qv;
       }
       double dq = 0.0;
+      if (CHUNK) {
+        // dq = (chunk inverse) qf: the chunk's 120 values through shared memory (the tile buffers are idle in this
+        // phase), every thread one row of the symmetric block: left of the diagonal its own packed row, below it a
+        // column walk (consecutive threads read consecutive words)
+        double* y_sh = c_sh + 16;
+        if (lane < 30) y_sh[wid * 30 + lane] = ok ? qv : 0.0;
+        named_bar_sync(1, CTA);
+        if (ok) {
+          const int r = wid * 30 + lane;
+          const float* row = cpk_sh + (r * (r - 1)) / 2;
+          double a0 = pf_dv[0] * qv, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+          int k = 0;
+          for (; k + 3 < r; k += 4) {
+            a0 += (double)row[k] * y_sh[k];
+            a1 += (double)row[k + 1] * y_sh[k + 1];
+            a2 += (double)row[k + 2] * y_sh[k + 2];
+            a3 += (double)row[k + 3] * y_sh[k + 3];
+          }
+          for (; k < r; k++) a0 += (double)row[k] * y_sh[k];
+          int idx = ((r + 1) * r) / 2 + r;  // entry (r + 1, r)
+          for (k = r + 1; k + 1 < CHB; k += 2) {
+            a1 += (double)cpk_sh[idx] * y_sh[k];
+            a2 += (double)cpk_sh[idx + k] * y_sh[k + 1];
+            idx += 2 * k + 1;
+          }
+          if (k < CHB) a3 += (double)cpk_sh[idx] * y_sh[k];
+          dq = (a0 + a1) + (a2 + a3);
+        }
+      } else {
 #pragma unroll
-      for (int k = 0; k < 6; k++) {
-        const double qk = __shfl_sync(FULL, qv, vbase + k);
-        dq += dv[k] * qk;
+        for (int k = 0; k < 6; k++) {
+          const double qk = __shfl_sync(FULL, qv, vbase + k);
+          dq += dv[k] * qk;
+        }
       }
       if (ok) A.dq[e] = dq;
       PROFP(11)

@@ -24,6 +24,7 @@
 
 #include "../../include/sqrtba.h"
 #include "sqrtba_kernels.cuh"
+#include "sqrtba_chunkprec.cuh"
 #include "sqrtba_poseopt.cuh"
 #include "sqrtba_lidar.cuh"
 #include "sqrtba_posegraph.cuh"
@@ -167,6 +168,11 @@ class Solver {
                                   (int)persist_smem_bytes(2, MAXSLOT, false)));
     CU_CHECK(cudaFuncSetAttribute(k_pcg_persist<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)persist_smem_bytes(3, MAXSLOT, false)));
+    CU_CHECK(cudaFuncSetAttribute(k_pcg_persist<2, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)persist_smem_bytes(2, 48, true, true)));
+    CU_CHECK(cudaFuncSetAttribute(k_pcg_persist<2, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)persist_smem_bytes(2, 48, true, true)));
+    CU_CHECK(cudaFuncSetAttribute(k_chunk_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_FACTOR_SMEM));
     CU_CHECK(cudaFuncSetAttribute(k_pg_factor_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU_CHECK(cudaFuncSetAttribute(k_qr_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QR_PIPE_SMEM));
     CU_CHECK(cudaFuncSetAttribute(k_qr_pipe2<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QR_PIPE2_SMEM));
@@ -708,6 +714,31 @@ class Solver {
       }
       // (4 CTAs/SM at 96 registers was measured SLOWER for the persistent kernel -- C0 5.4 vs 4.7 ms: every extra CTA adds
       // arrivals to the grid barrier, flush atomics on the q copies and a redundant vector update)
+      // Big single window (global BA): chunk preconditioner (sqrtba_chunkprec.cuh).  The owner CTA of a chunk keeps its
+      // 28.6 KB inverse block in shared memory, which leaves room for a 2-stage ring at the same residency; taken only
+      // if the residency holds and every chunk gets a CTA of its own.  pcg_mode = 5 keeps the 6x6 blocks (A/B).
+      chunk_active_ = false;
+      if (!pq_shared && n_win == 1 && n_slot > 0 && cfg_.pcg_mode != 5 && cfg_.pcg_mode != 1 && cfg_.pcg_mode != 4 &&
+          (cfg_.reserved[2] == 0 || cfg_.reserved[2] == 2)) {
+        const int nchunk = (n_slot + VSLOT - 1) / VSLOT;
+        for (int slots : {48, 40, 32}) {
+          int per_sm = 0;
+          const size_t pbytes = persist_smem_bytes(2, slots, true, true);
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist<2, true, false, true>, PIPE_THREADS, pbytes) != cudaSuccess) {
+            cudaGetLastError();
+            per_sm = 0;
+          }
+          if (std::getenv("SQRTBA_HOST_TIMING"))
+            std::fprintf(stderr, "[sqrtba host] chunk preconditioner: %zu B of shared memory at %d window slots -> %d CTAs/SM (6x6 path: %d)\n",
+                         pbytes, slots, per_sm, best);
+          if (per_sm >= best && best > 0 && std::min(n_tile, per_sm * n_sm_) >= nchunk) {
+            chunk_active_ = true;
+            persist_stages_ = 2;
+            persist_slots_ = slots;
+            break;
+          }
+        }
+      }
       if (const char* e = std::getenv("SQRTBA_PERSIST_CTAS_PER_SM")) best = std::max(1, std::min(best, std::atoi(e)));  // A/B
       persist_ctas_ = best * n_sm_;
     }
@@ -752,6 +783,13 @@ class Solver {
       CU_CHECK(d_gbar_.ensure(2));
       CU_CHECK(d_q3_.ensure((size_t)3 * KQ * 6 * std::max(n_slot, 1)));
       CU_CHECK(d_dq_.ensure((size_t)12 * std::max(n_slot, 1)));  // Dq and qf
+      if (chunk_active_ && std::min(n_tile, persist_ctas_) < nchunk) chunk_active_ = false;
+      if (chunk_active_) {
+        CU_CHECK(d_chunk_M_.ensure((size_t)nchunk * CH_MSIZE));
+        CU_CHECK(d_chunk_pack_.ensure((size_t)nchunk * CH_PACK));
+        CU_CHECK(d_chunk_diag_.ensure((size_t)nchunk * CHB));
+        CU_CHECK(d_chunk_rz_.ensure((size_t)nchunk));
+      }
       if (comm_) {
         if (int rc = peer_setup((size_t)std::max(n_slot, 1) * 6)) return rc;
       }
@@ -1827,9 +1865,28 @@ class Solver {
     return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + (big ? 6 : 15) * (size_t)maxslot) * sizeof(double) +
            2 * (2 * CTA + 4) * sizeof(int) + 2 * S * sizeof(uint64_t);
   }
-  static size_t persist_smem_bytes(int S, int maxslot, bool big) {
+  static size_t persist_smem_bytes(int S, int maxslot, bool big, bool chunk = false) {
     return ((size_t)S * JQ_STAGE_D + 12 * (CTA + 1) + 2 + (big ? 6 : 18) * (size_t)maxslot + 16) * sizeof(double) +
-           2 * S * sizeof(uint64_t) + 4 * sizeof(int) + 2 * (size_t)pipe_run_cap(maxslot, big) * sizeof(int);
+           2 * S * sizeof(uint64_t) + 4 * sizeof(int) + 2 * (size_t)pipe_run_cap(maxslot, big) * sizeof(int) +
+           (chunk ? (size_t)CH_PACK * sizeof(float) : 0);
+  }
+  // the chunk preconditioner is live for this solve: decided per problem, and only the persistent kernel applies it
+  bool chunk_on() const { return chunk_active_ && use_persist(); }
+  // off-diagonal blocks of every chunk -> [all-reduce] -> inverse + CG start vectors + r0.z0
+  int enqueue_chunk_prec() {
+    const int nchunk = (P_.n_slot + VSLOT - 1) / VSLOT;
+    CU_CHECK(cudaMemsetAsync(d_chunk_M_.p, 0, (size_t)nchunk * CH_MSIZE * sizeof(float), stream_));
+    k_chunk_blocks<<<P_.n_tile, CTA, 0, stream_>>>(P_, d_chunk_M_.p);
+    if (comm_) {  // every rank adds its landmarks' pairs; the sum is the same bits everywhere
+      const int rc = g_nccl.AllReduce(d_chunk_M_.p, d_chunk_M_.p, (size_t)nchunk * CH_MSIZE, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm_, stream_);
+      if (rc != 0) {
+        err_ = std::string("ncclAllReduce (chunk blocks) failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+        return SQRTBA_ERR_COMM;
+      }
+    }
+    k_chunk_factor<<<nchunk, CH_FACTOR_THREADS, CH_FACTOR_SMEM, stream_>>>(P_, d_chunk_M_.p, d_chunk_pack_.p, d_chunk_diag_.p, d_chunk_rz_.p);
+    k_chunk_rz<<<1, 32, 0, stream_>>>(P_, d_chunk_rz_.p, nchunk);
+    return SQRTBA_OK;
   }
   void launch_linearize(int robust, double d2, double d3, int force_all) {
     if (cfg_.reserved[7] == 1) k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
@@ -1911,11 +1968,15 @@ class Solver {
     const bool big = !P_.pq_shared;
     const int grid = persist_grid_;
     A.tile_ptr = d_ptile_.p;
-    const size_t bytes = persist_smem_bytes(persist_stages_, persist_slots_, big);
+    const bool chunk = big && chunk_on();
+    A.cpack = chunk ? d_chunk_pack_.p : nullptr;
+    A.cdiag = chunk ? d_chunk_diag_.p : nullptr;
+    const size_t bytes = persist_smem_bytes(persist_stages_, persist_slots_, big, chunk);
     int maxslot = persist_slots_;
     void* args[] = {(void*)&P_, (void*)&A, (void*)&maxslot, (void*)&lam_override, (void*)&use_override};
     const bool multi = A.nranks > 1;  // use_persist() admits several ranks only for big windows
-    const void* fn = big ? (multi ? (persist_stages_ == 2 ? (const void*)k_pcg_persist<2, true, true> : (const void*)k_pcg_persist<3, true, true>)
+    const void* fn = chunk ? (multi ? (const void*)k_pcg_persist<2, true, true, true> : (const void*)k_pcg_persist<2, true, false, true>)
+                     : big ? (multi ? (persist_stages_ == 2 ? (const void*)k_pcg_persist<2, true, true> : (const void*)k_pcg_persist<3, true, true>)
                                   : (persist_stages_ == 2 ? (const void*)k_pcg_persist<2, true> : (const void*)k_pcg_persist<3, true>))
                          : (persist_stages_ == 2 ? (const void*)k_pcg_persist<2, false> : (const void*)k_pcg_persist<3, false>);
     CU_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PIPE_THREADS), args, bytes, stream_));
@@ -2016,6 +2077,10 @@ class Solver {
     CU_CHECK(cudaMemsetAsync(P_.counters + 1, 0, sizeof(int), stream_));
     k_cg_init<<<P_.n_win, RCTA, 0, stream_>>>(P_, 0);
     launches_ += 2;
+    if (chunk_on()) {
+      if (int rc = enqueue_chunk_prec()) return rc;
+      launches_ += 3;
+    }
     const double tol2 = cfg_.pcg_rtol * cfg_.pcg_rtol;
     const int check = std::max(1, cfg_.pcg_check_every);
     const size_t qbytes = (size_t)P_.n_slot * 6 * sizeof(double);
@@ -2075,6 +2140,9 @@ class Solver {
     launch_qr(0, 0.0);
     if (P_.pq_shared) k_cg_prep<<<1, RCTA, 0, stream_>>>(P_, d_q3_.p, 3 * KQ * n6, nullptr, 0, d_gbar_.p);
     else k_cg_prep<<<1, RCTA, 0, stream_>>>(P_, P_.q, n6, d_dq_.p, 2 * n6, d_gbar_.p);
+    if (chunk_on()) {
+      if (int rc = enqueue_chunk_prec()) return rc;
+    }
     const double tol2 = cfg_.pcg_rtol * cfg_.pcg_rtol;
     if (int rc = launch_pcg_persist(tol2, 0, 0.0)) return rc;
     k_backsub<<<P_.n_tile, CTA, 0, stream_>>>(P_, 0, 0.0);
@@ -2149,7 +2217,7 @@ class Solver {
         }
         __builtin_ia32_pause();
       }
-      launches_ += STEP_NODES;
+      launches_ += STEP_NODES + (chunk_on() ? 3 : 0);
       lm_trials_++;
       cg_iters_total_ = h_ctl_->counters[2];
       if (h_ctl_->counters[0] >= P_.n_win) break;
@@ -2268,6 +2336,7 @@ class Solver {
       st->reserved[0] = use_persist() ? 1.0 : 0.0;           // the PCG solves ran in the persistent cooperative kernel
       st->reserved[1] = (comm_ && peer_ok_) ? 1.0 : 0.0;     // landmark-sharded: in-kernel NVLink exchange available
       st->reserved[2] = persist_grid_;
+      st->reserved[6] = chunk_on() ? 1.0 : 0.0;              // big window: the 20-pose chunk preconditioner was active
       st->reserved[5] = det_active_ ? 1.0 : 0.0;             // reproducible mode active (pcg_mode = 4 and the problem qualifies)
     }
     return SQRTBA_OK;
@@ -2285,6 +2354,7 @@ class Solver {
     d_tiles_.release(); d_obs_lp_.release(); d_tile_run_ptr_.release(); d_tile_runs_.release();
     d_win_tile_ptr_.release(); d_part_lin_.release(); d_part_qr_.release(); d_part_q_.release();
     d_gbar_.release(); d_part_.release(); d_q3_.release(); d_dq_.release(); d_ptile_.release();
+    d_chunk_M_.release(); d_chunk_rz_.release(); d_chunk_pack_.release(); d_chunk_diag_.release();
     d_l_pc_.release(); d_l_qw_.release(); d_l_nv_.release(); d_l_w_.release(); d_l_acc_.release(); d_l_match_.release();
     d_lm_flat_pose_.release(); d_lm_corner_pose_.release(); d_lc_flat_.release(); d_lc_normal_.release(); d_lc_corner_.release();
     d_lc_world_.release(); d_lm_flat_.release(); d_lm_flat_w_.release(); d_lm_corner_.release(); d_lm_corner_w_.release(); d_l_best_.release();
@@ -2342,6 +2412,9 @@ class Solver {
   size_t peer_nelem_cap_ = 0;
   DBuf<unsigned> d_gbar_;
   DBuf<double> d_part_, d_q3_, d_dq_;
+  bool chunk_active_ = false;  // big single window: 20-pose blocks as the PCG preconditioner (sqrtba_chunkprec.cuh)
+  DBuf<double> d_chunk_rz_;
+  DBuf<float> d_chunk_M_, d_chunk_pack_, d_chunk_diag_;
   // lidar pass
   LidarDev lidar_{};
   LidarAssoc assoc_{};

@@ -43,7 +43,7 @@ def main():
     dist.all_gather_object(parts, (tr, poses, pts))
     ok = True
     out = {"n_gpus": world, "n_pose": prob.n_pose, "n_obs": prob.n_obs, "persistent_pcg": st["persistent_pcg"],
-           "peer_exchange": st["peer_exchange"], "lm_trials": len(tr)}
+           "peer_exchange": st["peer_exchange"], "chunk_precond": st["chunk_precond"], "lm_trials": len(tr)}
     if rank == 0:
         from oracle import refba
         from test_gpu_parity import COST_RTOL, POSE_R_RMS, POSE_T_RMS, pose_rms

@@ -41,3 +41,4 @@ def test_sharded_global_ba_matches_oracle(robust):
     nproc = 2 if n < 4 else 4
     out = _run(nproc, ["--scale", "0.3", "--kf", "450", "--robust", str(robust), "--iters", "10"])
     assert out["n_gpus"] == nproc and out["persistent_pcg"] == 1 and out["peer_exchange"] == 1
+    assert out["chunk_precond"] == 1  # the sharded PCG runs with the 20-pose chunk preconditioner (all-reduced blocks)

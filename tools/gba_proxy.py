@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--kf", type=int, default=1500)
     ap.add_argument("--max-cg", type=int, default=300)
+    ap.add_argument("--pcg-mode", type=int, default=0, help="5 = 6x6 block-Jacobi instead of the chunk preconditioner (A/B)")
     args = ap.parse_args()
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -38,7 +39,7 @@ def main():
     pkg = load_pkg()
     prob = pkg.synth.config_c3(0, scale=args.scale, n_kf=args.kf)
     shard, _, _ = pkg.multi.shard_by_landmark(prob, rank, args.nshards)
-    ba = pkg.SqrtBA(device=local, pcg_max_iters=args.max_cg, stage_timing=True)
+    ba = pkg.SqrtBA(device=local, pcg_max_iters=args.max_cg, stage_timing=True, pcg_mode=args.pcg_mode)
     if world > 1:
         pkg.multi.init_comm(ba, rank, world)
     ba.set_problem(shard)

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--robust", type=int, default=0)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--skip-single", action="store_true")
+    ap.add_argument("--pcg-mode", type=int, default=0, help="5 = 6x6 block-Jacobi instead of the chunk preconditioner (A/B)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -38,7 +39,7 @@ def main():
     pkg = load_pkg()
     prob = pkg.synth.config_c3(0, scale=args.scale, n_kf=args.kf)   # same seed on every rank => identical problem
     shard, (l0, l1), _ = pkg.multi.shard_by_landmark(prob, rank, world)
-    ba = pkg.SqrtBA(device=local)
+    ba = pkg.SqrtBA(device=local, pcg_mode=args.pcg_mode)
     if world > 1:
         pkg.multi.init_comm(ba, rank, world)
     ba.set_problem(shard)
@@ -70,7 +71,7 @@ def main():
     else:
         pts_all = pts
     if rank == 0 and not args.skip_single and world > 1:
-        single = pkg.SqrtBA(device=local)
+        single = pkg.SqrtBA(device=local, pcg_mode=args.pcg_mode)
         single.set_problem(prob)
         single.solve_global(args.iters, bool(args.robust))
         ts = single.trace()
