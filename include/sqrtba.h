@@ -61,7 +61,9 @@ typedef struct {
                                 landmark with more than 32 observations, one GPU; otherwise the default path runs and
                                 stats.reserved[5] says 0;
                                 5 = like 0, but a big single window (global BA, more than 128 free poses) keeps the 6x6
-                                block-Jacobi preconditioner instead of the 20-pose chunk blocks (A/B; stats.reserved[6]) */
+                                block-Jacobi preconditioner instead of the 20-pose chunk blocks (A/B; stats.reserved[6]);
+                                6 = like 0, but the big-window preconditioner keeps its chunk level only, without the
+                                coarse correction over the chunks (A/B; stats.reserved[7]) */
   int32_t pcg_check_every;   /* multi-launch mode: host polls the convergence counter every N iterations */
   int32_t reserved[8];       /* tuning / A-B knobs, all 0 by default:
                                 [0] record per-stage CUDA-event times (stats.ms_linearize ...)
@@ -103,7 +105,8 @@ typedef struct {
   double reserved[8];       /* [0] 1 = the persistent PCG kernel ran, [1] 1 = in-kernel NVLink exchange was active,
                                [2] grid of the persistent kernel, [5] 1 = reproducible mode (pcg_mode 4) was active,
                                [6] 1 = global BA ran PCG with the chunk preconditioner (one 120x120 block of the reduced
-                               system per 20 consecutive keyframes; the persistent kernel's default for big windows) */
+                               system per 20 consecutive keyframes; the persistent kernel's default for big windows),
+                               [7] 1 = ... plus the additive coarse correction Z (Z^T S Z)^-1 Z^T over the chunks */
 } sqrtba_stats;
 
 int sqrtba_default_config(sqrtba_config* cfg);

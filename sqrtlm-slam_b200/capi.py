@@ -32,6 +32,7 @@ class Stats(C.Structure):
         d["peer_exchange"] = int(self.reserved[1])
         d["reproducible"] = int(self.reserved[5])
         d["chunk_precond"] = int(self.reserved[6])
+        d["coarse_level"] = int(self.reserved[7])
         return d
 
 

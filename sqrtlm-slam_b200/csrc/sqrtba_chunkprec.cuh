@@ -35,7 +35,7 @@ constexpr size_t CH_MSIZE = (size_t)VSLOT * VSLOT * CH_MBLK;  // floats per chun
 // in FP32 with vector reductions (REDG.ADD.F32x4: nine per pair instead of 36 scalar FP64 ones -- the kernel is bound by
 // the L2 atomic units); FP32 is what the PCG kernel keeps of the inverse anyway, and k_chunk_factor falls back to the 6x6
 // blocks should a chunk ever lose definiteness.
-__global__ void __launch_bounds__(CTA) k_chunk_blocks(Dev P, float* __restrict__ M) {
+__global__ void __launch_bounds__(CTA) k_chunk_blocks(Dev P, float* __restrict__ M, float* __restrict__ Cacc, int nchunk) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const TileInfo ti = P.tiles[blockIdx.x];
   if (ti.is_long || wid >= ti.nitem) return;
@@ -69,30 +69,70 @@ __global__ void __launch_bounds__(CTA) k_chunk_blocks(Dev P, float* __restrict__
   int maxlen = act ? sg.end - sg.start : 0;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL, maxlen, off));
+  // cross-chunk pairs towards the NEXT chunk (nearly all of them: the observations of a landmark follow the keyframe
+  // order) are first summed per lane, then per warp and chunk: the few blocks of the coarse matrix are hot addresses,
+  // and the L2 serialises reductions on one address (~30 cycles each)
+  float cn[36];
+#pragma unroll
+  for (int i = 0; i < 36; i++) cn[i] = 0.f;
+  bool has_cn = false;
   for (int d = 1; d < maxlen; d++) {
     const int sj = __shfl_down_sync(FULL, live ? slot : -1, d);
     float Gj[18];
 #pragma unroll
     for (int i = 0; i < 18; i++) Gj[i] = __shfl_down_sync(FULL, G[i], d);
-    const bool valid = live && lane + d < sg.end && sj >= 0 && sj != slot && sj / VSLOT == ch;
+    const bool pair = live && lane + d < sg.end && sj >= 0 && sj != slot;
+    const int chj = pair ? sj / VSLOT : -1;
+    const bool valid = pair && (chj == ch || Cacc != nullptr);
     if (valid) {
-      float4* blk = reinterpret_cast<float4*>(M + (size_t)ch * CH_MSIZE +
-                                              ((size_t)(slot - ch * VSLOT) * VSLOT + (sj - ch * VSLOT)) * CH_MBLK);
       float v[36];
 #pragma unroll
       for (int a = 0; a < 6; a++)
 #pragma unroll
         for (int b = 0; b < 6; b++)
           v[a * 6 + b] = -(G[a * 3] * Gj[b * 3] + G[a * 3 + 1] * Gj[b * 3 + 1] + G[a * 3 + 2] * Gj[b * 3 + 2]);
+      if (chj == ch + 1) {
 #pragma unroll
-      for (int q = 0; q < 9; q++) atomicAdd(blk + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        for (int i = 0; i < 36; i++) cn[i] += v[i];
+        has_cn = true;
+      } else {
+        // same chunk: the pair's 6x6 block of the chunk matrix; another chunk (loop closure, reversed order): its share
+        // of block (chunk_i, chunk_j) of the coarse matrix Z^T S Z
+        float4* blk = (chj == ch) ? reinterpret_cast<float4*>(M + (size_t)ch * CH_MSIZE +
+                                                              ((size_t)(slot - ch * VSLOT) * VSLOT + (sj - ch * VSLOT)) * CH_MBLK)
+                                  : reinterpret_cast<float4*>(Cacc + ((size_t)ch * nchunk + chj) * CH_MBLK);
+#pragma unroll
+        for (int q = 0; q < 9; q++) atomicAdd(blk + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+      }
+    }
+  }
+  if (Cacc != nullptr) {
+    unsigned todo = __ballot_sync(FULL, has_cn);
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int key = __shfl_sync(FULL, ch, leader);
+      const bool mine = has_cn && ch == key;
+      todo &= ~__ballot_sync(FULL, mine);
+#pragma unroll
+      for (int i = 0; i < 36; i++) {
+        float t = mine ? cn[i] : 0.f;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(FULL, t, off);
+        if (lane == leader) cn[i] = t;
+      }
+      if (lane == leader) {
+        float4* blk = reinterpret_cast<float4*>(Cacc + ((size_t)key * nchunk + key + 1) * CH_MBLK);
+#pragma unroll
+        for (int q = 0; q < 9; q++) atomicAdd(blk + q, make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]));
+      }
     }
   }
 }
 
 // One CTA per chunk.  rzpart[chunk] = this chunk's part of r0.z0.
 __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const float* __restrict__ M, float* __restrict__ cpack,
-                                                                    float* __restrict__ cdiag, double* __restrict__ rzpart) {
+                                                                    float* __restrict__ cdiag, double* __restrict__ rzpart,
+                                                                    double* __restrict__ dblk, unsigned* __restrict__ co_ctl) {
   extern __shared__ __align__(16) double ch_sm[];
   double* A = ch_sm;                   // [CHB][CH_LDA]
   double* colk = A + CHB * CH_LDA;     // pivot column of the current step
@@ -127,6 +167,15 @@ __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const
     }
   }
   for (int i = tid; i < n; i += CH_FACTOR_THREADS) vec[i] = P.bs[(size_t)s0 * 6 + i];
+  if (co_ctl && ch == 0 && tid < 2) co_ctl[tid] = 0u;  // grid-barrier counter and failure flag of k_coarse_invert
+  __syncthreads();
+  if (dblk && tid < 36) {  // Z^T (chunk matrix) Z: the 6x6 sum of all its 6x6 blocks, in a fixed order
+    const int a = tid / 6, b = tid - a * 6;
+    double sum = 0.0;
+    for (int bi = 0; bi < ns; bi++)
+      for (int bj = 0; bj < ns; bj++) sum += A[(bi * 6 + a) * CH_LDA + bj * 6 + b];
+    dblk[(size_t)ch * 36 + tid] = sum;
+  }
   __syncthreads();
   // in-place Gauss-Jordan inversion; the pivots of an SPD matrix are positive
   for (int k = 0; k < n; k++) {
@@ -201,6 +250,161 @@ __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const
     for (int i = 0; i < CH_FACTOR_THREADS / 32; i++) t += colk[i];  // fixed order
     rzpart[ch] = t;
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------- second level (coarse)
+// Block-Jacobi over chunks leaves the coupling BETWEEN chunks -- the smooth, loop-wide error modes -- to CG, and those
+// are exactly what a 1500-keyframe loop converges slowly on.  The second level is the classical additive coarse
+// correction  M^-1 = blockdiag(chunk inverses) + Z (Z^T S Z)^-1 Z^T  with Z = one column per (chunk, tangent component):
+// 6 nchunk unknowns (450 on C3).  Z^T S Z is assembled from sums that are already there: its diagonal blocks are the
+// 6x6 block sums of the chunk matrices (k_chunk_factor), block (c, c') the sum of the cross-chunk pair blocks
+// (k_chunk_blocks).  Measured on the KITTI-shaped loop at small lambda: another 3.7x fewer iterations on top of the chunks.
+constexpr int CO_MAXCH = 128;              // chunks (2560 free poses); beyond that only the chunk level is used
+constexpr int CO_LD = CO_MAXCH * 6;
+constexpr int CO_THREADS = 128;
+
+// Cooperative launch, one CTA per chunk = one 6-row block row of the coarse matrix in shared memory.  Block Gauss-Jordan
+// with 6x6 pivots: at step k the owner of row k inverts its pivot block and publishes R = P^-1 row_k; after a grid
+// barrier every other row eliminates its block column k.  nchunk barriers in all.
+__global__ void __launch_bounds__(CO_THREADS) k_coarse_invert(Dev P, const float* __restrict__ Cacc, const double* __restrict__ dblk,
+                                                              double* __restrict__ Rbuf, double* __restrict__ aci,
+                                                              unsigned* __restrict__ co_ctl, int nchunk) {
+  __shared__ double row[6][CO_LD];
+  __shared__ double Pm[36], Pinv[36], Cc[36];
+  __shared__ int bad;
+  const int tid = threadIdx.x, c = blockIdx.x;
+  if (P.ctl[0].phase != PH_TRIAL) return;  // grid-uniform
+  const int nc6 = nchunk * 6;
+  for (int k = tid; k < nc6; k += CO_THREADS) {
+    const int c2 = k / 6, b = k - c2 * 6;
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+      row[a][k] = (c2 == c) ? dblk[(size_t)c * 36 + a * 6 + b]
+                            : (double)Cacc[((size_t)c * nchunk + c2) * CH_MBLK + a * 6 + b] +
+                                  (double)Cacc[((size_t)c2 * nchunk + c) * CH_MBLK + b * 6 + a];
+  }
+  __syncthreads();
+  for (int kb = 0; kb < nchunk; kb++) {
+    double* R = Rbuf + (size_t)(kb & 1) * (6 * CO_LD + 36);
+    if (c == kb) {
+      if (tid < 36) Pm[tid] = row[tid / 6][kb * 6 + (tid % 6)];
+      if (tid == 0) bad = 0;
+      __syncthreads();
+      if (tid < 32) {  // 6x6 Gauss-Jordan by one warp: lane = entry (and entry + 32 for the first four lanes)
+        for (int k = 0; k < 6; k++) {
+          const double piv = Pm[k * 6 + k];
+          if (!(piv > 0.0) || !isfinite(piv)) { if (tid == 0) bad = 1; break; }
+          const double pinv = 1.0 / piv;
+          double nv[2];
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int en = tid + 32 * h;
+            nv[h] = 0.0;
+            if (en < 36) {
+              const int i = en / 6, j = en - i * 6;
+              if (i == k) nv[h] = (j == k) ? pinv : Pm[k * 6 + j] * pinv;
+              else if (j == k) nv[h] = -Pm[i * 6 + k] * pinv;
+              else nv[h] = Pm[en] - Pm[i * 6 + k] * Pm[k * 6 + j] * pinv;
+            }
+          }
+          __syncwarp();
+          Pm[tid] = nv[0];
+          if (tid < 4) Pm[tid + 32] = nv[1];
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      if (tid < 36) Pinv[tid] = bad ? 0.0 : Pm[tid];
+      if (bad && tid == 0) atomicExch(&co_ctl[1], 1u);
+      __syncthreads();
+      for (int k = tid; k < nc6; k += CO_THREADS) {
+        double rk[6];
+        const bool pc = k >= kb * 6 && k < kb * 6 + 6;
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+          double v = 0.0;
+          if (pc) v = Pinv[a * 6 + (k - kb * 6)];
+          else {
+#pragma unroll
+            for (int q = 0; q < 6; q++) v += Pinv[a * 6 + q] * row[q][k];
+          }
+          rk[a] = v;
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) { row[a][k] = rk[a]; R[(size_t)a * CO_LD + k] = rk[a]; }
+      }
+      if (tid < 36) R[6 * CO_LD + tid] = Pinv[tid];
+    }
+    grid_bar(co_ctl, gridDim.x, (unsigned)(kb + 1), tid);  // CO_THREADS == CTA: the same named barrier
+    if (c != kb) {
+      if (tid < 36) { Cc[tid] = row[tid / 6][kb * 6 + (tid % 6)]; Pinv[tid] = __ldcg(R + 6 * CO_LD + tid); }
+      __syncthreads();
+      for (int k = tid; k < nc6; k += CO_THREADS) {
+        const bool pc = k >= kb * 6 && k < kb * 6 + 6;
+        double rk[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) rk[q] = pc ? Pinv[q * 6 + (k - kb * 6)] : __ldcg(R + (size_t)q * CO_LD + k);
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+          double v = pc ? 0.0 : row[a][k];
+#pragma unroll
+          for (int q = 0; q < 6; q++) v -= Cc[a * 6 + q] * rk[q];
+          row[a][k] = v;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const bool failed = __ldcg(&co_ctl[1]) != 0u;  // written before some barrier every CTA has passed
+  for (int k = tid; k < nc6; k += CO_THREADS) {
+#pragma unroll
+    for (int a = 0; a < 6; a++) aci[(size_t)(c * 6 + a) * nc6 + k] = failed ? 0.0 : row[a][k];
+  }
+}
+
+// CG start with both levels: z0 = p0 = (chunk part, written by k_chunk_factor) + Z (Z^T S Z)^-1 Z^T b_s; r0.z0 per chunk
+__global__ void __launch_bounds__(CO_THREADS) k_chunk_z0(Dev P, const double* __restrict__ aci, double* __restrict__ rzpart, int nchunk) {
+  __shared__ double w[CO_LD];
+  __shared__ double ysh[4][6];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, ch = blockIdx.x;
+  if (P.ctl[0].phase != PH_TRIAL) return;
+  const int nc6 = nchunk * 6;
+  for (int k = tid; k < nc6; k += CO_THREADS) {
+    const int c2 = k / 6, a = k - c2 * 6;
+    const int ns = min(VSLOT, P.n_slot - c2 * VSLOT);
+    double sum = 0.0;
+    for (int sl = 0; sl < ns; sl++) sum += P.bs[(size_t)(c2 * VSLOT + sl) * 6 + a];
+    w[k] = sum;
+  }
+  __syncthreads();
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = tid; k < nc6; k += CO_THREADS) {
+#pragma unroll
+    for (int a = 0; a < 6; a++) acc[a] += aci[(size_t)(ch * 6 + a) * nc6 + k] * w[k];
+  }
+#pragma unroll
+  for (int a = 0; a < 6; a++) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc[a] += __shfl_down_sync(FULL, acc[a], off);
+    if (lane == 0) ysh[wid][a] = acc[a];
+  }
+  __syncthreads();
+  const int n = min(VSLOT, P.n_slot - ch * VSLOT) * 6;
+  double part = 0.0;
+  if (tid < n) {
+    const int a = tid % 6;
+    const size_t e = (size_t)ch * CHB + tid;
+    const double z = P.z[e] + ((ysh[0][a] + ysh[1][a]) + (ysh[2][a] + ysh[3][a]));
+    P.z[e] = z;
+    P.p[e] = z;
+    part = P.bs[e] * z;
+  }
+  part = warp_sum(part);
+  __syncthreads();
+  if (lane == 0) w[wid] = part;
+  __syncthreads();
+  if (tid == 0) rzpart[ch] = (w[0] + w[1]) + (w[2] + w[3]);
 }
 
 // r0.z0 of the chunk-preconditioned start, summed in chunk order; replaces what k_cg_init / k_cg_prep left in the

@@ -2221,6 +2221,9 @@ struct PcgArgs {
   int nelem_cap;
   const float* cpack;             // CHUNK: [nchunk][CH_PACK] strictly-lower triangle of every chunk's inverse block (FP32)
   const float* cdiag;             // CHUNK: [nchunk][CHB] its diagonal
+  const double* aci;              // CHUNK, optional: inverse of the coarse matrix Z^T S Z, [6 nchunk][6 nchunk] (Z = one
+                                  // column per chunk and tangent component: the second level of the preconditioner)
+  double* wvec;                   // CHUNK + coarse: Z^T qf of the current iteration, [6 nchunk]
 };
 
 __device__ __forceinline__ void st_volatile_v4(uint4* p, const uint4& v) {
@@ -2560,7 +2563,9 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
         }
       }
     }
-    grid_bar(A.gbar, gridDim.x, (unsigned)(BIG ? 2 * it + 1 : it + 1), tid);  // B1: q complete
+    const bool coarse = CHUNK && A.aci != nullptr;  // grid-uniform
+    const int nbar = BIG ? (coarse ? 3 : 2) : 1;     // grid barriers per iteration
+    grid_bar(A.gbar, gridDim.x, (unsigned)(nbar * it + 1), tid);  // B1: q complete
     PROFP(0)
     const double lam = st_sh[2], rz0 = st_sh[1];
     double rz = st_sh[0];
@@ -2667,6 +2672,30 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
     const int vsl = wid * 5 + lane / 6, vcc = lane - (lane / 6) * 6;
     const int vbase = min((lane / 6) * 6, 24);
     exch_out = it + 1;
+    // partial dot products of one chunk: r.z, p.qf, qf.z, qf.Dq -> A.part[chunk]
+    auto chunk_dots = [&](int ch, double rv, double zv, double pv, double qv, double dq) {
+      double d0 = rv * zv, d1 = pv * qv, d2 = qv * zv, d3 = qv * dq;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        d0 += __shfl_down_sync(FULL, d0, off);
+        d1 += __shfl_down_sync(FULL, d1, off);
+        d2 += __shfl_down_sync(FULL, d2, off);
+        d3 += __shfl_down_sync(FULL, d3, off);
+      }
+      PROFP(6)
+      named_bar_sync(1, CTA);  // scratch free (previous chunk's partials consumed)
+      PROFP(8)
+      if (lane == 0) { red_sh[wid] = d0; red_sh[4 + wid] = d1; c_sh[wid] = d2; c_sh[4 + wid] = d3; }
+      named_bar_sync(1, CTA);
+      if (tid < 4) {
+        const double* src = (tid < 2) ? red_sh + tid * 4 : c_sh + (tid - 2) * 4;
+        A.part[(size_t)ch * 4 + tid] = (src[0] + src[1]) + (src[2] + src[3]);
+      }
+    };
+    // two-level preconditioner: the owner's state between the chunk-local and the coarse part (one chunk per CTA)
+    bool co_ok = false;
+    int co_e = 0;
+    double co_qv = 0.0, co_pv = 0.0, co_zv = 0.0, co_rv = 0.0, co_dq = 0.0;
     for (int ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
       const int slot = ch * VSLOT + vsl;
       const bool ok = lane < 30 && slot < P.n_slot;
@@ -2735,28 +2764,54 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
           dq += dv[k] * qk;
         }
       }
+      if (coarse) {
+        // second level: publish Z^T qf of this chunk (the chunk's qf is in y_sh), finish after the extra grid barrier
+        if (tid < 6) {
+          const double* y_sh = c_sh + 16;
+          double w = 0.0;
+#pragma unroll
+          for (int sl = 0; sl < VSLOT; sl++) w += y_sh[sl * 6 + tid];
+          A.wvec[(size_t)ch * 6 + tid] = w;
+        }
+        co_ok = ok; co_e = e; co_qv = qv; co_pv = pv; co_zv = zv; co_rv = rv; co_dq = dq;
+        break;  // CHUNK: at most one chunk per CTA
+      }
       if (ok) A.dq[e] = dq;
       PROFP(11)
-      double d0 = rv * zv, d1 = pv * qv, d2 = qv * zv, d3 = qv * dq;
+      chunk_dots(ch, rv, zv, pv, qv, dq);
+    }
+    if (coarse) {
+      grid_bar(A.gbar, gridDim.x, (unsigned)(nbar * it + 2), tid);  // Bx: Z^T qf complete
+      const int ch = blockIdx.x;
+      if (ch < nchunk) {
+        // y = rows [6 ch, 6 ch + 6) of (Z^T S Z)^-1 times Z^T qf; every element of the chunk gets its component of y
+        const int nc6 = nchunk * 6;
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        const double* arow = A.aci + (size_t)ch * 6 * nc6;
+        for (int k = tid; k < nc6; k += CTA) {
+          const double wk = __ldcg(&A.wvec[k]);
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        d0 += __shfl_down_sync(FULL, d0, off);
-        d1 += __shfl_down_sync(FULL, d1, off);
-        d2 += __shfl_down_sync(FULL, d2, off);
-        d3 += __shfl_down_sync(FULL, d3, off);
-      }
-      PROFP(6)
-      named_bar_sync(1, CTA);  // scratch free (previous chunk's partials consumed)
-      PROFP(8)
-      if (lane == 0) { red_sh[wid] = d0; red_sh[4 + wid] = d1; c_sh[wid] = d2; c_sh[4 + wid] = d3; }
-      named_bar_sync(1, CTA);
-      if (tid < 4) {
-        const double* src = (tid < 2) ? red_sh + tid * 4 : c_sh + (tid - 2) * 4;
-        A.part[(size_t)ch * 4 + tid] = (src[0] + src[1]) + (src[2] + src[3]);
+          for (int a = 0; a < 6; a++) acc[a] += __ldg(arow + (size_t)a * nc6 + k) * wk;
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) acc[a] += __shfl_down_sync(FULL, acc[a], off);
+        }
+        double* yc_sh = c_sh + 16 + CHB;  // [4 warps][6]
+        if (lane == 0) {
+#pragma unroll
+          for (int a = 0; a < 6; a++) yc_sh[wid * 6 + a] = acc[a];
+        }
+        named_bar_sync(1, CTA);
+        const double yc = (yc_sh[vcc] + yc_sh[6 + vcc]) + (yc_sh[12 + vcc] + yc_sh[18 + vcc]);
+        const double dq = co_dq + yc;
+        if (co_ok) A.dq[co_e] = dq;
+        chunk_dots(ch, co_rv, co_zv, co_pv, co_qv, co_ok ? dq : 0.0);
       }
     }
     PROFP(1)
-    grid_bar(A.gbar, gridDim.x, (unsigned)(2 * it + 2), tid);  // B2: state of this iterate and the partial dot products complete
+    grid_bar(A.gbar, gridDim.x, (unsigned)(nbar * it + nbar), tid);  // B2: state of this iterate and the partial dot products complete
     PROFP(2)
     if (wid == 0) {  // one warp per CTA reads the partials (every CTA reads the same few lines)
       // three records per lane in flight at a time (96 chunks = 1920 poses per L2 round trip instead of one round trip

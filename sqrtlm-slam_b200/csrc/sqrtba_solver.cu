@@ -784,8 +784,17 @@ class Solver {
       CU_CHECK(d_q3_.ensure((size_t)3 * KQ * 6 * std::max(n_slot, 1)));
       CU_CHECK(d_dq_.ensure((size_t)12 * std::max(n_slot, 1)));  // Dq and qf
       if (chunk_active_ && std::min(n_tile, persist_ctas_) < nchunk) chunk_active_ = false;
+      // second level (coarse correction over the chunks): pcg_mode = 6 keeps the chunk level only (A/B)
+      coarse_active_ = chunk_active_ && nchunk >= 2 && nchunk <= CO_MAXCH && cfg_.pcg_mode != 6 && nchunk <= n_sm_;
       if (chunk_active_) {
-        CU_CHECK(d_chunk_M_.ensure((size_t)nchunk * CH_MSIZE));
+        CU_CHECK(d_chunk_M_.ensure((size_t)nchunk * CH_MSIZE + (coarse_active_ ? (size_t)nchunk * nchunk * CH_MBLK : 0)));
+        if (coarse_active_) {
+          CU_CHECK(d_co_dblk_.ensure((size_t)nchunk * 36));
+          CU_CHECK(d_co_R_.ensure((size_t)2 * (6 * CO_LD + 36)));
+          CU_CHECK(d_co_aci_.ensure((size_t)36 * nchunk * nchunk));
+          CU_CHECK(d_co_w_.ensure((size_t)6 * nchunk));
+          CU_CHECK(d_co_ctl_.ensure(2));
+        }
         CU_CHECK(d_chunk_pack_.ensure((size_t)nchunk * CH_PACK));
         CU_CHECK(d_chunk_diag_.ensure((size_t)nchunk * CHB));
         CU_CHECK(d_chunk_rz_.ensure((size_t)nchunk));
@@ -1874,20 +1883,35 @@ class Solver {
   bool chunk_on() const { return chunk_active_ && use_persist(); }
   // off-diagonal blocks of every chunk -> [all-reduce] -> inverse + CG start vectors + r0.z0
   int enqueue_chunk_prec() {
-    const int nchunk = (P_.n_slot + VSLOT - 1) / VSLOT;
-    CU_CHECK(cudaMemsetAsync(d_chunk_M_.p, 0, (size_t)nchunk * CH_MSIZE * sizeof(float), stream_));
-    k_chunk_blocks<<<P_.n_tile, CTA, 0, stream_>>>(P_, d_chunk_M_.p);
+    int nchunk = (P_.n_slot + VSLOT - 1) / VSLOT;
+    const size_t m_floats = (size_t)nchunk * CH_MSIZE, c_floats = coarse_active_ ? (size_t)nchunk * nchunk * CH_MBLK : 0;
+    float* cacc = coarse_active_ ? d_chunk_M_.p + m_floats : nullptr;
+    CU_CHECK(cudaMemsetAsync(d_chunk_M_.p, 0, (m_floats + c_floats) * sizeof(float), stream_));
+    k_chunk_blocks<<<P_.n_tile, CTA, 0, stream_>>>(P_, d_chunk_M_.p, cacc, nchunk);
     if (comm_) {  // every rank adds its landmarks' pairs; the sum is the same bits everywhere
-      const int rc = g_nccl.AllReduce(d_chunk_M_.p, d_chunk_M_.p, (size_t)nchunk * CH_MSIZE, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm_, stream_);
+      const int rc = g_nccl.AllReduce(d_chunk_M_.p, d_chunk_M_.p, m_floats + c_floats, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm_, stream_);
       if (rc != 0) {
         err_ = std::string("ncclAllReduce (chunk blocks) failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
         return SQRTBA_ERR_COMM;
       }
     }
-    k_chunk_factor<<<nchunk, CH_FACTOR_THREADS, CH_FACTOR_SMEM, stream_>>>(P_, d_chunk_M_.p, d_chunk_pack_.p, d_chunk_diag_.p, d_chunk_rz_.p);
+    k_chunk_factor<<<nchunk, CH_FACTOR_THREADS, CH_FACTOR_SMEM, stream_>>>(P_, d_chunk_M_.p, d_chunk_pack_.p, d_chunk_diag_.p, d_chunk_rz_.p,
+                                                                         coarse_active_ ? d_co_dblk_.p : nullptr,
+                                                                         coarse_active_ ? d_co_ctl_.p : nullptr);
+    if (coarse_active_) {
+      const float* cacc_c = cacc;
+      const double* dblk = d_co_dblk_.p;
+      double* rbuf = d_co_R_.p;
+      double* aci = d_co_aci_.p;
+      unsigned* ctl = d_co_ctl_.p;
+      void* args[] = {(void*)&P_, (void*)&cacc_c, (void*)&dblk, (void*)&rbuf, (void*)&aci, (void*)&ctl, (void*)&nchunk};
+      CU_CHECK(cudaLaunchCooperativeKernel((const void*)k_coarse_invert, dim3(nchunk), dim3(CO_THREADS), args, 0, stream_));
+      k_chunk_z0<<<nchunk, CO_THREADS, 0, stream_>>>(P_, d_co_aci_.p, d_chunk_rz_.p, nchunk);
+    }
     k_chunk_rz<<<1, 32, 0, stream_>>>(P_, d_chunk_rz_.p, nchunk);
     return SQRTBA_OK;
   }
+  int chunk_prec_launches() const { return coarse_active_ ? 5 : 3; }
   void launch_linearize(int robust, double d2, double d3, int force_all) {
     if (cfg_.reserved[7] == 1) k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
     else if (cfg_.reserved[7] == 2) k_linearize_pipe<false><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
@@ -1971,6 +1995,8 @@ class Solver {
     const bool chunk = big && chunk_on();
     A.cpack = chunk ? d_chunk_pack_.p : nullptr;
     A.cdiag = chunk ? d_chunk_diag_.p : nullptr;
+    A.aci = (chunk && coarse_active_) ? d_co_aci_.p : nullptr;
+    A.wvec = (chunk && coarse_active_) ? d_co_w_.p : nullptr;
     const size_t bytes = persist_smem_bytes(persist_stages_, persist_slots_, big, chunk);
     int maxslot = persist_slots_;
     void* args[] = {(void*)&P_, (void*)&A, (void*)&maxslot, (void*)&lam_override, (void*)&use_override};
@@ -2079,7 +2105,7 @@ class Solver {
     launches_ += 2;
     if (chunk_on()) {
       if (int rc = enqueue_chunk_prec()) return rc;
-      launches_ += 3;
+      launches_ += chunk_prec_launches();
     }
     const double tol2 = cfg_.pcg_rtol * cfg_.pcg_rtol;
     const int check = std::max(1, cfg_.pcg_check_every);
@@ -2217,7 +2243,7 @@ class Solver {
         }
         __builtin_ia32_pause();
       }
-      launches_ += STEP_NODES + (chunk_on() ? 3 : 0);
+      launches_ += STEP_NODES + (chunk_on() ? chunk_prec_launches() : 0);
       lm_trials_++;
       cg_iters_total_ = h_ctl_->counters[2];
       if (h_ctl_->counters[0] >= P_.n_win) break;
@@ -2336,6 +2362,7 @@ class Solver {
       st->reserved[0] = use_persist() ? 1.0 : 0.0;           // the PCG solves ran in the persistent cooperative kernel
       st->reserved[1] = (comm_ && peer_ok_) ? 1.0 : 0.0;     // landmark-sharded: in-kernel NVLink exchange available
       st->reserved[2] = persist_grid_;
+      st->reserved[7] = (chunk_on() && coarse_active_) ? 1.0 : 0.0;  // ... with the coarse (second) level
       st->reserved[6] = chunk_on() ? 1.0 : 0.0;              // big window: the 20-pose chunk preconditioner was active
       st->reserved[5] = det_active_ ? 1.0 : 0.0;             // reproducible mode active (pcg_mode = 4 and the problem qualifies)
     }
@@ -2355,6 +2382,7 @@ class Solver {
     d_win_tile_ptr_.release(); d_part_lin_.release(); d_part_qr_.release(); d_part_q_.release();
     d_gbar_.release(); d_part_.release(); d_q3_.release(); d_dq_.release(); d_ptile_.release();
     d_chunk_M_.release(); d_chunk_rz_.release(); d_chunk_pack_.release(); d_chunk_diag_.release();
+    d_co_dblk_.release(); d_co_R_.release(); d_co_aci_.release(); d_co_w_.release(); d_co_ctl_.release();
     d_l_pc_.release(); d_l_qw_.release(); d_l_nv_.release(); d_l_w_.release(); d_l_acc_.release(); d_l_match_.release();
     d_lm_flat_pose_.release(); d_lm_corner_pose_.release(); d_lc_flat_.release(); d_lc_normal_.release(); d_lc_corner_.release();
     d_lc_world_.release(); d_lm_flat_.release(); d_lm_flat_w_.release(); d_lm_corner_.release(); d_lm_corner_w_.release(); d_l_best_.release();
@@ -2413,7 +2441,9 @@ class Solver {
   DBuf<unsigned> d_gbar_;
   DBuf<double> d_part_, d_q3_, d_dq_;
   bool chunk_active_ = false;  // big single window: 20-pose blocks as the PCG preconditioner (sqrtba_chunkprec.cuh)
-  DBuf<double> d_chunk_rz_;
+  bool coarse_active_ = false;  // ... plus the coarse correction over the chunks (second level)
+  DBuf<double> d_chunk_rz_, d_co_dblk_, d_co_R_, d_co_aci_, d_co_w_;
+  DBuf<unsigned> d_co_ctl_;
   DBuf<float> d_chunk_M_, d_chunk_pack_, d_chunk_diag_;
   // lidar pass
   LidarDev lidar_{};
