@@ -25,9 +25,12 @@
 
 namespace sqrtba {
 
+constexpr int CO_MAXCH = 128;              // second level: chunks (2560 free poses); beyond that only the chunk level is used
+constexpr int CO_LD = CO_MAXCH * 6;
+constexpr int CO_THREADS = 128;
 constexpr int CH_LDA = CHB + 1;     // padded row of the shared-memory block (column walks without bank conflicts)
 constexpr int CH_FACTOR_THREADS = 512;
-constexpr size_t CH_FACTOR_SMEM = ((size_t)CHB * CH_LDA + 3 * CHB + 16) * sizeof(double);
+constexpr size_t CH_FACTOR_SMEM = ((size_t)CHB * CH_LDA + 6 * CHB + CH_FACTOR_THREADS + 16) * sizeof(double);
 constexpr int CH_MBLK = 36;                              // one 6x6 block, row-major, contiguous: nine 16-byte vectors
 constexpr size_t CH_MSIZE = (size_t)VSLOT * VSLOT * CH_MBLK;  // floats per chunk: [pose i][pose j][6x6]
 
@@ -130,15 +133,24 @@ __global__ void __launch_bounds__(CTA) k_chunk_blocks(Dev P, float* __restrict__
 }
 
 // One CTA per chunk.  rzpart[chunk] = this chunk's part of r0.z0.
+// The Gauss-Jordan sweep keeps the matrix in REGISTERS (a 5 x 6 tile per thread, 480 of the 512 threads): with the
+// matrix in shared memory every step moved all 14 400 entries through the SM's 128 B/clk shared-memory port (1.2 us per
+// step); now a step writes the pivot row and column (240 doubles), one barrier, and every thread reads 11 of them.
+constexpr int CH_TR = 5, CH_TC = 6;
+constexpr int CH_NTC = CHB / CH_TC;                 // 20 tile columns
+constexpr int CH_TILES = (CHB / CH_TR) * CH_NTC;    // 480
+static_assert(CHB % CH_TR == 0 && CHB % CH_TC == 0 && CH_TILES <= CH_FACTOR_THREADS, "register tiling of the chunk block");
+
 __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const float* __restrict__ M, float* __restrict__ cpack,
                                                                     float* __restrict__ cdiag, double* __restrict__ rzpart,
                                                                     double* __restrict__ dblk, unsigned* __restrict__ co_ctl) {
   extern __shared__ __align__(16) double ch_sm[];
   double* A = ch_sm;                   // [CHB][CH_LDA]
-  double* colk = A + CHB * CH_LDA;     // pivot column of the current step
-  double* rowk = colk + CHB;           // scaled pivot row
-  double* vec = rowk + CHB;            // b_s of the chunk
-  __shared__ int fail;
+  double* colk = A + CHB * CH_LDA;     // [2][CHB] pivot column of the current step (two parities)
+  double* rowk = colk + 2 * CHB;       // [2][CHB] pivot row
+  double* vec = rowk + 2 * CHB;        // b_s of the chunk
+  double* dsc = vec + CHB;             // Jacobi scaling 1 / sqrt(diagonal): the sweep runs on the unit-diagonal matrix
+  double* scr = dsc + CHB;             // [CH_FACTOR_THREADS] reduction scratch
   const int tid = threadIdx.x;
   const int ch = blockIdx.x;
   const WinCtl& c = P.ctl[0];
@@ -147,17 +159,17 @@ __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const
   const int s0 = ch * VSLOT;
   const int ns = min(VSLOT, P.n_slot - s0), n = ns * 6;
   const float* Mc = M + (size_t)ch * CH_MSIZE;
-  // thread -> (column j, rows i0, i0 + RG, ...): no index arithmetic inside the elimination loop
   constexpr int RG = CH_FACTOR_THREADS / 128;
-  static_assert((RG & (RG - 1)) == 0, "row groups: power of two");
   const int j = tid & 127, i0 = tid >> 7;
-  if (tid == 0) fail = 0;
-  if (j < n) {
+  // ---- assemble (a partly filled last chunk is padded with the identity: the sweep always runs over 120 pivots)
+  if (j < CHB) {
     const int bc = j / 6, b = j - bc * 6;
-    for (int r = i0; r < n; r += RG) {
+#pragma unroll 2
+    for (int r = i0; r < CHB; r += RG) {
       const int br = r / 6, a = r - br * 6;
       double v;
-      if (br == bc) {
+      if (r >= n || j >= n) v = (r == j) ? 1.0 : 0.0;
+      else if (br == bc) {
         const int lo = min(a, b), hi = max(a, b);
         v = P.D[(size_t)(s0 + br) * 21 + lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo)] + (r == j ? lam : 0.0);
       } else {  // every pair was added once, at one of the two places
@@ -166,58 +178,142 @@ __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const
       A[r * CH_LDA + j] = v;
     }
   }
-  for (int i = tid; i < n; i += CH_FACTOR_THREADS) vec[i] = P.bs[(size_t)s0 * 6 + i];
-  if (co_ctl && ch == 0 && tid < 2) co_ctl[tid] = 0u;  // grid-barrier counter and failure flag of k_coarse_invert
+  for (int i = tid; i < CHB; i += CH_FACTOR_THREADS) vec[i] = (i < n) ? P.bs[(size_t)s0 * 6 + i] : 0.0;
+  if (co_ctl && ch == 0 && tid < 2 + CO_MAXCH) co_ctl[tid] = 0u;  // failure flag and per-step flags of k_coarse_invert
   __syncthreads();
-  if (dblk && tid < 36) {  // Z^T (chunk matrix) Z: the 6x6 sum of all its 6x6 blocks, in a fixed order
-    const int a = tid / 6, b = tid - a * 6;
-    double sum = 0.0;
-    for (int bi = 0; bi < ns; bi++)
-      for (int bj = 0; bj < ns; bj++) sum += A[(bi * 6 + a) * CH_LDA + bj * 6 + b];
-    dblk[(size_t)ch * 36 + tid] = sum;
-  }
-  __syncthreads();
-  // in-place Gauss-Jordan inversion; the pivots of an SPD matrix are positive
-  for (int k = 0; k < n; k++) {
-    const double piv = A[k * CH_LDA + k];
-    if (!(piv > 0.0) || !isfinite(piv)) {
-      if (tid == 0) fail = 1;
-      break;  // uniform: every thread reads the same pivot
-    }
-    const double pinv = 1.0 / piv;
-    if (tid < n) {
-      colk[tid] = A[tid * CH_LDA + k];
-      rowk[tid] = (tid == k) ? pinv : A[k * CH_LDA + tid] * pinv;
+  if (dblk) {  // Z^T (chunk matrix) Z: the 6x6 sum of all its 6x6 blocks -- 14 partial sums per entry, added in order
+    constexpr int NP = CH_FACTOR_THREADS / 36;
+    if (tid < NP * 36) {
+      const int en = tid % 36, part = tid / 36, a = en / 6, b = en - a * 6;
+      double sum = 0.0;
+      for (int q = part; q < ns * ns; q += NP) {
+        const int bi = q / ns, bj = q - bi * ns;
+        sum += A[(bi * 6 + a) * CH_LDA + bj * 6 + b];
+      }
+      scr[part * 36 + en] = sum;
     }
     __syncthreads();
-    if (j < n) {  // thread = one column, every RG-th row; the pivot row / column cases stay outside the inner loops
-      const double rj = rowk[j];
-      if (j == k) {
-        for (int i = i0; i < n; i += RG)
-          if (i != k) A[i * CH_LDA + k] = -colk[i] * pinv;
-      } else {
-        double* a = A + j;
-#pragma unroll 5
-        for (int i = i0; i < n; i += RG) {
-          const double v = a[i * CH_LDA] - colk[i] * rj;
-          if (i != k) a[i * CH_LDA] = v;
+    if (tid < 36) {
+      double sum = 0.0;
+      for (int part = 0; part < NP; part++) sum += scr[part * 36 + tid];
+      dblk[(size_t)ch * 36 + tid] = sum;
+    }
+    __syncthreads();
+  }
+  // ---- Gauss-Jordan sweep over all pivots; the pivots of an SPD matrix are positive.
+  // The matrix is first scaled to unit diagonal (pivots in (0, 1]).  That makes it safe to fold the special cases of a
+  // sweep step -- pivot row, pivot column, pivot -- into the SAME rank-one update as everything else:
+  //   a_ij <- a_ij - c_i r_j   with  r_j = a_kj / p (j != k),  r_k = 1 + 1/p,  c_i = a_ik (i != k),  c_k = p - 1
+  // gives a_kj / p on the pivot row, -a_ik / p on the pivot column and 1/p at the pivot, without cancellation for p <= 1.
+  // A step is then 30 DFMA per thread and no branches on the position of the pivot (every warp holds a piece of the
+  // pivot column, so any special-casing is paid by all warps).
+  for (int i = tid; i < CHB; i += CH_FACTOR_THREADS) {
+    const double d = A[i * CH_LDA + i];
+    dsc[i] = (d > 0.0 && isfinite(d)) ? rsqrt(d) : 0.0;   // 0: the first pivot check fails -> fallback
+  }
+  __syncthreads();
+  if (j < CHB) {
+    const double dj = dsc[j];
+    for (int r = i0; r < CHB; r += RG) A[r * CH_LDA + j] *= dsc[r] * dj;
+  }
+  __syncthreads();
+  const bool worker = tid < CH_TILES;
+  const int tr = tid / CH_NTC, tc = tid - tr * CH_NTC;
+  double t[CH_TR][CH_TC];
+  if (worker) {
+#pragma unroll
+    for (int a = 0; a < CH_TR; a++)
+#pragma unroll
+      for (int b = 0; b < CH_TC; b++) t[a][b] = A[(tr * CH_TR + a) * CH_LDA + tc * CH_TC + b];
+  }
+  bool failed = false;
+  double* pvs = scr;  // [2][2]: pivot and its reciprocal, by parity
+  for (int k = 0; k < CHB; k++) {
+    double* ck = colk + (k & 1) * CHB;
+    double* rk = rowk + (k & 1) * CHB;
+    const int ik = k - tr * CH_TR, jk = k - tc * CH_TC;  // position of the pivot row / column inside this thread's tile
+    const bool has_row = worker && (unsigned)ik < (unsigned)CH_TR, has_col = worker && (unsigned)jk < (unsigned)CH_TC;
+    if (has_row) {
+#pragma unroll
+      for (int a = 0; a < CH_TR; a++)
+        if (a == ik) {
+#pragma unroll
+          for (int b = 0; b < CH_TC; b++) rk[tc * CH_TC + b] = t[a][b];
         }
-      }
-      if (((k - i0) & (RG - 1)) == 0) A[k * CH_LDA + j] = (j == k) ? pinv : rj;
+    }
+    if (has_col) {
+#pragma unroll
+      for (int b = 0; b < CH_TC; b++)
+        if (b == jk) {
+#pragma unroll
+          for (int a = 0; a < CH_TR; a++) ck[tr * CH_TR + a] = t[a][b];
+        }
+    }
+    if (has_row && has_col) {  // the thread that holds the pivot patches the two special entries behind its own writes
+      double pv = 0.0;
+#pragma unroll
+      for (int a = 0; a < CH_TR; a++)
+#pragma unroll
+        for (int b = 0; b < CH_TC; b++)
+          if (a == ik && b == jk) pv = t[a][b];
+      rk[k] = pv + 1.0;  // times 1/p: r_k = 1 + 1/p
+      ck[k] = pv - 1.0;  // c_k = p - 1
+      pvs[(k & 1) * 2] = pv;
+      pvs[(k & 1) * 2 + 1] = 1.0 / pv;
     }
     __syncthreads();
+    const double piv = pvs[(k & 1) * 2];
+    if (!(piv > 0.0) || !isfinite(piv)) { failed = true; break; }  // uniform: every thread reads the same pivot
+    const double pinv = pvs[(k & 1) * 2 + 1];
+    if (worker) {
+      double cc[CH_TR], rr[CH_TC];
+#pragma unroll
+      for (int a = 0; a < CH_TR; a++) cc[a] = ck[tr * CH_TR + a];
+#pragma unroll
+      for (int b = 0; b < CH_TC; b++) rr[b] = rk[tc * CH_TC + b] * pinv;
+#pragma unroll
+      for (int a = 0; a < CH_TR; a++)
+#pragma unroll
+        for (int b = 0; b < CH_TC; b++) t[a][b] -= cc[a] * rr[b];
+    }
+    // no second barrier: the next step writes the other parity, and nobody reaches the step after it before everyone
+    // has passed the next barrier
   }
   __syncthreads();
-  if (fail) {  // not positive definite in floating point: this chunk falls back to the 6x6 block-Jacobi inverses
-    if (j < n) {
-      const int bc = j / 6;
-      for (int r = i0; r < n; r += RG) {
-        const int br = r / 6;
-        A[r * CH_LDA + j] = (br == bc) ? P.Dinv[(size_t)(s0 + br) * 36 + (r - br * 6) * 6 + (j - bc * 6)] : 0.0;
-      }
+  if (!failed) {
+    if (worker) {
+#pragma unroll
+      for (int a = 0; a < CH_TR; a++)
+#pragma unroll
+        for (int b = 0; b < CH_TC; b++) A[(tr * CH_TR + a) * CH_LDA + tc * CH_TC + b] = t[a][b];
     }
     __syncthreads();
+    if (j < CHB) {  // undo the scaling: inverse of the original block
+      const double dj = dsc[j];
+      for (int r = i0; r < CHB; r += RG) A[r * CH_LDA + j] *= dsc[r] * dj;
+    }
+  } else {  // not positive definite in floating point: this chunk falls back to 6x6 block-Jacobi inverses
+    for (int idx = tid; idx < CHB * CHB; idx += CH_FACTOR_THREADS) A[(idx / CHB) * CH_LDA + (idx % CHB)] = 0.0;
+    __syncthreads();
+    if (tid < ns) {
+      double B6[36], Bi[36];
+      int idx = 0;
+      for (int a = 0; a < 6; a++)
+        for (int b = a; b < 6; b++) {
+          const double v = P.D[(size_t)(s0 + tid) * 21 + idx] + (a == b ? lam : 0.0);
+          B6[a * 6 + b] = v;
+          B6[b * 6 + a] = v;
+          idx++;
+        }
+      if (!spd6_inverse(B6, Bi)) {
+        for (int i = 0; i < 36; i++) Bi[i] = 0.0;
+        for (int i = 0; i < 6; i++) Bi[i * 6 + i] = 1.0 / fmax(fabs(B6[i * 6 + i]), 1e-300);
+      }
+      for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) A[(tid * 6 + a) * CH_LDA + tid * 6 + b] = Bi[a * 6 + b];
+    }
   }
+  __syncthreads();
   // symmetrise, round to the precision the PCG kernel keeps, publish
   float* pk = cpack + (size_t)ch * CH_PACK;
   if (j < CHB) {
@@ -233,9 +329,12 @@ __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const
   double part = 0.0;
   if (tid < n) {
     const int r = tid;
-    double z = (double)(float)A[r * CH_LDA + r] * vec[r];
-    for (int k = 0; k < n; k++)
-      if (k != r) z += (double)(float)(0.5 * (A[r * CH_LDA + k] + A[k * CH_LDA + r])) * vec[k];
+    double z0 = (double)(float)A[r * CH_LDA + r] * vec[r], z1 = 0.0;
+    for (int k = 0; k + 1 < n; k += 2) {
+      if (k != r) z0 += (double)(float)(0.5 * (A[r * CH_LDA + k] + A[k * CH_LDA + r])) * vec[k];
+      if (k + 1 != r) z1 += (double)(float)(0.5 * (A[r * CH_LDA + k + 1] + A[(k + 1) * CH_LDA + r])) * vec[k + 1];
+    }
+    const double z = z0 + z1;  // n is even (6 per pose)
     const size_t e = (size_t)s0 * 6 + r;
     P.z[e] = z;
     P.p[e] = z;
@@ -243,15 +342,14 @@ __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const
   }
   __syncthreads();
   part = warp_sum(part);
-  if ((tid & 31) == 0) colk[tid >> 5] = part;
+  if ((tid & 31) == 0) scr[tid >> 5] = part;
   __syncthreads();
   if (tid == 0) {
-    double t = 0.0;
-    for (int i = 0; i < CH_FACTOR_THREADS / 32; i++) t += colk[i];  // fixed order
-    rzpart[ch] = t;
+    double tsum = 0.0;
+    for (int i = 0; i < CH_FACTOR_THREADS / 32; i++) tsum += scr[i];  // fixed order
+    rzpart[ch] = tsum;
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------- second level (coarse)
 // Block-Jacobi over chunks leaves the coupling BETWEEN chunks -- the smooth, loop-wide error modes -- to CG, and those
@@ -260,13 +358,11 @@ __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const
 // 6 nchunk unknowns (450 on C3).  Z^T S Z is assembled from sums that are already there: its diagonal blocks are the
 // 6x6 block sums of the chunk matrices (k_chunk_factor), block (c, c') the sum of the cross-chunk pair blocks
 // (k_chunk_blocks).  Measured on the KITTI-shaped loop at small lambda: another 3.7x fewer iterations on top of the chunks.
-constexpr int CO_MAXCH = 128;              // chunks (2560 free poses); beyond that only the chunk level is used
-constexpr int CO_LD = CO_MAXCH * 6;
-constexpr int CO_THREADS = 128;
 
-// Cooperative launch, one CTA per chunk = one 6-row block row of the coarse matrix in shared memory.  Block Gauss-Jordan
-// with 6x6 pivots: at step k the owner of row k inverts its pivot block and publishes R = P^-1 row_k; after a grid
-// barrier every other row eliminates its block column k.  nchunk barriers in all.
+// Cooperative launch (co-residency), one CTA per chunk = one 6-row block row of the coarse matrix in shared memory.  Block
+// Gauss-Jordan with 6x6 pivots: at step k the owner of row k inverts its pivot block, publishes R = P^-1 row_k in the
+// step's own buffer and raises the step's flag; every other row waits for that flag (no grid barrier: the critical path
+// is the chain owner k -> owner k+1) and eliminates its block column k.
 __global__ void __launch_bounds__(CO_THREADS) k_coarse_invert(Dev P, const float* __restrict__ Cacc, const double* __restrict__ dblk,
                                                               double* __restrict__ Rbuf, double* __restrict__ aci,
                                                               unsigned* __restrict__ co_ctl, int nchunk) {
@@ -286,7 +382,7 @@ __global__ void __launch_bounds__(CO_THREADS) k_coarse_invert(Dev P, const float
   }
   __syncthreads();
   for (int kb = 0; kb < nchunk; kb++) {
-    double* R = Rbuf + (size_t)(kb & 1) * (6 * CO_LD + 36);
+    double* R = Rbuf + (size_t)kb * (6 * CO_LD + 36);
     if (c == kb) {
       if (tid < 36) Pm[tid] = row[tid / 6][kb * 6 + (tid % 6)];
       if (tid == 0) bad = 0;
@@ -335,28 +431,46 @@ __global__ void __launch_bounds__(CO_THREADS) k_coarse_invert(Dev P, const float
         for (int a = 0; a < 6; a++) { row[a][k] = rk[a]; R[(size_t)a * CO_LD + k] = rk[a]; }
       }
       if (tid < 36) R[6 * CO_LD + tid] = Pinv[tid];
-    }
-    grid_bar(co_ctl, gridDim.x, (unsigned)(kb + 1), tid);  // CO_THREADS == CTA: the same named barrier
-    if (c != kb) {
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(co_ctl + 2 + kb), "r"(1u) : "memory");
+      }
+    } else {
+      if (tid == 0) {
+        while (ld_acquire_gpu(co_ctl + 2 + kb) == 0u) {}
+      }
+      __syncthreads();
       if (tid < 36) { Cc[tid] = row[tid / 6][kb * 6 + (tid % 6)]; Pinv[tid] = __ldcg(R + 6 * CO_LD + tid); }
       __syncthreads();
-      for (int k = tid; k < nc6; k += CO_THREADS) {
+      // all of R this thread needs in flight at once (one L2 round trip), then the arithmetic
+      constexpr int KU = CO_LD / CO_THREADS;
+      double rk[KU][6];
+#pragma unroll
+      for (int u = 0; u < KU; u++) {
+        const int k = tid + u * CO_THREADS;
         const bool pc = k >= kb * 6 && k < kb * 6 + 6;
-        double rk[6];
 #pragma unroll
-        for (int q = 0; q < 6; q++) rk[q] = pc ? Pinv[q * 6 + (k - kb * 6)] : __ldcg(R + (size_t)q * CO_LD + k);
+        for (int q = 0; q < 6; q++) rk[u][q] = (k < nc6 && !pc) ? __ldcg(R + (size_t)q * CO_LD + k) : 0.0;
+      }
 #pragma unroll
-        for (int a = 0; a < 6; a++) {
-          double v = pc ? 0.0 : row[a][k];
+      for (int u = 0; u < KU; u++) {
+        const int k = tid + u * CO_THREADS;
+        if (k < nc6) {
+          const bool pc = k >= kb * 6 && k < kb * 6 + 6;
 #pragma unroll
-          for (int q = 0; q < 6; q++) v -= Cc[a * 6 + q] * rk[q];
-          row[a][k] = v;
+          for (int a = 0; a < 6; a++) {
+            double v = pc ? 0.0 : row[a][k];
+#pragma unroll
+            for (int q = 0; q < 6; q++) v -= Cc[a * 6 + q] * (pc ? Pinv[q * 6 + (k - kb * 6)] : rk[u][q]);
+            row[a][k] = v;
+          }
         }
       }
       __syncthreads();
     }
   }
-  const bool failed = __ldcg(&co_ctl[1]) != 0u;  // written before some barrier every CTA has passed
+  const bool failed = __ldcg(&co_ctl[1]) != 0u;  // written before the flag of a step every CTA has waited for (or by this CTA)
   for (int k = tid; k < nc6; k += CO_THREADS) {
 #pragma unroll
     for (int a = 0; a < 6; a++) aci[(size_t)(c * 6 + a) * nc6 + k] = failed ? 0.0 : row[a][k];

@@ -2902,7 +2902,9 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
 
 // ------------------------------------------------------------------------------------------------ K4/K5: PCG vector ops
 // One CTA owns one window's pose-sized vectors, so dot products are block reductions with no global sync.
-__device__ __forceinline__ void cg_init_body(const Dev& P, int win, int force_all, double* sh) {
+// no_dinv: the chunk preconditioner (sqrtba_chunkprec.cuh) writes z, p and r.z itself afterwards -- the 6x6 inverses were
+// not computed, so start from z = b
+__device__ __forceinline__ void cg_init_body(const Dev& P, int win, int force_all, double* sh, bool no_dinv = false) {
   WinCtl& c = P.ctl[win];
   if (!force_all && c.phase != PH_TRIAL) return;
   const int s0 = P.win_slot_ptr[win], s1 = P.win_slot_ptr[win + 1];
@@ -2910,8 +2912,11 @@ __device__ __forceinline__ void cg_init_body(const Dev& P, int win, int force_al
   for (int e = s0 * 6 + threadIdx.x; e < s1 * 6; e += RCTA) {
     const int s = e / 6, rr = e - s * 6;
     double z = 0.0;
+    if (no_dinv) z = P.bs[e];
+    else {
 #pragma unroll
-    for (int k = 0; k < 6; k++) z += P.Dinv[s * 36 + rr * 6 + k] * P.bs[s * 6 + k];
+      for (int k = 0; k < 6; k++) z += P.Dinv[s * 36 + rr * 6 + k] * P.bs[s * 6 + k];
+    }
     const double b = P.bs[e];
     P.x[e] = 0.0;
     P.res[e] = b;
@@ -2928,15 +2933,15 @@ __device__ __forceinline__ void cg_init_body(const Dev& P, int win, int force_al
     if (c.cg_active) atomicAdd(&P.counters[1], 1);
   }
 }
-__global__ void __launch_bounds__(RCTA) k_cg_init(Dev P, int force_all) {
+__global__ void __launch_bounds__(RCTA) k_cg_init(Dev P, int force_all, int no_dinv) {
   __shared__ double sh[RWARPS];
-  cg_init_body(P, blockIdx.x, force_all, sh);
+  cg_init_body(P, blockIdx.x, force_all, sh, no_dinv != 0);
 }
 
 // Single-window fusion of everything between the landmark QR and the persistent PCG kernel (CUDA-graph macro step):
 // block-Jacobi inverses, CG start vectors, and the zeroing the host used to enqueue as memset nodes (q buffers of the
 // persistent kernel, its grid-barrier counter, the "PCG active" counter).  One CTA (the problem has one window).
-__global__ void __launch_bounds__(RCTA) k_cg_prep(Dev P, double* zero_a, int n_a, double* zero_b, int n_b, unsigned* gbar) {
+__global__ void __launch_bounds__(RCTA) k_cg_prep(Dev P, double* zero_a, int n_a, double* zero_b, int n_b, unsigned* gbar, int no_dinv) {
   __shared__ double sh[RWARPS];
   const WinCtl& c = P.ctl[0];
   if (threadIdx.x == 0) { P.counters[1] = 0; gbar[0] = 0u; gbar[1] = 0u; }
@@ -2944,9 +2949,11 @@ __global__ void __launch_bounds__(RCTA) k_cg_prep(Dev P, double* zero_a, int n_a
   for (int i = threadIdx.x; i < n_b; i += RCTA) zero_b[i] = 0.0;
   if (c.phase != PH_TRIAL) return;
   const double lam = c.lambda;
-  for (int s = threadIdx.x; s < P.n_slot; s += RCTA) dinv_slot(P, s, lam);
+  if (!no_dinv) {
+    for (int s = threadIdx.x; s < P.n_slot; s += RCTA) dinv_slot(P, s, lam);
+  }
   __syncthreads();
-  cg_init_body(P, 0, 0, sh);
+  cg_init_body(P, 0, 0, sh, no_dinv != 0);
 }
 
 __global__ void __launch_bounds__(RCTA) k_cg_step(Dev P, double tol2, int max_iters, int force_all, double lam_override,

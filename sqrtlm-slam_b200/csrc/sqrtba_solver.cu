@@ -790,10 +790,10 @@ class Solver {
         CU_CHECK(d_chunk_M_.ensure((size_t)nchunk * CH_MSIZE + (coarse_active_ ? (size_t)nchunk * nchunk * CH_MBLK : 0)));
         if (coarse_active_) {
           CU_CHECK(d_co_dblk_.ensure((size_t)nchunk * 36));
-          CU_CHECK(d_co_R_.ensure((size_t)2 * (6 * CO_LD + 36)));
+          CU_CHECK(d_co_R_.ensure((size_t)nchunk * (6 * CO_LD + 36)));
           CU_CHECK(d_co_aci_.ensure((size_t)36 * nchunk * nchunk));
           CU_CHECK(d_co_w_.ensure((size_t)6 * nchunk));
-          CU_CHECK(d_co_ctl_.ensure(2));
+          CU_CHECK(d_co_ctl_.ensure(2 + CO_MAXCH));
         }
         CU_CHECK(d_chunk_pack_.ensure((size_t)nchunk * CH_PACK));
         CU_CHECK(d_chunk_diag_.ensure((size_t)nchunk * CHB));
@@ -2098,10 +2098,10 @@ class Solver {
     if (!P_.n_slot) return SQRTBA_OK;
     if (int rc = allreduce(P_.bs, (size_t)P_.n_slot * 27, false)) return rc;  // reduced rhs + block-Jacobi blocks
     if (lidar_active_) { k_lidar_trial_add<<<1, 32, 0, stream_>>>(P_, lidar_); launches_++; }
-    k_dinv<<<cdiv(P_.n_slot, 64), 64, 0, stream_>>>(P_, 0, 0.0);
+    if (!chunk_on()) k_dinv<<<cdiv(P_.n_slot, 64), 64, 0, stream_>>>(P_, 0, 0.0);
     stage_begin(2);
     CU_CHECK(cudaMemsetAsync(P_.counters + 1, 0, sizeof(int), stream_));
-    k_cg_init<<<P_.n_win, RCTA, 0, stream_>>>(P_, 0);
+    k_cg_init<<<P_.n_win, RCTA, 0, stream_>>>(P_, 0, chunk_on() ? 1 : 0);
     launches_ += 2;
     if (chunk_on()) {
       if (int rc = enqueue_chunk_prec()) return rc;
@@ -2164,8 +2164,8 @@ class Solver {
     if (P_.fused) launch_linqr(-1, d2, d3);
     k_trial_begin<<<1, RCTA, 0, stream_>>>(P_);
     launch_qr(0, 0.0);
-    if (P_.pq_shared) k_cg_prep<<<1, RCTA, 0, stream_>>>(P_, d_q3_.p, 3 * KQ * n6, nullptr, 0, d_gbar_.p);
-    else k_cg_prep<<<1, RCTA, 0, stream_>>>(P_, P_.q, n6, d_dq_.p, 2 * n6, d_gbar_.p);
+    if (P_.pq_shared) k_cg_prep<<<1, RCTA, 0, stream_>>>(P_, d_q3_.p, 3 * KQ * n6, nullptr, 0, d_gbar_.p, 0);
+    else k_cg_prep<<<1, RCTA, 0, stream_>>>(P_, P_.q, n6, d_dq_.p, 2 * n6, d_gbar_.p, chunk_on() ? 1 : 0);
     if (chunk_on()) {
       if (int rc = enqueue_chunk_prec()) return rc;
     }
