@@ -269,7 +269,9 @@ class Solver {
     int max_win_slots = 0;
     for (int w = 0; w < n_win; w++) max_win_slots = std::max(max_win_slots, win_slot_ptr[w + 1] - win_slot_ptr[w]);
     const int smallwin = (max_win_slots < 65535) ? 1 : 0;       // window-relative slots fit the 16-bit meta field
-    const int pq_shared = (max_win_slots <= MAXSLOT) ? 1 : 0;  // p/q of a window fit the matvec CTA's shared memory
+    // p/q of a window fit the matvec CTA's shared memory -- unless it is ONE window with enough keyframes for the chunked
+    // vector phase of global BA to pay (owner CTAs, two-level preconditioner): big_window_min_slots_
+    const int pq_shared = (max_win_slots <= MAXSLOT && !(n_win == 1 && max_win_slots >= big_window_min_slots())) ? 1 : 0;
     if (h_obs_slot_.ensure(n_obs, !plan_only_) || h_obs_lp_.ensure(n_obs, !plan_only_)) { err_ = "pinned host allocation failed"; return SQRTBA_ERR_ALLOC; }
     int* obs_slot = h_obs_slot_.p;
     unsigned* obs_lp = h_obs_lp_.p;
@@ -1881,6 +1883,13 @@ class Solver {
   }
   // the chunk preconditioner is live for this solve: decided per problem, and only the persistent kernel applies it
   bool chunk_on() const { return chunk_active_ && use_persist(); }
+  static int big_window_min_slots() {
+    static const int v = [] {
+      const char* e = std::getenv("SQRTBA_BIG_MIN_SLOTS");
+      return e ? std::max(2, std::atoi(e)) : MAXSLOT + 1;
+    }();
+    return v;
+  }
   // off-diagonal blocks of every chunk -> [all-reduce] -> inverse + CG start vectors + r0.z0
   int enqueue_chunk_prec() {
     int nchunk = (P_.n_slot + VSLOT - 1) / VSLOT;
