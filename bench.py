@@ -184,7 +184,8 @@ WORKLOAD = ("C4: batch of independent KITTI-00-shaped stereo local-BA windows (C
 
 def bench_config(args, n_obs_rank=None, nobs_all=None):
     cfg = {"workload": WORKLOAD, "windows_per_gpu": args.windows_per_gpu, "l2_policy": "inputs_larger_than_l2",
-           "pcg_rtol": 1e-9, "pcg_mode": args.pcg_mode}
+           "pcg_rtol": "auto (1e-7 for windows of up to 128 free keyframes, 1e-9 for global BA; include/sqrtba.h)",
+           "pcg_mode": args.pcg_mode}
     if n_obs_rank is not None:
         cfg["observations_per_gpu"] = n_obs_rank
         cfg["observations_total"] = int(nobs_all)

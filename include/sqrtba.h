@@ -44,7 +44,11 @@ typedef enum {
 
 typedef struct {
   int32_t device;            /* CUDA device ordinal */
-  double pcg_rtol;           /* PCG stops when sqrt(r'M^-1 r / r0'M^-1 r0) <= pcg_rtol (default 1e-9) */
+  double pcg_rtol;           /* PCG stops when sqrt(r'M^-1 r / r0'M^-1 r0) <= pcg_rtol.  0 (default) = automatic: 1e-7 for
+                                two-pass local BA on windows of up to 128 free keyframes (single or batched), 1e-9 for
+                                global BA and for handles with a third pass (third_pass_iters > 0: the fork's schedule,
+                                lidar edges with central-difference Jacobians); the value in effect is stats.reserved[4].  The result tolerances (identical trial sequence and
+                                outlier flags, cost 1e-6, pose RMS 1e-5 m) hold unchanged up to 1e-6 on local windows */
   int32_t pcg_max_iters;     /* hard cap per linear solve (default 2000; a safety net -- global BA needs a few hundred) */
   int32_t third_pass_iters;  /* 0 = ORB-SLAM2 two-pass 5+10 (default); 20 = this fork's extra pass (g2oOptimizer.cc:1113) */
   int32_t pcg_mode;          /* 0 = auto: single-window problems run the whole PCG solve in ONE persistent cooperative
@@ -103,7 +107,8 @@ typedef struct {
   double ms_linearize, ms_qr, ms_pcg, ms_backsub, ms_cost; /* per-stage device time (events) */
   double ms_matvec;         /* sum of matvec kernel time (multi-launch mode; 0 in persistent mode) */
   double reserved[8];       /* [0] 1 = the persistent PCG kernel ran, [1] 1 = in-kernel NVLink exchange was active,
-                               [2] grid of the persistent kernel, [5] 1 = reproducible mode (pcg_mode 4) was active,
+                               [2] grid of the persistent kernel, [4] PCG tolerance in effect,
+                               [5] 1 = reproducible mode (pcg_mode 4) was active,
                                [6] 1 = global BA ran PCG with the chunk preconditioner (one 120x120 block of the reduced
                                system per 20 consecutive keyframes; the persistent kernel's default for big windows),
                                [7] 1 = ... plus the additive coarse correction Z (Z^T S Z)^-1 Z^T over the chunks */

@@ -31,6 +31,7 @@ class Stats(C.Structure):
         d["persistent_pcg"] = int(self.reserved[0])
         d["peer_exchange"] = int(self.reserved[1])
         d["reproducible"] = int(self.reserved[5])
+        d["pcg_rtol"] = float(self.reserved[4])
         d["chunk_precond"] = int(self.reserved[6])
         d["coarse_level"] = int(self.reserved[7])
         return d
@@ -117,7 +118,7 @@ class SqrtBAError(RuntimeError):
 class SqrtBA:
     """Thin owner of one sqrtba_handle.  Method names follow the C ABI."""
 
-    def __init__(self, device: int = 0, pcg_rtol: float = 1e-9, pcg_max_iters: int = 2000, third_pass_iters: int = 0,
+    def __init__(self, device: int = 0, pcg_rtol: float = 0.0, pcg_max_iters: int = 2000, third_pass_iters: int = 0,
                  pcg_mode: int = 0, pcg_check_every: int = 4, stage_timing: bool = False,
                  general_matvec: bool = False, pipe_stages: int = 0, host_threads: int = 0,
                  no_reorder: bool = False, pipe_slots: int = 0, plain_qr: bool = False, qr_variant: int = 0):

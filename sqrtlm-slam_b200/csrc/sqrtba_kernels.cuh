@@ -38,6 +38,7 @@ struct WinCtl {
   double lambda, ni, cur_chi, ini_chi, tmp_chi, rho;
   unsigned long long maxdiag_bits;  // landmark-side max |diag(Hll)| as ordered bits (non-negative doubles)
   double rz, rz0;
+  double tol2;  // square of the PCG tolerance of this pass (set by k_pass_init; kernels launched with tol2 <= 0 read it here)
   int iter, qmax, nbad, phase;
   int max_iter, pass, cg_active, cg_iters;
   int trace_len, need_restore, lin_count;
@@ -2454,6 +2455,7 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
     st_sh[0] = c.rz;
     st_sh[1] = c.rz0;
     st_sh[2] = use_override ? lam_override : c.lambda;
+    st_sh[3] = A.tol2 > 0.0 ? A.tol2 : (c.tol2 > 0.0 ? c.tol2 : 1e-18);  // tolerance of this pass (WinCtl::tol2)
   }
   const int n6 = P.n_slot * 6;
   int n = 0, abase = 0;
@@ -2643,7 +2645,7 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
       }
       PROFP(2)
       const double rzn = cta_sum(d, red_sh, 1, lane, wid);
-      const bool last = !(rzn > A.tol2 * rz0) || it + 1 >= A.max_iters;
+      const bool last = !(rzn > st_sh[3] * rz0) || it + 1 >= A.max_iters;
       if (tid == 0) {
         if (last) { sig[2] = n; __threadfence_block(); sig[1] = 1; }
         else sig[0] = it + 1;
@@ -2856,7 +2858,7 @@ __global__ void __maxnreg__(120) k_pcg_persist(Dev P, PcgArgs A, int maxslot, do
     }
     double rzn = rz - 2.0 * alpha * s2 + alpha * alpha * s3;  // r'.z' after the step (exact in exact arithmetic)
     if (!(rzn > 0.0)) rzn = 0.0;
-    const bool last = !(rzn > A.tol2 * rz0) || it + 1 >= A.max_iters;
+    const bool last = !(rzn > st_sh[3] * rz0) || it + 1 >= A.max_iters;
     if (tid == 0) {
       if (last) { sig[2] = n; __threadfence_block(); sig[1] = 1; }
       else sig[0] = it + 1;
@@ -2963,6 +2965,7 @@ __global__ void __launch_bounds__(RCTA) k_cg_step(Dev P, double tol2, int max_it
   WinCtl& c = P.ctl[win];
   if (!c.cg_active) return;
   const double lam = force_all ? lam_override : c.lambda;
+  if (!(tol2 > 0.0)) tol2 = c.tol2 > 0.0 ? c.tol2 : 1e-18;  // tolerance of this pass
   const int e0 = P.win_slot_ptr[win] * 6, e1 = P.win_slot_ptr[win + 1] * 6;
   // reproducible mode (det_grid = grid of the matvec launch): q of the window = the partial vectors of the matvec CTAs
   // that own its tiles, in CTA order.  CTA c owns tiles [n_tile c / G, n_tile (c+1) / G): tile t belongs to
@@ -3302,7 +3305,7 @@ __global__ void k_terminate(Dev P) {
 }
 
 // start of one optimize(n) call: SparseOptimizer::optimize + the iteration==0 re-initialisation of lambda
-__global__ void k_pass_init(Dev P, int max_iter, int pass, int robust) {
+__global__ void k_pass_init(Dev P, int max_iter, int pass, int robust, double tol2) {
   const int win = blockIdx.x * blockDim.x + threadIdx.x;
   if (win >= P.n_win) return;
   WinCtl& c = P.ctl[win];
@@ -3313,6 +3316,7 @@ __global__ void k_pass_init(Dev P, int max_iter, int pass, int robust) {
   c.max_iter = max_iter;
   c.pass = pass;
   c.robust = robust;
+  c.tol2 = tol2;
   c.need_restore = 0;
   c.cg_active = 0;
   c.maxdiag_bits = 0ull;
