@@ -98,7 +98,7 @@ def test_hot_kernels_carry_the_blackwell_instructions(pkg):
         if m:
             fn = m.group(1)
             continue
-        for k in ("UBLKCP", "UBLKPF", "SYNCS", "LDGSTS", "DFMA"):
+        for k in ("UBLKCP", "UBLKPF", "SYNCS", "LDGSTS", "DFMA", "REDG.E.ADD.F32x4", "STL", "LDL"):
             if k in line:
                 cnt[fn][k] += 1
 
@@ -113,3 +113,10 @@ def test_hot_kernels_carry_the_blackwell_instructions(pkg):
         assert c["LDGSTS"] >= 14 and c["UBLKPF"] >= 1 and c["DFMA"] > 300, c
     for c in kernels("k_linearize_pipeILb1E"):
         assert c["LDGSTS"] >= 2 and c["UBLKPF"] >= 1 and c["DFMA"] > 150, c
+    # global-BA preconditioner: the pair blocks leave the SMs as 16-byte vector reductions; the Gauss-Jordan sweep of a
+    # chunk block keeps its 5x6 tile in registers (no local-memory traffic in the sweep: the only stack use is the 6x6
+    # fallback, which spills nothing) and the chunk instantiation of the PCG kernel spills nothing either
+    for c in kernels("k_chunk_blocks"):
+        assert c["REDG.E.ADD.F32x4"] >= 18, c
+    for c in kernels("k_pcg_persistILi2ELb1ELb0ELb1E") + kernels("k_pcg_persistILi2ELb1ELb1ELb1E"):
+        assert c["STL"] == 0 and c["LDL"] == 0 and c["UBLKCP"] >= 1, c

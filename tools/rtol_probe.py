@@ -8,7 +8,7 @@ from test_gpu_parity import pose_rms
 prob = pkg.synth.make_problem(17, 200, 1, 8000, 9.0, stereo=True, loop=True, cand_halfwidth=15)
 for robust in (False, True):
     ref = refba.RefBA(prob); ref.solve_global(10, robust)
-    for rtol in (1e-9, 1e-10, 1e-11, 1e-12, 1e-13):
+    for rtol in tuple(float(x) for x in __import__("os").environ.get("RTOLS", "1e-9,1e-10,1e-11,1e-12,1e-13").split(",")):
         ba = pkg.SqrtBA(pcg_rtol=rtol, pcg_max_iters=2000)
         ba.set_problem(prob)
         st = ba.solve_global(10, robust)
