@@ -45,9 +45,10 @@ typedef enum {
 typedef struct {
   int32_t device;            /* CUDA device ordinal */
   double pcg_rtol;           /* PCG stops when sqrt(r'M^-1 r / r0'M^-1 r0) <= pcg_rtol.  0 (default) = automatic: 1e-7 for
-                                two-pass local BA on windows of up to 128 free keyframes (single or batched), 1e-9 for
-                                global BA and for handles with a third pass (third_pass_iters > 0: the fork's schedule,
-                                lidar edges with central-difference Jacobians); the value in effect is stats.reserved[4].  The result tolerances (identical trial sequence and
+                                two-pass local BA on windows of up to 128 free keyframes (single or batched), 1e-8 for
+                                global BA with its two-level preconditioner (1e-9 with the 6x6 blocks), 1e-9 for handles
+                                with a third pass (third_pass_iters > 0: the fork's schedule, lidar edges with
+                                central-difference Jacobians); the value in effect is stats.reserved[4].  The result tolerances (identical trial sequence and
                                 outlier flags, cost 1e-6, pose RMS 1e-5 m) hold unchanged up to 1e-6 on local windows */
   int32_t pcg_max_iters;     /* hard cap per linear solve (default 2000; a safety net -- global BA needs a few hundred) */
   int32_t third_pass_iters;  /* 0 = ORB-SLAM2 two-pass 5+10 (default); 20 = this fork's extra pass (g2oOptimizer.cc:1113) */
