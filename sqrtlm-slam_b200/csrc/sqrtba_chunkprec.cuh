@@ -34,15 +34,26 @@ constexpr size_t CH_FACTOR_SMEM = ((size_t)CHB * CH_LDA + 6 * CHB + CH_FACTOR_TH
 constexpr int CH_MBLK = 36;                              // one 6x6 block, row-major, contiguous: nine 16-byte vectors
 constexpr size_t CH_MSIZE = (size_t)VSLOT * VSLOT * CH_MBLK;  // floats per chunk: [pose i][pose j][6x6]
 
+// Any SPD preconditioner gives the same PCG solution to tolerance, so a block that is one LM iteration old only costs
+// iterations, never correctness.  A level is rebuilt on the first trial of a pass and then every `refresh`-th outer
+// iteration; retries after a rejected trial (only lambda changed) reuse it as well.  Grid-uniform.
+__device__ __forceinline__ bool prec_is_stale_ok(const WinCtl& c, int refresh) {
+  return refresh > 1 && (c.qmax > 0 || (c.iter % refresh) != 0);
+}
+
 // One CTA per tile, one warp per item, one lane per observation (the layout of k_backsub).  The blocks are accumulated
 // in FP32 with vector reductions (REDG.ADD.F32x4: nine per pair instead of 36 scalar FP64 ones -- the kernel is bound by
 // the L2 atomic units); FP32 is what the PCG kernel keeps of the inverse anyway, and k_chunk_factor falls back to the 6x6
 // blocks should a chunk ever lose definiteness.
-__global__ void __launch_bounds__(CTA) k_chunk_blocks(Dev P, float* __restrict__ M, float* __restrict__ Cacc, int nchunk) {
+__global__ void __launch_bounds__(CTA) k_chunk_blocks(Dev P, float* __restrict__ M, float* __restrict__ Cacc, int nchunk,
+                                                      int refresh_chunk, int refresh_coarse) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const TileInfo ti = P.tiles[blockIdx.x];
   if (ti.is_long || wid >= ti.nitem) return;
   if (P.ctl[ti.win].phase != PH_TRIAL) return;
+  const bool skip_chunk = prec_is_stale_ok(P.ctl[ti.win], refresh_chunk);
+  if (Cacc != nullptr && prec_is_stale_ok(P.ctl[ti.win], refresh_coarse)) Cacc = nullptr;
+  if (skip_chunk && Cacc == nullptr) return;
   const int cnt = tile_item_cnt(ti, wid), start = tile_item_start(ti, wid);
   const bool act = lane < cnt;
   const int o = start + (act ? lane : 0);
@@ -86,7 +97,7 @@ __global__ void __launch_bounds__(CTA) k_chunk_blocks(Dev P, float* __restrict__
     for (int i = 0; i < 18; i++) Gj[i] = __shfl_down_sync(FULL, G[i], d);
     const bool pair = live && lane + d < sg.end && sj >= 0 && sj != slot;
     const int chj = pair ? sj / VSLOT : -1;
-    const bool valid = pair && (chj == ch || Cacc != nullptr);
+    const bool valid = pair && (chj == ch ? !skip_chunk : Cacc != nullptr);
     if (valid) {
       float v[36];
 #pragma unroll
@@ -143,7 +154,8 @@ static_assert(CHB % CH_TR == 0 && CHB % CH_TC == 0 && CH_TILES <= CH_FACTOR_THRE
 
 __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const float* __restrict__ M, float* __restrict__ cpack,
                                                                     float* __restrict__ cdiag, double* __restrict__ rzpart,
-                                                                    double* __restrict__ dblk, unsigned* __restrict__ co_ctl) {
+                                                                    double* __restrict__ dblk, unsigned* __restrict__ co_ctl,
+                                                                    int refresh_chunk) {
   extern __shared__ __align__(16) double ch_sm[];
   double* A = ch_sm;                   // [CHB][CH_LDA]
   double* colk = A + CHB * CH_LDA;     // [2][CHB] pivot column of the current step (two parities)
@@ -155,6 +167,8 @@ __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const
   const int ch = blockIdx.x;
   const WinCtl& c = P.ctl[0];
   if (c.phase != PH_TRIAL) return;
+  if (co_ctl && ch == 0 && tid < 2 + CO_MAXCH) co_ctl[tid] = 0u;  // failure flag and per-step flags of k_coarse_invert
+  if (prec_is_stale_ok(c, refresh_chunk)) return;  // (the coarse level is never fresher than the chunk level: dblk stays too)
   const double lam = c.lambda;
   const int s0 = ch * VSLOT;
   const int ns = min(VSLOT, P.n_slot - s0), n = ns * 6;
@@ -179,7 +193,6 @@ __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const
     }
   }
   for (int i = tid; i < CHB; i += CH_FACTOR_THREADS) vec[i] = (i < n) ? P.bs[(size_t)s0 * 6 + i] : 0.0;
-  if (co_ctl && ch == 0 && tid < 2 + CO_MAXCH) co_ctl[tid] = 0u;  // failure flag and per-step flags of k_coarse_invert
   __syncthreads();
   if (dblk) {  // Z^T (chunk matrix) Z: the 6x6 sum of all its 6x6 blocks -- 14 partial sums per entry, added in order
     constexpr int NP = CH_FACTOR_THREADS / 36;
@@ -325,30 +338,8 @@ __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const
       else pk[(r * (r - 1)) / 2 + j] = f;
     }
   }
-  // CG start of the chunk with the same (rounded) operator the PCG kernel applies: z0 = p0 = M^-1 b_s
-  double part = 0.0;
-  if (tid < n) {
-    const int r = tid;
-    double z0 = (double)(float)A[r * CH_LDA + r] * vec[r], z1 = 0.0;
-    for (int k = 0; k + 1 < n; k += 2) {
-      if (k != r) z0 += (double)(float)(0.5 * (A[r * CH_LDA + k] + A[k * CH_LDA + r])) * vec[k];
-      if (k + 1 != r) z1 += (double)(float)(0.5 * (A[r * CH_LDA + k + 1] + A[(k + 1) * CH_LDA + r])) * vec[k + 1];
-    }
-    const double z = z0 + z1;  // n is even (6 per pose)
-    const size_t e = (size_t)s0 * 6 + r;
-    P.z[e] = z;
-    P.p[e] = z;
-    part = vec[r] * z;
-  }
-  __syncthreads();
-  part = warp_sum(part);
-  if ((tid & 31) == 0) scr[tid >> 5] = part;
-  __syncthreads();
-  if (tid == 0) {
-    double tsum = 0.0;
-    for (int i = 0; i < CH_FACTOR_THREADS / 32; i++) tsum += scr[i];  // fixed order
-    rzpart[ch] = tsum;
-  }
+  (void)rzpart;
+  (void)vec;
 }
 
 // ---------------------------------------------------------------------------------------------- second level (coarse)
@@ -365,12 +356,16 @@ __global__ void __launch_bounds__(CH_FACTOR_THREADS) k_chunk_factor(Dev P, const
 // is the chain owner k -> owner k+1) and eliminates its block column k.
 __global__ void __launch_bounds__(CO_THREADS) k_coarse_invert(Dev P, const float* __restrict__ Cacc, const double* __restrict__ dblk,
                                                               double* __restrict__ Rbuf, double* __restrict__ aci,
-                                                              unsigned* __restrict__ co_ctl, int nchunk) {
+                                                              unsigned* __restrict__ co_ctl, int nchunk, int refresh) {
   __shared__ double row[6][CO_LD];
   __shared__ double Pm[36], Pinv[36], Cc[36];
   __shared__ int bad;
   const int tid = threadIdx.x, c = blockIdx.x;
   if (P.ctl[0].phase != PH_TRIAL) return;  // grid-uniform
+  // Any symmetric positive semi-definite coarse operator keeps the preconditioner SPD, so a slightly stale one only costs
+  // iterations, never correctness: refresh on the first trial of a pass and then every `refresh`-th outer iteration
+  // (retries after a rejected trial only change lambda and reuse it as well).
+  if (prec_is_stale_ok(P.ctl[0], refresh)) return;  // grid-uniform
   const int nc6 = nchunk * 6;
   for (int k = tid; k < nc6; k += CO_THREADS) {
     const int c2 = k / 6, b = k - c2 * 6;
@@ -477,25 +472,34 @@ __global__ void __launch_bounds__(CO_THREADS) k_coarse_invert(Dev P, const float
   }
 }
 
-// CG start with both levels: z0 = p0 = (chunk part, written by k_chunk_factor) + Z (Z^T S Z)^-1 Z^T b_s; r0.z0 per chunk
-__global__ void __launch_bounds__(CO_THREADS) k_chunk_z0(Dev P, const double* __restrict__ aci, double* __restrict__ rzpart, int nchunk) {
+// CG start with the operator the PCG kernel applies: z0 = p0 = (packed FP32 chunk inverse) b_s + Z (Z^T S Z)^-1 Z^T b_s;
+// r0.z0 per chunk.  Reads the PUBLISHED inverses, so it is the same whether they were rebuilt for this trial or not.
+__global__ void __launch_bounds__(CO_THREADS) k_chunk_z0(Dev P, const float* __restrict__ cpack, const float* __restrict__ cdiag,
+                                                         const double* __restrict__ aci, double* __restrict__ rzpart, int nchunk) {
   __shared__ double w[CO_LD];
   __shared__ double ysh[4][6];
+  __shared__ double bsh[CHB];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, ch = blockIdx.x;
   if (P.ctl[0].phase != PH_TRIAL) return;
   const int nc6 = nchunk * 6;
-  for (int k = tid; k < nc6; k += CO_THREADS) {
-    const int c2 = k / 6, a = k - c2 * 6;
-    const int ns = min(VSLOT, P.n_slot - c2 * VSLOT);
-    double sum = 0.0;
-    for (int sl = 0; sl < ns; sl++) sum += P.bs[(size_t)(c2 * VSLOT + sl) * 6 + a];
-    w[k] = sum;
+  const int n = min(VSLOT, P.n_slot - ch * VSLOT) * 6;
+  if (tid < CHB) bsh[tid] = (tid < n) ? P.bs[(size_t)ch * CHB + tid] : 0.0;
+  if (aci != nullptr) {
+    for (int k = tid; k < nc6; k += CO_THREADS) {
+      const int c2 = k / 6, a = k - c2 * 6;
+      const int ns = min(VSLOT, P.n_slot - c2 * VSLOT);
+      double sum = 0.0;
+      for (int sl = 0; sl < ns; sl++) sum += P.bs[(size_t)(c2 * VSLOT + sl) * 6 + a];
+      w[k] = sum;
+    }
   }
   __syncthreads();
   double acc[6] = {0, 0, 0, 0, 0, 0};
-  for (int k = tid; k < nc6; k += CO_THREADS) {
+  if (aci != nullptr) {
+    for (int k = tid; k < nc6; k += CO_THREADS) {
 #pragma unroll
-    for (int a = 0; a < 6; a++) acc[a] += aci[(size_t)(ch * 6 + a) * nc6 + k] * w[k];
+      for (int a = 0; a < 6; a++) acc[a] += aci[(size_t)(ch * 6 + a) * nc6 + k] * w[k];
+    }
   }
 #pragma unroll
   for (int a = 0; a < 6; a++) {
@@ -504,15 +508,28 @@ __global__ void __launch_bounds__(CO_THREADS) k_chunk_z0(Dev P, const double* __
     if (lane == 0) ysh[wid][a] = acc[a];
   }
   __syncthreads();
-  const int n = min(VSLOT, P.n_slot - ch * VSLOT) * 6;
   double part = 0.0;
   if (tid < n) {
-    const int a = tid % 6;
+    const int r = tid, a = tid % 6;
+    const float* pk = cpack + (size_t)ch * CH_PACK;
+    double z0 = (double)cdiag[(size_t)ch * CHB + r] * bsh[r], z1 = 0.0;
+    const float* row = pk + (r * (r - 1)) / 2;
+    int k = 0;
+    for (; k + 1 < r; k += 2) {
+      z0 += (double)row[k] * bsh[k];
+      z1 += (double)row[k + 1] * bsh[k + 1];
+    }
+    if (k < r) z0 += (double)row[k] * bsh[k];
+    int idx = ((r + 1) * r) / 2 + r;
+    for (k = r + 1; k < n; k++) {
+      z1 += (double)pk[idx] * bsh[k];
+      idx += k;
+    }
+    const double z = (z0 + z1) + ((ysh[0][a] + ysh[1][a]) + (ysh[2][a] + ysh[3][a]));
     const size_t e = (size_t)ch * CHB + tid;
-    const double z = P.z[e] + ((ysh[0][a] + ysh[1][a]) + (ysh[2][a] + ysh[3][a]));
     P.z[e] = z;
     P.p[e] = z;
-    part = P.bs[e] * z;
+    part = bsh[r] * z;
   }
   part = warp_sum(part);
   __syncthreads();

@@ -1912,7 +1912,16 @@ class Solver {
     const size_t m_floats = (size_t)nchunk * CH_MSIZE, c_floats = coarse_active_ ? (size_t)nchunk * nchunk * CH_MBLK : 0;
     float* cacc = coarse_active_ ? d_chunk_M_.p + m_floats : nullptr;
     CU_CHECK(cudaMemsetAsync(d_chunk_M_.p, 0, (m_floats + c_floats) * sizeof(float), stream_));
-    k_chunk_blocks<<<P_.n_tile, CTA, 0, stream_>>>(P_, d_chunk_M_.p, cacc, nchunk);
+    // how old a level of the preconditioner may be, in outer LM iterations (1 = rebuilt for every trial).  Measured on C3,
+    // one GPU: both levels every 2nd iteration cost 8 CG iterations of 490 and save five block builds (1.9 ms), chunk
+    // inversions and coarse inversions (0.54 ms): 96.6 -> 84.7 ms; every 3rd: 507 iterations, 83.4 ms; a coarse level that
+    // is never refreshed within the pass: 1148 iterations (lambda falls by 3^9 over the pass and sits on its diagonal)
+    static const int refresh_chunk_env = [] { const char* e = std::getenv("SQRTBA_CHUNK_REFRESH"); return e ? std::max(1, std::atoi(e)) : 2; }();
+    static const int refresh_coarse_env = [] { const char* e = std::getenv("SQRTBA_COARSE_REFRESH"); return e ? std::max(1, std::atoi(e)) : 2; }();
+    const int refresh_chunk = refresh_chunk_env;
+    int refresh = std::max(refresh_coarse_env, refresh_chunk);  // the coarse level is built from the chunk level's sums
+    if (refresh % refresh_chunk != 0) refresh = refresh_chunk * ((refresh + refresh_chunk - 1) / refresh_chunk);
+    k_chunk_blocks<<<P_.n_tile, CTA, 0, stream_>>>(P_, d_chunk_M_.p, cacc, nchunk, refresh_chunk, refresh);
     if (comm_) {  // every rank adds its landmarks' pairs; the sum is the same bits everywhere
       const int rc = g_nccl.AllReduce(d_chunk_M_.p, d_chunk_M_.p, m_floats + c_floats, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm_, stream_);
       if (rc != 0) {
@@ -1922,21 +1931,22 @@ class Solver {
     }
     k_chunk_factor<<<nchunk, CH_FACTOR_THREADS, CH_FACTOR_SMEM, stream_>>>(P_, d_chunk_M_.p, d_chunk_pack_.p, d_chunk_diag_.p, d_chunk_rz_.p,
                                                                          coarse_active_ ? d_co_dblk_.p : nullptr,
-                                                                         coarse_active_ ? d_co_ctl_.p : nullptr);
+                                                                         coarse_active_ ? d_co_ctl_.p : nullptr, refresh_chunk);
     if (coarse_active_) {
       const float* cacc_c = cacc;
       const double* dblk = d_co_dblk_.p;
       double* rbuf = d_co_R_.p;
       double* aci = d_co_aci_.p;
       unsigned* ctl = d_co_ctl_.p;
-      void* args[] = {(void*)&P_, (void*)&cacc_c, (void*)&dblk, (void*)&rbuf, (void*)&aci, (void*)&ctl, (void*)&nchunk};
+      void* args[] = {(void*)&P_, (void*)&cacc_c, (void*)&dblk, (void*)&rbuf, (void*)&aci, (void*)&ctl, (void*)&nchunk, (void*)&refresh};
       CU_CHECK(cudaLaunchCooperativeKernel((const void*)k_coarse_invert, dim3(nchunk), dim3(CO_THREADS), args, 0, stream_));
-      k_chunk_z0<<<nchunk, CO_THREADS, 0, stream_>>>(P_, d_co_aci_.p, d_chunk_rz_.p, nchunk);
     }
+    k_chunk_z0<<<nchunk, CO_THREADS, 0, stream_>>>(P_, d_chunk_pack_.p, d_chunk_diag_.p, coarse_active_ ? d_co_aci_.p : nullptr,
+                                                   d_chunk_rz_.p, nchunk);
     k_chunk_rz<<<1, 32, 0, stream_>>>(P_, d_chunk_rz_.p, nchunk);
     return SQRTBA_OK;
   }
-  int chunk_prec_launches() const { return coarse_active_ ? 5 : 3; }
+  int chunk_prec_launches() const { return coarse_active_ ? 5 : 4; }
   void launch_linearize(int robust, double d2, double d3, int force_all) {
     if (cfg_.reserved[7] == 1) k_linearize<<<P_.n_tile, CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
     else if (cfg_.reserved[7] == 2) k_linearize_pipe<false><<<cdiv(P_.n_tile, LIN_TPB), CTA, 0, stream_>>>(P_, robust, d2, d3, force_all);
