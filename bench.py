@@ -184,7 +184,7 @@ WORKLOAD = ("C4: batch of independent KITTI-00-shaped stereo local-BA windows (C
 
 def bench_config(args, n_obs_rank=None, nobs_all=None):
     cfg = {"workload": WORKLOAD, "windows_per_gpu": args.windows_per_gpu, "l2_policy": "inputs_larger_than_l2",
-           "pcg_rtol": "auto (1e-7 for windows of up to 128 free keyframes, 1e-9 for global BA; include/sqrtba.h)",
+           "pcg_rtol": "auto (1e-7 for two-pass local BA on windows of up to 128 free keyframes, 1e-8 for global BA; include/sqrtba.h)",
            "pcg_mode": args.pcg_mode}
     if n_obs_rank is not None:
         cfg["observations_per_gpu"] = n_obs_rank
@@ -616,7 +616,7 @@ def main():
                           "note": "the operand stores {x/z, y/z, 1/z, w} + Q1 (104 B per free-pose observation) and rebuilds "
                                   "the 3x6 pose block in registers: DRAM traffic is about half of the algorithmic figure, and "
                                   "the kernel is bound by the per-tile dependency chain (issue slots 58 % busy at 20 warps/SM, "
-                                  "profiles/r02_matvec_compactJ_ncu_full.txt), no longer by HBM"},
+                                  "profiles/r02_matvec_final_ncu_full.txt), no longer by HBM"},
                 "note": "achieved = SURVEY 8(d)'s 216 B per free-pose stereo observation (Jp 3x6 + Q1 3x3, FP64) x the "
                         "launch's observations / time, as in round 1; observations of fixed keyframes have no pose columns",
                 "other_kernels_ms": {"k_linearize": ms_lin, "k_qr": ms_qr},

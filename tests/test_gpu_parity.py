@@ -386,14 +386,23 @@ def test_stop_flag_and_errors(pkg, synth):
     h.close()
 
 
-def test_repeatable_after_reset(ba, synth):
+# The next tests compare two GPU runs of the SAME problem (a reset, graph against plain launches, kernel variants).  Their
+# sums are re-ordered by atomics, so PCG stops at slightly different points and the runs agree to about the PCG tolerance
+# times the step: they pin the tolerance (1e-10) instead of inheriting the automatic one, which is chosen against the
+# ORACLE's tolerances, not against 1e-9.
+TIGHT = 1e-10
+
+
+def test_repeatable_after_reset(pkg, synth):
     prob = synth.small_window(2, n_points=300)
+    ba = pkg.SqrtBA(pcg_rtol=TIGHT)
     ba.set_problem(prob)
     ba.solve_local()
     a = ba.poses().copy()
     ba.reset_state()
     ba.solve_local()
     np.testing.assert_allclose(ba.poses(), a, rtol=0, atol=1e-9)  # atomics reorder sums: not bit-identical
+    ba.close()
 
 
 def test_graph_step_equals_plain_launches(pkg, synth):
@@ -402,7 +411,7 @@ def test_graph_step_equals_plain_launches(pkg, synth):
     for prob, glob in ((synth.config_c0(3), False), (big_window_problem(synth, seed=29, n_kf=140, n_points=3000), True)):
         out = []
         for mode in (0, 3):
-            h = pkg.SqrtBA(pcg_mode=mode)
+            h = pkg.SqrtBA(pcg_mode=mode, pcg_rtol=TIGHT)
             h.set_problem(prob)
             st = h.solve_global(6, True) if glob else h.solve_local()
             assert st["persistent_pcg"] == 1
@@ -458,7 +467,7 @@ def test_fused_linearize_qr_variant(pkg, synth):
     for mode in ("single", "batch", "big"):
         out = []
         for variant in (0, 7):
-            h = pkg.SqrtBA(qr_variant=variant)
+            h = pkg.SqrtBA(qr_variant=variant, pcg_rtol=TIGHT)
             if mode == "single":
                 h.set_problem(wins[0])
                 h.solve_local()
