@@ -57,7 +57,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
 
 HOST_LIB = os.path.join(HERE, "libsqrtba_host.so")
 HOST_SOURCES = [os.path.join(HERE, "host", f) for f in ("sqrtbaOptimizer.cc", "harness.cc")]
-HOST_DEPS = HOST_SOURCES + [os.path.join(HERE, "host", f) for f in ("Optimizer.h", "map_types.h", "host_pool.h")]
+HOST_DEPS = HOST_SOURCES + [os.path.join(HERE, "host", f) for f in ("Optimizer.h", "map_types.h", "host_pool.h", "map_mirror.h")]
 
 
 def build_host(force: bool = False) -> str:

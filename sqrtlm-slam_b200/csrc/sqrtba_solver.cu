@@ -1889,7 +1889,7 @@ class Solver {
   // A handle with a third pass (the fork's schedule: 20 more iterations at the minimum, lidar edges with central-difference
   // Jacobians of step 1e-9, g2oOptimizer.cc:979-1117) keeps 1e-9 throughout: finite differences of step 1e-9 turn a 1e-8
   // difference of the state that enters the pass into per-trial cost differences above 1e-6 (tests/test_gpu_lidar.py).
-  // Global BA with the two-level preconditioner: 1e-8.  Full C3 against the oracle (tools/rtol_probe_c3.py): pose RMS
+  // Global BA with the two-level preconditioner: 1e-8.  Full C3 against the reference algorithm's exact solve (tools/rtol_probe_c3.py): pose RMS
   // 1.6e-7 / 2.0e-7 / 2.4e-7 / 5.2e-7 m at 1e-9 / 1e-8 / 1e-7 / 1e-6, identical trial sequences, 553 / 490 / 431 / 366
   // iterations -- the preconditioned residual of a strong preconditioner is close to the energy norm of the error.  The
   // 6x6 blocks (pcg_mode 5, sharded runs without peer access) keep 1e-9.

@@ -116,6 +116,9 @@ class sqrtbaOptimizer {
   void static ApplyLocalResult(KeyFrame* pKF, Map* pMap, const std::vector<double>& pose_qt,
                                const std::vector<double>& point_xyz, const std::vector<unsigned char>& outlier);
   void static GatherGlobal(const std::vector<KeyFrame*>& vpKF, const std::vector<MapPoint*>& vpMP, FlatProblem& out);
+  // incremental observation mirror (host/map_mirror.h): attach to an existing map / switch off again
+  void static AttachMirror(Map* pMap);
+  void static DetachMirror();
 };
 
 }  // namespace ORB_SLAM2

@@ -7,6 +7,9 @@
 #include <memory>
 
 #include "Optimizer.h"
+#include <atomic>
+#include <chrono>
+#include <thread>
 
 using namespace ORB_SLAM2;
 
@@ -358,6 +361,99 @@ void hh_pose_opt_batch(hh_frame** fs, int n, int32_t* inliers) {
 void hh_frame_get(hh_frame* f, float* Tcw16, uint8_t* outlier) {
   for (int i = 0; i < 16; i++) Tcw16[i] = f->frame.mTcw.at<float>(i / 4, i % 4);
   for (int i = 0; i < f->frame.N; i++) outlier[i] = f->frame.mvbOutlier[i] ? 1 : 0;
+}
+
+
+// ---- incremental observation mirror (host/map_mirror.h): attach / detach, mutations through the map's own methods (which
+// carry the hook lines), consistency of the mirror with the map, a concurrent stress run and the cost of the two paths
+void hh_mirror_attach(hh_map* m) { sqrtbaOptimizer::AttachMirror(&m->map); }
+void hh_mirror_detach() { sqrtbaOptimizer::DetachMirror(); }
+int hh_mirror_points() { return (int)sqrtba::MapMirror::Global().NumPoints(); }
+// a new keypoint of keyframe kf observing map point mp (MapPoint::AddObservation + KeyFrame::AddMapPoint)
+void hh_add_observation(hh_map* m, int kf, int mp, float u, float v, float ur, int octave) {
+  KeyFrame* k = m->kfs[kf].get();
+  MapPoint* p = m->mps[mp].get();
+  cv::KeyPoint kp;
+  kp.pt.x = u; kp.pt.y = v; kp.octave = octave;
+  const size_t idx = k->mvKeysUn.size();
+  k->mvKeysUn.push_back(kp);
+  k->mvuRight.push_back(ur);
+  k->mvpMapPoints.push_back(p);
+  p->AddObservation(k, idx);
+}
+void hh_erase_observation(hh_map* m, int kf, int mp) {
+  m->kfs[kf]->EraseMapPointMatch(m->mps[mp].get());
+  m->mps[mp]->EraseObservation(m->kfs[kf].get());
+}
+void hh_set_point_bad(hh_map* m, int mp) { m->mps[mp]->SetBadFlag(); }
+// number of map points whose mirrored list differs from MapPoint::GetObservations() (order included); -1: unknown point
+int hh_mirror_mismatches(hh_map* m) {
+  std::vector<MapPoint*> mps = m->map.GetAllMapPoints();
+  std::vector<size_t> ptr;
+  std::vector<sqrtba::MapMirror::Obs> rec;
+  if (!sqrtba::MapMirror::Global().Snapshot(mps.data(), mps.size(), ptr, rec)) return -1;
+  int bad = 0;
+  for (size_t i = 0; i < mps.size(); i++) {
+    const std::map<KeyFrame*, size_t> obs = mps[i]->GetObservations();
+    bool same = obs.size() == ptr[i + 1] - ptr[i];
+    size_t k = ptr[i];
+    if (same)
+      for (auto& kv : obs) {
+        if (rec[k].kf != (const void*)kv.first || rec[k].idx != kv.second) { same = false; break; }
+        k++;
+      }
+    bad += same ? 0 : 1;
+  }
+  return bad;
+}
+// writers add / erase observations of disjoint slices of the map points through the hooked methods while one reader
+// keeps taking snapshots; returns the number of snapshots taken (the caller checks hh_mirror_mismatches afterwards)
+int hh_mirror_stress(hh_map* m, int n_writers, int rounds) {
+  std::atomic<bool> done(false);
+  std::atomic<int> snaps(0);
+  std::vector<MapPoint*> mps = m->map.GetAllMapPoints();
+  std::thread reader([&] {
+    std::vector<size_t> ptr;
+    std::vector<sqrtba::MapMirror::Obs> rec;
+    while (!done.load()) {
+      if (sqrtba::MapMirror::Global().Snapshot(mps.data(), mps.size(), ptr, rec)) snaps++;
+    }
+  });
+  std::vector<std::thread> ws;
+  const int nk = (int)m->kfs.size();
+  for (int w = 0; w < n_writers; w++)
+    ws.emplace_back([&, w] {
+      unsigned rng = 12345u + 977u * (unsigned)w;
+      for (int r = 0; r < rounds; r++)
+        for (size_t i = (size_t)w; i < mps.size(); i += (size_t)n_writers) {
+          rng = rng * 1664525u + 1013904223u;
+          KeyFrame* k = m->kfs[(rng >> 8) % nk].get();
+          if ((rng >> 4) & 1) mps[i]->AddObservation(k, (size_t)(rng >> 20) % std::max<size_t>(1, k->mvKeysUn.size()));
+          else mps[i]->EraseObservation(k);
+        }
+    });
+  for (auto& t : ws) t.join();
+  done.store(true);
+  reader.join();
+  return snaps.load();
+}
+// the window-selection markers are per-call stamps (mnBALocalForKF == current keyframe id means "already taken",
+// g2oOptimizer.cc:713-775): selecting the same window twice needs them cleared in between
+void hh_reset_markers(hh_map* m) {
+  for (auto& k : m->kfs) { k->mnBALocalForKF = ~0ul; k->mnBAFixedForKF = ~0ul; }
+  for (auto& p : m->mps) p->mnBALocalForKF = ~0ul;
+}
+// microseconds per gather of the local window of keyframe kf (best of reps), with whatever path is active
+double hh_time_gather(hh_map* m, int kf, int reps) {
+  double best = 1e30;
+  sqrtbaOptimizer::FlatProblem f;
+  for (int r = 0; r < reps; r++) {
+    hh_reset_markers(m);
+    const auto t0 = std::chrono::steady_clock::now();
+    sqrtbaOptimizer::GatherLocalWindow(m->kfs[kf].get(), f);
+    best = std::min(best, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+  }
+  return best;
 }
 
 }  // extern "C"

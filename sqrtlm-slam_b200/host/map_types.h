@@ -13,6 +13,8 @@
 #include <set>
 #include <vector>
 
+#include "map_mirror.h"   // the hook lines below are the ones INTEGRATION.md adds to the reference's MapPoint.cc
+
 #define CV_32F 5
 namespace cv {
 struct Point2f { float x = 0, y = 0; };
@@ -157,7 +159,24 @@ class MapPoint {
   cv::Mat GetWorldPos() { std::unique_lock<std::mutex> l(mMutexPos); return mWorldPos.clone(); }
   void SetWorldPos(const cv::Mat& P) { std::unique_lock<std::mutex> l(mMutexPos); P.copyTo(mWorldPos); }
   std::map<KeyFrame*, size_t> GetObservations() { std::unique_lock<std::mutex> l(mMutexFeatures); return mObservations; }
-  void EraseObservation(KeyFrame* pKF) { std::unique_lock<std::mutex> l(mMutexFeatures); mObservations.erase(pKF); }
+  void AddObservation(KeyFrame* pKF, size_t idx) {  // MapPoint.cc:178-189
+    std::unique_lock<std::mutex> l(mMutexFeatures);
+    if (mObservations.count(pKF)) return;
+    mObservations[pKF] = idx;
+    sqrtba::MapMirror::Global().OnAddObservation(this, pKF, idx);   // <- hook
+  }
+  void EraseObservation(KeyFrame* pKF) {            // MapPoint.cc:191-215
+    std::unique_lock<std::mutex> l(mMutexFeatures);
+    mObservations.erase(pKF);
+    sqrtba::MapMirror::Global().OnEraseObservation(this, pKF);      // <- hook
+  }
+  void SetBadFlag() {                               // MapPoint.cc:228-246
+    std::unique_lock<std::mutex> l(mMutexFeatures);
+    mbBad = true;
+    mObservations.clear();
+    sqrtba::MapMirror::Global().OnClearObservations(this);          // <- hook
+  }
+  ~MapPoint() { sqrtba::MapMirror::Global().OnDeletePoint(this); }
   bool isBad() { return mbBad; }
   int GetIndexInKeyFrame(KeyFrame* pKF) {  // MapPoint.h:137, MapPoint.cc:493-500
     std::unique_lock<std::mutex> l(mMutexFeatures);

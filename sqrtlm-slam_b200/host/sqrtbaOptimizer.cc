@@ -15,6 +15,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
+#include <cstddef>
 #include <cstdint>
 #include <cstdio>
 #include <list>
@@ -25,6 +27,7 @@
 #include "../../include/sqrtba.h"
 #include "../csrc/sqrtba_sim3.cuh"  // g2o::Sim3's product / inverse restated (host build of the device arithmetic)
 #include "host_pool.h"
+#include "map_mirror.h"
 
 namespace ORB_SLAM2 {
 
@@ -156,7 +159,42 @@ void parallel_ranges(size_t n, int n_thr, F f) {   // f(part, begin, end) over n
   tl_pool.ranges(n, n_thr, f);
 }
 
+// With the incremental mirror switched on (host/map_mirror.h: the map's mutation sites keep flat per-point lists up to
+// date) the lists are read from it -- same order, same content, no std::map copies; a point the mirror does not know
+// sends the whole call back to the map copies.
+bool fill_obs_cache_from_mirror(const std::vector<MapPoint*>& mps, ObsCache& c) {
+  sqrtba::MapMirror& mm = sqrtba::MapMirror::Global();
+  if (!mm.enabled() || mps.empty()) return false;
+  // a snapshot is ~0.25 us per point (one shard lock, one hash lookup, one small copy): a few threads saturate it
+  const int T = std::min(4, host_threads(mps.size() / 4));
+  std::vector<std::vector<size_t>> ptr(T);
+  std::vector<std::vector<sqrtba::MapMirror::Obs>> rec(T);
+  std::vector<uint8_t> ok(T, 1);
+  parallel_ranges(mps.size(), T, [&](int t, size_t a, size_t b) {
+    ok[t] = mm.Snapshot(mps.data() + a, b - a, ptr[t], rec[t]) ? 1 : 0;
+  });
+  for (int t = 0; t < T; t++)
+    if (!ok[t]) return false;
+  size_t total = 0;
+  for (auto& r : rec) total += r.size();
+  c.ptr.assign(1, 0);
+  c.ptr.reserve(mps.size() + 1);
+  c.rec.clear();
+  c.rec.reserve(total);
+  static_assert(sizeof(ObsRec) == sizeof(sqrtba::MapMirror::Obs) && offsetof(ObsRec, idx) == offsetof(sqrtba::MapMirror::Obs, idx),
+                "the mirror's records are copied as they are");
+  c.rec.resize(total);
+  size_t base = 0;
+  for (int t = 0; t < T; t++) {
+    for (size_t i = 1; i < ptr[t].size(); i++) c.ptr.push_back(base + ptr[t][i]);
+    if (!rec[t].empty()) std::memcpy((void*)(c.rec.data() + base), rec[t].data(), rec[t].size() * sizeof(ObsRec));
+    base += rec[t].size();
+  }
+  return c.ptr.size() == mps.size() + 1;
+}
+
 void fill_obs_cache(const std::vector<MapPoint*>& mps, ObsCache& c) {
+  if (fill_obs_cache_from_mirror(mps, c)) return;
   const int T = host_threads(mps.size());
   std::vector<std::vector<ObsRec>> part(T);
   std::vector<std::vector<size_t>> cnt(T);
@@ -797,6 +835,30 @@ static void to_flat(const Gathered& g, sqrtbaOptimizer::FlatProblem& out) {
   for (KeyFrame* kf : g.kfs) out.kf_ids.push_back(kf->mnId);
   for (MapPoint* mp : g.mps) out.mp_ids.push_back(mp->mnId);
 }
+// Switch the incremental observation mirror on for a map that already exists: one pass over its points (the last time
+// their std::maps are copied), after which the hook lines in MapPoint keep it current (host/map_mirror.h).
+void sqrtbaOptimizer::AttachMirror(Map* pMap) {
+  sqrtba::MapMirror& mm = sqrtba::MapMirror::Global();
+  mm.Enable(false);
+  mm.Clear();
+  const std::vector<MapPoint*> mps = pMap->GetAllMapPoints();
+  parallel_ranges(mps.size(), host_threads(mps.size()), [&](int, size_t a, size_t b) {
+    std::vector<sqrtba::MapMirror::Obs> obs;
+    for (size_t i = a; i < b; i++) {
+      if (!mps[i]) continue;
+      const std::map<KeyFrame*, size_t> m = mps[i]->GetObservations();
+      obs.clear();
+      for (auto& kv : m) obs.push_back(sqrtba::MapMirror::Obs{kv.first, kv.second});
+      mm.SetPoint(mps[i], obs);
+    }
+  });
+  mm.Enable(true);
+}
+void sqrtbaOptimizer::DetachMirror() {
+  sqrtba::MapMirror::Global().Enable(false);
+  sqrtba::MapMirror::Global().Clear();
+}
+
 void sqrtbaOptimizer::GatherLocalWindow(KeyFrame* pKF, FlatProblem& out) {
   Gathered g;
   gather_local_window(pKF, g);

@@ -60,6 +60,15 @@ def lib():
                                         C.c_double, C.c_double]
         L.hh_pose_opt_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, ip]
         L.hh_frame_get.argtypes = [C.c_void_p, fp, up]
+        L.hh_mirror_attach.argtypes = [C.c_void_p]
+        L.hh_reset_markers.argtypes = [C.c_void_p]
+        L.hh_add_observation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
+        L.hh_erase_observation.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hh_set_point_bad.argtypes = [C.c_void_p, C.c_int]
+        L.hh_mirror_mismatches.argtypes = [C.c_void_p]
+        L.hh_mirror_stress.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hh_time_gather.restype = C.c_double
+        L.hh_time_gather.argtypes = [C.c_void_p, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -242,11 +251,49 @@ class MockMap:
         L.hh_set_lidar_config(self.h, int(ld.use_flat), int(ld.use_corner), ld.distance_sq_threshold, ld.flat_weight,
                               ld.corner_weight)
 
+    # ---- incremental observation mirror (host/map_mirror.h)
+    def mirror_attach(self):
+        lib().hh_mirror_attach(self.h)
+
+    @staticmethod
+    def mirror_detach():
+        lib().hh_mirror_detach()
+
+    @staticmethod
+    def mirror_points() -> int:
+        return int(lib().hh_mirror_points())
+
+    def add_observation(self, kf, mp, u, v, ur=-1.0, octave=0):
+        lib().hh_add_observation(self.h, int(kf), int(mp), float(u), float(v), float(ur), int(octave))
+
+    def erase_observation(self, kf, mp):
+        lib().hh_erase_observation(self.h, int(kf), int(mp))
+
+    def set_point_bad(self, mp):
+        lib().hh_set_point_bad(self.h, int(mp))
+
+    def mirror_mismatches(self) -> int:
+        return int(lib().hh_mirror_mismatches(self.h))
+
+    def mirror_stress(self, n_writers=4, rounds=3) -> int:
+        return int(lib().hh_mirror_stress(self.h, int(n_writers), int(rounds)))
+
+    def time_gather(self, kf, reps=5) -> float:
+        L = lib()
+        set_options(True, True)
+        return float(L.hh_time_gather(self.h, int(kf), int(reps)))
+
+    def reset_markers(self):
+        """Clear the per-call window-selection stamps so that the same local window can be selected again."""
+        lib().hh_reset_markers(self.h)
+
     def gather(self, kf=-1, stereo_edges=True):
         """The flat problem the adapter builds for LocalBundleAdjustment(kf) (kf >= 0) or for the whole map (-1),
         without solving it -- needs no GPU.  Returns a dict of arrays in the layout of sqrtba_set_problem + the ids."""
         L = lib()
         set_options(stereo_edges, True)
+        if kf >= 0:
+            self.reset_markers()
         sz = np.zeros(3, np.int32)
         L.hh_gather(self.h, kf, _i(sz))
         nk, nm, no = (int(v) for v in sz)
