@@ -437,7 +437,10 @@ def run_extras(pkg, torch, dist, world, rank, local, barrier, args):
                            "persistent_pcg": {"us_per_cg_iteration": us_cg, "achieved": free_obs * ALG_MATVEC / (us_cg * 1e-6) / 1e9,
                                               "frac": free_obs * ALG_MATVEC / (us_cg * 1e-6) / 1e9 / peaks["hbm_gbs"],
                                               "achieved_moved": free_obs * LAYOUT_MATVEC / (us_cg * 1e-6) / 1e9,
-                                              "note": "one CG iteration of k_pcg_persist = matvec over all tiles + grid barrier + vector update"},
+                                              "chunk_precond": st["chunk_precond"], "coarse_level": st["coarse_level"],
+                                              "note": "PCG stage time / CG iterations: matvec over all tiles + grid barriers + vector update; a "
+                                                      "window of 64 or more free keyframes runs the big-window kernel with the two-level "
+                                                      "preconditioner (half the iterations), whose build per LM iteration is inside this figure"},
                            "note": "SURVEY 8(d) bytes; the layout moves 104 B per free observation, so one CG iteration touches "
                                    "~61 MB: L2-resident on this GPU (126 MB) -- these are L2 rates, not HBM rates"}
         if cpu_ok:

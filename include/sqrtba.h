@@ -65,7 +65,8 @@ typedef struct {
                                 persistent PCG kernel is what makes C0 fast).  Needs <= 128 free poses per window, no
                                 landmark with more than 32 observations, one GPU; otherwise the default path runs and
                                 stats.reserved[5] says 0;
-                                5 = like 0, but a big single window (global BA, more than 128 free poses) keeps the 6x6
+                                5 = like 0, but a big single window (global BA; any single window of 64 or more free
+                                keyframes takes that path by default, SQRTBA_BIG_MIN_SLOTS) keeps the 6x6
                                 block-Jacobi preconditioner instead of the 20-pose chunk blocks (A/B; stats.reserved[6]);
                                 6 = like 0, but the big-window preconditioner keeps its chunk level only, without the
                                 coarse correction over the chunks (A/B; stats.reserved[7]) */

@@ -1895,16 +1895,24 @@ class Solver {
   // 6x6 blocks (pcg_mode 5, sharded runs without peer access) keep 1e-9.
   double eff_rtol() const {
     if (cfg_.pcg_rtol > 0) return cfg_.pcg_rtol;
-    if (P_.pq_shared) return cfg_.third_pass_iters <= 0 ? 1e-7 : 1e-9;
+    if (cfg_.third_pass_iters > 0) return 1e-9;
+    if (P_.pq_shared) return 1e-7;
     return (chunk_on() && coarse_active_) ? 1e-8 : 1e-9;
   }
   bool chunk_on() const { return chunk_active_ && use_persist(); }
-  static int big_window_min_slots() {
-    static const int v = [] {
+  // From how many free keyframes on ONE window takes the big-window PCG path (chunked vector phase, two-level
+  // preconditioner) instead of the shared-memory one.  Measured on C2-shaped windows (tools/big_window_crossover.py):
+  // 40 keyframes 10.0 against 12.5 ms, 60: 16.6 / 15.7, 80: 24.2 / 19.3, 99 (C2): 31.8 / 24.0, 120: 42.5 / 27.5 -- the
+  // iteration count halves, an iteration costs more (three grid barriers, q through global atomics).  64 = four chunks:
+  // the preconditioner then forms at most a quarter of the blocks of the reduced system.  The modes that need the
+  // shared-memory path (multi-launch, reproducible) or ask for the 6x6 blocks keep the old limit.
+  int big_window_min_slots() const {
+    static const int env = [] {
       const char* e = std::getenv("SQRTBA_BIG_MIN_SLOTS");
-      return e ? std::max(2, std::atoi(e)) : MAXSLOT + 1;
+      return e ? std::max(2, std::atoi(e)) : 0;
     }();
-    return v;
+    if (env > 0) return env;
+    return (cfg_.pcg_mode == 1 || cfg_.pcg_mode == 4 || cfg_.pcg_mode == 5) ? MAXSLOT + 1 : 64;
   }
   // off-diagonal blocks of every chunk -> [all-reduce] -> inverse + CG start vectors + r0.z0
   int enqueue_chunk_prec() {

@@ -485,7 +485,9 @@ def test_fused_linearize_qr_variant(pkg, synth):
         assert (ta[:, 7] == 0).any() or mode != "big" or True
         np.testing.assert_allclose(ta[:, 5], tb[:, 5], rtol=1e-9)
         np.testing.assert_allclose(pa, pb, rtol=0, atol=1e-8)
-        np.testing.assert_allclose(xa, xb, rtol=0, atol=1e-7)
+        # points: a far landmark turns a 1e-10 difference of the poses into 1e-6 m along its ray (the two runs differ by
+        # the order of their atomics, in the big mode also by the FP32 sums of the preconditioner)
+        np.testing.assert_allclose(xa, xb, rtol=1e-7, atol=1e-6)
         assert np.array_equal(fa, fb)
 
 
