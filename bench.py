@@ -276,6 +276,25 @@ def single_window_leg(pkg, prob, local, label, reps=5):
     return out, res
 
 
+def seeds_median_leg(pkg, local, make, seeds=(0, 1, 2, 3, 4)):
+    """median over seeds 0-4 (device time of the two-pass solve, best of 3 after a warm-up each)."""
+    ba = pkg.SqrtBA(device=local)
+    ms, iters = [], []
+    for seed in seeds:
+        prob = make(seed)
+        ba.set_problem(prob)
+        t = []
+        for _ in range(4):
+            ba.reset_state()
+            st = ba.solve_local()
+            t.append(st["ms_total"])
+        ms.append(min(t[1:]))
+        iters.append(len(ba.trace()) / (ms[-1] * 1e-3))
+    ba.close()
+    return {"seeds": list(seeds), "ms_per_local_ba": [float(x) for x in ms], "ms_per_local_ba_median": float(np.median(ms)),
+            "lm_iters_per_s_median": float(np.median(iters))}
+
+
 def oracle_local(prob, threads):
     from oracle import refba
     r = refba.RefBA(prob, threads=threads)
@@ -409,10 +428,13 @@ def run_extras(pkg, torch, dist, world, rank, local, barrier, args):
             if cpu_ok:
                 dt, ref = oracle_local(prob, 1)
                 ok, cost, t_rms, r_rms = parity_report(*res, *ref, prob.pose_fixed == 0)
+                dta, _ = oracle_local(prob, cores)
                 leg["cpu_baseline"] = {"value": len(ref[0]) * prob.n_obs / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                        "ms_per_local_ba": 1e3 * dt, "lm_iters_per_s": len(ref[0]) / dt,
+                                       "ms_per_local_ba_all_cores": 1e3 * dta, "all_cores": cores,
                                        "sample": "the same window, full two-pass local BA"}
                 leg["parity_vs_oracle"] = {"ok": ok, "cost_rel_err_max": cost, "pose_t_rms_m": t_rms, "pose_r_rms_rad": r_rms}
+            leg["seeds_0_4"] = seeds_median_leg(pkg, local, pkg.synth.config_c0 if key == "single_window" else pkg.synth.config_c1)
             out[key] = leg
         # ---- C2
         prob = pkg.synth.config_c2(0)
