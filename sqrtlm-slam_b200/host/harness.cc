@@ -419,6 +419,7 @@ int hh_mirror_stress(hh_map* m, int n_writers, int rounds) {
       if (sqrtba::MapMirror::Global().Snapshot(mps.data(), mps.size(), ptr, rec)) snaps++;
     }
   });
+  while (snaps.load() == 0) std::this_thread::yield();  // the reader is running before the writers start
   std::vector<std::thread> ws;
   const int nk = (int)m->kfs.size();
   for (int w = 0; w < n_writers; w++)
